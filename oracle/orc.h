@@ -1,0 +1,201 @@
+/*
+ * oracle/orc.h -- CPU oracle for the RANSAC pose-estimation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it, and only as the checker / CPU baseline.
+ *
+ * What it is: a dependency-free plain-C restatement of the reference's
+ *   src/PnPsolver.cpp, src/Sim3Solver.cpp, src/MLPnPsolver.cpp and
+ *   Thirdparty/DBoW2/DUtils/Random.cpp:47-50
+ * following the reference function by function (each function cites file:line).
+ *
+ * PARITY UNPINNED for every Eigen-backed step: the reference cannot be compiled
+ * here (it needs Eigen, OpenCV C++ headers and Pangolin, none installed, no
+ * network) and ships no tests or golden vectors.  Eigen calls
+ * (SelfAdjointEigenSolver, bdcSvd().solve, JacobiSVD, inverse(), LDLT,
+ * FullPivHouseholderQR::rank, Quaternion::toRotationMatrix) are restated by the
+ * published algorithm class they implement (cyclic Jacobi eigen-solver,
+ * one-sided Jacobi SVD with Eigen's rank threshold, cofactor inverse, ...).
+ * What IS pinned: the glibc rand() stream and the draw-without-replacement idiom
+ * (known answers in tests/golden/), ground-truth recovery on noise-free data,
+ * cv2.solvePnP(SOLVEPNP_EPNP) for n>=6, numpy eigh/svd/lstsq on the same
+ * matrices, and a numpy emulation of the three mixed-precision scoring
+ * expressions.
+ *
+ * Arithmetic contract shared with the CUDA kernels (DESIGN.md "arithmetic
+ * contract"): only + - * / sqrt in IEEE double/float, no FMA contraction
+ * (-ffp-contract=off here, -fmad=false there), identical operation order.  For
+ * 4-point EPnP this is a hard requirement.
+ */
+#ifndef ORC_H
+#define ORC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ RNG (R01) */
+void orc_rng_seed(unsigned seed);             /* DUtils::Random::SeedRand(int), Random.cpp:33-36 */
+int orc_random_int(int min, int max);         /* DUtils::Random::RandomInt, Random.cpp:47-50 */
+/* H draws of k distinct indices out of [0,n) with the reference's
+ * vAvailableIndices idiom (PnPsolver.cpp:125-138, Sim3Solver.cpp:136-149,
+ * MLPnPsolver.cpp:76-96).  srand(seed) first.  out is H*k uint32. */
+void orc_index_table(unsigned seed, int n, int k, int H, uint32_t *out);
+
+/* ------------------------------------------------------------ small dense solves */
+/* symmetric eigen-solve, eigenvalues ascending, eigenvectors = columns of v
+ * (restates Eigen::SelfAdjointEigenSolver as used at PnPsolver.cpp:311,380,469,
+ * Sim3Solver.cpp:238-241, MLPnPsolver.cpp:359).  a is n*n row-major, upper
+ * triangle read, destroyed. */
+void orc_jacobi_eig_d(int n, double *a, double *w, double *v);
+void orc_jacobi_eig_f(int n, float *a, float *w, float *v);
+/* minimum-norm least squares of an m x k system through a one-sided Jacobi SVD
+ * with Eigen's rank threshold (restates A.bdcSvd(ThinU|ThinV).solve(b),
+ * PnPsolver.cpp:531,559,590).  L row-major m*k, m<=8, k<=6. */
+void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x);
+/* closed-form cofactor inverse (restates Matrix3d::inverse(), PnPsolver.cpp:331) */
+void orc_inv3_d(const double m[9], double out[9]);
+/* orthogonal polar factor U*V^T of a 3x3 (restates JacobiSVD U*V^T,
+ * MLPnPsolver.cpp:511-512,570-571) */
+void orc_polar3_d(const double a[9], double r[9]);
+/* rank of a 3x3 by full-pivot Householder QR with Eigen's threshold
+ * (restates FullPivHouseholderQR<Matrix3d>::rank(), MLPnPsolver.cpp:347,354) */
+int orc_rank3_fullpiv_d(const double a[9]);
+/* LDL^T solve of a symmetric 6x6 (restates Eigen::LDLT::solve, MLPnPsolver.cpp:705-706) */
+void orc_ldlt6_solve_d(const double a[36], const double g[6], double x[6]);
+
+/* --------------------------------------------------------------- RANSAC set-up */
+typedef struct {
+    double prob;
+    int min_inliers;
+    int max_its;
+    int min_set;
+    float eps;
+    float th2;
+} orc_ransac_params;
+
+/* PnPsolver::SetRansacParameters (PnPsolver.cpp:58-94) / MLPnPsolver.cpp:185-220.
+ * Returns adjusted minInliers and iteration count. */
+void orc_pnp_ransac_setup(int n, const orc_ransac_params *p, int *min_inl, int *max_its);
+/* Sim3Solver::SetRansacParameters (Sim3Solver.cpp:87-111) */
+void orc_sim3_ransac_setup(int n, double prob, int min_inliers, int max_its_in, int *max_its);
+
+/* ------------------------------------------------------------------- PnPsolver */
+typedef struct {
+    int n;                 /* valid correspondences (mvP2D.size()) */
+    const float *p3d;      /* [n][3] mvP3Dw */
+    const float *p2d;      /* [n][2] mvP2D */
+    const float *sigma2;   /* [n]    mvSigma2 */
+    double fx, fy, cx, cy; /* PnPsolver.hpp:71 keeps them double */
+} orc_pnp_problem;
+
+#define ORC_FLAG_STALE_ROWS 1   /* Q1: reproduce colwise().sum() over all allocated rows */
+#define ORC_FLAG_EXHAUSTIVE 2   /* evaluate all H hypotheses (no early return), for throughput + per-hyp parity */
+#define ORC_FLAG_MLPNP_DISCARD_REFINE 4 /* Q6: reproduce MLPnP Refine() not storing its pose */
+
+typedef struct {
+    int ok;           /* return value of iterate() */
+    int no_more;      /* bNoMore */
+    int n_inliers;    /* nInliers */
+    int best_hyp;     /* index of the hypothesis that set mBestTcw (strict >, first max), -1 if none */
+    int refined;      /* 1 if T is the refined pose */
+    int n_hyp;        /* hypotheses actually evaluated */
+    int n_refines;    /* Refine() calls made */
+    int n_failed_refines;
+    int best_count;   /* mnBestInliers when the call ended */
+    float T[16];      /* row-major 4x4 [R t]; Sim3: mBestRotation/mBestTranslation, scale kept in `scale` */
+    float scale;      /* Sim3 only */
+} orc_result;
+
+/* PnPsolver::iterate as called the first time (PnPsolver.cpp:102-191; the `||`
+ * at :119 makes the first call consume the whole budget).  table is H*min_set
+ * indices.  mask (n bytes, compact index, NOT scattered to keypoint indices)
+ * receives the returned inlier set.  Optional per-hypothesis outputs (may be
+ * NULL): hyp_counts[H], hyp_pose[H*12] (R row-major 9 + t 3, float). */
+void orc_pnp_ransac(const orc_pnp_problem *pb, const orc_ransac_params *prm, const uint32_t *table,
+                    int flags, orc_result *res, uint8_t *mask, int *hyp_counts, float *hyp_pose);
+
+/* One EPnP solve on the subset idx[0..m) (PnPsolver::compute_pose, :359-415).
+ * Returns the reprojection error of the chosen solution. */
+double orc_epnp_pose(const orc_pnp_problem *pb, const uint32_t *idx, int m, float R[9], float t[3]);
+/* PnPsolver::CheckInliers (:241-268) for one pose; max_err[i] = sigma2[i]*th2 (f32*f32).
+ * err2 (optional) receives the f32 squared errors. */
+int orc_pnp_check_inliers(const orc_pnp_problem *pb, const float *max_err, const float R[9],
+                          const float t[3], uint8_t *mask, float *err2);
+/* scoring stress (cfg5): H poses x n correspondences, masks as bytes [H][n], counts[H] */
+void orc_pnp_score(const orc_pnp_problem *pb, const float *max_err, int H, const float *poses,
+                   uint8_t *masks, int *counts);
+
+/* ------------------------------------------------------------------ Sim3Solver */
+typedef struct {
+    int n;
+    const float *x1c;   /* [n][3] mvX3Dc1 */
+    const float *x2c;   /* [n][3] mvX3Dc2 */
+    const float *sigma2_1; /* [n] level sigma^2 of kp1 (threshold = size_t(9.210*sigma2), Q4) */
+    const float *sigma2_2;
+    float K1[4];        /* fx, fy, cx, cy of KF1 (mK1 is Matrix3f) */
+    float K2[4];
+    int fix_scale;      /* reference: always 1 (Sim3Solver.cpp:250); 0 = Horn scale step (Q7, parity unpinned) */
+} orc_sim3_problem;
+
+/* Sim3Solver::iterate called repeatedly with n_its_per_call until it returns
+ * true or bNoMore (Sim3Solver.cpp:113-178); because the loop condition is `&&`
+ * the outcome does not depend on n_its_per_call, only calls_made does. */
+void orc_sim3_ransac(const orc_sim3_problem *pb, double prob, int min_inliers, int max_its,
+                     const uint32_t *table, int flags, orc_result *res, uint8_t *mask,
+                     int *hyp_counts, float *hyp_pose /* H*13: R9,t3,s */);
+/* Sim3Solver::ComputeSim3 (:196-266) on three pairs */
+void orc_sim3_compute(const float P1[9] /*3 pts x xyz*/, const float P2[9], int fix_scale,
+                      float R12[9], float t12[3], float *s12);
+/* Sim3Solver::CheckInliers (:269-293) for a given (s,R,t) */
+int orc_sim3_check_inliers(const orc_sim3_problem *pb, const float R12[9], const float t12[3],
+                           float s12, uint8_t *mask, float *err /* optional [n][2] */);
+
+/* ----------------------------------------------------------------- MLPnPsolver */
+typedef struct {
+    int n;
+    const float *p3d;     /* [n][3] world points (stored as double in the solver, MLPnPsolver.cpp:40-42) */
+    const float *p2d;     /* [n][2] */
+    const float *sigma2;  /* [n] */
+    float fx, fy, cx, cy; /* MLPnPsolver.hpp:198 keeps them float */
+    const double *cov;    /* optional [n][9] bearing covariances (use_cov branch, MLPnPsolver.cpp:375-388); NULL = off */
+} orc_mlpnp_problem;
+
+void orc_mlpnp_ransac(const orc_mlpnp_problem *pb, const orc_ransac_params *prm, const uint32_t *table,
+                      int flags, orc_result *res, uint8_t *mask, int *hyp_counts,
+                      double *hyp_pose /* H*12 double: R9,t3 */);
+/* MLPnPsolver::computePose (:321-623) on subset idx[0..m); result R(9) t(3) double */
+void orc_mlpnp_pose(const orc_mlpnp_problem *pb, const uint32_t *idx, int m, double R[9], double t[3]);
+/* MLPnPsolver::CheckInliers (:222-255) */
+int orc_mlpnp_check_inliers(const orc_mlpnp_problem *pb, const float *max_err, const double R[9],
+                            const double t[3], uint8_t *mask, float *err2);
+void orc_rodrigues2rot(const double w[3], double R[9]);   /* MLPnPsolver.cpp:625-640 */
+void orc_rot2rodrigues(const double R[9], double w[3]);   /* MLPnPsolver.cpp:642-657 */
+/* residuals + analytic Jacobian of one point (MLPnPsolver.cpp:725-771, 773-1020) */
+void orc_mlpnp_res_jac(const double pt[3], const double nr[3], const double ns[3],
+                       const double w[3], const double t[3], double r[2], double J[12]);
+
+/* -------------------------------------------------- CPU baseline drivers (bench) */
+/* Runs C independent PnP problems on nthreads host threads (one solver call per
+ * task, as BASELINE.md mode B; nthreads=1 is mode A).  Returns wall seconds of
+ * the iterate() calls only (solver set-up excluded, like the reference's
+ * timers at Tracking.cpp:313-316 / LoopClosing.cpp:285-288). */
+double orc_pnp_batch(int C, const orc_pnp_problem *pbs, const orc_ransac_params *prm,
+                     const uint32_t *const *tables, int flags, int nthreads,
+                     orc_result *res, long long *evals_done);
+double orc_sim3_batch(int C, const orc_sim3_problem *pbs, double prob, int min_inliers, int max_its,
+                      const uint32_t *const *tables, int flags, int nthreads,
+                      orc_result *res, long long *evals_done);
+double orc_mlpnp_batch(int C, const orc_mlpnp_problem *pbs, const orc_ransac_params *prm,
+                       const uint32_t *const *tables, int flags, int nthreads,
+                       orc_result *res, long long *evals_done);
+double orc_pnp_score_timed(const orc_pnp_problem *pb, const float *max_err, int H, const float *poses,
+                           int nthreads, int *counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,290 @@
+/*
+ * oracle/orc_linalg.c -- TEST INFRASTRUCTURE ONLY (see orc.h).
+ *
+ * Small dense solves that the reference delegates to Eigen (un-vendored, no
+ * pinned version: CMakeLists.txt:49).  Each routine restates the published
+ * algorithm class of the Eigen call it stands in for; PARITY UNPINNED against
+ * an Eigen-built binary.  Only + - * / sqrt, fixed operation
+ * order: the CUDA kernels implement the same sequences (arithmetic
+ * contract) so that 4-point EPnP hypotheses are bit-identical on both sides.
+ */
+#include <math.h>
+#include <float.h>
+#include <string.h>
+#include "orc.h"
+
+#define ORC_MAX_SWEEPS 30
+
+/* ---- cyclic Jacobi (Rutishauser rotation), upper triangle, threshold tol ---- */
+#define ORC_JACOBI_IMPL(NAME, T, SQRT, FABS, TOLSCALE, ONE, TWO, ZERO)                          \
+void NAME(int n, T *a, T *w, T *v)                                                              \
+{                                                                                               \
+    for (int i = 0; i < n; ++i)                                                                 \
+        for (int j = 0; j < n; ++j) v[i * n + j] = (i == j) ? ONE : ZERO;                       \
+    T fro2 = ZERO;                                                                              \
+    for (int i = 0; i < n; ++i)                                                                 \
+        for (int j = i; j < n; ++j) fro2 += a[i * n + j] * a[i * n + j];                        \
+    const T tol = SQRT(fro2) * TOLSCALE;                                                        \
+    for (int sweep = 0; sweep < ORC_MAX_SWEEPS; ++sweep) {                                      \
+        int rotated = 0;                                                                        \
+        for (int p = 0; p < n - 1; ++p) {                                                       \
+            for (int q = p + 1; q < n; ++q) {                                                   \
+                const T apq = a[p * n + q];                                                     \
+                if (!(FABS(apq) > tol)) continue;                                               \
+                rotated = 1;                                                                    \
+                const T app = a[p * n + p], aqq = a[q * n + q];                                 \
+                const T theta = (aqq - app) / (TWO * apq);                                      \
+                T t = ONE / (FABS(theta) + SQRT(theta * theta + ONE));                          \
+                if (theta < ZERO) t = -t;                                                       \
+                const T c = ONE / SQRT(t * t + ONE);                                            \
+                const T s = t * c;                                                              \
+                const T tau = s / (ONE + c);                                                    \
+                const T h = t * apq;                                                            \
+                a[p * n + p] = app - h;                                                         \
+                a[q * n + q] = aqq + h;                                                         \
+                a[p * n + q] = ZERO;                                                            \
+                for (int j = 0; j < p; ++j) {                                                   \
+                    const T g = a[j * n + p], k = a[j * n + q];                                 \
+                    a[j * n + p] = g - s * (k + g * tau);                                       \
+                    a[j * n + q] = k + s * (g - k * tau);                                       \
+                }                                                                               \
+                for (int j = p + 1; j < q; ++j) {                                               \
+                    const T g = a[p * n + j], k = a[j * n + q];                                 \
+                    a[p * n + j] = g - s * (k + g * tau);                                       \
+                    a[j * n + q] = k + s * (g - k * tau);                                       \
+                }                                                                               \
+                for (int j = q + 1; j < n; ++j) {                                               \
+                    const T g = a[p * n + j], k = a[q * n + j];                                 \
+                    a[p * n + j] = g - s * (k + g * tau);                                       \
+                    a[q * n + j] = k + s * (g - k * tau);                                       \
+                }                                                                               \
+                for (int j = 0; j < n; ++j) {                                                   \
+                    const T g = v[j * n + p], k = v[j * n + q];                                 \
+                    v[j * n + p] = g - s * (k + g * tau);                                       \
+                    v[j * n + q] = k + s * (g - k * tau);                                       \
+                }                                                                               \
+            }                                                                                   \
+        }                                                                                       \
+        if (!rotated) break;                                                                    \
+    }                                                                                           \
+    for (int i = 0; i < n; ++i) w[i] = a[i * n + i];                                            \
+    /* ascending order, stable selection sort (SelfAdjointEigenSolver sorts ascending) */       \
+    for (int i = 0; i < n - 1; ++i) {                                                           \
+        int k = i;                                                                              \
+        for (int j = i + 1; j < n; ++j)                                                         \
+            if (w[j] < w[k]) k = j;                                                             \
+        if (k != i) {                                                                           \
+            T tw = w[i]; w[i] = w[k]; w[k] = tw;                                                \
+            for (int r = 0; r < n; ++r) {                                                       \
+                T tv = v[r * n + i]; v[r * n + i] = v[r * n + k]; v[r * n + k] = tv;            \
+            }                                                                                   \
+        }                                                                                       \
+    }                                                                                           \
+}
+
+ORC_JACOBI_IMPL(orc_jacobi_eig_d, double, sqrt, fabs, 0x1p-56, 1.0, 2.0, 0.0)
+ORC_JACOBI_IMPL(orc_jacobi_eig_f, float, sqrtf, fabsf, 0x1p-27f, 1.0f, 2.0f, 0.0f)
+
+/* ---- one-sided (Hestenes) Jacobi SVD: columns of U orthogonalised, V accumulated ---- */
+static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k */)
+{
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) V[i * k + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < ORC_MAX_SWEEPS; ++sweep) {
+        int rotated = 0;
+        for (int i = 0; i < k - 1; ++i) {
+            for (int j = i + 1; j < k; ++j) {
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+                for (int r = 0; r < m; ++r) {
+                    const double ui = U[r * k + i], uj = U[r * k + j];
+                    alpha += ui * ui;
+                    beta += uj * uj;
+                    gamma += ui * uj;
+                }
+                if (!(fabs(gamma) > DBL_EPSILON * sqrt(alpha * beta))) continue;
+                rotated = 1;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                double t = 1.0 / (fabs(zeta) + sqrt(zeta * zeta + 1.0));
+                if (zeta < 0.0) t = -t;
+                const double c = 1.0 / sqrt(t * t + 1.0);
+                const double s = c * t;
+                for (int r = 0; r < m; ++r) {
+                    const double ui = U[r * k + i], uj = U[r * k + j];
+                    U[r * k + i] = c * ui - s * uj;
+                    U[r * k + j] = s * ui + c * uj;
+                }
+                for (int r = 0; r < k; ++r) {
+                    const double vi = V[r * k + i], vj = V[r * k + j];
+                    V[r * k + i] = c * vi - s * vj;
+                    V[r * k + j] = s * vi + c * vj;
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+}
+
+/* PnPsolver.cpp:531,559,590: x = L.bdcSvd(ThinU|ThinV).solve(b).  For < 16
+ * columns Eigen's BDCSVD delegates to JacobiSVD; solve() is the minimum-norm
+ * least-squares solution with singular values <= sigma_max * diagSize * eps
+ * treated as zero. */
+void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
+{
+    double U[8 * 6], V[6 * 6], sig2[6], sig[6];
+    memcpy(U, L, sizeof(double) * (size_t)(m * k));
+    onesided_jacobi(m, k, U, V);
+    double smax = 0.0;
+    for (int j = 0; j < k; ++j) {
+        double s2 = 0.0;
+        for (int r = 0; r < m; ++r) s2 += U[r * k + j] * U[r * k + j];
+        sig2[j] = s2;
+        sig[j] = sqrt(s2);
+        if (sig[j] > smax) smax = sig[j];
+    }
+    const double thresh = smax * ((double)k * DBL_EPSILON);
+    for (int r = 0; r < k; ++r) x[r] = 0.0;
+    for (int j = 0; j < k; ++j) {
+        if (!(sig[j] > thresh)) continue;
+        double ub = 0.0;
+        for (int r = 0; r < m; ++r) ub += U[r * k + j] * b[r];
+        const double coef = ub / sig2[j];
+        for (int r = 0; r < k; ++r) x[r] += coef * V[r * k + j];
+    }
+}
+
+/* PnPsolver.cpp:331: CC.inverse() -- closed-form cofactor inverse, no pivoting,
+ * singular => inf/NaN propagate. */
+void orc_inv3_d(const double m[9], double out[9])
+{
+    const double c00 = m[4] * m[8] - m[5] * m[7];
+    const double c01 = m[5] * m[6] - m[3] * m[8];
+    const double c02 = m[3] * m[7] - m[4] * m[6];
+    const double c10 = m[2] * m[7] - m[1] * m[8];
+    const double c11 = m[0] * m[8] - m[2] * m[6];
+    const double c12 = m[1] * m[6] - m[0] * m[7];
+    const double c20 = m[1] * m[5] - m[2] * m[4];
+    const double c21 = m[2] * m[3] - m[0] * m[5];
+    const double c22 = m[0] * m[4] - m[1] * m[3];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const double id = 1.0 / det;
+    out[0] = c00 * id; out[1] = c10 * id; out[2] = c20 * id;
+    out[3] = c01 * id; out[4] = c11 * id; out[5] = c21 * id;
+    out[6] = c02 * id; out[7] = c12 * id; out[8] = c22 * id;
+}
+
+/* MLPnPsolver.cpp:511-512,570-571: JacobiSVD(tmp).matrixU() * matrixV()^T, the
+ * orthogonal polar factor.  A V = U_work (orthogonal columns of norm sigma_j),
+ * so U V^T = sum_j (U_work_j / sigma_j) V_j^T. */
+void orc_polar3_d(const double a[9], double r[9])
+{
+    double U[9], V[9], inv[3];
+    memcpy(U, a, sizeof(U));
+    onesided_jacobi(3, 3, U, V);
+    for (int j = 0; j < 3; ++j) {
+        double s2 = 0.0;
+        for (int i = 0; i < 3; ++i) s2 += U[i * 3 + j] * U[i * 3 + j];
+        inv[j] = 1.0 / sqrt(s2);
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) {
+            double acc = 0.0;
+            for (int j = 0; j < 3; ++j) acc += (U[i * 3 + j] * inv[j]) * V[c * 3 + j];
+            r[i * 3 + c] = acc;
+        }
+}
+
+/* MLPnPsolver.cpp:347,354: FullPivHouseholderQR<Matrix3d>(planarTest).rank().
+ * Eigen: at step k pick the largest |entry| of the trailing corner, stop early
+ * when it is much smaller than the first one (eps*size), Householder the
+ * column; rank = #{ |r_ii| > |maxpivot| * eps * 3 }. */
+int orc_rank3_fullpiv_d(const double a_in[9])
+{
+    double a[9];
+    memcpy(a, a_in, sizeof(a));
+    double diag[3] = {0.0, 0.0, 0.0};
+    int nonzero = 3;
+    double maxpivot = 0.0, biggest = 0.0;
+    const double precision = DBL_EPSILON * 3.0;
+    for (int k = 0; k < 3; ++k) {
+        int pr = k, pc = k;
+        double big = -1.0;
+        for (int c = k; c < 3; ++c)      /* Eigen visits column-major */
+            for (int r = k; r < 3; ++r)
+                if (fabs(a[r * 3 + c]) > big) { big = fabs(a[r * 3 + c]); pr = r; pc = c; }
+        if (k == 0) biggest = big;
+        if (!(big > biggest * precision)) { nonzero = k; break; }   /* isMuchSmallerThan */
+        if (pr != k)
+            for (int c = 0; c < 3; ++c) { double t = a[k * 3 + c]; a[k * 3 + c] = a[pr * 3 + c]; a[pr * 3 + c] = t; }
+        if (pc != k)
+            for (int r = 0; r < 3; ++r) { double t = a[r * 3 + k]; a[r * 3 + k] = a[r * 3 + pc]; a[r * 3 + pc] = t; }
+        /* Householder on column k, rows k..2 */
+        double tail2 = 0.0;
+        for (int r = k + 1; r < 3; ++r) tail2 += a[r * 3 + k] * a[r * 3 + k];
+        const double c0 = a[k * 3 + k];
+        double beta, tau;
+        double vv[3] = {0.0, 0.0, 0.0};
+        if (tail2 <= DBL_MIN) {
+            beta = c0; tau = 0.0;
+        } else {
+            beta = sqrt(c0 * c0 + tail2);
+            if (c0 >= 0.0) beta = -beta;
+            for (int r = k + 1; r < 3; ++r) vv[r] = a[r * 3 + k] / (c0 - beta);
+            tau = (beta - c0) / beta;
+        }
+        vv[k] = 1.0;
+        diag[k] = beta;
+        if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+        for (int c = k + 1; c < 3; ++c) {
+            double dot = 0.0;
+            for (int r = k; r < 3; ++r) dot += vv[r] * a[r * 3 + c];
+            for (int r = k; r < 3; ++r) a[r * 3 + c] -= tau * vv[r] * dot;
+        }
+    }
+    int rank = 0;
+    const double thr = maxpivot * (DBL_EPSILON * 3.0);
+    for (int i = 0; i < nonzero; ++i)
+        if (fabs(diag[i]) > thr) ++rank;
+    return rank;
+}
+
+/* MLPnPsolver.cpp:705-706: Eigen::LDLT<MatrixXd>(A).solve(g) -- LDL^T with
+ * diagonal pivoting (largest |a_ii| first); D entries that are not larger than
+ * the smallest normal number are treated as zero in the solve. */
+void orc_ldlt6_solve_d(const double a_in[36], const double g[6], double x[6])
+{
+    enum { N = 6 };
+    double a[36];
+    int perm[N];
+    memcpy(a, a_in, sizeof(a));
+    for (int i = 0; i < N; ++i) perm[i] = i;
+    for (int k = 0; k < N; ++k) {
+        int piv = k;
+        double big = fabs(a[k * N + k]);
+        for (int i = k + 1; i < N; ++i)
+            if (fabs(a[i * N + i]) > big) { big = fabs(a[i * N + i]); piv = i; }
+        if (piv != k) {   /* symmetric row+column swap */
+            for (int c = 0; c < N; ++c) { double t = a[k * N + c]; a[k * N + c] = a[piv * N + c]; a[piv * N + c] = t; }
+            for (int r = 0; r < N; ++r) { double t = a[r * N + k]; a[r * N + k] = a[r * N + piv]; a[r * N + piv] = t; }
+            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        const double d = a[k * N + k];
+        if (!(fabs(d) > DBL_MIN)) continue;   /* zero pivot: leave column, handled in solve */
+        for (int i = k + 1; i < N; ++i) a[i * N + k] = a[i * N + k] / d;          /* L column */
+        for (int i = k + 1; i < N; ++i)
+            for (int j = k + 1; j <= i; ++j) {
+                a[i * N + j] -= a[i * N + k] * d * a[j * N + k];
+                a[j * N + i] = a[i * N + j];
+            }
+    }
+    double y[N];
+    for (int i = 0; i < N; ++i) y[i] = g[perm[i]];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < i; ++j) y[i] -= a[i * N + j] * y[j];
+    for (int i = 0; i < N; ++i) {
+        const double d = a[i * N + i];
+        y[i] = (fabs(d) > DBL_MIN) ? y[i] / d : 0.0;
+    }
+    for (int i = N - 1; i >= 0; --i)
+        for (int j = i + 1; j < N; ++j) y[i] -= a[j * N + i] * y[j];
+    for (int i = 0; i < N; ++i) x[perm[i]] = y[i];
+}

@@ -1,0 +1,169 @@
+"""Seeded synthetic correspondence sets for the RANSAC hot path.
+
+No datasets are available offline, so every workload in BASELINE.json is
+generated here: 2D-3D sets for PnPsolver / MLPnPsolver (reference
+src/PnPsolver.cpp:11-55 and src/MLPnPsolver.cpp:5-53 define the fields a solver
+snapshots from a Frame) and 3D-3D sets for Sim3Solver (src/Sim3Solver.cpp:6-85).
+
+Conventions
+-----------
+* camera: EuRoC intrinsics (reference Examples/Stereo/EuRoC.yaml), 752x480
+* seed of problem `i` of config `cfg`: 1000*cfg + i  (numpy default_rng)
+* octave of a match: 0..7 with probability ~ 1.2**(-2*level);
+  sigma2 = (1.2**level)**2 evaluated as f32 products like
+  reference src/ORBextractor.cpp:352-359
+* inlier pixel noise N(0, sigma2 px^2); outliers: pixel uniform in the image
+  (PnP/MLPnP) or the second 3-D point replaced by an unrelated frustum sample (Sim3)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EUROC = dict(fx=435.2046959714599, fy=435.2046959714599, cx=367.4517211914062, cy=252.2008514404297,
+             width=752, height=480)
+KITTI = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, width=1241, height=376)
+
+N_LEVELS = 8
+SCALE_FACTOR = np.float32(1.2)
+
+
+def level_sigma2() -> np.ndarray:
+    """mvLevelSigma2 as ORBextractor builds it: f32 running products (ORBextractor.cpp:352-359)."""
+    sf = np.empty(N_LEVELS, np.float32)
+    s2 = np.empty(N_LEVELS, np.float32)
+    sf[0] = 1.0
+    s2[0] = 1.0
+    for i in range(1, N_LEVELS):
+        sf[i] = np.float32(sf[i - 1] * SCALE_FACTOR)
+        s2[i] = np.float32(sf[i] * sf[i])
+    return s2
+
+
+_SIGMA2 = level_sigma2()
+_LEVEL_P = (1.2 ** (-2.0 * np.arange(N_LEVELS)))
+_LEVEL_P = _LEVEL_P / _LEVEL_P.sum()
+
+
+def rodrigues(w: np.ndarray) -> np.ndarray:
+    th = float(np.linalg.norm(w))
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], float)
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+
+
+def random_pose(rng: np.random.Generator, max_angle: float = 0.5, max_t: float = 1.0):
+    """rotation vector uniform in the ball |w| <= max_angle, translation uniform in [-max_t, max_t]^3."""
+    d = rng.normal(size=3)
+    d /= np.linalg.norm(d)
+    w = d * max_angle * rng.uniform() ** (1.0 / 3.0)
+    return rodrigues(w), rng.uniform(-max_t, max_t, size=3)
+
+
+def frustum_points(rng: np.random.Generator, n: int, cam=EUROC, zmin=2.0, zmax=20.0) -> np.ndarray:
+    """points in the camera frame, uniform pixel x uniform depth in [zmin, zmax]."""
+    u = rng.uniform(0, cam["width"], size=n)
+    v = rng.uniform(0, cam["height"], size=n)
+    z = rng.uniform(zmin, zmax, size=n)
+    return np.stack([(u - cam["cx"]) / cam["fx"] * z, (v - cam["cy"]) / cam["fy"] * z, z], axis=1)
+
+
+def project(Xc: np.ndarray, cam=EUROC) -> np.ndarray:
+    return np.stack([cam["fx"] * Xc[:, 0] / Xc[:, 2] + cam["cx"], cam["fy"] * Xc[:, 1] / Xc[:, 2] + cam["cy"]], axis=1)
+
+
+def pnp_problem(seed: int, n: int = 500, outlier_ratio: float = 0.5, cam=EUROC, noise: bool = True):
+    """One 2D-3D correspondence set with ground truth.
+
+    Returns dict(p3d f32 [n,3], p2d f32 [n,2], sigma2 f32 [n], octave, inlier bool [n],
+                 R [3,3], t [3], K=(fx,fy,cx,cy))."""
+    rng = np.random.default_rng(seed)
+    R, t = random_pose(rng)
+    Xc = frustum_points(rng, n, cam)
+    Xw = (Xc - t) @ R          # R^T (Xc - t)
+    octave = rng.choice(N_LEVELS, size=n, p=_LEVEL_P)
+    sigma2 = _SIGMA2[octave]
+    uv = project(Xc, cam)
+    if noise:
+        uv = uv + rng.normal(size=(n, 2)) * np.sqrt(sigma2.astype(float))[:, None]
+    n_out = int(round(n * outlier_ratio))
+    inlier = np.ones(n, bool)
+    out_idx = rng.permutation(n)[:n_out]
+    inlier[out_idx] = False
+    uv[out_idx, 0] = rng.uniform(0, cam["width"], size=n_out)
+    uv[out_idx, 1] = rng.uniform(0, cam["height"], size=n_out)
+    return dict(p3d=np.ascontiguousarray(Xw, np.float32), p2d=np.ascontiguousarray(uv, np.float32),
+                sigma2=np.ascontiguousarray(sigma2, np.float32), octave=octave, inlier=inlier, R=R, t=t,
+                K=(cam["fx"], cam["fy"], cam["cx"], cam["cy"]))
+
+
+def pnp_batch(cfg: int, C: int, n: int = 500, outlier_ratio: float = 0.5, cam=EUROC, first: int = 0):
+    """C independent problems, seeds 1000*cfg + first + i, stacked: p3d [C,n,3], p2d [C,n,2], sigma2 [C,n]."""
+    ps = [pnp_problem(1000 * cfg + first + i, n, outlier_ratio, cam) for i in range(C)]
+    return dict(p3d=np.stack([p["p3d"] for p in ps]), p2d=np.stack([p["p2d"] for p in ps]),
+                sigma2=np.stack([p["sigma2"] for p in ps]), inlier=np.stack([p["inlier"] for p in ps]),
+                R=np.stack([p["R"] for p in ps]), t=np.stack([p["t"] for p in ps]), K=ps[0]["K"],
+                seeds=np.array([1000 * cfg + first + i for i in range(C)], np.uint32))
+
+
+def bearing_covariances(p: dict) -> np.ndarray:
+    """cfg2: Sigma_i = diag(sigma_i^2/fx^2, sigma_i^2/fy^2, 0) for the MLPnP use_cov branch
+    (reference src/MLPnPsolver.cpp:375-388)."""
+    fx, fy = p["K"][0], p["K"][1]
+    s2 = p["sigma2"].astype(np.float64)
+    cov = np.zeros(s2.shape + (3, 3))
+    cov[..., 0, 0] = s2 / fx ** 2
+    cov[..., 1, 1] = s2 / fy ** 2
+    return cov
+
+
+def sim3_problem(seed: int, n: int = 200, outlier_ratio: float = 0.4, scale: float = 1.0, cam=EUROC):
+    """One 3D-3D correspondence set: camera-frame points of two keyframes observing the same
+    landmarks (reference src/Sim3Solver.cpp:57-63), X1c = s*R12*X2c + t12 up to noise.
+
+    Returns dict(x1c, x2c f32 [n,3], sigma2_1, sigma2_2 f32 [n], inlier, R12, t12, s, K)."""
+    rng = np.random.default_rng(seed)
+    R1, t1 = random_pose(rng, 0.3, 0.5)
+    Rrel, trel = random_pose(rng, 0.3, 0.5)
+    X1 = frustum_points(rng, n, cam, 3.0, 15.0)              # camera-1 frame
+    # camera 2 = camera 1 moved by (Rrel, trel):  X2 = Rrel X1 + trel ; then X1 = R12 (s X2') + t12
+    X2 = X1 @ Rrel.T + trel
+    # keep only geometry in front of camera 2
+    X2[:, 2] = np.maximum(X2[:, 2], 1.0)
+    X1 = (X2 - trel) @ Rrel
+    R12 = Rrel.T
+    t12 = -Rrel.T @ trel
+    oct1 = rng.choice(N_LEVELS, size=n, p=_LEVEL_P)
+    oct2 = rng.choice(N_LEVELS, size=n, p=_LEVEL_P)
+    s1, s2 = _SIGMA2[oct1], _SIGMA2[oct2]
+    # lateral noise giving ~sigma px of reprojection noise in each image
+    X1n = X1.copy()
+    X2n = X2.copy()
+    X1n[:, :2] += rng.normal(size=(n, 2)) * (0.5 * np.sqrt(s1.astype(float)) * X1[:, 2] / cam["fx"])[:, None]
+    X2n[:, :2] += rng.normal(size=(n, 2)) * (0.5 * np.sqrt(s2.astype(float)) * X2[:, 2] / cam["fx"])[:, None]
+    n_out = int(round(n * outlier_ratio))
+    inlier = np.ones(n, bool)
+    out_idx = rng.permutation(n)[:n_out]
+    inlier[out_idx] = False
+    X2n[out_idx] = frustum_points(rng, n_out, cam, 3.0, 15.0)
+    X2n = X2n / scale                                       # monocular map 2 lives at another scale
+    K = (np.float32(cam["fx"]), np.float32(cam["fy"]), np.float32(cam["cx"]), np.float32(cam["cy"]))
+    return dict(x1c=np.ascontiguousarray(X1n, np.float32), x2c=np.ascontiguousarray(X2n, np.float32),
+                sigma2_1=np.ascontiguousarray(s1, np.float32), sigma2_2=np.ascontiguousarray(s2, np.float32),
+                inlier=inlier, R12=R12, t12=t12, s=scale, K=K)
+
+
+def scoring_stress(seed: int = 5000, H: int = 4096, n: int = 10000, cam=EUROC):
+    """cfg5: one 50%-outlier correspondence set of size n and H poses = ground truth perturbed by
+    N(0, 0.02) in rotation vector and translation."""
+    p = pnp_problem(seed, n, 0.5, cam)
+    rng = np.random.default_rng(seed + 1)
+    poses = np.empty((H, 12), np.float32)
+    for h in range(H):
+        dR = rodrigues(rng.normal(size=3) * 0.02)
+        R = dR @ p["R"]
+        t = p["t"] + rng.normal(size=3) * 0.02
+        poses[h, :9] = R.reshape(-1)
+        poses[h, 9:] = t
+    p["poses"] = poses
+    return p

@@ -1,0 +1,361 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+The oracle is the checker; only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module.  The product path
+(orb-slam2-optimized_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB = None
+
+FLAG_STALE_ROWS = 1
+FLAG_EXHAUSTIVE = 2
+FLAG_MLPNP_DISCARD_REFINE = 4
+
+
+class RansacParams(C.Structure):
+    _fields_ = [("prob", C.c_double), ("min_inliers", C.c_int), ("max_its", C.c_int),
+                ("min_set", C.c_int), ("eps", C.c_float), ("th2", C.c_float)]
+
+
+class PnPProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("p3d", C.c_void_p), ("p2d", C.c_void_p), ("sigma2", C.c_void_p),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double)]
+
+
+class Sim3Problem(C.Structure):
+    _fields_ = [("n", C.c_int), ("x1c", C.c_void_p), ("x2c", C.c_void_p), ("sigma2_1", C.c_void_p),
+                ("sigma2_2", C.c_void_p), ("K1", C.c_float * 4), ("K2", C.c_float * 4), ("fix_scale", C.c_int)]
+
+
+class MLPnPProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("p3d", C.c_void_p), ("p2d", C.c_void_p), ("sigma2", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("cov", C.c_void_p)]
+
+
+class Result(C.Structure):
+    _fields_ = [("ok", C.c_int), ("no_more", C.c_int), ("n_inliers", C.c_int), ("best_hyp", C.c_int),
+                ("refined", C.c_int), ("n_hyp", C.c_int), ("n_refines", C.c_int), ("n_failed_refines", C.c_int),
+                ("best_count", C.c_int), ("T", C.c_float * 16), ("scale", C.c_float)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "T"}
+        d["T"] = np.array(self.T, np.float32).reshape(4, 4)
+        return d
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_epnp_pose.restype = C.c_double
+        for f in ("orc_pnp_batch", "orc_sim3_batch", "orc_mlpnp_batch", "orc_pnp_score_timed"):
+            getattr(_LIB, f).restype = C.c_double
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def index_table(seed, n, k, H):
+    out = np.empty((H, k), np.uint32)
+    lib().orc_index_table(C.c_uint(seed), C.c_int(n), C.c_int(k), C.c_int(H), _p(out))
+    return out
+
+
+def random_ints(seed, lo, hi, count):
+    L = lib()
+    L.orc_rng_seed(C.c_uint(seed))
+    return [L.orc_random_int(C.c_int(lo), C.c_int(hi)) for _ in range(count)]
+
+
+def jacobi_eig(a, dtype=np.float64):
+    a = np.array(a, dtype, order="C", copy=True)
+    n = a.shape[0]
+    w = np.empty(n, dtype)
+    v = np.empty((n, n), dtype)
+    fn = lib().orc_jacobi_eig_d if dtype == np.float64 else lib().orc_jacobi_eig_f
+    fn(C.c_int(n), _p(a), _p(w), _p(v))
+    return w, v
+
+
+def svd_lstsq(L, b):
+    L = np.ascontiguousarray(L, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    x = np.empty(L.shape[1])
+    lib().orc_svd_lstsq_d(C.c_int(L.shape[0]), C.c_int(L.shape[1]), _p(L), _p(b), _p(x))
+    return x
+
+
+def inv3(m):
+    m = np.ascontiguousarray(m, np.float64)
+    o = np.empty((3, 3))
+    lib().orc_inv3_d(_p(m), _p(o))
+    return o
+
+
+def polar3(m):
+    m = np.ascontiguousarray(m, np.float64)
+    o = np.empty((3, 3))
+    lib().orc_polar3_d(_p(m), _p(o))
+    return o
+
+
+def rank3(m):
+    m = np.ascontiguousarray(m, np.float64)
+    return lib().orc_rank3_fullpiv_d(_p(m))
+
+
+def ldlt6_solve(a, g):
+    a = np.ascontiguousarray(a, np.float64)
+    g = np.ascontiguousarray(g, np.float64)
+    x = np.empty(6)
+    lib().orc_ldlt6_solve_d(_p(a), _p(g), _p(x))
+    return x
+
+
+def ransac_setup_pnp(n, prm: RansacParams):
+    mi, it = C.c_int(), C.c_int()
+    lib().orc_pnp_ransac_setup(C.c_int(n), C.byref(prm), C.byref(mi), C.byref(it))
+    return mi.value, it.value
+
+
+def ransac_setup_sim3(n, prob, min_inl, max_its):
+    it = C.c_int()
+    lib().orc_sim3_ransac_setup(C.c_int(n), C.c_double(prob), C.c_int(min_inl), C.c_int(max_its), C.byref(it))
+    return it.value
+
+
+class _Keep:
+    """a ctypes struct plus the numpy arrays it points into"""
+
+    def __init__(self, st, *arrs):
+        self.st = st
+        self.arrs = arrs
+
+
+def pnp_problem(p3d, p2d, sigma2, K):
+    p3d, p2d, sigma2 = _f32(p3d), _f32(p2d), _f32(sigma2)
+    st = PnPProblem(p3d.shape[0], _p(p3d), _p(p2d), _p(sigma2), K[0], K[1], K[2], K[3])
+    return _Keep(st, p3d, p2d, sigma2)
+
+
+def mlpnp_problem(p3d, p2d, sigma2, K, cov=None):
+    p3d, p2d, sigma2 = _f32(p3d), _f32(p2d), _f32(sigma2)
+    covc = None if cov is None else np.ascontiguousarray(cov, np.float64)
+    st = MLPnPProblem(p3d.shape[0], _p(p3d), _p(p2d), _p(sigma2), K[0], K[1], K[2], K[3],
+                      None if covc is None else _p(covc))
+    return _Keep(st, p3d, p2d, sigma2, covc)
+
+
+def sim3_problem(x1c, x2c, s1, s2, K1, K2, fix_scale=True):
+    x1c, x2c, s1, s2 = _f32(x1c), _f32(x2c), _f32(s1), _f32(s2)
+    st = Sim3Problem(x1c.shape[0], _p(x1c), _p(x2c), _p(s1), _p(s2), (C.c_float * 4)(*K1), (C.c_float * 4)(*K2),
+                     1 if fix_scale else 0)
+    return _Keep(st, x1c, x2c, s1, s2)
+
+
+def params(prob=0.99, min_inliers=8, max_its=300, min_set=4, eps=0.4, th2=5.991):
+    return RansacParams(prob, min_inliers, max_its, min_set, eps, th2)
+
+
+def epnp_pose(pb: _Keep, idx):
+    idx = np.ascontiguousarray(idx, np.uint32)
+    R = np.empty(9, np.float32)
+    t = np.empty(3, np.float32)
+    err = lib().orc_epnp_pose(C.byref(pb.st), _p(idx), C.c_int(len(idx)), _p(R), _p(t))
+    return R.reshape(3, 3), t, err
+
+
+def pnp_check_inliers(pb: _Keep, max_err, R, t):
+    max_err, R, t = _f32(max_err), _f32(R).reshape(-1), _f32(t)
+    n = pb.st.n
+    mask = np.empty(n, np.uint8)
+    err2 = np.empty(n, np.float32)
+    cnt = lib().orc_pnp_check_inliers(C.byref(pb.st), _p(max_err), _p(R), _p(t), _p(mask), _p(err2))
+    return cnt, mask.astype(bool), err2
+
+
+def pnp_score(pb: _Keep, max_err, poses, want_masks=True):
+    max_err, poses = _f32(max_err), _f32(poses)
+    H = poses.shape[0]
+    masks = np.empty((H, pb.st.n), np.uint8) if want_masks else None
+    counts = np.empty(H, np.int32)
+    lib().orc_pnp_score(C.byref(pb.st), _p(max_err), C.c_int(H), _p(poses), None if masks is None else _p(masks), _p(counts))
+    return counts, masks
+
+
+def pnp_ransac(pb: _Keep, prm: RansacParams, table, flags=0, per_hyp=False):
+    table = np.ascontiguousarray(table, np.uint32)
+    n = pb.st.n
+    res = Result()
+    mask = np.zeros(max(n, 1), np.uint8)
+    _, H = ransac_setup_pnp(n, prm)
+    hc = np.full(H, -1, np.int32) if per_hyp else None
+    hp = np.full((H, 12), np.nan, np.float32) if per_hyp else None
+    lib().orc_pnp_ransac(C.byref(pb.st), C.byref(prm), _p(table), C.c_int(flags), C.byref(res), _p(mask),
+                         None if hc is None else _p(hc), None if hp is None else _p(hp))
+    out = res.as_dict()
+    out["mask"] = mask[:n].astype(bool)
+    if per_hyp:
+        out["hyp_counts"], out["hyp_pose"] = hc, hp
+    return out
+
+
+def mlpnp_pose(pb: _Keep, idx):
+    idx = np.ascontiguousarray(idx, np.uint32)
+    R = np.empty(9)
+    t = np.empty(3)
+    lib().orc_mlpnp_pose(C.byref(pb.st), _p(idx), C.c_int(len(idx)), _p(R), _p(t))
+    return R.reshape(3, 3), t
+
+
+def mlpnp_check_inliers(pb: _Keep, max_err, R, t):
+    max_err = _f32(max_err)
+    R = np.ascontiguousarray(R, np.float64).reshape(-1)
+    t = np.ascontiguousarray(t, np.float64)
+    n = pb.st.n
+    mask = np.empty(n, np.uint8)
+    err2 = np.empty(n, np.float32)
+    cnt = lib().orc_mlpnp_check_inliers(C.byref(pb.st), _p(max_err), _p(R), _p(t), _p(mask), _p(err2))
+    return cnt, mask.astype(bool), err2
+
+
+def mlpnp_ransac(pb: _Keep, prm: RansacParams, table, flags=0, per_hyp=False):
+    table = np.ascontiguousarray(table, np.uint32)
+    n = pb.st.n
+    res = Result()
+    mask = np.zeros(max(n, 1), np.uint8)
+    _, H = ransac_setup_pnp(n, prm)
+    hc = np.full(H, -1, np.int32) if per_hyp else None
+    hp = np.full((H, 12), np.nan, np.float64) if per_hyp else None
+    lib().orc_mlpnp_ransac(C.byref(pb.st), C.byref(prm), _p(table), C.c_int(flags), C.byref(res), _p(mask),
+                           None if hc is None else _p(hc), None if hp is None else _p(hp))
+    out = res.as_dict()
+    out["mask"] = mask[:n].astype(bool)
+    if per_hyp:
+        out["hyp_counts"], out["hyp_pose"] = hc, hp
+    return out
+
+
+def mlpnp_res_jac(pt, nr, ns, w, t):
+    a = [np.ascontiguousarray(x, np.float64) for x in (pt, nr, ns, w, t)]
+    r = np.empty(2)
+    J = np.empty((2, 6))
+    lib().orc_mlpnp_res_jac(*[_p(x) for x in a], _p(r), _p(J))
+    return r, J
+
+
+def rodrigues2rot(w):
+    w = np.ascontiguousarray(w, np.float64)
+    R = np.empty((3, 3))
+    lib().orc_rodrigues2rot(_p(w), _p(R))
+    return R
+
+
+def rot2rodrigues(R):
+    R = np.ascontiguousarray(R, np.float64)
+    w = np.empty(3)
+    lib().orc_rot2rodrigues(_p(R), _p(w))
+    return w
+
+
+def sim3_compute(P1, P2, fix_scale=True):
+    P1, P2 = _f32(P1), _f32(P2)
+    R = np.empty(9, np.float32)
+    t = np.empty(3, np.float32)
+    s = C.c_float()
+    lib().orc_sim3_compute(_p(P1), _p(P2), C.c_int(1 if fix_scale else 0), _p(R), _p(t), C.byref(s))
+    return R.reshape(3, 3), t, s.value
+
+
+def sim3_check_inliers(pb: _Keep, R, t, s=1.0):
+    R, t = _f32(R).reshape(-1), _f32(t)
+    n = pb.st.n
+    mask = np.empty(n, np.uint8)
+    err = np.empty((n, 2), np.float32)
+    cnt = lib().orc_sim3_check_inliers(C.byref(pb.st), _p(R), _p(t), C.c_float(s), _p(mask), _p(err))
+    return cnt, mask.astype(bool), err
+
+
+def sim3_ransac(pb: _Keep, prob, min_inliers, max_its, table, flags=0, per_hyp=False):
+    table = np.ascontiguousarray(table, np.uint32)
+    n = pb.st.n
+    res = Result()
+    mask = np.zeros(max(n, 1), np.uint8)
+    H = ransac_setup_sim3(n, prob, min_inliers, max_its) if n > 0 else 1
+    hc = np.full(H, -1, np.int32) if per_hyp else None
+    hp = np.full((H, 13), np.nan, np.float32) if per_hyp else None
+    lib().orc_sim3_ransac(C.byref(pb.st), C.c_double(prob), C.c_int(min_inliers), C.c_int(max_its), _p(table),
+                          C.c_int(flags), C.byref(res), _p(mask), None if hc is None else _p(hc),
+                          None if hp is None else _p(hp))
+    out = res.as_dict()
+    out["mask"] = mask[:n].astype(bool)
+    if per_hyp:
+        out["hyp_counts"], out["hyp_pose"] = hc, hp
+    return out
+
+
+def _tables_ptr(tables):
+    arrs = [np.ascontiguousarray(t, np.uint32) for t in tables]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    return arrs, ptrs
+
+
+def pnp_batch(pbs, prm, tables, flags=0, nthreads=1):
+    """returns (seconds, evals_done, list of result dicts)"""
+    n = len(pbs)
+    arr = (PnPProblem * n)(*[p.st for p in pbs])
+    keep, ptrs = _tables_ptr(tables)
+    res = (Result * n)()
+    ev = C.c_longlong()
+    dt = lib().orc_pnp_batch(C.c_int(n), arr, C.byref(prm), ptrs, C.c_int(flags), C.c_int(nthreads), res, C.byref(ev))
+    return dt, ev.value, [r.as_dict() for r in res]
+
+
+def sim3_batch(pbs, prob, min_inliers, max_its, tables, flags=0, nthreads=1):
+    n = len(pbs)
+    arr = (Sim3Problem * n)(*[p.st for p in pbs])
+    keep, ptrs = _tables_ptr(tables)
+    res = (Result * n)()
+    ev = C.c_longlong()
+    dt = lib().orc_sim3_batch(C.c_int(n), arr, C.c_double(prob), C.c_int(min_inliers), C.c_int(max_its), ptrs,
+                              C.c_int(flags), C.c_int(nthreads), res, C.byref(ev))
+    return dt, ev.value, [r.as_dict() for r in res]
+
+
+def mlpnp_batch(pbs, prm, tables, flags=0, nthreads=1):
+    n = len(pbs)
+    arr = (MLPnPProblem * n)(*[p.st for p in pbs])
+    keep, ptrs = _tables_ptr(tables)
+    res = (Result * n)()
+    ev = C.c_longlong()
+    dt = lib().orc_mlpnp_batch(C.c_int(n), arr, C.byref(prm), ptrs, C.c_int(flags), C.c_int(nthreads), res, C.byref(ev))
+    return dt, ev.value, [r.as_dict() for r in res]
+
+
+def pnp_score_timed(pb: _Keep, max_err, poses, nthreads=1):
+    max_err, poses = _f32(max_err), _f32(poses)
+    counts = np.empty(poses.shape[0], np.int32)
+    dt = lib().orc_pnp_score_timed(C.byref(pb.st), _p(max_err), C.c_int(poses.shape[0]), _p(poses), C.c_int(nthreads), _p(counts))
+    return dt, counts
