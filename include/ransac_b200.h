@@ -1,0 +1,257 @@
+/*
+ * ransac_b200.h -- C ABI of the B200-native batched RANSAC pose-estimation engine.
+ *
+ * This is the drop-in boundary for ORB-SLAM2's geometric-verification hot path
+ * (reference: Luigi940260/orb-slam2-optimized).  The reference has no FFI layer: the
+ * path is three C++ classes -- PnPsolver (include/PnPsolver.hpp:21-31), MLPnPsolver
+ * (include/MLPnPsolver.hpp:10-21) and Sim3Solver (include/Sim3Solver.hpp:16-30) --
+ * constructed per candidate keyframe by Tracking::Relocalization
+ * (src/Tracking.cpp:1225-1255) and LoopClosing::ComputeSim3 (src/LoopClosing.cpp:260-308).
+ * The C++ classes of the same names in include/ransac_b200/*.hpp keep that API and are
+ * thin wrappers over the entry points below; the *_batch entry points are what the two
+ * callers use to verify all candidates in one device pass.
+ *
+ * Conventions: extern "C", POD structs, plain pointers and sizes, caller-allocated
+ * outputs, integer status codes (never throws across the ABI).  Host pointers unless a
+ * parameter is named d_* (device pointer).  All matrices row-major.  There is no CPU
+ * fallback: without a CUDA device every compute entry point returns RSAC_ERR_NO_DEVICE.
+ */
+#ifndef RANSAC_B200_H
+#define RANSAC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSAC_VERSION 100
+
+/* status codes */
+#define RSAC_OK 0
+#define RSAC_ERR_INVALID 1    /* bad argument */
+#define RSAC_ERR_NO_DEVICE 2  /* no usable CUDA device */
+#define RSAC_ERR_CUDA 3       /* CUDA runtime error (rsac_last_error has the text) */
+#define RSAC_ERR_STATE 4      /* call order (e.g. run before upload) */
+#define RSAC_ERR_ALLOC 5
+
+/* run flags */
+#define RSAC_FLAG_KEEP_MASKS 1      /* also keep per-hypothesis inlier bitmasks (debug / rsac_*_get_hypotheses) */
+#define RSAC_FLAG_MLPNP_DISCARD_REFINE 4 /* reproduce MLPnPsolver::Refine not storing its pose (MLPnPsolver.cpp:290-296) */
+
+typedef struct rsac_engine rsac_engine;
+
+/* RANSAC parameters exactly as PnPsolver::SetRansacParameters takes them
+ * (PnPsolver.hpp:26-27; MLPnPsolver.hpp:16-17 with min_set = 6) */
+typedef struct {
+    double prob;
+    int32_t min_inliers;
+    int32_t max_its;
+    int32_t min_set;
+    float eps;
+    float th2;
+} rsac_ransac_params;
+
+/* Sim3Solver::SetRansacParameters(probability, minInliers, maxIterations) (Sim3Solver.hpp:23)
+ * + the bFixScale constructor flag of upstream ORB-SLAM2 (absent from the reference,
+ * which is fixed-scale only: Sim3Solver.cpp:250) */
+typedef struct {
+    double prob;
+    int32_t min_inliers;
+    int32_t max_its;
+    int32_t fix_scale;
+} rsac_sim3_params;
+
+/* Per-problem outcome: what iterate()/find() return plus what the getters expose.
+ * 96-byte POD; this is the record gathered across GPUs. */
+typedef struct {
+    int32_t ok;          /* return value of iterate()/find() */
+    int32_t no_more;     /* bNoMore */
+    int32_t n_inliers;   /* nInliers (0 when !ok) */
+    int32_t best_hyp;    /* hypothesis that set the best pose (-1 if none) */
+    int32_t refined;     /* pose comes from Refine() */
+    int32_t n_refines;   /* Refine() calls the sequential reference would have made */
+    int32_t best_count;  /* mnBestInliers */
+    int32_t n_hyp;       /* hypotheses the sequential reference would have evaluated */
+    float R[9];          /* rotation (PnP/MLPnP: Tcw top-left; Sim3: GetEstimatedRotation) */
+    float t[3];          /* translation */
+    float s;             /* Sim3 scale (1 for PnP/MLPnP and fix_scale) */
+    int32_t problem;     /* global problem index (set by the sharding layer) */
+    int32_t reserved[2];
+} rsac_result;
+
+/* ------------------------------------------------------------------ engine */
+int rsac_version(void);
+int rsac_device_count(void);
+/* creates an engine on `device` with its own non-blocking stream */
+int rsac_create(int device, rsac_engine** out);
+void rsac_destroy(rsac_engine* e);
+const char* rsac_last_error(rsac_engine* e);
+/* use an external cudaStream_t (passed as void*) for all work; NULL restores the own stream */
+int rsac_set_stream(rsac_engine* e, void* cuda_stream);
+int rsac_sync(rsac_engine* e);
+/* pinned host memory for callers that want asynchronous H2D/D2H */
+int rsac_host_alloc(void** ptr, uint64_t bytes);
+int rsac_host_free(void* ptr);
+/* device facts for roofline arithmetic */
+typedef struct {
+    int32_t sm_count;
+    int32_t sm_clock_khz;     /* cudaDevAttrClockRate */
+    int32_t mem_clock_khz;
+    int32_t cc_major, cc_minor;
+    uint64_t total_mem;
+    char name[64];
+} rsac_device_info;
+int rsac_get_device_info(rsac_engine* e, rsac_device_info* info);
+/* CUDA-event stopwatch on the engine stream */
+int rsac_timer_begin(rsac_engine* e);
+int rsac_timer_end(rsac_engine* e, float* ms);   /* synchronises */
+/* per-stage kernel timing with CUDA events around each launch (off by default) */
+#define RSAC_STAGE_PACK 0
+#define RSAC_STAGE_RNG 1
+#define RSAC_STAGE_SOLVE 2     /* minimal solver kernel */
+#define RSAC_STAGE_SCORE 3     /* CheckInliers kernel */
+#define RSAC_STAGE_SELECT 4    /* replay + refine kernel */
+#define RSAC_STAGE_COUNT 5
+int rsac_profile_enable(rsac_engine* e, int on);
+int rsac_profile_reset(rsac_engine* e);
+int rsac_profile_get(rsac_engine* e, int stage, double* total_ms, int64_t* launches);
+/* number of this library's kernels launched since creation / last reset */
+int64_t rsac_launch_count(rsac_engine* e);
+/* FFMA / DFMA saturating micro-kernels: measured FP32 / FP64 CUDA-core peaks (TFLOP/s) */
+int rsac_measure_peaks(rsac_engine* e, double* fp32_tflops, double* fp64_tflops);
+
+/* ------------------------------------------------ host helpers (no device needed) */
+/* PnPsolver::SetRansacParameters arithmetic (PnPsolver.cpp:58-94, MLPnPsolver.cpp:185-220) */
+int rsac_pnp_ransac_setup(int n, const rsac_ransac_params* p, int* min_inliers, int* max_its);
+/* Sim3Solver::SetRansacParameters arithmetic (Sim3Solver.cpp:87-111) */
+int rsac_sim3_ransac_setup(int n, const rsac_sim3_params* p, int* max_its);
+/* H minimal sets of k distinct indices in [0,n): DUtils::Random::RandomInt
+ * (Thirdparty/DBoW2/DUtils/Random.cpp:47-50) over a private glibc-TYPE_3 stream seeded
+ * like srand(seed), with the reference's swap-remove draw (PnPsolver.cpp:125-138) */
+int rsac_index_table(uint32_t seed, int n, int k, int H, uint32_t* out);
+/* the raw stream: count outputs of rand() after srand(seed) */
+int rsac_rand_stream(uint32_t seed, int count, int32_t* out);
+
+/* ----------------------------------------------------------------- PnPsolver */
+/* A batch of C independent 2D-3D problems, ragged, concatenated.  Fields are the ones the
+ * PnPsolver constructor snapshots from Frame/MapPoint (PnPsolver.cpp:11-55). */
+typedef struct {
+    int32_t C;
+    const int32_t* offsets;      /* [C+1] first correspondence of each problem */
+    const float* p3d;            /* [total][3] mvP3Dw */
+    const float* p2d;            /* [total][2] mvP2D  */
+    const float* sigma2;         /* [total]    mvSigma2 */
+    const double* K;             /* [C][4] fx, fy, cx, cy (double, PnPsolver.hpp:71) */
+    const rsac_ransac_params* params;   /* [n_params]: one per problem, or one shared */
+    int32_t n_params;
+    const uint32_t* seeds;       /* [C] per-problem srand() seed; used when tables == NULL */
+    const uint32_t* tables;      /* optional explicit minimal-set tables, concatenated H_c*min_set each */
+    const int64_t* table_offsets;/* [C+1] offsets into tables (in uint32 units) */
+} rsac_pnp_batch;
+
+/* stage 1: host -> device (async on the engine stream) and device-side packing */
+int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b);
+/* stage 2: all hypotheses of all problems: EPnP minimal solves, CheckInliers scoring,
+ * sequential-semantics replay with Refine (PnPsolver::iterate, PnPsolver.cpp:102-238).
+ * Device-resident, asynchronous.  d_results_out: optional device buffer of C rsac_result
+ * that also receives the records (for a collective); may be NULL. */
+int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out);
+/* stage 3: device -> host, synchronises.  masks: optional, concatenated inlier bitmasks,
+ * ceil(n_c/32) words per problem in problem order (bit i of word w = correspondence 32w+i,
+ * COMPACT index; the C++ wrapper scatters to keypoint indices like PnPsolver.cpp:160-165) */
+int rsac_pnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks);
+/* the reference-facing call: 1+2+3 with host buffers */
+int rsac_pnp_solve(rsac_engine* e, const rsac_pnp_batch* b, int flags, rsac_result* results, uint32_t* masks);
+/* parity/debug: per-hypothesis poses ([sumH][12]: R 9, t 3) and inlier counts ([sumH]) of the last run */
+int rsac_pnp_get_hypotheses(rsac_engine* e, float* poses, int32_t* counts);
+int64_t rsac_pnp_total_hypotheses(rsac_engine* e);
+
+/* CheckInliers for H given poses x n correspondences of ONE problem (PnPsolver.cpp:241-268):
+ * masks [H][ceil(n/32)] and counts [H].  max_err[i] = mvMaxError[i]. */
+int rsac_score_pnp_upload(rsac_engine* e, int H, const float* poses, int n, const float* p3d,
+                          const float* p2d, const float* max_err, const double K[4]);
+int rsac_score_pnp_run(rsac_engine* e, int want_masks);
+int rsac_score_pnp_download(rsac_engine* e, uint32_t* masks, int32_t* counts);
+int rsac_score_pnp(rsac_engine* e, int H, const float* poses, int n, const float* p3d, const float* p2d,
+                   const float* max_err, const double K[4], uint32_t* masks, int32_t* counts);
+/* diagnostic: evaluations that took the exact (reference-arithmetic) path in the last scoring run */
+int64_t rsac_score_exact_evals(rsac_engine* e);
+
+/* ---------------------------------------------------------------- Sim3Solver */
+/* Fields the Sim3Solver constructor snapshots from the two keyframes (Sim3Solver.cpp:6-85):
+ * camera-frame points of both keyframes, level sigma^2 of both keypoints, calibrations. */
+typedef struct {
+    int32_t C;
+    const int32_t* offsets;      /* [C+1] */
+    const float* x1c;            /* [total][3] mvX3Dc1 */
+    const float* x2c;            /* [total][3] mvX3Dc2 */
+    const float* sigma2_1;       /* [total] mvLevelSigma2[kp1.octave]; threshold = size_t(9.210*sigma2) */
+    const float* sigma2_2;       /* [total] */
+    const float* K1;             /* [C][4] fx, fy, cx, cy of keyframe 1 (float, mK1) */
+    const float* K2;             /* [C][4] */
+    const rsac_sim3_params* params; /* [n_params] */
+    int32_t n_params;
+    const uint32_t* seeds;       /* [C] */
+    const uint32_t* tables;      /* optional, H_c*3 each */
+    const int64_t* table_offsets;
+} rsac_sim3_batch;
+
+int rsac_sim3_upload(rsac_engine* e, const rsac_sim3_batch* b);
+int rsac_sim3_run(rsac_engine* e, int flags, void* d_results_out);
+int rsac_sim3_download(rsac_engine* e, rsac_result* results, uint32_t* masks);
+int rsac_sim3_solve(rsac_engine* e, const rsac_sim3_batch* b, int flags, rsac_result* results, uint32_t* masks);
+/* per-hypothesis ([sumH][13]: R 9, t 3, s) poses, counts, and masks ([sumH][words_c]) of the last run;
+ * Sim3Solver::iterate(5,...) round-robin is replayed on the host from these (Sim3Solver.cpp:113-178) */
+int rsac_sim3_get_hypotheses(rsac_engine* e, float* poses, int32_t* counts, uint32_t* masks);
+int64_t rsac_sim3_total_hypotheses(rsac_engine* e);
+
+/* --------------------------------------------------------------- MLPnPsolver */
+typedef struct {
+    int32_t C;
+    const int32_t* offsets;
+    const float* p3d;            /* [total][3] */
+    const float* p2d;            /* [total][2] */
+    const float* sigma2;         /* [total] */
+    const float* K;              /* [C][4] fx, fy, cx, cy (float, MLPnPsolver.hpp:198) */
+    const double* cov;           /* optional [total][9] bearing covariances (use_cov branch, MLPnPsolver.cpp:375-388) */
+    const rsac_ransac_params* params;
+    int32_t n_params;
+    const uint32_t* seeds;
+    const uint32_t* tables;      /* optional, H_c*min_set each */
+    const int64_t* table_offsets;
+} rsac_mlpnp_batch;
+
+int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b);
+int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out);
+int rsac_mlpnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks);
+int rsac_mlpnp_solve(rsac_engine* e, const rsac_mlpnp_batch* b, int flags, rsac_result* results, uint32_t* masks);
+/* per-hypothesis poses in double ([sumH][12]) and counts */
+int rsac_mlpnp_get_hypotheses(rsac_engine* e, double* poses, int32_t* counts);
+int64_t rsac_mlpnp_total_hypotheses(rsac_engine* e);
+
+/* ------------------------------------------------ multi-GPU (candidates shard) */
+/* contiguous block partition of C problems over `world` ranks: rank r owns [*first, *first + *count) */
+int rsac_shard_range(int C, int rank, int world, int* first, int* count);
+/* NCCL all-gather of the per-problem records of the last PnP/MLPnP/Sim3 run (kind 0/1/2).
+ * comm: an initialised ncclComm_t passed as void*; every rank contributes `count_per_rank`
+ * records (pad with problem = -1) and receives world*count_per_rank into d_gathered. */
+int rsac_nccl_get_unique_id(void* id128);
+int rsac_nccl_init(rsac_engine* e, const void* id128, int rank, int world);
+int rsac_nccl_allgather_results(rsac_engine* e, const void* d_send, int count_per_rank, void* d_gathered);
+int rsac_nccl_destroy(rsac_engine* e);
+
+/* ------------------------------------------------------- host-side debug hooks */
+/* The device numerical core compiled for the host (same templates, same arithmetic
+ * contract).  Test-only: lets the CPU test-suite compare the solver source with the
+ * oracle bit-for-bit without a GPU.  Not a fallback: nothing in the engine calls these. */
+int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3]);
+int rsac_debug_host_jacobi12(const double a[144], double w[12], double v[144]);
+int rsac_debug_host_sim3(const float P1[9], const float P2[9], int fix_scale, float R[9], float t[3], float* s);
+int rsac_debug_host_mlpnp6(const float K[4], const float p3d[18], const float p2d[12], const double* cov54,
+                           double R[9], double t[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANSAC_B200_H */

@@ -1,0 +1,691 @@
+// engine.cu -- C ABI (include/ransac_b200.h) and host orchestration of the batched RANSAC
+// engine.  One engine = one device + one stream + grow-only device buffers.  No CPU
+// fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ransac_b200.h"
+#include "common.cuh"
+#include "engine_state.cuh"
+#include "pnp_pipeline.cuh"
+#include "score.cuh"
+
+using namespace rsac;
+
+// ------------------------------------------------------------------ helpers
+int rsac_version(void) { return RSAC_VERSION; }
+
+int rsac_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rsac_create(int device, rsac_engine** out)
+{
+    if (!out) return RSAC_ERR_INVALID;
+    *out = nullptr;
+    int n = rsac_device_count();
+    if (n <= 0 || device < 0 || device >= n) return RSAC_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return RSAC_ERR_NO_DEVICE; }
+    rsac_engine* e = new rsac_engine();
+    e->device = device;
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return RSAC_ERR_CUDA; }
+    e->stream = e->own_stream;
+    cudaEventCreate(&e->t0);
+    cudaEventCreate(&e->t1);
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = e;
+    return RSAC_OK;
+}
+
+void rsac_destroy(rsac_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->free_all();
+    for (auto& p : e->prof_events) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto& p : e->prof_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    cudaEventDestroy(e->t0);
+    cudaEventDestroy(e->t1);
+    cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+const char* rsac_last_error(rsac_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int rsac_set_stream(rsac_engine* e, void* s)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    e->stream = s ? (cudaStream_t)s : e->own_stream;
+    return RSAC_OK;
+}
+
+int rsac_sync(rsac_engine* e)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_host_alloc(void** ptr, uint64_t bytes)
+{
+    if (!ptr) return RSAC_ERR_INVALID;
+    if (cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return RSAC_ERR_ALLOC; }
+    return RSAC_OK;
+}
+
+int rsac_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? RSAC_OK : RSAC_ERR_CUDA; }
+
+int rsac_get_device_info(rsac_engine* e, rsac_device_info* info)
+{
+    if (!e || !info) return RSAC_ERR_INVALID;
+    cudaDeviceProp p;
+    RSAC_CUDA(e, cudaGetDeviceProperties(&p, e->device));
+    memset(info, 0, sizeof(*info));
+    info->sm_count = p.multiProcessorCount;
+    cudaDeviceGetAttribute(&info->sm_clock_khz, cudaDevAttrClockRate, e->device);
+    cudaDeviceGetAttribute(&info->mem_clock_khz, cudaDevAttrMemoryClockRate, e->device);
+    info->cc_major = p.major;
+    info->cc_minor = p.minor;
+    info->total_mem = p.totalGlobalMem;
+    strncpy(info->name, p.name, sizeof(info->name) - 1);
+    return RSAC_OK;
+}
+
+int rsac_timer_begin(rsac_engine* e)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaEventRecord(e->t0, e->stream));
+    return RSAC_OK;
+}
+
+int rsac_timer_end(rsac_engine* e, float* ms)
+{
+    if (!e || !ms) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaEventRecord(e->t1, e->stream));
+    RSAC_CUDA(e, cudaEventSynchronize(e->t1));
+    RSAC_CUDA(e, cudaEventElapsedTime(ms, e->t0, e->t1));
+    return RSAC_OK;
+}
+
+int rsac_profile_enable(rsac_engine* e, int on)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    e->profile = on != 0;
+    return RSAC_OK;
+}
+
+static int profile_drain(rsac_engine* e)
+{
+    if (e->prof_events.empty()) return RSAC_OK;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (auto& p : e->prof_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            e->stage_ms[p.stage] += ms;
+            e->stage_launches[p.stage] += 1;
+        } else {
+            cudaGetLastError();
+        }
+        e->prof_pool.push_back(p);
+    }
+    e->prof_events.clear();
+    return RSAC_OK;
+}
+
+int rsac_profile_reset(rsac_engine* e)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    int rc = profile_drain(e);
+    for (int i = 0; i < RSAC_STAGE_COUNT; ++i) { e->stage_ms[i] = 0.0; e->stage_launches[i] = 0; }
+    e->launches = 0;
+    return rc;
+}
+
+int rsac_profile_get(rsac_engine* e, int stage, double* total_ms, int64_t* launches)
+{
+    if (!e || stage < 0 || stage >= RSAC_STAGE_COUNT) return RSAC_ERR_INVALID;
+    int rc = profile_drain(e);
+    if (total_ms) *total_ms = e->stage_ms[stage];
+    if (launches) *launches = e->stage_launches[stage];
+    return rc;
+}
+
+int64_t rsac_launch_count(rsac_engine* e) { return e ? e->launches : 0; }
+
+// ------------------------------------------------------------ host helpers
+int rsac_pnp_ransac_setup(int N, const rsac_ransac_params* p, int* min_inl, int* max_its)
+{
+    if (!p) return RSAC_ERR_INVALID;
+    // PnPsolver::SetRansacParameters (PnPsolver.cpp:58-94); same arithmetic in MLPnPsolver.cpp:185-220
+    float eps = p->eps;
+    int nMinInliers = (int)((float)N * eps);
+    if (nMinInliers < p->min_inliers) nMinInliers = p->min_inliers;
+    if (nMinInliers < p->min_set) nMinInliers = p->min_set;
+    if (eps < (float)nMinInliers / N) eps = (float)nMinInliers / N;
+    int nIterations;
+    if (nMinInliers == N)
+        nIterations = 1;
+    else
+        nIterations = (int)std::ceil(std::log(1 - p->prob) / std::log(1 - std::pow(eps, 3)));
+    int its = std::min(nIterations, p->max_its);
+    if (max_its) *max_its = std::max(1, its);
+    if (min_inl) *min_inl = nMinInliers;
+    return RSAC_OK;
+}
+
+int rsac_sim3_ransac_setup(int N, const rsac_sim3_params* p, int* max_its)
+{
+    if (!p) return RSAC_ERR_INVALID;
+    // Sim3Solver::SetRansacParameters (Sim3Solver.cpp:87-111)
+    const float epsilon = (float)p->min_inliers / N;
+    int nIterations;
+    if (p->min_inliers == N)
+        nIterations = 1;
+    else
+        nIterations = (int)std::ceil(std::log(1 - p->prob) / std::log(1 - std::pow(epsilon, 3)));
+    int its = std::min(nIterations, p->max_its);
+    if (max_its) *max_its = std::max(1, its);
+    return RSAC_OK;
+}
+
+int rsac_index_table(uint32_t seed, int n, int k, int H, uint32_t* out)
+{
+    if (!out || k < 1 || k > 8 || n < k || H < 0) return RSAC_ERR_INVALID;
+    GlibcRand g;
+    g.seed(seed);
+    for (int h = 0; h < H; ++h) draw_minimal_set<8>(g, n, k, out + (size_t)h * k);
+    return RSAC_OK;
+}
+
+int rsac_rand_stream(uint32_t seed, int count, int32_t* out)
+{
+    if (!out || count < 0) return RSAC_ERR_INVALID;
+    GlibcRand g;
+    g.seed(seed);
+    for (int i = 0; i < count; ++i) out[i] = g.next();
+    return RSAC_OK;
+}
+
+int rsac_shard_range(int C, int rank, int world, int* first, int* count)
+{
+    if (world < 1 || rank < 0 || rank >= world || C < 0) return RSAC_ERR_INVALID;
+    const int per = (C + world - 1) / world;           // contiguous blocks of ceil(C/world)
+    const int f = std::min(C, rank * per);
+    const int l = std::min(C, f + per);
+    if (first) *first = f;
+    if (count) *count = l - f;
+    return RSAC_OK;
+}
+
+// --------------------------------------------------------- tile planning
+// CTA shape for the scoring kernel: HPL = 2 hypotheses per lane.
+static constexpr int kHPL = 2;
+static constexpr int kChunkCapMax = 2048;   // correspondences per shared-memory tile (64 KB)
+
+static int score_threads_for(int maxH)
+{
+    int warps = (maxH + 32 * kHPL - 1) / (32 * kHPL);
+    warps = std::max(1, std::min(8, warps));
+    return warps * 32;
+}
+
+// Splits each problem into (hypothesis tile) x (correspondence chunk) CTAs.  Chunks are
+// whole mask words; when the batch is too small to fill the SMs the correspondences are
+// cut finer so that the grid is about `waves` x SM count.
+static void plan_tiles(const std::vector<ProblemMeta>& metas, int threads, int sm_count,
+                       std::vector<ScoreTile>& tiles, int* chunk_cap_out)
+{
+    tiles.clear();
+    const int hyp_per_tile = (threads / 32) * 32 * kHPL;
+    long long base_tiles = 0;
+    for (const auto& m : metas) {
+        if (m.n <= 0 || m.H <= 0) continue;
+        const int ht = (m.H + hyp_per_tile - 1) / hyp_per_tile;
+        const int ch = (m.n + kChunkCapMax - 1) / kChunkCapMax;
+        base_tiles += (long long)ht * ch;
+    }
+    const long long target = 2LL * sm_count;
+    int cap = 32;
+    for (const auto& m : metas) {
+        if (m.n <= 0 || m.H <= 0) continue;
+        const int ht = (m.H + hyp_per_tile - 1) / hyp_per_tile;
+        const int words = (m.n + 31) / 32;
+        int chunks = (m.n + kChunkCapMax - 1) / kChunkCapMax;
+        if (base_tiles < target) {
+            // spread this problem over more CTAs (only matters for few, large problems)
+            const long long want = (target * (long long)ht * chunks + base_tiles - 1) / base_tiles;
+            chunks = (int)std::max<long long>(chunks, std::min<long long>(words, (want + ht - 1) / ht));
+        }
+        const int wbase = words / chunks, wrem = words % chunks;
+        for (int t = 0; t < ht; ++t) {
+            int w0 = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int wn = wbase + (c < wrem ? 1 : 0);
+                if (wn == 0) continue;
+                ScoreTile st;
+                st.problem = (int)(&m - metas.data());
+                st.hyp0 = t * hyp_per_tile;
+                st.corr0 = w0 * 32;
+                st.nc = std::min(m.n - w0 * 32, wn * 32);
+                cap = std::max(cap, wn * 32);
+                tiles.push_back(st);
+                w0 += wn;
+            }
+        }
+    }
+    *chunk_cap_out = cap;
+}
+
+template <int MODEL>
+static int launch_score(rsac_engine* e, const ScoreArgs& args, int ntiles, int threads)
+{
+    if (ntiles <= 0) return RSAC_OK;
+    const size_t smem = (size_t)args.chunk_cap * 32;
+    auto kern = score_kernel<kHPL, MODEL>;
+    if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    e->stage_begin(RSAC_STAGE_SCORE);
+    kern<<<ntiles, threads, smem, e->stream>>>(args);
+    e->stage_end(RSAC_STAGE_SCORE);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+// ------------------------------------------------------------------- PnP
+static int pnp_build_metas(rsac_engine* e, int C, const int32_t* offsets, const rsac_ransac_params* params, int n_params,
+                           const uint32_t* seeds, const int64_t* table_offsets, bool have_tables,
+                           std::vector<ProblemMeta>& metas, std::vector<float>& th2, BatchDims& d)
+{
+    metas.assign(C, ProblemMeta());
+    th2.assign(C, 0.f);
+    d = BatchDims();
+    d.C = C;
+    for (int c = 0; c < C; ++c) {
+        const rsac_ransac_params& p = params[n_params == 1 ? 0 : c];
+        ProblemMeta& m = metas[c];
+        memset(&m, 0, sizeof(m));
+        m.corr_off = offsets[c];
+        m.n = offsets[c + 1] - offsets[c];
+        if (m.n < 0 || p.min_set < 1 || p.min_set > 8) { e->err = "bad offsets or min_set"; return RSAC_ERR_INVALID; }
+        int minInl = 0, H = 1;
+        if (m.n > 0) rsac_pnp_ransac_setup(m.n, &p, &minInl, &H); else { minInl = std::max(p.min_inliers, p.min_set); H = 0; }
+        if (m.n < minInl || m.n < p.min_set) H = 0;       // iterate() returns at once (PnPsolver.cpp:110-114)
+        m.H = H;
+        m.min_inl = minInl;
+        m.min_set = p.min_set;
+        m.hyp_off = (int32_t)d.sumH;
+        m.words = (m.n + 31) / 32;
+        m.word_off = (int32_t)d.total_words;
+        m.hmask_off = d.total_hwords;
+        m.seed = seeds ? seeds[c] : 0u;
+        if (have_tables) {
+            m.table_off = table_offsets[c];
+            if (table_offsets[c + 1] - table_offsets[c] < (int64_t)H * p.min_set) { e->err = "index table too short"; return RSAC_ERR_INVALID; }
+        } else {
+            m.table_off = d.table_len;
+        }
+        th2[c] = p.th2;
+        d.table_len += (int64_t)H * p.min_set;
+        d.sumH += H;
+        d.total_words += m.words;
+        d.total_hwords += (int64_t)H * m.words;
+        d.maxH = std::max(d.maxH, H);
+        d.maxN = std::max(d.maxN, m.n);
+        d.maxWords = std::max(d.maxWords, m.words);
+    }
+    d.total = offsets[C];
+    if (have_tables) d.table_len = table_offsets[C];
+    return RSAC_OK;
+}
+
+int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
+{
+    if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
+    if (!b->seeds && !b->tables) { if (e) e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    PnpState& s = e->pnp;
+    s.uploaded = false; s.ran = false;
+    std::vector<float> th2;
+    int rc = pnp_build_metas(e, b->C, b->offsets, b->params, b->n_params, b->seeds, b->table_offsets, b->tables != nullptr, s.metas, th2, s.d);
+    if (rc) return rc;
+    for (int c = 0; c < b->C; ++c) {
+        s.metas[c].fx = b->K[4 * c]; s.metas[c].fy = b->K[4 * c + 1]; s.metas[c].cx = b->K[4 * c + 2]; s.metas[c].cy = b->K[4 * c + 3];
+    }
+    const BatchDims& d = s.d;
+    const size_t tot = (size_t)std::max(d.total, 1);
+    s.threads = score_threads_for(d.maxH);
+    plan_tiles(s.metas, s.threads, e->sm_count, s.tiles, &s.chunk_cap);
+
+    RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreTile) * std::max<size_t>(s.tiles.size(), 1)));
+    RSAC_TRY(s.d_th2.ensure(e, sizeof(float) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
+    RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
+    RSAC_TRY(s.d_sigma2.ensure(e, tot * 4));
+    RSAC_TRY(s.d_cA.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cB.ensure(e, tot * 16));
+    RSAC_TRY(s.d_uv.ensure(e, tot * 8));
+    RSAC_TRY(s.d_tables.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.table_len, 1)));
+    RSAC_TRY(s.d_poses.ensure(e, sizeof(float) * 12 * (size_t)std::max<int64_t>(d.sumH, 1)));
+    RSAC_TRY(s.d_counts.ensure(e, sizeof(int32_t) * (size_t)std::max<int64_t>(d.sumH, 1)));
+    RSAC_TRY(s.d_results.ensure(e, sizeof(rsac_result) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_masks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_words, 1)));
+    RSAC_TRY(s.d_sel.ensure(e, tot * 4));
+    RSAC_TRY(s.d_pw.ensure(e, tot * 24));
+    RSAC_TRY(s.d_us.ensure(e, tot * 16));
+    RSAC_TRY(s.d_al.ensure(e, tot * 32));
+
+    cudaStream_t st = e->stream;
+    if (d.C > 0) {
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, s.metas.data(), sizeof(ProblemMeta) * d.C, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_th2.p, th2.data(), sizeof(float) * d.C, cudaMemcpyHostToDevice, st));
+    }
+    if (!s.tiles.empty())
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, s.tiles.data(), sizeof(ScoreTile) * s.tiles.size(), cudaMemcpyHostToDevice, st));
+    if (d.total > 0) {
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, b->p3d, (size_t)d.total * 12, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, b->p2d, (size_t)d.total * 8, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_sigma2.p, b->sigma2, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));
+    }
+    s.have_tables = b->tables != nullptr;
+    if (s.have_tables && d.table_len > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tables.p, b->tables, sizeof(uint32_t) * (size_t)d.table_len, cudaMemcpyHostToDevice, st));
+    // the metas/tiles/th2 staging vectors must outlive the async copies from pageable memory:
+    // cudaMemcpyAsync from pageable host memory returns after the data is staged, so they do.
+    s.h2d_bytes = (uint64_t)d.total * 24 + sizeof(ProblemMeta) * (uint64_t)d.C + sizeof(float) * (uint64_t)d.C +
+                  sizeof(ScoreTile) * s.tiles.size() + (s.have_tables ? sizeof(uint32_t) * (uint64_t)d.table_len : 0);
+    if (d.total > 0 && d.C > 0) {
+        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)d.C);
+        e->stage_begin(RSAC_STAGE_PACK);
+        pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
+                                              (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 0,
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float2*)s.d_uv.p);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.uploaded = true;
+    return RSAC_OK;
+}
+
+int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    if (!s.uploaded) { e->err = "rsac_pnp_run before rsac_pnp_upload"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    const BatchDims& d = s.d;
+    cudaStream_t st = e->stream;
+    const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
+    if (d.C == 0) { s.ran = true; return RSAC_OK; }
+
+    if (!s.have_tables && d.table_len > 0) {
+        e->stage_begin(RSAC_STAGE_RNG);
+        rng_tables_kernel<<<(d.C + 63) / 64, 64, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
+        e->stage_end(RSAC_STAGE_RNG);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    if (d.sumH > 0) {
+        const int threads = 128;
+        const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
+        e->stage_begin(RSAC_STAGE_SOLVE);
+        epnp_minimal_kernel<<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
+                                                        (const float4*)s.d_cA.p, (const float2*)s.d_uv.p, (float*)s.d_poses.p);
+        e->stage_end(RSAC_STAGE_SOLVE);
+        RSAC_CUDA(e, cudaGetLastError());
+
+        RSAC_CUDA(e, cudaMemsetAsync(s.d_counts.p, 0, sizeof(int32_t) * (size_t)d.sumH, st));
+        ScoreArgs sa;
+        sa.metas = metas; sa.tiles = (const ScoreTile*)s.d_tiles.p;
+        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.uv = (const float2*)s.d_uv.p;
+        sa.poses = s.d_poses.p; sa.counts = (int32_t*)s.d_counts.p;
+        sa.hmasks = nullptr;
+        if (flags & RSAC_FLAG_KEEP_MASKS) {
+            RSAC_TRY(s.d_hmasks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_hwords, 1)));
+            sa.hmasks = (uint32_t*)s.d_hmasks.p;
+        }
+        RSAC_TRY(e->d_exact.ensure(e, sizeof(unsigned long long)));
+        RSAC_CUDA(e, cudaMemsetAsync(e->d_exact.p, 0, sizeof(unsigned long long), st));
+        sa.exact_counter = (unsigned long long*)e->d_exact.p;
+        sa.chunk_cap = s.chunk_cap;
+        int rc = launch_score<0>(e, sa, (int)s.tiles.size(), s.threads);
+        if (rc) return rc;
+    }
+    {
+        SelectArgs a;
+        a.metas = metas; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.uv = (const float2*)s.d_uv.p;
+        a.poses = (const float*)s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p;
+        a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p;
+        a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
+        a.problem_base = e->problem_base;
+        const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
+        if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(pnp_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        e->stage_begin(RSAC_STAGE_SELECT);
+        pnp_select_kernel<<<d.C, kSelectThreads, smem, st>>>(a);
+        e->stage_end(RSAC_STAGE_SELECT);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.ran = true;
+    return RSAC_OK;
+}
+
+int rsac_pnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    if (!s.ran) { e->err = "rsac_pnp_download before rsac_pnp_run"; return RSAC_ERR_STATE; }
+    const BatchDims& d = s.d;
+    if (results && d.C > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(results, s.d_results.p, sizeof(rsac_result) * d.C, cudaMemcpyDeviceToHost, e->stream));
+    if (masks && d.total_words > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(masks, s.d_masks.p, sizeof(uint32_t) * (size_t)d.total_words, cudaMemcpyDeviceToHost, e->stream));
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_pnp_solve(rsac_engine* e, const rsac_pnp_batch* b, int flags, rsac_result* results, uint32_t* masks)
+{
+    int rc = rsac_pnp_upload(e, b);
+    if (rc) return rc;
+    rc = rsac_pnp_run(e, flags, nullptr);
+    if (rc) return rc;
+    return rsac_pnp_download(e, results, masks);
+}
+
+int64_t rsac_pnp_total_hypotheses(rsac_engine* e) { return e ? e->pnp.d.sumH : 0; }
+
+int rsac_pnp_get_hypotheses(rsac_engine* e, float* poses, int32_t* counts)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    if (!s.ran) return RSAC_ERR_STATE;
+    if (s.d.sumH > 0) {
+        if (poses) RSAC_CUDA(e, cudaMemcpyAsync(poses, s.d_poses.p, sizeof(float) * 12 * (size_t)s.d.sumH, cudaMemcpyDeviceToHost, e->stream));
+        if (counts) RSAC_CUDA(e, cudaMemcpyAsync(counts, s.d_counts.p, sizeof(int32_t) * (size_t)s.d.sumH, cudaMemcpyDeviceToHost, e->stream));
+    }
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+// ------------------------------------------------------- scoring stress (cfg5)
+int rsac_score_pnp_upload(rsac_engine* e, int H, const float* poses, int n, const float* p3d, const float* p2d,
+                          const float* max_err, const double K[4])
+{
+    if (!e || H < 0 || n < 0 || !K || (H > 0 && !poses) || (n > 0 && (!p3d || !p2d || !max_err))) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    ScoreState& s = e->score;
+    s.uploaded = false; s.ran = false;
+    s.metas.assign(1, ProblemMeta());
+    ProblemMeta& m = s.metas[0];
+    memset(&m, 0, sizeof(m));
+    m.n = n; m.H = H; m.words = (n + 31) / 32;
+    m.fx = K[0]; m.fy = K[1]; m.cx = K[2]; m.cy = K[3];
+    s.H = H; s.n = n;
+    s.threads = score_threads_for(H);
+    plan_tiles(s.metas, s.threads, e->sm_count, s.tiles, &s.chunk_cap);
+    const size_t tot = (size_t)std::max(n, 1), hh = (size_t)std::max(H, 1);
+    RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta)));
+    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreTile) * std::max<size_t>(s.tiles.size(), 1)));
+    RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
+    RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
+    RSAC_TRY(s.d_maxerr.ensure(e, tot * 4));
+    RSAC_TRY(s.d_cA.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cB.ensure(e, tot * 16));
+    RSAC_TRY(s.d_uv.ensure(e, tot * 8));
+    RSAC_TRY(s.d_poses.ensure(e, hh * 48));
+    RSAC_TRY(s.d_counts.ensure(e, hh * 4));
+    RSAC_TRY(s.d_hmasks.ensure(e, hh * (size_t)std::max(m.words, 1) * 4));
+    cudaStream_t st = e->stream;
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, s.metas.data(), sizeof(ProblemMeta), cudaMemcpyHostToDevice, st));
+    if (!s.tiles.empty())
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, s.tiles.data(), sizeof(ScoreTile) * s.tiles.size(), cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, p3d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, p2d, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_maxerr.p, max_err, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (H > 0) RSAC_CUDA(e, cudaMemcpyAsync(s.d_poses.p, poses, (size_t)H * 48, cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        dim3 grid((unsigned)std::max(1, std::min(256, (n + 255) / 256)), 1);
+        e->stage_begin(RSAC_STAGE_PACK);
+        pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
+                                              nullptr, nullptr, (const float*)s.d_maxerr.p, 0,
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float2*)s.d_uv.p);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.uploaded = true;
+    return RSAC_OK;
+}
+
+int rsac_score_pnp_run(rsac_engine* e, int want_masks)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    ScoreState& s = e->score;
+    if (!s.uploaded) { e->err = "rsac_score_pnp_run before upload"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    if (s.H > 0) RSAC_CUDA(e, cudaMemsetAsync(s.d_counts.p, 0, sizeof(int32_t) * (size_t)s.H, st));
+    RSAC_TRY(e->d_exact.ensure(e, sizeof(unsigned long long)));
+    RSAC_CUDA(e, cudaMemsetAsync(e->d_exact.p, 0, sizeof(unsigned long long), st));
+    if (s.H > 0 && s.n > 0) {
+        ScoreArgs sa;
+        sa.metas = (const ProblemMeta*)s.d_metas.p; sa.tiles = (const ScoreTile*)s.d_tiles.p;
+        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.uv = (const float2*)s.d_uv.p;
+        sa.poses = s.d_poses.p; sa.counts = (int32_t*)s.d_counts.p;
+        sa.hmasks = want_masks ? (uint32_t*)s.d_hmasks.p : nullptr;
+        sa.exact_counter = (unsigned long long*)e->d_exact.p;
+        sa.chunk_cap = s.chunk_cap;
+        int rc = launch_score<0>(e, sa, (int)s.tiles.size(), s.threads);
+        if (rc) return rc;
+    }
+    s.ran = true;
+    s.with_masks = want_masks != 0;
+    return RSAC_OK;
+}
+
+int rsac_score_pnp_download(rsac_engine* e, uint32_t* masks, int32_t* counts)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    ScoreState& s = e->score;
+    if (!s.ran) return RSAC_ERR_STATE;
+    const int words = (s.n + 31) / 32;
+    if (counts && s.H > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(counts, s.d_counts.p, sizeof(int32_t) * (size_t)s.H, cudaMemcpyDeviceToHost, e->stream));
+    if (masks && s.with_masks && s.H > 0 && words > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(masks, s.d_hmasks.p, sizeof(uint32_t) * (size_t)s.H * words, cudaMemcpyDeviceToHost, e->stream));
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_score_pnp(rsac_engine* e, int H, const float* poses, int n, const float* p3d, const float* p2d,
+                   const float* max_err, const double K[4], uint32_t* masks, int32_t* counts)
+{
+    int rc = rsac_score_pnp_upload(e, H, poses, n, p3d, p2d, max_err, K);
+    if (rc) return rc;
+    rc = rsac_score_pnp_run(e, masks != nullptr);
+    if (rc) return rc;
+    return rsac_score_pnp_download(e, masks, counts);
+}
+
+int64_t rsac_score_exact_evals(rsac_engine* e)
+{
+    if (!e || !e->d_exact.p) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, e->d_exact.p, sizeof(v), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) return -1;
+    cudaStreamSynchronize(e->stream);
+    return (int64_t)v;
+}
+
+// ------------------------------------------------------------ peak probes
+template <typename T>
+__global__ void fma_peak_kernel(T* out, int iters)
+{
+    T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3;
+    T a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6, a7 = a0 + (T)7;
+    const T b = (T)0.999, c = (T)1e-4;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int rsac_measure_peaks(rsac_engine* e, double* fp32_tflops, double* fp64_tflops)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    const int blocks = e->sm_count * 8, threads = 256;
+    RSAC_TRY(e->d_scratch.ensure(e, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    auto run = [&](bool dbl, int iters) -> double {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(a, e->stream);
+            if (dbl) fma_peak_kernel<double><<<blocks, threads, 0, e->stream>>>((double*)e->d_scratch.p, iters);
+            else fma_peak_kernel<float><<<blocks, threads, 0, e->stream>>>((float*)e->d_scratch.p, iters);
+            cudaEventRecord(b, e->stream);
+            cudaEventSynchronize(b);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, a, b);
+            if (rep > 0) best = std::min(best, ms);
+        }
+        e->launches += 4;
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        return flops / (best * 1e-3) / 1e12;
+    };
+    if (fp32_tflops) *fp32_tflops = run(false, 4096);
+    if (fp64_tflops) *fp64_tflops = run(true, 1024);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+// ------------------------------------------------------- host debug hooks
+int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3])
+{
+    double pw[12], us[8];
+    for (int i = 0; i < 12; ++i) pw[i] = (double)p3d[i];
+    for (int i = 0; i < 8; ++i) us[i] = (double)p2d[i];
+    const Cam k = {K[0], K[1], K[2], K[3]};
+    epnp_compute_pose_small<4>(pw, us, k, R, t);
+    return RSAC_OK;
+}
+
+int rsac_debug_host_jacobi12(const double a[144], double w[12], double v[144])
+{
+    double A[144];
+    memcpy(A, a, sizeof(A));
+    jacobi_eig<double, 12>(A, w, v);
+    return RSAC_OK;
+}

@@ -1,0 +1,161 @@
+// engine_state.cuh -- host-side state of an engine: stream, grow-only device buffers,
+// per-batch bookkeeping, kernel-stage profiling with CUDA events.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/ransac_b200.h"
+#include "common.cuh"
+
+#define RSAC_CUDA(e, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t _err = (call);                                                                \
+        if (_err != cudaSuccess) {                                                                \
+            (e)->err = std::string(#call) + ": " + cudaGetErrorString(_err);                      \
+            cudaGetLastError();                                                                   \
+            return (_err == cudaErrorNoDevice || _err == cudaErrorInsufficientDriver) ? RSAC_ERR_NO_DEVICE : RSAC_ERR_CUDA; \
+        }                                                                                         \
+    } while (0)
+
+#define RSAC_TRY(expr)                       \
+    do {                                     \
+        int _rc = (expr);                    \
+        if (_rc != RSAC_OK) return _rc;      \
+    } while (0)
+
+struct rsac_engine;
+
+namespace rsac {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(rsac_engine* e, size_t bytes);
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct BatchDims {
+    int C = 0;
+    int total = 0;             // correspondences
+    int64_t sumH = 0;          // hypotheses
+    int64_t total_words = 0;   // final-mask words
+    int64_t total_hwords = 0;  // per-hypothesis mask words
+    int64_t table_len = 0;
+    int maxH = 0, maxN = 0, maxWords = 0;
+};
+
+struct PnpState {
+    bool uploaded = false, ran = false, have_tables = false;
+    BatchDims d;
+    std::vector<ProblemMeta> metas;
+    std::vector<ScoreTile> tiles;
+    int threads = 32, chunk_cap = 32;
+    uint64_t h2d_bytes = 0;
+    DevBuf d_metas, d_tiles, d_th2, d_p3d, d_p2d, d_sigma2, d_cA, d_cB, d_uv, d_tables, d_poses, d_counts,
+        d_results, d_masks, d_hmasks, d_sel, d_pw, d_us, d_al, d_cov, d_extra;
+    void release()
+    {
+        DevBuf* all[] = {&d_metas, &d_tiles, &d_th2, &d_p3d, &d_p2d, &d_sigma2, &d_cA, &d_cB, &d_uv, &d_tables, &d_poses,
+                         &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+struct ScoreState {
+    bool uploaded = false, ran = false, with_masks = false;
+    int H = 0, n = 0, threads = 32, chunk_cap = 32;
+    std::vector<ProblemMeta> metas;
+    std::vector<ScoreTile> tiles;
+    DevBuf d_metas, d_tiles, d_p3d, d_p2d, d_maxerr, d_cA, d_cB, d_uv, d_poses, d_counts, d_hmasks;
+    void release()
+    {
+        DevBuf* all[] = {&d_metas, &d_tiles, &d_p3d, &d_p2d, &d_maxerr, &d_cA, &d_cB, &d_uv, &d_poses, &d_counts, &d_hmasks};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+struct Sim3State {
+    bool uploaded = false, ran = false, have_tables = false;
+    BatchDims d;
+    std::vector<ProblemMeta> metas;
+    DevBuf d_metas, d_x1, d_x2, d_s1, d_s2, d_c1, d_c2, d_tables, d_poses, d_counts, d_hmasks, d_results, d_masks;
+    void release()
+    {
+        DevBuf* all[] = {&d_metas, &d_x1, &d_x2, &d_s1, &d_s2, &d_c1, &d_c2, &d_tables, &d_poses, &d_counts, &d_hmasks, &d_results, &d_masks};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+struct ProfPair {
+    int stage;
+    cudaEvent_t a, b;
+};
+
+}  // namespace rsac
+
+struct rsac_engine {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // per-stage profiling
+    bool profile = false;
+    std::vector<rsac::ProfPair> prof_events, prof_pool;
+    rsac::ProfPair cur{};
+    double stage_ms[RSAC_STAGE_COUNT] = {0, 0, 0, 0, 0};
+    int64_t stage_launches[RSAC_STAGE_COUNT] = {0, 0, 0, 0, 0};
+    int64_t launches = 0;
+    int32_t problem_base = 0;
+    rsac::PnpState pnp;
+    rsac::PnpState mlpnp;
+    rsac::ScoreState score;
+    rsac::Sim3State sim3;
+    rsac::DevBuf d_exact, d_scratch;
+    void* nccl_comm = nullptr;
+    void* nccl_lib = nullptr;
+
+    void stage_begin(int stage)
+    {
+        ++launches;
+        if (!profile) return;
+        if (!prof_pool.empty()) { cur = prof_pool.back(); prof_pool.pop_back(); }
+        else { cudaEventCreate(&cur.a); cudaEventCreate(&cur.b); }
+        cur.stage = stage;
+        cudaEventRecord(cur.a, stream);
+    }
+    void stage_end(int)
+    {
+        if (!profile) return;
+        cudaEventRecord(cur.b, stream);
+        prof_events.push_back(cur);
+    }
+    void free_all()
+    {
+        pnp.release(); mlpnp.release(); score.release(); sim3.release();
+        d_exact.release(); d_scratch.release();
+    }
+};
+
+inline int rsac::DevBuf::ensure(rsac_engine* e, size_t bytes)
+{
+    if (bytes <= cap) return RSAC_OK;
+    if (p) { cudaStreamSynchronize(e->stream); cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4;   // head-room so that ragged batches do not reallocate every call
+    cudaError_t err = cudaMalloc(&p, want);
+    if (err != cudaSuccess) {
+        e->err = std::string("cudaMalloc: ") + cudaGetErrorString(err);
+        cudaGetLastError();
+        p = nullptr;
+        return RSAC_ERR_ALLOC;
+    }
+    cap = want;
+    return RSAC_OK;
+}

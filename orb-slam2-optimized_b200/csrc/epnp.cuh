@@ -1,0 +1,388 @@
+// epnp.cuh -- EPnP building blocks (device), following reference src/PnPsolver.cpp.
+//
+// The same pieces serve two schedules:
+//   * minimal solve (n = 4): one thread per hypothesis, everything thread-private;
+//   * n-point refine: one CTA per problem, sums evaluated "entry-parallel" -- one thread
+//     per OUTPUT entry walks the points in index order -- so that every sum is formed in
+//     exactly the serial order of the CPU checker, and the dense tail (12x12 eigen-solve,
+//     betas, Gauss-Newton, Horn) runs on one thread with the functions below.
+// FP64, -fmad=false, operation order fixed (arithmetic contract).
+#pragma once
+#include "linalg.cuh"
+
+namespace rsac {
+
+struct Cam { double fx, fy, cx, cy; };
+
+// PnPsolver::choose_control_points (PnPsolver.cpp:296-321) after the sums:
+// C0 = centroid (already divided by n), A = upper triangle of PW0^T PW0.
+__host__ __device__ inline void epnp_control_points(const double* C0, double* A, int n, double* cws /*4x3*/)
+{
+    for (int c = 0; c < 3; ++c) cws[c] = C0[c];
+    double DC[3], UCt[9];
+    jacobi_eig<double, 3>(A, DC, UCt);
+    for (int i = 0; i < 3; ++i) {
+        const double k = sqrt(DC[i] / (double)n);
+        for (int c = 0; c < 3; ++c) cws[(i + 1) * 3 + c] = cws[c] + k * UCt[c * 3 + i];
+    }
+}
+
+// PnPsolver::compute_barycentric_coordinates (:323-331): CC and its inverse
+__host__ __device__ inline void epnp_cc_inverse(const double* cws, double* CCi)
+{
+    double CC[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 1; j < 4; ++j) CC[i * 3 + (j - 1)] = cws[j * 3 + i] - cws[i];
+    inv3(CC, CCi);
+}
+
+// (:334-342) alphas of one point
+__host__ __device__ inline void epnp_alphas(const double* pw, const double* cws, const double* CCi, double* a)
+{
+    const double d0 = pw[0] - cws[0], d1 = pw[1] - cws[1], d2 = pw[2] - cws[2];
+    for (int j = 0; j < 3; ++j) a[j + 1] = CCi[j * 3 + 0] * d0 + CCi[j * 3 + 1] * d1 + CCi[j * 3 + 2] * d2;
+    a[0] = 1.0 - a[1] - a[2] - a[3];
+}
+
+// the two rows of M contributed by one correspondence (PnPsolver.cpp:367-377)
+__host__ __device__ inline void epnp_m_rows(const double* a, double u, double v, const Cam& k, double* r0, double* r1)
+{
+    for (int j = 0; j < 4; ++j) {
+        r0[3 * j] = a[j] * k.fx; r0[3 * j + 1] = 0.0;        r0[3 * j + 2] = a[j] * (k.cx - u);
+        r1[3 * j] = 0.0;         r1[3 * j + 1] = a[j] * k.fy; r1[3 * j + 2] = a[j] * (k.cy - v);
+    }
+}
+
+// one entry of a row of M without materialising the row (entry-parallel MtM in the refine stage)
+__host__ __device__ inline void epnp_m_entry(const double* a, double u, double v, const Cam& k, int col, double& e0, double& e1)
+{
+    const int j = col / 3, c = col - 3 * j;
+    if (c == 0)      { e0 = a[j] * k.fx;       e1 = 0.0; }
+    else if (c == 1) { e0 = 0.0;               e1 = a[j] * k.fy; }
+    else             { e0 = a[j] * (k.cx - u); e1 = a[j] * (k.cy - v); }
+}
+
+// PnPsolver::compute_L_6x10 (:604-637), U4[r*4+i] = i-th smallest eigenvector, row r
+__host__ __device__ inline void epnp_L_6x10(const double* U4, double* L /*6x10*/)
+{
+    double dv[4][6][3];
+    for (int i = 0; i < 4; ++i) {
+        int a = 0, b = 1;
+        for (int j = 0; j < 6; ++j) {
+            for (int c = 0; c < 3; ++c) dv[i][j][c] = U4[(3 * a + c) * 4 + i] - U4[(3 * b + c) * 4 + i];
+            b++;
+            if (b > 3) { a++; b = a + 1; }
+        }
+    }
+#define RSAC_DOT3(x, y) ((x)[0] * (y)[0] + (x)[1] * (y)[1] + (x)[2] * (y)[2])
+    for (int i = 0; i < 6; ++i) {
+        double* l = L + i * 10;
+        l[0] = RSAC_DOT3(dv[0][i], dv[0][i]);
+        l[1] = 2.0 * RSAC_DOT3(dv[0][i], dv[1][i]);
+        l[2] = RSAC_DOT3(dv[1][i], dv[1][i]);
+        l[3] = 2.0 * RSAC_DOT3(dv[0][i], dv[2][i]);
+        l[4] = 2.0 * RSAC_DOT3(dv[1][i], dv[2][i]);
+        l[5] = RSAC_DOT3(dv[2][i], dv[2][i]);
+        l[6] = 2.0 * RSAC_DOT3(dv[0][i], dv[3][i]);
+        l[7] = 2.0 * RSAC_DOT3(dv[1][i], dv[3][i]);
+        l[8] = 2.0 * RSAC_DOT3(dv[2][i], dv[3][i]);
+        l[9] = RSAC_DOT3(dv[3][i], dv[3][i]);
+    }
+#undef RSAC_DOT3
+}
+
+__host__ __device__ inline double sqdist3(const double* a, const double* b)
+{
+    const double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+    return d0 * d0 + d1 * d1 + d2 * d2;
+}
+
+// PnPsolver::compute_rho (:639-647)
+__host__ __device__ inline void epnp_rho(const double* cws, double* rho)
+{
+    rho[0] = sqdist3(cws + 0, cws + 3);
+    rho[1] = sqdist3(cws + 0, cws + 6);
+    rho[2] = sqdist3(cws + 0, cws + 9);
+    rho[3] = sqdist3(cws + 3, cws + 6);
+    rho[4] = sqdist3(cws + 3, cws + 9);
+    rho[5] = sqdist3(cws + 6, cws + 9);
+}
+
+// find_betas_approx_{1,2,3} (:520-602)
+__host__ __device__ inline void epnp_betas_approx_1(const double* L, const double* rho, double* betas)
+{
+    double L4[24], b4[4];
+    for (int i = 0; i < 6; ++i) {
+        L4[i * 4 + 0] = L[i * 10 + 0]; L4[i * 4 + 1] = L[i * 10 + 1]; L4[i * 4 + 2] = L[i * 10 + 3]; L4[i * 4 + 3] = L[i * 10 + 6];
+    }
+    svd_lstsq<6, 4>(L4, rho, b4);
+    if (b4[0] < 0) {
+        betas[0] = sqrt(-b4[0]);
+        betas[1] = -b4[1] / betas[0];
+        betas[2] = -b4[2] / betas[0];
+        betas[3] = -b4[3] / betas[0];
+    } else {
+        betas[0] = sqrt(b4[0]);
+        betas[1] = b4[1] / betas[0];
+        betas[2] = b4[2] / betas[0];
+        betas[3] = b4[3] / betas[0];
+    }
+}
+
+__host__ __device__ inline void epnp_betas_approx_2(const double* L, const double* rho, double* betas)
+{
+    double L3[18], b3[3];
+    for (int i = 0; i < 6; ++i) {
+        L3[i * 3 + 0] = L[i * 10 + 0]; L3[i * 3 + 1] = L[i * 10 + 1]; L3[i * 3 + 2] = L[i * 10 + 2];
+    }
+    svd_lstsq<6, 3>(L3, rho, b3);
+    if (b3[0] < 0) {
+        betas[0] = sqrt(-b3[0]);
+        betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0;
+    } else {
+        betas[0] = sqrt(b3[0]);
+        betas[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0;
+    }
+    if (b3[1] < 0) betas[0] = -betas[0];
+    betas[2] = 0.0;
+    betas[3] = 0.0;
+}
+
+__host__ __device__ inline void epnp_betas_approx_3(const double* L, const double* rho, double* betas)
+{
+    double L5[30], b5[5];
+    for (int i = 0; i < 6; ++i)
+        for (int c = 0; c < 5; ++c) L5[i * 5 + c] = L[i * 10 + c];
+    svd_lstsq<6, 5>(L5, rho, b5);
+    if (b5[0] < 0) {
+        betas[0] = sqrt(-b5[0]);
+        betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0;
+    } else {
+        betas[0] = sqrt(b5[0]);
+        betas[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0;
+    }
+    if (b5[1] < 0) betas[0] = -betas[0];
+    betas[2] = b5[3] / betas[0];
+    betas[3] = 0.0;
+}
+
+// PnPsolver::compute_A_and_b_gauss_newton (:649-673)
+__host__ __device__ inline void epnp_gn_system(const double* L, const double* rho, const double* bt, double* A /*6x4*/, double* b)
+{
+    for (int i = 0; i < 6; ++i) {
+        const double* l = L + i * 10;
+        const double Lt[4][4] = {{2 * l[0], l[1], l[3], l[6]},
+                                 {l[1], 2 * l[2], l[4], l[7]},
+                                 {l[3], l[4], 2 * l[5], l[8]},
+                                 {l[6], l[7], l[8], 2 * l[9]}};
+        for (int r = 0; r < 4; ++r)
+            A[i * 4 + r] = Lt[r][0] * bt[0] + Lt[r][1] * bt[1] + Lt[r][2] * bt[2] + Lt[r][3] * bt[3];
+        b[i] = rho[i] - (l[0] * bt[0] * bt[0] + l[1] * bt[0] * bt[1] + l[2] * bt[1] * bt[1] +
+                         l[3] * bt[0] * bt[2] + l[4] * bt[1] * bt[2] + l[5] * bt[2] * bt[2] +
+                         l[6] * bt[0] * bt[3] + l[7] * bt[1] * bt[3] + l[8] * bt[2] * bt[3] +
+                         l[9] * bt[3] * bt[3]);
+    }
+}
+
+// PnPsolver::qr_solve (:693-796): Householder QR of the 6x4 system with max-abs column
+// scaling; a zero column returns with X untouched (:722-727).  Thread-private scratch
+// replaces the reference's function-static A1/A2 (:696-697).
+__host__ __device__ inline void epnp_qr_solve(double* A /*6x4*/, double* b, double* X)
+{
+    constexpr int nr = 6, nc = 4;
+    double A1[nc], A2[nc];
+    for (int k = 0; k < nc; ++k) {
+        double eta = fabs(A[k * nc + k]);
+        for (int i = k + 1; i < nr; ++i) {
+            const double elt = fabs(A[i * nc + k]);
+            if (eta < elt) eta = elt;
+        }
+        if (eta == 0) return;
+        const double inv_eta = 1. / eta;
+        double sum = 0.0;
+        for (int i = k; i < nr; ++i) {
+            A[i * nc + k] *= inv_eta;
+            sum += A[i * nc + k] * A[i * nc + k];
+        }
+        double sigma = sqrt(sum);
+        if (A[k * nc + k] < 0) sigma = -sigma;
+        A[k * nc + k] += sigma;
+        A1[k] = sigma * A[k * nc + k];
+        A2[k] = -eta * sigma;
+        for (int j = k + 1; j < nc; ++j) {
+            double s = 0;
+            for (int i = k; i < nr; ++i) s += A[i * nc + k] * A[i * nc + j];
+            const double tau = s / A1[k];
+            for (int i = k; i < nr; ++i) A[i * nc + j] -= tau * A[i * nc + k];
+        }
+    }
+    for (int j = 0; j < nc; ++j) {
+        double tau = 0;
+        for (int i = j; i < nr; ++i) tau += A[i * nc + j] * b[i];
+        tau /= A1[j];
+        for (int i = j; i < nr; ++i) b[i] -= tau * A[i * nc + j];
+    }
+    X[nc - 1] = b[nc - 1] / A2[nc - 1];
+    for (int i = nc - 2; i >= 0; --i) {
+        double sum = 0;
+        for (int j = i + 1; j < nc; ++j) sum += A[i * nc + j] * X[j];
+        X[i] = (b[i] - sum) / A2[i];
+    }
+}
+
+// PnPsolver::gauss_newton (:675-691): exactly five steps
+__host__ __device__ inline void epnp_gauss_newton(const double* L, const double* rho, double* betas)
+{
+    double A[24], B[6], X[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < 5; ++k) {
+        epnp_gn_system(L, rho, betas, A, B);
+        epnp_qr_solve(A, B, X);
+        for (int i = 0; i < 4; ++i) betas[i] += X[i];
+    }
+}
+
+// From MtM (upper triangle, destroyed) to the null-space basis U4 (12x4) and the three
+// refined beta vectors: 12x12 eigen-solve (:380), L, rho, approx_k + gauss_newton (:395-405).
+__host__ __device__ inline void epnp_solve_betas(double* MtM, const double* cws, double* U4, double* betas /*3x4*/)
+{
+    double w[12], U[144];
+    jacobi_eig<double, 12>(MtM, w, U);
+    for (int r = 0; r < 12; ++r)
+        for (int j = 0; j < 4; ++j) U4[r * 4 + j] = U[r * 12 + j];
+    double L[60], rho[6];
+    epnp_L_6x10(U4, L);
+    epnp_rho(cws, rho);
+    epnp_betas_approx_1(L, rho, betas + 0);
+    epnp_gauss_newton(L, rho, betas + 0);
+    epnp_betas_approx_2(L, rho, betas + 4);
+    epnp_gauss_newton(L, rho, betas + 4);
+    epnp_betas_approx_3(L, rho, betas + 8);
+    epnp_gauss_newton(L, rho, betas + 8);
+}
+
+// PnPsolver::compute_ccs (:345-352)
+__host__ __device__ inline void epnp_ccs(const double* betas, const double* U4, double* ccs /*4x3*/)
+{
+    for (int i = 0; i < 4; ++i)
+        for (int c = 0; c < 3; ++c) {
+            double s = 0.0;
+            for (int j = 0; j < 4; ++j) s += betas[j] * U4[(3 * i + c) * 4 + j];
+            ccs[i * 3 + c] = s;
+        }
+}
+
+// one row of pcs = alphas * ccs (:354-357)
+__host__ __device__ inline void epnp_pc(const double* a, const double* ccs, double* pc)
+{
+    for (int c = 0; c < 3; ++c) pc[c] = a[0] * ccs[c] + a[1] * ccs[3 + c] + a[2] * ccs[6 + c] + a[3] * ccs[9 + c];
+}
+
+// tail of PnPsolver::estimate_R_and_t (:449-492) given M = sum (pc-pc0)^T (pw-pw0):
+// Horn's 4x4 with float-truncated entries, last eigenvector, q = (w,-x,-y,-z)
+__host__ __device__ inline void epnp_horn(const double* M, const double* pc0, const double* pw0, double* R, double* t)
+{
+    const float N11 = (float)(M[0] + M[4] + M[8]);
+    const float N12 = (float)(M[5] - M[7]);
+    const float N13 = (float)(M[6] - M[2]);
+    const float N14 = (float)(M[1] - M[3]);
+    const float N22 = (float)(M[0] - M[4] - M[8]);
+    const float N23 = (float)(M[1] + M[3]);
+    const float N24 = (float)(M[6] + M[2]);
+    const float N33 = (float)(-M[0] + M[4] - M[8]);
+    const float N34 = (float)(M[5] + M[7]);
+    const float N44 = (float)(-M[0] - M[4] + M[8]);
+    double N[16] = {N11, N12, N13, N14, N12, N22, N23, N24, N13, N23, N33, N34, N14, N24, N34, N44};
+    double w[4], V[16];
+    jacobi_eig<double, 4>(N, w, V);
+    quat_to_rot<double>(V[0 * 4 + 3], -V[1 * 4 + 3], -V[2 * 4 + 3], -V[3 * 4 + 3], R);
+    if (det3(R) < 0) { R[6] = -R[6]; R[7] = -R[7]; R[8] = -R[8]; }
+    for (int r = 0; r < 3; ++r)
+        t[r] = pc0[r] - (R[r * 3 + 0] * pw0[0] + R[r * 3 + 1] * pw0[1] + R[r * 3 + 2] * pw0[2]);
+}
+
+// one term of PnPsolver::reprojection_error (:421-428)
+__host__ __device__ inline double epnp_reproj_term(const double* R, const double* t, const double* pw, double u, double v, const Cam& k)
+{
+    const double X = R[0] * pw[0] + R[1] * pw[1] + R[2] * pw[2] + t[0];
+    const double Y = R[3] * pw[0] + R[4] * pw[1] + R[5] * pw[2] + t[1];
+    const double Z = R[6] * pw[0] + R[7] * pw[1] + R[8] * pw[2] + t[2];
+    const double inv_Zc = 1.0 / Z;
+    const double ue = k.cx + k.fx * X * inv_Zc;
+    const double ve = k.cy + k.fy * Y * inv_Zc;
+    const double du = u - ue, dv = v - ve;
+    return sqrt(du * du + dv * dv);
+}
+
+// Whole PnPsolver::compute_pose (:359-415) for NPTS thread-private correspondences.
+// pw: NPTS x 3, us: NPTS x 2 (already widened to double).  Writes R (9) t (3) as float.
+template <int NPTS>
+__host__ __device__ inline double epnp_compute_pose_small(const double* pw, const double* us, const Cam& k, float* Rf, float* tf)
+{
+    double cws[12], C0[3];
+    for (int c = 0; c < 3; ++c) {
+        double s = 0.0;
+        for (int i = 0; i < NPTS; ++i) s += pw[i * 3 + c];
+        C0[c] = s / (double)NPTS;
+    }
+    double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < NPTS; ++i) {
+        const double d0 = pw[i * 3 + 0] - C0[0], d1 = pw[i * 3 + 1] - C0[1], d2 = pw[i * 3 + 2] - C0[2];
+        A[0] += d0 * d0; A[1] += d0 * d1; A[2] += d0 * d2;
+        A[4] += d1 * d1; A[5] += d1 * d2;
+        A[8] += d2 * d2;
+    }
+    epnp_control_points(C0, A, NPTS, cws);
+    double CCi[9];
+    epnp_cc_inverse(cws, CCi);
+    double alphas[NPTS * 4];
+    for (int i = 0; i < NPTS; ++i) epnp_alphas(pw + 3 * i, cws, CCi, alphas + 4 * i);
+
+    double MtM[144];
+    for (int i = 0; i < 144; ++i) MtM[i] = 0.0;
+    for (int i = 0; i < NPTS; ++i) {
+        double r0[12], r1[12];
+        epnp_m_rows(alphas + 4 * i, us[2 * i], us[2 * i + 1], k, r0, r1);
+        for (int a = 0; a < 12; ++a)
+            for (int b = a; b < 12; ++b) {
+                MtM[a * 12 + b] += r0[a] * r0[b];
+                MtM[a * 12 + b] += r1[a] * r1[b];
+            }
+    }
+    double U4[48], betas[12];
+    epnp_solve_betas(MtM, cws, U4, betas);
+
+    double rep[3], Rs[3][9], ts[3][3];
+    for (int kk = 0; kk < 3; ++kk) {
+        double ccs[12], pcs[NPTS * 3];
+        epnp_ccs(betas + 4 * kk, U4, ccs);
+        for (int i = 0; i < NPTS; ++i) epnp_pc(alphas + 4 * i, ccs, pcs + 3 * i);
+        if (pcs[2] < 0.0) {                                   // solve_for_sign (:495-502)
+            for (int i = 0; i < 12; ++i) ccs[i] = -ccs[i];
+            for (int i = 0; i < NPTS * 3; ++i) pcs[i] = -pcs[i];
+        }
+        double pc0[3], pw0[3];
+        for (int c = 0; c < 3; ++c) {
+            double sc = 0.0, sw = 0.0;
+            for (int i = 0; i < NPTS; ++i) sc += pcs[i * 3 + c];
+            for (int i = 0; i < NPTS; ++i) sw += pw[i * 3 + c];
+            pc0[c] = sc / (double)NPTS;
+            pw0[c] = sw / (double)NPTS;
+        }
+        double M[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < NPTS; ++i)
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) M[r * 3 + c] += (pcs[i * 3 + r] - pc0[r]) * (pw[i * 3 + c] - pw0[c]);
+        epnp_horn(M, pc0, pw0, Rs[kk], ts[kk]);
+        double sum2 = 0.0;
+        for (int i = 0; i < NPTS; ++i) sum2 += epnp_reproj_term(Rs[kk], ts[kk], pw + 3 * i, us[2 * i], us[2 * i + 1], k);
+        rep[kk] = sum2 / (double)NPTS;
+    }
+    int N = 0;                                                // :407-409 (index shifted by one)
+    if (rep[1] < rep[0]) N = 1;
+    if (rep[2] < rep[N]) N = 2;
+    for (int i = 0; i < 9; ++i) Rf[i] = (float)Rs[N][i];
+    for (int i = 0; i < 3; ++i) tf[i] = (float)ts[N][i];
+    return rep[N];
+}
+
+}  // namespace rsac

@@ -1,0 +1,314 @@
+// linalg.cuh -- fixed-size dense solves for the RANSAC minimal solvers (device side).
+//
+// These stand in for the Eigen calls of the reference (SelfAdjointEigenSolver at
+// src/PnPsolver.cpp:311,380,469 / src/Sim3Solver.cpp:238-241 / src/MLPnPsolver.cpp:359,
+// bdcSvd().solve at PnPsolver.cpp:531,559,590, Matrix3d::inverse at :331, JacobiSVD /
+// FullPivHouseholderQR / LDLT in MLPnPsolver.cpp).  Arithmetic contract:
+// only + - * / sqrt, IEEE round-to-nearest, NO FMA contraction (this TU is compiled
+// with -fmad=false), fixed operation order -- the CPU checker evaluates the same
+// sequences, which is what makes 4-point EPnP hypotheses comparable at all.
+#pragma once
+#include <cfloat>
+#include <cmath>
+
+namespace rsac {
+
+template <typename T> struct JacobiTol;
+template <> struct JacobiTol<double> { __host__ __device__ static double scale() { return 0x1p-56; } };
+template <> struct JacobiTol<float>  { __host__ __device__ static float scale() { return 0x1p-27f; } };
+
+__host__ __device__ inline double rsqrt_exact(double x) { return sqrt(x); }
+__host__ __device__ inline float rsqrt_exact(float x) { return sqrtf(x); }
+__host__ __device__ inline double rabs(double x) { return fabs(x); }
+__host__ __device__ inline float rabs(float x) { return fabsf(x); }
+
+constexpr int kMaxSweeps = 30;
+
+// Cyclic Jacobi with Rutishauser's rotation on the upper triangle of the symmetric
+// N x N matrix a (row-major, destroyed).  Eigenvalues ascending in w, eigenvectors in
+// the columns of v.  Rotations with |a_pq| <= ||a||_F * 2^-56 (2^-27 in float) are
+// skipped; the solve ends after a sweep without rotations.
+template <typename T, int N>
+__host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
+{
+    const T one = T(1), zero = T(0), two = T(2);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? one : zero;
+    T fro2 = zero;
+    for (int i = 0; i < N; ++i)
+        for (int j = i; j < N; ++j) fro2 += a[i * N + j] * a[i * N + j];
+    const T tol = rsqrt_exact(fro2) * JacobiTol<T>::scale();
+    for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < N - 1; ++p) {
+            for (int q = p + 1; q < N; ++q) {
+                const T apq = a[p * N + q];
+                if (!(rabs(apq) > tol)) continue;
+                rotated = true;
+                const T app = a[p * N + p], aqq = a[q * N + q];
+                const T theta = (aqq - app) / (two * apq);
+                T t = one / (rabs(theta) + rsqrt_exact(theta * theta + one));
+                if (theta < zero) t = -t;
+                const T c = one / rsqrt_exact(t * t + one);
+                const T s = t * c;
+                const T tau = s / (one + c);
+                const T h = t * apq;
+                a[p * N + p] = app - h;
+                a[q * N + q] = aqq + h;
+                a[p * N + q] = zero;
+                for (int j = 0; j < p; ++j) {
+                    const T g = a[j * N + p], k = a[j * N + q];
+                    a[j * N + p] = g - s * (k + g * tau);
+                    a[j * N + q] = k + s * (g - k * tau);
+                }
+                for (int j = p + 1; j < q; ++j) {
+                    const T g = a[p * N + j], k = a[j * N + q];
+                    a[p * N + j] = g - s * (k + g * tau);
+                    a[j * N + q] = k + s * (g - k * tau);
+                }
+                for (int j = q + 1; j < N; ++j) {
+                    const T g = a[p * N + j], k = a[q * N + j];
+                    a[p * N + j] = g - s * (k + g * tau);
+                    a[q * N + j] = k + s * (g - k * tau);
+                }
+                for (int j = 0; j < N; ++j) {
+                    const T g = v[j * N + p], k = v[j * N + q];
+                    v[j * N + p] = g - s * (k + g * tau);
+                    v[j * N + q] = k + s * (g - k * tau);
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+    for (int i = 0; i < N; ++i) w[i] = a[i * N + i];
+    for (int i = 0; i < N - 1; ++i) {
+        int k = i;
+        for (int j = i + 1; j < N; ++j)
+            if (w[j] < w[k]) k = j;
+        if (k != i) {
+            const T tw = w[i]; w[i] = w[k]; w[k] = tw;
+            for (int r = 0; r < N; ++r) {
+                const T tv = v[r * N + i]; v[r * N + i] = v[r * N + k]; v[r * N + k] = tv;
+            }
+        }
+    }
+}
+
+// One-sided (Hestenes) Jacobi: orthogonalises the columns of U (M x K), accumulates V (K x K).
+template <int M, int K>
+__host__ __device__ inline void onesided_jacobi(double* U, double* V)
+{
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) V[i * K + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+        bool rotated = false;
+        for (int i = 0; i < K - 1; ++i) {
+            for (int j = i + 1; j < K; ++j) {
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+                for (int r = 0; r < M; ++r) {
+                    const double ui = U[r * K + i], uj = U[r * K + j];
+                    alpha += ui * ui;
+                    beta += uj * uj;
+                    gamma += ui * uj;
+                }
+                if (!(fabs(gamma) > DBL_EPSILON * sqrt(alpha * beta))) continue;
+                rotated = true;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                double t = 1.0 / (fabs(zeta) + sqrt(zeta * zeta + 1.0));
+                if (zeta < 0.0) t = -t;
+                const double c = 1.0 / sqrt(t * t + 1.0);
+                const double s = c * t;
+                for (int r = 0; r < M; ++r) {
+                    const double ui = U[r * K + i], uj = U[r * K + j];
+                    U[r * K + i] = c * ui - s * uj;
+                    U[r * K + j] = s * ui + c * uj;
+                }
+                for (int r = 0; r < K; ++r) {
+                    const double vi = V[r * K + i], vj = V[r * K + j];
+                    V[r * K + i] = c * vi - s * vj;
+                    V[r * K + j] = s * vi + c * vj;
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+}
+
+// Minimum-norm least squares through the one-sided Jacobi SVD; singular values not larger
+// than sigma_max * K * eps count as zero (Eigen's SVDBase threshold, diagSize = K).
+// Stands in for L.bdcSvd(ThinU|ThinV).solve(b) (PnPsolver.cpp:531,559,590).
+template <int M, int K>
+__host__ __device__ inline void svd_lstsq(const double* L, const double* b, double* x)
+{
+    double U[M * K], V[K * K], sig2[K], sig[K];
+    for (int i = 0; i < M * K; ++i) U[i] = L[i];
+    onesided_jacobi<M, K>(U, V);
+    double smax = 0.0;
+    for (int j = 0; j < K; ++j) {
+        double s2 = 0.0;
+        for (int r = 0; r < M; ++r) s2 += U[r * K + j] * U[r * K + j];
+        sig2[j] = s2;
+        sig[j] = sqrt(s2);
+        if (sig[j] > smax) smax = sig[j];
+    }
+    const double thresh = smax * ((double)K * DBL_EPSILON);
+    for (int r = 0; r < K; ++r) x[r] = 0.0;
+    for (int j = 0; j < K; ++j) {
+        if (!(sig[j] > thresh)) continue;
+        double ub = 0.0;
+        for (int r = 0; r < M; ++r) ub += U[r * K + j] * b[r];
+        const double coef = ub / sig2[j];
+        for (int r = 0; r < K; ++r) x[r] += coef * V[r * K + j];
+    }
+}
+
+// closed-form cofactor inverse (Matrix3d::inverse(), PnPsolver.cpp:331); singular => inf/NaN
+__host__ __device__ inline void inv3(const double* m, double* out)
+{
+    const double c00 = m[4] * m[8] - m[5] * m[7];
+    const double c01 = m[5] * m[6] - m[3] * m[8];
+    const double c02 = m[3] * m[7] - m[4] * m[6];
+    const double c10 = m[2] * m[7] - m[1] * m[8];
+    const double c11 = m[0] * m[8] - m[2] * m[6];
+    const double c12 = m[1] * m[6] - m[0] * m[7];
+    const double c20 = m[1] * m[5] - m[2] * m[4];
+    const double c21 = m[2] * m[3] - m[0] * m[5];
+    const double c22 = m[0] * m[4] - m[1] * m[3];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const double id = 1.0 / det;
+    out[0] = c00 * id; out[1] = c10 * id; out[2] = c20 * id;
+    out[3] = c01 * id; out[4] = c11 * id; out[5] = c21 * id;
+    out[6] = c02 * id; out[7] = c12 * id; out[8] = c22 * id;
+}
+
+__host__ __device__ inline double det3(const double* R)
+{
+    return R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) +
+           R[2] * (R[3] * R[7] - R[4] * R[6]);
+}
+
+// Eigen::Quaternion::toRotationMatrix (PnPsolver.cpp:478, Sim3Solver.cpp:248), no normalisation
+template <typename T>
+__host__ __device__ inline void quat_to_rot(T w, T x, T y, T z, T* R)
+{
+    const T two = T(2), one = T(1);
+    const T tx = two * x, ty = two * y, tz = two * z;
+    const T twx = tx * w, twy = ty * w, twz = tz * w;
+    const T txx = tx * x, txy = ty * x, txz = tz * x;
+    const T tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = one - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
+    R[3] = txy + twz;         R[4] = one - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = one - (txx + tyy);
+}
+
+// orthogonal polar factor U V^T of a 3x3 (JacobiSVD, MLPnPsolver.cpp:511-512,570-571)
+__host__ __device__ inline void polar3(const double* a, double* r)
+{
+    double U[9], V[9], inv[3];
+    for (int i = 0; i < 9; ++i) U[i] = a[i];
+    onesided_jacobi<3, 3>(U, V);
+    for (int j = 0; j < 3; ++j) {
+        double s2 = 0.0;
+        for (int i = 0; i < 3; ++i) s2 += U[i * 3 + j] * U[i * 3 + j];
+        inv[j] = 1.0 / sqrt(s2);
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) {
+            double acc = 0.0;
+            for (int j = 0; j < 3; ++j) acc += (U[i * 3 + j] * inv[j]) * V[c * 3 + j];
+            r[i * 3 + c] = acc;
+        }
+}
+
+// rank of a 3x3 by full-pivot Householder QR with Eigen's thresholds
+// (FullPivHouseholderQR<Matrix3d>::rank(), MLPnPsolver.cpp:347,354)
+__host__ __device__ inline int rank3_fullpiv(const double* a_in)
+{
+    double a[9];
+    for (int i = 0; i < 9; ++i) a[i] = a_in[i];
+    double diag[3] = {0.0, 0.0, 0.0};
+    int nonzero = 3;
+    double maxpivot = 0.0, biggest = 0.0;
+    const double precision = DBL_EPSILON * 3.0;
+    for (int k = 0; k < 3; ++k) {
+        int pr = k, pc = k;
+        double big = -1.0;
+        for (int c = k; c < 3; ++c)
+            for (int r = k; r < 3; ++r)
+                if (fabs(a[r * 3 + c]) > big) { big = fabs(a[r * 3 + c]); pr = r; pc = c; }
+        if (k == 0) biggest = big;
+        if (!(big > biggest * precision)) { nonzero = k; break; }
+        if (pr != k)
+            for (int c = 0; c < 3; ++c) { const double t = a[k * 3 + c]; a[k * 3 + c] = a[pr * 3 + c]; a[pr * 3 + c] = t; }
+        if (pc != k)
+            for (int r = 0; r < 3; ++r) { const double t = a[r * 3 + k]; a[r * 3 + k] = a[r * 3 + pc]; a[r * 3 + pc] = t; }
+        double tail2 = 0.0;
+        for (int r = k + 1; r < 3; ++r) tail2 += a[r * 3 + k] * a[r * 3 + k];
+        const double c0 = a[k * 3 + k];
+        double beta, tau;
+        double vv[3] = {0.0, 0.0, 0.0};
+        if (tail2 <= DBL_MIN) {
+            beta = c0; tau = 0.0;
+        } else {
+            beta = sqrt(c0 * c0 + tail2);
+            if (c0 >= 0.0) beta = -beta;
+            for (int r = k + 1; r < 3; ++r) vv[r] = a[r * 3 + k] / (c0 - beta);
+            tau = (beta - c0) / beta;
+        }
+        vv[k] = 1.0;
+        diag[k] = beta;
+        if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+        for (int c = k + 1; c < 3; ++c) {
+            double dot = 0.0;
+            for (int r = k; r < 3; ++r) dot += vv[r] * a[r * 3 + c];
+            for (int r = k; r < 3; ++r) a[r * 3 + c] -= tau * vv[r] * dot;
+        }
+    }
+    int rank = 0;
+    const double thr = maxpivot * (DBL_EPSILON * 3.0);
+    for (int i = 0; i < nonzero; ++i)
+        if (fabs(diag[i]) > thr) ++rank;
+    return rank;
+}
+
+// LDL^T with diagonal pivoting, 6x6 (Eigen::LDLT::solve, MLPnPsolver.cpp:705-706)
+__host__ __device__ inline void ldlt6_solve(const double* a_in, const double* g, double* x)
+{
+    constexpr int N = 6;
+    double a[36];
+    int perm[N];
+    for (int i = 0; i < 36; ++i) a[i] = a_in[i];
+    for (int i = 0; i < N; ++i) perm[i] = i;
+    for (int k = 0; k < N; ++k) {
+        int piv = k;
+        double big = fabs(a[k * N + k]);
+        for (int i = k + 1; i < N; ++i)
+            if (fabs(a[i * N + i]) > big) { big = fabs(a[i * N + i]); piv = i; }
+        if (piv != k) {
+            for (int c = 0; c < N; ++c) { const double t = a[k * N + c]; a[k * N + c] = a[piv * N + c]; a[piv * N + c] = t; }
+            for (int r = 0; r < N; ++r) { const double t = a[r * N + k]; a[r * N + k] = a[r * N + piv]; a[r * N + piv] = t; }
+            const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        const double d = a[k * N + k];
+        if (!(fabs(d) > DBL_MIN)) continue;
+        for (int i = k + 1; i < N; ++i) a[i * N + k] = a[i * N + k] / d;
+        for (int i = k + 1; i < N; ++i)
+            for (int j = k + 1; j <= i; ++j) {
+                a[i * N + j] -= a[i * N + k] * d * a[j * N + k];
+                a[j * N + i] = a[i * N + j];
+            }
+    }
+    double y[N];
+    for (int i = 0; i < N; ++i) y[i] = g[perm[i]];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < i; ++j) y[i] -= a[i * N + j] * y[j];
+    for (int i = 0; i < N; ++i) {
+        const double d = a[i * N + i];
+        y[i] = (fabs(d) > DBL_MIN) ? y[i] / d : 0.0;
+    }
+    for (int i = N - 1; i >= 0; --i)
+        for (int j = i + 1; j < N; ++j) y[i] -= a[j * N + i] * y[j];
+    for (int i = 0; i < N; ++i) x[perm[i]] = y[i];
+}
+
+}  // namespace rsac

@@ -1,0 +1,303 @@
+"""ctypes binding of libransac_b200.so (the C ABI in include/ransac_b200.h).
+
+This is plumbing for bench.py / tests; the product is the shared library.  There is no
+fallback: if the library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libransac_b200.so")
+_LIB = None
+
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = range(6)
+FLAG_KEEP_MASKS = 1
+FLAG_MLPNP_DISCARD_REFINE = 4
+STAGE_PACK, STAGE_RNG, STAGE_SOLVE, STAGE_SCORE, STAGE_SELECT = range(5)
+STAGE_NAMES = ["pack", "rng", "solve", "score", "select"]
+
+
+class RansacParams(C.Structure):
+    _fields_ = [("prob", C.c_double), ("min_inliers", C.c_int32), ("max_its", C.c_int32),
+                ("min_set", C.c_int32), ("eps", C.c_float), ("th2", C.c_float)]
+
+
+class Sim3Params(C.Structure):
+    _fields_ = [("prob", C.c_double), ("min_inliers", C.c_int32), ("max_its", C.c_int32), ("fix_scale", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("no_more", C.c_int32), ("n_inliers", C.c_int32), ("best_hyp", C.c_int32),
+                ("refined", C.c_int32), ("n_refines", C.c_int32), ("best_count", C.c_int32), ("n_hyp", C.c_int32),
+                ("R", C.c_float * 9), ("t", C.c_float * 3), ("s", C.c_float), ("problem", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
+
+
+RESULT_DTYPE = np.dtype([("ok", "<i4"), ("no_more", "<i4"), ("n_inliers", "<i4"), ("best_hyp", "<i4"),
+                         ("refined", "<i4"), ("n_refines", "<i4"), ("best_count", "<i4"), ("n_hyp", "<i4"),
+                         ("R", "<f4", (9,)), ("t", "<f4", (3,)), ("s", "<f4"), ("problem", "<i4"),
+                         ("reserved", "<i4", (2,))])
+assert RESULT_DTYPE.itemsize == 96 == C.sizeof(Result)
+
+
+class DeviceInfo(C.Structure):
+    _fields_ = [("sm_count", C.c_int32), ("sm_clock_khz", C.c_int32), ("mem_clock_khz", C.c_int32),
+                ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("total_mem", C.c_uint64), ("name", C.c_char * 64)]
+
+
+class PnPBatch(C.Structure):
+    _fields_ = [("C", C.c_int32), ("offsets", C.c_void_p), ("p3d", C.c_void_p), ("p2d", C.c_void_p),
+                ("sigma2", C.c_void_p), ("K", C.c_void_p), ("params", C.c_void_p), ("n_params", C.c_int32),
+                ("seeds", C.c_void_p), ("tables", C.c_void_p), ("table_offsets", C.c_void_p)]
+
+
+class Sim3Batch(C.Structure):
+    _fields_ = [("C", C.c_int32), ("offsets", C.c_void_p), ("x1c", C.c_void_p), ("x2c", C.c_void_p),
+                ("sigma2_1", C.c_void_p), ("sigma2_2", C.c_void_p), ("K1", C.c_void_p), ("K2", C.c_void_p),
+                ("params", C.c_void_p), ("n_params", C.c_int32), ("seeds", C.c_void_p), ("tables", C.c_void_p),
+                ("table_offsets", C.c_void_p)]
+
+
+class MLPnPBatch(C.Structure):
+    _fields_ = [("C", C.c_int32), ("offsets", C.c_void_p), ("p3d", C.c_void_p), ("p2d", C.c_void_p),
+                ("sigma2", C.c_void_p), ("K", C.c_void_p), ("cov", C.c_void_p), ("params", C.c_void_p),
+                ("n_params", C.c_int32), ("seeds", C.c_void_p), ("tables", C.c_void_p), ("table_offsets", C.c_void_p)]
+
+
+class RsacError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__(f"ransac_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Loads the library; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is missing: run __graft_entry__.build() "
+                                    "(python orb-slam2-optimized_b200/build.py); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.rsac_last_error.restype = C.c_char_p
+        L.rsac_launch_count.restype = C.c_int64
+        for f in ("rsac_pnp_total_hypotheses", "rsac_sim3_total_hypotheses", "rsac_mlpnp_total_hypotheses",
+                  "rsac_score_exact_evals"):
+            if hasattr(L, f):
+                getattr(L, f).restype = C.c_int64
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pnp_ransac_setup(n, prm: RansacParams):
+    mi, it = C.c_int(), C.c_int()
+    lib().rsac_pnp_ransac_setup(C.c_int(n), C.byref(prm), C.byref(mi), C.byref(it))
+    return mi.value, it.value
+
+
+def sim3_ransac_setup(n, prm: Sim3Params):
+    it = C.c_int()
+    lib().rsac_sim3_ransac_setup(C.c_int(n), C.byref(prm), C.byref(it))
+    return it.value
+
+
+def index_table(seed, n, k, H):
+    out = np.empty((H, k), np.uint32)
+    rc = lib().rsac_index_table(C.c_uint32(seed), C.c_int(n), C.c_int(k), C.c_int(H), _p(out))
+    if rc:
+        raise RsacError(rc, "rsac_index_table")
+    return out
+
+
+def rand_stream(seed, count):
+    out = np.empty(count, np.int32)
+    lib().rsac_rand_stream(C.c_uint32(seed), C.c_int(count), _p(out))
+    return out
+
+
+def shard_range(Cn, rank, world):
+    f, c = C.c_int(), C.c_int()
+    rc = lib().rsac_shard_range(C.c_int(Cn), C.c_int(rank), C.c_int(world), C.byref(f), C.byref(c))
+    if rc:
+        raise RsacError(rc, "rsac_shard_range")
+    return f.value, c.value
+
+
+def ransac_params(prob=0.99, min_inliers=8, max_its=300, min_set=4, eps=0.4, th2=5.991):
+    return RansacParams(prob, min_inliers, max_its, min_set, eps, th2)
+
+
+class Engine:
+    """Owns one rsac_engine handle."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        rc = self.L.rsac_create(C.c_int(device), C.byref(self.h))
+        if rc:
+            raise RsacError(rc, "rsac_create: no usable CUDA device" if rc == ERR_NO_DEVICE else "rsac_create")
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.rsac_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc:
+            raise RsacError(rc, f"{what}: {self.L.rsac_last_error(self.h).decode()}")
+
+    # -- plumbing
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(self.L.rsac_set_stream(self.h, C.c_void_p(cuda_stream or 0)), "set_stream")
+
+    def sync(self):
+        self._ck(self.L.rsac_sync(self.h), "sync")
+
+    def device_info(self):
+        info = DeviceInfo()
+        self._ck(self.L.rsac_get_device_info(self.h, C.byref(info)), "device_info")
+        return dict(sm_count=info.sm_count, sm_clock_khz=info.sm_clock_khz, mem_clock_khz=info.mem_clock_khz,
+                    cc=(info.cc_major, info.cc_minor), total_mem=info.total_mem, name=info.name.decode())
+
+    def timer_begin(self):
+        self._ck(self.L.rsac_timer_begin(self.h), "timer_begin")
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        self._ck(self.L.rsac_timer_end(self.h, C.byref(ms)), "timer_end")
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.rsac_profile_enable(self.h, C.c_int(1 if on else 0)), "profile_enable")
+
+    def profile_reset(self):
+        self._ck(self.L.rsac_profile_reset(self.h), "profile_reset")
+
+    def profile(self):
+        out = {}
+        for i, nm in enumerate(STAGE_NAMES):
+            ms, n = C.c_double(), C.c_int64()
+            self._ck(self.L.rsac_profile_get(self.h, C.c_int(i), C.byref(ms), C.byref(n)), "profile_get")
+            out[nm] = (ms.value, n.value)
+        return out
+
+    def launch_count(self) -> int:
+        return self.L.rsac_launch_count(self.h)
+
+    def measure_peaks(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.rsac_measure_peaks(self.h, C.byref(a), C.byref(b)), "measure_peaks")
+        return a.value, b.value
+
+    # -- PnP
+    def _pnp_desc(self, offsets, p3d, p2d, sigma2, K, params, seeds=None, tables=None, table_offsets=None):
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        Cn = len(offsets) - 1
+        p3d = np.ascontiguousarray(p3d, np.float32).reshape(-1, 3)
+        p2d = np.ascontiguousarray(p2d, np.float32).reshape(-1, 2)
+        sigma2 = np.ascontiguousarray(sigma2, np.float32).reshape(-1)
+        K = np.ascontiguousarray(K, np.float64).reshape(-1, 4)
+        if K.shape[0] == 1 and Cn != 1:
+            K = np.ascontiguousarray(np.repeat(K, max(Cn, 1), axis=0))
+        if isinstance(params, RansacParams):
+            parr = (RansacParams * 1)(params)
+            npar = 1
+        else:
+            parr = (RansacParams * len(params))(*params)
+            npar = len(params)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, np.uint32)
+        tables = None if tables is None else np.ascontiguousarray(tables, np.uint32).reshape(-1)
+        table_offsets = None if table_offsets is None else np.ascontiguousarray(table_offsets, np.int64)
+        desc = PnPBatch(Cn, _p(offsets), _p(p3d), _p(p2d), _p(sigma2), _p(K), C.cast(parr, C.c_void_p), npar,
+                        _p(seeds), _p(tables), _p(table_offsets))
+        self._keep = [offsets, p3d, p2d, sigma2, K, parr, seeds, tables, table_offsets]
+        return desc, Cn, offsets
+
+    def pnp_upload(self, offsets, p3d, p2d, sigma2, K, params, seeds=None, tables=None, table_offsets=None):
+        desc, Cn, offsets = self._pnp_desc(offsets, p3d, p2d, sigma2, K, params, seeds, tables, table_offsets)
+        self._ck(self.L.rsac_pnp_upload(self.h, C.byref(desc)), "pnp_upload")
+        self._pnp_C = Cn
+        self._pnp_words = ((np.diff(offsets) + 31) // 32).astype(np.int64)
+        return Cn
+
+    def pnp_run(self, flags=0, d_results_out: int | None = None):
+        self._ck(self.L.rsac_pnp_run(self.h, C.c_int(flags), C.c_void_p(d_results_out or 0)), "pnp_run")
+
+    def pnp_download(self, want_masks=True):
+        res = np.zeros(self._pnp_C, RESULT_DTYPE)
+        masks = np.zeros(int(self._pnp_words.sum()), np.uint32) if want_masks else None
+        self._ck(self.L.rsac_pnp_download(self.h, _p(res), _p(masks)), "pnp_download")
+        return res, masks
+
+    def pnp_solve(self, offsets, p3d, p2d, sigma2, K, params, seeds=None, tables=None, table_offsets=None, flags=0):
+        self.pnp_upload(offsets, p3d, p2d, sigma2, K, params, seeds, tables, table_offsets)
+        self.pnp_run(flags)
+        return self.pnp_download()
+
+    def pnp_hypotheses(self):
+        n = self.L.rsac_pnp_total_hypotheses(self.h)
+        poses = np.zeros((n, 12), np.float32)
+        counts = np.zeros(n, np.int32)
+        self._ck(self.L.rsac_pnp_get_hypotheses(self.h, _p(poses), _p(counts)), "pnp_get_hypotheses")
+        return poses, counts
+
+    def split_masks(self, masks, offsets):
+        """concatenated words -> list of bool arrays (compact correspondence index)"""
+        out = []
+        w0 = 0
+        for c in range(len(offsets) - 1):
+            n = int(offsets[c + 1] - offsets[c])
+            nw = (n + 31) // 32
+            out.append(unpack_mask(masks[w0:w0 + nw], n))
+            w0 += nw
+        return out
+
+    # -- scoring stress
+    def score_pnp_upload(self, poses, p3d, p2d, max_err, K):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
+        p3d = np.ascontiguousarray(p3d, np.float32).reshape(-1, 3)
+        p2d = np.ascontiguousarray(p2d, np.float32).reshape(-1, 2)
+        max_err = np.ascontiguousarray(max_err, np.float32).reshape(-1)
+        Kd = (C.c_double * 4)(*[float(k) for k in K])
+        self._score_H, self._score_n = poses.shape[0], p3d.shape[0]
+        self._ck(self.L.rsac_score_pnp_upload(self.h, C.c_int(poses.shape[0]), _p(poses), C.c_int(p3d.shape[0]), _p(p3d),
+                                              _p(p2d), _p(max_err), Kd), "score_pnp_upload")
+
+    def score_pnp_run(self, want_masks=True):
+        self._ck(self.L.rsac_score_pnp_run(self.h, C.c_int(1 if want_masks else 0)), "score_pnp_run")
+
+    def score_pnp_download(self, want_masks=True):
+        words = (self._score_n + 31) // 32
+        counts = np.zeros(self._score_H, np.int32)
+        masks = np.zeros((self._score_H, words), np.uint32) if want_masks else None
+        self._ck(self.L.rsac_score_pnp_download(self.h, _p(masks), _p(counts)), "score_pnp_download")
+        return counts, masks
+
+    def score_pnp(self, poses, p3d, p2d, max_err, K, want_masks=True):
+        self.score_pnp_upload(poses, p3d, p2d, max_err, K)
+        self.score_pnp_run(want_masks)
+        return self.score_pnp_download(want_masks)
+
+    def score_exact_evals(self) -> int:
+        return self.L.rsac_score_exact_evals(self.h)
+
+
+def unpack_mask(words: np.ndarray, n: int) -> np.ndarray:
+    """uint32 words (bit i of word w = item 32w+i) -> bool[n]"""
+    words = np.ascontiguousarray(words, np.uint32)
+    b = ((words[..., :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)
+    return b.reshape(words.shape[:-1] + (-1,))[..., :n]

@@ -1,0 +1,143 @@
+"""GPU parity: batched EPnP RANSAC (CUDA, through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): identical minimal sets => inlier counts and masks
+bit-exact (no near-threshold allowance is needed: the scoring kernel reproduces the
+reference's inlier bit exactly), poses of 4-point hypotheses bit-identical (shared
+arithmetic contract), final R/t within 1e-4 relative.
+"""
+import numpy as np
+import pytest
+
+from ransac_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+PRM = dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.2, th2=5.991)   # cfg1: H = 300, minInl = 100
+
+
+def _batch(cfg, C, n, outl=0.5, first=0):
+    b = synth.pnp_batch(cfg, C, n, outl, first=first)
+    offsets = np.arange(C + 1, dtype=np.int32) * n
+    return b, offsets
+
+
+def _oracle_all(oracle, b, C, prm, tables, flags=0, per_hyp=True):
+    out = []
+    for c in range(C):
+        pb = oracle.pnp_problem(b["p3d"][c], b["p2d"][c], b["sigma2"][c], b["K"])
+        out.append(oracle.pnp_ransac(pb, oracle.params(**prm), tables[c], flags | oracle.FLAG_EXHAUSTIVE, per_hyp=per_hyp))
+    return out
+
+
+def _check_results(res, masks_list, orc):
+    for c, o in enumerate(orc):
+        r = res[c]
+        assert r["ok"] == o["ok"], c
+        assert r["no_more"] == o["no_more"], c
+        assert r["n_inliers"] == o["n_inliers"], c
+        assert r["best_hyp"] == o["best_hyp"], c
+        assert r["refined"] == o["refined"], c
+        assert r["best_count"] == o["best_count"], c
+        assert (masks_list[c] == o["mask"]).all(), c
+        if o["ok"]:
+            T = o["T"]
+            # north_star tolerance: 1e-4 relative on R, t (observed: bit-identical)
+            assert np.allclose(r["R"].reshape(3, 3), T[:3, :3], rtol=1e-4, atol=1e-6), c
+            assert np.allclose(r["t"], T[:3, 3], rtol=1e-4, atol=1e-6), c
+
+
+def test_pnp_cfg1_per_hypothesis_bit_exact(engine, oracle):
+    """cfg1: N=500, 50% outliers, H=300; 8 problems; explicit index tables."""
+    C, n = 8, 500
+    b, offsets = _batch(1, C, n)
+    tables = [oracle.index_table(int(s), n, 4, 300) for s in b["seeds"]]
+    toff = np.arange(C + 1, dtype=np.int64) * 1200
+    res, masks = engine.pnp_solve(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**PRM),
+                                  tables=np.concatenate(tables), table_offsets=toff)
+    poses, counts = engine.pnp_hypotheses()
+    orc = _oracle_all(oracle, b, C, PRM, tables)
+    for c in range(C):
+        hp = poses[c * 300:(c + 1) * 300]
+        op = orc[c]["hyp_pose"]
+        same = (hp.view(np.uint32) == op.view(np.uint32)) | (np.isnan(hp) & np.isnan(op))
+        assert same.all(), f"problem {c}: {np.argwhere(~same.all(axis=1)).ravel()[:5]} differ"
+        assert (counts[c * 300:(c + 1) * 300] == orc[c]["hyp_counts"]).all()
+    _check_results(res, engine.split_masks(masks, offsets), orc)
+    assert sum(o["ok"] for o in orc) >= C - 1          # the synthetic problems are solvable
+
+
+def test_pnp_device_generated_tables_match_libc(engine, oracle):
+    """seeds only: the device restatement of glibc rand() must give the oracle's tables"""
+    C, n = 5, 300
+    b, offsets = _batch(11, C, n)
+    res, masks = engine.pnp_solve(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**PRM), seeds=b["seeds"])
+    minInl, H = capi.pnp_ransac_setup(n, capi.ransac_params(**PRM))
+    tables = [oracle.index_table(int(s), n, 4, H) for s in b["seeds"]]
+    orc = _oracle_all(oracle, b, C, PRM, tables, per_hyp=False)
+    _check_results(res, engine.split_masks(masks, offsets), orc)
+
+
+def test_pnp_ragged_and_edge_cases(engine, oracle):
+    """ragged batch incl. an empty problem, n < minInliers, n == minSet, all-outlier and noise-free sets"""
+    sizes = [0, 3, 4, 9, 37, 64, 65, 500, 257]
+    prm = dict(PRM)
+    parts = []
+    for i, n in enumerate(sizes):
+        outl = 1.0 if i == 4 else (0.0 if i == 5 else 0.4)
+        parts.append(synth.pnp_problem(7000 + i, max(n, 1), outl, noise=(i != 6)))
+    p3d = np.concatenate([p["p3d"][:n] for p, n in zip(parts, sizes)])
+    p2d = np.concatenate([p["p2d"][:n] for p, n in zip(parts, sizes)])
+    s2 = np.concatenate([p["sigma2"][:n] for p, n in zip(parts, sizes)])
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    seeds = np.arange(len(sizes), dtype=np.uint32) + 77
+    res, masks = engine.pnp_solve(offsets, p3d, p2d, s2, [parts[0]["K"]], capi.ransac_params(**prm), seeds=seeds)
+    ml = engine.split_masks(masks, offsets)
+    for c, n in enumerate(sizes):
+        minInl, H = (capi.pnp_ransac_setup(n, capi.ransac_params(**prm)) if n > 0 else (10, 0))
+        if n < max(minInl, 4):
+            assert res[c]["ok"] == 0 and res[c]["no_more"] == 1 and res[c]["n_inliers"] == 0
+            assert not ml[c].any()
+            continue
+        pb = oracle.pnp_problem(parts[c]["p3d"][:n], parts[c]["p2d"][:n], parts[c]["sigma2"][:n], parts[c]["K"])
+        o = oracle.pnp_ransac(pb, oracle.params(**prm), oracle.index_table(int(seeds[c]), n, 4, H))
+        _check_results(res[c:c + 1], ml[c:c + 1], [o])
+
+
+def test_pnp_tracking_parameters_failed_refines(engine, oracle):
+    """Tracking's own call (src/Tracking.cpp:1226): eps=0.5 => H=35, minInl=N/2: refines do fail here;
+    the engine must follow the clean (n-bounded) semantics through them."""
+    prm = dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.5, th2=5.991)
+    C, n = 48, 200
+    b, offsets = _batch(12, C, n, outl=0.45)
+    res, masks = engine.pnp_solve(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**prm), seeds=b["seeds"])
+    minInl, H = capi.pnp_ransac_setup(n, capi.ransac_params(**prm))
+    assert (minInl, H) == (100, 35)
+    tables = [oracle.index_table(int(s), n, 4, H) for s in b["seeds"]]
+    orc = _oracle_all(oracle, b, C, prm, tables, per_hyp=False)
+    _check_results(res, engine.split_masks(masks, offsets), orc)
+    for c in range(C):
+        assert res[c]["n_refines"] == orc[c]["n_refines"]
+
+
+def test_score_pnp_bit_exact_small(engine, oracle):
+    """CheckInliers kernel vs oracle, masks and counts, incl. ragged N (not a multiple of 32), NaN / zero /
+    behind-camera poses and points on the camera plane."""
+    rng = np.random.default_rng(3)
+    for (H, n) in ((1, 1), (33, 31), (70, 1000), (300, 4097)):
+        p = synth.scoring_stress(5000 + n, H, n)
+        poses = p["poses"].copy()
+        if H > 8:
+            poses[1] = np.nan
+            poses[2] = 0.0
+            poses[3, 9:] = [0, 0, -30]          # everything behind the camera
+            poses[4, :9] *= 1e-3                # degenerate scale
+            poses[5, 11] = -p["poses"][5, 6:9] @ p["p3d"][0]   # point 0 exactly on the camera plane (z ~ 0)
+            poses[6] = rng.normal(size=12) * 100
+        max_err = (p["sigma2"] * np.float32(5.991)).astype(np.float32)
+        counts, masks = engine.score_pnp(poses, p["p3d"], p["p2d"], max_err, p["K"])
+        pb = oracle.pnp_problem(p["p3d"], p["p2d"], p["sigma2"], p["K"])
+        oc, om = oracle.pnp_score(pb, max_err, poses)
+        assert (counts == oc).all(), (H, n)
+        assert (capi.unpack_mask(masks, n) == om.astype(bool)).all(), (H, n)
+        ex = engine.score_exact_evals()
+        assert 0 <= ex <= H * n
