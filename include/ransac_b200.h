@@ -90,6 +90,8 @@ const char* rsac_last_error(rsac_engine* e);
 /* use an external cudaStream_t (passed as void*) for all work; NULL restores the own stream */
 int rsac_set_stream(rsac_engine* e, void* cuda_stream);
 int rsac_sync(rsac_engine* e);
+/* global index of this engine's problem 0 (written to rsac_result.problem; used when candidates are sharded) */
+int rsac_set_problem_base(rsac_engine* e, int base);
 /* pinned host memory for callers that want asynchronous H2D/D2H */
 int rsac_host_alloc(void** ptr, uint64_t bytes);
 int rsac_host_free(void* ptr);
@@ -161,6 +163,8 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out);
  * ceil(n_c/32) words per problem in problem order (bit i of word w = correspondence 32w+i,
  * COMPACT index; the C++ wrapper scatters to keypoint indices like PnPsolver.cpp:160-165) */
 int rsac_pnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks);
+/* same without the final synchronisation (pinned destinations; pipelined sweeps) */
+int rsac_pnp_download_async(rsac_engine* e, rsac_result* results, uint32_t* masks);
 /* the reference-facing call: 1+2+3 with host buffers */
 int rsac_pnp_solve(rsac_engine* e, const rsac_pnp_batch* b, int flags, rsac_result* results, uint32_t* masks);
 /* parity/debug: per-hypothesis poses ([sumH][12]: R 9, t 3) and inlier counts ([sumH]) of the last run */

@@ -121,6 +121,9 @@ void orc_pnp_ransac(const orc_pnp_problem *pb, const orc_ransac_params *prm, con
 /* One EPnP solve on the subset idx[0..m) (PnPsolver::compute_pose, :359-415).
  * Returns the reprojection error of the chosen solution. */
 double orc_epnp_pose(const orc_pnp_problem *pb, const uint32_t *idx, int m, float R[9], float t[3]);
+/* average algorithmic FP64 FLOP (+,-,*,/,sqrt = 1 each) of one minimal EPnP solve over a table of H sets */
+double orc_epnp_flops(const orc_pnp_problem *pb, const uint32_t *table, int H, int min_set);
+long long orc_flops_take(void);
 /* PnPsolver::CheckInliers (:241-268) for one pose; max_err[i] = sigma2[i]*th2 (f32*f32).
  * err2 (optional) receives the f32 squared errors. */
 int orc_pnp_check_inliers(const orc_pnp_problem *pb, const float *max_err, const float R[9],

@@ -13,6 +13,12 @@
 #include <string.h>
 #include "orc.h"
 
+/* Algorithmic FLOP counter (bench.py's roofline numerator for the solver kernels).
+ * Convention of SURVEY 8(d): + - * / sqrt count 1 each; comparisons, negations and copies 0. */
+__thread long long orc_flops = 0;
+#define FL(n) (orc_flops += (n))
+long long orc_flops_take(void) { long long v = orc_flops; orc_flops = 0; return v; }
+
 #define ORC_MAX_SWEEPS 30
 
 /* ---- cyclic Jacobi (Rutishauser rotation), upper triangle, threshold tol ---- */
@@ -24,6 +30,7 @@ void NAME(int n, T *a, T *w, T *v)                                              
     T fro2 = ZERO;                                                                              \
     for (int i = 0; i < n; ++i)                                                                 \
         for (int j = i; j < n; ++j) fro2 += a[i * n + j] * a[i * n + j];                        \
+    FL(n * (n + 1) + 2);                                                                        \
     const T tol = SQRT(fro2) * TOLSCALE;                                                        \
     for (int sweep = 0; sweep < ORC_MAX_SWEEPS; ++sweep) {                                      \
         int rotated = 0;                                                                        \
@@ -32,6 +39,7 @@ void NAME(int n, T *a, T *w, T *v)                                              
                 const T apq = a[p * n + q];                                                     \
                 if (!(FABS(apq) > tol)) continue;                                               \
                 rotated = 1;                                                                    \
+                FL(18 + 6 * (n - 2) + 6 * n); /* angle 15 + diag 3; 6 per rotated pair */       \
                 const T app = a[p * n + p], aqq = a[q * n + q];                                 \
                 const T theta = (aqq - app) / (TWO * apq);                                      \
                 T t = ONE / (FABS(theta) + SQRT(theta * theta + ONE));                          \
@@ -101,8 +109,10 @@ static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k 
                     beta += uj * uj;
                     gamma += ui * uj;
                 }
+                FL(6 * m + 3);
                 if (!(fabs(gamma) > DBL_EPSILON * sqrt(alpha * beta))) continue;
                 rotated = 1;
+                FL(13 + 6 * m + 6 * k);
                 const double zeta = (beta - alpha) / (2.0 * gamma);
                 double t = 1.0 / (fabs(zeta) + sqrt(zeta * zeta + 1.0));
                 if (zeta < 0.0) t = -t;
@@ -141,6 +151,7 @@ void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
         sig[j] = sqrt(s2);
         if (sig[j] > smax) smax = sig[j];
     }
+    FL(k * (2 * m + 1) + 2);
     const double thresh = smax * ((double)k * DBL_EPSILON);
     for (int r = 0; r < k; ++r) x[r] = 0.0;
     for (int j = 0; j < k; ++j) {
@@ -148,6 +159,7 @@ void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
         double ub = 0.0;
         for (int r = 0; r < m; ++r) ub += U[r * k + j] * b[r];
         const double coef = ub / sig2[j];
+        FL(2 * m + 1 + 2 * k);
         for (int r = 0; r < k; ++r) x[r] += coef * V[r * k + j];
     }
 }
@@ -167,6 +179,7 @@ void orc_inv3_d(const double m[9], double out[9])
     const double c22 = m[0] * m[4] - m[1] * m[3];
     const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
     const double id = 1.0 / det;
+    FL(27 + 5 + 1 + 9);
     out[0] = c00 * id; out[1] = c10 * id; out[2] = c20 * id;
     out[3] = c01 * id; out[4] = c11 * id; out[5] = c21 * id;
     out[6] = c02 * id; out[7] = c12 * id; out[8] = c22 * id;

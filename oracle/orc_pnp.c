@@ -11,6 +11,10 @@
 #include <stdio.h>
 #include "orc.h"
 
+extern __thread long long orc_flops;
+#define FL(n) (orc_flops += (n))
+long long orc_flops_take(void);
+
 /* mirrors the solver state of include/PnPsolver.hpp:71-136 that the arithmetic touches */
 typedef struct {
     double fx, fy, cx, cy;
@@ -87,8 +91,10 @@ static void choose_control_points(epnp_t *e)
         A[4] += d1 * d1; A[5] += d1 * d2;
         A[8] += d2 * d2;
     }
+    FL(3 * ns + 3 + n * 15);
     double DC[3], UCt[9];
     orc_jacobi_eig_d(3, A, DC, UCt);                           /* :311 */
+    FL(3 * (2 + 6));
     for (int i = 0; i < 3; ++i) {
         const double k = sqrt(DC[i] / (double)n);              /* :318 (negative => NaN) */
         for (int c = 0; c < 3; ++c) e->cws[i + 1][c] = e->cws[0][c] + k * UCt[c * 3 + i];
@@ -102,6 +108,7 @@ static void compute_barycentric_coordinates(epnp_t *e)
     for (int i = 0; i < 3; ++i)
         for (int j = 1; j < 4; ++j) CC[i * 3 + (j - 1)] = e->cws[j][i] - e->cws[0][i];
     orc_inv3_d(CC, CCi);                                       /* :331 */
+    FL(9 + e->n * (3 + 15 + 3));
     for (int i = 0; i < e->n; ++i) {
         const double d0 = e->pws[i * 3 + 0] - e->cws[0][0];
         const double d1 = e->pws[i * 3 + 1] - e->cws[0][1];
@@ -274,6 +281,8 @@ static void qr_solve(double A[6][4], double b[6], double X[4])
             for (int i = k; i < nr; ++i) A[i][j] -= tau * A[i][k];
         }
     }
+    FL(4 * 6 + 2 * (6 + 5 + 4 + 3) + 4 * 5 + (3 * 6 + 2 * 5 + 1 * 4) * 4 + 6);   /* column scaling, norms, reflections */
+    FL(2 * (6 + 5 + 4 + 3) * 2 + 4 + 4 + 12);                                      /* Qt b, back substitution */
     /* b <- Qt b (:762-780) */
     for (int j = 0; j < nc; ++j) {
         double tau = 0;
@@ -440,8 +449,11 @@ static double compute_pose(epnp_t *e, float Rf[9], float tf[3])
                 MtM[a * 12 + b] += r1[a] * r1[b];
             }
     }
+    FL(e->n * (4 * 6 + 2 + 78 * 4));
     double w[12], U[144];
     orc_jacobi_eig_d(12, MtM, w, U);                                   /* :380 */
+    FL(4 * 6 * 3 + 6 * (10 * 5 + 6) + 6 * 8);   /* L_6x10, rho */
+    FL(3 * (8 + 5 * (6 * (16 + 4 * 7 + 20 + 1) + 4)));   /* betas post-processing, 5 x (A,b build + beta update); QR counted below */
 
     double L[6][10], rho[6];
     compute_L_6x10(U, L);
@@ -518,6 +530,15 @@ void orc_pnp_score(const orc_pnp_problem *pb, const float *max_err, int H, const
     for (int h = 0; h < H; ++h)
         counts[h] = orc_pnp_check_inliers(pb, max_err, poses + (size_t)h * 12, poses + (size_t)h * 12 + 9,
                                           masks ? masks + (size_t)h * pb->n : NULL, NULL);
+}
+
+/* average algorithmic FP64 FLOP of one minimal (min_set-point) EPnP solve over the H rows of a table */
+double orc_epnp_flops(const orc_pnp_problem *pb, const uint32_t *table, int H, int min_set)
+{
+    float R[9], t[3];
+    orc_flops_take();
+    for (int h = 0; h < H; ++h) orc_epnp_pose(pb, table + (size_t)h * min_set, min_set, R, t);
+    return (double)orc_flops_take() / (double)(H > 0 ? H : 1);
 }
 
 double orc_epnp_pose(const orc_pnp_problem *pb, const uint32_t *idx, int m, float R[9], float t[3])

@@ -67,6 +67,13 @@ int rsac_set_stream(rsac_engine* e, void* s)
     return RSAC_OK;
 }
 
+int rsac_set_problem_base(rsac_engine* e, int base)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    e->problem_base = base;
+    return RSAC_OK;
+}
+
 int rsac_sync(rsac_engine* e)
 {
     if (!e) return RSAC_ERR_INVALID;
@@ -475,7 +482,7 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
     return RSAC_OK;
 }
 
-int rsac_pnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks)
+int rsac_pnp_download_async(rsac_engine* e, rsac_result* results, uint32_t* masks)
 {
     if (!e) return RSAC_ERR_INVALID;
     PnpState& s = e->pnp;
@@ -485,6 +492,13 @@ int rsac_pnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks)
         RSAC_CUDA(e, cudaMemcpyAsync(results, s.d_results.p, sizeof(rsac_result) * d.C, cudaMemcpyDeviceToHost, e->stream));
     if (masks && d.total_words > 0)
         RSAC_CUDA(e, cudaMemcpyAsync(masks, s.d_masks.p, sizeof(uint32_t) * (size_t)d.total_words, cudaMemcpyDeviceToHost, e->stream));
+    return RSAC_OK;
+}
+
+int rsac_pnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks)
+{
+    int rc = rsac_pnp_download_async(e, results, masks);
+    if (rc) return rc;
     RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
     return RSAC_OK;
 }

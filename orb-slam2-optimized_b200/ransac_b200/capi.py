@@ -167,6 +167,9 @@ class Engine:
     def sync(self):
         self._ck(self.L.rsac_sync(self.h), "sync")
 
+    def set_problem_base(self, base: int):
+        self._ck(self.L.rsac_set_problem_base(self.h, C.c_int(base)), "set_problem_base")
+
     def device_info(self):
         info = DeviceInfo()
         self._ck(self.L.rsac_get_device_info(self.h, C.byref(info)), "device_info")
@@ -242,6 +245,11 @@ class Engine:
         masks = np.zeros(int(self._pnp_words.sum()), np.uint32) if want_masks else None
         self._ck(self.L.rsac_pnp_download(self.h, _p(res), _p(masks)), "pnp_download")
         return res, masks
+
+    def pnp_download_async(self, results_ptr: int | None, masks_ptr: int | None):
+        """D2H into caller-owned PINNED host memory (raw addresses), no synchronisation"""
+        self._ck(self.L.rsac_pnp_download_async(self.h, C.c_void_p(results_ptr or 0), C.c_void_p(masks_ptr or 0)),
+                 "pnp_download_async")
 
     def pnp_solve(self, offsets, p3d, p2d, sigma2, K, params, seeds=None, tables=None, table_offsets=None, flags=0):
         self.pnp_upload(offsets, p3d, p2d, sigma2, K, params, seeds, tables, table_offsets)

@@ -1,0 +1,65 @@
+"""Developer timing probe (not the bench contract): stage times of the PnP sweep (cfg4) and the
+scoring stress (cfg5) with CUDA events, plus measured FP32/FP64 CUDA-core peaks."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "orb-slam2-optimized_b200"))
+from ransac_b200 import capi, synth  # noqa: E402
+
+C = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+eng = capi.Engine(0)
+print(eng.device_info())
+print("peaks TFLOP/s fp32, fp64:", eng.measure_peaks())
+
+n = 500
+t0 = time.time()
+b = synth.pnp_batch(4, C, n, 0.5)
+print("synth %.2fs" % (time.time() - t0))
+offsets = np.arange(C + 1, dtype=np.int32) * n
+prm = capi.ransac_params(0.99, 10, 300, 4, 0.2, 5.991)
+eng.pnp_upload(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], prm, seeds=b["seeds"])
+for it in range(3):
+    eng.pnp_run()
+eng.sync()
+eng.profile_enable(True)
+eng.profile_reset()
+eng.timer_begin()
+K = 5
+for it in range(K):
+    eng.pnp_run()
+ms = eng.timer_end()
+print("cfg4 C=%d: %.3f ms/sweep, %.3g evals/s, %.3g cand/s" % (C, ms / K, C * 300 * n / (ms / K * 1e-3), C / (ms / K * 1e-3)))
+for k, (tms, nl) in eng.profile().items():
+    if nl:
+        print("   %-7s %8.3f ms/launch (%d launches)" % (k, tms / nl, nl))
+res, masks = eng.pnp_download()
+print("   ok:", int(res["ok"].sum()), "refined:", int(res["refined"].sum()), "mean n_hyp", res["n_hyp"].mean(), "exact evals", eng.score_exact_evals())
+# e2e through host buffers
+t0 = time.time()
+for it in range(3):
+    eng.pnp_solve(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], prm, seeds=b["seeds"])
+dt = (time.time() - t0) / 3
+print("   e2e (pageable host buffers, wall): %.3f ms" % (dt * 1e3))
+
+# cfg5
+H, N = 4096, 10000
+p = synth.scoring_stress(5000, H, N)
+max_err = (p["sigma2"] * np.float32(5.991)).astype(np.float32)
+eng.profile_enable(False)
+eng.score_pnp_upload(p["poses"], p["p3d"], p["p2d"], max_err, p["K"])
+for want in (True, False):
+    for it in range(5):
+        eng.score_pnp_run(want)
+    eng.sync()
+    eng.timer_begin()
+    K = 50
+    for it in range(K):
+        eng.score_pnp_run(want)
+    ms = eng.timer_end() / K
+    ev = H * N / (ms * 1e-3)
+    print("cfg5 masks=%s: %.4f ms, %.3g evals/s, %.2f TFLOP/s (31 FLOP/eval), exact evals %d (%.2e)" %
+          (want, ms, ev, ev * 31 / 1e12, eng.score_exact_evals(), eng.score_exact_evals() / (H * N)))

@@ -64,6 +64,7 @@ def lib():
             build()
         _LIB = C.CDLL(path)
         _LIB.orc_epnp_pose.restype = C.c_double
+        _LIB.orc_epnp_flops.restype = C.c_double
         for f in ("orc_pnp_batch", "orc_sim3_batch", "orc_mlpnp_batch", "orc_pnp_score_timed"):
             getattr(_LIB, f).restype = C.c_double
     return _LIB
@@ -185,6 +186,11 @@ def epnp_pose(pb: _Keep, idx):
     t = np.empty(3, np.float32)
     err = lib().orc_epnp_pose(C.byref(pb.st), _p(idx), C.c_int(len(idx)), _p(R), _p(t))
     return R.reshape(3, 3), t, err
+
+
+def epnp_flops(pb: _Keep, table):
+    table = np.ascontiguousarray(table, np.uint32)
+    return lib().orc_epnp_flops(C.byref(pb.st), _p(table), C.c_int(table.shape[0]), C.c_int(table.shape[1]))
 
 
 def pnp_check_inliers(pb: _Keep, max_err, R, t):
