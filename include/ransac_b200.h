@@ -250,7 +250,8 @@ int rsac_nccl_destroy(rsac_engine* e);
  * contract).  Test-only: lets the CPU test-suite compare the solver source with the
  * oracle bit-for-bit without a GPU.  Not a fallback: nothing in the engine calls these. */
 int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3]);
-int rsac_debug_host_jacobi12(const double a[144], double w[12], double v[144]);
+/* the 4 smallest eigenpairs of a symmetric 12x12 (upper triangle read): w[4], v[12][4] */
+int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48]);
 int rsac_debug_host_sim3(const float P1[9], const float P2[9], int fix_scale, float R[9], float t[3], float* s);
 int rsac_debug_host_mlpnp6(const float K[4], const float p3d[18], const float p2d[12], const double* cov54,
                            double R[9], double t[3]);

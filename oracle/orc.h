@@ -52,6 +52,8 @@ void orc_index_table(unsigned seed, int n, int k, int H, uint32_t *out);
  * triangle read, destroyed. */
 void orc_jacobi_eig_d(int n, double *a, double *w, double *v);
 void orc_jacobi_eig_f(int n, float *a, float *w, float *v);
+/* the nv smallest eigenpairs of a symmetric n x n (n <= 12), recorded-rotation variant; v is n x nv */
+void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v);
 /* minimum-norm least squares of an m x k system through a one-sided Jacobi SVD
  * with Eigen's rank threshold (restates A.bdcSvd(ThinU|ThinV).solve(b),
  * PnPsolver.cpp:531,559,590).  L row-major m*k, m<=8, k<=6. */

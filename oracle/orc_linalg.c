@@ -21,8 +21,26 @@ long long orc_flops_take(void) { long long v = orc_flops; orc_flops = 0; return 
 
 #define ORC_MAX_SWEEPS 30
 
-/* ---- cyclic Jacobi (Rutishauser rotation), upper triangle, threshold tol ---- */
-#define ORC_JACOBI_IMPL(NAME, T, SQRT, FABS, TOLSCALE, ONE, TWO, ZERO)                          \
+#define ORC_MAX_SWEEPS_REC 12
+
+/* ---- cyclic Jacobi on the upper triangle, rotations below ||a||_F * 2^-56 (2^-27) skipped ----
+ * Rotation of the 2x2 block [app apq; apq aqq] (arithmetic contract):
+ *   h = aqq - app, r = sqrt(h*h + 4*(apq*apq)), cos(2t) = |h|/r,
+ *   c = sqrt(0.5 + 0.5*cos(2t)), s = apq/(r*c) with the sign of h,
+ *   new diagonal = (app+aqq)/2 -/+ r/2. */
+#define ORC_ANGLE(T, SQRT, FABS, HALF, FOUR, ZERO)                                              \
+    const T h = aqq - app;                                                                      \
+    const T r = SQRT(h * h + FOUR * (apq * apq));                                               \
+    const T c2 = FABS(h) / r;                                                                   \
+    const T c = SQRT(HALF + HALF * c2);                                                         \
+    const T s0 = apq / (r * c);                                                                 \
+    const T m = HALF * (app + aqq);                                                             \
+    const T hr = HALF * r;                                                                      \
+    T s, napp, naqq;                                                                            \
+    if (h < ZERO) { s = -s0; napp = m + hr; naqq = m - hr; }                                    \
+    else          { s = s0;  napp = m - hr; naqq = m + hr; }
+
+#define ORC_JACOBI_IMPL(NAME, T, SQRT, FABS, TOLSCALE, ONE, HALF, FOUR, ZERO)                   \
 void NAME(int n, T *a, T *w, T *v)                                                              \
 {                                                                                               \
     for (int i = 0; i < n; ++i)                                                                 \
@@ -39,37 +57,24 @@ void NAME(int n, T *a, T *w, T *v)                                              
                 const T apq = a[p * n + q];                                                     \
                 if (!(FABS(apq) > tol)) continue;                                               \
                 rotated = 1;                                                                    \
-                FL(18 + 6 * (n - 2) + 6 * n); /* angle 15 + diag 3; 6 per rotated pair */       \
+                FL(19 + 6 * (n - 2) + 6 * n);                                                   \
                 const T app = a[p * n + p], aqq = a[q * n + q];                                 \
-                const T theta = (aqq - app) / (TWO * apq);                                      \
-                T t = ONE / (FABS(theta) + SQRT(theta * theta + ONE));                          \
-                if (theta < ZERO) t = -t;                                                       \
-                const T c = ONE / SQRT(t * t + ONE);                                            \
-                const T s = t * c;                                                              \
-                const T tau = s / (ONE + c);                                                    \
-                const T h = t * apq;                                                            \
-                a[p * n + p] = app - h;                                                         \
-                a[q * n + q] = aqq + h;                                                         \
+                ORC_ANGLE(T, SQRT, FABS, HALF, FOUR, ZERO)                                      \
+                a[p * n + p] = napp;                                                            \
+                a[q * n + q] = naqq;                                                            \
                 a[p * n + q] = ZERO;                                                            \
-                for (int j = 0; j < p; ++j) {                                                   \
-                    const T g = a[j * n + p], k = a[j * n + q];                                 \
-                    a[j * n + p] = g - s * (k + g * tau);                                       \
-                    a[j * n + q] = k + s * (g - k * tau);                                       \
-                }                                                                               \
-                for (int j = p + 1; j < q; ++j) {                                               \
-                    const T g = a[p * n + j], k = a[j * n + q];                                 \
-                    a[p * n + j] = g - s * (k + g * tau);                                       \
-                    a[j * n + q] = k + s * (g - k * tau);                                       \
-                }                                                                               \
-                for (int j = q + 1; j < n; ++j) {                                               \
-                    const T g = a[p * n + j], k = a[q * n + j];                                 \
-                    a[p * n + j] = g - s * (k + g * tau);                                       \
-                    a[q * n + j] = k + s * (g - k * tau);                                       \
+                for (int j = 0; j < n; ++j) {                                                   \
+                    if (j == p || j == q) continue;                                             \
+                    const int ip = (j < p) ? j * n + p : p * n + j;                             \
+                    const int iq = (j < q) ? j * n + q : q * n + j;                             \
+                    const T g = a[ip], k = a[iq];                                               \
+                    a[ip] = c * g - s * k;                                                      \
+                    a[iq] = s * g + c * k;                                                      \
                 }                                                                               \
                 for (int j = 0; j < n; ++j) {                                                   \
                     const T g = v[j * n + p], k = v[j * n + q];                                 \
-                    v[j * n + p] = g - s * (k + g * tau);                                       \
-                    v[j * n + q] = k + s * (g - k * tau);                                       \
+                    v[j * n + p] = c * g - s * k;                                               \
+                    v[j * n + q] = s * g + c * k;                                               \
                 }                                                                               \
             }                                                                                   \
         }                                                                                       \
@@ -90,8 +95,89 @@ void NAME(int n, T *a, T *w, T *v)                                              
     }                                                                                           \
 }
 
-ORC_JACOBI_IMPL(orc_jacobi_eig_d, double, sqrt, fabs, 0x1p-56, 1.0, 2.0, 0.0)
-ORC_JACOBI_IMPL(orc_jacobi_eig_f, float, sqrtf, fabsf, 0x1p-27f, 1.0f, 2.0f, 0.0f)
+ORC_JACOBI_IMPL(orc_jacobi_eig_d, double, sqrt, fabs, 0x1p-56, 1.0, 0.5, 4.0, 0.0)
+ORC_JACOBI_IMPL(orc_jacobi_eig_f, float, sqrtf, fabsf, 0x1p-27f, 1.0f, 0.5f, 4.0f, 0.0f)
+
+/* The same eigen-solve when only the nv eigenvectors of the smallest eigenvalues are wanted
+ * (EPnP null-space basis, PnPsolver.cpp:379-382; MLPnP last singular vector, MLPnPsolver.cpp:488-489).
+ * The (c, s) of every rotation of at most ORC_MAX_SWEEPS_REC sweeps is recorded and the wanted
+ * eigenvectors are formed by applying the rotations in reverse order to unit vectors.
+ * a: n x n row-major, upper triangle read, destroyed.  w: nv eigenvalues ascending.
+ * v: n x nv row-major. */
+void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
+{
+    const int np = n * (n - 1) / 2;
+    static __thread double rc[ORC_MAX_SWEEPS_REC * 66], rs[ORC_MAX_SWEEPS_REC * 66];
+    double fro2 = 0.0;
+    for (int i = 0; i < n; ++i)
+        for (int j = i; j < n; ++j) fro2 += a[i * n + j] * a[i * n + j];
+    FL(n * (n + 1) + 2);
+    const double tol = sqrt(fro2) * 0x1p-56;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < ORC_MAX_SWEEPS_REC; ++sweep) {
+        int rotated = 0, slot = 0;
+        for (int p = 0; p < n - 1; ++p) {
+            for (int q = p + 1; q < n; ++q, ++slot) {
+                const double apq = a[p * n + q];
+                rc[sweep * np + slot] = 1.0;
+                rs[sweep * np + slot] = 0.0;
+                if (!(fabs(apq) > tol)) continue;
+                rotated = 1;
+                FL(19 + 6 * (n - 2));
+                const double app = a[p * n + p], aqq = a[q * n + q];
+                ORC_ANGLE(double, sqrt, fabs, 0.5, 4.0, 0.0)
+                a[p * n + p] = napp;
+                a[q * n + q] = naqq;
+                a[p * n + q] = 0.0;
+                for (int j = 0; j < n; ++j) {
+                    if (j == p || j == q) continue;
+                    const int ip = (j < p) ? j * n + p : p * n + j;
+                    const int iq = (j < q) ? j * n + q : q * n + j;
+                    const double g = a[ip], k = a[iq];
+                    a[ip] = c * g - s * k;
+                    a[iq] = s * g + c * k;
+                }
+                rc[sweep * np + slot] = c;
+                rs[sweep * np + slot] = s;
+            }
+        }
+        if (!rotated) break;
+        sweeps = sweep + 1;
+    }
+    /* the nv smallest diagonal entries, ascending, ties to the lower index */
+    unsigned usedmask = 0u;
+    int sel[12];
+    for (int k = 0; k < nv; ++k) {
+        int best = -1;
+        double bv = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if ((usedmask >> i) & 1u) continue;
+            if (best < 0 || a[i * n + i] < bv) { best = i; bv = a[i * n + i]; }
+        }
+        usedmask |= 1u << best;
+        sel[k] = best;
+        w[k] = bv;
+    }
+    double x[12][12];
+    for (int k = 0; k < nv; ++k)
+        for (int i = 0; i < n; ++i) x[k][i] = (i == sel[k]) ? 1.0 : 0.0;
+    for (int sweep = sweeps - 1; sweep >= 0; --sweep)
+        for (int p = n - 2; p >= 0; --p)
+            for (int q = n - 1; q > p; --q) {
+                const int slot = p * n - (p * (p + 1)) / 2 + (q - p - 1);
+                const double c = rc[sweep * np + slot], s = rs[sweep * np + slot];
+                if (s != 0.0) {
+                    FL(6 * nv);
+                    for (int k = 0; k < nv; ++k) {
+                        const double xp = x[k][p], xq = x[k][q];
+                        x[k][p] = c * xp + s * xq;
+                        x[k][q] = c * xq - s * xp;
+                    }
+                }
+            }
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < nv; ++k) v[i * nv + k] = x[k][i];
+}
 
 /* ---- one-sided (Hestenes) Jacobi SVD: columns of U orthogonalised, V accumulated ---- */
 static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k */)

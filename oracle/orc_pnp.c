@@ -120,14 +120,14 @@ static void compute_barycentric_coordinates(epnp_t *e)
     }
 }
 
-/* PnPsolver::compute_L_6x10 (PnPsolver.cpp:604-637); U is 12x12 row-major, columns = eigenvectors */
+/* PnPsolver::compute_L_6x10 (PnPsolver.cpp:604-637); U is 12x4 row-major: the 4 smallest eigenvectors (:382 uses columns 0..3 only) */
 static void compute_L_6x10(const double *U, double L[6][10])
 {
     double dv[4][6][3];
     for (int i = 0; i < 4; ++i) {
         int a = 0, b = 1;
         for (int j = 0; j < 6; ++j) {
-            for (int c = 0; c < 3; ++c) dv[i][j][c] = U[(3 * a + c) * 12 + i] - U[(3 * b + c) * 12 + i];
+            for (int c = 0; c < 3; ++c) dv[i][j][c] = U[(3 * a + c) * 4 + i] - U[(3 * b + c) * 4 + i];
             b++;
             if (b > 3) { a++; b = a + 1; }
         }
@@ -318,7 +318,7 @@ static void compute_ccs(epnp_t *e, const double betas[4], const double *U)
     for (int i = 0; i < 4; ++i)
         for (int c = 0; c < 3; ++c) {
             double s = 0.0;
-            for (int j = 0; j < 4; ++j) s += betas[j] * U[(3 * i + c) * 12 + j];
+            for (int j = 0; j < 4; ++j) s += betas[j] * U[(3 * i + c) * 4 + j];
             e->ccs[i][c] = s;
         }
 }
@@ -450,8 +450,8 @@ static double compute_pose(epnp_t *e, float Rf[9], float tf[3])
             }
     }
     FL(e->n * (4 * 6 + 2 + 78 * 4));
-    double w[12], U[144];
-    orc_jacobi_eig_d(12, MtM, w, U);                                   /* :380 */
+    double w[4], U[48];
+    orc_jacobi_lowest_d(12, 4, MtM, w, U);                             /* :380-382: eigenvectors 0..3 */
     FL(4 * 6 * 3 + 6 * (10 * 5 + 6) + 6 * 8);   /* L_6x10, rho */
     FL(3 * (8 + 5 * (6 * (16 + 4 * 7 + 20 + 1) + 4)));   /* betas post-processing, 5 x (A,b build + beta update); QR counted below */
 

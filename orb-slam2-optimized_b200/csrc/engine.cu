@@ -388,6 +388,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     RSAC_TRY(s.d_pw.ensure(e, tot * 24));
     RSAC_TRY(s.d_us.ensure(e, tot * 16));
     RSAC_TRY(s.d_al.ensure(e, tot * 32));
+    RSAC_TRY(s.d_extra.ensure(e, sizeof(double2) * (size_t)(kMaxSweepsRec * 66) * std::max(d.C, 1)));
 
     cudaStream_t st = e->stream;
     if (d.C > 0) {
@@ -468,7 +469,7 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         SelectArgs a;
         a.metas = metas; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.uv = (const float2*)s.d_uv.p;
         a.poses = (const float*)s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p;
-        a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p;
+        a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p; a.rec = (double2*)s.d_extra.p;
         a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
         a.problem_base = e->problem_base;
         const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
@@ -696,10 +697,12 @@ int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2
     return RSAC_OK;
 }
 
-int rsac_debug_host_jacobi12(const double a[144], double w[12], double v[144])
+int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48])
 {
-    double A[144];
-    memcpy(A, a, sizeof(A));
-    jacobi_eig<double, 12>(A, w, v);
+    double A[78];
+    for (int i = 0; i < 12; ++i)
+        for (int j = i; j < 12; ++j) A[tri_idx(12, i, j)] = a[i * 12 + j];
+    std::vector<double2> rec(kMaxSweepsRec * 66);
+    jacobi_lowest<12, 4>(A, w, v, rec.data());
     return RSAC_OK;
 }

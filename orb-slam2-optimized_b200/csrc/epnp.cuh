@@ -241,14 +241,13 @@ __host__ __device__ inline void epnp_gauss_newton(const double* L, const double*
     }
 }
 
-// From MtM (upper triangle, destroyed) to the null-space basis U4 (12x4) and the three
-// refined beta vectors: 12x12 eigen-solve (:380), L, rho, approx_k + gauss_newton (:395-405).
-__host__ __device__ inline void epnp_solve_betas(double* MtM, const double* cws, double* U4, double* betas /*3x4*/)
+// From MtM (PACKED upper triangle, 78 entries, destroyed) to the null-space basis U4 (12x4) and
+// the three refined beta vectors: 12x12 eigen-solve (:380), L, rho, approx_k + gauss_newton (:395-405).
+// rec: scratch for the recorded rotations (kMaxSweepsRec * 66 double2).
+__host__ __device__ inline void epnp_solve_betas(double* MtM, const double* cws, double* U4, double* betas /*3x4*/, double2* rec)
 {
-    double w[12], U[144];
-    jacobi_eig<double, 12>(MtM, w, U);
-    for (int r = 0; r < 12; ++r)
-        for (int j = 0; j < 4; ++j) U4[r * 4 + j] = U[r * 12 + j];
+    double w4[4];
+    jacobi_lowest<12, 4>(MtM, w4, U4, rec);
     double L[60], rho[6];
     epnp_L_6x10(U4, L);
     epnp_rho(cws, rho);
@@ -337,19 +336,24 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
     double alphas[NPTS * 4];
     for (int i = 0; i < NPTS; ++i) epnp_alphas(pw + 3 * i, cws, CCi, alphas + 4 * i);
 
-    double MtM[144];
-    for (int i = 0; i < 144; ++i) MtM[i] = 0.0;
+    double MtM[78];   // packed upper triangle
+#pragma unroll
+    for (int i = 0; i < 78; ++i) MtM[i] = 0.0;
+#pragma unroll
     for (int i = 0; i < NPTS; ++i) {
         double r0[12], r1[12];
         epnp_m_rows(alphas + 4 * i, us[2 * i], us[2 * i + 1], k, r0, r1);
+#pragma unroll
         for (int a = 0; a < 12; ++a)
+#pragma unroll
             for (int b = a; b < 12; ++b) {
-                MtM[a * 12 + b] += r0[a] * r0[b];
-                MtM[a * 12 + b] += r1[a] * r1[b];
+                MtM[tri_idx(12, a, b)] += r0[a] * r0[b];
+                MtM[tri_idx(12, a, b)] += r1[a] * r1[b];
             }
     }
     double U4[48], betas[12];
-    epnp_solve_betas(MtM, cws, U4, betas);
+    double2 rec[kMaxSweepsRec * 66];
+    epnp_solve_betas(MtM, cws, U4, betas, rec);
 
     double rep[3], Rs[3][9], ts[3][3];
     for (int kk = 0; kk < 3; ++kk) {

@@ -23,63 +23,81 @@ __host__ __device__ inline double rabs(double x) { return fabs(x); }
 __host__ __device__ inline float rabs(float x) { return fabsf(x); }
 
 constexpr int kMaxSweeps = 30;
+constexpr int kMaxSweepsRec = 12;   // recorded-rotation variant: rotations of at most 12 sweeps are kept
 
-// Cyclic Jacobi with Rutishauser's rotation on the upper triangle of the symmetric
-// N x N matrix a (row-major, destroyed).  Eigenvalues ascending in w, eigenvectors in
-// the columns of v.  Rotations with |a_pq| <= ||a||_F * 2^-56 (2^-27 in float) are
-// skipped; the solve ends after a sweep without rotations.
+// One Jacobi rotation for the symmetric 2x2 block [app apq; apq aqq] (arithmetic contract):
+//   h = aqq - app,  r = sqrt(h*h + 4*(apq*apq)),  cos(2t) = |h|/r,
+//   c = sqrt(0.5 + 0.5*cos(2t)),  s = apq/(r*c) with the sign of h,
+//   new diagonal = (app+aqq)/2 -/+ r/2 (the smaller entry stays the smaller).
+// 2 sqrt + 2 div; the angle satisfies |t| <= pi/4.
+template <typename T>
+__host__ __device__ inline void jacobi_angle(T app, T aqq, T apq, T& c, T& s, T& napp, T& naqq)
+{
+    const T half = T(0.5), four = T(4);
+    const T h = aqq - app;
+    const T r = rsqrt_exact(h * h + four * (apq * apq));
+    const T c2 = rabs(h) / r;
+    c = rsqrt_exact(half + half * c2);
+    const T s0 = apq / (r * c);
+    const T m = half * (app + aqq);
+    const T hr = half * r;
+    if (h < T(0)) { s = -s0; napp = m + hr; naqq = m - hr; }
+    else          { s = s0;  napp = m - hr; naqq = m + hr; }
+}
+
+// Cyclic Jacobi on the upper triangle of the symmetric N x N matrix a (row-major,
+// destroyed).  Eigenvalues ascending in w, eigenvectors in the columns of v (accumulated
+// forward).  Rotations with |a_pq| <= ||a||_F * 2^-56 (2^-27 in float) are skipped; the
+// solve ends after a sweep without rotations.  Used for the small solves (N = 3, 4).
 template <typename T, int N>
 __host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
 {
-    const T one = T(1), zero = T(0), two = T(2);
+    const T one = T(1), zero = T(0);
+#pragma unroll
     for (int i = 0; i < N; ++i)
+#pragma unroll
         for (int j = 0; j < N; ++j) v[i * N + j] = (i == j) ? one : zero;
     T fro2 = zero;
+#pragma unroll
     for (int i = 0; i < N; ++i)
+#pragma unroll
         for (int j = i; j < N; ++j) fro2 += a[i * N + j] * a[i * N + j];
     const T tol = rsqrt_exact(fro2) * JacobiTol<T>::scale();
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         bool rotated = false;
+#pragma unroll
         for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
             for (int q = p + 1; q < N; ++q) {
                 const T apq = a[p * N + q];
                 if (!(rabs(apq) > tol)) continue;
                 rotated = true;
-                const T app = a[p * N + p], aqq = a[q * N + q];
-                const T theta = (aqq - app) / (two * apq);
-                T t = one / (rabs(theta) + rsqrt_exact(theta * theta + one));
-                if (theta < zero) t = -t;
-                const T c = one / rsqrt_exact(t * t + one);
-                const T s = t * c;
-                const T tau = s / (one + c);
-                const T h = t * apq;
-                a[p * N + p] = app - h;
-                a[q * N + q] = aqq + h;
+                T c, s, napp, naqq;
+                jacobi_angle<T>(a[p * N + p], a[q * N + q], apq, c, s, napp, naqq);
+                a[p * N + p] = napp;
+                a[q * N + q] = naqq;
                 a[p * N + q] = zero;
-                for (int j = 0; j < p; ++j) {
-                    const T g = a[j * N + p], k = a[j * N + q];
-                    a[j * N + p] = g - s * (k + g * tau);
-                    a[j * N + q] = k + s * (g - k * tau);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    if (j == p || j == q) continue;
+                    // upper-triangle storage of the symmetric entries (j,p) and (j,q)
+                    const int ip = (j < p) ? j * N + p : p * N + j;
+                    const int iq = (j < q) ? j * N + q : q * N + j;
+                    const T g = a[ip], k = a[iq];
+                    a[ip] = c * g - s * k;
+                    a[iq] = s * g + c * k;
                 }
-                for (int j = p + 1; j < q; ++j) {
-                    const T g = a[p * N + j], k = a[j * N + q];
-                    a[p * N + j] = g - s * (k + g * tau);
-                    a[j * N + q] = k + s * (g - k * tau);
-                }
-                for (int j = q + 1; j < N; ++j) {
-                    const T g = a[p * N + j], k = a[q * N + j];
-                    a[p * N + j] = g - s * (k + g * tau);
-                    a[q * N + j] = k + s * (g - k * tau);
-                }
+#pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const T g = v[j * N + p], k = v[j * N + q];
-                    v[j * N + p] = g - s * (k + g * tau);
-                    v[j * N + q] = k + s * (g - k * tau);
+                    v[j * N + p] = c * g - s * k;
+                    v[j * N + q] = s * g + c * k;
                 }
             }
         }
         if (!rotated) break;
     }
+#pragma unroll
     for (int i = 0; i < N; ++i) w[i] = a[i * N + i];
     for (int i = 0; i < N - 1; ++i) {
         int k = i;
@@ -94,6 +112,111 @@ __host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
     }
 }
 
+// Same eigen-solve for the large matrices (N = 12, 9) when only the NV eigenvectors of the
+// smallest eigenvalues are wanted (EPnP: the 4-dimensional null-space basis, PnPsolver.cpp:379-382;
+// MLPnP: the last right-singular vector, MLPnPsolver.cpp:488-489).  The matrix is kept as a
+// packed upper triangle with compile-time indices (registers on the device), the (c, s) of
+// every rotation is recorded, and the wanted eigenvectors are obtained by applying the recorded
+// rotations in reverse order to unit vectors: V e_j = J_1 (J_2 ( ... (J_K e_j))).
+// a: packed upper triangle, row-major, N(N+1)/2 entries (destroyed).  w: the NV smallest
+// eigenvalues ascending; v: N x NV (row-major), column j = eigenvector of w[j].
+__host__ __device__ constexpr int tri_idx(int N, int i, int j) { return i * N - (i * (i - 1)) / 2 + (j - i); }
+
+template <int N, int NV>
+__host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, double2* rec /* kMaxSweepsRec*N*(N-1)/2 */)
+{
+    constexpr int NP = N * (N - 1) / 2;
+    double fro2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i; j < N; ++j) fro2 += a[tri_idx(N, i, j)] * a[tri_idx(N, i, j)];
+    const double tol = sqrt(fro2) * 0x1p-56;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < kMaxSweepsRec; ++sweep) {
+        bool rotated = false;
+        double2* rs = rec + sweep * NP;
+        int slot = 0;
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) {
+                const double apq = a[tri_idx(N, p, q)];
+                double c = 1.0, s = 0.0;
+                if (fabs(apq) > tol) {
+                    rotated = true;
+                    double napp, naqq;
+                    jacobi_angle<double>(a[tri_idx(N, p, p)], a[tri_idx(N, q, q)], apq, c, s, napp, naqq);
+                    a[tri_idx(N, p, p)] = napp;
+                    a[tri_idx(N, q, q)] = naqq;
+                    a[tri_idx(N, p, q)] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        if (j == p || j == q) continue;
+                        const int ip = (j < p) ? tri_idx(N, j, p) : tri_idx(N, p, j);
+                        const int iq = (j < q) ? tri_idx(N, j, q) : tri_idx(N, q, j);
+                        const double g = a[ip], k = a[iq];
+                        a[ip] = c * g - s * k;
+                        a[iq] = s * g + c * k;
+                    }
+                }
+                rs[slot] = make_double2(c, s);
+                ++slot;
+            }
+        }
+        if (!rotated) break;
+        sweeps = sweep + 1;
+    }
+    // the NV smallest diagonal entries, ascending, ties to the lower index (static indexing only)
+    double d[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) d[i] = a[tri_idx(N, i, i)];
+    unsigned usedmask = 0u;
+    int sel[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        int best = -1;
+        double bv = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if ((usedmask >> i) & 1u) continue;
+            if (best < 0 || d[i] < bv) { best = i; bv = d[i]; }
+        }
+        usedmask |= 1u << best;
+        sel[k] = best;
+        w[k] = bv;
+    }
+    double x[NV][N];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[k][i] = (i == sel[k]) ? 1.0 : 0.0;
+    for (int sweep = sweeps - 1; sweep >= 0; --sweep) {
+        const double2* rs = rec + sweep * NP;
+        // static (p,q) order reversed
+#pragma unroll
+        for (int p = N - 2; p >= 0; --p) {
+#pragma unroll
+            for (int q = N - 1; q > p; --q) {
+                const int slot = p * N - (p * (p + 1)) / 2 + (q - p - 1);
+                const double2 cs = rs[slot];
+                if (cs.y != 0.0) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        const double xp = x[k][p], xq = x[k][q];
+                        x[k][p] = cs.x * xp + cs.y * xq;
+                        x[k][q] = cs.x * xq - cs.y * xp;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[i * NV + k] = x[k][i];
+}
+
 // One-sided (Hestenes) Jacobi: orthogonalises the columns of U (M x K), accumulates V (K x K).
 template <int M, int K>
 __host__ __device__ inline void onesided_jacobi(double* U, double* V)
@@ -102,9 +225,12 @@ __host__ __device__ inline void onesided_jacobi(double* U, double* V)
         for (int j = 0; j < K; ++j) V[i * K + j] = (i == j) ? 1.0 : 0.0;
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         bool rotated = false;
+#pragma unroll
         for (int i = 0; i < K - 1; ++i) {
+#pragma unroll
             for (int j = i + 1; j < K; ++j) {
                 double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
                 for (int r = 0; r < M; ++r) {
                     const double ui = U[r * K + i], uj = U[r * K + j];
                     alpha += ui * ui;
@@ -118,11 +244,13 @@ __host__ __device__ inline void onesided_jacobi(double* U, double* V)
                 if (zeta < 0.0) t = -t;
                 const double c = 1.0 / sqrt(t * t + 1.0);
                 const double s = c * t;
+#pragma unroll
                 for (int r = 0; r < M; ++r) {
                     const double ui = U[r * K + i], uj = U[r * K + j];
                     U[r * K + i] = c * ui - s * uj;
                     U[r * K + j] = s * ui + c * uj;
                 }
+#pragma unroll
                 for (int r = 0; r < K; ++r) {
                     const double vi = V[r * K + i], vj = V[r * K + j];
                     V[r * K + i] = c * vi - s * vj;

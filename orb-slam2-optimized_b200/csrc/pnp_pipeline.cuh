@@ -78,6 +78,7 @@ struct SelectArgs {
     double* pw_s;            // [total][3]
     double* us_s;            // [total][2]
     double* al_s;            // [total][4]
+    double2* rec;            // [C][kMaxSweepsRec*66] recorded Jacobi rotations of the refine solve
     // outputs
     void* results;           // rsac_result[C] (layout in ransac_b200.h)
     void* results2;          // optional second copy (collective send buffer)
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kSelectThreads) pnp_select_kernel(SelectArgs a
     int* prefix = reinterpret_cast<int*>(refmask + words);        // [words+1]
 
     __shared__ int s_found, s_cnt;
-    __shared__ double s_C0[3], s_A[9], s_cws[12], s_CCi[9], s_MtM[144], s_U4[48], s_betas[12];
+    __shared__ double s_C0[3], s_A[9], s_cws[12], s_CCi[9], s_MtM[78], s_U4[48], s_betas[12];
     __shared__ double s_ccs[3][12], s_sign[3], s_pc0[3][3], s_pw0[3], s_M[3][9], s_R[3][9], s_t[3][3], s_rep[3];
     __shared__ float s_pose[12], s_bestpose[12];
 
@@ -250,13 +251,14 @@ __global__ void __launch_bounds__(kSelectThreads) pnp_select_kernel(SelectArgs a
                     s += a0 * b0;
                     s += a1 * b1;
                 }
-                s_MtM[ea * 12 + eb] = s;
+                s_MtM[tri_idx(12, ea, eb)] = s;
             }
             __syncthreads();
             if (tid == 0) {
-                double MtM[144];
-                for (int i = 0; i < 144; ++i) MtM[i] = s_MtM[i];
-                epnp_solve_betas(MtM, s_cws, s_U4, s_betas);
+                double MtM[78];
+#pragma unroll
+                for (int i = 0; i < 78; ++i) MtM[i] = s_MtM[i];
+                epnp_solve_betas(MtM, s_cws, s_U4, s_betas, a.rec + (size_t)blockIdx.x * (kMaxSweepsRec * 66));
                 for (int k = 0; k < 3; ++k) epnp_ccs(s_betas + 4 * k, s_U4, s_ccs[k]);
             }
             __syncthreads();

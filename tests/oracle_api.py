@@ -100,6 +100,15 @@ def jacobi_eig(a, dtype=np.float64):
     return w, v
 
 
+def jacobi_lowest(a, nv):
+    a = np.array(a, np.float64, order="C", copy=True)
+    n = a.shape[0]
+    w = np.empty(nv)
+    v = np.empty((n, nv))
+    lib().orc_jacobi_lowest_d(C.c_int(n), C.c_int(nv), _p(a), _p(w), _p(v))
+    return w, v
+
+
 def svd_lstsq(L, b):
     L = np.ascontiguousarray(L, np.float64)
     b = np.ascontiguousarray(b, np.float64)
