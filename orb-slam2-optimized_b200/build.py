@@ -18,7 +18,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libransac_b200.so")
-SOURCES = ["engine.cu", "engine_sim3.cu", "engine_mlpnp.cu", "engine_nccl.cu"]
+SOURCES = ["engine.cu"]   # one translation unit; engine_*.inl are included by it
 
 
 def _newer(src_dir: str, out: str) -> bool:

@@ -706,3 +706,6 @@ int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48])
     jacobi_lowest<12, 4>(A, w, v, rec.data());
     return RSAC_OK;
 }
+
+// ------------------------------------------------- remaining solver families (same TU)
+#include "engine_sim3.inl"

@@ -274,6 +274,58 @@ class Engine:
             w0 += nw
         return out
 
+    # -- Sim3
+    def sim3_upload(self, offsets, x1c, x2c, s1, s2, K1, K2, params, seeds=None, tables=None, table_offsets=None):
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        Cn = len(offsets) - 1
+        x1c = np.ascontiguousarray(x1c, np.float32).reshape(-1, 3)
+        x2c = np.ascontiguousarray(x2c, np.float32).reshape(-1, 3)
+        s1 = np.ascontiguousarray(s1, np.float32).reshape(-1)
+        s2 = np.ascontiguousarray(s2, np.float32).reshape(-1)
+        K1 = np.ascontiguousarray(K1, np.float32).reshape(-1, 4)
+        K2 = np.ascontiguousarray(K2, np.float32).reshape(-1, 4)
+        if K1.shape[0] == 1 and Cn != 1:
+            K1 = np.ascontiguousarray(np.repeat(K1, max(Cn, 1), axis=0))
+        if K2.shape[0] == 1 and Cn != 1:
+            K2 = np.ascontiguousarray(np.repeat(K2, max(Cn, 1), axis=0))
+        if isinstance(params, Sim3Params):
+            parr, npar = (Sim3Params * 1)(params), 1
+        else:
+            parr, npar = (Sim3Params * len(params))(*params), len(params)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, np.uint32)
+        tables = None if tables is None else np.ascontiguousarray(tables, np.uint32).reshape(-1)
+        table_offsets = None if table_offsets is None else np.ascontiguousarray(table_offsets, np.int64)
+        desc = Sim3Batch(Cn, _p(offsets), _p(x1c), _p(x2c), _p(s1), _p(s2), _p(K1), _p(K2), C.cast(parr, C.c_void_p), npar,
+                         _p(seeds), _p(tables), _p(table_offsets))
+        self._keep_sim3 = [offsets, x1c, x2c, s1, s2, K1, K2, parr, seeds, tables, table_offsets]
+        self._ck(self.L.rsac_sim3_upload(self.h, C.byref(desc)), "sim3_upload")
+        self._sim3_C = Cn
+        self._sim3_words = ((np.diff(offsets) + 31) // 32).astype(np.int64)
+        return Cn
+
+    def sim3_run(self, flags=0, d_results_out: int | None = None):
+        self._ck(self.L.rsac_sim3_run(self.h, C.c_int(flags), C.c_void_p(d_results_out or 0)), "sim3_run")
+
+    def sim3_download(self, want_masks=True):
+        res = np.zeros(self._sim3_C, RESULT_DTYPE)
+        masks = np.zeros(int(self._sim3_words.sum()), np.uint32) if want_masks else None
+        self._ck(self.L.rsac_sim3_download(self.h, _p(res), _p(masks)), "sim3_download")
+        return res, masks
+
+    def sim3_solve(self, offsets, x1c, x2c, s1, s2, K1, K2, params, seeds=None, tables=None, table_offsets=None, flags=0):
+        self.sim3_upload(offsets, x1c, x2c, s1, s2, K1, K2, params, seeds, tables, table_offsets)
+        self.sim3_run(flags)
+        return self.sim3_download()
+
+    def sim3_hypotheses(self, hyp_words: int):
+        """poses [sumH,13], counts [sumH], masks (flat words; hyp_words = total per-hypothesis words)"""
+        n = self.L.rsac_sim3_total_hypotheses(self.h)
+        poses = np.zeros((n, 13), np.float32)
+        counts = np.zeros(n, np.int32)
+        masks = np.zeros(max(hyp_words, 1), np.uint32)
+        self._ck(self.L.rsac_sim3_get_hypotheses(self.h, _p(poses), _p(counts), _p(masks)), "sim3_get_hypotheses")
+        return poses, counts, masks
+
     # -- scoring stress
     def score_pnp_upload(self, poses, p3d, p2d, max_err, K):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
