@@ -280,9 +280,8 @@ static void compute_pose(int n, const double *f, const double *p, const double *
                 AtPA[a * cols + b] += a1[a] * w1[b];
             }
     }
-    double ev[12], V[144], result1[12];
-    orc_jacobi_eig_d(cols, AtPA, ev, V);   /* :488-489 last right-singular vector = eigenvector of the smallest eigenvalue */
-    for (int r = 0; r < cols; ++r) result1[r] = V[r * cols + 0];
+    double ev[1], result1[12];
+    orc_jacobi_lowest_d(cols, 1, AtPA, ev, result1);   /* :488-489 last right-singular vector = eigenvector of the smallest eigenvalue */
 
     double Rout[9], tout[3];
     if (planar) {                                                       /* :497-558 */

@@ -13,6 +13,7 @@
 #include "engine_state.cuh"
 #include "pnp_pipeline.cuh"
 #include "score.cuh"
+#include "select.cuh"
 
 using namespace rsac;
 
@@ -468,14 +469,14 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
     {
         SelectArgs a;
         a.metas = metas; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.uv = (const float2*)s.d_uv.p;
-        a.poses = (const float*)s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p;
+        a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = nullptr; a.flags = flags;
         a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p; a.rec = (double2*)s.d_extra.p;
         a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
         a.problem_base = e->problem_base;
         const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
-        if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(pnp_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         e->stage_begin(RSAC_STAGE_SELECT);
-        pnp_select_kernel<<<d.C, kSelectThreads, smem, st>>>(a);
+        ransac_select_kernel<0><<<d.C, kSelectThreads, smem, st>>>(a);
         e->stage_end(RSAC_STAGE_SELECT);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -709,3 +710,4 @@ int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48])
 
 // ------------------------------------------------- remaining solver families (same TU)
 #include "engine_sim3.inl"
+#include "engine_mlpnp.inl"

@@ -1,0 +1,178 @@
+// engine_mlpnp.inl -- C ABI for the batched MLPnPsolver (include/ransac_b200.h, "MLPnPsolver").
+// (included at the end of engine.cu: the library is one translation unit)
+
+int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
+{
+    if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
+    if (!b->seeds && !b->tables) { e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    PnpState& s = e->mlpnp;
+    s.uploaded = false; s.ran = false;
+    std::vector<float> th2;
+    for (int c = 0; c < b->C; ++c)
+        if (b->params[b->n_params == 1 ? 0 : c].min_set != 6) { e->err = "MLPnP needs min_set = 6"; return RSAC_ERR_INVALID; }
+    int rc = pnp_build_metas(e, b->C, b->offsets, b->params, b->n_params, b->seeds, b->table_offsets, b->tables != nullptr, s.metas, th2, s.d);
+    if (rc) return rc;
+    for (int c = 0; c < b->C; ++c)
+        for (int k = 0; k < 4; ++k) s.metas[c].k1[k] = b->K[4 * c + k];
+    const BatchDims& d = s.d;
+    const size_t tot = (size_t)std::max(d.total, 1);
+    s.threads = score_threads_for(d.maxH);
+    plan_tiles(s.metas, s.threads, e->sm_count, s.tiles, &s.chunk_cap);
+
+    RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreTile) * std::max<size_t>(s.tiles.size(), 1)));
+    RSAC_TRY(s.d_th2.ensure(e, sizeof(float) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
+    RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
+    RSAC_TRY(s.d_sigma2.ensure(e, tot * 4));
+    RSAC_TRY(s.d_cA.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cB.ensure(e, tot * 16));
+    RSAC_TRY(s.d_uv.ensure(e, tot * 8));
+    RSAC_TRY(s.d_tables.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.table_len, 1)));
+    RSAC_TRY(s.d_poses.ensure(e, sizeof(double) * 12 * (size_t)std::max<int64_t>(d.sumH, 1)));
+    RSAC_TRY(s.d_counts.ensure(e, sizeof(int32_t) * (size_t)std::max<int64_t>(d.sumH, 1)));
+    RSAC_TRY(s.d_results.ensure(e, sizeof(rsac_result) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_masks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_words, 1)));
+    RSAC_TRY(s.d_sel.ensure(e, tot * 4));
+    RSAC_TRY(s.d_pw.ensure(e, tot * sizeof(double) * kMlpnpScratch));
+    RSAC_TRY(s.d_extra.ensure(e, sizeof(double2) * (size_t)(kMaxSweepsRec * 66) * std::max(d.C, 1)));
+    if (b->cov) RSAC_TRY(s.d_cov.ensure(e, tot * 72));
+
+    cudaStream_t st = e->stream;
+    if (d.C > 0) {
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, s.metas.data(), sizeof(ProblemMeta) * d.C, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_th2.p, th2.data(), sizeof(float) * d.C, cudaMemcpyHostToDevice, st));
+    }
+    if (!s.tiles.empty())
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, s.tiles.data(), sizeof(ScoreTile) * s.tiles.size(), cudaMemcpyHostToDevice, st));
+    if (d.total > 0) {
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, b->p3d, (size_t)d.total * 12, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, b->p2d, (size_t)d.total * 8, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_sigma2.p, b->sigma2, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));
+        if (b->cov) RSAC_CUDA(e, cudaMemcpyAsync(s.d_cov.p, b->cov, (size_t)d.total * 72, cudaMemcpyHostToDevice, st));
+    }
+    s.have_cov = b->cov != nullptr;
+    s.have_tables = b->tables != nullptr;
+    if (s.have_tables && d.table_len > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tables.p, b->tables, sizeof(uint32_t) * (size_t)d.table_len, cudaMemcpyHostToDevice, st));
+    if (d.total > 0 && d.C > 0) {
+        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)d.C);
+        e->stage_begin(RSAC_STAGE_PACK);
+        pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
+                                              (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 1,
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float2*)s.d_uv.p);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.uploaded = true;
+    return RSAC_OK;
+}
+
+int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->mlpnp;
+    if (!s.uploaded) { e->err = "rsac_mlpnp_run before rsac_mlpnp_upload"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    const BatchDims& d = s.d;
+    cudaStream_t st = e->stream;
+    const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
+    if (d.C == 0) { s.ran = true; return RSAC_OK; }
+    const double* cov = s.have_cov ? (const double*)s.d_cov.p : nullptr;
+
+    if (!s.have_tables && d.table_len > 0) {
+        e->stage_begin(RSAC_STAGE_RNG);
+        rng_tables_kernel<<<(d.C + 63) / 64, 64, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
+        e->stage_end(RSAC_STAGE_RNG);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    if (d.sumH > 0) {
+        const int threads = 128;
+        const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
+        e->stage_begin(RSAC_STAGE_SOLVE);
+        mlpnp_minimal_kernel<<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
+                                                         (const float4*)s.d_cA.p, (const float2*)s.d_uv.p, cov, (double*)s.d_poses.p);
+        e->stage_end(RSAC_STAGE_SOLVE);
+        RSAC_CUDA(e, cudaGetLastError());
+
+        RSAC_CUDA(e, cudaMemsetAsync(s.d_counts.p, 0, sizeof(int32_t) * (size_t)d.sumH, st));
+        ScoreArgs sa;
+        sa.metas = metas; sa.tiles = (const ScoreTile*)s.d_tiles.p;
+        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.uv = (const float2*)s.d_uv.p;
+        sa.poses = s.d_poses.p; sa.counts = (int32_t*)s.d_counts.p;
+        sa.hmasks = nullptr;
+        RSAC_TRY(e->d_exact.ensure(e, sizeof(unsigned long long)));
+        RSAC_CUDA(e, cudaMemsetAsync(e->d_exact.p, 0, sizeof(unsigned long long), st));
+        sa.exact_counter = (unsigned long long*)e->d_exact.p;
+        sa.chunk_cap = s.chunk_cap;
+        int rc = launch_score<1>(e, sa, (int)s.tiles.size(), s.threads);
+        if (rc) return rc;
+    }
+    {
+        SelectArgs a;
+        a.metas = metas; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.uv = (const float2*)s.d_uv.p;
+        a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = cov;
+        a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = nullptr; a.al_s = nullptr; a.rec = (double2*)s.d_extra.p;
+        a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
+        a.problem_base = e->problem_base; a.flags = flags;
+        const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
+        if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        e->stage_begin(RSAC_STAGE_SELECT);
+        ransac_select_kernel<1><<<d.C, kSelectThreads, smem, st>>>(a);
+        e->stage_end(RSAC_STAGE_SELECT);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.ran = true;
+    return RSAC_OK;
+}
+
+int rsac_mlpnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->mlpnp;
+    if (!s.ran) { e->err = "rsac_mlpnp_download before rsac_mlpnp_run"; return RSAC_ERR_STATE; }
+    const BatchDims& d = s.d;
+    if (results && d.C > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(results, s.d_results.p, sizeof(rsac_result) * d.C, cudaMemcpyDeviceToHost, e->stream));
+    if (masks && d.total_words > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(masks, s.d_masks.p, sizeof(uint32_t) * (size_t)d.total_words, cudaMemcpyDeviceToHost, e->stream));
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_mlpnp_solve(rsac_engine* e, const rsac_mlpnp_batch* b, int flags, rsac_result* results, uint32_t* masks)
+{
+    int rc = rsac_mlpnp_upload(e, b);
+    if (rc) return rc;
+    rc = rsac_mlpnp_run(e, flags, nullptr);
+    if (rc) return rc;
+    return rsac_mlpnp_download(e, results, masks);
+}
+
+int64_t rsac_mlpnp_total_hypotheses(rsac_engine* e) { return e ? e->mlpnp.d.sumH : 0; }
+
+int rsac_mlpnp_get_hypotheses(rsac_engine* e, double* poses, int32_t* counts)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->mlpnp;
+    if (!s.ran) return RSAC_ERR_STATE;
+    if (s.d.sumH > 0) {
+        if (poses) RSAC_CUDA(e, cudaMemcpyAsync(poses, s.d_poses.p, sizeof(double) * 12 * (size_t)s.d.sumH, cudaMemcpyDeviceToHost, e->stream));
+        if (counts) RSAC_CUDA(e, cudaMemcpyAsync(counts, s.d_counts.p, sizeof(int32_t) * (size_t)s.d.sumH, cudaMemcpyDeviceToHost, e->stream));
+    }
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_debug_host_mlpnp6(const float K[4], const float p3d[18], const float p2d[12], const double* cov54, double R[9], double t[3])
+{
+    double f[18], pw[18];
+    for (int i = 0; i < 6; ++i) {
+        mlpnp_bearing(p2d[2 * i], p2d[2 * i + 1], K, f + 3 * i);
+        for (int c = 0; c < 3; ++c) pw[3 * i + c] = (double)p3d[3 * i + c];
+    }
+    std::vector<double2> rec(kMaxSweepsRec * 66);
+    mlpnp_compute_pose_small<6>(f, pw, cov54, R, t, rec.data());
+    return RSAC_OK;
+}

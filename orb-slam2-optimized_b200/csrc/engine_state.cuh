@@ -52,7 +52,7 @@ struct BatchDims {
 };
 
 struct PnpState {
-    bool uploaded = false, ran = false, have_tables = false;
+    bool uploaded = false, ran = false, have_tables = false, have_cov = false;
     BatchDims d;
     std::vector<ProblemMeta> metas;
     std::vector<ScoreTile> tiles;

@@ -1,0 +1,511 @@
+// select.cuh -- sequential-semantics replay + Refine for PnPsolver and MLPnPsolver.
+//
+// Reference control flow: PnPsolver::iterate / Refine (src/PnPsolver.cpp:102-238) and
+// MLPnPsolver::iterate / Refine (src/MLPnPsolver.cpp:56-183, 257-318) -- identical logic
+// (SURVEY Appendix C): scan the hypotheses in draw order; every hypothesis with
+// cnt >= minInliers (i) replaces the best set on a strict '>' and (ii) triggers Refine() =
+// an n-point solve on the CURRENT BEST set followed by CheckInliers; the first refine with
+// cnt > minInliers wins; if the budget is exhausted the unrefined best is returned.
+//
+// One CTA per problem.  The n-point solves evaluate every sum "entry-parallel": one thread per
+// output entry walks the selected points in index order, which reproduces the serial summation
+// order of the CPU checker exactly; the dense tails run on thread 0 with the same device
+// functions as the minimal solvers.
+#pragma once
+#include <type_traits>
+#include "common.cuh"
+#include "epnp.cuh"
+#include "mlpnp.cuh"
+#include "score.cuh"
+
+namespace rsac {
+
+struct SelectArgs {
+    const ProblemMeta* metas;
+    const float4* cA;
+    const float4* cB;
+    const float2* uv;
+    const void* poses;       // [sumH][12] float (PnP) / double (MLPnP)
+    const int32_t* counts;   // [sumH]
+    const double* cov;       // MLPnP: optional [total][9]
+    // scratch, indexed like the correspondences
+    uint32_t* sel;           // compacted indices of the best set
+    double* pw_s;            // EPnP [total][3]          MLPnP: [total][33] f3 p3 N6 P4 q3 J12 r2
+    double* us_s;            // EPnP [total][2]
+    double* al_s;            // EPnP [total][4]
+    double2* rec;            // [C][kMaxSweepsRec*66] recorded Jacobi rotations of the refine solve
+    // outputs
+    void* results;           // rsac_result[C] (layout in ransac_b200.h)
+    void* results2;          // optional second copy (collective send buffer)
+    uint32_t* masks;         // final masks, word_off per problem
+    int32_t problem_base;    // global index of problem 0 (sharding)
+    int32_t flags;
+};
+
+struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
+    int32_t ok, no_more, n_inliers, best_hyp, refined, n_refines, best_count, n_hyp;
+    float R[9], t[3], s;
+    int32_t problem, reserved[2];
+};
+static_assert(sizeof(ResultRec) == 96, "rsac_result layout");
+
+constexpr int kSelectThreads = 128;
+constexpr int kMlpnpScratch = 33;   // doubles per selected observation
+
+// exact CheckInliers of one pose over all correspondences of the problem by the whole CTA
+template <int MODEL>
+__device__ inline void cta_score_exact(const ProblemMeta* m, const SelectArgs& a,
+                                       const typename ScoreModel<MODEL>::pose_t* pose, uint32_t* mask_out, int* s_cnt)
+{
+    if (threadIdx.x == 0) *s_cnt = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int local = 0;
+    for (int base = (threadIdx.x >> 5) * 32; base < m->words * 32; base += blockDim.x) {
+        const int i = base + lane;
+        bool in = false;
+        if (i < m->n) {
+            const size_t g = (size_t)m->corr_off + i;
+            const float4 c = a.cA[g];
+            const float2 q = a.uv[g];
+            in = ScoreModel<MODEL>::exact(pose, c.x, c.y, c.z, q.x, q.y, a.cB[g].y, m);
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) { mask_out[base >> 5] = word; local += __popc(word); }
+    }
+    if (lane == 0 && local) atomicAdd(s_cnt, local);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ EPnP refine
+struct EpnpShared {
+    double C0[3], A[9], cws[12], CCi[9], MtM[78], U4[48], betas[12];
+    double ccs[3][12], sign[3], pc0[3][3], pw0[3], M[3][9], R[3][9], t[3][3], rep[3];
+};
+
+// PnPsolver::Refine's compute_pose on the n selected points (PnPsolver.cpp:206-217, 359-415);
+// result as float R|t in pose_out[12] (shared)
+__device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, int n, EpnpShared& S, float* pose_out)
+{
+    const int tid = threadIdx.x;
+    const Cam cam = {m->fx, m->fy, m->cx, m->cy};
+    const uint32_t* sel = a.sel + m->corr_off;
+    double* pw = a.pw_s + (size_t)m->corr_off * 3;
+    double* us = a.us_s + (size_t)m->corr_off * 2;
+    double* al = a.al_s + (size_t)m->corr_off * 4;
+    for (int i = tid; i < n; i += blockDim.x) {       // add_correspondence
+        const size_t g = (size_t)m->corr_off + sel[i];
+        const float4 c = a.cA[g];
+        const float2 q = a.uv[g];
+        pw[3 * i] = (double)c.x; pw[3 * i + 1] = (double)c.y; pw[3 * i + 2] = (double)c.z;
+        us[2 * i] = (double)q.x; us[2 * i + 1] = (double)q.y;
+    }
+    __syncthreads();
+    if (tid < 3) {                                     // centroid (:301-303)
+        double s = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) s += pw[3 * i + tid];
+        S.C0[tid] = s / (double)n;
+    }
+    __syncthreads();
+    if (tid < 6) {                                     // PW0^T PW0 upper triangle (:306-310)
+        const int r = (tid < 3) ? 0 : (tid < 5 ? 1 : 2);
+        const int c = (tid < 3) ? tid : (tid < 5 ? tid - 2 : 2);
+        double s = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) s += (pw[3 * i + r] - S.C0[r]) * (pw[3 * i + c] - S.C0[c]);
+        S.A[r * 3 + c] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double A[9];
+        for (int i = 0; i < 9; ++i) A[i] = S.A[i];
+        epnp_control_points(S.C0, A, n, S.cws);
+        epnp_cc_inverse(S.cws, S.CCi);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) epnp_alphas(pw + 3 * i, S.cws, S.CCi, al + 4 * i);
+    __syncthreads();
+    if (tid < 78) {                                    // MtM upper triangle, one entry per thread (:379)
+        int ea = 0, rem = tid;
+        while (rem >= 12 - ea) { rem -= 12 - ea; ++ea; }
+        const int eb = ea + rem;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double a0, a1, b0, b1;
+            epnp_m_entry(al + 4 * i, us[2 * i], us[2 * i + 1], cam, ea, a0, a1);
+            epnp_m_entry(al + 4 * i, us[2 * i], us[2 * i + 1], cam, eb, b0, b1);
+            s += a0 * b0;
+            s += a1 * b1;
+        }
+        S.MtM[tri_idx(12, ea, eb)] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double MtM[78];
+#pragma unroll
+        for (int i = 0; i < 78; ++i) MtM[i] = S.MtM[i];
+        epnp_solve_betas(MtM, S.cws, S.U4, S.betas, a.rec + (size_t)blockIdx.x * (kMaxSweepsRec * 66));
+        for (int k = 0; k < 3; ++k) epnp_ccs(S.betas + 4 * k, S.U4, S.ccs[k]);
+    }
+    __syncthreads();
+    if (tid < 3) {                                     // solve_for_sign on pcs(0,2) (:495-502)
+        double pc[3];
+        epnp_pc(al, S.ccs[tid], pc);
+        S.sign[tid] = (pc[2] < 0.0) ? -1.0 : 1.0;
+    }
+    __syncthreads();
+    if (tid < 9) {                                     // pc0 of the three candidates (:435,438)
+        const int k = tid / 3, c = tid % 3;
+        const bool neg = S.sign[k] < 0.0;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double pc[3];
+            epnp_pc(al + 4 * i, S.ccs[k], pc);
+            s += neg ? -pc[c] : pc[c];
+        }
+        S.pc0[k][c] = s / (double)n;
+    } else if (tid < 12) {                             // pw0 (:436,439)
+        const int c = tid - 9;
+        double s = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) s += pw[3 * i + c];
+        S.pw0[c] = s / (double)n;
+    }
+    __syncthreads();
+    if (tid < 27) {                                    // M = sum (pc-pc0)^T (pw-pw0) (:443-447)
+        const int k = tid / 9, r = (tid % 9) / 3, c = tid % 3;
+        const bool neg = S.sign[k] < 0.0;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double pc[3];
+            epnp_pc(al + 4 * i, S.ccs[k], pc);
+            const double pcr = neg ? -pc[r] : pc[r];
+            s += (pcr - S.pc0[k][r]) * (pw[3 * i + c] - S.pw0[c]);
+        }
+        S.M[k][r * 3 + c] = s;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        epnp_horn(S.M[tid], S.pc0[tid], S.pw0, S.R[tid], S.t[tid]);
+        double sum2 = 0.0;                             // reprojection_error (:417-431)
+        for (int i = 0; i < n; ++i) sum2 += epnp_reproj_term(S.R[tid], S.t[tid], pw + 3 * i, us[2 * i], us[2 * i + 1], cam);
+        S.rep[tid] = sum2 / (double)n;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int Nn = 0;                                    // :407-409
+        if (S.rep[1] < S.rep[0]) Nn = 1;
+        if (S.rep[2] < S.rep[Nn]) Nn = 2;
+        for (int i = 0; i < 9; ++i) pose_out[i] = (float)S.R[Nn][i];
+        for (int i = 0; i < 3; ++i) pose_out[9 + i] = (float)S.t[Nn][i];
+    }
+    __syncthreads();
+}
+
+// ----------------------------------------------------------------- MLPnP refine
+struct MlpnpShared {
+    double planarTest[9], eigenRot[9], AtPA[78], x[6], A[36], g[6], dx[6];
+    unsigned long long maxdl_bits;
+    int planar, dec;
+};
+
+// one design-matrix column entry of observation (N, pt): rows a0[col], a1[col] (MLPnPsolver.cpp:404-476)
+__device__ inline void mlpnp_row_entry(const double* N, const double* pt, bool planar, int col, double& e0, double& e1)
+{
+    if (planar) {
+        if (col < 6) { const int r = col >> 1, c = 1 + (col & 1); e0 = N[r * 2 + 0] * pt[c]; e1 = N[r * 2 + 1] * pt[c]; }
+        else { const int r = col - 6; e0 = N[r * 2 + 0]; e1 = N[r * 2 + 1]; }
+    } else {
+        if (col < 9) { const int r = col / 3, c = col - 3 * r; e0 = N[r * 2 + 0] * pt[c]; e1 = N[r * 2 + 1] * pt[c]; }
+        else { const int r = col - 9; e0 = N[r * 2 + 0]; e1 = N[r * 2 + 1]; }
+    }
+}
+
+// MLPnPsolver::Refine's computePose on the n selected observations (MLPnPsolver.cpp:269-290,
+// 321-623); result as double R|t in pose_out[12] (shared)
+__device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, int n, MlpnpShared& S, double* pose_out)
+{
+    const int tid = threadIdx.x;
+    const uint32_t* sel = a.sel + m->corr_off;
+    double* sc = a.pw_s + (size_t)m->corr_off * kMlpnpScratch;   // per observation: f3 p3 N6 P4 q3 J12 r2
+    const bool use_cov = a.cov != nullptr;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const size_t g = (size_t)m->corr_off + sel[i];
+        const float4 c = a.cA[g];
+        const float2 q = a.uv[g];
+        double* o = sc + (size_t)i * kMlpnpScratch;
+        mlpnp_bearing(q.x, q.y, m->k1, o);                                  // f
+        o[3] = (double)c.x; o[4] = (double)c.y; o[5] = (double)c.z;          // p
+        mlpnp_nullspace(o, o + 6);                                           // N
+        if (use_cov) mlpnp_weight(o + 6, a.cov + 9 * g, o + 12);             // P
+    }
+    __syncthreads();
+    if (tid < 9) {                                     // planarTest = sum p p^T (:346)
+        const int r = tid / 3, c = tid % 3;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += sc[(size_t)i * kMlpnpScratch + 3 + r] * sc[(size_t)i * kMlpnpScratch + 3 + c];
+        S.planarTest[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 0; i < 9; ++i) S.eigenRot[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        S.planar = 0;
+        if (rank3_fullpiv(S.planarTest) == 2) {        // :354
+            S.planar = 1;
+            double A[9], w[3], V[9];
+            for (int i = 0; i < 9; ++i) A[i] = S.planarTest[i];
+            jacobi_eig<double, 3>(A, w, V);
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) S.eigenRot[r * 3 + c] = V[c * 3 + r];
+        }
+    }
+    __syncthreads();
+    const bool planar = S.planar != 0;
+    for (int i = tid; i < n; i += blockDim.x) {        // points3 (:362-363)
+        double* o = sc + (size_t)i * kMlpnpScratch;
+        if (planar) {
+            for (int r = 0; r < 3; ++r)
+                o[16 + r] = S.eigenRot[r * 3 + 0] * o[3] + S.eigenRot[r * 3 + 1] * o[4] + S.eigenRot[r * 3 + 2] * o[5];
+        } else {
+            o[16] = o[3]; o[17] = o[4]; o[18] = o[5];
+        }
+    }
+    __syncthreads();
+    const int cols = planar ? 9 : 12;
+    const int nent = cols * (cols + 1) / 2;
+    if (tid < nent) {                                  // A^T P A upper triangle, one entry per thread (:482-486)
+        int ea = 0, rem = tid;
+        while (rem >= cols - ea) { rem -= cols - ea; ++ea; }
+        const int eb = ea + rem;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double* o = sc + (size_t)i * kMlpnpScratch;
+            double a0, a1, b0, b1;
+            mlpnp_row_entry(o + 6, o + 16, planar, ea, a0, a1);
+            mlpnp_row_entry(o + 6, o + 16, planar, eb, b0, b1);
+            double w0 = b0, w1 = b1;
+            if (use_cov) {
+                w0 = o[12] * b0 + o[13] * b1;
+                w1 = o[14] * b0 + o[15] * b1;
+            }
+            s += a0 * w0;
+            s += a1 * w1;
+        }
+        S.AtPA[tri_idx(cols, ea, eb)] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double result1[12], ev[1];
+        double2* rec = a.rec + (size_t)blockIdx.x * (kMaxSweepsRec * 66);
+        if (planar) {
+            double T[45];
+            for (int i = 0; i < 45; ++i) T[i] = S.AtPA[i];
+            jacobi_lowest<9, 1>(T, ev, result1, rec);
+        } else {
+            double T[78];
+            for (int i = 0; i < 78; ++i) T[i] = S.AtPA[i];
+            jacobi_lowest<12, 1>(T, ev, result1, rec);
+        }
+        // first six observations for the +-t / 4-candidate test (:547-551, :590-594)
+        double p6[18], f6[18];
+        for (int q = 0; q < 6; ++q)
+            for (int c = 0; c < 3; ++c) {
+                f6[3 * q + c] = sc[(size_t)q * kMlpnpScratch + c];
+                p6[3 * q + c] = sc[(size_t)q * kMlpnpScratch + 3 + c];
+            }
+        double Rout[9], tout[3];
+        mlpnp_recover(result1, planar, S.eigenRot, p6, f6, Rout, tout);
+        rot2rodrigues(Rout, S.x);
+        S.x[3] = tout[0]; S.x[4] = tout[1]; S.x[5] = tout[2];
+    }
+    __syncthreads();
+    // Gauss-Newton (MLPnPsolver.cpp:659-723)
+    for (int it_cnt = 0; it_cnt < 5;) {
+        for (int i = tid; i < n; i += blockDim.x) {
+            double* o = sc + (size_t)i * kMlpnpScratch;
+            const double nr[3] = {o[6], o[8], o[10]}, ns[3] = {o[7], o[9], o[11]};
+            mlpnp_res_jac(o + 3, nr, ns, S.x, S.x + 3, o + 31, o + 19);
+        }
+        if (tid == 0) S.maxdl_bits = 0ull;
+        __syncthreads();
+        if (tid < 42) {                                // A = J^T P J (36 entries) and g = J^T P r (6 entries)
+            const bool isg = tid >= 36;
+            const int ea = isg ? tid - 36 : tid / 6, eb = isg ? 0 : tid % 6;
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double* o = sc + (size_t)i * kMlpnpScratch;
+                const double* J = o + 19;
+                double W0 = J[ea], W1 = J[6 + ea];
+                if (use_cov) {
+                    W0 = J[ea] * o[12] + J[6 + ea] * o[14];
+                    W1 = J[ea] * o[13] + J[6 + ea] * o[15];
+                }
+                if (isg) { s += W0 * o[31]; s += W1 * o[32]; }
+                else     { s += W0 * J[eb]; s += W1 * J[6 + eb]; }
+            }
+            if (isg) S.g[ea] = s; else S.A[ea * 6 + eb] = s;
+        }
+        __syncthreads();
+        if (tid == 0) ldlt6_solve(S.A, S.g, S.dx);
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) {    // max |J dx| (:712-713)
+            const double* J = sc + (size_t)i * kMlpnpScratch + 19;
+            for (int k = 0; k < 2; ++k) {
+                const double* Jk = J + 6 * k;
+                const double dl = Jk[0] * S.dx[0] + Jk[1] * S.dx[1] + Jk[2] * S.dx[2] + Jk[3] * S.dx[3] + Jk[4] * S.dx[4] + Jk[5] * S.dx[5];
+                const double v = fabs(dl);
+                if (v > 0.0) atomicMax(&S.maxdl_bits, (unsigned long long)__double_as_longlong(v));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double mdl = __longlong_as_double((long long)S.maxdl_bits);
+            S.dec = mlpnp_gn_decide(S.dx, mdl);
+            if (S.dec != 0)
+                for (int c = 0; c < 6; ++c) S.x[c] = S.x[c] - S.dx[c];
+        }
+        __syncthreads();
+        if (S.dec != 1) break;
+        ++it_cnt;
+    }
+    if (tid == 0) {
+        rodrigues2rot(S.x, pose_out);
+        pose_out[9] = S.x[3]; pose_out[10] = S.x[4]; pose_out[11] = S.x[5];
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------- the replay kernel
+template <int MODEL>
+__global__ void __launch_bounds__(kSelectThreads) ransac_select_kernel(SelectArgs a)
+{
+    using PT = typename ScoreModel<MODEL>::pose_t;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const ProblemMeta* m = a.metas + blockIdx.x;
+    const int tid = threadIdx.x;
+    const int words = m->words;
+    uint32_t* bestmask = reinterpret_cast<uint32_t*>(smem_raw);   // [words]
+    uint32_t* refmask = bestmask + words;                         // [words]
+    int* prefix = reinterpret_cast<int*>(refmask + words);        // [words+1]
+
+    __shared__ int s_found, s_cnt;
+    __shared__ PT s_pose[12], s_bestpose[12];
+    __shared__ typename std::conditional<MODEL == 0, EpnpShared, MlpnpShared>::type S;
+
+    ResultRec res;
+    res.ok = 0; res.no_more = 0; res.n_inliers = 0; res.best_hyp = -1; res.refined = 0; res.n_refines = 0;
+    res.best_count = 0; res.n_hyp = 0;
+    for (int i = 0; i < 9; ++i) res.R[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    res.t[0] = res.t[1] = res.t[2] = 0.0f; res.s = 1.0f;
+    res.problem = a.problem_base + blockIdx.x; res.reserved[0] = res.reserved[1] = 0;
+
+    const int N = m->n, H = m->H, minInl = m->min_inl;
+    uint32_t* final_mask = a.masks + m->word_off;
+    const int32_t* counts = a.counts + m->hyp_off;
+    const PT* poses = reinterpret_cast<const PT*>(a.poses) + (size_t)m->hyp_off * 12;
+    const bool discard = (MODEL == 1) && (a.flags & 4) != 0;   // RSAC_FLAG_MLPNP_DISCARD_REFINE (Q6)
+    bool finished = false;
+
+    if (N < minInl || H == 0) {              // PnPsolver.cpp:110-114 / MLPnPsolver.cpp:62-66
+        res.no_more = 1;
+        for (int w = tid; w < words; w += blockDim.x) final_mask[w] = 0u;
+        finished = true;
+    }
+
+    int best = 0, bestH = -1, lastRefBestH = -2, lastRefH = -2, lastCntR = 0, mSel = 0;
+    int cursor = 0;
+    while (!finished) {
+        // next hypothesis with cnt >= minInliers (PnPsolver.cpp:146)
+        if (tid == 0) s_found = H;
+        __syncthreads();
+        int h = H;
+        for (int base = cursor; base < H; base += blockDim.x) {   // uniform trip count: h is read after a barrier
+            const int hc = base + tid;
+            if (hc < H && counts[hc] >= minInl) atomicMin(&s_found, hc);
+            __syncthreads();
+            h = s_found;
+            __syncthreads();
+            if (h < H) break;
+        }
+        if (h >= H) break;
+
+        if (counts[h] > best) {              // :149 strict: first maximum wins
+            best = counts[h];
+            bestH = h;
+            if (tid < 12) s_bestpose[tid] = poses[(size_t)h * 12 + tid];
+            __syncthreads();
+            cta_score_exact<MODEL>(m, a, s_bestpose, bestmask, &s_cnt);
+            // ordered compaction of the best set -> sel (Refine, :195-204)
+            if (tid == 0) {
+                int acc = 0;
+                for (int w = 0; w < words; ++w) { prefix[w] = acc; acc += __popc(bestmask[w]); }
+                prefix[words] = acc;
+            }
+            __syncthreads();
+            mSel = prefix[words];
+            uint32_t* sel = a.sel + m->corr_off;
+            for (int w = tid; w < words; w += blockDim.x) {
+                uint32_t bits = bestmask[w];
+                int o = prefix[w];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    sel[o++] = (uint32_t)(w * 32 + b);
+                }
+            }
+            __syncthreads();
+        }
+        res.n_refines++;
+
+        if (discard) {
+            // MLPnPsolver::Refine as shipped never copies its result into mRi/mti
+            // (MLPnPsolver.cpp:290-296): the "refined" pose and inliers are the current hypothesis'
+            if (h != lastRefH) {
+                if (tid < 12) s_pose[tid] = poses[(size_t)h * 12 + tid];
+                __syncthreads();
+                cta_score_exact<MODEL>(m, a, s_pose, refmask, &s_cnt);
+                lastCntR = s_cnt;
+                lastRefH = h;
+            }
+        } else if (bestH != lastRefBestH) {
+            if constexpr (MODEL == 0) refine_epnp(m, a, mSel, S, s_pose);
+            else refine_mlpnp(m, a, mSel, S, s_pose);
+            cta_score_exact<MODEL>(m, a, s_pose, refmask, &s_cnt);   // :220
+            lastCntR = s_cnt;
+            lastRefBestH = bestH;
+        }
+
+        if (lastCntR > minInl) {                               // :225 strict
+            res.ok = 1; res.refined = 1; res.n_inliers = lastCntR; res.n_hyp = h + 1;
+            for (int i = 0; i < 9; ++i) res.R[i] = (float)s_pose[i];
+            for (int i = 0; i < 3; ++i) res.t[i] = (float)s_pose[9 + i];
+            for (int w = tid; w < words; w += blockDim.x) final_mask[w] = refmask[w];
+            finished = true;
+            break;
+        }
+        cursor = h + 1;
+    }
+
+    if (!finished) {                                           // :173-188 budget exhausted
+        res.no_more = 1;
+        res.n_hyp = H;
+        if (best >= minInl) {
+            res.ok = 1;
+            res.n_inliers = best;
+            for (int i = 0; i < 9; ++i) res.R[i] = (float)s_bestpose[i];
+            for (int i = 0; i < 3; ++i) res.t[i] = (float)s_bestpose[9 + i];
+            for (int w = tid; w < words; w += blockDim.x) final_mask[w] = bestmask[w];
+        } else {
+            for (int w = tid; w < words; w += blockDim.x) final_mask[w] = 0u;
+        }
+    }
+    res.best_hyp = bestH;
+    res.best_count = best;
+    if (tid == 0) {
+        reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
+        if (a.results2) reinterpret_cast<ResultRec*>(a.results2)[blockIdx.x] = res;
+    }
+}
+
+}  // namespace rsac

@@ -11,7 +11,8 @@
 #pragma once
 #include "common.cuh"
 #include "linalg.cuh"
-#include "pnp_pipeline.cuh"   // ResultRec
+#include "pnp_pipeline.cuh"   // rng_tables_kernel
+#include "select.cuh"         // ResultRec
 
 namespace rsac {
 

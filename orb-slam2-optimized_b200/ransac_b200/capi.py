@@ -274,6 +274,53 @@ class Engine:
             w0 += nw
         return out
 
+    # -- MLPnP
+    def mlpnp_upload(self, offsets, p3d, p2d, sigma2, K, params, cov=None, seeds=None, tables=None, table_offsets=None):
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        Cn = len(offsets) - 1
+        p3d = np.ascontiguousarray(p3d, np.float32).reshape(-1, 3)
+        p2d = np.ascontiguousarray(p2d, np.float32).reshape(-1, 2)
+        sigma2 = np.ascontiguousarray(sigma2, np.float32).reshape(-1)
+        K = np.ascontiguousarray(K, np.float32).reshape(-1, 4)
+        if K.shape[0] == 1 and Cn != 1:
+            K = np.ascontiguousarray(np.repeat(K, max(Cn, 1), axis=0))
+        cov = None if cov is None else np.ascontiguousarray(cov, np.float64).reshape(-1, 9)
+        if isinstance(params, RansacParams):
+            parr, npar = (RansacParams * 1)(params), 1
+        else:
+            parr, npar = (RansacParams * len(params))(*params), len(params)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, np.uint32)
+        tables = None if tables is None else np.ascontiguousarray(tables, np.uint32).reshape(-1)
+        table_offsets = None if table_offsets is None else np.ascontiguousarray(table_offsets, np.int64)
+        desc = MLPnPBatch(Cn, _p(offsets), _p(p3d), _p(p2d), _p(sigma2), _p(K), _p(cov), C.cast(parr, C.c_void_p), npar,
+                          _p(seeds), _p(tables), _p(table_offsets))
+        self._keep_mlpnp = [offsets, p3d, p2d, sigma2, K, cov, parr, seeds, tables, table_offsets]
+        self._ck(self.L.rsac_mlpnp_upload(self.h, C.byref(desc)), "mlpnp_upload")
+        self._mlpnp_C = Cn
+        self._mlpnp_words = ((np.diff(offsets) + 31) // 32).astype(np.int64)
+        return Cn
+
+    def mlpnp_run(self, flags=0, d_results_out: int | None = None):
+        self._ck(self.L.rsac_mlpnp_run(self.h, C.c_int(flags), C.c_void_p(d_results_out or 0)), "mlpnp_run")
+
+    def mlpnp_download(self, want_masks=True):
+        res = np.zeros(self._mlpnp_C, RESULT_DTYPE)
+        masks = np.zeros(int(self._mlpnp_words.sum()), np.uint32) if want_masks else None
+        self._ck(self.L.rsac_mlpnp_download(self.h, _p(res), _p(masks)), "mlpnp_download")
+        return res, masks
+
+    def mlpnp_solve(self, offsets, p3d, p2d, sigma2, K, params, cov=None, seeds=None, tables=None, table_offsets=None, flags=0):
+        self.mlpnp_upload(offsets, p3d, p2d, sigma2, K, params, cov, seeds, tables, table_offsets)
+        self.mlpnp_run(flags)
+        return self.mlpnp_download()
+
+    def mlpnp_hypotheses(self):
+        n = self.L.rsac_mlpnp_total_hypotheses(self.h)
+        poses = np.zeros((n, 12), np.float64)
+        counts = np.zeros(n, np.int32)
+        self._ck(self.L.rsac_mlpnp_get_hypotheses(self.h, _p(poses), _p(counts)), "mlpnp_get_hypotheses")
+        return poses, counts
+
     # -- Sim3
     def sim3_upload(self, offsets, x1c, x2c, s1, s2, K1, K2, params, seeds=None, tables=None, table_offsets=None):
         offsets = np.ascontiguousarray(offsets, np.int32)
