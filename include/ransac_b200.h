@@ -7,7 +7,7 @@
  * (include/MLPnPsolver.hpp:10-21) and Sim3Solver (include/Sim3Solver.hpp:16-30) --
  * constructed per candidate keyframe by Tracking::Relocalization
  * (src/Tracking.cpp:1225-1255) and LoopClosing::ComputeSim3 (src/LoopClosing.cpp:260-308).
- * The C++ classes of the same names in include/ransac_b200/*.hpp keep that API and are
+ * The C++ classes of the same names in include/ransac_b200/solvers.hpp keep that API and are
  * thin wrappers over the entry points below; the *_batch entry points are what the two
  * callers use to verify all candidates in one device pass.
  *
@@ -159,6 +159,10 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b);
  * Device-resident, asynchronous.  d_results_out: optional device buffer of C rsac_result
  * that also receives the records (for a collective); may be NULL. */
 int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out);
+/* later iterate() calls on solvers that already ran (Tracking.cpp:1239-1334 keeps calling iterate(5)
+ * on a candidate whose pose failed PoseOptimization): replays only the sequential stage, starting at
+ * resume_from[c] = hypotheses already consumed by problem c (host array of C ints) */
+int rsac_pnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* d_results_out);
 /* stage 3: device -> host, synchronises.  masks: optional, concatenated inlier bitmasks,
  * ceil(n_c/32) words per problem in problem order (bit i of word w = correspondence 32w+i,
  * COMPACT index; the C++ wrapper scatters to keypoint indices like PnPsolver.cpp:160-165) */
@@ -228,6 +232,7 @@ typedef struct {
 
 int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b);
 int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out);
+int rsac_mlpnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* d_results_out);
 int rsac_mlpnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks);
 int rsac_mlpnp_solve(rsac_engine* e, const rsac_mlpnp_batch* b, int flags, rsac_result* results, uint32_t* masks);
 /* per-hypothesis poses in double ([sumH][12]) and counts */

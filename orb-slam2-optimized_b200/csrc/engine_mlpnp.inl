@@ -69,6 +69,37 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
     return RSAC_OK;
 }
 
+static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out)
+{
+    PnpState& s = e->mlpnp;
+    const BatchDims& d = s.d;
+    SelectArgs a;
+    a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.uv = (const float2*)s.d_uv.p;
+    a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = s.have_cov ? (const double*)s.d_cov.p : nullptr;
+    a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = nullptr; a.al_s = nullptr; a.rec = (double2*)s.d_extra.p;
+    a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
+    a.problem_base = e->problem_base; a.flags = flags; a.resume = d_resume;
+    const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
+    if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    e->stage_begin(RSAC_STAGE_SELECT);
+    ransac_select_kernel<1><<<d.C, kSelectThreads, smem, e->stream>>>(a);
+    e->stage_end(RSAC_STAGE_SELECT);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+int rsac_mlpnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* d_results_out)
+{
+    if (!e || !resume_from) return RSAC_ERR_INVALID;
+    PnpState& s = e->mlpnp;
+    if (!s.ran) { e->err = "rsac_mlpnp_rerun before rsac_mlpnp_run"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    if (s.d.C == 0) return RSAC_OK;
+    RSAC_TRY(e->d_resume.ensure(e, sizeof(int32_t) * (size_t)s.d.C));
+    RSAC_CUDA(e, cudaMemcpyAsync(e->d_resume.p, resume_from, sizeof(int32_t) * (size_t)s.d.C, cudaMemcpyHostToDevice, e->stream));
+    return mlpnp_launch_select(e, flags, (const int32_t*)e->d_resume.p, d_results_out);
+}
+
 int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
 {
     if (!e) return RSAC_ERR_INVALID;
@@ -110,18 +141,8 @@ int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
         if (rc) return rc;
     }
     {
-        SelectArgs a;
-        a.metas = metas; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.uv = (const float2*)s.d_uv.p;
-        a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = cov;
-        a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = nullptr; a.al_s = nullptr; a.rec = (double2*)s.d_extra.p;
-        a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
-        a.problem_base = e->problem_base; a.flags = flags;
-        const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
-        if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        e->stage_begin(RSAC_STAGE_SELECT);
-        ransac_select_kernel<1><<<d.C, kSelectThreads, smem, st>>>(a);
-        e->stage_end(RSAC_STAGE_SELECT);
-        RSAC_CUDA(e, cudaGetLastError());
+        int rc = mlpnp_launch_select(e, flags, nullptr, d_results_out);
+        if (rc) return rc;
     }
     s.ran = true;
     return RSAC_OK;

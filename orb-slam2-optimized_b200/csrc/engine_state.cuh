@@ -118,7 +118,7 @@ struct rsac_engine {
     rsac::PnpState mlpnp;
     rsac::ScoreState score;
     rsac::Sim3State sim3;
-    rsac::DevBuf d_exact, d_scratch;
+    rsac::DevBuf d_exact, d_scratch, d_resume;
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
 
@@ -140,7 +140,7 @@ struct rsac_engine {
     void free_all()
     {
         pnp.release(); mlpnp.release(); score.release(); sim3.release();
-        d_exact.release(); d_scratch.release();
+        d_exact.release(); d_scratch.release(); d_resume.release();
     }
 };
 

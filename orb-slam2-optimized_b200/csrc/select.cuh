@@ -40,6 +40,7 @@ struct SelectArgs {
     uint32_t* masks;         // final masks, word_off per problem
     int32_t problem_base;    // global index of problem 0 (sharding)
     int32_t flags;
+    const int32_t* resume;   // optional [C]: hypotheses already consumed by earlier iterate() calls
 };
 
 struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
@@ -415,6 +416,50 @@ __global__ void __launch_bounds__(kSelectThreads) ransac_select_kernel(SelectArg
 
     int best = 0, bestH = -1, lastRefBestH = -2, lastRefH = -2, lastCntR = 0, mSel = 0;
     int cursor = 0;
+    __shared__ unsigned long long s_key;
+
+    // the best set becomes hypothesis h: its mask (exact re-evaluation) and the ordered index list
+    auto set_best = [&](int h) {
+        best = counts[h];
+        bestH = h;
+        if (tid < 12) s_bestpose[tid] = poses[(size_t)h * 12 + tid];
+        __syncthreads();
+        cta_score_exact<MODEL>(m, a, s_bestpose, bestmask, &s_cnt);
+        if (tid == 0) {
+            int acc = 0;
+            for (int w = 0; w < words; ++w) { prefix[w] = acc; acc += __popc(bestmask[w]); }
+            prefix[words] = acc;
+        }
+        __syncthreads();
+        mSel = prefix[words];
+        uint32_t* sel = a.sel + m->corr_off;
+        for (int w = tid; w < words; w += blockDim.x) {
+            uint32_t bits = bestmask[w];
+            int o = prefix[w];
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                sel[o++] = (uint32_t)(w * 32 + b);
+            }
+        }
+        __syncthreads();
+    };
+
+    if (!finished && a.resume && a.resume[blockIdx.x] > 0) {
+        // a later iterate() call: rebuild mnBestInliers / mvbBestInliers as the scan left them before
+        // `cursor` (first strict maximum among the hypotheses with cnt >= minInliers)
+        cursor = min(a.resume[blockIdx.x], H);
+        if (tid == 0) s_key = 0ull;
+        __syncthreads();
+        for (int h = tid; h < cursor; h += blockDim.x)
+            if (counts[h] >= minInl)
+                atomicMax(&s_key, ((unsigned long long)(unsigned)counts[h] << 32) | (unsigned long long)(0xffffffffu - (unsigned)h));
+        __syncthreads();
+        const unsigned long long key = s_key;
+        __syncthreads();
+        if (key != 0ull) set_best((int)(0xffffffffu - (unsigned)(key & 0xffffffffull)));
+    }
+
     while (!finished) {
         // next hypothesis with cnt >= minInliers (PnPsolver.cpp:146)
         if (tid == 0) s_found = H;
@@ -430,32 +475,7 @@ __global__ void __launch_bounds__(kSelectThreads) ransac_select_kernel(SelectArg
         }
         if (h >= H) break;
 
-        if (counts[h] > best) {              // :149 strict: first maximum wins
-            best = counts[h];
-            bestH = h;
-            if (tid < 12) s_bestpose[tid] = poses[(size_t)h * 12 + tid];
-            __syncthreads();
-            cta_score_exact<MODEL>(m, a, s_bestpose, bestmask, &s_cnt);
-            // ordered compaction of the best set -> sel (Refine, :195-204)
-            if (tid == 0) {
-                int acc = 0;
-                for (int w = 0; w < words; ++w) { prefix[w] = acc; acc += __popc(bestmask[w]); }
-                prefix[words] = acc;
-            }
-            __syncthreads();
-            mSel = prefix[words];
-            uint32_t* sel = a.sel + m->corr_off;
-            for (int w = tid; w < words; w += blockDim.x) {
-                uint32_t bits = bestmask[w];
-                int o = prefix[w];
-                while (bits) {
-                    const int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    sel[o++] = (uint32_t)(w * 32 + b);
-                }
-            }
-            __syncthreads();
-        }
+        if (counts[h] > best) set_best(h);   // :149 strict: first maximum wins (Refine uses this set, :195-204)
         res.n_refines++;
 
         if (discard) {

@@ -1,0 +1,170 @@
+// class_driver.cpp -- exercises the C++ class API (include/ransac_b200/solvers.hpp) the way
+// Tracking::Relocalization / LoopClosing::ComputeSim3 drive the reference's solvers, and prints
+// what every call returned as JSON lines.  tests/test_gpu_classes.py feeds it seeded problems and
+// checks the output against the CPU oracle.  (The oracle is NOT linked here.)
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "ransac_b200/solvers.hpp"
+
+using namespace ransac_b200;
+
+template <typename T> static void rd(std::ifstream& f, T* p, size_t n) { f.read(reinterpret_cast<char*>(p), sizeof(T) * n); }
+
+static void print_inliers(const std::vector<bool>& v)
+{
+    std::printf("[");
+    bool first = true;
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i]) { std::printf(first ? "%zu" : ",%zu", i); first = false; }
+    std::printf("]");
+}
+
+static void print_T(const Matrix4f& T)
+{
+    std::printf("[");
+    for (int i = 0; i < 16; ++i) std::printf(i ? ",%.9g" : "%.9g", T.m[i]);
+    std::printf("]");
+}
+
+struct FrameData {
+    int n = 0;
+    float K[4];
+    std::vector<float> xy, world, sigma2;
+    std::vector<int> octave;
+    std::vector<unsigned char> valid;
+    FrameView frame() const
+    {
+        FrameView F;
+        F.n_keypoints = n; F.keys_xy = xy.data(); F.octave = octave.data(); F.level_sigma2 = sigma2.data();
+        F.fx = K[0]; F.fy = K[1]; F.cx = K[2]; F.cy = K[3];
+        return F;
+    }
+    MapPointMatches matches() const
+    {
+        MapPointMatches M;
+        M.n = n; M.valid = valid.data(); M.world_pos = world.data();
+        return M;
+    }
+};
+
+static FrameData read_frame(std::ifstream& f)
+{
+    FrameData d;
+    rd(f, &d.n, 1);
+    rd(f, d.K, 4);
+    d.xy.resize(2 * d.n); d.world.resize(3 * d.n); d.octave.resize(d.n); d.valid.resize(d.n); d.sigma2.resize(8);
+    rd(f, d.xy.data(), d.xy.size());
+    rd(f, d.octave.data(), d.octave.size());
+    rd(f, d.valid.data(), d.valid.size());
+    rd(f, d.world.data(), d.world.size());
+    rd(f, d.sigma2.data(), 8);
+    return d;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { std::fprintf(stderr, "usage: class_driver pnp|pnp_batch|mlpnp|sim3 file\n"); return 2; }
+    const std::string mode = argv[1];
+    std::ifstream f(argv[2], std::ios::binary);
+    if (!f) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
+    try {
+        if (mode == "pnp" || mode == "mlpnp") {
+            FrameData d = read_frame(f);
+            double prob; int minInl, maxIts, minSet; float eps, th2; unsigned seed; int step;
+            rd(f, &prob, 1); rd(f, &minInl, 1); rd(f, &maxIts, 1); rd(f, &minSet, 1); rd(f, &eps, 1); rd(f, &th2, 1); rd(f, &seed, 1); rd(f, &step, 1);
+            std::vector<bool> inl; int n; bool noMore; Matrix4f T;
+            if (mode == "pnp") {
+                PnPsolver s(d.frame(), d.matches());
+                s.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);
+                s.SetSeed(seed);
+                std::printf("{\"H\":%d,\"minInl\":%d,\"N\":%d}\n", s.GetIterations(), s.GetMinInliers(), s.GetNumCorrespondences());
+                for (int call = 0; call < 400; ++call) {     // Tracking.cpp:1255 keeps calling iterate(5,...)
+                    const bool ok = s.iterate(step, noMore, inl, n, T);
+                    std::printf("{\"call\":%d,\"ok\":%d,\"noMore\":%d,\"nInliers\":%d,\"T\":", call, (int)ok, (int)noMore, n);
+                    print_T(T);
+                    std::printf(",\"inliers\":");
+                    print_inliers(inl);
+                    std::printf("}\n");
+                    if (noMore) break;
+                }
+            } else {
+                MLPnPsolver s(d.frame(), d.matches());
+                s.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);
+                s.SetSeed(seed);
+                for (int call = 0; call < 400; ++call) {
+                    const bool ok = s.iterate(step, noMore, inl, n, T);
+                    std::printf("{\"call\":%d,\"ok\":%d,\"noMore\":%d,\"nInliers\":%d,\"T\":", call, (int)ok, (int)noMore, n);
+                    print_T(T);
+                    std::printf(",\"inliers\":");
+                    print_inliers(inl);
+                    std::printf("}\n");
+                    if (noMore) break;
+                }
+            }
+        } else if (mode == "pnp_batch") {
+            int C;
+            rd(f, &C, 1);
+            std::vector<FrameData> ds;
+            std::vector<unsigned> seeds(C);
+            for (int c = 0; c < C; ++c) { ds.push_back(read_frame(f)); rd(f, &seeds[c], 1); }
+            std::vector<std::unique_ptr<PnPsolver>> solvers;
+            std::vector<PnPsolver*> ptrs;
+            for (int c = 0; c < C; ++c) {
+                solvers.emplace_back(new PnPsolver(ds[c].frame(), ds[c].matches()));
+                solvers.back()->SetRansacParameters(0.99, 10, 300, 4, 0.2f, 5.991f);
+                solvers.back()->SetSeed(seeds[c]);
+                ptrs.push_back(solvers.back().get());
+            }
+            PnPsolver::SolveBatch(ptrs);          // one device pass for all candidates
+            for (int c = 0; c < C; ++c) {
+                std::vector<bool> inl; int n; Matrix4f T;
+                const bool ok = solvers[c]->find(inl, n, T);
+                std::printf("{\"cand\":%d,\"ok\":%d,\"nInliers\":%d,\"T\":", c, (int)ok, n);
+                print_T(T);
+                std::printf(",\"inliers\":");
+                print_inliers(inl);
+                std::printf("}\n");
+            }
+        } else if (mode == "sim3") {
+            int n, fix; unsigned seed; int minInl, maxIts, step; double prob;
+            KeyFrameView K1, K2;
+            rd(f, &n, 1); rd(f, &fix, 1); rd(f, &seed, 1); rd(f, &prob, 1); rd(f, &minInl, 1); rd(f, &maxIts, 1); rd(f, &step, 1);
+            float Kc[4];
+            rd(f, K1.Rcw, 9); rd(f, K1.tcw, 3); rd(f, K2.Rcw, 9); rd(f, K2.tcw, 3); rd(f, Kc, 4);
+            std::vector<float> w1(3 * n), w2(3 * n), sig(8);
+            std::vector<int> o1(n), o2(n), i1(n), i2(n);
+            std::vector<unsigned char> v1(n), v2(n);
+            rd(f, w1.data(), w1.size()); rd(f, w2.data(), w2.size()); rd(f, o1.data(), n); rd(f, o2.data(), n);
+            rd(f, i1.data(), n); rd(f, i2.data(), n); rd(f, v1.data(), n); rd(f, v2.data(), n); rd(f, sig.data(), 8);
+            K1.n_keypoints = K2.n_keypoints = n;
+            K1.octave = o1.data(); K2.octave = o2.data(); K1.level_sigma2 = K2.level_sigma2 = sig.data();
+            K1.fx = K2.fx = Kc[0]; K1.fy = K2.fy = Kc[1]; K1.cx = K2.cx = Kc[2]; K1.cy = K2.cy = Kc[3];
+            Sim3Matches M;
+            M.n = n; M.valid1 = v1.data(); M.valid2 = v2.data(); M.world_pos1 = w1.data(); M.world_pos2 = w2.data();
+            M.index_in_kf1 = i1.data(); M.index_in_kf2 = i2.data();
+            Sim3Solver s(K1, K2, M, fix != 0);
+            s.SetRansacParameters(prob, minInl, maxIts);
+            s.SetSeed(seed);
+            std::vector<bool> inl; int nin; bool noMore;
+            for (int call = 0; call < 400; ++call) {          // LoopClosing.cpp:286 iterate(5,...)
+                const bool ok = s.iterate(step, noMore, inl, nin);
+                const Matrix3f R = s.GetEstimatedRotation();
+                const Vector3f t = s.GetEstimatedTranslation();
+                std::printf("{\"call\":%d,\"ok\":%d,\"noMore\":%d,\"nInliers\":%d,\"s\":%.9g,\"R\":[", call, (int)ok, (int)noMore, nin, s.GetEstimatedScale());
+                for (int i = 0; i < 9; ++i) std::printf(i ? ",%.9g" : "%.9g", R.m[i]);
+                std::printf("],\"t\":[%.9g,%.9g,%.9g],\"inliers\":", t.v[0], t.v[1], t.v[2]);
+                print_inliers(inl);
+                std::printf("}\n");
+                if (ok || noMore) break;
+            }
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,181 @@
+"""GPU: the C++ class API (include/ransac_b200/solvers.hpp: PnPsolver / MLPnPsolver / Sim3Solver with the
+reference's method names) driven like Tracking::Relocalization and LoopClosing::ComputeSim3 drive the
+reference, checked call by call against a replay built from oracle primitives."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from ransac_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "tests", "cpp", "class_driver")
+
+
+@pytest.fixture(scope="module")
+def driver(built_lib):
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")], check=True)
+    return DRIVER
+
+
+def _frame_bytes(p, n_slots, slot_of, rng):
+    """a Frame with n_slots keypoints; correspondence i of the problem sits in slot slot_of[i]; the other
+    slots have no (or a bad) MapPoint"""
+    xy = rng.uniform(0, 700, size=(n_slots, 2)).astype(np.float32)
+    octave = rng.integers(0, 8, size=n_slots).astype(np.int32)
+    valid = np.zeros(n_slots, np.uint8)
+    world = rng.normal(size=(n_slots, 3)).astype(np.float32)
+    s2 = synth.level_sigma2()
+    xy[slot_of] = p["p2d"]
+    octave[slot_of] = p["octave"]
+    valid[slot_of] = 1
+    world[slot_of] = p["p3d"]
+    K = np.array(p["K"], np.float32)
+    return struct.pack("<i", n_slots) + K.tobytes() + xy.tobytes() + octave.tobytes() + valid.tobytes() + world.tobytes() + s2.tobytes()
+
+
+def _run(driver, mode, blob, tmp_path):
+    f = tmp_path / (mode + ".bin")
+    f.write_bytes(blob)
+    out = subprocess.run([driver, mode, str(f)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    return [json.loads(l) for l in out.stdout.splitlines() if l.strip()]
+
+
+def _pnp_replay(oracle, p, prm, seed):
+    """PnPsolver::iterate called repeatedly (PnPsolver.cpp:102-191), rebuilt from oracle primitives"""
+    Kd = tuple(float(np.float32(k)) for k in p["K"])        # Frame::fx.. are floats, widened by the solver
+    pb = oracle.pnp_problem(p["p3d"], p["p2d"], p["sigma2"], Kd)
+    oprm = oracle.params(*prm)
+    n = len(p["p3d"])
+    minInl, H = oracle.ransac_setup_pnp(n, oprm)
+    tab = oracle.index_table(seed, n, 4, H)
+    ex = oracle.pnp_ransac(pb, oprm, tab, oracle.FLAG_EXHAUSTIVE, per_hyp=True)
+    counts, poses = ex["hyp_counts"], ex["hyp_pose"]
+    thr = (p["sigma2"] * np.float32(prm[5])).astype(np.float32)
+    calls, best, bestmask, bestpose, h = [], 0, None, None, 0
+    while True:
+        ret = None
+        while h < H:
+            cur = h
+            h += 1
+            if counts[cur] >= minInl:
+                if counts[cur] > best:
+                    best = counts[cur]
+                    bestpose = poses[cur]
+                    _, bestmask, _ = oracle.pnp_check_inliers(pb, thr, poses[cur][:9], poses[cur][9:])
+                R, t, _ = oracle.epnp_pose(pb, np.flatnonzero(bestmask))
+                cnt, mask, _ = oracle.pnp_check_inliers(pb, thr, R, t)
+                if cnt > minInl:
+                    ret = dict(ok=1, noMore=0, n=cnt, R=R, t=t, mask=mask)
+                    break
+        if ret is None:
+            if best >= minInl:
+                ret = dict(ok=1, noMore=1, n=best, R=bestpose[:9].reshape(3, 3), t=bestpose[9:], mask=bestmask)
+            else:
+                ret = dict(ok=0, noMore=1, n=0, R=None, t=None, mask=None)
+        calls.append(ret)
+        if ret["noMore"] or len(calls) > 400:
+            return calls, (minInl, H)
+
+
+def test_pnpsolver_iterate_sequence(driver, oracle, tmp_path):
+    rng = np.random.default_rng(0)
+    for seed, n, outl, prm in ((1000, 500, 0.5, (0.99, 10, 300, 4, 0.2, 5.991)),        # cfg1
+                               (12003, 200, 0.3, (0.99, 10, 300, 4, 0.5, 5.991))):      # Tracking.cpp:1226
+        p = synth.pnp_problem(seed, n, outl)
+        n_slots = n + 300
+        slot_of = np.sort(rng.permutation(n_slots)[:n])
+        blob = _frame_bytes(p, n_slots, slot_of, rng) + struct.pack("<diiiffIi", prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], seed, 5)
+        got = _run(driver, "pnp", blob, tmp_path)
+        ref, (minInl, H) = _pnp_replay(oracle, p, prm, seed)
+        assert got[0] == {"H": H, "minInl": minInl, "N": n}
+        got = got[1:]
+        assert len(got) == len(ref)
+        for g, r in zip(got, ref):
+            assert (g["ok"], g["noMore"], g["nInliers"]) == (r["ok"], r["noMore"], r["n"])
+            if r["ok"]:
+                T = np.array(g["T"], np.float32).reshape(4, 4)
+                assert np.allclose(T[:3, :3], r["R"], rtol=1e-4, atol=1e-6) and np.allclose(T[:3, 3], r["t"], rtol=1e-4, atol=1e-6)
+                assert (T[3] == [0, 0, 0, 1]).all()
+                assert g["inliers"] == slot_of[np.flatnonzero(r["mask"])].tolist()       # scattered to keypoint indices
+        assert len(ref) >= 2                                                             # the resumed path was exercised
+
+
+def test_pnpsolver_batch_entry_point(driver, oracle, tmp_path):
+    rng = np.random.default_rng(1)
+    C, n = 5, 300
+    blob = struct.pack("<i", C)
+    ps, slots = [], []
+    for c in range(C):
+        p = synth.pnp_problem(4000 + c, n, 0.5)
+        slot_of = np.sort(rng.permutation(n + 50)[:n])
+        blob += _frame_bytes(p, n + 50, slot_of, rng) + struct.pack("<I", 4000 + c)
+        ps.append(p); slots.append(slot_of)
+    got = _run(driver, "pnp_batch", blob, tmp_path)
+    for c in range(C):
+        ref, _ = _pnp_replay(oracle, ps[c], (0.99, 10, 300, 4, 0.2, 5.991), 4000 + c)
+        g, r = got[c], ref[0]
+        assert (g["ok"], g["nInliers"]) == (r["ok"], r["n"])
+        if r["ok"]:
+            assert g["inliers"] == slots[c][np.flatnonzero(r["mask"])].tolist()
+
+
+def test_mlpnpsolver_iterate(driver, oracle, tmp_path):
+    rng = np.random.default_rng(2)
+    seed, n = 2000, 400
+    p = synth.pnp_problem(seed, n, 0.5)
+    slot_of = np.sort(rng.permutation(n + 100)[:n])
+    prm = (0.99, 10, 300, 6, 0.2, 5.991)
+    blob = _frame_bytes(p, n + 100, slot_of, rng) + struct.pack("<diiiffIi", *prm, seed, 5)
+    got = _run(driver, "mlpnp", blob, tmp_path)
+    Kf = tuple(np.float32(k) for k in p["K"])
+    pb = oracle.mlpnp_problem(p["p3d"], p["p2d"], p["sigma2"], Kf)
+    _, H = oracle.ransac_setup_pnp(n, oracle.params(*prm))
+    o = oracle.mlpnp_ransac(pb, oracle.params(*prm), oracle.index_table(seed, n, 6, H))
+    g = got[0]
+    assert (g["ok"], g["noMore"], g["nInliers"]) == (o["ok"], o["no_more"], o["n_inliers"])
+    T = np.array(g["T"], np.float32).reshape(4, 4)
+    assert np.allclose(T, o["T"], rtol=1e-4, atol=1e-6)
+    assert g["inliers"] == slot_of[np.flatnonzero(o["mask"])].tolist()
+
+
+@pytest.mark.parametrize("scale", [1.0, 1.6])
+def test_sim3solver_iterate_five_at_a_time(driver, oracle, tmp_path, scale):
+    """LoopClosing.cpp:286 calls iterate(5, ...) until it returns true or bNoMore"""
+    rng = np.random.default_rng(3)
+    seed, n = 3000, 200
+    q = synth.sim3_problem(seed, n, 0.4, scale)
+    n_slots = n + 40
+    slot_of = np.sort(rng.permutation(n_slots)[:n])
+    # synthesise keyframes: identity poses, so camera-frame points == world points for both
+    R1 = np.eye(3, dtype=np.float32).reshape(-1); t0 = np.zeros(3, np.float32)
+    w1 = rng.normal(size=(n_slots, 3)).astype(np.float32); w2 = w1.copy()
+    v1 = np.zeros(n_slots, np.uint8); v2 = np.zeros(n_slots, np.uint8)
+    o1 = rng.integers(0, 8, n_slots).astype(np.int32); o2 = o1.copy()
+    w1[slot_of], w2[slot_of] = q["x1c"], q["x2c"]
+    v1[slot_of] = 1; v2[slot_of] = 1
+    s2 = synth.level_sigma2()
+    lv1 = np.array([int(np.flatnonzero(s2 == x)[0]) for x in q["sigma2_1"]], np.int32)
+    lv2 = np.array([int(np.flatnonzero(s2 == x)[0]) for x in q["sigma2_2"]], np.int32)
+    o1[slot_of], o2[slot_of] = lv1, lv2
+    i1 = np.arange(n_slots, dtype=np.int32); i2 = np.arange(n_slots, dtype=np.int32)
+    K = np.array(q["K"], np.float32)
+    blob = struct.pack("<iiIdiii", n_slots, 1 if scale == 1.0 else 0, seed, 0.99, 20, 300, 5)
+    blob += R1.tobytes() + t0.tobytes() + R1.tobytes() + t0.tobytes() + K.tobytes()
+    blob += w1.tobytes() + w2.tobytes() + o1.tobytes() + o2.tobytes() + i1.tobytes() + i2.tobytes() + v1.tobytes() + v2.tobytes() + s2.tobytes()
+    got = _run(driver, "sim3", blob, tmp_path)
+    pb = oracle.sim3_problem(q["x1c"], q["x2c"], q["sigma2_1"], q["sigma2_2"], q["K"], q["K"], fix_scale=(scale == 1.0))
+    H = oracle.ransac_setup_sim3(n, 0.99, 20, 300)
+    o = oracle.sim3_ransac(pb, 0.99, 20, 300, oracle.index_table(seed, n, 3, H))
+    assert len(got) == (o["n_hyp"] + 4) // 5                      # iterate(5) calls made
+    assert all(g["ok"] == 0 and g["noMore"] == 0 for g in got[:-1])
+    g = got[-1]
+    assert (g["ok"], g["nInliers"]) == (o["ok"], o["n_inliers"])
+    assert np.array_equal(np.array(g["R"], np.float32), o["T"][:3, :3].reshape(-1)) and np.array_equal(np.array(g["t"], np.float32), o["T"][:3, 3])
+    assert np.float32(g["s"]) == np.float32(o["scale"])
+    assert g["inliers"] == slot_of[np.flatnonzero(o["mask"])].tolist()
