@@ -23,14 +23,6 @@ struct ProblemMeta {
     float k1[4], k2[4];          // MLPnP: k1 = float intrinsics; Sim3: both cameras
 };
 
-// A scoring tile: CTA <- (problem, first hypothesis, first correspondence, #correspondences)
-struct ScoreTile {
-    int32_t problem;
-    int32_t hyp0;
-    int32_t corr0;   // relative to the problem, multiple of 32
-    int32_t nc;      // correspondences in this chunk
-};
-
 constexpr float kUnitRoundoff = 5.9604644775390625e-08f;   // 2^-24
 
 }  // namespace rsac

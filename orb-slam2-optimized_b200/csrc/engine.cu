@@ -233,75 +233,176 @@ int rsac_shard_range(int C, int rank, int world, int* first, int* count)
     return RSAC_OK;
 }
 
-// --------------------------------------------------------- tile planning
-// CTA shape for the scoring kernel: HPL = 2 hypotheses per lane.
-static constexpr int kHPL = 2;
-static constexpr int kChunkCapMax = 2048;   // correspondences per shared-memory tile (64 KB)
+// --------------------------------------------------------- score planning
+// CTA shape for the scoring kernel: HPL hypotheses per lane (template), `warps` consumer warps per CTA
+// plus one producer warp.  RSAC_SCORE_HPL / RSAC_SCORE_WARPS / RSAC_SCORE_CTAS / RSAC_SCORE_CW override the
+// planner (tuning sweeps only).
+static constexpr int kChunkWordsMax = 8;     // 256 correspondences per ring slot (12 KB), 4 slots
 
-static int score_threads_for(int maxH)
+static int env_int(const char* name, int dflt)
 {
-    int warps = (maxH + 32 * kHPL - 1) / (32 * kHPL);
-    warps = std::max(1, std::min(8, warps));
-    return warps * 32;
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
 }
 
-// Splits each problem into (hypothesis tile) x (correspondence chunk) CTAs.  Chunks are
-// whole mask words; when the batch is too small to fill the SMs the correspondences are
-// cut finer so that the grid is about `waves` x SM count.
-static void plan_tiles(const std::vector<ProblemMeta>& metas, int threads, int sm_count,
-                       std::vector<ScoreTile>& tiles, int* chunk_cap_out)
+using ScorePlan = ScorePlanPOD;
+
+template <int MODEL>
+static size_t score_smem_bytes(int chunk_cap, int tile_hyps)
 {
-    tiles.clear();
-    const int hyp_per_tile = (threads / 32) * 32 * kHPL;
-    long long base_tiles = 0;
-    for (const auto& m : metas) {
-        if (m.n <= 0 || m.H <= 0) continue;
-        const int ht = (m.H + hyp_per_tile - 1) / hyp_per_tile;
-        const int ch = (m.n + kChunkCapMax - 1) / kChunkCapMax;
-        base_tiles += (long long)ht * ch;
-    }
-    const long long target = 2LL * sm_count;
-    int cap = 32;
-    for (const auto& m : metas) {
-        if (m.n <= 0 || m.H <= 0) continue;
-        const int ht = (m.H + hyp_per_tile - 1) / hyp_per_tile;
-        const int words = (m.n + 31) / 32;
-        int chunks = (m.n + kChunkCapMax - 1) / kChunkCapMax;
-        if (base_tiles < target) {
-            // spread this problem over more CTAs (only matters for few, large problems)
-            const long long want = (target * (long long)ht * chunks + base_tiles - 1) / base_tiles;
-            chunks = (int)std::max<long long>(chunks, std::min<long long>(words, (want + ht - 1) / ht));
-        }
-        const int wbase = words / chunks, wrem = words % chunks;
-        for (int t = 0; t < ht; ++t) {
-            int w0 = 0;
-            for (int c = 0; c < chunks; ++c) {
-                const int wn = wbase + (c < wrem ? 1 : 0);
-                if (wn == 0) continue;
-                ScoreTile st;
-                st.problem = (int)(&m - metas.data());
-                st.hyp0 = t * hyp_per_tile;
-                st.corr0 = w0 * 32;
-                st.nc = std::min(m.n - w0 * 32, wn * 32);
-                cap = std::max(cap, wn * 32);
-                tiles.push_back(st);
-                w0 += wn;
-            }
-        }
-    }
-    *chunk_cap_out = cap;
+    return (size_t)chunk_cap * 48 * kScoreStages + (size_t)tile_hyps * 12 * sizeof(typename ScoreModel<MODEL>::pose_t);
 }
 
 template <int MODEL>
-static int launch_score(rsac_engine* e, const ScoreArgs& args, int ntiles, int threads)
+static const void* score_kernel_ptr(int hpl)
 {
-    if (ntiles <= 0) return RSAC_OK;
-    const size_t smem = (size_t)args.chunk_cap * 32;
-    auto kern = score_kernel<kHPL, MODEL>;
-    if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    switch (hpl) {
+        case 1: return (const void*)score_kernel<1, MODEL>;
+        case 4: return (const void*)score_kernel<4, MODEL>;
+        default: return (const void*)score_kernel<2, MODEL>;
+    }
+}
+
+// Builds the work groups (problem x hypothesis tile), the chunking and each CTA's visit list.
+//  * many groups (a relocalisation sweep): CTAs own groups round-robin; a chunk is up to 256
+//    correspondences; the producer warp prefetches the next group's chunks while the current one is scored;
+//  * few groups (scoring stress: 8 tiles x 10 000 correspondences): the CTAs are dealt to the groups in
+//    proportion to their work and pull one-word chunks from the group's counter, which balances the SMs to
+//    within one word of work.
+template <int MODEL>
+static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int maxH, std::vector<ScoreGroup>& groups, ScorePlan& pl)
+{
+    groups.clear();
+    pl = ScorePlan();
+    pl.hpl = env_int("RSAC_SCORE_HPL", 2);
+    if (pl.hpl != 1 && pl.hpl != 2 && pl.hpl != 4) pl.hpl = 2;
+    int warps = (maxH + 32 * pl.hpl - 1) / (32 * pl.hpl);
+    warps = std::max(1, std::min(env_int("RSAC_SCORE_WARPS", 8), std::min(8, warps)));
+    pl.threads = warps * 32;
+    pl.tile_hyps = warps * 32 * pl.hpl;
+    std::vector<double> work;
+    for (size_t p = 0; p < metas.size(); ++p) {
+        const ProblemMeta& m = metas[p];
+        if (m.n <= 0 || m.H <= 0) continue;
+        for (int h0 = 0; h0 < m.H; h0 += pl.tile_hyps) {
+            ScoreGroup g;
+            g.problem = (int)p; g.hyp0 = h0; g.nchunks = 0; g.chunk_words = 0;
+            groups.push_back(g);
+            work.push_back((double)m.words * std::min(pl.tile_hyps, m.H - h0));
+        }
+    }
+    const int NG = (int)groups.size();
+    if (NG == 0) { pl.cta_first.assign(2, 0); pl.grid = 1; return RSAC_OK; }
+    const void* kern = score_kernel_ptr<MODEL>(pl.hpl);
+    auto resident = [&](int chunk_words) -> int {
+        const size_t smem = score_smem_bytes<MODEL>(chunk_words * 32, pl.tile_hyps);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, pl.threads + 32, smem) != cudaSuccess) { cudaGetLastError(); nb = 1; }
+        nb = std::max(1, nb);
+        const int cap_env = env_int("RSAC_SCORE_CTAS", 0);
+        if (cap_env > 0) nb = std::min(nb, cap_env);
+        return nb * e->sm_count;
+    };
+    int maxWords = 1;
+    for (const auto& m : metas) maxWords = std::max(maxWords, m.words);
+    int cw = std::min(kChunkWordsMax, maxWords);
+    int slots = resident(cw);
+    pl.visit.clear();
+    if (NG >= slots) {
+        pl.grid = slots;
+        pl.cta_first.assign(pl.grid + 1, 0);
+        for (int b = 0; b < pl.grid; ++b) {
+            pl.cta_first[b] = (int32_t)pl.visit.size();
+            for (int g = b; g < NG; g += pl.grid) pl.visit.push_back(g);
+        }
+        pl.cta_first[pl.grid] = (int32_t)pl.visit.size();
+    } else {
+        // few groups: deal the CTAs to the groups in proportion to their work, small chunks
+        cw = 1;
+        slots = resident(cw);
+        double total = 0;
+        for (double w : work) total += w;
+        const int cw_env = env_int("RSAC_SCORE_CW", 0);
+        if (cw_env > 0) cw = std::min(kChunkWordsMax, cw_env);
+        else cw = std::max(1, std::min(kChunkWordsMax, (int)(maxWords / (6.0 * std::max(1, slots / NG)))));
+        slots = resident(cw);
+        pl.grid = slots;
+        pl.cta_first.assign(pl.grid + 1, 0);
+        // largest-remainder apportionment, at least one CTA per group
+        std::vector<int> share(NG, 1);
+        int left = pl.grid - NG;
+        if (left < 0) { pl.grid = NG; left = 0; pl.cta_first.assign(pl.grid + 1, 0); }
+        std::vector<double> frac(NG);
+        for (int g = 0; g < NG; ++g) {
+            const double ideal = work[g] / total * left;
+            share[g] += (int)ideal;
+            frac[g] = ideal - (int)ideal;
+        }
+        int used = 0;
+        for (int g = 0; g < NG; ++g) used += share[g];
+        while (used < pl.grid) {
+            int best = 0;
+            for (int g = 1; g < NG; ++g) if (frac[g] > frac[best]) best = g;
+            share[best]++; frac[best] = -1; used++;
+        }
+        // interleave so that the CTAs of one group spread over the SMs
+        std::vector<int> cta_group;
+        std::vector<int> rem = share;
+        while ((int)cta_group.size() < pl.grid)
+            for (int g = 0; g < NG && (int)cta_group.size() < pl.grid; ++g)
+                if (rem[g] > 0) { cta_group.push_back(g); rem[g]--; }
+        for (int b = 0; b < pl.grid; ++b) { pl.cta_first[b] = b; pl.visit.push_back(cta_group[b]); }
+        pl.cta_first[pl.grid] = pl.grid;
+    }
+    for (auto& g : groups) {
+        g.chunk_words = std::min(cw, std::max(1, metas[g.problem].words));
+        g.nchunks = (metas[g.problem].words + g.chunk_words - 1) / g.chunk_words;
+    }
+    pl.chunk_cap = cw * 32;
+    pl.smem = score_smem_bytes<MODEL>(pl.chunk_cap, pl.tile_hyps);
+    return RSAC_OK;
+}
+
+// uploads the plan's visit lists (pinned staging is the caller's business for the hot path; these are tiny)
+static int upload_visit(rsac_engine* e, const ScorePlan& pl, DevBuf& d_visit)
+{
+    const size_t n1 = pl.cta_first.size(), n2 = std::max<size_t>(pl.visit.size(), 1);
+    RSAC_TRY(d_visit.ensure(e, sizeof(int32_t) * (n1 + n2)));
+    return RSAC_OK;
+}
+
+// counts, the diagnostic counter and the per-group chunk counters live in ONE buffer so that a single
+// memset node prepares a scoring launch: [counts: n ints][exact: 2 ints][group_next: ngroups ints]
+static int zero_score_region(rsac_engine* e, DevBuf& d_counts, int64_t n_counts, int ngroups, ScoreArgs& sa)
+{
+    const size_t n_al = ((size_t)std::max<int64_t>(n_counts, 1) + 1) & ~(size_t)1;     // keep the 8-byte counter aligned
+    const size_t total = (n_al + 2 + (size_t)std::max(ngroups, 1)) * sizeof(int32_t);
+    RSAC_TRY(d_counts.ensure(e, total));
+    RSAC_CUDA(e, cudaMemsetAsync(d_counts.p, 0, total, e->stream));
+    sa.counts = (int32_t*)d_counts.p;
+    sa.exact_counter = (unsigned long long*)((int32_t*)d_counts.p + n_al);
+    sa.group_next = (int32_t*)d_counts.p + n_al + 2;
+    e->last_exact = sa.exact_counter;
+    return RSAC_OK;
+}
+
+template <int MODEL>
+static int launch_score(rsac_engine* e, ScoreArgs& args, const ScorePlan& pl, int ngroups, DevBuf& d_visit)
+{
+    if (ngroups <= 0) return RSAC_OK;
+    const void* kern = score_kernel_ptr<MODEL>(pl.hpl);
+    if (pl.smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    args.ngroups = ngroups;
+    args.cta_first = (const int32_t*)d_visit.p;
+    args.visit = (const int32_t*)d_visit.p + pl.cta_first.size();
+    args.chunk_cap = pl.chunk_cap;
+    args.tile_hyps = pl.tile_hyps;
+    void* kargs[] = {&args};
     e->stage_begin(RSAC_STAGE_SCORE);
-    kern<<<ntiles, threads, smem, e->stream>>>(args);
+    cudaError_t err = cudaLaunchKernel(kern, dim3(pl.grid), dim3(pl.threads + 32), kargs, pl.smem, e->stream);   // + the producer warp
     e->stage_end(RSAC_STAGE_SCORE);
+    RSAC_CUDA(e, err);
     RSAC_CUDA(e, cudaGetLastError());
     return RSAC_OK;
 }
@@ -353,6 +454,36 @@ static int pnp_build_metas(rsac_engine* e, int C, const int32_t* offsets, const 
     return RSAC_OK;
 }
 
+// metas, thresholds and tiles go through one pinned staging buffer so that the H2D copies are truly
+// asynchronous (the host never waits for the stream's earlier sweeps)
+static int stage_small_tables(rsac_engine* e, PnpState& s, const std::vector<float>& th2)
+{
+    const BatchDims& d = s.d;
+    const size_t b_meta = sizeof(ProblemMeta) * (size_t)d.C, b_th = sizeof(float) * (size_t)d.C;
+    const size_t b_tile = sizeof(ScoreGroup) * s.groups.size();
+    const size_t b_cf = sizeof(int32_t) * s.plan.cta_first.size(), b_vis = sizeof(int32_t) * s.plan.visit.size();
+    const size_t o_th = (b_meta + 255) & ~(size_t)255, o_tile = (o_th + b_th + 255) & ~(size_t)255;
+    const size_t o_vis = (o_tile + b_tile + 255) & ~(size_t)255;
+    char* h = (char*)s.h_stage.ensure(o_vis + b_cf + b_vis + 256);
+    if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
+    if (d.C > 0) {
+        memcpy(h, s.metas.data(), b_meta);
+        memcpy(h + o_th, th2.data(), b_th);
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, h, b_meta, cudaMemcpyHostToDevice, e->stream));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_th2.p, h + o_th, b_th, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (b_tile) {
+        memcpy(h + o_tile, s.groups.data(), b_tile);
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, h + o_tile, b_tile, cudaMemcpyHostToDevice, e->stream));
+    }
+    RSAC_TRY(upload_visit(e, s.plan, s.d_visit));
+    memcpy(h + o_vis, s.plan.cta_first.data(), b_cf);
+    if (b_vis) memcpy(h + o_vis + b_cf, s.plan.visit.data(), b_vis);
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, h + o_vis, b_cf + b_vis, cudaMemcpyHostToDevice, e->stream));
+    s.h_stage.mark(e->stream);
+    return RSAC_OK;
+}
+
 int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
 {
     if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
@@ -368,21 +499,21 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     }
     const BatchDims& d = s.d;
     const size_t tot = (size_t)std::max(d.total, 1);
-    s.threads = score_threads_for(d.maxH);
-    plan_tiles(s.metas, s.threads, e->sm_count, s.tiles, &s.chunk_cap);
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groups, s.plan));
 
     RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta) * std::max(d.C, 1)));
-    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreTile) * std::max<size_t>(s.tiles.size(), 1)));
+    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreGroup) * std::max<size_t>(s.groups.size(), 1)));
+    RSAC_TRY(s.d_gnext.ensure(e, sizeof(int32_t) * std::max<size_t>(s.groups.size(), 1)));
     RSAC_TRY(s.d_th2.ensure(e, sizeof(float) * std::max(d.C, 1)));
     RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
     RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
     RSAC_TRY(s.d_sigma2.ensure(e, tot * 4));
     RSAC_TRY(s.d_cA.ensure(e, tot * 16));
     RSAC_TRY(s.d_cB.ensure(e, tot * 16));
-    RSAC_TRY(s.d_uv.ensure(e, tot * 8));
+    RSAC_TRY(s.d_uv.ensure(e, tot * 16));
     RSAC_TRY(s.d_tables.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.table_len, 1)));
     RSAC_TRY(s.d_poses.ensure(e, sizeof(float) * 12 * (size_t)std::max<int64_t>(d.sumH, 1)));
-    RSAC_TRY(s.d_counts.ensure(e, sizeof(int32_t) * (size_t)std::max<int64_t>(d.sumH, 1)));
+    RSAC_TRY(s.d_counts.ensure(e, sizeof(int32_t) * ((size_t)std::max<int64_t>(d.sumH, 1) + 8 + s.groups.size())));
     RSAC_TRY(s.d_results.ensure(e, sizeof(rsac_result) * std::max(d.C, 1)));
     RSAC_TRY(s.d_masks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_words, 1)));
     RSAC_TRY(s.d_sel.ensure(e, tot * 4));
@@ -392,12 +523,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     RSAC_TRY(s.d_extra.ensure(e, sizeof(double2) * (size_t)(kMaxSweepsRec * 66) * std::max(d.C, 1)));
 
     cudaStream_t st = e->stream;
-    if (d.C > 0) {
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, s.metas.data(), sizeof(ProblemMeta) * d.C, cudaMemcpyHostToDevice, st));
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_th2.p, th2.data(), sizeof(float) * d.C, cudaMemcpyHostToDevice, st));
-    }
-    if (!s.tiles.empty())
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, s.tiles.data(), sizeof(ScoreTile) * s.tiles.size(), cudaMemcpyHostToDevice, st));
+    RSAC_TRY(stage_small_tables(e, s, th2));
     if (d.total > 0) {
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, b->p3d, (size_t)d.total * 12, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, b->p2d, (size_t)d.total * 8, cudaMemcpyHostToDevice, st));
@@ -406,16 +532,14 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     s.have_tables = b->tables != nullptr;
     if (s.have_tables && d.table_len > 0)
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_tables.p, b->tables, sizeof(uint32_t) * (size_t)d.table_len, cudaMemcpyHostToDevice, st));
-    // the metas/tiles/th2 staging vectors must outlive the async copies from pageable memory:
-    // cudaMemcpyAsync from pageable host memory returns after the data is staged, so they do.
     s.h2d_bytes = (uint64_t)d.total * 24 + sizeof(ProblemMeta) * (uint64_t)d.C + sizeof(float) * (uint64_t)d.C +
-                  sizeof(ScoreTile) * s.tiles.size() + (s.have_tables ? sizeof(uint32_t) * (uint64_t)d.table_len : 0);
+                  sizeof(ScoreGroup) * s.groups.size() + (s.have_tables ? sizeof(uint32_t) * (uint64_t)d.table_len : 0);
     if (d.total > 0 && d.C > 0) {
         dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)d.C);
         e->stage_begin(RSAC_STAGE_PACK);
         pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
                                               (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 0,
-                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float2*)s.d_uv.p);
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -428,7 +552,7 @@ static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume,
     PnpState& s = e->pnp;
     const BatchDims& d = s.d;
     SelectArgs a;
-    a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.uv = (const float2*)s.d_uv.p;
+    a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.cC = (const float4*)s.d_uv.p;
     a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = nullptr; a.flags = flags; a.resume = d_resume;
     a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p; a.rec = (double2*)s.d_extra.p;
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
@@ -477,25 +601,21 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
         e->stage_begin(RSAC_STAGE_SOLVE);
         epnp_minimal_kernel<<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
-                                                        (const float4*)s.d_cA.p, (const float2*)s.d_uv.p, (float*)s.d_poses.p);
+                                                        (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
         e->stage_end(RSAC_STAGE_SOLVE);
         RSAC_CUDA(e, cudaGetLastError());
 
-        RSAC_CUDA(e, cudaMemsetAsync(s.d_counts.p, 0, sizeof(int32_t) * (size_t)d.sumH, st));
         ScoreArgs sa;
-        sa.metas = metas; sa.tiles = (const ScoreTile*)s.d_tiles.p;
-        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.uv = (const float2*)s.d_uv.p;
-        sa.poses = s.d_poses.p; sa.counts = (int32_t*)s.d_counts.p;
+        RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, (int)s.groups.size(), sa));
+        sa.metas = metas; sa.groups = (const ScoreGroup*)s.d_tiles.p;
+        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.cC = (const float4*)s.d_uv.p;
+        sa.poses = s.d_poses.p;
         sa.hmasks = nullptr;
         if (flags & RSAC_FLAG_KEEP_MASKS) {
             RSAC_TRY(s.d_hmasks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_hwords, 1)));
             sa.hmasks = (uint32_t*)s.d_hmasks.p;
         }
-        RSAC_TRY(e->d_exact.ensure(e, sizeof(unsigned long long)));
-        RSAC_CUDA(e, cudaMemsetAsync(e->d_exact.p, 0, sizeof(unsigned long long), st));
-        sa.exact_counter = (unsigned long long*)e->d_exact.p;
-        sa.chunk_cap = s.chunk_cap;
-        int rc = launch_score<0>(e, sa, (int)s.tiles.size(), s.threads);
+        int rc = launch_score<0>(e, sa, s.plan, (int)s.groups.size(), s.d_visit);
         if (rc) return rc;
     }
     {
@@ -565,24 +685,28 @@ int rsac_score_pnp_upload(rsac_engine* e, int H, const float* poses, int n, cons
     m.n = n; m.H = H; m.words = (n + 31) / 32;
     m.fx = K[0]; m.fy = K[1]; m.cx = K[2]; m.cy = K[3];
     s.H = H; s.n = n;
-    s.threads = score_threads_for(H);
-    plan_tiles(s.metas, s.threads, e->sm_count, s.tiles, &s.chunk_cap);
+    RSAC_TRY(plan_score<0>(e, s.metas, H, s.groups, s.plan));
     const size_t tot = (size_t)std::max(n, 1), hh = (size_t)std::max(H, 1);
     RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta)));
-    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreTile) * std::max<size_t>(s.tiles.size(), 1)));
+    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreGroup) * std::max<size_t>(s.groups.size(), 1)));
+    RSAC_TRY(s.d_gnext.ensure(e, sizeof(int32_t) * std::max<size_t>(s.groups.size(), 1)));
     RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
     RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
     RSAC_TRY(s.d_maxerr.ensure(e, tot * 4));
     RSAC_TRY(s.d_cA.ensure(e, tot * 16));
     RSAC_TRY(s.d_cB.ensure(e, tot * 16));
-    RSAC_TRY(s.d_uv.ensure(e, tot * 8));
+    RSAC_TRY(s.d_uv.ensure(e, tot * 16));
     RSAC_TRY(s.d_poses.ensure(e, hh * 48));
-    RSAC_TRY(s.d_counts.ensure(e, hh * 4));
+    RSAC_TRY(s.d_counts.ensure(e, (hh + 8 + s.groups.size()) * 4));
     RSAC_TRY(s.d_hmasks.ensure(e, hh * (size_t)std::max(m.words, 1) * 4));
     cudaStream_t st = e->stream;
     RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, s.metas.data(), sizeof(ProblemMeta), cudaMemcpyHostToDevice, st));
-    if (!s.tiles.empty())
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, s.tiles.data(), sizeof(ScoreTile) * s.tiles.size(), cudaMemcpyHostToDevice, st));
+    if (!s.groups.empty())
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, s.groups.data(), sizeof(ScoreGroup) * s.groups.size(), cudaMemcpyHostToDevice, st));
+    RSAC_TRY(upload_visit(e, s.plan, s.d_visit));
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, s.plan.cta_first.data(), sizeof(int32_t) * s.plan.cta_first.size(), cudaMemcpyHostToDevice, st));
+    if (!s.plan.visit.empty())
+        RSAC_CUDA(e, cudaMemcpyAsync((int32_t*)s.d_visit.p + s.plan.cta_first.size(), s.plan.visit.data(), sizeof(int32_t) * s.plan.visit.size(), cudaMemcpyHostToDevice, st));
     if (n > 0) {
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, p3d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, p2d, (size_t)n * 8, cudaMemcpyHostToDevice, st));
@@ -594,7 +718,7 @@ int rsac_score_pnp_upload(rsac_engine* e, int H, const float* poses, int n, cons
         e->stage_begin(RSAC_STAGE_PACK);
         pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
                                               nullptr, nullptr, (const float*)s.d_maxerr.p, 0,
-                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float2*)s.d_uv.p);
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -609,18 +733,15 @@ int rsac_score_pnp_run(rsac_engine* e, int want_masks)
     if (!s.uploaded) { e->err = "rsac_score_pnp_run before upload"; return RSAC_ERR_STATE; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
-    if (s.H > 0) RSAC_CUDA(e, cudaMemsetAsync(s.d_counts.p, 0, sizeof(int32_t) * (size_t)s.H, st));
-    RSAC_TRY(e->d_exact.ensure(e, sizeof(unsigned long long)));
-    RSAC_CUDA(e, cudaMemsetAsync(e->d_exact.p, 0, sizeof(unsigned long long), st));
+    ScoreArgs sa;
+    RSAC_TRY(zero_score_region(e, s.d_counts, s.H, (int)s.groups.size(), sa));
+    (void)st;
     if (s.H > 0 && s.n > 0) {
-        ScoreArgs sa;
-        sa.metas = (const ProblemMeta*)s.d_metas.p; sa.tiles = (const ScoreTile*)s.d_tiles.p;
-        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.uv = (const float2*)s.d_uv.p;
-        sa.poses = s.d_poses.p; sa.counts = (int32_t*)s.d_counts.p;
+        sa.metas = (const ProblemMeta*)s.d_metas.p; sa.groups = (const ScoreGroup*)s.d_tiles.p;
+        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.cC = (const float4*)s.d_uv.p;
+        sa.poses = s.d_poses.p;
         sa.hmasks = want_masks ? (uint32_t*)s.d_hmasks.p : nullptr;
-        sa.exact_counter = (unsigned long long*)e->d_exact.p;
-        sa.chunk_cap = s.chunk_cap;
-        int rc = launch_score<0>(e, sa, (int)s.tiles.size(), s.threads);
+        int rc = launch_score<0>(e, sa, s.plan, (int)s.groups.size(), s.d_visit);
         if (rc) return rc;
     }
     s.ran = true;
@@ -654,9 +775,9 @@ int rsac_score_pnp(rsac_engine* e, int H, const float* poses, int n, const float
 
 int64_t rsac_score_exact_evals(rsac_engine* e)
 {
-    if (!e || !e->d_exact.p) return -1;
+    if (!e || !e->last_exact) return -1;
     unsigned long long v = 0;
-    if (cudaMemcpyAsync(&v, e->d_exact.p, sizeof(v), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&v, e->last_exact, sizeof(v), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) return -1;
     cudaStreamSynchronize(e->stream);
     return (int64_t)v;
 }

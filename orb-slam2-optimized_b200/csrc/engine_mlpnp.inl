@@ -17,21 +17,21 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
         for (int k = 0; k < 4; ++k) s.metas[c].k1[k] = b->K[4 * c + k];
     const BatchDims& d = s.d;
     const size_t tot = (size_t)std::max(d.total, 1);
-    s.threads = score_threads_for(d.maxH);
-    plan_tiles(s.metas, s.threads, e->sm_count, s.tiles, &s.chunk_cap);
+    RSAC_TRY(plan_score<1>(e, s.metas, d.maxH, s.groups, s.plan));
 
     RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta) * std::max(d.C, 1)));
-    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreTile) * std::max<size_t>(s.tiles.size(), 1)));
+    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreGroup) * std::max<size_t>(s.groups.size(), 1)));
+    RSAC_TRY(s.d_gnext.ensure(e, sizeof(int32_t) * std::max<size_t>(s.groups.size(), 1)));
     RSAC_TRY(s.d_th2.ensure(e, sizeof(float) * std::max(d.C, 1)));
     RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
     RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
     RSAC_TRY(s.d_sigma2.ensure(e, tot * 4));
     RSAC_TRY(s.d_cA.ensure(e, tot * 16));
     RSAC_TRY(s.d_cB.ensure(e, tot * 16));
-    RSAC_TRY(s.d_uv.ensure(e, tot * 8));
+    RSAC_TRY(s.d_uv.ensure(e, tot * 16));
     RSAC_TRY(s.d_tables.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.table_len, 1)));
     RSAC_TRY(s.d_poses.ensure(e, sizeof(double) * 12 * (size_t)std::max<int64_t>(d.sumH, 1)));
-    RSAC_TRY(s.d_counts.ensure(e, sizeof(int32_t) * (size_t)std::max<int64_t>(d.sumH, 1)));
+    RSAC_TRY(s.d_counts.ensure(e, sizeof(int32_t) * ((size_t)std::max<int64_t>(d.sumH, 1) + 8 + s.groups.size())));
     RSAC_TRY(s.d_results.ensure(e, sizeof(rsac_result) * std::max(d.C, 1)));
     RSAC_TRY(s.d_masks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_words, 1)));
     RSAC_TRY(s.d_sel.ensure(e, tot * 4));
@@ -40,12 +40,7 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
     if (b->cov) RSAC_TRY(s.d_cov.ensure(e, tot * 72));
 
     cudaStream_t st = e->stream;
-    if (d.C > 0) {
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, s.metas.data(), sizeof(ProblemMeta) * d.C, cudaMemcpyHostToDevice, st));
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_th2.p, th2.data(), sizeof(float) * d.C, cudaMemcpyHostToDevice, st));
-    }
-    if (!s.tiles.empty())
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, s.tiles.data(), sizeof(ScoreTile) * s.tiles.size(), cudaMemcpyHostToDevice, st));
+    RSAC_TRY(stage_small_tables(e, s, th2));
     if (d.total > 0) {
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, b->p3d, (size_t)d.total * 12, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, b->p2d, (size_t)d.total * 8, cudaMemcpyHostToDevice, st));
@@ -61,7 +56,7 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
         e->stage_begin(RSAC_STAGE_PACK);
         pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
                                               (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 1,
-                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float2*)s.d_uv.p);
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -74,7 +69,7 @@ static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resum
     PnpState& s = e->mlpnp;
     const BatchDims& d = s.d;
     SelectArgs a;
-    a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.uv = (const float2*)s.d_uv.p;
+    a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.cC = (const float4*)s.d_uv.p;
     a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = s.have_cov ? (const double*)s.d_cov.p : nullptr;
     a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = nullptr; a.al_s = nullptr; a.rec = (double2*)s.d_extra.p;
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
@@ -123,21 +118,17 @@ int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
         e->stage_begin(RSAC_STAGE_SOLVE);
         mlpnp_minimal_kernel<<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
-                                                         (const float4*)s.d_cA.p, (const float2*)s.d_uv.p, cov, (double*)s.d_poses.p);
+                                                         (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, cov, (double*)s.d_poses.p);
         e->stage_end(RSAC_STAGE_SOLVE);
         RSAC_CUDA(e, cudaGetLastError());
 
-        RSAC_CUDA(e, cudaMemsetAsync(s.d_counts.p, 0, sizeof(int32_t) * (size_t)d.sumH, st));
         ScoreArgs sa;
-        sa.metas = metas; sa.tiles = (const ScoreTile*)s.d_tiles.p;
-        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.uv = (const float2*)s.d_uv.p;
-        sa.poses = s.d_poses.p; sa.counts = (int32_t*)s.d_counts.p;
+        RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, (int)s.groups.size(), sa));
+        sa.metas = metas; sa.groups = (const ScoreGroup*)s.d_tiles.p;
+        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.cC = (const float4*)s.d_uv.p;
+        sa.poses = s.d_poses.p;
         sa.hmasks = nullptr;
-        RSAC_TRY(e->d_exact.ensure(e, sizeof(unsigned long long)));
-        RSAC_CUDA(e, cudaMemsetAsync(e->d_exact.p, 0, sizeof(unsigned long long), st));
-        sa.exact_counter = (unsigned long long*)e->d_exact.p;
-        sa.chunk_cap = s.chunk_cap;
-        int rc = launch_score<1>(e, sa, (int)s.tiles.size(), s.threads);
+        int rc = launch_score<1>(e, sa, s.plan, (int)s.groups.size(), s.d_visit);
         if (rc) return rc;
     }
     {

@@ -8,6 +8,7 @@
 
 #include "../../include/ransac_b200.h"
 #include "common.cuh"
+#include "score.cuh"
 
 #define RSAC_CUDA(e, call)                                                                        \
     do {                                                                                          \
@@ -41,6 +42,40 @@ struct DevBuf {
     }
 };
 
+// pinned host staging for the small per-batch tables (metas, tiles, thresholds): a cudaMemcpyAsync from
+// pageable memory would make the host wait for the stream's earlier work and defeat sweep pipelining
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;   // recorded after the last async copy out of this buffer
+    void* ensure(size_t bytes)
+    {
+        if (done) cudaEventSynchronize(done);   // the previous copy out of this buffer has finished
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            if (cudaHostAlloc(&p, bytes + bytes / 4 + 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+            cap = bytes + bytes / 4 + 64;
+        }
+        if (!done) cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+        return p;
+    }
+    void mark(cudaStream_t st) { if (done) cudaEventRecord(done, st); }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        if (done) cudaEventDestroy(done);
+        p = nullptr; cap = 0; done = nullptr;
+    }
+};
+
+struct ScorePlanPOD {
+    int threads = 32, tile_hyps = 64, chunk_cap = 32, grid = 1, hpl = 2;
+    size_t smem = 0;
+    std::vector<int32_t> cta_first, visit;   // per-CTA work lists (host copy)
+};
+
 struct BatchDims {
     int C = 0;
     int total = 0;             // correspondences
@@ -55,28 +90,31 @@ struct PnpState {
     bool uploaded = false, ran = false, have_tables = false, have_cov = false;
     BatchDims d;
     std::vector<ProblemMeta> metas;
-    std::vector<ScoreTile> tiles;
-    int threads = 32, chunk_cap = 32;
+    std::vector<ScoreGroup> groups;
+    ScorePlanPOD plan;
     uint64_t h2d_bytes = 0;
     DevBuf d_metas, d_tiles, d_th2, d_p3d, d_p2d, d_sigma2, d_cA, d_cB, d_uv, d_tables, d_poses, d_counts,
-        d_results, d_masks, d_hmasks, d_sel, d_pw, d_us, d_al, d_cov, d_extra;
+        d_results, d_masks, d_hmasks, d_sel, d_pw, d_us, d_al, d_cov, d_extra, d_gnext, d_visit;
+    PinnedBuf h_stage;
     void release()
     {
+        h_stage.release();
         DevBuf* all[] = {&d_metas, &d_tiles, &d_th2, &d_p3d, &d_p2d, &d_sigma2, &d_cA, &d_cB, &d_uv, &d_tables, &d_poses,
-                         &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra};
+                         &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra, &d_gnext, &d_visit};
         for (DevBuf* b : all) b->release();
     }
 };
 
 struct ScoreState {
     bool uploaded = false, ran = false, with_masks = false;
-    int H = 0, n = 0, threads = 32, chunk_cap = 32;
+    int H = 0, n = 0;
+    ScorePlanPOD plan;
     std::vector<ProblemMeta> metas;
-    std::vector<ScoreTile> tiles;
-    DevBuf d_metas, d_tiles, d_p3d, d_p2d, d_maxerr, d_cA, d_cB, d_uv, d_poses, d_counts, d_hmasks;
+    std::vector<ScoreGroup> groups;
+    DevBuf d_metas, d_tiles, d_p3d, d_p2d, d_maxerr, d_cA, d_cB, d_uv, d_poses, d_counts, d_hmasks, d_gnext, d_visit;
     void release()
     {
-        DevBuf* all[] = {&d_metas, &d_tiles, &d_p3d, &d_p2d, &d_maxerr, &d_cA, &d_cB, &d_uv, &d_poses, &d_counts, &d_hmasks};
+        DevBuf* all[] = {&d_metas, &d_tiles, &d_p3d, &d_p2d, &d_maxerr, &d_cA, &d_cB, &d_uv, &d_poses, &d_counts, &d_hmasks, &d_gnext, &d_visit};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -119,6 +157,7 @@ struct rsac_engine {
     rsac::ScoreState score;
     rsac::Sim3State sim3;
     rsac::DevBuf d_exact, d_scratch, d_resume;
+    unsigned long long* last_exact = nullptr;   // diagnostic counter of the last scoring launch
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ int find_problem(const ProblemMeta* metas, int C, int
 // ---- EPnP minimal solve: one thread per hypothesis (PnPsolver.cpp:125-141) ----
 __global__ void __launch_bounds__(128) epnp_minimal_kernel(const ProblemMeta* metas, int C, int64_t sumH,
                                                            const uint32_t* tables, const float4* cA,
-                                                           const float2* uv, float* poses)
+                                                           const float4* cC, float* poses)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= sumH) return;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) epnp_minimal_kernel(const ProblemMeta* me
     for (int i = 0; i < 4; ++i) {
         const size_t ci = (size_t)m.corr_off + idx[i];
         const float4 a = cA[ci];
-        const float2 q = uv[ci];
+        const float4 q = cC[ci];
         pw[3 * i] = (double)a.x; pw[3 * i + 1] = (double)a.y; pw[3 * i + 2] = (double)a.z;   // add_correspondence (:288-294)
         us[2 * i] = (double)q.x; us[2 * i + 1] = (double)q.y;
     }
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) epnp_minimal_kernel(const ProblemMeta* me
 // ---- MLPnP minimal solve: one thread per hypothesis (MLPnPsolver.cpp:76-120) ----
 __global__ void __launch_bounds__(128) mlpnp_minimal_kernel(const ProblemMeta* metas, int C, int64_t sumH,
                                                             const uint32_t* tables, const float4* cA,
-                                                            const float2* uv, const double* cov, double* poses)
+                                                            const float4* cC, const double* cov, double* poses)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= sumH) return;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128) mlpnp_minimal_kernel(const ProblemMeta* m
     for (int i = 0; i < 6; ++i) {
         const size_t ci = (size_t)m.corr_off + idx[i];
         const float4 a = cA[ci];
-        const float2 q = uv[ci];
+        const float4 q = cC[ci];
         mlpnp_bearing(q.x, q.y, m.k1, f + 3 * i);                         // MLPnPsolver.cpp:33-37
         pw[3 * i] = (double)a.x; pw[3 * i + 1] = (double)a.y; pw[3 * i + 2] = (double)a.z;
         if (cov)

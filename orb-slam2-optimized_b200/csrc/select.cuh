@@ -24,7 +24,7 @@ struct SelectArgs {
     const ProblemMeta* metas;
     const float4* cA;
     const float4* cB;
-    const float2* uv;
+    const float4* cC;
     const void* poses;       // [sumH][12] float (PnP) / double (MLPnP)
     const int32_t* counts;   // [sumH]
     const double* cov;       // MLPnP: optional [total][9]
@@ -68,7 +68,7 @@ __device__ inline void cta_score_exact(const ProblemMeta* m, const SelectArgs& a
         if (i < m->n) {
             const size_t g = (size_t)m->corr_off + i;
             const float4 c = a.cA[g];
-            const float2 q = a.uv[g];
+            const float4 q = a.cC[g];
             in = ScoreModel<MODEL>::exact(pose, c.x, c.y, c.z, q.x, q.y, a.cB[g].y, m);
         }
         const uint32_t word = __ballot_sync(0xffffffffu, in);
@@ -97,7 +97,7 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     for (int i = tid; i < n; i += blockDim.x) {       // add_correspondence
         const size_t g = (size_t)m->corr_off + sel[i];
         const float4 c = a.cA[g];
-        const float2 q = a.uv[g];
+        const float4 q = a.cC[g];
         pw[3 * i] = (double)c.x; pw[3 * i + 1] = (double)c.y; pw[3 * i + 2] = (double)c.z;
         us[2 * i] = (double)q.x; us[2 * i + 1] = (double)q.y;
     }
@@ -234,7 +234,7 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
     for (int i = tid; i < n; i += blockDim.x) {
         const size_t g = (size_t)m->corr_off + sel[i];
         const float4 c = a.cA[g];
-        const float2 q = a.uv[g];
+        const float4 q = a.cC[g];
         double* o = sc + (size_t)i * kMlpnpScratch;
         mlpnp_bearing(q.x, q.y, m->k1, o);                                  // f
         o[3] = (double)c.x; o[4] = (double)c.y; o[5] = (double)c.z;          // p
@@ -379,7 +379,7 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
 
 // ------------------------------------------------------------- the replay kernel
 template <int MODEL>
-__global__ void __launch_bounds__(kSelectThreads) ransac_select_kernel(SelectArgs a)
+__global__ void __launch_bounds__(kSelectThreads, 4) ransac_select_kernel(SelectArgs a)
 {
     using PT = typename ScoreModel<MODEL>::pose_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
