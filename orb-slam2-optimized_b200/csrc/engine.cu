@@ -258,24 +258,24 @@ static const void* score_kernel_ptr(int hpl)
 {
     switch (hpl) {
         case 1: return (const void*)score_kernel<1, MODEL>;
-        case 4: return (const void*)score_kernel<4, MODEL>;
+        case 3: return (const void*)score_kernel<3, MODEL>;
         default: return (const void*)score_kernel<2, MODEL>;
     }
 }
 
-// Builds the work groups (problem x hypothesis tile), the chunking and each CTA's visit list.
+// Builds the work groups (problem x hypothesis tile), the chunking and each CTA's list of group records.
 //  * many groups (a relocalisation sweep): CTAs own groups round-robin; a chunk is up to 256
 //    correspondences; the producer warp prefetches the next group's chunks while the current one is scored;
 //  * few groups (scoring stress: 8 tiles x 10 000 correspondences): the CTAs are dealt to the groups in
-//    proportion to their work and pull one-word chunks from the group's counter, which balances the SMs to
-//    within one word of work.
+//    proportion to their work and pull small chunks from the group's counter, which balances the SMs to
+//    within one chunk of work.
 template <int MODEL>
 static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int maxH, std::vector<ScoreGroup>& groups, ScorePlan& pl)
 {
     groups.clear();
     pl = ScorePlan();
     pl.hpl = env_int("RSAC_SCORE_HPL", 2);
-    if (pl.hpl != 1 && pl.hpl != 2 && pl.hpl != 4) pl.hpl = 2;
+    if (pl.hpl != 1 && pl.hpl != 2 && pl.hpl != 3) pl.hpl = 2;
     int warps = (maxH + 32 * pl.hpl - 1) / (32 * pl.hpl);
     warps = std::max(1, std::min(env_int("RSAC_SCORE_WARPS", 8), std::min(8, warps)));
     pl.threads = warps * 32;
@@ -286,13 +286,21 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
         if (m.n <= 0 || m.H <= 0) continue;
         for (int h0 = 0; h0 < m.H; h0 += pl.tile_hyps) {
             ScoreGroup g;
-            g.problem = (int)p; g.hyp0 = h0; g.nchunks = 0; g.chunk_words = 0;
+            memset(&g, 0, sizeof(g));
+            g.gid = (int32_t)groups.size();
+            g.problem = (int)p; g.hyp0 = h0;
+            g.corr_off = m.corr_off; g.n = m.n; g.words = m.words; g.H = m.H;
+            g.hyp_off = m.hyp_off; g.word_off = m.word_off; g.hmask_off = m.hmask_off;
+            if (MODEL == 0) { g.fx = (float)m.fx; g.fy = (float)m.fy; } else { g.fx = m.k1[0]; g.fy = m.k1[1]; }
             groups.push_back(g);
             work.push_back((double)m.words * std::min(pl.tile_hyps, m.H - h0));
         }
     }
     const int NG = (int)groups.size();
-    if (NG == 0) { pl.cta_first.assign(2, 0); pl.grid = 1; return RSAC_OK; }
+    ScoreGroup end_rec;
+    memset(&end_rec, 0, sizeof(end_rec));
+    end_rec.gid = -1;
+    if (NG == 0) { pl.work.assign(1, end_rec); pl.vlen = 1; pl.grid = 1; return RSAC_OK; }
     const void* kern = score_kernel_ptr<MODEL>(pl.hpl);
     auto resident = [&](int chunk_words) -> int {
         const size_t smem = score_smem_bytes<MODEL>(chunk_words * 32, pl.tile_hyps);
@@ -308,15 +316,11 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
     for (const auto& m : metas) maxWords = std::max(maxWords, m.words);
     int cw = std::min(kChunkWordsMax, maxWords);
     int slots = resident(cw);
-    pl.visit.clear();
+    std::vector<std::vector<int>> lists;
     if (NG >= slots) {
         pl.grid = slots;
-        pl.cta_first.assign(pl.grid + 1, 0);
-        for (int b = 0; b < pl.grid; ++b) {
-            pl.cta_first[b] = (int32_t)pl.visit.size();
-            for (int g = b; g < NG; g += pl.grid) pl.visit.push_back(g);
-        }
-        pl.cta_first[pl.grid] = (int32_t)pl.visit.size();
+        lists.assign(pl.grid, {});
+        for (int g = 0; g < NG; ++g) lists[g % pl.grid].push_back(g);
     } else {
         // few groups: deal the CTAs to the groups in proportion to their work, small chunks
         cw = 1;
@@ -327,12 +331,10 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
         if (cw_env > 0) cw = std::min(kChunkWordsMax, cw_env);
         else cw = std::max(1, std::min(kChunkWordsMax, (int)(maxWords / (6.0 * std::max(1, slots / NG)))));
         slots = resident(cw);
-        pl.grid = slots;
-        pl.cta_first.assign(pl.grid + 1, 0);
+        pl.grid = std::max(slots, NG);
         // largest-remainder apportionment, at least one CTA per group
         std::vector<int> share(NG, 1);
-        int left = pl.grid - NG;
-        if (left < 0) { pl.grid = NG; left = 0; pl.cta_first.assign(pl.grid + 1, 0); }
+        const int left = pl.grid - NG;
         std::vector<double> frac(NG);
         for (int g = 0; g < NG; ++g) {
             const double ideal = work[g] / total * left;
@@ -347,28 +349,25 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
             share[best]++; frac[best] = -1; used++;
         }
         // interleave so that the CTAs of one group spread over the SMs
-        std::vector<int> cta_group;
+        lists.assign(pl.grid, {});
         std::vector<int> rem = share;
-        while ((int)cta_group.size() < pl.grid)
-            for (int g = 0; g < NG && (int)cta_group.size() < pl.grid; ++g)
-                if (rem[g] > 0) { cta_group.push_back(g); rem[g]--; }
-        for (int b = 0; b < pl.grid; ++b) { pl.cta_first[b] = b; pl.visit.push_back(cta_group[b]); }
-        pl.cta_first[pl.grid] = pl.grid;
+        int b = 0;
+        while (b < pl.grid)
+            for (int g = 0; g < NG && b < pl.grid; ++g)
+                if (rem[g] > 0) { lists[b++].push_back(g); rem[g]--; }
     }
     for (auto& g : groups) {
-        g.chunk_words = std::min(cw, std::max(1, metas[g.problem].words));
-        g.nchunks = (metas[g.problem].words + g.chunk_words - 1) / g.chunk_words;
+        g.chunk_words = std::min(cw, std::max(1, g.words));
+        g.nchunks = (g.words + g.chunk_words - 1) / g.chunk_words;
     }
+    size_t vlen = 1;
+    for (const auto& l : lists) vlen = std::max(vlen, l.size());
+    pl.vlen = (int)vlen;
+    pl.work.assign((size_t)pl.grid * vlen, end_rec);
+    for (int b = 0; b < pl.grid; ++b)
+        for (size_t k = 0; k < lists[b].size(); ++k) pl.work[(size_t)b * vlen + k] = groups[lists[b][k]];
     pl.chunk_cap = cw * 32;
     pl.smem = score_smem_bytes<MODEL>(pl.chunk_cap, pl.tile_hyps);
-    return RSAC_OK;
-}
-
-// uploads the plan's visit lists (pinned staging is the caller's business for the hot path; these are tiny)
-static int upload_visit(rsac_engine* e, const ScorePlan& pl, DevBuf& d_visit)
-{
-    const size_t n1 = pl.cta_first.size(), n2 = std::max<size_t>(pl.visit.size(), 1);
-    RSAC_TRY(d_visit.ensure(e, sizeof(int32_t) * (n1 + n2)));
     return RSAC_OK;
 }
 
@@ -393,9 +392,8 @@ static int launch_score(rsac_engine* e, ScoreArgs& args, const ScorePlan& pl, in
     if (ngroups <= 0) return RSAC_OK;
     const void* kern = score_kernel_ptr<MODEL>(pl.hpl);
     if (pl.smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    args.ngroups = ngroups;
-    args.cta_first = (const int32_t*)d_visit.p;
-    args.visit = (const int32_t*)d_visit.p + pl.cta_first.size();
+    args.work = (const ScoreGroup*)d_visit.p;
+    args.vlen = pl.vlen;
     args.chunk_cap = pl.chunk_cap;
     args.tile_hyps = pl.tile_hyps;
     void* kargs[] = {&args};
@@ -460,11 +458,9 @@ static int stage_small_tables(rsac_engine* e, PnpState& s, const std::vector<flo
 {
     const BatchDims& d = s.d;
     const size_t b_meta = sizeof(ProblemMeta) * (size_t)d.C, b_th = sizeof(float) * (size_t)d.C;
-    const size_t b_tile = sizeof(ScoreGroup) * s.groups.size();
-    const size_t b_cf = sizeof(int32_t) * s.plan.cta_first.size(), b_vis = sizeof(int32_t) * s.plan.visit.size();
-    const size_t o_th = (b_meta + 255) & ~(size_t)255, o_tile = (o_th + b_th + 255) & ~(size_t)255;
-    const size_t o_vis = (o_tile + b_tile + 255) & ~(size_t)255;
-    char* h = (char*)s.h_stage.ensure(o_vis + b_cf + b_vis + 256);
+    const size_t b_work = sizeof(ScoreGroup) * s.plan.work.size();
+    const size_t o_th = (b_meta + 255) & ~(size_t)255, o_work = (o_th + b_th + 255) & ~(size_t)255;
+    char* h = (char*)s.h_stage.ensure(o_work + b_work + 256);
     if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
     if (d.C > 0) {
         memcpy(h, s.metas.data(), b_meta);
@@ -472,14 +468,9 @@ static int stage_small_tables(rsac_engine* e, PnpState& s, const std::vector<flo
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, h, b_meta, cudaMemcpyHostToDevice, e->stream));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_th2.p, h + o_th, b_th, cudaMemcpyHostToDevice, e->stream));
     }
-    if (b_tile) {
-        memcpy(h + o_tile, s.groups.data(), b_tile);
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, h + o_tile, b_tile, cudaMemcpyHostToDevice, e->stream));
-    }
-    RSAC_TRY(upload_visit(e, s.plan, s.d_visit));
-    memcpy(h + o_vis, s.plan.cta_first.data(), b_cf);
-    if (b_vis) memcpy(h + o_vis + b_cf, s.plan.visit.data(), b_vis);
-    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, h + o_vis, b_cf + b_vis, cudaMemcpyHostToDevice, e->stream));
+    RSAC_TRY(s.d_visit.ensure(e, std::max<size_t>(b_work, sizeof(ScoreGroup))));
+    memcpy(h + o_work, s.plan.work.data(), b_work);
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, h + o_work, b_work, cudaMemcpyHostToDevice, e->stream));
     s.h_stage.mark(e->stream);
     return RSAC_OK;
 }
@@ -502,14 +493,13 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groups, s.plan));
 
     RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta) * std::max(d.C, 1)));
-    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreGroup) * std::max<size_t>(s.groups.size(), 1)));
-    RSAC_TRY(s.d_gnext.ensure(e, sizeof(int32_t) * std::max<size_t>(s.groups.size(), 1)));
     RSAC_TRY(s.d_th2.ensure(e, sizeof(float) * std::max(d.C, 1)));
     RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
     RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
     RSAC_TRY(s.d_sigma2.ensure(e, tot * 4));
     RSAC_TRY(s.d_cA.ensure(e, tot * 16));
     RSAC_TRY(s.d_cB.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cP.ensure(e, (size_t)std::max<int64_t>(d.total_words, 1) * 1024));
     RSAC_TRY(s.d_uv.ensure(e, tot * 16));
     RSAC_TRY(s.d_tables.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.table_len, 1)));
     RSAC_TRY(s.d_poses.ensure(e, sizeof(float) * 12 * (size_t)std::max<int64_t>(d.sumH, 1)));
@@ -539,7 +529,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
         e->stage_begin(RSAC_STAGE_PACK);
         pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
                                               (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 0,
-                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p);
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -607,8 +597,8 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
 
         ScoreArgs sa;
         RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, (int)s.groups.size(), sa));
-        sa.metas = metas; sa.groups = (const ScoreGroup*)s.d_tiles.p;
-        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.cC = (const float4*)s.d_uv.p;
+        sa.metas = metas;
+        sa.cP = (const float4*)s.d_cP.p; sa.cC = (const float4*)s.d_uv.p;
         sa.poses = s.d_poses.p;
         sa.hmasks = nullptr;
         if (flags & RSAC_FLAG_KEEP_MASKS) {
@@ -688,25 +678,20 @@ int rsac_score_pnp_upload(rsac_engine* e, int H, const float* poses, int n, cons
     RSAC_TRY(plan_score<0>(e, s.metas, H, s.groups, s.plan));
     const size_t tot = (size_t)std::max(n, 1), hh = (size_t)std::max(H, 1);
     RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta)));
-    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreGroup) * std::max<size_t>(s.groups.size(), 1)));
-    RSAC_TRY(s.d_gnext.ensure(e, sizeof(int32_t) * std::max<size_t>(s.groups.size(), 1)));
     RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
     RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
     RSAC_TRY(s.d_maxerr.ensure(e, tot * 4));
     RSAC_TRY(s.d_cA.ensure(e, tot * 16));
     RSAC_TRY(s.d_cB.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cP.ensure(e, (size_t)std::max<int64_t>((int64_t)m.words, 1) * 1024));
     RSAC_TRY(s.d_uv.ensure(e, tot * 16));
     RSAC_TRY(s.d_poses.ensure(e, hh * 48));
     RSAC_TRY(s.d_counts.ensure(e, (hh + 8 + s.groups.size()) * 4));
     RSAC_TRY(s.d_hmasks.ensure(e, hh * (size_t)std::max(m.words, 1) * 4));
     cudaStream_t st = e->stream;
     RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, s.metas.data(), sizeof(ProblemMeta), cudaMemcpyHostToDevice, st));
-    if (!s.groups.empty())
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tiles.p, s.groups.data(), sizeof(ScoreGroup) * s.groups.size(), cudaMemcpyHostToDevice, st));
-    RSAC_TRY(upload_visit(e, s.plan, s.d_visit));
-    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, s.plan.cta_first.data(), sizeof(int32_t) * s.plan.cta_first.size(), cudaMemcpyHostToDevice, st));
-    if (!s.plan.visit.empty())
-        RSAC_CUDA(e, cudaMemcpyAsync((int32_t*)s.d_visit.p + s.plan.cta_first.size(), s.plan.visit.data(), sizeof(int32_t) * s.plan.visit.size(), cudaMemcpyHostToDevice, st));
+    RSAC_TRY(s.d_visit.ensure(e, sizeof(ScoreGroup) * std::max<size_t>(s.plan.work.size(), 1)));
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, s.plan.work.data(), sizeof(ScoreGroup) * s.plan.work.size(), cudaMemcpyHostToDevice, st));
     if (n > 0) {
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, p3d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, p2d, (size_t)n * 8, cudaMemcpyHostToDevice, st));
@@ -718,7 +703,7 @@ int rsac_score_pnp_upload(rsac_engine* e, int H, const float* poses, int n, cons
         e->stage_begin(RSAC_STAGE_PACK);
         pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
                                               nullptr, nullptr, (const float*)s.d_maxerr.p, 0,
-                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p);
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -737,8 +722,8 @@ int rsac_score_pnp_run(rsac_engine* e, int want_masks)
     RSAC_TRY(zero_score_region(e, s.d_counts, s.H, (int)s.groups.size(), sa));
     (void)st;
     if (s.H > 0 && s.n > 0) {
-        sa.metas = (const ProblemMeta*)s.d_metas.p; sa.groups = (const ScoreGroup*)s.d_tiles.p;
-        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.cC = (const float4*)s.d_uv.p;
+        sa.metas = (const ProblemMeta*)s.d_metas.p;
+        sa.cP = (const float4*)s.d_cP.p; sa.cC = (const float4*)s.d_uv.p;
         sa.poses = s.d_poses.p;
         sa.hmasks = want_masks ? (uint32_t*)s.d_hmasks.p : nullptr;
         int rc = launch_score<0>(e, sa, s.plan, (int)s.groups.size(), s.d_visit);

@@ -20,14 +20,13 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
     RSAC_TRY(plan_score<1>(e, s.metas, d.maxH, s.groups, s.plan));
 
     RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta) * std::max(d.C, 1)));
-    RSAC_TRY(s.d_tiles.ensure(e, sizeof(ScoreGroup) * std::max<size_t>(s.groups.size(), 1)));
-    RSAC_TRY(s.d_gnext.ensure(e, sizeof(int32_t) * std::max<size_t>(s.groups.size(), 1)));
     RSAC_TRY(s.d_th2.ensure(e, sizeof(float) * std::max(d.C, 1)));
     RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
     RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
     RSAC_TRY(s.d_sigma2.ensure(e, tot * 4));
     RSAC_TRY(s.d_cA.ensure(e, tot * 16));
     RSAC_TRY(s.d_cB.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cP.ensure(e, (size_t)std::max<int64_t>(d.total_words, 1) * 1024));
     RSAC_TRY(s.d_uv.ensure(e, tot * 16));
     RSAC_TRY(s.d_tables.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.table_len, 1)));
     RSAC_TRY(s.d_poses.ensure(e, sizeof(double) * 12 * (size_t)std::max<int64_t>(d.sumH, 1)));
@@ -56,7 +55,7 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
         e->stage_begin(RSAC_STAGE_PACK);
         pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
                                               (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 1,
-                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p);
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -124,8 +123,8 @@ int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
 
         ScoreArgs sa;
         RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, (int)s.groups.size(), sa));
-        sa.metas = metas; sa.groups = (const ScoreGroup*)s.d_tiles.p;
-        sa.cA = (const float4*)s.d_cA.p; sa.cB = (const float4*)s.d_cB.p; sa.cC = (const float4*)s.d_uv.p;
+        sa.metas = metas;
+        sa.cP = (const float4*)s.d_cP.p; sa.cC = (const float4*)s.d_uv.p;
         sa.poses = s.d_poses.p;
         sa.hmasks = nullptr;
         int rc = launch_score<1>(e, sa, s.plan, (int)s.groups.size(), s.d_visit);

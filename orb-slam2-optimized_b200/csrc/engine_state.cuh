@@ -73,7 +73,8 @@ struct PinnedBuf {
 struct ScorePlanPOD {
     int threads = 32, tile_hyps = 64, chunk_cap = 32, grid = 1, hpl = 2;
     size_t smem = 0;
-    std::vector<int32_t> cta_first, visit;   // per-CTA work lists (host copy)
+    int vlen = 1;                            // records per CTA in `work`
+    std::vector<ScoreGroup> work;            // [grid][vlen] per-CTA lists of group records (host copy)
 };
 
 struct BatchDims {
@@ -93,14 +94,14 @@ struct PnpState {
     std::vector<ScoreGroup> groups;
     ScorePlanPOD plan;
     uint64_t h2d_bytes = 0;
-    DevBuf d_metas, d_tiles, d_th2, d_p3d, d_p2d, d_sigma2, d_cA, d_cB, d_uv, d_tables, d_poses, d_counts,
-        d_results, d_masks, d_hmasks, d_sel, d_pw, d_us, d_al, d_cov, d_extra, d_gnext, d_visit;
+    DevBuf d_metas, d_cP, d_th2, d_p3d, d_p2d, d_sigma2, d_cA, d_cB, d_uv, d_tables, d_poses, d_counts,
+        d_results, d_masks, d_hmasks, d_sel, d_pw, d_us, d_al, d_cov, d_extra, d_visit;
     PinnedBuf h_stage;
     void release()
     {
         h_stage.release();
-        DevBuf* all[] = {&d_metas, &d_tiles, &d_th2, &d_p3d, &d_p2d, &d_sigma2, &d_cA, &d_cB, &d_uv, &d_tables, &d_poses,
-                         &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra, &d_gnext, &d_visit};
+        DevBuf* all[] = {&d_metas, &d_cP, &d_th2, &d_p3d, &d_p2d, &d_sigma2, &d_cA, &d_cB, &d_uv, &d_tables, &d_poses,
+                         &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra, &d_visit};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -111,10 +112,10 @@ struct ScoreState {
     ScorePlanPOD plan;
     std::vector<ProblemMeta> metas;
     std::vector<ScoreGroup> groups;
-    DevBuf d_metas, d_tiles, d_p3d, d_p2d, d_maxerr, d_cA, d_cB, d_uv, d_poses, d_counts, d_hmasks, d_gnext, d_visit;
+    DevBuf d_metas, d_cP, d_p3d, d_p2d, d_maxerr, d_cA, d_cB, d_uv, d_poses, d_counts, d_hmasks, d_visit;
     void release()
     {
-        DevBuf* all[] = {&d_metas, &d_tiles, &d_p3d, &d_p2d, &d_maxerr, &d_cA, &d_cB, &d_uv, &d_poses, &d_counts, &d_hmasks, &d_gnext, &d_visit};
+        DevBuf* all[] = {&d_metas, &d_cP, &d_p3d, &d_p2d, &d_maxerr, &d_cA, &d_cB, &d_uv, &d_poses, &d_counts, &d_hmasks, &d_visit};
         for (DevBuf* b : all) b->release();
     }
 };

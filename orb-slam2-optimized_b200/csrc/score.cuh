@@ -27,30 +27,35 @@
 
 namespace rsac {
 
-// a group = (problem, hypothesis tile); its correspondences are cut into chunks of whole mask words
-struct ScoreGroup {
-    int32_t problem;
+// a group = (problem, hypothesis tile); its correspondences are cut into chunks of whole mask words.
+// The record is self-contained (everything the kernel needs about the problem), so a CTA starts with ONE
+// global load before its first TMA copy; each CTA owns a list of such records.
+struct __align__(16) ScoreGroup {
+    int32_t gid;         // index of the group's chunk counter; < 0 terminates a CTA's list
     int32_t hyp0;        // first hypothesis of the tile
     int32_t nchunks;
     int32_t chunk_words; // words per chunk (the last chunk may be shorter)
+    int32_t corr_off, n, words, H;     // copied from the problem's ProblemMeta
+    int32_t hyp_off, word_off;
+    int64_t hmask_off;
+    float fx, fy;        // f32 focal lengths folded into the fast-path rows
+    int32_t problem, pad;
 };
+static_assert(sizeof(ScoreGroup) == 64, "ScoreGroup is copied as four 16-byte words");
 
 struct ScoreArgs {
-    const ProblemMeta* metas;
-    const ScoreGroup* groups;
-    int32_t* group_next;     // [ngroups] chunk counters, zeroed before the launch
-    int32_t ngroups;
-    const int32_t* cta_first; // [grid+1] range of this CTA in `visit`
-    const int32_t* visit;     // group ids in the order each CTA works through them
-    const float4* cA;        // (X, Y, Z, cx-u)
-    const float4* cB;        // (cy-v, thr, band, 0)
-    const float4* cC;        // (u, v, 0, 0)   exact pixel coordinates (exact path, minimal solvers)
-    const void* poses;       // PnP: float[sumH][12]; MLPnP: double[sumH][12]
-    int32_t* counts;         // [sumH], atomically accumulated (zeroed before the launch)
-    uint32_t* hmasks;        // optional per-hypothesis masks
+    const ProblemMeta* metas;        // exact path only (f64 intrinsics)
+    const ScoreGroup* work;          // [grid][vlen] per-CTA lists of group records
+    int32_t vlen;
+    int32_t* group_next;             // [ngroups] chunk counters, zeroed before the launch
+    const float4* cP;                // pair-packed records, 4 x float4 per two correspondences (see pack kernel)
+    const float4* cC;                // (u, v, 0, 0)   exact pixel coordinates (exact path)
+    const void* poses;               // PnP: float[sumH][12]; MLPnP: double[sumH][12]
+    int32_t* counts;                 // [sumH], atomically accumulated (zeroed before the launch)
+    uint32_t* hmasks;                // optional per-hypothesis masks
     unsigned long long* exact_counter;   // optional diagnostic
-    int32_t chunk_cap;       // capacity of one shared-memory buffer in correspondences
-    int32_t tile_hyps;       // hypotheses per tile = warps * 32 * HPL
+    int32_t chunk_cap;               // capacity of one ring slot in correspondences
+    int32_t tile_hyps;               // hypotheses per tile = warps * 32 * HPL
 };
 
 // ---- exact (reference-arithmetic) evaluations ----
@@ -137,46 +142,61 @@ __device__ __forceinline__ void fold_pose(const PT* __restrict__ r, float fx, fl
     }
 }
 
-// One fast evaluation; shifts sign(D) (provisional inlier bit) and sign(t) (t >= 0: too close to
-// call) into the lane's words, most significant position first: call for i = 31 .. 0.
-__device__ __forceinline__ void eval_fast(const float* c, const float4& a, const float4& b, uint32_t& inl, uint32_t& cert)
+// Two fast evaluations of one hypothesis (correspondences 2p and 2p+1) with the packed FP32 pipe
+// (FFMA2 / FMUL2: one issue slot, two results).  C[k] = (c[k], c[k]).  Shifts sign(D) (provisional inlier
+// bit) and sign(t) (t >= 0: too close to call) into the lane's words, most significant position first:
+// call for p = 15 .. 0.  Component-wise the operation sequence is
+//   x = fma(c0,X,fma(c1,Y,fma(c2,Z,c3))) (same for y, z);  N = fma(cu,z,x);  M = fma(cv,z,y);
+//   q = thr*(z*z);  D = fma(M,M,fma(N,N,-q));  t = fma(band,|z|,-min(|D|,q))
+// which is what the band derivation in DESIGN.md assumes.
+__device__ __forceinline__ void eval_pair(const float2* C, const float4& q0, const float4& q1, const float4& q2,
+                                          const float2& band, uint32_t& inl, uint32_t& cert)
 {
-    const float x = fmaf(c[0], a.x, fmaf(c[1], a.y, fmaf(c[2], a.z, c[3])));
-    const float y = fmaf(c[4], a.x, fmaf(c[5], a.y, fmaf(c[6], a.z, c[7])));
-    const float z = fmaf(c[8], a.x, fmaf(c[9], a.y, fmaf(c[10], a.z, c[11])));
-    const float N = fmaf(a.w, z, x);                      // z * (u_est - u)
-    const float M = fmaf(b.x, z, y);
-    const float q = b.y * (z * z);                        // thr z^2
-    const float D = fmaf(M, M, fmaf(N, N, -q));           // z^2 (e - thr)
-    const float m = fminf(fabsf(D), q);                   // q <= band|z|: point on the camera plane
-    const float t = fmaf(b.z, fabsf(z), -m);              // >= 0 (or NaN): inside the rounding band
-    inl = __funnelshift_l(__float_as_uint(D), inl, 1);    // sign(D): e < thr   (NaN results are +qNaN: bit clear)
-    cert = __funnelshift_l(__float_as_uint(t), cert, 1);  // sign(t) set: decision is certain
+    const float2 X = make_float2(q0.x, q0.y), Y = make_float2(q0.z, q0.w), Z = make_float2(q1.x, q1.y);
+    const float2 cu = make_float2(q1.z, q1.w), cv = make_float2(q2.x, q2.y), nthr = make_float2(q2.z, q2.w);
+    const float2 x = __ffma2_rn(C[0], X, __ffma2_rn(C[1], Y, __ffma2_rn(C[2], Z, C[3])));
+    const float2 y = __ffma2_rn(C[4], X, __ffma2_rn(C[5], Y, __ffma2_rn(C[6], Z, C[7])));
+    const float2 z = __ffma2_rn(C[8], X, __ffma2_rn(C[9], Y, __ffma2_rn(C[10], Z, C[11])));
+    const float2 N = __ffma2_rn(cu, z, x);                 // z * (u_est - u)
+    const float2 M = __ffma2_rn(cv, z, y);
+    const float2 nq = __fmul2_rn(nthr, __fmul2_rn(z, z));  // -thr z^2
+    const float2 D = __ffma2_rn(M, M, __ffma2_rn(N, N, nq));   // z^2 (e - thr)
+    const float m1 = fminf(fabsf(D.y), -nq.y);             // thr z^2 <= band|z|: point on the camera plane
+    const float t1 = fmaf(band.y, fabsf(z.y), -m1);        // >= 0 (or NaN): inside the rounding band
+    inl = __funnelshift_l(__float_as_uint(D.y), inl, 1);   // sign(D): e < thr   (NaN results are +qNaN: bit clear)
+    cert = __funnelshift_l(__float_as_uint(t1), cert, 1);  // sign(t) set: decision is certain
+    const float m0 = fminf(fabsf(D.x), -nq.x);
+    const float t0 = fmaf(band.x, fabsf(z.x), -m0);
+    inl = __funnelshift_l(__float_as_uint(D.x), inl, 1);
+    cert = __funnelshift_l(__float_as_uint(t0), cert, 1);
 }
 
 constexpr int kScoreStages = 4;        // shared-memory ring of correspondence chunks
 constexpr int kScoreMaxThreads = 288;  // 8 consumer warps + 1 producer warp
 
 // Warp-specialised persistent kernel.  blockDim.x = (consumer warps + 1) * 32.
-//   producer (last warp, one lane): walks this CTA's groups, pulls chunk ids from the group's atomic
+//   producer (last warp, one lane): walks this CTA's group records, pulls chunk ids from the group's atomic
 //     counter (the next id is requested before the current TMA is issued, so the atomic's latency is
-//     off the critical path), waits for a free ring slot (empty barrier) and bulk-copies the chunk's
-//     three 16-byte record arrays into it (full barrier, transaction bytes);
-//   consumers: wait for the slot to fill, evaluate 32*HPL hypotheses per warp against the chunk, release
-//     the slot.  Warps never meet at a CTA barrier inside the loop; they drift up to kScoreStages-1
-//     chunks apart, which absorbs the rare exact-path excursions.
+//     off the critical path), waits for a free ring slot (empty barrier), writes the slot's header (chunk id,
+//     list position, group record) and bulk-copies the chunk's two record arrays into it (full barrier,
+//     transaction bytes);
+//   consumers: wait for the slot to fill, switch group when the header says so (flush counts, fold the new
+//     tile's poses), evaluate 32*HPL hypotheses per warp against the chunk, release the slot.  Warps never
+//     meet at a CTA barrier inside the loop; they drift up to kScoreStages-1 chunks apart, which absorbs
+//     the rare exact-path excursions.
 template <int HPL, int MODEL>
 __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs args)
 {
     using Model = ScoreModel<MODEL>;
     using PT = typename Model::pose_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: kScoreStages x [A | B | C] (cap records each), then raw poses: tile_hyps x 12 PT
+    // layout: kScoreStages x [P: cap/2 pairs x 64 B | C: cap x 16 B], then raw poses: tile_hyps x 12 PT
     const int cap = args.chunk_cap;
     float4* sbuf = reinterpret_cast<float4*>(smem_raw);
     PT* sraw = reinterpret_cast<PT*>(smem_raw + (size_t)cap * 48 * kScoreStages);
     __shared__ __align__(8) uint64_t full_bar[kScoreStages], empty_bar[kScoreStages];
-    __shared__ int s_chunk[kScoreStages];
+    __shared__ __align__(16) ScoreGroup s_grp[kScoreStages];
+    __shared__ int2 s_hdr[kScoreStages];                // (chunk id or -1, position in the CTA's list)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncons = (blockDim.x >> 5) - 1;            // consumer warps
@@ -190,82 +210,86 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
     }
     __syncthreads();
 
-    const int v_begin = args.cta_first[blockIdx.x], v_end = args.cta_first[blockIdx.x + 1];
-
     if (warp == ncons) {
         // ------------------------------------------------------------- producer
         if (lane == 0) {
+            const int4* work = reinterpret_cast<const int4*>(args.work + (size_t)blockIdx.x * args.vlen);
             uint32_t pit = 0;
-            for (int k = v_begin; k < v_end; ++k) {
-                const int g = args.visit[k];
-                const ScoreGroup grp = args.groups[g];
-                const ProblemMeta* mp = args.metas + grp.problem;
-                const int words_total = mp->words, n = mp->n;
-                const size_t base = (size_t)mp->corr_off;
-                int next_id = atomicAdd(args.group_next + g, 1);
-                for (;;) {
+            for (int k = 0; k < args.vlen; ++k) {
+                union { ScoreGroup g; int4 q[4]; } rec;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rec.q[i] = work[4 * k + i];
+                const ScoreGroup& grp = rec.g;
+                if (grp.gid < 0) break;
+                int next_id = atomicAdd(args.group_next + grp.gid, 1);
+                while (next_id < grp.nchunks) {
                     const int c = next_id;
                     const uint32_t stage = pit % kScoreStages;
                     mbar_wait(&empty_bar[stage], ((pit / kScoreStages) & 1u) ^ 1u);
-                    if (c < grp.nchunks) {
-                        s_chunk[stage] = c;
-                        next_id = atomicAdd(args.group_next + g, 1);     // consumed next iteration
-                        const int w0 = c * grp.chunk_words;
-                        const int nw = min(grp.chunk_words, words_total - w0);
-                        const int nc = min(nw * 32, n - w0 * 32);
-                        const uint32_t bytes = (uint32_t)nc * 16u;
-                        float4* dst = sbuf + (size_t)stage * cap * 3;
-                        const size_t off = base + (size_t)w0 * 32;
-                        mbar_arrive_expect_tx(&full_bar[stage], 3u * bytes);
-                        tma_load_1d(dst, args.cA + off, bytes, &full_bar[stage]);
-                        tma_load_1d(dst + cap, args.cB + off, bytes, &full_bar[stage]);
-                        tma_load_1d(dst + 2 * cap, args.cC + off, bytes, &full_bar[stage]);
-                        ++pit;
-                    } else {
-                        s_chunk[stage] = -1;                             // end of this group
-                        mbar_arrive(&full_bar[stage]);
-                        ++pit;
-                        break;
-                    }
+                    next_id = atomicAdd(args.group_next + grp.gid, 1);   // consumed next iteration
+                    s_hdr[stage] = make_int2(c, k);
+                    int4* gdst = reinterpret_cast<int4*>(&s_grp[stage]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gdst[i] = rec.q[i];
+                    const int w0 = c * grp.chunk_words;
+                    const int nw = min(grp.chunk_words, grp.words - w0);
+                    const int nc = min(nw * 32, grp.n - w0 * 32);
+                    float4* dst = sbuf + (size_t)stage * cap * 3;
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nw * 1024u + (uint32_t)nc * 16u);
+                    tma_load_1d(dst, args.cP + ((size_t)grp.word_off + w0) * 64, (uint32_t)nw * 1024u, &full_bar[stage]);
+                    tma_load_1d(dst + 2 * cap, args.cC + (size_t)grp.corr_off + (size_t)w0 * 32, (uint32_t)nc * 16u, &full_bar[stage]);
+                    ++pit;
                 }
             }
+            const uint32_t stage = pit % kScoreStages;             // end-of-work marker
+            mbar_wait(&empty_bar[stage], ((pit / kScoreStages) & 1u) ^ 1u);
+            s_hdr[stage] = make_int2(-1, -1);
+            mbar_arrive(&full_bar[stage]);
         }
         return;
     }
 
     // --------------------------------------------------------------- consumers
     const PT* poses = reinterpret_cast<const PT*>(args.poses);
-    uint32_t cit = 0;
-    for (int k = v_begin; k < v_end; ++k) {
-        const int g = args.visit[k];
-        const ScoreGroup grp = args.groups[g];
-        const ProblemMeta* mp = args.metas + grp.problem;
-        const int words_total = mp->words;
-        const int H = mp->H;
-        float c[HPL][12];
-        int hyp[HPL];
-        uint32_t live[HPL];
-        int cnt[HPL];
-        bool any_live = false;
+    float2 C[HPL][12];
+    int cnt[HPL];
+    uint32_t live[HPL];
+    int g_hyp0 = 0, g_cw = 0, g_n = 0, g_words = 0, g_hypoff = 0, g_problem = 0;
+    int64_t g_hmask = 0;
+    int cur_k = -1;
+#pragma unroll
+    for (int s = 0; s < HPL; ++s) { cnt[s] = 0; live[s] = 0u; }
+
+    auto flush = [&]() {
 #pragma unroll
         for (int s = 0; s < HPL; ++s) {
-            hyp[s] = grp.hyp0 + (warp * HPL + s) * 32 + lane;
-            live[s] = (hyp[s] < H) ? 0xffffffffu : 0u;
+            if (live[s] && cnt[s]) atomicAdd(args.counts + g_hypoff + g_hyp0 + (warp * HPL + s) * 32 + lane, cnt[s]);
             cnt[s] = 0;
-            any_live = any_live || (live[s] != 0u);
         }
-        const bool warp_live = __any_sync(0xffffffffu, any_live);
-        bool folded = false;
-        // poses are loaded and folded when the first chunk of the group arrives (a CTA may find its group
-        // already finished by others)
-        auto fold_all = [&]() {
-            float fx, fy;
-            Model::fold_f(*mp, fx, fy);
+    };
+
+    for (uint32_t cit = 0;; ++cit) {
+        const uint32_t stage = cit % kScoreStages;
+        mbar_wait(&full_bar[stage], (cit / kScoreStages) & 1u);
+        const int2 hdr = s_hdr[stage];
+        if (hdr.x < 0) break;
+        if (hdr.y != cur_k) {
+            // ---- new group: flush the finished tile, take the record, load and fold this warp's poses
+            if (cur_k >= 0) flush();
+            cur_k = hdr.y;
+            const ScoreGroup& grp = s_grp[stage];
+            g_hyp0 = grp.hyp0; g_cw = grp.chunk_words; g_n = grp.n; g_words = grp.words;
+            g_hypoff = grp.hyp_off; g_problem = grp.problem; g_hmask = grp.hmask_off;
+            const int H = grp.H;
+            const float fx = grp.fx, fy = grp.fy;
 #pragma unroll
             for (int s = 0; s < HPL; ++s) {
                 const int local = (warp * HPL + s) * 32 + lane;
+                const int hyp = g_hyp0 + local;
+                live[s] = (hyp < H) ? 0xffffffffu : 0u;
+                float c[12];
                 if (live[s]) {
-                    const PT* src = poses + (size_t)(mp->hyp_off + hyp[s]) * 12;
+                    const PT* src = poses + (size_t)(g_hypoff + hyp) * 12;
                     PT raw[12];
                     if constexpr (sizeof(PT) == 4) {
                         const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -277,77 +301,67 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
 #pragma unroll
                         for (int i = 0; i < 6; ++i) { const double2 v = s2[i]; raw[2 * i] = v.x; raw[2 * i + 1] = v.y; }
                     }
-                    fold_pose<PT>(raw, fx, fy, c[s]);
+                    fold_pose<PT>(raw, fx, fy, c);
                     // each thread keeps the raw poses of its own slots for the exact path (no other thread reads them)
 #pragma unroll
                     for (int i = 0; i < 12; ++i) sraw[(size_t)local * 12 + i] = raw[i];
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) c[s][i] = 0.0f;
+                    for (int i = 0; i < 12; ++i) c[i] = 0.0f;
                 }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) C[s][i] = make_float2(c[i], c[i]);
             }
-        };
-
-        for (;;) {
-            const uint32_t stage = cit % kScoreStages;
-            mbar_wait(&full_bar[stage], (cit / kScoreStages) & 1u);
-            const int chunk = s_chunk[stage];
-            if (chunk >= 0 && warp_live) {
-                if (!folded) { fold_all(); folded = true; }
-                const float4* sA = sbuf + (size_t)stage * cap * 3;
-                const float4* sB = sA + cap;
-                const float4* sC = sA + 2 * cap;
-                const int w0 = chunk * grp.chunk_words;
-                const int nw = min(grp.chunk_words, words_total - w0);
-                const int nc = min(nw * 32, mp->n - w0 * 32);
-                for (int w = 0; w < nw; ++w) {
-                    uint32_t inl[HPL], cert[HPL];
-#pragma unroll
-                    for (int s = 0; s < HPL; ++s) { inl[s] = 0u; cert[s] = 0u; }
-                    const float4* pa = sA + w * 32;
-                    const float4* pb = sB + w * 32;
-#pragma unroll
-                    for (int i = 31; i >= 0; --i) {
-                        const float4 a = pa[i];
-                        const float4 b = pb[i];
-#pragma unroll
-                        for (int s = 0; s < HPL; ++s) eval_fast(c[s], a, b, inl[s], cert[s]);
-                    }
-                    const int rem = nc - w * 32;
-                    const uint32_t valid = (rem >= 32) ? 0xffffffffu : ((1u << rem) - 1u);
-#pragma unroll
-                    for (int s = 0; s < HPL; ++s) {
-                        inl[s] &= valid & live[s];
-                        uint32_t u = ~cert[s] & valid & live[s];
-                        if (u) {
-                            if (args.exact_counter) atomicAdd(args.exact_counter, (unsigned long long)__popc(u));
-                            const PT* pose = sraw + (size_t)((warp * HPL + s) * 32 + lane) * 12;
-                            while (u) {
-                                const int i = __ffs(u) - 1;
-                                u &= u - 1;
-                                const int ci = w * 32 + i;
-                                const float4 a = sA[ci];
-                                const float4 b = sB[ci];
-                                const float4 p2 = sC[ci];
-                                const bool in = Model::exact(pose, a.x, a.y, a.z, p2.x, p2.y, b.y, mp);
-                                inl[s] = in ? (inl[s] | (1u << i)) : (inl[s] & ~(1u << i));
-                            }
-                        }
-                        cnt[s] += __popc(inl[s]);
-                        if (args.hmasks && live[s])
-                            args.hmasks[mp->hmask_off + (int64_t)hyp[s] * words_total + w0 + w] = inl[s];
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);     // slot may be refilled
-            ++cit;
-            if (chunk < 0) break;
         }
+        const bool warp_live = __any_sync(0xffffffffu, (live[0] != 0u));   // slot 0 holds the lowest hypotheses
+        if (warp_live) {
+            const float4* sP = sbuf + (size_t)stage * cap * 3;
+            const float4* sC = sP + 2 * cap;
+            const int w0 = hdr.x * g_cw;
+            const int nw = min(g_cw, g_words - w0);
+            const int nc = min(nw * 32, g_n - w0 * 32);
+            for (int w = 0; w < nw; ++w) {
+                uint32_t inl[HPL], cert[HPL];
 #pragma unroll
-        for (int s = 0; s < HPL; ++s)
-            if (live[s] && cnt[s]) atomicAdd(args.counts + mp->hyp_off + hyp[s], cnt[s]);
+                for (int s = 0; s < HPL; ++s) { inl[s] = 0u; cert[s] = 0u; }
+                const float4* pp = sP + w * 64;
+#pragma unroll
+                for (int p = 15; p >= 0; --p) {
+                    const float4 q0 = pp[4 * p], q1 = pp[4 * p + 1], q2 = pp[4 * p + 2];
+                    const float2 bd = *reinterpret_cast<const float2*>(pp + 4 * p + 3);
+#pragma unroll
+                    for (int s = 0; s < HPL; ++s) eval_pair(C[s], q0, q1, q2, bd, inl[s], cert[s]);
+                }
+                const int rem = nc - w * 32;
+                const uint32_t valid = (rem >= 32) ? 0xffffffffu : ((1u << rem) - 1u);
+#pragma unroll
+                for (int s = 0; s < HPL; ++s) {
+                    inl[s] &= valid & live[s];
+                    uint32_t u = ~cert[s] & valid & live[s];
+                    if (u) {
+                        if (args.exact_counter) atomicAdd(args.exact_counter, (unsigned long long)__popc(u));
+                        const PT* pose = sraw + (size_t)((warp * HPL + s) * 32 + lane) * 12;
+                        const ProblemMeta* mp = args.metas + g_problem;
+                        while (u) {
+                            const int i = __ffs(u) - 1;
+                            u &= u - 1;
+                            const int ci = w * 32 + i;
+                            const float* rec = reinterpret_cast<const float*>(sP + (size_t)(ci >> 1) * 4) + (ci & 1);
+                            const float4 p2 = sC[ci];
+                            const bool in = Model::exact(pose, rec[0], rec[2], rec[4], p2.x, p2.y, -rec[10], mp);
+                            inl[s] = in ? (inl[s] | (1u << i)) : (inl[s] & ~(1u << i));
+                        }
+                    }
+                    cnt[s] += __popc(inl[s]);
+                    if (args.hmasks && live[s])
+                        args.hmasks[g_hmask + (int64_t)(g_hyp0 + (warp * HPL + s) * 32 + lane) * g_words + w0 + w] = inl[s];
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);     // slot may be refilled
     }
+    if (cur_k >= 0) flush();
 }
 
 // ---- packing: raw correspondences -> (cA, cB, cC) records with thresholds and rounding bands ----
@@ -374,31 +388,67 @@ __device__ __forceinline__ float score_band(float X, float Y, float Z, float cu,
     return __double2float_ru(band);
 }
 
-// One thread per correspondence; blockIdx.y = problem.  thr = sigma2*th2 as an f32 product
+// One thread per correspondence pair; blockIdx.y = problem.  thr = sigma2*th2 as an f32 product
 // (PnPsolver.cpp:93) unless a ready-made max_err array is supplied (scoring stress).
+// Outputs:
+//   cA (X,Y,Z,cx-u), cB (cy-v,thr,band,0), cC (u,v,0,0): one record per correspondence, indexed by
+//       corr_off + i -- minimal solvers, refinement and the exact path read these;
+//   cP: the scoring kernel's stream, 64 B per PAIR of correspondences (2p, 2p+1) so that every operand of
+//       the packed-FP32 evaluation is an aligned register pair straight out of LDS.128:
+//         [X0 X1 Y0 Y1] [Z0 Z1 cu0 cu1] [cv0 cv1 -thr0 -thr1] [band0 band1 0 0]
+//       indexed by (word_off*16 + p); a problem's tail is zero-padded to a whole 32-correspondence word.
+struct PackedPoint { float X, Y, Z, cu, cv, thr, band, u, v; };
+
+__device__ __forceinline__ PackedPoint pack_point(const ProblemMeta& m, size_t g, const float* p3d, const float* p2d,
+                                                  const float* sigma2, float th2, const float* max_err, int model)
+{
+    PackedPoint r;
+    r.X = p3d[3 * g]; r.Y = p3d[3 * g + 1]; r.Z = p3d[3 * g + 2];
+    r.u = p2d[2 * g]; r.v = p2d[2 * g + 1];
+    r.thr = max_err ? max_err[g] : sigma2[g] * th2;
+    float fx, fy;
+    if (model == 0) {
+        r.cu = (float)(m.cx - (double)r.u);
+        r.cv = (float)(m.cy - (double)r.v);
+        fx = (float)m.fx; fy = (float)m.fy;
+    } else {
+        r.cu = m.k1[2] - r.u;
+        r.cv = m.k1[3] - r.v;
+        fx = m.k1[0]; fy = m.k1[1];
+    }
+    r.band = score_band(r.X, r.Y, r.Z, r.cu, r.cv, r.u, r.v, r.thr, fx, fy);
+    return r;
+}
+
 __global__ void pack_pnp_kernel(const ProblemMeta* metas, const float* p3d, const float* p2d, const float* sigma2,
                                 const float* th2_per_problem, const float* max_err, int model,
-                                float4* cA, float4* cB, float4* cC)
+                                float4* cA, float4* cB, float4* cC, float4* cP)
 {
     const ProblemMeta& m = metas[blockIdx.y];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.n; i += gridDim.x * blockDim.x) {
-        const size_t g = (size_t)m.corr_off + i;
-        const float X = p3d[3 * g], Y = p3d[3 * g + 1], Z = p3d[3 * g + 2];
-        const float u = p2d[2 * g], v = p2d[2 * g + 1];
-        const float thr = max_err ? max_err[g] : sigma2[g] * th2_per_problem[blockIdx.y];
-        float cu, cv, fx, fy;
-        if (model == 0) {
-            cu = (float)(m.cx - (double)u);
-            cv = (float)(m.cy - (double)v);
-            fx = (float)m.fx; fy = (float)m.fy;
-        } else {
-            cu = m.k1[2] - u;
-            cv = m.k1[3] - v;
-            fx = m.k1[0]; fy = m.k1[1];
+    const float th2 = th2_per_problem ? th2_per_problem[blockIdx.y] : 0.0f;
+    const int npairs = m.words * 16;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
+        PackedPoint a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b = a;
+        const int i0 = 2 * p, i1 = 2 * p + 1;
+        if (i0 < m.n) {
+            const size_t g = (size_t)m.corr_off + i0;
+            a = pack_point(m, g, p3d, p2d, sigma2, th2, max_err, model);
+            cA[g] = make_float4(a.X, a.Y, a.Z, a.cu);
+            cB[g] = make_float4(a.cv, a.thr, a.band, 0.0f);
+            cC[g] = make_float4(a.u, a.v, 0.0f, 0.0f);
         }
-        cA[g] = make_float4(X, Y, Z, cu);
-        cB[g] = make_float4(cv, thr, score_band(X, Y, Z, cu, cv, u, v, thr, fx, fy), 0.0f);
-        cC[g] = make_float4(u, v, 0.0f, 0.0f);
+        if (i1 < m.n) {
+            const size_t g = (size_t)m.corr_off + i1;
+            b = pack_point(m, g, p3d, p2d, sigma2, th2, max_err, model);
+            cA[g] = make_float4(b.X, b.Y, b.Z, b.cu);
+            cB[g] = make_float4(b.cv, b.thr, b.band, 0.0f);
+            cC[g] = make_float4(b.u, b.v, 0.0f, 0.0f);
+        }
+        float4* dst = cP + ((size_t)m.word_off * 16 + p) * 4;
+        dst[0] = make_float4(a.X, b.X, a.Y, b.Y);
+        dst[1] = make_float4(a.Z, b.Z, a.cu, b.cu);
+        dst[2] = make_float4(a.cv, b.cv, -a.thr, -b.thr);
+        dst[3] = make_float4(a.band, b.band, 0.0f, 0.0f);
     }
 }
 
