@@ -44,7 +44,7 @@ PRM = dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.2, th2=5.991
 H_HYP = 300
 METRIC = "relocalization candidates/s (PnP EPnP RANSAC sweep; hyp x corr evals/s in extras)"
 FLOP_PER_EVAL = 31            # PnP CheckInliers
-PIPE = 4                      # sweeps in flight
+PIPE = int(os.environ.get("RSAC_BENCH_PIPE", "1"))   # sweeps in flight
 
 
 def measured_peaks():
