@@ -108,7 +108,7 @@ int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
 
     if (!s.have_tables && d.table_len > 0) {
         e->stage_begin(RSAC_STAGE_RNG);
-        rng_tables_kernel<<<(d.C + 63) / 64, 64, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
+        rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
         e->stage_end(RSAC_STAGE_RNG);
         RSAC_CUDA(e, cudaGetLastError());
     }
