@@ -38,6 +38,8 @@ extern "C" {
 /* run flags */
 #define RSAC_FLAG_KEEP_MASKS 1      /* also keep per-hypothesis inlier bitmasks (debug / rsac_*_get_hypotheses) */
 #define RSAC_FLAG_MLPNP_DISCARD_REFINE 4 /* reproduce MLPnPsolver::Refine not storing its pose (MLPnPsolver.cpp:290-296) */
+#define RSAC_FLAG_EPNP_EIGEN 8      /* 4-point EPnP: null-space basis from the 12x12 M^T M eigen-solve (PnPsolver.cpp:380)
+                                       instead of the default Householder QR of M^T (same subspace, different basis) */
 
 typedef struct rsac_engine rsac_engine;
 
@@ -255,6 +257,8 @@ int rsac_nccl_destroy(rsac_engine* e);
  * contract).  Test-only: lets the CPU test-suite compare the solver source with the
  * oracle bit-for-bit without a GPU.  Not a fallback: nothing in the engine calls these. */
 int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3]);
+/* the same with the default QR null space (RSAC_FLAG_EPNP_EIGEN clear) */
+int rsac_debug_host_epnp4_qr(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3]);
 /* the 4 smallest eigenpairs of a symmetric 12x12 (upper triangle read): w[4], v[12][4] */
 int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48]);
 int rsac_debug_host_sim3(const float P1[9], const float P2[9], int fix_scale, float R[9], float t[3], float* s);

@@ -54,6 +54,8 @@ void orc_jacobi_eig_d(int n, double *a, double *w, double *v);
 void orc_jacobi_eig_f(int n, float *a, float *w, float *v);
 /* the nv smallest eigenpairs of a symmetric n x n (n <= 12), recorded-rotation variant; v is n x nv */
 void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v);
+/* orthonormal basis of the null space of an 8 x 12 matrix (4-point EPnP) by Householder QR of its transpose */
+void orc_nullspace_qr_d(const double *Mrows /*8x12*/, double *U4 /*12x4*/);
 /* minimum-norm least squares of an m x k system through a one-sided Jacobi SVD
  * with Eigen's rank threshold (restates A.bdcSvd(ThinU|ThinV).solve(b),
  * PnPsolver.cpp:531,559,590).  L row-major m*k, m<=8, k<=6. */
@@ -97,6 +99,7 @@ typedef struct {
 #define ORC_FLAG_STALE_ROWS 1   /* Q1: reproduce colwise().sum() over all allocated rows */
 #define ORC_FLAG_EXHAUSTIVE 2   /* evaluate all H hypotheses (no early return), for throughput + per-hyp parity */
 #define ORC_FLAG_MLPNP_DISCARD_REFINE 4 /* Q6: reproduce MLPnP Refine() not storing its pose */
+#define ORC_FLAG_EPNP_QR_NULLSPACE 8    /* 4-point EPnP: null-space basis by Householder QR instead of the 12x12 eigen-solve */
 
 typedef struct {
     int ok;           /* return value of iterate() */
@@ -123,8 +126,10 @@ void orc_pnp_ransac(const orc_pnp_problem *pb, const orc_ransac_params *prm, con
 /* One EPnP solve on the subset idx[0..m) (PnPsolver::compute_pose, :359-415).
  * Returns the reprojection error of the chosen solution. */
 double orc_epnp_pose(const orc_pnp_problem *pb, const uint32_t *idx, int m, float R[9], float t[3]);
+double orc_epnp_pose_mode(const orc_pnp_problem *pb, const uint32_t *idx, int m, int flags, float R[9], float t[3]);
 /* average algorithmic FP64 FLOP (+,-,*,/,sqrt = 1 each) of one minimal EPnP solve over a table of H sets */
 double orc_epnp_flops(const orc_pnp_problem *pb, const uint32_t *table, int H, int min_set);
+double orc_epnp_flops_mode(const orc_pnp_problem *pb, const uint32_t *table, int H, int min_set, int flags);
 long long orc_flops_take(void);
 /* PnPsolver::CheckInliers (:241-268) for one pose; max_err[i] = sigma2[i]*th2 (f32*f32).
  * err2 (optional) receives the f32 squared errors. */

@@ -387,3 +387,49 @@ void orc_ldlt6_solve_d(const double a_in[36], const double g[6], double x[6])
         for (int j = i + 1; j < N; ++j) y[i] -= a[j * N + i] * y[j];
     for (int i = 0; i < N; ++i) x[perm[i]] = y[i];
 }
+
+/* Null space of an 8 x 12 matrix (the M of a 4-point EPnP system, PnPsolver.cpp:365-379) by Householder QR
+ * of its transpose: M^T = Q [R; 0], null(M) = span of the last four columns of Q = H0 H1 ... H7 e_{8..11}.
+ * For four correspondences M^T M has an exact four-dimensional null space, so "the four eigenvectors of
+ * the smallest eigenvalues" (PnPsolver.cpp:380-382) are ANY orthonormal basis of that space -- which one
+ * the reference's eigen-solver returns is decided by rounding noise.  This routine returns a
+ * deterministic one for 2.4 kFLOP instead of a 37 kFLOP 12 x 12 eigen-solve.  Operation order is part of
+ * the arithmetic contract (mirrored by csrc/linalg.cuh nullspace_qr_8x12).
+ * Mrows: 8 x 12 row-major.  U4: 12 x 4 row-major, column i = basis vector i. */
+void orc_nullspace_qr_d(const double *Mrows, double *U4)
+{
+    double A[12][8], tau[8];
+    for (int r = 0; r < 12; ++r)
+        for (int c = 0; c < 8; ++c) A[r][c] = Mrows[c * 12 + r];
+    for (int k = 0; k < 8; ++k) {
+        double s = 0.0;
+        for (int r = k; r < 12; ++r) s += A[r][k] * A[r][k];
+        const double norm = sqrt(s);
+        if (norm == 0.0) { tau[k] = 0.0; continue; }
+        const double alpha = (A[k][k] > 0.0) ? -norm : norm;
+        A[k][k] = A[k][k] - alpha;
+        double vtv = 0.0;
+        for (int r = k; r < 12; ++r) vtv += A[r][k] * A[r][k];
+        tau[k] = 2.0 / vtv;
+        for (int j = k + 1; j < 8; ++j) {
+            double d = 0.0;
+            for (int r = k; r < 12; ++r) d += A[r][k] * A[r][j];
+            d = d * tau[k];
+            for (int r = k; r < 12; ++r) A[r][j] = A[r][j] - d * A[r][k];
+        }
+        FL(2 * (12 - k) + 1 + 1 + 2 * (12 - k) + 1 + (7 - k) * (4 * (12 - k) + 1));
+    }
+    for (int i = 0; i < 4; ++i) {
+        double y[12];
+        for (int r = 0; r < 12; ++r) y[r] = (r == 8 + i) ? 1.0 : 0.0;
+        for (int k = 7; k >= 0; --k) {
+            if (tau[k] == 0.0) continue;
+            double d = 0.0;
+            for (int r = k; r < 12; ++r) d += A[r][k] * y[r];
+            d = d * tau[k];
+            for (int r = k; r < 12; ++r) y[r] = y[r] - d * A[r][k];
+            FL(4 * (12 - k) + 1);
+        }
+        for (int r = 0; r < 12; ++r) U4[r * 4 + i] = y[r];
+    }
+}

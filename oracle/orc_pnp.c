@@ -22,6 +22,7 @@ typedef struct {
     double *pws, *us, *alphas, *pcs;   /* max_n rows, grow-only (PnPsolver.cpp:271-281) */
     int max_n, n;
     int stale_rows;                    /* Q1 */
+    int qr_nullspace;                  /* ORC_FLAG_EPNP_QR_NULLSPACE: n == 4 uses orc_nullspace_qr_d */
 } epnp_t;
 
 static void epnp_init(epnp_t *e, double fx, double fy, double cx, double cy, int stale_rows)
@@ -434,9 +435,10 @@ static double compute_pose(epnp_t *e, float Rf[9], float tf[3])
     compute_barycentric_coordinates(e);
 
     /* :365-379  M (2n x 12) and MtM = M^T M, accumulated row by row, upper triangle */
+    const int use_qr = e->qr_nullspace && e->n == 4;
     double MtM[144];
     memset(MtM, 0, sizeof(MtM));
-    for (int i = 0; i < e->n; ++i) {
+    for (int i = 0; i < e->n && !use_qr; ++i) {
         double r0[12], r1[12];
         for (int j = 0; j < 4; ++j) {
             const double a = e->alphas[i * 4 + j];
@@ -449,9 +451,23 @@ static double compute_pose(epnp_t *e, float Rf[9], float tf[3])
                 MtM[a * 12 + b] += r1[a] * r1[b];
             }
     }
-    FL(e->n * (4 * 6 + 2 + 78 * 4));
     double w[4], U[48];
-    orc_jacobi_lowest_d(12, 4, MtM, w, U);                             /* :380-382: eigenvectors 0..3 */
+    if (use_qr) {
+        /* the same 8 x 12 M, null space taken directly (see orc_nullspace_qr_d) */
+        double Mrows[8 * 12];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                const double a = e->alphas[i * 4 + j];
+                double *r0 = &Mrows[(2 * i) * 12], *r1 = &Mrows[(2 * i + 1) * 12];
+                r0[3 * j] = a * e->fx; r0[3 * j + 1] = 0.0;      r0[3 * j + 2] = a * (e->cx - e->us[i * 2 + 0]);
+                r1[3 * j] = 0.0;       r1[3 * j + 1] = a * e->fy; r1[3 * j + 2] = a * (e->cy - e->us[i * 2 + 1]);
+            }
+        FL(4 * 4 * 6);
+        orc_nullspace_qr_d(Mrows, U);
+    } else {
+        FL(e->n * (4 * 6 + 2 + 78 * 4));
+        orc_jacobi_lowest_d(12, 4, MtM, w, U);                         /* :380-382: eigenvectors 0..3 */
+    }
     FL(4 * 6 * 3 + 6 * (10 * 5 + 6) + 6 * 8);   /* L_6x10, rho */
     FL(3 * (8 + 5 * (6 * (16 + 4 * 7 + 20 + 1) + 4)));   /* betas post-processing, 5 x (A,b build + beta update); QR counted below */
 
@@ -533,18 +549,29 @@ void orc_pnp_score(const orc_pnp_problem *pb, const float *max_err, int H, const
 }
 
 /* average algorithmic FP64 FLOP of one minimal (min_set-point) EPnP solve over the H rows of a table */
-double orc_epnp_flops(const orc_pnp_problem *pb, const uint32_t *table, int H, int min_set)
+double orc_epnp_flops_mode(const orc_pnp_problem *pb, const uint32_t *table, int H, int min_set, int flags)
 {
     float R[9], t[3];
     orc_flops_take();
-    for (int h = 0; h < H; ++h) orc_epnp_pose(pb, table + (size_t)h * min_set, min_set, R, t);
+    for (int h = 0; h < H; ++h) orc_epnp_pose_mode(pb, table + (size_t)h * min_set, min_set, flags, R, t);
     return (double)orc_flops_take() / (double)(H > 0 ? H : 1);
+}
+
+double orc_epnp_flops(const orc_pnp_problem *pb, const uint32_t *table, int H, int min_set)
+{
+    return orc_epnp_flops_mode(pb, table, H, min_set, 0);
 }
 
 double orc_epnp_pose(const orc_pnp_problem *pb, const uint32_t *idx, int m, float R[9], float t[3])
 {
+    return orc_epnp_pose_mode(pb, idx, m, 0, R, t);
+}
+
+double orc_epnp_pose_mode(const orc_pnp_problem *pb, const uint32_t *idx, int m, int flags, float R[9], float t[3])
+{
     epnp_t e;
     epnp_init(&e, pb->fx, pb->fy, pb->cx, pb->cy, 0);
+    e.qr_nullspace = (flags & ORC_FLAG_EPNP_QR_NULLSPACE) != 0;
     set_maximum_number_of_correspondences(&e, m);
     reset_correspondences(&e);
     for (int i = 0; i < m; ++i) add_correspondence(&e, pb->p3d + 3 * idx[i], pb->p2d + 2 * idx[i]);
@@ -595,6 +622,7 @@ void orc_pnp_ransac(const orc_pnp_problem *pb, const orc_ransac_params *prm, con
 
     epnp_t e;
     epnp_init(&e, pb->fx, pb->fy, pb->cx, pb->cy, (flags & ORC_FLAG_STALE_ROWS) != 0);
+    e.qr_nullspace = (flags & ORC_FLAG_EPNP_QR_NULLSPACE) != 0;
     set_maximum_number_of_correspondences(&e, minSet);                  /* :108 */
 
     for (int h = 0; h < H; ++h) {                                       /* :119 */

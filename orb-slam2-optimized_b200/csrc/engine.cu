@@ -590,8 +590,12 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         const int threads = 128;
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
         e->stage_begin(RSAC_STAGE_SOLVE);
-        epnp_minimal_kernel<<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
-                                                        (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+        if (flags & RSAC_FLAG_EPNP_EIGEN)
+            epnp_minimal_kernel<false><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
+                                                                   (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+        else
+            epnp_minimal_kernel<true><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
+                                                                  (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
         e->stage_end(RSAC_STAGE_SOLVE);
         RSAC_CUDA(e, cudaGetLastError());
 
@@ -822,7 +826,17 @@ int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2
     for (int i = 0; i < 12; ++i) pw[i] = (double)p3d[i];
     for (int i = 0; i < 8; ++i) us[i] = (double)p2d[i];
     const Cam k = {K[0], K[1], K[2], K[3]};
-    epnp_compute_pose_small<4>(pw, us, k, R, t);
+    epnp_compute_pose_small<4, false>(pw, us, k, R, t);
+    return RSAC_OK;
+}
+
+int rsac_debug_host_epnp4_qr(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3])
+{
+    double pw[12], us[8];
+    for (int i = 0; i < 12; ++i) pw[i] = (double)p3d[i];
+    for (int i = 0; i < 8; ++i) us[i] = (double)p2d[i];
+    const Cam k = {K[0], K[1], K[2], K[3]};
+    epnp_compute_pose_small<4, true>(pw, us, k, R, t);
     return RSAC_OK;
 }
 

@@ -241,13 +241,9 @@ __host__ __device__ inline void epnp_gauss_newton(const double* L, const double*
     }
 }
 
-// From MtM (PACKED upper triangle, 78 entries, destroyed) to the null-space basis U4 (12x4) and
-// the three refined beta vectors: 12x12 eigen-solve (:380), L, rho, approx_k + gauss_newton (:395-405).
-// rec: scratch for the recorded rotations (kMaxSweepsRec * 66 double2).
-__host__ __device__ inline void epnp_solve_betas(double* MtM, const double* cws, double* U4, double* betas /*3x4*/, double2* rec)
+// L, rho, approx_k + gauss_newton (PnPsolver.cpp:395-405) from the null-space basis U4 (12x4)
+__host__ __device__ inline void epnp_betas_from_basis(const double* U4, const double* cws, double* betas /*3x4*/)
 {
-    double w4[4];
-    jacobi_lowest<12, 4>(MtM, w4, U4, rec);
     double L[60], rho[6];
     epnp_L_6x10(U4, L);
     epnp_rho(cws, rho);
@@ -257,6 +253,34 @@ __host__ __device__ inline void epnp_solve_betas(double* MtM, const double* cws,
     epnp_gauss_newton(L, rho, betas + 4);
     epnp_betas_approx_3(L, rho, betas + 8);
     epnp_gauss_newton(L, rho, betas + 8);
+}
+
+// From MtM (PACKED upper triangle, 78 entries, destroyed) to the null-space basis U4 (12x4) and
+// the three refined beta vectors: 12x12 eigen-solve (:380), then the above.
+// rec: scratch for the recorded rotations (kMaxSweepsRec * 66 double2).
+__host__ __device__ inline void epnp_solve_betas(double* MtM, const double* cws, double* U4, double* betas /*3x4*/, double2* rec)
+{
+    double w4[4];
+    jacobi_lowest<12, 4>(MtM, w4, U4, rec);
+    epnp_betas_from_basis(U4, cws, betas);
+}
+
+// 4-point variant: the null space of the 8 x 12 M directly (Householder QR of M^T) -- for four
+// correspondences M^T M is exactly rank 8 and any orthonormal null-space basis is as good as the
+// eigen-solver's.  al: 4 x 4 alphas, us: 4 x 2.
+__host__ __device__ inline void epnp_solve_betas_qr4(const double* al, const double* us, const Cam& k, const double* cws,
+                                                     double* U4, double* betas /*3x4*/)
+{
+    double A[96];   // M^T, row-major 12 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double r0[12], r1[12];
+        epnp_m_rows(al + 4 * i, us[2 * i], us[2 * i + 1], k, r0, r1);
+#pragma unroll
+        for (int r = 0; r < 12; ++r) { A[r * 8 + 2 * i] = r0[r]; A[r * 8 + 2 * i + 1] = r1[r]; }
+    }
+    nullspace_qr_8x12(A, U4);
+    epnp_betas_from_basis(U4, cws, betas);
 }
 
 // PnPsolver::compute_ccs (:345-352)
@@ -314,7 +338,8 @@ __host__ __device__ inline double epnp_reproj_term(const double* R, const double
 
 // Whole PnPsolver::compute_pose (:359-415) for NPTS thread-private correspondences.
 // pw: NPTS x 3, us: NPTS x 2 (already widened to double).  Writes R (9) t (3) as float.
-template <int NPTS>
+// QR: take the null space of a 4-point system by Householder QR instead of the 12x12 eigen-solve.
+template <int NPTS, bool QR = false>
 __host__ __device__ inline double epnp_compute_pose_small(const double* pw, const double* us, const Cam& k, float* Rf, float* tf)
 {
     double cws[12], C0[3];
@@ -336,24 +361,28 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
     double alphas[NPTS * 4];
     for (int i = 0; i < NPTS; ++i) epnp_alphas(pw + 3 * i, cws, CCi, alphas + 4 * i);
 
-    double MtM[78];   // packed upper triangle
-#pragma unroll
-    for (int i = 0; i < 78; ++i) MtM[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < NPTS; ++i) {
-        double r0[12], r1[12];
-        epnp_m_rows(alphas + 4 * i, us[2 * i], us[2 * i + 1], k, r0, r1);
-#pragma unroll
-        for (int a = 0; a < 12; ++a)
-#pragma unroll
-            for (int b = a; b < 12; ++b) {
-                MtM[tri_idx(12, a, b)] += r0[a] * r0[b];
-                MtM[tri_idx(12, a, b)] += r1[a] * r1[b];
-            }
-    }
     double U4[48], betas[12];
-    double2 rec[kMaxSweepsRec * 66];
-    epnp_solve_betas(MtM, cws, U4, betas, rec);
+    if constexpr (QR && NPTS == 4) {
+        epnp_solve_betas_qr4(alphas, us, k, cws, U4, betas);
+    } else {
+        double MtM[78];   // packed upper triangle
+#pragma unroll
+        for (int i = 0; i < 78; ++i) MtM[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPTS; ++i) {
+            double r0[12], r1[12];
+            epnp_m_rows(alphas + 4 * i, us[2 * i], us[2 * i + 1], k, r0, r1);
+#pragma unroll
+            for (int a = 0; a < 12; ++a)
+#pragma unroll
+                for (int b = a; b < 12; ++b) {
+                    MtM[tri_idx(12, a, b)] += r0[a] * r0[b];
+                    MtM[tri_idx(12, a, b)] += r1[a] * r1[b];
+                }
+        }
+        double2 rec[kMaxSweepsRec * 66];
+        epnp_solve_betas(MtM, cws, U4, betas, rec);
+    }
 
     double rep[3], Rs[3][9], ts[3][3];
     for (int kk = 0; kk < 3; ++kk) {

@@ -217,6 +217,56 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
         for (int k = 0; k < NV; ++k) v[i * NV + k] = x[k][i];
 }
 
+// Orthonormal basis of the null space of an 8 x 12 matrix M (4-point EPnP) by Householder QR of
+// A = M^T (12 x 8, row-major A[r*8+c], destroyed): null(M) = last four columns of Q = H0..H7 e_{8..11}.
+// U4[r*4+i] = component r of basis vector i.  Operation order mirrors oracle/orc_linalg.c
+// orc_nullspace_qr_d exactly (arithmetic contract).  2.4 kFLOP, fully unrolled: A stays in registers.
+__host__ __device__ inline void nullspace_qr_8x12(double* A, double* U4)
+{
+    double tau[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = k; r < 12; ++r) s += A[r * 8 + k] * A[r * 8 + k];
+        const double norm = sqrt(s);
+        if (norm == 0.0) { tau[k] = 0.0; continue; }
+        const double alpha = (A[k * 8 + k] > 0.0) ? -norm : norm;
+        A[k * 8 + k] = A[k * 8 + k] - alpha;
+        double vtv = 0.0;
+#pragma unroll
+        for (int r = k; r < 12; ++r) vtv += A[r * 8 + k] * A[r * 8 + k];
+        tau[k] = 2.0 / vtv;
+#pragma unroll
+        for (int j = k + 1; j < 8; ++j) {
+            double d = 0.0;
+#pragma unroll
+            for (int r = k; r < 12; ++r) d += A[r * 8 + k] * A[r * 8 + j];
+            d = d * tau[k];
+#pragma unroll
+            for (int r = k; r < 12; ++r) A[r * 8 + j] = A[r * 8 + j] - d * A[r * 8 + k];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double y[12];
+#pragma unroll
+        for (int r = 0; r < 12; ++r) y[r] = (r == 8 + i) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            if (tau[k] == 0.0) continue;
+            double d = 0.0;
+#pragma unroll
+            for (int r = k; r < 12; ++r) d += A[r * 8 + k] * y[r];
+            d = d * tau[k];
+#pragma unroll
+            for (int r = k; r < 12; ++r) y[r] = y[r] - d * A[r * 8 + k];
+        }
+#pragma unroll
+        for (int r = 0; r < 12; ++r) U4[r * 4 + i] = y[r];
+    }
+}
+
 // One-sided (Hestenes) Jacobi: orthogonalises the columns of U (M x K), accumulates V (K x K).
 template <int M, int K>
 __host__ __device__ inline void onesided_jacobi(double* U, double* V)

@@ -136,6 +136,9 @@ __device__ __forceinline__ int find_problem(const ProblemMeta* metas, int C, int
 }
 
 // ---- EPnP minimal solve: one thread per hypothesis (PnPsolver.cpp:125-141) ----
+// QR = true: null space of the 4-point system by Householder QR (default); false: 12x12 eigen-solve
+// (RSAC_FLAG_EPNP_EIGEN, the reference's structure)
+template <bool QR>
 __global__ void __launch_bounds__(128) epnp_minimal_kernel(const ProblemMeta* metas, int C, int64_t sumH,
                                                            const uint32_t* tables, const float4* cA,
                                                            const float4* cC, float* poses)
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(128) epnp_minimal_kernel(const ProblemMeta* me
     }
     const Cam k = {m.fx, m.fy, m.cx, m.cy};
     float R[9], t[3];
-    epnp_compute_pose_small<4>(pw, us, k, R, t);
+    epnp_compute_pose_small<4, QR>(pw, us, k, R, t);
     float* out = poses + g * 12;
 #pragma unroll
     for (int i = 0; i < 9; ++i) out[i] = R[i];

@@ -146,7 +146,10 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         double MtM[78];
 #pragma unroll
         for (int i = 0; i < 78; ++i) MtM[i] = S.MtM[i];
-        epnp_solve_betas(MtM, S.cws, S.U4, S.betas, a.rec + (size_t)blockIdx.x * (kMaxSweepsRec * 66));
+        if (n == 4 && !(a.flags & 8))   // RSAC_FLAG_EPNP_EIGEN clear: QR null space for a 4-point system
+            epnp_solve_betas_qr4(al, us, cam, S.cws, S.U4, S.betas);
+        else
+            epnp_solve_betas(MtM, S.cws, S.U4, S.betas, a.rec + (size_t)blockIdx.x * (kMaxSweepsRec * 66));
         for (int k = 0; k < 3; ++k) epnp_ccs(S.betas + 4 * k, S.U4, S.ccs[k]);
     }
     __syncthreads();

@@ -17,6 +17,7 @@ _LIB = None
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = range(6)
 FLAG_KEEP_MASKS = 1
 FLAG_MLPNP_DISCARD_REFINE = 4
+FLAG_EPNP_EIGEN = 8          # 4-point EPnP null space from the 12x12 eigen-solve (default: Householder QR)
 STAGE_PACK, STAGE_RNG, STAGE_SOLVE, STAGE_SCORE, STAGE_SELECT = range(5)
 STAGE_NAMES = ["pack", "rng", "solve", "score", "select"]
 

@@ -19,6 +19,7 @@ _LIB = None
 FLAG_STALE_ROWS = 1
 FLAG_EXHAUSTIVE = 2
 FLAG_MLPNP_DISCARD_REFINE = 4
+FLAG_EPNP_QR_NULLSPACE = 8
 
 
 class RansacParams(C.Structure):
@@ -65,6 +66,8 @@ def lib():
         _LIB = C.CDLL(path)
         _LIB.orc_epnp_pose.restype = C.c_double
         _LIB.orc_epnp_flops.restype = C.c_double
+        _LIB.orc_epnp_pose_mode.restype = C.c_double
+        _LIB.orc_epnp_flops_mode.restype = C.c_double
         for f in ("orc_pnp_batch", "orc_sim3_batch", "orc_mlpnp_batch", "orc_pnp_score_timed"):
             getattr(_LIB, f).restype = C.c_double
     return _LIB
@@ -189,17 +192,18 @@ def params(prob=0.99, min_inliers=8, max_its=300, min_set=4, eps=0.4, th2=5.991)
     return RansacParams(prob, min_inliers, max_its, min_set, eps, th2)
 
 
-def epnp_pose(pb: _Keep, idx):
+def epnp_pose(pb: _Keep, idx, flags=0):
+    """flags: FLAG_EPNP_QR_NULLSPACE selects the QR null space for 4-point sets"""
     idx = np.ascontiguousarray(idx, np.uint32)
     R = np.empty(9, np.float32)
     t = np.empty(3, np.float32)
-    err = lib().orc_epnp_pose(C.byref(pb.st), _p(idx), C.c_int(len(idx)), _p(R), _p(t))
+    err = lib().orc_epnp_pose_mode(C.byref(pb.st), _p(idx), C.c_int(len(idx)), C.c_int(flags), _p(R), _p(t))
     return R.reshape(3, 3), t, err
 
 
-def epnp_flops(pb: _Keep, table):
+def epnp_flops(pb: _Keep, table, flags=0):
     table = np.ascontiguousarray(table, np.uint32)
-    return lib().orc_epnp_flops(C.byref(pb.st), _p(table), C.c_int(table.shape[0]), C.c_int(table.shape[1]))
+    return lib().orc_epnp_flops_mode(C.byref(pb.st), _p(table), C.c_int(table.shape[0]), C.c_int(table.shape[1]), C.c_int(flags))
 
 
 def pnp_check_inliers(pb: _Keep, max_err, R, t):

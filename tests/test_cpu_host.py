@@ -97,6 +97,10 @@ def test_host_compiled_core_is_bit_identical_to_oracle(built_lib, oracle):
         R, t = np.empty(9, np.float32), np.empty(3, np.float32)
         L.rsac_debug_host_epnp4(K, capi._p(p3), capi._p(p2), capi._p(R), capi._p(t))
         assert np.array_equal(R.view(np.uint32), Ro.reshape(-1).view(np.uint32)) and np.array_equal(t.view(np.uint32), to.view(np.uint32)), h
+        # default device mode: null space of the 4-point system by Householder QR
+        Rq, tq, _ = oracle.epnp_pose(pb, idx, oracle.FLAG_EPNP_QR_NULLSPACE)
+        L.rsac_debug_host_epnp4_qr(K, capi._p(p3), capi._p(p2), capi._p(R), capi._p(t))
+        assert np.array_equal(R.view(np.uint32), Rq.reshape(-1).view(np.uint32)) and np.array_equal(t.view(np.uint32), tq.view(np.uint32)), h
     # 12x12 eigen-solve: 4 smallest eigenpairs
     rng = np.random.default_rng(1)
     for _ in range(20):

@@ -54,7 +54,7 @@ def _pnp_replay(oracle, p, prm, seed):
     n = len(p["p3d"])
     minInl, H = oracle.ransac_setup_pnp(n, oprm)
     tab = oracle.index_table(seed, n, 4, H)
-    ex = oracle.pnp_ransac(pb, oprm, tab, oracle.FLAG_EXHAUSTIVE, per_hyp=True)
+    ex = oracle.pnp_ransac(pb, oprm, tab, oracle.FLAG_EXHAUSTIVE | oracle.FLAG_EPNP_QR_NULLSPACE, per_hyp=True)
     counts, poses = ex["hyp_counts"], ex["hyp_pose"]
     thr = (p["sigma2"] * np.float32(prm[5])).astype(np.float32)
     calls, best, bestmask, bestpose, h = [], 0, None, None, 0

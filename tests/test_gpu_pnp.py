@@ -21,7 +21,10 @@ def _batch(cfg, C, n, outl=0.5, first=0):
     return b, offsets
 
 
-def _oracle_all(oracle, b, C, prm, tables, flags=0, per_hyp=True):
+def _oracle_all(oracle, b, C, prm, tables, flags=None, per_hyp=True):
+    """flags=None: the engine's default mode (QR null space for the 4-point sets)"""
+    if flags is None:
+        flags = oracle.FLAG_EPNP_QR_NULLSPACE
     out = []
     for c in range(C):
         pb = oracle.pnp_problem(b["p3d"][c], b["p2d"][c], b["sigma2"][c], b["K"])
@@ -46,16 +49,20 @@ def _check_results(res, masks_list, orc):
             assert np.allclose(r["t"], T[:3, 3], rtol=1e-4, atol=1e-6), c
 
 
-def test_pnp_cfg1_per_hypothesis_bit_exact(engine, oracle):
-    """cfg1: N=500, 50% outliers, H=300; 8 problems; explicit index tables."""
+@pytest.mark.parametrize("mode", ["qr", "eigen"])
+def test_pnp_cfg1_per_hypothesis_bit_exact(engine, oracle, mode):
+    """cfg1: N=500, 50% outliers, H=300; 8 problems; explicit index tables.  Both null-space modes:
+    the default Householder QR of the 4-point M^T and the 12x12 M^T M eigen-solve (RSAC_FLAG_EPNP_EIGEN)."""
     C, n = 8, 500
     b, offsets = _batch(1, C, n)
     tables = [oracle.index_table(int(s), n, 4, 300) for s in b["seeds"]]
     toff = np.arange(C + 1, dtype=np.int64) * 1200
+    dev_flags = capi.FLAG_EPNP_EIGEN if mode == "eigen" else 0
+    orc_flags = 0 if mode == "eigen" else oracle.FLAG_EPNP_QR_NULLSPACE
     res, masks = engine.pnp_solve(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**PRM),
-                                  tables=np.concatenate(tables), table_offsets=toff)
+                                  tables=np.concatenate(tables), table_offsets=toff, flags=dev_flags)
     poses, counts = engine.pnp_hypotheses()
-    orc = _oracle_all(oracle, b, C, PRM, tables)
+    orc = _oracle_all(oracle, b, C, PRM, tables, flags=orc_flags)
     for c in range(C):
         hp = poses[c * 300:(c + 1) * 300]
         op = orc[c]["hyp_pose"]
@@ -99,7 +106,7 @@ def test_pnp_ragged_and_edge_cases(engine, oracle):
             assert not ml[c].any()
             continue
         pb = oracle.pnp_problem(parts[c]["p3d"][:n], parts[c]["p2d"][:n], parts[c]["sigma2"][:n], parts[c]["K"])
-        o = oracle.pnp_ransac(pb, oracle.params(**prm), oracle.index_table(int(seeds[c]), n, 4, H))
+        o = oracle.pnp_ransac(pb, oracle.params(**prm), oracle.index_table(int(seeds[c]), n, 4, H), oracle.FLAG_EPNP_QR_NULLSPACE)
         _check_results(res[c:c + 1], ml[c:c + 1], [o])
 
 
