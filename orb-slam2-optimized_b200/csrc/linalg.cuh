@@ -217,6 +217,98 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
         for (int k = 0; k < NV; ++k) v[i * NV + k] = x[k][i];
 }
 
+#ifdef __CUDACC__
+// Warp-cooperative schedule of jacobi_lowest<N,NV> for the refine stage (one problem per CTA, warp 0):
+// the same cyclic rotation order, the same rotation parameters and the same per-element arithmetic --
+// only the 2(N-2) independent element updates of one rotation are spread over lanes 0..N-1 and the NV
+// back-substitutions over lanes 0..NV-1, so the result is bit-identical to the serial routine.
+// a: packed upper triangle in SHARED memory (destroyed); w: NV smallest eigenvalues; v: N x NV
+// (row-major) in shared memory; rec: kMaxSweepsRec*N(N-1)/2 double2 in shared memory.
+// Loops are real loops (indices are data here, not register names): ~2 KB of code instead of the
+// fully unrolled 200 KB the register-resident version needs.
+template <int N, int NV>
+__device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, double2* rec, int lane)
+{
+    constexpr int NP = N * (N - 1) / 2;
+    constexpr unsigned FULL = 0xffffffffu;
+    double fro2 = 0.0;
+    if (lane == 0) {
+        for (int i = 0; i < N; ++i)
+            for (int j = i; j < N; ++j) fro2 += a[tri_idx(N, i, j)] * a[tri_idx(N, i, j)];
+    }
+    fro2 = __shfl_sync(FULL, fro2, 0);
+    const double tol = sqrt(fro2) * 0x1p-56;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < kMaxSweepsRec; ++sweep) {
+        bool rotated = false;
+        double2* rs = rec + sweep * NP;
+        int slot = 0;
+        for (int p = 0; p < N - 1; ++p) {
+            for (int q = p + 1; q < N; ++q, ++slot) {
+                const int ipp = tri_idx(N, p, p), iqq = tri_idx(N, q, q), ipq = tri_idx(N, p, q);
+                const double apq = a[ipq];
+                double c = 1.0, s = 0.0;
+                if (fabs(apq) > tol) {                       // warp-uniform
+                    rotated = true;
+                    double napp, naqq;
+                    jacobi_angle<double>(a[ipp], a[iqq], apq, c, s, napp, naqq);
+                    __syncwarp();                            // all lanes have read (pp, qq, pq)
+                    if (lane == 0) { a[ipp] = napp; a[iqq] = naqq; a[ipq] = 0.0; }
+                    if (lane < N && lane != p && lane != q) {
+                        const int j = lane;
+                        const int ip = (j < p) ? tri_idx(N, j, p) : tri_idx(N, p, j);
+                        const int iq = (j < q) ? tri_idx(N, j, q) : tri_idx(N, q, j);
+                        const double g = a[ip], k = a[iq];
+                        a[ip] = c * g - s * k;
+                        a[iq] = s * g + c * k;
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) rs[slot] = make_double2(c, s);
+            }
+        }
+        if (!rotated) break;
+        sweeps = sweep + 1;
+    }
+    __syncwarp();
+    // the NV smallest diagonal entries, ascending, ties to the lower index
+    int sel = -1;
+    {
+        unsigned usedmask = 0u;
+        for (int k = 0; k < NV; ++k) {
+            int best = -1;
+            double bv = 0.0;
+            for (int i = 0; i < N; ++i) {
+                if ((usedmask >> i) & 1u) continue;
+                const double di = a[tri_idx(N, i, i)];
+                if (best < 0 || di < bv) { best = i; bv = di; }
+            }
+            usedmask |= 1u << best;
+            if (lane == k) sel = best;
+            if (lane == 0) w[k] = bv;
+        }
+    }
+    if (lane < NV) {
+        for (int i = 0; i < N; ++i) v[i * NV + lane] = (i == sel) ? 1.0 : 0.0;
+        for (int sweep = sweeps - 1; sweep >= 0; --sweep) {
+            const double2* rs = rec + sweep * NP;
+            for (int p = N - 2; p >= 0; --p) {
+                for (int q = N - 1; q > p; --q) {
+                    const int slot = p * N - (p * (p + 1)) / 2 + (q - p - 1);
+                    const double2 cs = rs[slot];
+                    if (cs.y != 0.0) {
+                        const double xp = v[p * NV + lane], xq = v[q * NV + lane];
+                        v[p * NV + lane] = cs.x * xp + cs.y * xq;
+                        v[q * NV + lane] = cs.x * xq - cs.y * xp;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+#endif  // __CUDACC__
+
 // Orthonormal basis of the null space of an 8 x 12 matrix M (4-point EPnP) by Householder QR of
 // A = M^T (12 x 8, row-major A[r*8+c], destroyed): null(M) = last four columns of Q = H0..H7 e_{8..11}.
 // U4[r*4+i] = component r of basis vector i.  Operation order mirrors oracle/orc_linalg.c

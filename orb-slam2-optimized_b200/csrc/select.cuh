@@ -80,13 +80,13 @@ __device__ inline void cta_score_exact(const ProblemMeta* m, const SelectArgs& a
 
 // ------------------------------------------------------------------ EPnP refine
 struct EpnpShared {
-    double C0[3], A[9], cws[12], CCi[9], MtM[78], U4[48], betas[12];
+    double C0[3], A[9], cws[12], CCi[9], MtM[78], U4[48], betas[12], w4[4];
     double ccs[3][12], sign[3], pc0[3][3], pw0[3], M[3][9], R[3][9], t[3][3], rep[3];
 };
 
 // PnPsolver::Refine's compute_pose on the n selected points (PnPsolver.cpp:206-217, 359-415);
 // result as float R|t in pose_out[12] (shared)
-__device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, int n, EpnpShared& S, float* pose_out)
+__device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, int n, EpnpShared& S, double2* s_rec, float* pose_out)
 {
     const int tid = threadIdx.x;
     const Cam cam = {m->fx, m->fy, m->cx, m->cy};
@@ -142,16 +142,28 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         S.MtM[tri_idx(12, ea, eb)] = s;
     }
     __syncthreads();
-    if (tid == 0) {
-        double MtM[78];
-#pragma unroll
-        for (int i = 0; i < 78; ++i) MtM[i] = S.MtM[i];
-        if (n == 4 && !(a.flags & 8))   // RSAC_FLAG_EPNP_EIGEN clear: QR null space for a 4-point system
-            epnp_solve_betas_qr4(al, us, cam, S.cws, S.U4, S.betas);
-        else
-            epnp_solve_betas(MtM, S.cws, S.U4, S.betas, a.rec + (size_t)blockIdx.x * (kMaxSweepsRec * 66));
-        for (int k = 0; k < 3; ++k) epnp_ccs(S.betas + 4 * k, S.U4, S.ccs[k]);
+    if (n == 4 && !(a.flags & 8)) {                    // RSAC_FLAG_EPNP_EIGEN clear: QR null space for a 4-point system
+        if (tid == 0) epnp_solve_betas_qr4(al, us, cam, S.cws, S.U4, S.betas);
+    } else {
+        // 12x12 eigen-solve (:380): warp 0, cooperative schedule of the same rotations
+        if (tid < 32) jacobi_lowest_warp<12, 4>(S.MtM, S.w4, S.U4, s_rec, tid);
+        __syncthreads();
+        // the three beta approximations + Gauss-Newton (:395-405) are independent: one thread each, in three warps
+        if ((tid & 31) == 0 && tid < 96) {
+            const int kk = tid >> 5;
+            double L[60], rho[6], U4[48], bt[4];
+            for (int i = 0; i < 48; ++i) U4[i] = S.U4[i];
+            epnp_L_6x10(U4, L);
+            epnp_rho(S.cws, rho);
+            if (kk == 0) epnp_betas_approx_1(L, rho, bt);
+            else if (kk == 1) epnp_betas_approx_2(L, rho, bt);
+            else epnp_betas_approx_3(L, rho, bt);
+            epnp_gauss_newton(L, rho, bt);
+            for (int i = 0; i < 4; ++i) S.betas[4 * kk + i] = bt[i];
+        }
     }
+    __syncthreads();
+    if (tid < 3) epnp_ccs(S.betas + 4 * tid, S.U4, S.ccs[tid]);
     __syncthreads();
     if (tid < 3) {                                     // solve_for_sign on pcs(0,2) (:495-502)
         double pc[3];
@@ -209,7 +221,7 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
 
 // ----------------------------------------------------------------- MLPnP refine
 struct MlpnpShared {
-    double planarTest[9], eigenRot[9], AtPA[78], x[6], A[36], g[6], dx[6];
+    double planarTest[9], eigenRot[9], AtPA[78], x[6], A[36], g[6], dx[6], ev[1], result1[12];
     unsigned long long maxdl_bits;
     int planar, dec;
 };
@@ -228,7 +240,7 @@ __device__ inline void mlpnp_row_entry(const double* N, const double* pt, bool p
 
 // MLPnPsolver::Refine's computePose on the n selected observations (MLPnPsolver.cpp:269-290,
 // 321-623); result as double R|t in pose_out[12] (shared)
-__device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, int n, MlpnpShared& S, double* pose_out)
+__device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, int n, MlpnpShared& S, double2* s_rec, double* pose_out)
 {
     const int tid = threadIdx.x;
     const uint32_t* sel = a.sel + m->corr_off;
@@ -299,18 +311,14 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
         S.AtPA[tri_idx(cols, ea, eb)] = s;
     }
     __syncthreads();
+    if (tid < 32) {                                    // smallest eigenvector of A^T P A (:488-493), warp-cooperative
+        if (planar) jacobi_lowest_warp<9, 1>(S.AtPA, S.ev, S.result1, s_rec, tid);
+        else jacobi_lowest_warp<12, 1>(S.AtPA, S.ev, S.result1, s_rec, tid);
+    }
+    __syncthreads();
     if (tid == 0) {
-        double result1[12], ev[1];
-        double2* rec = a.rec + (size_t)blockIdx.x * (kMaxSweepsRec * 66);
-        if (planar) {
-            double T[45];
-            for (int i = 0; i < 45; ++i) T[i] = S.AtPA[i];
-            jacobi_lowest<9, 1>(T, ev, result1, rec);
-        } else {
-            double T[78];
-            for (int i = 0; i < 78; ++i) T[i] = S.AtPA[i];
-            jacobi_lowest<12, 1>(T, ev, result1, rec);
-        }
+        double result1[12];
+        for (int i = 0; i < 12; ++i) result1[i] = S.result1[i];
         // first six observations for the +-t / 4-candidate test (:547-551, :590-594)
         double p6[18], f6[18];
         for (int q = 0; q < 6; ++q)
@@ -396,6 +404,7 @@ __global__ void __launch_bounds__(kSelectThreads, 4) ransac_select_kernel(Select
     __shared__ int s_found, s_cnt;
     __shared__ PT s_pose[12], s_bestpose[12];
     __shared__ typename std::conditional<MODEL == 0, EpnpShared, MlpnpShared>::type S;
+    __shared__ double2 s_rec[kMaxSweepsRec * 66];       // recorded rotations of the refine eigen-solve
 
     ResultRec res;
     res.ok = 0; res.no_more = 0; res.n_inliers = 0; res.best_hyp = -1; res.refined = 0; res.n_refines = 0;
@@ -492,8 +501,8 @@ __global__ void __launch_bounds__(kSelectThreads, 4) ransac_select_kernel(Select
                 lastRefH = h;
             }
         } else if (bestH != lastRefBestH) {
-            if constexpr (MODEL == 0) refine_epnp(m, a, mSel, S, s_pose);
-            else refine_mlpnp(m, a, mSel, S, s_pose);
+            if constexpr (MODEL == 0) refine_epnp(m, a, mSel, S, s_rec, s_pose);
+            else refine_mlpnp(m, a, mSel, S, s_rec, s_pose);
             cta_score_exact<MODEL>(m, a, s_pose, refmask, &s_cnt);   // :220
             lastCntR = s_cnt;
             lastRefBestH = bestH;
