@@ -256,6 +256,8 @@ int rsac_nccl_destroy(rsac_engine* e);
 /* The device numerical core compiled for the host (same templates, same arithmetic
  * contract).  Test-only: lets the CPU test-suite compare the solver source with the
  * oracle bit-for-bit without a GPU.  Not a fallback: nothing in the engine calls these. */
+/* diagnostic: clock64() stamps of the replay kernel's phases (block 0 of the last launch) */
+int rsac_debug_select_clocks(rsac_engine* e, long long out[16]);
 int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3]);
 /* the same with the default QR null space (RSAC_FLAG_EPNP_EIGEN clear) */
 int rsac_debug_host_epnp4_qr(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3]);

@@ -38,15 +38,17 @@ def _newer(src_dir: str, out: str) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _newer(CSRC, OUT):
-        return OUT
+    out = os.environ.get("RSAC_LIB_OUT", OUT)            # tuning variants: another file name, extra -D flags
+    extra = os.environ.get("RSAC_EXTRA_NVCC", "").split()
+    if not force and not extra and not _newer(CSRC, out):
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc, "-shared", "-o", OUT, "-std=c++17", "-O3", "-lineinfo",
+    cmd = [nvcc, "-shared", "-o", out, "-std=c++17", "-O3", "-lineinfo",
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
            "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O3",
-           "-cudart", "static"] + srcs + ["-ldl"]
+           "-cudart", "static"] + extra + srcs + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -55,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libransac_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

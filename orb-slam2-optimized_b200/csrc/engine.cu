@@ -840,6 +840,14 @@ int rsac_debug_host_epnp4_qr(const double K[4], const float p3d[12], const float
     return RSAC_OK;
 }
 
+int rsac_debug_select_clocks(rsac_engine* e, long long out[16])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_select_clocks, sizeof(long long) * 16));
+    return RSAC_OK;
+}
+
 int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48])
 {
     double A[78];

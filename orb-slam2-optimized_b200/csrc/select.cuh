@@ -51,6 +51,14 @@ struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
 static_assert(sizeof(ResultRec) == 96, "rsac_result layout");
 
 constexpr int kSelectThreads = 128;
+#ifndef RSAC_SELECT_CTAS
+#define RSAC_SELECT_CTAS 7
+#endif
+constexpr int kSelectCtasPerSm = RSAC_SELECT_CTAS;   // 7 x 148 = 1036 resident candidates: a 1024-candidate sweep is one wave
+
+// diagnostic: clock64() at phase boundaries of block 0 (rsac_debug_select_clocks)
+__device__ long long g_select_clocks[16];
+#define RSAC_SEL_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_select_clocks[i] = clock64(); } while (0)
 constexpr int kMlpnpScratch = 33;   // doubles per selected observation
 
 // exact CheckInliers of one pose over all correspondences of the problem by the whole CTA
@@ -94,6 +102,7 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     double* pw = a.pw_s + (size_t)m->corr_off * 3;
     double* us = a.us_s + (size_t)m->corr_off * 2;
     double* al = a.al_s + (size_t)m->corr_off * 4;
+    RSAC_SEL_MARK(2);
     for (int i = tid; i < n; i += blockDim.x) {       // add_correspondence
         const size_t g = (size_t)m->corr_off + sel[i];
         const float4 c = a.cA[g];
@@ -127,6 +136,7 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) epnp_alphas(pw + 3 * i, S.cws, S.CCi, al + 4 * i);
     __syncthreads();
+    RSAC_SEL_MARK(3);
     if (tid < 78) {                                    // MtM upper triangle, one entry per thread (:379)
         int ea = 0, rem = tid;
         while (rem >= 12 - ea) { rem -= 12 - ea; ++ea; }
@@ -142,12 +152,14 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         S.MtM[tri_idx(12, ea, eb)] = s;
     }
     __syncthreads();
+    RSAC_SEL_MARK(4);
     if (n == 4 && !(a.flags & 8)) {                    // RSAC_FLAG_EPNP_EIGEN clear: QR null space for a 4-point system
         if (tid == 0) epnp_solve_betas_qr4(al, us, cam, S.cws, S.U4, S.betas);
     } else {
         // 12x12 eigen-solve (:380): warp 0, cooperative schedule of the same rotations
         if (tid < 32) jacobi_lowest_warp<12, 4>(S.MtM, S.w4, S.U4, s_rec, tid);
         __syncthreads();
+        RSAC_SEL_MARK(5);
         // the three beta approximations + Gauss-Newton (:395-405) are independent: one thread each, in three warps
         if ((tid & 31) == 0 && tid < 96) {
             const int kk = tid >> 5;
@@ -163,6 +175,7 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         }
     }
     __syncthreads();
+    RSAC_SEL_MARK(6);
     if (tid < 3) epnp_ccs(S.betas + 4 * tid, S.U4, S.ccs[tid]);
     __syncthreads();
     if (tid < 3) {                                     // solve_for_sign on pcs(0,2) (:495-502)
@@ -202,6 +215,7 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         S.M[k][r * 3 + c] = s;
     }
     __syncthreads();
+    RSAC_SEL_MARK(7);
     if (tid < 3) {
         epnp_horn(S.M[tid], S.pc0[tid], S.pw0, S.R[tid], S.t[tid]);
         double sum2 = 0.0;                             // reprojection_error (:417-431)
@@ -390,7 +404,7 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
 
 // ------------------------------------------------------------- the replay kernel
 template <int MODEL>
-__global__ void __launch_bounds__(kSelectThreads, 4) ransac_select_kernel(SelectArgs a)
+__global__ void __launch_bounds__(kSelectThreads, kSelectCtasPerSm) ransac_select_kernel(SelectArgs a)
 {
     using PT = typename ScoreModel<MODEL>::pose_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -413,6 +427,7 @@ __global__ void __launch_bounds__(kSelectThreads, 4) ransac_select_kernel(Select
     res.t[0] = res.t[1] = res.t[2] = 0.0f; res.s = 1.0f;
     res.problem = a.problem_base + blockIdx.x; res.reserved[0] = res.reserved[1] = 0;
 
+    RSAC_SEL_MARK(0);
     const int N = m->n, H = m->H, minInl = m->min_inl;
     uint32_t* final_mask = a.masks + m->word_off;
     const int32_t* counts = a.counts + m->hyp_off;
@@ -487,6 +502,7 @@ __global__ void __launch_bounds__(kSelectThreads, 4) ransac_select_kernel(Select
         }
         if (h >= H) break;
 
+        RSAC_SEL_MARK(1);
         if (counts[h] > best) set_best(h);   // :149 strict: first maximum wins (Refine uses this set, :195-204)
         res.n_refines++;
 
@@ -503,7 +519,9 @@ __global__ void __launch_bounds__(kSelectThreads, 4) ransac_select_kernel(Select
         } else if (bestH != lastRefBestH) {
             if constexpr (MODEL == 0) refine_epnp(m, a, mSel, S, s_rec, s_pose);
             else refine_mlpnp(m, a, mSel, S, s_rec, s_pose);
+            RSAC_SEL_MARK(8);
             cta_score_exact<MODEL>(m, a, s_pose, refmask, &s_cnt);   // :220
+            RSAC_SEL_MARK(9);
             lastCntR = s_cnt;
             lastRefBestH = bestH;
         }
@@ -534,6 +552,7 @@ __global__ void __launch_bounds__(kSelectThreads, 4) ransac_select_kernel(Select
     }
     res.best_hyp = bestH;
     res.best_count = best;
+    RSAC_SEL_MARK(10);
     if (tid == 0) {
         reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
         if (a.results2) reinterpret_cast<ResultRec*>(a.results2)[blockIdx.x] = res;

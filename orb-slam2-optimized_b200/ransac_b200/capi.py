@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libransac_b200.so")
+LIB_PATH = os.environ.get("RSAC_LIB", os.path.join(_PKG, "libransac_b200.so"))   # RSAC_LIB: tuning variants only
 _LIB = None
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = range(6)

@@ -63,3 +63,15 @@ for want in (True, False):
     ev = H * N / (ms * 1e-3)
     print("cfg5 masks=%s: %.4f ms, %.3g evals/s, %.2f TFLOP/s (31 FLOP/eval), exact evals %d (%.2e)" %
           (want, ms, ev, ev * 31 / 1e12, eng.score_exact_evals(), eng.score_exact_evals() / (H * N)))
+
+# phase clocks of the replay kernel (block 0)
+import ctypes
+clk = (ctypes.c_longlong * 16)()
+eng.profile_enable(False)
+eng.pnp_upload(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], prm, seeds=b["seeds"])
+eng.pnp_run()
+eng.sync()
+eng.L.rsac_debug_select_clocks(eng.h, clk)
+c = list(clk)
+names = ["start", "found", "refine:begin", "presums", "MtM", "jacobi", "betas", "sums2", "horn+reproj", "score", "end"]
+print("select phases (block 0, cycles):", [(names[i], c[i] - c[i - 1]) for i in range(1, 11)], "total", c[10] - c[0])
