@@ -510,7 +510,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     RSAC_TRY(s.d_pw.ensure(e, tot * 24));
     RSAC_TRY(s.d_us.ensure(e, tot * 16));
     RSAC_TRY(s.d_al.ensure(e, tot * 32));
-    RSAC_TRY(s.d_extra.ensure(e, sizeof(double2) * (size_t)(kMaxSweepsRec * 66) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_extra.ensure(e, tot * 96));   // refine scratch: 12 doubles per correspondence
 
     cudaStream_t st = e->stream;
     RSAC_TRY(stage_small_tables(e, s, th2));
@@ -544,7 +544,7 @@ static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume,
     SelectArgs a;
     a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.cC = (const float4*)s.d_uv.p;
     a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = nullptr; a.flags = flags; a.resume = d_resume;
-    a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p; a.rec = (double2*)s.d_extra.p;
+    a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p; a.tm_s = (double*)s.d_extra.p;
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;

@@ -35,7 +35,7 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
     RSAC_TRY(s.d_masks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_words, 1)));
     RSAC_TRY(s.d_sel.ensure(e, tot * 4));
     RSAC_TRY(s.d_pw.ensure(e, tot * sizeof(double) * kMlpnpScratch));
-    RSAC_TRY(s.d_extra.ensure(e, sizeof(double2) * (size_t)(kMaxSweepsRec * 66) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_extra.ensure(e, tot * 96));   // refine scratch: 12 doubles per correspondence
     if (b->cov) RSAC_TRY(s.d_cov.ensure(e, tot * 72));
 
     cudaStream_t st = e->stream;
@@ -70,7 +70,7 @@ static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resum
     SelectArgs a;
     a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.cC = (const float4*)s.d_uv.p;
     a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = s.have_cov ? (const double*)s.d_cov.p : nullptr;
-    a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = nullptr; a.al_s = nullptr; a.rec = (double2*)s.d_extra.p;
+    a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = nullptr; a.al_s = nullptr; a.tm_s = (double*)s.d_extra.p;
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base; a.flags = flags; a.resume = d_resume;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;

@@ -15,10 +15,9 @@
 //   * two-tier evaluation.  Fast path, division-free: with (x,y,z) = P X,
 //         D = (x + (cx-u) z)^2 + (y + (cy-v) z)^2 - thr z^2      (= z^2 (e - thr))
 //     is formed with 15 FFMA/FMUL; sign(D) is the provisional inlier bit.  A rigorous bound
-//     band*|z| on |D_fast - D_reference| (pack kernel below, derivation in DESIGN.md) marks the
-//     evaluations that are too close to call: |D| <= band |z|, or thr z^2 <= band |z| (point on
-//     the camera plane).  Only those are re-evaluated with the reference's exact operation
-//     sequence, from shared memory.  Result: the reference's inlier bit for every pair;
+//     band*|z| + eps2 on |D_fast - D_reference| (pack kernel below, derivation in DESIGN.md) marks the
+//     evaluations that are too close to call.  Only those are re-evaluated with the reference's exact
+//     operation sequence, from shared memory.  Result: the reference's inlier bit for every pair;
 //   * bits are shifted into per-lane 32-bit words (one SHF per evaluation), counted with POPC and
 //     optionally stored as the hypothesis' bitmask.
 #pragma once
@@ -115,7 +114,7 @@ template <> struct ScoreModel<1> {
 
 // Folded, scaled projective rows of one hypothesis: c[0..3] = fx*[r0|t0]/B, c[4..7] = fy*[r1|t1]/B,
 // c[8..11] = [r2|t2]/B with B = max_row|r|_1 + |t|_inf.  A non-finite or zero pose gets an all-zero
-// matrix: z = 0 for every point, which the band test sends to the exact path.
+// matrix: D = 0 for every point, which the certainty test (|D| > eps2) sends to the exact path.
 template <typename PT>
 __device__ __forceinline__ void fold_pose(const PT* __restrict__ r, float fx, float fy, float* c)
 {
@@ -147,13 +146,14 @@ __device__ __forceinline__ void fold_pose(const PT* __restrict__ r, float fx, fl
 // bit) and sign(t) (t >= 0: too close to call) into the lane's words, most significant position first:
 // call for p = 15 .. 0.  Component-wise the operation sequence is
 //   x = fma(c0,X,fma(c1,Y,fma(c2,Z,c3))) (same for y, z);  N = fma(cu,z,x);  M = fma(cv,z,y);
-//   q = thr*(z*z);  D = fma(M,M,fma(N,N,-q));  t = fma(band,|z|,-min(|D|,q))
+//   q = thr*(z*z);  D = fma(M,M,fma(N,N,-q));  t = fma(band,|z|,eps2-|D|)
 // which is what the band derivation in DESIGN.md assumes.
 __device__ __forceinline__ void eval_pair(const float2* C, const float4& q0, const float4& q1, const float4& q2,
-                                          const float2& band, uint32_t& inl, uint32_t& cert)
+                                          const float4& q3, uint32_t& inl, uint32_t& cert)
 {
     const float2 X = make_float2(q0.x, q0.y), Y = make_float2(q0.z, q0.w), Z = make_float2(q1.x, q1.y);
     const float2 cu = make_float2(q1.z, q1.w), cv = make_float2(q2.x, q2.y), nthr = make_float2(q2.z, q2.w);
+    const float2 band = make_float2(q3.x, q3.y), eps2 = make_float2(q3.z, q3.w);
     const float2 x = __ffma2_rn(C[0], X, __ffma2_rn(C[1], Y, __ffma2_rn(C[2], Z, C[3])));
     const float2 y = __ffma2_rn(C[4], X, __ffma2_rn(C[5], Y, __ffma2_rn(C[6], Z, C[7])));
     const float2 z = __ffma2_rn(C[8], X, __ffma2_rn(C[9], Y, __ffma2_rn(C[10], Z, C[11])));
@@ -161,12 +161,10 @@ __device__ __forceinline__ void eval_pair(const float2* C, const float4& q0, con
     const float2 M = __ffma2_rn(cv, z, y);
     const float2 nq = __fmul2_rn(nthr, __fmul2_rn(z, z));  // -thr z^2
     const float2 D = __ffma2_rn(M, M, __ffma2_rn(N, N, nq));   // z^2 (e - thr)
-    const float m1 = fminf(fabsf(D.y), -nq.y);             // thr z^2 <= band|z|: point on the camera plane
-    const float t1 = fmaf(band.y, fabsf(z.y), -m1);        // >= 0 (or NaN): inside the rounding band
+    const float t1 = fmaf(band.y, fabsf(z.y), eps2.y - fabsf(D.y));   // >= 0 (or NaN): inside the rounding band
     inl = __funnelshift_l(__float_as_uint(D.y), inl, 1);   // sign(D): e < thr   (NaN results are +qNaN: bit clear)
     cert = __funnelshift_l(__float_as_uint(t1), cert, 1);  // sign(t) set: decision is certain
-    const float m0 = fminf(fabsf(D.x), -nq.x);
-    const float t0 = fmaf(band.x, fabsf(z.x), -m0);
+    const float t0 = fmaf(band.x, fabsf(z.x), eps2.x - fabsf(D.x));
     inl = __funnelshift_l(__float_as_uint(D.x), inl, 1);
     cert = __funnelshift_l(__float_as_uint(t0), cert, 1);
 }
@@ -327,10 +325,9 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
                 const float4* pp = sP + w * 64;
 #pragma unroll
                 for (int p = 15; p >= 0; --p) {
-                    const float4 q0 = pp[4 * p], q1 = pp[4 * p + 1], q2 = pp[4 * p + 2];
-                    const float2 bd = *reinterpret_cast<const float2*>(pp + 4 * p + 3);
+                    const float4 q0 = pp[4 * p], q1 = pp[4 * p + 1], q2 = pp[4 * p + 2], q3 = pp[4 * p + 3];
 #pragma unroll
-                    for (int s = 0; s < HPL; ++s) eval_pair(C[s], q0, q1, q2, bd, inl[s], cert[s]);
+                    for (int s = 0; s < HPL; ++s) eval_pair(C[s], q0, q1, q2, q3, inl[s], cert[s]);
                 }
                 const int rem = nc - w * 32;
                 const uint32_t valid = (rem >= 32) ? 0xffffffffu : ((1u << rem) - 1u);
@@ -364,28 +361,42 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
     if (cur_k >= 0) flush();
 }
 
-// ---- packing: raw correspondences -> (cA, cB, cC) records with thresholds and rounding bands ----
-// band_i * |z| bounds |D_fast - z^2 (e_reference - thr)| for an evaluation that is near the threshold
-// (derivation in DESIGN.md).  With u = 2^-24, M = 1 + |X|_inf, s = sqrt(thr),
-// q = 1 + (|c|_inf + s)/f_min, c = (cx-u, cy-v):
-//   band = 2 u M [ s ((12 + 8 q)(fx + fy) + 16 (|cu| + |cv|) + 2 (|u| + |v|)) + 33 thr ]
-// and at least thr * 2^-10 * M, which makes "thr z^2 <= band |z|" cover |z| <= 2^-10 M (cancellation guard).
-__device__ __forceinline__ float score_band(float X, float Y, float Z, float cu, float cv, float u, float v,
-                                            float thr, float fx, float fy)
+// ---- packing: raw correspondences -> records with thresholds and rounding bounds ----
+// With u = 2^-24, M = 1 + |X|_inf, s = sqrt(thr), q = 1 + (|c|_inf + s)/f_min, c = (cx-u, cy-v), and all
+// quantities in the kernel's scaled units (rows of K[R|t] divided by B, so |z| <= M, |x| <= fx M, |y| <= fy M):
+//   * both sides evaluate N = x + cu z (resp. M) with an ABSOLUTE error <= eps_a = 12 u M (f_max + |c|_inf +
+//     |uv|_inf + s), whatever z is: the reference's z_ref^2 * error2 equals (N_ref')^2 + (M_ref')^2 with
+//     N_ref' = fx xc + cu zc + O(u)(fx|xc| + |zc||ue|) -- the division by zc cancels;
+//   * if R = sqrt(N^2 + M^2) >= s|z| + 3 eps_a both D_fast and D_ref are positive (outlier, certain);
+//   * otherwise |N|, |M| <= s|z| + 3 eps_a and
+//         |D_fast - z^2 (e_ref - thr)| <= band |z| + eps2,
+//     band = 2 u M [ s((12 + 8 q)(fx + fy) + 16(|cu| + |cv|) + 2(|u| + |v|)) + 33 thr ]   (first-order terms,
+//     >= 30 % head-room over the term-by-term derivation in DESIGN.md),  eps2 = 10 eps_a^2  (second-order).
+// An evaluation is certain iff |D| > band |z| + eps2.  No separate guard for points on the camera plane is
+// needed: there |z| -> 0 and the test degenerates to |D| > eps2, i.e. N, M must be clearly non-zero.
+struct ScoreBounds { float band, eps2; };
+
+__device__ __forceinline__ ScoreBounds score_bounds(float X, float Y, float Z, float cu, float cv, float u, float v,
+                                                    float thr, float fx, float fy)
 {
     const double uro = (double)kUnitRoundoff;
     const double M = 1.0 + fmax(fabs((double)X), fmax(fabs((double)Y), fabs((double)Z)));
     const double th = fmax((double)thr, 0.0);
     const double s = sqrt(th);
     const double fmin_ = fmin(fabs((double)fx), fabs((double)fy));
+    const double fmax_ = fmax(fabs((double)fx), fabs((double)fy));
     const double cinf = fmax(fabs((double)cu), fabs((double)cv));
+    const double uvinf = fmax(fabs((double)u), fabs((double)v));
     const double q = 1.0 + (cinf + s) / fmin_;
-    double band = 2.0 * uro * M * (s * ((12.0 + 8.0 * q) * (fabs((double)fx) + fabs((double)fy)) +
-                                        16.0 * (fabs((double)cu) + fabs((double)cv)) + 2.0 * (fabs((double)u) + fabs((double)v))) +
-                                   33.0 * th);
-    band = fmax(band, th * 0x1p-10 * M);
-    // round up to float; NaN/inf inputs give a NaN/inf band => those evaluations take the exact path
-    return __double2float_ru(band);
+    const double band = 2.0 * uro * M * (s * ((12.0 + 8.0 * q) * (fabs((double)fx) + fabs((double)fy)) +
+                                              16.0 * (fabs((double)cu) + fabs((double)cv)) + 2.0 * (fabs((double)u) + fabs((double)v))) +
+                                         33.0 * th);
+    const double eps_a = 12.0 * uro * M * (fmax_ + cinf + uvinf + s);
+    // round up to float; NaN/inf inputs give NaN/inf bounds => those evaluations take the exact path
+    ScoreBounds r;
+    r.band = __double2float_ru(band);
+    r.eps2 = __double2float_ru(fmax(10.0 * eps_a * eps_a, 1e-30));
+    return r;
 }
 
 // One thread per correspondence pair; blockIdx.y = problem.  thr = sigma2*th2 as an f32 product
@@ -395,9 +406,9 @@ __device__ __forceinline__ float score_band(float X, float Y, float Z, float cu,
 //       corr_off + i -- minimal solvers, refinement and the exact path read these;
 //   cP: the scoring kernel's stream, 64 B per PAIR of correspondences (2p, 2p+1) so that every operand of
 //       the packed-FP32 evaluation is an aligned register pair straight out of LDS.128:
-//         [X0 X1 Y0 Y1] [Z0 Z1 cu0 cu1] [cv0 cv1 -thr0 -thr1] [band0 band1 0 0]
+//         [X0 X1 Y0 Y1] [Z0 Z1 cu0 cu1] [cv0 cv1 -thr0 -thr1] [band0 band1 eps2_0 eps2_1]
 //       indexed by (word_off*16 + p); a problem's tail is zero-padded to a whole 32-correspondence word.
-struct PackedPoint { float X, Y, Z, cu, cv, thr, band, u, v; };
+struct PackedPoint { float X, Y, Z, cu, cv, thr, band, eps2, u, v; };
 
 __device__ __forceinline__ PackedPoint pack_point(const ProblemMeta& m, size_t g, const float* p3d, const float* p2d,
                                                   const float* sigma2, float th2, const float* max_err, int model)
@@ -416,7 +427,8 @@ __device__ __forceinline__ PackedPoint pack_point(const ProblemMeta& m, size_t g
         r.cv = m.k1[3] - r.v;
         fx = m.k1[0]; fy = m.k1[1];
     }
-    r.band = score_band(r.X, r.Y, r.Z, r.cu, r.cv, r.u, r.v, r.thr, fx, fy);
+    const ScoreBounds sb = score_bounds(r.X, r.Y, r.Z, r.cu, r.cv, r.u, r.v, r.thr, fx, fy);
+    r.band = sb.band; r.eps2 = sb.eps2;
     return r;
 }
 
@@ -428,7 +440,7 @@ __global__ void pack_pnp_kernel(const ProblemMeta* metas, const float* p3d, cons
     const float th2 = th2_per_problem ? th2_per_problem[blockIdx.y] : 0.0f;
     const int npairs = m.words * 16;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
-        PackedPoint a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b = a;
+        PackedPoint a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b = a;
         const int i0 = 2 * p, i1 = 2 * p + 1;
         if (i0 < m.n) {
             const size_t g = (size_t)m.corr_off + i0;
@@ -448,7 +460,7 @@ __global__ void pack_pnp_kernel(const ProblemMeta* metas, const float* p3d, cons
         dst[0] = make_float4(a.X, b.X, a.Y, b.Y);
         dst[1] = make_float4(a.Z, b.Z, a.cu, b.cu);
         dst[2] = make_float4(a.cv, b.cv, -a.thr, -b.thr);
-        dst[3] = make_float4(a.band, b.band, 0.0f, 0.0f);
+        dst[3] = make_float4(a.band, b.band, a.eps2, b.eps2);
     }
 }
 

@@ -33,7 +33,7 @@ struct SelectArgs {
     double* pw_s;            // EPnP [total][3]          MLPnP: [total][33] f3 p3 N6 P4 q3 J12 r2
     double* us_s;            // EPnP [total][2]
     double* al_s;            // EPnP [total][4]
-    double2* rec;            // [C][kMaxSweepsRec*66] recorded Jacobi rotations of the refine solve
+    double* tm_s;            // EPnP [total][12]: per-point pcs of the three candidates (9) + reprojection terms (3)
     // outputs
     void* results;           // rsac_result[C] (layout in ransac_b200.h)
     void* results2;          // optional second copy (collective send buffer)
@@ -137,19 +137,40 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     for (int i = tid; i < n; i += blockDim.x) epnp_alphas(pw + 3 * i, S.cws, S.CCi, al + 4 * i);
     __syncthreads();
     RSAC_SEL_MARK(3);
-    if (tid < 78) {                                    // MtM upper triangle, one entry per thread (:379)
-        int ea = 0, rem = tid;
-        while (rem >= 12 - ea) { rem -= 12 - ea; ++ea; }
-        const int eb = ea + rem;
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) {
-            double a0, a1, b0, b1;
-            epnp_m_entry(al + 4 * i, us[2 * i], us[2 * i + 1], cam, ea, a0, a1);
-            epnp_m_entry(al + 4 * i, us[2 * i], us[2 * i + 1], cam, eb, b0, b1);
-            s += a0 * b0;
-            s += a1 * b1;
+    {                                                  // MtM upper triangle, one entry per thread (:379)
+        // alphas and pixels are staged through shared memory in tiles; every entry still adds its
+        // per-point products in index order
+        __shared__ double s_tile[kSelectThreads * 6];
+        int ea = 0, eb = 0;
+        if (tid < 78) {
+            int rem = tid;
+            while (rem >= 12 - ea) { rem -= 12 - ea; ++ea; }
+            eb = ea + rem;
         }
-        S.MtM[tri_idx(12, ea, eb)] = s;
+        double acc = 0.0;
+        for (int base = 0; base < n; base += kSelectThreads) {
+            const int cnt = min(kSelectThreads, n - base);
+            __syncthreads();
+            if (tid < cnt) {
+                const int i = base + tid;
+                s_tile[tid * 6 + 0] = al[4 * i + 0]; s_tile[tid * 6 + 1] = al[4 * i + 1];
+                s_tile[tid * 6 + 2] = al[4 * i + 2]; s_tile[tid * 6 + 3] = al[4 * i + 3];
+                s_tile[tid * 6 + 4] = us[2 * i]; s_tile[tid * 6 + 5] = us[2 * i + 1];
+            }
+            __syncthreads();
+            if (tid < 78) {
+#pragma unroll 4
+                for (int i = 0; i < cnt; ++i) {
+                    const double* t6 = s_tile + i * 6;
+                    double a0, a1, b0, b1;
+                    epnp_m_entry(t6, t6[4], t6[5], cam, ea, a0, a1);
+                    epnp_m_entry(t6, t6[4], t6[5], cam, eb, b0, b1);
+                    acc += a0 * b0;
+                    acc += a1 * b1;
+                }
+            }
+        }
+        if (tid < 78) S.MtM[tri_idx(12, ea, eb)] = acc;
     }
     __syncthreads();
     RSAC_SEL_MARK(4);
@@ -184,16 +205,23 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         S.sign[tid] = (pc[2] < 0.0) ? -1.0 : 1.0;
     }
     __syncthreads();
-    if (tid < 9) {                                     // pc0 of the three candidates (:435,438)
-        const int k = tid / 3, c = tid % 3;
-        const bool neg = S.sign[k] < 0.0;
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) {
+    double* tm = a.tm_s + (size_t)m->corr_off * 12;
+    for (int i = tid; i < n; i += blockDim.x) {        // pcs of the three candidates, sign applied (:354-357, :495-502)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
             double pc[3];
             epnp_pc(al + 4 * i, S.ccs[k], pc);
-            s += neg ? -pc[c] : pc[c];
+            const bool neg = S.sign[k] < 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tm[(size_t)i * 12 + 3 * k + c] = neg ? -pc[c] : pc[c];
         }
-        S.pc0[k][c] = s / (double)n;
+    }
+    __syncthreads();
+    if (tid < 9) {                                     // pc0 of the three candidates (:435,438)
+        double s = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) s += tm[(size_t)i * 12 + tid];
+        S.pc0[tid / 3][tid % 3] = s / (double)n;
     } else if (tid < 12) {                             // pw0 (:436,439)
         const int c = tid - 9;
         double s = 0.0;
@@ -204,22 +232,26 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     __syncthreads();
     if (tid < 27) {                                    // M = sum (pc-pc0)^T (pw-pw0) (:443-447)
         const int k = tid / 9, r = (tid % 9) / 3, c = tid % 3;
-        const bool neg = S.sign[k] < 0.0;
+        const double p0 = S.pc0[k][r], w0 = S.pw0[c];
         double s = 0.0;
-        for (int i = 0; i < n; ++i) {
-            double pc[3];
-            epnp_pc(al + 4 * i, S.ccs[k], pc);
-            const double pcr = neg ? -pc[r] : pc[r];
-            s += (pcr - S.pc0[k][r]) * (pw[3 * i + c] - S.pw0[c]);
-        }
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) s += (tm[(size_t)i * 12 + 3 * k + r] - p0) * (pw[3 * i + c] - w0);
         S.M[k][r * 3 + c] = s;
     }
     __syncthreads();
     RSAC_SEL_MARK(7);
+    if (tid < 3) epnp_horn(S.M[tid], S.pc0[tid], S.pw0, S.R[tid], S.t[tid]);
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {        // reprojection_error terms (:417-431), summed in index order below
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            tm[(size_t)i * 12 + 9 + k] = epnp_reproj_term(S.R[k], S.t[k], pw + 3 * i, us[2 * i], us[2 * i + 1], cam);
+    }
+    __syncthreads();
     if (tid < 3) {
-        epnp_horn(S.M[tid], S.pc0[tid], S.pw0, S.R[tid], S.t[tid]);
-        double sum2 = 0.0;                             // reprojection_error (:417-431)
-        for (int i = 0; i < n; ++i) sum2 += epnp_reproj_term(S.R[tid], S.t[tid], pw + 3 * i, us[2 * i], us[2 * i + 1], cam);
+        double sum2 = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) sum2 += tm[(size_t)i * 12 + 9 + tid];
         S.rep[tid] = sum2 / (double)n;
     }
     __syncthreads();
