@@ -148,3 +148,53 @@ def test_score_pnp_bit_exact_small(engine, oracle):
         assert (capi.unpack_mask(masks, n) == om.astype(bool)).all(), (H, n)
         ex = engine.score_exact_evals()
         assert 0 <= ex <= H * n
+
+
+def test_score_pnp_adversarial_camera_plane_and_threshold(engine, oracle):
+    """The fast tier has no separate guard for points near the camera plane: its certainty test is
+    |D| > band|z| + eps2.  Stress exactly that regime -- camera centres placed on / next to world points
+    (x, y, z all ~ 0), points a hair in front of or behind the camera plane, poses scaled up and down by
+    2^+-20, and thresholds nudged so that many evaluations sit within an ulp of the decision boundary."""
+    rng = np.random.default_rng(77)
+    H, n = 192, 640
+    p = synth.scoring_stress(5900, H, n)
+    P3 = p["p3d"].astype(np.float32)
+    poses = p["poses"].copy()
+    for h in range(H):
+        R = poses[h, :9].reshape(3, 3).astype(np.float64)
+        k = rng.integers(0, n)
+        mode = h % 6
+        if mode == 0:      # camera centre at world point k, offset by 10^-e metres
+            d = rng.normal(size=3) * 10.0 ** (-rng.integers(0, 9))
+            poses[h, 9:] = (-(R @ P3[k].astype(np.float64)) + d).astype(np.float32)
+        elif mode == 1:    # point k on the camera plane up to rounding, others wherever they fall
+            t = poses[h, 9:].astype(np.float64)
+            t[2] = -(R[2] @ P3[k].astype(np.float64)) * (1.0 + rng.normal() * 1e-7)
+            poses[h, 9:] = t.astype(np.float32)
+        elif mode == 2:    # whole pose scaled: K[R|t]/B must be scale-free
+            poses[h] *= np.float32(2.0 ** rng.integers(-20, 21))
+        elif mode == 3:    # huge sideways translation: z stays small against B
+            poses[h, 9] += np.float32(10.0 ** rng.integers(2, 7))
+        elif mode == 4:    # tiny rotation rows, large t_z
+            poses[h, :9] *= np.float32(1e-4)
+            poses[h, 11] = np.float32(rng.uniform(1, 50))
+        # mode 5: unchanged (near ground truth)
+    # thresholds set to the reference's own error for one pose => evaluations exactly at / one ulp off the boundary
+    pb = oracle.pnp_problem(p["p3d"], p["p2d"], p["sigma2"], p["K"])
+    max_err = (p["sigma2"] * np.float32(5.991)).astype(np.float32)
+    ref = poses[5].astype(np.float64)
+    Xc = (P3.astype(np.float32) @ poses[5, :9].reshape(3, 3).T.astype(np.float32)) + poses[5, 9:]
+    with np.errstate(all="ignore"):
+        inv = np.float32(1) / Xc[:, 2]
+        ue = (p["K"][2] + p["K"][0] * Xc[:, 0].astype(np.float64) * inv.astype(np.float64)).astype(np.float32)
+        ve = (p["K"][3] + p["K"][1] * Xc[:, 1].astype(np.float64) * inv.astype(np.float64)).astype(np.float32)
+        e = ((ue - p["p2d"][:, 0]) ** 2 + (ve - p["p2d"][:, 1]) ** 2).astype(np.float32)
+    sel = np.isfinite(e) & (e > 0) & (e < 1e4)
+    nudged = max_err.copy()
+    nudged[sel] = np.nextafter(e[sel], np.where(rng.random(sel.sum()) < 0.5, np.float32(0), np.float32(np.inf))).astype(np.float32)
+    nudged[::7] = e[::7] if np.isfinite(e[::7]).all() else nudged[::7]
+    for thr in (max_err, nudged):
+        counts, masks = engine.score_pnp(poses, p["p3d"], p["p2d"], thr, p["K"])
+        oc, om = oracle.pnp_score(pb, thr, poses)
+        assert (counts == oc).all()
+        assert (capi.unpack_mask(masks, n) == om.astype(bool)).all()
