@@ -44,7 +44,7 @@ PRM = dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.2, th2=5.991
 H_HYP = 300
 METRIC = "relocalization candidates/s (PnP EPnP RANSAC sweep; hyp x corr evals/s in extras)"
 FLOP_PER_EVAL = 31            # PnP CheckInliers
-PIPE = int(os.environ.get("RSAC_BENCH_PIPE", "1"))   # sweeps in flight
+PIPE = int(os.environ.get("RSAC_BENCH_PIPE", "0"))   # sweeps in flight per GPU (0: default, one)
 
 
 def measured_peaks():
@@ -127,11 +127,12 @@ def run_reference(args):
     prm = O.params(**PRM)
     pbs = [O.pnp_problem(b["p3d"][c], b["p2d"][c], b["sigma2"][c], b["K"]) for c in range(C_TOTAL)]
     tables = [O.index_table(int(s), N_MATCH, 4, H_HYP) for s in b["seeds"]]
+    oflags = O.FLAG_EPNP_QR_NULLSPACE   # the port's faster mode (same arithmetic as the device path)
     for _ in range(max(1, min(args.warmup, 1))):
-        O.pnp_batch(pbs[:64], prm, tables[:64], 0, cores)
+        O.pnp_batch(pbs[:64], prm, tables[:64], oflags, cores)
     t_tot, ev_tot = 0.0, 0
     for _ in range(args.steps):
-        dt, ev, res = O.pnp_batch(pbs, prm, tables, 0, cores)
+        dt, ev, res = O.pnp_batch(pbs, prm, tables, oflags, cores)
         t_tot += dt
         ev_tot += ev
     val = C_TOTAL * args.steps / t_tot
@@ -141,7 +142,8 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": "cfg4", "candidates": C_TOTAL, "matches": N_MATCH,
                                             "hypotheses": H_HYP, "mode": "reference semantics (early exit)"},
             "cpu_baseline": {"value": val, "unit": "candidates/s", "cores": cores, "kind": "port",
-                             "sample": "full cfg4 sweep per step, one solver call per core (BASELINE.md mode B)",
+                             "sample": "full cfg4 sweep per step, one solver call per core (BASELINE.md mode B); "
+                                       "4-point null space by Householder QR as on the device (the port's faster mode)",
                              "evals_per_s": ev_tot / t_tot},
             "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -153,8 +155,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip cfg5/cfg1 side measurements and the CPU baseline")
     args = ap.parse_args()
@@ -177,6 +179,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
+    # sweeps in flight per GPU: one 1024-candidate sweep saturates the residency of one B200 (measured: more
+    # sweeps in flight only add contention), so one sweep at a time per GPU
+    global PIPE, C_TOTAL
+    if PIPE <= 0:
+        PIPE = 1
+    # weak scaling (task statement, section 5): the path shards by candidate with no data-path collective, so
+    # every GPU works on its own 1024-candidate sweep and the job processes 1024 x N candidates per step;
+    # RSAC_BENCH_STRONG=1 keeps the total at 1024 instead (each GPU then gets 1024/N candidates)
+    strong = os.environ.get("RSAC_BENCH_STRONG", "0") == "1"
+    C_PER_GPU = C_TOTAL
+    if not strong:
+        C_TOTAL = C_PER_GPU * world
     first, count = shard.block_range(C_TOTAL, rank, world)
     cap = shard.per_rank_capacity(C_TOTAL, world)
     b, offsets = make_shard(first, count)
@@ -292,12 +306,15 @@ def main():
     evals_per_sweep = C_TOTAL * H_HYP * N_MATCH
 
     line = {"metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64 solve / f32 score", "data": "synthetic",
-            "config": {"workload": "cfg4", "candidates": C_TOTAL, "matches": N_MATCH, "hypotheses": H_HYP,
-                       "outliers": 0.5, "mode": "exhaustive on device (all H scored) + reference-semantics replay",
+            "config": {"workload": "cfg4", "candidates": C_TOTAL, "candidates_per_gpu": count, "matches": N_MATCH,
+                       "hypotheses": H_HYP, "outliers": 0.5,
+                       "mode": "all H hypotheses solved and scored on the device (4-point null space by QR), then "
+                               "reference-semantics replay + Refine per candidate",
                        "parallelism": f"candidates sharded x{world}, {PIPE} sweeps in flight",
-                       "l2": "inputs 12.3 MB/sweep re-read from HBM/L2; scratch (hypothesis poses, local memory) > L2 churn: no flush"},
+                       "l2": "working set of a sweep (~90 MB) is L2-resident by design; every kernel is compute- or latency-bound: no flush"},
             "e2e": {"value": e2e_v, "unit": "candidates/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -312,16 +329,36 @@ def main():
         fp32_pk, fp64_pk = engines[0].measure_peaks()
         line["extras"]["measured_fp32_tflops"] = fp32_pk
         line["extras"]["measured_fp64_tflops"] = fp64_pk
-        # dominant kernel: EPnP minimal solver, FP64 CUDA cores.  Algorithmic FLOP per 4-point solve is
-        # counted by the oracle's instrumented build and averaged over this shard's problems.
+        # per-kernel rooflines; "roofline" is the kernel with the largest share of the sweep.
+        # Algorithmic FLOP per 4-point solve is counted by the oracle's instrumented build.
         flop_per_solve = epnp_flops_per_solve(b)
-        if stage.get("solve", [0, 0])[1]:
-            t_solve = stage["solve"][0] / stage["solve"][1] * 1e-3
-            ach = flop_per_solve * count * H_HYP / t_solve / 1e12
-            line["roofline"] = {"bound": "fp64", "kernel": "epnp_minimal_kernel", "achieved": ach, "peak": fp64_pk,
-                                "unit": "TFLOP/s", "frac": ach / fp64_pk, "traffic": None,
-                                "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                                "flop_per_solve": flop_per_solve, "launch_ms": t_solve * 1e3}
+        per = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in stage.items()}
+        total_ms = sum(per.values()) or 1.0
+        roofs = {}
+        if per.get("solve"):
+            t = per["solve"] * 1e-3
+            ach = flop_per_solve * count * H_HYP / t / 1e12
+            roofs["solve"] = {"bound": "fp64", "kernel": "epnp_minimal_kernel<QR>", "achieved": ach, "peak": fp64_pk,
+                              "unit": "TFLOP/s", "frac": ach / fp64_pk, "traffic": None,
+                              "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                              "flop_per_solve": flop_per_solve, "launch_ms": per["solve"], "share_of_sweep": per["solve"] / total_ms}
+        if per.get("score"):
+            t = per["score"] * 1e-3
+            ach = FLOP_PER_EVAL * count * H_HYP * N_MATCH / t / 1e12
+            roofs["score"] = {"bound": "fp32", "kernel": "score_kernel<2,0> (cfg4 sweep)", "achieved": ach, "peak": fp32_pk,
+                              "unit": "TFLOP/s", "frac": ach / fp32_pk, "traffic": None,
+                              "peak_source": "FFMA micro-kernel measured in this run", "flop_per_eval": FLOP_PER_EVAL,
+                              "launch_ms": per["score"], "share_of_sweep": per["score"] / total_ms}
+        if per.get("select"):
+            roofs["select"] = {"bound": "latency", "kernel": "ransac_select_kernel<0> (replay + Refine, one CTA per candidate)",
+                               "launch_ms": per["select"], "share_of_sweep": per["select"] / total_ms,
+                               "note": "serial dense tails (2 sqrt + 1-2 div chains); no meaningful FLOP roofline"}
+        dom = max(roofs, key=lambda k: roofs[k]["launch_ms"]) if roofs else None
+        if dom and "achieved" in roofs[dom]:
+            line["roofline"] = roofs[dom]
+        elif roofs.get("solve"):
+            line["roofline"] = roofs["solve"]
+        line["extras"]["rooflines"] = roofs
     if rank == 0 and world == 1 and not args.no_extras:
         line.update(extras_single_gpu(engines[0], peaks, peak_src, fp32_pk, line))
     if rank == 0:
@@ -340,7 +377,7 @@ def epnp_flops_per_solve(b):
         O.build()
         pb = O.pnp_problem(b["p3d"][0], b["p2d"][0], b["sigma2"][0], b["K"])
         tab = O.index_table(int(b["seeds"][0]), N_MATCH, 4, 64)
-        return float(O.epnp_flops(pb, tab))
+        return float(O.epnp_flops(pb, tab, O.FLAG_EPNP_QR_NULLSPACE))
     except Exception:
         return 9.0e4   # order-of-magnitude fallback
 
@@ -396,14 +433,64 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
     pbs = [O.pnp_problem(bb["p3d"][c], bb["p2d"][c], bb["sigma2"][c], bb["K"]) for c in range(nb)]
     tabs = [O.index_table(int(s), N_MATCH, 4, H_HYP) for s in bb["seeds"]]
     oprm = O.params(**PRM)
-    dt1, ev1, _ = O.pnp_batch(pbs[:64], oprm, tabs[:64], 0, 1)
-    dtn, evn, _ = O.pnp_batch(pbs, oprm, tabs, 0, cores)
-    dtx, evx, _ = O.pnp_batch(pbs[:32], oprm, tabs[:32], O.FLAG_EXHAUSTIVE, 1)
+    qr = O.FLAG_EPNP_QR_NULLSPACE
+    dt1, ev1, _ = O.pnp_batch(pbs[:64], oprm, tabs[:64], qr, 1)
+    dtn, evn, _ = O.pnp_batch(pbs, oprm, tabs, qr, cores)
+    dtx, evx, _ = O.pnp_batch(pbs[:32], oprm, tabs[:32], O.FLAG_EXHAUSTIVE | qr, 1)
+    dte, eve, _ = O.pnp_batch(pbs, oprm, tabs, 0, cores)
     out["cpu_baseline"] = {"value": nb / dtn, "unit": "candidates/s", "cores": cores, "kind": "port",
-                           "sample": f"{nb} cfg4 candidates, reference semantics (early exit), one solver call per core",
+                           "sample": f"{nb} cfg4 candidates, reference semantics (early exit), one solver call per core, "
+                                     "4-point null space by QR as on the device",
                            "single_thread_candidates_per_s": 64 / dt1, "single_thread_evals_per_s": ev1 / dt1,
                            "exhaustive_single_thread_evals_per_s": evx / dtx,
-                           "exhaustive_single_thread_candidates_per_s": 32 / dtx}
+                           "exhaustive_single_thread_candidates_per_s": 32 / dtx,
+                           "eigen_nullspace_candidates_per_s": nb / dte}
+
+    # ---- cfg2: MLPnP, 64 frames x 1000 matches with bearing covariances; cfg3: Sim3, 200 matches, 300 iterations
+    ex = out.setdefault("extras", dict(line["extras"]))
+    try:
+        C2, N2 = 64, 1000
+        b2 = synth.pnp_batch(2, C2, N2, 0.5)
+        cov = np.stack([synth.bearing_covariances(dict(K=b2["K"], sigma2=b2["sigma2"][c])) for c in range(C2)])
+        Kf = np.array([b2["K"]], np.float32)
+        off2 = (np.arange(C2 + 1) * N2).astype(np.int32)
+        prm2 = capi.ransac_params(0.99, 10, 300, 6, 0.2, 5.991)
+        eng.mlpnp_upload(off2, b2["p3d"], b2["p2d"], b2["sigma2"], Kf, prm2, cov=cov, seeds=b2["seeds"])
+        for _ in range(2):
+            eng.mlpnp_run()
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(5):
+            eng.mlpnp_run()
+        ms2 = eng.timer_end() / 5
+        _, H2 = capi.pnp_ransac_setup(N2, prm2)
+        res2, _ = eng.mlpnp_download()
+        ex["cfg2_mlpnp"] = {"frames": C2, "matches": N2, "hypotheses": H2, "ms_per_batch": ms2,
+                            "frames_per_s": C2 / (ms2 * 1e-3), "evals_per_s": C2 * H2 * N2 / (ms2 * 1e-3),
+                            "frames_ok": int(res2["ok"].sum())}
+        ps = [synth.sim3_problem(3000 + i, 200, 0.4, 1.0) for i in range(64)]
+        cat = lambda k: np.concatenate([q[k] for q in ps])
+        off3 = (np.arange(len(ps) + 1) * 200).astype(np.int32)
+        K3 = np.array([ps[0]["K"]], np.float32)
+        prm3 = capi.Sim3Params(0.99, 20, 300, 1)
+        seeds3 = np.arange(len(ps), dtype=np.uint32) + 3000
+        for C3 in (1, 64):
+            o3 = off3[:C3 + 1]
+            n3 = int(o3[-1])
+            eng.sim3_upload(o3, cat("x1c")[:n3], cat("x2c")[:n3], cat("sigma2_1")[:n3], cat("sigma2_2")[:n3], K3, K3, prm3,
+                            seeds=seeds3[:C3])
+            for _ in range(2):
+                eng.sim3_run()
+            eng.sync()
+            eng.timer_begin()
+            for _ in range(10):
+                eng.sim3_run()
+            ms3 = eng.timer_end() / 10
+            H3 = capi.sim3_ransac_setup(200, prm3)
+            ex["cfg3_sim3_x%d" % C3] = {"candidates": C3, "matches": 200, "hypotheses": H3, "ms_per_batch": ms3,
+                                        "evals_per_s": C3 * H3 * 200 / (ms3 * 1e-3)}
+    except Exception as err:   # the headline line must still be printed
+        ex["cfg2_cfg3_error"] = repr(err)
     return out
 
 
