@@ -25,15 +25,20 @@ long long orc_flops_take(void) { long long v = orc_flops; orc_flops = 0; return 
 
 /* ---- cyclic Jacobi on the upper triangle, rotations below ||a||_F * 2^-56 (2^-27) skipped ----
  * Rotation of the 2x2 block [app apq; apq aqq] (arithmetic contract):
- *   h = aqq - app, r = sqrt(h*h + 4*(apq*apq)), cos(2t) = |h|/r,
- *   c = sqrt(0.5 + 0.5*cos(2t)), s = apq/(r*c) with the sign of h,
- *   new diagonal = (app+aqq)/2 -/+ r/2. */
+ *   h = aqq - app, b = 2 apq, r = sqrt(h*h + b*b), u = 2r (r + |h|), w = 1/sqrt(u),
+ *   c = (r + |h|) w  (= sqrt((1 + |h|/r)/2)),  s = b w with the sign of h,
+ *   new diagonal = (app+aqq)/2 -/+ r/2.
+ * Two square roots and ONE division, the division last: the dependent chain is
+ * sqrt -> sqrt -> div instead of the textbook sqrt -> div -> sqrt -> div. */
 #define ORC_ANGLE(T, SQRT, FABS, HALF, FOUR, ZERO)                                              \
     const T h = aqq - app;                                                                      \
-    const T r = SQRT(h * h + FOUR * (apq * apq));                                               \
-    const T c2 = FABS(h) / r;                                                                   \
-    const T c = SQRT(HALF + HALF * c2);                                                         \
-    const T s0 = apq / (r * c);                                                                 \
+    const T b2 = apq + apq;                                                                     \
+    const T r = SQRT(h * h + b2 * b2);                                                          \
+    const T ah = FABS(h);                                                                       \
+    const T uu = (r + r) * (r + ah);                                                            \
+    const T ww = (HALF + HALF) / SQRT(uu);                                                      \
+    const T c = (r + ah) * ww;                                                                  \
+    const T s0 = b2 * ww;                                                                       \
     const T m = HALF * (app + aqq);                                                             \
     const T hr = HALF * r;                                                                      \
     T s, napp, naqq;                                                                            \
@@ -196,14 +201,21 @@ static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k 
                     gamma += ui * uj;
                 }
                 FL(6 * m + 3);
-                if (!(fabs(gamma) > DBL_EPSILON * sqrt(alpha * beta))) continue;
+                /* |gamma| > eps sqrt(alpha beta), tested on the squares (no square root) */
+                if (!(gamma * gamma > (DBL_EPSILON * DBL_EPSILON) * (alpha * beta))) continue;
                 rotated = 1;
                 FL(13 + 6 * m + 6 * k);
-                const double zeta = (beta - alpha) / (2.0 * gamma);
-                double t = 1.0 / (fabs(zeta) + sqrt(zeta * zeta + 1.0));
-                if (zeta < 0.0) t = -t;
-                const double c = 1.0 / sqrt(t * t + 1.0);
-                const double s = c * t;
+                /* rotation that zeroes gamma: tan(2t) = 2 gamma / (beta - alpha); same chain as ORC_ANGLE:
+                 * two square roots and one division */
+                const double h = beta - alpha;
+                const double b2 = gamma + gamma;
+                const double rr = sqrt(h * h + b2 * b2);
+                const double ah = fabs(h);
+                const double uu = (rr + rr) * (rr + ah);
+                const double ww = 1.0 / sqrt(uu);
+                const double c = (rr + ah) * ww;
+                double s = b2 * ww;
+                if (h < 0.0) s = -s;
                 for (int r = 0; r < m; ++r) {
                     const double ui = U[r * k + i], uj = U[r * k + j];
                     U[r * k + i] = c * ui - s * uj;

@@ -587,10 +587,11 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         RSAC_CUDA(e, cudaGetLastError());
     }
     if (d.sumH > 0) {
-        const int threads = 128;
+        const bool eigen = (flags & RSAC_FLAG_EPNP_EIGEN) != 0;
+        const int threads = eigen ? 128 : RSAC_SOLVE_THREADS;
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
         e->stage_begin(RSAC_STAGE_SOLVE);
-        if (flags & RSAC_FLAG_EPNP_EIGEN)
+        if (eigen)
             epnp_minimal_kernel<false><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
                                                                    (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
         else

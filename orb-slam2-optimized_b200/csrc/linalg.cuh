@@ -33,12 +33,15 @@ constexpr int kMaxSweepsRec = 12;   // recorded-rotation variant: rotations of a
 template <typename T>
 __host__ __device__ inline void jacobi_angle(T app, T aqq, T apq, T& c, T& s, T& napp, T& naqq)
 {
-    const T half = T(0.5), four = T(4);
+    const T half = T(0.5);
     const T h = aqq - app;
-    const T r = rsqrt_exact(h * h + four * (apq * apq));
-    const T c2 = rabs(h) / r;
-    c = rsqrt_exact(half + half * c2);
-    const T s0 = apq / (r * c);
+    const T b2 = apq + apq;
+    const T r = rsqrt_exact(h * h + b2 * b2);
+    const T ah = rabs(h);
+    const T uu = (r + r) * (r + ah);
+    const T ww = (half + half) / rsqrt_exact(uu);
+    c = (r + ah) * ww;
+    const T s0 = b2 * ww;
     const T m = half * (app + aqq);
     const T hr = half * r;
     if (h < T(0)) { s = -s0; napp = m + hr; naqq = m - hr; }
@@ -379,13 +382,18 @@ __host__ __device__ inline void onesided_jacobi(double* U, double* V)
                     beta += uj * uj;
                     gamma += ui * uj;
                 }
-                if (!(fabs(gamma) > DBL_EPSILON * sqrt(alpha * beta))) continue;
+                if (!(gamma * gamma > (DBL_EPSILON * DBL_EPSILON) * (alpha * beta))) continue;   // |gamma| > eps sqrt(alpha beta)
                 rotated = true;
-                const double zeta = (beta - alpha) / (2.0 * gamma);
-                double t = 1.0 / (fabs(zeta) + sqrt(zeta * zeta + 1.0));
-                if (zeta < 0.0) t = -t;
-                const double c = 1.0 / sqrt(t * t + 1.0);
-                const double s = c * t;
+                // rotation that zeroes gamma: tan(2t) = 2 gamma / (beta - alpha); two square roots, one division
+                const double h = beta - alpha;
+                const double b2 = gamma + gamma;
+                const double rr = sqrt(h * h + b2 * b2);
+                const double ah = fabs(h);
+                const double uu = (rr + rr) * (rr + ah);
+                const double ww = 1.0 / sqrt(uu);
+                const double c = (rr + ah) * ww;
+                double s = b2 * ww;
+                if (h < 0.0) s = -s;
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
                     const double ui = U[r * K + i], uj = U[r * K + j];

@@ -136,13 +136,16 @@ __device__ __forceinline__ int find_problem(const ProblemMeta* metas, int C, int
 }
 
 // ---- EPnP minimal solve: one thread per hypothesis (PnPsolver.cpp:125-141) ----
+#ifndef RSAC_SOLVE_THREADS
+#define RSAC_SOLVE_THREADS 128
+#endif
 #ifndef RSAC_SOLVE_BLOCKS
 #define RSAC_SOLVE_BLOCKS 4   // 128 registers: measured best (2: 1.60 ms, 3: 1.52, 4: 1.39, 5: 2.05 per 307k solves)
 #endif
 // QR = true: null space of the 4-point system by Householder QR (default); false: 12x12 eigen-solve
 // (RSAC_FLAG_EPNP_EIGEN, the reference's structure)
 template <bool QR>
-__global__ void __launch_bounds__(128, QR ? RSAC_SOLVE_BLOCKS : 2) epnp_minimal_kernel(const ProblemMeta* metas, int C, int64_t sumH,
+__global__ void __launch_bounds__(QR ? RSAC_SOLVE_THREADS : 128, QR ? RSAC_SOLVE_BLOCKS : 2) epnp_minimal_kernel(const ProblemMeta* metas, int C, int64_t sumH,
                                                            const uint32_t* tables, const float4* cA,
                                                            const float4* cC, float* poses)
 {

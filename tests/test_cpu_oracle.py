@@ -309,6 +309,12 @@ def test_oracle_frozen_vectors(oracle):
     assert np.array_equal(r["hyp_pose"].view(np.uint32), g["cfg1_pose"].view(np.uint32))
     assert [r["ok"], r["n_inliers"], r["best_hyp"], r["refined"], r["n_refines"]] == g["cfg1_meta"].tolist()
     assert (r["mask"] == g["cfg1_mask"]).all()
+    r = oracle.pnp_ransac(pb, oracle.params(0.99, 10, 300, 4, 0.2, 5.991), oracle.index_table(1000, 500, 4, 300),
+                          oracle.FLAG_EXHAUSTIVE | oracle.FLAG_EPNP_QR_NULLSPACE, per_hyp=True)
+    assert (r["hyp_counts"] == g["cfg1q_counts"]).all()
+    assert np.array_equal(r["hyp_pose"].view(np.uint32), g["cfg1q_pose"].view(np.uint32))
+    assert [r["ok"], r["n_inliers"], r["best_hyp"], r["refined"], r["n_refines"]] == g["cfg1q_meta"].tolist()
+    assert (r["mask"] == g["cfg1q_mask"]).all()
     for tag, sc in (("cfg3", 1.0), ("cfg3s", 1.6)):
         q = synth.sim3_problem(3000, 200, 0.4, sc)
         sb = oracle.sim3_problem(q["x1c"], q["x2c"], q["sigma2_1"], q["sigma2_2"], q["K"], q["K"], fix_scale=(sc == 1.0))
