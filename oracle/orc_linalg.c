@@ -109,9 +109,31 @@ ORC_JACOBI_IMPL(orc_jacobi_eig_f, float, sqrtf, fabsf, 0x1p-27f, 1.0f, 0.5f, 4.0
  * eigenvectors are formed by applying the rotations in reverse order to unit vectors.
  * a: n x n row-major, upper triangle read, destroyed.  w: nv eigenvalues ascending.
  * v: n x nv row-major. */
+/* Round-robin (tournament) ordering of the Jacobi pairs: m = n rounded up to even players, m-1 steps per
+ * sweep, m/2 disjoint pairs per step (circle method: player m-1 is fixed, the others rotate).  Every
+ * unordered pair appears exactly once per sweep.  For odd n the pair that contains the dummy player n is a
+ * bye.  Disjoint pairs are what lets the refine kernel compute the m/2 rotation parameters of a step on
+ * m/2 lanes at once; the arithmetic of every element is specified below and is the same in all three
+ * implementations (this one, csrc/linalg.cuh jacobi_lowest and jacobi_lowest_warp). */
+static void tour_pair(int m, int t, int i, int *p, int *q)
+{
+    const int r = m - 1;
+    int a, b;
+    if (i == 0) { a = r; b = t % r; }
+    else { a = (t + i) % r; b = (t - i + r) % r; }
+    if (a < b) { *p = a; *q = b; } else { *p = b; *q = a; }
+}
+
+#define ORC_E(x, y) a[((x) < (y) ? (x) : (y)) * n + ((x) < (y) ? (y) : (x))]
+
+/* One step: (1) the rotation of every pair from the current matrix (pairs are disjoint, so no pair's
+ * (app, aqq, apq) is touched by another pair's rotation) and its diagonal block; (2) for every two pairs
+ * i < j the 2x2 block of elements with one index in each: first pair i's rotation mixes the elements that
+ * share the other index, then pair j's -- which is exactly what applying rotation i and then rotation j to
+ * the whole matrix does to those four elements. */
 void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
 {
-    const int np = n * (n - 1) / 2;
+    const int m = n + (n & 1), h = m / 2, steps = m - 1, slots = steps * h;
     static __thread double rc[ORC_MAX_SWEEPS_REC * 66], rs[ORC_MAX_SWEEPS_REC * 66];
     double fro2 = 0.0;
     for (int i = 0; i < n; ++i)
@@ -120,13 +142,18 @@ void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
     const double tol = sqrt(fro2) * 0x1p-56;
     int sweeps = 0;
     for (int sweep = 0; sweep < ORC_MAX_SWEEPS_REC; ++sweep) {
-        int rotated = 0, slot = 0;
-        for (int p = 0; p < n - 1; ++p) {
-            for (int q = p + 1; q < n; ++q, ++slot) {
+        int rotated = 0;
+        for (int t = 0; t < steps; ++t) {
+            int P[6], Q[6], rot[6];
+            double C[6], S[6];
+            for (int i = 0; i < h; ++i) {
+                tour_pair(m, t, i, &P[i], &Q[i]);
+                rot[i] = 0; C[i] = 1.0; S[i] = 0.0;
+                if (Q[i] >= n) continue;                       /* bye */
+                const int p = P[i], q = Q[i];
                 const double apq = a[p * n + q];
-                rc[sweep * np + slot] = 1.0;
-                rs[sweep * np + slot] = 0.0;
                 if (!(fabs(apq) > tol)) continue;
+                rot[i] = 1;
                 rotated = 1;
                 FL(19 + 6 * (n - 2));
                 const double app = a[p * n + p], aqq = a[q * n + q];
@@ -134,16 +161,34 @@ void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
                 a[p * n + p] = napp;
                 a[q * n + q] = naqq;
                 a[p * n + q] = 0.0;
-                for (int j = 0; j < n; ++j) {
-                    if (j == p || j == q) continue;
-                    const int ip = (j < p) ? j * n + p : p * n + j;
-                    const int iq = (j < q) ? j * n + q : q * n + j;
-                    const double g = a[ip], k = a[iq];
-                    a[ip] = c * g - s * k;
-                    a[iq] = s * g + c * k;
+                C[i] = c; S[i] = s;
+            }
+            /* blocks; a bye (odd n: pair 0 = {player, dummy}) still has one real member whose elements are
+             * mixed by the other pairs' rotations */
+            for (int i = 0; i < h; ++i) {
+                const int ni = (Q[i] >= n) ? 1 : 2;            /* real members of pair i: P[i] (and Q[i]) */
+                for (int j = i + 1; j < h; ++j) {
+                    if (rot[i]) {                              /* rot[i] implies a real pair */
+                        const int ys[2] = {P[j], Q[j]};
+                        for (int e = 0; e < 2; ++e) {
+                            const double g = ORC_E(P[i], ys[e]), k = ORC_E(Q[i], ys[e]);
+                            ORC_E(P[i], ys[e]) = C[i] * g - S[i] * k;
+                            ORC_E(Q[i], ys[e]) = S[i] * g + C[i] * k;
+                        }
+                    }
+                    if (rot[j]) {
+                        const int xs[2] = {P[i], Q[i]};
+                        for (int e = 0; e < ni; ++e) {
+                            const double g = ORC_E(xs[e], P[j]), k = ORC_E(xs[e], Q[j]);
+                            ORC_E(xs[e], P[j]) = C[j] * g - S[j] * k;
+                            ORC_E(xs[e], Q[j]) = S[j] * g + C[j] * k;
+                        }
+                    }
                 }
-                rc[sweep * np + slot] = c;
-                rs[sweep * np + slot] = s;
+            }
+            for (int i = 0; i < h; ++i) {
+                rc[sweep * slots + t * h + i] = C[i];
+                rs[sweep * slots + t * h + i] = S[i];
             }
         }
         if (!rotated) break;
@@ -163,15 +208,18 @@ void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
         sel[k] = best;
         w[k] = bv;
     }
+    /* eigenvectors: the recorded rotations applied in reverse to unit vectors (rotations of one step act on
+     * disjoint index pairs, so their order within the step is immaterial) */
     double x[12][12];
     for (int k = 0; k < nv; ++k)
         for (int i = 0; i < n; ++i) x[k][i] = (i == sel[k]) ? 1.0 : 0.0;
     for (int sweep = sweeps - 1; sweep >= 0; --sweep)
-        for (int p = n - 2; p >= 0; --p)
-            for (int q = n - 1; q > p; --q) {
-                const int slot = p * n - (p * (p + 1)) / 2 + (q - p - 1);
-                const double c = rc[sweep * np + slot], s = rs[sweep * np + slot];
+        for (int t = steps - 1; t >= 0; --t)
+            for (int i = h - 1; i >= 0; --i) {
+                const double c = rc[sweep * slots + t * h + i], s = rs[sweep * slots + t * h + i];
                 if (s != 0.0) {
+                    int p, q;
+                    tour_pair(m, t, i, &p, &q);
                     FL(6 * nv);
                     for (int k = 0; k < nv; ++k) {
                         const double xp = x[k][p], xq = x[k][q];
@@ -183,6 +231,7 @@ void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
     for (int i = 0; i < n; ++i)
         for (int k = 0; k < nv; ++k) v[i * nv + k] = x[k][i];
 }
+#undef ORC_E
 
 /* ---- one-sided (Hestenes) Jacobi SVD: columns of U orthogonalised, V accumulated ---- */
 static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k */)

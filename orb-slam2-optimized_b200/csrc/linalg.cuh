@@ -125,10 +125,33 @@ __host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
 // eigenvalues ascending; v: N x NV (row-major), column j = eigenvector of w[j].
 __host__ __device__ constexpr int tri_idx(int N, int i, int j) { return i * N - (i * (i - 1)) / 2 + (j - i); }
 
-template <int N, int NV>
-__host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, double2* rec /* kMaxSweepsRec*N*(N-1)/2 */)
+// Round-robin (tournament) ordering of the Jacobi pairs (mirrors oracle/orc_linalg.c tour_pair): M = N rounded
+// up to even players, M-1 steps per sweep, M/2 disjoint pairs per step; for odd N the pair with the dummy
+// player N is a bye.  p < q.
+__host__ __device__ constexpr int tour_lo(int M, int t, int i)
 {
-    constexpr int NP = N * (N - 1) / 2;
+    const int r = M - 1;
+    const int a = (i == 0) ? r : (t + i) % r;
+    const int b = (i == 0) ? (t % r) : (t - i + r) % r;
+    return a < b ? a : b;
+}
+__host__ __device__ constexpr int tour_hi(int M, int t, int i)
+{
+    const int r = M - 1;
+    const int a = (i == 0) ? r : (t + i) % r;
+    const int b = (i == 0) ? (t % r) : (t - i + r) % r;
+    return a < b ? b : a;
+}
+__host__ __device__ constexpr int tri_sym(int N, int x, int y) { return x < y ? tri_idx(N, x, y) : tri_idx(N, y, x); }
+
+// One step = the rotations of M/2 disjoint pairs: (1) every pair's parameters from the current matrix and
+// its diagonal block, (2) for every two pairs i < j the 2x2 block with one index in each -- pair i's
+// rotation first, then pair j's (what applying rotation i and then rotation j to the whole matrix does to
+// those four elements).  rec holds (c, s) per (sweep, step, pair); identity for skipped pairs and byes.
+template <int N, int NV>
+__host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, double2* rec /* kMaxSweepsRec*66 */)
+{
+    constexpr int M = N + (N & 1), Hh = M / 2, STEPS = M - 1, SLOTS = STEPS * Hh;
     double fro2 = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -138,34 +161,64 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
     int sweeps = 0;
     for (int sweep = 0; sweep < kMaxSweepsRec; ++sweep) {
         bool rotated = false;
-        double2* rs = rec + sweep * NP;
-        int slot = 0;
+        double2* rs = rec + sweep * SLOTS;
 #pragma unroll
-        for (int p = 0; p < N - 1; ++p) {
+        for (int t = 0; t < STEPS; ++t) {
+            double C[Hh], S[Hh];
+            bool rot[Hh];
 #pragma unroll
-            for (int q = p + 1; q < N; ++q) {
-                const double apq = a[tri_idx(N, p, q)];
-                double c = 1.0, s = 0.0;
-                if (fabs(apq) > tol) {
-                    rotated = true;
-                    double napp, naqq;
-                    jacobi_angle<double>(a[tri_idx(N, p, p)], a[tri_idx(N, q, q)], apq, c, s, napp, naqq);
-                    a[tri_idx(N, p, p)] = napp;
-                    a[tri_idx(N, q, q)] = naqq;
-                    a[tri_idx(N, p, q)] = 0.0;
-#pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        if (j == p || j == q) continue;
-                        const int ip = (j < p) ? tri_idx(N, j, p) : tri_idx(N, p, j);
-                        const int iq = (j < q) ? tri_idx(N, j, q) : tri_idx(N, q, j);
-                        const double g = a[ip], k = a[iq];
-                        a[ip] = c * g - s * k;
-                        a[iq] = s * g + c * k;
+            for (int i = 0; i < Hh; ++i) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int p = tour_lo(M, t, i), q = tour_hi(M, t, i);
+                rot[i] = false; C[i] = 1.0; S[i] = 0.0;
+                if (q < N) {
+                    const double apq = a[tri_idx(N, p, q)];
+                    if (fabs(apq) > tol) {
+                        rot[i] = true;
+                        rotated = true;
+                        double napp, naqq;
+                        jacobi_angle<double>(a[tri_idx(N, p, p)], a[tri_idx(N, q, q)], apq, C[i], S[i], napp, naqq);
+                        a[tri_idx(N, p, p)] = napp;
+                        a[tri_idx(N, q, q)] = naqq;
+                        a[tri_idx(N, p, q)] = 0.0;
                     }
                 }
-                rs[slot] = make_double2(c, s);
-                ++slot;
             }
+#pragma unroll
+            for (int i = 0; i < Hh; ++i) {
+                const int pi = tour_lo(M, t, i), qi = tour_hi(M, t, i);
+#pragma unroll
+                for (int j = i + 1; j < Hh; ++j) {
+                    const int pj = tour_lo(M, t, j), qj = tour_hi(M, t, j);
+                    if (rot[i]) {                              // rot[i] implies a real pair
+                        {
+                            const double g = a[tri_sym(N, pi, pj)], k = a[tri_sym(N, qi < N ? qi : pi, pj)];
+                            a[tri_sym(N, pi, pj)] = C[i] * g - S[i] * k;
+                            a[tri_sym(N, qi < N ? qi : pi, pj)] = S[i] * g + C[i] * k;
+                        }
+                        {
+                            const double g = a[tri_sym(N, pi, qj)], k = a[tri_sym(N, qi < N ? qi : pi, qj)];
+                            a[tri_sym(N, pi, qj)] = C[i] * g - S[i] * k;
+                            a[tri_sym(N, qi < N ? qi : pi, qj)] = S[i] * g + C[i] * k;
+                        }
+                    }
+                    if (rot[j]) {
+                        {
+                            const double g = a[tri_sym(N, pi, pj)], k = a[tri_sym(N, pi, qj)];
+                            a[tri_sym(N, pi, pj)] = C[j] * g - S[j] * k;
+                            a[tri_sym(N, pi, qj)] = S[j] * g + C[j] * k;
+                        }
+                        if (qi < N) {                          // a bye has one real member only
+                            const double g = a[tri_sym(N, qi < N ? qi : pi, pj)], k = a[tri_sym(N, qi < N ? qi : pi, qj)];
+                            a[tri_sym(N, qi < N ? qi : pi, pj)] = C[j] * g - S[j] * k;
+                            a[tri_sym(N, qi < N ? qi : pi, qj)] = S[j] * g + C[j] * k;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < Hh; ++i) rs[t * Hh + i] = make_double2(C[i], S[i]);
         }
         if (!rotated) break;
         sweeps = sweep + 1;
@@ -195,20 +248,19 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
 #pragma unroll
         for (int i = 0; i < N; ++i) x[k][i] = (i == sel[k]) ? 1.0 : 0.0;
     for (int sweep = sweeps - 1; sweep >= 0; --sweep) {
-        const double2* rs = rec + sweep * NP;
-        // static (p,q) order reversed
+        const double2* rs = rec + sweep * SLOTS;
 #pragma unroll
-        for (int p = N - 2; p >= 0; --p) {
+        for (int t = STEPS - 1; t >= 0; --t) {
 #pragma unroll
-            for (int q = N - 1; q > p; --q) {
-                const int slot = p * N - (p * (p + 1)) / 2 + (q - p - 1);
-                const double2 cs = rs[slot];
-                if (cs.y != 0.0) {
+            for (int i = Hh - 1; i >= 0; --i) {
+                const int p = tour_lo(M, t, i), q = tour_hi(M, t, i);
+                const double2 cs = rs[t * Hh + i];
+                if (q < N && cs.y != 0.0) {
 #pragma unroll
                     for (int k = 0; k < NV; ++k) {
-                        const double xp = x[k][p], xq = x[k][q];
+                        const double xp = x[k][p], xq = x[k][q < N ? q : p];
                         x[k][p] = cs.x * xp + cs.y * xq;
-                        x[k][q] = cs.x * xq - cs.y * xp;
+                        x[k][q < N ? q : p] = cs.x * xq - cs.y * xp;
                     }
                 }
             }
@@ -221,19 +273,18 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
 }
 
 #ifdef __CUDACC__
-// Warp-cooperative schedule of jacobi_lowest<N,NV> for the refine stage (one problem per CTA, warp 0):
-// the same cyclic rotation order, the same rotation parameters and the same per-element arithmetic --
-// only the 2(N-2) independent element updates of one rotation are spread over lanes 0..N-1 and the NV
-// back-substitutions over lanes 0..NV-1, so the result is bit-identical to the serial routine.
-// a: packed upper triangle in SHARED memory (destroyed); w: NV smallest eigenvalues; v: N x NV
-// (row-major) in shared memory; rec: kMaxSweepsRec*N(N-1)/2 double2 in shared memory.
-// Loops are real loops (indices are data here, not register names): ~2 KB of code instead of the
-// fully unrolled 200 KB the register-resident version needs.
+// Warp-cooperative schedule of jacobi_lowest<N,NV> for the refine stage (one problem per CTA, warp 0): the
+// M/2 rotation parameters of a step -- each a sqrt -> sqrt -> div chain -- are computed on M/2 lanes at once,
+// the (M/2 choose 2) 2x2 blocks on as many lanes, the NV back-substitutions on NV lanes.  Every element sees
+// the operations of the serial routine in the same order, so the result is bit-identical.
+// a: packed upper triangle in SHARED memory (destroyed); w: NV smallest eigenvalues; v: N x NV (row-major)
+// in shared memory; rec: kMaxSweepsRec*66 double2 in shared memory.
 template <int N, int NV>
 __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, double2* rec, int lane)
 {
-    constexpr int NP = N * (N - 1) / 2;
+    constexpr int M = N + (N & 1), Hh = M / 2, STEPS = M - 1, SLOTS = STEPS * Hh, NB = Hh * (Hh - 1) / 2;
     constexpr unsigned FULL = 0xffffffffu;
+    static_assert(NB <= 32 && Hh <= 32, "one lane per pair / per block");
     double fro2 = 0.0;
     if (lane == 0) {
         for (int i = 0; i < N; ++i)
@@ -241,34 +292,70 @@ __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, doubl
     }
     fro2 = __shfl_sync(FULL, fro2, 0);
     const double tol = sqrt(fro2) * 0x1p-56;
+    // this lane's block (bi < bj), fixed for the whole solve
+    int bi = 0, bj = 1;
+    if (lane < NB) {
+        int rem = lane;
+        while (rem >= Hh - 1 - bi) { rem -= Hh - 1 - bi; ++bi; }
+        bj = bi + 1 + rem;
+    }
     int sweeps = 0;
     for (int sweep = 0; sweep < kMaxSweepsRec; ++sweep) {
         bool rotated = false;
-        double2* rs = rec + sweep * NP;
-        int slot = 0;
-        for (int p = 0; p < N - 1; ++p) {
-            for (int q = p + 1; q < N; ++q, ++slot) {
-                const int ipp = tri_idx(N, p, p), iqq = tri_idx(N, q, q), ipq = tri_idx(N, p, q);
-                const double apq = a[ipq];
-                double c = 1.0, s = 0.0;
-                if (fabs(apq) > tol) {                       // warp-uniform
-                    rotated = true;
-                    double napp, naqq;
-                    jacobi_angle<double>(a[ipp], a[iqq], apq, c, s, napp, naqq);
-                    __syncwarp();                            // all lanes have read (pp, qq, pq)
-                    if (lane == 0) { a[ipp] = napp; a[iqq] = naqq; a[ipq] = 0.0; }
-                    if (lane < N && lane != p && lane != q) {
-                        const int j = lane;
-                        const int ip = (j < p) ? tri_idx(N, j, p) : tri_idx(N, p, j);
-                        const int iq = (j < q) ? tri_idx(N, j, q) : tri_idx(N, q, j);
-                        const double g = a[ip], k = a[iq];
-                        a[ip] = c * g - s * k;
-                        a[iq] = s * g + c * k;
+        double2* rs = rec + sweep * SLOTS;
+        for (int t = 0; t < STEPS; ++t) {
+            // (1) lane i < Hh: pair i
+            int p = 0, q = N;
+            double c = 1.0, s = 0.0;
+            bool rot = false;
+            if (lane < Hh) {
+                p = tour_lo(M, t, lane); q = tour_hi(M, t, lane);
+                if (q < N) {
+                    const double apq = a[tri_idx(N, p, q)];
+                    if (fabs(apq) > tol) {
+                        rot = true;
+                        double napp, naqq;
+                        jacobi_angle<double>(a[tri_idx(N, p, p)], a[tri_idx(N, q, q)], apq, c, s, napp, naqq);
+                        a[tri_idx(N, p, p)] = napp;          // diagonal blocks are private to their pair
+                        a[tri_idx(N, q, q)] = naqq;
+                        a[tri_idx(N, p, q)] = 0.0;
                     }
-                    __syncwarp();
                 }
-                if (lane == 0) rs[slot] = make_double2(c, s);
+                rs[t * Hh + lane] = make_double2(c, s);
             }
+            const unsigned anyrot = __ballot_sync(FULL, rot);
+            if (anyrot) {
+                rotated = true;
+                // (2) lane b < NB: block (bi, bj)
+                const int pi = __shfl_sync(FULL, p, bi), qi = __shfl_sync(FULL, q, bi);
+                const int pj = __shfl_sync(FULL, p, bj), qj = __shfl_sync(FULL, q, bj);
+                const double ci = __shfl_sync(FULL, c, bi), si = __shfl_sync(FULL, s, bi);
+                const double cj = __shfl_sync(FULL, c, bj), sj = __shfl_sync(FULL, s, bj);
+                const bool roti = (anyrot >> bi) & 1u, rotj = (anyrot >> bj) & 1u;
+                if (lane < NB && (roti || rotj)) {
+                    const bool real_i = qi < N;                   // pair i is a bye when qi == N (then !roti)
+                    const int qir = real_i ? qi : pi;
+                    const int e00 = tri_sym(N, pi, pj), e01 = tri_sym(N, pi, qj);
+                    const int e10 = tri_sym(N, qir, pj), e11 = tri_sym(N, qir, qj);
+                    double x00 = a[e00], x01 = a[e01], x10 = a[e10], x11 = a[e11];
+                    if (roti) {
+                        const double g0 = x00, k0 = x10, g1 = x01, k1 = x11;
+                        x00 = ci * g0 - si * k0; x10 = si * g0 + ci * k0;
+                        x01 = ci * g1 - si * k1; x11 = si * g1 + ci * k1;
+                    }
+                    if (rotj) {
+                        const double g0 = x00, k0 = x01;
+                        x00 = cj * g0 - sj * k0; x01 = sj * g0 + cj * k0;
+                        if (real_i) {
+                            const double g1 = x10, k1 = x11;
+                            x10 = cj * g1 - sj * k1; x11 = sj * g1 + cj * k1;
+                        }
+                    }
+                    a[e00] = x00; a[e01] = x01;
+                    if (real_i) { a[e10] = x10; a[e11] = x11; }
+                }
+            }
+            __syncwarp();
         }
         if (!rotated) break;
         sweeps = sweep + 1;
@@ -294,12 +381,12 @@ __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, doubl
     if (lane < NV) {
         for (int i = 0; i < N; ++i) v[i * NV + lane] = (i == sel) ? 1.0 : 0.0;
         for (int sweep = sweeps - 1; sweep >= 0; --sweep) {
-            const double2* rs = rec + sweep * NP;
-            for (int p = N - 2; p >= 0; --p) {
-                for (int q = N - 1; q > p; --q) {
-                    const int slot = p * N - (p * (p + 1)) / 2 + (q - p - 1);
-                    const double2 cs = rs[slot];
+            const double2* rs = rec + sweep * SLOTS;
+            for (int t = STEPS - 1; t >= 0; --t) {
+                for (int i = Hh - 1; i >= 0; --i) {
+                    const double2 cs = rs[t * Hh + i];
                     if (cs.y != 0.0) {
+                        const int p = tour_lo(M, t, i), q = tour_hi(M, t, i);
                         const double xp = v[p * NV + lane], xq = v[q * NV + lane];
                         v[p * NV + lane] = cs.x * xp + cs.y * xq;
                         v[q * NV + lane] = cs.x * xq - cs.y * xp;

@@ -50,11 +50,17 @@ struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
 };
 static_assert(sizeof(ResultRec) == 96, "rsac_result layout");
 
-constexpr int kSelectThreads = 128;
+#ifndef RSAC_SELECT_THREADS
+#define RSAC_SELECT_THREADS 128
+#endif
 #ifndef RSAC_SELECT_CTAS
 #define RSAC_SELECT_CTAS 7
 #endif
-constexpr int kSelectCtasPerSm = RSAC_SELECT_CTAS;   // 7 x 148 = 1036 resident candidates: a 1024-candidate sweep is one wave
+// 128 threads x 7 CTAs/SM: 1036 resident candidates, so a 1024-candidate sweep is one wave (measured: 4 CTAs/SM
+// at 128 registers 1.05 ms, 7 CTAs/SM at 72 registers 0.91 ms, 64 threads x 8 CTAs/SM at 128 registers 0.65 vs
+// 0.56 ms for this shape after the later changes)
+constexpr int kSelectThreads = RSAC_SELECT_THREADS;
+constexpr int kSelectCtasPerSm = RSAC_SELECT_CTAS;
 
 // diagnostic: clock64() at phase boundaries of block 0 (rsac_debug_select_clocks)
 __device__ long long g_select_clocks[16];
@@ -141,13 +147,20 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         // alphas and pixels are staged through shared memory in tiles; every entry still adds its
         // per-point products in index order
         __shared__ double s_tile[kSelectThreads * 6];
-        int ea = 0, eb = 0;
-        if (tid < 78) {
-            int rem = tid;
-            while (rem >= 12 - ea) { rem -= 12 - ea; ++ea; }
-            eb = ea + rem;
+        // entries e = tid and tid + blockDim.x (78 entries over >= 64 threads)
+        int ea[2] = {0, 0}, eb[2] = {0, 0};
+        bool have[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int e = tid + k * blockDim.x;
+            have[k] = e < 78;
+            if (have[k]) {
+                int rem = e;
+                while (rem >= 12 - ea[k]) { rem -= 12 - ea[k]; ++ea[k]; }
+                eb[k] = ea[k] + rem;
+            }
         }
-        double acc = 0.0;
+        double acc[2] = {0.0, 0.0};
         for (int base = 0; base < n; base += kSelectThreads) {
             const int cnt = min(kSelectThreads, n - base);
             __syncthreads();
@@ -158,19 +171,23 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
                 s_tile[tid * 6 + 4] = us[2 * i]; s_tile[tid * 6 + 5] = us[2 * i + 1];
             }
             __syncthreads();
-            if (tid < 78) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (!have[k]) continue;
 #pragma unroll 4
                 for (int i = 0; i < cnt; ++i) {
                     const double* t6 = s_tile + i * 6;
                     double a0, a1, b0, b1;
-                    epnp_m_entry(t6, t6[4], t6[5], cam, ea, a0, a1);
-                    epnp_m_entry(t6, t6[4], t6[5], cam, eb, b0, b1);
-                    acc += a0 * b0;
-                    acc += a1 * b1;
+                    epnp_m_entry(t6, t6[4], t6[5], cam, ea[k], a0, a1);
+                    epnp_m_entry(t6, t6[4], t6[5], cam, eb[k], b0, b1);
+                    acc[k] += a0 * b0;
+                    acc[k] += a1 * b1;
                 }
             }
         }
-        if (tid < 78) S.MtM[tri_idx(12, ea, eb)] = acc;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (have[k]) S.MtM[tri_idx(12, ea[k], eb[k])] = acc[k];
     }
     __syncthreads();
     RSAC_SEL_MARK(4);
@@ -181,18 +198,30 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         if (tid < 32) jacobi_lowest_warp<12, 4>(S.MtM, S.w4, S.U4, s_rec, tid);
         __syncthreads();
         RSAC_SEL_MARK(5);
-        // the three beta approximations + Gauss-Newton (:395-405) are independent: one thread each, in three warps
-        if ((tid & 31) == 0 && tid < 96) {
-            const int kk = tid >> 5;
+        // the three beta approximations + Gauss-Newton (:395-405) are independent: one thread each in three
+        // warps (two warps when the CTA has only two: approx_3 alone, approx_1 + approx_2 together)
+        const bool three = blockDim.x >= 96;
+        if ((tid & 31) == 0 && tid < (three ? 96 : 64)) {
+            const int wk = tid >> 5;
             double L[60], rho[6], U4[48], bt[4];
             for (int i = 0; i < 48; ++i) U4[i] = S.U4[i];
             epnp_L_6x10(U4, L);
             epnp_rho(S.cws, rho);
-            if (kk == 0) epnp_betas_approx_1(L, rho, bt);
-            else if (kk == 1) epnp_betas_approx_2(L, rho, bt);
-            else epnp_betas_approx_3(L, rho, bt);
-            epnp_gauss_newton(L, rho, bt);
-            for (int i = 0; i < 4; ++i) S.betas[4 * kk + i] = bt[i];
+            if (wk == 0) {
+                epnp_betas_approx_3(L, rho, bt);
+                epnp_gauss_newton(L, rho, bt);
+                for (int i = 0; i < 4; ++i) S.betas[8 + i] = bt[i];
+            }
+            if (wk == 1) {
+                epnp_betas_approx_1(L, rho, bt);
+                epnp_gauss_newton(L, rho, bt);
+                for (int i = 0; i < 4; ++i) S.betas[i] = bt[i];
+            }
+            if (wk == 2 || (wk == 1 && !three)) {
+                epnp_betas_approx_2(L, rho, bt);
+                epnp_gauss_newton(L, rho, bt);
+                for (int i = 0; i < 4; ++i) S.betas[4 + i] = bt[i];
+            }
         }
     }
     __syncthreads();
@@ -336,8 +365,8 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
     __syncthreads();
     const int cols = planar ? 9 : 12;
     const int nent = cols * (cols + 1) / 2;
-    if (tid < nent) {                                  // A^T P A upper triangle, one entry per thread (:482-486)
-        int ea = 0, rem = tid;
+    for (int e = tid; e < nent; e += blockDim.x) {     // A^T P A upper triangle, entry-parallel (:482-486)
+        int ea = 0, rem = e;
         while (rem >= cols - ea) { rem -= cols - ea; ++ea; }
         const int eb = ea + rem;
         double s = 0.0;
