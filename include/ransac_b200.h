@@ -258,6 +258,11 @@ int rsac_nccl_destroy(rsac_engine* e);
  * oracle bit-for-bit without a GPU.  Not a fallback: nothing in the engine calls these. */
 /* diagnostic: clock64() stamps of the replay kernel's phases (block 0 of the last launch) */
 int rsac_debug_select_clocks(rsac_engine* e, long long out[16]);
+/* diagnostic: globaltimer stamps (ns) of the first and last four CTAs of the last scoring launch:
+ * [cta][0] entry, [1] first chunk landed, [2] poses folded, [3] last chunk done, [4] exit, [5] chunks processed */
+int rsac_debug_score_clocks(rsac_engine* e, unsigned long long out[64]);
+/* per CTA (first 1024) of the last scoring launch: entry ns, exit ns, chunks processed, SM id */
+int rsac_debug_score_all(rsac_engine* e, unsigned long long out[4096]);
 int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3]);
 /* the same with the default QR null space (RSAC_FLAG_EPNP_EIGEN clear) */
 int rsac_debug_host_epnp4_qr(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3]);

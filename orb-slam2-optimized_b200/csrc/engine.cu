@@ -277,7 +277,7 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
     pl.hpl = env_int("RSAC_SCORE_HPL", 2);
     if (pl.hpl != 1 && pl.hpl != 2 && pl.hpl != 3) pl.hpl = 2;
     int warps = (maxH + 32 * pl.hpl - 1) / (32 * pl.hpl);
-    warps = std::max(1, std::min(env_int("RSAC_SCORE_WARPS", 8), std::min(8, warps)));
+    warps = std::max(1, std::min(env_int("RSAC_SCORE_WARPS", 16), std::min(16, warps)));
     pl.threads = warps * 32;
     pl.tile_hyps = warps * 32 * pl.hpl;
     std::vector<double> work;
@@ -364,24 +364,32 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
     for (const auto& l : lists) vlen = std::max(vlen, l.size());
     pl.vlen = (int)vlen;
     pl.work.assign((size_t)pl.grid * vlen, end_rec);
+    // chunks of a group are dealt round-robin to the CTAs that visit it (one CTA per group in the many-groups case)
+    std::vector<int> visitors(NG, 0), seen(NG, 0);
     for (int b = 0; b < pl.grid; ++b)
-        for (size_t k = 0; k < lists[b].size(); ++k) pl.work[(size_t)b * vlen + k] = groups[lists[b][k]];
+        for (int g : lists[b]) visitors[g]++;
+    for (int b = 0; b < pl.grid; ++b)
+        for (size_t k = 0; k < lists[b].size(); ++k) {
+            const int g = lists[b][k];
+            ScoreGroup rec = groups[g];
+            rec.first_stride = (seen[g]++ & 0xffff) | (std::min(visitors[g], 0x7fff) << 16);
+            pl.work[(size_t)b * vlen + k] = rec;
+        }
     pl.chunk_cap = cw * 32;
     pl.smem = score_smem_bytes<MODEL>(pl.chunk_cap, pl.tile_hyps);
     return RSAC_OK;
 }
 
-// counts, the diagnostic counter and the per-group chunk counters live in ONE buffer so that a single
-// memset node prepares a scoring launch: [counts: n ints][exact: 2 ints][group_next: ngroups ints]
-static int zero_score_region(rsac_engine* e, DevBuf& d_counts, int64_t n_counts, int ngroups, ScoreArgs& sa)
+// counts and the diagnostic counter live in ONE buffer so that a single memset node prepares a scoring
+// launch: [counts: n ints][exact: 2 ints]
+static int zero_score_region(rsac_engine* e, DevBuf& d_counts, int64_t n_counts, int /*ngroups*/, ScoreArgs& sa)
 {
     const size_t n_al = ((size_t)std::max<int64_t>(n_counts, 1) + 1) & ~(size_t)1;     // keep the 8-byte counter aligned
-    const size_t total = (n_al + 2 + (size_t)std::max(ngroups, 1)) * sizeof(int32_t);
+    const size_t total = (n_al + 2) * sizeof(int32_t);
     RSAC_TRY(d_counts.ensure(e, total));
     RSAC_CUDA(e, cudaMemsetAsync(d_counts.p, 0, total, e->stream));
     sa.counts = (int32_t*)d_counts.p;
     sa.exact_counter = (unsigned long long*)((int32_t*)d_counts.p + n_al);
-    sa.group_next = (int32_t*)d_counts.p + n_al + 2;
     e->last_exact = sa.exact_counter;
     return RSAC_OK;
 }
@@ -838,6 +846,22 @@ int rsac_debug_host_epnp4_qr(const double K[4], const float p3d[12], const float
     for (int i = 0; i < 8; ++i) us[i] = (double)p2d[i];
     const Cam k = {K[0], K[1], K[2], K[3]};
     epnp_compute_pose_small<4, true>(pw, us, k, R, t);
+    return RSAC_OK;
+}
+
+int rsac_debug_score_clocks(rsac_engine* e, unsigned long long out[64])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_score_clocks, sizeof(unsigned long long) * 64));
+    return RSAC_OK;
+}
+
+int rsac_debug_score_all(rsac_engine* e, unsigned long long out[4096])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_score_all, sizeof(unsigned long long) * 4096));
     return RSAC_OK;
 }
 

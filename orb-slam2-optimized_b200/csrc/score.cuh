@@ -7,10 +7,13 @@
 // Design (DESIGN.md "scoring kernel"):
 //   * lane <-> hypothesis: each lane keeps HPL poses in registers as 3x4 projective rows with the
 //     intrinsics folded in and the whole matrix scaled by 1/(|R|_1 + |t|_inf);
-//   * persistent, warp-specialised CTAs: a producer warp pulls (hypothesis tile, correspondence chunk)
-//     work items from per-group atomic counters -- SMs stay balanced at word (32-correspondence)
-//     granularity -- and stages each chunk in a 4-slot shared-memory ring with 1-D TMA bulk copies
-//     (full/empty mbarriers); consumer warps never meet at a CTA-wide barrier;
+//   * persistent, warp-specialised CTAs, one per SM (up to 16 consumer warps + a producer warp): the
+//     producer walks the CTA's statically dealt (hypothesis tile, correspondence chunk) work items and
+//     stages each chunk in a 4-slot shared-memory ring with 1-D TMA bulk copies (full/empty mbarriers);
+//     consumer warps never meet at a CTA-wide barrier.  (Measured alternatives: two 8-warp CTAs per SM
+//     starve one another -- the warp arbiter favours one CTA, which then leaves the SM half empty for the
+//     last third of the launch; a per-chunk atomic work counter costs an L2 round trip per 32
+//     correspondences and only papers over that imbalance);
 //   * correspondences are read back as warp-broadcast LDS.128: two loads serve 32*HPL evaluations;
 //   * two-tier evaluation.  Fast path, division-free: with (x,y,z) = P X,
 //         D = (x + (cx-u) z)^2 + (y + (cy-v) z)^2 - thr z^2      (= z^2 (e - thr))
@@ -30,7 +33,7 @@ namespace rsac {
 // The record is self-contained (everything the kernel needs about the problem), so a CTA starts with ONE
 // global load before its first TMA copy; each CTA owns a list of such records.
 struct __align__(16) ScoreGroup {
-    int32_t gid;         // index of the group's chunk counter; < 0 terminates a CTA's list
+    int32_t gid;         // group index; < 0 terminates a CTA's list
     int32_t hyp0;        // first hypothesis of the tile
     int32_t nchunks;
     int32_t chunk_words; // words per chunk (the last chunk may be shorter)
@@ -38,7 +41,8 @@ struct __align__(16) ScoreGroup {
     int32_t hyp_off, word_off;
     int64_t hmask_off;
     float fx, fy;        // f32 focal lengths folded into the fast-path rows
-    int32_t problem, pad;
+    int32_t problem;
+    int32_t first_stride; // this CTA's chunks of the group: first | (stride << 16) -- static round-robin deal
 };
 static_assert(sizeof(ScoreGroup) == 64, "ScoreGroup is copied as four 16-byte words");
 
@@ -46,7 +50,6 @@ struct ScoreArgs {
     const ProblemMeta* metas;        // exact path only (f64 intrinsics)
     const ScoreGroup* work;          // [grid][vlen] per-CTA lists of group records
     int32_t vlen;
-    int32_t* group_next;             // [ngroups] chunk counters, zeroed before the launch
     const float4* cP;                // pair-packed records, 4 x float4 per two correspondences (see pack kernel)
     const float4* cC;                // (u, v, 0, 0)   exact pixel coordinates (exact path)
     const void* poses;               // PnP: float[sumH][12]; MLPnP: double[sumH][12]
@@ -169,13 +172,25 @@ __device__ __forceinline__ void eval_pair(const float2* C, const float4& q0, con
     cert = __funnelshift_l(__float_as_uint(t0), cert, 1);
 }
 
+// diagnostic: globaltimer (ns) stamps of consumer warp 0 in a few CTAs (rsac_debug_score_clocks):
+// [cta][0] kernel entry, [1] first chunk landed, [2] poses folded, [3] last chunk done, [4] exit, [5] chunks
+__device__ unsigned long long g_score_clocks[8][8];
+__device__ unsigned long long g_score_all[1024][4];   // per CTA (first 1024): entry, exit (globaltimer ns), chunks, SM id
+__device__ __forceinline__ unsigned long long rsac_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define RSAC_SCORE_MARK(i) do { if (dbg_slot >= 0 && threadIdx.x == 0) g_score_clocks[dbg_slot][i] = rsac_globaltimer(); } while (0)
+
 constexpr int kScoreStages = 4;        // shared-memory ring of correspondence chunks
-constexpr int kScoreMaxThreads = 288;  // 8 consumer warps + 1 producer warp
+constexpr int kScoreMaxThreads = 544;  // up to 16 consumer warps + 1 producer warp (one CTA per SM)
 
 // Warp-specialised persistent kernel.  blockDim.x = (consumer warps + 1) * 32.
-//   producer (last warp, one lane): walks this CTA's group records, pulls chunk ids from the group's atomic
-//     counter (the next id is requested before the current TMA is issued, so the atomic's latency is
-//     off the critical path), waits for a free ring slot (empty barrier), writes the slot's header (chunk id,
+//   producer (last warp, one lane): walks this CTA's group records and its statically dealt chunks of each
+//     group (a per-chunk atomic counter was measured to BE the critical path: one L2 round trip per 32
+//     correspondences), waits for a free ring slot (empty barrier), writes the slot's header (chunk id,
 //     list position, group record) and bulk-copies the chunk's two record arrays into it (full barrier,
 //     transaction bytes);
 //   consumers: wait for the slot to fill, switch group when the header says so (flush counts, fold the new
@@ -183,7 +198,7 @@ constexpr int kScoreMaxThreads = 288;  // 8 consumer warps + 1 producer warp
 //     meet at a CTA barrier inside the loop; they drift up to kScoreStages-1 chunks apart, which absorbs
 //     the rare exact-path excursions.
 template <int HPL, int MODEL>
-__global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs args)
+__global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs args)
 {
     using Model = ScoreModel<MODEL>;
     using PT = typename Model::pose_t;
@@ -198,6 +213,10 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncons = (blockDim.x >> 5) - 1;            // consumer warps
+    const int dbg_slot = (blockIdx.x < 4) ? (int)blockIdx.x : ((blockIdx.x + 4 >= gridDim.x) ? (int)(blockIdx.x + 8 - gridDim.x) : -1);
+    RSAC_SCORE_MARK(0);
+    const unsigned long long t_entry = rsac_globaltimer();
+    int dbg_chunks = 0;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < kScoreStages; ++i) {
@@ -219,12 +238,12 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
                 for (int i = 0; i < 4; ++i) rec.q[i] = work[4 * k + i];
                 const ScoreGroup& grp = rec.g;
                 if (grp.gid < 0) break;
-                int next_id = atomicAdd(args.group_next + grp.gid, 1);
-                while (next_id < grp.nchunks) {
-                    const int c = next_id;
+                // this CTA's share of the group's chunks: first, first + stride, ... (dealt by the host; no
+                // global round trip between chunks, so the ring runs kScoreStages chunks ahead of the consumers)
+                const int c_first = grp.first_stride & 0xffff, c_stride = max(1, grp.first_stride >> 16);
+                for (int c = c_first; c < grp.nchunks; c += c_stride) {
                     const uint32_t stage = pit % kScoreStages;
                     mbar_wait(&empty_bar[stage], ((pit / kScoreStages) & 1u) ^ 1u);
-                    next_id = atomicAdd(args.group_next + grp.gid, 1);   // consumed next iteration
                     s_hdr[stage] = make_int2(c, k);
                     int4* gdst = reinterpret_cast<int4*>(&s_grp[stage]);
 #pragma unroll
@@ -271,6 +290,8 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
         mbar_wait(&full_bar[stage], (cit / kScoreStages) & 1u);
         const int2 hdr = s_hdr[stage];
         if (hdr.x < 0) break;
+        if (cit == 0) RSAC_SCORE_MARK(1);
+        ++dbg_chunks;
         if (hdr.y != cur_k) {
             // ---- new group: flush the finished tile, take the record, load and fold this warp's poses
             if (cur_k >= 0) flush();
@@ -311,6 +332,7 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
                 for (int i = 0; i < 12; ++i) C[s][i] = make_float2(c[i], c[i]);
             }
         }
+        if (cit == 0) RSAC_SCORE_MARK(2);
         const bool warp_live = __any_sync(0xffffffffu, (live[0] != 0u));   // slot 0 holds the lowest hypotheses
         if (warp_live) {
             const float4* sP = sbuf + (size_t)stage * cap * 3;
@@ -358,7 +380,18 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 2) score_kernel(ScoreArgs ar
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);     // slot may be refilled
     }
+    RSAC_SCORE_MARK(3);
     if (cur_k >= 0) flush();
+    RSAC_SCORE_MARK(4);
+    if (dbg_slot >= 0 && threadIdx.x == 0) g_score_clocks[dbg_slot][5] = (unsigned long long)dbg_chunks;
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_score_all[blockIdx.x][0] = t_entry;
+        g_score_all[blockIdx.x][1] = rsac_globaltimer();
+        g_score_all[blockIdx.x][2] = (unsigned long long)dbg_chunks;
+        g_score_all[blockIdx.x][3] = smid;
+    }
 }
 
 // ---- packing: raw correspondences -> records with thresholds and rounding bounds ----

@@ -75,3 +75,50 @@ eng.L.rsac_debug_select_clocks(eng.h, clk)
 c = list(clk)
 names = ["start", "found", "refine:begin", "presums", "MtM", "jacobi", "betas", "sums2", "horn+reproj", "score", "end"]
 print("select phases (block 0, cycles):", [(names[i], c[i] - c[i - 1]) for i in range(1, 11)], "total", c[10] - c[0])
+
+# cfg5 kernel-only duration (events bracket the kernel launch, not the memset)
+eng.score_pnp_upload(p["poses"], p["p3d"], p["p2d"], max_err, p["K"])
+for want in (True, False):
+    for it in range(5):
+        eng.score_pnp_run(want)
+    eng.sync()
+    eng.profile_enable(True)
+    eng.profile_reset()
+    for it in range(50):
+        eng.score_pnp_run(want)
+    eng.sync()
+    tms, nl = eng.profile()["score"]
+    eng.profile_enable(False)
+    ms = tms / nl
+    print("cfg5 masks=%s kernel only: %.4f ms -> %.2f TFLOP/s (%.1f%% of 71.7)" % (want, ms, H * N * 31 / (ms * 1e-3) / 1e12, H * N * 31 / (ms * 1e-3) / 1e12 / 71.7 * 100))
+
+eng.score_pnp_run(True)
+eng.sync()
+sc = (ctypes.c_ulonglong * 64)()
+eng.L.rsac_debug_score_clocks(eng.h, sc)
+sc = np.array(list(sc), dtype=np.int64).reshape(8, 8)
+t0 = sc[:, 0].min()
+print("score CTA timelines (ns from first entry): entry, first chunk, folded, last chunk done, exit, chunks")
+for r in sc:
+    print("   ", [int(x - t0) for x in r[:5]], int(r[5]))
+al = (ctypes.c_ulonglong * 4096)()
+eng.L.rsac_debug_score_all(eng.h, al)
+al = np.array(list(al), dtype=np.int64).reshape(1024, 4)[:296]
+t0 = al[:, 0].min()
+dur = al[:, 1] - al[:, 0]
+print("all CTAs: entry spread %d ns, exit min/median/max %d/%d/%d ns, chunks min/max %d/%d" %
+      (al[:, 0].max() - t0, (al[:, 1] - t0).min(), np.median(al[:, 1] - t0), (al[:, 1] - t0).max(), al[:, 2].min(), al[:, 2].max()))
+per = dur / np.maximum(al[:, 2], 1)
+order = np.argsort(per)
+print("ns per chunk: fastest", per[order[:5]].astype(int), "slowest", per[order[-5:]].astype(int))
+print("slowest CTAs (blockIdx, smid, chunks):", [(int(i), int(al[i, 3]), int(al[i, 2])) for i in order[-8:]])
+print("fastest CTAs (blockIdx, smid, chunks):", [(int(i), int(al[i, 3]), int(al[i, 2])) for i in order[:8]])
+sm_counts = np.bincount(al[:, 3].astype(int), minlength=148)
+print("CTAs per SM histogram:", np.bincount(sm_counts))
+# per-SM: sum of chunks and max exit
+import collections
+bysm = collections.defaultdict(list)
+for i in range(296):
+    bysm[int(al[i, 3])].append((int(al[i, 1] - t0), int(al[i, 2]), i))
+late = sorted(bysm.items(), key=lambda kv: -max(x[0] for x in kv[1]))[:5]
+print("latest SMs:", late)
