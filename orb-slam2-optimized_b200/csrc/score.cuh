@@ -285,6 +285,53 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
         }
     };
 
+    // take a group record: tile geometry, then load and fold this warp's poses
+    auto enter_group = [&](const ScoreGroup& grp) {
+        g_hyp0 = grp.hyp0; g_cw = grp.chunk_words; g_n = grp.n; g_words = grp.words;
+        g_hypoff = grp.hyp_off; g_problem = grp.problem; g_hmask = grp.hmask_off;
+        const int H = grp.H;
+        const float fx = grp.fx, fy = grp.fy;
+#pragma unroll
+        for (int s = 0; s < HPL; ++s) {
+            const int local = (warp * HPL + s) * 32 + lane;
+            const int hyp = g_hyp0 + local;
+            live[s] = (hyp < H) ? 0xffffffffu : 0u;
+            float c[12];
+            if (live[s]) {
+                const PT* src = poses + (size_t)(g_hypoff + hyp) * 12;
+                PT raw[12];
+                if constexpr (sizeof(PT) == 4) {
+                    const float4* s4 = reinterpret_cast<const float4*>(src);
+                    const float4 r0 = s4[0], r1 = s4[1], r2 = s4[2];
+                    raw[0] = r0.x; raw[1] = r0.y; raw[2] = r0.z; raw[3] = r0.w; raw[4] = r1.x; raw[5] = r1.y;
+                    raw[6] = r1.z; raw[7] = r1.w; raw[8] = r2.x; raw[9] = r2.y; raw[10] = r2.z; raw[11] = r2.w;
+                } else {
+                    const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { const double2 v = s2[i]; raw[2 * i] = v.x; raw[2 * i + 1] = v.y; }
+                }
+                fold_pose<PT>(raw, fx, fy, c);
+                // each thread keeps the raw poses of its own slots for the exact path (no other thread reads them)
+#pragma unroll
+                for (int i = 0; i < 12; ++i) sraw[(size_t)local * 12 + i] = raw[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) c[i] = 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) C[s][i] = make_float2(c[i], c[i]);
+        }
+    };
+
+    // the CTA's first group is known without the producer: fold its poses while the first chunk is in flight
+    {
+        union { ScoreGroup g; int4 q[4]; } rec;
+        const int4* w0 = reinterpret_cast<const int4*>(args.work + (size_t)blockIdx.x * args.vlen);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rec.q[i] = w0[i];
+        if (rec.g.gid >= 0) { enter_group(rec.g); cur_k = 0; }
+    }
+
     for (uint32_t cit = 0;; ++cit) {
         const uint32_t stage = cit % kScoreStages;
         mbar_wait(&full_bar[stage], (cit / kScoreStages) & 1u);
@@ -293,44 +340,10 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
         if (cit == 0) RSAC_SCORE_MARK(1);
         ++dbg_chunks;
         if (hdr.y != cur_k) {
-            // ---- new group: flush the finished tile, take the record, load and fold this warp's poses
+            // ---- new group: flush the finished tile, take the record from the slot header
             if (cur_k >= 0) flush();
             cur_k = hdr.y;
-            const ScoreGroup& grp = s_grp[stage];
-            g_hyp0 = grp.hyp0; g_cw = grp.chunk_words; g_n = grp.n; g_words = grp.words;
-            g_hypoff = grp.hyp_off; g_problem = grp.problem; g_hmask = grp.hmask_off;
-            const int H = grp.H;
-            const float fx = grp.fx, fy = grp.fy;
-#pragma unroll
-            for (int s = 0; s < HPL; ++s) {
-                const int local = (warp * HPL + s) * 32 + lane;
-                const int hyp = g_hyp0 + local;
-                live[s] = (hyp < H) ? 0xffffffffu : 0u;
-                float c[12];
-                if (live[s]) {
-                    const PT* src = poses + (size_t)(g_hypoff + hyp) * 12;
-                    PT raw[12];
-                    if constexpr (sizeof(PT) == 4) {
-                        const float4* s4 = reinterpret_cast<const float4*>(src);
-                        const float4 r0 = s4[0], r1 = s4[1], r2 = s4[2];
-                        raw[0] = r0.x; raw[1] = r0.y; raw[2] = r0.z; raw[3] = r0.w; raw[4] = r1.x; raw[5] = r1.y;
-                        raw[6] = r1.z; raw[7] = r1.w; raw[8] = r2.x; raw[9] = r2.y; raw[10] = r2.z; raw[11] = r2.w;
-                    } else {
-                        const double2* s2 = reinterpret_cast<const double2*>(src);
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) { const double2 v = s2[i]; raw[2 * i] = v.x; raw[2 * i + 1] = v.y; }
-                    }
-                    fold_pose<PT>(raw, fx, fy, c);
-                    // each thread keeps the raw poses of its own slots for the exact path (no other thread reads them)
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) sraw[(size_t)local * 12 + i] = raw[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) c[i] = 0.0f;
-                }
-#pragma unroll
-                for (int i = 0; i < 12; ++i) C[s][i] = make_float2(c[i], c[i]);
-            }
+            enter_group(s_grp[stage]);
         }
         if (cit == 0) RSAC_SCORE_MARK(2);
         const bool warp_live = __any_sync(0xffffffffu, (live[0] != 0u));   // slot 0 holds the lowest hypotheses
