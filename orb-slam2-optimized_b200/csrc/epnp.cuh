@@ -234,6 +234,7 @@ __host__ __device__ inline void epnp_qr_solve(double* A /*6x4*/, double* b, doub
 __host__ __device__ inline void epnp_gauss_newton(const double* L, const double* rho, double* betas)
 {
     double A[24], B[6], X[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
     for (int k = 0; k < 5; ++k) {
         epnp_gn_system(L, rho, betas, A, B);
         epnp_qr_solve(A, B, X);
@@ -385,6 +386,7 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
     }
 
     double rep[3], Rs[3][9], ts[3][3];
+#pragma unroll 1
     for (int kk = 0; kk < 3; ++kk) {
         double ccs[12], pcs[NPTS * 3];
         epnp_ccs(betas + 4 * kk, U4, ccs);
