@@ -60,6 +60,8 @@ void orc_nullspace_qr_d(const double *Mrows /*8x12*/, double *U4 /*12x4*/);
  * with Eigen's rank threshold (restates A.bdcSvd(ThinU|ThinV).solve(b),
  * PnPsolver.cpp:531,559,590).  L row-major m*k, m<=8, k<=6. */
 void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x);
+/* Householder-QR least squares with the SVD solve above as the rank-deficient fallback */
+void orc_lstsq_d(int m, int k, const double *L, const double *b, double *x);
 /* closed-form cofactor inverse (restates Matrix3d::inverse(), PnPsolver.cpp:331) */
 void orc_inv3_d(const double m[9], double out[9]);
 /* orthogonal polar factor U*V^T of a 3x3 (restates JacobiSVD U*V^T,

@@ -285,6 +285,13 @@ static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k 
  * columns Eigen's BDCSVD delegates to JacobiSVD; solve() is the minimum-norm
  * least-squares solution with singular values <= sigma_max * diagSize * eps
  * treated as zero. */
+long long orc_cond_hist[8][16];
+void orc_lstsq_cond_hist(long long *out /* 8*16 */, int reset)
+{
+    memcpy(out, orc_cond_hist, sizeof(orc_cond_hist));
+    if (reset) memset(orc_cond_hist, 0, sizeof(orc_cond_hist));
+}
+
 void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
 {
     double U[8 * 6], V[6 * 6], sig2[6], sig[6];
@@ -299,6 +306,13 @@ void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
         if (sig[j] > smax) smax = sig[j];
     }
     FL(k * (2 * m + 1) + 2);
+    {   /* diagnostic histogram of log10(sigma_min / sigma_max) per column count (orc_lstsq_cond_hist) */
+        double smin = smax;
+        for (int j = 0; j < k; ++j) if (sig[j] < smin) smin = sig[j];
+        int bin = 0;
+        if (smax > 0.0 && smin > 0.0) { bin = (int)(-log10(smin / smax)); if (bin < 0) bin = 0; if (bin > 15) bin = 15; } else bin = 15;
+        __atomic_fetch_add(&orc_cond_hist[k][bin], 1, __ATOMIC_RELAXED);
+    }
     const double thresh = smax * ((double)k * DBL_EPSILON);
     for (int r = 0; r < k; ++r) x[r] = 0.0;
     for (int j = 0; j < k; ++j) {
@@ -309,6 +323,62 @@ void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
         FL(2 * m + 1 + 2 * k);
         for (int r = 0; r < k; ++r) x[r] += coef * V[r * k + j];
     }
+}
+
+/* Least squares of an m x k system (m <= 8, k <= 6) by Householder QR without pivoting.  For a system of
+ * full column rank the least-squares solution is unique, so this is the value L.bdcSvd().solve(b) returns
+ * (PnPsolver.cpp:531,559,590) up to rounding -- at ~1/30 of the cost of a Jacobi SVD.  Returns 0, x
+ * untouched, when the triangular factor is numerically rank deficient (min |R_kk| <= 1e-7 max |R_kk|; the
+ * cfg4 systems have sigma_min/sigma_max >= 1e-5): the caller then takes the minimum-norm SVD solve, which
+ * is what the reference's call means for a rank-deficient system.  Mirrored by csrc/linalg.cuh qr_lstsq. */
+static int qr_lstsq(int m, int k, const double *L, const double *b, double *x)
+{
+    double A[8 * 6], bb[8], rd[6];
+    memcpy(A, L, sizeof(double) * (size_t)(m * k));
+    memcpy(bb, b, sizeof(double) * (size_t)m);
+    for (int c = 0; c < k; ++c) {
+        double s = 0.0;
+        for (int r = c; r < m; ++r) s += A[r * k + c] * A[r * k + c];
+        const double norm = sqrt(s);
+        if (norm == 0.0) return 0;
+        const double alpha = (A[c * k + c] > 0.0) ? -norm : norm;
+        A[c * k + c] = A[c * k + c] - alpha;
+        double vtv = 0.0;
+        for (int r = c; r < m; ++r) vtv += A[r * k + c] * A[r * k + c];
+        const double tau = 2.0 / vtv;
+        for (int j = c + 1; j < k; ++j) {
+            double d = 0.0;
+            for (int r = c; r < m; ++r) d += A[r * k + c] * A[r * k + j];
+            d = d * tau;
+            for (int r = c; r < m; ++r) A[r * k + j] = A[r * k + j] - d * A[r * k + c];
+        }
+        double d = 0.0;
+        for (int r = c; r < m; ++r) d += A[r * k + c] * bb[r];
+        d = d * tau;
+        for (int r = c; r < m; ++r) bb[r] = bb[r] - d * A[r * k + c];
+        rd[c] = alpha;
+        FL(4 * (m - c) + 3 + (k - c) * (4 * (m - c) + 1));
+    }
+    double rmax = 0.0, rmin = fabs(rd[0]);
+    for (int c = 0; c < k; ++c) {
+        const double a = fabs(rd[c]);
+        if (a > rmax) rmax = a;
+        if (a < rmin) rmin = a;
+    }
+    if (!(rmin > rmax * 1e-7)) return 0;
+    for (int i = k - 1; i >= 0; --i) {
+        double sum = 0.0;
+        for (int j = i + 1; j < k; ++j) sum += A[i * k + j] * x[j];
+        x[i] = (bb[i] - sum) / rd[i];
+    }
+    FL(k * k + k);
+    return 1;
+}
+
+/* the least-squares solve of find_betas_approx_{1,2,3}: QR, minimum-norm SVD only if rank deficient */
+void orc_lstsq_d(int m, int k, const double *L, const double *b, double *x)
+{
+    if (!qr_lstsq(m, k, L, b, x)) orc_svd_lstsq_d(m, k, L, b, x);
 }
 
 /* PnPsolver.cpp:331: CC.inverse() -- closed-form cofactor inverse, no pivoting,

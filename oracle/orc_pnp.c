@@ -173,7 +173,7 @@ static void find_betas_approx_1(const double L[6][10], const double rho[6], doub
     for (int i = 0; i < 6; ++i) {
         L4[i * 4 + 0] = L[i][0]; L4[i * 4 + 1] = L[i][1]; L4[i * 4 + 2] = L[i][3]; L4[i * 4 + 3] = L[i][6];
     }
-    orc_svd_lstsq_d(6, 4, L4, rho, b4);
+    orc_lstsq_d(6, 4, L4, rho, b4);
     if (b4[0] < 0) {
         betas[0] = sqrt(-b4[0]);
         betas[1] = -b4[1] / betas[0];
@@ -194,7 +194,7 @@ static void find_betas_approx_2(const double L[6][10], const double rho[6], doub
     for (int i = 0; i < 6; ++i) {
         L3[i * 3 + 0] = L[i][0]; L3[i * 3 + 1] = L[i][1]; L3[i * 3 + 2] = L[i][2];
     }
-    orc_svd_lstsq_d(6, 3, L3, rho, b3);
+    orc_lstsq_d(6, 3, L3, rho, b3);
     if (b3[0] < 0) {
         betas[0] = sqrt(-b3[0]);
         betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0;
@@ -213,7 +213,7 @@ static void find_betas_approx_3(const double L[6][10], const double rho[6], doub
     double L5[6 * 5], b5[5];
     for (int i = 0; i < 6; ++i)
         for (int c = 0; c < 5; ++c) L5[i * 5 + c] = L[i][c];
-    orc_svd_lstsq_d(6, 5, L5, rho, b5);
+    orc_lstsq_d(6, 5, L5, rho, b5);
     if (b5[0] < 0) {
         betas[0] = sqrt(-b5[0]);
         betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0;

@@ -115,7 +115,7 @@ __host__ __device__ inline void epnp_betas_approx_1(const double* L, const doubl
     for (int i = 0; i < 6; ++i) {
         L4[i * 4 + 0] = L[i * 10 + 0]; L4[i * 4 + 1] = L[i * 10 + 1]; L4[i * 4 + 2] = L[i * 10 + 3]; L4[i * 4 + 3] = L[i * 10 + 6];
     }
-    svd_lstsq<6, 4>(L4, rho, b4);
+    lstsq<6, 4>(L4, rho, b4);
     if (b4[0] < 0) {
         betas[0] = sqrt(-b4[0]);
         betas[1] = -b4[1] / betas[0];
@@ -135,7 +135,7 @@ __host__ __device__ inline void epnp_betas_approx_2(const double* L, const doubl
     for (int i = 0; i < 6; ++i) {
         L3[i * 3 + 0] = L[i * 10 + 0]; L3[i * 3 + 1] = L[i * 10 + 1]; L3[i * 3 + 2] = L[i * 10 + 2];
     }
-    svd_lstsq<6, 3>(L3, rho, b3);
+    lstsq<6, 3>(L3, rho, b3);
     if (b3[0] < 0) {
         betas[0] = sqrt(-b3[0]);
         betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0;
@@ -153,7 +153,7 @@ __host__ __device__ inline void epnp_betas_approx_3(const double* L, const doubl
     double L5[30], b5[5];
     for (int i = 0; i < 6; ++i)
         for (int c = 0; c < 5; ++c) L5[i * 5 + c] = L[i * 10 + c];
-    svd_lstsq<6, 5>(L5, rho, b5);
+    lstsq<6, 5>(L5, rho, b5);
     if (b5[0] < 0) {
         betas[0] = sqrt(-b5[0]);
         betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0;

@@ -527,6 +527,80 @@ __host__ __device__ inline void svd_lstsq(const double* L, const double* b, doub
     }
 }
 
+// Least squares of an M x K system by Householder QR without pivoting (mirrors oracle/orc_linalg.c qr_lstsq):
+// for full column rank the least-squares solution is unique, so this is what the SVD solve returns up to
+// rounding at ~1/30 of the cost.  Returns false, x untouched, when min |R_kk| <= 1e-7 max |R_kk|.
+template <int M, int K>
+__host__ __device__ inline bool qr_lstsq(const double* L, const double* b, double* x)
+{
+    double A[M * K], bb[M], rd[K];
+#pragma unroll
+    for (int i = 0; i < M * K; ++i) A[i] = L[i];
+#pragma unroll
+    for (int i = 0; i < M; ++i) bb[i] = b[i];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = c; r < M; ++r) s += A[r * K + c] * A[r * K + c];
+        const double norm = sqrt(s);
+        if (norm == 0.0) return false;
+        const double alpha = (A[c * K + c] > 0.0) ? -norm : norm;
+        A[c * K + c] = A[c * K + c] - alpha;
+        double vtv = 0.0;
+#pragma unroll
+        for (int r = c; r < M; ++r) vtv += A[r * K + c] * A[r * K + c];
+        const double tau = 2.0 / vtv;
+#pragma unroll
+        for (int j = c + 1; j < K; ++j) {
+            double d = 0.0;
+#pragma unroll
+            for (int r = c; r < M; ++r) d += A[r * K + c] * A[r * K + j];
+            d = d * tau;
+#pragma unroll
+            for (int r = c; r < M; ++r) A[r * K + j] = A[r * K + j] - d * A[r * K + c];
+        }
+        double d = 0.0;
+#pragma unroll
+        for (int r = c; r < M; ++r) d += A[r * K + c] * bb[r];
+        d = d * tau;
+#pragma unroll
+        for (int r = c; r < M; ++r) bb[r] = bb[r] - d * A[r * K + c];
+        rd[c] = alpha;
+    }
+    double rmax = 0.0, rmin = fabs(rd[0]);
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const double a = fabs(rd[c]);
+        if (a > rmax) rmax = a;
+        if (a < rmin) rmin = a;
+    }
+    if (!(rmin > rmax * 1e-7)) return false;
+#pragma unroll
+    for (int i = K - 1; i >= 0; --i) {
+        double sum = 0.0;
+#pragma unroll
+        for (int j = i + 1; j < K; ++j) sum += A[i * K + j] * x[j];
+        x[i] = (bb[i] - sum) / rd[i];
+    }
+    return true;
+}
+
+// rank-deficient fallback kept out of line: it is (almost) never taken and its unrolled Jacobi sweeps would
+// otherwise sit in the middle of the hot instruction stream
+template <int M, int K>
+__host__ __device__ __noinline__ void svd_lstsq_cold(const double* L, const double* b, double* x)
+{
+    svd_lstsq<M, K>(L, b, x);
+}
+
+// the least-squares solve of find_betas_approx_{1,2,3} (PnPsolver.cpp:531,559,590)
+template <int M, int K>
+__host__ __device__ inline void lstsq(const double* L, const double* b, double* x)
+{
+    if (!qr_lstsq<M, K>(L, b, x)) svd_lstsq_cold<M, K>(L, b, x);
+}
+
 // closed-form cofactor inverse (Matrix3d::inverse(), PnPsolver.cpp:331); singular => inf/NaN
 __host__ __device__ inline void inv3(const double* m, double* out)
 {
