@@ -258,6 +258,8 @@ int rsac_nccl_destroy(rsac_engine* e);
  * oracle bit-for-bit without a GPU.  Not a fallback: nothing in the engine calls these. */
 /* diagnostic: clock64() stamps of the replay kernel's phases (block 0 of the last launch) */
 int rsac_debug_select_clocks(rsac_engine* e, long long out[16]);
+/* diagnostic: clock64() stamps of the EPnP minimal solve's phases (thread 0 of block 0 of the last launch) */
+int rsac_debug_solve_clocks(rsac_engine* e, long long out[16]);
 /* diagnostic: globaltimer stamps (ns) of the first and last four CTAs of the last scoring launch:
  * [cta][0] entry, [1] first chunk landed, [2] poses folded, [3] last chunk done, [4] exit, [5] chunks processed */
 int rsac_debug_score_clocks(rsac_engine* e, unsigned long long out[64]);

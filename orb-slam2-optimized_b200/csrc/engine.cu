@@ -857,6 +857,14 @@ int rsac_debug_score_clocks(rsac_engine* e, unsigned long long out[64])
     return RSAC_OK;
 }
 
+int rsac_debug_solve_clocks(rsac_engine* e, long long out[16])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_solve_clocks, sizeof(long long) * 16));
+    return RSAC_OK;
+}
+
 int rsac_debug_score_all(rsac_engine* e, unsigned long long out[4096])
 {
     if (!e || !out) return RSAC_ERR_INVALID;

@@ -12,6 +12,16 @@
 
 namespace rsac {
 
+// diagnostic: clock64() at the phase boundaries of the minimal solve, thread 0 of block 0 (rsac_debug_solve_clocks)
+#ifdef __CUDACC__
+__device__ long long g_solve_clocks[16];
+#endif
+#ifdef __CUDA_ARCH__
+#define RSAC_SOLVE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_solve_clocks[i] = clock64(); } while (0)
+#else
+#define RSAC_SOLVE_MARK(i) do { } while (0)
+#endif
+
 struct Cam { double fx, fy, cx, cy; };
 
 // PnPsolver::choose_control_points (PnPsolver.cpp:296-321) after the sums:
@@ -248,12 +258,17 @@ __host__ __device__ inline void epnp_betas_from_basis(const double* U4, const do
     double L[60], rho[6];
     epnp_L_6x10(U4, L);
     epnp_rho(cws, rho);
+    RSAC_SOLVE_MARK(3);
     epnp_betas_approx_1(L, rho, betas + 0);
+    RSAC_SOLVE_MARK(4);
     epnp_gauss_newton(L, rho, betas + 0);
+    RSAC_SOLVE_MARK(5);
     epnp_betas_approx_2(L, rho, betas + 4);
     epnp_gauss_newton(L, rho, betas + 4);
+    RSAC_SOLVE_MARK(6);
     epnp_betas_approx_3(L, rho, betas + 8);
     epnp_gauss_newton(L, rho, betas + 8);
+    RSAC_SOLVE_MARK(7);
 }
 
 // From MtM (PACKED upper triangle, 78 entries, destroyed) to the null-space basis U4 (12x4) and
@@ -281,6 +296,7 @@ __host__ __device__ inline void epnp_solve_betas_qr4(const double* al, const dou
         for (int r = 0; r < 12; ++r) { A[r * 8 + 2 * i] = r0[r]; A[r * 8 + 2 * i + 1] = r1[r]; }
     }
     nullspace_qr_8x12(A, U4);
+    RSAC_SOLVE_MARK(2);
     epnp_betas_from_basis(U4, cws, betas);
 }
 
@@ -343,6 +359,7 @@ __host__ __device__ inline double epnp_reproj_term(const double* R, const double
 template <int NPTS, bool QR = false>
 __host__ __device__ inline double epnp_compute_pose_small(const double* pw, const double* us, const Cam& k, float* Rf, float* tf)
 {
+    RSAC_SOLVE_MARK(0);
     double cws[12], C0[3];
     for (int c = 0; c < 3; ++c) {
         double s = 0.0;
@@ -362,6 +379,7 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
     double alphas[NPTS * 4];
     for (int i = 0; i < NPTS; ++i) epnp_alphas(pw + 3 * i, cws, CCi, alphas + 4 * i);
 
+    RSAC_SOLVE_MARK(1);
     double U4[48], betas[12];
     if constexpr (QR && NPTS == 4) {
         epnp_solve_betas_qr4(alphas, us, k, cws, U4, betas);
@@ -407,11 +425,14 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
         for (int i = 0; i < NPTS; ++i)
             for (int r = 0; r < 3; ++r)
                 for (int c = 0; c < 3; ++c) M[r * 3 + c] += (pcs[i * 3 + r] - pc0[r]) * (pw[i * 3 + c] - pw0[c]);
+        if (kk == 0) RSAC_SOLVE_MARK(8);
         epnp_horn(M, pc0, pw0, Rs[kk], ts[kk]);
+        if (kk == 0) RSAC_SOLVE_MARK(9);
         double sum2 = 0.0;
         for (int i = 0; i < NPTS; ++i) sum2 += epnp_reproj_term(Rs[kk], ts[kk], pw + 3 * i, us[2 * i], us[2 * i + 1], k);
         rep[kk] = sum2 / (double)NPTS;
     }
+    RSAC_SOLVE_MARK(10);
     int N = 0;                                                // :407-409 (index shifted by one)
     if (rep[1] < rep[0]) N = 1;
     if (rep[2] < rep[N]) N = 2;

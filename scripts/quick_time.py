@@ -122,3 +122,11 @@ for i in range(296):
     bysm[int(al[i, 3])].append((int(al[i, 1] - t0), int(al[i, 2]), i))
 late = sorted(bysm.items(), key=lambda kv: -max(x[0] for x in kv[1]))[:5]
 print("latest SMs:", late)
+
+eng.pnp_upload(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], prm, seeds=b["seeds"])
+eng.pnp_run()
+eng.sync()
+eng.L.rsac_debug_solve_clocks(eng.h, clk)
+c = list(clk)
+names = ["ctrl pts+alphas", "QR nullspace", "L,rho", "approx1", "GN1", "approx2+GN2", "approx3+GN3", "ccs/pcs/M (k=0)", "horn (k=0)", "rest (reproj k=0, k=1,2)"]
+print("solve phases (block 0 warp 0, cycles):", [(names[i - 1], c[i] - c[i - 1]) for i in range(1, 11)], "total", c[10] - c[0])
