@@ -123,9 +123,11 @@ def run_reference(args):
     import oracle_api as O
     O.build()
     cores = os.cpu_count() or 1
-    b, _ = make_shard(0, C_TOTAL)
+    strong = os.environ.get("RSAC_BENCH_STRONG", "0") == "1"
+    n_cand = C_TOTAL if strong else C_TOTAL * max(1, args.gpus)     # the GPU arm's config at this N
+    b, _ = make_shard(0, n_cand)
     prm = O.params(**PRM)
-    pbs = [O.pnp_problem(b["p3d"][c], b["p2d"][c], b["sigma2"][c], b["K"]) for c in range(C_TOTAL)]
+    pbs = [O.pnp_problem(b["p3d"][c], b["p2d"][c], b["sigma2"][c], b["K"]) for c in range(n_cand)]
     tables = [O.index_table(int(s), N_MATCH, 4, H_HYP) for s in b["seeds"]]
     oflags = O.FLAG_EPNP_QR_NULLSPACE   # the port's faster mode (same arithmetic as the device path)
     for _ in range(max(1, min(args.warmup, 1))):
@@ -135,11 +137,11 @@ def run_reference(args):
         dt, ev, res = O.pnp_batch(pbs, prm, tables, oflags, cores)
         t_tot += dt
         ev_tot += ev
-    val = C_TOTAL * args.steps / t_tot
+    val = n_cand * args.steps / t_tot
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "candidates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": "cfg4", "candidates": C_TOTAL, "matches": N_MATCH,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": "cfg4", "candidates": n_cand, "matches": N_MATCH,
                                             "hypotheses": H_HYP, "mode": "reference semantics (early exit)"},
             "cpu_baseline": {"value": val, "unit": "candidates/s", "cores": cores, "kind": "port",
                              "sample": "full cfg4 sweep per step, one solver call per core (BASELINE.md mode B); "
@@ -221,11 +223,30 @@ def main():
     def upload(i):
         engines[i].pnp_upload(offsets, h_p3d.numpy(), h_p2d.numpy(), h_s2.numpy(), [b["K"]], prm, seeds=seeds)
 
+    # multi-GPU: the all-gather of sweep k (98 KB per rank, latency-bound) runs on a side stream under the
+    # kernels of sweep k+1; two record buffers alternate so that a sweep never overwrites records in flight
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    d_loc2 = [torch.full((cap, shard.REC_WORDS), -1, dtype=torch.int32, device=dev) for _ in range(2)]
+    d_gat2 = [torch.empty((world * cap, shard.REC_WORDS), dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else d_loc2
+    gather_done = [None, None]
+    step_no = [0]
+
     def step_resident(i):
+        k = step_no[0] & 1
+        step_no[0] += 1
         with torch.cuda.stream(streams[i]):
-            engines[i].pnp_run(0, d_local[i].data_ptr())
+            if gather_done[k] is not None:
+                streams[i].wait_event(gather_done[k])      # the gather that last read this buffer (two sweeps ago)
+            engines[i].pnp_run(0, d_loc2[k].data_ptr())
             if world > 1:
-                dist.all_gather_into_tensor(d_gath[i], d_local[i])
+                ev = torch.cuda.Event()
+                ev.record(streams[i])
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ev)
+                    dist.all_gather_into_tensor(d_gat2[k], d_loc2[k])
+                    gd = torch.cuda.Event()
+                    gd.record(comm_stream)
+                    gather_done[k] = gd
 
     def step_e2e(i):
         with torch.cuda.stream(streams[i]):
@@ -256,7 +277,7 @@ def main():
             s.wait_event(ev0)
         for k in range(steps):
             fn(k % nslot)
-        for s in streams:
+        for s in streams + ([comm_stream] if comm_stream is not None else []):
             e = torch.cuda.Event()
             e.record(s)
             main_s.wait_event(e)
@@ -300,7 +321,7 @@ def main():
 
     # correctness guard on the gathered records (cheap): every candidate reported once, in order
     torch.cuda.synchronize()
-    rec = shard.records_from_tensor(d_gath[0])
+    rec = shard.records_from_tensor(d_gat2[(step_no[0] - 1) & 1] if step_no[0] else d_gath[0])
     assert len(rec) == C_TOTAL and (rec["problem"] == np.arange(C_TOTAL)).all(), "gather lost candidates"
     n_ok = int(rec["ok"].sum())
 
