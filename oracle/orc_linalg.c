@@ -19,6 +19,11 @@ __thread long long orc_flops = 0;
 #define FL(n) (orc_flops += (n))
 long long orc_flops_take(void) { long long v = orc_flops; orc_flops = 0; return v; }
 
+/* Arithmetic contract: only + - * / sqrt and EXPLICIT fused multiply-adds, in a fixed order.  Every fma below
+ * has a twin in csrc/linalg.cuh (rfma); compilers are forbidden to contract anything else (-ffp-contract=off,
+ * nvcc -fmad=false).  fma()/fmaf() are correctly rounded whether they compile to a vfmadd or call libm. */
+#define ORC_FMA(a, b, c) _Generic((a), float: fmaf, default: fma)((a), (b), (c))
+
 #define ORC_MAX_SWEEPS 30
 
 #define ORC_MAX_SWEEPS_REC 12
@@ -33,7 +38,7 @@ long long orc_flops_take(void) { long long v = orc_flops; orc_flops = 0; return 
 #define ORC_ANGLE(T, SQRT, FABS, HALF, FOUR, ZERO)                                              \
     const T h = aqq - app;                                                                      \
     const T b2 = apq + apq;                                                                     \
-    const T r = SQRT(h * h + b2 * b2);                                                          \
+    const T r = SQRT(ORC_FMA(h, h, b2 * b2));                                                   \
     const T ah = FABS(h);                                                                       \
     const T uu = (r + r) * (r + ah);                                                            \
     const T ww = (HALF + HALF) / SQRT(uu);                                                      \
@@ -52,7 +57,7 @@ void NAME(int n, T *a, T *w, T *v)                                              
         for (int j = 0; j < n; ++j) v[i * n + j] = (i == j) ? ONE : ZERO;                       \
     T fro2 = ZERO;                                                                              \
     for (int i = 0; i < n; ++i)                                                                 \
-        for (int j = i; j < n; ++j) fro2 += a[i * n + j] * a[i * n + j];                        \
+        for (int j = i; j < n; ++j) fro2 = ORC_FMA(a[i * n + j], a[i * n + j], fro2);                        \
     FL(n * (n + 1) + 2);                                                                        \
     const T tol = SQRT(fro2) * TOLSCALE;                                                        \
     for (int sweep = 0; sweep < ORC_MAX_SWEEPS; ++sweep) {                                      \
@@ -73,13 +78,13 @@ void NAME(int n, T *a, T *w, T *v)                                              
                     const int ip = (j < p) ? j * n + p : p * n + j;                             \
                     const int iq = (j < q) ? j * n + q : q * n + j;                             \
                     const T g = a[ip], k = a[iq];                                               \
-                    a[ip] = c * g - s * k;                                                      \
-                    a[iq] = s * g + c * k;                                                      \
+                    a[ip] = ORC_FMA(c, g, -(s * k));                                                      \
+                    a[iq] = ORC_FMA(s, g, c * k);                                                      \
                 }                                                                               \
                 for (int j = 0; j < n; ++j) {                                                   \
                     const T g = v[j * n + p], k = v[j * n + q];                                 \
-                    v[j * n + p] = c * g - s * k;                                               \
-                    v[j * n + q] = s * g + c * k;                                               \
+                    v[j * n + p] = ORC_FMA(c, g, -(s * k));                                               \
+                    v[j * n + q] = ORC_FMA(s, g, c * k);                                               \
                 }                                                                               \
             }                                                                                   \
         }                                                                                       \
@@ -137,7 +142,7 @@ void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
     static __thread double rc[ORC_MAX_SWEEPS_REC * 66], rs[ORC_MAX_SWEEPS_REC * 66];
     double fro2 = 0.0;
     for (int i = 0; i < n; ++i)
-        for (int j = i; j < n; ++j) fro2 += a[i * n + j] * a[i * n + j];
+        for (int j = i; j < n; ++j) fro2 = ORC_FMA(a[i * n + j], a[i * n + j], fro2);
     FL(n * (n + 1) + 2);
     const double tol = sqrt(fro2) * 0x1p-56;
     int sweeps = 0;
@@ -172,16 +177,16 @@ void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
                         const int ys[2] = {P[j], Q[j]};
                         for (int e = 0; e < 2; ++e) {
                             const double g = ORC_E(P[i], ys[e]), k = ORC_E(Q[i], ys[e]);
-                            ORC_E(P[i], ys[e]) = C[i] * g - S[i] * k;
-                            ORC_E(Q[i], ys[e]) = S[i] * g + C[i] * k;
+                            ORC_E(P[i], ys[e]) = ORC_FMA(C[i], g, -(S[i] * k));
+                            ORC_E(Q[i], ys[e]) = ORC_FMA(S[i], g, C[i] * k);
                         }
                     }
                     if (rot[j]) {
                         const int xs[2] = {P[i], Q[i]};
                         for (int e = 0; e < ni; ++e) {
                             const double g = ORC_E(xs[e], P[j]), k = ORC_E(xs[e], Q[j]);
-                            ORC_E(xs[e], P[j]) = C[j] * g - S[j] * k;
-                            ORC_E(xs[e], Q[j]) = S[j] * g + C[j] * k;
+                            ORC_E(xs[e], P[j]) = ORC_FMA(C[j], g, -(S[j] * k));
+                            ORC_E(xs[e], Q[j]) = ORC_FMA(S[j], g, C[j] * k);
                         }
                     }
                 }
@@ -223,8 +228,8 @@ void orc_jacobi_lowest_d(int n, int nv, double *a, double *w, double *v)
                     FL(6 * nv);
                     for (int k = 0; k < nv; ++k) {
                         const double xp = x[k][p], xq = x[k][q];
-                        x[k][p] = c * xp + s * xq;
-                        x[k][q] = c * xq - s * xp;
+                        x[k][p] = ORC_FMA(c, xp, s * xq);
+                        x[k][q] = ORC_FMA(c, xq, -(s * xp));
                     }
                 }
             }
@@ -245,9 +250,9 @@ static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k 
                 double alpha = 0.0, beta = 0.0, gamma = 0.0;
                 for (int r = 0; r < m; ++r) {
                     const double ui = U[r * k + i], uj = U[r * k + j];
-                    alpha += ui * ui;
-                    beta += uj * uj;
-                    gamma += ui * uj;
+                    alpha = ORC_FMA(ui, ui, alpha);
+                    beta = ORC_FMA(uj, uj, beta);
+                    gamma = ORC_FMA(ui, uj, gamma);
                 }
                 FL(6 * m + 3);
                 /* |gamma| > eps sqrt(alpha beta), tested on the squares (no square root) */
@@ -258,7 +263,7 @@ static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k 
                  * two square roots and one division */
                 const double h = beta - alpha;
                 const double b2 = gamma + gamma;
-                const double rr = sqrt(h * h + b2 * b2);
+                const double rr = sqrt(ORC_FMA(h, h, b2 * b2));
                 const double ah = fabs(h);
                 const double uu = (rr + rr) * (rr + ah);
                 const double ww = 1.0 / sqrt(uu);
@@ -267,13 +272,13 @@ static void onesided_jacobi(int m, int k, double *U /* m*k */, double *V /* k*k 
                 if (h < 0.0) s = -s;
                 for (int r = 0; r < m; ++r) {
                     const double ui = U[r * k + i], uj = U[r * k + j];
-                    U[r * k + i] = c * ui - s * uj;
-                    U[r * k + j] = s * ui + c * uj;
+                    U[r * k + i] = ORC_FMA(c, ui, -(s * uj));
+                    U[r * k + j] = ORC_FMA(s, ui, c * uj);
                 }
                 for (int r = 0; r < k; ++r) {
                     const double vi = V[r * k + i], vj = V[r * k + j];
-                    V[r * k + i] = c * vi - s * vj;
-                    V[r * k + j] = s * vi + c * vj;
+                    V[r * k + i] = ORC_FMA(c, vi, -(s * vj));
+                    V[r * k + j] = ORC_FMA(s, vi, c * vj);
                 }
             }
         }
@@ -300,7 +305,7 @@ void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
     double smax = 0.0;
     for (int j = 0; j < k; ++j) {
         double s2 = 0.0;
-        for (int r = 0; r < m; ++r) s2 += U[r * k + j] * U[r * k + j];
+        for (int r = 0; r < m; ++r) s2 = ORC_FMA(U[r * k + j], U[r * k + j], s2);
         sig2[j] = s2;
         sig[j] = sqrt(s2);
         if (sig[j] > smax) smax = sig[j];
@@ -318,10 +323,10 @@ void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
     for (int j = 0; j < k; ++j) {
         if (!(sig[j] > thresh)) continue;
         double ub = 0.0;
-        for (int r = 0; r < m; ++r) ub += U[r * k + j] * b[r];
+        for (int r = 0; r < m; ++r) ub = ORC_FMA(U[r * k + j], b[r], ub);
         const double coef = ub / sig2[j];
         FL(2 * m + 1 + 2 * k);
-        for (int r = 0; r < k; ++r) x[r] += coef * V[r * k + j];
+        for (int r = 0; r < k; ++r) x[r] = ORC_FMA(coef, V[r * k + j], x[r]);
     }
 }
 
@@ -338,24 +343,24 @@ static int qr_lstsq(int m, int k, const double *L, const double *b, double *x)
     memcpy(bb, b, sizeof(double) * (size_t)m);
     for (int c = 0; c < k; ++c) {
         double s = 0.0;
-        for (int r = c; r < m; ++r) s += A[r * k + c] * A[r * k + c];
+        for (int r = c; r < m; ++r) s = ORC_FMA(A[r * k + c], A[r * k + c], s);
         const double norm = sqrt(s);
         if (norm == 0.0) return 0;
         const double alpha = (A[c * k + c] > 0.0) ? -norm : norm;
         A[c * k + c] = A[c * k + c] - alpha;
         double vtv = 0.0;
-        for (int r = c; r < m; ++r) vtv += A[r * k + c] * A[r * k + c];
+        for (int r = c; r < m; ++r) vtv = ORC_FMA(A[r * k + c], A[r * k + c], vtv);
         const double tau = 2.0 / vtv;
         for (int j = c + 1; j < k; ++j) {
             double d = 0.0;
-            for (int r = c; r < m; ++r) d += A[r * k + c] * A[r * k + j];
+            for (int r = c; r < m; ++r) d = ORC_FMA(A[r * k + c], A[r * k + j], d);
             d = d * tau;
-            for (int r = c; r < m; ++r) A[r * k + j] = A[r * k + j] - d * A[r * k + c];
+            for (int r = c; r < m; ++r) A[r * k + j] = ORC_FMA(-d, A[r * k + c], A[r * k + j]);
         }
         double d = 0.0;
-        for (int r = c; r < m; ++r) d += A[r * k + c] * bb[r];
+        for (int r = c; r < m; ++r) d = ORC_FMA(A[r * k + c], bb[r], d);
         d = d * tau;
-        for (int r = c; r < m; ++r) bb[r] = bb[r] - d * A[r * k + c];
+        for (int r = c; r < m; ++r) bb[r] = ORC_FMA(-d, A[r * k + c], bb[r]);
         rd[c] = alpha;
         FL(4 * (m - c) + 3 + (k - c) * (4 * (m - c) + 1));
     }
@@ -368,7 +373,7 @@ static int qr_lstsq(int m, int k, const double *L, const double *b, double *x)
     if (!(rmin > rmax * 1e-7)) return 0;
     for (int i = k - 1; i >= 0; --i) {
         double sum = 0.0;
-        for (int j = i + 1; j < k; ++j) sum += A[i * k + j] * x[j];
+        for (int j = i + 1; j < k; ++j) sum = ORC_FMA(A[i * k + j], x[j], sum);
         x[i] = (bb[i] - sum) / rd[i];
     }
     FL(k * k + k);
@@ -385,15 +390,15 @@ void orc_lstsq_d(int m, int k, const double *L, const double *b, double *x)
  * singular => inf/NaN propagate. */
 void orc_inv3_d(const double m[9], double out[9])
 {
-    const double c00 = m[4] * m[8] - m[5] * m[7];
-    const double c01 = m[5] * m[6] - m[3] * m[8];
-    const double c02 = m[3] * m[7] - m[4] * m[6];
-    const double c10 = m[2] * m[7] - m[1] * m[8];
-    const double c11 = m[0] * m[8] - m[2] * m[6];
-    const double c12 = m[1] * m[6] - m[0] * m[7];
-    const double c20 = m[1] * m[5] - m[2] * m[4];
-    const double c21 = m[2] * m[3] - m[0] * m[5];
-    const double c22 = m[0] * m[4] - m[1] * m[3];
+    const double c00 = ORC_FMA(m[4], m[8], -(m[5] * m[7]));
+    const double c01 = ORC_FMA(m[5], m[6], -(m[3] * m[8]));
+    const double c02 = ORC_FMA(m[3], m[7], -(m[4] * m[6]));
+    const double c10 = ORC_FMA(m[2], m[7], -(m[1] * m[8]));
+    const double c11 = ORC_FMA(m[0], m[8], -(m[2] * m[6]));
+    const double c12 = ORC_FMA(m[1], m[6], -(m[0] * m[7]));
+    const double c20 = ORC_FMA(m[1], m[5], -(m[2] * m[4]));
+    const double c21 = ORC_FMA(m[2], m[3], -(m[0] * m[5]));
+    const double c22 = ORC_FMA(m[0], m[4], -(m[1] * m[3]));
     const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
     const double id = 1.0 / det;
     FL(27 + 5 + 1 + 9);
@@ -412,7 +417,7 @@ void orc_polar3_d(const double a[9], double r[9])
     onesided_jacobi(3, 3, U, V);
     for (int j = 0; j < 3; ++j) {
         double s2 = 0.0;
-        for (int i = 0; i < 3; ++i) s2 += U[i * 3 + j] * U[i * 3 + j];
+        for (int i = 0; i < 3; ++i) s2 = ORC_FMA(U[i * 3 + j], U[i * 3 + j], s2);
         inv[j] = 1.0 / sqrt(s2);
     }
     for (int i = 0; i < 3; ++i)
@@ -449,7 +454,7 @@ int orc_rank3_fullpiv_d(const double a_in[9])
             for (int r = 0; r < 3; ++r) { double t = a[r * 3 + k]; a[r * 3 + k] = a[r * 3 + pc]; a[r * 3 + pc] = t; }
         /* Householder on column k, rows k..2 */
         double tail2 = 0.0;
-        for (int r = k + 1; r < 3; ++r) tail2 += a[r * 3 + k] * a[r * 3 + k];
+        for (int r = k + 1; r < 3; ++r) tail2 = ORC_FMA(a[r * 3 + k], a[r * 3 + k], tail2);
         const double c0 = a[k * 3 + k];
         double beta, tau;
         double vv[3] = {0.0, 0.0, 0.0};
@@ -466,7 +471,7 @@ int orc_rank3_fullpiv_d(const double a_in[9])
         if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
         for (int c = k + 1; c < 3; ++c) {
             double dot = 0.0;
-            for (int r = k; r < 3; ++r) dot += vv[r] * a[r * 3 + c];
+            for (int r = k; r < 3; ++r) dot = ORC_FMA(vv[r], a[r * 3 + c], dot);
             for (int r = k; r < 3; ++r) a[r * 3 + c] -= tau * vv[r] * dot;
         }
     }
@@ -509,13 +514,13 @@ void orc_ldlt6_solve_d(const double a_in[36], const double g[6], double x[6])
     double y[N];
     for (int i = 0; i < N; ++i) y[i] = g[perm[i]];
     for (int i = 0; i < N; ++i)
-        for (int j = 0; j < i; ++j) y[i] -= a[i * N + j] * y[j];
+        for (int j = 0; j < i; ++j) y[i] = ORC_FMA(-a[i * N + j], y[j], y[i]);
     for (int i = 0; i < N; ++i) {
         const double d = a[i * N + i];
         y[i] = (fabs(d) > DBL_MIN) ? y[i] / d : 0.0;
     }
     for (int i = N - 1; i >= 0; --i)
-        for (int j = i + 1; j < N; ++j) y[i] -= a[j * N + i] * y[j];
+        for (int j = i + 1; j < N; ++j) y[i] = ORC_FMA(-a[j * N + i], y[j], y[i]);
     for (int i = 0; i < N; ++i) x[perm[i]] = y[i];
 }
 
@@ -534,19 +539,19 @@ void orc_nullspace_qr_d(const double *Mrows, double *U4)
         for (int c = 0; c < 8; ++c) A[r][c] = Mrows[c * 12 + r];
     for (int k = 0; k < 8; ++k) {
         double s = 0.0;
-        for (int r = k; r < 12; ++r) s += A[r][k] * A[r][k];
+        for (int r = k; r < 12; ++r) s = ORC_FMA(A[r][k], A[r][k], s);
         const double norm = sqrt(s);
         if (norm == 0.0) { tau[k] = 0.0; continue; }
         const double alpha = (A[k][k] > 0.0) ? -norm : norm;
         A[k][k] = A[k][k] - alpha;
         double vtv = 0.0;
-        for (int r = k; r < 12; ++r) vtv += A[r][k] * A[r][k];
+        for (int r = k; r < 12; ++r) vtv = ORC_FMA(A[r][k], A[r][k], vtv);
         tau[k] = 2.0 / vtv;
         for (int j = k + 1; j < 8; ++j) {
             double d = 0.0;
-            for (int r = k; r < 12; ++r) d += A[r][k] * A[r][j];
+            for (int r = k; r < 12; ++r) d = ORC_FMA(A[r][k], A[r][j], d);
             d = d * tau[k];
-            for (int r = k; r < 12; ++r) A[r][j] = A[r][j] - d * A[r][k];
+            for (int r = k; r < 12; ++r) A[r][j] = ORC_FMA(-d, A[r][k], A[r][j]);
         }
         FL(2 * (12 - k) + 1 + 1 + 2 * (12 - k) + 1 + (7 - k) * (4 * (12 - k) + 1));
     }
@@ -556,9 +561,9 @@ void orc_nullspace_qr_d(const double *Mrows, double *U4)
         for (int k = 7; k >= 0; --k) {
             if (tau[k] == 0.0) continue;
             double d = 0.0;
-            for (int r = k; r < 12; ++r) d += A[r][k] * y[r];
+            for (int r = k; r < 12; ++r) d = ORC_FMA(A[r][k], y[r], d);
             d = d * tau[k];
-            for (int r = k; r < 12; ++r) y[r] = y[r] - d * A[r][k];
+            for (int r = k; r < 12; ++r) y[r] = ORC_FMA(-d, A[r][k], y[r]);
             FL(4 * (12 - k) + 1);
         }
         for (int r = 0; r < 12; ++r) U4[r * 4 + i] = y[r];

@@ -49,9 +49,9 @@ void orc_rot2rodrigues(const double R[9], double w[3])
 
 static void cross3(const double a[3], const double b[3], double o[3])
 {
-    o[0] = a[1] * b[2] - a[2] * b[1];
-    o[1] = a[2] * b[0] - a[0] * b[2];
-    o[2] = a[0] * b[1] - a[1] * b[0];
+    o[0] = fma(a[1], b[2], -(a[2] * b[1]));
+    o[1] = fma(a[2], b[0], -(a[0] * b[2]));
+    o[2] = fma(a[0], b[1], -(a[1] * b[0]));
 }
 
 /* residual pair and 2x6 Jacobian of one observation
@@ -148,8 +148,8 @@ static void mlpnp_gn(double x[6], int n, const double *pts, const double *nulls,
             if (P) {
                 const double *p = P + 4 * i;
                 for (int c = 0; c < 6; ++c) {
-                    W0[c] = J[c] * p[0] + J[6 + c] * p[2];
-                    W1[c] = J[c] * p[1] + J[6 + c] * p[3];
+                    W0[c] = fma(J[c], p[0], J[6 + c] * p[2]);
+                    W1[c] = fma(J[c], p[1], J[6 + c] * p[3]);
                 }
             } else {
                 for (int c = 0; c < 6; ++c) { W0[c] = J[c]; W1[c] = J[6 + c]; }
@@ -157,11 +157,11 @@ static void mlpnp_gn(double x[6], int n, const double *pts, const double *nulls,
             wr0 = r[0]; wr1 = r[1];
             for (int a = 0; a < 6; ++a) {
                 for (int b = 0; b < 6; ++b) {
-                    A[a * 6 + b] += W0[a] * J[b];
-                    A[a * 6 + b] += W1[a] * J[6 + b];
+                    A[a * 6 + b] = fma(W0[a], J[b], A[a * 6 + b]);
+                    A[a * 6 + b] = fma(W1[a], J[6 + b], A[a * 6 + b]);
                 }
-                g[a] += W0[a] * wr0;
-                g[a] += W1[a] * wr1;
+                g[a] = fma(W0[a], wr0, g[a]);
+                g[a] = fma(W1[a], wr1, g[a]);
             }
         }
         orc_ldlt6_solve_d(A, g, dx);                                   /* :705-706 */
@@ -202,7 +202,7 @@ static void compute_pose(int n, const double *f, const double *p, const double *
     memset(planarTest, 0, sizeof(planarTest));
     for (int i = 0; i < n; ++i)
         for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) planarTest[r * 3 + c] += p[3 * i + r] * p[3 * i + c];
+            for (int c = 0; c < 3; ++c) planarTest[r * 3 + c] = fma(p[3 * i + r], p[3 * i + c], planarTest[r * 3 + c]);
     double eigenRot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     int planar = 0;
     if (orc_rank3_fullpiv_d(planarTest) == 2) {
@@ -231,7 +231,7 @@ static void compute_pose(int n, const double *f, const double *p, const double *
             for (int r = 0; r < 2; ++r)
                 for (int c = 0; c < 2; ++c)
                     T[r * 2 + c] = N[0 * 2 + r] * SN[0 * 2 + c] + N[1 * 2 + r] * SN[1 * 2 + c] + N[2 * 2 + r] * SN[2 * 2 + c];
-            const double det = T[0] * T[3] - T[1] * T[2];
+            const double det = fma(T[0], T[3], -(T[1] * T[2]));
             const double id = 1.0 / det;                               /* Matrix2d::inverse() :381 */
             P[4 * i + 0] = T[3] * id;
             P[4 * i + 1] = -T[1] * id;
@@ -267,8 +267,8 @@ static void compute_pose(int n, const double *f, const double *p, const double *
         if (P) {
             const double *pp = P + 4 * i;
             for (int c = 0; c < cols; ++c) {
-                w0[c] = pp[0] * a0[c] + pp[1] * a1[c];
-                w1[c] = pp[2] * a0[c] + pp[3] * a1[c];
+                w0[c] = fma(pp[0], a0[c], pp[1] * a1[c]);
+                w1[c] = fma(pp[2], a0[c], pp[3] * a1[c]);
             }
         } else {
             memcpy(w0, a0, sizeof(double) * (size_t)cols);
@@ -276,8 +276,8 @@ static void compute_pose(int n, const double *f, const double *p, const double *
         }
         for (int a = 0; a < cols; ++a)
             for (int b = a; b < cols; ++b) {
-                AtPA[a * cols + b] += a0[a] * w0[b];
-                AtPA[a * cols + b] += a1[a] * w1[b];
+                AtPA[a * cols + b] = fma(a0[a], w0[b], AtPA[a * cols + b]);
+                AtPA[a * cols + b] = fma(a1[a], w1[b], AtPA[a * cols + b]);
             }
     }
     double ev[1], result1[12];

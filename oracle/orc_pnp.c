@@ -88,9 +88,9 @@ static void choose_control_points(epnp_t *e)
         const double d0 = e->pws[i * 3 + 0] - e->cws[0][0];
         const double d1 = e->pws[i * 3 + 1] - e->cws[0][1];
         const double d2 = e->pws[i * 3 + 2] - e->cws[0][2];
-        A[0] += d0 * d0; A[1] += d0 * d1; A[2] += d0 * d2;
-        A[4] += d1 * d1; A[5] += d1 * d2;
-        A[8] += d2 * d2;
+        A[0] = fma(d0, d0, A[0]); A[1] = fma(d0, d1, A[1]); A[2] = fma(d0, d2, A[2]);
+        A[4] = fma(d1, d1, A[4]); A[5] = fma(d1, d2, A[5]);
+        A[8] = fma(d2, d2, A[8]);
     }
     FL(3 * ns + 3 + n * 15);
     double DC[3], UCt[9];
@@ -268,7 +268,7 @@ static void qr_solve(double A[6][4], double b[6], double X[4])
         double sum = 0.0;
         for (int i = k; i < nr; ++i) {
             A[i][k] *= inv_eta;
-            sum += A[i][k] * A[i][k];
+            sum = fma(A[i][k], A[i][k], sum);
         }
         double sigma = sqrt(sum);
         if (A[k][k] < 0) sigma = -sigma;
@@ -277,9 +277,9 @@ static void qr_solve(double A[6][4], double b[6], double X[4])
         A2[k] = -eta * sigma;
         for (int j = k + 1; j < nc; ++j) {
             double s = 0;
-            for (int i = k; i < nr; ++i) s += A[i][k] * A[i][j];
+            for (int i = k; i < nr; ++i) s = fma(A[i][k], A[i][j], s);
             const double tau = s / A1[k];
-            for (int i = k; i < nr; ++i) A[i][j] -= tau * A[i][k];
+            for (int i = k; i < nr; ++i) A[i][j] = fma(-tau, A[i][k], A[i][j]);
         }
     }
     FL(4 * 6 + 2 * (6 + 5 + 4 + 3) + 4 * 5 + (3 * 6 + 2 * 5 + 1 * 4) * 4 + 6);   /* column scaling, norms, reflections */
@@ -287,15 +287,15 @@ static void qr_solve(double A[6][4], double b[6], double X[4])
     /* b <- Qt b (:762-780) */
     for (int j = 0; j < nc; ++j) {
         double tau = 0;
-        for (int i = j; i < nr; ++i) tau += A[i][j] * b[i];
+        for (int i = j; i < nr; ++i) tau = fma(A[i][j], b[i], tau);
         tau /= A1[j];
-        for (int i = j; i < nr; ++i) b[i] -= tau * A[i][j];
+        for (int i = j; i < nr; ++i) b[i] = fma(-tau, A[i][j], b[i]);
     }
     /* X = R^-1 b (:782-795) */
     X[nc - 1] = b[nc - 1] / A2[nc - 1];
     for (int i = nc - 2; i >= 0; --i) {
         double sum = 0;
-        for (int j = i + 1; j < nc; ++j) sum += A[i][j] * X[j];
+        for (int j = i + 1; j < nc; ++j) sum = fma(A[i][j], X[j], sum);
         X[i] = (b[i] - sum) / A2[i];
     }
 }
@@ -319,7 +319,7 @@ static void compute_ccs(epnp_t *e, const double betas[4], const double *U)
     for (int i = 0; i < 4; ++i)
         for (int c = 0; c < 3; ++c) {
             double s = 0.0;
-            for (int j = 0; j < 4; ++j) s += betas[j] * U[(3 * i + c) * 4 + j];
+            for (int j = 0; j < 4; ++j) s = fma(betas[j], U[(3 * i + c) * 4 + j], s);
             e->ccs[i][c] = s;
         }
 }
@@ -447,8 +447,8 @@ static double compute_pose(epnp_t *e, float Rf[9], float tf[3])
         }
         for (int a = 0; a < 12; ++a)
             for (int b = a; b < 12; ++b) {
-                MtM[a * 12 + b] += r0[a] * r0[b];
-                MtM[a * 12 + b] += r1[a] * r1[b];
+                MtM[a * 12 + b] = fma(r0[a], r0[b], MtM[a * 12 + b]);
+                MtM[a * 12 + b] = fma(r1[a], r1[b], MtM[a * 12 + b]);
             }
     }
     double w[4], U[48];

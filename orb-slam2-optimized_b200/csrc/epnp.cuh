@@ -212,7 +212,7 @@ __host__ __device__ inline void epnp_qr_solve(double* A /*6x4*/, double* b, doub
         double sum = 0.0;
         for (int i = k; i < nr; ++i) {
             A[i * nc + k] *= inv_eta;
-            sum += A[i * nc + k] * A[i * nc + k];
+            sum = rfma(A[i * nc + k], A[i * nc + k], sum);
         }
         double sigma = sqrt(sum);
         if (A[k * nc + k] < 0) sigma = -sigma;
@@ -221,21 +221,21 @@ __host__ __device__ inline void epnp_qr_solve(double* A /*6x4*/, double* b, doub
         A2[k] = -eta * sigma;
         for (int j = k + 1; j < nc; ++j) {
             double s = 0;
-            for (int i = k; i < nr; ++i) s += A[i * nc + k] * A[i * nc + j];
+            for (int i = k; i < nr; ++i) s = rfma(A[i * nc + k], A[i * nc + j], s);
             const double tau = s / A1[k];
-            for (int i = k; i < nr; ++i) A[i * nc + j] -= tau * A[i * nc + k];
+            for (int i = k; i < nr; ++i) A[i * nc + j] = rfma(-tau, A[i * nc + k], A[i * nc + j]);
         }
     }
     for (int j = 0; j < nc; ++j) {
         double tau = 0;
-        for (int i = j; i < nr; ++i) tau += A[i * nc + j] * b[i];
+        for (int i = j; i < nr; ++i) tau = rfma(A[i * nc + j], b[i], tau);
         tau /= A1[j];
-        for (int i = j; i < nr; ++i) b[i] -= tau * A[i * nc + j];
+        for (int i = j; i < nr; ++i) b[i] = rfma(-tau, A[i * nc + j], b[i]);
     }
     X[nc - 1] = b[nc - 1] / A2[nc - 1];
     for (int i = nc - 2; i >= 0; --i) {
         double sum = 0;
-        for (int j = i + 1; j < nc; ++j) sum += A[i * nc + j] * X[j];
+        for (int j = i + 1; j < nc; ++j) sum = rfma(A[i * nc + j], X[j], sum);
         X[i] = (b[i] - sum) / A2[i];
     }
 }
@@ -306,7 +306,7 @@ __host__ __device__ inline void epnp_ccs(const double* betas, const double* U4, 
     for (int i = 0; i < 4; ++i)
         for (int c = 0; c < 3; ++c) {
             double s = 0.0;
-            for (int j = 0; j < 4; ++j) s += betas[j] * U4[(3 * i + c) * 4 + j];
+            for (int j = 0; j < 4; ++j) s = rfma(betas[j], U4[(3 * i + c) * 4 + j], s);
             ccs[i * 3 + c] = s;
         }
 }
@@ -369,9 +369,9 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
     double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < NPTS; ++i) {
         const double d0 = pw[i * 3 + 0] - C0[0], d1 = pw[i * 3 + 1] - C0[1], d2 = pw[i * 3 + 2] - C0[2];
-        A[0] += d0 * d0; A[1] += d0 * d1; A[2] += d0 * d2;
-        A[4] += d1 * d1; A[5] += d1 * d2;
-        A[8] += d2 * d2;
+        A[0] = rfma(d0, d0, A[0]); A[1] = rfma(d0, d1, A[1]); A[2] = rfma(d0, d2, A[2]);
+        A[4] = rfma(d1, d1, A[4]); A[5] = rfma(d1, d2, A[5]);
+        A[8] = rfma(d2, d2, A[8]);
     }
     epnp_control_points(C0, A, NPTS, cws);
     double CCi[9];
@@ -395,8 +395,8 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
             for (int a = 0; a < 12; ++a)
 #pragma unroll
                 for (int b = a; b < 12; ++b) {
-                    MtM[tri_idx(12, a, b)] += r0[a] * r0[b];
-                    MtM[tri_idx(12, a, b)] += r1[a] * r1[b];
+                    MtM[tri_idx(12, a, b)] = rfma(r0[a], r0[b], MtM[tri_idx(12, a, b)]);
+                    MtM[tri_idx(12, a, b)] = rfma(r1[a], r1[b], MtM[tri_idx(12, a, b)]);
                 }
         }
         double2 rec[kMaxSweepsRec * 66];

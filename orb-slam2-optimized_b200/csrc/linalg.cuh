@@ -19,6 +19,10 @@ template <> struct JacobiTol<float>  { __host__ __device__ static float scale() 
 
 __host__ __device__ inline double rsqrt_exact(double x) { return sqrt(x); }
 __host__ __device__ inline float rsqrt_exact(float x) { return sqrtf(x); }
+// explicit fused multiply-add: the only contraction allowed by the arithmetic contract (the build uses
+// -fmad=false); every rfma below has a twin in oracle/orc_linalg.c (ORC_FMA)
+__host__ __device__ inline double rfma(double a, double b, double c) { return fma(a, b, c); }
+__host__ __device__ inline float rfma(float a, float b, float c) { return fmaf(a, b, c); }
 __host__ __device__ inline double rabs(double x) { return fabs(x); }
 __host__ __device__ inline float rabs(float x) { return fabsf(x); }
 
@@ -36,7 +40,7 @@ __host__ __device__ inline void jacobi_angle(T app, T aqq, T apq, T& c, T& s, T&
     const T half = T(0.5);
     const T h = aqq - app;
     const T b2 = apq + apq;
-    const T r = rsqrt_exact(h * h + b2 * b2);
+    const T r = rsqrt_exact(rfma(h, h, b2 * b2));
     const T ah = rabs(h);
     const T uu = (r + r) * (r + ah);
     const T ww = (half + half) / rsqrt_exact(uu);
@@ -64,7 +68,7 @@ __host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = i; j < N; ++j) fro2 += a[i * N + j] * a[i * N + j];
+        for (int j = i; j < N; ++j) fro2 = rfma(a[i * N + j], a[i * N + j], fro2);
     const T tol = rsqrt_exact(fro2) * JacobiTol<T>::scale();
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         bool rotated = false;
@@ -87,14 +91,14 @@ __host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
                     const int ip = (j < p) ? j * N + p : p * N + j;
                     const int iq = (j < q) ? j * N + q : q * N + j;
                     const T g = a[ip], k = a[iq];
-                    a[ip] = c * g - s * k;
-                    a[iq] = s * g + c * k;
+                    a[ip] = rfma(c, g, -(s * k));
+                    a[iq] = rfma(s, g, c * k);
                 }
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const T g = v[j * N + p], k = v[j * N + q];
-                    v[j * N + p] = c * g - s * k;
-                    v[j * N + q] = s * g + c * k;
+                    v[j * N + p] = rfma(c, g, -(s * k));
+                    v[j * N + q] = rfma(s, g, c * k);
                 }
             }
         }
@@ -156,7 +160,7 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = i; j < N; ++j) fro2 += a[tri_idx(N, i, j)] * a[tri_idx(N, i, j)];
+        for (int j = i; j < N; ++j) fro2 = rfma(a[tri_idx(N, i, j)], a[tri_idx(N, i, j)], fro2);
     const double tol = sqrt(fro2) * 0x1p-56;
     int sweeps = 0;
     for (int sweep = 0; sweep < kMaxSweepsRec; ++sweep) {
@@ -194,25 +198,25 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
                     if (rot[i]) {                              // rot[i] implies a real pair
                         {
                             const double g = a[tri_sym(N, pi, pj)], k = a[tri_sym(N, qi < N ? qi : pi, pj)];
-                            a[tri_sym(N, pi, pj)] = C[i] * g - S[i] * k;
-                            a[tri_sym(N, qi < N ? qi : pi, pj)] = S[i] * g + C[i] * k;
+                            a[tri_sym(N, pi, pj)] = rfma(C[i], g, -(S[i] * k));
+                            a[tri_sym(N, qi < N ? qi : pi, pj)] = rfma(S[i], g, C[i] * k);
                         }
                         {
                             const double g = a[tri_sym(N, pi, qj)], k = a[tri_sym(N, qi < N ? qi : pi, qj)];
-                            a[tri_sym(N, pi, qj)] = C[i] * g - S[i] * k;
-                            a[tri_sym(N, qi < N ? qi : pi, qj)] = S[i] * g + C[i] * k;
+                            a[tri_sym(N, pi, qj)] = rfma(C[i], g, -(S[i] * k));
+                            a[tri_sym(N, qi < N ? qi : pi, qj)] = rfma(S[i], g, C[i] * k);
                         }
                     }
                     if (rot[j]) {
                         {
                             const double g = a[tri_sym(N, pi, pj)], k = a[tri_sym(N, pi, qj)];
-                            a[tri_sym(N, pi, pj)] = C[j] * g - S[j] * k;
-                            a[tri_sym(N, pi, qj)] = S[j] * g + C[j] * k;
+                            a[tri_sym(N, pi, pj)] = rfma(C[j], g, -(S[j] * k));
+                            a[tri_sym(N, pi, qj)] = rfma(S[j], g, C[j] * k);
                         }
                         if (qi < N) {                          // a bye has one real member only
                             const double g = a[tri_sym(N, qi < N ? qi : pi, pj)], k = a[tri_sym(N, qi < N ? qi : pi, qj)];
-                            a[tri_sym(N, qi < N ? qi : pi, pj)] = C[j] * g - S[j] * k;
-                            a[tri_sym(N, qi < N ? qi : pi, qj)] = S[j] * g + C[j] * k;
+                            a[tri_sym(N, qi < N ? qi : pi, pj)] = rfma(C[j], g, -(S[j] * k));
+                            a[tri_sym(N, qi < N ? qi : pi, qj)] = rfma(S[j], g, C[j] * k);
                         }
                     }
                 }
@@ -259,8 +263,8 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
 #pragma unroll
                     for (int k = 0; k < NV; ++k) {
                         const double xp = x[k][p], xq = x[k][q < N ? q : p];
-                        x[k][p] = cs.x * xp + cs.y * xq;
-                        x[k][q < N ? q : p] = cs.x * xq - cs.y * xp;
+                        x[k][p] = rfma(cs.x, xp, cs.y * xq);
+                        x[k][q < N ? q : p] = rfma(cs.x, xq, -(cs.y * xp));
                     }
                 }
             }
@@ -288,7 +292,7 @@ __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, doubl
     double fro2 = 0.0;
     if (lane == 0) {
         for (int i = 0; i < N; ++i)
-            for (int j = i; j < N; ++j) fro2 += a[tri_idx(N, i, j)] * a[tri_idx(N, i, j)];
+            for (int j = i; j < N; ++j) fro2 = rfma(a[tri_idx(N, i, j)], a[tri_idx(N, i, j)], fro2);
     }
     fro2 = __shfl_sync(FULL, fro2, 0);
     const double tol = sqrt(fro2) * 0x1p-56;
@@ -340,15 +344,15 @@ __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, doubl
                     double x00 = a[e00], x01 = a[e01], x10 = a[e10], x11 = a[e11];
                     if (roti) {
                         const double g0 = x00, k0 = x10, g1 = x01, k1 = x11;
-                        x00 = ci * g0 - si * k0; x10 = si * g0 + ci * k0;
-                        x01 = ci * g1 - si * k1; x11 = si * g1 + ci * k1;
+                        x00 = rfma(ci, g0, -(si * k0)); x10 = rfma(si, g0, ci * k0);
+                        x01 = rfma(ci, g1, -(si * k1)); x11 = rfma(si, g1, ci * k1);
                     }
                     if (rotj) {
                         const double g0 = x00, k0 = x01;
-                        x00 = cj * g0 - sj * k0; x01 = sj * g0 + cj * k0;
+                        x00 = rfma(cj, g0, -(sj * k0)); x01 = rfma(sj, g0, cj * k0);
                         if (real_i) {
                             const double g1 = x10, k1 = x11;
-                            x10 = cj * g1 - sj * k1; x11 = sj * g1 + cj * k1;
+                            x10 = rfma(cj, g1, -(sj * k1)); x11 = rfma(sj, g1, cj * k1);
                         }
                     }
                     a[e00] = x00; a[e01] = x01;
@@ -388,8 +392,8 @@ __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, doubl
                     if (cs.y != 0.0) {
                         const int p = tour_lo(M, t, i), q = tour_hi(M, t, i);
                         const double xp = v[p * NV + lane], xq = v[q * NV + lane];
-                        v[p * NV + lane] = cs.x * xp + cs.y * xq;
-                        v[q * NV + lane] = cs.x * xq - cs.y * xp;
+                        v[p * NV + lane] = rfma(cs.x, xp, cs.y * xq);
+                        v[q * NV + lane] = rfma(cs.x, xq, -(cs.y * xp));
                     }
                 }
             }
@@ -410,23 +414,23 @@ __host__ __device__ inline void nullspace_qr_8x12(double* A, double* U4)
     for (int k = 0; k < 8; ++k) {
         double s = 0.0;
 #pragma unroll
-        for (int r = k; r < 12; ++r) s += A[r * 8 + k] * A[r * 8 + k];
+        for (int r = k; r < 12; ++r) s = rfma(A[r * 8 + k], A[r * 8 + k], s);
         const double norm = sqrt(s);
         if (norm == 0.0) { tau[k] = 0.0; continue; }
         const double alpha = (A[k * 8 + k] > 0.0) ? -norm : norm;
         A[k * 8 + k] = A[k * 8 + k] - alpha;
         double vtv = 0.0;
 #pragma unroll
-        for (int r = k; r < 12; ++r) vtv += A[r * 8 + k] * A[r * 8 + k];
+        for (int r = k; r < 12; ++r) vtv = rfma(A[r * 8 + k], A[r * 8 + k], vtv);
         tau[k] = 2.0 / vtv;
 #pragma unroll
         for (int j = k + 1; j < 8; ++j) {
             double d = 0.0;
 #pragma unroll
-            for (int r = k; r < 12; ++r) d += A[r * 8 + k] * A[r * 8 + j];
+            for (int r = k; r < 12; ++r) d = rfma(A[r * 8 + k], A[r * 8 + j], d);
             d = d * tau[k];
 #pragma unroll
-            for (int r = k; r < 12; ++r) A[r * 8 + j] = A[r * 8 + j] - d * A[r * 8 + k];
+            for (int r = k; r < 12; ++r) A[r * 8 + j] = rfma(-d, A[r * 8 + k], A[r * 8 + j]);
         }
     }
 #pragma unroll
@@ -439,10 +443,10 @@ __host__ __device__ inline void nullspace_qr_8x12(double* A, double* U4)
             if (tau[k] == 0.0) continue;
             double d = 0.0;
 #pragma unroll
-            for (int r = k; r < 12; ++r) d += A[r * 8 + k] * y[r];
+            for (int r = k; r < 12; ++r) d = rfma(A[r * 8 + k], y[r], d);
             d = d * tau[k];
 #pragma unroll
-            for (int r = k; r < 12; ++r) y[r] = y[r] - d * A[r * 8 + k];
+            for (int r = k; r < 12; ++r) y[r] = rfma(-d, A[r * 8 + k], y[r]);
         }
 #pragma unroll
         for (int r = 0; r < 12; ++r) U4[r * 4 + i] = y[r];
@@ -465,16 +469,16 @@ __host__ __device__ inline void onesided_jacobi(double* U, double* V)
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
                     const double ui = U[r * K + i], uj = U[r * K + j];
-                    alpha += ui * ui;
-                    beta += uj * uj;
-                    gamma += ui * uj;
+                    alpha = rfma(ui, ui, alpha);
+                    beta = rfma(uj, uj, beta);
+                    gamma = rfma(ui, uj, gamma);
                 }
                 if (!(gamma * gamma > (DBL_EPSILON * DBL_EPSILON) * (alpha * beta))) continue;   // |gamma| > eps sqrt(alpha beta)
                 rotated = true;
                 // rotation that zeroes gamma: tan(2t) = 2 gamma / (beta - alpha); two square roots, one division
                 const double h = beta - alpha;
                 const double b2 = gamma + gamma;
-                const double rr = sqrt(h * h + b2 * b2);
+                const double rr = sqrt(rfma(h, h, b2 * b2));
                 const double ah = fabs(h);
                 const double uu = (rr + rr) * (rr + ah);
                 const double ww = 1.0 / sqrt(uu);
@@ -484,14 +488,14 @@ __host__ __device__ inline void onesided_jacobi(double* U, double* V)
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
                     const double ui = U[r * K + i], uj = U[r * K + j];
-                    U[r * K + i] = c * ui - s * uj;
-                    U[r * K + j] = s * ui + c * uj;
+                    U[r * K + i] = rfma(c, ui, -(s * uj));
+                    U[r * K + j] = rfma(s, ui, c * uj);
                 }
 #pragma unroll
                 for (int r = 0; r < K; ++r) {
                     const double vi = V[r * K + i], vj = V[r * K + j];
-                    V[r * K + i] = c * vi - s * vj;
-                    V[r * K + j] = s * vi + c * vj;
+                    V[r * K + i] = rfma(c, vi, -(s * vj));
+                    V[r * K + j] = rfma(s, vi, c * vj);
                 }
             }
         }
@@ -511,7 +515,7 @@ __host__ __device__ inline void svd_lstsq(const double* L, const double* b, doub
     double smax = 0.0;
     for (int j = 0; j < K; ++j) {
         double s2 = 0.0;
-        for (int r = 0; r < M; ++r) s2 += U[r * K + j] * U[r * K + j];
+        for (int r = 0; r < M; ++r) s2 = rfma(U[r * K + j], U[r * K + j], s2);
         sig2[j] = s2;
         sig[j] = sqrt(s2);
         if (sig[j] > smax) smax = sig[j];
@@ -521,9 +525,9 @@ __host__ __device__ inline void svd_lstsq(const double* L, const double* b, doub
     for (int j = 0; j < K; ++j) {
         if (!(sig[j] > thresh)) continue;
         double ub = 0.0;
-        for (int r = 0; r < M; ++r) ub += U[r * K + j] * b[r];
+        for (int r = 0; r < M; ++r) ub = rfma(U[r * K + j], b[r], ub);
         const double coef = ub / sig2[j];
-        for (int r = 0; r < K; ++r) x[r] += coef * V[r * K + j];
+        for (int r = 0; r < K; ++r) x[r] = rfma(coef, V[r * K + j], x[r]);
     }
 }
 
@@ -542,30 +546,30 @@ __host__ __device__ inline bool qr_lstsq(const double* L, const double* b, doubl
     for (int c = 0; c < K; ++c) {
         double s = 0.0;
 #pragma unroll
-        for (int r = c; r < M; ++r) s += A[r * K + c] * A[r * K + c];
+        for (int r = c; r < M; ++r) s = rfma(A[r * K + c], A[r * K + c], s);
         const double norm = sqrt(s);
         if (norm == 0.0) return false;
         const double alpha = (A[c * K + c] > 0.0) ? -norm : norm;
         A[c * K + c] = A[c * K + c] - alpha;
         double vtv = 0.0;
 #pragma unroll
-        for (int r = c; r < M; ++r) vtv += A[r * K + c] * A[r * K + c];
+        for (int r = c; r < M; ++r) vtv = rfma(A[r * K + c], A[r * K + c], vtv);
         const double tau = 2.0 / vtv;
 #pragma unroll
         for (int j = c + 1; j < K; ++j) {
             double d = 0.0;
 #pragma unroll
-            for (int r = c; r < M; ++r) d += A[r * K + c] * A[r * K + j];
+            for (int r = c; r < M; ++r) d = rfma(A[r * K + c], A[r * K + j], d);
             d = d * tau;
 #pragma unroll
-            for (int r = c; r < M; ++r) A[r * K + j] = A[r * K + j] - d * A[r * K + c];
+            for (int r = c; r < M; ++r) A[r * K + j] = rfma(-d, A[r * K + c], A[r * K + j]);
         }
         double d = 0.0;
 #pragma unroll
-        for (int r = c; r < M; ++r) d += A[r * K + c] * bb[r];
+        for (int r = c; r < M; ++r) d = rfma(A[r * K + c], bb[r], d);
         d = d * tau;
 #pragma unroll
-        for (int r = c; r < M; ++r) bb[r] = bb[r] - d * A[r * K + c];
+        for (int r = c; r < M; ++r) bb[r] = rfma(-d, A[r * K + c], bb[r]);
         rd[c] = alpha;
     }
     double rmax = 0.0, rmin = fabs(rd[0]);
@@ -580,7 +584,7 @@ __host__ __device__ inline bool qr_lstsq(const double* L, const double* b, doubl
     for (int i = K - 1; i >= 0; --i) {
         double sum = 0.0;
 #pragma unroll
-        for (int j = i + 1; j < K; ++j) sum += A[i * K + j] * x[j];
+        for (int j = i + 1; j < K; ++j) sum = rfma(A[i * K + j], x[j], sum);
         x[i] = (bb[i] - sum) / rd[i];
     }
     return true;
@@ -604,15 +608,15 @@ __host__ __device__ inline void lstsq(const double* L, const double* b, double* 
 // closed-form cofactor inverse (Matrix3d::inverse(), PnPsolver.cpp:331); singular => inf/NaN
 __host__ __device__ inline void inv3(const double* m, double* out)
 {
-    const double c00 = m[4] * m[8] - m[5] * m[7];
-    const double c01 = m[5] * m[6] - m[3] * m[8];
-    const double c02 = m[3] * m[7] - m[4] * m[6];
-    const double c10 = m[2] * m[7] - m[1] * m[8];
-    const double c11 = m[0] * m[8] - m[2] * m[6];
-    const double c12 = m[1] * m[6] - m[0] * m[7];
-    const double c20 = m[1] * m[5] - m[2] * m[4];
-    const double c21 = m[2] * m[3] - m[0] * m[5];
-    const double c22 = m[0] * m[4] - m[1] * m[3];
+    const double c00 = rfma(m[4], m[8], -(m[5] * m[7]));
+    const double c01 = rfma(m[5], m[6], -(m[3] * m[8]));
+    const double c02 = rfma(m[3], m[7], -(m[4] * m[6]));
+    const double c10 = rfma(m[2], m[7], -(m[1] * m[8]));
+    const double c11 = rfma(m[0], m[8], -(m[2] * m[6]));
+    const double c12 = rfma(m[1], m[6], -(m[0] * m[7]));
+    const double c20 = rfma(m[1], m[5], -(m[2] * m[4]));
+    const double c21 = rfma(m[2], m[3], -(m[0] * m[5]));
+    const double c22 = rfma(m[0], m[4], -(m[1] * m[3]));
     const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
     const double id = 1.0 / det;
     out[0] = c00 * id; out[1] = c10 * id; out[2] = c20 * id;
@@ -648,7 +652,7 @@ __host__ __device__ inline void polar3(const double* a, double* r)
     onesided_jacobi<3, 3>(U, V);
     for (int j = 0; j < 3; ++j) {
         double s2 = 0.0;
-        for (int i = 0; i < 3; ++i) s2 += U[i * 3 + j] * U[i * 3 + j];
+        for (int i = 0; i < 3; ++i) s2 = rfma(U[i * 3 + j], U[i * 3 + j], s2);
         inv[j] = 1.0 / sqrt(s2);
     }
     for (int i = 0; i < 3; ++i)
@@ -682,7 +686,7 @@ __host__ __device__ inline int rank3_fullpiv(const double* a_in)
         if (pc != k)
             for (int r = 0; r < 3; ++r) { const double t = a[r * 3 + k]; a[r * 3 + k] = a[r * 3 + pc]; a[r * 3 + pc] = t; }
         double tail2 = 0.0;
-        for (int r = k + 1; r < 3; ++r) tail2 += a[r * 3 + k] * a[r * 3 + k];
+        for (int r = k + 1; r < 3; ++r) tail2 = rfma(a[r * 3 + k], a[r * 3 + k], tail2);
         const double c0 = a[k * 3 + k];
         double beta, tau;
         double vv[3] = {0.0, 0.0, 0.0};
@@ -699,7 +703,7 @@ __host__ __device__ inline int rank3_fullpiv(const double* a_in)
         if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
         for (int c = k + 1; c < 3; ++c) {
             double dot = 0.0;
-            for (int r = k; r < 3; ++r) dot += vv[r] * a[r * 3 + c];
+            for (int r = k; r < 3; ++r) dot = rfma(vv[r], a[r * 3 + c], dot);
             for (int r = k; r < 3; ++r) a[r * 3 + c] -= tau * vv[r] * dot;
         }
     }
@@ -740,13 +744,13 @@ __host__ __device__ inline void ldlt6_solve(const double* a_in, const double* g,
     double y[N];
     for (int i = 0; i < N; ++i) y[i] = g[perm[i]];
     for (int i = 0; i < N; ++i)
-        for (int j = 0; j < i; ++j) y[i] -= a[i * N + j] * y[j];
+        for (int j = 0; j < i; ++j) y[i] = rfma(-a[i * N + j], y[j], y[i]);
     for (int i = 0; i < N; ++i) {
         const double d = a[i * N + i];
         y[i] = (fabs(d) > DBL_MIN) ? y[i] / d : 0.0;
     }
     for (int i = N - 1; i >= 0; --i)
-        for (int j = i + 1; j < N; ++j) y[i] -= a[j * N + i] * y[j];
+        for (int j = i + 1; j < N; ++j) y[i] = rfma(-a[j * N + i], y[j], y[i]);
     for (int i = 0; i < N; ++i) x[perm[i]] = y[i];
 }
 

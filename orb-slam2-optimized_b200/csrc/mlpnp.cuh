@@ -13,9 +13,9 @@ namespace rsac {
 
 __host__ __device__ inline void cross3(const double* a, const double* b, double* o)
 {
-    o[0] = a[1] * b[2] - a[2] * b[1];
-    o[1] = a[2] * b[0] - a[0] * b[2];
-    o[2] = a[0] * b[1] - a[1] * b[0];
+    o[0] = rfma(a[1], b[2], -(a[2] * b[1]));
+    o[1] = rfma(a[2], b[0], -(a[0] * b[2]));
+    o[2] = rfma(a[0], b[1], -(a[1] * b[0]));
 }
 
 __host__ __device__ inline double norm3(const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
@@ -131,7 +131,7 @@ __host__ __device__ inline void mlpnp_weight(const double* N, const double* S, d
     for (int r = 0; r < 2; ++r)
         for (int c = 0; c < 2; ++c)
             T[r * 2 + c] = N[0 * 2 + r] * SN[0 * 2 + c] + N[1 * 2 + r] * SN[1 * 2 + c] + N[2 * 2 + r] * SN[2 * 2 + c];
-    const double det = T[0] * T[3] - T[1] * T[2];
+    const double det = rfma(T[0], T[3], -(T[1] * T[2]));
     const double id = 1.0 / det;
     P[0] = T[3] * id;
     P[1] = -T[1] * id;
@@ -162,8 +162,8 @@ __host__ __device__ inline void mlpnp_rows(const double* N, const double* pt, co
     }
     if (P) {
         for (int c = 0; c < cols; ++c) {
-            w0[c] = P[0] * a0[c] + P[1] * a1[c];
-            w1[c] = P[2] * a0[c] + P[3] * a1[c];
+            w0[c] = rfma(P[0], a0[c], P[1] * a1[c]);
+            w1[c] = rfma(P[2], a0[c], P[3] * a1[c]);
         }
     } else {
         for (int c = 0; c < cols; ++c) { w0[c] = a0[c]; w1[c] = a1[c]; }
@@ -281,7 +281,7 @@ __host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const 
     double planarTest[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < NPTS; ++i)
         for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) planarTest[r * 3 + c] += p[3 * i + r] * p[3 * i + c];
+            for (int c = 0; c < 3; ++c) planarTest[r * 3 + c] = rfma(p[3 * i + r], p[3 * i + c], planarTest[r * 3 + c]);
     double eigenRot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     bool planar = false;
     if (rank3_fullpiv(planarTest) == 2) {
@@ -311,8 +311,8 @@ __host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const 
             for (int a = 0; a < 9; ++a)
 #pragma unroll
                 for (int b = a; b < 9; ++b) {
-                    AtPA[tri_idx(9, a, b)] += a0[a] * w0[b];
-                    AtPA[tri_idx(9, a, b)] += a1[a] * w1[b];
+                    AtPA[tri_idx(9, a, b)] = rfma(a0[a], w0[b], AtPA[tri_idx(9, a, b)]);
+                    AtPA[tri_idx(9, a, b)] = rfma(a1[a], w1[b], AtPA[tri_idx(9, a, b)]);
                 }
         }
         jacobi_lowest<9, 1>(AtPA, ev, result1, rec);
@@ -326,8 +326,8 @@ __host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const 
             for (int a = 0; a < 12; ++a)
 #pragma unroll
                 for (int b = a; b < 12; ++b) {
-                    AtPA[tri_idx(12, a, b)] += a0[a] * w0[b];
-                    AtPA[tri_idx(12, a, b)] += a1[a] * w1[b];
+                    AtPA[tri_idx(12, a, b)] = rfma(a0[a], w0[b], AtPA[tri_idx(12, a, b)]);
+                    AtPA[tri_idx(12, a, b)] = rfma(a1[a], w1[b], AtPA[tri_idx(12, a, b)]);
                 }
         }
         jacobi_lowest<12, 1>(AtPA, ev, result1, rec);
@@ -355,19 +355,19 @@ __host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const 
             if (cov) {
                 const double* pp = P + 4 * i;
                 for (int c = 0; c < 6; ++c) {
-                    W0[c] = J[c] * pp[0] + J[6 + c] * pp[2];
-                    W1[c] = J[c] * pp[1] + J[6 + c] * pp[3];
+                    W0[c] = rfma(J[c], pp[0], J[6 + c] * pp[2]);
+                    W1[c] = rfma(J[c], pp[1], J[6 + c] * pp[3]);
                 }
             } else {
                 for (int c = 0; c < 6; ++c) { W0[c] = J[c]; W1[c] = J[6 + c]; }
             }
             for (int a = 0; a < 6; ++a) {
                 for (int b = 0; b < 6; ++b) {
-                    A[a * 6 + b] += W0[a] * J[b];
-                    A[a * 6 + b] += W1[a] * J[6 + b];
+                    A[a * 6 + b] = rfma(W0[a], J[b], A[a * 6 + b]);
+                    A[a * 6 + b] = rfma(W1[a], J[6 + b], A[a * 6 + b]);
                 }
-                g[a] += W0[a] * r[0];
-                g[a] += W1[a] * r[1];
+                g[a] = rfma(W0[a], r[0], g[a]);
+                g[a] = rfma(W1[a], r[1], g[a]);
             }
         }
         ldlt6_solve(A, g, dx);

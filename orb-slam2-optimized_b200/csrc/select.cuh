@@ -129,7 +129,7 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         const int c = (tid < 3) ? tid : (tid < 5 ? tid - 2 : 2);
         double s = 0.0;
 #pragma unroll 8
-        for (int i = 0; i < n; ++i) s += (pw[3 * i + r] - S.C0[r]) * (pw[3 * i + c] - S.C0[c]);
+        for (int i = 0; i < n; ++i) s = rfma(pw[3 * i + r] - S.C0[r], pw[3 * i + c] - S.C0[c], s);   // fma as in epnp_compute_pose_small
         S.A[r * 3 + c] = s;
     }
     __syncthreads();
@@ -180,8 +180,8 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
                     double a0, a1, b0, b1;
                     epnp_m_entry(t6, t6[4], t6[5], cam, ea[k], a0, a1);
                     epnp_m_entry(t6, t6[4], t6[5], cam, eb[k], b0, b1);
-                    acc[k] += a0 * b0;
-                    acc[k] += a1 * b1;
+                    acc[k] = rfma(a0, b0, acc[k]);
+                    acc[k] = rfma(a1, b1, acc[k]);
                 }
             }
         }
@@ -335,7 +335,7 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
     if (tid < 9) {                                     // planarTest = sum p p^T (:346)
         const int r = tid / 3, c = tid % 3;
         double s = 0.0;
-        for (int i = 0; i < n; ++i) s += sc[(size_t)i * kMlpnpScratch + 3 + r] * sc[(size_t)i * kMlpnpScratch + 3 + c];
+        for (int i = 0; i < n; ++i) s = rfma(sc[(size_t)i * kMlpnpScratch + 3 + r], sc[(size_t)i * kMlpnpScratch + 3 + c], s);
         S.planarTest[tid] = s;
     }
     __syncthreads();
@@ -377,11 +377,11 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
             mlpnp_row_entry(o + 6, o + 16, planar, eb, b0, b1);
             double w0 = b0, w1 = b1;
             if (use_cov) {
-                w0 = o[12] * b0 + o[13] * b1;
-                w1 = o[14] * b0 + o[15] * b1;
+                w0 = rfma(o[12], b0, o[13] * b1);
+                w1 = rfma(o[14], b0, o[15] * b1);
             }
-            s += a0 * w0;
-            s += a1 * w1;
+            s = rfma(a0, w0, s);
+            s = rfma(a1, w1, s);
         }
         S.AtPA[tri_idx(cols, ea, eb)] = s;
     }
@@ -425,11 +425,11 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
                 const double* J = o + 19;
                 double W0 = J[ea], W1 = J[6 + ea];
                 if (use_cov) {
-                    W0 = J[ea] * o[12] + J[6 + ea] * o[14];
-                    W1 = J[ea] * o[13] + J[6 + ea] * o[15];
+                    W0 = rfma(J[ea], o[12], J[6 + ea] * o[14]);
+                    W1 = rfma(J[ea], o[13], J[6 + ea] * o[15]);
                 }
-                if (isg) { s += W0 * o[31]; s += W1 * o[32]; }
-                else     { s += W0 * J[eb]; s += W1 * J[6 + eb]; }
+                if (isg) { s = rfma(W0, o[31], s); s = rfma(W1, o[32], s); }
+                else     { s = rfma(W0, J[eb], s); s = rfma(W1, J[6 + eb], s); }
             }
             if (isg) S.g[ea] = s; else S.A[ea * 6 + eb] = s;
         }

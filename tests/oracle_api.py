@@ -53,7 +53,19 @@ class Result(C.Structure):
         return d
 
 
+def _host_has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " fma " in f.read().replace("\n", " ")
+    except OSError:
+        return False
+
+
 def build():
+    """make; a library built with -mfma on another host is rebuilt when this host has no FMA3"""
+    flag_file = os.path.join(ORACLE_DIR, ".fmaflag")
+    if os.path.exists(flag_file) and "-mfma" in open(flag_file).read() and not _host_has_fma():
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "clean"], check=True)
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
 
 
@@ -61,7 +73,8 @@ def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(ORACLE_DIR, "liboracle.so")
-        if not os.path.exists(path):
+        flag_file = os.path.join(ORACLE_DIR, ".fmaflag")
+        if not os.path.exists(path) or (os.path.exists(flag_file) and "-mfma" in open(flag_file).read() and not _host_has_fma()):
             build()
         _LIB = C.CDLL(path)
         _LIB.orc_epnp_pose.restype = C.c_double
