@@ -237,11 +237,18 @@ static void compute_A_and_b_gauss_newton(const double L[6][10], const double rho
                                  {l[3], l[4], 2 * l[5], l[8]},
                                  {l[6], l[7], l[8], 2 * l[9]}};
         for (int r = 0; r < 4; ++r)
-            A[i][r] = Lt[r][0] * bt[0] + Lt[r][1] * bt[1] + Lt[r][2] * bt[2] + Lt[r][3] * bt[3];   /* :659 */
-        b[i] = rho[i] - (l[0] * bt[0] * bt[0] + l[1] * bt[0] * bt[1] + l[2] * bt[1] * bt[1] +
-                         l[3] * bt[0] * bt[2] + l[4] * bt[1] * bt[2] + l[5] * bt[2] * bt[2] +
-                         l[6] * bt[0] * bt[3] + l[7] * bt[1] * bt[3] + l[8] * bt[2] * bt[3] +
-                         l[9] * bt[3] * bt[3]);                                                      /* :661-671 */
+            A[i][r] = fma(Lt[r][3], bt[3], fma(Lt[r][2], bt[2], fma(Lt[r][1], bt[1], Lt[r][0] * bt[0])));   /* :659 */
+        double q = (l[0] * bt[0]) * bt[0];                                                          /* :661-671 */
+        q = fma(l[1] * bt[0], bt[1], q);
+        q = fma(l[2] * bt[1], bt[1], q);
+        q = fma(l[3] * bt[0], bt[2], q);
+        q = fma(l[4] * bt[1], bt[2], q);
+        q = fma(l[5] * bt[2], bt[2], q);
+        q = fma(l[6] * bt[0], bt[3], q);
+        q = fma(l[7] * bt[1], bt[3], q);
+        q = fma(l[8] * bt[2], bt[3], q);
+        q = fma(l[9] * bt[3], bt[3], q);
+        b[i] = rho[i] - q;
     }
 }
 

@@ -186,11 +186,18 @@ __host__ __device__ inline void epnp_gn_system(const double* L, const double* rh
                                  {l[3], l[4], 2 * l[5], l[8]},
                                  {l[6], l[7], l[8], 2 * l[9]}};
         for (int r = 0; r < 4; ++r)
-            A[i * 4 + r] = Lt[r][0] * bt[0] + Lt[r][1] * bt[1] + Lt[r][2] * bt[2] + Lt[r][3] * bt[3];
-        b[i] = rho[i] - (l[0] * bt[0] * bt[0] + l[1] * bt[0] * bt[1] + l[2] * bt[1] * bt[1] +
-                         l[3] * bt[0] * bt[2] + l[4] * bt[1] * bt[2] + l[5] * bt[2] * bt[2] +
-                         l[6] * bt[0] * bt[3] + l[7] * bt[1] * bt[3] + l[8] * bt[2] * bt[3] +
-                         l[9] * bt[3] * bt[3]);
+            A[i * 4 + r] = rfma(Lt[r][3], bt[3], rfma(Lt[r][2], bt[2], rfma(Lt[r][1], bt[1], Lt[r][0] * bt[0])));   /* :659 */
+        double q = (l[0] * bt[0]) * bt[0];                                                          /* :661-671 */
+        q = rfma(l[1] * bt[0], bt[1], q);
+        q = rfma(l[2] * bt[1], bt[1], q);
+        q = rfma(l[3] * bt[0], bt[2], q);
+        q = rfma(l[4] * bt[1], bt[2], q);
+        q = rfma(l[5] * bt[2], bt[2], q);
+        q = rfma(l[6] * bt[0], bt[3], q);
+        q = rfma(l[7] * bt[1], bt[3], q);
+        q = rfma(l[8] * bt[2], bt[3], q);
+        q = rfma(l[9] * bt[3], bt[3], q);
+        b[i] = rho[i] - q;
     }
 }
 
