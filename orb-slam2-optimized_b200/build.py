@@ -2,9 +2,9 @@
 
 Flags that matter:
   -gencode arch=compute_100a,code=sm_100a   B200 only, no other targets
-  -fmad=false                               no FMA contraction anywhere; fast paths ask for
-                                            FMA explicitly (fmaf/__fma_rn).  This is the
-                                            arithmetic contract shared with the CPU checker
+  -fmad=false                               no FMA contraction by the compiler anywhere; code asks for
+                                            fused multiply-adds explicitly (rfma / fmaf / __ffma2_rn).
+                                            This is the arithmetic contract shared with the CPU checker
                                             
   -Xcompiler -ffp-contract=off              same for the host-compiled debug hooks
   -lineinfo                                 so that ncu's source page maps to these files
