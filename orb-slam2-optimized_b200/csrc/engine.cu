@@ -603,7 +603,7 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
             epnp_minimal_kernel<false><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
                                                                    (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
         else
-            epnp_minimal_kernel<true><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
+            epnp_minimal_kernel<true><<<blocks, threads, sizeof(double) * 48 * threads, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
                                                                   (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
         e->stage_end(RSAC_STAGE_SOLVE);
         RSAC_CUDA(e, cudaGetLastError());

@@ -73,13 +73,13 @@ __host__ __device__ inline void epnp_m_entry(const double* a, double u, double v
 }
 
 // PnPsolver::compute_L_6x10 (:604-637), U4[r*4+i] = i-th smallest eigenvector, row r
-__host__ __device__ inline void epnp_L_6x10(const double* U4, double* L /*6x10*/)
+__host__ __device__ inline void epnp_L_6x10(const double* U4, double* L /*6x10*/, int ust = 1)
 {
     double dv[4][6][3];
     for (int i = 0; i < 4; ++i) {
         int a = 0, b = 1;
         for (int j = 0; j < 6; ++j) {
-            for (int c = 0; c < 3; ++c) dv[i][j][c] = U4[(3 * a + c) * 4 + i] - U4[(3 * b + c) * 4 + i];
+            for (int c = 0; c < 3; ++c) dv[i][j][c] = U4[((3 * a + c) * 4 + i) * ust] - U4[((3 * b + c) * 4 + i) * ust];
             b++;
             if (b > 3) { a++; b = a + 1; }
         }
@@ -260,10 +260,10 @@ __host__ __device__ inline void epnp_gauss_newton(const double* L, const double*
 }
 
 // L, rho, approx_k + gauss_newton (PnPsolver.cpp:395-405) from the null-space basis U4 (12x4)
-__host__ __device__ inline void epnp_betas_from_basis(const double* U4, const double* cws, double* betas /*3x4*/)
+__host__ __device__ inline void epnp_betas_from_basis(const double* U4, const double* cws, double* betas /*3x4*/, int ust = 1)
 {
     double L[60], rho[6];
-    epnp_L_6x10(U4, L);
+    epnp_L_6x10(U4, L, ust);
     epnp_rho(cws, rho);
     RSAC_SOLVE_MARK(3);
     epnp_betas_approx_1(L, rho, betas + 0);
@@ -292,7 +292,7 @@ __host__ __device__ inline void epnp_solve_betas(double* MtM, const double* cws,
 // correspondences M^T M is exactly rank 8 and any orthonormal null-space basis is as good as the
 // eigen-solver's.  al: 4 x 4 alphas, us: 4 x 2.
 __host__ __device__ inline void epnp_solve_betas_qr4(const double* al, const double* us, const Cam& k, const double* cws,
-                                                     double* U4, double* betas /*3x4*/)
+                                                     double* U4, double* betas /*3x4*/, int ust = 1)
 {
     double A[96];   // M^T, row-major 12 x 8
 #pragma unroll
@@ -302,18 +302,18 @@ __host__ __device__ inline void epnp_solve_betas_qr4(const double* al, const dou
 #pragma unroll
         for (int r = 0; r < 12; ++r) { A[r * 8 + 2 * i] = r0[r]; A[r * 8 + 2 * i + 1] = r1[r]; }
     }
-    nullspace_qr_8x12(A, U4);
+    nullspace_qr_8x12(A, U4, ust);
     RSAC_SOLVE_MARK(2);
-    epnp_betas_from_basis(U4, cws, betas);
+    epnp_betas_from_basis(U4, cws, betas, ust);
 }
 
 // PnPsolver::compute_ccs (:345-352)
-__host__ __device__ inline void epnp_ccs(const double* betas, const double* U4, double* ccs /*4x3*/)
+__host__ __device__ inline void epnp_ccs(const double* betas, const double* U4, double* ccs /*4x3*/, int ust = 1)
 {
     for (int i = 0; i < 4; ++i)
         for (int c = 0; c < 3; ++c) {
             double s = 0.0;
-            for (int j = 0; j < 4; ++j) s = rfma(betas[j], U4[(3 * i + c) * 4 + j], s);
+            for (int j = 0; j < 4; ++j) s = rfma(betas[j], U4[((3 * i + c) * 4 + j) * ust], s);
             ccs[i * 3 + c] = s;
         }
 }
@@ -363,8 +363,11 @@ __host__ __device__ inline double epnp_reproj_term(const double* R, const double
 // Whole PnPsolver::compute_pose (:359-415) for NPTS thread-private correspondences.
 // pw: NPTS x 3, us: NPTS x 2 (already widened to double).  Writes R (9) t (3) as float.
 // QR: take the null space of a 4-point system by Householder QR instead of the 12x12 eigen-solve.
+// u4_ext/ust: optional external storage for the 12x4 basis (shared memory, element stride ust) -- keeps 48
+// long-lived doubles out of the register file / local memory in the one-thread-per-hypothesis kernel
 template <int NPTS, bool QR = false>
-__host__ __device__ inline double epnp_compute_pose_small(const double* pw, const double* us, const Cam& k, float* Rf, float* tf)
+__host__ __device__ inline double epnp_compute_pose_small(const double* pw, const double* us, const Cam& k, float* Rf, float* tf,
+                                                          double* u4_ext = nullptr, int ust = 1)
 {
     RSAC_SOLVE_MARK(0);
     double cws[12], C0[3];
@@ -387,9 +390,11 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
     for (int i = 0; i < NPTS; ++i) epnp_alphas(pw + 3 * i, cws, CCi, alphas + 4 * i);
 
     RSAC_SOLVE_MARK(1);
-    double U4[48], betas[12];
+    double U4_priv[48], betas[12];
+    double* U4 = u4_ext ? u4_ext : U4_priv;
+    if (!u4_ext) ust = 1;
     if constexpr (QR && NPTS == 4) {
-        epnp_solve_betas_qr4(alphas, us, k, cws, U4, betas);
+        epnp_solve_betas_qr4(alphas, us, k, cws, U4, betas, ust);
     } else {
         double MtM[78];   // packed upper triangle
 #pragma unroll
@@ -414,7 +419,7 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
 #pragma unroll 1
     for (int kk = 0; kk < 3; ++kk) {
         double ccs[12], pcs[NPTS * 3];
-        epnp_ccs(betas + 4 * kk, U4, ccs);
+        epnp_ccs(betas + 4 * kk, U4, ccs, ust);
         for (int i = 0; i < NPTS; ++i) epnp_pc(alphas + 4 * i, ccs, pcs + 3 * i);
         if (pcs[2] < 0.0) {                                   // solve_for_sign (:495-502)
             for (int i = 0; i < 12; ++i) ccs[i] = -ccs[i];

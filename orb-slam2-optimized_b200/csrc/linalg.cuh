@@ -407,7 +407,9 @@ __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, doubl
 // A = M^T (12 x 8, row-major A[r*8+c], destroyed): null(M) = last four columns of Q = H0..H7 e_{8..11}.
 // U4[r*4+i] = component r of basis vector i.  Operation order mirrors oracle/orc_linalg.c
 // orc_nullspace_qr_d exactly (arithmetic contract).  2.4 kFLOP, fully unrolled: A stays in registers.
-__host__ __device__ inline void nullspace_qr_8x12(double* A, double* U4)
+// ust: element stride of U4 (1 for a private array; blockDim.x when the basis lives in shared memory, one
+// column of doubles per thread)
+__host__ __device__ inline void nullspace_qr_8x12(double* A, double* U4, int ust = 1)
 {
     double tau[8];
 #pragma unroll
@@ -449,7 +451,7 @@ __host__ __device__ inline void nullspace_qr_8x12(double* A, double* U4)
             for (int r = k; r < 12; ++r) y[r] = rfma(-d, A[r * 8 + k], y[r]);
         }
 #pragma unroll
-        for (int r = 0; r < 12; ++r) U4[r * 4 + i] = y[r];
+        for (int r = 0; r < 12; ++r) U4[(r * 4 + i) * ust] = y[r];
     }
 }
 

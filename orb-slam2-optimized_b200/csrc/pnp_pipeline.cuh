@@ -166,7 +166,12 @@ __global__ void __launch_bounds__(QR ? RSAC_SOLVE_THREADS : 128, QR ? RSAC_SOLVE
     }
     const Cam k = {m.fx, m.fy, m.cx, m.cy};
     float R[9], t[3];
-    epnp_compute_pose_small<4, QR>(pw, us, k, R, t);
+    if constexpr (QR) {
+        extern __shared__ double s_u4[];                 // [48][blockDim.x]: the null-space basis, one column per thread
+        epnp_compute_pose_small<4, true>(pw, us, k, R, t, s_u4 + threadIdx.x, (int)blockDim.x);
+    } else {
+        epnp_compute_pose_small<4, false>(pw, us, k, R, t);
+    }
     float* out = poses + g * 12;
 #pragma unroll
     for (int i = 0; i < 9; ++i) out[i] = R[i];
