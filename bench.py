@@ -370,7 +370,8 @@ def main():
             t = per["solve"] * 1e-3
             ach = flop_per_solve * count * H_HYP / t / 1e12
             roofs["solve"] = {"bound": "fp64", "kernel": "epnp_minimal_kernel<QR>", "achieved": ach, "peak": fp64_pk,
-                              "unit": "TFLOP/s", "frac": ach / fp64_pk, "traffic": None,
+                              "unit": "TFLOP/s", "frac": ach / fp64_pk,
+                              "traffic": ncu_traffic("epnp_minimal_kernel<QR>") if count == 1024 else None,
                               "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                               "flop_per_solve": flop_per_solve, "launch_ms": per["solve"], "share_of_sweep": per["solve"] / total_ms}
         if per.get("score"):
@@ -399,6 +400,18 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic(key):
+    """per-launch DRAM bytes of a kernel from the committed ncu capture (profiles/r01_traffic.json), or None"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        for k, v in d.items():
+            if k.startswith(key):
+                return int(v["dram_bytes"])
+    except Exception:
+        pass
+    return None
 
 
 def epnp_flops_per_solve(b):

@@ -140,7 +140,7 @@ __device__ __forceinline__ int find_problem(const ProblemMeta* metas, int C, int
 #define RSAC_SOLVE_THREADS 128
 #endif
 #ifndef RSAC_SOLVE_BLOCKS
-#define RSAC_SOLVE_BLOCKS 4   // 128 registers: measured best (2: 1.60 ms, 3: 1.52, 4: 1.39, 5: 2.05 per 307k solves)
+#define RSAC_SOLVE_BLOCKS 3   // with the basis in shared memory: 168 registers x 384 threads/SM measured best (blocks/SM 2: 0.99 ms, 3: 0.83, 4: 0.96 per 307k solves)
 #endif
 // QR = true: null space of the 4-point system by Householder QR (default); false: 12x12 eigen-solve
 // (RSAC_FLAG_EPNP_EIGEN, the reference's structure)
