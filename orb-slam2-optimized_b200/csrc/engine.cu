@@ -596,6 +596,9 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
     }
     if (d.sumH > 0) {
         const bool eigen = (flags & RSAC_FLAG_EPNP_EIGEN) != 0;
+        if (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS > 48 * 1024)
+            RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS)));
         const int threads = eigen ? 128 : RSAC_SOLVE_THREADS;
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
         e->stage_begin(RSAC_STAGE_SOLVE);
@@ -603,7 +606,7 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
             epnp_minimal_kernel<false><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
                                                                    (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
         else
-            epnp_minimal_kernel<true><<<blocks, threads, sizeof(double) * 48 * threads, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
+            epnp_minimal_kernel<true><<<blocks, threads, sizeof(double) * kSolveSmemDoubles * threads, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
                                                                   (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
         e->stage_end(RSAC_STAGE_SOLVE);
         RSAC_CUDA(e, cudaGetLastError());

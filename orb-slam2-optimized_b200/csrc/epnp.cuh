@@ -24,6 +24,14 @@ __device__ long long g_solve_clocks[16];
 
 struct Cam { double fx, fy, cx, cy; };
 
+// array view with an element stride: lets a thread keep an array in shared memory as one column of doubles
+// (element i of thread t at base[i * blockDim.x + t]: conflict-free) behind the same indexing code
+struct StridedD {
+    double* p;
+    int st;
+    __host__ __device__ double& operator[](int i) const { return p[(size_t)i * st]; }
+};
+
 // PnPsolver::choose_control_points (PnPsolver.cpp:296-321) after the sums:
 // C0 = centroid (already divided by n), A = upper triangle of PW0^T PW0.
 __host__ __device__ inline void epnp_control_points(const double* C0, double* A, int n, double* cws /*4x3*/)
@@ -73,7 +81,8 @@ __host__ __device__ inline void epnp_m_entry(const double* a, double u, double v
 }
 
 // PnPsolver::compute_L_6x10 (:604-637), U4[r*4+i] = i-th smallest eigenvector, row r
-__host__ __device__ inline void epnp_L_6x10(const double* U4, double* L /*6x10*/, int ust = 1)
+template <class LT>
+__host__ __device__ inline void epnp_L_6x10(const double* U4, LT L /*6x10*/, int ust = 1)
 {
     double dv[4][6][3];
     for (int i = 0; i < 4; ++i) {
@@ -86,17 +95,16 @@ __host__ __device__ inline void epnp_L_6x10(const double* U4, double* L /*6x10*/
     }
 #define RSAC_DOT3(x, y) ((x)[0] * (y)[0] + (x)[1] * (y)[1] + (x)[2] * (y)[2])
     for (int i = 0; i < 6; ++i) {
-        double* l = L + i * 10;
-        l[0] = RSAC_DOT3(dv[0][i], dv[0][i]);
-        l[1] = 2.0 * RSAC_DOT3(dv[0][i], dv[1][i]);
-        l[2] = RSAC_DOT3(dv[1][i], dv[1][i]);
-        l[3] = 2.0 * RSAC_DOT3(dv[0][i], dv[2][i]);
-        l[4] = 2.0 * RSAC_DOT3(dv[1][i], dv[2][i]);
-        l[5] = RSAC_DOT3(dv[2][i], dv[2][i]);
-        l[6] = 2.0 * RSAC_DOT3(dv[0][i], dv[3][i]);
-        l[7] = 2.0 * RSAC_DOT3(dv[1][i], dv[3][i]);
-        l[8] = 2.0 * RSAC_DOT3(dv[2][i], dv[3][i]);
-        l[9] = RSAC_DOT3(dv[3][i], dv[3][i]);
+        L[i * 10 + 0] = RSAC_DOT3(dv[0][i], dv[0][i]);
+        L[i * 10 + 1] = 2.0 * RSAC_DOT3(dv[0][i], dv[1][i]);
+        L[i * 10 + 2] = RSAC_DOT3(dv[1][i], dv[1][i]);
+        L[i * 10 + 3] = 2.0 * RSAC_DOT3(dv[0][i], dv[2][i]);
+        L[i * 10 + 4] = 2.0 * RSAC_DOT3(dv[1][i], dv[2][i]);
+        L[i * 10 + 5] = RSAC_DOT3(dv[2][i], dv[2][i]);
+        L[i * 10 + 6] = 2.0 * RSAC_DOT3(dv[0][i], dv[3][i]);
+        L[i * 10 + 7] = 2.0 * RSAC_DOT3(dv[1][i], dv[3][i]);
+        L[i * 10 + 8] = 2.0 * RSAC_DOT3(dv[2][i], dv[3][i]);
+        L[i * 10 + 9] = RSAC_DOT3(dv[3][i], dv[3][i]);
     }
 #undef RSAC_DOT3
 }
@@ -119,7 +127,8 @@ __host__ __device__ inline void epnp_rho(const double* cws, double* rho)
 }
 
 // find_betas_approx_{1,2,3} (:520-602)
-__host__ __device__ inline void epnp_betas_approx_1(const double* L, const double* rho, double* betas)
+template <class LT>
+__host__ __device__ inline void epnp_betas_approx_1(LT L, const double* rho, double* betas)
 {
     double L4[24], b4[4];
     for (int i = 0; i < 6; ++i) {
@@ -139,7 +148,8 @@ __host__ __device__ inline void epnp_betas_approx_1(const double* L, const doubl
     }
 }
 
-__host__ __device__ inline void epnp_betas_approx_2(const double* L, const double* rho, double* betas)
+template <class LT>
+__host__ __device__ inline void epnp_betas_approx_2(LT L, const double* rho, double* betas)
 {
     double L3[18], b3[3];
     for (int i = 0; i < 6; ++i) {
@@ -158,7 +168,8 @@ __host__ __device__ inline void epnp_betas_approx_2(const double* L, const doubl
     betas[3] = 0.0;
 }
 
-__host__ __device__ inline void epnp_betas_approx_3(const double* L, const double* rho, double* betas)
+template <class LT>
+__host__ __device__ inline void epnp_betas_approx_3(LT L, const double* rho, double* betas)
 {
     double L5[30], b5[5];
     for (int i = 0; i < 6; ++i)
@@ -177,10 +188,12 @@ __host__ __device__ inline void epnp_betas_approx_3(const double* L, const doubl
 }
 
 // PnPsolver::compute_A_and_b_gauss_newton (:649-673)
-__host__ __device__ inline void epnp_gn_system(const double* L, const double* rho, const double* bt, double* A /*6x4*/, double* b)
+template <class LT>
+__host__ __device__ inline void epnp_gn_system(LT L, const double* rho, const double* bt, double* A /*6x4*/, double* b)
 {
     for (int i = 0; i < 6; ++i) {
-        const double* l = L + i * 10;
+        double l[10];
+        for (int j = 0; j < 10; ++j) l[j] = L[i * 10 + j];
         const double Lt[4][4] = {{2 * l[0], l[1], l[3], l[6]},
                                  {l[1], 2 * l[2], l[4], l[7]},
                                  {l[3], l[4], 2 * l[5], l[8]},
@@ -248,7 +261,8 @@ __host__ __device__ inline void epnp_qr_solve(double* A /*6x4*/, double* b, doub
 }
 
 // PnPsolver::gauss_newton (:675-691): exactly five steps
-__host__ __device__ inline void epnp_gauss_newton(const double* L, const double* rho, double* betas)
+template <class LT>
+__host__ __device__ inline void epnp_gauss_newton(LT L, const double* rho, double* betas)
 {
     double A[24], B[6], X[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
@@ -260,9 +274,24 @@ __host__ __device__ inline void epnp_gauss_newton(const double* L, const double*
 }
 
 // L, rho, approx_k + gauss_newton (PnPsolver.cpp:395-405) from the null-space basis U4 (12x4)
-__host__ __device__ inline void epnp_betas_from_basis(const double* U4, const double* cws, double* betas /*3x4*/, int ust = 1)
+template <class LT>
+__host__ __device__ inline void epnp_betas_from_basis_L(const double* U4, const double* cws, double* betas /*3x4*/, int ust, LT L);
+
+__host__ __device__ inline void epnp_betas_from_basis(const double* U4, const double* cws, double* betas /*3x4*/, int ust = 1,
+                                                      double* l_ext = nullptr, int lst = 1)
 {
-    double L[60], rho[6];
+    if (l_ext) {
+        epnp_betas_from_basis_L(U4, cws, betas, ust, StridedD{l_ext, lst});
+    } else {
+        double Lp[60];
+        epnp_betas_from_basis_L(U4, cws, betas, ust, (double*)Lp);
+    }
+}
+
+template <class LT>
+__host__ __device__ inline void epnp_betas_from_basis_L(const double* U4, const double* cws, double* betas /*3x4*/, int ust, LT L)
+{
+    double rho[6];
     epnp_L_6x10(U4, L, ust);
     epnp_rho(cws, rho);
     RSAC_SOLVE_MARK(3);
@@ -292,7 +321,8 @@ __host__ __device__ inline void epnp_solve_betas(double* MtM, const double* cws,
 // correspondences M^T M is exactly rank 8 and any orthonormal null-space basis is as good as the
 // eigen-solver's.  al: 4 x 4 alphas, us: 4 x 2.
 __host__ __device__ inline void epnp_solve_betas_qr4(const double* al, const double* us, const Cam& k, const double* cws,
-                                                     double* U4, double* betas /*3x4*/, int ust = 1)
+                                                     double* U4, double* betas /*3x4*/, int ust = 1,
+                                                     double* l_ext = nullptr, int lst = 1)
 {
     double A[96];   // M^T, row-major 12 x 8
 #pragma unroll
@@ -304,7 +334,7 @@ __host__ __device__ inline void epnp_solve_betas_qr4(const double* al, const dou
     }
     nullspace_qr_8x12(A, U4, ust);
     RSAC_SOLVE_MARK(2);
-    epnp_betas_from_basis(U4, cws, betas, ust);
+    epnp_betas_from_basis(U4, cws, betas, ust, l_ext, lst);
 }
 
 // PnPsolver::compute_ccs (:345-352)
@@ -367,7 +397,7 @@ __host__ __device__ inline double epnp_reproj_term(const double* R, const double
 // long-lived doubles out of the register file / local memory in the one-thread-per-hypothesis kernel
 template <int NPTS, bool QR = false>
 __host__ __device__ inline double epnp_compute_pose_small(const double* pw, const double* us, const Cam& k, float* Rf, float* tf,
-                                                          double* u4_ext = nullptr, int ust = 1)
+                                                          double* u4_ext = nullptr, int ust = 1, double* l_ext = nullptr, int lst = 1)
 {
     RSAC_SOLVE_MARK(0);
     double cws[12], C0[3];
@@ -394,7 +424,7 @@ __host__ __device__ inline double epnp_compute_pose_small(const double* pw, cons
     double* U4 = u4_ext ? u4_ext : U4_priv;
     if (!u4_ext) ust = 1;
     if constexpr (QR && NPTS == 4) {
-        epnp_solve_betas_qr4(alphas, us, k, cws, U4, betas, ust);
+        epnp_solve_betas_qr4(alphas, us, k, cws, U4, betas, ust, l_ext, lst);
     } else {
         double MtM[78];   // packed upper triangle
 #pragma unroll

@@ -136,6 +136,10 @@ __device__ __forceinline__ int find_problem(const ProblemMeta* metas, int C, int
 }
 
 // ---- EPnP minimal solve: one thread per hypothesis (PnPsolver.cpp:125-141) ----
+#ifndef RSAC_SOLVE_SMEM
+#define RSAC_SOLVE_SMEM 0    // what lives in shared memory: 0 the basis U4 (48 doubles/thread), 1 L (60), 2 both (108)
+#endif
+constexpr int kSolveSmemDoubles = RSAC_SOLVE_SMEM == 0 ? 48 : (RSAC_SOLVE_SMEM == 1 ? 60 : 108);
 #ifndef RSAC_SOLVE_THREADS
 #define RSAC_SOLVE_THREADS 128
 #endif
@@ -167,8 +171,15 @@ __global__ void __launch_bounds__(QR ? RSAC_SOLVE_THREADS : 128, QR ? RSAC_SOLVE
     const Cam k = {m.fx, m.fy, m.cx, m.cy};
     float R[9], t[3];
     if constexpr (QR) {
-        extern __shared__ double s_u4[];                 // [48][blockDim.x]: the null-space basis, one column per thread
-        epnp_compute_pose_small<4, true>(pw, us, k, R, t, s_u4 + threadIdx.x, (int)blockDim.x);
+        extern __shared__ double s_cols[];               // per thread one column of doubles: basis U4 [48] (and L [60])
+#if RSAC_SOLVE_SMEM == 0
+        epnp_compute_pose_small<4, true>(pw, us, k, R, t, s_cols + threadIdx.x, (int)blockDim.x);
+#elif RSAC_SOLVE_SMEM == 1
+        epnp_compute_pose_small<4, true>(pw, us, k, R, t, nullptr, 1, s_cols + threadIdx.x, (int)blockDim.x);
+#else
+        epnp_compute_pose_small<4, true>(pw, us, k, R, t, s_cols + threadIdx.x, (int)blockDim.x,
+                                         s_cols + 48 * blockDim.x + threadIdx.x, (int)blockDim.x);
+#endif
     } else {
         epnp_compute_pose_small<4, false>(pw, us, k, R, t);
     }

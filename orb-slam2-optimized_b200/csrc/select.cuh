@@ -205,21 +205,21 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
             const int wk = tid >> 5;
             double L[60], rho[6], U4[48], bt[4];
             for (int i = 0; i < 48; ++i) U4[i] = S.U4[i];
-            epnp_L_6x10(U4, L);
+            epnp_L_6x10(U4, (double*)L);
             epnp_rho(S.cws, rho);
             if (wk == 0) {
-                epnp_betas_approx_3(L, rho, bt);
-                epnp_gauss_newton(L, rho, bt);
+                epnp_betas_approx_3((const double*)L, rho, bt);
+                epnp_gauss_newton((const double*)L, rho, bt);
                 for (int i = 0; i < 4; ++i) S.betas[8 + i] = bt[i];
             }
             if (wk == 1) {
-                epnp_betas_approx_1(L, rho, bt);
-                epnp_gauss_newton(L, rho, bt);
+                epnp_betas_approx_1((const double*)L, rho, bt);
+                epnp_gauss_newton((const double*)L, rho, bt);
                 for (int i = 0; i < 4; ++i) S.betas[i] = bt[i];
             }
             if (wk == 2 || (wk == 1 && !three)) {
-                epnp_betas_approx_2(L, rho, bt);
-                epnp_gauss_newton(L, rho, bt);
+                epnp_betas_approx_2((const double*)L, rho, bt);
+                epnp_gauss_newton((const double*)L, rho, bt);
                 for (int i = 0; i < 4; ++i) S.betas[4 + i] = bt[i];
             }
         }
