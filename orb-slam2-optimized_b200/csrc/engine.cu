@@ -557,6 +557,13 @@ static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume,
     a.problem_base = e->problem_base;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
     if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        cudaFuncAttributes fa;
+        RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<0>));
+        const size_t need = (fa.sharedSizeBytes + smem + 1024) * kSelectCtasPerSm;
+        const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
+        RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     e->stage_begin(RSAC_STAGE_SELECT);
     ransac_select_kernel<0><<<d.C, kSelectThreads, smem, e->stream>>>(a);
     e->stage_end(RSAC_STAGE_SELECT);
@@ -599,6 +606,14 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         if (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS > 48 * 1024)
             RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)(sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS)));
+        {
+            // ask for exactly the shared-memory carve-out that keeps RSAC_SOLVE_BLOCKS blocks resident (the rest of
+            // the 228 KB stays L1 for the kernel's local memory); left to its own devices the driver was seen to pick
+            // a smaller carve-out in some processes, which silently drops a block per SM (0.96 vs 0.82 ms)
+            const size_t need = (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS + 1024) * RSAC_SOLVE_BLOCKS;
+            const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
+            RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
         const int threads = eigen ? 128 : RSAC_SOLVE_THREADS;
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
         e->stage_begin(RSAC_STAGE_SOLVE);

@@ -76,6 +76,13 @@ static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resum
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
     if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     e->stage_begin(RSAC_STAGE_SELECT);
+    {
+        cudaFuncAttributes fa;
+        RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<1>));
+        const size_t need = (fa.sharedSizeBytes + smem + 1024) * kSelectCtasPerSm;
+        const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
+        RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     ransac_select_kernel<1><<<d.C, kSelectThreads, smem, e->stream>>>(a);
     e->stage_end(RSAC_STAGE_SELECT);
     RSAC_CUDA(e, cudaGetLastError());
