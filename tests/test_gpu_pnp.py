@@ -198,3 +198,35 @@ def test_score_pnp_adversarial_camera_plane_and_threshold(engine, oracle):
         oc, om = oracle.pnp_score(pb, thr, poses)
         assert (counts == oc).all()
         assert (capi.unpack_mask(masks, n) == om.astype(bool)).all()
+
+
+def test_pnp_many_hypotheses_multiple_tiles_per_problem(engine, oracle):
+    """maxIterations = 2500 with eps = 0.08 keeps H > 1024, so every problem spans several hypothesis tiles of the
+    scoring kernel, and 160 problems give more (problem x tile) groups than there are CTAs: the round-robin
+    work lists, tile tails (H not a multiple of the tile) and ragged n are all exercised; per-hypothesis counts
+    must equal the oracle's."""
+    prm = dict(prob=0.99, min_inliers=10, max_its=2500, min_set=4, eps=0.08, th2=5.991)
+    sizes = [64 + 7 * (i % 9) for i in range(160)]
+    parts = [synth.pnp_problem(9100 + i, n, 0.5) for i, n in enumerate(sizes)]
+    p3d = np.concatenate([p["p3d"] for p in parts])
+    p2d = np.concatenate([p["p2d"] for p in parts])
+    s2 = np.concatenate([p["sigma2"] for p in parts])
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    seeds = np.arange(len(sizes), dtype=np.uint32) + 500
+    res, masks = engine.pnp_solve(offsets, p3d, p2d, s2, [parts[0]["K"]], capi.ransac_params(**prm), seeds=seeds)
+    poses, counts = engine.pnp_hypotheses()
+    ml = engine.split_masks(masks, offsets)
+    h0 = 0
+    checked = 0
+    for c, n in enumerate(sizes):
+        minInl, H = capi.pnp_ransac_setup(n, capi.ransac_params(**prm))
+        assert H > 1024
+        if c % 8 == 0:            # the oracle's exhaustive pass over 1000+ hypotheses is slow: every 8th problem
+            pb = oracle.pnp_problem(parts[c]["p3d"], parts[c]["p2d"], parts[c]["sigma2"], parts[c]["K"])
+            o = oracle.pnp_ransac(pb, oracle.params(**prm), oracle.index_table(int(seeds[c]), n, 4, H),
+                                  oracle.FLAG_EXHAUSTIVE | oracle.FLAG_EPNP_QR_NULLSPACE, per_hyp=True)
+            assert (counts[h0:h0 + H] == o["hyp_counts"]).all(), c
+            _check_results(res[c:c + 1], ml[c:c + 1], [o])
+            checked += 1
+        h0 += H
+    assert checked == 20 and h0 == len(counts)
