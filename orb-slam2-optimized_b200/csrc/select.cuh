@@ -56,9 +56,10 @@ static_assert(sizeof(ResultRec) == 96, "rsac_result layout");
 #ifndef RSAC_SELECT_CTAS
 #define RSAC_SELECT_CTAS 7
 #endif
-// 128 threads x 7 CTAs/SM: 1036 resident candidates, so a 1024-candidate sweep is one wave (measured: 4 CTAs/SM
-// at 128 registers 1.05 ms, 7 CTAs/SM at 72 registers 0.91 ms, 64 threads x 8 CTAs/SM at 128 registers 0.65 vs
-// 0.56 ms for this shape after the later changes)
+// 128 threads x 7 CTAs/SM: 1036 resident candidates, so a 1024-candidate sweep is one wave.  Measured per 1024
+// candidates: 128 x 4 (128 registers) 1.05 ms before the other changes; then 128 x 7 (72 registers) 0.37,
+// 96 x 7 (80 registers) 0.34, 96 x 8 0.36, 128 x 6 0.46, 64 x 10 0.42 -- but the 96-thread shapes (larger stack)
+// slow the NEXT sweep's local-memory-bound solve kernel down by 0.14 ms, so 128 x 7 wins per sweep
 constexpr int kSelectThreads = RSAC_SELECT_THREADS;
 constexpr int kSelectCtasPerSm = RSAC_SELECT_CTAS;
 
