@@ -2,7 +2,9 @@
 // engine.  One engine = one device + one stream + grow-only device buffers.  No CPU
 // fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -72,6 +74,13 @@ int rsac_set_problem_base(rsac_engine* e, int base)
 {
     if (!e) return RSAC_ERR_INVALID;
     e->problem_base = base;
+    return RSAC_OK;
+}
+
+int rsac_set_first_phase(rsac_engine* e, int hypotheses)
+{
+    if (!e || hypotheses < 0) return RSAC_ERR_INVALID;
+    e->first_phase = hypotheses;
     return RSAC_OK;
 }
 
@@ -270,12 +279,18 @@ static const void* score_kernel_ptr(int hpl)
 //    proportion to their work and pull small chunks from the group's counter, which balances the SMs to
 //    within one chunk of work.
 template <int MODEL>
-static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int maxH, std::vector<ScoreGroup>& groups, ScorePlan& pl)
+static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int maxH, std::vector<ScoreGroup>& groups, ScorePlan& pl,
+                      int h_lo = 0, int h_hi = INT32_MAX, int hpl_want = 0, int cw_want = 0)
 {
+    // [h_lo, min(H, h_hi)) of every problem: the early-exit phases score hypothesis ranges (pnp_run_early)
     groups.clear();
     pl = ScorePlan();
-    pl.hpl = env_int("RSAC_SCORE_HPL", 2);
+    pl.hpl = hpl_want > 0 ? hpl_want : env_int("RSAC_SCORE_HPL", 2);
     if (pl.hpl != 1 && pl.hpl != 2 && pl.hpl != 3) pl.hpl = 2;
+    if (h_lo > 0 || h_hi != INT32_MAX) {
+        maxH = 0;
+        for (const auto& m : metas) maxH = std::max(maxH, std::min(m.H, h_hi) - h_lo);
+    }
     int warps = (maxH + 32 * pl.hpl - 1) / (32 * pl.hpl);
     warps = std::max(1, std::min(env_int("RSAC_SCORE_WARPS", 16), std::min(16, warps)));
     pl.threads = warps * 32;
@@ -284,16 +299,17 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
     for (size_t p = 0; p < metas.size(); ++p) {
         const ProblemMeta& m = metas[p];
         if (m.n <= 0 || m.H <= 0) continue;
-        for (int h0 = 0; h0 < m.H; h0 += pl.tile_hyps) {
+        const int h_end = std::min(m.H, h_hi);
+        for (int h0 = h_lo; h0 < h_end; h0 += pl.tile_hyps) {
             ScoreGroup g;
             memset(&g, 0, sizeof(g));
             g.gid = (int32_t)groups.size();
             g.problem = (int)p; g.hyp0 = h0;
-            g.corr_off = m.corr_off; g.n = m.n; g.words = m.words; g.H = m.H;
+            g.corr_off = m.corr_off; g.n = m.n; g.words = m.words; g.H = h_end;
             g.hyp_off = m.hyp_off; g.word_off = m.word_off; g.hmask_off = m.hmask_off;
             if (MODEL == 0) { g.fx = (float)m.fx; g.fy = (float)m.fy; } else { g.fx = m.k1[0]; g.fy = m.k1[1]; }
             groups.push_back(g);
-            work.push_back((double)m.words * std::min(pl.tile_hyps, m.H - h0));
+            work.push_back((double)m.words * std::min(pl.tile_hyps, h_end - h0));
         }
     }
     const int NG = (int)groups.size();
@@ -315,6 +331,7 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
     int maxWords = 1;
     for (const auto& m : metas) maxWords = std::max(maxWords, m.words);
     int cw = std::min(kChunkWordsMax, maxWords);
+    if (cw_want > 0) cw = std::min(cw, cw_want);
     int slots = resident(cw);
     std::vector<std::vector<int>> lists;
     if (NG >= slots) {
@@ -489,7 +506,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     if (!b->seeds && !b->tables) { if (e) e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     PnpState& s = e->pnp;
-    s.uploaded = false; s.ran = false;
+    s.uploaded = false; s.ran = false; s.ee_planned = false; s.ee_mode = false;
     std::vector<float> th2;
     int rc = pnp_build_metas(e, b->C, b->offsets, b->params, b->n_params, b->seeds, b->table_offsets, b->tables != nullptr, s.metas, th2, s.d);
     if (rc) return rc;
@@ -545,11 +562,125 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     return RSAC_OK;
 }
 
-static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out)
+// ---- early exit in phases (pnp_pipeline.cuh) ----
+static int solve_range_setup(rsac_engine* e)
+{
+    const size_t smem = sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS;
+    if (smem > 48 * 1024)
+        RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t need = (smem + 1024) * RSAC_SOLVE_BLOCKS;
+    const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
+    RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_range_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    return RSAC_OK;
+}
+
+static int pnp_early_flag(rsac_engine* e, int mode)
+{
+    PnpState& s = e->pnp;
+    e->stage_begin(RSAC_STAGE_RNG);
+    early_exit_flag_kernel<<<(s.d.C + 3) / 4, 128, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, s.d.C, (const int32_t*)s.d_counts.p,
+                                                                  s.ee_HA, (int32_t*)s.d_ee.p, mode);
+    e->stage_end(RSAC_STAGE_RNG);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+// minimal solves + scoring of hypotheses [HA, H) of the problems in `list` (device-side count) whose phase is `want`
+static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* list_count, int want)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    const int span = d.maxH - s.ee_HA;
+    if (span <= 0) return RSAC_OK;
+    const int64_t most = (int64_t)d.C * span;
+    const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
+    e->stage_begin(RSAC_STAGE_SOLVE);
+    epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, e->stream>>>(
+        (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, s.ee_HA, span, (const uint32_t*)s.d_tables.p,
+        (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+    e->stage_end(RSAC_STAGE_SOLVE);
+    RSAC_CUDA(e, cudaGetLastError());
+    ScoreArgs sa = s.ee_sa;
+    sa.phase = (const int32_t*)s.d_ee.p;
+    sa.phase_want = want;
+    return launch_score<0>(e, sa, s.planB, (int)s.groupsB.size(), s.d_visitB);
+}
+
+static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase);
+
+static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, int HA)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    cudaStream_t st = e->stream;
+    const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
+    if (!s.ee_planned || s.ee_HA != HA) {
+        s.ee_HA = HA;
+        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsA, s.planA, 0, HA, env_int("RSAC_EE_HPL_A", 0), env_int("RSAC_EE_CW_A", 0)));
+        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB, s.planB, HA, INT32_MAX, env_int("RSAC_EE_HPL_B", 0), env_int("RSAC_EE_CW_B", 0)));
+        const size_t bA = sizeof(ScoreGroup) * s.planA.work.size(), bB = sizeof(ScoreGroup) * s.planB.work.size();
+        const size_t oB = (bA + 255) & ~(size_t)255;
+        char* h = (char*)s.h_stageEE.ensure(oB + bB + 256);
+        if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
+        RSAC_TRY(s.d_visitA.ensure(e, std::max<size_t>(bA, sizeof(ScoreGroup))));
+        RSAC_TRY(s.d_visitB.ensure(e, std::max<size_t>(bB, sizeof(ScoreGroup))));
+        memcpy(h, s.planA.work.data(), bA);
+        memcpy(h + oB, s.planB.work.data(), bB);
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_visitA.p, h, bA, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_visitB.p, h + oB, bB, cudaMemcpyHostToDevice, st));
+        s.h_stageEE.mark(st);
+        s.ee_planned = true;
+    }
+    s.ee_mode = true;
+    s.ee_complete = false;
+    RSAC_TRY(s.d_ee.ensure(e, sizeof(int32_t) * (3 * (size_t)d.C + 4)));
+    RSAC_CUDA(e, cudaMemsetAsync(s.d_ee.p, 0, sizeof(int32_t) * (3 * (size_t)d.C + 4), st));
+    int32_t* ee = (int32_t*)s.d_ee.p;
+    RSAC_TRY(solve_range_setup(e));
+
+    ScoreArgs sa;
+    RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, 0, sa));
+    sa.metas = metas;
+    sa.cP = (const float4*)s.d_cP.p; sa.cC = (const float4*)s.d_uv.p;
+    sa.poses = s.d_poses.p;
+    sa.hmasks = nullptr;
+    if (flags & RSAC_FLAG_KEEP_MASKS) {
+        RSAC_TRY(s.d_hmasks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_hwords, 1)));
+        sa.hmasks = (uint32_t*)s.d_hmasks.p;
+    }
+    s.ee_sa = sa;
+
+    // phase A: hypotheses [0, HA) of every problem
+    {
+        const int64_t most = (int64_t)d.C * HA;
+        const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
+        e->stage_begin(RSAC_STAGE_SOLVE);
+        epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, st>>>(
+            metas, d.C, nullptr, nullptr, 0, HA, (const uint32_t*)s.d_tables.p, (const float4*)s.d_cA.p, (const float4*)s.d_uv.p,
+            (float*)s.d_poses.p);
+        e->stage_end(RSAC_STAGE_SOLVE);
+        RSAC_CUDA(e, cudaGetLastError());
+        RSAC_TRY(launch_score<0>(e, sa, s.planA, (int)s.groupsA.size(), s.d_visitA));
+    }
+    // who needs the rest right away; phase B
+    RSAC_TRY(pnp_early_flag(e, 0));
+    RSAC_TRY(pnp_early_range(e, ee + d.C, ee + 3 * (size_t)d.C, 1));
+    // replay; problems it cannot decide go to phase C
+    RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, -1));
+    RSAC_TRY(pnp_early_range(e, ee + 2 * (size_t)d.C, ee + 3 * (size_t)d.C + 1, 2));
+    RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, 2));
+    s.ran = true;
+    return RSAC_OK;
+}
+
+static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase)
 {
     PnpState& s = e->pnp;
     const BatchDims& d = s.d;
     SelectArgs a;
+    if (s.ee_mode) { a.ee = (int32_t*)s.d_ee.p; a.C = d.C; a.first_phase = s.ee_HA; a.only_phase = only_phase; }
     a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.cC = (const float4*)s.d_uv.p;
     a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = nullptr; a.flags = flags; a.resume = d_resume;
     a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p; a.tm_s = (double*)s.d_extra.p;
@@ -581,7 +712,16 @@ int rsac_pnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* 
     if (s.d.C == 0) return RSAC_OK;
     RSAC_TRY(e->d_resume.ensure(e, sizeof(int32_t) * (size_t)s.d.C));
     RSAC_CUDA(e, cudaMemcpyAsync(e->d_resume.p, resume_from, sizeof(int32_t) * (size_t)s.d.C, cudaMemcpyHostToDevice, e->stream));
-    return pnp_launch_select(e, flags, (const int32_t*)e->d_resume.p, d_results_out);
+    if (s.ee_mode && !s.ee_complete) {
+        // the last run stopped early: problems that were decided inside their first HA hypotheses get the rest
+        // now, so that the scan can go on wherever the caller resumes it
+        int32_t* ee = (int32_t*)s.d_ee.p;
+        RSAC_CUDA(e, cudaMemsetAsync(ee + 3 * (size_t)s.d.C, 0, 4 * sizeof(int32_t), e->stream));
+        RSAC_TRY(pnp_early_flag(e, 1));
+        RSAC_TRY(pnp_early_range(e, ee + s.d.C, ee + 3 * (size_t)s.d.C, 3));
+        s.ee_complete = true;
+    }
+    return pnp_launch_select(e, flags, (const int32_t*)e->d_resume.p, d_results_out, -1);
 }
 
 int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
@@ -600,6 +740,13 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
         e->stage_end(RSAC_STAGE_RNG);
         RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.ee_mode = false;
+    if ((flags & RSAC_FLAG_EARLY_EXIT) && !(flags & RSAC_FLAG_EPNP_EIGEN) && d.sumH > 0) {
+        // phase A sized to one wave of the minimal solver unless the caller chose
+        int HA = e->first_phase > 0 ? e->first_phase : env_int("RSAC_EE_HA", 0);
+        if (HA <= 0) HA = std::max(32, (RSAC_SOLVE_THREADS * RSAC_SOLVE_BLOCKS * e->sm_count / std::max(d.C, 1)) & ~7);
+        if (HA < d.maxH) return pnp_run_early(e, flags, d_results_out, HA);
     }
     if (d.sumH > 0) {
         const bool eigen = (flags & RSAC_FLAG_EPNP_EIGEN) != 0;
@@ -640,10 +787,31 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         if (rc) return rc;
     }
     {
-        int rc = pnp_launch_select(e, flags, nullptr, d_results_out);
+        int rc = pnp_launch_select(e, flags, nullptr, d_results_out, -1);
         if (rc) return rc;
     }
     s.ran = true;
+    return RSAC_OK;
+}
+
+int rsac_pnp_phase_stats(rsac_engine* e, int64_t out[4])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    out[0] = out[1] = out[2] = 0;
+    out[3] = s.d.sumH;
+    if (!s.ran) { e->err = "rsac_pnp_phase_stats before rsac_pnp_run"; return RSAC_ERR_STATE; }
+    if (!s.ee_mode) return RSAC_OK;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    std::vector<int32_t> ee(3 * (size_t)s.d.C + 4);
+    RSAC_CUDA(e, cudaMemcpyAsync(ee.data(), s.d_ee.p, sizeof(int32_t) * ee.size(), cudaMemcpyDeviceToHost, e->stream));
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    out[0] = s.ee_HA;
+    out[1] = ee[3 * (size_t)s.d.C];
+    out[2] = ee[3 * (size_t)s.d.C + 1];
+    int64_t done = 0;
+    for (int c = 0; c < s.d.C; ++c) done += (ee[c] == 0) ? std::min(s.metas[c].H, s.ee_HA) : s.metas[c].H;
+    out[3] = done;
     return RSAC_OK;
 }
 

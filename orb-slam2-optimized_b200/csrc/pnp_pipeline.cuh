@@ -189,6 +189,102 @@ __global__ void __launch_bounds__(QR ? RSAC_SOLVE_THREADS : 128, QR ? RSAC_SOLVE
     out[9] = t[0]; out[10] = t[1]; out[11] = t[2];
 }
 
+// ---- early exit in phases (RSAC_FLAG_EARLY_EXIT) ----
+// The sequential reference stops at the first hypothesis whose Refine() succeeds (PnPsolver.cpp:225-236), on
+// average after 35-40 of cfg4's 300; hypotheses behind it never influence the result.  The batched engine keeps
+// that property without a host round trip:
+//   phase A  every problem: hypotheses [0, HA)            (HA sized so that C * HA is about one wave of the solver)
+//   flag     problems WITHOUT a hypothesis of cnt >= minInliers in [0, HA) get the rest now (phase 1, list B);
+//            the others are predicted to finish inside [0, HA) (phase 0)
+//   phase B  list B: hypotheses [HA, H)
+//   replay   all problems; a phase-0 problem whose refines all failed before HA is not decided yet: it is
+//            appended to list C (phase 2) instead of reporting "budget exhausted"
+//   phase C  list C: hypotheses [HA, H), then the replay resumes at HA for those problems only (normally empty:
+//            the kernels find a zero count and return)
+// ee[] layout: [phase: C][listB: C][listC: C][nB, nC, 0, 0]
+struct EarlyExit {
+    int32_t* phase;
+    int32_t* listB;
+    int32_t* listC;
+    int32_t* counters;   // [0] nB, [1] nC
+};
+__host__ __device__ inline EarlyExit early_exit_view(int32_t* ee, int C)
+{
+    EarlyExit v;
+    v.phase = ee; v.listB = ee + C; v.listC = ee + 2 * (size_t)C; v.counters = ee + 3 * (size_t)C;
+    return v;
+}
+
+// one warp per problem.  mode 0 (after phase A): decide who needs the rest now.  mode 1 (before a later
+// iterate() call resumes past HA): everything that has only its first HA hypotheses gets the rest (phase 3).
+__global__ void __launch_bounds__(128) early_exit_flag_kernel(const ProblemMeta* metas, int C, const int32_t* counts, int HA,
+                                                              int32_t* ee, int mode)
+{
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= C) return;
+    const EarlyExit v = early_exit_view(ee, C);
+    const ProblemMeta& m = metas[p];
+    if (mode == 0) {
+        int ph = 1;                                  // complete (H <= HA, or nothing to do)
+        if (m.H > HA) {
+            bool any = false;
+            for (int h = lane; h < HA; h += 32) any = any || (counts[m.hyp_off + h] >= m.min_inl);
+            any = __any_sync(0xffffffffu, any);
+            ph = any ? 0 : 1;
+            if (!any && lane == 0) v.listB[atomicAdd(v.counters, 1)] = p;
+        }
+        if (lane == 0) v.phase[p] = ph;
+    } else {
+        if (lane == 0 && v.phase[p] == 0 && m.H > HA) {
+            v.phase[p] = 3;
+            v.listB[atomicAdd(v.counters, 1)] = p;   // counters[0] was reset by the host
+        }
+    }
+}
+
+// EPnP minimal solves of hypotheses [h_lo, h_lo + span) of the listed problems (list == nullptr: all C problems).
+// Persistent grid-stride form: the amount of work is only known on the device.
+__global__ void __launch_bounds__(RSAC_SOLVE_THREADS, RSAC_SOLVE_BLOCKS)
+epnp_minimal_range_kernel(const ProblemMeta* metas, int C, const int32_t* list, const int32_t* list_count, int h_lo, int span,
+                          const uint32_t* tables, const float4* cA, const float4* cC, float* poses)
+{
+    extern __shared__ double s_cols[];
+    const int np = list ? *list_count : C;
+    const int64_t total = (int64_t)np * span;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t / span);
+        const int h = h_lo + (int)(t - (int64_t)k * span);
+        const int p = list ? list[k] : k;
+        const ProblemMeta& m = metas[p];
+        if (h >= m.H) continue;
+        const uint32_t* idx = tables + m.table_off + (size_t)h * 4;
+        double pw[12], us[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t ci = (size_t)m.corr_off + idx[i];
+            const float4 a = cA[ci];
+            const float4 q = cC[ci];
+            pw[3 * i] = (double)a.x; pw[3 * i + 1] = (double)a.y; pw[3 * i + 2] = (double)a.z;
+            us[2 * i] = (double)q.x; us[2 * i + 1] = (double)q.y;
+        }
+        const Cam kk = {m.fx, m.fy, m.cx, m.cy};
+        float R[9], tr[3];
+#if RSAC_SOLVE_SMEM == 0
+        epnp_compute_pose_small<4, true>(pw, us, kk, R, tr, s_cols + threadIdx.x, (int)blockDim.x);
+#elif RSAC_SOLVE_SMEM == 1
+        epnp_compute_pose_small<4, true>(pw, us, kk, R, tr, nullptr, 1, s_cols + threadIdx.x, (int)blockDim.x);
+#else
+        epnp_compute_pose_small<4, true>(pw, us, kk, R, tr, s_cols + threadIdx.x, (int)blockDim.x,
+                                         s_cols + 48 * blockDim.x + threadIdx.x, (int)blockDim.x);
+#endif
+        float* out = poses + ((int64_t)m.hyp_off + h) * 12;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) out[i] = R[i];
+        out[9] = tr[0]; out[10] = tr[1]; out[11] = tr[2];
+    }
+}
+
 // ---- MLPnP minimal solve: one thread per hypothesis (MLPnPsolver.cpp:76-120) ----
 __global__ void __launch_bounds__(128) mlpnp_minimal_kernel(const ProblemMeta* metas, int C, int64_t sumH,
                                                             const uint32_t* tables, const float4* cA,

@@ -58,6 +58,10 @@ struct ScoreArgs {
     unsigned long long* exact_counter;   // optional diagnostic
     int32_t chunk_cap;               // capacity of one ring slot in correspondences
     int32_t tile_hyps;               // hypotheses per tile = warps * 32 * HPL
+    // early-exit phases (pnp_pipeline.cuh): when `phase` is set, only the groups of problems with
+    // phase[problem] == phase_want are scored; producer and consumers read the same stable flag
+    const int32_t* phase = nullptr;
+    int32_t phase_want = 0;
 };
 
 // ---- exact (reference-arithmetic) evaluations ----
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
                 for (int i = 0; i < 4; ++i) rec.q[i] = work[4 * k + i];
                 const ScoreGroup& grp = rec.g;
                 if (grp.gid < 0) break;
+                if (args.phase && args.phase[grp.problem] != args.phase_want) continue;   // not in this phase
                 // this CTA's share of the group's chunks: first, first + stride, ... (dealt by the host; no
                 // global round trip between chunks, so the ring runs kScoreStages chunks ahead of the consumers)
                 const int c_first = grp.first_stride & 0xffff, c_stride = max(1, grp.first_stride >> 16);
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
         const int4* w0 = reinterpret_cast<const int4*>(args.work + (size_t)blockIdx.x * args.vlen);
 #pragma unroll
         for (int i = 0; i < 4; ++i) rec.q[i] = w0[i];
-        if (rec.g.gid >= 0) { enter_group(rec.g); cur_k = 0; }
+        if (rec.g.gid >= 0 && !(args.phase && args.phase[rec.g.problem] != args.phase_want)) { enter_group(rec.g); cur_k = 0; }
     }
 
     for (uint32_t cit = 0;; ++cit) {

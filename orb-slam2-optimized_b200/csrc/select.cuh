@@ -41,6 +41,11 @@ struct SelectArgs {
     int32_t problem_base;    // global index of problem 0 (sharding)
     int32_t flags;
     const int32_t* resume;   // optional [C]: hypotheses already consumed by earlier iterate() calls
+    // early exit in phases (pnp_pipeline.cuh): ee = [phase: C][listB: C][listC: C][nB, nC, ..] or nullptr
+    int32_t* ee = nullptr;
+    int32_t C = 0;
+    int32_t first_phase = 0;   // HA: hypotheses every problem has after phase A
+    int32_t only_phase = -1;   // >= 0: only problems in this phase run (the phase-C replay resumes them at HA)
 };
 
 struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
@@ -490,7 +495,20 @@ __global__ void __launch_bounds__(kSelectThreads, kSelectCtasPerSm) ransac_selec
     res.problem = a.problem_base + blockIdx.x; res.reserved[0] = res.reserved[1] = 0;
 
     RSAC_SEL_MARK(0);
-    const int N = m->n, H = m->H, minInl = m->min_inl;
+    const int N = m->n, Hfull = m->H, minInl = m->min_inl;
+    // early exit: a phase-0 problem has only its first HA hypotheses; the scan must not look past them
+    int H = Hfull;
+    bool resume_phase = false;
+    if (a.ee) {
+        const int ph = a.ee[blockIdx.x];
+        if (a.only_phase >= 0) {
+            if (ph != a.only_phase) return;
+            resume_phase = true;
+            res.n_refines = reinterpret_cast<const ResultRec*>(a.results)[blockIdx.x].n_refines;   // carried over
+        } else if (ph == 0 && Hfull > a.first_phase) {
+            H = a.first_phase;
+        }
+    }
     uint32_t* final_mask = a.masks + m->word_off;
     const int32_t* counts = a.counts + m->hyp_off;
     const PT* poses = reinterpret_cast<const PT*>(a.poses) + (size_t)m->hyp_off * 12;
@@ -534,10 +552,11 @@ __global__ void __launch_bounds__(kSelectThreads, kSelectCtasPerSm) ransac_selec
         __syncthreads();
     };
 
-    if (!finished && a.resume && a.resume[blockIdx.x] > 0) {
-        // a later iterate() call: rebuild mnBestInliers / mvbBestInliers as the scan left them before
-        // `cursor` (first strict maximum among the hypotheses with cnt >= minInliers)
-        cursor = min(a.resume[blockIdx.x], H);
+    const int resume_at = resume_phase ? a.first_phase : ((a.resume && !finished) ? a.resume[blockIdx.x] : 0);
+    if (!finished && resume_at > 0) {
+        // a later iterate() call (or the phase-C continuation): rebuild mnBestInliers / mvbBestInliers as the
+        // scan left them before `cursor` (first strict maximum among the hypotheses with cnt >= minInliers)
+        cursor = min(resume_at, H);
         if (tid == 0) s_key = 0ull;
         __syncthreads();
         for (int h = tid; h < cursor; h += blockDim.x)
@@ -599,6 +618,18 @@ __global__ void __launch_bounds__(kSelectThreads, kSelectCtasPerSm) ransac_selec
         cursor = h + 1;
     }
 
+    if (!finished && H < Hfull) {
+        // early exit: every refine before HA failed and the rest of the hypotheses has not been computed yet:
+        // hand the problem to phase C; only the refine counter survives (in the result record)
+        if (tid == 0) {
+            int32_t* counters = a.ee + 3 * (size_t)a.C;
+            a.ee[blockIdx.x] = 2;
+            (a.ee + 2 * (size_t)a.C)[atomicAdd(counters + 1, 1)] = blockIdx.x;
+            res.reserved[0] = 1;   // not decided yet
+            reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
+        }
+        return;
+    }
     if (!finished) {                                           // :173-188 budget exhausted
         res.no_more = 1;
         res.n_hyp = H;

@@ -18,6 +18,7 @@ OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_ALLOC = range(6)
 FLAG_KEEP_MASKS = 1
 FLAG_MLPNP_DISCARD_REFINE = 4
 FLAG_EPNP_EIGEN = 8          # 4-point EPnP null space from the 12x12 eigen-solve (default: Householder QR)
+FLAG_EARLY_EXIT = 16         # PnP: hypotheses in phases, nothing behind the reference's stopping point is computed
 STAGE_PACK, STAGE_RNG, STAGE_SOLVE, STAGE_SCORE, STAGE_SELECT = range(5)
 STAGE_NAMES = ["pack", "rng", "solve", "score", "select"]
 
@@ -170,6 +171,19 @@ class Engine:
 
     def set_problem_base(self, base: int):
         self._ck(self.L.rsac_set_problem_base(self.h, C.c_int(base)), "set_problem_base")
+
+    def set_first_phase(self, hypotheses: int):
+        self._ck(self.L.rsac_set_first_phase(self.h, C.c_int(hypotheses)), "set_first_phase")
+
+    def pnp_phase_stats(self):
+        """(first_phase, problems in phase B, problems in phase C, hypotheses solved) of the last early-exit run"""
+        out = (C.c_int64 * 4)()
+        self._ck(self.L.rsac_pnp_phase_stats(self.h, out), "pnp_phase_stats")
+        return tuple(int(v) for v in out)
+
+    def pnp_rerun(self, resume_from, flags=0, d_results_out: int | None = None):
+        r = np.ascontiguousarray(resume_from, np.int32)
+        self._ck(self.L.rsac_pnp_rerun(self.h, C.c_int(flags), _p(r), C.c_void_p(d_results_out or 0)), "pnp_rerun")
 
     def device_info(self):
         info = DeviceInfo()

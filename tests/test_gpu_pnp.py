@@ -230,3 +230,126 @@ def test_pnp_many_hypotheses_multiple_tiles_per_problem(engine, oracle):
             checked += 1
         h0 += H
     assert checked == 20 and h0 == len(counts)
+
+
+# ---------------------------------------------------------------- early exit in phases (RSAC_FLAG_EARLY_EXIT)
+_REC_FIELDS = ("ok", "no_more", "n_inliers", "best_hyp", "refined", "n_refines", "best_count", "n_hyp")
+
+
+def _same_records(a, b):
+    for f in _REC_FIELDS:
+        assert (a[f] == b[f]).all(), (f, np.argwhere(a[f] != b[f]).ravel()[:8])
+    assert (a["R"].view(np.uint32) == b["R"].view(np.uint32)).all()
+    assert (a["t"].view(np.uint32) == b["t"].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("first_phase", [8, 32, 56, 299])
+def test_pnp_early_exit_equals_exhaustive_and_oracle(engine, oracle, first_phase):
+    """The phased run (first `first_phase` hypotheses of every problem, the rest only where still needed) must
+    return the exhaustive run's records and masks bit for bit, and the sequential oracle's (early exit is what
+    the reference does: PnPsolver.cpp:225-236)."""
+    C, n = 96, 500
+    b, offsets = _batch(4, C, n)
+    args = (offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**PRM))
+    res0, masks0 = engine.pnp_solve(*args, seeds=b["seeds"])
+    engine.set_first_phase(first_phase)
+    try:
+        res1, masks1 = engine.pnp_solve(*args, seeds=b["seeds"], flags=capi.FLAG_EARLY_EXIT)
+        ha, nB, nC, solved = engine.pnp_phase_stats()
+    finally:
+        engine.set_first_phase(0)
+    assert ha == first_phase
+    _same_records(res0, res1)
+    assert (masks0 == masks1).all()
+    assert 0 <= nB <= C and solved <= C * 300
+    if first_phase <= 56:
+        assert solved < C * 300          # work was actually skipped
+    tables = [oracle.index_table(int(s), n, 4, 300) for s in b["seeds"][:16]]
+    orc = [oracle.pnp_ransac(oracle.pnp_problem(b["p3d"][c], b["p2d"][c], b["sigma2"][c], b["K"]), oracle.params(**PRM),
+                             tables[c], oracle.FLAG_EPNP_QR_NULLSPACE) for c in range(16)]
+    _check_results(res1[:16], engine.split_masks(masks1, offsets)[:16], orc)
+    for c in range(16):
+        assert res1[c]["n_refines"] == orc[c]["n_refines"] and res1[c]["n_hyp"] == orc[c]["n_hyp"]
+
+
+def test_pnp_early_exit_failed_refines_reach_the_cleanup_phase(engine, oracle):
+    """Tracking's parameters (H = 35, minInl = N/2): refines fail, so problems predicted to finish inside the
+    first phase do not; the replay hands them to the clean-up phase, which must continue the scan exactly where
+    the sequential reference would be (same refine count, same result)."""
+    prm = dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.5, th2=5.991)
+    C, n = 192, 200
+    b, offsets = _batch(12, C, n, outl=0.45)
+    args = (offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**prm))
+    res0, masks0 = engine.pnp_solve(*args, seeds=b["seeds"])
+    seen_c = 0
+    for first_phase in (4, 9, 20):
+        engine.set_first_phase(first_phase)
+        try:
+            res1, masks1 = engine.pnp_solve(*args, seeds=b["seeds"], flags=capi.FLAG_EARLY_EXIT)
+            ha, nB, nC, solved = engine.pnp_phase_stats()
+        finally:
+            engine.set_first_phase(0)
+        _same_records(res0, res1)
+        assert (masks0 == masks1).all()
+        assert (res1["reserved"] == 0).all()      # nothing left undecided
+        seen_c += nC
+    assert seen_c > 0, "the clean-up phase was never exercised"
+    minInl, H = capi.pnp_ransac_setup(n, capi.ransac_params(**prm))
+    orc = [oracle.pnp_ransac(oracle.pnp_problem(b["p3d"][c], b["p2d"][c], b["sigma2"][c], b["K"]), oracle.params(**prm),
+                             oracle.index_table(int(b["seeds"][c]), n, 4, H), oracle.FLAG_EPNP_QR_NULLSPACE) for c in range(24)]
+    _check_results(res1[:24], engine.split_masks(masks1, offsets)[:24], orc)
+    for c in range(24):
+        assert res1[c]["n_refines"] == orc[c]["n_refines"]
+
+
+def test_pnp_early_exit_ragged_batch(engine):
+    """ragged problems (empty, n < minInliers, H = 0, H < first_phase) through the phased run"""
+    sizes = [0, 3, 4, 9, 37, 64, 65, 500, 257, 130]
+    parts = [synth.pnp_problem(7100 + i, max(n, 1), 0.4 if i != 4 else 1.0) for i, n in enumerate(sizes)]
+    p3d = np.concatenate([p["p3d"][:n] for p, n in zip(parts, sizes)])
+    p2d = np.concatenate([p["p2d"][:n] for p, n in zip(parts, sizes)])
+    s2 = np.concatenate([p["sigma2"][:n] for p, n in zip(parts, sizes)])
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    seeds = np.arange(len(sizes), dtype=np.uint32) + 177
+    prms = [capi.ransac_params(**PRM), capi.ransac_params(prob=0.99, min_inliers=10, max_its=20, min_set=4, eps=0.5, th2=5.991)]
+    for prm in prms:
+        args = (offsets, p3d, p2d, s2, [parts[0]["K"]], prm)
+        res0, masks0 = engine.pnp_solve(*args, seeds=seeds)
+        for first_phase in (1, 7, 40):
+            engine.set_first_phase(first_phase)
+            try:
+                res1, masks1 = engine.pnp_solve(*args, seeds=seeds, flags=capi.FLAG_EARLY_EXIT)
+            finally:
+                engine.set_first_phase(0)
+            _same_records(res0, res1)
+            assert (masks0 == masks1).all()
+
+
+def test_pnp_early_exit_then_later_iterate_calls(engine):
+    """rsac_pnp_rerun after a phased run: the hypotheses that were skipped are computed on demand, and the scan
+    continues like after an exhaustive run (Tracking.cpp:1239-1334 keeps calling iterate on a candidate whose
+    pose failed PoseOptimization)."""
+    C, n = 64, 400
+    b, offsets = _batch(14, C, n)
+    args = (offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**PRM))
+    res0, _ = engine.pnp_solve(*args, seeds=b["seeds"])
+    resume = res0["n_hyp"].astype(np.int32)
+    engine.pnp_rerun(resume)
+    ref, refm = engine.pnp_download()
+    engine.set_first_phase(24)
+    try:
+        res1, _ = engine.pnp_solve(*args, seeds=b["seeds"], flags=capi.FLAG_EARLY_EXIT)
+        _same_records(res0, res1)
+        engine.pnp_rerun(resume)
+        got, gotm = engine.pnp_download()
+        _same_records(ref, got)
+        assert (refm == gotm).all()
+        engine.pnp_rerun(got["n_hyp"].astype(np.int32))       # and once more, now with everything computed
+        engine.pnp_download()
+    finally:
+        engine.set_first_phase(0)
+    poses1, counts1 = engine.pnp_hypotheses()
+    engine.pnp_solve(*args, seeds=b["seeds"])
+    poses0, counts0 = engine.pnp_hypotheses()
+    assert (counts0 == counts1).all()                          # after the rerun every hypothesis exists
+    assert (poses0.view(np.uint32) == poses1.view(np.uint32)).all()
