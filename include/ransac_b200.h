@@ -133,6 +133,9 @@ int rsac_timer_end(rsac_engine* e, float* ms);   /* synchronises */
 int rsac_profile_enable(rsac_engine* e, int on);
 int rsac_profile_reset(rsac_engine* e);
 int rsac_profile_get(rsac_engine* e, int stage, double* total_ms, int64_t* launches);
+/* the profiled launches since the last reset in launch order (first 4096): stage id and milliseconds of each;
+ * returns the number of entries written, -1 on error */
+int rsac_profile_trace(rsac_engine* e, int max_entries, int32_t* stages, float* ms);
 /* number of this library's kernels launched since creation / last reset */
 int64_t rsac_launch_count(rsac_engine* e);
 /* FFMA / DFMA saturating micro-kernels: measured FP32 / FP64 CUDA-core peaks (TFLOP/s) */

@@ -148,6 +148,7 @@ static int profile_drain(rsac_engine* e)
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
             e->stage_ms[p.stage] += ms;
             e->stage_launches[p.stage] += 1;
+            if (e->prof_trace.size() < 4096) e->prof_trace.push_back({p.stage, ms});
         } else {
             cudaGetLastError();
         }
@@ -163,7 +164,20 @@ int rsac_profile_reset(rsac_engine* e)
     int rc = profile_drain(e);
     for (int i = 0; i < RSAC_STAGE_COUNT; ++i) { e->stage_ms[i] = 0.0; e->stage_launches[i] = 0; }
     e->launches = 0;
+    e->prof_trace.clear();
     return rc;
+}
+
+int rsac_profile_trace(rsac_engine* e, int max_entries, int32_t* stages, float* ms)
+{
+    if (!e || max_entries < 0) return -1;
+    if (profile_drain(e) != RSAC_OK) return -1;
+    const int n = (int)std::min<size_t>(e->prof_trace.size(), (size_t)max_entries);
+    for (int i = 0; i < n; ++i) {
+        if (stages) stages[i] = e->prof_trace[i].first;
+        if (ms) ms[i] = e->prof_trace[i].second;
+    }
+    return n;
 }
 
 int rsac_profile_get(rsac_engine* e, int stage, double* total_ms, int64_t* launches)
@@ -280,7 +294,7 @@ static const void* score_kernel_ptr(int hpl)
 //    within one chunk of work.
 template <int MODEL>
 static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int maxH, std::vector<ScoreGroup>& groups, ScorePlan& pl,
-                      int h_lo = 0, int h_hi = INT32_MAX, int hpl_want = 0, int cw_want = 0)
+                      int h_lo = 0, int h_hi = INT32_MAX, int hpl_want = 0, int cw_want = 0, bool by_list = false)
 {
     // [h_lo, min(H, h_hi)) of every problem: the early-exit phases score hypothesis ranges (pnp_run_early)
     groups.clear();
@@ -333,6 +347,25 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
     int cw = std::min(kChunkWordsMax, maxWords);
     if (cw_want > 0) cw = std::min(cw, cw_want);
     int slots = resident(cw);
+    if (by_list) {
+        // which problems are scored is decided on the device (early-exit phases B, C): one record per
+        // (problem, tile), whole groups per CTA, the CTAs stride over the device-side list
+        const int T = std::max(1, (maxH + pl.tile_hyps - 1) / pl.tile_hyps);
+        pl.by_list = true;
+        pl.tiles = T;
+        pl.vlen = T;
+        pl.grid = slots;
+        pl.work.assign(metas.size() * (size_t)T, end_rec);
+        for (auto& g : groups) {
+            g.chunk_words = std::min(cw, std::max(1, g.words));
+            g.nchunks = (g.words + g.chunk_words - 1) / g.chunk_words;
+            g.first_stride = 1 << 16;
+            pl.work[(size_t)g.problem * T + (g.hyp0 - h_lo) / pl.tile_hyps] = g;
+        }
+        pl.chunk_cap = cw * 32;
+        pl.smem = score_smem_bytes<MODEL>(pl.chunk_cap, pl.tile_hyps);
+        return RSAC_OK;
+    }
     std::vector<std::vector<int>> lists;
     if (NG >= slots) {
         pl.grid = slots;
@@ -419,6 +452,8 @@ static int launch_score(rsac_engine* e, ScoreArgs& args, const ScorePlan& pl, in
     if (pl.smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     args.work = (const ScoreGroup*)d_visit.p;
     args.vlen = pl.vlen;
+    args.tiles_per_problem = pl.tiles;
+    if (pl.by_list != (args.list != nullptr)) { e->err = "scoring plan and launch disagree about list mode"; return RSAC_ERR_STATE; }
     args.chunk_cap = pl.chunk_cap;
     args.tile_hyps = pl.tile_hyps;
     void* kargs[] = {&args};
@@ -602,8 +637,9 @@ static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* l
     e->stage_end(RSAC_STAGE_SOLVE);
     RSAC_CUDA(e, cudaGetLastError());
     ScoreArgs sa = s.ee_sa;
-    sa.phase = (const int32_t*)s.d_ee.p;
-    sa.phase_want = want;
+    sa.list = list;
+    sa.list_count = list_count;
+    (void)want;
     return launch_score<0>(e, sa, s.planB, (int)s.groupsB.size(), s.d_visitB);
 }
 
@@ -617,8 +653,10 @@ static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, int HA)
     const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
     if (!s.ee_planned || s.ee_HA != HA) {
         s.ee_HA = HA;
-        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsA, s.planA, 0, HA, env_int("RSAC_EE_HPL_A", 0), env_int("RSAC_EE_CW_A", 0)));
-        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB, s.planB, HA, INT32_MAX, env_int("RSAC_EE_HPL_B", 0), env_int("RSAC_EE_CW_B", 0)));
+        // phase A: few hypotheses per problem -- one hypothesis per lane (two consumer warps per problem) measured
+        // best (0.045 ms against 0.066 with two per lane at 1024 x 55)
+        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsA, s.planA, 0, HA, env_int("RSAC_EE_HPL_A", 1), env_int("RSAC_EE_CW_A", 0)));
+        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB, s.planB, HA, INT32_MAX, env_int("RSAC_EE_HPL_B", 0), env_int("RSAC_EE_CW_B", 0), true));
         const size_t bA = sizeof(ScoreGroup) * s.planA.work.size(), bB = sizeof(ScoreGroup) * s.planB.work.size();
         const size_t oB = (bA + 255) & ~(size_t)255;
         char* h = (char*)s.h_stageEE.ensure(oB + bB + 256);
@@ -745,7 +783,11 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
     if ((flags & RSAC_FLAG_EARLY_EXIT) && !(flags & RSAC_FLAG_EPNP_EIGEN) && d.sumH > 0) {
         // phase A sized to one wave of the minimal solver unless the caller chose
         int HA = e->first_phase > 0 ? e->first_phase : env_int("RSAC_EE_HA", 0);
-        if (HA <= 0) HA = std::max(32, (RSAC_SOLVE_THREADS * RSAC_SOLVE_BLOCKS * e->sm_count / std::max(d.C, 1)) & ~7);
+        if (HA <= 0) {
+            // whole blocks only: 1024 problems x 55 hypotheses = 440 blocks of 128 <= 444 resident
+            const int blocks = RSAC_SOLVE_BLOCKS * e->sm_count;
+            HA = std::max(32, (int)(((int64_t)blocks * RSAC_SOLVE_THREADS) / std::max(d.C, 1)));
+        }
         if (HA < d.maxH) return pnp_run_early(e, flags, d_results_out, HA);
     }
     if (d.sumH > 0) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -74,6 +75,8 @@ struct ScorePlanPOD {
     int threads = 32, tile_hyps = 64, chunk_cap = 32, grid = 1, hpl = 2;
     size_t smem = 0;
     int vlen = 1;                            // records per CTA in `work`
+    bool by_list = false;                    // `work` is [problem][tiles]; the CTAs stride over a device-side problem list
+    int tiles = 1;
     std::vector<ScoreGroup> work;            // [grid][vlen] per-CTA lists of group records (host copy)
 };
 
@@ -159,6 +162,7 @@ struct rsac_engine {
     bool profile = false;
     std::vector<rsac::ProfPair> prof_events, prof_pool;
     rsac::ProfPair cur{};
+    std::vector<std::pair<int, float>> prof_trace;   // (stage, ms) of every profiled launch since the last reset, in order
     double stage_ms[RSAC_STAGE_COUNT] = {0, 0, 0, 0, 0};
     int64_t stage_launches[RSAC_STAGE_COUNT] = {0, 0, 0, 0, 0};
     int64_t launches = 0;

@@ -62,6 +62,11 @@ struct ScoreArgs {
     // phase[problem] == phase_want are scored; producer and consumers read the same stable flag
     const int32_t* phase = nullptr;
     int32_t phase_want = 0;
+    // list mode (phases B and C): the problems to score are only known on the device.  `work` is then
+    // [problem][tiles_per_problem] and the CTAs stride over list[0 .. *list_count) x tiles
+    const int32_t* list = nullptr;
+    const int32_t* list_count = nullptr;
+    int32_t tiles_per_problem = 1;
 };
 
 // ---- exact (reference-arithmetic) evaluations ----
@@ -234,15 +239,19 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
     if (warp == ncons) {
         // ------------------------------------------------------------- producer
         if (lane == 0) {
-            const int4* work = reinterpret_cast<const int4*>(args.work + (size_t)blockIdx.x * args.vlen);
+            const bool by_list = args.list != nullptr;
+            const int4* work = reinterpret_cast<const int4*>(by_list ? args.work : args.work + (size_t)blockIdx.x * args.vlen);
+            const int T = args.tiles_per_problem;
+            const int k_end = by_list ? *args.list_count * T : args.vlen;
             uint32_t pit = 0;
-            for (int k = 0; k < args.vlen; ++k) {
+            for (int k = by_list ? (int)blockIdx.x : 0; k < k_end; k += by_list ? (int)gridDim.x : 1) {
                 union { ScoreGroup g; int4 q[4]; } rec;
+                const int4* src = by_list ? work + 4 * ((size_t)args.list[k / T] * T + k % T) : work + 4 * k;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) rec.q[i] = work[4 * k + i];
+                for (int i = 0; i < 4; ++i) rec.q[i] = src[i];
                 const ScoreGroup& grp = rec.g;
-                if (grp.gid < 0) break;
-                if (args.phase && args.phase[grp.problem] != args.phase_want) continue;   // not in this phase
+                if (grp.gid < 0) { if (by_list) continue; else break; }
+                if (!by_list && args.phase && args.phase[grp.problem] != args.phase_want) continue;   // not in this phase
                 // this CTA's share of the group's chunks: first, first + stride, ... (dealt by the host; no
                 // global round trip between chunks, so the ring runs kScoreStages chunks ahead of the consumers)
                 const int c_first = grp.first_stride & 0xffff, c_stride = max(1, grp.first_stride >> 16);
@@ -329,7 +338,16 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
     };
 
     // the CTA's first group is known without the producer: fold its poses while the first chunk is in flight
-    {
+    if (args.list) {
+        const int T = args.tiles_per_problem, k = (int)blockIdx.x;
+        if (k < *args.list_count * T) {
+            union { ScoreGroup g; int4 q[4]; } rec;
+            const int4* w0 = reinterpret_cast<const int4*>(args.work + ((size_t)args.list[k / T] * T + k % T));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rec.q[i] = w0[i];
+            if (rec.g.gid >= 0) { enter_group(rec.g); cur_k = k; }
+        }
+    } else {
         union { ScoreGroup g; int4 q[4]; } rec;
         const int4* w0 = reinterpret_cast<const int4*>(args.work + (size_t)blockIdx.x * args.vlen);
 #pragma unroll

@@ -213,6 +213,14 @@ class Engine:
             out[nm] = (ms.value, n.value)
         return out
 
+    def profile_trace(self, max_entries=4096):
+        st = np.zeros(max_entries, np.int32)
+        ms = np.zeros(max_entries, np.float32)
+        n = self.L.rsac_profile_trace(self.h, C.c_int(max_entries), _p(st), _p(ms))
+        if n < 0:
+            raise RsacError(3, "profile_trace")
+        return [(STAGE_NAMES[int(s)], float(m)) for s, m in zip(st[:n], ms[:n])]
+
     def launch_count(self) -> int:
         return self.L.rsac_launch_count(self.h)
 

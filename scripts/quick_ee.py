@@ -33,6 +33,9 @@ def run(flags, K=8):
         eng.pnp_run(flags)
     eng.sync()
     prof = {k: (t / 4, nl // 4) for k, (t, nl) in eng.profile().items() if nl}
+    tr = eng.profile_trace()
+    per = len(tr) // 4
+    print("      last sweep:", " ".join("%s %.3f" % (k, m) for k, m in tr[-per:]))
     eng.profile_enable(False)
     return ms, prof
 
@@ -48,3 +51,13 @@ for ha in HAS:
     same = all((res0[f] == res1[f]).all() for f in ("ok", "n_inliers", "best_hyp", "n_refines", "n_hyp")) and (m0 == m1).all()
     print("HA=%3d (used %3d): %.3f ms/sweep  %.0f cand/s  B=%d C=%d solved=%.1f%%  same=%s  %s" % (
         ha, st[0], ms, C / ms * 1e3, st[1], st[2], 100.0 * st[3] / (C * 300), same, {k: "%.3f/%d" % v for k, v in prof.items()}))
+
+import ctypes
+clk = (ctypes.c_longlong * 16)()
+eng.set_first_phase(0)
+eng.pnp_run()
+eng.sync()
+eng.L.rsac_debug_select_clocks(eng.h, clk)
+c = list(clk)
+names = ["start", "found", "refine:begin", "presums", "MtM", "jacobi", "betas", "sums2", "horn+reproj", "score", "end"]
+print("select phases (block 0, cycles):", [(names[i], c[i] - c[i - 1]) for i in range(1, 11)], "total", c[10] - c[0])
