@@ -3,11 +3,13 @@
 
 Workload (config.workload = "cfg4"): 1024 candidate keyframes x 500 2D-3D matches, 50 % outliers,
 PnPsolver EPnP RANSAC with SetRansacParameters(0.99,10,300,4,0.2,5.991) => H = 300 hypotheses per
-candidate, all of them solved and scored on the device (153.6 M hypothesis x correspondence
-evaluations + 307 200 EPnP minimal solves per sweep), then the reference's sequential semantics
-(PnPsolver::iterate / Refine) are replayed per candidate.  With N GPUs the 1024 candidates are
-sharded in contiguous blocks (strong scaling, as BASELINE.json's config says) and the
-per-candidate records (96 B) are all-gathered over NCCL every sweep.
+candidate.  The reference stops at the first hypothesis whose Refine() succeeds; the device does the same
+in phases (RSAC_FLAG_EARLY_EXIT: the first 55 hypotheses of every candidate, the rest only for the candidates
+that still need them), then replays the reference's sequential semantics (PnPsolver::iterate / Refine) per
+candidate -- records and masks are identical to solving and scoring all 300 (RSAC_BENCH_EXHAUSTIVE=1 times
+that mode: 153.6 M evaluations + 307 200 minimal solves per sweep).  With N GPUs every GPU works on its own
+1024-candidate sweep (weak scaling; RSAC_BENCH_STRONG=1 shards one sweep instead) and the per-candidate
+records (96 B) are all-gathered over NCCL every sweep.
 
 A "step" is one sweep.  Sweeps are independent, so they are pipelined over a few engine
 instances / CUDA streams; the timed region is K sweeps between barriers, timed with CUDA events,
@@ -45,6 +47,7 @@ H_HYP = 300
 METRIC = "relocalization candidates/s (PnP EPnP RANSAC sweep; hyp x corr evals/s in extras)"
 FLOP_PER_EVAL = 31            # PnP CheckInliers
 PIPE = int(os.environ.get("RSAC_BENCH_PIPE", "0"))   # sweeps in flight per GPU (0: default, one)
+EXHAUSTIVE = os.environ.get("RSAC_BENCH_EXHAUSTIVE", "0") == "1"   # solve and score all 300 hypotheses of every candidate
 
 
 def measured_peaks():
@@ -193,6 +196,7 @@ def main():
     C_PER_GPU = C_TOTAL
     if not strong:
         C_TOTAL = C_PER_GPU * world
+    RUN_FLAGS = 0 if EXHAUSTIVE else capi.FLAG_EARLY_EXIT
     first, count = shard.block_range(C_TOTAL, rank, world)
     cap = shard.per_rank_capacity(C_TOTAL, world)
     b, offsets = make_shard(first, count)
@@ -237,7 +241,7 @@ def main():
         with torch.cuda.stream(streams[i]):
             if gather_done[k] is not None:
                 streams[i].wait_event(gather_done[k])      # the gather that last read this buffer (two sweeps ago)
-            engines[i].pnp_run(0, d_loc2[k].data_ptr())
+            engines[i].pnp_run(RUN_FLAGS, d_loc2[k].data_ptr())
             if world > 1:
                 ev = torch.cuda.Event()
                 ev.record(streams[i])
@@ -253,7 +257,7 @@ def main():
             upload(i)                                   # H2D + pack: overlaps the previous sweep's kernels
             if compute_done[0] is not None:             # ... but the sweeps' kernels run one sweep at a time
                 streams[i].wait_event(compute_done[0])
-            engines[i].pnp_run(0, d_local[i].data_ptr())
+            engines[i].pnp_run(RUN_FLAGS, d_local[i].data_ptr())
             if world > 1:
                 dist.all_gather_into_tensor(d_gath[i], d_local[i])
             ev = torch.cuda.Event()
@@ -313,11 +317,14 @@ def main():
     nprof = max(3, min(10, args.steps))
     with torch.cuda.stream(streams[0]):
         for _ in range(nprof):
-            e0.pnp_run(0, d_local[0].data_ptr())
+            e0.pnp_run(RUN_FLAGS, d_local[0].data_ptr())
     torch.cuda.synchronize()
     for k, (tms, nl) in e0.profile().items():
         stage[k] = [tms, nl]
+    trace = e0.profile_trace()
+    trace = trace[-(len(trace) // nprof):] if trace else []      # the launches of the last sweep, in order
     e0.profile_enable(False)
+    ha, n_b, n_c, hyp_done = e0.pnp_phase_stats()               # hypotheses actually solved and scored (this rank)
 
     # correctness guard on the gathered records (cheap): every candidate reported once, in order
     torch.cuda.synchronize()
@@ -333,7 +340,7 @@ def main():
 
     value = C_TOTAL * args.steps / (ms * 1e-3)
     e2e_v = C_TOTAL * args.steps / (ms_e2e * 1e-3)
-    evals_per_sweep = C_TOTAL * H_HYP * N_MATCH
+    hyp_frac = hyp_done / float(count * H_HYP)                   # share of the 300 x candidates hypotheses computed
 
     line = {"metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -341,16 +348,25 @@ def main():
             "vs_baseline": None, "dtype": "f64 solve / f32 score", "data": "synthetic",
             "config": {"workload": "cfg4", "candidates": C_TOTAL, "candidates_per_gpu": count, "matches": N_MATCH,
                        "hypotheses": H_HYP, "outliers": 0.5,
-                       "mode": "all H hypotheses solved and scored on the device (4-point null space by QR), then "
-                               "reference-semantics replay + Refine per candidate",
+                       "mode": ("all H hypotheses solved and scored on the device (4-point null space by QR), then "
+                                "reference-semantics replay + Refine per candidate") if EXHAUSTIVE else
+                               (f"reference semantics with early exit in phases: hypotheses [0,{ha}) of every candidate, the "
+                                f"remaining ones for the {n_b} of {count} candidates without an acceptable hypothesis so far "
+                                f"({100 * hyp_frac:.1f} % of the 300 x {count} hypotheses solved and scored), replay + Refine per "
+                                "candidate; records identical to the exhaustive run"),
                        "parallelism": f"candidates sharded x{world}, {PIPE} sweep(s) in flight per GPU; e2e double-buffers the "
                                       "H2D copy of the next sweep under the kernels of the current one",
                        "l2": "working set of a sweep (~90 MB) is L2-resident by design; every kernel is compute- or latency-bound: no flush"},
             "e2e": {"value": e2e_v, "unit": "candidates/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "extras": {"evals_per_s": value * H_HYP * N_MATCH, "e2e_evals_per_s": e2e_v * H_HYP * N_MATCH,
+            "extras": {"evals_per_s": value * H_HYP * N_MATCH * hyp_frac, "e2e_evals_per_s": e2e_v * H_HYP * N_MATCH * hyp_frac,
+                       "evals_note": "hypothesis x correspondence evaluations actually performed (early exit skips the rest)",
                        "candidates_ok": n_ok,
+                       "phases": {"first_phase": ha, "candidates_phase_b": n_b, "candidates_phase_c": n_c,
+                                  "hypotheses_done_frac": hyp_frac},
+                       "sweep_launches_ms": [[k, round(m, 4)] for k, m in trace],
+                       "stage_ms_per_sweep": {k: v[0] / nprof for k, v in stage.items() if v[1]},
                        "stage_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in stage.items()}}}
     if clocks is not None:
         line["clocks"] = clocks
@@ -363,27 +379,39 @@ def main():
         # per-kernel rooflines; "roofline" is the kernel with the largest share of the sweep.
         # Algorithmic FLOP per 4-point solve is counted by the oracle's instrumented build.
         flop_per_solve = epnp_flops_per_solve(b)
-        per = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in stage.items()}
+        # per sweep: with early exit a kernel is launched once per phase (A, B, clean-up); work = what the launches
+        # of a sweep actually did, time = their summed durations, so achieved = work / time is the launch-weighted
+        # average; the first launch of each kind (phase A: count x first_phase hypotheses) is also given alone
+        per = {k: v[0] / nprof for k, v in stage.items() if v[1]}
+        nl = {k: v[1] / nprof for k, v in stage.items() if v[1]}
         total_ms = sum(per.values()) or 1.0
+        first = {}
+        for k, m in trace:
+            first.setdefault(k, m)
         roofs = {}
         if per.get("solve"):
             t = per["solve"] * 1e-3
-            ach = flop_per_solve * count * H_HYP / t / 1e12
-            roofs["solve"] = {"bound": "fp64", "kernel": "epnp_minimal_kernel<QR>", "achieved": ach, "peak": fp64_pk,
+            ach = flop_per_solve * hyp_done / t / 1e12
+            roofs["solve"] = {"bound": "fp64", "kernel": "epnp_minimal_kernel<QR>" if EXHAUSTIVE else "epnp_minimal_range_kernel",
+                              "achieved": ach, "peak": fp64_pk,
                               "unit": "TFLOP/s", "frac": ach / fp64_pk,
-                              "traffic": ncu_traffic("epnp_minimal_kernel<QR>") if count == 1024 else None,
+                              "traffic": ncu_traffic("epnp_minimal_kernel<QR>" if EXHAUSTIVE else "epnp_minimal_range_kernel") if count == 1024 else None,
                               "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                              "flop_per_solve": flop_per_solve, "launch_ms": per["solve"], "share_of_sweep": per["solve"] / total_ms}
+                              "flop_per_solve": flop_per_solve, "solves_per_sweep": hyp_done, "launch_ms": per["solve"],
+                              "launches_per_sweep": nl["solve"], "share_of_sweep": per["solve"] / total_ms}
+            if not EXHAUSTIVE and first.get("solve"):
+                a1 = flop_per_solve * count * ha / (first["solve"] * 1e-3) / 1e12
+                roofs["solve"]["phase_a_launch"] = {"solves": count * ha, "launch_ms": first["solve"], "achieved": a1, "frac": a1 / fp64_pk}
         if per.get("score"):
             t = per["score"] * 1e-3
-            ach = FLOP_PER_EVAL * count * H_HYP * N_MATCH / t / 1e12
-            roofs["score"] = {"bound": "fp32", "kernel": "score_kernel<2,0> (cfg4 sweep)", "achieved": ach, "peak": fp32_pk,
+            ach = FLOP_PER_EVAL * hyp_done * N_MATCH / t / 1e12
+            roofs["score"] = {"bound": "fp32", "kernel": "score_kernel<HPL,0> (cfg4 sweep)", "achieved": ach, "peak": fp32_pk,
                               "unit": "TFLOP/s", "frac": ach / fp32_pk, "traffic": None,
                               "peak_source": "FFMA micro-kernel measured in this run", "flop_per_eval": FLOP_PER_EVAL,
-                              "launch_ms": per["score"], "share_of_sweep": per["score"] / total_ms}
+                              "launch_ms": per["score"], "launches_per_sweep": nl["score"], "share_of_sweep": per["score"] / total_ms}
         if per.get("select"):
             roofs["select"] = {"bound": "latency", "kernel": "ransac_select_kernel<0> (replay + Refine, one CTA per candidate)",
-                               "launch_ms": per["select"], "share_of_sweep": per["select"] / total_ms,
+                               "launch_ms": per["select"], "launches_per_sweep": nl["select"], "share_of_sweep": per["select"] / total_ms,
                                "note": "serial dense tails (2 sqrt + 1-2 div chains); no meaningful FLOP roofline"}
         dom = max(roofs, key=lambda k: roofs[k]["launch_ms"]) if roofs else None
         if dom and "achieved" in roofs[dom]:

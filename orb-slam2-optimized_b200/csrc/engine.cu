@@ -40,6 +40,9 @@ int rsac_create(int device, rsac_engine** out)
     e->device = device;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return RSAC_ERR_CUDA; }
     e->stream = e->own_stream;
+    if (cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); e->aux_stream = nullptr; }
+    cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
     cudaEventCreate(&e->t0);
     cudaEventCreate(&e->t1);
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -57,6 +60,9 @@ void rsac_destroy(rsac_engine* e)
     for (auto& p : e->prof_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     cudaEventDestroy(e->t0);
     cudaEventDestroy(e->t1);
+    if (e->aux_stream) { cudaStreamSynchronize(e->aux_stream); cudaStreamDestroy(e->aux_stream); }
+    cudaEventDestroy(e->ev_fork);
+    cudaEventDestroy(e->ev_join);
     cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -535,6 +541,62 @@ static int stage_small_tables(rsac_engine* e, PnpState& s, const std::vector<flo
     return RSAC_OK;
 }
 
+static int pnp_first_phase(rsac_engine* e, const BatchDims& d)
+{
+    // phase A sized to one wave of the minimal solver unless the caller chose
+    int HA = e->first_phase > 0 ? e->first_phase : env_int("RSAC_EE_HA", 0);
+    if (HA <= 0) {
+        // whole blocks only: 1024 problems x 55 hypotheses = 440 blocks of 128 <= 444 resident
+        const int blocks = RSAC_SOLVE_BLOCKS * e->sm_count;
+        HA = std::max(32, (int)(((int64_t)blocks * RSAC_SOLVE_THREADS) / std::max(d.C, 1)));
+    }
+    return HA;
+}
+
+// scoring plans of the two hypothesis ranges [0, HA) and [HA, H) and their work lists (H2D through pinned staging)
+static int pnp_plan_early(rsac_engine* e, int HA)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    cudaStream_t st = e->stream;
+    s.ee_HA = HA;
+    // phase A: few hypotheses per problem -- one hypothesis per lane (two consumer warps per problem) measured
+    // best (0.045 ms against 0.066 with two per lane at 1024 x 55)
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsA, s.planA, 0, HA, env_int("RSAC_EE_HPL_A", 1), env_int("RSAC_EE_CW_A", 0)));
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB, s.planB, HA, INT32_MAX, env_int("RSAC_EE_HPL_B", 0), env_int("RSAC_EE_CW_B", 0), true));
+    const size_t bA = sizeof(ScoreGroup) * s.planA.work.size(), bB = sizeof(ScoreGroup) * s.planB.work.size();
+    const size_t oB = (bA + 255) & ~(size_t)255;
+    char* h = (char*)s.h_stageEE.ensure(oB + bB + 256);
+    if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
+    RSAC_TRY(s.d_visitA.ensure(e, std::max<size_t>(bA, sizeof(ScoreGroup))));
+    RSAC_TRY(s.d_visitB.ensure(e, std::max<size_t>(bB, sizeof(ScoreGroup))));
+    memcpy(h, s.planA.work.data(), bA);
+    memcpy(h + oB, s.planB.work.data(), bB);
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visitA.p, h, bA, cudaMemcpyHostToDevice, st));
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visitB.p, h + oB, bB, cudaMemcpyHostToDevice, st));
+    s.h_stageEE.mark(st);
+    s.ee_planned = true;
+    return RSAC_OK;
+}
+
+static int pnp_pack(rsac_engine* e)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    if (s.packed) return RSAC_OK;
+    if (d.total > 0 && d.C > 0) {
+        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)d.C);
+        e->stage_begin(RSAC_STAGE_PACK);
+        pack_pnp_kernel<<<grid, 256, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
+                                                     (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 0,
+                                                     (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.packed = true;
+    return RSAC_OK;
+}
+
 int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
 {
     if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
@@ -584,14 +646,16 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_tables.p, b->tables, sizeof(uint32_t) * (size_t)d.table_len, cudaMemcpyHostToDevice, st));
     s.h2d_bytes = (uint64_t)d.total * 24 + sizeof(ProblemMeta) * (uint64_t)d.C + sizeof(float) * (uint64_t)d.C +
                   sizeof(ScoreGroup) * s.groups.size() + (s.have_tables ? sizeof(uint32_t) * (uint64_t)d.table_len : 0);
-    if (d.total > 0 && d.C > 0) {
-        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)d.C);
-        e->stage_begin(RSAC_STAGE_PACK);
-        pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
-                                              (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 0,
-                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p);
-        e->stage_end(RSAC_STAGE_PACK);
-        RSAC_CUDA(e, cudaGetLastError());
+    // the packing kernel is launched by the first run: a caller that uploads sweep k+1 while sweep k computes
+    // (two engines) then overlaps only DMA with the kernels of sweep k -- a concurrent packing kernel takes block
+    // slots from the solver and replay kernels, whose grids are sized to exactly one wave
+    s.packed = false;
+    s.tables_ready = false;
+    {
+        // the early-exit plans travel with the upload: no H2D copy is left for the run (copies issued by a run wait
+        // for the previous sweep in the copy queue, in front of the next sweep's inputs)
+        const int HA = pnp_first_phase(e, d);
+        if (d.sumH > 0 && HA < d.maxH) RSAC_TRY(pnp_plan_early(e, HA));
     }
     s.uploaded = true;
     return RSAC_OK;
@@ -651,25 +715,7 @@ static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, int HA)
     const BatchDims& d = s.d;
     cudaStream_t st = e->stream;
     const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
-    if (!s.ee_planned || s.ee_HA != HA) {
-        s.ee_HA = HA;
-        // phase A: few hypotheses per problem -- one hypothesis per lane (two consumer warps per problem) measured
-        // best (0.045 ms against 0.066 with two per lane at 1024 x 55)
-        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsA, s.planA, 0, HA, env_int("RSAC_EE_HPL_A", 1), env_int("RSAC_EE_CW_A", 0)));
-        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB, s.planB, HA, INT32_MAX, env_int("RSAC_EE_HPL_B", 0), env_int("RSAC_EE_CW_B", 0), true));
-        const size_t bA = sizeof(ScoreGroup) * s.planA.work.size(), bB = sizeof(ScoreGroup) * s.planB.work.size();
-        const size_t oB = (bA + 255) & ~(size_t)255;
-        char* h = (char*)s.h_stageEE.ensure(oB + bB + 256);
-        if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
-        RSAC_TRY(s.d_visitA.ensure(e, std::max<size_t>(bA, sizeof(ScoreGroup))));
-        RSAC_TRY(s.d_visitB.ensure(e, std::max<size_t>(bB, sizeof(ScoreGroup))));
-        memcpy(h, s.planA.work.data(), bA);
-        memcpy(h + oB, s.planB.work.data(), bB);
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_visitA.p, h, bA, cudaMemcpyHostToDevice, st));
-        RSAC_CUDA(e, cudaMemcpyAsync(s.d_visitB.p, h + oB, bB, cudaMemcpyHostToDevice, st));
-        s.h_stageEE.mark(st);
-        s.ee_planned = true;
-    }
+    if (!s.ee_planned || s.ee_HA != HA) RSAC_TRY(pnp_plan_early(e, HA));   // normally done by the upload
     s.ee_mode = true;
     s.ee_complete = false;
     RSAC_TRY(s.d_ee.ensure(e, sizeof(int32_t) * (3 * (size_t)d.C + 4)));
@@ -772,22 +818,34 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
     cudaStream_t st = e->stream;
     const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
     if (d.C == 0) { s.ran = true; return RSAC_OK; }
-
-    if (!s.have_tables && d.table_len > 0) {
-        e->stage_begin(RSAC_STAGE_RNG);
-        rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
-        e->stage_end(RSAC_STAGE_RNG);
+    // the minimal-set tables depend on the seeds only: generated once per upload, later runs of the same
+    // batch reuse them (like tables passed in by the host)
+    const bool need_rng = !s.have_tables && d.table_len > 0 && !s.tables_ready;
+    if (need_rng && !s.packed && e->aux_stream && !e->profile) {
+        // first run after an upload: table generation (one warp per problem, latency-bound) and packing
+        // (bandwidth-bound) are independent: fork the former onto the side stream
+        RSAC_CUDA(e, cudaEventRecord(e->ev_fork, st));
+        RSAC_CUDA(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        ++e->launches;
+        rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, e->aux_stream>>>(metas, d.C, (uint32_t*)s.d_tables.p);
         RSAC_CUDA(e, cudaGetLastError());
+        RSAC_CUDA(e, cudaEventRecord(e->ev_join, e->aux_stream));
+        RSAC_TRY(pnp_pack(e));
+        RSAC_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
+        s.tables_ready = true;
+    } else {
+        RSAC_TRY(pnp_pack(e));
+        if (need_rng) {
+            e->stage_begin(RSAC_STAGE_RNG);
+            rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
+            e->stage_end(RSAC_STAGE_RNG);
+            RSAC_CUDA(e, cudaGetLastError());
+            s.tables_ready = true;
+        }
     }
     s.ee_mode = false;
     if ((flags & RSAC_FLAG_EARLY_EXIT) && !(flags & RSAC_FLAG_EPNP_EIGEN) && d.sumH > 0) {
-        // phase A sized to one wave of the minimal solver unless the caller chose
-        int HA = e->first_phase > 0 ? e->first_phase : env_int("RSAC_EE_HA", 0);
-        if (HA <= 0) {
-            // whole blocks only: 1024 problems x 55 hypotheses = 440 blocks of 128 <= 444 resident
-            const int blocks = RSAC_SOLVE_BLOCKS * e->sm_count;
-            HA = std::max(32, (int)(((int64_t)blocks * RSAC_SOLVE_THREADS) / std::max(d.C, 1)));
-        }
+        const int HA = pnp_first_phase(e, d);
         if (HA < d.maxH) return pnp_run_early(e, flags, d_results_out, HA);
     }
     if (d.sumH > 0) {

@@ -91,7 +91,7 @@ struct BatchDims {
 };
 
 struct PnpState {
-    bool uploaded = false, ran = false, have_tables = false, have_cov = false;
+    bool uploaded = false, ran = false, have_tables = false, have_cov = false, packed = false, tables_ready = false;
     BatchDims d;
     std::vector<ProblemMeta> metas;
     std::vector<ScoreGroup> groups;
@@ -156,6 +156,8 @@ struct rsac_engine {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t aux_stream = nullptr;           // fork/join side stream for independent preparation kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     // per-stage profiling
