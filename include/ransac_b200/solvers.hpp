@@ -244,7 +244,9 @@ public:
         int64_t nwords = 0;
         for (auto* s : solvers) nwords += (s->N + 31) / 32;
         std::vector<uint32_t> masks((size_t)std::max<int64_t>(nwords, 1));
-        check(rsac_pnp_solve(eng->handle(), &b, 0, res.data(), masks.data()), eng->handle(), "rsac_pnp_solve");
+        // early exit in phases: identical records, hypotheses behind the reference's stopping point are not computed
+        // (batches too small to fill one solver wave run all hypotheses at once)
+        check(rsac_pnp_solve(eng->handle(), &b, RSAC_FLAG_EARLY_EXIT, res.data(), masks.data()), eng->handle(), "rsac_pnp_solve");
         eng->next_epoch();
         size_t w0 = 0;
         for (int c = 0; c < C; ++c) {

@@ -115,6 +115,13 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     double* us = a.us_s + (size_t)m->corr_off * 2;
     double* al = a.al_s + (size_t)m->corr_off * 4;
     RSAC_SEL_MARK(2);
+    // Every n-point sum below is formed by ONE thread per output entry that adds the per-point terms in index
+    // order (the checker's serial order).  The terms travel through a shared-memory tile: the whole CTA loads /
+    // computes the terms of kTile points (coalesced, independent), then the few summing threads add them from
+    // shared memory -- the dependent chain is the additions alone, not a global-memory load per point.
+    constexpr int kTile = 64, kTP = kTile + 1;          // padded rows: entries of different rows fall into different banks
+    constexpr int kRowTile = 32, kRP = kRowTile + 1;    // MtM: 24 row entries per point
+    __shared__ double s_tile[24 * kRP > 12 * kTP ? 24 * kRP : 12 * kTP];
     for (int i = tid; i < n; i += blockDim.x) {       // add_correspondence
         const size_t g = (size_t)m->corr_off + sel[i];
         const float4 c = a.cA[g];
@@ -123,20 +130,33 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         us[2 * i] = (double)q.x; us[2 * i + 1] = (double)q.y;
     }
     __syncthreads();
-    if (tid < 3) {                                     // centroid (:301-303)
+    {                                                  // centroid (:301-303)
         double s = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) s += pw[3 * i + tid];
-        S.C0[tid] = s / (double)n;
+        for (int base = 0; base < n; base += kTile) {
+            const int cnt = min(kTile, n - base);
+            __syncthreads();
+            for (int e = tid; e < cnt * 3; e += blockDim.x) s_tile[(e % 3) * kTP + e / 3] = pw[3 * base + e];
+            __syncthreads();
+            if (tid < 3)
+                for (int i = 0; i < cnt; ++i) s += s_tile[tid * kTP + i];
+        }
+        if (tid < 3) S.C0[tid] = s / (double)n;
     }
     __syncthreads();
-    if (tid < 6) {                                     // PW0^T PW0 upper triangle (:306-310)
+    {                                                  // PW0^T PW0 upper triangle (:306-310)
         const int r = (tid < 3) ? 0 : (tid < 5 ? 1 : 2);
         const int c = (tid < 3) ? tid : (tid < 5 ? tid - 2 : 2);
+        const double c0r = S.C0[r], c0c = S.C0[c < 3 ? c : 0];
         double s = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) s = rfma(pw[3 * i + r] - S.C0[r], pw[3 * i + c] - S.C0[c], s);   // fma as in epnp_compute_pose_small
-        S.A[r * 3 + c] = s;
+        for (int base = 0; base < n; base += kTile) {
+            const int cnt = min(kTile, n - base);
+            __syncthreads();
+            for (int e = tid; e < cnt * 3; e += blockDim.x) s_tile[(e % 3) * kTP + e / 3] = pw[3 * base + e];
+            __syncthreads();
+            if (tid < 6)
+                for (int i = 0; i < cnt; ++i) s = rfma(s_tile[r * kTP + i] - c0r, s_tile[c * kTP + i] - c0c, s);   // fma as in epnp_compute_pose_small
+        }
+        if (tid < 6) S.A[r * 3 + c] = s;
     }
     __syncthreads();
     if (tid == 0) {
@@ -150,9 +170,8 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     __syncthreads();
     RSAC_SEL_MARK(3);
     {                                                  // MtM upper triangle, one entry per thread (:379)
-        // alphas and pixels are staged through shared memory in tiles; every entry still adds its
-        // per-point products in index order
-        __shared__ double s_tile[kSelectThreads * 6];
+        // the two rows of M of every point of a tile are materialised in shared memory (epnp_m_rows, zeros
+        // included); every entry adds its two products per point in index order
         // entries e = tid and tid + blockDim.x (78 entries over >= 64 threads)
         int ea[2] = {0, 0}, eb[2] = {0, 0};
         bool have[2];
@@ -167,27 +186,31 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
             }
         }
         double acc[2] = {0.0, 0.0};
-        for (int base = 0; base < n; base += kSelectThreads) {
-            const int cnt = min(kSelectThreads, n - base);
+        for (int base = 0; base < n; base += kRowTile) {
+            const int cnt = min(kRowTile, n - base);
             __syncthreads();
-            if (tid < cnt) {
-                const int i = base + tid;
-                s_tile[tid * 6 + 0] = al[4 * i + 0]; s_tile[tid * 6 + 1] = al[4 * i + 1];
-                s_tile[tid * 6 + 2] = al[4 * i + 2]; s_tile[tid * 6 + 3] = al[4 * i + 3];
-                s_tile[tid * 6 + 4] = us[2 * i]; s_tile[tid * 6 + 5] = us[2 * i + 1];
+            for (int e = tid; e < cnt * 4; e += blockDim.x) {      // (point, control point j): six row entries
+                const int pt = e >> 2, j = e & 3, i = base + pt;
+                const double aj = al[4 * i + j], u = us[2 * i], v = us[2 * i + 1];
+                s_tile[(3 * j + 0) * kRP + pt] = aj * cam.fx;
+                s_tile[(3 * j + 1) * kRP + pt] = 0.0;
+                s_tile[(3 * j + 2) * kRP + pt] = aj * (cam.cx - u);
+                s_tile[(12 + 3 * j + 0) * kRP + pt] = 0.0;
+                s_tile[(12 + 3 * j + 1) * kRP + pt] = aj * cam.fy;
+                s_tile[(12 + 3 * j + 2) * kRP + pt] = aj * (cam.cy - v);
             }
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (!have[k]) continue;
+                const double* r0a = s_tile + ea[k] * kRP;
+                const double* r0b = s_tile + eb[k] * kRP;
+                const double* r1a = r0a + 12 * kRP;
+                const double* r1b = r0b + 12 * kRP;
 #pragma unroll 4
                 for (int i = 0; i < cnt; ++i) {
-                    const double* t6 = s_tile + i * 6;
-                    double a0, a1, b0, b1;
-                    epnp_m_entry(t6, t6[4], t6[5], cam, ea[k], a0, a1);
-                    epnp_m_entry(t6, t6[4], t6[5], cam, eb[k], b0, b1);
-                    acc[k] = rfma(a0, b0, acc[k]);
-                    acc[k] = rfma(a1, b1, acc[k]);
+                    acc[k] = rfma(r0a[i], r0b[i], acc[k]);
+                    acc[k] = rfma(r1a[i], r1b[i], acc[k]);
                 }
             }
         }
@@ -241,53 +264,69 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     }
     __syncthreads();
     double* tm = a.tm_s + (size_t)m->corr_off * 12;
-    for (int i = tid; i < n; i += blockDim.x) {        // pcs of the three candidates, sign applied (:354-357, :495-502)
+    {
+        // pcs of the three candidates, sign applied (:354-357, :495-502), computed tile by tile into shared
+        // memory (and kept in `tm` for the M sums); pc0 of the three candidates (:435,438) and pw0 (:436,439)
+        double s = 0.0;
+        for (int base = 0; base < n; base += kTile) {
+            const int cnt = min(kTile, n - base);
+            __syncthreads();
+            for (int e = tid; e < cnt * 3; e += blockDim.x) {
+                const int pt = e / 3, k = e - 3 * pt, i = base + pt;
+                double pc[3];
+                epnp_pc(al + 4 * i, S.ccs[k], pc);
+                const bool neg = S.sign[k] < 0.0;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            double pc[3];
-            epnp_pc(al + 4 * i, S.ccs[k], pc);
-            const bool neg = S.sign[k] < 0.0;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) tm[(size_t)i * 12 + 3 * k + c] = neg ? -pc[c] : pc[c];
+                for (int c = 0; c < 3; ++c) {
+                    const double v = neg ? -pc[c] : pc[c];
+                    tm[(size_t)i * 12 + 3 * k + c] = v;
+                    s_tile[(3 * k + c) * kTP + pt] = v;
+                }
+                s_tile[(9 + k) * kTP + pt] = pw[3 * i + k];
+            }
+            __syncthreads();
+            if (tid < 12)
+                for (int i = 0; i < cnt; ++i) s += s_tile[tid * kTP + i];
         }
+        if (tid < 9) S.pc0[tid / 3][tid % 3] = s / (double)n;
+        else if (tid < 12) S.pw0[tid - 9] = s / (double)n;
     }
     __syncthreads();
-    if (tid < 9) {                                     // pc0 of the three candidates (:435,438)
-        double s = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) s += tm[(size_t)i * 12 + tid];
-        S.pc0[tid / 3][tid % 3] = s / (double)n;
-    } else if (tid < 12) {                             // pw0 (:436,439)
-        const int c = tid - 9;
-        double s = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) s += pw[3 * i + c];
-        S.pw0[c] = s / (double)n;
-    }
-    __syncthreads();
-    if (tid < 27) {                                    // M = sum (pc-pc0)^T (pw-pw0) (:443-447)
-        const int k = tid / 9, r = (tid % 9) / 3, c = tid % 3;
+    {                                                  // M = sum (pc-pc0)^T (pw-pw0) (:443-447)
+        const int k = (tid < 27) ? tid / 9 : 0, r = (tid % 9) / 3, c = tid % 3;
         const double p0 = S.pc0[k][r], w0 = S.pw0[c];
         double s = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) s += (tm[(size_t)i * 12 + 3 * k + r] - p0) * (pw[3 * i + c] - w0);
-        S.M[k][r * 3 + c] = s;
+        for (int base = 0; base < n; base += kTile) {
+            const int cnt = min(kTile, n - base);
+            __syncthreads();
+            for (int e = tid; e < cnt * 12; e += blockDim.x) {
+                const int pt = e / 12, j = e - 12 * pt, i = base + pt;
+                s_tile[j * kTP + pt] = (j < 9) ? tm[(size_t)i * 12 + j] : pw[3 * i + (j - 9)];
+            }
+            __syncthreads();
+            if (tid < 27)
+                for (int i = 0; i < cnt; ++i) s += (s_tile[(3 * k + r) * kTP + i] - p0) * (s_tile[(9 + c) * kTP + i] - w0);
+        }
+        if (tid < 27) S.M[k][r * 3 + c] = s;
     }
     __syncthreads();
     RSAC_SEL_MARK(7);
     if (tid < 3) epnp_horn(S.M[tid], S.pc0[tid], S.pw0, S.R[tid], S.t[tid]);
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) {        // reprojection_error terms (:417-431), summed in index order below
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            tm[(size_t)i * 12 + 9 + k] = epnp_reproj_term(S.R[k], S.t[k], pw + 3 * i, us[2 * i], us[2 * i + 1], cam);
-    }
-    __syncthreads();
-    if (tid < 3) {
+    {                                                  // reprojection_error terms (:417-431), summed in index order
         double sum2 = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) sum2 += tm[(size_t)i * 12 + 9 + tid];
-        S.rep[tid] = sum2 / (double)n;
+        for (int base = 0; base < n; base += kTile) {
+            const int cnt = min(kTile, n - base);
+            __syncthreads();
+            for (int e = tid; e < cnt * 3; e += blockDim.x) {
+                const int pt = e / 3, k = e - 3 * pt, i = base + pt;
+                s_tile[k * kTP + pt] = epnp_reproj_term(S.R[k], S.t[k], pw + 3 * i, us[2 * i], us[2 * i + 1], cam);
+            }
+            __syncthreads();
+            if (tid < 3)
+                for (int i = 0; i < cnt; ++i) sum2 += s_tile[tid * kTP + i];
+        }
+        if (tid < 3) S.rep[tid] = sum2 / (double)n;
     }
     __syncthreads();
     if (tid == 0) {
