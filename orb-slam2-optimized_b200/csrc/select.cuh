@@ -104,6 +104,121 @@ struct EpnpShared {
     double ccs[3][12], sign[3], pc0[3][3], pw0[3], M[3][9], R[3][9], t[3][3], rep[3];
 };
 
+// PnPsolver::gauss_newton (:675-691) by one warp: the same arithmetic as epnp_gauss_newton / epnp_gn_system /
+// epnp_qr_solve element for element, spread over lanes.
+//   * rows of the 6x4 system: lane i < 6 builds row i and b[i] (epnp_gn_system's row body);
+//   * Householder QR column-wise: lane j < 4 owns column j, lane 4 owns the right-hand side.  At step k lane k
+//     scales its column and forms the reflector (eta, sigma, A1, A2), broadcasts it, and the lanes j > k apply it
+//     to their columns in parallel.  The reference applies the reflectors to b after the factorisation
+//     (:763-773), one after another, using entries of column j that no later step touches -- applying reflector k
+//     to b at step k is the same sequence of operations on b;
+//   * back substitution is redundant on every lane so that the betas stay warp-uniform.
+// scratch: 40 doubles of shared memory private to the warp.
+__device__ inline void epnp_gauss_newton_warp(const double* L, const double* rho, double* betas, double* scratch, int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    double X[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int it = 0; it < 5; ++it) {
+        if (lane < 6) {
+            const int i = lane;
+            double l[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) l[j] = L[i * 10 + j];
+            const double Lt[4][4] = {{2 * l[0], l[1], l[3], l[6]},
+                                     {l[1], 2 * l[2], l[4], l[7]},
+                                     {l[3], l[4], 2 * l[5], l[8]},
+                                     {l[6], l[7], l[8], 2 * l[9]}};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                scratch[r * 6 + i] = rfma(Lt[r][3], betas[3], rfma(Lt[r][2], betas[2], rfma(Lt[r][1], betas[1], Lt[r][0] * betas[0])));
+            double q = (l[0] * betas[0]) * betas[0];
+            q = rfma(l[1] * betas[0], betas[1], q);
+            q = rfma(l[2] * betas[1], betas[1], q);
+            q = rfma(l[3] * betas[0], betas[2], q);
+            q = rfma(l[4] * betas[1], betas[2], q);
+            q = rfma(l[5] * betas[2], betas[2], q);
+            q = rfma(l[6] * betas[0], betas[3], q);
+            q = rfma(l[7] * betas[1], betas[3], q);
+            q = rfma(l[8] * betas[2], betas[3], q);
+            q = rfma(l[9] * betas[3], betas[3], q);
+            scratch[4 * 6 + i] = rho[i] - q;
+        }
+        __syncwarp();
+        double col[6];                    // lane j < 4: column j of A; lane 4: b
+#pragma unroll
+        for (int i = 0; i < 6; ++i) col[i] = scratch[(lane < 5 ? lane : 0) * 6 + i];
+        double A2 = 0.0;
+        bool zero_col = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double A1 = 0.0;
+            bool z = false;
+            if (lane == k) {
+                double eta = fabs(col[k]);
+#pragma unroll
+                for (int i = k + 1; i < 6; ++i) {
+                    const double elt = fabs(col[i]);
+                    if (eta < elt) eta = elt;
+                }
+                if (eta == 0) {
+                    z = true;
+                } else {
+                    const double inv_eta = 1. / eta;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int i = k; i < 6; ++i) {
+                        col[i] *= inv_eta;
+                        sum = rfma(col[i], col[i], sum);
+                    }
+                    double sigma = sqrt(sum);
+                    if (col[k] < 0) sigma = -sigma;
+                    col[k] += sigma;
+                    A1 = sigma * col[k];
+                    A2 = -eta * sigma;
+                }
+            }
+            z = __shfl_sync(FULL, z, k);
+            if (z) { zero_col = true; break; }             // :722-727: returns with X untouched
+            A1 = __shfl_sync(FULL, A1, k);
+            double v[6];
+#pragma unroll
+            for (int i = k; i < 6; ++i) v[i] = __shfl_sync(FULL, col[i], k);
+            if (lane > k && lane < 5) {
+                double sdot = 0;
+#pragma unroll
+                for (int i = k; i < 6; ++i) sdot = rfma(v[i], col[i], sdot);
+                const double tau = sdot / A1;
+#pragma unroll
+                for (int i = k; i < 6; ++i) col[i] = rfma(-tau, v[i], col[i]);
+            }
+        }
+        if (!zero_col) {
+            // R (upper triangle, held column-wise), its diagonal A2 and the transformed b to every lane
+            double Rm[4][4], bb[4], d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                d[j] = __shfl_sync(FULL, A2, j);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Rm[i][j] = __shfl_sync(FULL, col[i], j);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bb[i] = __shfl_sync(FULL, col[i], 4);
+            X[3] = bb[3] / d[3];
+#pragma unroll
+            for (int i = 2; i >= 0; --i) {
+                double sum = 0;
+#pragma unroll
+                for (int j = i + 1; j < 4; ++j) sum = rfma(Rm[i][j], X[j], sum);
+                X[i] = (bb[i] - sum) / d[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) betas[i] += X[i];
+        __syncwarp();
+    }
+}
+
 // PnPsolver::Refine's compute_pose on the n selected points (PnPsolver.cpp:206-217, 359-415);
 // result as float R|t in pose_out[12] (shared)
 __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, int n, EpnpShared& S, double2* s_rec, float* pose_out)
@@ -227,29 +342,48 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         if (tid < 32) jacobi_lowest_warp<12, 4>(S.MtM, S.w4, S.U4, s_rec, tid);
         __syncthreads();
         RSAC_SEL_MARK(5);
-        // the three beta approximations + Gauss-Newton (:395-405) are independent: one thread each in three
-        // warps (two warps when the CTA has only two: approx_3 alone, approx_1 + approx_2 together)
+        // L (6x10, :604-637) and rho (:639-647) entry-parallel into shared memory: 72 control-point differences,
+        // then 60 dot products (same expressions as epnp_L_6x10)
+        __shared__ double s_dv[72], s_L[60], s_rho[6], s_gn[3][40];
+        for (int e = tid; e < 72; e += blockDim.x) {
+            const int i = e / 18, j = (e % 18) / 3, c = e % 3;
+            const int pa = (j < 3) ? 0 : (j < 5 ? 1 : 2);
+            const int pb = (j < 3) ? j + 1 : (j < 5 ? j - 1 : 3);
+            s_dv[e] = S.U4[(3 * pa + c) * 4 + i] - S.U4[(3 * pb + c) * 4 + i];
+        }
+        if (tid == blockDim.x - 1) epnp_rho(S.cws, s_rho);
+        __syncthreads();
+        for (int e = tid; e < 60; e += blockDim.x) {
+            const int row = e / 10, col = e % 10;
+            const int xs[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3}, ys[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3};
+            const double* x = s_dv + (xs[col] * 6 + row) * 3;
+            const double* y = s_dv + (ys[col] * 6 + row) * 3;
+            const double d = x[0] * y[0] + x[1] * y[1] + x[2] * y[2];
+            s_L[e] = (xs[col] == ys[col]) ? d : 2.0 * d;
+        }
+        __syncthreads();
+        // the three beta approximations + Gauss-Newton (:395-405) are independent: one warp each (two warps when
+        // the CTA has only two: approx_3 alone, approx_1 + approx_2 one after the other); the initial guess on
+        // lane 0, the five Gauss-Newton steps on the warp (epnp_gauss_newton_warp)
         const bool three = blockDim.x >= 96;
-        if ((tid & 31) == 0 && tid < (three ? 96 : 64)) {
-            const int wk = tid >> 5;
-            double L[60], rho[6], U4[48], bt[4];
-            for (int i = 0; i < 48; ++i) U4[i] = S.U4[i];
-            epnp_L_6x10(U4, (double*)L);
-            epnp_rho(S.cws, rho);
-            if (wk == 0) {
-                epnp_betas_approx_3((const double*)L, rho, bt);
-                epnp_gauss_newton((const double*)L, rho, bt);
-                for (int i = 0; i < 4; ++i) S.betas[8 + i] = bt[i];
-            }
-            if (wk == 1) {
-                epnp_betas_approx_1((const double*)L, rho, bt);
-                epnp_gauss_newton((const double*)L, rho, bt);
-                for (int i = 0; i < 4; ++i) S.betas[i] = bt[i];
-            }
-            if (wk == 2 || (wk == 1 && !three)) {
-                epnp_betas_approx_2((const double*)L, rho, bt);
-                epnp_gauss_newton((const double*)L, rho, bt);
-                for (int i = 0; i < 4; ++i) S.betas[4 + i] = bt[i];
+        if (tid < (three ? 96 : 64)) {
+            const int wk = tid >> 5, lane = tid & 31;
+            for (int pass = 0; pass < 2; ++pass) {
+                int which = -1;                          // 0: approx_1, 1: approx_2, 2: approx_3
+                if (pass == 0) which = (wk == 0) ? 2 : (wk == 1 ? 0 : 1);
+                else if (!three && wk == 1) which = 1;
+                if (which < 0) break;
+                double bt[4] = {0.0, 0.0, 0.0, 0.0};
+                if (lane == 0) {
+                    if (which == 0) epnp_betas_approx_1((const double*)s_L, s_rho, bt);
+                    else if (which == 1) epnp_betas_approx_2((const double*)s_L, s_rho, bt);
+                    else epnp_betas_approx_3((const double*)s_L, s_rho, bt);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bt[i] = __shfl_sync(0xffffffffu, bt[i], 0);
+                epnp_gauss_newton_warp(s_L, s_rho, bt, s_gn[wk], lane);
+                if (lane == 0)
+                    for (int i = 0; i < 4; ++i) S.betas[4 * which + i] = bt[i];
             }
         }
     }
