@@ -160,7 +160,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip cfg5/cfg1 side measurements and the CPU baseline")
@@ -566,5 +566,19 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
     return out
 
 
+def _quiet_main():
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    out = sys.stdout
+    sys.stdout = os.fdopen(saved, "w")
+    try:
+        return main()
+    finally:
+        sys.stdout.flush()
+        sys.stdout = out
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_quiet_main())

@@ -1,4 +1,5 @@
-"""Short program for ncu: one PnP sweep (C candidates) and a few cfg5 scoring launches."""
+"""Short program for ncu: PnP sweeps (C candidates, early exit in phases unless RSAC_PROF_EXHAUSTIVE=1) and a few cfg5
+scoring launches."""
 import os
 import sys
 
@@ -16,8 +17,9 @@ b = synth.pnp_batch(4, C, n, 0.5)
 offsets = (np.arange(C + 1) * n).astype(np.int32)
 prm = capi.ransac_params(0.99, 10, 300, 4, 0.2, 5.991)
 eng.pnp_upload(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], prm, seeds=b["seeds"])
+FLAGS = 0 if os.environ.get("RSAC_PROF_EXHAUSTIVE") == "1" else capi.FLAG_EARLY_EXIT
 for _ in range(reps):
-    eng.pnp_run()
+    eng.pnp_run(FLAGS)
 res, _ = eng.pnp_download()
 p = synth.scoring_stress(5000, 4096, 10000)
 max_err = (p["sigma2"] * np.float32(5.991)).astype(np.float32)

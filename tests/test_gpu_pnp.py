@@ -353,3 +353,31 @@ def test_pnp_early_exit_then_later_iterate_calls(engine):
     poses0, counts0 = engine.pnp_hypotheses()
     assert (counts0 == counts1).all()                          # after the rerun every hypothesis exists
     assert (poses0.view(np.uint32) == poses1.view(np.uint32)).all()
+
+
+def test_pnp_early_exit_many_hypotheses_several_tiles(engine):
+    """H > 1024 per problem: the second phase spans several hypothesis tiles per problem (list-driven scoring with
+    more than one record per problem), ragged n; a hard batch (70 % outliers) so that many problems need it."""
+    prm = capi.ransac_params(prob=0.99, min_inliers=10, max_its=2500, min_set=4, eps=0.08, th2=5.991)
+    sizes = [64 + 7 * (i % 9) for i in range(96)]
+    parts = [synth.pnp_problem(9300 + i, n, 0.7) for i, n in enumerate(sizes)]
+    p3d = np.concatenate([p["p3d"] for p in parts])
+    p2d = np.concatenate([p["p2d"] for p in parts])
+    s2 = np.concatenate([p["sigma2"] for p in parts])
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    seeds = np.arange(len(sizes), dtype=np.uint32) + 900
+    args = (offsets, p3d, p2d, s2, [parts[0]["K"]], prm)
+    res0, masks0 = engine.pnp_solve(*args, seeds=seeds)
+    seen_b = 0
+    for first_phase in (16, 100, 1500):
+        engine.set_first_phase(first_phase)
+        try:
+            res1, masks1 = engine.pnp_solve(*args, seeds=seeds, flags=capi.FLAG_EARLY_EXIT)
+            ha, nB, nC, solved = engine.pnp_phase_stats()
+        finally:
+            engine.set_first_phase(0)
+        assert ha == first_phase
+        _same_records(res0, res1)
+        assert (masks0 == masks1).all()
+        seen_b += nB
+    assert seen_b > 0
