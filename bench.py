@@ -435,7 +435,7 @@ def ncu_traffic(key):
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         for k, v in d.items():
-            if k.startswith(key):
+            if k.startswith(key) and "phase B" not in k:
                 return int(v["dram_bytes"])
     except Exception:
         pass

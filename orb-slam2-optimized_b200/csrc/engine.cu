@@ -266,6 +266,8 @@ int rsac_shard_range(int C, int rank, int world, int* first, int* count)
 // CTA shape for the scoring kernel: HPL hypotheses per lane (template), `warps` consumer warps per CTA
 // plus one producer warp.  RSAC_SCORE_HPL / RSAC_SCORE_WARPS / RSAC_SCORE_CTAS / RSAC_SCORE_CW override the
 // planner (tuning sweeps only).
+// dynamic shared memory above 32 KB is always opted in (cudaFuncAttributeMaxDynamicSharedMemorySize): the 48 KB default
+// limit counts the kernel's static shared memory too, so a request of exactly 48 KB fails without it
 static constexpr int kChunkWordsMax = 8;     // 256 correspondences per ring slot (12 KB), 4 slots
 
 static int env_int(const char* name, int dflt)
@@ -340,7 +342,7 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
     const void* kern = score_kernel_ptr<MODEL>(pl.hpl);
     auto resident = [&](int chunk_words) -> int {
         const size_t smem = score_smem_bytes<MODEL>(chunk_words * 32, pl.tile_hyps);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 32 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, pl.threads + 32, smem) != cudaSuccess) { cudaGetLastError(); nb = 1; }
         nb = std::max(1, nb);
@@ -455,7 +457,7 @@ static int launch_score(rsac_engine* e, ScoreArgs& args, const ScorePlan& pl, in
 {
     if (ngroups <= 0) return RSAC_OK;
     const void* kern = score_kernel_ptr<MODEL>(pl.hpl);
-    if (pl.smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    if (pl.smem > 32 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     args.work = (const ScoreGroup*)d_visit.p;
     args.vlen = pl.vlen;
     args.tiles_per_problem = pl.tiles;
@@ -466,7 +468,14 @@ static int launch_score(rsac_engine* e, ScoreArgs& args, const ScorePlan& pl, in
     e->stage_begin(RSAC_STAGE_SCORE);
     cudaError_t err = cudaLaunchKernel(kern, dim3(pl.grid), dim3(pl.threads + 32), kargs, pl.smem, e->stream);   // + the producer warp
     e->stage_end(RSAC_STAGE_SCORE);
-    RSAC_CUDA(e, err);
+    if (err != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "score launch (grid %d, threads %d, smem %zu, hpl %d, list %d): %s", pl.grid, pl.threads + 32,
+                 pl.smem, pl.hpl, (int)pl.by_list, cudaGetErrorString(err));
+        e->err = buf;
+        cudaGetLastError();
+        return RSAC_ERR_CUDA;
+    }
     RSAC_CUDA(e, cudaGetLastError());
     return RSAC_OK;
 }
@@ -665,7 +674,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
 static int solve_range_setup(rsac_engine* e)
 {
     const size_t smem = sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS;
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t need = (smem + 1024) * RSAC_SOLVE_BLOCKS;
     const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
@@ -771,7 +780,7 @@ static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume,
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
-    if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         cudaFuncAttributes fa;
         RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<0>));
@@ -850,7 +859,7 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
     }
     if (d.sumH > 0) {
         const bool eigen = (flags & RSAC_FLAG_EPNP_EIGEN) != 0;
-        if (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS > 48 * 1024)
+        if (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS > 32 * 1024)
             RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)(sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS)));
         {

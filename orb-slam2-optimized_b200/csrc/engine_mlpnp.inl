@@ -74,7 +74,7 @@ static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resum
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base; a.flags = flags; a.resume = d_resume;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
-    if (smem > 48 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     e->stage_begin(RSAC_STAGE_SELECT);
     {
         cudaFuncAttributes fa;
