@@ -128,15 +128,29 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     strong = os.environ.get("RSAC_BENCH_STRONG", "0") == "1"
     n_cand = C_TOTAL if strong else C_TOTAL * max(1, args.gpus)     # the GPU arm's config at this N
-    b, _ = make_shard(0, n_cand)
+    # the GPU arm's data: NBLOCK blocks of 1024 candidates; step k works on blocks (k + r) mod NBLOCK, r < gpus
+    nblock = 1 if strong else max(1, int(os.environ.get("RSAC_BENCH_BLOCKS", "8")))
     prm = O.params(**PRM)
-    pbs = [O.pnp_problem(b["p3d"][c], b["p2d"][c], b["sigma2"][c], b["K"]) for c in range(n_cand)]
-    tables = [O.index_table(int(s), N_MATCH, 4, H_HYP) for s in b["seeds"]]
     oflags = O.FLAG_EPNP_QR_NULLSPACE   # the port's faster mode (same arithmetic as the device path)
+    blocks = []
+    for j in range(nblock):
+        bj, _ = make_shard(j * C_TOTAL, C_TOTAL)
+        blocks.append(([O.pnp_problem(bj["p3d"][c], bj["p2d"][c], bj["sigma2"][c], bj["K"]) for c in range(C_TOTAL)],
+                       [O.index_table(int(sd), N_MATCH, 4, H_HYP) for sd in bj["seeds"]]))
+
+    def step_work(k):
+        pbs, tabs = [], []
+        for r in range(1 if strong else max(1, args.gpus)):
+            p_, t_ = blocks[(k + r) % nblock]
+            pbs += p_
+            tabs += t_
+        return pbs, tabs
+
     for _ in range(max(1, min(args.warmup, 1))):
-        O.pnp_batch(pbs[:64], prm, tables[:64], oflags, cores)
+        O.pnp_batch(blocks[0][0][:64], prm, blocks[0][1][:64], oflags, cores)
     t_tot, ev_tot = 0.0, 0
-    for _ in range(args.steps):
+    for k in range(args.steps):
+        pbs, tables = step_work(k)
         dt, ev, res = O.pnp_batch(pbs, prm, tables, oflags, cores)
         t_tot += dt
         ev_tot += ev
@@ -145,7 +159,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": "cfg4", "candidates": n_cand, "matches": N_MATCH,
-                                            "hypotheses": H_HYP, "mode": "reference semantics (early exit)"},
+                                            "hypotheses": H_HYP, "mode": "reference semantics (early exit)",
+                                            "blocks": f"{nblock} blocks of {C_TOTAL} synthetic candidates; step k works on blocks (k + r) mod {nblock}, r < {max(1, args.gpus)}"},
             "cpu_baseline": {"value": val, "unit": "candidates/s", "cores": cores, "kind": "port",
                              "sample": "full cfg4 sweep per step, one solver call per core (BASELINE.md mode B); "
                                        "4-point null space by Householder QR as on the device (the port's faster mode)",
@@ -184,11 +199,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
-    # sweeps in flight per GPU: one 1024-candidate sweep saturates the residency of one B200 (measured: more
-    # sweeps in flight only add contention), so one sweep at a time per GPU
+    # Sweeps are independent, so several are in flight per GPU (one engine + stream each): every phase of a sweep is
+    # one latency-bound wave, and a rare candidate that needs several Refine() calls, or the clean-up phase, stretches
+    # a whole sweep (0.52 -> 1.16 ms for one such candidate) -- overlapping sweeps fills those holes
+    # (measured on the 8-block mix, resident: 1 in flight 0.72 ms per sweep, 2: 0.59, 3: 0.55, 4: 0.56, 6: 0.54)
     global PIPE, C_TOTAL
     if PIPE <= 0:
-        PIPE = 1
+        PIPE = 4
     # weak scaling (task statement, section 5): the path shards by candidate with no data-path collective, so
     # every GPU works on its own 1024-candidate sweep and the job processes 1024 x N candidates per step;
     # RSAC_BENCH_STRONG=1 keeps the total at 1024 instead (each GPU then gets 1024/N candidates)
@@ -199,76 +216,103 @@ def main():
     RUN_FLAGS = 0 if EXHAUSTIVE else capi.FLAG_EARLY_EXIT
     first, count = shard.block_range(C_TOTAL, rank, world)
     cap = shard.per_rank_capacity(C_TOTAL, world)
-    b, offsets = make_shard(first, count)
+    # The synthetic set is NBLOCK blocks of 1024 candidates; at step k rank r works on block (k + r) mod NBLOCK, so
+    # every rank meets every block equally often at every N (blocks differ: some hold a candidate whose refines
+    # fail, which costs the clean-up phase) and the ranks of one step work on different blocks.
+    NBLOCK = 1 if strong else max(1, int(os.environ.get("RSAC_BENCH_BLOCKS", "8")))
     prm = capi.ransac_params(**PRM)
-
-    # pinned host staging (one copy per pipeline slot is not needed: inputs are read-only)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_p3d, h_p2d, h_s2 = pin(b["p3d"].reshape(-1, 3)), pin(b["p2d"].reshape(-1, 2)), pin(b["sigma2"].reshape(-1))
-    seeds = b["seeds"]
+    blocks = []
+    for j in range(NBLOCK):
+        bj = (j + rank) % NBLOCK
+        bb, offsets = make_shard(first if strong else bj * C_PER_GPU, count)
+        blocks.append(dict(p3d=pin(bb["p3d"].reshape(-1, 3)), p2d=pin(bb["p2d"].reshape(-1, 2)), s2=pin(bb["sigma2"].reshape(-1)),
+                           seeds=bb["seeds"], K=bb["K"], block=bj))
+    b = dict(K=blocks[0]["K"], p3d=blocks[0]["p3d"].numpy().reshape(count, N_MATCH, 3), p2d=blocks[0]["p2d"].numpy().reshape(count, N_MATCH, 2),
+             sigma2=blocks[0]["s2"].numpy().reshape(count, N_MATCH), seeds=blocks[0]["seeds"])
 
-    engines, streams, d_local, d_gath = [], [], [], []
-    NSLOT = max(PIPE, 2)    # the end-to-end pass double-buffers: H2D of sweep k+1 under the kernels of sweep k
-    for i in range(NSLOT):
+    NRES = max(NBLOCK, PIPE)             # resident pass: one engine per block (block j of this rank stays uploaded in engine j)
+    NSLOT = PIPE + 1                     # end-to-end pass: engines 0 .. PIPE are re-uploaded every step
+    NENG = max(NRES, NSLOT)
+    engines, streams, d_local = [], [], []
+    for i in range(NENG):
         e = capi.Engine(local_rank)
         s = torch.cuda.Stream(device=dev)
         e.set_stream(s.cuda_stream)
         e.set_problem_base(first)
         engines.append(e)
         streams.append(s)
-        t = torch.full((cap, shard.REC_WORDS), -1, dtype=torch.int32, device=dev)
-        d_local.append(t)
-        d_gath.append(torch.empty((world * cap, shard.REC_WORDS), dtype=torch.int32, device=dev) if world > 1 else t)
+        d_local.append(torch.full((cap, shard.REC_WORDS), -1, dtype=torch.int32, device=dev))
     words_total = int(((np.diff(offsets) + 31) // 32).sum())
     h_res = [torch.empty((count, shard.REC_WORDS), dtype=torch.int32).pin_memory() for _ in range(NSLOT)]
     h_msk = [torch.empty((max(words_total, 1),), dtype=torch.int32).pin_memory() for _ in range(NSLOT)]
-    compute_done = [None]   # event after the kernels of the previous end-to-end step
 
-    def upload(i):
-        engines[i].pnp_upload(offsets, h_p3d.numpy(), h_p2d.numpy(), h_s2.numpy(), [b["K"]], prm, seeds=seeds)
+    def upload(i, j):
+        blk = blocks[j % NBLOCK]
+        engines[i].pnp_upload(offsets, blk["p3d"].numpy(), blk["p2d"].numpy(), blk["s2"].numpy(), [blk["K"]], prm, seeds=blk["seeds"])
 
-    # multi-GPU: the all-gather of sweep k (98 KB per rank, latency-bound) runs on a side stream under the
-    # kernels of sweep k+1; two record buffers alternate so that a sweep never overwrites records in flight
+    # multi-GPU: the all-gather of a sweep's records (98 KB per rank, latency-bound) runs on a side stream, in
+    # issue order; a ring of gather buffers, and every engine waits for the gather that last read its records
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    d_loc2 = [torch.full((cap, shard.REC_WORDS), -1, dtype=torch.int32, device=dev) for _ in range(2)]
-    d_gat2 = [torch.empty((world * cap, shard.REC_WORDS), dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else d_loc2
-    gather_done = [None, None]
-    step_no = [0]
+    NG = NENG + 2
+    d_gath = [torch.empty((world * cap, shard.REC_WORDS), dtype=torch.int32, device=dev) for _ in range(NG)] if world > 1 else None
+    gather_done = [None] * NENG
+    slot_done = [None] * NENG          # completion of the last sweep that ran on engine i
+    last_gather = [None]
+    GATHER = os.environ.get("RSAC_BENCH_GATHER", "overlap")   # overlap | none (diagnostic)
 
-    def step_resident(i):
-        k = step_no[0] & 1
-        step_no[0] += 1
-        with torch.cuda.stream(streams[i]):
-            if gather_done[k] is not None:
-                streams[i].wait_event(gather_done[k])      # the gather that last read this buffer (two sweeps ago)
-            engines[i].pnp_run(RUN_FLAGS, d_loc2[k].data_ptr())
-            if world > 1:
-                ev = torch.cuda.Event()
-                ev.record(streams[i])
-                with torch.cuda.stream(comm_stream):
-                    comm_stream.wait_event(ev)
-                    dist.all_gather_into_tensor(d_gat2[k], d_loc2[k])
-                    gd = torch.cuda.Event()
-                    gd.record(comm_stream)
-                    gather_done[k] = gd
+    def run_and_gather(i, k):
+        st = streams[i]
+        if gather_done[i] is not None:
+            st.wait_event(gather_done[i])              # the gather that last read this engine's records
+        engines[i].pnp_run(RUN_FLAGS, d_local[i].data_ptr())
+        if world > 1 and GATHER != "none":
+            ev = torch.cuda.Event()
+            ev.record(st)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev)
+                dist.all_gather_into_tensor(d_gath[k % NG], d_local[i])
+                gd = torch.cuda.Event()
+                gd.record(comm_stream)
+                gather_done[i] = gd
+            last_gather[0] = d_gath[k % NG]
+        else:
+            last_gather[0] = d_local[i]
 
-    def step_e2e(i):
+    def bound_in_flight(i, k, ring):
+        # at most PIPE sweeps in flight: sweep k starts after sweep k - PIPE has finished
+        prev = ring[(k - PIPE) % len(ring)] if k >= PIPE else None
+        if prev is not None:
+            streams[i].wait_event(prev)
+
+    res_ring = [None] * (NRES + PIPE)
+    e2e_ring = [None] * (NSLOT + PIPE)
+
+    def step_resident(k):
+        i = k % NRES
         with torch.cuda.stream(streams[i]):
-            upload(i)                                   # H2D + pack: overlaps the previous sweep's kernels
-            if compute_done[0] is not None:             # ... but the sweeps' kernels run one sweep at a time
-                streams[i].wait_event(compute_done[0])
-            engines[i].pnp_run(RUN_FLAGS, d_local[i].data_ptr())
-            if world > 1:
-                dist.all_gather_into_tensor(d_gath[i], d_local[i])
+            bound_in_flight(i, k, res_ring)
+            run_and_gather(i, k)
             ev = torch.cuda.Event()
             ev.record(streams[i])
-            compute_done[0] = ev
+            res_ring[k % len(res_ring)] = ev
+
+    def step_e2e(k):
+        i = k % NSLOT
+        with torch.cuda.stream(streams[i]):
+            upload(i, k)                                # H2D of block (k + rank) mod NBLOCK, plans, tables
+            bound_in_flight(i, k, e2e_ring)
+            run_and_gather(i, k)
+            ev = torch.cuda.Event()
+            ev.record(streams[i])
+            e2e_ring[k % len(e2e_ring)] = ev
             # D2H of this sweep's records and inlier masks into pinned memory (async on the sweep's stream)
             engines[i].pnp_download_async(h_res[i].data_ptr(), h_msk[i].data_ptr())
 
-    def timed(fn, steps, nslot=None):
-        nslot = nslot or PIPE
-        compute_done[0] = None
+    def timed(fn, steps):
+        for r in (res_ring, e2e_ring):
+            for q in range(len(r)):
+                r[q] = None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -280,7 +324,7 @@ def main():
         for s in streams:
             s.wait_event(ev0)
         for k in range(steps):
-            fn(k % nslot)
+            fn(k)
         for s in streams + ([comm_stream] if comm_stream is not None else []):
             e = torch.cuda.Event()
             e.record(s)
@@ -295,10 +339,10 @@ def main():
             ms = float(t.item())
         return ms
 
-    for i in range(NSLOT):
-        upload(i)
+    for i in range(NRES):
+        upload(i, i)
     torch.cuda.synchronize()
-    timed(step_resident, max(args.warmup, PIPE))
+    timed(step_resident, max(args.warmup, NRES))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -324,17 +368,25 @@ def main():
     trace = e0.profile_trace()
     trace = trace[-(len(trace) // nprof):] if trace else []      # the launches of the last sweep, in order
     e0.profile_enable(False)
-    ha, n_b, n_c, hyp_done = e0.pnp_phase_stats()               # hypotheses actually solved and scored (this rank)
+    # phases and hypotheses actually solved and scored: mean over the blocks this rank holds
+    stats = [engines[i].pnp_phase_stats() for i in range(NRES)]
+    ha = stats[0][0]
+    n_b = float(np.mean([st[1] for st in stats]))
+    n_c = float(np.mean([st[2] for st in stats]))
+    hyp_done = float(np.mean([st[3] for st in stats]))
 
     # correctness guard on the gathered records (cheap): every candidate reported once, in order
     torch.cuda.synchronize()
-    rec = shard.records_from_tensor(d_gat2[(step_no[0] - 1) & 1] if step_no[0] else d_gath[0])
-    assert len(rec) == C_TOTAL and (rec["problem"] == np.arange(C_TOTAL)).all(), "gather lost candidates"
-    n_ok = int(rec["ok"].sum())
+    if world > 1 and GATHER == "none":
+        n_ok = -1
+    else:
+        rec = shard.records_from_tensor(last_gather[0])
+        assert len(rec) == C_TOTAL and (rec["problem"] == np.arange(C_TOTAL)).all(), "gather lost candidates"
+        n_ok = int(rec["ok"].sum())
 
     # end-to-end through host buffers
-    timed(step_e2e, max(4, NSLOT), NSLOT)
-    ms_e2e = timed(step_e2e, args.steps, NSLOT)
+    timed(step_e2e, max(4, 2 * NSLOT))
+    ms_e2e = timed(step_e2e, args.steps)
     h2d = int(count * N_MATCH * 24 + count * 4 + count * 152)
     d2h = int(count * 96 + words_total * 4)
 
@@ -351,11 +403,13 @@ def main():
                        "mode": ("all H hypotheses solved and scored on the device (4-point null space by QR), then "
                                 "reference-semantics replay + Refine per candidate") if EXHAUSTIVE else
                                (f"reference semantics with early exit in phases: hypotheses [0,{ha}) of every candidate, the "
-                                f"remaining ones for the {n_b} of {count} candidates without an acceptable hypothesis so far "
-                                f"({100 * hyp_frac:.1f} % of the 300 x {count} hypotheses solved and scored), replay + Refine per "
-                                "candidate; records identical to the exhaustive run"),
-                       "parallelism": f"candidates sharded x{world}, {PIPE} sweep(s) in flight per GPU; e2e double-buffers the "
-                                      "H2D copy of the next sweep under the kernels of the current one",
+                                f"remaining ones for the {n_b:.0f} of {count} candidates (mean over blocks) without an acceptable "
+                                f"hypothesis so far ({100 * hyp_frac:.1f} % of the 300 x {count} hypotheses solved and scored), "
+                                "replay + Refine per candidate; records identical to the exhaustive run"),
+                       "blocks": f"{NBLOCK} blocks of {C_PER_GPU} synthetic candidates; at step k rank r works on block (k + r) mod {NBLOCK}",
+                       "parallelism": f"one 1024-candidate sweep per GPU and step (x{world} GPUs), {PIPE} independent sweeps in flight per "
+                                      "GPU (one engine + stream each); e2e uploads every step's block from pinned host memory and "
+                                      "reads records + masks back inside the timed region",
                        "l2": "working set of a sweep (~90 MB) is L2-resident by design; every kernel is compute- or latency-bound: no flush"},
             "e2e": {"value": e2e_v, "unit": "candidates/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps},
