@@ -83,7 +83,7 @@ static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resum
         const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
         RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
-    ransac_select_kernel<1><<<d.C, kSelectThreads, smem, e->stream>>>(a);
+    ransac_select_kernel<1><<<d.C, kSelectThreadsMlpnp, smem, e->stream>>>(a);
     e->stage_end(RSAC_STAGE_SELECT);
     RSAC_CUDA(e, cudaGetLastError());
     return RSAC_OK;

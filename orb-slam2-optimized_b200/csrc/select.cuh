@@ -56,16 +56,19 @@ struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
 static_assert(sizeof(ResultRec) == 96, "rsac_result layout");
 
 #ifndef RSAC_SELECT_THREADS
-#define RSAC_SELECT_THREADS 128
+#define RSAC_SELECT_THREADS 96
 #endif
 #ifndef RSAC_SELECT_CTAS
 #define RSAC_SELECT_CTAS 7
 #endif
-// 128 threads x 7 CTAs/SM: 1036 resident candidates, so a 1024-candidate sweep is one wave.  Measured per 1024
-// candidates: 128 x 4 (128 registers) 1.05 ms before the other changes; then 128 x 7 (72 registers) 0.37,
-// 96 x 7 (80 registers) 0.34, 96 x 8 0.36, 128 x 6 0.46, 64 x 10 0.42 -- but the 96-thread shapes (larger stack)
-// slow the NEXT sweep's local-memory-bound solve kernel down by 0.14 ms, so 128 x 7 wins per sweep
+// 7 CTAs/SM: 1036 resident candidates, so a 1024-candidate sweep is one wave.  Three warps are what the phases can
+// use (78 MtM entries, three beta branches, one eigen-solve); with several sweeps in flight per GPU (bench.py) what
+// counts is register-file share x time, and 96 x 7 (80 registers) beats 128 x 7 (72 registers): 0.538 against 0.558 ms
+// per sweep, the kernel alone 0.193 against 0.205 ms; 64 x 9 (96 registers): 0.571, 96 x 9: 0.552.  (With ONE
+// exhaustive sweep at a time 128 x 7 had won because the 96-thread shapes slowed the following solve kernel down.)
 constexpr int kSelectThreads = RSAC_SELECT_THREADS;
+constexpr int kSelectThreadsMlpnp = 128;   // MLPnP's refine (cfg2: 64 frames, one partial wave) is faster with four warps: 0.46 against 0.54 ms
+template <int MODEL> constexpr int select_threads() { return MODEL == 0 ? kSelectThreads : kSelectThreadsMlpnp; }
 constexpr int kSelectCtasPerSm = RSAC_SELECT_CTAS;
 
 // diagnostic: clock64() at phase boundaries of block 0 (rsac_debug_select_clocks)
@@ -644,7 +647,7 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
 
 // ------------------------------------------------------------- the replay kernel
 template <int MODEL>
-__global__ void __launch_bounds__(kSelectThreads, kSelectCtasPerSm) ransac_select_kernel(SelectArgs a)
+__global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ransac_select_kernel(SelectArgs a)
 {
     using PT = typename ScoreModel<MODEL>::pose_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
