@@ -41,8 +41,9 @@ extern "C" {
 #define RSAC_FLAG_EPNP_EIGEN 8      /* 4-point EPnP: null-space basis from the 12x12 M^T M eigen-solve (PnPsolver.cpp:380)
                                        instead of the default Householder QR of M^T (same subspace, different basis) */
 #define RSAC_FLAG_EARLY_EXIT 16     /* PnP: stop where the sequential reference stops (PnPsolver.cpp:225-236 returns at the
-                                       first successful Refine): hypotheses are solved and scored in phases -- the first
-                                       `first_phase` of every problem, the rest only for the problems that still need them.
+                                       first successful Refine): hypotheses are solved and scored in stages -- the first
+                                       `first_phase` of every problem, the next ones, then the rest, only for the problems
+                                       that still need them.
                                        Results are identical to the exhaustive run; hypotheses behind the stopping point
                                        are simply never computed (rsac_pnp_get_hypotheses returns zeros/stale data there;
                                        rsac_pnp_rerun computes them on demand).  Ignored with RSAC_FLAG_EPNP_EIGEN. */
@@ -103,9 +104,13 @@ int rsac_set_problem_base(rsac_engine* e, int base);
 /* RSAC_FLAG_EARLY_EXIT: hypotheses per problem in the first phase; 0 (default) = as many as make one wave of the
  * minimal-solver kernel over the batch (>= 32; a batch small enough runs all hypotheses in one phase) */
 int rsac_set_first_phase(rsac_engine* e, int hypotheses);
+/* both stage boundaries: hypotheses [0, first) for every problem, [first, second) for the problems still without an
+ * acceptable hypothesis, [second, H) for those still without one after that; 0 = automatic (second: half of what
+ * remains after the first stage; second >= H: two stages only, the lower latency for a single sweep) */
+int rsac_set_phases(rsac_engine* e, int first, int second);
 /* diagnostic (synchronises): after an early-exit run: out[0] = first_phase used (0: the run was exhaustive),
- * out[1] = problems that needed the remaining hypotheses right after phase A, out[2] = problems handed to the
- * clean-up phase by the replay, out[3] = hypotheses solved and scored in total */
+ * out[1] = problems that went on to the second stage, out[2] = problems handed to the clean-up phase by the
+ * replay, out[3] = hypotheses solved and scored in total */
 int rsac_pnp_phase_stats(rsac_engine* e, int64_t out[4]);
 /* pinned host memory for callers that want asynchronous H2D/D2H */
 int rsac_host_alloc(void** ptr, uint64_t bytes);

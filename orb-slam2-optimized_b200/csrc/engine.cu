@@ -90,6 +90,14 @@ int rsac_set_first_phase(rsac_engine* e, int hypotheses)
     return RSAC_OK;
 }
 
+int rsac_set_phases(rsac_engine* e, int first, int second)
+{
+    if (!e || first < 0 || second < 0 || (second > 0 && first > 0 && second <= first)) return RSAC_ERR_INVALID;
+    e->first_phase = first;
+    e->second_phase = second;
+    return RSAC_OK;
+}
+
 int rsac_sync(rsac_engine* e)
 {
     if (!e) return RSAC_ERR_INVALID;
@@ -562,27 +570,43 @@ static int pnp_first_phase(rsac_engine* e, const BatchDims& d)
     return HA;
 }
 
-// scoring plans of the two hypothesis ranges [0, HA) and [HA, H) and their work lists (H2D through pinned staging)
+static int pnp_second_phase(rsac_engine* e, const BatchDims& d, int HA)
+{
+    // end of the second stage: half of the remaining hypotheses (cfg4: [55, 177)) unless the caller chose; measured
+    // with four sweeps in flight: second stage up to 100: 0.497 ms per sweep, 136: 0.491, 180: 0.486, none: 0.537
+    int HB = e->second_phase > 0 ? e->second_phase : env_int("RSAC_EE_HB", 0);
+    if (HB <= 0) HB = HA + std::max(32, (d.maxH - HA) / 2);
+    return std::max(HB, HA + 1);
+}
+
+// scoring plans of the hypothesis ranges [0, HA) (static work lists), [HA, HB), [HB, H) and [HA, H) (driven by
+// device-side lists) and their work arrays (H2D through pinned staging)
 static int pnp_plan_early(rsac_engine* e, int HA)
 {
     PnpState& s = e->pnp;
     const BatchDims& d = s.d;
     cudaStream_t st = e->stream;
     s.ee_HA = HA;
+    s.ee_HB = std::min(pnp_second_phase(e, d, HA), d.maxH);
     // phase A: few hypotheses per problem -- one hypothesis per lane (two consumer warps per problem) measured
     // best (0.045 ms against 0.066 with two per lane at 1024 x 55)
     RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsA, s.planA, 0, HA, env_int("RSAC_EE_HPL_A", 1), env_int("RSAC_EE_CW_A", 0)));
-    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB, s.planB, HA, INT32_MAX, env_int("RSAC_EE_HPL_B", 0), env_int("RSAC_EE_CW_B", 0), true));
-    const size_t bA = sizeof(ScoreGroup) * s.planA.work.size(), bB = sizeof(ScoreGroup) * s.planB.work.size();
-    const size_t oB = (bA + 255) & ~(size_t)255;
-    char* h = (char*)s.h_stageEE.ensure(oB + bB + 256);
+    const int hplB = env_int("RSAC_EE_HPL_B", 0), cwB = env_int("RSAC_EE_CW_B", 0);
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB1, s.planB1, HA, s.ee_HB, hplB, cwB, true));
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB2, s.planB2, s.ee_HB, INT32_MAX, hplB, cwB, true));
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB, s.planB, HA, INT32_MAX, hplB, cwB, true));
+    const ScorePlanPOD* plans[4] = {&s.planA, &s.planB1, &s.planB2, &s.planB};
+    DevBuf* bufs[4] = {&s.d_visitA, &s.d_visitB1, &s.d_visitB2, &s.d_visitB};
+    size_t off[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) off[i + 1] = (off[i] + sizeof(ScoreGroup) * plans[i]->work.size() + 255) & ~(size_t)255;
+    char* h = (char*)s.h_stageEE.ensure(off[4] + 256);
     if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
-    RSAC_TRY(s.d_visitA.ensure(e, std::max<size_t>(bA, sizeof(ScoreGroup))));
-    RSAC_TRY(s.d_visitB.ensure(e, std::max<size_t>(bB, sizeof(ScoreGroup))));
-    memcpy(h, s.planA.work.data(), bA);
-    memcpy(h + oB, s.planB.work.data(), bB);
-    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visitA.p, h, bA, cudaMemcpyHostToDevice, st));
-    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visitB.p, h + oB, bB, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < 4; ++i) {
+        const size_t bytes = sizeof(ScoreGroup) * plans[i]->work.size();
+        RSAC_TRY(bufs[i]->ensure(e, std::max<size_t>(bytes, sizeof(ScoreGroup))));
+        memcpy(h + off[i], plans[i]->work.data(), bytes);
+        RSAC_CUDA(e, cudaMemcpyAsync(bufs[i]->p, h + off[i], bytes, cudaMemcpyHostToDevice, st));
+    }
     s.h_stageEE.mark(st);
     s.ee_planned = true;
     return RSAC_OK;
@@ -687,33 +711,34 @@ static int pnp_early_flag(rsac_engine* e, int mode)
     PnpState& s = e->pnp;
     e->stage_begin(RSAC_STAGE_RNG);
     early_exit_flag_kernel<<<(s.d.C + 3) / 4, 128, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, s.d.C, (const int32_t*)s.d_counts.p,
-                                                                  s.ee_HA, (int32_t*)s.d_ee.p, mode);
+                                                                  s.ee_HA, s.ee_HB, (int32_t*)s.d_ee.p, mode);
     e->stage_end(RSAC_STAGE_RNG);
     RSAC_CUDA(e, cudaGetLastError());
     return RSAC_OK;
 }
 
-// minimal solves + scoring of hypotheses [HA, H) of the problems in `list` (device-side count) whose phase is `want`
-static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* list_count, int want)
+// minimal solves + scoring of hypotheses [lo, hi) of the problems in `list` (device-side count); `plan` is the
+// list-driven scoring plan of that range
+static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* list_count, int lo, int hi, const ScorePlanPOD& plan,
+                           int ngroups, DevBuf& d_visit)
 {
     PnpState& s = e->pnp;
     const BatchDims& d = s.d;
-    const int span = d.maxH - s.ee_HA;
+    const int span = std::min(hi, d.maxH) - lo;
     if (span <= 0) return RSAC_OK;
     const int64_t most = (int64_t)d.C * span;
     const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
     e->stage_begin(RSAC_STAGE_SOLVE);
     epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, e->stream>>>(
-        (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, s.ee_HA, span, (const uint32_t*)s.d_tables.p,
+        (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, lo, span, (const uint32_t*)s.d_tables.p,
         (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
     e->stage_end(RSAC_STAGE_SOLVE);
     RSAC_CUDA(e, cudaGetLastError());
     ScoreArgs sa = s.ee_sa;
     sa.list = list;
     sa.list_count = list_count;
-    (void)want;
-    return launch_score<0>(e, sa, s.planB, (int)s.groupsB.size(), s.d_visitB);
+    return launch_score<0>(e, sa, plan, ngroups, d_visit);
 }
 
 static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase);
@@ -724,12 +749,13 @@ static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, int HA)
     const BatchDims& d = s.d;
     cudaStream_t st = e->stream;
     const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
-    if (!s.ee_planned || s.ee_HA != HA) RSAC_TRY(pnp_plan_early(e, HA));   // normally done by the upload
+    if (!s.ee_planned || s.ee_HA != HA || s.ee_HB != std::min(pnp_second_phase(e, d, HA), d.maxH))
+        RSAC_TRY(pnp_plan_early(e, HA));   // normally done by the upload
     s.ee_mode = true;
     s.ee_complete = false;
-    RSAC_TRY(s.d_ee.ensure(e, sizeof(int32_t) * (3 * (size_t)d.C + 4)));
-    RSAC_CUDA(e, cudaMemsetAsync(s.d_ee.p, 0, sizeof(int32_t) * (3 * (size_t)d.C + 4), st));
-    int32_t* ee = (int32_t*)s.d_ee.p;
+    RSAC_TRY(s.d_ee.ensure(e, sizeof(int32_t) * early_exit_words(d.C)));
+    RSAC_CUDA(e, cudaMemsetAsync(s.d_ee.p, 0, sizeof(int32_t) * early_exit_words(d.C), st));
+    const EarlyExit v = early_exit_view((int32_t*)s.d_ee.p, d.C);
     RSAC_TRY(solve_range_setup(e));
 
     ScoreArgs sa;
@@ -757,12 +783,17 @@ static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, int HA)
         RSAC_CUDA(e, cudaGetLastError());
         RSAC_TRY(launch_score<0>(e, sa, s.planA, (int)s.groupsA.size(), s.d_visitA));
     }
-    // who needs the rest right away; phase B
+    // who goes on; phase B1 [HA, HB); who still goes on; phase B2 [HB, H)
     RSAC_TRY(pnp_early_flag(e, 0));
-    RSAC_TRY(pnp_early_range(e, ee + d.C, ee + 3 * (size_t)d.C, 1));
+    RSAC_TRY(pnp_early_range(e, v.listX, v.counters + 0, HA, s.ee_HB, s.planB1, (int)s.groupsB1.size(), s.d_visitB1));
+    RSAC_TRY(pnp_early_flag(e, 1));
+    if (s.ee_HB < d.maxH) {
+        RSAC_TRY(pnp_early_range(e, v.listY, v.counters + 1, s.ee_HB, d.maxH, s.planB2, (int)s.groupsB2.size(), s.d_visitB2));
+        RSAC_TRY(pnp_early_flag(e, 3));
+    }
     // replay; problems it cannot decide go to phase C
     RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, -1));
-    RSAC_TRY(pnp_early_range(e, ee + 2 * (size_t)d.C, ee + 3 * (size_t)d.C + 1, 2));
+    RSAC_TRY(pnp_early_range(e, v.listC, v.counters + 2, HA, d.maxH, s.planB, (int)s.groupsB.size(), s.d_visitB));
     RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, 2));
     s.ran = true;
     return RSAC_OK;
@@ -808,10 +839,10 @@ int rsac_pnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* 
     if (s.ee_mode && !s.ee_complete) {
         // the last run stopped early: problems that were decided inside their first HA hypotheses get the rest
         // now, so that the scan can go on wherever the caller resumes it
-        int32_t* ee = (int32_t*)s.d_ee.p;
-        RSAC_CUDA(e, cudaMemsetAsync(ee + 3 * (size_t)s.d.C, 0, 4 * sizeof(int32_t), e->stream));
-        RSAC_TRY(pnp_early_flag(e, 1));
-        RSAC_TRY(pnp_early_range(e, ee + s.d.C, ee + 3 * (size_t)s.d.C, 3));
+        const EarlyExit v = early_exit_view((int32_t*)s.d_ee.p, s.d.C);
+        RSAC_CUDA(e, cudaMemsetAsync(v.counters, 0, 4 * sizeof(int32_t), e->stream));
+        RSAC_TRY(pnp_early_flag(e, 2));
+        RSAC_TRY(pnp_early_range(e, v.listC, v.counters + 2, s.ee_HA, s.d.maxH, s.planB, (int)s.groupsB.size(), s.d_visitB));
         s.ee_complete = true;
     }
     return pnp_launch_select(e, flags, (const int32_t*)e->d_resume.p, d_results_out, -1);
@@ -912,14 +943,15 @@ int rsac_pnp_phase_stats(rsac_engine* e, int64_t out[4])
     if (!s.ran) { e->err = "rsac_pnp_phase_stats before rsac_pnp_run"; return RSAC_ERR_STATE; }
     if (!s.ee_mode) return RSAC_OK;
     RSAC_CUDA(e, cudaSetDevice(e->device));
-    std::vector<int32_t> ee(3 * (size_t)s.d.C + 4);
+    std::vector<int32_t> ee(early_exit_words(s.d.C));
     RSAC_CUDA(e, cudaMemcpyAsync(ee.data(), s.d_ee.p, sizeof(int32_t) * ee.size(), cudaMemcpyDeviceToHost, e->stream));
     RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
     out[0] = s.ee_HA;
-    out[1] = ee[3 * (size_t)s.d.C];
-    out[2] = ee[3 * (size_t)s.d.C + 1];
+    out[1] = ee[4 * (size_t)s.d.C];
+    out[2] = ee[4 * (size_t)s.d.C + 2];
     int64_t done = 0;
-    for (int c = 0; c < s.d.C; ++c) done += (ee[c] == 0) ? std::min(s.metas[c].H, s.ee_HA) : s.metas[c].H;
+    for (int c = 0; c < s.d.C; ++c) done += std::min(s.metas[c].H, std::max(ee[c], 0));
+    done += (int64_t)out[2] * 0;   // (problems of the clean-up phase end with upto = H)
     out[3] = done;
     return RSAC_OK;
 }

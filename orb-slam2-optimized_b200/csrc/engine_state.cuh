@@ -102,17 +102,17 @@ struct PnpState {
     PinnedBuf h_stage;
     // early exit in phases (RSAC_FLAG_EARLY_EXIT): plans of the two hypothesis ranges, per-problem phase state
     bool ee_planned = false, ee_mode = false, ee_complete = false;
-    int ee_HA = 0;
-    ScorePlanPOD planA, planB;
-    std::vector<ScoreGroup> groupsA, groupsB;
+    int ee_HA = 0, ee_HB = 0;
+    ScorePlanPOD planA, planB1, planB2, planB;     // [0,HA) static; [HA,HB), [HB,H), [HA,H) list-driven
+    std::vector<ScoreGroup> groupsA, groupsB1, groupsB2, groupsB;
     ScoreArgs ee_sa;
-    DevBuf d_ee, d_visitA, d_visitB;
+    DevBuf d_ee, d_visitA, d_visitB1, d_visitB2, d_visitB;
     PinnedBuf h_stageEE;
     void release()
     {
         h_stage.release();
         h_stageEE.release();
-        d_ee.release(); d_visitA.release(); d_visitB.release();
+        d_ee.release(); d_visitA.release(); d_visitB1.release(); d_visitB2.release(); d_visitB.release();
         DevBuf* all[] = {&d_metas, &d_cP, &d_th2, &d_p3d, &d_p2d, &d_sigma2, &d_cA, &d_cB, &d_uv, &d_tables, &d_poses,
                          &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra, &d_visit};
         for (DevBuf* b : all) b->release();
@@ -170,6 +170,7 @@ struct rsac_engine {
     int64_t launches = 0;
     int32_t problem_base = 0;
     int32_t first_phase = 0;   // early exit: hypotheses per problem in phase A (0 = one solver wave)
+    int32_t second_phase = 0;  // early exit: end of the second stage (0 = a third of what remains)
     rsac::PnpState pnp;
     rsac::PnpState mlpnp;
     rsac::ScoreState score;

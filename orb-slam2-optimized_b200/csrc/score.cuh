@@ -291,10 +291,13 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
 #pragma unroll
     for (int s = 0; s < HPL; ++s) { cnt[s] = 0; live[s] = 0u; }
 
+    bool g_owned = false;    // this CTA scores every chunk of the current group: counts are stored, not accumulated
     auto flush = [&]() {
 #pragma unroll
         for (int s = 0; s < HPL; ++s) {
-            if (live[s] && cnt[s]) atomicAdd(args.counts + g_hypoff + g_hyp0 + (warp * HPL + s) * 32 + lane, cnt[s]);
+            int32_t* dst = args.counts + g_hypoff + g_hyp0 + (warp * HPL + s) * 32 + lane;
+            if (g_owned) { if (live[s]) *dst = cnt[s]; }
+            else if (live[s] && cnt[s]) atomicAdd(dst, cnt[s]);
             cnt[s] = 0;
         }
     };
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
     auto enter_group = [&](const ScoreGroup& grp) {
         g_hyp0 = grp.hyp0; g_cw = grp.chunk_words; g_n = grp.n; g_words = grp.words;
         g_hypoff = grp.hyp_off; g_problem = grp.problem; g_hmask = grp.hmask_off;
+        g_owned = grp.first_stride == (1 << 16);      // first chunk 0, stride 1
         const int H = grp.H;
         const float fx = grp.fx, fy = grp.fy;
 #pragma unroll

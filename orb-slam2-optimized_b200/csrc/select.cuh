@@ -41,11 +41,11 @@ struct SelectArgs {
     int32_t problem_base;    // global index of problem 0 (sharding)
     int32_t flags;
     const int32_t* resume;   // optional [C]: hypotheses already consumed by earlier iterate() calls
-    // early exit in phases (pnp_pipeline.cuh): ee = [phase: C][listB: C][listC: C][nB, nC, ..] or nullptr
+    // early exit in phases (pnp_pipeline.cuh): ee = [upto: C][listX: C][listY: C][listC: C][nX, nY, nC, 0] or nullptr
     int32_t* ee = nullptr;
     int32_t C = 0;
     int32_t first_phase = 0;   // HA: hypotheses every problem has after phase A
-    int32_t only_phase = -1;   // >= 0: only problems in this phase run (the phase-C replay resumes them at HA)
+    int32_t only_phase = -1;   // >= 0: the phase-C replay: only problems marked undecided run; they resume where they stopped
 };
 
 struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
@@ -672,19 +672,20 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
 
     RSAC_SEL_MARK(0);
     const int N = m->n, Hfull = m->H, minInl = m->min_inl;
-    // early exit: a phase-0 problem has only its first HA hypotheses; the scan must not look past them
+    // early exit: a problem may only look at the upto[p] hypotheses it has
     int H = Hfull;
-    bool resume_phase = false;
+    int resume_stop = 0;
     if (a.ee) {
-        const int ph = a.ee[blockIdx.x];
+        const int up = a.ee[blockIdx.x];
         if (a.only_phase >= 0) {
-            if (ph != a.only_phase) return;
-            resume_phase = true;
+            if (up >= 0) return;                       // decided in the main replay
+            resume_stop = -up - 1;                     // where the main replay stopped
             res.n_refines = reinterpret_cast<const ResultRec*>(a.results)[blockIdx.x].n_refines;   // carried over
-        } else if (ph == 0 && Hfull > a.first_phase) {
-            H = a.first_phase;
+        } else {
+            H = min(Hfull, up);
         }
     }
+    const bool resume_phase = a.ee && a.only_phase >= 0;
     uint32_t* final_mask = a.masks + m->word_off;
     const int32_t* counts = a.counts + m->hyp_off;
     const PT* poses = reinterpret_cast<const PT*>(a.poses) + (size_t)m->hyp_off * 12;
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
         __syncthreads();
     };
 
-    const int resume_at = resume_phase ? a.first_phase : ((a.resume && !finished) ? a.resume[blockIdx.x] : 0);
+    const int resume_at = resume_phase ? resume_stop : ((a.resume && !finished) ? a.resume[blockIdx.x] : 0);
     if (!finished && resume_at > 0) {
         // a later iterate() call (or the phase-C continuation): rebuild mnBestInliers / mvbBestInliers as the
         // scan left them before `cursor` (first strict maximum among the hypotheses with cnt >= minInliers)
@@ -795,12 +796,12 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
     }
 
     if (!finished && H < Hfull) {
-        // early exit: every refine before HA failed and the rest of the hypotheses has not been computed yet:
+        // early exit: every refine so far failed and the rest of the hypotheses has not been computed yet:
         // hand the problem to phase C; only the refine counter survives (in the result record)
         if (tid == 0) {
-            int32_t* counters = a.ee + 3 * (size_t)a.C;
-            a.ee[blockIdx.x] = 2;
-            (a.ee + 2 * (size_t)a.C)[atomicAdd(counters + 1, 1)] = blockIdx.x;
+            int32_t* counters = a.ee + 4 * (size_t)a.C;
+            a.ee[blockIdx.x] = -(H + 1);
+            (a.ee + 3 * (size_t)a.C)[atomicAdd(counters + 2, 1)] = blockIdx.x;
             res.reserved[0] = 1;   // not decided yet
             reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
         }
@@ -825,6 +826,7 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
     if (tid == 0) {
         reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
         if (a.results2) reinterpret_cast<ResultRec*>(a.results2)[blockIdx.x] = res;
+        if (resume_phase) a.ee[blockIdx.x] = Hfull;     // everything of this problem exists now
     }
 }
 

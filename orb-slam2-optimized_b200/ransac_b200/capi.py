@@ -175,6 +175,9 @@ class Engine:
     def set_first_phase(self, hypotheses: int):
         self._ck(self.L.rsac_set_first_phase(self.h, C.c_int(hypotheses)), "set_first_phase")
 
+    def set_phases(self, first: int, second: int):
+        self._ck(self.L.rsac_set_phases(self.h, C.c_int(first), C.c_int(second)), "set_phases")
+
     def pnp_phase_stats(self):
         """(first_phase, problems in phase B, problems in phase C, hypotheses solved) of the last early-exit run"""
         out = (C.c_int64 * 4)()

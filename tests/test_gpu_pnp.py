@@ -302,6 +302,30 @@ def test_pnp_early_exit_failed_refines_reach_the_cleanup_phase(engine, oracle):
         assert res1[c]["n_refines"] == orc[c]["n_refines"]
 
 
+@pytest.mark.parametrize("phases", [(6, 13), (20, 21), (40, 120), (55, 300)])
+def test_pnp_early_exit_three_stages(engine, phases):
+    """explicit stage boundaries [0, first), [first, second), [second, H): both device-side lists (second and third
+    stage) are exercised on a hard batch (65 % outliers: many candidates go on), and with Tracking's parameters
+    (failing refines after the second stage as well)"""
+    first, second = phases
+    for (cfgno, C, n, outl, prm) in ((15, 128, 300, 0.65, PRM),
+                                     (12, 96, 200, 0.45, dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.5, th2=5.991))):
+        b, offsets = _batch(cfgno, C, n, outl=outl)
+        args = (offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**prm))
+        res0, masks0 = engine.pnp_solve(*args, seeds=b["seeds"])
+        engine.set_phases(first, second)
+        try:
+            res1, masks1 = engine.pnp_solve(*args, seeds=b["seeds"], flags=capi.FLAG_EARLY_EXIT)
+            ha, nB, nC, solved = engine.pnp_phase_stats()
+        finally:
+            engine.set_phases(0, 0)
+        _same_records(res0, res1)
+        assert (masks0 == masks1).all()
+        assert (res1["reserved"] == 0).all()
+        H = capi.pnp_ransac_setup(n, capi.ransac_params(**prm))[1]
+        assert solved <= C * H
+
+
 def test_pnp_early_exit_ragged_batch(engine):
     """ragged problems (empty, n < minInliers, H = 0, H < first_phase) through the phased run"""
     sizes = [0, 3, 4, 9, 37, 64, 65, 500, 257, 130]
