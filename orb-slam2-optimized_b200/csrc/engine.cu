@@ -537,7 +537,7 @@ static int pnp_build_metas(rsac_engine* e, int C, const int32_t* offsets, const 
 
 // metas, thresholds and tiles go through one pinned staging buffer so that the H2D copies are truly
 // asynchronous (the host never waits for the stream's earlier sweeps)
-static int stage_small_tables(rsac_engine* e, PnpState& s, const std::vector<float>& th2)
+static int stage_small_tables(rsac_engine* e, PnpState& s, const std::vector<float>& th2, bool with_plan = true)
 {
     const BatchDims& d = s.d;
     const size_t b_meta = sizeof(ProblemMeta) * (size_t)d.C, b_th = sizeof(float) * (size_t)d.C;
@@ -551,9 +551,11 @@ static int stage_small_tables(rsac_engine* e, PnpState& s, const std::vector<flo
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, h, b_meta, cudaMemcpyHostToDevice, e->stream));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_th2.p, h + o_th, b_th, cudaMemcpyHostToDevice, e->stream));
     }
-    RSAC_TRY(s.d_visit.ensure(e, std::max<size_t>(b_work, sizeof(ScoreGroup))));
-    memcpy(h + o_work, s.plan.work.data(), b_work);
-    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, h + o_work, b_work, cudaMemcpyHostToDevice, e->stream));
+    if (with_plan) {
+        RSAC_TRY(s.d_visit.ensure(e, std::max<size_t>(b_work, sizeof(ScoreGroup))));
+        memcpy(h + o_work, s.plan.work.data(), b_work);
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, h + o_work, b_work, cudaMemcpyHostToDevice, e->stream));
+    }
     s.h_stage.mark(e->stream);
     return RSAC_OK;
 }
@@ -636,7 +638,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     if (!b->seeds && !b->tables) { if (e) e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     PnpState& s = e->pnp;
-    s.uploaded = false; s.ran = false; s.ee_planned = false; s.ee_mode = false;
+    s.uploaded = false; s.ran = false; s.ee_mode = false;
     std::vector<float> th2;
     int rc = pnp_build_metas(e, b->C, b->offsets, b->params, b->n_params, b->seeds, b->table_offsets, b->tables != nullptr, s.metas, th2, s.d);
     if (rc) return rc;
@@ -645,7 +647,26 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     }
     const BatchDims& d = s.d;
     const size_t tot = (size_t)std::max(d.total, 1);
-    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groups, s.plan));
+    // The scoring plans (tiles, chunking, per-CTA work lists) depend only on the batch's shape -- n, H and the focal
+    // lengths of every problem, and the stage boundaries -- so a batch shaped like the previous one reuses them,
+    // including the work arrays already on the device (a relocalisation loop with a fixed match budget per candidate)
+    const int HA_now = pnp_first_phase(e, d);
+    const int HB_now = std::min(pnp_second_phase(e, d, HA_now), d.maxH);
+    std::vector<int32_t> sig;
+    sig.reserve(4 * (size_t)b->C + 4);
+    for (int c = 0; c < b->C; ++c) {
+        const float fx = (float)s.metas[c].fx, fy = (float)s.metas[c].fy;
+        int32_t fxb, fyb;
+        memcpy(&fxb, &fx, 4); memcpy(&fyb, &fy, 4);
+        sig.push_back(s.metas[c].n); sig.push_back(s.metas[c].H); sig.push_back(fxb); sig.push_back(fyb);
+    }
+    sig.push_back(HA_now); sig.push_back(HB_now); sig.push_back(b->C);
+    const bool same_shape = s.plans_valid && sig == s.shape_sig;
+    if (!same_shape) {
+        s.plans_valid = false;
+        s.ee_planned = false;
+        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groups, s.plan));
+    }
 
     RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta) * std::max(d.C, 1)));
     RSAC_TRY(s.d_th2.ensure(e, sizeof(float) * std::max(d.C, 1)));
@@ -668,7 +689,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     RSAC_TRY(s.d_extra.ensure(e, tot * 96));   // refine scratch: 12 doubles per correspondence
 
     cudaStream_t st = e->stream;
-    RSAC_TRY(stage_small_tables(e, s, th2));
+    RSAC_TRY(stage_small_tables(e, s, th2, !same_shape));
     if (d.total > 0) {
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, b->p3d, (size_t)d.total * 12, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, b->p2d, (size_t)d.total * 8, cudaMemcpyHostToDevice, st));
@@ -687,9 +708,10 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     {
         // the early-exit plans travel with the upload: no H2D copy is left for the run (copies issued by a run wait
         // for the previous sweep in the copy queue, in front of the next sweep's inputs)
-        const int HA = pnp_first_phase(e, d);
-        if (d.sumH > 0 && HA < d.maxH) RSAC_TRY(pnp_plan_early(e, HA));
+        if (d.sumH > 0 && HA_now < d.maxH && !s.ee_planned) RSAC_TRY(pnp_plan_early(e, HA_now));
     }
+    s.shape_sig.swap(sig);
+    s.plans_valid = true;
     s.uploaded = true;
     return RSAC_OK;
 }

@@ -102,6 +102,8 @@ struct PnpState {
     PinnedBuf h_stage;
     // early exit in phases (RSAC_FLAG_EARLY_EXIT): plans of the two hypothesis ranges, per-problem phase state
     bool ee_planned = false, ee_mode = false, ee_complete = false;
+    bool plans_valid = false;               // plans and device work arrays match shape_sig
+    std::vector<int32_t> shape_sig;         // n, H, fx, fy of every problem + stage boundaries
     int ee_HA = 0, ee_HB = 0;
     ScorePlanPOD planA, planB1, planB2, planB;     // [0,HA) static; [HA,HB), [HB,H), [HA,H) list-driven
     std::vector<ScoreGroup> groupsA, groupsB1, groupsB2, groupsB;
