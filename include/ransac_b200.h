@@ -101,13 +101,17 @@ int rsac_set_stream(rsac_engine* e, void* cuda_stream);
 int rsac_sync(rsac_engine* e);
 /* global index of this engine's problem 0 (written to rsac_result.problem; used when candidates are sharded) */
 int rsac_set_problem_base(rsac_engine* e, int base);
-/* RSAC_FLAG_EARLY_EXIT: hypotheses per problem in the first phase; 0 (default) = as many as make one wave of the
- * minimal-solver kernel over the batch (>= 32; a batch small enough runs all hypotheses in one phase) */
+/* RSAC_FLAG_EARLY_EXIT: hypotheses per problem in the first stage (later stages double); 0 (default) = three quarters
+ * of one wave of the minimal-solver kernel over the batch (a batch that fits one wave runs all hypotheses at once) */
 int rsac_set_first_phase(rsac_engine* e, int hypotheses);
-/* both stage boundaries: hypotheses [0, first) for every problem, [first, second) for the problems still without an
- * acceptable hypothesis, [second, H) for those still without one after that; 0 = automatic (second: half of what
- * remains after the first stage; second >= H: two stages only, the lower latency for a single sweep) */
+/* two explicit boundaries: hypotheses [0, first) for every problem, [first, second) for the problems still without an
+ * acceptable hypothesis, [second, H) for those still without one after that (second >= H: two stages only, the lower
+ * latency for a single sweep); 0, 0 = automatic */
 int rsac_set_phases(rsac_engine* e, int first, int second);
+/* any number of stages (n <= 7 boundaries, strictly increasing; [b(n-1), H) is the last stage); n = 0: automatic =
+ * first stage three quarters of a solver wave, every further stage doubles the hypotheses a problem has (cfg4: 41, 82,
+ * 164, 300); fewer stages = lower latency of a single sweep, more stages = less work when sweeps overlap */
+int rsac_set_stages(rsac_engine* e, int n, const int32_t* bounds);
 /* diagnostic (synchronises): after an early-exit run: out[0] = first_phase used (0: the run was exhaustive),
  * out[1] = problems that went on to the second stage, out[2] = problems handed to the clean-up phase by the
  * replay, out[3] = hypotheses solved and scored in total */

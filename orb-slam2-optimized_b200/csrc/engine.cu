@@ -87,6 +87,8 @@ int rsac_set_first_phase(rsac_engine* e, int hypotheses)
 {
     if (!e || hypotheses < 0) return RSAC_ERR_INVALID;
     e->first_phase = hypotheses;
+    e->second_phase = 0;
+    e->stage_bounds.clear();
     return RSAC_OK;
 }
 
@@ -95,6 +97,16 @@ int rsac_set_phases(rsac_engine* e, int first, int second)
     if (!e || first < 0 || second < 0 || (second > 0 && first > 0 && second <= first)) return RSAC_ERR_INVALID;
     e->first_phase = first;
     e->second_phase = second;
+    e->stage_bounds.clear();
+    return RSAC_OK;
+}
+
+int rsac_set_stages(rsac_engine* e, int n, const int32_t* bounds)
+{
+    if (!e || n < 0 || n > 7 || (n > 0 && !bounds)) return RSAC_ERR_INVALID;
+    for (int i = 0; i < n; ++i)
+        if (bounds[i] <= 0 || (i > 0 && bounds[i] <= bounds[i - 1])) return RSAC_ERR_INVALID;
+    e->stage_bounds.assign(bounds, bounds + n);
     return RSAC_OK;
 }
 
@@ -562,52 +574,82 @@ static int stage_small_tables(rsac_engine* e, PnpState& s, const std::vector<flo
 
 static int pnp_first_phase(rsac_engine* e, const BatchDims& d)
 {
-    // phase A sized to one wave of the minimal solver unless the caller chose
+    // first stage: three quarters of one wave of the minimal solver unless the caller chose (whole blocks: 1024
+    // problems x 55 hypotheses = 440 blocks of 128 <= 444 resident is a full wave).  Measured on cfg4 with six sweeps in
+    // flight, ms per sweep resident / end to end: (55,177) 0.449 / 0.504, (55,110,220) 0.440 / 0.512,
+    // (40,80,160) 0.421 / 0.474, (28,55,110,220) 0.420 / 0.498, (20,40,80,160) 0.428 / 0.500
     int HA = e->first_phase > 0 ? e->first_phase : env_int("RSAC_EE_HA", 0);
     if (HA <= 0) {
-        // whole blocks only: 1024 problems x 55 hypotheses = 440 blocks of 128 <= 444 resident
         const int blocks = RSAC_SOLVE_BLOCKS * e->sm_count;
-        HA = std::max(32, (int)(((int64_t)blocks * RSAC_SOLVE_THREADS) / std::max(d.C, 1)));
+        const int wave = (int)(((int64_t)blocks * RSAC_SOLVE_THREADS) / std::max(d.C, 1));
+        HA = wave >= d.maxH ? wave : std::max(16, wave * 3 / 4);
     }
     return HA;
 }
 
-static int pnp_second_phase(rsac_engine* e, const BatchDims& d, int HA)
+// stage boundaries b0 < b1 < ... < b(K-1) = maxH: hypotheses [0, b0) for every problem, [b(j-1), bj) for the problems
+// still without an acceptable hypothesis.  Caller's choice (rsac_set_stages / rsac_set_phases / RSAC_EE_STAGES), else
+// b0 = three quarters of a solver wave and every further stage doubles what exists (cfg4: 41, 82, 164, 300)
+static std::vector<int> pnp_stage_bounds(rsac_engine* e, const BatchDims& d)
 {
-    // end of the second stage: half of the remaining hypotheses (cfg4: [55, 177)) unless the caller chose; measured
-    // with four sweeps in flight: second stage up to 100: 0.497 ms per sweep, 136: 0.491, 180: 0.486, none: 0.537
-    int HB = e->second_phase > 0 ? e->second_phase : env_int("RSAC_EE_HB", 0);
-    if (HB <= 0) HB = HA + std::max(32, (d.maxH - HA) / 2);
-    return std::max(HB, HA + 1);
+    std::vector<int> b;
+    const char* env = getenv("RSAC_EE_STAGES");
+    if (!e->stage_bounds.empty()) {
+        b = e->stage_bounds;
+    } else if (env && *env) {
+        for (const char* p = env; *p;) {
+            b.push_back(atoi(p));
+            while (*p && *p != ',') ++p;
+            if (*p == ',') ++p;
+        }
+    } else {
+        const int HA = pnp_first_phase(e, d);
+        b.push_back(HA);
+        if (e->second_phase > 0) b.push_back(e->second_phase);
+        else
+            while (b.back() < d.maxH && (int)b.size() < kMaxStages - 1) b.push_back(b.back() * 2);
+    }
+    // sanitise: strictly increasing, inside (0, maxH), last = maxH
+    std::vector<int> out;
+    for (int v : b) {
+        v = std::min(v, d.maxH);
+        if (v <= 0 || (!out.empty() && v <= out.back())) continue;
+        out.push_back(v);
+        if (v >= d.maxH || (int)out.size() == kMaxStages - 1) break;
+    }
+    if (out.empty() || out.back() < d.maxH) out.push_back(std::max(d.maxH, 1));
+    return out;
 }
 
-// scoring plans of the hypothesis ranges [0, HA) (static work lists), [HA, HB), [HB, H) and [HA, H) (driven by
-// device-side lists) and their work arrays (H2D through pinned staging)
-static int pnp_plan_early(rsac_engine* e, int HA)
+// scoring plans of the stages: [0, b0) with static work lists, [b(j-1), bj) and the clean-up range [b0, H) driven by
+// device-side lists; their work arrays go H2D through pinned staging
+static int pnp_plan_early(rsac_engine* e, const std::vector<int>& bounds)
 {
     PnpState& s = e->pnp;
     const BatchDims& d = s.d;
     cudaStream_t st = e->stream;
-    s.ee_HA = HA;
-    s.ee_HB = std::min(pnp_second_phase(e, d, HA), d.maxH);
-    // phase A: few hypotheses per problem -- one hypothesis per lane (two consumer warps per problem) measured
+    const int K = (int)bounds.size();
+    s.ee_bounds = bounds;
+    s.ee_HA = bounds[0];
+    s.ee_plans.assign(K + 1, ScorePlanPOD());
+    s.ee_groups.assign(K + 1, std::vector<ScoreGroup>());
+    if ((int)s.ee_visit.size() < K + 1) s.ee_visit.resize(K + 1);
+    // stage 0: few hypotheses per problem -- one hypothesis per lane (two consumer warps per problem) measured
     // best (0.045 ms against 0.066 with two per lane at 1024 x 55)
-    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsA, s.planA, 0, HA, env_int("RSAC_EE_HPL_A", 1), env_int("RSAC_EE_CW_A", 0)));
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.ee_groups[0], s.ee_plans[0], 0, bounds[0], env_int("RSAC_EE_HPL_A", 1), env_int("RSAC_EE_CW_A", 0)));
     const int hplB = env_int("RSAC_EE_HPL_B", 0), cwB = env_int("RSAC_EE_CW_B", 0);
-    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB1, s.planB1, HA, s.ee_HB, hplB, cwB, true));
-    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB2, s.planB2, s.ee_HB, INT32_MAX, hplB, cwB, true));
-    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groupsB, s.planB, HA, INT32_MAX, hplB, cwB, true));
-    const ScorePlanPOD* plans[4] = {&s.planA, &s.planB1, &s.planB2, &s.planB};
-    DevBuf* bufs[4] = {&s.d_visitA, &s.d_visitB1, &s.d_visitB2, &s.d_visitB};
-    size_t off[5] = {0, 0, 0, 0, 0};
-    for (int i = 0; i < 4; ++i) off[i + 1] = (off[i] + sizeof(ScoreGroup) * plans[i]->work.size() + 255) & ~(size_t)255;
-    char* h = (char*)s.h_stageEE.ensure(off[4] + 256);
+    for (int j = 1; j < K; ++j)
+        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.ee_groups[j], s.ee_plans[j], bounds[j - 1], bounds[j], hplB, cwB, true));
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.ee_groups[K], s.ee_plans[K], bounds[0], INT32_MAX, hplB, cwB, true));   // clean-up
+    std::vector<size_t> off(K + 2, 0);
+    for (int i = 0; i <= K; ++i) off[i + 1] = (off[i] + sizeof(ScoreGroup) * s.ee_plans[i].work.size() + 255) & ~(size_t)255;
+    char* h = (char*)s.h_stageEE.ensure(off[K + 1] + 256);
     if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
-    for (int i = 0; i < 4; ++i) {
-        const size_t bytes = sizeof(ScoreGroup) * plans[i]->work.size();
-        RSAC_TRY(bufs[i]->ensure(e, std::max<size_t>(bytes, sizeof(ScoreGroup))));
-        memcpy(h + off[i], plans[i]->work.data(), bytes);
-        RSAC_CUDA(e, cudaMemcpyAsync(bufs[i]->p, h + off[i], bytes, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i <= K; ++i) {
+        const size_t bytes = sizeof(ScoreGroup) * s.ee_plans[i].work.size();
+        RSAC_TRY(s.ee_visit[i].ensure(e, std::max<size_t>(bytes, sizeof(ScoreGroup))));
+        memcpy(h + off[i], s.ee_plans[i].work.data(), bytes);
+        RSAC_CUDA(e, cudaMemcpyAsync(s.ee_visit[i].p, h + off[i], bytes, cudaMemcpyHostToDevice, st));
     }
     s.h_stageEE.mark(st);
     s.ee_planned = true;
@@ -650,8 +692,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     // The scoring plans (tiles, chunking, per-CTA work lists) depend only on the batch's shape -- n, H and the focal
     // lengths of every problem, and the stage boundaries -- so a batch shaped like the previous one reuses them,
     // including the work arrays already on the device (a relocalisation loop with a fixed match budget per candidate)
-    const int HA_now = pnp_first_phase(e, d);
-    const int HB_now = std::min(pnp_second_phase(e, d, HA_now), d.maxH);
+    const std::vector<int> bounds_now = pnp_stage_bounds(e, d);
     std::vector<int32_t> sig;
     sig.reserve(4 * (size_t)b->C + 4);
     for (int c = 0; c < b->C; ++c) {
@@ -660,7 +701,8 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
         memcpy(&fxb, &fx, 4); memcpy(&fyb, &fy, 4);
         sig.push_back(s.metas[c].n); sig.push_back(s.metas[c].H); sig.push_back(fxb); sig.push_back(fyb);
     }
-    sig.push_back(HA_now); sig.push_back(HB_now); sig.push_back(b->C);
+    for (int v : bounds_now) sig.push_back(v);
+    sig.push_back(b->C);
     const bool same_shape = s.plans_valid && sig == s.shape_sig;
     if (!same_shape) {
         s.plans_valid = false;
@@ -708,7 +750,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     {
         // the early-exit plans travel with the upload: no H2D copy is left for the run (copies issued by a run wait
         // for the previous sweep in the copy queue, in front of the next sweep's inputs)
-        if (d.sumH > 0 && HA_now < d.maxH && !s.ee_planned) RSAC_TRY(pnp_plan_early(e, HA_now));
+        if (d.sumH > 0 && bounds_now.size() > 1 && !s.ee_planned) RSAC_TRY(pnp_plan_early(e, bounds_now));
     }
     s.shape_sig.swap(sig);
     s.plans_valid = true;
@@ -728,21 +770,20 @@ static int solve_range_setup(rsac_engine* e)
     return RSAC_OK;
 }
 
-static int pnp_early_flag(rsac_engine* e, int mode)
+static int pnp_early_flag(rsac_engine* e, int stage, int lim, int mode)
 {
     PnpState& s = e->pnp;
     e->stage_begin(RSAC_STAGE_RNG);
     early_exit_flag_kernel<<<(s.d.C + 3) / 4, 128, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, s.d.C, (const int32_t*)s.d_counts.p,
-                                                                  s.ee_HA, s.ee_HB, (int32_t*)s.d_ee.p, mode);
+                                                                  stage, lim, (int32_t*)s.d_ee.p, mode);
     e->stage_end(RSAC_STAGE_RNG);
     RSAC_CUDA(e, cudaGetLastError());
     return RSAC_OK;
 }
 
-// minimal solves + scoring of hypotheses [lo, hi) of the problems in `list` (device-side count); `plan` is the
-// list-driven scoring plan of that range
-static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* list_count, int lo, int hi, const ScorePlanPOD& plan,
-                           int ngroups, DevBuf& d_visit)
+// minimal solves + scoring of hypotheses [lo, hi) of the problems in `list` (device-side count); plan index `pi` is
+// the list-driven scoring plan of that range
+static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* list_count, int lo, int hi, int pi)
 {
     PnpState& s = e->pnp;
     const BatchDims& d = s.d;
@@ -760,19 +801,19 @@ static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* l
     ScoreArgs sa = s.ee_sa;
     sa.list = list;
     sa.list_count = list_count;
-    return launch_score<0>(e, sa, plan, ngroups, d_visit);
+    return launch_score<0>(e, sa, s.ee_plans[pi], (int)s.ee_groups[pi].size(), s.ee_visit[pi]);
 }
 
 static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase);
 
-static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, int HA)
+static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, const std::vector<int>& bounds)
 {
     PnpState& s = e->pnp;
     const BatchDims& d = s.d;
     cudaStream_t st = e->stream;
     const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
-    if (!s.ee_planned || s.ee_HA != HA || s.ee_HB != std::min(pnp_second_phase(e, d, HA), d.maxH))
-        RSAC_TRY(pnp_plan_early(e, HA));   // normally done by the upload
+    if (!s.ee_planned || s.ee_bounds != bounds) RSAC_TRY(pnp_plan_early(e, bounds));   // normally done by the upload
+    const int K = (int)bounds.size();
     s.ee_mode = true;
     s.ee_complete = false;
     RSAC_TRY(s.d_ee.ensure(e, sizeof(int32_t) * early_exit_words(d.C)));
@@ -792,30 +833,28 @@ static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, int HA)
     }
     s.ee_sa = sa;
 
-    // phase A: hypotheses [0, HA) of every problem
+    // stage 0: hypotheses [0, b0) of every problem
     {
-        const int64_t most = (int64_t)d.C * HA;
+        const int64_t most = (int64_t)d.C * bounds[0];
         const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
         const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
         e->stage_begin(RSAC_STAGE_SOLVE);
         epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, st>>>(
-            metas, d.C, nullptr, nullptr, 0, HA, (const uint32_t*)s.d_tables.p, (const float4*)s.d_cA.p, (const float4*)s.d_uv.p,
+            metas, d.C, nullptr, nullptr, 0, bounds[0], (const uint32_t*)s.d_tables.p, (const float4*)s.d_cA.p, (const float4*)s.d_uv.p,
             (float*)s.d_poses.p);
         e->stage_end(RSAC_STAGE_SOLVE);
         RSAC_CUDA(e, cudaGetLastError());
-        RSAC_TRY(launch_score<0>(e, sa, s.planA, (int)s.groupsA.size(), s.d_visitA));
+        RSAC_TRY(launch_score<0>(e, sa, s.ee_plans[0], (int)s.ee_groups[0].size(), s.ee_visit[0]));
     }
-    // who goes on; phase B1 [HA, HB); who still goes on; phase B2 [HB, H)
-    RSAC_TRY(pnp_early_flag(e, 0));
-    RSAC_TRY(pnp_early_range(e, v.listX, v.counters + 0, HA, s.ee_HB, s.planB1, (int)s.groupsB1.size(), s.d_visitB1));
-    RSAC_TRY(pnp_early_flag(e, 1));
-    if (s.ee_HB < d.maxH) {
-        RSAC_TRY(pnp_early_range(e, v.listY, v.counters + 1, s.ee_HB, d.maxH, s.planB2, (int)s.groupsB2.size(), s.d_visitB2));
-        RSAC_TRY(pnp_early_flag(e, 3));
+    // who goes on after stage j-1 (list j); stage j: [b(j-1), bj) of list j
+    for (int j = 1; j < K; ++j) {
+        RSAC_TRY(pnp_early_flag(e, j - 1, bounds[j - 1], 0));
+        RSAC_TRY(pnp_early_range(e, v.list(j), v.counters + j, bounds[j - 1], bounds[j], j));
     }
-    // replay; problems it cannot decide go to phase C
+    RSAC_TRY(pnp_early_flag(e, K - 1, bounds[K - 1], 0));     // the members of the last list have everything
+    // replay; problems it cannot decide go to the clean-up
     RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, -1));
-    RSAC_TRY(pnp_early_range(e, v.listC, v.counters + 2, HA, d.maxH, s.planB, (int)s.groupsB.size(), s.d_visitB));
+    RSAC_TRY(pnp_early_range(e, v.listC, v.counters + kCleanupCounter, bounds[0], d.maxH, K));
     RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, 2));
     s.ran = true;
     return RSAC_OK;
@@ -862,9 +901,9 @@ int rsac_pnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* 
         // the last run stopped early: problems that were decided inside their first HA hypotheses get the rest
         // now, so that the scan can go on wherever the caller resumes it
         const EarlyExit v = early_exit_view((int32_t*)s.d_ee.p, s.d.C);
-        RSAC_CUDA(e, cudaMemsetAsync(v.counters, 0, 4 * sizeof(int32_t), e->stream));
-        RSAC_TRY(pnp_early_flag(e, 2));
-        RSAC_TRY(pnp_early_range(e, v.listC, v.counters + 2, s.ee_HA, s.d.maxH, s.planB, (int)s.groupsB.size(), s.d_visitB));
+        RSAC_CUDA(e, cudaMemsetAsync(v.counters + kCleanupCounter, 0, sizeof(int32_t), e->stream));
+        RSAC_TRY(pnp_early_flag(e, 0, 0, 2));
+        RSAC_TRY(pnp_early_range(e, v.listC, v.counters + kCleanupCounter, s.ee_HA, s.d.maxH, (int)s.ee_bounds.size()));
         s.ee_complete = true;
     }
     return pnp_launch_select(e, flags, (const int32_t*)e->d_resume.p, d_results_out, -1);
@@ -907,8 +946,8 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
     }
     s.ee_mode = false;
     if ((flags & RSAC_FLAG_EARLY_EXIT) && !(flags & RSAC_FLAG_EPNP_EIGEN) && d.sumH > 0) {
-        const int HA = pnp_first_phase(e, d);
-        if (HA < d.maxH) return pnp_run_early(e, flags, d_results_out, HA);
+        const std::vector<int> bounds = pnp_stage_bounds(e, d);
+        if (bounds.size() > 1) return pnp_run_early(e, flags, d_results_out, bounds);
     }
     if (d.sumH > 0) {
         const bool eigen = (flags & RSAC_FLAG_EPNP_EIGEN) != 0;
@@ -969,8 +1008,8 @@ int rsac_pnp_phase_stats(rsac_engine* e, int64_t out[4])
     RSAC_CUDA(e, cudaMemcpyAsync(ee.data(), s.d_ee.p, sizeof(int32_t) * ee.size(), cudaMemcpyDeviceToHost, e->stream));
     RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
     out[0] = s.ee_HA;
-    out[1] = ee[4 * (size_t)s.d.C];
-    out[2] = ee[4 * (size_t)s.d.C + 2];
+    out[1] = ee[4 * (size_t)s.d.C + 1];
+    out[2] = ee[4 * (size_t)s.d.C + kCleanupCounter];
     int64_t done = 0;
     for (int c = 0; c < s.d.C; ++c) done += std::min(s.metas[c].H, std::max(ee[c], 0));
     done += (int64_t)out[2] * 0;   // (problems of the clean-up phase end with upto = H)

@@ -104,17 +104,20 @@ struct PnpState {
     bool ee_planned = false, ee_mode = false, ee_complete = false;
     bool plans_valid = false;               // plans and device work arrays match shape_sig
     std::vector<int32_t> shape_sig;         // n, H, fx, fy of every problem + stage boundaries
-    int ee_HA = 0, ee_HB = 0;
-    ScorePlanPOD planA, planB1, planB2, planB;     // [0,HA) static; [HA,HB), [HB,H), [HA,H) list-driven
-    std::vector<ScoreGroup> groupsA, groupsB1, groupsB2, groupsB;
+    int ee_HA = 0;
+    std::vector<int> ee_bounds;                      // stage boundaries b0 < ... < b(K-1) = maxH
+    std::vector<ScorePlanPOD> ee_plans;              // [0,b0) static; [b(j-1),bj) list-driven; last: clean-up [b0,H)
+    std::vector<std::vector<ScoreGroup>> ee_groups;
+    std::vector<DevBuf> ee_visit;
     ScoreArgs ee_sa;
-    DevBuf d_ee, d_visitA, d_visitB1, d_visitB2, d_visitB;
+    DevBuf d_ee;
     PinnedBuf h_stageEE;
     void release()
     {
         h_stage.release();
         h_stageEE.release();
-        d_ee.release(); d_visitA.release(); d_visitB1.release(); d_visitB2.release(); d_visitB.release();
+        d_ee.release();
+        for (auto& b : ee_visit) b.release();
         DevBuf* all[] = {&d_metas, &d_cP, &d_th2, &d_p3d, &d_p2d, &d_sigma2, &d_cA, &d_cB, &d_uv, &d_tables, &d_poses,
                          &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra, &d_visit};
         for (DevBuf* b : all) b->release();
@@ -172,7 +175,8 @@ struct rsac_engine {
     int64_t launches = 0;
     int32_t problem_base = 0;
     int32_t first_phase = 0;   // early exit: hypotheses per problem in phase A (0 = one solver wave)
-    int32_t second_phase = 0;  // early exit: end of the second stage (0 = a third of what remains)
+    int32_t second_phase = 0;  // early exit: end of the second stage when the caller fixed it (rsac_set_phases)
+    std::vector<int> stage_bounds;   // early exit: explicit stage boundaries (rsac_set_stages); empty = automatic
     rsac::PnpState pnp;
     rsac::PnpState mlpnp;
     rsac::ScoreState score;

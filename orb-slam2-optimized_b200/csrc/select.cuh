@@ -41,7 +41,7 @@ struct SelectArgs {
     int32_t problem_base;    // global index of problem 0 (sharding)
     int32_t flags;
     const int32_t* resume;   // optional [C]: hypotheses already consumed by earlier iterate() calls
-    // early exit in phases (pnp_pipeline.cuh): ee = [upto: C][listX: C][listY: C][listC: C][nX, nY, nC, 0] or nullptr
+    // early exit in stages (pnp_pipeline.cuh): ee = [upto: C][listX: C][listY: C][listC: C][counters: 16] or nullptr
     int32_t* ee = nullptr;
     int32_t C = 0;
     int32_t first_phase = 0;   // HA: hypotheses every problem has after phase A
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
         if (tid == 0) {
             int32_t* counters = a.ee + 4 * (size_t)a.C;
             a.ee[blockIdx.x] = -(H + 1);
-            (a.ee + 3 * (size_t)a.C)[atomicAdd(counters + 2, 1)] = blockIdx.x;
+            (a.ee + 3 * (size_t)a.C)[atomicAdd(counters + 15, 1)] = blockIdx.x;   // kCleanupCounter
             res.reserved[0] = 1;   // not decided yet
             reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
         }

@@ -178,6 +178,10 @@ class Engine:
     def set_phases(self, first: int, second: int):
         self._ck(self.L.rsac_set_phases(self.h, C.c_int(first), C.c_int(second)), "set_phases")
 
+    def set_stages(self, bounds):
+        b = np.ascontiguousarray(bounds, np.int32)
+        self._ck(self.L.rsac_set_stages(self.h, C.c_int(len(b)), _p(b) if len(b) else None), "set_stages")
+
     def pnp_phase_stats(self):
         """(first_phase, problems in phase B, problems in phase C, hypotheses solved) of the last early-exit run"""
         out = (C.c_int64 * 4)()

@@ -405,3 +405,30 @@ def test_pnp_early_exit_many_hypotheses_several_tiles(engine):
         assert (masks0 == masks1).all()
         seen_b += nB
     assert seen_b > 0
+
+
+@pytest.mark.parametrize("bounds", [[3, 6, 12, 24, 48, 96, 192], [10, 11, 12, 250], [64, 128]])
+def test_pnp_early_exit_many_stages(engine, bounds):
+    """up to eight stages: the candidate lists alternate between two device buffers, boundaries beyond H are clipped
+    (Tracking's parameters give H = 35); records must not depend on the staging"""
+    for (cfgno, C, n, outl, prm) in ((16, 160, 250, 0.6, PRM),
+                                     (12, 64, 200, 0.45, dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.5, th2=5.991))):
+        b, offsets = _batch(cfgno, C, n, outl=outl)
+        args = (offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**prm))
+        res0, masks0 = engine.pnp_solve(*args, seeds=b["seeds"])
+        engine.set_stages(bounds)
+        try:
+            res1, masks1 = engine.pnp_solve(*args, seeds=b["seeds"], flags=capi.FLAG_EARLY_EXIT)
+            ha, nB, nC, solved = engine.pnp_phase_stats()
+            engine.pnp_rerun(res1["n_hyp"].astype(np.int32))
+            after, _ = engine.pnp_download()
+        finally:
+            engine.set_stages([])
+        H = capi.pnp_ransac_setup(n, capi.ransac_params(**prm))[1]
+        assert ha == (bounds[0] if bounds[0] < H else 0)      # a first stage that covers H is the exhaustive run
+        _same_records(res0, res1)
+        assert (masks0 == masks1).all()
+        engine.pnp_solve(*args, seeds=b["seeds"])
+        engine.pnp_rerun(res0["n_hyp"].astype(np.int32))
+        ref, _ = engine.pnp_download()
+        _same_records(ref, after)
