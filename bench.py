@@ -605,6 +605,25 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
         ex["cfg2_mlpnp"] = {"frames": C2, "matches": N2, "hypotheses": H2, "ms_per_batch": ms2,
                             "frames_per_s": C2 / (ms2 * 1e-3), "evals_per_s": C2 * H2 * N2 / (ms2 * 1e-3),
                             "frames_ok": int(res2["ok"].sum())}
+        # a 64-frame batch is a fraction of one wave: independent batches in flight (one engine + stream each)
+        pool = [capi.Engine(0) for _ in range(6)]
+        for q in pool:
+            q.mlpnp_upload(off2, b2["p3d"], b2["p2d"], b2["sigma2"], Kf, prm2, cov=cov, seeds=b2["seeds"])
+            q.mlpnp_run()
+        for q in pool:
+            q.sync()
+        t0 = time.perf_counter()
+        reps2 = 20
+        for _ in range(reps2):
+            for q in pool:
+                q.mlpnp_run()
+        for q in pool:
+            q.sync()
+        dt2 = (time.perf_counter() - t0) / (reps2 * len(pool))
+        ex["cfg2_mlpnp"]["batches_in_flight_6"] = {"ms_per_batch": dt2 * 1e3, "frames_per_s": C2 / dt2,
+                                                   "evals_per_s": C2 * H2 * N2 / dt2, "timing": "wall clock around 120 batches, synchronised"}
+        for q in pool:
+            q.close()
         ps = [synth.sim3_problem(3000 + i, 200, 0.4, 1.0) for i in range(64)]
         cat = lambda k: np.concatenate([q[k] for q in ps])
         off3 = (np.arange(len(ps) + 1) * 200).astype(np.int32)
