@@ -411,7 +411,9 @@ def main():
                        "parallelism": f"one 1024-candidate sweep per GPU and step (x{world} GPUs), {PIPE} independent sweeps in flight per "
                                       "GPU (one engine + stream each); e2e uploads every step's block from pinned host memory and "
                                       "reads records + masks back inside the timed region",
-                       "l2": "working set of a sweep (~90 MB) is L2-resident by design; every kernel is compute- or latency-bound: no flush"},
+                       "l2": (f"no explicit flush: {NBLOCK} blocks are cycled, each in its own engine (~90 MB of device buffers per block, "
+                              f"{NBLOCK * 90} MB in total against 126 MB of L2), so a step's data was last touched {NBLOCK} steps earlier; "
+                              "within a sweep the working set is L2-resident by design and every kernel is compute- or latency-bound")},
             "e2e": {"value": e2e_v, "unit": "candidates/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
