@@ -7,7 +7,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/ransac_b200.h"
@@ -290,6 +293,21 @@ int rsac_shard_range(int C, int rank, int world, int* first, int* count)
 // limit counts the kernel's static shared memory too, so a request of exactly 48 KB fails without it
 static constexpr int kChunkWordsMax = 8;     // 256 correspondences per ring slot (12 KB), 4 slots
 
+// Kernel attributes are per device and process-wide, not per engine: engines on different host threads (Tracking and
+// LoopClosing each own one) must not lower what another engine's launch relies on -- monotonic maxima under a lock
+static int set_func_attr_max(rsac_engine* e, const void* kern, cudaFuncAttribute attr, int value)
+{
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void*, int>, int> cur;
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_tuple(e->device, kern, (int)attr);
+    const auto it = cur.find(key);
+    if (it != cur.end() && it->second >= value) return RSAC_OK;
+    RSAC_CUDA(e, cudaFuncSetAttribute(kern, attr, value));
+    cur[key] = value;
+    return RSAC_OK;
+}
+
 static int env_int(const char* name, int dflt)
 {
     const char* v = getenv(name);
@@ -362,7 +380,7 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
     const void* kern = score_kernel_ptr<MODEL>(pl.hpl);
     auto resident = [&](int chunk_words) -> int {
         const size_t smem = score_smem_bytes<MODEL>(chunk_words * 32, pl.tile_hyps);
-        if (smem > 32 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 32 * 1024) (void)set_func_attr_max(e, kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, pl.threads + 32, smem) != cudaSuccess) { cudaGetLastError(); nb = 1; }
         nb = std::max(1, nb);
@@ -477,7 +495,7 @@ static int launch_score(rsac_engine* e, ScoreArgs& args, const ScorePlan& pl, in
 {
     if (ngroups <= 0) return RSAC_OK;
     const void* kern = score_kernel_ptr<MODEL>(pl.hpl);
-    if (pl.smem > 32 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    if (pl.smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     args.work = (const ScoreGroup*)d_visit.p;
     args.vlen = pl.vlen;
     args.tiles_per_problem = pl.tiles;
@@ -763,10 +781,10 @@ static int solve_range_setup(rsac_engine* e)
 {
     const size_t smem = sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS;
     if (smem > 32 * 1024)
-        RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t need = (smem + 1024) * RSAC_SOLVE_BLOCKS;
     const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
-    RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_range_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     return RSAC_OK;
 }
 
@@ -872,13 +890,13 @@ static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume,
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
-    if (smem > 32 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         cudaFuncAttributes fa;
         RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<0>));
         const size_t need = (fa.sharedSizeBytes + smem + 1024) * kSelectCtasPerSm;
         const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
-        RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     e->stage_begin(RSAC_STAGE_SELECT);
     ransac_select_kernel<0><<<d.C, kSelectThreads, smem, e->stream>>>(a);
@@ -952,7 +970,7 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
     if (d.sumH > 0) {
         const bool eigen = (flags & RSAC_FLAG_EPNP_EIGEN) != 0;
         if (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS > 32 * 1024)
-            RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)(sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS)));
         {
             // ask for exactly the shared-memory carve-out that keeps RSAC_SOLVE_BLOCKS blocks resident (the rest of
@@ -960,7 +978,7 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
             // a smaller carve-out in some processes, which silently drops a block per SM (0.96 vs 0.82 ms)
             const size_t need = (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS + 1024) * RSAC_SOLVE_BLOCKS;
             const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
-            RSAC_CUDA(e, cudaFuncSetAttribute(epnp_minimal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         }
         const int threads = eigen ? 128 : RSAC_SOLVE_THREADS;
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);

@@ -74,14 +74,14 @@ static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resum
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base; a.flags = flags; a.resume = d_resume;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
-    if (smem > 32 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     e->stage_begin(RSAC_STAGE_SELECT);
     {
         cudaFuncAttributes fa;
         RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<1>));
         const size_t need = (fa.sharedSizeBytes + smem + 1024) * kSelectCtasPerSm;
         const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
-        RSAC_CUDA(e, cudaFuncSetAttribute(ransac_select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     ransac_select_kernel<1><<<d.C, kSelectThreadsMlpnp, smem, e->stream>>>(a);
     e->stage_end(RSAC_STAGE_SELECT);

@@ -114,7 +114,7 @@ int rsac_sim3_run(rsac_engine* e, int flags, void* d_results_out)
     a.tile = std::max(32, std::min(1024, ((d.maxN + 31) / 32) * 32));
     const int threads = std::max(32, std::min(512, ((d.maxH + 31) / 32) * 32));
     const size_t smem = (size_t)a.tile * 48;
-    if (smem > 32 * 1024) RSAC_CUDA(e, cudaFuncSetAttribute(sim3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)sim3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     e->stage_begin(RSAC_STAGE_SOLVE);
     sim3_kernel<<<d.C, threads, smem, st>>>(a);
     e->stage_end(RSAC_STAGE_SOLVE);
