@@ -7,7 +7,7 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
     if (!b->seeds && !b->tables) { e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     PnpState& s = e->mlpnp;
-    s.uploaded = false; s.ran = false;
+    s.uploaded = false; s.ran = false; s.tables_ready = false;
     std::vector<float> th2;
     for (int c = 0; c < b->C; ++c)
         if (b->params[b->n_params == 1 ? 0 : c].min_set != 6) { e->err = "MLPnP needs min_set = 6"; return RSAC_ERR_INVALID; }
@@ -113,11 +113,12 @@ int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
     if (d.C == 0) { s.ran = true; return RSAC_OK; }
     const double* cov = s.have_cov ? (const double*)s.d_cov.p : nullptr;
 
-    if (!s.have_tables && d.table_len > 0) {
+    if (!s.have_tables && d.table_len > 0 && !s.tables_ready) {   // once per upload: the tables depend on the seeds only
         e->stage_begin(RSAC_STAGE_RNG);
         rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
         e->stage_end(RSAC_STAGE_RNG);
         RSAC_CUDA(e, cudaGetLastError());
+        s.tables_ready = true;
     }
     if (d.sumH > 0) {
         const int threads = 128;

@@ -68,6 +68,7 @@ static_assert(sizeof(ResultRec) == 96, "rsac_result layout");
 // exhaustive sweep at a time 128 x 7 had won because the 96-thread shapes slowed the following solve kernel down.)
 constexpr int kSelectThreads = RSAC_SELECT_THREADS;
 constexpr int kSelectThreadsMlpnp = 128;   // MLPnP's refine (cfg2: 64 frames, one partial wave) is faster with four warps: 0.46 against 0.54 ms
+static_assert(kSelectThreadsMlpnp >= 78, "refine_mlpnp maps the 78 A^T P A entries to one thread each");
 template <int MODEL> constexpr int select_threads() { return MODEL == 0 ? kSelectThreads : kSelectThreadsMlpnp; }
 constexpr int kSelectCtasPerSm = RSAC_SELECT_CTAS;
 
@@ -514,11 +515,23 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
         if (use_cov) mlpnp_weight(o + 6, a.cov + 9 * g, o + 12);             // P
     }
     __syncthreads();
-    if (tid < 9) {                                     // planarTest = sum p p^T (:346)
-        const int r = tid / 3, c = tid % 3;
+    // n-point sums: one thread per output entry adds the per-observation terms in index order (the checker's serial
+    // order); the terms travel through a shared-memory tile staged by the whole CTA (see refine_epnp)
+    constexpr int kTa = 24, kTPa = kTa + 1;            // A^T P A: two design-matrix rows (12 + 12) and P (4) per observation
+    constexpr int kTg = 38, kTPg = kTg + 1;            // Gauss-Newton: J (12), P (4), r (2) per observation
+    __shared__ double m_tile[28 * kTPa > 18 * kTPg ? 28 * kTPa : 18 * kTPg];
+    {                                                  // planarTest = sum p p^T (:346)
+        const int r = (tid % 9) / 3, c = tid % 3;
         double s = 0.0;
-        for (int i = 0; i < n; ++i) s = rfma(sc[(size_t)i * kMlpnpScratch + 3 + r], sc[(size_t)i * kMlpnpScratch + 3 + c], s);
-        S.planarTest[tid] = s;
+        for (int base = 0; base < n; base += kTg) {
+            const int cnt = min(kTg, n - base);
+            __syncthreads();
+            for (int e = tid; e < cnt * 3; e += blockDim.x) m_tile[(e % 3) * kTPg + e / 3] = sc[(size_t)(base + e / 3) * kMlpnpScratch + 3 + e % 3];
+            __syncthreads();
+            if (tid < 9)
+                for (int i = 0; i < cnt; ++i) s = rfma(m_tile[r * kTPg + i], m_tile[c * kTPg + i], s);
+        }
+        if (tid < 9) S.planarTest[tid] = s;
     }
     __syncthreads();
     if (tid == 0) {
@@ -547,25 +560,45 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
     __syncthreads();
     const int cols = planar ? 9 : 12;
     const int nent = cols * (cols + 1) / 2;
-    for (int e = tid; e < nent; e += blockDim.x) {     // A^T P A upper triangle, entry-parallel (:482-486)
-        int ea = 0, rem = e;
-        while (rem >= cols - ea) { rem -= cols - ea; ++ea; }
-        const int eb = ea + rem;
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) {
-            const double* o = sc + (size_t)i * kMlpnpScratch;
-            double a0, a1, b0, b1;
-            mlpnp_row_entry(o + 6, o + 16, planar, ea, a0, a1);
-            mlpnp_row_entry(o + 6, o + 16, planar, eb, b0, b1);
-            double w0 = b0, w1 = b1;
-            if (use_cov) {
-                w0 = rfma(o[12], b0, o[13] * b1);
-                w1 = rfma(o[14], b0, o[15] * b1);
-            }
-            s = rfma(a0, w0, s);
-            s = rfma(a1, w1, s);
+    {                                                  // A^T P A upper triangle, entry-parallel (:482-486)
+        int ea = 0, eb = 0;
+        const bool have = tid < nent;                  // nent <= 78 <= blockDim.x
+        if (have) {
+            int rem = tid;
+            while (rem >= cols - ea) { rem -= cols - ea; ++ea; }
+            eb = ea + rem;
         }
-        S.AtPA[tri_idx(cols, ea, eb)] = s;
+        double s = 0.0;
+        for (int base = 0; base < n; base += kTa) {
+            const int cnt = min(kTa, n - base);
+            __syncthreads();
+            for (int e = tid; e < cnt * cols; e += blockDim.x) {       // the two rows of every observation of the tile
+                const int pt = e / cols, col = e - pt * cols;
+                const double* o = sc + (size_t)(base + pt) * kMlpnpScratch;
+                double e0, e1;
+                mlpnp_row_entry(o + 6, o + 16, planar, col, e0, e1);
+                m_tile[col * kTPa + pt] = e0;
+                m_tile[(12 + col) * kTPa + pt] = e1;
+            }
+            if (use_cov)
+                for (int e = tid; e < cnt * 4; e += blockDim.x)
+                    m_tile[(24 + (e & 3)) * kTPa + (e >> 2)] = sc[(size_t)(base + (e >> 2)) * kMlpnpScratch + 12 + (e & 3)];
+            __syncthreads();
+            if (have) {
+                for (int i = 0; i < cnt; ++i) {
+                    const double a0 = m_tile[ea * kTPa + i], a1 = m_tile[(12 + ea) * kTPa + i];
+                    const double b0 = m_tile[eb * kTPa + i], b1 = m_tile[(12 + eb) * kTPa + i];
+                    double w0 = b0, w1 = b1;
+                    if (use_cov) {
+                        w0 = rfma(m_tile[24 * kTPa + i], b0, m_tile[25 * kTPa + i] * b1);
+                        w1 = rfma(m_tile[26 * kTPa + i], b0, m_tile[27 * kTPa + i] * b1);
+                    }
+                    s = rfma(a0, w0, s);
+                    s = rfma(a1, w1, s);
+                }
+            }
+        }
+        if (have) S.AtPA[tri_idx(cols, ea, eb)] = s;
     }
     __syncthreads();
     if (tid < 32) {                                    // smallest eigenvector of A^T P A (:488-493), warp-cooperative
@@ -598,22 +631,33 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
         }
         if (tid == 0) S.maxdl_bits = 0ull;
         __syncthreads();
-        if (tid < 42) {                                // A = J^T P J (36 entries) and g = J^T P r (6 entries)
+        {                                              // A = J^T P J (36 entries) and g = J^T P r (6 entries)
             const bool isg = tid >= 36;
-            const int ea = isg ? tid - 36 : tid / 6, eb = isg ? 0 : tid % 6;
+            const int ea = isg ? (tid - 36) % 6 : tid / 6, eb = isg ? 0 : tid % 6;
             double s = 0.0;
-            for (int i = 0; i < n; ++i) {
-                const double* o = sc + (size_t)i * kMlpnpScratch;
-                const double* J = o + 19;
-                double W0 = J[ea], W1 = J[6 + ea];
-                if (use_cov) {
-                    W0 = rfma(J[ea], o[12], J[6 + ea] * o[14]);
-                    W1 = rfma(J[ea], o[13], J[6 + ea] * o[15]);
+            for (int base = 0; base < n; base += kTg) {
+                const int cnt = min(kTg, n - base);
+                __syncthreads();
+                for (int e = tid; e < cnt * 18; e += blockDim.x) {
+                    const int pt = e / 18, j = e - 18 * pt;        // j < 12: J; 12..15: P; 16, 17: r
+                    const double* o = sc + (size_t)(base + pt) * kMlpnpScratch;
+                    m_tile[j * kTPg + pt] = (j < 12) ? o[19 + j] : (j < 16 ? o[12 + (j - 12)] : o[31 + (j - 16)]);
                 }
-                if (isg) { s = rfma(W0, o[31], s); s = rfma(W1, o[32], s); }
-                else     { s = rfma(W0, J[eb], s); s = rfma(W1, J[6 + eb], s); }
+                __syncthreads();
+                if (tid < 42) {
+                    for (int i = 0; i < cnt; ++i) {
+                        const double Ja = m_tile[ea * kTPg + i], Jb = m_tile[(6 + ea) * kTPg + i];
+                        double W0 = Ja, W1 = Jb;
+                        if (use_cov) {
+                            W0 = rfma(Ja, m_tile[12 * kTPg + i], Jb * m_tile[14 * kTPg + i]);
+                            W1 = rfma(Ja, m_tile[13 * kTPg + i], Jb * m_tile[15 * kTPg + i]);
+                        }
+                        if (isg) { s = rfma(W0, m_tile[16 * kTPg + i], s); s = rfma(W1, m_tile[17 * kTPg + i], s); }
+                        else     { s = rfma(W0, m_tile[eb * kTPg + i], s); s = rfma(W1, m_tile[(6 + eb) * kTPg + i], s); }
+                    }
+                }
             }
-            if (isg) S.g[ea] = s; else S.A[ea * 6 + eb] = s;
+            if (tid < 42) { if (isg) S.g[ea] = s; else S.A[ea * 6 + eb] = s; }
         }
         __syncthreads();
         if (tid == 0) ldlt6_solve(S.A, S.g, S.dx);
