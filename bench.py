@@ -553,6 +553,52 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                                      "peak_gbs": peaks["hbm_gbs"], "peak_source": peak_src + " (MEASURED_PEAKS.json)"},
                              "exact_path_evals": eng.score_exact_evals(),
                              "note": "launches run back to back on 5.6 MB of data: L2-resident by design (compute-bound kernel)"}
+    # independent scoring jobs in flight (one engine + stream each), like the sweeps of the headline number: the ramp
+    # and tail of one launch (19 % of its duration: sm__cycles_active 60.5 k of 74.5 k elapsed,
+    # profiles/r01_score_cfg5_ncu_full.txt) overlap its neighbours.  Timed on the device: one event before all streams
+    # start, one after they have all finished.
+    single = dict(out["roofline_score"])
+    try:
+        NF = 6
+        pool, pstreams = [], []
+        for _ in range(NF):
+            q = capi.Engine(0)
+            st_ = torch.cuda.Stream()
+            q.set_stream(st_.cuda_stream)
+            q.score_pnp_upload(p["poses"], p["p3d"], p["p2d"], max_err, p["K"])
+            for _ in range(3):
+                q.score_pnp_run(True)
+            pool.append(q)
+            pstreams.append(st_)
+        torch.cuda.synchronize()
+        main_s = torch.cuda.current_stream()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(main_s)
+        for st_ in pstreams:
+            st_.wait_event(ev0)
+        per = 100
+        for _ in range(per):
+            for q in pool:
+                q.score_pnp_run(True)
+        for st_ in pstreams:
+            e_ = torch.cuda.Event()
+            e_.record(st_)
+            main_s.wait_event(e_)
+        ev1.record(main_s)
+        torch.cuda.synchronize()
+        msf = ev0.elapsed_time(ev1) / (per * NF)
+        evf = H * N / (msf * 1e-3)
+        out["roofline_score"].update({
+            "kernel": "score_kernel<2,0> (cfg5: 4096 x 10000, masks + counts), %d independent scoring jobs in flight" % NF,
+            "achieved": evf * FLOP_PER_EVAL / 1e12, "frac": evf * FLOP_PER_EVAL / 1e12 / fp32_pk, "evals_per_s": evf,
+            "launch_ms": msf, "launches_timed": per * NF,
+            "timing": "CUDA events around %d launches on %d streams; launch_ms = timed region / launches" % (per * NF, NF),
+            "single_stream": {k: single[k] for k in ("achieved", "frac", "evals_per_s", "launch_ms")}})
+        out["roofline_score"]["hbm"]["achieved_gbs"] = alg_bytes / (msf * 1e-3) / 1e9
+        for q in pool:
+            q.close()
+    except Exception as err:
+        out["roofline_score"]["in_flight_error"] = repr(err)
     # ---- cfg1: one frame, one candidate (latency of the reference-facing call)
     b1 = synth.pnp_batch(1, 1, N_MATCH, 0.5)
     off1 = np.array([0, N_MATCH], np.int32)

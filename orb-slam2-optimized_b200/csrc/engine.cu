@@ -352,7 +352,10 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
         for (const auto& m : metas) maxH = std::max(maxH, std::min(m.H, h_hi) - h_lo);
     }
     int warps = (maxH + 32 * pl.hpl - 1) / (32 * pl.hpl);
-    warps = std::max(1, std::min(env_int("RSAC_SCORE_WARPS", 16), std::min(16, warps)));
+    // at most 8 consumer warps per CTA (two CTAs per SM): alone it scores cfg5 like one 16-warp CTA per SM (46-47 % of
+    // the FP32 peak), with independent scoring jobs in flight it is ahead (64 % against 59 %: a CTA that waits for its
+    // first chunk or drains its last one has a neighbour on the SM)
+    warps = std::max(1, std::min(env_int("RSAC_SCORE_WARPS", 8), std::min(16, warps)));
     pl.threads = warps * 32;
     pl.tile_hyps = warps * 32 * pl.hpl;
     std::vector<double> work;
@@ -425,7 +428,7 @@ static int plan_score(rsac_engine* e, const std::vector<ProblemMeta>& metas, int
         for (double w : work) total += w;
         const int cw_env = env_int("RSAC_SCORE_CW", 0);
         if (cw_env > 0) cw = std::min(kChunkWordsMax, cw_env);
-        else cw = std::max(1, std::min(kChunkWordsMax, (int)(maxWords / (6.0 * std::max(1, slots / NG)))));
+        else cw = std::max(1, std::min(kChunkWordsMax, (int)(maxWords / (3.0 * std::max(1, slots / NG)))));   // cfg5: 2 words
         slots = resident(cw);
         pl.grid = std::max(slots, NG);
         // largest-remainder apportionment, at least one CTA per group
