@@ -266,6 +266,40 @@ int rsac_mlpnp_solve(rsac_engine* e, const rsac_mlpnp_batch* b, int flags, rsac_
 int rsac_mlpnp_get_hypotheses(rsac_engine* e, double* poses, int32_t* counts);
 int64_t rsac_mlpnp_total_hypotheses(rsac_engine* e);
 
+/* -------------------------------------------- Optimizer::PoseOptimization (batched) */
+/* the consumer of every pose the RANSAC engine accepts (Tracking.cpp:1284,1300,1315 call
+ * Optimizer::PoseOptimization(&mCurrentFrame) per candidate; src/Optimizer.cpp:205-424).  One problem = one frame:
+ * the keypoints that have a MapPoint (Optimizer.cpp:250-323), in keypoint order.  4 rounds of <= 10
+ * Levenberg-Marquardt iterations with the Huber kernel (dropped for the last round), every round restarted from
+ * the initial pose on the edges the previous round classified as inliers -- g2o's step control reproduced
+ * (Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:59-179).  One warp per frame. */
+typedef struct {
+    int32_t C;
+    const int32_t* offsets;      /* [C+1] */
+    const float* p3d;            /* [total][3] MapPoint::GetWorldPos() */
+    const float* obs;            /* [total][3] kpUn.pt.x, kpUn.pt.y, mvuRight[i] (< 0: monocular edge, else stereo) */
+    const float* inv_sigma2;     /* [total] mvInvLevelSigma2[kpUn.octave] */
+    const float* K;              /* [C][5] fx, fy, cx, cy, mbf */
+    const float* Tcw;            /* [C][12] initial pose pFrame->mTcw: R row-major (9), t (3) */
+} rsac_poseopt_batch;
+
+typedef struct {
+    int32_t n_inliers;           /* return value of PoseOptimization: nInitialCorrespondences - nBad */
+    int32_t n_bad;
+    int32_t rounds;              /* outer rounds executed (4; 1 with fewer than 10 edges; 0 with fewer than 3) */
+    int32_t iterations;          /* LM iterations over all rounds */
+    int32_t trials;              /* LM trials (6x6 solves) over all rounds */
+    int32_t reserved;
+    double R[9], t[3];           /* SE3quat_recov.to_homogeneous_matrix() */
+    float Rf[9], tf[3];          /* Converter::toIso(...) as handed to Frame::SetPose (Optimizer.cpp:418-421) */
+} rsac_poseopt_result;
+
+int rsac_poseopt_upload(rsac_engine* e, const rsac_poseopt_batch* b);
+int rsac_poseopt_run(rsac_engine* e);
+/* outlier: [total] pFrame->mvbOutlier of the matched keypoints (1 = outlier) */
+int rsac_poseopt_download(rsac_engine* e, rsac_poseopt_result* results, uint8_t* outlier);
+int rsac_poseopt_solve(rsac_engine* e, const rsac_poseopt_batch* b, rsac_poseopt_result* results, uint8_t* outlier);
+
 /* ------------------------------------------------ multi-GPU (candidates shard) */
 /* contiguous block partition of C problems over `world` ranks: rank r owns [*first, *first + *count) */
 int rsac_shard_range(int C, int rank, int world, int* first, int* count);
@@ -296,6 +330,9 @@ int rsac_debug_host_epnp4_qr(const double K[4], const float p3d[12], const float
 /* the 4 smallest eigenpairs of a symmetric 12x12 (upper triangle read): w[4], v[12][4] */
 int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48]);
 int rsac_debug_host_sim3(const float P1[9], const float P2[9], int fix_scale, float R[9], float t[3], float* s);
+/* PoseOptimization of one frame with the device source compiled for the host (one lane, edges summed in order) */
+int rsac_debug_host_poseopt(int n, const float* p3d, const float* obs, const float* inv_sigma2, const float K[5],
+                            const float Tcw[12], rsac_poseopt_result* result, uint8_t* outlier);
 int rsac_debug_host_mlpnp6(const float K[4], const float p3d[18], const float p2d[12], const double* cov54,
                            double R[9], double t[3]);
 

@@ -207,6 +207,32 @@ double orc_mlpnp_batch(int C, const orc_mlpnp_problem *pbs, const orc_ransac_par
 double orc_pnp_score_timed(const orc_pnp_problem *pb, const float *max_err, int H, const float *poses,
                            int nthreads, int *counts);
 
+/* ------------------------------------------------ Optimizer::PoseOptimization */
+/* one frame: what Optimizer.cpp:244-323 reads from the Frame and its MapPoints */
+typedef struct {
+    int n;                    /* keypoints with a MapPoint (nInitialCorrespondences) */
+    const float *p3d;         /* [n][3] MapPoint::GetWorldPos() */
+    const float *obs;         /* [n][3] kpUn.pt.x, kpUn.pt.y, mvuRight (< 0: monocular edge) */
+    const float *inv_sigma2;  /* [n] mvInvLevelSigma2[kpUn.octave] */
+    float K[5];               /* fx, fy, cx, cy, mbf */
+    float Rcw[9], tcw[3];     /* pFrame->mTcw */
+} orc_poseopt_problem;
+
+typedef struct {
+    int32_t n_inliers;        /* return value: nInitialCorrespondences - nBad */
+    int32_t n_bad;
+    int32_t rounds;           /* outer rounds executed */
+    int32_t iterations;       /* LM iterations (solve() calls) */
+    int32_t trials;           /* LM trials (linear solves + chi2 passes) */
+    int32_t reserved;
+    double R[9], t[3];        /* SE3quat_recov.to_homogeneous_matrix() */
+    float Rf[9], tf[3];       /* Converter::toIso -> Frame::SetPose */
+} orc_poseopt_result;
+
+/* outlier: [n] pFrame->mvbOutlier of the matched keypoints */
+void orc_pose_optimization(const orc_poseopt_problem *pb, orc_poseopt_result *res, uint8_t *outlier);
+void orc_pose_optimization_batch(int C, const orc_poseopt_problem *pbs, orc_poseopt_result *res, uint8_t **outliers);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1303,4 +1303,5 @@ int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48])
 // ------------------------------------------------- remaining solver families (same TU)
 #include "engine_sim3.inl"
 #include "engine_mlpnp.inl"
+#include "engine_poseopt.inl"
 #include "engine_nccl.inl"

@@ -150,6 +150,20 @@ struct Sim3State {
     }
 };
 
+struct PoseOptState {
+    bool uploaded = false, ran = false;
+    int C = 0;
+    int64_t total = 0;
+    DevBuf d_metas, d_p3d, d_obs, d_isig, d_outlier, d_results;
+    PinnedBuf h_metas;
+    void release()
+    {
+        DevBuf* all[] = {&d_metas, &d_p3d, &d_obs, &d_isig, &d_outlier, &d_results};
+        for (DevBuf* b : all) b->release();
+        h_metas.release();
+    }
+};
+
 struct ProfPair {
     int stage;
     cudaEvent_t a, b;
@@ -181,6 +195,7 @@ struct rsac_engine {
     rsac::PnpState mlpnp;
     rsac::ScoreState score;
     rsac::Sim3State sim3;
+    rsac::PoseOptState poseopt;
     rsac::DevBuf d_exact, d_scratch, d_resume;
     unsigned long long* last_exact = nullptr;   // diagnostic counter of the last scoring launch
     void* nccl_comm = nullptr;
@@ -203,7 +218,7 @@ struct rsac_engine {
     }
     void free_all()
     {
-        pnp.release(); mlpnp.release(); score.release(); sim3.release();
+        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release();
         d_exact.release(); d_scratch.release(); d_resume.release();
     }
 };

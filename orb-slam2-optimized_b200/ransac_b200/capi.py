@@ -70,6 +70,17 @@ class MLPnPBatch(C.Structure):
                 ("n_params", C.c_int32), ("seeds", C.c_void_p), ("tables", C.c_void_p), ("table_offsets", C.c_void_p)]
 
 
+class PoseOptBatch(C.Structure):
+    _fields_ = [("C", C.c_int32), ("offsets", C.c_void_p), ("p3d", C.c_void_p), ("obs", C.c_void_p),
+                ("inv_sigma2", C.c_void_p), ("K", C.c_void_p), ("Tcw", C.c_void_p)]
+
+
+# rsac_poseopt_result (include/ransac_b200.h)
+POSEOPT_DTYPE = np.dtype([("n_inliers", np.int32), ("n_bad", np.int32), ("rounds", np.int32), ("iterations", np.int32),
+                          ("trials", np.int32), ("reserved", np.int32), ("R", np.float64, (9,)), ("t", np.float64, (3,)),
+                          ("Rf", np.float32, (9,)), ("tf", np.float32, (3,))], align=True)
+
+
 class RsacError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__(f"ransac_b200 error {code}: {msg}")
@@ -403,6 +414,37 @@ class Engine:
         self._ck(self.L.rsac_sim3_get_hypotheses(self.h, _p(poses), _p(counts), _p(masks)), "sim3_get_hypotheses")
         return poses, counts, masks
 
+    # -- Optimizer::PoseOptimization (batched)
+    def poseopt_upload(self, offsets, p3d, obs, inv_sigma2, K, Tcw):
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        Cn = len(offsets) - 1
+        p3d = np.ascontiguousarray(p3d, np.float32).reshape(-1, 3)
+        obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3)
+        inv_sigma2 = np.ascontiguousarray(inv_sigma2, np.float32).reshape(-1)
+        K = np.ascontiguousarray(K, np.float32).reshape(-1, 5)
+        if K.shape[0] == 1 and Cn != 1:
+            K = np.ascontiguousarray(np.repeat(K, max(Cn, 1), axis=0))
+        Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 12)
+        desc = PoseOptBatch(Cn, _p(offsets), _p(p3d), _p(obs), _p(inv_sigma2), _p(K), _p(Tcw))
+        self._keep_poseopt = [offsets, p3d, obs, inv_sigma2, K, Tcw]
+        self._ck(self.L.rsac_poseopt_upload(self.h, C.byref(desc)), "poseopt_upload")
+        self._poseopt_C, self._poseopt_total = Cn, int(offsets[-1])
+        return Cn
+
+    def poseopt_run(self):
+        self._ck(self.L.rsac_poseopt_run(self.h), "poseopt_run")
+
+    def poseopt_download(self):
+        res = np.zeros(self._poseopt_C, POSEOPT_DTYPE)
+        outlier = np.zeros(max(self._poseopt_total, 1), np.uint8)
+        self._ck(self.L.rsac_poseopt_download(self.h, _p(res), _p(outlier)), "poseopt_download")
+        return res, outlier[:self._poseopt_total]
+
+    def poseopt_solve(self, offsets, p3d, obs, inv_sigma2, K, Tcw):
+        self.poseopt_upload(offsets, p3d, obs, inv_sigma2, K, Tcw)
+        self.poseopt_run()
+        return self.poseopt_download()
+
     # -- scoring stress
     def score_pnp_upload(self, poses, p3d, p2d, max_err, K):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
@@ -431,6 +473,21 @@ class Engine:
 
     def score_exact_evals(self) -> int:
         return self.L.rsac_score_exact_evals(self.h)
+
+
+def debug_host_poseopt(p3d, obs, inv_sigma2, K, Tcw):
+    """the device source of PoseOptimization compiled for the host, one frame (test hook, not a fallback)"""
+    p3d = np.ascontiguousarray(p3d, np.float32).reshape(-1, 3)
+    obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3)
+    inv_sigma2 = np.ascontiguousarray(inv_sigma2, np.float32).reshape(-1)
+    K = np.ascontiguousarray(K, np.float32).reshape(5)
+    Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(12)
+    res = np.zeros(1, POSEOPT_DTYPE)
+    outlier = np.zeros(max(p3d.shape[0], 1), np.uint8)
+    rc = lib().rsac_debug_host_poseopt(C.c_int(p3d.shape[0]), _p(p3d), _p(obs), _p(inv_sigma2), _p(K), _p(Tcw), _p(res), _p(outlier))
+    if rc:
+        raise RsacError(rc, "debug_host_poseopt")
+    return res[0], outlier[:p3d.shape[0]]
 
 
 def unpack_mask(words: np.ndarray, n: int) -> np.ndarray:

@@ -167,3 +167,34 @@ def scoring_stress(seed: int = 5000, H: int = 4096, n: int = 10000, cam=EUROC):
         poses[h, 9:] = t
     p["poses"] = poses
     return p
+
+
+def poseopt_problem(seed: int, n: int = 250, outlier_ratio: float = 0.2, stereo_ratio: float = 0.0, cam=EUROC,
+                    bf: float = 47.9, pose_noise=(0.02, 0.05)):
+    """One Optimizer::PoseOptimization input (Optimizer.cpp:244-323): matched map points, observations
+    (u, v, uR; uR < 0 for monocular keypoints), 1/sigma^2 per keypoint level, and an initial pose = ground truth
+    perturbed by a rotation of `pose_noise[0]` rad and a translation of `pose_noise[1]` m (what RANSAC + Refine
+    hands over).  Returns dict(p3d [n,3], obs [n,3], inv_sigma2 [n], K (fx,fy,cx,cy,bf) f32, Rcw [3,3] f32,
+    tcw [3] f32, R, t ground truth, inlier [n])."""
+    p = pnp_problem(seed, n, outlier_ratio, cam)
+    rng = np.random.default_rng(seed + 77_000_000)
+    Xc = p["p3d"].astype(float) @ p["R"].T + p["t"]
+    ur = np.full(n, -1.0)
+    is_st = rng.uniform(size=n) < stereo_ratio
+    ur_true = p["p2d"][:, 0].astype(float) - bf / Xc[:, 2]
+    ur[is_st] = ur_true[is_st] + rng.normal(size=int(is_st.sum())) * np.sqrt(p["sigma2"][is_st].astype(float))
+    bad = is_st & ~p["inlier"]
+    ur[bad] = rng.uniform(0, cam["width"], size=int(bad.sum()))
+    ur[is_st & (ur < 0)] = 0.0
+    d = rng.normal(size=3)
+    d /= np.linalg.norm(d)
+    dR = rodrigues(d * pose_noise[0])
+    dt = rng.normal(size=3) * pose_noise[1]
+    R0 = dR @ p["R"]
+    t0 = dR @ p["t"] + dt
+    inv_sigma2 = (np.float32(1.0) / p["sigma2"]).astype(np.float32)      # mvInvLevelSigma2 (ORBextractor.cpp:361-365)
+    obs = np.concatenate([p["p2d"], ur[:, None].astype(np.float32)], axis=1).astype(np.float32)
+    return dict(p3d=p["p3d"], obs=np.ascontiguousarray(obs), inv_sigma2=inv_sigma2,
+                K=np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"], bf], np.float32),
+                Rcw=np.ascontiguousarray(R0, np.float32), tcw=np.ascontiguousarray(t0, np.float32),
+                R=p["R"], t=p["t"], inlier=p["inlier"])

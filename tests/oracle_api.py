@@ -391,3 +391,35 @@ def pnp_score_timed(pb: _Keep, max_err, poses, nthreads=1):
     counts = np.empty(poses.shape[0], np.int32)
     dt = lib().orc_pnp_score_timed(C.byref(pb.st), _p(max_err), C.c_int(poses.shape[0]), _p(poses), C.c_int(nthreads), _p(counts))
     return dt, counts
+
+
+class PoseOptProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("p3d", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p),
+                ("K", C.c_float * 5), ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3)]
+
+
+class PoseOptResult(C.Structure):
+    _fields_ = [("n_inliers", C.c_int32), ("n_bad", C.c_int32), ("rounds", C.c_int32), ("iterations", C.c_int32),
+                ("trials", C.c_int32), ("reserved", C.c_int32), ("R", C.c_double * 9), ("t", C.c_double * 3),
+                ("Rf", C.c_float * 9), ("tf", C.c_float * 3)]
+
+
+def poseopt_problem(p3d, obs, inv_sigma2, K, Rcw, tcw):
+    p3d, obs, inv_sigma2 = _f32(p3d), _f32(obs), _f32(inv_sigma2)
+    st = PoseOptProblem(int(p3d.shape[0]), _p(p3d), _p(obs), _p(inv_sigma2), (C.c_float * 5)(*[float(k) for k in K]),
+                        (C.c_float * 9)(*[float(x) for x in np.asarray(Rcw, np.float32).ravel()]),
+                        (C.c_float * 3)(*[float(x) for x in np.asarray(tcw, np.float32).ravel()]))
+    return _Keep(st, p3d, obs, inv_sigma2)
+
+
+def pose_optimization(pb: _Keep):
+    """Optimizer::PoseOptimization on one frame -> (dict, outlier flags uint8 [n])"""
+    res = PoseOptResult()
+    out = np.zeros(max(pb.st.n, 1), np.uint8)
+    lib().orc_pose_optimization(C.byref(pb.st), C.byref(res), _p(out))
+    d = {k: getattr(res, k) for k in ("n_inliers", "n_bad", "rounds", "iterations", "trials")}
+    d["R"] = np.array(res.R).reshape(3, 3)
+    d["t"] = np.array(res.t)
+    d["Rf"] = np.array(res.Rf, np.float32).reshape(3, 3)
+    d["tf"] = np.array(res.tf, np.float32)
+    return d, out[:pb.st.n]
