@@ -170,19 +170,21 @@ def scoring_stress(seed: int = 5000, H: int = 4096, n: int = 10000, cam=EUROC):
 
 
 def poseopt_problem(seed: int, n: int = 250, outlier_ratio: float = 0.2, stereo_ratio: float = 0.0, cam=EUROC,
-                    bf: float = 47.9, pose_noise=(0.02, 0.05)):
+                    bf: float = 47.9, pose_noise=(0.02, 0.05), noise_scale: float = 1.0):
     """One Optimizer::PoseOptimization input (Optimizer.cpp:244-323): matched map points, observations
     (u, v, uR; uR < 0 for monocular keypoints), 1/sigma^2 per keypoint level, and an initial pose = ground truth
     perturbed by a rotation of `pose_noise[0]` rad and a translation of `pose_noise[1]` m (what RANSAC + Refine
-    hands over).  Returns dict(p3d [n,3], obs [n,3], inv_sigma2 [n], K (fx,fy,cx,cy,bf) f32, Rcw [3,3] f32,
+    hands over); inlier pixel noise is `noise_scale` x the level's sigma.  Returns dict(p3d [n,3], obs [n,3], inv_sigma2 [n], K (fx,fy,cx,cy,bf) f32, Rcw [3,3] f32,
     tcw [3] f32, R, t ground truth, inlier [n])."""
-    p = pnp_problem(seed, n, outlier_ratio, cam)
+    p = pnp_problem(seed, n, outlier_ratio, cam, noise=False)
     rng = np.random.default_rng(seed + 77_000_000)
+    sig = np.sqrt(p["sigma2"].astype(float)) * noise_scale
+    p["p2d"] = (p["p2d"] + np.where(p["inlier"][:, None], rng.normal(size=(n, 2)) * sig[:, None], 0.0)).astype(np.float32)
     Xc = p["p3d"].astype(float) @ p["R"].T + p["t"]
     ur = np.full(n, -1.0)
     is_st = rng.uniform(size=n) < stereo_ratio
     ur_true = p["p2d"][:, 0].astype(float) - bf / Xc[:, 2]
-    ur[is_st] = ur_true[is_st] + rng.normal(size=int(is_st.sum())) * np.sqrt(p["sigma2"][is_st].astype(float))
+    ur[is_st] = ur_true[is_st] + rng.normal(size=int(is_st.sum())) * sig[is_st]
     bad = is_st & ~p["inlier"]
     ur[bad] = rng.uniform(0, cam["width"], size=int(bad.sum()))
     ur[is_st & (ur < 0)] = 0.0

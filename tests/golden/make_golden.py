@@ -10,6 +10,10 @@ Sources of truth, in order of independence:
                                Sim3Solver.cpp:269-293) on seeded inputs
   * oracle_frozen.npz       -- outputs of the oracle itself on the BASELINE configs (regression pin:
                                RANSAC outcomes, per-hypothesis counts, poses)
+  * poseopt_scipy.npz       -- Optimizer::PoseOptimization: scipy.optimize.least_squares optimum of the same
+                               weighted reprojection cost on outlier-free frames (every edge stays an inlier, so
+                               the reference's last, kernel-free round minimises exactly that cost), and the
+                               oracle's own outputs on noisy frames with outliers (regression pin)
 The reference cannot be run to generate vectors: it needs Eigen/OpenCV C++ headers.
 """
 import ctypes
@@ -119,10 +123,52 @@ def oracle_frozen():
     np.savez_compressed(os.path.join(HERE, "oracle_frozen.npz"), **out)
 
 
+def _poseopt_cases():
+    return [dict(seed=9500 + i, n=n, outl=0.0, stereo=sr, noise_scale=0.3) for i, (n, sr) in
+            enumerate([(60, 0.0), (200, 0.0), (200, 1.0), (400, 0.5)])]
+
+
+def poseopt_scipy():
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+
+    out = {}
+    for k, c in enumerate(_poseopt_cases()):
+        p = synth.poseopt_problem(c["seed"], c["n"], c["outl"], c["stereo"], noise_scale=c["noise_scale"])
+        X = p["p3d"].astype(np.float64)
+        obs = p["obs"].astype(np.float64)
+        w = np.sqrt(p["inv_sigma2"].astype(np.float64))
+        fx, fy, cx, cy, bf = [float(v) for v in p["K"]]
+        st = obs[:, 2] >= 0
+
+        def resid(x):
+            R = Rotation.from_rotvec(x[:3]).as_matrix()
+            Xc = X @ R.T + x[3:]
+            u = fx * Xc[:, 0] / Xc[:, 2] + cx
+            v = fy * Xc[:, 1] / Xc[:, 2] + cy
+            r = [w * (obs[:, 0] - u), w * (obs[:, 1] - v), np.where(st, w * (obs[:, 2] - (u - bf / Xc[:, 2])), 0.0)]
+            return np.concatenate(r)
+
+        x0 = np.concatenate([Rotation.from_matrix(p["Rcw"].astype(np.float64)).as_rotvec(), p["tcw"].astype(np.float64)])
+        sol = least_squares(resid, x0, method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15)
+        out[f"case{k}_R"] = Rotation.from_rotvec(sol.x[:3]).as_matrix()
+        out[f"case{k}_t"] = sol.x[3:]
+        out[f"case{k}_cost"] = 2.0 * sol.cost
+    # regression pin: the oracle on noisy frames with outliers, monocular / stereo / mixed
+    for k, (seed, n, outl, sr) in enumerate([(9600, 250, 0.2, 0.0), (9601, 250, 0.3, 1.0), (9602, 500, 0.4, 0.5), (9603, 9, 0.2, 0.0)]):
+        p = synth.poseopt_problem(seed, n, outl, sr)
+        d, o = O.pose_optimization(O.poseopt_problem(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], p["Rcw"], p["tcw"]))
+        out[f"frozen{k}_R"] = d["R"]; out[f"frozen{k}_t"] = d["t"]; out[f"frozen{k}_outlier"] = o
+        out[f"frozen{k}_meta"] = np.array([d["n_inliers"], d["n_bad"], d["rounds"], d["iterations"], d["trials"]])
+    np.savez_compressed(os.path.join(HERE, "poseopt_scipy.npz"), **out)
+
+
 if __name__ == "__main__":
     O.build()
-    if "frozen" in sys.argv:      # after a deliberate change of the arithmetic contract: only the regression pin
+    if "poseopt" in sys.argv:
+        poseopt_scipy()
+    elif "frozen" in sys.argv:      # after a deliberate change of the arithmetic contract: only the regression pin
         oracle_frozen()
     else:
-        rng(); cv2_epnp(); scoring_numpy(); oracle_frozen()
+        rng(); cv2_epnp(); scoring_numpy(); oracle_frozen(); poseopt_scipy()
     print(sorted(os.listdir(HERE)))

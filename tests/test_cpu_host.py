@@ -137,6 +137,24 @@ def test_host_compiled_core_is_bit_identical_to_oracle(built_lib, oracle):
             assert np.array_equal(R.view(np.uint64), Ro.reshape(-1).view(np.uint64)) and np.array_equal(t.view(np.uint64), to.view(np.uint64))
 
 
+def test_host_compiled_poseopt_is_bit_identical_to_oracle(built_lib, oracle):
+    """csrc/poseopt.cuh compiled for the host with one lane (edges summed in order) against oracle/orc_poseopt.c:
+    separate sources, same operation sequence, same libm -> identical poses, flags and step-control trajectory"""
+    from ransac_b200 import capi, synth
+
+    for seed, n, outl, sr, pn in [(1, 250, 0.2, 0.0, (0.02, 0.05)), (2, 250, 0.3, 0.5, (0.02, 0.05)), (3, 400, 0.3, 1.0, (0.02, 0.05)),
+                                  (4, 8, 0.2, 0.3, (0.02, 0.05)), (5, 2, 0.0, 0.0, (0.02, 0.05)), (6, 1200, 0.2, 0.2, (0.02, 0.05)),
+                                  (7, 0, 0.0, 0.0, (0.02, 0.05)), (8, 200, 0.5, 0.0, (0.3, 1.0)), (9, 200, 0.5, 1.0, (0.3, 1.0))]:
+        p = synth.poseopt_problem(seed, n, outl, sr, pose_noise=pn)
+        d, out = oracle.pose_optimization(oracle.poseopt_problem(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], p["Rcw"], p["tcw"]))
+        r, o2 = capi.debug_host_poseopt(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], np.concatenate([p["Rcw"].ravel(), p["tcw"]]))
+        for k in ("n_inliers", "n_bad", "rounds", "iterations", "trials"):
+            assert int(r[k]) == int(d[k]), (seed, k)
+        assert np.array_equal(r["R"], d["R"].ravel()) and np.array_equal(r["t"], d["t"]), seed
+        assert np.array_equal(r["Rf"], d["Rf"].ravel()) and np.array_equal(r["tf"], d["tf"]), seed
+        assert np.array_equal(out, o2), seed
+
+
 def test_no_gpu_means_loud_failure_not_fallback(built_lib):
     if _has_gpu():
         pytest.skip("a CUDA device is present")

@@ -329,3 +329,64 @@ def test_oracle_frozen_vectors(oracle):
     assert (r["hyp_counts"] == g["cfg2_counts"]).all()
     assert np.allclose(r["hyp_pose"], g["cfg2_pose"], rtol=1e-12, atol=1e-14, equal_nan=True)
     assert [r["ok"], r["n_inliers"], r["best_hyp"], r["refined"], r["n_refines"]] == g["cfg2_meta"].tolist()
+
+
+# ------------------------------------------------ Optimizer::PoseOptimization
+def _po(oracle, p):
+    return oracle.pose_optimization(oracle.poseopt_problem(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], p["Rcw"], p["tcw"]))
+
+
+def test_poseopt_matches_scipy_least_squares_on_outlier_free_frames(oracle):
+    """every edge stays an inlier, so the last (kernel-free) round minimises the plain weighted reprojection cost:
+    scipy's Levenberg-Marquardt optimum frozen in tests/golden/poseopt_scipy.npz (made by make_golden.py) is an
+    independent pin.  Stereo edges use a float 1/z in the reference (types_six_dof_expmap.cpp:300), scipy a double
+    one, hence the looser bound there."""
+    cases = [dict(seed=9500 + i, n=n, outl=0.0, stereo=sr, noise_scale=0.3) for i, (n, sr) in
+             enumerate([(60, 0.0), (200, 0.0), (200, 1.0), (400, 0.5)])]     # = make_golden._poseopt_cases()
+    g = np.load(os.path.join(GOLD, "poseopt_scipy.npz"))
+    for k, c in enumerate(cases):
+        p = synth.poseopt_problem(c["seed"], c["n"], c["outl"], c["stereo"], noise_scale=c["noise_scale"])
+        d, out = _po(oracle, p)
+        assert d["n_bad"] == 0 and d["rounds"] == 4 and not out.any()
+        tol = 1e-8 if c["stereo"] == 0.0 else 5e-6
+        assert np.abs(d["R"] - g[f"case{k}_R"]).max() < tol, k
+        assert np.abs(d["t"] - g[f"case{k}_t"]).max() < tol, k
+        assert np.abs(d["R"] - p["R"]).max() < 1e-3          # and that optimum is the ground truth up to the noise
+
+
+def test_poseopt_rejects_gross_outliers_and_recovers_the_pose(oracle):
+    for seed, sr in ((9700, 0.0), (9701, 1.0), (9702, 0.4)):
+        p = synth.poseopt_problem(seed, 300, 0.3, sr)
+        d, out = _po(oracle, p)
+        gross = ~p["inlier"]
+        assert out[gross].mean() > 0.97                       # a random pixel is almost never within the chi2 gate
+        assert out[~gross].mean() < 0.12                      # ~5 % (mono) of true inliers exceed a 95 % gate
+        assert d["n_inliers"] == 300 - int(out.sum()) and d["n_bad"] == int(out.sum())
+        assert np.abs(d["R"] - p["R"]).max() < 5e-3 and np.abs(d["t"] - p["t"]).max() < 5e-2
+        assert np.abs(d["R"] @ d["R"].T - np.eye(3)).max() < 1e-12
+        assert np.array_equal(d["Rf"], d["R"].astype(np.float32)) and np.array_equal(d["tf"], d["t"].astype(np.float32))
+
+
+def test_poseopt_control_flow_edge_cases(oracle):
+    # fewer than 3 correspondences: return 0, pose untouched (Optimizer.cpp:326-327)
+    p = synth.poseopt_problem(9710, 2, 0.0)
+    d, out = _po(oracle, p)
+    assert d["n_inliers"] == 0 and d["rounds"] == 0 and d["iterations"] == 0
+    assert np.abs(d["R"] - p["Rcw"].astype(np.float64)).max() < 1e-6
+    # fewer than 10 edges: one round only (Optimizer.cpp:409-410)
+    d, _ = _po(oracle, synth.poseopt_problem(9711, 9, 0.0))
+    assert d["rounds"] == 1
+    d, _ = _po(oracle, synth.poseopt_problem(9712, 10, 0.0))
+    assert d["rounds"] == 4
+    # every round restarts from the initial pose: at most 10 LM iterations per round, rejected trials on top
+    d, _ = _po(oracle, synth.poseopt_problem(9713, 200, 0.5, pose_noise=(0.3, 1.0)))
+    assert d["iterations"] <= 40 and d["trials"] >= d["iterations"]
+
+
+def test_poseopt_frozen_vectors(oracle):
+    g = np.load(os.path.join(GOLD, "poseopt_scipy.npz"))
+    for k, (seed, n, outl, sr) in enumerate([(9600, 250, 0.2, 0.0), (9601, 250, 0.3, 1.0), (9602, 500, 0.4, 0.5), (9603, 9, 0.2, 0.0)]):
+        d, out = _po(oracle, synth.poseopt_problem(seed, n, outl, sr))
+        assert np.allclose(d["R"], g[f"frozen{k}_R"], rtol=0, atol=1e-9) and np.allclose(d["t"], g[f"frozen{k}_t"], rtol=0, atol=1e-9)
+        assert (out != g[f"frozen{k}_outlier"]).sum() <= 1
+        assert [d["n_inliers"], d["n_bad"], d["rounds"]] == g[f"frozen{k}_meta"][:3].tolist() or (out != g[f"frozen{k}_outlier"]).sum() == 1
