@@ -552,4 +552,83 @@ private:
     std::vector<uint32_t> hmasks_;
 };
 
+// =========================================================================== Optimizer
+// Mirror of `int Optimizer::PoseOptimization(Frame* pFrame)` (include/Optimizer.hpp, src/Optimizer.cpp:205-424):
+// reads pFrame->mTcw, mvpMapPoints, mvKeysUn, mvuRight, mvInvLevelSigma2, fx/fy/cx/cy/mbf; writes pFrame->mvbOutlier
+// for every keypoint that has a MapPoint, sets the pose (Frame::SetPose) and returns nInitialCorrespondences - nBad.
+// Tracking::Relocalization calls it for every candidate RANSAC accepts (Tracking.cpp:1284,1300,1315):
+// `PoseOptimizationBatch` optimises all of them in one device pass.
+struct PoseOptFrame {
+    // in
+    int n_keypoints = 0;                       // pFrame->N
+    const float* keys_xy = nullptr;            // [N][2] mvKeysUn[i].pt
+    const int* octave = nullptr;               // [N]    mvKeysUn[i].octave
+    const float* u_right = nullptr;            // [N]    mvuRight[i] (< 0: monocular); nullptr = all monocular
+    const float* inv_level_sigma2 = nullptr;   // mvInvLevelSigma2
+    const unsigned char* has_map_point = nullptr;  // [N] pFrame->mvpMapPoints[i] != nullptr
+    const float* world_pos = nullptr;          // [N][3] pMP->GetWorldPos()
+    float fx = 0, fy = 0, cx = 0, cy = 0, bf = 0;
+    // in/out
+    Matrix4f Tcw;                              // pFrame->mTcw (SetPose on return)
+    std::vector<bool>* outlier = nullptr;      // pFrame->mvbOutlier (size N; entries with a MapPoint are written)
+    // out
+    int n_inliers = 0;                         // return value
+};
+
+class Optimizer {
+public:
+    static int PoseOptimization(PoseOptFrame* pFrame, Engine& engine = Engine::Default())
+    {
+        std::vector<PoseOptFrame*> v{pFrame};
+        PoseOptimizationBatch(v, engine);
+        return pFrame->n_inliers;
+    }
+
+    static void PoseOptimizationBatch(const std::vector<PoseOptFrame*>& frames, Engine& engine = Engine::Default())
+    {
+        if (frames.empty()) return;
+        std::lock_guard<std::mutex> lock(engine.mutex());
+        const int C = (int)frames.size();
+        std::vector<int32_t> offsets(C + 1, 0);
+        std::vector<float> p3d, obs, isig, K, T;
+        std::vector<std::vector<int>> index(C);
+        for (int c = 0; c < C; ++c) {
+            const PoseOptFrame& f = *frames[c];
+            for (int i = 0; i < f.n_keypoints; ++i) {
+                if (!f.has_map_point[i]) continue;
+                index[c].push_back(i);
+                p3d.insert(p3d.end(), f.world_pos + 3 * i, f.world_pos + 3 * i + 3);
+                obs.push_back(f.keys_xy[2 * i]);
+                obs.push_back(f.keys_xy[2 * i + 1]);
+                obs.push_back(f.u_right ? f.u_right[i] : -1.0f);
+                isig.push_back(f.inv_level_sigma2[f.octave[i]]);
+            }
+            offsets[c + 1] = offsets[c] + (int32_t)index[c].size();
+            const float k[5] = {f.fx, f.fy, f.cx, f.cy, f.bf};
+            K.insert(K.end(), k, k + 5);
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q) T.push_back(f.Tcw(r, q));
+            for (int r = 0; r < 3; ++r) T.push_back(f.Tcw(r, 3));
+        }
+        rsac_poseopt_batch b;
+        std::memset(&b, 0, sizeof(b));
+        b.C = C; b.offsets = offsets.data(); b.p3d = p3d.data(); b.obs = obs.data(); b.inv_sigma2 = isig.data();
+        b.K = K.data(); b.Tcw = T.data();
+        std::vector<rsac_poseopt_result> res(C);
+        std::vector<uint8_t> out((size_t)std::max(offsets[C], 1));
+        check(rsac_poseopt_solve(engine.handle(), &b, res.data(), out.data()), engine.handle(), "rsac_poseopt_solve");
+        for (int c = 0; c < C; ++c) {
+            PoseOptFrame& f = *frames[c];
+            f.n_inliers = res[c].n_inliers;
+            if (f.outlier)
+                for (size_t k = 0; k < index[c].size(); ++k) (*f.outlier)[(size_t)index[c][k]] = out[(size_t)offsets[c] + k] != 0;
+            if (index[c].size() < 3) continue;      // `return 0` before the pose is touched (Optimizer.cpp:326-327)
+            for (int r = 0; r < 3; ++r) {
+                for (int q = 0; q < 3; ++q) f.Tcw.m[4 * r + q] = res[c].Rf[3 * r + q];
+                f.Tcw.m[4 * r + 3] = res[c].tf[r];
+            }
+        }
+    }
+};
+
 }  // namespace ransac_b200

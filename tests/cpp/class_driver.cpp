@@ -67,7 +67,7 @@ static FrameData read_frame(std::ifstream& f)
 
 int main(int argc, char** argv)
 {
-    if (argc < 3) { std::fprintf(stderr, "usage: class_driver pnp|pnp_batch|mlpnp|sim3 file\n"); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: class_driver pnp|pnp_batch|mlpnp|sim3|poseopt file\n"); return 2; }
     const std::string mode = argv[1];
     std::ifstream f(argv[2], std::ios::binary);
     if (!f) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
@@ -161,6 +161,40 @@ int main(int argc, char** argv)
                 std::printf("}\n");
                 if (ok || noMore) break;
             }
+        }
+        else if (mode == "poseopt") {
+            // Optimizer::PoseOptimization(&frame) per candidate, as Tracking.cpp:1284 does, in one batch
+            int C;
+            rd(f, &C, 1);
+            struct Data { int n; float K[5]; float T[12]; std::vector<float> xy, ur, world, isig; std::vector<int> oct; std::vector<unsigned char> has; std::vector<bool> outl; };
+            std::vector<Data> ds(C);
+            std::vector<PoseOptFrame> frames(C);
+            std::vector<PoseOptFrame*> ptrs;
+            for (int c = 0; c < C; ++c) {
+                Data& d = ds[c];
+                rd(f, &d.n, 1); rd(f, d.K, 5); rd(f, d.T, 12);
+                d.xy.resize(2 * d.n); d.ur.resize(d.n); d.world.resize(3 * d.n); d.isig.resize(8); d.oct.resize(d.n); d.has.resize(d.n);
+                rd(f, d.xy.data(), d.xy.size()); rd(f, d.ur.data(), d.n); rd(f, d.oct.data(), d.n); rd(f, d.has.data(), d.n);
+                rd(f, d.world.data(), d.world.size()); rd(f, d.isig.data(), 8);
+                d.outl.assign(d.n, true);             // stale flags: only keypoints with a MapPoint are rewritten
+                PoseOptFrame& F = frames[c];
+                F.n_keypoints = d.n; F.keys_xy = d.xy.data(); F.octave = d.oct.data(); F.u_right = d.ur.data();
+                F.inv_level_sigma2 = d.isig.data(); F.has_map_point = d.has.data(); F.world_pos = d.world.data();
+                F.fx = d.K[0]; F.fy = d.K[1]; F.cx = d.K[2]; F.cy = d.K[3]; F.bf = d.K[4];
+                for (int r = 0; r < 3; ++r) { for (int q = 0; q < 3; ++q) F.Tcw(r, q) = d.T[3 * r + q]; F.Tcw(r, 3) = d.T[9 + r]; }
+                F.outlier = &d.outl;
+                ptrs.push_back(&F);
+            }
+            Optimizer::PoseOptimizationBatch(ptrs);
+            const int single = Optimizer::PoseOptimization(ptrs[0]) ;   // the per-frame form, from the optimised pose
+            for (int c = 0; c < C; ++c) {
+                std::printf("{\"cand\":%d,\"nInliers\":%d,\"T\":", c, c == 0 ? -1 : frames[c].n_inliers);
+                print_T(frames[c].Tcw);
+                std::printf(",\"outliers\":");
+                print_inliers(ds[c].outl);
+                std::printf("}\n");
+            }
+            std::printf("{\"single\":%d}\n", single);
         }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());

@@ -179,3 +179,58 @@ def test_sim3solver_iterate_five_at_a_time(driver, oracle, tmp_path, scale):
     assert np.array_equal(np.array(g["R"], np.float32), o["T"][:3, :3].reshape(-1)) and np.array_equal(np.array(g["t"], np.float32), o["T"][:3, 3])
     assert np.float32(g["s"]) == np.float32(o["scale"])
     assert g["inliers"] == slot_of[np.flatnonzero(o["mask"])].tolist()
+
+
+def test_optimizer_pose_optimization_batch_and_single(driver, oracle, tmp_path):
+    """Optimizer::PoseOptimization(Frame*) mirror: frames with empty keypoint slots, stale mvbOutlier flags,
+    monocular and stereo keypoints; one batched call for all candidates, then the per-frame form again on
+    candidate 0 from its optimised pose (Tracking.cpp:1284 then :1300)."""
+    rng = np.random.default_rng(77)
+    C = 6
+    blob = struct.pack("<i", C)
+    frames = []
+    for c in range(C):
+        n = [250, 300, 120, 8, 2, 400][c]
+        p = synth.poseopt_problem(9800 + c, n, 0.25, [0.0, 1.0, 0.5, 0.0, 0.0, 0.3][c])
+        n_slots = n + 60
+        slot_of = np.sort(rng.permutation(n_slots)[:n])
+        octave_of = np.array([int(np.argmin(np.abs(synth.level_sigma2() - 1.0 / s))) for s in p["inv_sigma2"]], np.int32)
+        xy = rng.uniform(0, 700, size=(n_slots, 2)).astype(np.float32)
+        ur = np.full(n_slots, -1.0, np.float32)
+        octv = rng.integers(0, 8, size=n_slots).astype(np.int32)
+        has = np.zeros(n_slots, np.uint8)
+        world = rng.normal(size=(n_slots, 3)).astype(np.float32)
+        xy[slot_of] = p["obs"][:, :2]
+        ur[slot_of] = p["obs"][:, 2]
+        octv[slot_of] = octave_of
+        has[slot_of] = 1
+        world[slot_of] = p["p3d"]
+        isig = (np.float32(1.0) / synth.level_sigma2()).astype(np.float32)
+        assert np.array_equal(isig[octave_of], p["inv_sigma2"])
+        T = np.concatenate([p["Rcw"].ravel(), p["tcw"]]).astype(np.float32)
+        blob += struct.pack("<i", n_slots) + p["K"].tobytes() + T.tobytes() + xy.tobytes() + ur.tobytes() + octv.tobytes() \
+            + has.tobytes() + world.tobytes() + isig.tobytes()
+        frames.append((p, slot_of, n_slots))
+    lines = _run(driver, "poseopt", blob, tmp_path)
+    assert len(lines) == C + 1
+    for c, (p, slot_of, n_slots) in enumerate(frames):
+        o, oout = oracle.pose_optimization(oracle.poseopt_problem(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], p["Rcw"], p["tcw"]))
+        n = len(p["p3d"])
+        if c == 0:      # optimised twice: replay the second call from the first call's float pose
+            o2, oout = oracle.pose_optimization(oracle.poseopt_problem(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], o["Rf"], o["tf"]))
+            assert abs(lines[C]["single"] - o2["n_inliers"]) <= 1
+            o = o2
+        else:
+            assert abs(lines[c]["nInliers"] - o["n_inliers"]) <= 1, c
+        T = np.array(lines[c]["T"], np.float32).reshape(4, 4)
+        if n >= 3:
+            assert np.abs(T[:3, :3] - o["Rf"]).max() < 2e-6 and np.abs(T[:3, 3] - o["tf"]).max() < 2e-5, c
+        else:           # returned before the pose was touched
+            assert np.array_equal(T[:3, :3], p["Rcw"]) and np.array_equal(T[:3, 3], p["tcw"]), c
+        assert np.array_equal(T[3], np.array([0, 0, 0, 1], np.float32))
+        flags = np.zeros(n_slots, bool)
+        flags[lines[c]["outliers"]] = True
+        empty = np.ones(n_slots, bool)
+        empty[slot_of] = False
+        assert flags[empty].all()                                   # slots without a MapPoint keep their stale flag
+        assert (flags[slot_of] != oout.astype(bool)).sum() <= 1, c  # at most one edge on the chi2 boundary
