@@ -695,6 +695,44 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                                         "evals_per_s": C3 * H3 * 200 / (ms3 * 1e-3)}
     except Exception as err:   # the headline line must still be printed
         ex["cfg2_cfg3_error"] = repr(err)
+    # ---- Optimizer::PoseOptimization for every candidate of a cfg4-sized sweep (1024 frames x 250 matched
+    # map points, 20 % outliers, monocular), one warp per frame; CPU port on a 64-frame sample beside it
+    try:
+        CP, NP = 1024, 250
+        pp = [synth.poseopt_problem(4000 + i, NP, 0.2, 0.0) for i in range(CP)]
+        offp = (np.arange(CP + 1) * NP).astype(np.int32)
+        catp = lambda k: np.concatenate([q[k] for q in pp])
+        Kp = np.stack([q["K"] for q in pp])
+        Tp = np.stack([np.concatenate([q["Rcw"].ravel(), q["tcw"]]) for q in pp])
+        argsp = (offp, catp("p3d"), catp("obs"), catp("inv_sigma2"), Kp, Tp)
+        eng.poseopt_upload(*argsp)
+        for _ in range(3):
+            eng.poseopt_run()
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(20):
+            eng.poseopt_run()
+        msp = eng.timer_end() / 20
+        resp, _ = eng.poseopt_download()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            eng.poseopt_solve(*argsp)
+        dte = (time.perf_counter() - t0) / 10
+        passes = float(resp["iterations"].sum() + resp["trials"].sum()) * NP       # edge visits of the LM loops
+        import oracle_api as _O          # CPU baseline only (bench.py cpu_baseline leg)
+        pbs = [_O.poseopt_problem(q["p3d"], q["obs"], q["inv_sigma2"], q["K"], q["Rcw"], q["tcw"]) for q in pp[:64]]
+        t0 = time.perf_counter()
+        for pb in pbs:
+            _O.pose_optimization(pb)
+        dtc = (time.perf_counter() - t0) / len(pbs)
+        ex["pose_optimization"] = {"frames": CP, "edges_per_frame": NP, "ms_per_batch": msp, "frames_per_s": CP / (msp * 1e-3),
+                                   "e2e_ms_per_batch": dte * 1e3, "e2e_frames_per_s": CP / dte,
+                                   "lm_iterations_mean": float(resp["iterations"].mean()), "lm_trials_mean": float(resp["trials"].mean()),
+                                   "edge_visits_per_s": passes / (msp * 1e-3), "inliers_mean": float(resp["n_inliers"].mean()),
+                                   "cpu_port_single_thread_frames_per_s": 1.0 / dtc,
+                                   "note": "Optimizer.cpp:205-424 batched; e2e = upload from host buffers + kernel + records and flags back"}
+    except Exception as err:
+        ex["pose_optimization_error"] = repr(err)
     return out
 
 
