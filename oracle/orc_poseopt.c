@@ -182,17 +182,18 @@ static double edge_chi2(const double e[3], int dim, double s)
 /* no-pivot LDL^T of a symmetric positive definite 6x6; returns 0 when a pivot is not positive (isPositive() false) */
 static int ldlt6(const double Hin[36], const double b[6], double x[6])
 {
-    double L[36], d[6], y[6];
+    double L[36], d[6], r[6], y[6];
     memcpy(L, Hin, sizeof L);
     for (int j = 0; j < 6; ++j) {
         double dj = L[7 * j];
         for (int k = 0; k < j; ++k) dj -= L[6 * j + k] * L[6 * j + k] * d[k];
         if (!(dj > 0.0)) return 0;
         d[j] = dj;
+        r[j] = 1.0 / dj;               /* one reciprocal per pivot (shared with the device core) */
         for (int i = j + 1; i < 6; ++i) {
             double v = L[6 * i + j];
             for (int k = 0; k < j; ++k) v -= L[6 * i + k] * L[6 * j + k] * d[k];
-            L[6 * i + j] = v / dj;
+            L[6 * i + j] = v * r[j];
         }
     }
     for (int i = 0; i < 6; ++i) {
@@ -200,7 +201,7 @@ static int ldlt6(const double Hin[36], const double b[6], double x[6])
         for (int k = 0; k < i; ++k) v -= L[6 * i + k] * y[k];
         y[i] = v;
     }
-    for (int i = 0; i < 6; ++i) y[i] /= d[i];
+    for (int i = 0; i < 6; ++i) y[i] *= r[i];
     for (int i = 5; i >= 0; --i) {
         double v = y[i];
         for (int k = i + 1; k < 6; ++k) v -= L[6 * k + i] * x[k];

@@ -95,6 +95,6 @@ int rsac_debug_host_poseopt(int n, const float* p3d, const float* obs, const flo
     for (int k = 0; k < 5; ++k) m.K[k] = K[k];
     for (int k = 0; k < 9; ++k) m.Rcw[k] = Tcw[k];
     for (int k = 0; k < 3; ++k) m.tcw[k] = Tcw[9 + k];
-    po::pose_optimization<1>(m, p3d, obs, inv_sigma2, outlier, 0, result);
+    po::pose_optimization<1>(m, p3d, obs, inv_sigma2, outlier, 0, nullptr, result);
     return RSAC_OK;
 }

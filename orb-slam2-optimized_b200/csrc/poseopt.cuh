@@ -193,24 +193,60 @@ __host__ __device__ inline double huber_delta(bool stereo)
     return stereo ? 0x1.65d4p+1 : 0x1.394ca8p+1;   // (double)(float)sqrt(7.815) = 2.7955322265625, (double)(float)sqrt(5.991) = 2.4476518630981445
 }
 
+// Sum over the 32 lanes that share a frame.  Host (LANES = 1): identity.
+// One value: shuffle butterfly (every lane ends with the identical total).  The 28 accumulators of the normal
+// equations: a butterfly would cost 280 SHFL (each with its WARPSYNC / ENDCOLLECTIVE pair, the loops around it
+// have data-dependent exits) -- instead every lane parks its partials in shared memory ([28][33] doubles, padded
+// against bank conflicts), lane k adds the 32 partials of accumulator k in lane order (two interleaved chains), and
+// all lanes read the 28 totals back: ~130 instructions, and every lane holds bit-identical totals, which the
+// redundant 6x6 solve and step control need to take the same branches.
+constexpr int kRedStride = 33;
+constexpr int kRedDoubles = 28 * kRedStride + 28;     // partials + totals, per warp
+
+template <int LANES>
+struct Reducer {
+    double* sm;     // this warp's kRedDoubles
+    __host__ __device__ inline void sum1(double& v)
+    {
 #ifdef __CUDA_ARCH__
-template <int LANES>
-__device__ inline double lane_sum(double v)
-{
-    if (LANES == 32) {
+        if (LANES == 32) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    }
-    return v;
-}
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        }
 #else
-template <int LANES>
-inline double lane_sum(double v) { return v; }
+        (void)v;
 #endif
+    }
+    __host__ __device__ inline void sum28(double* v)
+    {
+#ifdef __CUDA_ARCH__
+        if (LANES == 32) {
+            const int lane = threadIdx.x & 31;
+            __syncwarp();                                   // the previous totals have been read by every lane
+#pragma unroll
+            for (int k = 0; k < 28; ++k) sm[k * kRedStride + lane] = v[k];
+            __syncwarp();
+            if (lane < 28) {
+                const double* row = sm + lane * kRedStride;
+                double t0 = row[0], t1 = row[1];
+#pragma unroll
+                for (int l = 2; l < 32; l += 2) { t0 += row[l]; t1 += row[l + 1]; }
+                sm[28 * kRedStride + lane] = t0 + t1;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 28; ++k) v[k] = sm[28 * kRedStride + k];
+        }
+#else
+        (void)v;
+#endif
+    }
+};
 
 // computeActiveErrors + activeRobustChi2 at pose T
 template <int LANES>
-__host__ __device__ inline double active_chi2(const FrameView& f, const uint8_t* level, bool robust, const Se3& T, int lane)
+__host__ __device__ inline double active_chi2(const FrameView& f, const uint8_t* level, bool robust, const Se3& T, int lane,
+                                              Reducer<LANES>& red)
 {
     double sum = 0.0;
     for (int i = lane; i < f.n; i += LANES) {
@@ -226,19 +262,21 @@ __host__ __device__ inline double active_chi2(const FrameView& f, const uint8_t*
             sum += c;
         }
     }
-    return lane_sum<LANES>(sum);
+    red.sum1(sum);
+    return sum;
 }
 
 // errors at T + linearizeOplus + constructQuadraticForm: upper triangle of H (21), b (6), robust chi2
 template <int LANES>
 __host__ __device__ inline double build_system(const FrameView& f, const uint8_t* level, bool robust, const Se3& T, int lane,
-                                               double* H /*36, symmetric on return*/, double* b)
+                                               Reducer<LANES>& red, double* H /*36, symmetric on return*/, double* b)
 {
-    double acc[21], bb[6], chi = 0.0;
+    double all[28];                       // acc[21] | bb[6] | chi : reduced together
+    double* acc = all;
+    double* bb = all + 21;
+    double& chi = all[27];
 #pragma unroll
-    for (int k = 0; k < 21; ++k) acc[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) bb[k] = 0.0;
+    for (int k = 0; k < 28; ++k) all[k] = 0.0;
     for (int i = lane; i < f.n; i += LANES) {
         if (level[i]) continue;
         const Edge e = load_edge(f, i);
@@ -297,24 +335,25 @@ __host__ __device__ inline double build_system(const FrameView& f, const uint8_t
             }
         }
     }
+    red.sum28(all);
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-        b[a] = lane_sum<LANES>(bb[a]);
+        b[a] = bb[a];
 #pragma unroll
         for (int c2 = a; c2 < 6; ++c2) {
-            const double h = lane_sum<LANES>(acc[k++]);
+            const double h = acc[k++];
             H[6 * a + c2] = h;
             H[6 * c2 + a] = h;
         }
     }
-    return lane_sum<LANES>(chi);
+    return chi;
 }
 
 // LDL^T without pivoting of (H + lambda I); false when a pivot is not positive (Eigen LDLT::isPositive())
 __host__ __device__ inline bool ldlt6(const double* Hin, double lambda, const double* b, double* x)
 {
-    double L[36], d[6], y[6];
+    double L[36], d[6], r[6], y[6];
 #pragma unroll
     for (int i = 0; i < 36; ++i) L[i] = Hin[i];
 #pragma unroll
@@ -326,12 +365,14 @@ __host__ __device__ inline bool ldlt6(const double* Hin, double lambda, const do
         for (int k = 0; k < j; ++k) dj -= L[6 * j + k] * L[6 * j + k] * d[k];
         if (!(dj > 0.0)) return false;
         d[j] = dj;
+        const double rj = 1.0 / dj;          // one reciprocal per pivot; the column and the diagonal solve multiply by it
+        r[j] = rj;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double v = L[6 * i + j];
 #pragma unroll
             for (int k = 0; k < j; ++k) v -= L[6 * i + k] * L[6 * j + k] * d[k];
-            L[6 * i + j] = v / dj;
+            L[6 * i + j] = v * rj;
         }
     }
 #pragma unroll
@@ -342,7 +383,7 @@ __host__ __device__ inline bool ldlt6(const double* Hin, double lambda, const do
         y[i] = v;
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] /= d[i];
+    for (int i = 0; i < 6; ++i) y[i] *= r[i];
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double v = y[i];
@@ -358,14 +399,14 @@ struct Stats { int iterations, trials; };
 // SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg.  T: estimate; Terr: pose of the last error pass.
 template <int LANES>
 __host__ __device__ inline void optimize(const FrameView& f, const uint8_t* level, bool robust, Se3& T, Se3& Terr, int iterations,
-                                         int lane, Stats& st)
+                                         int lane, Reducer<LANES>& red, Stats& st)
 {
     double lambda = 0.0, ni = 2.0;
     int nBad = 0;
     double x[6] = {0, 0, 0, 0, 0, 0};
     for (int it = 0; it < iterations; ++it) {
         double H[36], b[6];
-        double currentChi = build_system<LANES>(f, level, robust, T, lane, H, b);
+        double currentChi = build_system<LANES>(f, level, robust, T, lane, red, H, b);
         Terr = T;
         const double iniChi = currentChi;
         ++st.iterations;
@@ -383,7 +424,7 @@ __host__ __device__ inline void optimize(const FrameView& f, const uint8_t* leve
             const bool ok2 = ldlt6(H, lambda, b, x);
             ++st.trials;
             se3_oplus(x, T);
-            double tempChi = active_chi2<LANES>(f, level, robust, T, lane);
+            double tempChi = active_chi2<LANES>(f, level, robust, T, lane, red);
             Terr = T;
             if (!ok2) tempChi = DBL_MAX;
             rho = currentChi - tempChi;
@@ -416,8 +457,10 @@ __host__ __device__ inline void optimize(const FrameView& f, const uint8_t* leve
 // after every classification, Optimizer.cpp:341-352).  Returns nInitialCorrespondences - nBad.
 template <int LANES>
 __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const float* p3d, const float* obs, const float* isig,
-                                                  uint8_t* outlier, int lane, rsac_poseopt_result* out)
+                                                  uint8_t* outlier, int lane, double* red_smem, rsac_poseopt_result* out)
 {
+    Reducer<LANES> red;
+    red.sm = red_smem;
     FrameView f;
     f.p3d = p3d + 3 * m.off; f.obs = obs + 3 * m.off; f.isig = isig + m.off;
     f.fx = (double)m.K[0]; f.fy = (double)m.K[1]; f.cx = (double)m.K[2]; f.cy = (double)m.K[3]; f.bf = (double)m.K[4];
@@ -426,9 +469,6 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
     Se3 T;
     se3_from_float(m.Rcw, m.tcw, T);
     for (int i = lane; i < f.n; i += LANES) flag[i] = 0;
-#ifdef __CUDA_ARCH__
-    __syncwarp();
-#endif
     Stats st = {0, 0};
     int nBad = 0, rounds = 0;
     bool robust = true;
@@ -437,7 +477,7 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
         for (int it = 0; it < 4; ++it) {
             se3_from_float(m.Rcw, m.tcw, T);
             Se3 Terr = T;
-            if (active > 0) optimize<LANES>(f, flag, robust, T, Terr, 10, lane, st);
+            if (active > 0) optimize<LANES>(f, flag, robust, T, Terr, 10, lane, red, st);
             int bad = 0;
             for (int i = lane; i < f.n; i += LANES) {
                 const Edge e = load_edge(f, i);
@@ -447,13 +487,9 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
                 flag[i] = is_out ? 1 : 0;
                 bad += is_out ? 1 : 0;
             }
-#ifdef __CUDA_ARCH__
-            if (LANES == 32) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
-            }
-            __syncwarp();
-#endif
+            double badd = (double)bad;     // exact: counts are far below 2^53
+            red.sum1(badd);
+            bad = (int)badd;
             nBad = bad;
             active = f.n - bad;
             if (it == 2) robust = false;
@@ -477,18 +513,19 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
 
 }  // namespace po
 
-constexpr int kPoseOptWarps = 4;
+constexpr int kPoseOptWarps = 4;      // frames per CTA (one warp per frame)
 
-// one warp per frame, kPoseOptWarps frames per CTA
 __global__ void __launch_bounds__(kPoseOptWarps * 32) poseopt_kernel(const PoseOptMeta* __restrict__ metas, int C,
                                                                      const float* __restrict__ p3d, const float* __restrict__ obs,
                                                                      const float* __restrict__ isig, uint8_t* __restrict__ outlier,
                                                                      rsac_poseopt_result* __restrict__ results)
 {
-    const int c = blockIdx.x * kPoseOptWarps + (threadIdx.x >> 5);
+    __shared__ double red_smem[kPoseOptWarps * po::kRedDoubles];
+    const int w = threadIdx.x >> 5;
+    const int c = blockIdx.x * kPoseOptWarps + w;
     if (c >= C) return;
     const PoseOptMeta m = metas[c];
-    po::pose_optimization<32>(m, p3d, obs, isig, outlier, threadIdx.x & 31, results + c);
+    po::pose_optimization<32>(m, p3d, obs, isig, outlier, threadIdx.x & 31, red_smem + w * po::kRedDoubles, results + c);
 }
 
 }  // namespace rsac
