@@ -282,15 +282,25 @@ static void build_system(const graph_t *g, const se3_t *T, double H[36], double 
             const double delta = (double)(dim == 2 ? sqrtf(5.991f) : sqrtf(7.815f));
             if (c > delta * delta) rho1 = delta / sqrt(c);
         }
+        /* explicit fused multiply-adds (arithmetic contract shared with csrc/poseopt.cuh); the exact zeros of the
+         * Jacobian (column 4 of rows 0 and 2, column 3 of row 1) are skipped */
         const double wo = rho1 * s;
+        const int st = dim == 3;
+        double w0[6], w1[6], w2[6];
+        for (int c2 = 0; c2 < 6; ++c2) { w0[c2] = wo * J[c2]; w1[c2] = wo * J[6 + c2]; w2[c2] = st ? wo * J[12 + c2] : 0.0; }
+        const double we0 = s * e[0], we1 = s * e[1], we2 = s * e[2];
         for (int a = 0; a < 6; ++a) {
             double be = 0.0;
-            for (int rr = 0; rr < dim; ++rr) be += J[6 * rr + a] * (s * e[rr]);
+            if (a != 4) be = J[a] * we0;
+            if (a != 3) be = fma(J[6 + a], we1, be);
+            if (st && a != 4) be = fma(J[12 + a], we2, be);
             b[a] -= rho1 * be;
             for (int c2 = a; c2 < 6; ++c2) {
-                double h = 0.0;
-                for (int rr = 0; rr < dim; ++rr) h += J[6 * rr + a] * (wo * J[6 * rr + c2]);
-                H[6 * a + c2] += h;
+                double h = H[6 * a + c2];
+                if (a != 4 && c2 != 4) h = fma(J[a], w0[c2], h);
+                if (a != 3 && c2 != 3) h = fma(J[6 + a], w1[c2], h);
+                if (st && a != 4 && c2 != 4) h = fma(J[12 + a], w2[c2], h);
+                H[6 * a + c2] = h;
             }
         }
     }

@@ -40,6 +40,8 @@ struct Se3 { double q[4]; double t[3]; };   // quaternion (w, x, y, z) + transla
 
 namespace po {
 
+__host__ __device__ inline double po_fma(double a, double b, double c) { return fma(a, b, c); }   // twin: fma() in oracle/orc_poseopt.c
+
 __host__ __device__ inline void quat_from_rot(const double* m, double* q)
 {
     double t = m[0] + m[4] + m[8];
@@ -317,21 +319,29 @@ __host__ __device__ inline double build_system(const FrameView& f, const uint8_t
 #pragma unroll
             for (int k = 12; k < 18; ++k) J[k] = 0.0;
         }
+        // constructQuadraticForm: H += J^T (rho' Omega) J, b -= rho' J^T Omega e, accumulated with explicit fused
+        // multiply-adds (arithmetic contract).  Column 4 of rows 0 and 2 and column 3 of row 1 are exact
+        // zeros (J[4] = J[9] = J[16] = 0): their products are skipped -- 30 of 42 (45 of 63 with the stereo row) remain.
         const double wo = rho1 * e.s;
-        const int dim = stereo ? 3 : 2;
+        double w0[6], w1[6], w2[6];
+#pragma unroll
+        for (int c2 = 0; c2 < 6; ++c2) { w0[c2] = wo * J[c2]; w1[c2] = wo * J[6 + c2]; w2[c2] = wo * J[12 + c2]; }
+        const double we0 = e.s * er[0], we1 = e.s * er[1], we2 = e.s * er[2];
         int k = 0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            double be = J[a] * (e.s * er[0]);
-            be += J[6 + a] * (e.s * er[1]);
-            if (dim == 3) be += J[12 + a] * (e.s * er[2]);
+            double be = 0.0;
+            if (a != 4) be = J[a] * we0;
+            if (a != 3) be = po_fma(J[6 + a], we1, be);
+            if (stereo && a != 4) be = po_fma(J[12 + a], we2, be);
             bb[a] -= rho1 * be;
 #pragma unroll
             for (int c2 = a; c2 < 6; ++c2) {
-                double h = J[a] * (wo * J[c2]);
-                h += J[6 + a] * (wo * J[6 + c2]);
-                if (dim == 3) h += J[12 + a] * (wo * J[12 + c2]);
-                acc[k++] += h;
+                double h = acc[k];
+                if (a != 4 && c2 != 4) h = po_fma(J[a], w0[c2], h);
+                if (a != 3 && c2 != 3) h = po_fma(J[6 + a], w1[c2], h);
+                if (stereo && a != 4 && c2 != 4) h = po_fma(J[12 + a], w2[c2], h);
+                acc[k++] = h;
             }
         }
     }
