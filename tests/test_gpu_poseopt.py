@@ -89,6 +89,37 @@ def test_poseopt_bad_initial_pose_and_heavy_outliers(engine, oracle):
     assert (res["trials"] > res["iterations"]).any()
 
 
+def test_poseopt_points_behind_the_camera_and_non_finite_input(engine, oracle):
+    """no positive-depth test in the reference (EdgeSE3ProjectXYZOnlyPose::isDepthPositive is never called): a point
+    behind the camera or at the camera centre is an ordinary (huge) residual; a NaN observation or an infinite point
+    makes every chi2 sum NaN, every LM step is rejected (rho > 0 is false), the pose stays where it started and the NaN
+    edge counts as an inlier (`chi2 > th` is false) -- the kernel must do exactly the same."""
+    ps = []
+    for k in range(4):
+        p = synth.poseopt_problem(9400 + k, 120, 0.2, 0.5 * (k % 2))
+        cam_centre = -(p["R"].T @ p["t"])
+        p["p3d"][3] = (cam_centre + p["R"].T @ np.array([0.1, 0.2, -3.0])).astype(np.float32)
+        p["p3d"][7] = cam_centre.astype(np.float32)
+        if k >= 2:
+            p["obs"][11, 0] = np.nan
+            p["p3d"][15] = np.float32(np.inf)
+        ps.append(p)
+    sizes = [120] * 4
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    cat = lambda k: np.concatenate([p[k] for p in ps])
+    res, outlier = engine.poseopt_solve(offsets, cat("p3d"), cat("obs"), cat("inv_sigma2"), np.stack([p["K"] for p in ps]),
+                                        np.stack([np.concatenate([p["Rcw"].ravel(), p["tcw"]]) for p in ps]))
+    for c, p in enumerate(ps):
+        o, oout = oracle.pose_optimization(oracle.poseopt_problem(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], p["Rcw"], p["tcw"]))
+        g = outlier[offsets[c]:offsets[c + 1]]
+        assert res[c]["rounds"] == o["rounds"]
+        assert np.abs(res[c]["R"].reshape(3, 3) - o["R"]).max() < POSE_TOL and np.abs(res[c]["t"] - o["t"]).max() < POSE_TOL, c
+        assert (g != oout).sum() <= 1 and abs(int(res[c]["n_inliers"]) - o["n_inliers"]) <= 1, c
+        assert g[3] == 1 and g[7] == 1
+        if c >= 2:
+            assert res[c]["iterations"] == 40 and res[c]["trials"] == 40 and g[11] == 0
+
+
 def test_poseopt_empty_batch(engine):
     res, out = engine.poseopt_solve(np.zeros(1, np.int32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32),
                                     np.zeros(0, np.float32), np.zeros((0, 5), np.float32), np.zeros((0, 12), np.float32))
