@@ -300,6 +300,46 @@ int rsac_poseopt_run(rsac_engine* e);
 int rsac_poseopt_download(rsac_engine* e, rsac_poseopt_result* results, uint8_t* outlier);
 int rsac_poseopt_solve(rsac_engine* e, const rsac_poseopt_batch* b, rsac_poseopt_result* results, uint8_t* outlier);
 
+/* ------------------------------------------------ Optimizer::OptimizeSim3 (batched) */
+/* SURVEY 8(f) N1, second half: LoopClosing::ComputeSim3 refines every Sim3 that RANSAC accepts
+ * (LoopClosing.cpp:311: Optimizer::OptimizeSim3(mpCurrentKF, pKF, vpMapPointMatches, gScm, 10); src/Optimizer.cpp:1054-1249).
+ * One problem = one keyframe pair: the matches that pass the validity tests of Optimizer.cpp:1107-1143, in order.
+ * 5 LM iterations with Huber(sqrt(th2)), matches with a chi2 > th2 on either edge removed, 5 (no outlier) or 10 more
+ * iterations, final inlier count; g2o's numeric Jacobians (central differences, delta 1e-9) and step control
+ * reproduced.  One warp per pair. */
+typedef struct {
+    int32_t C;
+    const int32_t* offsets;      /* [C+1] */
+    const float* x1c;            /* [total][3] R1w*P3D1w + t1w (map point of keyframe 1 in camera 1, float as in the reference) */
+    const float* x2c;            /* [total][3] R2w*P3D2w + t2w */
+    const float* obs1;           /* [total][2] pKF1->mvKeysUn[i].pt */
+    const float* obs2;           /* [total][2] pKF2->mvKeysUn[i2].pt */
+    const float* inv_sigma2_1;   /* [total] pKF1->mvInvLevelSigma2[kpUn1.octave] */
+    const float* inv_sigma2_2;   /* [total] */
+    const float* K1;             /* [C][4] fx, fy, cx, cy of keyframe 1 */
+    const float* K2;             /* [C][4] */
+    const float* S12;            /* [C][13] g2oS12 on entry: R row-major (9), t (3), s */
+    const float* th2;            /* [C] (LoopClosing passes 10) */
+    const int32_t* fix_scale;    /* [C] or NULL = 1 (the reference hard-codes _fix_scale = true, Optimizer.cpp:1076) */
+} rsac_sim3opt_batch;
+
+typedef struct {
+    int32_t n_inliers;           /* return value nIn (0 when fewer than 10 matches survive the first pass) */
+    int32_t n_bad;               /* matches removed after the first optimisation */
+    int32_t optimized;           /* 1 when the second optimisation ran and g2oS12 was written back */
+    int32_t iterations;          /* LM iterations */
+    int32_t trials;              /* LM trials */
+    int32_t reserved;
+    double R[9], t[3], s;        /* g2oS12 on return (rotation().toRotationMatrix(), translation(), scale()) */
+    double q[4];                 /* rotation() as (w, x, y, z), not normalised (g2o::Sim3 never normalises) */
+} rsac_sim3opt_result;
+
+int rsac_sim3opt_upload(rsac_engine* e, const rsac_sim3opt_batch* b);
+int rsac_sim3opt_run(rsac_engine* e);
+/* removed: [total] 1 where the reference sets vpMatches1[idx] = nullptr */
+int rsac_sim3opt_download(rsac_engine* e, rsac_sim3opt_result* results, uint8_t* removed);
+int rsac_sim3opt_solve(rsac_engine* e, const rsac_sim3opt_batch* b, rsac_sim3opt_result* results, uint8_t* removed);
+
 /* ------------------------------------------------ multi-GPU (candidates shard) */
 /* contiguous block partition of C problems over `world` ranks: rank r owns [*first, *first + *count) */
 int rsac_shard_range(int C, int rank, int world, int* first, int* count);
@@ -333,6 +373,10 @@ int rsac_debug_host_sim3(const float P1[9], const float P2[9], int fix_scale, fl
 /* PoseOptimization of one frame with the device source compiled for the host (one lane, edges summed in order) */
 int rsac_debug_host_poseopt(int n, const float* p3d, const float* obs, const float* inv_sigma2, const float K[5],
                             const float Tcw[12], rsac_poseopt_result* result, uint8_t* outlier);
+/* OptimizeSim3 of one keyframe pair with the device source compiled for the host (one lane) */
+int rsac_debug_host_sim3opt(int n, const float* x1c, const float* x2c, const float* obs1, const float* obs2,
+                            const float* inv_sigma2_1, const float* inv_sigma2_2, const float K1[4], const float K2[4],
+                            const float S12[13], float th2, int fix_scale, rsac_sim3opt_result* result, uint8_t* removed);
 int rsac_debug_host_mlpnp6(const float K[4], const float p3d[18], const float p2d[12], const double* cov54,
                            double R[9], double t[3]);
 

@@ -233,6 +233,26 @@ typedef struct {
 void orc_pose_optimization(const orc_poseopt_problem *pb, orc_poseopt_result *res, uint8_t *outlier);
 void orc_pose_optimization_batch(int C, const orc_poseopt_problem *pbs, orc_poseopt_result *res, uint8_t **outliers);
 
+/* ------------------------------------------------ Optimizer::OptimizeSim3 */
+typedef struct {
+    int n;                        /* matches that pass Optimizer.cpp:1107-1143 (nCorrespondences) */
+    const float *x1c, *x2c;       /* [n][3] P3D1c, P3D2c */
+    const float *obs1, *obs2;     /* [n][2] kpUn1.pt, kpUn2.pt */
+    const float *inv_sigma2_1, *inv_sigma2_2;   /* [n] */
+    float K1[4], K2[4];           /* fx, fy, cx, cy */
+    float S12[13];                /* g2oS12 on entry: R (9), t (3), s */
+    float th2;
+    int fix_scale;
+} orc_sim3opt_problem;
+
+typedef struct {
+    int32_t n_inliers, n_bad, optimized, iterations, trials, reserved;
+    double R[9], t[3], s;
+    double q[4];
+} orc_sim3opt_result;
+
+void orc_optimize_sim3(const orc_sim3opt_problem *pb, orc_sim3opt_result *res, uint8_t *removed);
+
 #ifdef __cplusplus
 }
 #endif

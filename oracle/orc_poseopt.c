@@ -419,3 +419,333 @@ void orc_pose_optimization_batch(int C, const orc_poseopt_problem *pbs, orc_pose
 {
     for (int c = 0; c < C; ++c) orc_pose_optimization(&pbs[c], &res[c], outliers[c]);
 }
+
+/* ===================================================================================================
+ * Optimizer::OptimizeSim3 (src/Optimizer.cpp:1054-1249) -- SURVEY 8(f) N1, second half.
+ *   Thirdparty/g2o/g2o/types/sim3.h:69-143 (exp), :145-147 (map), :232-235 (inverse), :263-269 (product)
+ *   Thirdparty/g2o/g2o/types/types_seven_dof_expmap.h:60-69 (oplus, _fix_scale), :74-88, :138-167 (edges)
+ *   Thirdparty/g2o/g2o/core/base_binary_edge.hpp:131-205 (numeric Jacobians, delta = 1e-9), :55-115 (quadratic form)
+ * The map points are fixed vertices: one free 7-dof vertex.  g2o::Sim3 never normalises its quaternion.
+ * Both classifications read the edges' stored errors (those of the last LM trial, accepted or not).
+ * PARITY UNPINNED (Eigen arithmetic restated by formula; accumulation with explicit fma as in PoseOptimization).
+ * =================================================================================================== */
+typedef struct { double q[4]; double t[3]; double s; } sim3_t;
+
+static void sim3_exp(const double x[7], sim3_t *E)
+{
+    const double w0 = x[0], w1 = x[1], w2 = x[2];
+    const double sigma = x[6];
+    const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    const double O[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+    double O2[9], R[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) O2[3 * i + j] = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
+    const double s = exp(sigma);
+    const double eps = 0.00001;
+    double A, B, C;
+    if (fabs(sigma) < eps) {
+        C = 1.0;
+        if (theta < eps) {
+            A = 1.0 / 2.0;
+            B = 1.0 / 6.0;
+            for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i];
+        } else {
+            const double theta2 = theta * theta;
+            A = (1.0 - cos(theta)) / theta2;
+            B = (theta - sin(theta)) / (theta2 * theta);
+            const double a = sin(theta) / theta, b = (1.0 - cos(theta)) / (theta * theta);
+            for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * O[i] + b * O2[i];
+        }
+    } else {
+        C = (s - 1.0) / sigma;
+        if (theta < eps) {
+            const double sigma2 = sigma * sigma;
+            A = ((sigma - 1.0) * s + 1.0) / sigma2;
+            B = ((0.5 * sigma2 - sigma + 1.0) * s) / (sigma2 * sigma);
+            for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i];
+        } else {
+            const double ra = sin(theta) / theta, rb = (1.0 - cos(theta)) / (theta * theta);
+            for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + ra * O[i] + rb * O2[i];
+            const double a = s * sin(theta);
+            const double b = s * cos(theta);
+            const double theta2 = theta * theta;
+            const double sigma2 = sigma * sigma;
+            const double c = theta2 + sigma2;
+            A = (a * sigma + (1.0 - b) * theta) / (theta * c);
+            B = (C - ((b - 1.0) * sigma + a * theta) / c) * 1.0 / theta2;
+        }
+    }
+    quat_from_rot(R, E->q);
+    for (int i = 0; i < 3; ++i) {
+        const double W0 = A * O[3 * i] + B * O2[3 * i] + ((i == 0) ? C : 0.0);
+        const double W1 = A * O[3 * i + 1] + B * O2[3 * i + 1] + ((i == 1) ? C : 0.0);
+        const double W2 = A * O[3 * i + 2] + B * O2[3 * i + 2] + ((i == 2) ? C : 0.0);
+        E->t[i] = W0 * x[3] + W1 * x[4] + W2 * x[5];
+    }
+    E->s = s;
+}
+
+static void sim3_mul(const sim3_t *a, const sim3_t *b, sim3_t *o)
+{
+    double r[3], q[4];
+    quat_rotate(a->q, b->t, r);
+    quat_mul(a->q, b->q, q);
+    sim3_t out;
+    memcpy(out.q, q, sizeof q);
+    for (int i = 0; i < 3; ++i) out.t[i] = a->s * r[i] + a->t[i];
+    out.s = a->s * b->s;
+    *o = out;
+}
+
+static void sim3_inverse(const sim3_t *a, sim3_t *o)
+{
+    o->q[0] = a->q[0]; o->q[1] = -a->q[1]; o->q[2] = -a->q[2]; o->q[3] = -a->q[3];
+    const double m = -1.0 / a->s;
+    const double v[3] = {m * a->t[0], m * a->t[1], m * a->t[2]};
+    quat_rotate(o->q, v, o->t);
+    o->s = 1.0 / a->s;
+}
+
+static void sim3_edge_err(const sim3_t *S, const float *X, const float *obs, const double K[4], double e[2])
+{
+    const double v[3] = {(double)X[0], (double)X[1], (double)X[2]};
+    double r[3];
+    quat_rotate(S->q, v, r);
+    const double p0 = S->s * r[0] + S->t[0], p1 = S->s * r[1] + S->t[1], p2 = S->s * r[2] + S->t[2];
+    e[0] = (double)obs[0] - ((p0 / p2) * K[0] + K[2]);
+    e[1] = (double)obs[1] - ((p1 / p2) * K[1] + K[3]);
+}
+
+typedef struct {
+    const orc_sim3opt_problem *pb;
+    const uint8_t *removed;
+    double K1[4], K2[4], delta, dsqr;
+    double *err;             /* [n][4]: e12 (2), e21 (2) -- the edges' stored _error */
+} sgraph_t;
+
+static double s_huber(double c, double delta, double dsqr) { return (c <= dsqr) ? c : 2.0 * sqrt(c) * delta - dsqr; }
+
+static double s_active_chi2(const sgraph_t *g, const sim3_t *S)
+{
+    const orc_sim3opt_problem *pb = g->pb;
+    sim3_t Si;
+    sim3_inverse(S, &Si);
+    double sum = 0.0;
+    for (int i = 0; i < pb->n; ++i) {
+        if (g->removed[i]) continue;
+        double *e = g->err + 4 * i;
+        sim3_edge_err(S, pb->x2c + 3 * i, pb->obs1 + 2 * i, g->K1, e);
+        const double s1 = (double)pb->inv_sigma2_1[i];
+        sum += s_huber(e[0] * (s1 * e[0]) + e[1] * (s1 * e[1]), g->delta, g->dsqr);
+        sim3_edge_err(&Si, pb->x1c + 3 * i, pb->obs2 + 2 * i, g->K2, e + 2);
+        const double s2 = (double)pb->inv_sigma2_2[i];
+        sum += s_huber(e[2] * (s2 * e[2]) + e[3] * (s2 * e[3]), g->delta, g->dsqr);
+    }
+    return sum;
+}
+
+static void s_build_system(const sgraph_t *g, const sim3_t *S, double H[49], double b[7])
+{
+    const orc_sim3opt_problem *pb = g->pb;
+    sim3_t fwd[15], inv[15];
+    fwd[0] = *S;
+    for (int p = 1; p < 15; ++p) {
+        double x[7] = {0, 0, 0, 0, 0, 0, 0};
+        const int d = (p - 1) >> 1;
+        x[d] = ((p - 1) & 1) ? -1e-9 : 1e-9;
+        if (pb->fix_scale) x[6] = 0.0;
+        sim3_t E;
+        sim3_exp(x, &E);
+        sim3_mul(&E, S, &fwd[p]);
+    }
+    for (int p = 0; p < 15; ++p) sim3_inverse(&fwd[p], &inv[p]);
+    memset(H, 0, 49 * sizeof(double));
+    memset(b, 0, 7 * sizeof(double));
+    const double scalar = 1.0 / (2.0 * 1e-9);
+    for (int i = 0; i < pb->n; ++i) {
+        if (g->removed[i]) continue;
+        for (int side = 0; side < 2; ++side) {
+            const float *X = side ? pb->x1c + 3 * i : pb->x2c + 3 * i;
+            const float *ob = side ? pb->obs2 + 2 * i : pb->obs1 + 2 * i;
+            const double *K = side ? g->K2 : g->K1;
+            const sim3_t *P = side ? inv : fwd;
+            const double s = (double)(side ? pb->inv_sigma2_2[i] : pb->inv_sigma2_1[i]);
+            const double *e = g->err + 4 * i + 2 * side;
+            double J0[7], J1[7];
+            for (int d = 0; d < 7; ++d) {
+                double ea[2], eb[2];
+                sim3_edge_err(&P[1 + 2 * d], X, ob, K, ea);
+                sim3_edge_err(&P[2 + 2 * d], X, ob, K, eb);
+                J0[d] = scalar * (ea[0] - eb[0]);
+                J1[d] = scalar * (ea[1] - eb[1]);
+            }
+            const double c = e[0] * (s * e[0]) + e[1] * (s * e[1]);
+            double rho1 = 1.0;
+            if (c > g->dsqr) rho1 = g->delta / sqrt(c);
+            const double wo = rho1 * s;
+            const double we0 = s * e[0], we1 = s * e[1];
+            for (int a = 0; a < 7; ++a) {
+                const double be = fma(J1[a], we1, J0[a] * we0);
+                b[a] -= rho1 * be;
+                for (int c2 = a; c2 < 7; ++c2) {
+                    double h = H[7 * a + c2];
+                    h = fma(J0[a], wo * J0[c2], h);
+                    h = fma(J1[a], wo * J1[c2], h);
+                    H[7 * a + c2] = h;
+                }
+            }
+        }
+    }
+    for (int a = 0; a < 7; ++a)
+        for (int c2 = 0; c2 < a; ++c2) H[7 * a + c2] = H[7 * c2 + a];
+}
+
+static int ldlt7(const double Hin[49], const double b[7], double x[7])
+{
+    double L[49], d[7], r[7], y[7];
+    memcpy(L, Hin, sizeof L);
+    for (int j = 0; j < 7; ++j) {
+        double dj = L[8 * j];
+        for (int k = 0; k < j; ++k) dj -= L[7 * j + k] * L[7 * j + k] * d[k];
+        if (!(dj > 0.0)) return 0;
+        d[j] = dj;
+        r[j] = 1.0 / dj;
+        for (int i = j + 1; i < 7; ++i) {
+            double v = L[7 * i + j];
+            for (int k = 0; k < j; ++k) v -= L[7 * i + k] * L[7 * j + k] * d[k];
+            L[7 * i + j] = v * r[j];
+        }
+    }
+    for (int i = 0; i < 7; ++i) {
+        double v = b[i];
+        for (int k = 0; k < i; ++k) v -= L[7 * i + k] * y[k];
+        y[i] = v;
+    }
+    for (int i = 0; i < 7; ++i) y[i] *= r[i];
+    for (int i = 6; i >= 0; --i) {
+        double v = y[i];
+        for (int k = i + 1; k < 7; ++k) v -= L[7 * k + i] * x[k];
+        x[i] = v;
+    }
+    return 1;
+}
+
+static void s_optimize(const sgraph_t *g, sim3_t *S, int iterations, int *n_iter, int *n_trials)
+{
+    double lambda = 0.0, ni = 2.0;
+    int nBad = 0;
+    double x[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int it = 0; it < iterations; ++it) {
+        double currentChi = s_active_chi2(g, S);
+        const double iniChi = currentChi;
+        double H[49], b[7];
+        s_build_system(g, S, H, b);
+        ++*n_iter;
+        if (it == 0) {
+            double maxDiag = 0.0;
+            for (int j = 0; j < 7; ++j) maxDiag = fmax(fabs(H[8 * j]), maxDiag);
+            lambda = 1e-5 * maxDiag;
+            ni = 2.0;
+            nBad = 0;
+        }
+        double rho = 0.0;
+        int qmax = 0;
+        do {
+            const sim3_t backup = *S;
+            double Hl[49];
+            memcpy(Hl, H, sizeof Hl);
+            for (int j = 0; j < 7; ++j) Hl[8 * j] += lambda;
+            const int ok2 = ldlt7(Hl, b, x);
+            ++*n_trials;
+            if (g->pb->fix_scale) x[6] = 0.0;
+            sim3_t E, Sn;
+            sim3_exp(x, &E);
+            sim3_mul(&E, S, &Sn);
+            *S = Sn;
+            double tempChi = s_active_chi2(g, S);
+            if (!ok2) tempChi = DBL_MAX;
+            rho = currentChi - tempChi;
+            double scale = 0.0;
+            for (int j = 0; j < 7; ++j) scale += x[j] * (lambda * x[j] + b[j]);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0.0 && isfinite(tempChi)) {
+                const double d = 2.0 * rho - 1.0;
+                double alpha = 1.0 - d * d * d;
+                alpha = fmin(alpha, 2.0 / 3.0);
+                lambda *= fmax(1.0 / 3.0, alpha);
+                ni = 2.0;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni;
+                ni *= 2.0;
+                *S = backup;
+            }
+            ++qmax;
+        } while (rho < 0.0 && qmax < 10);
+        if (qmax == 10 || rho == 0.0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+        if (nBad >= 3) break;
+    }
+}
+
+static int s_classify(const sgraph_t *g, uint8_t *removed, int *kept)
+{
+    const orc_sim3opt_problem *pb = g->pb;
+    int bad = 0, good = 0;
+    const double th2 = (double)pb->th2;
+    for (int i = 0; i < pb->n; ++i) {
+        if (removed[i]) continue;
+        const double *e = g->err + 4 * i;
+        const double s1 = (double)pb->inv_sigma2_1[i], s2 = (double)pb->inv_sigma2_2[i];
+        const double c12 = e[0] * (s1 * e[0]) + e[1] * (s1 * e[1]);
+        const double c21 = e[2] * (s2 * e[2]) + e[3] * (s2 * e[3]);
+        if (c12 > th2 || c21 > th2) { removed[i] = 1; ++bad; }
+        else ++good;
+    }
+    *kept = good;
+    return bad;
+}
+
+void orc_optimize_sim3(const orc_sim3opt_problem *pb, orc_sim3opt_result *res, uint8_t *removed)
+{
+    memset(res, 0, sizeof *res);
+    const int n = pb->n;
+    for (int i = 0; i < n; ++i) removed[i] = 0;
+    sim3_t S;
+    {
+        double R[9];
+        for (int i = 0; i < 9; ++i) R[i] = (double)pb->S12[i];
+        quat_from_rot(R, S.q);
+        for (int i = 0; i < 3; ++i) S.t[i] = (double)pb->S12[9 + i];
+        S.s = (double)pb->S12[12];
+    }
+    const sim3_t S0 = S;
+    int second = 0, nBad = 0, nIn = 0;
+    if (n > 0) {
+        sgraph_t g;
+        g.pb = pb; g.removed = removed;
+        for (int k = 0; k < 4; ++k) { g.K1[k] = (double)pb->K1[k]; g.K2[k] = (double)pb->K2[k]; }
+        g.delta = (double)sqrtf(pb->th2);
+        g.dsqr = g.delta * g.delta;
+        g.err = (double *)calloc((size_t)n * 4, sizeof(double));
+        s_optimize(&g, &S, 5, &res->iterations, &res->trials);
+        int kept = 0;
+        nBad = s_classify(&g, removed, &kept);
+        if (n - nBad >= 10) {
+            second = 1;
+            s_optimize(&g, &S, nBad > 0 ? 10 : 5, &res->iterations, &res->trials);
+            s_classify(&g, removed, &kept);
+            nIn = kept;
+        }
+        free(g.err);
+    }
+    const sim3_t *F = second ? &S : &S0;
+    res->n_inliers = second ? nIn : 0;
+    res->n_bad = nBad;
+    res->optimized = second;
+    quat_to_rot(F->q, res->R);
+    for (int i = 0; i < 3; ++i) res->t[i] = F->t[i];
+    res->s = F->s;
+    for (int i = 0; i < 4; ++i) res->q[i] = F->q[i];
+}

@@ -1304,4 +1304,5 @@ int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48])
 #include "engine_sim3.inl"
 #include "engine_mlpnp.inl"
 #include "engine_poseopt.inl"
+#include "engine_sim3opt.inl"
 #include "engine_nccl.inl"

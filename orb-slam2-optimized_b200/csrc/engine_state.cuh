@@ -164,6 +164,20 @@ struct PoseOptState {
     }
 };
 
+struct Sim3OptState {
+    bool uploaded = false, ran = false;
+    int C = 0;
+    int64_t total = 0;
+    DevBuf d_metas, d_x1, d_x2, d_o1, d_o2, d_is1, d_is2, d_removed, d_results;
+    PinnedBuf h_metas;
+    void release()
+    {
+        DevBuf* all[] = {&d_metas, &d_x1, &d_x2, &d_o1, &d_o2, &d_is1, &d_is2, &d_removed, &d_results};
+        for (DevBuf* b : all) b->release();
+        h_metas.release();
+    }
+};
+
 struct ProfPair {
     int stage;
     cudaEvent_t a, b;
@@ -196,6 +210,7 @@ struct rsac_engine {
     rsac::ScoreState score;
     rsac::Sim3State sim3;
     rsac::PoseOptState poseopt;
+    rsac::Sim3OptState sim3opt;
     rsac::DevBuf d_exact, d_scratch, d_resume;
     unsigned long long* last_exact = nullptr;   // diagnostic counter of the last scoring launch
     void* nccl_comm = nullptr;
@@ -218,7 +233,7 @@ struct rsac_engine {
     }
     void free_all()
     {
-        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release();
+        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release(); sim3opt.release();
         d_exact.release(); d_scratch.release(); d_resume.release();
     }
 };

@@ -81,6 +81,18 @@ POSEOPT_DTYPE = np.dtype([("n_inliers", np.int32), ("n_bad", np.int32), ("rounds
                           ("Rf", np.float32, (9,)), ("tf", np.float32, (3,))], align=True)
 
 
+class Sim3OptBatch(C.Structure):
+    _fields_ = [("C", C.c_int32), ("offsets", C.c_void_p), ("x1c", C.c_void_p), ("x2c", C.c_void_p), ("obs1", C.c_void_p),
+                ("obs2", C.c_void_p), ("inv_sigma2_1", C.c_void_p), ("inv_sigma2_2", C.c_void_p), ("K1", C.c_void_p),
+                ("K2", C.c_void_p), ("S12", C.c_void_p), ("th2", C.c_void_p), ("fix_scale", C.c_void_p)]
+
+
+# rsac_sim3opt_result (include/ransac_b200.h)
+SIM3OPT_DTYPE = np.dtype([("n_inliers", np.int32), ("n_bad", np.int32), ("optimized", np.int32), ("iterations", np.int32),
+                          ("trials", np.int32), ("reserved", np.int32), ("R", np.float64, (9,)), ("t", np.float64, (3,)),
+                          ("s", np.float64), ("q", np.float64, (4,))], align=True)
+
+
 class RsacError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__(f"ransac_b200 error {code}: {msg}")
@@ -445,6 +457,27 @@ class Engine:
         self.poseopt_run()
         return self.poseopt_download()
 
+    # -- Optimizer::OptimizeSim3 (batched)
+    def sim3opt_solve(self, offsets, x1c, x2c, obs1, obs2, is1, is2, K1, K2, S12, th2, fix_scale=None):
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        Cn = len(offsets) - 1
+        f = lambda a, w: np.ascontiguousarray(a, np.float32).reshape(-1, w)
+        x1c, x2c, obs1, obs2 = f(x1c, 3), f(x2c, 3), f(obs1, 2), f(obs2, 2)
+        is1, is2 = np.ascontiguousarray(is1, np.float32).reshape(-1), np.ascontiguousarray(is2, np.float32).reshape(-1)
+        K1, K2, S12 = f(K1, 4), f(K2, 4), f(S12, 13)
+        th2 = np.ascontiguousarray(np.broadcast_to(np.asarray(th2, np.float32), (max(Cn, 1),)))
+        fs = None if fix_scale is None else np.ascontiguousarray(fix_scale, np.int32)
+        desc = Sim3OptBatch(Cn, _p(offsets), _p(x1c), _p(x2c), _p(obs1), _p(obs2), _p(is1), _p(is2), _p(K1), _p(K2), _p(S12), _p(th2), _p(fs))
+        self._ck(self.L.rsac_sim3opt_upload(self.h, C.byref(desc)), "sim3opt_upload")
+        self._ck(self.L.rsac_sim3opt_run(self.h), "sim3opt_run")
+        res = np.zeros(Cn, SIM3OPT_DTYPE)
+        removed = np.zeros(max(int(offsets[-1]), 1), np.uint8)
+        self._ck(self.L.rsac_sim3opt_download(self.h, _p(res), _p(removed)), "sim3opt_download")
+        return res, removed[:int(offsets[-1])]
+
+    def sim3opt_run(self):
+        self._ck(self.L.rsac_sim3opt_run(self.h), "sim3opt_run")
+
     # -- scoring stress
     def score_pnp_upload(self, poses, p3d, p2d, max_err, K):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
@@ -488,6 +521,21 @@ def debug_host_poseopt(p3d, obs, inv_sigma2, K, Tcw):
     if rc:
         raise RsacError(rc, "debug_host_poseopt")
     return res[0], outlier[:p3d.shape[0]]
+
+
+def debug_host_sim3opt(x1c, x2c, obs1, obs2, is1, is2, K1, K2, S12, th2=10.0, fix_scale=True):
+    """the device source of OptimizeSim3 compiled for the host, one keyframe pair (test hook, not a fallback)"""
+    f = lambda a, w: np.ascontiguousarray(a, np.float32).reshape(-1, w)
+    x1c, x2c, obs1, obs2 = f(x1c, 3), f(x2c, 3), f(obs1, 2), f(obs2, 2)
+    is1, is2 = np.ascontiguousarray(is1, np.float32).reshape(-1), np.ascontiguousarray(is2, np.float32).reshape(-1)
+    K1, K2, S12 = f(K1, 4).ravel(), f(K2, 4).ravel(), f(S12, 13).ravel()
+    res = np.zeros(1, SIM3OPT_DTYPE)
+    removed = np.zeros(max(x1c.shape[0], 1), np.uint8)
+    rc = lib().rsac_debug_host_sim3opt(C.c_int(x1c.shape[0]), _p(x1c), _p(x2c), _p(obs1), _p(obs2), _p(is1), _p(is2), _p(K1), _p(K2),
+                                       _p(S12), C.c_float(th2), C.c_int(1 if fix_scale else 0), _p(res), _p(removed))
+    if rc:
+        raise RsacError(rc, "debug_host_sim3opt")
+    return res[0], removed[:x1c.shape[0]]
 
 
 def unpack_mask(words: np.ndarray, n: int) -> np.ndarray:

@@ -200,3 +200,25 @@ def poseopt_problem(seed: int, n: int = 250, outlier_ratio: float = 0.2, stereo_
                 K=np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"], bf], np.float32),
                 Rcw=np.ascontiguousarray(R0, np.float32), tcw=np.ascontiguousarray(t0, np.float32),
                 R=p["R"], t=p["t"], inlier=p["inlier"])
+
+
+def sim3opt_problem(seed: int, n: int = 100, outlier_ratio: float = 0.15, cam=EUROC, pose_noise=(0.01, 0.03), scale: float = 1.0):
+    """One Optimizer::OptimizeSim3 input (Optimizer.cpp:1054-1160): matched map points of two keyframes in their own
+    camera frames, their keypoints (projection + sigma px of noise per level), 1/sigma^2, and an initial S12 = ground
+    truth perturbed by `pose_noise` (rad, m) -- what Sim3Solver hands over.  Returns dict(x1c, x2c [n,3], obs1, obs2
+    [n,2], inv_sigma2_1/2 [n], K (fx,fy,cx,cy) f32, S12 [13] f32 (R, t, s), R12, t12, s, inlier)."""
+    q = sim3_problem(seed, n, outlier_ratio, scale, cam)
+    rng = np.random.default_rng(seed + 55_000_000)
+    sg1 = np.sqrt(q["sigma2_1"].astype(float))
+    sg2 = np.sqrt(q["sigma2_2"].astype(float))
+    obs1 = project(q["x1c"].astype(float), cam) + rng.normal(size=(n, 2)) * 0.5 * sg1[:, None]
+    obs2 = project(q["x2c"].astype(float) * scale, cam) + rng.normal(size=(n, 2)) * 0.5 * sg2[:, None]
+    d = rng.normal(size=3)
+    d /= np.linalg.norm(d)
+    dR = rodrigues(d * pose_noise[0])
+    R0 = dR @ q["R12"]
+    t0 = dR @ q["t12"] + rng.normal(size=3) * pose_noise[1]
+    S12 = np.concatenate([R0.ravel(), t0, [q["s"]]]).astype(np.float32)
+    return dict(x1c=q["x1c"], x2c=q["x2c"], obs1=np.ascontiguousarray(obs1, np.float32), obs2=np.ascontiguousarray(obs2, np.float32),
+                inv_sigma2_1=(np.float32(1) / q["sigma2_1"]).astype(np.float32), inv_sigma2_2=(np.float32(1) / q["sigma2_2"]).astype(np.float32),
+                K=np.array(q["K"], np.float32), S12=S12, R12=q["R12"], t12=q["t12"], s=q["s"], inlier=q["inlier"])

@@ -423,3 +423,35 @@ def pose_optimization(pb: _Keep):
     d["Rf"] = np.array(res.Rf, np.float32).reshape(3, 3)
     d["tf"] = np.array(res.tf, np.float32)
     return d, out[:pb.st.n]
+
+
+class Sim3OptProblem(C.Structure):
+    _fields_ = [("n", C.c_int), ("x1c", C.c_void_p), ("x2c", C.c_void_p), ("obs1", C.c_void_p), ("obs2", C.c_void_p),
+                ("inv_sigma2_1", C.c_void_p), ("inv_sigma2_2", C.c_void_p), ("K1", C.c_float * 4), ("K2", C.c_float * 4),
+                ("S12", C.c_float * 13), ("th2", C.c_float), ("fix_scale", C.c_int)]
+
+
+class Sim3OptResult(C.Structure):
+    _fields_ = [("n_inliers", C.c_int32), ("n_bad", C.c_int32), ("optimized", C.c_int32), ("iterations", C.c_int32),
+                ("trials", C.c_int32), ("reserved", C.c_int32), ("R", C.c_double * 9), ("t", C.c_double * 3), ("s", C.c_double),
+                ("q", C.c_double * 4)]
+
+
+def sim3opt_problem(x1c, x2c, obs1, obs2, is1, is2, K1, K2, S12, th2=10.0, fix_scale=True):
+    arrs = [_f32(a) for a in (x1c, x2c, obs1, obs2, is1, is2)]
+    st = Sim3OptProblem(int(arrs[0].shape[0]), *[_p(a) for a in arrs], (C.c_float * 4)(*[float(k) for k in K1]),
+                        (C.c_float * 4)(*[float(k) for k in K2]), (C.c_float * 13)(*[float(x) for x in np.asarray(S12, np.float32).ravel()]),
+                        C.c_float(th2), 1 if fix_scale else 0)
+    return _Keep(st, *arrs)
+
+
+def optimize_sim3(pb: _Keep):
+    """Optimizer::OptimizeSim3 on one keyframe pair -> (dict, removed flags uint8 [n])"""
+    res = Sim3OptResult()
+    rem = np.zeros(max(pb.st.n, 1), np.uint8)
+    lib().orc_optimize_sim3(C.byref(pb.st), C.byref(res), _p(rem))
+    d = {k: getattr(res, k) for k in ("n_inliers", "n_bad", "optimized", "iterations", "trials", "s")}
+    d["R"] = np.array(res.R).reshape(3, 3)
+    d["t"] = np.array(res.t)
+    d["q"] = np.array(res.q)
+    return d, rem[:pb.st.n]

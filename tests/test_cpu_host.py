@@ -183,3 +183,19 @@ def test_synthetic_generator_is_seeded_and_shaped():
     assert s[0] == 1.0 and abs(float(s[1]) - 1.44) < 1e-6
     q = synth.sim3_problem(3000, 200, 0.4, 1.6)
     assert q["x1c"].shape == (200, 3) and q["inlier"].sum() == 120 and q["s"] == 1.6
+
+
+def test_host_compiled_sim3opt_is_bit_identical_to_oracle(built_lib, oracle):
+    """csrc/sim3opt.cuh compiled for the host with one lane against oracle/orc_poseopt.c (OptimizeSim3 half)"""
+    from ransac_b200 import capi, synth
+
+    for seed, n, outl, fs, sc in [(1, 100, 0.15, True, 1.0), (2, 200, 0.3, True, 1.0), (3, 60, 0.0, True, 1.0), (4, 12, 0.5, True, 1.0),
+                                  (5, 100, 0.15, False, 1.6), (6, 0, 0.0, True, 1.0), (7, 5, 0.0, True, 1.0)]:
+        p = synth.sim3opt_problem(seed, n, outl, scale=sc)
+        a = (p["x1c"], p["x2c"], p["obs1"], p["obs2"], p["inv_sigma2_1"], p["inv_sigma2_2"], p["K"], p["K"], p["S12"])
+        d, rem = oracle.optimize_sim3(oracle.sim3opt_problem(*a, th2=10.0, fix_scale=fs))
+        r, rem2 = capi.debug_host_sim3opt(*a, th2=10.0, fix_scale=fs)
+        for k in ("n_inliers", "n_bad", "optimized", "iterations", "trials"):
+            assert int(r[k]) == int(d[k]), (seed, k)
+        assert np.array_equal(r["R"], d["R"].ravel()) and np.array_equal(r["t"], d["t"]) and r["s"] == d["s"], seed
+        assert np.array_equal(rem, rem2), seed

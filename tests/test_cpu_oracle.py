@@ -390,3 +390,59 @@ def test_poseopt_frozen_vectors(oracle):
         assert np.allclose(d["R"], g[f"frozen{k}_R"], rtol=0, atol=1e-9) and np.allclose(d["t"], g[f"frozen{k}_t"], rtol=0, atol=1e-9)
         assert (out != g[f"frozen{k}_outlier"]).sum() <= 1
         assert [d["n_inliers"], d["n_bad"], d["rounds"]] == g[f"frozen{k}_meta"][:3].tolist() or (out != g[f"frozen{k}_outlier"]).sum() == 1
+
+
+# ------------------------------------------------ Optimizer::OptimizeSim3
+def _so(oracle, p, **kw):
+    return oracle.optimize_sim3(oracle.sim3opt_problem(p["x1c"], p["x2c"], p["obs1"], p["obs2"], p["inv_sigma2_1"], p["inv_sigma2_2"],
+                                                       p["K"], p["K"], p["S12"], **kw))
+
+
+def test_sim3opt_improves_the_estimate_and_removes_outliers(oracle):
+    for seed in range(8600, 8606):
+        p = synth.sim3opt_problem(seed, 150, 0.2)
+        d, rem = _so(oracle, p)
+        assert d["optimized"] == 1 and d["s"] == 1.0
+        assert np.abs(d["R"] - p["R12"]).max() < 0.5 * np.abs(p["S12"][:9].reshape(3, 3) - p["R12"]).max()
+        assert rem[~p["inlier"]].mean() > 0.9 and rem[p["inlier"]].mean() < 0.1
+        assert d["n_inliers"] == 150 - int(rem.sum())
+        assert abs(np.linalg.norm(d["q"]) - 1.0) < 1e-6      # never normalised by g2o, stays near 1 over 15 steps
+
+
+def test_sim3opt_free_scale_and_early_return(oracle):
+    p = synth.sim3opt_problem(8610, 150, 0.1, scale=1.5)
+    d, _ = _so(oracle, p, fix_scale=False)
+    assert abs(d["s"] - 1.5) < 0.05
+    d, rem = _so(oracle, synth.sim3opt_problem(8611, 9, 0.0))       # fewer than 10 matches: return 0, estimate untouched
+    assert d["optimized"] == 0 and d["n_inliers"] == 0
+    d, rem = _so(oracle, synth.sim3opt_problem(8612, 0, 0.0))
+    assert d["optimized"] == 0 and d["iterations"] == 0
+
+
+def test_sim3opt_matches_scipy_on_outlier_free_pairs(oracle):
+    """independent pin: with no outliers and noise well inside the Huber band the cost is plain weighted least squares
+    over both edge families; scipy's optimum (computed here, seconds) against the oracle after its 5 + 5 iterations"""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+
+    p = synth.sim3opt_problem(8620, 80, 0.0)
+    K = [float(k) for k in p["K"]]
+    X1, X2 = p["x1c"].astype(np.float64), p["x2c"].astype(np.float64)
+    w1, w2 = np.sqrt(p["inv_sigma2_1"].astype(np.float64)), np.sqrt(p["inv_sigma2_2"].astype(np.float64))
+
+    def proj(X):
+        return np.stack([K[0] * X[:, 0] / X[:, 2] + K[2], K[1] * X[:, 1] / X[:, 2] + K[3]], axis=1)
+
+    def resid(x):
+        R = Rotation.from_rotvec(x[:3]).as_matrix()
+        e12 = (p["obs1"] - proj(X2 @ R.T + x[3:])) * w1[:, None]
+        e21 = (p["obs2"] - proj((X1 - x[3:]) @ R)) * w2[:, None]
+        return np.concatenate([e12.ravel(), e21.ravel()])
+
+    R0 = p["S12"][:9].reshape(3, 3).astype(np.float64)
+    sol = least_squares(resid, np.concatenate([Rotation.from_matrix(R0).as_rotvec(), p["S12"][9:12].astype(np.float64)]), method="lm",
+                        xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    d, rem = _so(oracle, p)
+    if rem.sum() == 0:
+        assert np.abs(d["R"] - Rotation.from_rotvec(sol.x[:3]).as_matrix()).max() < 1e-5
+        assert np.abs(d["t"] - sol.x[3:]).max() < 1e-4
