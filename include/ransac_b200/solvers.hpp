@@ -631,4 +631,98 @@ public:
     }
 };
 
+// Mirror of `int Optimizer::OptimizeSim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches1, g2o::Sim3& g2oS12,
+// const float th2)` (src/Optimizer.cpp:1054-1249; LoopClosing.cpp:311 calls it with th2 = 10 for every candidate whose
+// Sim3Solver succeeded).  Reads both keyframes' poses, calibrations, undistorted keypoints and level sigmas and the two
+// map points of every match; nulls the matches it rejects, writes the refined Sim3 back, returns the inlier count.
+struct Sim3Value {                 // g2o::Sim3 as the caller holds it
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double t[3] = {0, 0, 0};
+    double s = 1.0;
+};
+struct Sim3OptPair {
+    // in
+    KeyFrameView kf1, kf2;                     // GetRotation/GetTranslation, mK, mvKeysUn (keys_xy), octave, level_sigma2
+    const float* inv_level_sigma2_1 = nullptr; // pKF1->mvInvLevelSigma2
+    const float* inv_level_sigma2_2 = nullptr;
+    int n = 0;                                 // vpMatches1.size()
+    const unsigned char* valid1 = nullptr;     // [n] pKF1's map point i exists and is not bad
+    const float* world_pos1 = nullptr;         // [n][3]
+    const unsigned char* valid2 = nullptr;     // [n] vpMatches1[i] exists and is not bad
+    const float* world_pos2 = nullptr;         // [n][3]
+    const int* index_in_kf2 = nullptr;         // [n] pMP2->GetIndexInKeyFrame(pKF2) (< 0: skipped)
+    float th2 = 10.0f;
+    bool fix_scale = true;                     // the reference hard-codes true (Optimizer.cpp:1076)
+    // in/out
+    Sim3Value S12;                             // g2oS12
+    std::vector<bool>* match_alive = nullptr;  // [n] false where the reference sets vpMatches1[i] = nullptr
+    // out
+    int n_inliers = 0;
+};
+
+class Sim3Optimizer {
+public:
+    static int OptimizeSim3(Sim3OptPair* pair, Engine& engine = Engine::Default())
+    {
+        std::vector<Sim3OptPair*> v{pair};
+        OptimizeSim3Batch(v, engine);
+        return pair->n_inliers;
+    }
+
+    static void OptimizeSim3Batch(const std::vector<Sim3OptPair*>& pairs, Engine& engine = Engine::Default())
+    {
+        if (pairs.empty()) return;
+        std::lock_guard<std::mutex> lock(engine.mutex());
+        const int C = (int)pairs.size();
+        std::vector<int32_t> offsets(C + 1, 0), fix(C);
+        std::vector<float> x1, x2, o1, o2, is1, is2, K1, K2, S, th;
+        std::vector<std::vector<int>> index(C);
+        auto to_cam = [](const float* R, const float* t, const float* X, std::vector<float>& out) {
+            for (int r = 0; r < 3; ++r) out.push_back(R[3 * r] * X[0] + R[3 * r + 1] * X[1] + R[3 * r + 2] * X[2] + t[r]);   // f32, Optimizer.cpp:1114,1122
+        };
+        for (int c = 0; c < C; ++c) {
+            const Sim3OptPair& p = *pairs[c];
+            for (int i = 0; i < p.n; ++i) {
+                if (!p.valid2[i] || !p.valid1[i] || p.index_in_kf2[i] < 0) continue;      // Optimizer.cpp:1096-1143
+                const int i2 = p.index_in_kf2[i];
+                index[c].push_back(i);
+                to_cam(p.kf1.Rcw, p.kf1.tcw, p.world_pos1 + 3 * i, x1);
+                to_cam(p.kf2.Rcw, p.kf2.tcw, p.world_pos2 + 3 * i, x2);
+                o1.push_back(p.kf1.keys_xy[2 * i]); o1.push_back(p.kf1.keys_xy[2 * i + 1]);
+                o2.push_back(p.kf2.keys_xy[2 * i2]); o2.push_back(p.kf2.keys_xy[2 * i2 + 1]);
+                is1.push_back(p.inv_level_sigma2_1[p.kf1.octave[i]]);
+                is2.push_back(p.inv_level_sigma2_2[p.kf2.octave[i2]]);
+            }
+            offsets[c + 1] = offsets[c] + (int32_t)index[c].size();
+            const float k1[4] = {p.kf1.fx, p.kf1.fy, p.kf1.cx, p.kf1.cy}, k2[4] = {p.kf2.fx, p.kf2.fy, p.kf2.cx, p.kf2.cy};
+            K1.insert(K1.end(), k1, k1 + 4);
+            K2.insert(K2.end(), k2, k2 + 4);
+            for (int k = 0; k < 9; ++k) S.push_back((float)p.S12.R[k]);
+            for (int k = 0; k < 3; ++k) S.push_back((float)p.S12.t[k]);
+            S.push_back((float)p.S12.s);
+            th.push_back(p.th2);
+            fix[c] = p.fix_scale ? 1 : 0;
+        }
+        rsac_sim3opt_batch b;
+        std::memset(&b, 0, sizeof(b));
+        b.C = C; b.offsets = offsets.data(); b.x1c = x1.data(); b.x2c = x2.data(); b.obs1 = o1.data(); b.obs2 = o2.data();
+        b.inv_sigma2_1 = is1.data(); b.inv_sigma2_2 = is2.data(); b.K1 = K1.data(); b.K2 = K2.data(); b.S12 = S.data();
+        b.th2 = th.data(); b.fix_scale = fix.data();
+        std::vector<rsac_sim3opt_result> res(C);
+        std::vector<uint8_t> removed((size_t)std::max(offsets[C], 1));
+        check(rsac_sim3opt_solve(engine.handle(), &b, res.data(), removed.data()), engine.handle(), "rsac_sim3opt_solve");
+        for (int c = 0; c < C; ++c) {
+            Sim3OptPair& p = *pairs[c];
+            p.n_inliers = res[c].n_inliers;
+            if (p.match_alive)
+                for (size_t k = 0; k < index[c].size(); ++k)
+                    if (removed[(size_t)offsets[c] + k]) (*p.match_alive)[(size_t)index[c][k]] = false;
+            if (!res[c].optimized) continue;          // `return 0` before g2oS12 is written (Optimizer.cpp:1203-1204)
+            for (int k = 0; k < 9; ++k) p.S12.R[k] = res[c].R[k];
+            for (int k = 0; k < 3; ++k) p.S12.t[k] = res[c].t[k];
+            p.S12.s = res[c].s;
+        }
+    }
+};
+
 }  // namespace ransac_b200

@@ -67,7 +67,7 @@ static FrameData read_frame(std::ifstream& f)
 
 int main(int argc, char** argv)
 {
-    if (argc < 3) { std::fprintf(stderr, "usage: class_driver pnp|pnp_batch|mlpnp|sim3|poseopt file\n"); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: class_driver pnp|pnp_batch|mlpnp|sim3|poseopt|sim3opt file\n"); return 2; }
     const std::string mode = argv[1];
     std::ifstream f(argv[2], std::ios::binary);
     if (!f) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
@@ -195,6 +195,47 @@ int main(int argc, char** argv)
                 std::printf("}\n");
             }
             std::printf("{\"single\":%d}\n", single);
+        }
+        else if (mode == "sim3opt") {
+            // Optimizer::OptimizeSim3 for every loop candidate (LoopClosing.cpp:311), one batch
+            int C;
+            rd(f, &C, 1);
+            struct Data { int n, nk2; KeyFrameView k1, k2; std::vector<float> xy1, xy2, w1, w2, isig; std::vector<int> o1, o2, i2;
+                          std::vector<unsigned char> v1, v2; std::vector<bool> alive; float S[13]; float K[4]; };
+            std::vector<Data> ds(C);
+            std::vector<Sim3OptPair> pairs(C);
+            std::vector<Sim3OptPair*> ptrs;
+            for (int c = 0; c < C; ++c) {
+                Data& d = ds[c];
+                rd(f, &d.n, 1); rd(f, &d.nk2, 1);
+                rd(f, d.k1.Rcw, 9); rd(f, d.k1.tcw, 3); rd(f, d.k2.Rcw, 9); rd(f, d.k2.tcw, 3); rd(f, d.K, 4); rd(f, d.S, 13);
+                d.xy1.resize(2 * d.n); d.xy2.resize(2 * d.nk2); d.w1.resize(3 * d.n); d.w2.resize(3 * d.n); d.isig.resize(8);
+                d.o1.resize(d.n); d.o2.resize(d.nk2); d.i2.resize(d.n); d.v1.resize(d.n); d.v2.resize(d.n);
+                rd(f, d.xy1.data(), d.xy1.size()); rd(f, d.xy2.data(), d.xy2.size()); rd(f, d.w1.data(), d.w1.size()); rd(f, d.w2.data(), d.w2.size());
+                rd(f, d.o1.data(), d.n); rd(f, d.o2.data(), d.nk2); rd(f, d.i2.data(), d.n); rd(f, d.v1.data(), d.n); rd(f, d.v2.data(), d.n);
+                rd(f, d.isig.data(), 8);
+                d.alive.assign(d.n, true);
+                Sim3OptPair& P = pairs[c];
+                d.k1.keys_xy = d.xy1.data(); d.k1.octave = d.o1.data(); d.k1.n_keypoints = d.n;
+                d.k2.keys_xy = d.xy2.data(); d.k2.octave = d.o2.data(); d.k2.n_keypoints = d.nk2;
+                d.k1.fx = d.k2.fx = d.K[0]; d.k1.fy = d.k2.fy = d.K[1]; d.k1.cx = d.k2.cx = d.K[2]; d.k1.cy = d.k2.cy = d.K[3];
+                P.kf1 = d.k1; P.kf2 = d.k2; P.inv_level_sigma2_1 = P.inv_level_sigma2_2 = d.isig.data();
+                P.n = d.n; P.valid1 = d.v1.data(); P.valid2 = d.v2.data(); P.world_pos1 = d.w1.data(); P.world_pos2 = d.w2.data();
+                P.index_in_kf2 = d.i2.data(); P.th2 = 10.0f;
+                for (int k = 0; k < 9; ++k) P.S12.R[k] = d.S[k];
+                for (int k = 0; k < 3; ++k) P.S12.t[k] = d.S[9 + k];
+                P.S12.s = d.S[12];
+                P.match_alive = &d.alive;
+                ptrs.push_back(&P);
+            }
+            Sim3Optimizer::OptimizeSim3Batch(ptrs);
+            for (int c = 0; c < C; ++c) {
+                std::printf("{\"cand\":%d,\"nIn\":%d,\"s\":%.17g,\"R\":[", c, pairs[c].n_inliers, pairs[c].S12.s);
+                for (int i = 0; i < 9; ++i) std::printf(i ? ",%.17g" : "%.17g", pairs[c].S12.R[i]);
+                std::printf("],\"t\":[%.17g,%.17g,%.17g],\"alive\":", pairs[c].S12.t[0], pairs[c].S12.t[1], pairs[c].S12.t[2]);
+                print_inliers(ds[c].alive);
+                std::printf("}\n");
+            }
         }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());

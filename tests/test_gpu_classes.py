@@ -234,3 +234,57 @@ def test_optimizer_pose_optimization_batch_and_single(driver, oracle, tmp_path):
         empty[slot_of] = False
         assert flags[empty].all()                                   # slots without a MapPoint keep their stale flag
         assert (flags[slot_of] != oout.astype(bool)).sum() <= 1, c  # at most one edge on the chi2 boundary
+
+
+def test_optimizer_optimize_sim3_batch(driver, oracle, tmp_path):
+    """Optimizer::OptimizeSim3 mirror (Sim3Optimizer::OptimizeSim3Batch): keyframe poses + world points in, camera-frame
+    points computed in float as Optimizer.cpp:1114,1122 do, invalid / unobserved matches skipped, rejected matches nulled."""
+    rng = np.random.default_rng(91)
+    C = 4
+    blob = struct.pack("<i", C)
+    cases = []
+    isig = (np.float32(1.0) / synth.level_sigma2()).astype(np.float32)
+    f32 = np.float32
+    for c in range(C):
+        n_ok = [100, 150, 12, 60][c]
+        p = synth.sim3opt_problem(8700 + c, n_ok, [0.15, 0.3, 0.5, 0.0][c])
+        n = n_ok + 10                                        # 10 extra slots that must be skipped
+        nk2 = n + 7
+        slot = np.sort(rng.permutation(n)[:n_ok])
+        i2 = np.full(n, -1, np.int32)
+        i2[slot] = rng.permutation(nk2)[:n_ok].astype(np.int32)
+        v1 = np.zeros(n, np.uint8); v2 = np.zeros(n, np.uint8)
+        v1[slot] = 1; v2[slot] = 1
+        skipped = np.setdiff1d(np.arange(n), slot)
+        v2[skipped[:4]] = 1; v1[skipped[:4]] = 0             # pMP1 missing
+        v1[skipped[4:7]] = 1; v2[skipped[4:7]] = 1           # both there but not observed in KF2 (i2 < 0)
+        R1, t1 = synth.random_pose(rng); R2, t2 = synth.random_pose(rng)
+        R1, t1, R2, t2 = R1.astype(f32), t1.astype(f32), R2.astype(f32), t2.astype(f32)
+        w1 = rng.normal(size=(n, 3)).astype(f32); w2 = rng.normal(size=(n, 3)).astype(f32)
+        w1[slot] = ((p["x1c"].astype(np.float64) - t1) @ R1.astype(np.float64)).astype(f32)
+        w2[slot] = ((p["x2c"].astype(np.float64) - t2) @ R2.astype(np.float64)).astype(f32)
+        cam = lambda R, t, X: np.stack([((R[r, 0] * X[:, 0] + R[r, 1] * X[:, 1]) + R[r, 2] * X[:, 2]) + t[r] for r in range(3)], axis=1).astype(f32)
+        x1c, x2c = cam(R1, t1, w1[slot]), cam(R2, t2, w2[slot])
+        oct1 = rng.integers(0, 8, size=n).astype(np.int32); oct2 = rng.integers(0, 8, size=nk2).astype(np.int32)
+        lv = lambda s: np.array([int(np.argmin(np.abs(isig - v))) for v in s], np.int32)
+        oct1[slot] = lv(p["inv_sigma2_1"]); oct2[i2[slot]] = lv(p["inv_sigma2_2"])
+        xy1 = rng.uniform(0, 700, size=(n, 2)).astype(f32); xy2 = rng.uniform(0, 700, size=(nk2, 2)).astype(f32)
+        xy1[slot] = p["obs1"]; xy2[i2[slot]] = p["obs2"]
+        blob += struct.pack("<ii", n, nk2) + R1.tobytes() + t1.tobytes() + R2.tobytes() + t2.tobytes() + p["K"].tobytes() + p["S12"].tobytes() \
+            + xy1.tobytes() + xy2.tobytes() + w1.tobytes() + w2.tobytes() + oct1.tobytes() + oct2.tobytes() + i2.tobytes() + v1.tobytes() \
+            + v2.tobytes() + isig.tobytes()
+        cases.append((p, slot, n, x1c, x2c))
+    lines = _run(driver, "sim3opt", blob, tmp_path)
+    assert len(lines) == C
+    for c, (p, slot, n, x1c, x2c) in enumerate(cases):
+        o, orem = oracle.optimize_sim3(oracle.sim3opt_problem(x1c, x2c, p["obs1"], p["obs2"], p["inv_sigma2_1"], p["inv_sigma2_2"],
+                                                              p["K"], p["K"], p["S12"], th2=10.0, fix_scale=True))
+        alive = np.zeros(n, bool)
+        alive[lines[c]["alive"]] = True
+        skipped = np.setdiff1d(np.arange(n), slot)
+        assert alive[skipped].all()                           # untouched: the reference `continue`s over them
+        if (alive[slot] != ~orem.astype(bool)).sum() > 0:
+            continue                                          # a match on the chi2 boundary (see test_gpu_sim3opt.py)
+        assert lines[c]["nIn"] == o["n_inliers"], c
+        assert np.abs(np.array(lines[c]["R"]).reshape(3, 3) - o["R"]).max() < 1e-6 and np.abs(np.array(lines[c]["t"]) - o["t"]).max() < 1e-6, c
+        assert lines[c]["s"] == 1.0
