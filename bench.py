@@ -733,6 +733,36 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                                    "note": "Optimizer.cpp:205-424 batched; e2e = upload from host buffers + kernel + records and flags back"}
     except Exception as err:
         ex["pose_optimization_error"] = repr(err)
+    # ---- Optimizer::OptimizeSim3 for 256 loop candidates x 100 matches (fixed scale, th2 = 10)
+    try:
+        CS, NS = 256, 100
+        sp = [synth.sim3opt_problem(8000 + i, NS, 0.15) for i in range(CS)]
+        offs = (np.arange(CS + 1) * NS).astype(np.int32)
+        cats = lambda k: np.concatenate([q[k] for q in sp])
+        Ks = np.stack([q["K"] for q in sp])
+        argss = (offs, cats("x1c"), cats("x2c"), cats("obs1"), cats("obs2"), cats("inv_sigma2_1"), cats("inv_sigma2_2"), Ks, Ks,
+                 np.stack([q["S12"] for q in sp]), 10.0)
+        ress, _ = eng.sim3opt_solve(*argss)
+        for _ in range(3):
+            eng.sim3opt_run()
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(20):
+            eng.sim3opt_run()
+        mss = eng.timer_end() / 20
+        import oracle_api as _O          # CPU baseline only
+        pbs = [_O.sim3opt_problem(q["x1c"], q["x2c"], q["obs1"], q["obs2"], q["inv_sigma2_1"], q["inv_sigma2_2"], q["K"], q["K"], q["S12"])
+               for q in sp[:32]]
+        t0 = time.perf_counter()
+        for pb in pbs:
+            _O.optimize_sim3(pb)
+        dts = (time.perf_counter() - t0) / len(pbs)
+        ex["optimize_sim3"] = {"pairs": CS, "matches_per_pair": NS, "ms_per_batch": mss, "pairs_per_s": CS / (mss * 1e-3),
+                               "lm_iterations_mean": float(ress["iterations"].mean()), "lm_trials_mean": float(ress["trials"].mean()),
+                               "inliers_mean": float(ress["n_inliers"].mean()), "cpu_port_single_thread_pairs_per_s": 1.0 / dts,
+                               "note": "Optimizer.cpp:1054-1249 batched, numeric Jacobians (30 projections per match and build pass)"}
+    except Exception as err:
+        ex["optimize_sim3_error"] = repr(err)
     return out
 
 

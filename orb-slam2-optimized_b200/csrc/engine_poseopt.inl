@@ -52,8 +52,11 @@ int rsac_poseopt_run(rsac_engine* e)
     if (!s.uploaded) { e->err = "rsac_poseopt_run before rsac_poseopt_upload"; return RSAC_ERR_STATE; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     if (s.C > 0) {
+        // a batch that cannot give every SM four CTAs is spread one frame per CTA (a loop-closure-sized batch of
+        // 64 frames would otherwise sit on 16 SMs)
+        const int W = s.C >= 4 * e->sm_count ? kPoseOptWarps : 1;
         e->stage_begin(RSAC_STAGE_SELECT);
-        poseopt_kernel<<<(s.C + kPoseOptWarps - 1) / kPoseOptWarps, kPoseOptWarps * 32, 0, e->stream>>>(
+        poseopt_kernel<<<(s.C + W - 1) / W, W * 32, 0, e->stream>>>(
             (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)s.d_p3d.p, (const float*)s.d_obs.p, (const float*)s.d_isig.p,
             (uint8_t*)s.d_outlier.p, (rsac_poseopt_result*)s.d_results.p);
         e->stage_end(RSAC_STAGE_SELECT);

@@ -66,10 +66,11 @@ int rsac_sim3opt_run(rsac_engine* e)
     if (!s.uploaded) { e->err = "rsac_sim3opt_run before rsac_sim3opt_upload"; return RSAC_ERR_STATE; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     if (s.C > 0) {
-        const size_t smem = sizeof(double) * (size_t)kSim3OptWarps * so::kSimSmemDoubles;
+        const int W = s.C >= 4 * e->sm_count ? kSim3OptWarps : 1;      // small batches: one pair per CTA, spread over the SMs
+        const size_t smem = sizeof(double) * (size_t)W * so::kSimSmemDoubles;
         if (smem > 48 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)sim3opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         e->stage_begin(RSAC_STAGE_SELECT);
-        sim3opt_kernel<<<(s.C + kSim3OptWarps - 1) / kSim3OptWarps, kSim3OptWarps * 32, smem, e->stream>>>(
+        sim3opt_kernel<<<(s.C + W - 1) / W, W * 32, smem, e->stream>>>(
             (const Sim3OptMeta*)s.d_metas.p, s.C, (const float*)s.d_x1.p, (const float*)s.d_x2.p, (const float*)s.d_o1.p,
             (const float*)s.d_o2.p, (const float*)s.d_is1.p, (const float*)s.d_is2.p, (uint8_t*)s.d_removed.p,
             (rsac_sim3opt_result*)s.d_results.p);

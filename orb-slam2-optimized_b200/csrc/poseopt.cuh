@@ -523,7 +523,7 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
 
 }  // namespace po
 
-constexpr int kPoseOptWarps = 4;      // frames per CTA (one warp per frame)
+constexpr int kPoseOptWarps = 4;      // frames per CTA at most (one warp per frame); small batches get one frame per CTA
 
 __global__ void __launch_bounds__(kPoseOptWarps * 32) poseopt_kernel(const PoseOptMeta* __restrict__ metas, int C,
                                                                      const float* __restrict__ p3d, const float* __restrict__ obs,
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kPoseOptWarps * 32) poseopt_kernel(const PoseO
 {
     __shared__ double red_smem[kPoseOptWarps * po::kRedDoubles];
     const int w = threadIdx.x >> 5;
-    const int c = blockIdx.x * kPoseOptWarps + w;
+    const int c = blockIdx.x * (blockDim.x >> 5) + w;      // the host launches 1 or kPoseOptWarps frames per CTA
     if (c >= C) return;
     const PoseOptMeta m = metas[c];
     po::pose_optimization<32>(m, p3d, obs, isig, outlier, threadIdx.x & 31, red_smem + w * po::kRedDoubles, results + c);

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kSim3OptWarps * 32) sim3opt_kernel(const Sim3O
 {
     extern __shared__ double sim3opt_smem[];
     const int w = threadIdx.x >> 5;
-    const int c = blockIdx.x * kSim3OptWarps + w;
+    const int c = blockIdx.x * (blockDim.x >> 5) + w;      // 1 or kSim3OptWarps pairs per CTA
     if (c >= C) return;
     const Sim3OptMeta m = metas[c];
     so::optimize_sim3<32>(m, x1, x2, o1, o2, is1, is2, removed, threadIdx.x & 31, sim3opt_smem + w * so::kSimSmemDoubles, results + c);
