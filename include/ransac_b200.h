@@ -289,7 +289,7 @@ typedef struct {
     int32_t rounds;              /* outer rounds executed (4; 1 with fewer than 10 edges; 0 with fewer than 3) */
     int32_t iterations;          /* LM iterations over all rounds */
     int32_t trials;              /* LM trials (6x6 solves) over all rounds */
-    int32_t reserved;
+    int32_t problem;             /* global frame index (rsac_set_problem_base + local index): the sharding layer's key */
     double R[9], t[3];           /* SE3quat_recov.to_homogeneous_matrix() */
     float Rf[9], tf[3];          /* Converter::toIso(...) as handed to Frame::SetPose (Optimizer.cpp:418-421) */
 } rsac_poseopt_result;
@@ -329,7 +329,7 @@ typedef struct {
     int32_t optimized;           /* 1 when the second optimisation ran and g2oS12 was written back */
     int32_t iterations;          /* LM iterations */
     int32_t trials;              /* LM trials */
-    int32_t reserved;
+    int32_t problem;             /* global pair index (rsac_set_problem_base + local index) */
     double R[9], t[3], s;        /* g2oS12 on return (rotation().toRotationMatrix(), translation(), scale()) */
     double q[4];                 /* rotation() as (w, x, y, z), not normalised (g2o::Sim3 never normalises) */
 } rsac_sim3opt_result;

@@ -58,7 +58,7 @@ int rsac_poseopt_run(rsac_engine* e)
         e->stage_begin(RSAC_STAGE_SELECT);
         poseopt_kernel<<<(s.C + W - 1) / W, W * 32, 0, e->stream>>>(
             (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)s.d_p3d.p, (const float*)s.d_obs.p, (const float*)s.d_isig.p,
-            (uint8_t*)s.d_outlier.p, (rsac_poseopt_result*)s.d_results.p);
+            (uint8_t*)s.d_outlier.p, (rsac_poseopt_result*)s.d_results.p, e->problem_base);
         e->stage_end(RSAC_STAGE_SELECT);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -98,6 +98,6 @@ int rsac_debug_host_poseopt(int n, const float* p3d, const float* obs, const flo
     for (int k = 0; k < 5; ++k) m.K[k] = K[k];
     for (int k = 0; k < 9; ++k) m.Rcw[k] = Tcw[k];
     for (int k = 0; k < 3; ++k) m.tcw[k] = Tcw[9 + k];
-    po::pose_optimization<1>(m, p3d, obs, inv_sigma2, outlier, 0, nullptr, result);
+    po::pose_optimization<1>(m, p3d, obs, inv_sigma2, outlier, 0, nullptr, 0, result);
     return RSAC_OK;
 }

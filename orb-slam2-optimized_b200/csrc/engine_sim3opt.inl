@@ -73,7 +73,7 @@ int rsac_sim3opt_run(rsac_engine* e)
         sim3opt_kernel<<<(s.C + W - 1) / W, W * 32, smem, e->stream>>>(
             (const Sim3OptMeta*)s.d_metas.p, s.C, (const float*)s.d_x1.p, (const float*)s.d_x2.p, (const float*)s.d_o1.p,
             (const float*)s.d_o2.p, (const float*)s.d_is1.p, (const float*)s.d_is2.p, (uint8_t*)s.d_removed.p,
-            (rsac_sim3opt_result*)s.d_results.p);
+            (rsac_sim3opt_result*)s.d_results.p, e->problem_base);
         e->stage_end(RSAC_STAGE_SELECT);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -111,6 +111,6 @@ int rsac_debug_host_sim3opt(int n, const float* x1c, const float* x2c, const flo
     Sim3OptMeta m;
     sim3opt_fill_meta(m, 0, n, K1, K2, S12, th2, fix_scale);
     std::vector<double> scratch((size_t)so::kSimSmemDoubles);
-    so::optimize_sim3<1>(m, x1c, x2c, obs1, obs2, inv_sigma2_1, inv_sigma2_2, removed, 0, scratch.data(), result);
+    so::optimize_sim3<1>(m, x1c, x2c, obs1, obs2, inv_sigma2_1, inv_sigma2_2, removed, 0, scratch.data(), 0, result);
     return RSAC_OK;
 }

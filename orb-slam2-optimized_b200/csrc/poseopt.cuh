@@ -467,7 +467,7 @@ __host__ __device__ inline void optimize(const FrameView& f, const uint8_t* leve
 // after every classification, Optimizer.cpp:341-352).  Returns nInitialCorrespondences - nBad.
 template <int LANES>
 __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const float* p3d, const float* obs, const float* isig,
-                                                  uint8_t* outlier, int lane, double* red_smem, rsac_poseopt_result* out)
+                                                  uint8_t* outlier, int lane, double* red_smem, int problem, rsac_poseopt_result* out)
 {
     Reducer<LANES> red;
     red.sm = red_smem;
@@ -513,7 +513,7 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
         out->rounds = rounds;
         out->iterations = st.iterations;
         out->trials = st.trials;
-        out->reserved = 0;
+        out->problem = problem;
         quat_to_rot_d(T.q, out->R);
         for (int i = 0; i < 3; ++i) out->t[i] = T.t[i];
         for (int i = 0; i < 9; ++i) out->Rf[i] = (float)out->R[i];
@@ -528,14 +528,14 @@ constexpr int kPoseOptWarps = 4;      // frames per CTA at most (one warp per fr
 __global__ void __launch_bounds__(kPoseOptWarps * 32) poseopt_kernel(const PoseOptMeta* __restrict__ metas, int C,
                                                                      const float* __restrict__ p3d, const float* __restrict__ obs,
                                                                      const float* __restrict__ isig, uint8_t* __restrict__ outlier,
-                                                                     rsac_poseopt_result* __restrict__ results)
+                                                                     rsac_poseopt_result* __restrict__ results, int problem_base)
 {
     __shared__ double red_smem[kPoseOptWarps * po::kRedDoubles];
     const int w = threadIdx.x >> 5;
     const int c = blockIdx.x * (blockDim.x >> 5) + w;      // the host launches 1 or kPoseOptWarps frames per CTA
     if (c >= C) return;
     const PoseOptMeta m = metas[c];
-    po::pose_optimization<32>(m, p3d, obs, isig, outlier, threadIdx.x & 31, red_smem + w * po::kRedDoubles, results + c);
+    po::pose_optimization<32>(m, p3d, obs, isig, outlier, threadIdx.x & 31, red_smem + w * po::kRedDoubles, problem_base + c, results + c);
 }
 
 }  // namespace rsac

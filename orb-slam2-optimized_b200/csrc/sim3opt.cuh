@@ -424,7 +424,7 @@ __host__ __device__ inline int classify(const PairView& f, uint8_t* flag, const 
 template <int LANES>
 __host__ __device__ inline void optimize_sim3(const Sim3OptMeta& m, const float* x1, const float* x2, const float* o1, const float* o2,
                                               const float* is1, const float* is2, uint8_t* removed, int lane, double* smem,
-                                              rsac_sim3opt_result* out)
+                                              int problem, rsac_sim3opt_result* out)
 {
     PairView f;
     f.x1 = x1 + 3 * m.off; f.x2 = x2 + 3 * m.off; f.o1 = o1 + 2 * m.off; f.o2 = o2 + 2 * m.off; f.is1 = is1 + m.off; f.is2 = is2 + m.off;
@@ -472,7 +472,7 @@ __host__ __device__ inline void optimize_sim3(const Sim3OptMeta& m, const float*
         out->optimized = second ? 1 : 0;
         out->iterations = st.iterations;
         out->trials = st.trials;
-        out->reserved = 0;
+        out->problem = problem;
         po::quat_to_rot_d(F.q, out->R);
         for (int i = 0; i < 3; ++i) out->t[i] = F.t[i];
         out->s = F.s;
@@ -488,14 +488,14 @@ __global__ void __launch_bounds__(kSim3OptWarps * 32) sim3opt_kernel(const Sim3O
                                                                      const float* __restrict__ x1, const float* __restrict__ x2,
                                                                      const float* __restrict__ o1, const float* __restrict__ o2,
                                                                      const float* __restrict__ is1, const float* __restrict__ is2,
-                                                                     uint8_t* __restrict__ removed, rsac_sim3opt_result* __restrict__ results)
+                                                                     uint8_t* __restrict__ removed, rsac_sim3opt_result* __restrict__ results, int problem_base)
 {
     extern __shared__ double sim3opt_smem[];
     const int w = threadIdx.x >> 5;
     const int c = blockIdx.x * (blockDim.x >> 5) + w;      // 1 or kSim3OptWarps pairs per CTA
     if (c >= C) return;
     const Sim3OptMeta m = metas[c];
-    so::optimize_sim3<32>(m, x1, x2, o1, o2, is1, is2, removed, threadIdx.x & 31, sim3opt_smem + w * so::kSimSmemDoubles, results + c);
+    so::optimize_sim3<32>(m, x1, x2, o1, o2, is1, is2, removed, threadIdx.x & 31, sim3opt_smem + w * so::kSimSmemDoubles, problem_base + c, results + c);
 }
 
 }  // namespace rsac

@@ -77,7 +77,7 @@ class PoseOptBatch(C.Structure):
 
 # rsac_poseopt_result (include/ransac_b200.h)
 POSEOPT_DTYPE = np.dtype([("n_inliers", np.int32), ("n_bad", np.int32), ("rounds", np.int32), ("iterations", np.int32),
-                          ("trials", np.int32), ("reserved", np.int32), ("R", np.float64, (9,)), ("t", np.float64, (3,)),
+                          ("trials", np.int32), ("problem", np.int32), ("R", np.float64, (9,)), ("t", np.float64, (3,)),
                           ("Rf", np.float32, (9,)), ("tf", np.float32, (3,))], align=True)
 
 
@@ -89,7 +89,7 @@ class Sim3OptBatch(C.Structure):
 
 # rsac_sim3opt_result (include/ransac_b200.h)
 SIM3OPT_DTYPE = np.dtype([("n_inliers", np.int32), ("n_bad", np.int32), ("optimized", np.int32), ("iterations", np.int32),
-                          ("trials", np.int32), ("reserved", np.int32), ("R", np.float64, (9,)), ("t", np.float64, (3,)),
+                          ("trials", np.int32), ("problem", np.int32), ("R", np.float64, (9,)), ("t", np.float64, (3,)),
                           ("s", np.float64), ("q", np.float64, (4,))], align=True)
 
 

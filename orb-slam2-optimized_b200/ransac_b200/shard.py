@@ -44,11 +44,12 @@ def gather_records(local: "torch.Tensor", C: int, world: int, group=None):
     return out
 
 
-def records_from_tensor(t) -> np.ndarray:
-    """int32 [n, 24] tensor/array -> structured rsac_result array, padding rows (problem < 0) dropped,
-    ordered by global problem index."""
+def records_from_tensor(t, dtype=None) -> np.ndarray:
+    """int32 [n, words] tensor/array -> structured record array (rsac_result by default; capi.POSEOPT_DTYPE /
+    capi.SIM3OPT_DTYPE for the two optimisers, whose frames / keyframe pairs shard the same way), padding rows
+    (problem < 0) dropped, ordered by global problem index."""
     a = t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
-    rec = np.ascontiguousarray(a, np.int32).view(capi.RESULT_DTYPE).reshape(-1)
+    rec = np.ascontiguousarray(a, np.int32).view(dtype or capi.RESULT_DTYPE).reshape(-1)
     rec = rec[rec["problem"] >= 0]
     return rec[np.argsort(rec["problem"], kind="stable")]
 

@@ -76,3 +76,45 @@ def test_gloo_world2_gather_equals_single_rank(tmp_path, C, oracle):
         assert np.array_equal(r0[g]["R"], r["T"][:3, :3].reshape(-1)) and np.array_equal(r0[g]["t"], r["T"][:3, 3])
     first = shard.first_verified(r0, 30)
     assert first == next((int(x["problem"]) for x in r0 if x["ok"] and x["n_inliers"] >= 30), -1)
+
+
+def _worker_poseopt(rank, world, port, C, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "orb-slam2-optimized_b200"))
+    import oracle_api as O
+    from ransac_b200 import capi, shard, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, count = shard.block_range(C, rank, world)
+    cap = shard.per_rank_capacity(C, world)
+    rec = np.zeros(cap, capi.POSEOPT_DTYPE)
+    rec["problem"] = -1
+    for i in range(count):
+        g = first + i
+        p = synth.poseopt_problem(4100 + g, 80, 0.2, 0.5 * (g % 2))
+        d, _ = O.pose_optimization(O.poseopt_problem(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], p["Rcw"], p["tcw"]))
+        for k in ("n_inliers", "n_bad", "rounds", "iterations", "trials"):
+            rec[i][k] = d[k]
+        rec[i]["R"], rec[i]["t"], rec[i]["Rf"], rec[i]["tf"] = d["R"].ravel(), d["t"], d["Rf"].ravel(), d["tf"]
+        rec[i]["problem"] = g
+    words = capi.POSEOPT_DTYPE.itemsize // 4
+    local = torch.from_numpy(rec.view(np.int32).reshape(cap, words).copy())
+    out = shard.records_from_tensor(shard.gather_records(local, C, world), capi.POSEOPT_DTYPE)
+    np.save(os.path.join(out_dir, f"po_rank{rank}.npy"), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_pose_optimization_records(tmp_path, oracle):
+    """frames of a PoseOptimization batch shard like candidates: contiguous blocks, one all-gather of the 168-byte
+    records, index order restored on every rank"""
+    from ransac_b200 import synth
+    C, world = 5, 2
+    mp.spawn(_worker_poseopt, args=(world, _free_port(), C, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "po_rank0.npy"), np.load(tmp_path / "po_rank1.npy")
+    assert r0.tobytes() == r1.tobytes() and (r0["problem"] == np.arange(C)).all()
+    for g in range(C):
+        p = synth.poseopt_problem(4100 + g, 80, 0.2, 0.5 * (g % 2))
+        d, _ = oracle.pose_optimization(oracle.poseopt_problem(p["p3d"], p["obs"], p["inv_sigma2"], p["K"], p["Rcw"], p["tcw"]))
+        assert r0[g]["n_inliers"] == d["n_inliers"] and np.array_equal(r0[g]["R"], d["R"].ravel()) and np.array_equal(r0[g]["t"], d["t"])

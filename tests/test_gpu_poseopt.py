@@ -115,7 +115,7 @@ def test_poseopt_points_behind_the_camera_and_non_finite_input(engine, oracle):
         assert res[c]["rounds"] == o["rounds"]
         assert np.abs(res[c]["R"].reshape(3, 3) - o["R"]).max() < POSE_TOL and np.abs(res[c]["t"] - o["t"]).max() < POSE_TOL, c
         assert (g != oout).sum() <= 1 and abs(int(res[c]["n_inliers"]) - o["n_inliers"]) <= 1, c
-        assert g[3] == 1 and g[7] == 1
+        assert g[3] == oout[3] and g[7] == oout[7] and g[3] == 1      # the mirrored projection of a point behind the camera is far off
         if c >= 2:
             assert res[c]["iterations"] == 40 and res[c]["trials"] == 40 and g[11] == 0
 
