@@ -52,13 +52,19 @@ int rsac_poseopt_run(rsac_engine* e)
     if (!s.uploaded) { e->err = "rsac_poseopt_run before rsac_poseopt_upload"; return RSAC_ERR_STATE; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     if (s.C > 0) {
-        // a batch that cannot give every SM four CTAs is spread one frame per CTA (a loop-closure-sized batch of
-        // 64 frames would otherwise sit on 16 SMs)
-        const int W = s.C >= 4 * e->sm_count ? kPoseOptWarps : 1;
+        // large batches: one warp per frame, four frames per CTA (throughput); batches that cannot give every SM four
+        // CTAs: one frame per CTA with four warps on its edges (latency -- a relocalisation hands over a few frames)
+        const bool wide = s.C < 4 * e->sm_count;
         e->stage_begin(RSAC_STAGE_SELECT);
-        poseopt_kernel<<<(s.C + W - 1) / W, W * 32, 0, e->stream>>>(
-            (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)s.d_p3d.p, (const float*)s.d_obs.p, (const float*)s.d_isig.p,
-            (uint8_t*)s.d_outlier.p, (rsac_poseopt_result*)s.d_results.p, e->problem_base);
+        if (wide)
+            poseopt_kernel<128><<<s.C, 128, sizeof(double) * po::red_doubles(128), e->stream>>>(
+                (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)s.d_p3d.p, (const float*)s.d_obs.p, (const float*)s.d_isig.p,
+                (uint8_t*)s.d_outlier.p, (rsac_poseopt_result*)s.d_results.p, e->problem_base);
+        else
+            poseopt_kernel<32><<<(s.C + kPoseOptWarps - 1) / kPoseOptWarps, kPoseOptWarps * 32,
+                                 sizeof(double) * kPoseOptWarps * po::red_doubles(32), e->stream>>>(
+                (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)s.d_p3d.p, (const float*)s.d_obs.p, (const float*)s.d_isig.p,
+                (uint8_t*)s.d_outlier.p, (rsac_poseopt_result*)s.d_results.p, e->problem_base);
         e->stage_end(RSAC_STAGE_SELECT);
         RSAC_CUDA(e, cudaGetLastError());
     }

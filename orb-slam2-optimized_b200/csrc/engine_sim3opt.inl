@@ -66,14 +66,23 @@ int rsac_sim3opt_run(rsac_engine* e)
     if (!s.uploaded) { e->err = "rsac_sim3opt_run before rsac_sim3opt_upload"; return RSAC_ERR_STATE; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     if (s.C > 0) {
-        const int W = s.C >= 4 * e->sm_count ? kSim3OptWarps : 1;      // small batches: one pair per CTA, spread over the SMs
-        const size_t smem = sizeof(double) * (size_t)W * so::kSimSmemDoubles;
-        if (smem > 48 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)sim3opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // large batches: one warp per pair, four pairs per CTA; otherwise (a loop closure hands over a few candidates)
+        // one pair per CTA with four warps on its matches
+        const bool wide = s.C < 4 * e->sm_count;
+        const size_t smem = sizeof(double) * (size_t)(wide ? so::sim_smem_doubles(128) : kSim3OptWarps * so::sim_smem_doubles(32));
+        const void* kern = wide ? (const void*)sim3opt_kernel<128> : (const void*)sim3opt_kernel<32>;
+        if (smem > 48 * 1024) RSAC_TRY(set_func_attr_max(e, kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         e->stage_begin(RSAC_STAGE_SELECT);
-        sim3opt_kernel<<<(s.C + W - 1) / W, W * 32, smem, e->stream>>>(
-            (const Sim3OptMeta*)s.d_metas.p, s.C, (const float*)s.d_x1.p, (const float*)s.d_x2.p, (const float*)s.d_o1.p,
-            (const float*)s.d_o2.p, (const float*)s.d_is1.p, (const float*)s.d_is2.p, (uint8_t*)s.d_removed.p,
-            (rsac_sim3opt_result*)s.d_results.p, e->problem_base);
+        if (wide)
+            sim3opt_kernel<128><<<s.C, 128, smem, e->stream>>>(
+                (const Sim3OptMeta*)s.d_metas.p, s.C, (const float*)s.d_x1.p, (const float*)s.d_x2.p, (const float*)s.d_o1.p,
+                (const float*)s.d_o2.p, (const float*)s.d_is1.p, (const float*)s.d_is2.p, (uint8_t*)s.d_removed.p,
+                (rsac_sim3opt_result*)s.d_results.p, e->problem_base);
+        else
+            sim3opt_kernel<32><<<(s.C + kSim3OptWarps - 1) / kSim3OptWarps, kSim3OptWarps * 32, smem, e->stream>>>(
+                (const Sim3OptMeta*)s.d_metas.p, s.C, (const float*)s.d_x1.p, (const float*)s.d_x2.p, (const float*)s.d_o1.p,
+                (const float*)s.d_o2.p, (const float*)s.d_is1.p, (const float*)s.d_is2.p, (uint8_t*)s.d_removed.p,
+                (rsac_sim3opt_result*)s.d_results.p, e->problem_base);
         e->stage_end(RSAC_STAGE_SELECT);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -110,7 +119,7 @@ int rsac_debug_host_sim3opt(int n, const float* x1c, const float* x2c, const flo
     if (n < 0 || !K1 || !K2 || !S12 || !result) return RSAC_ERR_INVALID;
     Sim3OptMeta m;
     sim3opt_fill_meta(m, 0, n, K1, K2, S12, th2, fix_scale);
-    std::vector<double> scratch((size_t)so::kSimSmemDoubles);
+    std::vector<double> scratch((size_t)so::sim_smem_doubles(32));
     so::optimize_sim3<1>(m, x1c, x2c, obs1, obs2, inv_sigma2_1, inv_sigma2_2, removed, 0, scratch.data(), 0, result);
     return RSAC_OK;
 }

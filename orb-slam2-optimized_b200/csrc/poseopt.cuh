@@ -203,17 +203,41 @@ __host__ __device__ inline double huber_delta(bool stereo)
 // all lanes read the 28 totals back: ~130 instructions, and every lane holds bit-identical totals, which the
 // redundant 6x6 solve and step control need to take the same branches.
 constexpr int kRedStride = 33;
-constexpr int kRedDoubles = 28 * kRedStride + 28;     // partials + totals, per warp
+// per problem: W warps x (partials [28][33] + warp totals [28]) + W single-value slots
+__host__ __device__ constexpr int red_doubles(int lanes) { return (lanes / 32) * (28 * kRedStride + 28) + (lanes / 32); }
+constexpr int kRedDoubles = red_doubles(32);
 
+// LANES = 32: one warp per problem (throughput shape, __syncwarp only).  LANES = 128: four warps per problem, one
+// problem per CTA (latency shape for small batches): every warp reduces its own rows, the warp totals meet in shared
+// memory across __syncthreads() and every thread adds them in warp order -- all 128 threads hold bit-identical totals
+// and follow identical control flow, which is what makes the block-wide barriers legal.
 template <int LANES>
 struct Reducer {
-    double* sm;     // this warp's kRedDoubles
+    double* sm;     // this problem's red_doubles(LANES)
+    static constexpr int W = LANES >= 32 ? LANES / 32 : 1;
+    __host__ __device__ inline void barrier() const
+    {
+#ifdef __CUDA_ARCH__
+        if (LANES > 32) __syncthreads(); else __syncwarp();
+#endif
+    }
     __host__ __device__ inline void sum1(double& v)
     {
 #ifdef __CUDA_ARCH__
-        if (LANES == 32) {
+        if (LANES >= 32) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        }
+        if (LANES > 32) {
+            double* s1 = sm + W * (28 * kRedStride + 28);
+            const int w = (threadIdx.x % LANES) >> 5;
+            __syncthreads();                                // the previous totals have been read
+            if ((threadIdx.x & 31) == 0) s1[w] = v;
+            __syncthreads();
+            double t = s1[0];
+#pragma unroll
+            for (int k = 1; k < W; ++k) t += s1[k];
+            v = t;
         }
 #else
         (void)v;
@@ -222,22 +246,29 @@ struct Reducer {
     __host__ __device__ inline void sum28(double* v)
     {
 #ifdef __CUDA_ARCH__
-        if (LANES == 32) {
+        if (LANES >= 32) {
             const int lane = threadIdx.x & 31;
-            __syncwarp();                                   // the previous totals have been read by every lane
+            const int w = (threadIdx.x % LANES) >> 5;
+            double* part = sm + w * (28 * kRedStride + 28);
+            barrier();                                      // the previous totals have been read by every lane
 #pragma unroll
-            for (int k = 0; k < 28; ++k) sm[k * kRedStride + lane] = v[k];
+            for (int k = 0; k < 28; ++k) part[k * kRedStride + lane] = v[k];
             __syncwarp();
             if (lane < 28) {
-                const double* row = sm + lane * kRedStride;
+                const double* row = part + lane * kRedStride;
                 double t0 = row[0], t1 = row[1];
 #pragma unroll
                 for (int l = 2; l < 32; l += 2) { t0 += row[l]; t1 += row[l + 1]; }
-                sm[28 * kRedStride + lane] = t0 + t1;
+                part[28 * kRedStride + lane] = t0 + t1;
             }
-            __syncwarp();
+            barrier();
 #pragma unroll
-            for (int k = 0; k < 28; ++k) v[k] = sm[28 * kRedStride + k];
+            for (int k = 0; k < 28; ++k) {
+                double t = sm[28 * kRedStride + k];
+#pragma unroll
+                for (int x = 1; x < W; ++x) t += sm[x * (28 * kRedStride + 28) + 28 * kRedStride + k];
+                v[k] = t;
+            }
         }
 #else
         (void)v;
@@ -523,19 +554,23 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
 
 }  // namespace po
 
-constexpr int kPoseOptWarps = 4;      // frames per CTA at most (one warp per frame); small batches get one frame per CTA
+constexpr int kPoseOptWarps = 4;      // warps per CTA: four frames (LANES = 32) or one frame (LANES = 128)
 
+// LANES = 32: one warp per frame, blockDim/32 frames per CTA (large batches).  LANES = 128: one frame per CTA, four warps
+// on its edges (batches too small to fill the machine: a relocalisation with a handful of accepted candidates).
+template <int LANES>
 __global__ void __launch_bounds__(kPoseOptWarps * 32) poseopt_kernel(const PoseOptMeta* __restrict__ metas, int C,
                                                                      const float* __restrict__ p3d, const float* __restrict__ obs,
                                                                      const float* __restrict__ isig, uint8_t* __restrict__ outlier,
                                                                      rsac_poseopt_result* __restrict__ results, int problem_base)
 {
-    __shared__ double red_smem[kPoseOptWarps * po::kRedDoubles];
-    const int w = threadIdx.x >> 5;
-    const int c = blockIdx.x * (blockDim.x >> 5) + w;      // the host launches 1 or kPoseOptWarps frames per CTA
-    if (c >= C) return;
+    extern __shared__ double poseopt_smem[];
+    const int w = threadIdx.x / LANES;
+    const int c = blockIdx.x * (blockDim.x / LANES) + w;
+    if (c >= C) return;                                    // uniform over the LANES threads of a frame (and over the CTA when LANES = 128)
     const PoseOptMeta m = metas[c];
-    po::pose_optimization<32>(m, p3d, obs, isig, outlier, threadIdx.x & 31, red_smem + w * po::kRedDoubles, problem_base + c, results + c);
+    po::pose_optimization<LANES>(m, p3d, obs, isig, outlier, threadIdx.x % LANES, poseopt_smem + w * po::red_doubles(LANES),
+                                 problem_base + c, results + c);
 }
 
 }  // namespace rsac

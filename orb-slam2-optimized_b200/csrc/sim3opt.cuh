@@ -145,25 +145,44 @@ struct PairView {
 constexpr int kSimPoses = 15;                      // estimate + 14 perturbations
 constexpr int kSimAcc = 36;                        // H upper triangle 28 | b 7 | chi2
 constexpr int kSimRedStride = 33;
-constexpr int kSimSmemDoubles = kSimAcc * kSimRedStride + kSimAcc + 2 * kSimPoses * 8;   // per warp
+// per pair: W warps x (partials [36][33] + warp totals [36]) + W single-value slots + 2 x 15 transforms
+__host__ __device__ constexpr int sim_smem_doubles(int lanes)
+{
+    return (lanes / 32) * (kSimAcc * kSimRedStride + kSimAcc) + 8 + 2 * kSimPoses * 8;
+}
+constexpr int kSimSmemDoubles = sim_smem_doubles(32);
 
+// LANES = 32: one warp per pair (__syncwarp only); LANES = 128: four warps per pair, one pair per CTA (see poseopt.cuh)
 template <int LANES>
 struct SimShared {
-    double* red;        // [36][33] + [36]
+    double* red;        // W x ([36][33] + [36]), then 8 single-value slots
     Sim3T* fwd;         // [15]
     Sim3T* inv;         // [15]
+    static constexpr int W = LANES >= 32 ? LANES / 32 : 1;
+    static constexpr int kWarpDoubles = kSimAcc * kSimRedStride + kSimAcc;
     __host__ __device__ inline void sync() const
     {
 #ifdef __CUDA_ARCH__
-        __syncwarp();
+        if (LANES > 32) __syncthreads(); else __syncwarp();
 #endif
     }
     __host__ __device__ inline void sum1(double& v) const
     {
 #ifdef __CUDA_ARCH__
-        if (LANES == 32) {
+        if (LANES >= 32) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        }
+        if (LANES > 32) {
+            double* s1 = red + W * kWarpDoubles;
+            const int w = (threadIdx.x % LANES) >> 5;
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) s1[w] = v;
+            __syncthreads();
+            double t = s1[0];
+#pragma unroll
+            for (int k = 1; k < W; ++k) t += s1[k];
+            v = t;
         }
 #else
         (void)v;
@@ -172,22 +191,29 @@ struct SimShared {
     __host__ __device__ inline void sum36(double* v) const
     {
 #ifdef __CUDA_ARCH__
-        if (LANES == 32) {
+        if (LANES >= 32) {
             const int lane = threadIdx.x & 31;
-            __syncwarp();
+            const int w = (threadIdx.x % LANES) >> 5;
+            double* part = red + w * kWarpDoubles;
+            sync();
 #pragma unroll
-            for (int k = 0; k < kSimAcc; ++k) red[k * kSimRedStride + lane] = v[k];
+            for (int k = 0; k < kSimAcc; ++k) part[k * kSimRedStride + lane] = v[k];
             __syncwarp();
             for (int k = lane; k < kSimAcc; k += 32) {
-                const double* row = red + k * kSimRedStride;
+                const double* row = part + k * kSimRedStride;
                 double t0 = row[0], t1 = row[1];
 #pragma unroll
                 for (int l = 2; l < 32; l += 2) { t0 += row[l]; t1 += row[l + 1]; }
-                red[kSimAcc * kSimRedStride + k] = t0 + t1;
+                part[kSimAcc * kSimRedStride + k] = t0 + t1;
             }
-            __syncwarp();
+            sync();
 #pragma unroll
-            for (int k = 0; k < kSimAcc; ++k) v[k] = red[kSimAcc * kSimRedStride + k];
+            for (int k = 0; k < kSimAcc; ++k) {
+                double t = red[kSimAcc * kSimRedStride + k];
+#pragma unroll
+                for (int x = 1; x < W; ++x) t += red[x * kWarpDoubles + kSimAcc * kSimRedStride + k];
+                v[k] = t;
+            }
         }
 #else
         (void)v;
@@ -435,7 +461,7 @@ __host__ __device__ inline void optimize_sim3(const Sim3OptMeta& m, const float*
     f.n = m.n;
     SimShared<LANES> sh;
     sh.red = smem;
-    sh.fwd = reinterpret_cast<Sim3T*>(smem + kSimAcc * kSimRedStride + kSimAcc);
+    sh.fwd = reinterpret_cast<Sim3T*>(smem + SimShared<LANES>::W * SimShared<LANES>::kWarpDoubles + 8);
     sh.inv = sh.fwd + kSimPoses;
     uint8_t* flag = removed + m.off;
     for (int i = lane; i < f.n; i += LANES) flag[i] = 0;
@@ -482,8 +508,9 @@ __host__ __device__ inline void optimize_sim3(const Sim3OptMeta& m, const float*
 
 }  // namespace so
 
-constexpr int kSim3OptWarps = 4;      // keyframe pairs per CTA (one warp per pair)
+constexpr int kSim3OptWarps = 4;      // warps per CTA: four pairs (LANES = 32) or one pair (LANES = 128)
 
+template <int LANES>
 __global__ void __launch_bounds__(kSim3OptWarps * 32) sim3opt_kernel(const Sim3OptMeta* __restrict__ metas, int C,
                                                                      const float* __restrict__ x1, const float* __restrict__ x2,
                                                                      const float* __restrict__ o1, const float* __restrict__ o2,
@@ -491,11 +518,12 @@ __global__ void __launch_bounds__(kSim3OptWarps * 32) sim3opt_kernel(const Sim3O
                                                                      uint8_t* __restrict__ removed, rsac_sim3opt_result* __restrict__ results, int problem_base)
 {
     extern __shared__ double sim3opt_smem[];
-    const int w = threadIdx.x >> 5;
-    const int c = blockIdx.x * (blockDim.x >> 5) + w;      // 1 or kSim3OptWarps pairs per CTA
+    const int w = threadIdx.x / LANES;
+    const int c = blockIdx.x * (blockDim.x / LANES) + w;
     if (c >= C) return;
     const Sim3OptMeta m = metas[c];
-    so::optimize_sim3<32>(m, x1, x2, o1, o2, is1, is2, removed, threadIdx.x & 31, sim3opt_smem + w * so::kSimSmemDoubles, problem_base + c, results + c);
+    so::optimize_sim3<LANES>(m, x1, x2, o1, o2, is1, is2, removed, threadIdx.x % LANES, sim3opt_smem + w * so::sim_smem_doubles(LANES),
+                             problem_base + c, results + c);
 }
 
 }  // namespace rsac

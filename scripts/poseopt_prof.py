@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.join(ROOT, "orb-slam2-optimized_b200"))
 from ransac_b200 import capi, synth  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-C, N = 1024, 250
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 250
 pp = [synth.poseopt_problem(4000 + i, N, 0.2, 0.0) for i in range(C)]
 off = (np.arange(C + 1) * N).astype(np.int32)
 cat = lambda k: np.concatenate([q[k] for q in pp])

@@ -120,6 +120,13 @@ def test_poseopt_points_behind_the_camera_and_non_finite_input(engine, oracle):
             assert res[c]["iterations"] == 40 and res[c]["trials"] == 40 and g[11] == 0
 
 
+def test_poseopt_large_batch_takes_the_one_warp_per_frame_kernel(engine, oracle):
+    """batches of at least 4 x SM-count frames run one warp per frame (four frames per CTA), smaller ones four warps
+    per frame: both shapes must agree with the oracle (every other test here is a small batch)"""
+    ps = [synth.poseopt_problem(9900 + i, 40 + (i % 7), 0.2, 0.5 * (i % 2)) for i in range(640)]
+    _run(engine, oracle, ps)
+
+
 def test_poseopt_empty_batch(engine):
     res, out = engine.poseopt_solve(np.zeros(1, np.int32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32),
                                     np.zeros(0, np.float32), np.zeros((0, 5), np.float32), np.zeros((0, 12), np.float32))

@@ -82,3 +82,8 @@ def test_sim3opt_ragged_and_early_return(engine, oracle):
 def test_sim3opt_far_initial_estimate(engine, oracle):
     ps = [synth.sim3opt_problem(8300 + i, 120, 0.4, pose_noise=(0.1, 0.3)) for i in range(12)]
     _run(engine, oracle, ps)
+
+
+def test_sim3opt_large_batch_takes_the_one_warp_per_pair_kernel(engine, oracle):
+    ps = [synth.sim3opt_problem(8400 + i, 30 + (i % 5), 0.2) for i in range(640)]
+    _run(engine, oracle, ps)
