@@ -295,6 +295,12 @@ typedef struct {
 } rsac_poseopt_result;
 
 int rsac_poseopt_upload(rsac_engine* e, const rsac_poseopt_batch* b);
+/* Device-side chaining behind a PnP sweep (Tracking.cpp:1258-1284: the inliers of the accepted RANSAC pose become the
+ * frame's map points, the pose becomes mTcw, then PoseOptimization): frame c = PnP problem c of the engine's last run,
+ * edges = the correspondences of its final inlier mask (monocular), initial pose = its result; problems without a pose
+ * get an empty frame.  Nothing crosses PCIe.  After rsac_poseopt_run, rsac_poseopt_download returns one flag per PnP
+ * correspondence: 0 inlier, 1 outlier, 2 not an edge.  bf is only recorded (no stereo edges arise). */
+int rsac_poseopt_from_pnp(rsac_engine* e, float bf);
 int rsac_poseopt_run(rsac_engine* e);
 /* outlier: [total] pFrame->mvbOutlier of the matched keypoints (1 = outlier) */
 int rsac_poseopt_download(rsac_engine* e, rsac_poseopt_result* results, uint8_t* outlier);

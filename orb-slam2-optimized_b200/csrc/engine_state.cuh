@@ -152,6 +152,7 @@ struct Sim3State {
 
 struct PoseOptState {
     bool uploaded = false, ran = false;
+    bool chained = false;      // edges are the PnP engine's correspondences (rsac_poseopt_from_pnp)
     int C = 0;
     int64_t total = 0;
     DevBuf d_metas, d_p3d, d_obs, d_isig, d_outlier, d_results;

@@ -34,6 +34,7 @@ struct PoseOptMeta {
     float K[5];        // fx, fy, cx, cy, bf
     float Rcw[9];      // Frame::mTcw
     float tcw[3];
+    int32_t preset;    // 1: the flag array arrives initialised (2 = this slot is not an edge), see rsac_poseopt_from_pnp
 };
 
 struct Se3 { double q[4]; double t[3]; };   // quaternion (w, x, y, z) + translation, as g2o::SE3Quat
@@ -509,18 +510,30 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
     uint8_t* flag = outlier + m.off;
     Se3 T;
     se3_from_float(m.Rcw, m.tcw, T);
-    for (int i = lane; i < f.n; i += LANES) flag[i] = 0;
+    // nEdges: the keypoints that have a map point.  Chained behind the PnP engine (preset) the slots are all
+    // correspondences of the RANSAC problem and only the final inliers are edges: flag 2 = not an edge, skipped by every
+    // pass (`if (level[i]) continue`) and by the classification.
+    int nEdges = f.n;
+    if (m.preset) {
+        double cnt = 0.0;
+        for (int i = lane; i < f.n; i += LANES) cnt += flag[i] == 2 ? 0.0 : 1.0;
+        red.sum1(cnt);
+        nEdges = (int)cnt;
+    } else {
+        for (int i = lane; i < f.n; i += LANES) flag[i] = 0;
+    }
     Stats st = {0, 0};
     int nBad = 0, rounds = 0;
     bool robust = true;
-    if (f.n >= 3) {
-        int active = f.n;
+    if (nEdges >= 3) {
+        int active = nEdges;
         for (int it = 0; it < 4; ++it) {
             se3_from_float(m.Rcw, m.tcw, T);
             Se3 Terr = T;
             if (active > 0) optimize<LANES>(f, flag, robust, T, Terr, 10, lane, red, st);
             int bad = 0;
             for (int i = lane; i < f.n; i += LANES) {
+                if (flag[i] == 2) continue;
                 const Edge e = load_edge(f, i);
                 double x, y, z, e0, e1, e2;
                 const float chi2 = (float)edge_error(f, e, flag[i] ? T : Terr, x, y, z, e0, e1, e2);
@@ -532,14 +545,14 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
             red.sum1(badd);
             bad = (int)badd;
             nBad = bad;
-            active = f.n - bad;
+            active = nEdges - bad;
             if (it == 2) robust = false;
             ++rounds;
-            if (f.n < 10) break;
+            if (nEdges < 10) break;
         }
     }
     if (lane == 0) {
-        out->n_inliers = f.n >= 3 ? f.n - nBad : 0;
+        out->n_inliers = nEdges >= 3 ? nEdges - nBad : 0;
         out->n_bad = nBad;
         out->rounds = rounds;
         out->iterations = st.iterations;
@@ -553,6 +566,41 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
 }
 
 }  // namespace po
+
+// Chains PoseOptimization behind a PnP sweep without leaving the device (Tracking.cpp:1258-1284: the inliers of the
+// accepted RANSAC pose become the frame's map points, the pose becomes mTcw, then Optimizer::PoseOptimization): one CTA
+// per candidate writes the frame record and, per correspondence, the observation (u, v, -1: monocular),
+// 1/sigma^2 (float division, as ORBextractor fills mvInvLevelSigma2) and the edge flag (0 = inlier of the final mask,
+// 2 = not an edge).  Candidates without a pose get n = 0.
+__global__ void poseopt_from_pnp_kernel(const ProblemMeta* __restrict__ metas, int C, const rsac_result* __restrict__ results,
+                                        const uint32_t* __restrict__ masks, const float* __restrict__ p2d,
+                                        const float* __restrict__ sigma2, float bf, PoseOptMeta* __restrict__ out_metas,
+                                        float* __restrict__ obs, float* __restrict__ isig, uint8_t* __restrict__ flag)
+{
+    const int c = blockIdx.x;
+    if (c >= C) return;
+    const ProblemMeta m = metas[c];
+    const rsac_result r = results[c];
+    if (threadIdx.x == 0) {
+        PoseOptMeta o;
+        o.off = m.corr_off;
+        o.n = r.ok ? m.n : 0;
+        o.K[0] = (float)m.fx; o.K[1] = (float)m.fy; o.K[2] = (float)m.cx; o.K[3] = (float)m.cy; o.K[4] = bf;
+        for (int k = 0; k < 9; ++k) o.Rcw[k] = r.R[k];
+        for (int k = 0; k < 3; ++k) o.tcw[k] = r.t[k];
+        o.preset = 1;
+        out_metas[c] = o;
+    }
+    for (int i = threadIdx.x; i < m.n; i += blockDim.x) {
+        const size_t g = (size_t)m.corr_off + i;
+        const bool inl = r.ok && ((masks[m.word_off + (i >> 5)] >> (i & 31)) & 1u);
+        obs[3 * g] = p2d[2 * g];
+        obs[3 * g + 1] = p2d[2 * g + 1];
+        obs[3 * g + 2] = -1.0f;
+        isig[g] = 1.0f / sigma2[g];
+        flag[g] = inl ? 0 : 2;
+    }
+}
 
 constexpr int kPoseOptWarps = 4;      // warps per CTA: four frames (LANES = 32) or one frame (LANES = 128)
 

@@ -287,6 +287,7 @@ class Engine:
         desc, Cn, offsets = self._pnp_desc(offsets, p3d, p2d, sigma2, K, params, seeds, tables, table_offsets)
         self._ck(self.L.rsac_pnp_upload(self.h, C.byref(desc)), "pnp_upload")
         self._pnp_C = Cn
+        self._pnp_total = int(offsets[-1])
         self._pnp_words = ((np.diff(offsets) + 31) // 32).astype(np.int64)
         return Cn
 
@@ -442,6 +443,11 @@ class Engine:
         self._ck(self.L.rsac_poseopt_upload(self.h, C.byref(desc)), "poseopt_upload")
         self._poseopt_C, self._poseopt_total = Cn, int(offsets[-1])
         return Cn
+
+    def poseopt_from_pnp(self, bf=0.0):
+        """chain PoseOptimization behind the engine's last PnP run on the device (flags come back per PnP correspondence)"""
+        self._ck(self.L.rsac_poseopt_from_pnp(self.h, C.c_float(bf)), "poseopt_from_pnp")
+        self._poseopt_C, self._poseopt_total = self._pnp_C, self._pnp_total
 
     def poseopt_run(self):
         self._ck(self.L.rsac_poseopt_run(self.h), "poseopt_run")

@@ -132,3 +132,36 @@ def test_poseopt_empty_batch(engine):
                                     np.zeros(0, np.float32), np.zeros((0, 5), np.float32), np.zeros((0, 12), np.float32))
     assert res.shape[0] == 0 and out.shape[0] == 0
     print("poseopt GPU vs oracle:", STATS)
+
+
+def test_poseopt_chained_behind_a_pnp_sweep_on_the_device(engine, oracle):
+    """rsac_poseopt_from_pnp: the frames are built on the device from the PnP engine's resident correspondences, final
+    inlier masks and poses (Tracking.cpp:1258-1284); result = PoseOptimization of the compacted inlier sets from the
+    RANSAC poses, as the oracle computes it from the downloaded records."""
+    C, n = 12, 300
+    b = synth.pnp_batch(11, C, n, 0.5)
+    b["p2d"][5] += 400.0                                     # one candidate that RANSAC cannot verify: empty frame
+    offsets = (np.arange(C + 1) * n).astype(np.int32)
+    prm = capi.ransac_params(0.99, 10, 300, 4, 0.2, 5.991)
+    res, masks = engine.pnp_solve(offsets, b["p3d"], b["p2d"], b["sigma2"], [b["K"]], prm, seeds=b["seeds"], flags=capi.FLAG_EARLY_EXIT)
+    ml = engine.split_masks(masks, offsets)
+    engine.poseopt_from_pnp(bf=0.0)
+    engine.poseopt_run()
+    pres, flags = engine.poseopt_download()
+    assert flags.shape[0] == C * n
+    n_ok = 0
+    for c in range(C):
+        f = flags[c * n:(c + 1) * n]
+        if not res[c]["ok"]:
+            assert pres[c]["rounds"] == 0 and pres[c]["n_inliers"] == 0
+            continue
+        n_ok += 1
+        m = ml[c].astype(bool)
+        assert (f[~m] == 2).all() and (f[m] < 2).all()
+        p = dict(p3d=b["p3d"][c][m], obs=np.concatenate([b["p2d"][c][m], np.full((int(m.sum()), 1), -1, np.float32)], axis=1),
+                 isig=(np.float32(1) / b["sigma2"][c][m]).astype(np.float32), K=np.array(list(b["K"]) + [0.0], np.float32))
+        o, oout = oracle.pose_optimization(oracle.poseopt_problem(p["p3d"], p["obs"], p["isig"], p["K"], res[c]["R"].reshape(3, 3), res[c]["t"]))
+        assert pres[c]["rounds"] == o["rounds"]
+        assert np.abs(pres[c]["R"].reshape(3, 3) - o["R"]).max() < POSE_TOL and np.abs(pres[c]["t"] - o["t"]).max() < POSE_TOL, c
+        assert (f[m] != oout).sum() <= 1 and abs(int(pres[c]["n_inliers"]) - o["n_inliers"]) <= 1, c
+    assert n_ok >= C - 2 and not res[5]["ok"]
