@@ -733,6 +733,35 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                                    "note": "Optimizer.cpp:205-424 batched; e2e = upload from host buffers + kernel + records and flags back"}
     except Exception as err:
         ex["pose_optimization_error"] = repr(err)
+    # ---- the relocalisation chain on the device: cfg4 sweep (early exit) -> PoseOptimization of every verified candidate's
+    # inliers from its RANSAC pose (rsac_poseopt_from_pnp: nothing crosses PCIe between the two)
+    try:
+        bc = synth.pnp_batch(4, 1024, 500, 0.5)
+        offc = (np.arange(1025) * 500).astype(np.int32)
+        prmc = capi.ransac_params(0.99, 10, 300, 4, 0.2, 5.991)
+        eng.pnp_upload(offc, bc["p3d"], bc["p2d"], bc["sigma2"], [bc["K"]], prmc, seeds=bc["seeds"])
+        def chain():
+            eng.pnp_run(capi.FLAG_EARLY_EXIT)
+            eng.poseopt_from_pnp(0.0)
+            eng.poseopt_run()
+        for _ in range(3):
+            chain()
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(10):
+            chain()
+        msc = eng.timer_end() / 10
+        eng.timer_begin()
+        for _ in range(10):
+            eng.pnp_run(capi.FLAG_EARLY_EXIT)
+        msr = eng.timer_end() / 10
+        presc, _ = eng.poseopt_download()
+        ex["relocalisation_chain"] = {"candidates": 1024, "matches": 500, "ms_per_sweep_ransac_only": msr, "ms_per_sweep_with_pose_optimization": msc,
+                                      "candidates_per_s": 1024 / (msc * 1e-3), "frames_optimised": int((presc["rounds"] > 0).sum()),
+                                      "inliers_after_optimization_mean": float(presc["n_inliers"].mean()),
+                                      "note": "one engine, one sweep at a time (no sweeps in flight), inputs resident"}
+    except Exception as err:
+        ex["relocalisation_chain_error"] = repr(err)
     # ---- Optimizer::OptimizeSim3 for 256 loop candidates x 100 matches (fixed scale, th2 = 10)
     try:
         CS, NS = 256, 100
