@@ -21,7 +21,6 @@ int rsac_poseopt_upload(rsac_engine* e, const rsac_poseopt_batch* b)
         for (int k = 0; k < 5; ++k) m.K[k] = b->K[5 * c + k];
         for (int k = 0; k < 9; ++k) m.Rcw[k] = b->Tcw[12 * c + k];
         for (int k = 0; k < 3; ++k) m.tcw[k] = b->Tcw[12 * c + 9 + k];
-        m.preset = 0;
     }
     s.C = C;
     s.chained = false;
@@ -62,16 +61,19 @@ int rsac_poseopt_from_pnp(rsac_engine* e, float bf)
     s.chained = true;
     const size_t tot = (size_t)std::max<int64_t>(total, 1);
     RSAC_TRY(s.d_metas.ensure(e, sizeof(PoseOptMeta) * (size_t)std::max(C, 1)));
+    RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
     RSAC_TRY(s.d_obs.ensure(e, tot * 12));
     RSAC_TRY(s.d_isig.ensure(e, tot * 4));
     RSAC_TRY(s.d_outlier.ensure(e, tot));
+    RSAC_TRY(s.d_src.ensure(e, tot * 4));
+    RSAC_TRY(s.d_full.ensure(e, tot));
     RSAC_TRY(s.d_results.ensure(e, sizeof(rsac_poseopt_result) * (size_t)std::max(C, 1)));
     if (C > 0) {
         e->stage_begin(RSAC_STAGE_PACK);
         poseopt_from_pnp_kernel<<<C, 128, 0, e->stream>>>((const ProblemMeta*)p.d_metas.p, C, (const rsac_result*)p.d_results.p,
-                                                          (const uint32_t*)p.d_masks.p, (const float*)p.d_p2d.p, (const float*)p.d_sigma2.p,
-                                                          bf, (PoseOptMeta*)s.d_metas.p, (float*)s.d_obs.p, (float*)s.d_isig.p,
-                                                          (uint8_t*)s.d_outlier.p);
+                                                          (const uint32_t*)p.d_masks.p, (const float*)p.d_p3d.p, (const float*)p.d_p2d.p,
+                                                          (const float*)p.d_sigma2.p, bf, (PoseOptMeta*)s.d_metas.p, (float*)s.d_p3d.p,
+                                                          (float*)s.d_obs.p, (float*)s.d_isig.p, (int32_t*)s.d_src.p);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -92,15 +94,22 @@ int rsac_poseopt_run(rsac_engine* e)
         e->stage_begin(RSAC_STAGE_SELECT);
         if (wide)
             poseopt_kernel<128><<<s.C, 128, sizeof(double) * po::red_doubles(128), e->stream>>>(
-                (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)(s.chained ? e->pnp.d_p3d.p : s.d_p3d.p), (const float*)s.d_obs.p, (const float*)s.d_isig.p,
+                (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)s.d_p3d.p, (const float*)s.d_obs.p, (const float*)s.d_isig.p,
                 (uint8_t*)s.d_outlier.p, (rsac_poseopt_result*)s.d_results.p, e->problem_base);
         else
             poseopt_kernel<32><<<(s.C + kPoseOptWarps - 1) / kPoseOptWarps, kPoseOptWarps * 32,
                                  sizeof(double) * kPoseOptWarps * po::red_doubles(32), e->stream>>>(
-                (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)(s.chained ? e->pnp.d_p3d.p : s.d_p3d.p), (const float*)s.d_obs.p, (const float*)s.d_isig.p,
+                (const PoseOptMeta*)s.d_metas.p, s.C, (const float*)s.d_p3d.p, (const float*)s.d_obs.p, (const float*)s.d_isig.p,
                 (uint8_t*)s.d_outlier.p, (rsac_poseopt_result*)s.d_results.p, e->problem_base);
         e->stage_end(RSAC_STAGE_SELECT);
         RSAC_CUDA(e, cudaGetLastError());
+        if (s.chained) {
+            e->stage_begin(RSAC_STAGE_PACK);
+            poseopt_scatter_flags_kernel<<<s.C, 128, 0, e->stream>>>((const ProblemMeta*)e->pnp.d_metas.p, s.C, (const PoseOptMeta*)s.d_metas.p,
+                                                                     (const uint8_t*)s.d_outlier.p, (const int32_t*)s.d_src.p, (uint8_t*)s.d_full.p);
+            e->stage_end(RSAC_STAGE_PACK);
+            RSAC_CUDA(e, cudaGetLastError());
+        }
     }
     s.ran = true;
     return RSAC_OK;
@@ -114,7 +123,7 @@ int rsac_poseopt_download(rsac_engine* e, rsac_poseopt_result* results, uint8_t*
     if (results && s.C > 0)
         RSAC_CUDA(e, cudaMemcpyAsync(results, s.d_results.p, sizeof(rsac_poseopt_result) * (size_t)s.C, cudaMemcpyDeviceToHost, e->stream));
     if (outlier && s.total > 0)
-        RSAC_CUDA(e, cudaMemcpyAsync(outlier, s.d_outlier.p, (size_t)s.total, cudaMemcpyDeviceToHost, e->stream));
+        RSAC_CUDA(e, cudaMemcpyAsync(outlier, s.chained ? s.d_full.p : s.d_outlier.p, (size_t)s.total, cudaMemcpyDeviceToHost, e->stream));
     RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
     return RSAC_OK;
 }
@@ -138,7 +147,6 @@ int rsac_debug_host_poseopt(int n, const float* p3d, const float* obs, const flo
     for (int k = 0; k < 5; ++k) m.K[k] = K[k];
     for (int k = 0; k < 9; ++k) m.Rcw[k] = Tcw[k];
     for (int k = 0; k < 3; ++k) m.tcw[k] = Tcw[9 + k];
-    m.preset = 0;
     po::pose_optimization<1>(m, p3d, obs, inv_sigma2, outlier, 0, nullptr, 0, result);
     return RSAC_OK;
 }

@@ -155,11 +155,11 @@ struct PoseOptState {
     bool chained = false;      // edges are the PnP engine's correspondences (rsac_poseopt_from_pnp)
     int C = 0;
     int64_t total = 0;
-    DevBuf d_metas, d_p3d, d_obs, d_isig, d_outlier, d_results;
+    DevBuf d_metas, d_p3d, d_obs, d_isig, d_outlier, d_results, d_src, d_full;
     PinnedBuf h_metas;
     void release()
     {
-        DevBuf* all[] = {&d_metas, &d_p3d, &d_obs, &d_isig, &d_outlier, &d_results};
+        DevBuf* all[] = {&d_metas, &d_p3d, &d_obs, &d_isig, &d_outlier, &d_results, &d_src, &d_full};
         for (DevBuf* b : all) b->release();
         h_metas.release();
     }

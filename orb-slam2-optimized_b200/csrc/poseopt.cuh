@@ -34,7 +34,6 @@ struct PoseOptMeta {
     float K[5];        // fx, fy, cx, cy, bf
     float Rcw[9];      // Frame::mTcw
     float tcw[3];
-    int32_t preset;    // 1: the flag array arrives initialised (2 = this slot is not an edge), see rsac_poseopt_from_pnp
 };
 
 struct Se3 { double q[4]; double t[3]; };   // quaternion (w, x, y, z) + translation, as g2o::SE3Quat
@@ -510,18 +509,8 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
     uint8_t* flag = outlier + m.off;
     Se3 T;
     se3_from_float(m.Rcw, m.tcw, T);
-    // nEdges: the keypoints that have a map point.  Chained behind the PnP engine (preset) the slots are all
-    // correspondences of the RANSAC problem and only the final inliers are edges: flag 2 = not an edge, skipped by every
-    // pass (`if (level[i]) continue`) and by the classification.
-    int nEdges = f.n;
-    if (m.preset) {
-        double cnt = 0.0;
-        for (int i = lane; i < f.n; i += LANES) cnt += flag[i] == 2 ? 0.0 : 1.0;
-        red.sum1(cnt);
-        nEdges = (int)cnt;
-    } else {
-        for (int i = lane; i < f.n; i += LANES) flag[i] = 0;
-    }
+    const int nEdges = f.n;
+    for (int i = lane; i < f.n; i += LANES) flag[i] = 0;
     Stats st = {0, 0};
     int nBad = 0, rounds = 0;
     bool robust = true;
@@ -533,7 +522,6 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
             if (active > 0) optimize<LANES>(f, flag, robust, T, Terr, 10, lane, red, st);
             int bad = 0;
             for (int i = lane; i < f.n; i += LANES) {
-                if (flag[i] == 2) continue;
                 const Edge e = load_edge(f, i);
                 double x, y, z, e0, e1, e2;
                 const float chi2 = (float)edge_error(f, e, flag[i] ? T : Terr, x, y, z, e0, e1, e2);
@@ -569,37 +557,61 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
 
 // Chains PoseOptimization behind a PnP sweep without leaving the device (Tracking.cpp:1258-1284: the inliers of the
 // accepted RANSAC pose become the frame's map points, the pose becomes mTcw, then Optimizer::PoseOptimization): one CTA
-// per candidate writes the frame record and, per correspondence, the observation (u, v, -1: monocular),
-// 1/sigma^2 (float division, as ORBextractor fills mvInvLevelSigma2) and the edge flag (0 = inlier of the final mask,
-// 2 = not an edge).  Candidates without a pose get n = 0.
-__global__ void poseopt_from_pnp_kernel(const ProblemMeta* __restrict__ metas, int C, const rsac_result* __restrict__ results,
-                                        const uint32_t* __restrict__ masks, const float* __restrict__ p2d,
-                                        const float* __restrict__ sigma2, float bf, PoseOptMeta* __restrict__ out_metas,
-                                        float* __restrict__ obs, float* __restrict__ isig, uint8_t* __restrict__ flag)
+// per candidate compacts the inliers of the final mask, in correspondence order, into the optimiser's own arrays --
+// point, observation (u, v, -1: monocular), 1/sigma^2 (float division, as ORBextractor fills mvInvLevelSigma2) -- at the
+// problem's correspondence offset, remembers where each came from (`src`) and writes the frame record.  Candidates
+// without a pose get an empty frame.
+__global__ void __launch_bounds__(128) poseopt_from_pnp_kernel(const ProblemMeta* __restrict__ metas, int C,
+                                                              const rsac_result* __restrict__ results, const uint32_t* __restrict__ masks,
+                                                              const float* __restrict__ p3d_in, const float* __restrict__ p2d,
+                                                              const float* __restrict__ sigma2, float bf, PoseOptMeta* __restrict__ out_metas,
+                                                              float* __restrict__ p3d, float* __restrict__ obs, float* __restrict__ isig,
+                                                              int32_t* __restrict__ src)
 {
+    __shared__ int s_pre[2049];                 // exclusive popcount prefix over the mask words (n <= 65536)
     const int c = blockIdx.x;
     if (c >= C) return;
     const ProblemMeta m = metas[c];
     const rsac_result r = results[c];
+    const int words = r.ok ? min(m.words, 2048) : 0;
     if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int w = 0; w < words; ++w) { s_pre[w] = acc; acc += __popc(masks[m.word_off + w]); }
+        s_pre[words] = acc;
         PoseOptMeta o;
         o.off = m.corr_off;
-        o.n = r.ok ? m.n : 0;
+        o.n = acc;
         o.K[0] = (float)m.fx; o.K[1] = (float)m.fy; o.K[2] = (float)m.cx; o.K[3] = (float)m.cy; o.K[4] = bf;
         for (int k = 0; k < 9; ++k) o.Rcw[k] = r.R[k];
         for (int k = 0; k < 3; ++k) o.tcw[k] = r.t[k];
-        o.preset = 1;
         out_metas[c] = o;
     }
-    for (int i = threadIdx.x; i < m.n; i += blockDim.x) {
-        const size_t g = (size_t)m.corr_off + i;
-        const bool inl = r.ok && ((masks[m.word_off + (i >> 5)] >> (i & 31)) & 1u);
-        obs[3 * g] = p2d[2 * g];
-        obs[3 * g + 1] = p2d[2 * g + 1];
-        obs[3 * g + 2] = -1.0f;
-        isig[g] = 1.0f / sigma2[g];
-        flag[g] = inl ? 0 : 2;
+    __syncthreads();
+    const int n = min(m.n, words * 32);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t wv = masks[m.word_off + (i >> 5)];
+        if (!((wv >> (i & 31)) & 1u)) continue;
+        const int k = s_pre[i >> 5] + __popc(wv & ((1u << (i & 31)) - 1u));
+        const size_t g = (size_t)m.corr_off + i, d = (size_t)m.corr_off + k;
+        p3d[3 * d] = p3d_in[3 * g]; p3d[3 * d + 1] = p3d_in[3 * g + 1]; p3d[3 * d + 2] = p3d_in[3 * g + 2];
+        obs[3 * d] = p2d[2 * g]; obs[3 * d + 1] = p2d[2 * g + 1]; obs[3 * d + 2] = -1.0f;
+        isig[d] = 1.0f / sigma2[g];
+        src[d] = i;
     }
+}
+
+// flags of a chained run back in the PnP correspondence index space: 2 = not an edge, else the optimiser's flag
+__global__ void __launch_bounds__(128) poseopt_scatter_flags_kernel(const ProblemMeta* __restrict__ metas, int C,
+                                                                   const PoseOptMeta* __restrict__ frames, const uint8_t* __restrict__ flag,
+                                                                   const int32_t* __restrict__ src, uint8_t* __restrict__ full)
+{
+    const int c = blockIdx.x;
+    if (c >= C) return;
+    const ProblemMeta m = metas[c];
+    const int n_edges = frames[c].n;
+    for (int i = threadIdx.x; i < m.n; i += blockDim.x) full[(size_t)m.corr_off + i] = 2;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_edges; k += blockDim.x) full[(size_t)m.corr_off + src[(size_t)m.corr_off + k]] = flag[(size_t)m.corr_off + k];
 }
 
 constexpr int kPoseOptWarps = 4;      // warps per CTA: four frames (LANES = 32) or one frame (LANES = 128)
