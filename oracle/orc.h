@@ -8,6 +8,8 @@
  * What it is: a dependency-free plain-C restatement of the reference's
  *   src/PnPsolver.cpp, src/Sim3Solver.cpp, src/MLPnPsolver.cpp and
  *   Thirdparty/DBoW2/DUtils/Random.cpp:47-50
+ * and, for SURVEY 8(f) N1, of src/Optimizer.cpp:205-424 (PoseOptimization) and :1054-1249 (OptimizeSim3) over the
+ * vendored g2o's Levenberg-Marquardt, SE3/Sim3 exponential maps and numeric Jacobians (oracle/orc_poseopt.c),
  * following the reference function by function (each function cites file:line).
  *
  * PARITY UNPINNED for every Eigen-backed step: the reference cannot be compiled
