@@ -338,7 +338,7 @@ void orc_svd_lstsq_d(int m, int k, const double *L, const double *b, double *x)
  * is what the reference's call means for a rank-deficient system.  Mirrored by csrc/linalg.cuh qr_lstsq. */
 static int qr_lstsq(int m, int k, const double *L, const double *b, double *x)
 {
-    double A[8 * 6], bb[8], rd[6];
+    double A[8 * 6], bb[8], rd[6] = {0, 0, 0, 0, 0, 0};   /* k >= 1 always; the initialiser only quiets -Wmaybe-uninitialized */
     memcpy(A, L, sizeof(double) * (size_t)(m * k));
     memcpy(bb, b, sizeof(double) * (size_t)m);
     for (int c = 0; c < k; ++c) {
