@@ -40,6 +40,12 @@ struct Se3 { double q[4]; double t[3]; };   // quaternion (w, x, y, z) + transla
 
 namespace po {
 
+#ifndef RSAC_PO_UNROLL
+#define RSAC_PO_UNROLL 1
+#endif
+constexpr int kEdgeUnroll = RSAC_PO_UNROLL;     // edges of a lane unrolled together; measured on B200 (1024 x 250): 1: 0.53 ms, 2: 0.70, 3: 0.81
+                                                // -- the code outgrows the instruction cache faster than the ILP pays
+
 __host__ __device__ inline double po_fma(double a, double b, double c) { return fma(a, b, c); }   // twin: fma() in oracle/orc_poseopt.c
 
 __host__ __device__ inline void quat_from_rot(const double* m, double* q)
@@ -282,6 +288,7 @@ __host__ __device__ inline double active_chi2(const FrameView& f, const uint8_t*
                                               Reducer<LANES>& red)
 {
     double sum = 0.0;
+#pragma unroll(kEdgeUnroll)
     for (int i = lane; i < f.n; i += LANES) {
         if (level[i]) continue;
         const Edge e = load_edge(f, i);
@@ -310,6 +317,7 @@ __host__ __device__ inline double build_system(const FrameView& f, const uint8_t
     double& chi = all[27];
 #pragma unroll
     for (int k = 0; k < 28; ++k) all[k] = 0.0;
+#pragma unroll(kEdgeUnroll)
     for (int i = lane; i < f.n; i += LANES) {
         if (level[i]) continue;
         const Edge e = load_edge(f, i);
