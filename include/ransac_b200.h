@@ -9,7 +9,9 @@
  * (src/Tracking.cpp:1225-1255) and LoopClosing::ComputeSim3 (src/LoopClosing.cpp:260-308).
  * The C++ classes of the same names in include/ransac_b200/solvers.hpp keep that API and are
  * thin wrappers over the entry points below; the *_batch entry points are what the two
- * callers use to verify all candidates in one device pass.
+ * callers use to verify all candidates in one device pass.  The two consumers of the accepted poses,
+ * Optimizer::PoseOptimization (src/Optimizer.cpp:205-424) and Optimizer::OptimizeSim3 (src/Optimizer.cpp:1054-1249),
+ * are batched behind rsac_poseopt_* / rsac_sim3opt_* (SURVEY 8(f) N1).
  *
  * Conventions: extern "C", POD structs, plain pointers and sizes, caller-allocated
  * outputs, integer status codes (never throws across the ABI).  Host pointers unless a
