@@ -351,9 +351,13 @@ int rsac_sim3opt_solve(rsac_engine* e, const rsac_sim3opt_batch* b, rsac_sim3opt
 /* ------------------------------------------------ multi-GPU (candidates shard) */
 /* contiguous block partition of C problems over `world` ranks: rank r owns [*first, *first + *count) */
 int rsac_shard_range(int C, int rank, int world, int* first, int* count);
-/* NCCL all-gather of the per-problem records of the last PnP/MLPnP/Sim3 run (kind 0/1/2).
- * comm: an initialised ncclComm_t passed as void*; every rank contributes `count_per_rank`
- * records (pad with problem = -1) and receives world*count_per_rank into d_gathered. */
+/* NCCL all-gather of per-problem records (the one exchange step of the path).
+ * rsac_nccl_get_unique_id on rank 0 -> broadcast the 128 bytes by any means -> rsac_nccl_init on every rank
+ * (persistent communicator owned by the engine; released by rsac_nccl_destroy or rsac_destroy).
+ * rsac_nccl_allgather_results: enqueued on the engine's stream, so it orders after the replay kernel without a
+ * host round trip; d_send = this rank's `count_per_rank` rsac_result records on the device (e.g. the
+ * d_results_out buffer of rsac_*_run; pad with problem = -1), d_gathered receives world*count_per_rank records
+ * in rank order. */
 int rsac_nccl_get_unique_id(void* id128);
 int rsac_nccl_init(rsac_engine* e, const void* id128, int rank, int world);
 int rsac_nccl_allgather_results(rsac_engine* e, const void* d_send, int count_per_rank, void* d_gathered);

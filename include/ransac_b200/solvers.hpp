@@ -173,7 +173,11 @@ public:
         vbInliers.clear();
         nInliers = 0;
         if (N < mRansacMinInliers) { bNoMore = true; return false; }
-        if (cursor_ >= mRansacMaxIts) { bNoMore = true; return false; }   // budget spent by earlier calls
+        // Budget spent by earlier calls: the reference's loop (`mnIterations<mRansacMaxIts || nCurrentIterations<nIterations`,
+        // PnPsolver.cpp:119) would draw nIterations FRESH minimal sets beyond the budget and then fall back to the best
+        // set so far (:173-188).  The extra draws are not performed here (deviations); the fallback is:
+        // the rerun below resumes at the end of the table, finds nothing and returns mBestTcw / mvbBestInliers with
+        // bNoMore = true when mnBestInliers >= mRansacMinInliers.
         std::lock_guard<std::mutex> lock(eng_->mutex());
         rsac_result r;
         std::vector<uint32_t> words((size_t)(N + 31) / 32);
@@ -346,7 +350,7 @@ public:
         vbInliers.clear();
         nInliers = 0;
         if (N < mRansacMinInliers) { bNoMore = true; return false; }
-        if (cursor_ >= mRansacMaxIts) { bNoMore = true; return false; }
+        // budget spent: best-so-far fallback with bNoMore = true (see PnPsolver::iterate above; MLPnPsolver.cpp:71,165-180)
         std::lock_guard<std::mutex> lock(eng_->mutex());
         if (!(epoch_ != 0 && epoch_ == eng_->epoch())) {
             int32_t offsets[2] = {0, N};

@@ -143,6 +143,10 @@ int orc_pnp_check_inliers(const orc_pnp_problem *pb, const float *max_err, const
 void orc_pnp_score(const orc_pnp_problem *pb, const float *max_err, int H, const float *poses,
                    uint8_t *masks, int *counts);
 
+/* test hooks for the null-space-basis experiments ("The 4-point null space") */
+void orc_epnp_mtm(const orc_pnp_problem *pb, const uint32_t *idx, int m, double MtM[144]);
+double orc_epnp_pose_basis(const orc_pnp_problem *pb, const uint32_t *idx, int m, const double U[48], float R[9], float t[3]);
+
 /* ------------------------------------------------------------------ Sim3Solver */
 typedef struct {
     int n;
@@ -200,6 +204,12 @@ void orc_mlpnp_res_jac(const double pt[3], const double nr[3], const double ns[3
 double orc_pnp_batch(int C, const orc_pnp_problem *pbs, const orc_ransac_params *prm,
                      const uint32_t *const *tables, int flags, int nthreads,
                      orc_result *res, long long *evals_done);
+double orc_pnp_batch_masks(int C, const orc_pnp_problem *pbs, const orc_ransac_params *prm,
+                           const uint32_t *const *tables, int flags, int nthreads,
+                           orc_result *res, uint8_t **masks, long long *evals_done);
+double orc_mlpnp_batch_masks(int C, const orc_mlpnp_problem *pbs, const orc_ransac_params *prm,
+                             const uint32_t *const *tables, int flags, int nthreads,
+                             orc_result *res, uint8_t **masks, long long *evals_done);
 double orc_sim3_batch(int C, const orc_sim3_problem *pbs, double prob, int min_inliers, int max_its,
                       const uint32_t *const *tables, int flags, int nthreads,
                       orc_result *res, long long *evals_done);

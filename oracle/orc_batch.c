@@ -31,6 +31,7 @@ typedef struct {
     const uint32_t *const *tables;
     int flags;
     orc_result *res;
+    uint8_t **masks;    /* optional: per-problem inlier masks (n bytes each) */
     long long *evals;   /* per task */
     int next;           /* atomic task counter */
     /* score */
@@ -54,15 +55,15 @@ static void *worker(void *arg)
         if (i >= j->C) break;
         if (j->kind == 0) {
             const orc_pnp_problem *pb = (const orc_pnp_problem *)j->pbs + i;
-            orc_pnp_ransac(pb, j->prm, j->tables[i], j->flags, &j->res[i], NULL, NULL, NULL);
+            orc_pnp_ransac(pb, j->prm, j->tables[i], j->flags, &j->res[i], j->masks ? j->masks[i] : NULL, NULL, NULL);
             j->evals[i] = (long long)(j->res[i].n_hyp + j->res[i].n_refines) * pb->n;
         } else if (j->kind == 1) {
             const orc_sim3_problem *pb = (const orc_sim3_problem *)j->pbs + i;
-            orc_sim3_ransac(pb, j->prob, j->min_inliers, j->max_its, j->tables[i], j->flags, &j->res[i], NULL, NULL, NULL);
+            orc_sim3_ransac(pb, j->prob, j->min_inliers, j->max_its, j->tables[i], j->flags, &j->res[i], j->masks ? j->masks[i] : NULL, NULL, NULL);
             j->evals[i] = (long long)j->res[i].n_hyp * pb->n;
         } else {
             const orc_mlpnp_problem *pb = (const orc_mlpnp_problem *)j->pbs + i;
-            orc_mlpnp_ransac(pb, j->prm, j->tables[i], j->flags, &j->res[i], NULL, NULL, NULL);
+            orc_mlpnp_ransac(pb, j->prm, j->tables[i], j->flags, &j->res[i], j->masks ? j->masks[i] : NULL, NULL, NULL);
             j->evals[i] = (long long)(j->res[i].n_hyp + j->res[i].n_refines) * pb->n;
         }
     }
@@ -97,6 +98,27 @@ double orc_pnp_batch(int C, const orc_pnp_problem *pbs, const orc_ransac_params 
     job_t j;
     memset(&j, 0, sizeof(j));
     j.kind = 0; j.C = C; j.pbs = pbs; j.prm = prm; j.tables = tables; j.flags = flags; j.res = res;
+    return run_job(&j, nthreads, evals_done);
+}
+
+/* same with the returned inlier masks (masks[i]: n_i bytes), for full-size parity tests */
+double orc_pnp_batch_masks(int C, const orc_pnp_problem *pbs, const orc_ransac_params *prm,
+                           const uint32_t *const *tables, int flags, int nthreads,
+                           orc_result *res, uint8_t **masks, long long *evals_done)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.kind = 0; j.C = C; j.pbs = pbs; j.prm = prm; j.tables = tables; j.flags = flags; j.res = res; j.masks = masks;
+    return run_job(&j, nthreads, evals_done);
+}
+
+double orc_mlpnp_batch_masks(int C, const orc_mlpnp_problem *pbs, const orc_ransac_params *prm,
+                             const uint32_t *const *tables, int flags, int nthreads,
+                             orc_result *res, uint8_t **masks, long long *evals_done)
+{
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.kind = 2; j.C = C; j.pbs = pbs; j.prm = prm; j.tables = tables; j.flags = flags; j.res = res; j.masks = masks;
     return run_job(&j, nthreads, evals_done);
 }
 

@@ -23,6 +23,8 @@ typedef struct {
     int max_n, n;
     int stale_rows;                    /* Q1 */
     int qr_nullspace;                  /* ORC_FLAG_EPNP_QR_NULLSPACE: n == 4 uses orc_nullspace_qr_d */
+    const double *ext_basis;           /* test hook: null-space basis supplied by the caller (12 x 4, row-major) */
+    double *mtm_out;                   /* test hook: receives the full symmetric 12 x 12 M^T M */
 } epnp_t;
 
 static void epnp_init(epnp_t *e, double fx, double fy, double cx, double cy, int stale_rows)
@@ -459,7 +461,14 @@ static double compute_pose(epnp_t *e, float Rf[9], float tf[3])
             }
     }
     double w[4], U[48];
-    if (use_qr) {
+    if (e->mtm_out)
+        for (int a = 0; a < 12; ++a)
+            for (int b = a; b < 12; ++b) e->mtm_out[a * 12 + b] = e->mtm_out[b * 12 + a] = MtM[a * 12 + b];
+    if (e->ext_basis) {
+        /* basis-sensitivity experiments (tests/test_cpu_basis_agreement.py): everything downstream of :380-382
+         * runs on a caller-supplied orthonormal basis of the (near-)null space, e.g. LAPACK's */
+        memcpy(U, e->ext_basis, sizeof(U));
+    } else if (use_qr) {
         /* the same 8 x 12 M, null space taken directly (see orc_nullspace_qr_d) */
         double Mrows[8 * 12];
         for (int i = 0; i < 4; ++i)
@@ -579,6 +588,34 @@ double orc_epnp_pose_mode(const orc_pnp_problem *pb, const uint32_t *idx, int m,
     epnp_t e;
     epnp_init(&e, pb->fx, pb->fy, pb->cx, pb->cy, 0);
     e.qr_nullspace = (flags & ORC_FLAG_EPNP_QR_NULLSPACE) != 0;
+    set_maximum_number_of_correspondences(&e, m);
+    reset_correspondences(&e);
+    for (int i = 0; i < m; ++i) add_correspondence(&e, pb->p3d + 3 * idx[i], pb->p2d + 2 * idx[i]);
+    const double err = compute_pose(&e, R, t);
+    epnp_free(&e);
+    return err;
+}
+
+/* test hooks for the null-space-basis experiments: M^T M of the subset (12 x 12, symmetric, row-major) and the
+ * solve of PnPsolver::compute_pose (:383-415) downstream of a caller-supplied basis U (12 x 4, column j = vector j) */
+void orc_epnp_mtm(const orc_pnp_problem *pb, const uint32_t *idx, int m, double MtM[144])
+{
+    epnp_t e;
+    float R[9], t[3];
+    epnp_init(&e, pb->fx, pb->fy, pb->cx, pb->cy, 0);
+    e.mtm_out = MtM;
+    set_maximum_number_of_correspondences(&e, m);
+    reset_correspondences(&e);
+    for (int i = 0; i < m; ++i) add_correspondence(&e, pb->p3d + 3 * idx[i], pb->p2d + 2 * idx[i]);
+    compute_pose(&e, R, t);
+    epnp_free(&e);
+}
+
+double orc_epnp_pose_basis(const orc_pnp_problem *pb, const uint32_t *idx, int m, const double U[48], float R[9], float t[3])
+{
+    epnp_t e;
+    epnp_init(&e, pb->fx, pb->fy, pb->cx, pb->cy, 0);
+    e.ext_basis = U;
     set_maximum_number_of_correspondences(&e, m);
     reset_correspondences(&e);
     for (int i = 0; i < m; ++i) add_correspondence(&e, pb->p3d + 3 * idx[i], pb->p2d + 2 * idx[i]);

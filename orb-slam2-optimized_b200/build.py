@@ -1,5 +1,7 @@
 """Builds libransac_b200.so in-tree with nvcc for sm_100a.
 
+One object per translation unit (csrc/engine*.cu), compiled in parallel, then linked.
+
 Flags that matter:
   -gencode arch=compute_100a,code=sm_100a   B200 only, no other targets
   -fmad=false                               no FMA contraction by the compiler anywhere; code asks for
@@ -11,52 +13,73 @@ Flags that matter:
 """
 from __future__ import annotations
 
+import concurrent.futures
+import glob
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libransac_b200.so")
-SOURCES = ["engine.cu"]   # one translation unit; engine_*.inl are included by it
 
 
-def _newer(src_dir: str, out: str) -> bool:
-    if not os.path.exists(out):
-        return True
-    t = os.path.getmtime(out)
-    for root, _, files in os.walk(src_dir):
-        for f in files:
-            if os.path.getmtime(os.path.join(root, f)) > t:
-                return True
+def _sources():
+    return sorted(glob.glob(os.path.join(CSRC, "engine*.cu")) + glob.glob(os.path.join(CSRC, "bow*.cu")))
+
+
+def _headers_mtime() -> float:
+    t = os.path.getmtime(__file__)
     inc = os.path.join(os.path.dirname(HERE), "include")
-    for root, _, files in os.walk(inc):
-        for f in files:
-            if os.path.getmtime(os.path.join(root, f)) > t:
-                return True
-    return os.path.getmtime(__file__) > t
+    for d in (CSRC, inc):
+        for root, _, files in os.walk(d):
+            for f in files:
+                if f.endswith((".cuh", ".h", ".hpp", ".inl")):
+                    t = max(t, os.path.getmtime(os.path.join(root, f)))
+    return t
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     out = os.environ.get("RSAC_LIB_OUT", OUT)            # tuning variants: another file name, extra -D flags
     extra = os.environ.get("RSAC_EXTRA_NVCC", "").split()
-    if not force and not extra and not _newer(CSRC, out):
-        return out
+    objdir = OBJ if not extra else OBJ + "_" + str(abs(hash(tuple(extra))) % 100000)
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc, "-shared", "-o", out, "-std=c++17", "-O3", "-lineinfo",
-           "-gencode", "arch=compute_100a,code=sm_100a",
-           "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-           "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O3",
-           "-cudart", "static"] + extra + srcs + ["-ldl"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
+    hdr_t = _headers_mtime()
+    flags = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+             "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+             "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O3"] + extra
+    jobs, objs = [], []
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(hdr_t, os.path.getmtime(src)):
+            cmd = [nvcc, "-c", "-o", obj] + flags + [src]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append(cmd)
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return cmd, r
+
+    failed = False
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for cmd, r in ex.map(run, jobs):
+                if verbose or r.returncode != 0:
+                    sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+                failed = failed or r.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libransac_b200.so")
+    if jobs or not os.path.exists(out) or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs):
+        cmd = [nvcc, "-shared", "-o", out, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"] + objs + ["-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("link failed for libransac_b200.so")
     return out
 
 

@@ -25,4 +25,17 @@ struct ProblemMeta {
 
 constexpr float kUnitRoundoff = 5.9604644775390625e-08f;   // 2^-24
 
+#ifdef __CUDACC__
+// problem that owns global hypothesis g (binary search over hyp_off)
+__device__ __forceinline__ int find_problem(const ProblemMeta* metas, int C, int64_t g)
+{
+    int lo = 0, hi = C - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int64_t)metas[mid].hyp_off <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+#endif
+
 }  // namespace rsac

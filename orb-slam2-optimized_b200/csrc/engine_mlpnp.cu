@@ -1,10 +1,13 @@
-// engine_mlpnp.inl -- C ABI for the batched MLPnPsolver (include/ransac_b200.h, "MLPnPsolver").
-// (included at the end of engine.cu: the library is one translation unit)
+// engine_mlpnp.cu -- C ABI for the batched MLPnPsolver (include/ransac_b200.h, "MLPnPsolver").
+#include "engine_shared.cuh"
+#include "mlpnp_pipeline.cuh"
+#include "select.cuh"
 
 int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
 {
     if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
     if (!b->seeds && !b->tables) { e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
+    if (b->C > 0 && !b->K) { e->err = "K is NULL"; return RSAC_ERR_INVALID; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     PnpState& s = e->mlpnp;
     s.uploaded = false; s.ran = false; s.tables_ready = false;
@@ -51,11 +54,11 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
     if (s.have_tables && d.table_len > 0)
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_tables.p, b->tables, sizeof(uint32_t) * (size_t)d.table_len, cudaMemcpyHostToDevice, st));
     if (d.total > 0 && d.C > 0) {
-        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)d.C);
+        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)std::min(d.C, 65535));
         e->stage_begin(RSAC_STAGE_PACK);
         pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
                                               (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 1,
-                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p);
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p, d.C);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }
@@ -75,7 +78,6 @@ static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resum
     a.problem_base = e->problem_base; a.flags = flags; a.resume = d_resume;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
     if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    e->stage_begin(RSAC_STAGE_SELECT);
     {
         cudaFuncAttributes fa;
         RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<1>));
@@ -83,6 +85,7 @@ static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resum
         const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
         RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
+    e->stage_begin(RSAC_STAGE_SELECT);
     ransac_select_kernel<1><<<d.C, kSelectThreadsMlpnp, smem, e->stream>>>(a);
     e->stage_end(RSAC_STAGE_SELECT);
     RSAC_CUDA(e, cudaGetLastError());

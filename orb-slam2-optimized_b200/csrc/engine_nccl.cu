@@ -1,5 +1,4 @@
-// engine_nccl.inl -- native NCCL exchange of the per-candidate records.
-// (included at the end of engine.cu: the library is one translation unit)
+// engine_nccl.cu -- native NCCL exchange of the per-candidate records.
 //
 // The only exchange step of the path is one all-gather of fixed-size records (rsac_result, 96 B
 // per candidate) per sweep; the communicator is persistent and the collective is enqueued on
@@ -7,6 +6,11 @@
 // libnccl.so.2 is resolved at run time (dlopen): the library has no link-time NCCL dependency
 // and picks up the copy the host process already loaded (e.g. the one bundled with torch).
 #include <dlfcn.h>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include "../../include/ransac_b200.h"
+#include "engine_state.cuh"
 
 namespace {
 typedef struct { char internal[128]; } nccl_unique_id_t;
@@ -30,7 +34,8 @@ struct NcclApi {
 NcclApi& nccl_api()
 {
     static NcclApi api;
-    if (!api.lib) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (api.lib) {
@@ -40,7 +45,7 @@ NcclApi& nccl_api()
             api.comm_destroy = (fn_comm_destroy)dlsym(api.lib, "ncclCommDestroy");
             api.get_error_string = (fn_get_error_string)dlsym(api.lib, "ncclGetErrorString");
         }
-    }
+    });
     return api;
 }
 }  // namespace

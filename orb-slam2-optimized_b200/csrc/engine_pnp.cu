@@ -1,0 +1,669 @@
+// engine_pnp.cu -- C ABI for the batched PnPsolver (EPnP RANSAC sweep, early exit in stages) and the cfg5 scoring
+// entry points (include/ransac_b200.h, "PnPsolver").
+#include "engine_shared.cuh"
+#include "pnp_pipeline.cuh"
+#include "select.cuh"
+
+static int pnp_first_phase(rsac_engine* e, const BatchDims& d)
+{
+    // first stage: three quarters of one wave of the minimal solver unless the caller chose (whole blocks: 1024
+    // problems x 55 hypotheses = 440 blocks of 128 <= 444 resident is a full wave).  Measured on cfg4 with six sweeps in
+    // flight, ms per sweep resident / end to end: (55,177) 0.449 / 0.504, (55,110,220) 0.440 / 0.512,
+    // (40,80,160) 0.421 / 0.474, (28,55,110,220) 0.420 / 0.498, (20,40,80,160) 0.428 / 0.500
+    int HA = e->first_phase > 0 ? e->first_phase : env_int("RSAC_EE_HA", 0);
+    if (HA <= 0) {
+        const int blocks = RSAC_SOLVE_BLOCKS * e->sm_count;
+        const int wave = (int)(((int64_t)blocks * RSAC_SOLVE_THREADS) / std::max(d.C, 1));
+        HA = wave >= d.maxH ? wave : std::max(16, wave * 3 / 4);
+    }
+    return HA;
+}
+
+// stage boundaries b0 < b1 < ... < b(K-1) = maxH: hypotheses [0, b0) for every problem, [b(j-1), bj) for the problems
+// still without an acceptable hypothesis.  Caller's choice (rsac_set_stages / rsac_set_phases / RSAC_EE_STAGES), else
+// b0 = three quarters of a solver wave and every further stage doubles what exists (cfg4: 41, 82, 164, 300)
+static std::vector<int> pnp_stage_bounds(rsac_engine* e, const BatchDims& d)
+{
+    std::vector<int> b;
+    const char* env = getenv("RSAC_EE_STAGES");
+    if (!e->stage_bounds.empty()) {
+        b = e->stage_bounds;
+    } else if (env && *env) {
+        for (const char* p = env; *p;) {
+            b.push_back(atoi(p));
+            while (*p && *p != ',') ++p;
+            if (*p == ',') ++p;
+        }
+    } else {
+        const int HA = pnp_first_phase(e, d);
+        b.push_back(HA);
+        if (e->second_phase > 0) b.push_back(e->second_phase);
+        else
+            while (b.back() < d.maxH && (int)b.size() < kMaxStages - 1) b.push_back(b.back() * 2);
+    }
+    // sanitise: strictly increasing, inside (0, maxH), last = maxH
+    std::vector<int> out;
+    for (int v : b) {
+        v = std::min(v, d.maxH);
+        if (v <= 0 || (!out.empty() && v <= out.back())) continue;
+        out.push_back(v);
+        if (v >= d.maxH || (int)out.size() == kMaxStages - 1) break;
+    }
+    if (out.empty() || out.back() < d.maxH) out.push_back(std::max(d.maxH, 1));
+    return out;
+}
+
+// scoring plans of the stages: [0, b0) with static work lists, [b(j-1), bj) and the clean-up range [b0, H) driven by
+// device-side lists; their work arrays go H2D through pinned staging
+static int pnp_plan_early(rsac_engine* e, const std::vector<int>& bounds)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    cudaStream_t st = e->stream;
+    const int K = (int)bounds.size();
+    s.ee_bounds = bounds;
+    s.ee_HA = bounds[0];
+    s.ee_plans.assign(K + 1, ScorePlanPOD());
+    s.ee_groups.assign(K + 1, std::vector<ScoreGroup>());
+    if ((int)s.ee_visit.size() < K + 1) s.ee_visit.resize(K + 1);
+    // stage 0: few hypotheses per problem -- one hypothesis per lane (two consumer warps per problem) measured
+    // best (0.045 ms against 0.066 with two per lane at 1024 x 55)
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.ee_groups[0], s.ee_plans[0], 0, bounds[0], env_int("RSAC_EE_HPL_A", 1), env_int("RSAC_EE_CW_A", 0)));
+    const int hplB = env_int("RSAC_EE_HPL_B", 0), cwB = env_int("RSAC_EE_CW_B", 0);
+    for (int j = 1; j < K; ++j)
+        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.ee_groups[j], s.ee_plans[j], bounds[j - 1], bounds[j], hplB, cwB, true));
+    RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.ee_groups[K], s.ee_plans[K], bounds[0], INT32_MAX, hplB, cwB, true));   // clean-up
+    std::vector<size_t> off(K + 2, 0);
+    for (int i = 0; i <= K; ++i) off[i + 1] = (off[i] + sizeof(ScoreGroup) * s.ee_plans[i].work.size() + 255) & ~(size_t)255;
+    char* h = (char*)s.h_stageEE.ensure(off[K + 1] + 256);
+    if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
+    for (int i = 0; i <= K; ++i) {
+        const size_t bytes = sizeof(ScoreGroup) * s.ee_plans[i].work.size();
+        RSAC_TRY(s.ee_visit[i].ensure(e, std::max<size_t>(bytes, sizeof(ScoreGroup))));
+        memcpy(h + off[i], s.ee_plans[i].work.data(), bytes);
+        RSAC_CUDA(e, cudaMemcpyAsync(s.ee_visit[i].p, h + off[i], bytes, cudaMemcpyHostToDevice, st));
+    }
+    s.h_stageEE.mark(st);
+    s.ee_planned = true;
+    return RSAC_OK;
+}
+
+static int pnp_pack(rsac_engine* e)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    if (s.packed) return RSAC_OK;
+    if (d.total > 0 && d.C > 0) {
+        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)std::min(d.C, 65535));
+        e->stage_begin(RSAC_STAGE_PACK);
+        pack_pnp_kernel<<<grid, 256, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
+                                                     (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 0,
+                                                     (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p, d.C);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.packed = true;
+    return RSAC_OK;
+}
+
+int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
+{
+    if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
+    if (!b->seeds && !b->tables) { if (e) e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
+    if (b->C > 0 && !b->K) { e->err = "K is NULL"; return RSAC_ERR_INVALID; }
+    // the minimal solver is the reference's call shape: mRansacMinSet = 4 (Tracking.cpp:1226; PnPsolver.hpp:27 default).
+    // Other sizes would need an n-point minimal kernel and a different table stride: refused, not silently misread
+    for (int c = 0; c < b->n_params; ++c)
+        if (b->params[c].min_set != 4) { e->err = "PnP needs min_set = 4"; return RSAC_ERR_INVALID; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    PnpState& s = e->pnp;
+    s.uploaded = false; s.ran = false; s.ee_mode = false;
+    std::vector<float> th2;
+    int rc = pnp_build_metas(e, b->C, b->offsets, b->params, b->n_params, b->seeds, b->table_offsets, b->tables != nullptr, s.metas, th2, s.d);
+    if (rc) return rc;
+    for (int c = 0; c < b->C; ++c) {
+        s.metas[c].fx = b->K[4 * c]; s.metas[c].fy = b->K[4 * c + 1]; s.metas[c].cx = b->K[4 * c + 2]; s.metas[c].cy = b->K[4 * c + 3];
+    }
+    const BatchDims& d = s.d;
+    const size_t tot = (size_t)std::max(d.total, 1);
+    // The scoring plans (tiles, chunking, per-CTA work lists) depend only on the batch's shape -- n, H and the focal
+    // lengths of every problem, and the stage boundaries -- so a batch shaped like the previous one reuses them,
+    // including the work arrays already on the device (a relocalisation loop with a fixed match budget per candidate)
+    const std::vector<int> bounds_now = pnp_stage_bounds(e, d);
+    std::vector<int32_t> sig;
+    sig.reserve(4 * (size_t)b->C + 4);
+    for (int c = 0; c < b->C; ++c) {
+        const float fx = (float)s.metas[c].fx, fy = (float)s.metas[c].fy;
+        int32_t fxb, fyb;
+        memcpy(&fxb, &fx, 4); memcpy(&fyb, &fy, 4);
+        sig.push_back(s.metas[c].n); sig.push_back(s.metas[c].H); sig.push_back(fxb); sig.push_back(fyb);
+    }
+    for (int v : bounds_now) sig.push_back(v);
+    sig.push_back(b->C);
+    const bool same_shape = s.plans_valid && sig == s.shape_sig;
+    if (!same_shape) {
+        s.plans_valid = false;
+        s.ee_planned = false;
+        RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groups, s.plan));
+    }
+
+    RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_th2.ensure(e, sizeof(float) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
+    RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
+    RSAC_TRY(s.d_sigma2.ensure(e, tot * 4));
+    RSAC_TRY(s.d_cA.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cB.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cP.ensure(e, (size_t)std::max<int64_t>(d.total_words, 1) * 1024));
+    RSAC_TRY(s.d_uv.ensure(e, tot * 16));
+    RSAC_TRY(s.d_tables.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.table_len, 1)));
+    RSAC_TRY(s.d_poses.ensure(e, sizeof(float) * 12 * (size_t)std::max<int64_t>(d.sumH, 1)));
+    RSAC_TRY(s.d_counts.ensure(e, sizeof(int32_t) * ((size_t)std::max<int64_t>(d.sumH, 1) + 8 + s.groups.size())));
+    RSAC_TRY(s.d_results.ensure(e, sizeof(rsac_result) * std::max(d.C, 1)));
+    RSAC_TRY(s.d_masks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_words, 1)));
+    RSAC_TRY(s.d_sel.ensure(e, tot * 4));
+    RSAC_TRY(s.d_pw.ensure(e, tot * 24));
+    RSAC_TRY(s.d_us.ensure(e, tot * 16));
+    RSAC_TRY(s.d_al.ensure(e, tot * 32));
+    RSAC_TRY(s.d_extra.ensure(e, tot * 96));   // refine scratch: 12 doubles per correspondence
+
+    cudaStream_t st = e->stream;
+    RSAC_TRY(stage_small_tables(e, s, th2, !same_shape));
+    if (d.total > 0) {
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, b->p3d, (size_t)d.total * 12, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, b->p2d, (size_t)d.total * 8, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_sigma2.p, b->sigma2, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));
+    }
+    s.have_tables = b->tables != nullptr;
+    if (s.have_tables && d.table_len > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_tables.p, b->tables, sizeof(uint32_t) * (size_t)d.table_len, cudaMemcpyHostToDevice, st));
+    s.h2d_bytes = (uint64_t)d.total * 24 + sizeof(ProblemMeta) * (uint64_t)d.C + sizeof(float) * (uint64_t)d.C +
+                  sizeof(ScoreGroup) * s.groups.size() + (s.have_tables ? sizeof(uint32_t) * (uint64_t)d.table_len : 0);
+    // the packing kernel is launched by the first run: a caller that uploads sweep k+1 while sweep k computes
+    // (two engines) then overlaps only DMA with the kernels of sweep k -- a concurrent packing kernel takes block
+    // slots from the solver and replay kernels, whose grids are sized to exactly one wave
+    s.packed = false;
+    s.tables_ready = false;
+    {
+        // the early-exit plans travel with the upload: no H2D copy is left for the run (copies issued by a run wait
+        // for the previous sweep in the copy queue, in front of the next sweep's inputs)
+        if (d.sumH > 0 && bounds_now.size() > 1 && !s.ee_planned) RSAC_TRY(pnp_plan_early(e, bounds_now));
+    }
+    s.shape_sig.swap(sig);
+    s.plans_valid = true;
+    s.uploaded = true;
+    return RSAC_OK;
+}
+
+// ---- early exit in phases (pnp_pipeline.cuh) ----
+static int solve_range_setup(rsac_engine* e)
+{
+    const size_t smem = sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS;
+    if (smem > 32 * 1024)
+        RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t need = (smem + 1024) * RSAC_SOLVE_BLOCKS;
+    const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
+    RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    return RSAC_OK;
+}
+
+static int pnp_early_flag(rsac_engine* e, int stage, int lim, int mode)
+{
+    PnpState& s = e->pnp;
+    e->stage_begin(RSAC_STAGE_RNG);
+    early_exit_flag_kernel<<<(s.d.C + 3) / 4, 128, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, s.d.C, (const int32_t*)s.d_counts.p,
+                                                                  stage, lim, (int32_t*)s.d_ee.p, mode);
+    e->stage_end(RSAC_STAGE_RNG);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+// minimal solves + scoring of hypotheses [lo, hi) of the problems in `list` (device-side count); plan index `pi` is
+// the list-driven scoring plan of that range
+static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* list_count, int lo, int hi, int pi)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    const int span = std::min(hi, d.maxH) - lo;
+    if (span <= 0) return RSAC_OK;
+    const int64_t most = (int64_t)d.C * span;
+    const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
+    e->stage_begin(RSAC_STAGE_SOLVE);
+    epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, e->stream>>>(
+        (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, lo, span, (const uint32_t*)s.d_tables.p,
+        (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+    e->stage_end(RSAC_STAGE_SOLVE);
+    RSAC_CUDA(e, cudaGetLastError());
+    ScoreArgs sa = s.ee_sa;
+    sa.list = list;
+    sa.list_count = list_count;
+    return launch_score<0>(e, sa, s.ee_plans[pi], (int)s.ee_groups[pi].size(), s.ee_visit[pi]);
+}
+
+static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase);
+
+static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, const std::vector<int>& bounds)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    cudaStream_t st = e->stream;
+    const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
+    if (!s.ee_planned || s.ee_bounds != bounds) RSAC_TRY(pnp_plan_early(e, bounds));   // normally done by the upload
+    const int K = (int)bounds.size();
+    s.ee_mode = true;
+    s.ee_complete = false;
+    RSAC_TRY(s.d_ee.ensure(e, sizeof(int32_t) * early_exit_words(d.C)));
+    RSAC_CUDA(e, cudaMemsetAsync(s.d_ee.p, 0, sizeof(int32_t) * early_exit_words(d.C), st));
+    const EarlyExit v = early_exit_view((int32_t*)s.d_ee.p, d.C);
+    RSAC_TRY(solve_range_setup(e));
+
+    ScoreArgs sa;
+    RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, 0, sa));
+    sa.metas = metas;
+    sa.cP = (const float4*)s.d_cP.p; sa.cC = (const float4*)s.d_uv.p;
+    sa.poses = s.d_poses.p;
+    sa.hmasks = nullptr;
+    if (flags & RSAC_FLAG_KEEP_MASKS) {
+        RSAC_TRY(s.d_hmasks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_hwords, 1)));
+        sa.hmasks = (uint32_t*)s.d_hmasks.p;
+    }
+    s.ee_sa = sa;
+
+    // stage 0: hypotheses [0, b0) of every problem
+    {
+        const int64_t most = (int64_t)d.C * bounds[0];
+        const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
+        e->stage_begin(RSAC_STAGE_SOLVE);
+        epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, st>>>(
+            metas, d.C, nullptr, nullptr, 0, bounds[0], (const uint32_t*)s.d_tables.p, (const float4*)s.d_cA.p, (const float4*)s.d_uv.p,
+            (float*)s.d_poses.p);
+        e->stage_end(RSAC_STAGE_SOLVE);
+        RSAC_CUDA(e, cudaGetLastError());
+        RSAC_TRY(launch_score<0>(e, sa, s.ee_plans[0], (int)s.ee_groups[0].size(), s.ee_visit[0]));
+    }
+    // who goes on after stage j-1 (list j); stage j: [b(j-1), bj) of list j
+    for (int j = 1; j < K; ++j) {
+        RSAC_TRY(pnp_early_flag(e, j - 1, bounds[j - 1], 0));
+        RSAC_TRY(pnp_early_range(e, v.list(j), v.counters + j, bounds[j - 1], bounds[j], j));
+    }
+    RSAC_TRY(pnp_early_flag(e, K - 1, bounds[K - 1], 0));     // the members of the last list have everything
+    // replay; problems it cannot decide go to the clean-up
+    RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, -1));
+    RSAC_TRY(pnp_early_range(e, v.listC, v.counters + kCleanupCounter, bounds[0], d.maxH, K));
+    RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, 2));
+    s.ran = true;
+    return RSAC_OK;
+}
+
+static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    SelectArgs a;
+    if (s.ee_mode) { a.ee = (int32_t*)s.d_ee.p; a.C = d.C; a.first_phase = s.ee_HA; a.only_phase = only_phase; }
+    a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.cC = (const float4*)s.d_uv.p;
+    a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = nullptr; a.flags = flags; a.resume = d_resume;
+    a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p; a.tm_s = (double*)s.d_extra.p;
+    a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
+    a.problem_base = e->problem_base;
+    const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
+    if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        cudaFuncAttributes fa;
+        RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<0>));
+        const size_t need = (fa.sharedSizeBytes + smem + 1024) * kSelectCtasPerSm;
+        const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
+        RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+    e->stage_begin(RSAC_STAGE_SELECT);
+    ransac_select_kernel<0><<<d.C, kSelectThreads, smem, e->stream>>>(a);
+    e->stage_end(RSAC_STAGE_SELECT);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+// later iterate() calls on solvers that already ran: only the replay stage, from per-problem cursors
+int rsac_pnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* d_results_out)
+{
+    if (!e || !resume_from) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    if (!s.ran) { e->err = "rsac_pnp_rerun before rsac_pnp_run"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    if (s.d.C == 0) return RSAC_OK;
+    RSAC_TRY(e->d_resume.ensure(e, sizeof(int32_t) * (size_t)s.d.C));
+    RSAC_CUDA(e, cudaMemcpyAsync(e->d_resume.p, resume_from, sizeof(int32_t) * (size_t)s.d.C, cudaMemcpyHostToDevice, e->stream));
+    if (s.ee_mode && !s.ee_complete) {
+        // the last run stopped early: problems that were decided inside their first HA hypotheses get the rest
+        // now, so that the scan can go on wherever the caller resumes it
+        const EarlyExit v = early_exit_view((int32_t*)s.d_ee.p, s.d.C);
+        RSAC_CUDA(e, cudaMemsetAsync(v.counters + kCleanupCounter, 0, sizeof(int32_t), e->stream));
+        RSAC_TRY(pnp_early_flag(e, 0, 0, 2));
+        RSAC_TRY(pnp_early_range(e, v.listC, v.counters + kCleanupCounter, s.ee_HA, s.d.maxH, (int)s.ee_bounds.size()));
+        s.ee_complete = true;
+    }
+    return pnp_launch_select(e, flags, (const int32_t*)e->d_resume.p, d_results_out, -1);
+}
+
+int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    if (!s.uploaded) { e->err = "rsac_pnp_run before rsac_pnp_upload"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    const BatchDims& d = s.d;
+    cudaStream_t st = e->stream;
+    const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
+    if (d.C == 0) { s.ran = true; return RSAC_OK; }
+    // the minimal-set tables depend on the seeds only: generated once per upload, later runs of the same
+    // batch reuse them (like tables passed in by the host)
+    const bool need_rng = !s.have_tables && d.table_len > 0 && !s.tables_ready;
+    if (need_rng && !s.packed && e->aux_stream && !e->profile) {
+        // first run after an upload: table generation (one warp per problem, latency-bound) and packing
+        // (bandwidth-bound) are independent: fork the former onto the side stream
+        RSAC_CUDA(e, cudaEventRecord(e->ev_fork, st));
+        RSAC_CUDA(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        ++e->launches;
+        rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, e->aux_stream>>>(metas, d.C, (uint32_t*)s.d_tables.p);
+        RSAC_CUDA(e, cudaGetLastError());
+        RSAC_CUDA(e, cudaEventRecord(e->ev_join, e->aux_stream));
+        RSAC_TRY(pnp_pack(e));
+        RSAC_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
+        s.tables_ready = true;
+    } else {
+        RSAC_TRY(pnp_pack(e));
+        if (need_rng) {
+            e->stage_begin(RSAC_STAGE_RNG);
+            rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
+            e->stage_end(RSAC_STAGE_RNG);
+            RSAC_CUDA(e, cudaGetLastError());
+            s.tables_ready = true;
+        }
+    }
+    s.ee_mode = false;
+    if ((flags & RSAC_FLAG_EARLY_EXIT) && !(flags & RSAC_FLAG_EPNP_EIGEN) && d.sumH > 0) {
+        const std::vector<int> bounds = pnp_stage_bounds(e, d);
+        if (bounds.size() > 1) return pnp_run_early(e, flags, d_results_out, bounds);
+    }
+    if (d.sumH > 0) {
+        const bool eigen = (flags & RSAC_FLAG_EPNP_EIGEN) != 0;
+        if (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS > 32 * 1024)
+            RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS)));
+        {
+            // ask for exactly the shared-memory carve-out that keeps RSAC_SOLVE_BLOCKS blocks resident (the rest of
+            // the 228 KB stays L1 for the kernel's local memory); left to its own devices the driver was seen to pick
+            // a smaller carve-out in some processes, which silently drops a block per SM (0.96 vs 0.82 ms)
+            const size_t need = (sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS + 1024) * RSAC_SOLVE_BLOCKS;
+            const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
+            RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
+        const int threads = eigen ? 128 : RSAC_SOLVE_THREADS;
+        const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
+        e->stage_begin(RSAC_STAGE_SOLVE);
+        if (eigen)
+            epnp_minimal_kernel<false><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
+                                                                   (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+        else
+            epnp_minimal_kernel<true><<<blocks, threads, sizeof(double) * kSolveSmemDoubles * threads, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
+                                                                  (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+        e->stage_end(RSAC_STAGE_SOLVE);
+        RSAC_CUDA(e, cudaGetLastError());
+
+        ScoreArgs sa;
+        RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, (int)s.groups.size(), sa));
+        sa.metas = metas;
+        sa.cP = (const float4*)s.d_cP.p; sa.cC = (const float4*)s.d_uv.p;
+        sa.poses = s.d_poses.p;
+        sa.hmasks = nullptr;
+        if (flags & RSAC_FLAG_KEEP_MASKS) {
+            RSAC_TRY(s.d_hmasks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_hwords, 1)));
+            sa.hmasks = (uint32_t*)s.d_hmasks.p;
+        }
+        int rc = launch_score<0>(e, sa, s.plan, (int)s.groups.size(), s.d_visit);
+        if (rc) return rc;
+    }
+    {
+        int rc = pnp_launch_select(e, flags, nullptr, d_results_out, -1);
+        if (rc) return rc;
+    }
+    s.ran = true;
+    return RSAC_OK;
+}
+
+int rsac_pnp_phase_stats(rsac_engine* e, int64_t out[4])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    out[0] = out[1] = out[2] = 0;
+    out[3] = s.d.sumH;
+    if (!s.ran) { e->err = "rsac_pnp_phase_stats before rsac_pnp_run"; return RSAC_ERR_STATE; }
+    if (!s.ee_mode) return RSAC_OK;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    std::vector<int32_t> ee(early_exit_words(s.d.C));
+    RSAC_CUDA(e, cudaMemcpyAsync(ee.data(), s.d_ee.p, sizeof(int32_t) * ee.size(), cudaMemcpyDeviceToHost, e->stream));
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    out[0] = s.ee_HA;
+    out[1] = ee[4 * (size_t)s.d.C + 1];
+    out[2] = ee[4 * (size_t)s.d.C + kCleanupCounter];
+    int64_t done = 0;
+    for (int c = 0; c < s.d.C; ++c) done += std::min(s.metas[c].H, std::max(ee[c], 0));
+    done += (int64_t)out[2] * 0;   // (problems of the clean-up phase end with upto = H)
+    out[3] = done;
+    return RSAC_OK;
+}
+
+int rsac_pnp_download_async(rsac_engine* e, rsac_result* results, uint32_t* masks)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    if (!s.ran) { e->err = "rsac_pnp_download before rsac_pnp_run"; return RSAC_ERR_STATE; }
+    const BatchDims& d = s.d;
+    if (results && d.C > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(results, s.d_results.p, sizeof(rsac_result) * d.C, cudaMemcpyDeviceToHost, e->stream));
+    if (masks && d.total_words > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(masks, s.d_masks.p, sizeof(uint32_t) * (size_t)d.total_words, cudaMemcpyDeviceToHost, e->stream));
+    return RSAC_OK;
+}
+
+int rsac_pnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks)
+{
+    int rc = rsac_pnp_download_async(e, results, masks);
+    if (rc) return rc;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_pnp_solve(rsac_engine* e, const rsac_pnp_batch* b, int flags, rsac_result* results, uint32_t* masks)
+{
+    int rc = rsac_pnp_upload(e, b);
+    if (rc) return rc;
+    rc = rsac_pnp_run(e, flags, nullptr);
+    if (rc) return rc;
+    return rsac_pnp_download(e, results, masks);
+}
+
+int64_t rsac_pnp_total_hypotheses(rsac_engine* e) { return e ? e->pnp.d.sumH : 0; }
+
+int rsac_pnp_get_hypotheses(rsac_engine* e, float* poses, int32_t* counts)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    PnpState& s = e->pnp;
+    if (!s.ran) return RSAC_ERR_STATE;
+    if (s.d.sumH > 0) {
+        if (poses) RSAC_CUDA(e, cudaMemcpyAsync(poses, s.d_poses.p, sizeof(float) * 12 * (size_t)s.d.sumH, cudaMemcpyDeviceToHost, e->stream));
+        if (counts) RSAC_CUDA(e, cudaMemcpyAsync(counts, s.d_counts.p, sizeof(int32_t) * (size_t)s.d.sumH, cudaMemcpyDeviceToHost, e->stream));
+    }
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+// ------------------------------------------------------- scoring stress (cfg5)
+int rsac_score_pnp_upload(rsac_engine* e, int H, const float* poses, int n, const float* p3d, const float* p2d,
+                          const float* max_err, const double K[4])
+{
+    if (!e || H < 0 || n < 0 || !K || (H > 0 && !poses) || (n > 0 && (!p3d || !p2d || !max_err))) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    ScoreState& s = e->score;
+    s.uploaded = false; s.ran = false;
+    s.metas.assign(1, ProblemMeta());
+    ProblemMeta& m = s.metas[0];
+    memset(&m, 0, sizeof(m));
+    m.n = n; m.H = H; m.words = (n + 31) / 32;
+    m.fx = K[0]; m.fy = K[1]; m.cx = K[2]; m.cy = K[3];
+    s.H = H; s.n = n;
+    RSAC_TRY(plan_score<0>(e, s.metas, H, s.groups, s.plan));
+    const size_t tot = (size_t)std::max(n, 1), hh = (size_t)std::max(H, 1);
+    RSAC_TRY(s.d_metas.ensure(e, sizeof(ProblemMeta)));
+    RSAC_TRY(s.d_p3d.ensure(e, tot * 12));
+    RSAC_TRY(s.d_p2d.ensure(e, tot * 8));
+    RSAC_TRY(s.d_maxerr.ensure(e, tot * 4));
+    RSAC_TRY(s.d_cA.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cB.ensure(e, tot * 16));
+    RSAC_TRY(s.d_cP.ensure(e, (size_t)std::max<int64_t>((int64_t)m.words, 1) * 1024));
+    RSAC_TRY(s.d_uv.ensure(e, tot * 16));
+    RSAC_TRY(s.d_poses.ensure(e, hh * 48));
+    RSAC_TRY(s.d_counts.ensure(e, (hh + 8 + s.groups.size()) * 4));
+    RSAC_TRY(s.d_hmasks.ensure(e, hh * (size_t)std::max(m.words, 1) * 4));
+    cudaStream_t st = e->stream;
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_metas.p, s.metas.data(), sizeof(ProblemMeta), cudaMemcpyHostToDevice, st));
+    RSAC_TRY(s.d_visit.ensure(e, sizeof(ScoreGroup) * std::max<size_t>(s.plan.work.size(), 1)));
+    RSAC_CUDA(e, cudaMemcpyAsync(s.d_visit.p, s.plan.work.data(), sizeof(ScoreGroup) * s.plan.work.size(), cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, p3d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, p2d, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_maxerr.p, max_err, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (H > 0) RSAC_CUDA(e, cudaMemcpyAsync(s.d_poses.p, poses, (size_t)H * 48, cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        dim3 grid((unsigned)std::max(1, std::min(256, (n + 255) / 256)), 1);
+        e->stage_begin(RSAC_STAGE_PACK);
+        pack_pnp_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
+                                              nullptr, nullptr, (const float*)s.d_maxerr.p, 0,
+                                              (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p, 1);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.uploaded = true;
+    return RSAC_OK;
+}
+
+int rsac_score_pnp_run(rsac_engine* e, int want_masks)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    ScoreState& s = e->score;
+    if (!s.uploaded) { e->err = "rsac_score_pnp_run before upload"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    ScoreArgs sa;
+    RSAC_TRY(zero_score_region(e, s.d_counts, s.H, (int)s.groups.size(), sa));
+    (void)st;
+    if (s.H > 0 && s.n > 0) {
+        sa.metas = (const ProblemMeta*)s.d_metas.p;
+        sa.cP = (const float4*)s.d_cP.p; sa.cC = (const float4*)s.d_uv.p;
+        sa.poses = s.d_poses.p;
+        sa.hmasks = want_masks ? (uint32_t*)s.d_hmasks.p : nullptr;
+        int rc = launch_score<0>(e, sa, s.plan, (int)s.groups.size(), s.d_visit);
+        if (rc) return rc;
+    }
+    s.ran = true;
+    s.with_masks = want_masks != 0;
+    return RSAC_OK;
+}
+
+int rsac_score_pnp_download(rsac_engine* e, uint32_t* masks, int32_t* counts)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    ScoreState& s = e->score;
+    if (!s.ran) return RSAC_ERR_STATE;
+    const int words = (s.n + 31) / 32;
+    if (counts && s.H > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(counts, s.d_counts.p, sizeof(int32_t) * (size_t)s.H, cudaMemcpyDeviceToHost, e->stream));
+    if (masks && s.with_masks && s.H > 0 && words > 0)
+        RSAC_CUDA(e, cudaMemcpyAsync(masks, s.d_hmasks.p, sizeof(uint32_t) * (size_t)s.H * words, cudaMemcpyDeviceToHost, e->stream));
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_score_pnp(rsac_engine* e, int H, const float* poses, int n, const float* p3d, const float* p2d,
+                   const float* max_err, const double K[4], uint32_t* masks, int32_t* counts)
+{
+    int rc = rsac_score_pnp_upload(e, H, poses, n, p3d, p2d, max_err, K);
+    if (rc) return rc;
+    rc = rsac_score_pnp_run(e, masks != nullptr);
+    if (rc) return rc;
+    return rsac_score_pnp_download(e, masks, counts);
+}
+
+int64_t rsac_score_exact_evals(rsac_engine* e)
+{
+    if (!e || !e->last_exact) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, e->last_exact, sizeof(v), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) return -1;
+    cudaStreamSynchronize(e->stream);
+    return (int64_t)v;
+}
+
+// ------------------------------------------------------- host debug hooks
+int rsac_debug_host_epnp4(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3])
+{
+    double pw[12], us[8];
+    for (int i = 0; i < 12; ++i) pw[i] = (double)p3d[i];
+    for (int i = 0; i < 8; ++i) us[i] = (double)p2d[i];
+    const Cam k = {K[0], K[1], K[2], K[3]};
+    epnp_compute_pose_small<4, false>(pw, us, k, R, t);
+    return RSAC_OK;
+}
+
+int rsac_debug_host_epnp4_qr(const double K[4], const float p3d[12], const float p2d[8], float R[9], float t[3])
+{
+    double pw[12], us[8];
+    for (int i = 0; i < 12; ++i) pw[i] = (double)p3d[i];
+    for (int i = 0; i < 8; ++i) us[i] = (double)p2d[i];
+    const Cam k = {K[0], K[1], K[2], K[3]};
+    epnp_compute_pose_small<4, true>(pw, us, k, R, t);
+    return RSAC_OK;
+}
+
+int rsac_debug_score_clocks(rsac_engine* e, unsigned long long out[64])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_score_clocks, sizeof(unsigned long long) * 64));
+    return RSAC_OK;
+}
+
+int rsac_debug_solve_clocks(rsac_engine* e, long long out[16])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_solve_clocks, sizeof(long long) * 16));
+    return RSAC_OK;
+}
+
+int rsac_debug_score_all(rsac_engine* e, unsigned long long out[4096])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_score_all, sizeof(unsigned long long) * 4096));
+    return RSAC_OK;
+}
+
+int rsac_debug_select_clocks(rsac_engine* e, long long out[16])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_select_clocks, sizeof(long long) * 16));
+    return RSAC_OK;
+}
+
+int rsac_debug_host_jacobi12(const double a[144], double w[4], double v[48])
+{
+    double A[78];
+    for (int i = 0; i < 12; ++i)
+        for (int j = i; j < 12; ++j) A[tri_idx(12, i, j)] = a[i * 12 + j];
+    std::vector<double2> rec(kMaxSweepsRec * 66);
+    jacobi_lowest<12, 4>(A, w, v, rec.data());
+    return RSAC_OK;
+}

@@ -1,5 +1,5 @@
-// engine_poseopt.inl -- C ABI for the batched Optimizer::PoseOptimization (include/ransac_b200.h).
-// (included at the end of engine.cu: the library is one translation unit)
+// engine_poseopt.cu -- C ABI for the batched Optimizer::PoseOptimization (include/ransac_b200.h).
+#include "engine_shared.cuh"
 #include "poseopt.cuh"
 
 int rsac_poseopt_upload(rsac_engine* e, const rsac_poseopt_batch* b)

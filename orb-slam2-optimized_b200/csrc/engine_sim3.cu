@@ -1,11 +1,13 @@
-// engine_sim3.inl -- C ABI for the batched Sim3Solver (include/ransac_b200.h, "Sim3Solver").
-// (included at the end of engine.cu: the library is one translation unit)
+// engine_sim3.cu -- C ABI for the batched Sim3Solver (include/ransac_b200.h, "Sim3Solver").
+#include "engine_shared.cuh"
 #include "sim3.cuh"
 
 int rsac_sim3_upload(rsac_engine* e, const rsac_sim3_batch* b)
 {
     if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
     if (!b->seeds && !b->tables) { e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
+    if (b->tables && !b->table_offsets) { e->err = "tables without table_offsets"; return RSAC_ERR_INVALID; }
+    if (b->C > 0 && (!b->K1 || !b->K2)) { e->err = "K1/K2 is NULL"; return RSAC_ERR_INVALID; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     Sim3State& s = e->sim3;
     s.uploaded = false; s.ran = false;
@@ -76,10 +78,10 @@ int rsac_sim3_upload(rsac_engine* e, const rsac_sim3_batch* b)
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_tables.p, b->tables, sizeof(uint32_t) * (size_t)d.table_len, cudaMemcpyHostToDevice, st));
     if (d.total > 0 && C > 0) {
         float4* c1 = (float4*)s.d_c1.p;
-        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)C);
+        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)std::min(C, 65535));
         e->stage_begin(RSAC_STAGE_PACK);
         sim3_pack_kernel<<<grid, 256, 0, st>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_x1.p, (const float*)s.d_x2.p,
-                                               (const float*)s.d_s1.p, (const float*)s.d_s2.p, c1, c1 + tot, c1 + 2 * tot);
+                                               (const float*)s.d_s1.p, (const float*)s.d_s2.p, c1, c1 + tot, c1 + 2 * tot, C);
         e->stage_end(RSAC_STAGE_PACK);
         RSAC_CUDA(e, cudaGetLastError());
     }

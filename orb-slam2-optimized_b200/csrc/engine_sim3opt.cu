@@ -1,5 +1,5 @@
-// engine_sim3opt.inl -- C ABI for the batched Optimizer::OptimizeSim3 (include/ransac_b200.h).
-// (included at the end of engine.cu: the library is one translation unit)
+// engine_sim3opt.cu -- C ABI for the batched Optimizer::OptimizeSim3 (include/ransac_b200.h).
+#include "engine_shared.cuh"
 #include "sim3opt.cuh"
 
 static void sim3opt_fill_meta(Sim3OptMeta& m, int64_t off, int n, const float* K1, const float* K2, const float* S12, float th2, int fix)

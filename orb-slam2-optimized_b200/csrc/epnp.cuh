@@ -14,7 +14,7 @@ namespace rsac {
 
 // diagnostic: clock64() at the phase boundaries of the minimal solve, thread 0 of block 0 (rsac_debug_solve_clocks)
 #ifdef __CUDACC__
-__device__ long long g_solve_clocks[16];
+static __device__ long long g_solve_clocks[16];
 #endif
 #ifdef __CUDA_ARCH__
 #define RSAC_SOLVE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_solve_clocks[i] = clock64(); } while (0)

@@ -10,130 +10,8 @@
 #include "epnp.cuh"
 #include "rng.cuh"
 #include "score.cuh"
-#include "mlpnp.cuh"
 
 namespace rsac {
-
-// ---- minimal-set tables from per-problem seeds: one warp per problem ----
-// The additive-feedback recurrence r[i] = r[i-31] + r[i-3] is advanced 31 values at a time: with the last
-// 31 values w[0..30] on lanes 0..30, the next 31 are y[j] = w[j] + y[j-3] (y[-3..-1] = w[28..30]) -- three
-// interleaved running sums, i.e. a stride-3 inclusive scan (4 shuffle steps) plus a carry.  Integer
-// arithmetic mod 2^32, so the result is the serial stream bit for bit.  The 310 discarded outputs are
-// exactly 10 such batches.  Every RANSAC iteration consumes exactly min_set values (PnPsolver.cpp:125-138),
-// so once the raw stream is in shared memory the draws of different iterations are independent: lane <->
-// iteration, `draw_from` restates draw_minimal_set over a given slice of the stream.
-constexpr int kRngWarps = 4;          // problems per CTA
-constexpr int kRngBuf = 32 * 8 + 32;  // raw values buffered per warp: one tile of 32 iterations x <= 8 draws + a partial batch
-
-template <int KMAX>
-__device__ inline void draw_from(const uint32_t* raw, int n, int k, uint32_t* out)
-{
-    int pos[KMAX];
-    uint32_t val[KMAX];
-    int nov = 0;
-    int size = n;
-    for (int i = 0; i < k; ++i) {
-        // DUtils::Random::RandomInt(0, size-1) over rand() = raw >> 1 (Random.cpp:47-50)
-        const int d = size;
-        const int randi = (int)(((double)(int32_t)(raw[i] >> 1) / ((double)2147483647 + 1.0)) * d);
-        uint32_t idx = (uint32_t)randi;
-        for (int j = nov - 1; j >= 0; --j)
-            if (pos[j] == randi) { idx = val[j]; break; }
-        out[i] = idx;
-        const int last = size - 1;
-        uint32_t lastv = (uint32_t)last;
-        for (int j = nov - 1; j >= 0; --j)
-            if (pos[j] == last) { lastv = val[j]; break; }
-        pos[nov] = randi;
-        val[nov] = lastv;
-        ++nov;
-        --size;
-    }
-}
-
-__global__ void __launch_bounds__(kRngWarps * 32) rng_tables_kernel(const ProblemMeta* metas, int C, uint32_t* tables)
-{
-    __shared__ uint32_t s_buf[kRngWarps][kRngBuf];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int p = blockIdx.x * kRngWarps + warp;
-    if (p >= C) return;
-    const ProblemMeta& m = metas[p];
-    const int n = m.n, k = m.min_set, H = m.H;
-    if (n < k || H <= 0) return;
-    uint32_t* buf = s_buf[warp];
-
-    // seeding (glibc srandom_r, TYPE_3): r[0] = seed, r[i] = 16807 r[i-1] mod (2^31-1), i < 31; r[31..33] = r[0..2].
-    // window w = r[3..33] on lanes 0..30
-    if (lane == 0) {
-        uint32_t sd = m.seed;
-        if (sd == 0) sd = 1;
-        int32_t r = (int32_t)sd;
-        buf[0] = (uint32_t)r;
-        for (int i = 1; i < 31; ++i) {
-            const int32_t hi = r / 127773, lo = r % 127773;
-            int32_t word = 16807 * lo - 2836 * hi;
-            if (word < 0) word += 2147483647;
-            r = word;
-            buf[i] = (uint32_t)r;
-        }
-    }
-    __syncwarp();
-    uint32_t w = 0;
-    if (lane < 28) w = buf[3 + lane];
-    else if (lane < 31) w = buf[lane - 28];
-    __syncwarp();
-
-    auto next_batch = [&]() -> uint32_t {       // lanes 0..30 return r[i+31]; w is advanced
-        const uint32_t carry = __shfl_sync(0xffffffffu, w, 28 + lane % 3);
-        uint32_t v = w;
-#pragma unroll
-        for (int d = 3; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) v += t;
-        }
-        v += carry;
-        w = v;
-        return v;
-    };
-    for (int b = 0; b < 10; ++b) (void)next_batch();   // the 310 discarded outputs
-
-    uint32_t* out = tables + m.table_off;
-    int have = 0;
-    for (int h0 = 0; h0 < H; h0 += 32) {
-        const int need = min(32, H - h0) * k;
-        while (have < need) {
-            const uint32_t y = next_batch();
-            if (lane < 31) buf[have + lane] = y;
-            have += 31;
-        }
-        __syncwarp();
-        const int h = h0 + lane;
-        if (h < H) {
-            uint32_t idx[8];
-            draw_from<8>(buf + lane * k, n, k, idx);
-            uint32_t* o = out + (size_t)h * k;
-            for (int i = 0; i < k; ++i) o[i] = idx[i];
-        }
-        __syncwarp();
-        const int rem = have - need;            // < 31: move the unconsumed tail to the front
-        uint32_t keep = 0;
-        if (lane < rem) keep = buf[need + lane];
-        __syncwarp();
-        if (lane < rem) buf[lane] = keep;
-        have = rem;
-        __syncwarp();
-    }
-}
-
-__device__ __forceinline__ int find_problem(const ProblemMeta* metas, int C, int64_t g)
-{
-    int lo = 0, hi = C - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int64_t)metas[mid].hyp_off <= g) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
 
 // ---- EPnP minimal solve: one thread per hypothesis (PnPsolver.cpp:125-141) ----
 #ifndef RSAC_SOLVE_SMEM
@@ -293,35 +171,6 @@ epnp_minimal_range_kernel(const ProblemMeta* metas, int C, const int32_t* list, 
         for (int i = 0; i < 9; ++i) out[i] = R[i];
         out[9] = tr[0]; out[10] = tr[1]; out[11] = tr[2];
     }
-}
-
-// ---- MLPnP minimal solve: one thread per hypothesis (MLPnPsolver.cpp:76-120) ----
-__global__ void __launch_bounds__(128) mlpnp_minimal_kernel(const ProblemMeta* metas, int C, int64_t sumH,
-                                                            const uint32_t* tables, const float4* cA,
-                                                            const float4* cC, const double* cov, double* poses)
-{
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= sumH) return;
-    const int p = find_problem(metas, C, g);
-    const ProblemMeta& m = metas[p];
-    const int h = (int)(g - m.hyp_off);
-    const uint32_t* idx = tables + m.table_off + (size_t)h * 6;
-    double f[18], pw[18], cv[54];
-    for (int i = 0; i < 6; ++i) {
-        const size_t ci = (size_t)m.corr_off + idx[i];
-        const float4 a = cA[ci];
-        const float4 q = cC[ci];
-        mlpnp_bearing(q.x, q.y, m.k1, f + 3 * i);                         // MLPnPsolver.cpp:33-37
-        pw[3 * i] = (double)a.x; pw[3 * i + 1] = (double)a.y; pw[3 * i + 2] = (double)a.z;
-        if (cov)
-            for (int k = 0; k < 9; ++k) cv[9 * i + k] = cov[9 * ci + k];
-    }
-    double R[9], t[3];
-    double2 rec[kMaxSweepsRec * 66];
-    mlpnp_compute_pose_small<6>(f, pw, cov ? cv : nullptr, R, t, rec);
-    double* out = poses + g * 12;
-    for (int i = 0; i < 9; ++i) out[i] = R[i];
-    out[9] = t[0]; out[10] = t[1]; out[11] = t[2];
 }
 
 }  // namespace rsac

@@ -569,7 +569,7 @@ __host__ __device__ inline void pose_optimization(const PoseOptMeta& m, const fl
 // point, observation (u, v, -1: monocular), 1/sigma^2 (float division, as ORBextractor fills mvInvLevelSigma2) -- at the
 // problem's correspondence offset, remembers where each came from (`src`) and writes the frame record.  Candidates
 // without a pose get an empty frame.
-__global__ void __launch_bounds__(128) poseopt_from_pnp_kernel(const ProblemMeta* __restrict__ metas, int C,
+static __global__ void __launch_bounds__(128) poseopt_from_pnp_kernel(const ProblemMeta* __restrict__ metas, int C,
                                                               const rsac_result* __restrict__ results, const uint32_t* __restrict__ masks,
                                                               const float* __restrict__ p3d_in, const float* __restrict__ p2d,
                                                               const float* __restrict__ sigma2, float bf, PoseOptMeta* __restrict__ out_metas,
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(128) poseopt_from_pnp_kernel(const ProblemMeta
 }
 
 // flags of a chained run back in the PnP correspondence index space: 2 = not an edge, else the optimiser's flag
-__global__ void __launch_bounds__(128) poseopt_scatter_flags_kernel(const ProblemMeta* __restrict__ metas, int C,
+static __global__ void __launch_bounds__(128) poseopt_scatter_flags_kernel(const ProblemMeta* __restrict__ metas, int C,
                                                                    const PoseOptMeta* __restrict__ frames, const uint8_t* __restrict__ flag,
                                                                    const int32_t* __restrict__ src, uint8_t* __restrict__ full)
 {

@@ -183,8 +183,8 @@ __device__ __forceinline__ void eval_pair(const float2* C, const float4& q0, con
 
 // diagnostic: globaltimer (ns) stamps of consumer warp 0 in a few CTAs (rsac_debug_score_clocks):
 // [cta][0] kernel entry, [1] first chunk landed, [2] poses folded, [3] last chunk done, [4] exit, [5] chunks
-__device__ unsigned long long g_score_clocks[8][8];
-__device__ unsigned long long g_score_all[1024][4];   // per CTA (first 1024): entry, exit (globaltimer ns), chunks, SM id
+static __device__ unsigned long long g_score_clocks[8][8];
+static __device__ unsigned long long g_score_all[1024][4];   // per CTA (first 1024): entry, exit (globaltimer ns), chunks, SM id
 __device__ __forceinline__ unsigned long long rsac_globaltimer()
 {
     unsigned long long t;
@@ -505,12 +505,13 @@ __device__ __forceinline__ PackedPoint pack_point(const ProblemMeta& m, size_t g
     return r;
 }
 
-__global__ void pack_pnp_kernel(const ProblemMeta* metas, const float* p3d, const float* p2d, const float* sigma2,
+static __global__ void pack_pnp_kernel(const ProblemMeta* metas, const float* p3d, const float* p2d, const float* sigma2,
                                 const float* th2_per_problem, const float* max_err, int model,
-                                float4* cA, float4* cB, float4* cC, float4* cP)
+                                float4* cA, float4* cB, float4* cC, float4* cP, int C)
 {
-    const ProblemMeta& m = metas[blockIdx.y];
-    const float th2 = th2_per_problem ? th2_per_problem[blockIdx.y] : 0.0f;
+  for (int pr = blockIdx.y; pr < C; pr += gridDim.y) {       // grid.y is capped at 65535 problems
+    const ProblemMeta& m = metas[pr];
+    const float th2 = th2_per_problem ? th2_per_problem[pr] : 0.0f;
     const int npairs = m.words * 16;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
         PackedPoint a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b = a;
@@ -535,6 +536,7 @@ __global__ void pack_pnp_kernel(const ProblemMeta* metas, const float* p3d, cons
         dst[2] = make_float4(a.cv, b.cv, -a.thr, -b.thr);
         dst[3] = make_float4(a.band, b.band, a.eps2, b.eps2);
     }
+  }
 }
 
 }  // namespace rsac

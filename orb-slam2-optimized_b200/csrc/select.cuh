@@ -73,7 +73,7 @@ template <int MODEL> constexpr int select_threads() { return MODEL == 0 ? kSelec
 constexpr int kSelectCtasPerSm = RSAC_SELECT_CTAS;
 
 // diagnostic: clock64() at phase boundaries of block 0 (rsac_debug_select_clocks)
-__device__ long long g_select_clocks[16];
+static __device__ long long g_select_clocks[16];
 #define RSAC_SEL_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_select_clocks[i] = clock64(); } while (0)
 constexpr int kMlpnpScratch = 33;   // doubles per selected observation
 

@@ -11,7 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "linalg.cuh"
-#include "pnp_pipeline.cuh"   // rng_tables_kernel
+#include "rng.cuh"            // rng_tables_kernel
 #include "select.cuh"         // ResultRec
 
 namespace rsac {
@@ -108,10 +108,11 @@ __host__ __device__ inline void sim3_cam2img(const float* K, float X0, float X1,
 
 // packed correspondence records (built once per problem, Sim3Solver.cpp:51-52,57-63,81-82):
 //   c1 = (X1c.xyz, thr1), c2 = (X2c.xyz, thr2), c3 = (p1im1.uv, p2im2.uv)
-__global__ void sim3_pack_kernel(const ProblemMeta* metas, const float* x1c, const float* x2c, const float* s1, const float* s2,
-                                 float4* c1, float4* c2, float4* c3)
+static __global__ void sim3_pack_kernel(const ProblemMeta* metas, const float* x1c, const float* x2c, const float* s1, const float* s2,
+                                 float4* c1, float4* c2, float4* c3, int C)
 {
-    const ProblemMeta& m = metas[blockIdx.y];
+  for (int pr = blockIdx.y; pr < C; pr += gridDim.y) {       // grid.y is capped at 65535 problems
+    const ProblemMeta& m = metas[pr];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.n; i += gridDim.x * blockDim.x) {
         const size_t g = (size_t)m.corr_off + i;
         const float a0 = x1c[3 * g], a1 = x1c[3 * g + 1], a2 = x1c[3 * g + 2];
@@ -126,6 +127,7 @@ __global__ void sim3_pack_kernel(const ProblemMeta* metas, const float* x1c, con
         c2[g] = make_float4(b0, b1, b2, thr2);
         c3[g] = make_float4(u1, v1, u2, v2);
     }
+  }
 }
 
 struct Sim3Args {

@@ -91,6 +91,14 @@ int main(int argc, char** argv)
                     std::printf("}\n");
                     if (noMore) break;
                 }
+                {   // one call past the budget: the best-so-far fallback with bNoMore (PnPsolver.cpp:119,173-188)
+                    const bool ok = s.iterate(step, noMore, inl, n, T);
+                    std::printf("{\"call\":-1,\"ok\":%d,\"noMore\":%d,\"nInliers\":%d,\"T\":", (int)ok, (int)noMore, n);
+                    print_T(T);
+                    std::printf(",\"inliers\":");
+                    print_inliers(inl);
+                    std::printf("}\n");
+                }
             } else {
                 MLPnPsolver s(d.frame(), d.matches());
                 s.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);

@@ -214,6 +214,24 @@ def epnp_pose(pb: _Keep, idx, flags=0):
     return R.reshape(3, 3), t, err
 
 
+def epnp_mtm(pb: _Keep, idx):
+    """M^T M (12 x 12) of the EPnP system on the subset idx"""
+    idx = np.ascontiguousarray(idx, np.uint32)
+    out = np.zeros((12, 12), np.float64)
+    lib().orc_epnp_mtm(C.byref(pb.st), _p(idx), C.c_int(len(idx)), _p(out))
+    return out
+
+
+def epnp_pose_basis(pb: _Keep, idx, U):
+    """compute_pose downstream of a caller-supplied null-space basis U (12 x 4)"""
+    idx = np.ascontiguousarray(idx, np.uint32)
+    U = np.ascontiguousarray(U, np.float64)
+    R, t = np.empty(9, np.float32), np.empty(3, np.float32)
+    lib().orc_epnp_pose_basis.restype = C.c_double
+    err = lib().orc_epnp_pose_basis(C.byref(pb.st), _p(idx), C.c_int(len(idx)), _p(U), _p(R), _p(t))
+    return R.reshape(3, 3), t, err
+
+
 def epnp_flops(pb: _Keep, table, flags=0):
     table = np.ascontiguousarray(table, np.uint32)
     return lib().orc_epnp_flops_mode(C.byref(pb.st), _p(table), C.c_int(table.shape[0]), C.c_int(table.shape[1]), C.c_int(flags))
@@ -363,6 +381,29 @@ def pnp_batch(pbs, prm, tables, flags=0, nthreads=1):
     ev = C.c_longlong()
     dt = lib().orc_pnp_batch(C.c_int(n), arr, C.byref(prm), ptrs, C.c_int(flags), C.c_int(nthreads), res, C.byref(ev))
     return dt, ev.value, [r.as_dict() for r in res]
+
+
+def _batch_masks(fn_name, arr_t, pbs, prm, tables, flags, nthreads):
+    """threaded batch driver that also returns the inlier masks: (list of result dicts, list of bool masks)"""
+    n = len(pbs)
+    arr = (arr_t * n)(*[p.st for p in pbs])
+    keep, ptrs = _tables_ptr(tables)
+    res = (Result * n)()
+    masks = [np.zeros(max(int(p.st.n), 1), np.uint8) for p in pbs]
+    mptr = (C.c_void_p * n)(*[m.ctypes.data for m in masks])
+    ev = C.c_longlong()
+    fn = getattr(lib(), fn_name)
+    fn.restype = C.c_double
+    fn(C.c_int(n), arr, C.byref(prm), ptrs, C.c_int(flags), C.c_int(nthreads), res, mptr, C.byref(ev))
+    return [r.as_dict() for r in res], [m[:int(p.st.n)].astype(bool) for m, p in zip(masks, pbs)]
+
+
+def pnp_batch_masks(pbs, prm, tables, flags=0, nthreads=1):
+    return _batch_masks("orc_pnp_batch_masks", PnPProblem, pbs, prm, tables, flags, nthreads)
+
+
+def mlpnp_batch_masks(pbs, prm, tables, flags=0, nthreads=1):
+    return _batch_masks("orc_mlpnp_batch_masks", MLPnPProblem, pbs, prm, tables, flags, nthreads)
 
 
 def sim3_batch(pbs, prob, min_inliers, max_its, tables, flags=0, nthreads=1):

@@ -95,6 +95,9 @@ def test_pnpsolver_iterate_sequence(driver, oracle, tmp_path):
         ref, (minInl, H) = _pnp_replay(oracle, p, prm, seed)
         assert got[0] == {"H": H, "minInl": minInl, "N": n}
         got = got[1:]
+        past = got.pop()                                  # the call after bNoMore: best-so-far fallback (PnPsolver.cpp:173-188)
+        assert past["call"] == -1 and past["noMore"] == 1
+        assert (past["ok"], past["nInliers"]) == (ref[-1]["ok"], ref[-1]["n"])      # ref[-1] is the exhausted call: the same fallback
         assert len(got) == len(ref)
         for g, r in zip(got, ref):
             assert (g["ok"], g["noMore"], g["nInliers"]) == (r["ok"], r["noMore"], r["n"])
