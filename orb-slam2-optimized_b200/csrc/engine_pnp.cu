@@ -2,7 +2,50 @@
 // entry points (include/ransac_b200.h, "PnPsolver").
 #include "engine_shared.cuh"
 #include "pnp_pipeline.cuh"
+#include "epnp_subwarp.cuh"
 #include "select.cuh"
+
+// The 4-point minimal solver: three lanes per hypothesis (epnp_subwarp.cuh); RSAC_SOLVE_IMPL=thread selects the
+// round-1 one-thread-per-hypothesis kernel (A/B timing only)
+static bool solve_subwarp()
+{
+    static const bool v = [] { const char* s = getenv("RSAC_SOLVE_IMPL"); return !(s && strcmp(s, "thread") == 0); }();
+    return v;
+}
+
+// hypotheses of one resident wave of the minimal solver
+static int64_t solve_wave_hyps(rsac_engine* e)
+{
+    return solve_subwarp() ? (int64_t)RSAC_SW_BLOCKS * e->sm_count * kSwHypsPerBlock
+                           : (int64_t)RSAC_SOLVE_BLOCKS * e->sm_count * RSAC_SOLVE_THREADS;
+}
+
+static int solve_range_setup(rsac_engine* e);
+
+// minimal solves of hypotheses [lo, lo + span) of the listed problems (list == nullptr: all C problems; `most` = upper
+// bound of the work items, for the grid)
+static int launch_solve_range(rsac_engine* e, PnpState& s, const int32_t* list, const int32_t* list_count, int lo, int span, int64_t most)
+{
+    const BatchDims& d = s.d;
+    RSAC_TRY(solve_range_setup(e));
+    e->stage_begin(RSAC_STAGE_SOLVE);
+    if (solve_subwarp()) {
+        const int resident = RSAC_SW_BLOCKS * e->sm_count;
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + kSwHypsPerBlock - 1) / kSwHypsPerBlock, resident));
+        epnp_minimal_subwarp_kernel<<<blocks, kSwThreads, kSwSmemBytes, e->stream>>>(
+            (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, lo, span, (const uint32_t*)s.d_tables.p,
+            (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+    } else {
+        const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
+        epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, e->stream>>>(
+            (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, lo, span, (const uint32_t*)s.d_tables.p,
+            (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+    }
+    e->stage_end(RSAC_STAGE_SOLVE);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
 
 static int pnp_first_phase(rsac_engine* e, const BatchDims& d)
 {
@@ -12,9 +55,13 @@ static int pnp_first_phase(rsac_engine* e, const BatchDims& d)
     // (40,80,160) 0.421 / 0.474, (28,55,110,220) 0.420 / 0.498, (20,40,80,160) 0.428 / 0.500
     int HA = e->first_phase > 0 ? e->first_phase : env_int("RSAC_EE_HA", 0);
     if (HA <= 0) {
-        const int blocks = RSAC_SOLVE_BLOCKS * e->sm_count;
-        const int wave = (int)(((int64_t)blocks * RSAC_SOLVE_THREADS) / std::max(d.C, 1));
-        HA = wave >= d.maxH ? wave : std::max(16, wave * 3 / 4);
+        // measured with the three-lane solver (wave = 160 hypotheses per SM), six sweeps in flight, M candidates/s
+        // resident / end to end: (17,34,...) 2.54 / 2.21, (23,46,92,184) 2.65 / 2.32, (46,92,184) 2.66 / 2.38,
+        // (41,82,164) 2.69 / 2.40, (35,70,140) 2.68 / 2.38, (30,60,120,240) 2.66 / 2.36: about 1.8 waves first
+        const int64_t wave_h = solve_wave_hyps(e);
+        const int wave = (int)(wave_h / std::max(d.C, 1));
+        const int first = (int)((solve_subwarp() ? wave_h * 9 / 5 : wave_h * 3 / 4) / std::max(d.C, 1));
+        HA = wave >= d.maxH ? wave : std::max(16, first);
     }
     return HA;
 }
@@ -198,6 +245,14 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
 // ---- early exit in phases (pnp_pipeline.cuh) ----
 static int solve_range_setup(rsac_engine* e)
 {
+    if (solve_subwarp()) {
+        if (kSwSmemBytes > 32 * 1024)
+            RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_subwarp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmemBytes));
+        const size_t need = (kSwSmemBytes + 1024) * RSAC_SW_BLOCKS;
+        const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 1);
+        RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_subwarp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        return RSAC_OK;
+    }
     const size_t smem = sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS;
     if (smem > 32 * 1024)
         RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -226,15 +281,7 @@ static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* l
     const BatchDims& d = s.d;
     const int span = std::min(hi, d.maxH) - lo;
     if (span <= 0) return RSAC_OK;
-    const int64_t most = (int64_t)d.C * span;
-    const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
-    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
-    e->stage_begin(RSAC_STAGE_SOLVE);
-    epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, e->stream>>>(
-        (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, lo, span, (const uint32_t*)s.d_tables.p,
-        (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
-    e->stage_end(RSAC_STAGE_SOLVE);
-    RSAC_CUDA(e, cudaGetLastError());
+    RSAC_TRY(launch_solve_range(e, s, list, list_count, lo, span, (int64_t)d.C * span));
     ScoreArgs sa = s.ee_sa;
     sa.list = list;
     sa.list_count = list_count;
@@ -272,15 +319,7 @@ static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, const s
 
     // stage 0: hypotheses [0, b0) of every problem
     {
-        const int64_t most = (int64_t)d.C * bounds[0];
-        const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
-        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
-        e->stage_begin(RSAC_STAGE_SOLVE);
-        epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, st>>>(
-            metas, d.C, nullptr, nullptr, 0, bounds[0], (const uint32_t*)s.d_tables.p, (const float4*)s.d_cA.p, (const float4*)s.d_uv.p,
-            (float*)s.d_poses.p);
-        e->stage_end(RSAC_STAGE_SOLVE);
-        RSAC_CUDA(e, cudaGetLastError());
+        RSAC_TRY(launch_solve_range(e, s, nullptr, nullptr, 0, bounds[0], (int64_t)d.C * bounds[0]));
         RSAC_TRY(launch_score<0>(e, sa, s.ee_plans[0], (int)s.ee_groups[0].size(), s.ee_visit[0]));
     }
     // who goes on after stage j-1 (list j); stage j: [b(j-1), bj) of list j
@@ -401,15 +440,21 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         }
         const int threads = eigen ? 128 : RSAC_SOLVE_THREADS;
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
-        e->stage_begin(RSAC_STAGE_SOLVE);
-        if (eigen)
+        if (eigen) {
+            e->stage_begin(RSAC_STAGE_SOLVE);
             epnp_minimal_kernel<false><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
                                                                    (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
-        else
+            e->stage_end(RSAC_STAGE_SOLVE);
+            RSAC_CUDA(e, cudaGetLastError());
+        } else if (solve_subwarp()) {
+            RSAC_TRY(launch_solve_range(e, s, nullptr, nullptr, 0, d.maxH, (int64_t)d.C * d.maxH));
+        } else {
+            e->stage_begin(RSAC_STAGE_SOLVE);
             epnp_minimal_kernel<true><<<blocks, threads, sizeof(double) * kSolveSmemDoubles * threads, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
                                                                   (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
-        e->stage_end(RSAC_STAGE_SOLVE);
-        RSAC_CUDA(e, cudaGetLastError());
+            e->stage_end(RSAC_STAGE_SOLVE);
+            RSAC_CUDA(e, cudaGetLastError());
+        }
 
         ScoreArgs sa;
         RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, (int)s.groups.size(), sa));

@@ -34,13 +34,14 @@ struct StridedD {
 
 // PnPsolver::choose_control_points (PnPsolver.cpp:296-321) after the sums:
 // C0 = centroid (already divided by n), A = upper triangle of PW0^T PW0.
+template <bool STATIC_SORT = false>
 __host__ __device__ inline void epnp_control_points(const double* C0, double* A, int n, double* cws /*4x3*/)
 {
     for (int c = 0; c < 3; ++c) cws[c] = C0[c];
     double DC[3], UCt[9];
-    jacobi_eig<double, 3>(A, DC, UCt);
+    jacobi_eig<double, 3, STATIC_SORT>(A, DC, UCt);
     for (int i = 0; i < 3; ++i) {
-        const double k = sqrt(DC[i] / (double)n);
+        const double k = rsqrt_exact(rdiv(DC[i], (double)n));
         for (int c = 0; c < 3; ++c) cws[(i + 1) * 3 + c] = cws[c] + k * UCt[c * 3 + i];
     }
 }
@@ -273,6 +274,107 @@ __host__ __device__ inline void epnp_gauss_newton(LT L, const double* rho, doubl
     }
 }
 
+// One Gauss-Newton step (epnp_gn_system + epnp_qr_solve) with every array in registers: all loops unrolled (static
+// indices only) and reflector k applied to b right after the columns -- column k is final then and b has seen
+// H_0..H_{k-1}, so b goes through the reference's operation sequence (PnPsolver.cpp:766-778) unchanged while A1 and
+// the lower part of the factor die early.  Element for element the arithmetic of the two routines above.
+template <class LT>
+__host__ __device__ __forceinline__ void epnp_gn_step_reg(LT L, const double* rho, const double (&bt)[4], double (&X)[4])
+{
+    double A[6][4], b[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double l[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) l[j] = L[i * 10 + j];
+        A[i][0] = rfma(l[6], bt[3], rfma(l[3], bt[2], rfma(l[1], bt[1], (2 * l[0]) * bt[0])));        /* :659 */
+        A[i][1] = rfma(l[7], bt[3], rfma(l[4], bt[2], rfma(2 * l[2], bt[1], l[1] * bt[0])));
+        A[i][2] = rfma(l[8], bt[3], rfma(2 * l[5], bt[2], rfma(l[4], bt[1], l[3] * bt[0])));
+        A[i][3] = rfma(2 * l[9], bt[3], rfma(l[8], bt[2], rfma(l[7], bt[1], l[6] * bt[0])));
+        double q = (l[0] * bt[0]) * bt[0];                                                           /* :661-671 */
+        q = rfma(l[1] * bt[0], bt[1], q);
+        q = rfma(l[2] * bt[1], bt[1], q);
+        q = rfma(l[3] * bt[0], bt[2], q);
+        q = rfma(l[4] * bt[1], bt[2], q);
+        q = rfma(l[5] * bt[2], bt[2], q);
+        q = rfma(l[6] * bt[0], bt[3], q);
+        q = rfma(l[7] * bt[1], bt[3], q);
+        q = rfma(l[8] * bt[2], bt[3], q);
+        q = rfma(l[9] * bt[3], bt[3], q);
+        b[i] = rho[i] - q;
+    }
+    double A2[4];
+    bool singular = false;                       // eta == 0: qr_solve returns with X untouched (:722-727)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!singular) {
+            double eta = fabs(A[k][k]);
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) {
+                const double elt = fabs(A[i][k]);
+                if (eta < elt) eta = elt;
+            }
+            if (eta == 0) {
+                singular = true;
+            } else {
+                const double inv_eta = rdiv(1., eta);
+                double sum = 0.0;
+#pragma unroll
+                for (int i = k; i < 6; ++i) {
+                    A[i][k] *= inv_eta;
+                    sum = rfma(A[i][k], A[i][k], sum);
+                }
+                double sigma = rsqrt_exact(sum);
+                if (A[k][k] < 0) sigma = -sigma;
+                A[k][k] += sigma;
+                const double A1k = sigma * A[k][k];
+                A2[k] = -eta * sigma;
+#pragma unroll
+                for (int j = k + 1; j < 4; ++j) {
+                    double s = 0;
+#pragma unroll
+                    for (int i = k; i < 6; ++i) s = rfma(A[i][k], A[i][j], s);
+                    const double tau = rdiv(s, A1k);
+#pragma unroll
+                    for (int i = k; i < 6; ++i) A[i][j] = rfma(-tau, A[i][k], A[i][j]);
+                }
+                double tau = 0;
+#pragma unroll
+                for (int i = k; i < 6; ++i) tau = rfma(A[i][k], b[i], tau);
+                tau = rdiv(tau, A1k);
+#pragma unroll
+                for (int i = k; i < 6; ++i) b[i] = rfma(-tau, A[i][k], b[i]);
+            }
+        }
+    }
+    if (singular) return;
+    X[3] = rdiv(b[3], A2[3]);
+#pragma unroll
+    for (int i = 2; i >= 0; --i) {
+        double sum = 0;
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) sum = rfma(A[i][j], X[j], sum);
+        X[i] = rdiv(b[i] - sum, A2[i]);
+    }
+}
+
+// PnPsolver::gauss_newton (:675-691) on epnp_gn_step_reg; L and rho may live in shared memory (the loads are kept
+// inside the loop: hoisted out of it they would be 66 live doubles)
+template <class LT>
+__host__ __device__ __forceinline__ void epnp_gauss_newton_reg(LT L, const double* rho, double (&betas)[4])
+{
+    double X[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+#ifdef __CUDA_ARCH__
+        asm volatile("" ::: "memory");
+#endif
+        epnp_gn_step_reg(L, rho, betas, X);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) betas[i] += X[i];
+    }
+}
+
 // L, rho, approx_k + gauss_newton (PnPsolver.cpp:395-405) from the null-space basis U4 (12x4)
 template <class LT>
 __host__ __device__ inline void epnp_betas_from_basis_L(const double* U4, const double* cws, double* betas /*3x4*/, int ust, LT L);
@@ -356,6 +458,7 @@ __host__ __device__ inline void epnp_pc(const double* a, const double* ccs, doub
 
 // tail of PnPsolver::estimate_R_and_t (:449-492) given M = sum (pc-pc0)^T (pw-pw0):
 // Horn's 4x4 with float-truncated entries, last eigenvector, q = (w,-x,-y,-z)
+template <bool STATIC_SORT = false>
 __host__ __device__ inline void epnp_horn(const double* M, const double* pc0, const double* pw0, double* R, double* t)
 {
     const float N11 = (float)(M[0] + M[4] + M[8]);
@@ -370,7 +473,7 @@ __host__ __device__ inline void epnp_horn(const double* M, const double* pc0, co
     const float N44 = (float)(-M[0] - M[4] + M[8]);
     double N[16] = {N11, N12, N13, N14, N12, N22, N23, N24, N13, N23, N33, N34, N14, N24, N34, N44};
     double w[4], V[16];
-    jacobi_eig<double, 4>(N, w, V);
+    jacobi_eig<double, 4, STATIC_SORT>(N, w, V);
     quat_to_rot<double>(V[0 * 4 + 3], -V[1 * 4 + 3], -V[2 * 4 + 3], -V[3 * 4 + 3], R);
     if (det3(R) < 0) { R[6] = -R[6]; R[7] = -R[7]; R[8] = -R[8]; }
     for (int r = 0; r < 3; ++r)
@@ -383,11 +486,11 @@ __host__ __device__ inline double epnp_reproj_term(const double* R, const double
     const double X = R[0] * pw[0] + R[1] * pw[1] + R[2] * pw[2] + t[0];
     const double Y = R[3] * pw[0] + R[4] * pw[1] + R[5] * pw[2] + t[1];
     const double Z = R[6] * pw[0] + R[7] * pw[1] + R[8] * pw[2] + t[2];
-    const double inv_Zc = 1.0 / Z;
+    const double inv_Zc = rdiv(1.0, Z);
     const double ue = k.cx + k.fx * X * inv_Zc;
     const double ve = k.cy + k.fy * Y * inv_Zc;
     const double du = u - ue, dv = v - ve;
-    return sqrt(du * du + dv * dv);
+    return rsqrt_exact(du * du + dv * dv);
 }
 
 // Whole PnPsolver::compute_pose (:359-415) for NPTS thread-private correspondences.

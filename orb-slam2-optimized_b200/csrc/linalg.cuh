@@ -17,8 +17,18 @@ template <typename T> struct JacobiTol;
 template <> struct JacobiTol<double> { __host__ __device__ static double scale() { return 0x1p-56; } };
 template <> struct JacobiTol<float>  { __host__ __device__ static float scale() { return 0x1p-27f; } };
 
+// IEEE division and square root behind one name each.  RSAC_NOINLINE_DIVSQRT compiles the FP64 ones as out-of-line device
+// functions: an inlined double division / square root is ~25 instructions plus a slow-path subroutine, and the solvers
+// contain ~200 of them -- out of line the 4-point solver's hot code shrinks by a third (instruction-cache footprint)
+#if defined(__CUDA_ARCH__) && defined(RSAC_NOINLINE_DIVSQRT)
+__device__ __noinline__ double rsqrt_exact(double x) { return sqrt(x); }
+__device__ __noinline__ double rdiv(double a, double b) { return a / b; }
+#else
 __host__ __device__ inline double rsqrt_exact(double x) { return sqrt(x); }
+__host__ __device__ inline double rdiv(double a, double b) { return a / b; }
+#endif
 __host__ __device__ inline float rsqrt_exact(float x) { return sqrtf(x); }
+__host__ __device__ inline float rdiv(float a, float b) { return a / b; }
 // explicit fused multiply-add: the only contraction allowed by the arithmetic contract (the build uses
 // -fmad=false); every rfma below has a twin in oracle/orc_linalg.c (ORC_FMA)
 __host__ __device__ inline double rfma(double a, double b, double c) { return fma(a, b, c); }
@@ -43,7 +53,7 @@ __host__ __device__ inline void jacobi_angle(T app, T aqq, T apq, T& c, T& s, T&
     const T r = rsqrt_exact(rfma(h, h, b2 * b2));
     const T ah = rabs(h);
     const T uu = (r + r) * (r + ah);
-    const T ww = (half + half) / rsqrt_exact(uu);
+    const T ww = rdiv(half + half, rsqrt_exact(uu));
     c = (r + ah) * ww;
     const T s0 = b2 * ww;
     const T m = half * (app + aqq);
@@ -56,7 +66,9 @@ __host__ __device__ inline void jacobi_angle(T app, T aqq, T apq, T& c, T& s, T&
 // destroyed).  Eigenvalues ascending in w, eigenvectors in the columns of v (accumulated
 // forward).  Rotations with |a_pq| <= ||a||_F * 2^-56 (2^-27 in float) are skipped; the
 // solve ends after a sweep without rotations.  Used for the small solves (N = 3, 4).
-template <typename T, int N>
+// STATIC_SORT: the final ordering with compile-time indices only, so that w and v stay in registers (the sub-warp
+// solver); the default keeps the run-time-indexed selection sort (w, v in local memory).  Same permutation.
+template <typename T, int N, bool STATIC_SORT = false>
 __host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
 {
     const T one = T(1), zero = T(0);
@@ -106,6 +118,7 @@ __host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) w[i] = a[i * N + i];
+    if constexpr (!STATIC_SORT) {
     for (int i = 0; i < N - 1; ++i) {
         int k = i;
         for (int j = i + 1; j < N; ++j)
@@ -114,6 +127,29 @@ __host__ __device__ inline void jacobi_eig(T* a, T* w, T* v)
             const T tw = w[i]; w[i] = w[k]; w[k] = tw;
             for (int r = 0; r < N; ++r) {
                 const T tv = v[r * N + i]; v[r * N + i] = v[r * N + k]; v[r * N + k] = tv;
+            }
+        }
+    }
+    return;
+    }
+    // selection sort, ascending, ties to the lower index.  Static indices only (the arrays stay in registers): the
+    // minimum of w[i..N) is tracked by value, the swap partner is found by comparing the (run-time) position with
+    // every (compile-time) j
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) {
+        int k = i;
+        T wk = w[i];
+#pragma unroll
+        for (int j = i + 1; j < N; ++j)
+            if (w[j] < wk) { k = j; wk = w[j]; }
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+            if (k == j) {
+                const T tw = w[i]; w[i] = w[j]; w[j] = tw;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    const T tv = v[r * N + i]; v[r * N + i] = v[r * N + j]; v[r * N + j] = tv;
+                }
             }
         }
     }
@@ -620,7 +656,7 @@ __host__ __device__ inline void inv3(const double* m, double* out)
     const double c21 = rfma(m[2], m[3], -(m[0] * m[5]));
     const double c22 = rfma(m[0], m[4], -(m[1] * m[3]));
     const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
-    const double id = 1.0 / det;
+    const double id = rdiv(1.0, det);
     out[0] = c00 * id; out[1] = c10 * id; out[2] = c20 * id;
     out[3] = c01 * id; out[4] = c11 * id; out[5] = c21 * id;
     out[6] = c02 * id; out[7] = c12 * id; out[8] = c22 * id;
