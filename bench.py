@@ -1,28 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- relocalisation-sweep throughput of the B200 RANSAC engine (BASELINE.json metric).
 
-Workload (config.workload = "cfg4"): 1024 candidate keyframes x 500 2D-3D matches, 50 % outliers,
-PnPsolver EPnP RANSAC with SetRansacParameters(0.99,10,300,4,0.2,5.991) => H = 300 hypotheses per
-candidate.  The reference stops at the first hypothesis whose Refine() succeeds; the device does the same
-in phases (RSAC_FLAG_EARLY_EXIT: the first 55 hypotheses of every candidate, the rest only for the candidates
-that still need them), then replays the reference's sequential semantics (PnPsolver::iterate / Refine) per
-candidate -- records and masks are identical to solving and scoring all 300 (RSAC_BENCH_EXHAUSTIVE=1 times
-that mode: 153.6 M evaluations + 307 200 minimal solves per sweep).  With N GPUs every GPU works on its own
-1024-candidate sweep (weak scaling; RSAC_BENCH_STRONG=1 shards one sweep instead) and the per-candidate
-records (96 B) are all-gathered over NCCL every sweep.
+Workload (config.workload = "cfg4"): relocalisation sweeps of 1024 candidate keyframes x 500 2D-3D matches, 50 %
+outliers, PnPsolver EPnP RANSAC with SetRansacParameters(0.99,10,300,4,0.2,5.991) => H = 300 hypotheses per candidate.
+The reference stops at the first hypothesis whose Refine() succeeds; the device does the same in stages
+(RSAC_FLAG_EARLY_EXIT), then replays the reference's sequential semantics (PnPsolver::iterate / Refine) per candidate
+-- records and masks are identical to solving and scoring all 300 (RSAC_BENCH_EXHAUSTIVE=1 times that mode).
 
-A "step" is one sweep.  Sweeps are independent, so they are pipelined over a few engine
-instances / CUDA streams; the timed region is K sweeps between barriers, timed with CUDA events,
-max over ranks.
+A STEP is a fixed bundle of 64 independent sweeps = 65 536 candidates, whatever the number of GPUs (STRONG scaling:
+BASELINE cfg4 "1024 candidates sharded at 1/2/4/8 GPUs with NCCL best-pose gather").  With N GPUs every sweep's
+candidates are sharded in contiguous blocks of 1024/N; a rank concatenates its shards of N consecutive
+sweeps into one device batch of 1024 candidates, and after every batch the per-candidate records (96 B) of the N sweeps
+are all-gathered over NCCL, so that every rank holds the N complete sweeps.  A step is 64/N batches per GPU.
   value : candidates/s, inputs resident in HBM
-  e2e   : the same through the host-buffer C-ABI call sequence (H2D of every sweep's inputs from
-          pinned memory, D2H of results + inlier masks inside the timed region)
+  e2e   : the same through the host-buffer C-ABI call sequence (H2D of every batch's inputs from pinned memory, D2H of
+          records + inlier masks inside the timed region)
   roofline      : dominant kernel of the sweep (EPnP minimal solver, FP64 CUDA cores)
   roofline_score: CheckInliers kernel on cfg5 (4096 poses x 10 000 correspondences, FP32 CUDA cores)
   cpu_baseline  : the CPU oracle (port of the reference, see oracle/) on the host cores
+After the timed passes rank 0 checks CONTENT: the end-to-end records and masks equal the resident run's, and (N > 1) the
+records gathered from N ranks -- through torch.distributed and through the library's own rsac_nccl_allgather_results --
+are byte-identical to a one-rank run of the same sweeps.
 
---impl reference runs the reference arm: the oracle port of PnPsolver on all host threads, same
-workload, same metric (the reference itself cannot be compiled here: it needs Eigen/OpenCV).
+--impl reference runs the reference arm: the oracle port of PnPsolver on all host threads, same workload, same metric,
+each step a bounded sample of the bundle (the reference itself cannot be compiled here: it needs Eigen/OpenCV).
 """
 from __future__ import annotations
 
@@ -40,14 +41,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "orb-slam2-optimized_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-C_TOTAL = 1024
+C_SWEEP = 1024                # candidates of one relocalisation sweep (BASELINE cfg4)
 N_MATCH = 500
 PRM = dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.2, th2=5.991)
 H_HYP = 300
+NBLOCK = 8                    # distinct synthetic sweeps ("blocks") that are cycled
+BUNDLE = int(os.environ.get("RSAC_BENCH_BUNDLE", "64"))   # sweeps per step (a multiple of 8): 65 536 candidates per step
 METRIC = "relocalization candidates/s (PnP EPnP RANSAC sweep; hyp x corr evals/s in extras)"
 FLOP_PER_EVAL = 31            # PnP CheckInliers
-PIPE = int(os.environ.get("RSAC_BENCH_PIPE", "0"))   # sweeps in flight per GPU (0: default, one)
+PIPE = int(os.environ.get("RSAC_BENCH_PIPE", "0"))   # device batches in flight per GPU (0: default, six)
 EXHAUSTIVE = os.environ.get("RSAC_BENCH_EXHAUSTIVE", "0") == "1"   # solve and score all 300 hypotheses of every candidate
+EIGEN = os.environ.get("RSAC_BENCH_EIGEN", "0") == "1"             # 12x12 eigen-solve null space (the reference's structure)
 
 
 def measured_peaks():
@@ -110,11 +114,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_shard(first, count):
+def make_block(j):
+    """synthetic sweep j: 1024 cfg1-style candidates (distinct seeds and poses)"""
     from ransac_b200 import synth
-    b = synth.pnp_batch(4, count, N_MATCH, 0.5, first=first)
-    offsets = (np.arange(count + 1, dtype=np.int64) * N_MATCH).astype(np.int32)
-    return b, offsets
+    return synth.pnp_batch(4, C_SWEEP, N_MATCH, 0.5, first=j * C_SWEEP)
+
+
+def shard_of(C, rank, world):
+    per = (C + world - 1) // world
+    first = min(C, rank * per)
+    return first, min(C, first + per) - first
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -126,44 +135,37 @@ def run_reference(args):
     import oracle_api as O
     O.build()
     cores = os.cpu_count() or 1
-    strong = os.environ.get("RSAC_BENCH_STRONG", "0") == "1"
-    n_cand = C_TOTAL if strong else C_TOTAL * max(1, args.gpus)     # the GPU arm's config at this N
-    # the GPU arm's data: NBLOCK blocks of 1024 candidates; step k works on blocks (k + r) mod NBLOCK, r < gpus
-    nblock = 1 if strong else max(1, int(os.environ.get("RSAC_BENCH_BLOCKS", "8")))
     prm = O.params(**PRM)
-    oflags = O.FLAG_EPNP_QR_NULLSPACE   # the port's faster mode (same arithmetic as the device path)
+    oflags = 0 if EIGEN else O.FLAG_EPNP_QR_NULLSPACE   # the port's faster mode (same arithmetic as the device path)
+    # bounded sample of a step: SAMPLE of the bundle's 64 sweeps (8 distinct blocks are cycled, like the GPU arm)
+    sample = max(1, int(os.environ.get("RSAC_BENCH_REF_SWEEPS", "4")))
     blocks = []
-    for j in range(nblock):
-        bj, _ = make_shard(j * C_TOTAL, C_TOTAL)
-        blocks.append(([O.pnp_problem(bj["p3d"][c], bj["p2d"][c], bj["sigma2"][c], bj["K"]) for c in range(C_TOTAL)],
+    for j in range(min(NBLOCK, sample)):
+        bj = make_block(j)
+        blocks.append(([O.pnp_problem(bj["p3d"][c], bj["p2d"][c], bj["sigma2"][c], bj["K"]) for c in range(C_SWEEP)],
                        [O.index_table(int(sd), N_MATCH, 4, H_HYP) for sd in bj["seeds"]]))
-
-    def step_work(k):
-        pbs, tabs = [], []
-        for r in range(1 if strong else max(1, args.gpus)):
-            p_, t_ = blocks[(k + r) % nblock]
-            pbs += p_
-            tabs += t_
-        return pbs, tabs
-
     for _ in range(max(1, min(args.warmup, 1))):
         O.pnp_batch(blocks[0][0][:64], prm, blocks[0][1][:64], oflags, cores)
-    t_tot, ev_tot = 0.0, 0
+    t_tot, ev_tot, n_tot = 0.0, 0, 0
     for k in range(args.steps):
-        pbs, tables = step_work(k)
-        dt, ev, res = O.pnp_batch(pbs, prm, tables, oflags, cores)
-        t_tot += dt
-        ev_tot += ev
-    val = n_cand * args.steps / t_tot
+        for q in range(sample):
+            pbs, tables = blocks[(k * sample + q) % len(blocks)]
+            dt, ev, res = O.pnp_batch(pbs, prm, tables, oflags, cores)
+            t_tot += dt
+            ev_tot += ev
+            n_tot += len(pbs)
+    val = n_tot / t_tot
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "candidates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": "cfg4", "candidates": n_cand, "matches": N_MATCH,
-                                            "hypotheses": H_HYP, "mode": "reference semantics (early exit)",
-                                            "blocks": f"{nblock} blocks of {C_TOTAL} synthetic candidates; step k works on blocks (k + r) mod {nblock}, r < {max(1, args.gpus)}"},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 solve / f32 score",
+            "data": "synthetic", "config": {"workload": "cfg4", "candidates_per_sweep": C_SWEEP, "sweeps_per_step": BUNDLE,
+                                            "candidates_per_step": BUNDLE * C_SWEEP, "matches": N_MATCH,
+                                            "hypotheses": H_HYP, "mode": "reference semantics (early exit)"},
             "cpu_baseline": {"value": val, "unit": "candidates/s", "cores": cores, "kind": "port",
-                             "sample": "full cfg4 sweep per step, one solver call per core (BASELINE.md mode B); "
-                                       "4-point null space by Householder QR as on the device (the port's faster mode)",
+                             "sample": f"{sample} of the {BUNDLE} sweeps of a step ({sample * C_SWEEP} candidates per step), one solver call "
+                                       "per core (BASELINE.md mode B); 4-point null space " +
+                                       ("by the 12x12 eigen-solve (the reference's structure)" if EIGEN else
+                                        "by Householder QR as on the device (the port's faster mode)"),
                              "evals_per_s": ev_tot / t_tot},
             "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -175,8 +177,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip cfg5/cfg1 side measurements and the CPU baseline")
     args = ap.parse_args()
@@ -198,76 +200,68 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    assert world in (1, 2, 4, 8) and BUNDLE % NBLOCK == 0, "sweeps are sharded over 1, 2, 4 or 8 ranks"
 
-    # Sweeps are independent, so several are in flight per GPU (one engine + stream each): every phase of a sweep is
-    # one latency-bound wave, and a rare candidate that needs several Refine() calls, or the clean-up phase, stretches
-    # a whole sweep (0.52 -> 1.16 ms for one such candidate) -- overlapping sweeps fills those holes
-    # (measured on the 8-block mix, resident, two stages: 1 in flight 0.72 ms per sweep, 2: 0.59, 3: 0.55; three stages: 4 in
-    # flight 0.48, 6: 0.45, 8: 0.46)
-    global PIPE, C_TOTAL
+    # Several device batches are in flight per GPU (one engine + stream each): every kernel of a sweep is one
+    # latency-bound wave (or a fraction of one), and a rare candidate that needs several Refine() calls, or the
+    # clean-up stage, stretches a whole sweep -- overlapping batches fills those holes
+    global PIPE
     if PIPE <= 0:
         PIPE = 6
-    # weak scaling (task statement, section 5): the path shards by candidate with no data-path collective, so
-    # every GPU works on its own 1024-candidate sweep and the job processes 1024 x N candidates per step;
-    # RSAC_BENCH_STRONG=1 keeps the total at 1024 instead (each GPU then gets 1024/N candidates)
-    strong = os.environ.get("RSAC_BENCH_STRONG", "0") == "1"
-    C_PER_GPU = C_TOTAL
-    if not strong:
-        C_TOTAL = C_PER_GPU * world
-    RUN_FLAGS = 0 if EXHAUSTIVE else capi.FLAG_EARLY_EXIT
-    first, count = shard.block_range(C_TOTAL, rank, world)
-    cap = shard.per_rank_capacity(C_TOTAL, world)
-    # The synthetic set is NBLOCK blocks of 1024 candidates; at step k rank r works on block (k + r) mod NBLOCK, so
-    # every rank meets every block equally often at every N (blocks differ: some hold a candidate whose refines
-    # fail, which costs the clean-up phase) and the ranks of one step work on different blocks.
-    NBLOCK = 1 if strong else max(1, int(os.environ.get("RSAC_BENCH_BLOCKS", "8")))
+    RUN_FLAGS = (0 if EXHAUSTIVE else capi.FLAG_EARLY_EXIT) | (capi.FLAG_EPNP_EIGEN if EIGEN else 0)
+    # strong scaling: rank r owns candidates [first, first + count) of EVERY sweep; its shards of `world` consecutive
+    # sweeps (blocks j*world .. j*world + world - 1) are concatenated into device batch j (1024 candidates)
+    first, count = shard_of(C_SWEEP, rank, world)
+    NB = NBLOCK // world                     # distinct device batches of this rank
+    RUNS = BUNDLE // world                   # batches per step and GPU
+    C_RUN = count * world                    # = 1024
     prm = capi.ransac_params(**PRM)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    blocks = []
-    for j in range(NBLOCK):
-        bj = (j + rank) % NBLOCK
-        bb, offsets = make_shard(first if strong else bj * C_PER_GPU, count)
-        blocks.append(dict(p3d=pin(bb["p3d"].reshape(-1, 3)), p2d=pin(bb["p2d"].reshape(-1, 2)), s2=pin(bb["sigma2"].reshape(-1)),
-                           seeds=bb["seeds"], K=bb["K"], block=bj))
-    b = dict(K=blocks[0]["K"], p3d=blocks[0]["p3d"].numpy().reshape(count, N_MATCH, 3), p2d=blocks[0]["p2d"].numpy().reshape(count, N_MATCH, 2),
-             sigma2=blocks[0]["s2"].numpy().reshape(count, N_MATCH), seeds=blocks[0]["seeds"])
+    offsets = (np.arange(C_RUN + 1, dtype=np.int64) * N_MATCH).astype(np.int32)
+    blocks_full = [make_block(j) for j in range(NBLOCK)]
+    batches = []
+    for j in range(NB):
+        sel = [blocks_full[j * world + i] for i in range(world)]
+        cat = lambda k, shp: np.concatenate([b_[k][first:first + count] for b_ in sel]).reshape(shp)
+        ids = np.concatenate([(j * world + i) * C_SWEEP + first + np.arange(count) for i in range(world)]).astype(np.int32)
+        batches.append(dict(p3d=pin(cat("p3d", (-1, 3))), p2d=pin(cat("p2d", (-1, 2))), s2=pin(cat("sigma2", (-1,))),
+                            seeds=np.concatenate([b_["seeds"][first:first + count] for b_ in sel]), K=sel[0]["K"], ids=ids))
+    b = blocks_full[0]
 
-    NRES = max(NBLOCK, PIPE)             # resident pass: one engine per block (block j of this rank stays uploaded in engine j)
-    NSLOT = PIPE + 1                     # end-to-end pass: engines 0 .. PIPE are re-uploaded every step
+    NRES = max(NB, PIPE)                 # resident pass: engine i keeps batch (i mod NB) uploaded
+    NSLOT = PIPE + 1                     # end-to-end pass: engines 0 .. PIPE are re-uploaded every run
     NENG = max(NRES, NSLOT)
     engines, streams, d_local = [], [], []
     for i in range(NENG):
         e = capi.Engine(local_rank)
         s = torch.cuda.Stream(device=dev)
         e.set_stream(s.cuda_stream)
-        e.set_problem_base(first)
         engines.append(e)
         streams.append(s)
-        d_local.append(torch.full((cap, shard.REC_WORDS), -1, dtype=torch.int32, device=dev))
+        d_local.append(torch.full((C_RUN, shard.REC_WORDS), -1, dtype=torch.int32, device=dev))
     words_total = int(((np.diff(offsets) + 31) // 32).sum())
-    h_res = [torch.empty((count, shard.REC_WORDS), dtype=torch.int32).pin_memory() for _ in range(NSLOT)]
+    h_res = [torch.empty((C_RUN, shard.REC_WORDS), dtype=torch.int32).pin_memory() for _ in range(NSLOT)]
     h_msk = [torch.empty((max(words_total, 1),), dtype=torch.int32).pin_memory() for _ in range(NSLOT)]
 
     def upload(i, j):
-        blk = blocks[j % NBLOCK]
+        blk = batches[j % NB]
+        engines[i].set_problem_ids(blk["ids"])
         engines[i].pnp_upload(offsets, blk["p3d"].numpy(), blk["p2d"].numpy(), blk["s2"].numpy(), [blk["K"]], prm, seeds=blk["seeds"])
 
-    # multi-GPU: the all-gather of a sweep's records (98 KB per rank, latency-bound) runs on a side stream, in
-    # issue order; a ring of gather buffers, and every engine waits for the gather that last read its records
+    # multi-GPU: the all-gather of a batch's records (98 KB per rank, latency-bound) runs on a side stream, in issue
+    # order; a ring of gather buffers, and every engine waits for the gather that last read its records
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     NG = NENG + 2
-    d_gath = [torch.empty((world * cap, shard.REC_WORDS), dtype=torch.int32, device=dev) for _ in range(NG)] if world > 1 else None
+    d_gath = [torch.empty((world * C_RUN, shard.REC_WORDS), dtype=torch.int32, device=dev) for _ in range(NG)] if world > 1 else None
     gather_done = [None] * NENG
-    slot_done = [None] * NENG          # completion of the last sweep that ran on engine i
     last_gather = [None]
-    GATHER = os.environ.get("RSAC_BENCH_GATHER", "overlap")   # overlap | none (diagnostic)
 
     def run_and_gather(i, k):
         st = streams[i]
         if gather_done[i] is not None:
             st.wait_event(gather_done[i])              # the gather that last read this engine's records
         engines[i].pnp_run(RUN_FLAGS, d_local[i].data_ptr())
-        if world > 1 and GATHER != "none":
+        if world > 1:
             ev = torch.cuda.Event()
             ev.record(st)
             with torch.cuda.stream(comm_stream):
@@ -281,7 +275,7 @@ def main():
             last_gather[0] = d_local[i]
 
     def bound_in_flight(i, k, ring):
-        # at most PIPE sweeps in flight: sweep k starts after sweep k - PIPE has finished
+        # at most PIPE batches in flight: batch k starts after batch k - PIPE has finished
         prev = ring[(k - PIPE) % len(ring)] if k >= PIPE else None
         if prev is not None:
             streams[i].wait_event(prev)
@@ -289,7 +283,7 @@ def main():
     res_ring = [None] * (NRES + PIPE)
     e2e_ring = [None] * (NSLOT + PIPE)
 
-    def step_resident(k):
+    def run_resident(k):
         i = k % NRES
         with torch.cuda.stream(streams[i]):
             bound_in_flight(i, k, res_ring)
@@ -298,19 +292,20 @@ def main():
             ev.record(streams[i])
             res_ring[k % len(res_ring)] = ev
 
-    def step_e2e(k):
+    def run_e2e(k):
         i = k % NSLOT
         with torch.cuda.stream(streams[i]):
-            upload(i, k)                                # H2D of block (k + rank) mod NBLOCK, plans, tables
+            upload(i, k)                                # H2D of batch k mod NB
             bound_in_flight(i, k, e2e_ring)
             run_and_gather(i, k)
             ev = torch.cuda.Event()
             ev.record(streams[i])
             e2e_ring[k % len(e2e_ring)] = ev
-            # D2H of this sweep's records and inlier masks into pinned memory (async on the sweep's stream)
+            # D2H of this batch's records and inlier masks into pinned memory (async on the batch's stream)
             engines[i].pnp_download_async(h_res[i].data_ptr(), h_msk[i].data_ptr())
 
     def timed(fn, steps):
+        """`steps` steps = steps * RUNS batches on this rank; device time, max over ranks"""
         for r in (res_ring, e2e_ring):
             for q in range(len(r)):
                 r[q] = None
@@ -324,7 +319,7 @@ def main():
         ev0.record(main_s)
         for s in streams:
             s.wait_event(ev0)
-        for k in range(steps):
+        for k in range(steps * RUNS):
             fn(k)
         for s in streams + ([comm_stream] if comm_stream is not None else []):
             e = torch.cuda.Event()
@@ -343,23 +338,22 @@ def main():
     for i in range(NRES):
         upload(i, i)
     torch.cuda.synchronize()
-    timed(step_resident, max(args.warmup, NRES))
+    timed(run_resident, max(1, (args.warmup * RUNS + RUNS - 1) // RUNS))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = sum(e.launch_count() for e in engines)
-    ms = timed(step_resident, args.steps)
+    ms = timed(run_resident, args.steps)
     launches = sum(e.launch_count() for e in engines) - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-kernel durations: CUDA events around every launch of a NON-pipelined pass (one sweep at a time on one
-    # stream), so that an event pair brackets exactly one kernel; in the pipelined region above kernels of
-    # different sweeps overlap and a bracket would also count the neighbours
+    # per-kernel durations: CUDA events around every launch of a NON-pipelined pass (one batch at a time on one
+    # stream, eager launches), so that an event pair brackets exactly one kernel
     stage = {}
     e0 = engines[0]
     e0.profile_reset()
     e0.profile_enable(True)
-    nprof = max(3, min(10, args.steps))
+    nprof = 8
     with torch.cuda.stream(streams[0]):
         for _ in range(nprof):
             e0.pnp_run(RUN_FLAGS, d_local[0].data_ptr())
@@ -367,58 +361,109 @@ def main():
     for k, (tms, nl) in e0.profile().items():
         stage[k] = [tms, nl]
     trace = e0.profile_trace()
-    trace = trace[-(len(trace) // nprof):] if trace else []      # the launches of the last sweep, in order
+    trace = trace[-(len(trace) // nprof):] if trace else []      # the launches of the last batch, in order
     e0.profile_enable(False)
-    # phases and hypotheses actually solved and scored: mean over the blocks this rank holds
-    stats = [engines[i].pnp_phase_stats() for i in range(NRES)]
+    # stages and hypotheses actually solved and scored: mean over the batches this rank holds
+    stats = [engines[i].pnp_phase_stats() for i in range(NB)]
     ha = stats[0][0]
     n_b = float(np.mean([st[1] for st in stats]))
     n_c = float(np.mean([st[2] for st in stats]))
     hyp_done = float(np.mean([st[3] for st in stats]))
 
-    # correctness guard on the gathered records (cheap): every candidate reported once, in order
+    # ---- content checks (rank 0 asserts; every rank takes part in the collectives)
     torch.cuda.synchronize()
-    if world > 1 and GATHER == "none":
-        n_ok = -1
+    checks = {}
+    # (1) the resident records of batch 0, as this rank computed them
+    with torch.cuda.stream(streams[0]):
+        engines[0].pnp_run(RUN_FLAGS, d_local[0].data_ptr())
+    torch.cuda.synchronize()
+    res_local, msk_local = engines[0].pnp_download()
+    # (2) end to end (timed), then one more end-to-end batch 0 whose downloaded records and masks must equal the resident run's
+    timed(run_e2e, 1)
+    ms_e2e = timed(run_e2e, args.steps)
+    with torch.cuda.stream(streams[0]):
+        upload(0, 0)
+        engines[0].pnp_run(RUN_FLAGS, d_local[0].data_ptr())
+        engines[0].pnp_download_async(h_res[0].data_ptr(), h_msk[0].data_ptr())
+    torch.cuda.synchronize()
+    got = h_res[0].numpy().view(capi.RESULT_DTYPE).reshape(-1)
+    assert got.tobytes() == res_local.tobytes(), "end-to-end records differ from the resident run's"
+    assert (h_msk[0].numpy().view(np.uint32)[:words_total] == msk_local).all(), "end-to-end masks differ from the resident run's"
+    checks["e2e_equals_resident"] = True
+    # (3) N ranks == 1 rank: gather batch 0 (= sweeps 0 .. world-1) through torch.distributed and through the library's own
+    # NCCL path; rank 0 recomputes those sweeps alone (unsharded) and compares byte for byte
+    if world > 1:
+        g_torch = torch.empty((world * C_RUN, shard.REC_WORDS), dtype=torch.int32, device=dev)
+        g_native = torch.zeros_like(g_torch)
+        dist.all_gather_into_tensor(g_torch, d_local[0])
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.Engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        engines[0].nccl_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        engines[0].nccl_allgather_results(d_local[0].data_ptr(), C_RUN, g_native.data_ptr())
+        engines[0].sync()
+        torch.cuda.synchronize()
+        engines[0].nccl_destroy()
+        rec_t = shard.records_from_tensor(g_torch)
+        rec_n = shard.records_from_tensor(g_native)
+        if rank == 0:
+            assert rec_t.tobytes() == rec_n.tobytes(), "rsac_nccl_allgather_results differs from torch.distributed's all-gather"
+            assert len(rec_t) == world * C_SWEEP and (rec_t["problem"] == np.arange(world * C_SWEEP)).all(), "gather lost candidates"
+            one = capi.Engine(local_rank)
+            for sw in range(world):
+                bs = blocks_full[sw]
+                one.set_problem_ids(None)
+                one.set_problem_base(sw * C_SWEEP)
+                r1, _ = one.pnp_solve((np.arange(C_SWEEP + 1) * N_MATCH).astype(np.int32), bs["p3d"], bs["p2d"], bs["sigma2"], [bs["K"]], prm,
+                                      seeds=bs["seeds"], flags=RUN_FLAGS)
+                assert r1.tobytes() == rec_t[sw * C_SWEEP:(sw + 1) * C_SWEEP].tobytes(), f"sweep {sw}: {world}-rank records differ from the 1-rank run"
+            one.close()
+            checks["n_rank_equals_1_rank_bytes"] = True
+            checks["native_nccl_allgather_equals_torch"] = True
+        n_ok = int(rec_t["ok"].sum())
     else:
         rec = shard.records_from_tensor(last_gather[0])
-        assert len(rec) == C_TOTAL and (rec["problem"] == np.arange(C_TOTAL)).all(), "gather lost candidates"
+        assert len(rec) == C_RUN
         n_ok = int(rec["ok"].sum())
 
-    # end-to-end through host buffers
-    timed(step_e2e, max(4, 2 * NSLOT))
-    ms_e2e = timed(step_e2e, args.steps)
-    h2d = int(count * N_MATCH * 24 + count * 4 + count * 152)
-    d2h = int(count * 96 + words_total * 4)
-
-    value = C_TOTAL * args.steps / (ms * 1e-3)
-    e2e_v = C_TOTAL * args.steps / (ms_e2e * 1e-3)
-    hyp_frac = hyp_done / float(count * H_HYP)                   # share of the 300 x candidates hypotheses computed
+    h2d = int(C_RUN * N_MATCH * 24 + C_RUN * 4 + C_RUN * 152 + C_RUN * 4)
+    d2h = int(C_RUN * 96 + words_total * 4)
+    C_STEP = BUNDLE * C_SWEEP
+    value = C_STEP * args.steps / (ms * 1e-3)
+    e2e_v = C_STEP * args.steps / (ms_e2e * 1e-3)
+    hyp_frac = hyp_done / float(C_RUN * H_HYP)                   # share of the 300 x candidates hypotheses computed
 
     line = {"metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak",
+            "scaling": "strong",
             "vs_baseline": None, "dtype": "f64 solve / f32 score", "data": "synthetic",
-            "config": {"workload": "cfg4", "candidates": C_TOTAL, "candidates_per_gpu": count, "matches": N_MATCH,
-                       "hypotheses": H_HYP, "outliers": 0.5,
-                       "mode": ("all H hypotheses solved and scored on the device (4-point null space by QR), then "
-                                "reference-semantics replay + Refine per candidate") if EXHAUSTIVE else
-                               (f"reference semantics with early exit in phases: hypotheses [0,{ha}) of every candidate, the "
-                                f"remaining ones for the {n_b:.0f} of {count} candidates (mean over blocks) without an acceptable "
-                                f"hypothesis so far ({100 * hyp_frac:.1f} % of the 300 x {count} hypotheses solved and scored), "
-                                "replay + Refine per candidate; records identical to the exhaustive run"),
-                       "blocks": f"{NBLOCK} blocks of {C_PER_GPU} synthetic candidates; at step k rank r works on block (k + r) mod {NBLOCK}",
-                       "parallelism": f"one 1024-candidate sweep per GPU and step (x{world} GPUs), {PIPE} independent sweeps in flight per "
-                                      "GPU (one engine + stream each); e2e uploads every step's block from pinned host memory and "
-                                      "reads records + masks back inside the timed region",
-                       "l2": (f"no explicit flush: {NBLOCK} blocks are cycled, each in its own engine (~90 MB of device buffers per block, "
-                              f"{NBLOCK * 90} MB in total against 126 MB of L2), so a step's data was last touched {NBLOCK} steps earlier; "
-                              "within a sweep the working set is L2-resident by design and every kernel is compute- or latency-bound")},
-            "e2e": {"value": e2e_v, "unit": "candidates/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+            "config": {"workload": "cfg4", "candidates_per_sweep": C_SWEEP, "sweeps_per_step": BUNDLE, "candidates_per_step": C_STEP,
+                       "candidates_per_gpu_per_sweep": count, "matches": N_MATCH, "hypotheses": H_HYP, "outliers": 0.5,
+                       "mode": ("all H hypotheses solved and scored on the device, then reference-semantics replay + Refine per candidate"
+                                if EXHAUSTIVE else
+                                (f"reference semantics with early exit in stages: hypotheses [0,{ha}) of every candidate, the "
+                                 f"following stages for the {n_b:.0f} of {C_RUN} candidates (mean over batches) without an acceptable "
+                                 f"hypothesis so far ({100 * hyp_frac:.1f} % of the 300 x {C_RUN} hypotheses solved and scored), "
+                                 "replay + Refine per candidate; records identical to the exhaustive run")) +
+                               ("; 4-point null space by the 12x12 eigen-solve (RSAC_FLAG_EPNP_EIGEN)" if EIGEN else
+                                "; 4-point null space by Householder QR (DESIGN.md section 2)"),
+                       "blocks": f"{NBLOCK} distinct synthetic sweeps of {C_SWEEP} candidates are cycled: sweep s of a step is block s mod {NBLOCK}",
+                       "parallelism": (f"every sweep sharded over {world} GPU(s) in contiguous blocks of {count} candidates; a rank concatenates its "
+                                       f"shards of {world} consecutive sweeps into one device batch of {C_RUN} candidates ({RUNS} batches per step "
+                                       f"and GPU, {PIPE} in flight, one engine + stream each; CUDA graph per batch); all-gather of the batch's "
+                                       "records (96 B per candidate) after every batch; e2e uploads every batch from pinned host memory and reads "
+                                       "records + masks back inside the timed region"),
+                       "l2": (f"no explicit flush: {NB} distinct batches per GPU are cycled, each in its own engine (~90 MB of device buffers per "
+                              "batch against 126 MB of L2); within a sweep the working set is L2-resident by design and every kernel is "
+                              "compute- or latency-bound")},
+            "e2e": {"value": e2e_v, "unit": "candidates/s", "h2d_bytes_per_step": h2d * RUNS * world, "d2h_bytes_per_step": d2h * RUNS * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "checks": checks,
             "extras": {"evals_per_s": value * H_HYP * N_MATCH * hyp_frac, "e2e_evals_per_s": e2e_v * H_HYP * N_MATCH * hyp_frac,
                        "evals_note": "hypothesis x correspondence evaluations actually performed (early exit skips the rest)",
+                       "ms_per_sweep": ms / args.steps / BUNDLE, "e2e_ms_per_sweep": ms_e2e / args.steps / BUNDLE,
                        "candidates_ok": n_ok,
                        "phases": {"first_phase": ha, "candidates_phase_b": n_b, "candidates_phase_c": n_c,
                                   "hypotheses_done_frac": hyp_frac},
@@ -435,38 +480,37 @@ def main():
         line["extras"]["measured_fp64_tflops"] = fp64_pk
         # per-kernel rooflines; "roofline" is the kernel with the largest share of the sweep.
         # Algorithmic FLOP per 4-point solve is counted by the oracle's instrumented build.
-        flop_per_solve = epnp_flops_per_solve(b)
-        # per sweep: with early exit a kernel is launched once per phase (A, B, clean-up); work = what the launches
-        # of a sweep actually did, time = their summed durations, so achieved = work / time is the launch-weighted
-        # average; the first launch of each kind (phase A: count x first_phase hypotheses) is also given alone
+        flop_per_solve = epnp_flops_per_solve(b, eigen=EIGEN)
         per = {k: v[0] / nprof for k, v in stage.items() if v[1]}
         nl = {k: v[1] / nprof for k, v in stage.items() if v[1]}
         total_ms = sum(per.values()) or 1.0
-        first = {}
+        first_l = {}
         for k, m in trace:
-            first.setdefault(k, m)
+            first_l.setdefault(k, m)
+        kern_solve = ("epnp_minimal_kernel<eigen>" if EIGEN else "epnp_minimal_subwarp_kernel")
         roofs = {}
         if per.get("solve"):
             t = per["solve"] * 1e-3
             ach = flop_per_solve * hyp_done / t / 1e12
-            roofs["solve"] = {"bound": "fp64", "kernel": "epnp_minimal_kernel<QR>" if EXHAUSTIVE else "epnp_minimal_range_kernel",
-                              "achieved": ach, "peak": fp64_pk,
+            roofs["solve"] = {"bound": "fp64", "kernel": kern_solve, "achieved": ach, "peak": fp64_pk,
                               "unit": "TFLOP/s", "frac": ach / fp64_pk,
-                              "traffic": ncu_traffic("epnp_minimal_kernel<QR>" if EXHAUSTIVE else "epnp_minimal_range_kernel") if count == 1024 else None,
+                              "traffic": None,
                               "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                               "flop_per_solve": flop_per_solve, "solves_per_sweep": hyp_done, "launch_ms": per["solve"],
                               "launches_per_sweep": nl["solve"], "share_of_sweep": per["solve"] / total_ms}
-            if not EXHAUSTIVE and first.get("solve"):
-                # the stage-A launch (every candidate's first hypotheses: one full resident wave) is the dominant launch
-                # of the sweep; the later stages launch the same kernel on a fraction of a wave (latency-bound by design,
-                # they overlap with other sweeps).  `roofline` quotes the stage-A launch; the launch-weighted figure over
-                # all launches of a sweep stays beside it
-                a1 = flop_per_solve * count * ha / (first["solve"] * 1e-3) / 1e12
+            if not EXHAUSTIVE and first_l.get("solve"):
+                # the stage-0 launch (every candidate's first hypotheses) is the dominant launch of the sweep; the later
+                # stages launch the same kernel on a fraction of a wave (latency-bound by design, they overlap with other
+                # sweeps).  `roofline` quotes the stage-0 launch; the launch-weighted figure over all launches stays beside it
+                a1 = flop_per_solve * C_RUN * ha / (first_l["solve"] * 1e-3) / 1e12
                 agg = dict(achieved=roofs["solve"]["achieved"], frac=roofs["solve"]["frac"], launch_ms=roofs["solve"]["launch_ms"],
                            solves=hyp_done, launches_per_sweep=nl["solve"])
-                roofs["solve"].update({"achieved": a1, "frac": a1 / fp64_pk, "launch_ms": first["solve"], "solves_per_launch": count * ha,
-                                       "launch": "stage A (hypotheses [0,%d) of %d candidates)" % (ha, count),
-                                       "all_launches_of_a_sweep": agg, "share_of_sweep": first["solve"] / total_ms})
+                tr = ncu_traffic(kern_solve)
+                roofs["solve"].update({"achieved": a1, "frac": a1 / fp64_pk, "launch_ms": first_l["solve"], "solves_per_launch": C_RUN * ha,
+                                       "launch": "stage 0 (hypotheses [0,%d) of %d candidates)" % (ha, C_RUN),
+                                       "all_launches_of_a_sweep": agg, "share_of_sweep": first_l["solve"] / total_ms,
+                                       "traffic": tr["dram_bytes"] if tr else None,
+                                       "traffic_source": (tr or {}).get("source")})
                 roofs["solve"].pop("solves_per_sweep", None)
                 roofs["solve"].pop("launches_per_sweep", None)
         if per.get("score"):
@@ -480,7 +524,7 @@ def main():
             roofs["select"] = {"bound": "latency", "kernel": "ransac_select_kernel<0> (replay + Refine, one CTA per candidate)",
                                "launch_ms": per["select"], "launches_per_sweep": nl["select"], "share_of_sweep": per["select"] / total_ms,
                                "note": "serial dense tails (2 sqrt + 1-2 div chains); no meaningful FLOP roofline"}
-        dom = max(roofs, key=lambda k: roofs[k]["launch_ms"] if "achieved" in roofs[k] else 0.0) if roofs else None
+        dom = max(roofs, key=lambda k: per.get(k, 0.0) if "achieved" in roofs[k] else 0.0) if roofs else None   # largest share of a sweep
         if dom and "achieved" in roofs[dom]:
             line["roofline"] = roofs[dom]
         elif roofs.get("solve"):
@@ -498,25 +542,26 @@ def main():
 
 
 def ncu_traffic(key):
-    """per-launch DRAM bytes of a kernel from the committed ncu capture (profiles/r01_traffic.json), or None"""
+    """per-launch DRAM bytes of a kernel from the committed ncu capture (profiles/r02_traffic.json): NOT measured in this
+    run -- the entry names the capture it comes from (kernel, launch shape, solves per launch)"""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         for k, v in d.items():
-            if k.startswith(key) and "phase B" not in k:
-                return int(v["dram_bytes"])
+            if k.startswith(key):
+                return {"dram_bytes": int(v["dram_bytes"]), "source": v.get("source", "profiles/r02_traffic.json")}
     except Exception:
         pass
     return None
 
 
-def epnp_flops_per_solve(b):
+def epnp_flops_per_solve(b, eigen=False):
     """algorithmic FP64 FLOP of one 4-point EPnP solve, from the oracle's operation counters"""
     try:
         import oracle_api as O
         O.build()
         pb = O.pnp_problem(b["p3d"][0], b["p2d"][0], b["sigma2"][0], b["K"])
         tab = O.index_table(int(b["seeds"][0]), N_MATCH, 4, 64)
-        return float(O.epnp_flops(pb, tab, O.FLAG_EPNP_QR_NULLSPACE))
+        return float(O.epnp_flops(pb, tab, 0 if eigen else O.FLAG_EPNP_QR_NULLSPACE))
     except Exception:
         return 9.0e4   # order-of-magnitude fallback (SURVEY 8(d))
 

@@ -48,7 +48,7 @@ extern "C" {
                                        that still need them.
                                        Results are identical to the exhaustive run; hypotheses behind the stopping point
                                        are simply never computed (rsac_pnp_get_hypotheses returns zeros/stale data there;
-                                       rsac_pnp_rerun computes them on demand).  Ignored with RSAC_FLAG_EPNP_EIGEN. */
+                                       rsac_pnp_rerun computes them on demand).  Works in both null-space modes. */
 
 typedef struct rsac_engine rsac_engine;
 
@@ -103,6 +103,12 @@ int rsac_set_stream(rsac_engine* e, void* cuda_stream);
 int rsac_sync(rsac_engine* e);
 /* global index of this engine's problem 0 (written to rsac_result.problem; used when candidates are sharded) */
 int rsac_set_problem_base(rsac_engine* e, int base);
+/* per-problem global indices written to rsac_result.problem instead of base + local index: ids[C] for the NEXT batches of
+ * exactly C problems (a rank whose batch concatenates its shards of several sweeps); C = 0 switches back to the base */
+int rsac_set_problem_ids(rsac_engine* e, const int32_t* ids, int C);
+/* CUDA graphs for the staged PnP sweep (default on; RSAC_GRAPH=0 in the environment turns them off): the second run of
+ * a (batch shape, flags, output buffer) combination captures its 18 launches, later runs replay them with one call */
+int rsac_set_graphs(rsac_engine* e, int on);
 /* RSAC_FLAG_EARLY_EXIT: hypotheses per problem in the first stage (later stages double); 0 (default) = three quarters
  * of one wave of the minimal-solver kernel over the batch (a batch that fits one wave runs all hypotheses at once) */
 int rsac_set_first_phase(rsac_engine* e, int hypotheses);

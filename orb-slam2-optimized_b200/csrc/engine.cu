@@ -39,6 +39,7 @@ int rsac_create(int device, rsac_engine** out)
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return RSAC_ERR_NO_DEVICE; }
     rsac_engine* e = new rsac_engine();
     e->device = device;
+    { const char* g = getenv("RSAC_GRAPH"); if (g && *g == '0') e->graphs = false; }
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return RSAC_ERR_CUDA; }
     e->stream = e->own_stream;
     if (cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); e->aux_stream = nullptr; }
@@ -82,6 +83,26 @@ int rsac_set_problem_base(rsac_engine* e, int base)
 {
     if (!e) return RSAC_ERR_INVALID;
     e->problem_base = base;
+    return RSAC_OK;
+}
+
+int rsac_set_problem_ids(rsac_engine* e, const int32_t* ids, int C)
+{
+    if (!e || C < 0 || (C > 0 && !ids)) return RSAC_ERR_INVALID;
+    e->n_problem_ids = 0;
+    if (C == 0) return RSAC_OK;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    RSAC_TRY(e->d_problem_ids.ensure(e, sizeof(int32_t) * (size_t)C));
+    RSAC_CUDA(e, cudaMemcpyAsync(e->d_problem_ids.p, ids, sizeof(int32_t) * (size_t)C, cudaMemcpyHostToDevice, e->stream));
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));       // ids may live on the caller's stack
+    e->n_problem_ids = C;
+    return RSAC_OK;
+}
+
+int rsac_set_graphs(rsac_engine* e, int on)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    e->graphs = on != 0;
     return RSAC_OK;
 }
 

@@ -16,6 +16,7 @@ static bool solve_subwarp()
 // hypotheses of one resident wave of the minimal solver
 static int64_t solve_wave_hyps(rsac_engine* e)
 {
+    if (e->pnp.run_eigen) return (int64_t)2 * e->sm_count * 128;
     return solve_subwarp() ? (int64_t)RSAC_SW_BLOCKS * e->sm_count * kSwHypsPerBlock
                            : (int64_t)RSAC_SOLVE_BLOCKS * e->sm_count * RSAC_SOLVE_THREADS;
 }
@@ -29,7 +30,13 @@ static int launch_solve_range(rsac_engine* e, PnpState& s, const int32_t* list, 
     const BatchDims& d = s.d;
     RSAC_TRY(solve_range_setup(e));
     e->stage_begin(RSAC_STAGE_SOLVE);
-    if (solve_subwarp()) {
+    if (s.run_eigen) {
+        const int resident = 2 * e->sm_count;
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + 127) / 128, resident));
+        epnp_minimal_range_kernel<false><<<blocks, 128, 0, e->stream>>>(
+            (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, lo, span, (const uint32_t*)s.d_tables.p,
+            (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
+    } else if (solve_subwarp()) {
         const int resident = RSAC_SW_BLOCKS * e->sm_count;
         const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + kSwHypsPerBlock - 1) / kSwHypsPerBlock, resident));
         epnp_minimal_subwarp_kernel<<<blocks, kSwThreads, kSwSmemBytes, e->stream>>>(
@@ -38,7 +45,7 @@ static int launch_solve_range(rsac_engine* e, PnpState& s, const int32_t* list, 
     } else {
         const int resident = RSAC_SOLVE_BLOCKS * e->sm_count;
         const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + RSAC_SOLVE_THREADS - 1) / RSAC_SOLVE_THREADS, resident));
-        epnp_minimal_range_kernel<<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, e->stream>>>(
+        epnp_minimal_range_kernel<true><<<blocks, RSAC_SOLVE_THREADS, sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS, e->stream>>>(
             (const ProblemMeta*)s.d_metas.p, d.C, list, list_count, lo, span, (const uint32_t*)s.d_tables.p,
             (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
     }
@@ -132,6 +139,7 @@ static int pnp_plan_early(rsac_engine* e, const std::vector<int>& bounds)
     }
     s.h_stageEE.mark(st);
     s.ee_planned = true;
+    ++s.plan_version;
     return RSAC_OK;
 }
 
@@ -191,6 +199,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     if (!same_shape) {
         s.plans_valid = false;
         s.ee_planned = false;
+        ++s.plan_version;
         RSAC_TRY(plan_score<0>(e, s.metas, d.maxH, s.groups, s.plan));
     }
 
@@ -245,6 +254,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
 // ---- early exit in phases (pnp_pipeline.cuh) ----
 static int solve_range_setup(rsac_engine* e)
 {
+    if (e->pnp.run_eigen) return RSAC_OK;
     if (solve_subwarp()) {
         if (kSwSmemBytes > 32 * 1024)
             RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_subwarp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmemBytes));
@@ -255,10 +265,10 @@ static int solve_range_setup(rsac_engine* e)
     }
     const size_t smem = sizeof(double) * kSolveSmemDoubles * RSAC_SOLVE_THREADS;
     if (smem > 32 * 1024)
-        RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t need = (smem + 1024) * RSAC_SOLVE_BLOCKS;
     const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
-    RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RSAC_TRY(set_func_attr_max(e, (const void*)epnp_minimal_range_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     return RSAC_OK;
 }
 
@@ -290,20 +300,17 @@ static int pnp_early_range(rsac_engine* e, const int32_t* list, const int32_t* l
 
 static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase);
 
-static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, const std::vector<int>& bounds)
+// the launches of one staged sweep (two memsets + 4 + 3 (K - 1) + 4 kernels); every buffer exists and every plan is on
+// the device: nothing here allocates, copies or synchronises, so the sequence can be captured into a CUDA graph
+static int pnp_issue_early(rsac_engine* e, int flags, void* d_results_out, const std::vector<int>& bounds)
 {
     PnpState& s = e->pnp;
     const BatchDims& d = s.d;
     cudaStream_t st = e->stream;
     const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
-    if (!s.ee_planned || s.ee_bounds != bounds) RSAC_TRY(pnp_plan_early(e, bounds));   // normally done by the upload
     const int K = (int)bounds.size();
-    s.ee_mode = true;
-    s.ee_complete = false;
-    RSAC_TRY(s.d_ee.ensure(e, sizeof(int32_t) * early_exit_words(d.C)));
     RSAC_CUDA(e, cudaMemsetAsync(s.d_ee.p, 0, sizeof(int32_t) * early_exit_words(d.C), st));
     const EarlyExit v = early_exit_view((int32_t*)s.d_ee.p, d.C);
-    RSAC_TRY(solve_range_setup(e));
 
     ScoreArgs sa;
     RSAC_TRY(zero_score_region(e, s.d_counts, d.sumH, 0, sa));
@@ -332,6 +339,72 @@ static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, const s
     RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, -1));
     RSAC_TRY(pnp_early_range(e, v.listC, v.counters + kCleanupCounter, bounds[0], d.maxH, K));
     RSAC_TRY(pnp_launch_select(e, flags, nullptr, d_results_out, 2));
+    return RSAC_OK;
+}
+
+static int pnp_run_early(rsac_engine* e, int flags, void* d_results_out, const std::vector<int>& bounds)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    if (!s.ee_planned || s.ee_bounds != bounds) RSAC_TRY(pnp_plan_early(e, bounds));   // normally done by the upload
+    s.ee_mode = true;
+    s.ee_complete = false;
+    // everything a sweep touches exists before the first launch (a captured sequence must not allocate)
+    RSAC_TRY(s.d_ee.ensure(e, sizeof(int32_t) * early_exit_words(d.C)));
+    {
+        const size_t n_al = ((size_t)std::max<int64_t>(d.sumH, 1) + 1) & ~(size_t)1;
+        RSAC_TRY(s.d_counts.ensure(e, (n_al + 2) * sizeof(int32_t)));
+    }
+    if (flags & RSAC_FLAG_KEEP_MASKS) RSAC_TRY(s.d_hmasks.ensure(e, sizeof(uint32_t) * (size_t)std::max<int64_t>(d.total_hwords, 1)));
+    RSAC_TRY(solve_range_setup(e));
+
+    // CUDA graph: the staged sweep is 18 dependent launches (K = 4) of 5-150 us each.  The first run of a key is eager;
+    // the second captures the same call sequence; later runs are one cudaGraphLaunch.  The key holds every value that
+    // ends up in a kernel argument or a launch shape; device contents (metas, tables, plans) are read at run time
+    std::vector<int64_t> key = {(int64_t)flags, (int64_t)(intptr_t)d_results_out, (int64_t)e->alloc_epoch, (int64_t)s.plan_version,
+                                (int64_t)e->problem_base, (int64_t)e->n_problem_ids, (int64_t)d.C, d.sumH, (int64_t)d.maxH, (int64_t)d.maxWords};
+    for (int b : bounds) key.push_back(b);
+    const bool want_graph = e->graphs && !e->profile && d.C > 0;
+    if (want_graph && s.graph && key == s.graph_key) {
+        RSAC_CUDA(e, cudaGraphLaunch(s.graph, e->stream));
+        e->launches += s.graph_nodes;
+        ScoreArgs sa;                                   // host-side state the eager path leaves behind
+        const size_t n_al = ((size_t)std::max<int64_t>(d.sumH, 1) + 1) & ~(size_t)1;
+        e->last_exact = (unsigned long long*)((int32_t*)s.d_counts.p + n_al);
+        (void)sa;
+        s.ran = true;
+        return RSAC_OK;
+    }
+    if (want_graph && key == s.graph_key && s.eager_runs >= 1) {
+        if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        const int64_t l0 = e->launches;
+        RSAC_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
+        const int rc = pnp_issue_early(e, flags, d_results_out, bounds);
+        const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        const int64_t nodes = e->launches - l0;
+        e->launches = l0;
+        if (rc == RSAC_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&s.graph, g, 0) == cudaSuccess) {
+            cudaGraphDestroy(g);
+            s.graph_nodes = nodes;
+            RSAC_CUDA(e, cudaGraphLaunch(s.graph, e->stream));
+            e->launches += nodes;
+            s.ran = true;
+            return RSAC_OK;
+        }
+        // capture failed: stay eager for this engine
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        s.graph = nullptr;
+        e->graphs = false;
+    }
+    if (key != s.graph_key) {
+        if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }
+        s.graph_key = key;
+        s.eager_runs = 0;
+    }
+    RSAC_TRY(pnp_issue_early(e, flags, d_results_out, bounds));
+    ++s.eager_runs;
     s.ran = true;
     return RSAC_OK;
 }
@@ -347,6 +420,7 @@ static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume,
     a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = (double*)s.d_us.p; a.al_s = (double*)s.d_al.p; a.tm_s = (double*)s.d_extra.p;
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base;
+    a.problem_ids = (e->n_problem_ids == d.C && d.C > 0) ? (const int32_t*)e->d_problem_ids.p : nullptr;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
     if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
@@ -421,7 +495,8 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         }
     }
     s.ee_mode = false;
-    if ((flags & RSAC_FLAG_EARLY_EXIT) && !(flags & RSAC_FLAG_EPNP_EIGEN) && d.sumH > 0) {
+    s.run_eigen = (flags & RSAC_FLAG_EPNP_EIGEN) != 0;
+    if ((flags & RSAC_FLAG_EARLY_EXIT) && d.sumH > 0) {
         const std::vector<int> bounds = pnp_stage_bounds(e, d);
         if (bounds.size() > 1) return pnp_run_early(e, flags, d_results_out, bounds);
     }
@@ -440,13 +515,7 @@ int rsac_pnp_run(rsac_engine* e, int flags, void* d_results_out)
         }
         const int threads = eigen ? 128 : RSAC_SOLVE_THREADS;
         const unsigned blocks = (unsigned)((d.sumH + threads - 1) / threads);
-        if (eigen) {
-            e->stage_begin(RSAC_STAGE_SOLVE);
-            epnp_minimal_kernel<false><<<blocks, threads, 0, st>>>(metas, d.C, d.sumH, (const uint32_t*)s.d_tables.p,
-                                                                   (const float4*)s.d_cA.p, (const float4*)s.d_uv.p, (float*)s.d_poses.p);
-            e->stage_end(RSAC_STAGE_SOLVE);
-            RSAC_CUDA(e, cudaGetLastError());
-        } else if (solve_subwarp()) {
+        if (eigen || solve_subwarp()) {
             RSAC_TRY(launch_solve_range(e, s, nullptr, nullptr, 0, d.maxH, (int64_t)d.C * d.maxH));
         } else {
             e->stage_begin(RSAC_STAGE_SOLVE);

@@ -102,6 +102,7 @@ struct PnpState {
     PinnedBuf h_stage;
     // early exit in phases (RSAC_FLAG_EARLY_EXIT): plans of the two hypothesis ranges, per-problem phase state
     bool ee_planned = false, ee_mode = false, ee_complete = false;
+    bool run_eigen = false;                 // the current / last run used RSAC_FLAG_EPNP_EIGEN (selects the solver kernel)
     bool plans_valid = false;               // plans and device work arrays match shape_sig
     std::vector<int32_t> shape_sig;         // n, H, fx, fy of every problem + stage boundaries
     int ee_HA = 0;
@@ -112,8 +113,17 @@ struct PnpState {
     ScoreArgs ee_sa;
     DevBuf d_ee;
     PinnedBuf h_stageEE;
+    // CUDA graph of the staged sweep (pnp_run_early): captured on the second run of a (shape, flags, output) key --
+    // the first run is eager and sizes every buffer -- and replayed until the key or a device pointer changes
+    cudaGraphExec_t graph = nullptr;
+    std::vector<int64_t> graph_key;
+    int64_t graph_nodes = 0;
+    uint64_t alloc_epoch_seen = 0;
+    int eager_runs = 0;
+    int64_t plan_version = 0;               // bumped whenever the scoring plans are rebuilt
     void release()
     {
+        if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
         h_stage.release();
         h_stageEE.release();
         d_ee.release();
@@ -212,7 +222,10 @@ struct rsac_engine {
     rsac::Sim3State sim3;
     rsac::PoseOptState poseopt;
     rsac::Sim3OptState sim3opt;
-    rsac::DevBuf d_exact, d_scratch, d_resume;
+    rsac::DevBuf d_exact, d_scratch, d_resume, d_problem_ids;
+    int32_t n_problem_ids = 0;                   // > 0: rsac_set_problem_ids is in force for batches of exactly this many problems
+    uint64_t alloc_epoch = 0;                    // bumped by every device (re)allocation: captured graphs hold raw pointers
+    bool graphs = true;                          // rsac_set_graphs / RSAC_GRAPH=0
     unsigned long long* last_exact = nullptr;   // diagnostic counter of the last scoring launch
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
@@ -235,7 +248,7 @@ struct rsac_engine {
     void free_all()
     {
         pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release(); sim3opt.release();
-        d_exact.release(); d_scratch.release(); d_resume.release();
+        d_exact.release(); d_scratch.release(); d_resume.release(); d_problem_ids.release();
     }
 };
 
@@ -252,5 +265,6 @@ inline int rsac::DevBuf::ensure(rsac_engine* e, size_t bytes)
         return RSAC_ERR_ALLOC;
     }
     cap = want;
+    ++e->alloc_epoch;
     return RSAC_OK;
 }

@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(128) early_exit_flag_kernel(const ProblemMeta*
 
 // EPnP minimal solves of hypotheses [h_lo, h_lo + span) of the listed problems (list == nullptr: all C problems).
 // Persistent grid-stride form: the amount of work is only known on the device.
-__global__ void __launch_bounds__(RSAC_SOLVE_THREADS, RSAC_SOLVE_BLOCKS)
+// QR = false: the 12x12 eigen-solve of M^T M per hypothesis (RSAC_FLAG_EPNP_EIGEN, the reference's structure)
+template <bool QR>
+__global__ void __launch_bounds__(QR ? RSAC_SOLVE_THREADS : 128, QR ? RSAC_SOLVE_BLOCKS : 2)
 epnp_minimal_range_kernel(const ProblemMeta* metas, int C, const int32_t* list, const int32_t* list_count, int h_lo, int span,
                           const uint32_t* tables, const float4* cA, const float4* cC, float* poses)
 {
@@ -158,6 +160,9 @@ epnp_minimal_range_kernel(const ProblemMeta* metas, int C, const int32_t* list, 
         }
         const Cam kk = {m.fx, m.fy, m.cx, m.cy};
         float R[9], tr[3];
+        if constexpr (!QR) {
+            epnp_compute_pose_small<4, false>(pw, us, kk, R, tr);
+        } else {
 #if RSAC_SOLVE_SMEM == 0
         epnp_compute_pose_small<4, true>(pw, us, kk, R, tr, s_cols + threadIdx.x, (int)blockDim.x);
 #elif RSAC_SOLVE_SMEM == 1
@@ -166,6 +171,7 @@ epnp_minimal_range_kernel(const ProblemMeta* metas, int C, const int32_t* list, 
         epnp_compute_pose_small<4, true>(pw, us, kk, R, tr, s_cols + threadIdx.x, (int)blockDim.x,
                                          s_cols + 48 * blockDim.x + threadIdx.x, (int)blockDim.x);
 #endif
+        }
         float* out = poses + ((int64_t)m.hyp_off + h) * 12;
 #pragma unroll
         for (int i = 0; i < 9; ++i) out[i] = R[i];

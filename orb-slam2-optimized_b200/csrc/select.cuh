@@ -46,6 +46,7 @@ struct SelectArgs {
     int32_t C = 0;
     int32_t first_phase = 0;   // HA: hypotheses every problem has after phase A
     int32_t only_phase = -1;   // >= 0: the phase-C replay: only problems marked undecided run; they resume where they stopped
+    const int32_t* problem_ids = nullptr;   // optional [C]: global problem index of every problem (rsac_set_problem_ids)
 };
 
 struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
@@ -712,7 +713,7 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
     res.best_count = 0; res.n_hyp = 0;
     for (int i = 0; i < 9; ++i) res.R[i] = (i % 4 == 0) ? 1.0f : 0.0f;
     res.t[0] = res.t[1] = res.t[2] = 0.0f; res.s = 1.0f;
-    res.problem = a.problem_base + blockIdx.x; res.reserved[0] = res.reserved[1] = 0;
+    res.problem = a.problem_ids ? a.problem_ids[blockIdx.x] : a.problem_base + blockIdx.x; res.reserved[0] = res.reserved[1] = 0;
 
     RSAC_SEL_MARK(0);
     const int N = m->n, Hfull = m->H, minInl = m->min_inl;

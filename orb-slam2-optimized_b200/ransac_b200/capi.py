@@ -195,6 +195,37 @@ class Engine:
     def set_problem_base(self, base: int):
         self._ck(self.L.rsac_set_problem_base(self.h, C.c_int(base)), "set_problem_base")
 
+    def set_problem_ids(self, ids):
+        """global problem index of every problem of the next batches (None / empty: base + local index)"""
+        if ids is None or len(ids) == 0:
+            self._ck(self.L.rsac_set_problem_ids(self.h, None, 0), "rsac_set_problem_ids")
+            return
+        a = np.ascontiguousarray(ids, np.int32)
+        self._ck(self.L.rsac_set_problem_ids(self.h, _p(a), C.c_int(len(a))), "rsac_set_problem_ids")
+
+    def set_graphs(self, on=True):
+        self._ck(self.L.rsac_set_graphs(self.h, C.c_int(1 if on else 0)), "rsac_set_graphs")
+
+    # ---- native NCCL exchange of the per-candidate records (include/ransac_b200.h, "multi-GPU")
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_char * 128)()
+        rc = lib().rsac_nccl_get_unique_id(buf)
+        if rc:
+            raise RsacError(rc, "rsac_nccl_get_unique_id")
+        return bytes(buf)
+
+    def nccl_init(self, uid: bytes, rank: int, world: int):
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        self._ck(self.L.rsac_nccl_init(self.h, buf, C.c_int(rank), C.c_int(world)), "rsac_nccl_init")
+
+    def nccl_allgather_results(self, d_send: int, count_per_rank: int, d_gathered: int):
+        self._ck(self.L.rsac_nccl_allgather_results(self.h, C.c_void_p(d_send), C.c_int(count_per_rank), C.c_void_p(d_gathered)),
+                 "rsac_nccl_allgather_results")
+
+    def nccl_destroy(self):
+        self._ck(self.L.rsac_nccl_destroy(self.h), "rsac_nccl_destroy")
+
     def set_first_phase(self, hypotheses: int):
         self._ck(self.L.rsac_set_first_phase(self.h, C.c_int(hypotheses)), "set_first_phase")
 
