@@ -10,7 +10,7 @@ int rsac_sim3_upload(rsac_engine* e, const rsac_sim3_batch* b)
     if (b->C > 0 && (!b->K1 || !b->K2)) { e->err = "K1/K2 is NULL"; return RSAC_ERR_INVALID; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     Sim3State& s = e->sim3;
-    s.uploaded = false; s.ran = false;
+    s.uploaded = false; s.ran = false; s.tables_ready = false;
     const int C = b->C;
     s.metas.assign(C, ProblemMeta());
     BatchDims d;
@@ -100,7 +100,8 @@ int rsac_sim3_run(rsac_engine* e, int flags, void* d_results_out)
     cudaStream_t st = e->stream;
     if (d.C == 0) { s.ran = true; return RSAC_OK; }
     const ProblemMeta* metas = (const ProblemMeta*)s.d_metas.p;
-    if (!s.have_tables && d.table_len > 0) {
+    if (!s.have_tables && d.table_len > 0 && !s.tables_ready) {     // once per upload: the tables depend on the seeds only
+        s.tables_ready = true;
         e->stage_begin(RSAC_STAGE_RNG);
         rng_tables_kernel<<<(d.C + kRngWarps - 1) / kRngWarps, kRngWarps * 32, 0, st>>>(metas, d.C, (uint32_t*)s.d_tables.p);
         e->stage_end(RSAC_STAGE_RNG);
@@ -114,11 +115,20 @@ int rsac_sim3_run(rsac_engine* e, int flags, void* d_results_out)
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base;
     a.tile = std::max(32, std::min(1024, ((d.maxN + 31) / 32) * 32));
-    const int threads = std::max(32, std::min(512, ((d.maxH + 31) / 32) * 32));
+    const int lanes = d.sumH <= 8192 ? 8 : 2;
+    const int hpc = sim3_hyps_per_cta(lanes);
+    a.tiles_h = std::max(1, (d.maxH + hpc - 1) / hpc);
+    if (s.d_done.cap < sizeof(int32_t) * (size_t)d.C) {
+        RSAC_TRY(s.d_done.ensure(e, sizeof(int32_t) * (size_t)d.C));
+        RSAC_CUDA(e, cudaMemsetAsync(s.d_done.p, 0, s.d_done.cap, st));     // the kernel leaves the counters at zero
+    }
+    a.done = (int32_t*)s.d_done.p;
     const size_t smem = (size_t)a.tile * 48;
-    if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)sim3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const void* kern = lanes == 8 ? (const void*)sim3_kernel<8> : (const void*)sim3_kernel<2>;
+    if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     e->stage_begin(RSAC_STAGE_SOLVE);
-    sim3_kernel<<<d.C, threads, smem, st>>>(a);
+    if (lanes == 8) sim3_kernel<8><<<(unsigned)d.C * (unsigned)a.tiles_h, kSim3Threads, smem, st>>>(a);
+    else sim3_kernel<2><<<(unsigned)d.C * (unsigned)a.tiles_h, kSim3Threads, smem, st>>>(a);
     e->stage_end(RSAC_STAGE_SOLVE);
     RSAC_CUDA(e, cudaGetLastError());
     s.ran = true;

@@ -149,13 +149,13 @@ struct ScoreState {
 };
 
 struct Sim3State {
-    bool uploaded = false, ran = false, have_tables = false;
+    bool uploaded = false, ran = false, have_tables = false, tables_ready = false;
     BatchDims d;
     std::vector<ProblemMeta> metas;
-    DevBuf d_metas, d_x1, d_x2, d_s1, d_s2, d_c1, d_c2, d_tables, d_poses, d_counts, d_hmasks, d_results, d_masks;
+    DevBuf d_metas, d_x1, d_x2, d_s1, d_s2, d_c1, d_c2, d_tables, d_poses, d_counts, d_hmasks, d_results, d_masks, d_done;
     void release()
     {
-        DevBuf* all[] = {&d_metas, &d_x1, &d_x2, &d_s1, &d_s2, &d_c1, &d_c2, &d_tables, &d_poses, &d_counts, &d_hmasks, &d_results, &d_masks};
+        DevBuf* all[] = {&d_metas, &d_x1, &d_x2, &d_s1, &d_s2, &d_c1, &d_c2, &d_tables, &d_poses, &d_counts, &d_hmasks, &d_results, &d_masks, &d_done};
         for (DevBuf* b : all) b->release();
     }
 };

@@ -142,43 +142,61 @@ struct Sim3Args {
     void* results;
     void* results2;
     uint32_t* masks;
+    int32_t* done;       // [C] CTAs of a candidate that have finished (zero on entry, zero again on exit)
     int32_t problem_base;
-    int32_t tile;        // correspondences per shared-memory tile
+    int32_t tile;        // correspondences per shared-memory tile (a multiple of 32)
+    int32_t tiles_h;     // CTAs per candidate in the grid = ceil(maxH / hypotheses per CTA)
 };
 
-// One CTA per problem; blockDim.x >= 32.  Hypotheses are processed in rounds of blockDim.x.
-__global__ void sim3_kernel(Sim3Args a)
+constexpr int kSim3Threads = 256;
+// LANES per hypothesis (each scores every LANES-th mask word): 8 for a loop-closure-sized batch (latency: cfg3, one
+// candidate, 0.023 ms), 2 once the batch fills the machine anyway (Horn is computed redundantly on the lanes of a hypothesis)
+__host__ __device__ constexpr int sim3_hyps_per_cta(int lanes) { return kSim3Threads / lanes; }
+
+// Sim3Solver::iterate for a batch of loop candidates.  Grid = candidates x hypothesis tiles: a CTA takes 32 hypotheses
+// of one candidate, EIGHT LANES per hypothesis -- Horn's closed form redundantly on the eight lanes (2 kFLOP), then the
+// two-way reprojection test of every 8th mask word on each lane (the correspondences are staged in shared memory), the
+// inlier count reduced over the eight lanes by shuffles.  A loop-closure attempt has a handful of candidates
+// (LoopClosing.cpp:238-265), so one CTA per candidate (round 1) left 147 SMs idle and ran 200 evaluations + Horn as ONE
+// thread's dependent chain: cfg3 (1 candidate x 300 hypotheses x 200 matches) 0.068 ms.  The CTA that finishes last for
+// a candidate (a per-candidate arrival counter) replays the selection rule (Sim3Solver.cpp:155,163) -- one launch.
+template <int kSim3Lanes>
+__global__ void __launch_bounds__(kSim3Threads) sim3_kernel(Sim3Args a)
 {
+    constexpr int kSim3HypsPerCta = sim3_hyps_per_cta(kSim3Lanes);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* s1 = reinterpret_cast<float4*>(smem_raw);
     float4* s2 = s1 + a.tile;
     float4* s3 = s2 + a.tile;
-    __shared__ int s_first, s_bestcnt, s_besth;
+    __shared__ int s_first, s_bestcnt, s_besth, s_last;
 
-    const ProblemMeta* m = a.metas + blockIdx.x;
+    const int prob = blockIdx.x / a.tiles_h, hb = blockIdx.x - prob * a.tiles_h;
+    const ProblemMeta* m = a.metas + prob;
     const int N = m->n, H = m->H, words = m->words, minInl = m->min_inl;
     const int tid = threadIdx.x;
+    const int my_tiles = (N < minInl || H == 0) ? 1 : (H + kSim3HypsPerCta - 1) / kSim3HypsPerCta;
+    if (hb >= my_tiles) return;                          // ragged batches: this candidate has fewer hypothesis tiles
     ResultRec res;
     res.ok = 0; res.no_more = 0; res.n_inliers = 0; res.best_hyp = -1; res.refined = 0; res.n_refines = 0;
     res.best_count = 0; res.n_hyp = 0;
     for (int i = 0; i < 9; ++i) res.R[i] = (i % 4 == 0) ? 1.0f : 0.0f;
     res.t[0] = res.t[1] = res.t[2] = 0.0f; res.s = 1.0f;
-    res.problem = a.problem_base + blockIdx.x; res.reserved[0] = res.reserved[1] = 0;
+    res.problem = a.problem_base + prob; res.reserved[0] = res.reserved[1] = 0;
     uint32_t* final_mask = a.masks + m->word_off;
 
     if (N < minInl || H == 0) {                 // Sim3Solver.cpp:119-123
         res.no_more = 1;
         for (int w = tid; w < words; w += blockDim.x) final_mask[w] = 0u;
         if (tid == 0) {
-            reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
-            if (a.results2) reinterpret_cast<ResultRec*>(a.results2)[blockIdx.x] = res;
+            reinterpret_cast<ResultRec*>(a.results)[prob] = res;
+            if (a.results2) reinterpret_cast<ResultRec*>(a.results2)[prob] = res;
         }
         return;
     }
-    if (tid == 0) { s_first = H; s_bestcnt = -1; s_besth = -1; }
 
-    for (int h0 = 0; h0 < H; h0 += blockDim.x) {
-        const int h = h0 + tid;
+    {
+        const int sub = tid & (kSim3Lanes - 1);
+        const int h = hb * kSim3HypsPerCta + tid / kSim3Lanes;
         const bool live = h < H;
         float R[9], t[3], s = 1.0f, A12[9], A21[9], t21[3];
         if (live) {
@@ -192,11 +210,13 @@ __global__ void sim3_kernel(Sim3Args a)
             }
             sim3_compute(P1, P2, m->fix_scale, R, t, &s);
             sim3_make_T(R, t, s, A12, A21, t21);
-            float* out = a.poses + (size_t)(m->hyp_off + h) * 13;
-            for (int i = 0; i < 9; ++i) out[i] = R[i];
-            out[9] = t[0]; out[10] = t[1]; out[11] = t[2]; out[12] = s;
+            if (sub == 0) {
+                float* out = a.poses + (size_t)(m->hyp_off + h) * 13;
+                for (int i = 0; i < 9; ++i) out[i] = R[i];
+                out[9] = t[0]; out[10] = t[1]; out[11] = t[2]; out[12] = s;
+            }
         }
-        // CheckInliers (Sim3Solver.cpp:269-293): correspondences staged tile by tile
+        // CheckInliers (Sim3Solver.cpp:269-293): correspondences staged tile by tile, mask words dealt to the eight lanes
         int cnt = 0;
         uint32_t* hm = a.hmasks + m->hmask_off + (int64_t)h * words;
         for (int c0 = 0; c0 < N; c0 += a.tile) {
@@ -208,7 +228,7 @@ __global__ void sim3_kernel(Sim3Args a)
             }
             __syncthreads();
             if (live) {
-                for (int w0 = 0; w0 < nc; w0 += 32) {
+                for (int w0 = sub * 32; w0 < nc; w0 += 32 * kSim3Lanes) {
                     uint32_t bits = 0u;
                     const int ne = min(32, nc - w0);
                     for (int i = 0; i < ne; ++i) {
@@ -227,23 +247,36 @@ __global__ void sim3_kernel(Sim3Args a)
                 }
             }
         }
-        if (live) {
-            a.counts[m->hyp_off + h] = cnt;
-            if (cnt > minInl) atomicMin(&s_first, h);      // first hypothesis that returns true (:163)
-        }
+#pragma unroll
+        for (int d = kSim3Lanes / 2; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (live && sub == 0) a.counts[m->hyp_off + h] = cnt;
     }
+    // arrival: the last CTA of this candidate replays the selection
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int prev = atomicAdd(a.done + prob, 1);
+        s_last = (prev == my_tiles - 1);
+        s_first = H; s_bestcnt = -1; s_besth = -1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile int32_t* counts = a.counts + m->hyp_off;
+    for (int h = tid; h < H; h += blockDim.x)
+        if (counts[h] > minInl) atomicMin(&s_first, h);    // first hypothesis that returns true (:163)
     __syncthreads();
     // outcome: first h with cnt > minInl; otherwise best = LAST arg-max over all H (>=, :155)
     const int first = s_first;
     const int limit = (first < H) ? first + 1 : H;         // hypotheses the reference evaluates
-    for (int h = tid; h < limit; h += blockDim.x) atomicMax(&s_bestcnt, a.counts[m->hyp_off + h]);
+    for (int h = tid; h < limit; h += blockDim.x) atomicMax(&s_bestcnt, counts[h]);
     __syncthreads();
     const int bestcnt = s_bestcnt;
     for (int h = tid; h < limit; h += blockDim.x)
-        if (a.counts[m->hyp_off + h] == bestcnt) atomicMax(&s_besth, h);
+        if (counts[h] == bestcnt) atomicMax(&s_besth, h);
     __syncthreads();
     const int besth = s_besth;
-    const float* bp = a.poses + (size_t)(m->hyp_off + besth) * 13;
+    const volatile float* bp = a.poses + (size_t)(m->hyp_off + besth) * 13;
     res.best_hyp = besth;
     res.best_count = bestcnt;
     res.n_hyp = limit;
@@ -251,16 +284,17 @@ __global__ void sim3_kernel(Sim3Args a)
     res.t[0] = bp[9]; res.t[1] = bp[10]; res.t[2] = bp[11]; res.s = bp[12];
     if (first < H) {
         res.ok = 1;
-        res.n_inliers = a.counts[m->hyp_off + first];
-        const uint32_t* hm = a.hmasks + m->hmask_off + (int64_t)first * words;
+        res.n_inliers = counts[first];
+        const volatile uint32_t* hm = a.hmasks + m->hmask_off + (int64_t)first * words;
         for (int w = tid; w < words; w += blockDim.x) final_mask[w] = hm[w];
     } else {
         res.no_more = 1;                                // :174-175
         for (int w = tid; w < words; w += blockDim.x) final_mask[w] = 0u;
     }
     if (tid == 0) {
-        reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
-        if (a.results2) reinterpret_cast<ResultRec*>(a.results2)[blockIdx.x] = res;
+        reinterpret_cast<ResultRec*>(a.results)[prob] = res;
+        if (a.results2) reinterpret_cast<ResultRec*>(a.results2)[prob] = res;
+        a.done[prob] = 0;                               // ready for the next run
     }
 }
 
