@@ -354,6 +354,43 @@ int rsac_sim3opt_run(rsac_engine* e);
 int rsac_sim3opt_download(rsac_engine* e, rsac_sim3opt_result* results, uint8_t* removed);
 int rsac_sim3opt_solve(rsac_engine* e, const rsac_sim3opt_batch* b, rsac_sim3opt_result* results, uint8_t* removed);
 
+/* ------------------------------------------------ ORBmatcher::SearchByBoW (batched) */
+/* the producer of every correspondence set the RANSAC engine verifies.  Both overloads of the reference:
+ *   mode 0  SearchByBoW(KeyFrame, Frame&, vpMapPointMatches)   src/ORBmatcher.cpp:110-239  (Tracking.cpp:611,1214)
+ *   mode 1  SearchByBoW(KeyFrame1, KeyFrame2, vpMatches12)     src/ORBmatcher.cpp:354-487  (LoopClosing.cpp:251)
+ * TH_LOW = 50, HISTO_LENGTH = 30 (ORBmatcher.cpp:9-10), DescriptorDistance :1492-1508, ComputeThreeMaxima :1445-1488.
+ * A feature set is what the function reads from a Frame / KeyFrame; sets are uploaded once and referenced by index, so
+ * the current frame of a relocalisation (or the current keyframe of a loop closure) is shared by all its candidates. */
+typedef struct {
+    int32_t n_feat;
+    const uint32_t* desc;        /* [n_feat][8] mDescriptors rows (256-bit ORB, 32 bytes, 16-byte aligned) */
+    const float* angle;          /* [n_feat] mvKeys[i].angle / mvKeysUn[i].angle */
+    const uint8_t* valid;        /* [n_feat] 1 = the feature has a MapPoint that is not bad; NULL = all (a Frame) */
+    int32_t n_nodes;             /* mFeatVec.size() */
+    const uint32_t* node_ids;    /* [n_nodes] NodeIds, ascending (std::map order) */
+    const int32_t* node_off;     /* [n_nodes + 1] */
+    const uint32_t* node_feat;   /* [node_off[n_nodes]] feature indices, per node in insertion order */
+} rsac_bow_features;
+
+typedef struct {
+    int32_t n_sets;
+    const rsac_bow_features* sets;
+    int32_t C;                   /* pairs */
+    const int32_t* query_set;    /* [C] the keyframe whose features drive the outer loop (pKF / pKF1) */
+    const int32_t* target_set;   /* [C] the other side (F / pKF2) */
+    float nn_ratio;              /* ORBmatcher(nnratio, ...): 0.75 in Relocalization and ComputeSim3 */
+    int32_t check_orientation;   /* mbCheckOrientation */
+    int32_t mode;                /* 0 / 1, see above */
+} rsac_bow_batch;
+
+int rsac_bow_upload(rsac_engine* e, const rsac_bow_batch* b);
+int rsac_bow_run(rsac_engine* e);
+/* matches: concatenated per pair.  mode 0: sets[target].n_feat entries, the keyframe feature matched to each frame feature
+ * (vpMapPointMatches[iF] = that feature's MapPoint), -1 = none; mode 1: sets[query].n_feat entries, the pKF2 feature matched
+ * to each pKF1 feature (vpMatches12[idx1] = its MapPoint).  n_matches: [C] the return values. */
+int rsac_bow_download(rsac_engine* e, int32_t* matches, int32_t* n_matches);
+int rsac_bow_match(rsac_engine* e, const rsac_bow_batch* b, int32_t* matches, int32_t* n_matches);
+
 /* ------------------------------------------------ multi-GPU (candidates shard) */
 /* contiguous block partition of C problems over `world` ranks: rank r owns [*first, *first + *count) */
 int rsac_shard_range(int C, int rank, int world, int* first, int* count);

@@ -219,6 +219,25 @@ double orc_mlpnp_batch(int C, const orc_mlpnp_problem *pbs, const orc_ransac_par
 double orc_pnp_score_timed(const orc_pnp_problem *pb, const float *max_err, int H, const float *poses,
                            int nthreads, int *counts);
 
+/* ------------------------------------------------ ORBmatcher::SearchByBoW */
+/* what SearchByBoW reads from a Frame / KeyFrame */
+typedef struct {
+    int n_feat;
+    const uint32_t *desc;        /* [n_feat][8] mDescriptors rows (256-bit ORB) */
+    const float *angle;          /* [n_feat] mvKeys / mvKeysUn [i].angle */
+    const uint8_t *valid;        /* [n_feat] feature has a MapPoint that is not bad; NULL = all (a Frame in mode 0) */
+    int n_nodes;                 /* mFeatVec.size() */
+    const uint32_t *node_ids;    /* [n_nodes] ascending NodeIds */
+    const int32_t *node_off;     /* [n_nodes + 1] */
+    const uint32_t *node_feat;   /* [node_off[n_nodes]] feature indices, per node in insertion order */
+} orc_bow_features;
+
+int orc_descriptor_distance(const uint32_t *a, const uint32_t *b);                    /* ORBmatcher.cpp:1492-1508 */
+void orc_three_maxima(const int *histo, int L, int *ind1, int *ind2, int *ind3);      /* :1445-1488 */
+/* mode 0: SearchByBoW(KF, Frame) (:110-239); mode 1: SearchByBoW(KF1, KF2) (:354-487) */
+int orc_search_by_bow(const orc_bow_features *q, const orc_bow_features *t, float nn_ratio, int check_orientation,
+                      int mode, int32_t *match_out);
+
 /* ------------------------------------------------ Optimizer::PoseOptimization */
 /* one frame: what Optimizer.cpp:244-323 reads from the Frame and its MapPoints */
 typedef struct {

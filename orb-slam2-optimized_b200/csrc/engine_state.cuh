@@ -189,6 +189,25 @@ struct Sim3OptState {
     }
 };
 
+struct BowState {
+    bool uploaded = false, ran = false;
+    int C = 0, n_items = 0, mode = 0, check_orientation = 1;
+    float nn_ratio = 0.6f;
+    int64_t total_t = 0, total_q = 0;          // sizes of the per-pair target- / query-indexed arrays
+    std::vector<int64_t> t2q_off, q2t_off;
+    DevBuf d_sets, d_qset, d_tset, d_t2q_off, d_q2t_off, d_items, d_desc, d_angle, d_valid, d_node_ids, d_node_start, d_node_feat,
+        d_t2q, d_q2t, d_bin, d_nmatches;
+    PinnedBuf h_stage;
+    bool have_valid = false;
+    void release()
+    {
+        DevBuf* all[] = {&d_sets, &d_qset, &d_tset, &d_t2q_off, &d_q2t_off, &d_items, &d_desc, &d_angle, &d_valid, &d_node_ids,
+                         &d_node_start, &d_node_feat, &d_t2q, &d_q2t, &d_bin, &d_nmatches};
+        for (DevBuf* b : all) b->release();
+        h_stage.release();
+    }
+};
+
 struct ProfPair {
     int stage;
     cudaEvent_t a, b;
@@ -222,6 +241,7 @@ struct rsac_engine {
     rsac::Sim3State sim3;
     rsac::PoseOptState poseopt;
     rsac::Sim3OptState sim3opt;
+    rsac::BowState bow;
     rsac::DevBuf d_exact, d_scratch, d_resume, d_problem_ids;
     int32_t n_problem_ids = 0;                   // > 0: rsac_set_problem_ids is in force for batches of exactly this many problems
     uint64_t alloc_epoch = 0;                    // bumped by every device (re)allocation: captured graphs hold raw pointers
@@ -247,7 +267,7 @@ struct rsac_engine {
     }
     void free_all()
     {
-        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release(); sim3opt.release();
+        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release(); sim3opt.release(); bow.release();
         d_exact.release(); d_scratch.release(); d_resume.release(); d_problem_ids.release();
     }
 };

@@ -93,6 +93,16 @@ SIM3OPT_DTYPE = np.dtype([("n_inliers", np.int32), ("n_bad", np.int32), ("optimi
                           ("s", np.float64), ("q", np.float64, (4,))], align=True)
 
 
+class BowFeatures(C.Structure):
+    _fields_ = [("n_feat", C.c_int32), ("desc", C.c_void_p), ("angle", C.c_void_p), ("valid", C.c_void_p),
+                ("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("node_off", C.c_void_p), ("node_feat", C.c_void_p)]
+
+
+class BowBatch(C.Structure):
+    _fields_ = [("n_sets", C.c_int32), ("sets", C.c_void_p), ("C", C.c_int32), ("query_set", C.c_void_p), ("target_set", C.c_void_p),
+                ("nn_ratio", C.c_float), ("check_orientation", C.c_int32), ("mode", C.c_int32)]
+
+
 class RsacError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__(f"ransac_b200 error {code}: {msg}")
@@ -540,6 +550,46 @@ class Engine:
         self.score_pnp_upload(poses, p3d, p2d, max_err, K)
         self.score_pnp_run(want_masks)
         return self.score_pnp_download(want_masks)
+
+    # ---- ORBmatcher::SearchByBoW
+    def _bow_desc(self, sets, query_set, target_set, nn_ratio, check_orientation, mode):
+        keep, arr = [], (BowFeatures * max(len(sets), 1))()
+        for i, f in enumerate(sets):
+            desc = np.ascontiguousarray(f["desc"], np.uint32).reshape(-1, 8)
+            ang = np.ascontiguousarray(f["angle"], np.float32)
+            val = None if f.get("valid") is None else np.ascontiguousarray(f["valid"], np.uint8)
+            nid = np.ascontiguousarray(f["node_ids"], np.uint32)
+            noff = np.ascontiguousarray(f["node_off"], np.int32)
+            nfe = np.ascontiguousarray(f["node_feat"], np.uint32)
+            keep += [desc, ang, val, nid, noff, nfe]
+            arr[i] = BowFeatures(desc.shape[0], _p(desc), _p(ang), _p(val), len(nid), _p(nid), _p(noff), _p(nfe))
+        qs, ts = np.ascontiguousarray(query_set, np.int32), np.ascontiguousarray(target_set, np.int32)
+        keep += [qs, ts, arr]
+        b = BowBatch(len(sets), C.cast(arr, C.c_void_p), len(qs), _p(qs), _p(ts), C.c_float(nn_ratio), int(check_orientation), int(mode))
+        n_out = [sets[t if mode == 0 else q]["desc"].shape[0] for q, t in zip(qs, ts)]
+        return b, keep, n_out
+
+    def bow_upload(self, sets, query_set, target_set, nn_ratio=0.75, check_orientation=True, mode=0):
+        b, keep, n_out = self._bow_desc(sets, query_set, target_set, nn_ratio, check_orientation, mode)
+        self._ck(self.L.rsac_bow_upload(self.h, C.byref(b)), "rsac_bow_upload")
+        self._bow_n_out = n_out
+
+    def bow_run(self):
+        self._ck(self.L.rsac_bow_run(self.h), "rsac_bow_run")
+
+    def bow_download(self):
+        """(list of per-pair match arrays, n_matches [C])"""
+        n_out = self._bow_n_out
+        flat = np.empty(max(int(sum(n_out)), 1), np.int32)
+        nm = np.empty(max(len(n_out), 1), np.int32)
+        self._ck(self.L.rsac_bow_download(self.h, _p(flat), _p(nm)), "rsac_bow_download")
+        offs = np.concatenate([[0], np.cumsum(n_out)]).astype(np.int64)
+        return [flat[offs[i]:offs[i + 1]] for i in range(len(n_out))], nm[:len(n_out)]
+
+    def bow_match(self, sets, query_set, target_set, nn_ratio=0.75, check_orientation=True, mode=0):
+        self.bow_upload(sets, query_set, target_set, nn_ratio, check_orientation, mode)
+        self.bow_run()
+        return self.bow_download()
 
     def score_exact_evals(self) -> int:
         return self.L.rsac_score_exact_evals(self.h)

@@ -222,3 +222,57 @@ def sim3opt_problem(seed: int, n: int = 100, outlier_ratio: float = 0.15, cam=EU
     return dict(x1c=q["x1c"], x2c=q["x2c"], obs1=np.ascontiguousarray(obs1, np.float32), obs2=np.ascontiguousarray(obs2, np.float32),
                 inv_sigma2_1=(np.float32(1) / q["sigma2_1"]).astype(np.float32), inv_sigma2_2=(np.float32(1) / q["sigma2_2"]).astype(np.float32),
                 K=np.array(q["K"], np.float32), S12=S12, R12=q["R12"], t12=q["t12"], s=q["s"], inlier=q["inlier"])
+
+
+# ---------------------------------------------------------------- ORB features + bag-of-words feature vectors (SearchByBoW)
+def _feature_vector(nodes: np.ndarray):
+    """DBoW2::FeatureVector as CSR: node ids ascending, per node the feature indices in insertion (= index) order"""
+    order = np.argsort(nodes, kind="stable")
+    ids, start = np.unique(nodes[order], return_index=True)
+    off = np.concatenate([start, [len(nodes)]]).astype(np.int32)
+    return ids.astype(np.uint32), off, order.astype(np.uint32)
+
+
+def bow_frame(seed: int, n_feat: int = 1500, n_nodes: int = 100):
+    """a frame: random 256-bit ORB descriptors, keypoint angles, every feature in one of n_nodes vocabulary nodes"""
+    rng = np.random.default_rng(seed)
+    desc = rng.integers(0, 2 ** 32, size=(n_feat, 8), dtype=np.uint64).astype(np.uint32)
+    angle = rng.uniform(0.0, 360.0, n_feat).astype(np.float32)
+    node_pool = np.sort(rng.choice(10 ** 6, n_nodes, replace=False)).astype(np.int64)
+    nodes = node_pool[rng.integers(0, n_nodes, n_feat)]
+    ids, off, feat = _feature_vector(nodes)
+    return dict(desc=desc, angle=angle, valid=None, node_ids=ids, node_off=off, node_feat=feat, nodes=nodes, node_pool=node_pool)
+
+
+def bow_keyframe(seed: int, frame: dict, n_feat: int = 1500, shared: float = 0.4, flip_bits: int = 25, rot: float = 33.0,
+                 valid_ratio: float = 0.7, wrong_node: float = 0.05, wrong_rot: float = 0.1):
+    """a keyframe that saw `shared` of the frame's features: their descriptors with up to flip_bits bits flipped, the same
+    vocabulary node (a few land in another node), angle = frame angle + rot (+ noise; some with an unrelated rotation);
+    the rest are unrelated features.  valid = the feature has a usable MapPoint."""
+    rng = np.random.default_rng(seed)
+    nF = frame["desc"].shape[0]
+    desc = rng.integers(0, 2 ** 32, size=(n_feat, 8), dtype=np.uint64).astype(np.uint32)
+    angle = rng.uniform(0.0, 360.0, n_feat).astype(np.float32)
+    pool = frame["node_pool"]
+    nodes = pool[rng.integers(0, len(pool), n_feat)]
+    ns = int(shared * min(n_feat, nF))
+    src = rng.choice(nF, ns, replace=False)
+    dst = rng.choice(n_feat, ns, replace=False)
+    d = frame["desc"][src].copy()
+    for i in range(ns):
+        nb = int(rng.integers(0, flip_bits + 1))
+        bits = rng.choice(256, nb, replace=False)
+        for b in bits:
+            d[i, b >> 5] ^= np.uint32(1) << np.uint32(b & 31)
+    desc[dst] = d
+    nodes[dst] = frame["nodes"][src]
+    moved = rng.random(ns) < wrong_node
+    nodes[dst[moved]] = pool[rng.integers(0, len(pool), int(moved.sum()))]
+    a = frame["angle"][src].astype(np.float64) + rot + rng.normal(0.0, 3.0, ns)
+    odd = rng.random(ns) < wrong_rot
+    a[odd] += rng.uniform(40.0, 320.0, int(odd.sum()))
+    angle[dst] = np.mod(a, 360.0).astype(np.float32)
+    valid = (rng.random(n_feat) < valid_ratio).astype(np.uint8)
+    ids, off, feat = _feature_vector(nodes)
+    return dict(desc=desc, angle=angle, valid=valid, node_ids=ids, node_off=off, node_feat=feat, nodes=nodes, node_pool=pool,
+                truth=(dst, src))

@@ -434,6 +434,42 @@ def pnp_score_timed(pb: _Keep, max_err, poses, nthreads=1):
     return dt, counts
 
 
+class BowFeatures(C.Structure):
+    _fields_ = [("n_feat", C.c_int), ("desc", C.c_void_p), ("angle", C.c_void_p), ("valid", C.c_void_p),
+                ("n_nodes", C.c_int), ("node_ids", C.c_void_p), ("node_off", C.c_void_p), ("node_feat", C.c_void_p)]
+
+
+def bow_features(f):
+    desc = np.ascontiguousarray(f["desc"], np.uint32).reshape(-1, 8)
+    ang = np.ascontiguousarray(f["angle"], np.float32)
+    val = None if f.get("valid") is None else np.ascontiguousarray(f["valid"], np.uint8)
+    nid = np.ascontiguousarray(f["node_ids"], np.uint32)
+    noff = np.ascontiguousarray(f["node_off"], np.int32)
+    nfe = np.ascontiguousarray(f["node_feat"], np.uint32)
+    st = BowFeatures(desc.shape[0], _p(desc), _p(ang), None if val is None else _p(val), len(nid), _p(nid), _p(noff), _p(nfe))
+    return _Keep(st, desc, ang, val, nid, noff, nfe)
+
+
+def descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint32), np.ascontiguousarray(b, np.uint32)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def three_maxima(histo):
+    h = np.ascontiguousarray(histo, np.int32)
+    i1, i2, i3 = C.c_int(), C.c_int(), C.c_int()
+    lib().orc_three_maxima(_p(h), C.c_int(len(h)), C.byref(i1), C.byref(i2), C.byref(i3))
+    return i1.value, i2.value, i3.value
+
+
+def search_by_bow(q: _Keep, t: _Keep, nn_ratio=0.75, check_orientation=True, mode=0):
+    """(match array, nmatches): mode 0 indexed by target (frame) feature, mode 1 by query (KF1) feature"""
+    n_out = t.st.n_feat if mode == 0 else q.st.n_feat
+    out = np.empty(max(n_out, 1), np.int32)
+    n = lib().orc_search_by_bow(C.byref(q.st), C.byref(t.st), C.c_float(nn_ratio), C.c_int(int(check_orientation)), C.c_int(mode), _p(out))
+    return out[:n_out], n
+
+
 class PoseOptProblem(C.Structure):
     _fields_ = [("n", C.c_int), ("p3d", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p),
                 ("K", C.c_float * 5), ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3)]
