@@ -189,6 +189,30 @@ typedef struct {
 
 /* stage 1: host -> device (async on the engine stream) and device-side packing */
 int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b);
+/* The same batch in the INDEXED wire format (first half): in a relocalisation all candidates match the SAME
+ * frame against ONE map (Tracking.cpp:1196-1232: vvpMapPointMatches[i][j] pairs keypoint j of mCurrentFrame with a MapPoint),
+ * so a correspondence is a (keypoint index, map-point index) pair -- 6 bytes instead of 24 -- over two tables that are
+ * uploaded once and stay resident: kp_uv / kp_sigma2 = Frame::mvKeysUn[j].pt and mvLevelSigma2[mvKeysUn[j].octave]
+ * (PnPsolver.cpp:33-36), mp_xyz = MapPoint::GetWorldPos() by map-point index (:38-39).  kp_uv == NULL / mp_xyz == NULL keep
+ * the tables of the previous upload.  The flat arrays are gathered on the device; everything behind is rsac_pnp_upload's. */
+typedef struct {
+    int32_t n_keypoints;         /* <= 65536 */
+    const float* kp_uv;          /* [n_keypoints][2] or NULL */
+    const float* kp_sigma2;      /* [n_keypoints] */
+    int32_t n_mappoints;
+    const float* mp_xyz;         /* [n_mappoints][3] or NULL */
+    int32_t C;
+    const int32_t* offsets;      /* [C+1] */
+    const uint16_t* kp_idx;      /* [total] */
+    const uint32_t* mp_idx;      /* [total] */
+    const double* K;             /* [4] fx, fy, cx, cy of the frame */
+    const rsac_ransac_params* params;
+    int32_t n_params;
+    const uint32_t* seeds;
+    const uint32_t* tables;
+    const int64_t* table_offsets;
+} rsac_pnp_indexed_batch;
+int rsac_pnp_upload_indexed(rsac_engine* e, const rsac_pnp_indexed_batch* b);
 /* stage 2: all hypotheses of all problems: EPnP minimal solves, CheckInliers scoring,
  * sequential-semantics replay with Refine (PnPsolver::iterate, PnPsolver.cpp:102-238).
  * Device-resident, asynchronous.  d_results_out: optional device buffer of C rsac_result

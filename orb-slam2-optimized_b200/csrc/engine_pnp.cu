@@ -161,7 +161,53 @@ static int pnp_pack(rsac_engine* e)
     return RSAC_OK;
 }
 
-int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
+// indexed wire format (rsac_pnp_upload_indexed): flat p3d / p2d / sigma2 arrays gathered on the device from the frame's
+// keypoint table and the map-point table through (keypoint index, map-point index) pairs
+static __global__ void pnp_gather_indexed_kernel(int64_t total, const uint16_t* __restrict__ kp_idx, const uint32_t* __restrict__ mp_idx,
+                                                 const float* __restrict__ kp_uv, const float* __restrict__ kp_sigma2,
+                                                 const float* __restrict__ mp_xyz, float* __restrict__ p3d, float* __restrict__ p2d,
+                                                 float* __restrict__ sigma2, int n_kp, int n_mp)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = kp_idx[i], m = mp_idx[i];
+        if (k >= (uint32_t)n_kp || m >= (uint32_t)n_mp) {
+            // an index outside the tables (a caller bug) never reads out of bounds: the correspondence becomes NaN, i.e.
+            // a certain outlier (CheckInliers: NaN compares false), and poisons any minimal set that draws it
+            const float qn = __int_as_float(0x7fc00000);
+            p2d[2 * i] = p2d[2 * i + 1] = sigma2[i] = p3d[3 * i] = p3d[3 * i + 1] = p3d[3 * i + 2] = qn;
+            continue;
+        }
+        p2d[2 * i] = kp_uv[2 * k]; p2d[2 * i + 1] = kp_uv[2 * k + 1];
+        sigma2[i] = kp_sigma2[k];
+        p3d[3 * i] = mp_xyz[3 * (size_t)m]; p3d[3 * i + 1] = mp_xyz[3 * (size_t)m + 1]; p3d[3 * i + 2] = mp_xyz[3 * (size_t)m + 2];
+    }
+}
+
+static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_pnp_indexed_batch* ib);
+
+int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b) { return pnp_upload_impl(e, b, nullptr); }
+
+int rsac_pnp_upload_indexed(rsac_engine* e, const rsac_pnp_indexed_batch* ib)
+{
+    if (!e || !ib || ib->C < 0 || !ib->offsets || !ib->K) return RSAC_ERR_INVALID;
+    const int64_t total = ib->offsets[ib->C];
+    if (total > 0 && (!ib->kp_idx || !ib->mp_idx)) { e->err = "kp_idx / mp_idx is NULL"; return RSAC_ERR_INVALID; }
+    PnpState& s = e->pnp;
+    if ((!ib->kp_uv && s.n_keypoints == 0) || (!ib->mp_xyz && s.n_mappoints == 0)) { e->err = "no resident keypoint / map-point table"; return RSAC_ERR_STATE; }
+    if ((ib->kp_uv && (ib->n_keypoints <= 0 || ib->n_keypoints > 65536 || !ib->kp_sigma2)) || (ib->mp_xyz && ib->n_mappoints <= 0)) {
+        e->err = "bad keypoint / map-point table"; return RSAC_ERR_INVALID;
+    }
+    std::vector<double> K((size_t)std::max(ib->C, 1) * 4);
+    for (int c = 0; c < ib->C; ++c)
+        for (int k = 0; k < 4; ++k) K[4 * (size_t)c + k] = ib->K[k];
+    rsac_pnp_batch b;
+    memset(&b, 0, sizeof(b));
+    b.C = ib->C; b.offsets = ib->offsets; b.K = K.data(); b.params = ib->params; b.n_params = ib->n_params;
+    b.seeds = ib->seeds; b.tables = ib->tables; b.table_offsets = ib->table_offsets;
+    return pnp_upload_impl(e, &b, ib);
+}
+
+static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_pnp_indexed_batch* ib)
 {
     if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
     if (!b->seeds && !b->tables) { if (e) e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
@@ -225,7 +271,34 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
 
     cudaStream_t st = e->stream;
     RSAC_TRY(stage_small_tables(e, s, th2, !same_shape));
-    if (d.total > 0) {
+    if (ib) {
+        // tables (when given) replace the resident ones; per sweep only 6 bytes per correspondence cross PCIe
+        if (ib->kp_uv) {
+            RSAC_TRY(s.d_kp_uv.ensure(e, (size_t)ib->n_keypoints * 8));
+            RSAC_TRY(s.d_kp_s2.ensure(e, (size_t)ib->n_keypoints * 4));
+            RSAC_CUDA(e, cudaMemcpyAsync(s.d_kp_uv.p, ib->kp_uv, (size_t)ib->n_keypoints * 8, cudaMemcpyHostToDevice, st));
+            RSAC_CUDA(e, cudaMemcpyAsync(s.d_kp_s2.p, ib->kp_sigma2, (size_t)ib->n_keypoints * 4, cudaMemcpyHostToDevice, st));
+            s.n_keypoints = ib->n_keypoints;
+        }
+        if (ib->mp_xyz) {
+            RSAC_TRY(s.d_mp_xyz.ensure(e, (size_t)ib->n_mappoints * 12));
+            RSAC_CUDA(e, cudaMemcpyAsync(s.d_mp_xyz.p, ib->mp_xyz, (size_t)ib->n_mappoints * 12, cudaMemcpyHostToDevice, st));
+            s.n_mappoints = ib->n_mappoints;
+        }
+        if (d.total > 0) {
+            RSAC_TRY(s.d_kp_idx.ensure(e, (size_t)d.total * 2));
+            RSAC_TRY(s.d_mp_idx.ensure(e, (size_t)d.total * 4));
+            RSAC_CUDA(e, cudaMemcpyAsync(s.d_kp_idx.p, ib->kp_idx, (size_t)d.total * 2, cudaMemcpyHostToDevice, st));
+            RSAC_CUDA(e, cudaMemcpyAsync(s.d_mp_idx.p, ib->mp_idx, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));
+            const int blocks = (int)std::min<int64_t>(((int64_t)d.total + 255) / 256, (int64_t)e->sm_count * 8);
+            ++e->launches;
+            pnp_gather_indexed_kernel<<<blocks, 256, 0, st>>>(d.total, (const uint16_t*)s.d_kp_idx.p, (const uint32_t*)s.d_mp_idx.p,
+                                                             (const float*)s.d_kp_uv.p, (const float*)s.d_kp_s2.p, (const float*)s.d_mp_xyz.p,
+                                                             (float*)s.d_p3d.p, (float*)s.d_p2d.p, (float*)s.d_sigma2.p,
+                                                             s.n_keypoints, s.n_mappoints);
+            RSAC_CUDA(e, cudaGetLastError());
+        }
+    } else if (d.total > 0) {
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, b->p3d, (size_t)d.total * 12, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, b->p2d, (size_t)d.total * 8, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_sigma2.p, b->sigma2, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));
@@ -233,7 +306,7 @@ int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b)
     s.have_tables = b->tables != nullptr;
     if (s.have_tables && d.table_len > 0)
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_tables.p, b->tables, sizeof(uint32_t) * (size_t)d.table_len, cudaMemcpyHostToDevice, st));
-    s.h2d_bytes = (uint64_t)d.total * 24 + sizeof(ProblemMeta) * (uint64_t)d.C + sizeof(float) * (uint64_t)d.C +
+    s.h2d_bytes = (uint64_t)d.total * (ib ? 6 : 24) + sizeof(ProblemMeta) * (uint64_t)d.C + sizeof(float) * (uint64_t)d.C +
                   sizeof(ScoreGroup) * s.groups.size() + (s.have_tables ? sizeof(uint32_t) * (uint64_t)d.table_len : 0);
     // the packing kernel is launched by the first run: a caller that uploads sweep k+1 while sweep k computes
     // (two engines) then overlaps only DMA with the kernels of sweep k -- a concurrent packing kernel takes block

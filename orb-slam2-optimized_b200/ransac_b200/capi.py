@@ -57,6 +57,13 @@ class PnPBatch(C.Structure):
                 ("seeds", C.c_void_p), ("tables", C.c_void_p), ("table_offsets", C.c_void_p)]
 
 
+class PnPIndexedBatch(C.Structure):
+    _fields_ = [("n_keypoints", C.c_int32), ("kp_uv", C.c_void_p), ("kp_sigma2", C.c_void_p), ("n_mappoints", C.c_int32),
+                ("mp_xyz", C.c_void_p), ("C", C.c_int32), ("offsets", C.c_void_p), ("kp_idx", C.c_void_p), ("mp_idx", C.c_void_p),
+                ("K", C.c_void_p), ("params", C.c_void_p), ("n_params", C.c_int32), ("seeds", C.c_void_p), ("tables", C.c_void_p),
+                ("table_offsets", C.c_void_p)]
+
+
 class Sim3Batch(C.Structure):
     _fields_ = [("C", C.c_int32), ("offsets", C.c_void_p), ("x1c", C.c_void_p), ("x2c", C.c_void_p),
                 ("sigma2_1", C.c_void_p), ("sigma2_2", C.c_void_p), ("K1", C.c_void_p), ("K2", C.c_void_p),
@@ -327,6 +334,28 @@ class Engine:
     def pnp_upload(self, offsets, p3d, p2d, sigma2, K, params, seeds=None, tables=None, table_offsets=None):
         desc, Cn, offsets = self._pnp_desc(offsets, p3d, p2d, sigma2, K, params, seeds, tables, table_offsets)
         self._ck(self.L.rsac_pnp_upload(self.h, C.byref(desc)), "pnp_upload")
+        self._pnp_C = Cn
+        self._pnp_total = int(offsets[-1])
+        self._pnp_words = ((np.diff(offsets) + 31) // 32).astype(np.int64)
+        return Cn
+
+    def pnp_upload_indexed(self, offsets, kp_idx, mp_idx, K, params, seeds=None, kp_uv=None, kp_sigma2=None, mp_xyz=None):
+        """indexed wire format: (keypoint index u16, map-point index u32) pairs over resident tables; kp_uv / mp_xyz None keeps
+        the tables of the previous upload"""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        Cn = len(offsets) - 1
+        kp_idx = np.ascontiguousarray(kp_idx, np.uint16).reshape(-1)
+        mp_idx = np.ascontiguousarray(mp_idx, np.uint32).reshape(-1)
+        K = np.ascontiguousarray(K, np.float64).reshape(4)
+        parr = (RansacParams * 1)(params)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, np.uint32)
+        kp_uv = None if kp_uv is None else np.ascontiguousarray(kp_uv, np.float32).reshape(-1, 2)
+        kp_sigma2 = None if kp_sigma2 is None else np.ascontiguousarray(kp_sigma2, np.float32).reshape(-1)
+        mp_xyz = None if mp_xyz is None else np.ascontiguousarray(mp_xyz, np.float32).reshape(-1, 3)
+        desc = PnPIndexedBatch(0 if kp_uv is None else kp_uv.shape[0], _p(kp_uv), _p(kp_sigma2), 0 if mp_xyz is None else mp_xyz.shape[0],
+                               _p(mp_xyz), Cn, _p(offsets), _p(kp_idx), _p(mp_idx), _p(K), C.cast(parr, C.c_void_p), 1, _p(seeds), None, None)
+        self._keep = [offsets, kp_idx, mp_idx, K, parr, seeds, kp_uv, kp_sigma2, mp_xyz]
+        self._ck(self.L.rsac_pnp_upload_indexed(self.h, C.byref(desc)), "pnp_upload_indexed")
         self._pnp_C = Cn
         self._pnp_total = int(offsets[-1])
         self._pnp_words = ((np.diff(offsets) + 31) // 32).astype(np.int64)

@@ -276,3 +276,31 @@ def bow_keyframe(seed: int, frame: dict, n_feat: int = 1500, shared: float = 0.4
     ids, off, feat = _feature_vector(nodes)
     return dict(desc=desc, angle=angle, valid=valid, node_ids=ids, node_off=off, node_feat=feat, nodes=nodes, node_pool=pool,
                 truth=(dst, src))
+
+
+# ---------------------------------------------------------------- one frame, many candidate keyframes (indexed wire format)
+def reloc_frame(seed: int, C: int, n_kp: int = 2000, n_match: int = 500, outlier_ratio: float = 0.5, n_map: int = 200000, cam=EUROC):
+    """A relocalisation as Tracking::Relocalization sees it: ONE frame (n_kp undistorted keypoints with octaves, one true
+    pose) and C candidate keyframes, each contributing n_match (keypoint, map point) pairs -- the true map point of the
+    keypoint (inliers) or an unrelated one (outliers).  Returns the tables, the index pairs and the equivalent flat arrays."""
+    rng = np.random.default_rng(seed)
+    R, t = random_pose(rng)
+    octave = rng.choice(N_LEVELS, size=n_kp, p=_LEVEL_P)
+    sigma2 = np.ascontiguousarray(_SIGMA2[octave], np.float32)
+    Xc = frustum_points(rng, n_kp, cam)
+    uv = (project(Xc, cam) + rng.normal(size=(n_kp, 2)) * np.sqrt(sigma2)[:, None]).astype(np.float32)
+    mp = np.empty((n_map, 3), np.float32)
+    true_id = rng.choice(n_map, n_kp, replace=False)
+    mp[:] = ((frustum_points(rng, n_map, cam) - t) @ R).astype(np.float32)
+    mp[true_id] = ((Xc - t) @ R).astype(np.float32)
+    kp_idx = np.empty((C, n_match), np.uint16)
+    mp_idx = np.empty((C, n_match), np.uint32)
+    for c in range(C):
+        ks = rng.choice(n_kp, n_match, replace=False)
+        ms = true_id[ks].copy()
+        out = rng.random(n_match) < outlier_ratio
+        ms[out] = rng.integers(0, n_map, int(out.sum()))
+        kp_idx[c], mp_idx[c] = ks, ms
+    flat = dict(p3d=mp[mp_idx], p2d=uv[kp_idx], sigma2=sigma2[kp_idx])
+    return dict(K=np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float64), R=R, t=t, kp_uv=uv, kp_sigma2=sigma2, mp_xyz=mp, kp_idx=kp_idx, mp_idx=mp_idx,
+                seeds=(np.arange(C) + 1000 * (seed % 1000) + 7).astype(np.uint32), **flat)

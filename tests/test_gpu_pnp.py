@@ -432,3 +432,34 @@ def test_pnp_early_exit_many_stages(engine, bounds):
         engine.pnp_rerun(res0["n_hyp"].astype(np.int32))
         ref, _ = engine.pnp_download()
         _same_records(ref, after)
+
+
+def test_pnp_indexed_wire_format_equals_flat_upload(engine):
+    """rsac_pnp_upload_indexed (6 B per correspondence over resident keypoint / map-point tables) must give the flat upload's
+    records and masks bit for bit; a second sweep re-uses the resident tables; an out-of-range index becomes an outlier."""
+    C, n = 48, 500
+    f = synth.reloc_frame(3, C, n_kp=2000, n_match=n, n_map=50000)
+    offsets = (np.arange(C + 1) * n).astype(np.int32)
+    prm = capi.ransac_params(**PRM)
+    res0, m0 = engine.pnp_solve(offsets, f["p3d"], f["p2d"], f["sigma2"], [f["K"]], prm, seeds=f["seeds"], flags=capi.FLAG_EARLY_EXIT)
+    engine.pnp_upload_indexed(offsets, f["kp_idx"], f["mp_idx"], f["K"], prm, seeds=f["seeds"], kp_uv=f["kp_uv"], kp_sigma2=f["kp_sigma2"],
+                              mp_xyz=f["mp_xyz"])
+    engine.pnp_run(capi.FLAG_EARLY_EXIT)
+    res1, m1 = engine.pnp_download()
+    _same_records(res0, res1)
+    assert (m0 == m1).all()
+    assert int(res1["ok"].sum()) >= C - 1 and np.abs(res1[0]["R"].reshape(3, 3) - f["R"]).max() < 0.02
+    # the second sweep of the same frame: tables stay resident, only the pairs travel (other candidates: a permutation)
+    perm = np.random.default_rng(0).permutation(C)
+    engine.pnp_upload_indexed(offsets, f["kp_idx"][perm], f["mp_idx"][perm], f["K"], prm, seeds=f["seeds"][perm])
+    engine.pnp_run(capi.FLAG_EARLY_EXIT)
+    res2, m2 = engine.pnp_download()
+    for fld in _REC_FIELDS:
+        assert (res2[fld] == res0[fld][perm]).all(), fld
+    # an index outside the tables is never dereferenced: that correspondence is a certain outlier
+    bad = f["mp_idx"].copy()
+    bad[0, :5] = 50000 + 17
+    engine.pnp_upload_indexed(offsets[:2], f["kp_idx"][:1], bad[:1], f["K"], prm, seeds=f["seeds"][:1])
+    engine.pnp_run(0)
+    res3, m3 = engine.pnp_download()
+    assert not capi.unpack_mask(m3[:16], n)[:5].any()
