@@ -698,6 +698,18 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
         ex["cfg2_mlpnp"] = {"frames": C2, "matches": N2, "hypotheses": H2, "ms_per_batch": ms2,
                             "frames_per_s": C2 / (ms2 * 1e-3), "evals_per_s": C2 * H2 * N2 / (ms2 * 1e-3),
                             "frames_ok": int(res2["ok"].sum())}
+        ex["cfg2_mlpnp"]["roofline"] = {"bound": "fp32 (scoring) / fp64 latency (one thread per 6-point solve)", "flop_per_eval": 30,
+                                        "achieved": C2 * H2 * N2 * 30 / (ms2 * 1e-3) / 1e12, "peak": fp32_pk, "unit": "TFLOP/s",
+                                        "frac": C2 * H2 * N2 * 30 / (ms2 * 1e-3) / 1e12 / fp32_pk,
+                                        "note": "exhaustive: all 300 hypotheses of every frame are solved and scored"}
+        # CPU port (oracle) on the host cores: reference semantics (stops at the first successful Refine)
+        pbs2 = [O.mlpnp_problem(b2["p3d"][c], b2["p2d"][c], b2["sigma2"][c], tuple(Kf[0]), cov[c]) for c in range(C2)]
+        tabs2 = [O.index_table(int(sd), N2, 6, H2) for sd in b2["seeds"]]
+        oprm2 = O.params(0.99, 10, 300, 6, 0.2, 5.991)
+        dta, eva, _ = O.mlpnp_batch(pbs2[:16], oprm2, tabs2[:16], 0, 1)
+        dtb, evb, _ = O.mlpnp_batch(pbs2, oprm2, tabs2, 0, cores)
+        ex["cfg2_mlpnp"]["cpu_port"] = {"single_thread_frames_per_s": 16 / dta, "single_thread_evals_per_s": eva / dta,
+                                        "all_cores_frames_per_s": C2 / dtb, "cores": cores, "sample": "16 / 64 frames, early exit"}
         # a 64-frame batch is a fraction of one wave: independent batches in flight (one engine + stream each)
         pool = [capi.Engine(0) for _ in range(6)]
         for q in pool:
@@ -737,9 +749,107 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
             ms3 = eng.timer_end() / 10
             H3 = capi.sim3_ransac_setup(200, prm3)
             ex["cfg3_sim3_x%d" % C3] = {"candidates": C3, "matches": 200, "hypotheses": H3, "ms_per_batch": ms3,
-                                        "evals_per_s": C3 * H3 * 200 / (ms3 * 1e-3)}
+                                        "evals_per_s": C3 * H3 * 200 / (ms3 * 1e-3),
+                                        "roofline": {"bound": "fp32", "flop_per_eval": 63, "achieved": C3 * H3 * 200 * 63 / (ms3 * 1e-3) / 1e12,
+                                                     "peak": fp32_pk, "unit": "TFLOP/s", "frac": C3 * H3 * 200 * 63 / (ms3 * 1e-3) / 1e12 / fp32_pk,
+                                                     "note": "every hypothesis is scored (the reference stops at the first accepted one)"}}
+        pbs3 = [O.sim3_problem(q["x1c"], q["x2c"], q["sigma2_1"], q["sigma2_2"], q["K"], q["K"], True) for q in ps]
+        tabs3 = [O.index_table(int(sd), 200, 3, H3) for sd in seeds3]
+        dt3a, ev3a, _ = O.sim3_batch(pbs3[:32], 0.99, 20, 300, tabs3[:32], 0, 1)
+        dt3x, ev3x, _ = O.sim3_batch(pbs3[:32], 0.99, 20, 300, tabs3[:32], O.FLAG_EXHAUSTIVE, 1)
+        ex["cfg3_sim3_cpu_port"] = {"single_thread_ms_per_candidate": 1e3 * dt3a / 32, "single_thread_evals_per_s": ev3a / dt3a,
+                                    "exhaustive_single_thread_ms_per_candidate": 1e3 * dt3x / 32,
+                                    "exhaustive_single_thread_evals_per_s": ev3x / dt3x, "sample": "32 candidates"}
     except Exception as err:   # the headline line must still be printed
         ex["cfg2_cfg3_error"] = repr(err)
+    # ---- the relocalisation of ONE frame in the indexed wire format (first half): 1024 candidates x 500
+    # (keypoint, map point) pairs over resident tables against the same sweep uploaded flat; one engine, one sweep at a time
+    try:
+        Ci, ni = 1024, 500
+        fr = synth.reloc_frame(9, Ci, n_kp=2000, n_match=ni, n_map=200000)
+        offi = (np.arange(Ci + 1) * ni).astype(np.int32)
+        prmi = capi.ransac_params(**PRM)
+        eng.pnp_upload_indexed(offi, fr["kp_idx"], fr["mp_idx"], fr["K"], prmi, seeds=fr["seeds"], kp_uv=fr["kp_uv"], kp_sigma2=fr["kp_sigma2"],
+                               mp_xyz=fr["mp_xyz"])
+        eng.pnp_run(capi.FLAG_EARLY_EXIT)
+        ri, mi = eng.pnp_download()
+        rf, mf = eng.pnp_solve(offi, fr["p3d"], fr["p2d"], fr["sigma2"], [fr["K"]], prmi, seeds=fr["seeds"], flags=capi.FLAG_EARLY_EXIT)
+        assert ri.tobytes() == rf.tobytes() and (mi == mf).all(), "indexed upload differs from the flat upload"
+
+        def sweep_indexed():
+            eng.pnp_upload_indexed(offi, fr["kp_idx"], fr["mp_idx"], fr["K"], prmi, seeds=fr["seeds"])
+            eng.pnp_run(capi.FLAG_EARLY_EXIT)
+            return eng.pnp_download()
+
+        def sweep_flat():
+            return eng.pnp_solve(offi, fr["p3d"], fr["p2d"], fr["sigma2"], [fr["K"]], prmi, seeds=fr["seeds"], flags=capi.FLAG_EARLY_EXIT)
+
+        tms = {}
+        for name, fn in (("indexed", sweep_indexed), ("flat", sweep_flat)):
+            for _ in range(3):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                fn()
+            tms[name] = (time.perf_counter() - t0) / 20 * 1e3
+        ex["indexed_wire_format"] = {"candidates": Ci, "matches": ni, "keypoints": 2000, "map_points": 200000,
+                                     "h2d_bytes_per_sweep_indexed": Ci * ni * 6, "h2d_bytes_per_sweep_flat": Ci * ni * 24,
+                                     "ms_per_sweep_end_to_end_indexed": tms["indexed"], "ms_per_sweep_end_to_end_flat": tms["flat"],
+                                     "records_identical": True, "candidates_ok": int(ri["ok"].sum()),
+                                     "note": "host buffers pageable, one sweep at a time (upload + run + download, synchronous)"}
+    except Exception as err:
+        ex["indexed_wire_format_error"] = repr(err)
+    # ---- ORBmatcher::SearchByBoW, 1024 candidate keyframes against one frame (Tracking.cpp:1207-1232)
+    try:
+        Fb = synth.bow_frame(11, 1500, 100)
+        kfs = [synth.bow_keyframe(1000 + i, Fb, 1200, shared=0.25, rot=7.0 * i) for i in range(16)]
+        setsb = [Fb] + kfs
+        qs = [1 + (i % 16) for i in range(1024)]
+        tsb = [0] * 1024
+        eng.bow_upload(setsb, qs, tsb, 0.75, True, 0)
+        for _ in range(3):
+            eng.bow_run()
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(20):
+            eng.bow_run()
+        msb = eng.timer_end() / 20
+        mt, nmb = eng.bow_download()
+        kq = [O.bow_features(s_) for s_ in setsb]
+        t0 = time.perf_counter()
+        for i in range(16):
+            want, nw = O.search_by_bow(kq[1 + i], kq[0], 0.75, True, 0)
+            assert nw == nmb[i] and (want == mt[i]).all(), "SearchByBoW differs from the oracle"
+        dtb_ = (time.perf_counter() - t0) / 16
+        # distances actually needed: per common node |KF features with a map point| x |frame features| (upper bound: none taken)
+        alg_bytes = 32 * (1500 + 1024 * 1200) + 4 * 1024 * 1500
+        ex["search_by_bow"] = {"pairs": 1024, "frame_features": 1500, "keyframe_features": 1200, "vocabulary_nodes": 100,
+                               "ms_per_batch": msb, "pairs_per_s": 1024 / (msb * 1e-3), "matches_mean": float(np.mean(nmb)),
+                               "cpu_port_single_thread_pairs_per_s": 1.0 / dtb_,
+                               "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (msb * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
+                               "note": "ORBmatcher.cpp:110-239 batched; 16 distinct synthetic keyframes cycled; bit-identical to the oracle"}
+    except Exception as err:
+        ex["search_by_bow_error"] = repr(err)
+    # ---- the reference's own null-space structure (RSAC_FLAG_EPNP_EIGEN: 12x12 eigen-solve per hypothesis), with early exit
+    try:
+        bce = synth.pnp_batch(4, 1024, 500, 0.5)
+        offe = (np.arange(1025) * 500).astype(np.int32)
+        eng.pnp_upload(offe, bce["p3d"], bce["p2d"], bce["sigma2"], [bce["K"]], capi.ransac_params(**PRM), seeds=bce["seeds"])
+        fl = capi.FLAG_EARLY_EXIT | capi.FLAG_EPNP_EIGEN
+        for _ in range(3):
+            eng.pnp_run(fl)
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(10):
+            eng.pnp_run(fl)
+        mse = eng.timer_end() / 10
+        rese, _ = eng.pnp_download()
+        ex["eigen_mode"] = {"candidates": 1024, "ms_per_sweep": mse, "candidates_per_s": 1024 / (mse * 1e-3), "candidates_ok": int(rese["ok"].sum()),
+                            "phases": list(eng.pnp_phase_stats()),
+                            "cpu_port_all_cores_candidates_per_s": out.get("cpu_baseline", {}).get("eigen_nullspace_candidates_per_s"),
+                            "note": "one engine, one sweep at a time; RSAC_BENCH_EIGEN=1 runs the whole bench in this mode"}
+    except Exception as err:
+        ex["eigen_mode_error"] = repr(err)
     # ---- Optimizer::PoseOptimization for every candidate of a cfg4-sized sweep (1024 frames x 250 matched
     # map points, 20 % outliers, monocular), one warp per frame; CPU port on a 64-frame sample beside it
     try:
