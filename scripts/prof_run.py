@@ -28,3 +28,29 @@ for _ in range(reps + 1):
     eng.score_pnp_run(True)
 eng.sync()
 print("ok", int(res["ok"].sum()))
+
+# ---- round 2: the other kernels north_star asks a capture for (RSAC_PROF_ALL=1)
+if os.environ.get("RSAC_PROF_ALL") == "1":
+    C2, N2 = 64, 1000
+    b2 = synth.pnp_batch(2, C2, N2, 0.5)
+    cov = np.stack([synth.bearing_covariances(dict(K=b2["K"], sigma2=b2["sigma2"][c])) for c in range(C2)])
+    eng.mlpnp_upload((np.arange(C2 + 1) * N2).astype(np.int32), b2["p3d"], b2["p2d"], b2["sigma2"], np.array([b2["K"]], np.float32),
+                     capi.ransac_params(0.99, 10, 300, 6, 0.2, 5.991), cov=cov, seeds=b2["seeds"])
+    for _ in range(reps):
+        eng.mlpnp_run()
+    ps = [synth.sim3_problem(3000 + i, 200, 0.4, 1.0) for i in range(64)]
+    cat = lambda k: np.concatenate([q[k] for q in ps])
+    K3 = np.array([ps[0]["K"]], np.float32)
+    for C3 in (1, 64):
+        n3 = 200 * C3
+        eng.sim3_upload((np.arange(C3 + 1) * 200).astype(np.int32), cat("x1c")[:n3], cat("x2c")[:n3], cat("sigma2_1")[:n3], cat("sigma2_2")[:n3],
+                        K3, K3, capi.Sim3Params(0.99, 20, 300, 1), seeds=np.arange(C3, dtype=np.uint32) + 3000)
+        for _ in range(reps):
+            eng.sim3_run()
+    Fb = synth.bow_frame(11, 1500, 100)
+    kfs = [synth.bow_keyframe(1000 + i, Fb, 1200, shared=0.25, rot=7.0 * i) for i in range(8)]
+    eng.bow_upload([Fb] + kfs, [1 + (i % 8) for i in range(1024)], [0] * 1024, 0.75, True, 0)
+    for _ in range(reps):
+        eng.bow_run()
+    eng.sync()
+    print("all ok")
