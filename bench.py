@@ -13,8 +13,9 @@ candidates are sharded in contiguous blocks of 1024/N; a rank conc
 sweeps into one device batch of 1024 candidates, and after every batch the per-candidate records (96 B) of the N sweeps
 are all-gathered over NCCL, so that every rank holds the N complete sweeps.  A step is 64/N batches per GPU.
   value : candidates/s, inputs resident in HBM
-  e2e   : the same through the host-buffer C-ABI call sequence (H2D of every batch's inputs from pinned memory, D2H of
-          records + inlier masks inside the timed region)
+  e2e   : the same through the host-buffer C-ABI call sequence (H2D of every batch's inputs from pinned memory in the
+          indexed wire format -- keypoint tables + (keypoint, map point) index pairs over the device-resident map --,
+          D2H of records + inlier masks inside the timed region)
   roofline      : dominant kernel of the sweep (EPnP minimal solver, FP64 CUDA cores)
   roofline_score: CheckInliers kernel on cfg5 (4096 poses x 10 000 correspondences, FP32 CUDA cores)
   cpu_baseline  : the CPU oracle (port of the reference, see oracle/) on the host cores
@@ -114,10 +115,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+N_KP = 2000                   # keypoints of the frame being relocalised
+N_MAP = 200000                # map points of one synthetic map (one map per block; the blocks' maps are concatenated)
+
+
 def make_block(j):
-    """synthetic sweep j: 1024 cfg1-style candidates (distinct seeds and poses)"""
+    """synthetic sweep j = ONE relocalisation as Tracking::Relocalization sees it (Tracking.cpp:1196-1232): one frame of 2000
+    keypoints, 1024 candidate keyframes, each contributing 500 (keypoint, map point) pairs, half of them wrong map points.
+    Carries the indexed form (tables + index pairs) and the equivalent flat arrays p3d [C,n,3], p2d [C,n,2], sigma2 [C,n]."""
     from ransac_b200 import synth
-    return synth.pnp_batch(4, C_SWEEP, N_MATCH, 0.5, first=j * C_SWEEP)
+    return synth.reloc_frame(4000 + j, C_SWEEP, n_kp=N_KP, n_match=N_MATCH, outlier_ratio=0.5, n_map=N_MAP)
 
 
 def bind_to_gpu_numa(local_rank):
@@ -249,8 +256,16 @@ def main():
         sel = [blocks_full[j * world + i] for i in range(world)]
         cat = lambda k, shp: np.concatenate([b_[k][first:first + count] for b_ in sel]).reshape(shp)
         ids = np.concatenate([(j * world + i) * C_SWEEP + first + np.arange(count) for i in range(world)]).astype(np.int32)
-        batches.append(dict(p3d=pin(cat("p3d", (-1, 3))), p2d=pin(cat("p2d", (-1, 2))), s2=pin(cat("sigma2", (-1,))),
+        # indexed wire format of the same batch: the keypoint tables of its `world` frames one after another, map-point
+        # indices into the resident map (the blocks' maps concatenated)
+        kpi = np.concatenate([b_["kp_idx"][first:first + count].astype(np.int64) + i * N_KP for i, b_ in enumerate(sel)]).astype(np.uint16)
+        mpi = np.concatenate([b_["mp_idx"][first:first + count].astype(np.int64) + (j * world + i) * N_MAP
+                              for i, b_ in enumerate(sel)]).astype(np.uint32)
+        batches.append(dict(p3d=cat("p3d", (-1, 3)), p2d=cat("p2d", (-1, 2)), s2=cat("sigma2", (-1,)),
+                            kp_idx=pin(kpi.reshape(-1)), mp_idx=pin(mpi.reshape(-1)),
+                            kp_uv=pin(np.concatenate([b_["kp_uv"] for b_ in sel])), kp_s2=pin(np.concatenate([b_["kp_sigma2"] for b_ in sel])),
                             seeds=np.concatenate([b_["seeds"][first:first + count] for b_ in sel]), K=sel[0]["K"], ids=ids))
+    the_map = np.ascontiguousarray(np.concatenate([b_["mp_xyz"] for b_ in blocks_full]), np.float32)     # resident on every engine
     b = blocks_full[0]
 
     NRES = max(NB, PIPE)                 # resident pass: engine i keeps batch (i mod NB) uploaded
@@ -269,9 +284,18 @@ def main():
     h_msk = [torch.empty((max(words_total, 1),), dtype=torch.int32).pin_memory() for _ in range(NSLOT)]
 
     def upload(i, j):
+        """flat arrays (24 B per correspondence): the resident pass, whose inputs are uploaded before the timed region"""
         blk = batches[j % NB]
         engines[i].set_problem_ids(blk["ids"])
-        engines[i].pnp_upload(offsets, blk["p3d"].numpy(), blk["p2d"].numpy(), blk["s2"].numpy(), [blk["K"]], prm, seeds=blk["seeds"])
+        engines[i].pnp_upload(offsets, blk["p3d"], blk["p2d"], blk["s2"], [blk["K"]], prm, seeds=blk["seeds"])
+
+    def upload_indexed(i, j, with_map=False):
+        """the end-to-end pass: per batch the frames' keypoint tables (12 B per keypoint) and 6 B per correspondence --
+        (keypoint u16, map point u32) -- from pinned memory; the map stays resident on the device"""
+        blk = batches[j % NB]
+        engines[i].set_problem_ids(blk["ids"])
+        engines[i].pnp_upload_indexed(offsets, blk["kp_idx"].numpy(), blk["mp_idx"].numpy(), blk["K"], prm, seeds=blk["seeds"],
+                                      kp_uv=blk["kp_uv"].numpy(), kp_sigma2=blk["kp_s2"].numpy(), mp_xyz=the_map if with_map else None)
 
     # multi-GPU: the all-gather of a batch's records (98 KB per rank, latency-bound) runs on a side stream, in issue
     # order; a ring of gather buffers, and every engine waits for the gather that last read its records
@@ -320,7 +344,7 @@ def main():
     def run_e2e(k):
         i = k % NSLOT
         with torch.cuda.stream(streams[i]):
-            upload(i, k)                                # H2D of batch k mod NB
+            upload_indexed(i, k)                        # H2D of batch k mod NB
             bound_in_flight(i, k, e2e_ring)
             run_and_gather(i, k)
             ev = torch.cuda.Event()
@@ -328,6 +352,8 @@ def main():
             e2e_ring[k % len(e2e_ring)] = ev
             # D2H of this batch's records and inlier masks into pinned memory (async on the batch's stream)
             engines[i].pnp_download_async(h_res[i].data_ptr(), h_msk[i].data_ptr())
+
+    issue_ms = [0.0]
 
     def timed(fn, steps):
         """`steps` steps = steps * RUNS batches on this rank; device time, max over ranks"""
@@ -344,8 +370,10 @@ def main():
         ev0.record(main_s)
         for s in streams:
             s.wait_event(ev0)
+        t_host = time.perf_counter()
         for k in range(steps * RUNS):
             fn(k)
+        issue_ms[0] = (time.perf_counter() - t_host) * 1e3 / max(1, steps * RUNS)    # host time to ISSUE one batch
         for s in streams + ([comm_stream] if comm_stream is not None else []):
             e = torch.cuda.Event()
             e.record(s)
@@ -369,6 +397,7 @@ def main():
         sampler.start()
     launches0 = sum(e.launch_count() for e in engines)
     ms = timed(run_resident, args.steps)
+    issue_res = issue_ms[0]
     launches = sum(e.launch_count() for e in engines) - launches0
     clocks = sampler.stop() if rank == 0 else None
 
@@ -404,10 +433,15 @@ def main():
     torch.cuda.synchronize()
     res_local, msk_local = engines[0].pnp_download()
     # (2) end to end (timed), then one more end-to-end batch 0 whose downloaded records and masks must equal the resident run's
+    for i in range(NSLOT):                              # the map becomes resident on the end-to-end engines (not timed)
+        with torch.cuda.stream(streams[i]):
+            upload_indexed(i, i, with_map=True)
+    torch.cuda.synchronize()
     timed(run_e2e, 1)
     ms_e2e = timed(run_e2e, args.steps)
+    issue_e2e = issue_ms[0]
     with torch.cuda.stream(streams[0]):
-        upload(0, 0)
+        upload_indexed(0, 0)
         engines[0].pnp_run(RUN_FLAGS, d_local[0].data_ptr())
         engines[0].pnp_download_async(h_res[0].data_ptr(), h_msk[0].data_ptr())
     torch.cuda.synchronize()
@@ -452,7 +486,7 @@ def main():
         assert len(rec) == C_RUN
         n_ok = int(rec["ok"].sum())
 
-    h2d = int(C_RUN * N_MATCH * 24 + C_RUN * 4 + C_RUN * 152 + C_RUN * 4)
+    h2d = int(C_RUN * N_MATCH * 6 + world * N_KP * 12 + C_RUN * 4 + C_RUN * 152 + C_RUN * 4)
     d2h = int(C_RUN * 96 + words_total * 4)
     C_STEP = BUNDLE * C_SWEEP
     value = C_STEP * args.steps / (ms * 1e-3)
@@ -473,17 +507,24 @@ def main():
                                  "replay + Refine per candidate; records identical to the exhaustive run")) +
                                ("; 4-point null space by the 12x12 eigen-solve (RSAC_FLAG_EPNP_EIGEN)" if EIGEN else
                                 "; 4-point null space by Householder QR (DESIGN.md section 2)"),
-                       "blocks": f"{NBLOCK} distinct synthetic sweeps of {C_SWEEP} candidates are cycled: sweep s of a step is block s mod {NBLOCK}",
+                       "blocks": (f"{NBLOCK} distinct synthetic sweeps are cycled (sweep s of a step is block s mod {NBLOCK}); a sweep is one frame of "
+                                  f"{N_KP} keypoints matched against {C_SWEEP} candidate keyframes of a {N_MAP}-point map, {N_MATCH} (keypoint, map point) "
+                                  "pairs per candidate, half of them wrong map points (Tracking.cpp:1196-1232)"),
                        "parallelism": (f"every sweep sharded over {world} GPU(s) in contiguous blocks of {count} candidates; a rank concatenates its "
                                        f"shards of {world} consecutive sweeps into one device batch of {C_RUN} candidates ({RUNS} batches per step "
                                        f"and GPU, {PIPE} in flight, one engine + stream each; CUDA graph per batch); all-gather of the batch's "
-                                       "records (96 B per candidate) after every batch; e2e uploads every batch from pinned host memory and reads "
-                                       "records + masks back inside the timed region"),
+                                       "records (96 B per candidate) after every batch; e2e uploads every batch from pinned host memory in the indexed "
+                                       "wire format (rsac_pnp_upload_indexed: the frames' keypoint tables + 6 B per correspondence; the map is "
+                                       "resident on the device, as the map of a running SLAM system is) and reads records + masks back inside the "
+                                       "timed region; the resident pass holds the same batches uploaded flat (24 B per correspondence), and the "
+                                       "content check compares the two"),
                        "l2": (f"no explicit flush: {NB} distinct batches per GPU are cycled, each in its own engine (~90 MB of device buffers per "
                               "batch against 126 MB of L2); within a sweep the working set is L2-resident by design and every kernel is "
                               "compute- or latency-bound")},
             "e2e": {"value": e2e_v, "unit": "candidates/s", "h2d_bytes_per_step": h2d * RUNS * world, "d2h_bytes_per_step": d2h * RUNS * world,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "ms_per_batch": ms_e2e / args.steps / RUNS, "host_issue_ms_per_batch": issue_e2e,
+                    "resident_ms_per_batch": ms / args.steps / RUNS, "resident_host_issue_ms_per_batch": issue_res},
             "gpu_launches": int(launches),
             "checks": checks,
             "host_binding": ("rank 0 bound to NUMA node %d of its GPU (every rank binds itself the same way)" % numa_node) if numa_node is not None

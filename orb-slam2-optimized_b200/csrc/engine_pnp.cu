@@ -143,24 +143,6 @@ static int pnp_plan_early(rsac_engine* e, const std::vector<int>& bounds)
     return RSAC_OK;
 }
 
-static int pnp_pack(rsac_engine* e)
-{
-    PnpState& s = e->pnp;
-    const BatchDims& d = s.d;
-    if (s.packed) return RSAC_OK;
-    if (d.total > 0 && d.C > 0) {
-        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)std::min(d.C, 65535));
-        e->stage_begin(RSAC_STAGE_PACK);
-        pack_pnp_kernel<<<grid, 256, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
-                                                     (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 0,
-                                                     (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p, d.C);
-        e->stage_end(RSAC_STAGE_PACK);
-        RSAC_CUDA(e, cudaGetLastError());
-    }
-    s.packed = true;
-    return RSAC_OK;
-}
-
 // indexed wire format (rsac_pnp_upload_indexed): flat p3d / p2d / sigma2 arrays gathered on the device from the frame's
 // keypoint table and the map-point table through (keypoint index, map-point index) pairs
 static __global__ void pnp_gather_indexed_kernel(int64_t total, const uint16_t* __restrict__ kp_idx, const uint32_t* __restrict__ mp_idx,
@@ -181,6 +163,158 @@ static __global__ void pnp_gather_indexed_kernel(int64_t total, const uint16_t* 
         sigma2[i] = kp_sigma2[k];
         p3d[3 * i] = mp_xyz[3 * (size_t)m]; p3d[3 * i + 1] = mp_xyz[3 * (size_t)m + 1]; p3d[3 * i + 2] = mp_xyz[3 * (size_t)m + 2];
     }
+}
+
+// Indexed wire format, fused path (one RANSAC parameter set for the whole batch -- the reference's call shape): everything
+// of a packed record that depends on the keypoint only -- u, v, cx-u, cy-v, the threshold sigma2*th2, and the two f64
+// factors of the scoring kernel's rounding bounds (score_bounds: the square root and the division live here) -- is
+// computed once per KEYPOINT (2000 per frame instead of 512 000 correspondences per sweep) ...
+struct KpRecord { double A, E; float thr, pad; };   // band = ru(2u M A), eps_a = 12u M E  (score_bounds, operation for operation)
+static __global__ void pnp_keypoint_table_kernel(int n_kp, const float* __restrict__ kp_uv, const float* __restrict__ kp_sigma2, float th2,
+                                                 double fxd, double fyd, double cxd, double cyd, float4* __restrict__ kpA,
+                                                 KpRecord* __restrict__ kpB)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_kp) return;
+    const float u = kp_uv[2 * k], v = kp_uv[2 * k + 1];
+    const float thr = kp_sigma2[k] * th2;                       // PnPsolver.cpp:93
+    const float cu = (float)(cxd - (double)u), cv = (float)(cyd - (double)v);
+    const float fx = (float)fxd, fy = (float)fyd;
+    // the keypoint-only part of score_bounds (score.cuh), same expressions in the same order
+    const double th = fmax((double)thr, 0.0);
+    const double s = sqrt(th);
+    const double fmin_ = fmin(fabs((double)fx), fabs((double)fy));
+    const double fmax_ = fmax(fabs((double)fx), fabs((double)fy));
+    const double cinf = fmax(fabs((double)cu), fabs((double)cv));
+    const double uvinf = fmax(fabs((double)u), fabs((double)v));
+    const double q = 1.0 + (cinf + s) / fmin_;
+    KpRecord r;
+    r.A = (s * ((12.0 + 8.0 * q) * (fabs((double)fx) + fabs((double)fy)) +
+                16.0 * (fabs((double)cu) + fabs((double)cv)) + 2.0 * (fabs((double)u) + fabs((double)v))) +
+           33.0 * th);
+    r.E = (fmax_ + cinf + uvinf + s);
+    r.thr = thr; r.pad = 0.0f;
+    kpA[k] = make_float4(u, v, cu, cv);
+    kpB[k] = r;
+}
+
+// ... and the packing kernel gathers: per correspondence the map point (12 B, L2-resident table), the keypoint record, two
+// f64 products for the bounds.  Writes exactly what pack_pnp_kernel writes (bit for bit: tests compare records, masks
+// and the number of exact-tier evaluations of the two paths); the flat p3d / p2d / sigma2 arrays are not materialised
+// (rsac_poseopt_from_pnp gathers them on demand).
+static __device__ __forceinline__ PackedPoint pack_point_indexed(size_t g, const uint16_t* kp_idx, const uint32_t* mp_idx,
+                                                                 const float4* kpA, const KpRecord* kpB, const float* mp_xyz,
+                                                                 int n_kp, int n_mp, float th2, const ProblemMeta& m)
+{
+    PackedPoint r;
+    const uint32_t k = kp_idx[g], mi = mp_idx[g];
+    if (k >= (uint32_t)n_kp || mi >= (uint32_t)n_mp) {
+        // an index outside the tables (a caller bug) never reads out of bounds: the correspondence becomes NaN -- a certain
+        // outlier (CheckInliers: NaN compares false) that poisons any minimal set drawing it; same record as the unfused path
+        const float qn = __int_as_float(0x7fc00000);
+        r.X = r.Y = r.Z = r.u = r.v = qn;
+        r.thr = qn * th2;
+        r.cu = (float)(m.cx - (double)r.u); r.cv = (float)(m.cy - (double)r.v);
+        const ScoreBounds sb = score_bounds(r.X, r.Y, r.Z, r.cu, r.cv, r.u, r.v, r.thr, (float)m.fx, (float)m.fy);
+        r.band = sb.band; r.eps2 = sb.eps2;
+        return r;
+    }
+    const float4 a = kpA[k];
+    const KpRecord b = kpB[k];
+    r.X = mp_xyz[3 * (size_t)mi]; r.Y = mp_xyz[3 * (size_t)mi + 1]; r.Z = mp_xyz[3 * (size_t)mi + 2];
+    r.u = a.x; r.v = a.y; r.cu = a.z; r.cv = a.w; r.thr = b.thr;
+    const double uro = (double)kUnitRoundoff;
+    const double M = 1.0 + fmax(fabs((double)r.X), fmax(fabs((double)r.Y), fabs((double)r.Z)));
+    const double band = 2.0 * uro * M * b.A;
+    const double eps_a = 12.0 * uro * M * b.E;
+    r.band = __double2float_ru(band);
+    r.eps2 = __double2float_ru(fmax(10.0 * eps_a * eps_a, 1e-30));
+    return r;
+}
+
+static __global__ void pack_pnp_indexed_kernel(const ProblemMeta* metas, int C, const uint16_t* __restrict__ kp_idx,
+                                               const uint32_t* __restrict__ mp_idx, const float4* __restrict__ kpA,
+                                               const KpRecord* __restrict__ kpB, const float* __restrict__ mp_xyz, int n_kp, int n_mp,
+                                               float th2, float4* cA, float4* cB, float4* cC, float4* cP)
+{
+    for (int pr = blockIdx.y; pr < C; pr += gridDim.y) {
+        const ProblemMeta& m = metas[pr];
+        const int npairs = m.words * 16;
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
+            PackedPoint a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b = a;
+            const int i0 = 2 * p, i1 = 2 * p + 1;
+            if (i0 < m.n) {
+                const size_t g = (size_t)m.corr_off + i0;
+                a = pack_point_indexed(g, kp_idx, mp_idx, kpA, kpB, mp_xyz, n_kp, n_mp, th2, m);
+                cA[g] = make_float4(a.X, a.Y, a.Z, a.cu);
+                cB[g] = make_float4(a.cv, a.thr, a.band, 0.0f);
+                cC[g] = make_float4(a.u, a.v, 0.0f, 0.0f);
+            }
+            if (i1 < m.n) {
+                const size_t g = (size_t)m.corr_off + i1;
+                b = pack_point_indexed(g, kp_idx, mp_idx, kpA, kpB, mp_xyz, n_kp, n_mp, th2, m);
+                cA[g] = make_float4(b.X, b.Y, b.Z, b.cu);
+                cB[g] = make_float4(b.cv, b.thr, b.band, 0.0f);
+                cC[g] = make_float4(b.u, b.v, 0.0f, 0.0f);
+            }
+            float4* dst = cP + ((size_t)m.word_off * 16 + p) * 4;
+            dst[0] = make_float4(a.X, b.X, a.Y, b.Y);
+            dst[1] = make_float4(a.Z, b.Z, a.cu, b.cu);
+            dst[2] = make_float4(a.cv, b.cv, -a.thr, -b.thr);
+            dst[3] = make_float4(a.band, b.band, a.eps2, b.eps2);
+        }
+    }
+}
+
+// flat p3d / p2d / sigma2 of an indexed batch, on demand (the chained PoseOptimization reads them)
+int rsac_internal_pnp_ensure_flat(rsac_engine* e)
+{
+    PnpState& s = e->pnp;
+    if (s.flat_valid || s.d.total <= 0) return RSAC_OK;
+    const int blocks = (int)std::min<int64_t>(((int64_t)s.d.total + 255) / 256, (int64_t)e->sm_count * 8);
+    ++e->launches;
+    pnp_gather_indexed_kernel<<<blocks, 256, 0, e->stream>>>(s.d.total, (const uint16_t*)s.d_kp_idx.p, (const uint32_t*)s.d_mp_idx.p,
+                                                               (const float*)s.d_kp_uv.p, (const float*)s.d_kp_s2.p, (const float*)s.d_mp_xyz.p,
+                                                               (float*)s.d_p3d.p, (float*)s.d_p2d.p, (float*)s.d_sigma2.p,
+                                                               s.n_keypoints, s.n_mappoints);
+    RSAC_CUDA(e, cudaGetLastError());
+    s.flat_valid = true;
+    return RSAC_OK;
+}
+
+static int pnp_pack(rsac_engine* e)
+{
+    PnpState& s = e->pnp;
+    const BatchDims& d = s.d;
+    if (s.packed) return RSAC_OK;
+    if (d.total > 0 && d.C > 0 && s.indexed_fused) {
+        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN / 2 + 255) / 256)), (unsigned)std::min(d.C, 65535));
+        e->stage_begin(RSAC_STAGE_PACK);
+        if (s.kp_table_dirty) {
+            ++e->launches;
+            pnp_keypoint_table_kernel<<<(s.n_keypoints + 255) / 256, 256, 0, e->stream>>>(
+                s.n_keypoints, (const float*)s.d_kp_uv.p, (const float*)s.d_kp_s2.p, s.kp_th2, s.metas[0].fx, s.metas[0].fy,
+                s.metas[0].cx, s.metas[0].cy, (float4*)s.d_kpA.p, (KpRecord*)s.d_kpB.p);
+            s.kp_table_dirty = false;
+        }
+        pack_pnp_indexed_kernel<<<grid, 256, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, d.C, (const uint16_t*)s.d_kp_idx.p,
+                                                             (const uint32_t*)s.d_mp_idx.p, (const float4*)s.d_kpA.p,
+                                                             (const KpRecord*)s.d_kpB.p, (const float*)s.d_mp_xyz.p, s.n_keypoints,
+                                                             s.n_mappoints, s.kp_th2, (float4*)s.d_cA.p, (float4*)s.d_cB.p,
+                                                             (float4*)s.d_uv.p, (float4*)s.d_cP.p);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+    } else if (d.total > 0 && d.C > 0) {
+        dim3 grid((unsigned)std::max(1, std::min(64, (d.maxN + 255) / 256)), (unsigned)std::min(d.C, 65535));
+        e->stage_begin(RSAC_STAGE_PACK);
+        pack_pnp_kernel<<<grid, 256, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, (const float*)s.d_p3d.p, (const float*)s.d_p2d.p,
+                                                     (const float*)s.d_sigma2.p, (const float*)s.d_th2.p, nullptr, 0,
+                                                     (float4*)s.d_cA.p, (float4*)s.d_cB.p, (float4*)s.d_uv.p, (float4*)s.d_cP.p, d.C);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    s.packed = true;
+    return RSAC_OK;
 }
 
 static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_pnp_indexed_batch* ib);
@@ -285,20 +419,29 @@ static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_p
             RSAC_CUDA(e, cudaMemcpyAsync(s.d_mp_xyz.p, ib->mp_xyz, (size_t)ib->n_mappoints * 12, cudaMemcpyHostToDevice, st));
             s.n_mappoints = ib->n_mappoints;
         }
+        // one parameter set for the whole batch (the reference's call shape): gather and packing are one kernel, fed by a
+        // per-keypoint table (pnp_pack); otherwise the flat arrays are gathered first and packed like a flat upload
+        s.indexed_fused = ib->n_params == 1 && env_int("RSAC_INDEXED_FUSED", 1) != 0;
+        s.flat_valid = false;
+        if (s.indexed_fused) {
+            const float th2v = th2.empty() ? 0.0f : th2[0];
+            const double kk[4] = {ib->K[0], ib->K[1], ib->K[2], ib->K[3]};
+            if (ib->kp_uv || th2v != s.kp_th2 || memcmp(kk, s.kp_K, sizeof(kk)) != 0) s.kp_table_dirty = true;
+            s.kp_th2 = th2v;
+            memcpy(s.kp_K, kk, sizeof(kk));
+            RSAC_TRY(s.d_kpA.ensure(e, (size_t)s.n_keypoints * 16));
+            RSAC_TRY(s.d_kpB.ensure(e, (size_t)s.n_keypoints * sizeof(KpRecord)));
+        }
         if (d.total > 0) {
             RSAC_TRY(s.d_kp_idx.ensure(e, (size_t)d.total * 2));
             RSAC_TRY(s.d_mp_idx.ensure(e, (size_t)d.total * 4));
             RSAC_CUDA(e, cudaMemcpyAsync(s.d_kp_idx.p, ib->kp_idx, (size_t)d.total * 2, cudaMemcpyHostToDevice, st));
             RSAC_CUDA(e, cudaMemcpyAsync(s.d_mp_idx.p, ib->mp_idx, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));
-            const int blocks = (int)std::min<int64_t>(((int64_t)d.total + 255) / 256, (int64_t)e->sm_count * 8);
-            ++e->launches;
-            pnp_gather_indexed_kernel<<<blocks, 256, 0, st>>>(d.total, (const uint16_t*)s.d_kp_idx.p, (const uint32_t*)s.d_mp_idx.p,
-                                                             (const float*)s.d_kp_uv.p, (const float*)s.d_kp_s2.p, (const float*)s.d_mp_xyz.p,
-                                                             (float*)s.d_p3d.p, (float*)s.d_p2d.p, (float*)s.d_sigma2.p,
-                                                             s.n_keypoints, s.n_mappoints);
-            RSAC_CUDA(e, cudaGetLastError());
+            if (!s.indexed_fused) RSAC_TRY(rsac_internal_pnp_ensure_flat(e));
         }
     } else if (d.total > 0) {
+        s.indexed_fused = false;
+        s.flat_valid = true;
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p3d.p, b->p3d, (size_t)d.total * 12, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_p2d.p, b->p2d, (size_t)d.total * 8, cudaMemcpyHostToDevice, st));
         RSAC_CUDA(e, cudaMemcpyAsync(s.d_sigma2.p, b->sigma2, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));

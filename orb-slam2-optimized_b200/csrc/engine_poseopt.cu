@@ -69,6 +69,7 @@ int rsac_poseopt_from_pnp(rsac_engine* e, float bf)
     RSAC_TRY(s.d_full.ensure(e, tot));
     RSAC_TRY(s.d_results.ensure(e, sizeof(rsac_poseopt_result) * (size_t)std::max(C, 1)));
     if (C > 0) {
+        RSAC_TRY(rsac_internal_pnp_ensure_flat(e));      // an indexed batch keeps no flat arrays until somebody asks
         e->stage_begin(RSAC_STAGE_PACK);
         poseopt_from_pnp_kernel<<<C, 128, 0, e->stream>>>((const ProblemMeta*)p.d_metas.p, C, (const rsac_result*)p.d_results.p,
                                                           (const uint32_t*)p.d_masks.p, (const float*)p.d_p3d.p, (const float*)p.d_p2d.p,

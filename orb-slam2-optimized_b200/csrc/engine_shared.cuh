@@ -53,6 +53,9 @@ static int env_int(const char* name, int dflt)
 
 using ScorePlan = ScorePlanPOD;
 
+// engine_pnp.cu: materialises the flat p3d / p2d / sigma2 arrays of an indexed PnP batch (no-op for flat uploads)
+int rsac_internal_pnp_ensure_flat(rsac_engine* e);
+
 template <int MODEL>
 static size_t score_smem_bytes(int chunk_cap, int tile_hyps)
 {

@@ -101,8 +101,13 @@ struct PnpState {
         d_results, d_masks, d_hmasks, d_sel, d_pw, d_us, d_al, d_cov, d_extra, d_visit;
     PinnedBuf h_stage;
     // indexed wire format: the frame's keypoint table and the map-point table stay resident between uploads
-    DevBuf d_kp_uv, d_kp_s2, d_mp_xyz, d_kp_idx, d_mp_idx;
+    DevBuf d_kp_uv, d_kp_s2, d_mp_xyz, d_kp_idx, d_mp_idx, d_kpA, d_kpB;
     int n_keypoints = 0, n_mappoints = 0;
+    bool indexed_fused = false;             // the batch is packed straight from the index pairs (pnp_pack)
+    bool flat_valid = true;                 // d_p3d / d_p2d / d_sigma2 hold the batch (always for flat uploads)
+    bool kp_table_dirty = true;             // per-keypoint records (d_kpA / d_kpB) must be rebuilt
+    float kp_th2 = -1.0f;
+    double kp_K[4] = {0, 0, 0, 0};
     // early exit in phases (RSAC_FLAG_EARLY_EXIT): plans of the two hypothesis ranges, per-problem phase state
     bool ee_planned = false, ee_mode = false, ee_complete = false;
     bool run_eigen = false;                 // the current / last run used RSAC_FLAG_EPNP_EIGEN (selects the solver kernel)
@@ -133,7 +138,7 @@ struct PnpState {
         for (auto& b : ee_visit) b.release();
         DevBuf* all[] = {&d_metas, &d_cP, &d_th2, &d_p3d, &d_p2d, &d_sigma2, &d_cA, &d_cB, &d_uv, &d_tables, &d_poses,
                          &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra, &d_visit,
-                         &d_kp_uv, &d_kp_s2, &d_mp_xyz, &d_kp_idx, &d_mp_idx};
+                         &d_kp_uv, &d_kp_s2, &d_mp_xyz, &d_kp_idx, &d_mp_idx, &d_kpA, &d_kpB};
         for (DevBuf* b : all) b->release();
     }
 };

@@ -285,11 +285,12 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
     float2 C[HPL][12];
     int cnt[HPL];
     uint32_t live[HPL];
+    uint32_t act[HPL];       // live and the pose holds no NaN (see enter_group)
     int g_hyp0 = 0, g_cw = 0, g_n = 0, g_words = 0, g_hypoff = 0, g_problem = 0;
     int64_t g_hmask = 0;
     int cur_k = -1;
 #pragma unroll
-    for (int s = 0; s < HPL; ++s) { cnt[s] = 0; live[s] = 0u; }
+    for (int s = 0; s < HPL; ++s) { cnt[s] = 0; live[s] = 0u; act[s] = 0u; }
 
     bool g_owned = false;    // this CTA scores every chunk of the current group: counts are stored, not accumulated
     auto flush = [&]() {
@@ -329,10 +330,21 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
                     for (int i = 0; i < 6; ++i) { const double2 v = s2[i]; raw[2 * i] = v.x; raw[2 * i + 1] = v.y; }
                 }
                 fold_pose<PT>(raw, fx, fy, c);
+                // A NaN anywhere in the pose makes xc, yc or zc NaN for every point, hence error2 NaN and the
+                // reference's `error2 < mvMaxError` false (PnPsolver.cpp:250-262, MLPnPsolver.cpp:231-249): count 0,
+                // empty mask, without sending n evaluations down the exact path one by one (a minimal set that holds
+                // one map point twice -- two keypoints matched to the same wrong point -- yields such a pose, and one
+                // of them used to stretch a whole scoring launch from 0.045 to 0.15 ms).  Inf entries are NOT
+                // shortcut: 1/Inf = 0 can leave a finite error2.
+                bool has_nan = false;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) has_nan = has_nan || (raw[i] != raw[i]);
+                act[s] = has_nan ? 0u : 0xffffffffu;
                 // each thread keeps the raw poses of its own slots for the exact path (no other thread reads them)
 #pragma unroll
                 for (int i = 0; i < 12; ++i) sraw[(size_t)local * 12 + i] = raw[i];
             } else {
+                act[s] = 0u;
 #pragma unroll
                 for (int i = 0; i < 12; ++i) c[i] = 0.0f;
             }
@@ -395,8 +407,8 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
                 const uint32_t valid = (rem >= 32) ? 0xffffffffu : ((1u << rem) - 1u);
 #pragma unroll
                 for (int s = 0; s < HPL; ++s) {
-                    inl[s] &= valid & live[s];
-                    uint32_t u = ~cert[s] & valid & live[s];
+                    inl[s] &= valid & act[s];
+                    uint32_t u = ~cert[s] & valid & act[s];
                     if (u) {
                         if (args.exact_counter) atomicAdd(args.exact_counter, (unsigned long long)__popc(u));
                         const PT* pose = sraw + (size_t)((warp * HPL + s) * 32 + lane) * 12;

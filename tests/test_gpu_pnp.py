@@ -73,6 +73,36 @@ def test_pnp_cfg1_per_hypothesis_bit_exact(engine, oracle, mode):
     assert sum(o["ok"] for o in orc) >= C - 1          # the synthetic problems are solvable
 
 
+def test_pnp_duplicate_map_points_nan_hypotheses(engine, oracle):
+    """Two keypoints matched to the SAME (wrong) map point: a minimal set that draws both is degenerate and EPnP returns a
+    NaN translation.  The reference scores such a pose as "no inliers" (NaN compares false, PnPsolver.cpp:258-262); the
+    scoring kernel takes a shortcut for NaN poses instead of the exact tier -- hypothesis poses, counts, records and masks
+    must still equal the oracle's, in the exhaustive and in the staged run."""
+    C, n = 6, 300
+    b, offsets = _batch(13, C, n)
+    p3d = b["p3d"].copy()
+    rng = np.random.default_rng(5)
+    tables = [np.asarray(oracle.index_table(int(s), n, 4, 300)).reshape(300, 4).copy() for s in b["seeds"]]
+    for c in range(C):
+        for h in rng.choice(300, 12, replace=False):          # 12 hypotheses per problem draw one map point twice
+            i, j = tables[c][h][0], tables[c][h][2]
+            p3d[c][j] = p3d[c][i]
+    tabs = [t.reshape(-1).astype(np.uint32) for t in tables]
+    toff = np.arange(C + 1, dtype=np.int64) * 1200
+    orc = _oracle_all(oracle, dict(b, p3d=p3d), C, PRM, tabs)
+    assert sum(int(np.isnan(o["hyp_pose"]).any(axis=1).sum()) for o in orc) >= C      # the case is really exercised
+    for flags in (0, capi.FLAG_EARLY_EXIT):
+        res, masks = engine.pnp_solve(offsets, p3d, b["p2d"], b["sigma2"], [b["K"]], capi.ransac_params(**PRM),
+                                      tables=np.concatenate(tabs), table_offsets=toff, flags=flags)
+        _check_results(res, engine.split_masks(masks, offsets), orc)
+        if flags == 0:
+            poses, counts = engine.pnp_hypotheses()
+            for c in range(C):
+                hp, op = poses[c * 300:(c + 1) * 300], orc[c]["hyp_pose"]
+                assert ((hp.view(np.uint32) == op.view(np.uint32)) | (np.isnan(hp) & np.isnan(op))).all(), c
+                assert (counts[c * 300:(c + 1) * 300] == orc[c]["hyp_counts"]).all(), c
+
+
 def test_pnp_device_generated_tables_match_libc(engine, oracle):
     """seeds only: the device restatement of glibc rand() must give the oracle's tables"""
     C, n = 5, 300
@@ -463,3 +493,33 @@ def test_pnp_indexed_wire_format_equals_flat_upload(engine):
     engine.pnp_run(0)
     res3, m3 = engine.pnp_download()
     assert not capi.unpack_mask(m3[:16], n)[:5].any()
+
+
+def test_pnp_indexed_fused_pack_equals_flat_pack(engine, oracle):
+    """The indexed batch is packed by one kernel straight from the index pairs (per-keypoint table of thresholds and bound
+    factors + two f64 products per correspondence).  Its packed records must be the flat path's bit for bit: same records
+    and masks, same per-hypothesis counts, and the same NUMBER of evaluations sent to the exact tier (the bounds decide that
+    and nothing else).  Also: the chained PoseOptimization still finds the flat arrays."""
+    C, n = 24, 411                      # ragged tail in every 32-correspondence word
+    f = synth.reloc_frame(5, C, n_kp=1500, n_match=n, n_map=30000)
+    offsets = (np.arange(C + 1) * n).astype(np.int32)
+    prm = capi.ransac_params(**PRM)
+    res0, m0 = engine.pnp_solve(offsets, f["p3d"], f["p2d"], f["sigma2"], [f["K"]], prm, seeds=f["seeds"], flags=0)
+    ex0 = engine.score_exact_evals()
+    _, cnt0 = engine.pnp_hypotheses()
+    engine.poseopt_from_pnp()
+    engine.poseopt_run()
+    po0, fl0 = engine.poseopt_download()
+    engine.pnp_upload_indexed(offsets, f["kp_idx"], f["mp_idx"], f["K"], prm, seeds=f["seeds"], kp_uv=f["kp_uv"], kp_sigma2=f["kp_sigma2"],
+                              mp_xyz=f["mp_xyz"])
+    engine.pnp_run(0)
+    res1, m1 = engine.pnp_download()
+    ex1 = engine.score_exact_evals()
+    _, cnt1 = engine.pnp_hypotheses()
+    _same_records(res0, res1)
+    assert (m0 == m1).all() and (cnt0 == cnt1).all()
+    assert ex0 == ex1 and ex0 > 0, (ex0, ex1)
+    engine.poseopt_from_pnp()
+    engine.poseopt_run()
+    po1, fl1 = engine.poseopt_download()
+    assert po0.tobytes() == po1.tobytes() and (fl0 == fl1).all()
