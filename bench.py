@@ -795,6 +795,39 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
         dt2 = (time.perf_counter() - t0) / (reps2 * len(pool))
         ex["cfg2_mlpnp"]["batches_in_flight_6"] = {"ms_per_batch": dt2 * 1e3, "frames_per_s": C2 / dt2,
                                                    "evals_per_s": C2 * H2 * N2 / dt2, "timing": "wall clock around 120 batches, synchronised"}
+        # the same with the staged early exit (RSAC_FLAG_EARLY_EXIT, MLPnPsolver.cpp:144-160: the reference returns at the first
+        # successful Refine): fewer hypotheses per batch, so more batches share a wave; records equal the exhaustive run's
+        try:
+            ee_stats = {}
+            for stg in ((32,), (24, 72), (48,)):
+                for q in pool:
+                    q.set_stages(list(stg))
+                    q.mlpnp_run(capi.FLAG_EARLY_EXIT)
+                    q.mlpnp_run(capi.FLAG_EARLY_EXIT)
+                for q in pool:
+                    q.sync()
+                r_ee, _ = pool[0].mlpnp_download()
+                same = all((r_ee[f] == res2[f]).all() for f in ("ok", "n_inliers", "best_hyp", "n_refines", "n_hyp"))
+                t0 = time.perf_counter()
+                for _ in range(reps2):
+                    for q in pool:
+                        q.mlpnp_run(capi.FLAG_EARLY_EXIT)
+                for q in pool:
+                    q.sync()
+                dte = (time.perf_counter() - t0) / (reps2 * len(pool))
+                st2 = pool[0].mlpnp_phase_stats()
+                ee_stats[",".join(str(v) for v in stg)] = {"ms_per_batch": dte * 1e3, "frames_per_s": C2 / dte, "records_equal_exhaustive": bool(same),
+                                                           "hypotheses_done_frac": st2[3] / float(C2 * H2), "frames_in_stage_1": st2[1]}
+            ex["cfg2_mlpnp"]["early_exit_batches_in_flight_6"] = ee_stats
+            eng.set_stages([32])
+            eng.mlpnp_run(capi.FLAG_EARLY_EXIT); eng.mlpnp_run(capi.FLAG_EARLY_EXIT); eng.sync()
+            eng.timer_begin()
+            for _ in range(5):
+                eng.mlpnp_run(capi.FLAG_EARLY_EXIT)
+            ex["cfg2_mlpnp"]["early_exit_one_batch_ms"] = eng.timer_end() / 5
+            eng.set_stages([])
+        except Exception as err:
+            ex["cfg2_mlpnp"]["early_exit_error"] = repr(err)
         for q in pool:
             q.close()
         ps = [synth.sim3_problem(3000 + i, 200, 0.4, 1.0) for i in range(64)]

@@ -42,8 +42,9 @@ extern "C" {
 #define RSAC_FLAG_MLPNP_DISCARD_REFINE 4 /* reproduce MLPnPsolver::Refine not storing its pose (MLPnPsolver.cpp:290-296) */
 #define RSAC_FLAG_EPNP_EIGEN 8      /* 4-point EPnP: null-space basis from the 12x12 M^T M eigen-solve (PnPsolver.cpp:380)
                                        instead of the default Householder QR of M^T (same subspace, different basis) */
-#define RSAC_FLAG_EARLY_EXIT 16     /* PnP: stop where the sequential reference stops (PnPsolver.cpp:225-236 returns at the
-                                       first successful Refine): hypotheses are solved and scored in stages -- the first
+#define RSAC_FLAG_EARLY_EXIT 16     /* PnP and MLPnP: stop where the sequential reference stops (PnPsolver.cpp:225-236 and
+                                       MLPnPsolver.cpp:144-160 return at the first successful Refine): hypotheses are solved
+                                       and scored in stages -- the first
                                        `first_phase` of every problem, the next ones, then the rest, only for the problems
                                        that still need them.
                                        Results are identical to the exhaustive run; hypotheses behind the stopping point
@@ -292,6 +293,11 @@ typedef struct {
 int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b);
 int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out);
 int rsac_mlpnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* d_results_out);
+/* RSAC_FLAG_EARLY_EXIT for MLPnP (MLPnPsolver::iterate returns at the first successful Refine, MLPnPsolver.cpp:144-160): the
+ * same staged scheme as rsac_pnp_run, same records and masks as the exhaustive run.  Stage boundaries: rsac_set_stages /
+ * rsac_set_phases / rsac_set_first_phase; automatic: a batch that fits one wave of the solver kernel runs all its
+ * hypotheses at once.  out[] as rsac_pnp_phase_stats. */
+int rsac_mlpnp_phase_stats(rsac_engine* e, int64_t out[4]);
 int rsac_mlpnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks);
 int rsac_mlpnp_solve(rsac_engine* e, const rsac_mlpnp_batch* b, int flags, rsac_result* results, uint32_t* masks);
 /* per-hypothesis poses in double ([sumH][12]) and counts */

@@ -1,5 +1,6 @@
 // engine_mlpnp.cu -- C ABI for the batched MLPnPsolver (include/ransac_b200.h, "MLPnPsolver").
 #include "engine_shared.cuh"
+#include "engine_early.cuh"
 #include "mlpnp_pipeline.cuh"
 #include "select.cuh"
 
@@ -10,7 +11,7 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
     if (b->C > 0 && !b->K) { e->err = "K is NULL"; return RSAC_ERR_INVALID; }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     PnpState& s = e->mlpnp;
-    s.uploaded = false; s.ran = false; s.tables_ready = false;
+    s.uploaded = false; s.ran = false; s.tables_ready = false; s.ee_mode = false; s.ee_planned = false;
     std::vector<float> th2;
     for (int c = 0; c < b->C; ++c)
         if (b->params[b->n_params == 1 ? 0 : c].min_set != 6) { e->err = "MLPnP needs min_set = 6"; return RSAC_ERR_INVALID; }
@@ -66,31 +67,89 @@ int rsac_mlpnp_upload(rsac_engine* e, const rsac_mlpnp_batch* b)
     return RSAC_OK;
 }
 
-static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out)
+// resident threads of the minimal solver: the staged early exit sizes its first stage from one wave
+static int64_t mlpnp_wave_hyps(rsac_engine* e)
+{
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlpnp_minimal_range_kernel, 128, 0) != cudaSuccess) { cudaGetLastError(); nb = 2; }
+        per_sm = std::max(1, nb) * 128;
+    }
+    return (int64_t)per_sm * e->sm_count;
+}
+
+// Stage boundaries (rsac_set_stages / rsac_set_phases / RSAC_MLPNP_EE_STAGES); automatic: a batch that fits one wave of the
+// solver runs every hypothesis at once (a stage costs one thread latency whatever its size -- cfg2, 64 frames x 300, is a
+// single partial wave), otherwise the first stage is three quarters of a wave and every further stage doubles
+static std::vector<int> mlpnp_stage_bounds(rsac_engine* e, const BatchDims& d)
+{
+    const int64_t wave_h = mlpnp_wave_hyps(e);
+    const int wave = (int)std::min<int64_t>(wave_h / std::max(d.C, 1), INT32_MAX);
+    const int first = e->first_phase > 0 ? e->first_phase : (wave >= d.maxH ? d.maxH : std::max(16, (int)(wave_h * 3 / 4 / std::max(d.C, 1))));
+    return early_stage_bounds(e, d, first, "RSAC_MLPNP_EE_STAGES");
+}
+
+static int mlpnp_launch_solve_range(rsac_engine* e, PnpState& s, const int32_t* list, const int32_t* list_count, int lo, int span, int64_t most)
+{
+    const BatchDims& d = s.d;
+    const int64_t resident = mlpnp_wave_hyps(e) / 128;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((most + 127) / 128, resident));
+    e->stage_begin(RSAC_STAGE_SOLVE);
+    mlpnp_minimal_range_kernel<<<blocks, 128, 0, e->stream>>>((const ProblemMeta*)s.d_metas.p, d.C, list, list_count, lo, span,
+                                                             (const uint32_t*)s.d_tables.p, (const float4*)s.d_cA.p, (const float4*)s.d_uv.p,
+                                                             s.have_cov ? (const double*)s.d_cov.p : nullptr, (double*)s.d_poses.p);
+    e->stage_end(RSAC_STAGE_SOLVE);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+static int mlpnp_select_setup(rsac_engine* e)
+{
+    const BatchDims& d = e->mlpnp.d;
+    const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
+    if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa;
+    RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<1>));
+    const size_t need = (fa.sharedSizeBytes + smem + 1024) * kSelectCtasPerSm;
+    const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
+    RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    return RSAC_OK;
+}
+
+static int mlpnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase = -1)
 {
     PnpState& s = e->mlpnp;
     const BatchDims& d = s.d;
     SelectArgs a;
+    if (s.ee_mode) { a.ee = (int32_t*)s.d_ee.p; a.C = d.C; a.first_phase = s.ee_HA; a.only_phase = only_phase; }
     a.metas = (const ProblemMeta*)s.d_metas.p; a.cA = (const float4*)s.d_cA.p; a.cB = (const float4*)s.d_cB.p; a.cC = (const float4*)s.d_uv.p;
     a.poses = s.d_poses.p; a.counts = (const int32_t*)s.d_counts.p; a.cov = s.have_cov ? (const double*)s.d_cov.p : nullptr;
     a.sel = (uint32_t*)s.d_sel.p; a.pw_s = (double*)s.d_pw.p; a.us_s = nullptr; a.al_s = nullptr; a.tm_s = (double*)s.d_extra.p;
     a.results = s.d_results.p; a.results2 = d_results_out; a.masks = (uint32_t*)s.d_masks.p;
     a.problem_base = e->problem_base; a.flags = flags; a.resume = d_resume;
+    a.problem_ids = (e->n_problem_ids == d.C && d.C > 0) ? (const int32_t*)e->d_problem_ids.p : nullptr;
     const size_t smem = (size_t)(3 * d.maxWords + 1) * 4 + 16;
-    if (smem > 32 * 1024) RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        cudaFuncAttributes fa;
-        RSAC_CUDA(e, cudaFuncGetAttributes(&fa, ransac_select_kernel<1>));
-        const size_t need = (fa.sharedSizeBytes + smem + 1024) * kSelectCtasPerSm;
-        const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
-        RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    }
+    // kernel attributes: a no-op after the first call of a shape; inside a graph capture nothing is left to set
+    // (early_run calls the set-up before it captures)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(e->stream, &cap);
+    if (cap == cudaStreamCaptureStatusNone) RSAC_TRY(mlpnp_select_setup(e));
     e->stage_begin(RSAC_STAGE_SELECT);
     ransac_select_kernel<1><<<d.C, kSelectThreadsMlpnp, smem, e->stream>>>(a);
     e->stage_end(RSAC_STAGE_SELECT);
     RSAC_CUDA(e, cudaGetLastError());
     return RSAC_OK;
 }
+
+template <> struct EarlyHooks<1> {
+    static int solve_range(rsac_engine* e, PnpState& s, const int32_t* list, const int32_t* list_count, int lo, int span, int64_t most)
+    { return mlpnp_launch_solve_range(e, s, list, list_count, lo, span, most); }
+    static int select(rsac_engine* e, int flags, const int32_t* d_resume, void* d_results_out, int only_phase)
+    { return mlpnp_launch_select(e, flags, d_resume, d_results_out, only_phase); }
+    static int setup(rsac_engine* e) { return mlpnp_select_setup(e); }
+    static int stage0_hpl() { return 0; }
+};
 
 int rsac_mlpnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* d_results_out)
 {
@@ -101,6 +160,7 @@ int rsac_mlpnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void
     if (s.d.C == 0) return RSAC_OK;
     RSAC_TRY(e->d_resume.ensure(e, sizeof(int32_t) * (size_t)s.d.C));
     RSAC_CUDA(e, cudaMemcpyAsync(e->d_resume.p, resume_from, sizeof(int32_t) * (size_t)s.d.C, cudaMemcpyHostToDevice, e->stream));
+    RSAC_TRY(early_complete<1>(e, s));     // the last run stopped early: compute what the resumed scan may need
     return mlpnp_launch_select(e, flags, (const int32_t*)e->d_resume.p, d_results_out);
 }
 
@@ -122,6 +182,11 @@ int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
         e->stage_end(RSAC_STAGE_RNG);
         RSAC_CUDA(e, cudaGetLastError());
         s.tables_ready = true;
+    }
+    s.ee_mode = false;
+    if ((flags & RSAC_FLAG_EARLY_EXIT) && d.sumH > 0) {
+        const std::vector<int> bounds = mlpnp_stage_bounds(e, d);
+        if (bounds.size() > 1) return early_run<1>(e, s, flags, d_results_out, bounds);
     }
     if (d.sumH > 0) {
         const int threads = 128;
@@ -147,6 +212,16 @@ int rsac_mlpnp_run(rsac_engine* e, int flags, void* d_results_out)
     }
     s.ran = true;
     return RSAC_OK;
+}
+
+int rsac_mlpnp_phase_stats(rsac_engine* e, int64_t out[4])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    PnpState& s = e->mlpnp;
+    out[0] = out[1] = out[2] = 0;
+    out[3] = s.d.sumH;
+    if (!s.ran) { e->err = "rsac_mlpnp_phase_stats before rsac_mlpnp_run"; return RSAC_ERR_STATE; }
+    return early_stats(e, s, out);
 }
 
 int rsac_mlpnp_download(rsac_engine* e, rsac_result* results, uint32_t* masks)

@@ -427,6 +427,15 @@ class Engine:
     def mlpnp_run(self, flags=0, d_results_out: int | None = None):
         self._ck(self.L.rsac_mlpnp_run(self.h, C.c_int(flags), C.c_void_p(d_results_out or 0)), "mlpnp_run")
 
+    def mlpnp_phase_stats(self):
+        out = (C.c_int64 * 4)()
+        self._ck(self.L.rsac_mlpnp_phase_stats(self.h, out), "mlpnp_phase_stats")
+        return tuple(int(v) for v in out)
+
+    def mlpnp_rerun(self, resume_from, flags=0, d_results_out: int | None = None):
+        r = np.ascontiguousarray(resume_from, np.int32)
+        self._ck(self.L.rsac_mlpnp_rerun(self.h, C.c_int(flags), _p(r), C.c_void_p(d_results_out or 0)), "mlpnp_rerun")
+
     def mlpnp_download(self, want_masks=True):
         res = np.zeros(self._mlpnp_C, RESULT_DTYPE)
         masks = np.zeros(int(self._mlpnp_words.sum()), np.uint32) if want_masks else None

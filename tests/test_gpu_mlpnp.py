@@ -126,3 +126,61 @@ def test_mlpnp_planar_scene(engine, oracle):
         rel = np.abs(gp - op) / np.maximum(1.0, np.abs(op))
         assert finite.mean() > 0.5 and np.nanmax(rel[finite]) < 1e-7
         assert res[c]["ok"] == o["ok"] and res[c]["best_hyp"] == o["best_hyp"]
+
+
+_REC_FIELDS = ("ok", "no_more", "n_inliers", "best_hyp", "refined", "n_refines", "best_count", "n_hyp")
+
+
+def _same_records(a, b):
+    for f in _REC_FIELDS:
+        assert (a[f] == b[f]).all(), (f, np.argwhere(a[f] != b[f]).ravel()[:8])
+    assert (a["R"].view(np.uint32) == b["R"].view(np.uint32)).all()
+    assert (a["t"].view(np.uint32) == b["t"].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("stages", [(8,), (16, 48), (5, 10, 20, 40, 80, 160), (299,)])
+@pytest.mark.parametrize("use_cov", [False, True])
+def test_mlpnp_early_exit_equals_exhaustive(engine, stages, use_cov):
+    """MLPnPsolver::iterate returns at the first successful Refine (MLPnPsolver.cpp:144-160).  The staged run (hypotheses
+    [0, b0) of every frame, later stages only for the frames still without an acceptable hypothesis, replay, clean-up) must
+    give the exhaustive run's records and masks bit for bit -- same device arithmetic, fewer hypotheses computed.  The batch
+    holds easy frames, frames with 70 % outliers (late or no success: the clean-up is exercised) and a frame too small to run."""
+    sizes = [300, 300, 257, 300, 64, 5, 300, 300]
+    outl = [0.3, 0.5, 0.7, 0.72, 0.4, 0.0, 0.75, 0.5]
+    parts = [synth.pnp_problem(8100 + i, max(n, 6), o) for i, (n, o) in enumerate(zip(sizes, outl))]
+    p3d = np.concatenate([p["p3d"][:n] for p, n in zip(parts, sizes)])
+    p2d = np.concatenate([p["p2d"][:n] for p, n in zip(parts, sizes)])
+    s2 = np.concatenate([p["sigma2"][:n] for p, n in zip(parts, sizes)])
+    cov = np.concatenate([synth.bearing_covariances(dict(K=p["K"], sigma2=p["sigma2"][:n])) for p, n in zip(parts, sizes)]) if use_cov else None
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    Kf = np.array([parts[0]["K"]], np.float32)
+    seeds = np.arange(len(sizes), dtype=np.uint32) + 901
+    prm = capi.ransac_params(**PRM)
+    engine.set_stages([])
+    ref, mref = engine.mlpnp_solve(offsets, p3d, p2d, s2, Kf, prm, cov=cov, seeds=seeds, flags=0)
+    try:
+        engine.set_stages(list(stages))
+        for rep in range(3):                      # eager, captured, replayed
+            res, m = engine.mlpnp_solve(offsets, p3d, p2d, s2, Kf, prm, cov=cov, seeds=seeds, flags=capi.FLAG_EARLY_EXIT) if rep == 0 else (None, None)
+            if rep > 0:
+                engine.mlpnp_run(capi.FLAG_EARLY_EXIT)
+                res, m = engine.mlpnp_download()
+            _same_records(ref, res)
+            assert (mref == m).all()
+        st = engine.mlpnp_phase_stats()
+        assert st[0] == stages[0]
+        H = sum(capi.pnp_ransac_setup(n, prm)[1] if n >= 60 else 0 for n in sizes)
+        if stages[0] < 100:
+            assert st[3] < H, "the staged run must skip hypotheses"
+            assert st[1] >= 1, "the hard frames must go on to the second stage"
+        # a later iterate() call resumes anywhere: first the skipped hypotheses are computed, then the replay resumes
+        resume = np.minimum(ref["n_hyp"], 7).astype(np.int32)
+        engine.mlpnp_rerun(resume, flags=capi.FLAG_EARLY_EXIT)
+        r_ee, m_ee = engine.mlpnp_download()
+    finally:
+        engine.set_stages([])
+    engine.mlpnp_solve(offsets, p3d, p2d, s2, Kf, prm, cov=cov, seeds=seeds, flags=0)
+    engine.mlpnp_rerun(resume, flags=0)
+    r_ex, m_ex = engine.mlpnp_download()
+    _same_records(r_ex, r_ee)
+    assert (m_ex == m_ee).all()
