@@ -799,7 +799,7 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
         # successful Refine): fewer hypotheses per batch, so more batches share a wave; records equal the exhaustive run's
         try:
             ee_stats = {}
-            for stg in ((32,), (24, 72), (48,)):
+            for stg in ((128,), (96, 192), (48, 96, 192)):
                 for q in pool:
                     q.set_stages(list(stg))
                     q.mlpnp_run(capi.FLAG_EARLY_EXIT)
@@ -819,7 +819,7 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                 ee_stats[",".join(str(v) for v in stg)] = {"ms_per_batch": dte * 1e3, "frames_per_s": C2 / dte, "records_equal_exhaustive": bool(same),
                                                            "hypotheses_done_frac": st2[3] / float(C2 * H2), "frames_in_stage_1": st2[1]}
             ex["cfg2_mlpnp"]["early_exit_batches_in_flight_6"] = ee_stats
-            eng.set_stages([32])
+            eng.set_stages([128])
             eng.mlpnp_run(capi.FLAG_EARLY_EXIT); eng.mlpnp_run(capi.FLAG_EARLY_EXIT); eng.sync()
             eng.timer_begin()
             for _ in range(5):

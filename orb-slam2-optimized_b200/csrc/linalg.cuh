@@ -320,7 +320,7 @@ __host__ __device__ inline void jacobi_lowest(double* a, double* w, double* v, d
 // a: packed upper triangle in SHARED memory (destroyed); w: NV smallest eigenvalues; v: N x NV (row-major)
 // in shared memory; rec: kMaxSweepsRec*66 double2 in shared memory.
 template <int N, int NV>
-__device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, double2* rec, int lane)
+__device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, double2* rec, int lane, long long* clk = nullptr)
 {
     constexpr int M = N + (N & 1), Hh = M / 2, STEPS = M - 1, SLOTS = STEPS * Hh, NB = Hh * (Hh - 1) / 2;
     constexpr unsigned FULL = 0xffffffffu;
@@ -401,6 +401,7 @@ __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, doubl
         sweeps = sweep + 1;
     }
     __syncwarp();
+    if (clk && lane == 0) { clk[0] = clock64(); clk[1] = sweeps; }     // diagnostic: end of the forward sweeps
     // the NV smallest diagonal entries, ascending, ties to the lower index
     int sel = -1;
     {
@@ -419,21 +420,34 @@ __device__ inline void jacobi_lowest_warp(double* a, double* w, double* v, doubl
         }
     }
     if (lane < NV) {
-        for (int i = 0; i < N; ++i) v[i * NV + lane] = (i == sel) ? 1.0 : 0.0;
+        // back-application of the recorded rotations to e_sel: the vector lives in registers (the pairs of a step are
+        // compile-time constants once the step loop is unrolled; only the sweep loop is dynamic) -- through shared memory
+        // this phase was a third of the eigen-solve (40 k of 125 k cycles: two dependent LDS/STS round trips per rotation)
+        double x[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = (i == sel) ? 1.0 : 0.0;
         for (int sweep = sweeps - 1; sweep >= 0; --sweep) {
             const double2* rs = rec + sweep * SLOTS;
+#pragma unroll
             for (int t = STEPS - 1; t >= 0; --t) {
+                double2 cs[Hh];
+#pragma unroll
+                for (int i = 0; i < Hh; ++i) cs[i] = rs[t * Hh + i];
+#pragma unroll
                 for (int i = Hh - 1; i >= 0; --i) {
-                    const double2 cs = rs[t * Hh + i];
-                    if (cs.y != 0.0) {
-                        const int p = tour_lo(M, t, i), q = tour_hi(M, t, i);
-                        const double xp = v[p * NV + lane], xq = v[q * NV + lane];
-                        v[p * NV + lane] = rfma(cs.x, xp, cs.y * xq);
-                        v[q * NV + lane] = rfma(cs.x, xq, -(cs.y * xp));
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int p = tour_lo(M, t, i), q = tour_hi(M, t, i);
+                    if (q < N && cs[i].y != 0.0) {
+                        const double xp = x[p], xq = x[q < N ? q : p];
+                        x[p] = rfma(cs[i].x, xp, cs[i].y * xq);
+                        x[q < N ? q : p] = rfma(cs[i].x, xq, -(cs[i].y * xp));
                     }
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i * NV + lane] = x[i];
     }
     __syncwarp();
 }

@@ -344,7 +344,7 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
         if (tid == 0) epnp_solve_betas_qr4(al, us, cam, S.cws, S.U4, S.betas);
     } else {
         // 12x12 eigen-solve (:380): warp 0, cooperative schedule of the same rotations
-        if (tid < 32) jacobi_lowest_warp<12, 4>(S.MtM, S.w4, S.U4, s_rec, tid);
+        if (tid < 32) jacobi_lowest_warp<12, 4>(S.MtM, S.w4, S.U4, s_rec, tid, blockIdx.x == 0 ? g_select_clocks + 11 : nullptr);
         __syncthreads();
         RSAC_SEL_MARK(5);
         // L (6x10, :604-637) and rho (:639-647) entry-parallel into shared memory: 72 control-point differences,

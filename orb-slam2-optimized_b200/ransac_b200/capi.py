@@ -123,7 +123,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise FileNotFoundError(f"{LIB_PATH} is missing: run __graft_entry__.build() "
                                     "(python orb-slam2-optimized_b200/build.py); there is no CPU fallback")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(os.environ.get("RSAC_LIB", LIB_PATH))     # RSAC_LIB: a tuning variant built by build.py (RSAC_LIB_OUT)
         L.rsac_last_error.restype = C.c_char_p
         L.rsac_launch_count.restype = C.c_int64
         for f in ("rsac_pnp_total_hypotheses", "rsac_sim3_total_hypotheses", "rsac_mlpnp_total_hypotheses",

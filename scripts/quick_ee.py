@@ -61,3 +61,4 @@ eng.L.rsac_debug_select_clocks(eng.h, clk)
 c = list(clk)
 names = ["start", "found", "refine:begin", "presums", "MtM", "jacobi", "betas", "sums2", "horn+reproj", "score", "end"]
 print("select phases (block 0, cycles):", [(names[i], c[i] - c[i - 1]) for i in range(1, 11)], "total", c[10] - c[0])
+print("12x12 eigen-solve: forward sweeps", c[11] - c[4], "cycles over", c[12], "sweeps; selection + back-application", c[5] - c[11])
