@@ -900,6 +900,40 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                                      "note": "host buffers pageable, one sweep at a time (upload + run + download, synchronous)"}
     except Exception as err:
         ex["indexed_wire_format_error"] = repr(err)
+    # ---- KeyFrameDatabase::DetectRelocalizationCandidates, 64 lost frames against a resident database of
+    # 4096 keyframes (KeyFrameDatabase.cpp:174-284); CPU port = the oracle's inverted-file walk, one thread
+    try:
+        Kd, Qd = 4096, 64
+        dbk = synth.kf_database(21, K=Kd, n_places=256)
+        qsk = [synth.kf_query(500 + i, dbk, (37 * i) % 256) for i in range(Qd)]
+        eng.kfdb_upload(dbk)
+        got = eng.kfdb_detect(qsk, mode=0)
+        for _ in range(2):
+            eng.kfdb_run()
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(10):
+            eng.kfdb_run()
+        msk = eng.timer_end() / 10
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.kfdb_detect(qsk, mode=0)
+        e2ek = (time.perf_counter() - t0) / 3 * 1e3
+        odbk = O.kfdb(dbk)
+        stk = np.zeros(Kd, np.float32)
+        t0 = time.perf_counter()
+        want = [O.detect_candidates(odbk, w, v, mode=0, score_state=stk) for (w, v) in qsk[:8]]
+        dck = (time.perf_counter() - t0) / 8
+        nnz_db = int(dbk["bow_off"][-1])
+        ex["candidate_retrieval"] = {"keyframes": Kd, "queries": Qd, "words_per_vector": nnz_db // Kd, "ms_per_batch": msk, "queries_per_s": Qd / (msk * 1e-3),
+                                     "e2e_ms_per_batch": e2ek, "candidates_mean": float(np.mean([len(g) for g in got])),
+                                     "first_8_equal_oracle": bool(all(g.tolist() == w.tolist() for g, w in zip(got[:8], want))),
+                                     "cpu_port_single_thread_queries_per_s": 1.0 / dck,
+                                     "hbm": {"algorithmic_bytes": Qd * nnz_db * 4, "achieved_gbs": Qd * nnz_db * 4 / (msk * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
+                                     "note": "KeyFrameDatabase.cpp:174-284 batched: every query against every keyframe's BowVector (the database is resident); "
+                                             "the oracle rebuilds its inverted file per call (that part is excluded from no figure: it is what a port would do per query batch)"}
+    except Exception as err:
+        ex["candidate_retrieval_error"] = repr(err)
     # ---- ORBmatcher::SearchByBoW, 1024 candidate keyframes against one frame (Tracking.cpp:1207-1232)
     try:
         Fb = synth.bow_frame(11, 1500, 100)

@@ -421,6 +421,45 @@ int rsac_bow_run(rsac_engine* e);
 int rsac_bow_download(rsac_engine* e, int32_t* matches, int32_t* n_matches);
 int rsac_bow_match(rsac_engine* e, const rsac_bow_batch* b, int32_t* matches, int32_t* n_matches);
 
+/* ------------------------------------------------ KeyFrameDatabase candidate retrieval (batched) */
+/* where the candidate keyframes of every relocalisation / loop closure come from.
+ *   mode 0  KeyFrameDatabase::DetectRelocalizationCandidates(Frame*)          src/KeyFrameDatabase.cpp:174-284  (Tracking.cpp:1199)
+ *   mode 1  KeyFrameDatabase::DetectLoopCandidates(KeyFrame, minScore)        src/KeyFrameDatabase.cpp:51-172   (LoopClosing.cpp:135)
+ * with DBoW2's L1 score (Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-66) and GetBestCovisibilityKeyFrames(10).
+ * The database -- what the two functions read from the keyframes -- is uploaded once and stays resident; keyframe index =
+ * insertion order into the inverted file (KeyFrameDatabase::add), which decides the ORDER of the returned candidates.
+ * score_state: KeyFrame::mRelocScore carried in (NULL = zeros): DetectRelocalizationCandidates reads it for covisible
+ * keyframes that share a word but were not scored by the current query (KeyFrameDatabase.cpp:243-246), i.e. it may hold an
+ * earlier query's score; the engine keeps it on the device from batch to batch and applies the queries of a batch in order. */
+typedef struct {
+    int32_t n_keyframes;
+    const int64_t* bow_off;      /* [n_keyframes + 1] */
+    const uint32_t* bow_word;    /* KeyFrame::mBowVec word ids, ascending per keyframe (std::map order) */
+    const double* bow_val;       /* word values (DBoW2::WordValue = double) */
+    const int32_t* covis;        /* [n_keyframes][10] GetBestCovisibilityKeyFrames(10), -1 padded */
+    const float* score_state;    /* optional [n_keyframes] */
+} rsac_kfdb;
+
+typedef struct {
+    int32_t Q;                   /* queries (<= 65535) */
+    const int64_t* bow_off;      /* [Q + 1] */
+    const uint32_t* bow_word;    /* Frame::mBowVec / KeyFrame::mBowVec of the queries, ascending per query */
+    const double* bow_val;
+    int32_t mode;                /* 0 relocalisation, 1 loop detection */
+    const float* min_score;      /* mode 1: [Q] minScore (LoopClosing.cpp:121-133) */
+    const int64_t* conn_off;     /* mode 1: [Q + 1] */
+    const int32_t* conn;         /* mode 1: pKF->GetConnectedKeyFrames() as database indices (any order) */
+} rsac_kfdb_queries;
+
+int rsac_kfdb_upload(rsac_engine* e, const rsac_kfdb* db);
+int rsac_kfdb_query_upload(rsac_engine* e, const rsac_kfdb_queries* q);
+int rsac_kfdb_run(rsac_engine* e);
+/* counts[Q]: candidates of every query (may exceed cap); candidates[Q][cap]: the first min(count, cap) in the reference's order */
+int rsac_kfdb_download(rsac_engine* e, int32_t* counts, int32_t* candidates, int32_t cap);
+int rsac_kfdb_detect(rsac_engine* e, const rsac_kfdb_queries* q, int32_t* counts, int32_t* candidates, int32_t cap);
+/* mRelocScore of every keyframe after the queries run so far */
+int rsac_kfdb_get_state(rsac_engine* e, float* score_state);
+
 /* ------------------------------------------------ multi-GPU (candidates shard) */
 /* contiguous block partition of C problems over `world` ranks: rank r owns [*first, *first + *count) */
 int rsac_shard_range(int C, int rank, int world, int* first, int* count);

@@ -238,6 +238,20 @@ void orc_three_maxima(const int *histo, int L, int *ind1, int *ind2, int *ind3);
 int orc_search_by_bow(const orc_bow_features *q, const orc_bow_features *t, float nn_ratio, int check_orientation,
                       int mode, int32_t *match_out);
 
+/* ------------------------------------------------ KeyFrameDatabase candidate retrieval */
+/* what DetectRelocalizationCandidates / DetectLoopCandidates read from the keyframe database: keyframe index =
+ * insertion order into the inverted file */
+typedef struct {
+    int K;
+    const int64_t *bow_off;      /* [K+1] */
+    const uint32_t *bow_word;    /* word ids, ascending per keyframe (DBoW2::BowVector is a std::map) */
+    const double *bow_val;       /* WordValue = double */
+    const int32_t *covis;        /* [K][10] KeyFrame::GetBestCovisibilityKeyFrames(10), -1 padded */
+} orc_kfdb;
+double orc_bow_l1_score(int n1, const uint32_t *w1, const double *v1, int n2, const uint32_t *w2, const double *v2);
+int orc_detect_candidates(const orc_kfdb *db, int mode, int nq, const uint32_t *qword, const double *qval, int n_conn,
+                          const int32_t *conn, float min_score, float *score_state, int32_t *out, int cap);
+
 /* ------------------------------------------------ Optimizer::PoseOptimization */
 /* one frame: what Optimizer.cpp:244-323 reads from the Frame and its MapPoints */
 typedef struct {

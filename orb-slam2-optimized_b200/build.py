@@ -26,7 +26,7 @@ OUT = os.path.join(HERE, "libransac_b200.so")
 
 
 def _sources():
-    return sorted(glob.glob(os.path.join(CSRC, "engine*.cu")) + glob.glob(os.path.join(CSRC, "bow*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "engine*.cu")))
 
 
 def _headers_mtime() -> float:

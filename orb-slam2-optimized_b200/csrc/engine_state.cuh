@@ -217,6 +217,23 @@ struct BowState {
     }
 };
 
+struct KfdbState {
+    bool db_ready = false, queries_ready = false, ran = false;
+    int K = 0, K2 = 1, Q = 0, mode = 0;
+    DevBuf d_kf_off, d_kf_word, d_kf_val, d_covis, d_state;
+    DevBuf d_q_off, d_q_word, d_q_val, d_min_score, d_conn_off, d_conn;
+    DevBuf d_cw, d_wstar, d_si, d_eff, d_acc, d_best, d_firstpos, d_keys, d_out, d_min_common, d_best_acc, d_n_out;
+    PinnedBuf h_stage;
+    void release()
+    {
+        DevBuf* all[] = {&d_kf_off, &d_kf_word, &d_kf_val, &d_covis, &d_state, &d_q_off, &d_q_word, &d_q_val, &d_min_score, &d_conn_off,
+                         &d_conn, &d_cw, &d_wstar, &d_si, &d_eff, &d_acc, &d_best, &d_firstpos, &d_keys, &d_out, &d_min_common,
+                         &d_best_acc, &d_n_out};
+        for (DevBuf* b : all) b->release();
+        h_stage.release();
+    }
+};
+
 struct ProfPair {
     int stage;
     cudaEvent_t a, b;
@@ -251,6 +268,7 @@ struct rsac_engine {
     rsac::PoseOptState poseopt;
     rsac::Sim3OptState sim3opt;
     rsac::BowState bow;
+    rsac::KfdbState kfdb;
     rsac::DevBuf d_exact, d_scratch, d_resume, d_problem_ids;
     int32_t n_problem_ids = 0;                   // > 0: rsac_set_problem_ids is in force for batches of exactly this many problems
     uint64_t alloc_epoch = 0;                    // bumped by every device (re)allocation: captured graphs hold raw pointers
@@ -276,7 +294,7 @@ struct rsac_engine {
     }
     void free_all()
     {
-        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release(); sim3opt.release(); bow.release();
+        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release(); sim3opt.release(); bow.release(); kfdb.release();
         d_exact.release(); d_scratch.release(); d_resume.release(); d_problem_ids.release();
     }
 };

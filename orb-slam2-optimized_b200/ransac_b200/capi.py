@@ -110,6 +110,16 @@ class BowBatch(C.Structure):
                 ("nn_ratio", C.c_float), ("check_orientation", C.c_int32), ("mode", C.c_int32)]
 
 
+class KfDb(C.Structure):
+    _fields_ = [("n_keyframes", C.c_int32), ("bow_off", C.c_void_p), ("bow_word", C.c_void_p), ("bow_val", C.c_void_p),
+                ("covis", C.c_void_p), ("score_state", C.c_void_p)]
+
+
+class KfDbQueries(C.Structure):
+    _fields_ = [("Q", C.c_int32), ("bow_off", C.c_void_p), ("bow_word", C.c_void_p), ("bow_val", C.c_void_p), ("mode", C.c_int32),
+                ("min_score", C.c_void_p), ("conn_off", C.c_void_p), ("conn", C.c_void_p)]
+
+
 class RsacError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__(f"ransac_b200 error {code}: {msg}")
@@ -628,6 +638,55 @@ class Engine:
         self.bow_upload(sets, query_set, target_set, nn_ratio, check_orientation, mode)
         self.bow_run()
         return self.bow_download()
+
+    # -- keyframe database: candidate retrieval
+    def kfdb_upload(self, db, score_state=None):
+        """db: dict(bow_off int64 [K+1], bow_word uint32, bow_val float64, covis int32 [K,10])"""
+        off = np.ascontiguousarray(db["bow_off"], np.int64)
+        w = np.ascontiguousarray(db["bow_word"], np.uint32)
+        v = np.ascontiguousarray(db["bow_val"], np.float64)
+        cv = np.ascontiguousarray(db["covis"], np.int32).reshape(-1, 10)
+        st = None if score_state is None else np.ascontiguousarray(score_state, np.float32)
+        d = KfDb(len(off) - 1, _p(off), _p(w), _p(v), _p(cv), _p(st))
+        self._ck(self.L.rsac_kfdb_upload(self.h, C.byref(d)), "rsac_kfdb_upload")
+        self._kfdb_K = len(off) - 1
+
+    def kfdb_query_upload(self, queries, mode=0, min_score=None, conn=None):
+        """queries: list of (words uint32 ascending, values float64); conn: list of connected-keyframe index lists (mode 1)"""
+        Q = len(queries)
+        off = np.concatenate([[0], np.cumsum([len(q[0]) for q in queries])]).astype(np.int64)
+        w = np.ascontiguousarray(np.concatenate([q[0] for q in queries]) if Q else [], np.uint32)
+        v = np.ascontiguousarray(np.concatenate([q[1] for q in queries]) if Q else [], np.float64)
+        ms = co = cn = None
+        if mode == 1:
+            ms = np.ascontiguousarray(min_score, np.float32).reshape(-1)
+            co = np.concatenate([[0], np.cumsum([len(c) for c in conn])]).astype(np.int64)
+            cn = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32) for c in conn]) if Q and co[-1] else [], np.int32)
+        d = KfDbQueries(Q, _p(off), _p(w) if len(w) else None, _p(v) if len(v) else None, mode, _p(ms), _p(co), _p(cn) if cn is not None and len(cn) else None)
+        self._ck(self.L.rsac_kfdb_query_upload(self.h, C.byref(d)), "rsac_kfdb_query_upload")
+        self._kfdb_Q = Q
+
+    def kfdb_run(self):
+        self._ck(self.L.rsac_kfdb_run(self.h), "rsac_kfdb_run")
+
+    def kfdb_download(self, cap=None):
+        """list of candidate index arrays, one per query, in the reference's order"""
+        Q = self._kfdb_Q
+        cap = max(1, self._kfdb_K if cap is None else cap)
+        counts = np.zeros(max(Q, 1), np.int32)
+        cand = np.full((max(Q, 1), cap), -1, np.int32)
+        self._ck(self.L.rsac_kfdb_download(self.h, _p(counts), _p(cand), C.c_int32(cap)), "rsac_kfdb_download")
+        return [cand[q, :min(int(counts[q]), cap)].copy() for q in range(Q)], counts[:Q]
+
+    def kfdb_detect(self, queries, mode=0, min_score=None, conn=None):
+        self.kfdb_query_upload(queries, mode, min_score, conn)
+        self.kfdb_run()
+        return self.kfdb_download()[0]
+
+    def kfdb_state(self):
+        st = np.zeros(max(self._kfdb_K, 1), np.float32)
+        self._ck(self.L.rsac_kfdb_get_state(self.h, _p(st)), "rsac_kfdb_get_state")
+        return st[:self._kfdb_K]
 
     def score_exact_evals(self) -> int:
         return self.L.rsac_score_exact_evals(self.h)

@@ -304,3 +304,55 @@ def reloc_frame(seed: int, C: int, n_kp: int = 2000, n_match: int = 500, outlier
     flat = dict(p3d=mp[mp_idx], p2d=uv[kp_idx], sigma2=sigma2[kp_idx])
     return dict(K=np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float64), R=R, t=t, kp_uv=uv, kp_sigma2=sigma2, mp_xyz=mp, kp_idx=kp_idx, mp_idx=mp_idx,
                 seeds=(np.arange(C) + 1000 * (seed % 1000) + 7).astype(np.uint32), **flat)
+
+
+# ---------------------------------------------------------------- keyframe database (candidate retrieval)
+def _bow_vector(rng, words):
+    """an L1-normalised TF-IDF style BowVector over the given word ids (ascending, unique)"""
+    words = np.unique(np.asarray(words, np.uint32))
+    w = rng.gamma(2.0, 1.0, len(words)) + 0.05
+    return words, (w / w.sum()).astype(np.float64)
+
+
+def kf_database(seed: int, K: int = 400, n_places: int = 40, vocab: int = 100000, words_per_kf: int = 900, pool: int = 2500):
+    """A keyframe database as KeyFrameDatabase sees it: K keyframes along a trajectory through n_places places.  A place owns a
+    pool of vocabulary words; a keyframe draws most of its words from the pools of the (one or two) places it sees and a few
+    from anywhere (words shared by unrelated keyframes).  Covisibility: the ten nearest keyframes of the same stretch of the
+    trajectory, nearest first.  Returns the CSR arrays (bow_off, bow_word, bow_val), covis [K,10], and the place of every keyframe."""
+    rng = np.random.default_rng(seed)
+    pools = [rng.choice(vocab, pool, replace=False) for _ in range(n_places)]
+    place = np.minimum((np.arange(K) * n_places) // max(K, 1), n_places - 1)
+    # revisits: the last tenth of the trajectory goes back to the first places (what loop closing looks for)
+    nrev = K // 10
+    if nrev:
+        place[K - nrev:] = place[:nrev]
+    offs, ws, vs = [0], [], []
+    for k in range(K):
+        p = place[k]
+        q = min(p + 1, n_places - 1)
+        mix = rng.random()
+        n_local = int(words_per_kf * 0.85)
+        a = rng.choice(pools[p], int(n_local * (0.5 + 0.5 * mix)), replace=False)
+        b = rng.choice(pools[q], max(1, n_local - len(a)), replace=False)
+        c = rng.integers(0, vocab, words_per_kf - n_local)
+        w, v = _bow_vector(rng, np.concatenate([a, b, c]))
+        ws.append(w); vs.append(v); offs.append(offs[-1] + len(w))
+    covis = np.full((K, 10), -1, np.int32)
+    for k in range(K):
+        near = [j for d in range(1, 9) for j in (k - d, k + d) if 0 <= j < K and abs(int(place[j]) - int(place[k])) <= 1]
+        if rng.random() < 0.3:
+            near = near[:rng.integers(0, 6)]                  # young keyframes have few connections
+        covis[k, :min(10, len(near))] = near[:10]
+    return dict(K=K, bow_off=np.array(offs, np.int64), bow_word=np.concatenate(ws), bow_val=np.concatenate(vs), covis=covis,
+                place=place, pools=pools, vocab=vocab)
+
+
+def kf_query(seed: int, db: dict, place: int, n_words: int = 1000):
+    """the BowVector of a frame that looks at `place`"""
+    rng = np.random.default_rng(seed)
+    p = int(place)
+    q = min(p + 1, len(db["pools"]) - 1)
+    a = rng.choice(db["pools"][p], int(n_words * 0.6), replace=False)
+    b = rng.choice(db["pools"][q], int(n_words * 0.25), replace=False)
+    c = rng.integers(0, db["vocab"], n_words - len(a) - len(b))
+    return _bow_vector(rng, np.concatenate([a, b, c]))

@@ -470,6 +470,43 @@ def search_by_bow(q: _Keep, t: _Keep, nn_ratio=0.75, check_orientation=True, mod
     return out[:n_out], n
 
 
+class KfDb(C.Structure):
+    _fields_ = [("K", C.c_int), ("bow_off", C.c_void_p), ("bow_word", C.c_void_p), ("bow_val", C.c_void_p), ("covis", C.c_void_p)]
+
+
+def kfdb(db):
+    """db: dict(bow_off int64 [K+1], bow_word uint32, bow_val float64, covis int32 [K,10])"""
+    off = np.ascontiguousarray(db["bow_off"], np.int64)
+    w = np.ascontiguousarray(db["bow_word"], np.uint32)
+    v = np.ascontiguousarray(db["bow_val"], np.float64)
+    cv = np.ascontiguousarray(db["covis"], np.int32).reshape(-1, 10)
+    st = KfDb(len(off) - 1, _p(off), _p(w), _p(v), _p(cv))
+    return _Keep(st, off, w, v, cv)
+
+
+def bow_l1_score(w1, v1, w2, v2):
+    w1, w2 = np.ascontiguousarray(w1, np.uint32), np.ascontiguousarray(w2, np.uint32)
+    v1, v2 = np.ascontiguousarray(v1, np.float64), np.ascontiguousarray(v2, np.float64)
+    f = lib().orc_bow_l1_score
+    f.restype = C.c_double
+    return f(C.c_int(len(w1)), _p(w1), _p(v1), C.c_int(len(w2)), _p(w2), _p(v2))
+
+
+def detect_candidates(db: _Keep, qword, qval, mode=0, conn=None, min_score=0.0, score_state=None):
+    """KeyFrameDatabase::DetectRelocalizationCandidates (mode 0) / DetectLoopCandidates (mode 1): candidate keyframe
+    indices in the reference's order.  score_state (float32 [K]) is updated in place (mode 0)."""
+    qw = np.ascontiguousarray(qword, np.uint32)
+    qv = np.ascontiguousarray(qval, np.float64)
+    cn = np.ascontiguousarray(conn if conn is not None else [], np.int32)
+    out = np.empty(max(db.st.K, 1), np.int32)
+    if score_state is not None:
+        assert score_state.dtype == np.float32 and score_state.flags.c_contiguous
+    n = lib().orc_detect_candidates(C.byref(db.st), C.c_int(mode), C.c_int(len(qw)), _p(qw), _p(qv), C.c_int(len(cn)), _p(cn) if len(cn) else None,
+                                    C.c_float(min_score), None if score_state is None else _p(score_state), _p(out), C.c_int(len(out)))
+    assert n >= 0
+    return out[:n].copy()
+
+
 class PoseOptProblem(C.Structure):
     _fields_ = [("n", C.c_int), ("p3d", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p),
                 ("K", C.c_float * 5), ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3)]
