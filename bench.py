@@ -921,9 +921,10 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
         e2ek = (time.perf_counter() - t0) / 3 * 1e3
         odbk = O.kfdb(dbk)
         stk = np.zeros(Kd, np.float32)
-        t0 = time.perf_counter()
-        want = [O.detect_candidates(odbk, w, v, mode=0, score_state=stk) for (w, v) in qsk[:8]]
-        dck = (time.perf_counter() - t0) / 8
+        want, dck = [], 0.0
+        for (w, v) in qsk[:8]:
+            want.append(O.detect_candidates(odbk, w, v, mode=0, score_state=stk))
+            dck += O.kfdb_last_query_seconds() / 8
         nnz_db = int(dbk["bow_off"][-1])
         ex["candidate_retrieval"] = {"keyframes": Kd, "queries": Qd, "words_per_vector": nnz_db // Kd, "ms_per_batch": msk, "queries_per_s": Qd / (msk * 1e-3),
                                      "e2e_ms_per_batch": e2ek, "candidates_mean": float(np.mean([len(g) for g in got])),
@@ -931,9 +932,38 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                                      "cpu_port_single_thread_queries_per_s": 1.0 / dck,
                                      "hbm": {"algorithmic_bytes": Qd * nnz_db * 4, "achieved_gbs": Qd * nnz_db * 4 / (msk * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
                                      "note": "KeyFrameDatabase.cpp:174-284 batched: every query against every keyframe's BowVector (the database is resident); "
-                                             "the oracle rebuilds its inverted file per call (that part is excluded from no figure: it is what a port would do per query batch)"}
+                                             "CPU figure: the oracle's inverted-file walk + scoring of one query, the (per-call) rebuild of its inverted file excluded"}
     except Exception as err:
         ex["candidate_retrieval_error"] = repr(err)
+    # ---- ORBmatcher::SearchBySim3 (ORBmatcher.cpp:948-1171), 64 keyframe pairs of ~1500 features each
+    try:
+        prs = [synth.kf_view_pair(700 + i, n_points=1200, n_extra=400, prematched=0.3) for i in range(8)]
+        vws = [v for p_ in prs for v in (p_["kf1"], p_["kf2"])]
+        NP = 64
+        k1i, k2i = [2 * (i % 8) for i in range(NP)], [2 * (i % 8) + 1 for i in range(NP)]
+        eng.sim3_search_upload(vws, k1i, k2i, [prs[i % 8]["K"] for i in range(NP)], [prs[i % 8]["R12"] for i in range(NP)],
+                               [prs[i % 8]["t12"] for i in range(NP)], 7.5, [prs[i % 8]["matched12_in"] for i in range(NP)])
+        for _ in range(3):
+            eng.sim3_search_run()
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(20):
+            eng.sim3_search_run()
+        mss = eng.timer_end() / 20
+        gm, gn = eng.sim3_search_download()
+        ok1, ok2 = O.kf_view(prs[0]["kf1"]), O.kf_view(prs[0]["kf2"])
+        t0 = time.perf_counter()
+        for _ in range(5):
+            wm, wn = O.search_by_sim3(ok1, ok2, prs[0]["K"], prs[0]["R12"], prs[0]["t12"], 7.5, prs[0]["matched12_in"])
+        dcs = (time.perf_counter() - t0) / 5
+        feats = sum(vws[a]["n_feat"] + vws[b_]["n_feat"] for a, b_ in zip(k1i, k2i))
+        ex["search_by_sim3"] = {"pairs": NP, "features_per_keyframe_mean": feats / (2.0 * NP), "ms_per_batch": mss, "pairs_per_s": NP / (mss * 1e-3),
+                                "matches_mean": float(np.mean(gn)), "pair_0_equals_oracle": bool(gm[0].tolist() == wm.tolist() and int(gn[0]) == wn),
+                                "cpu_port_single_thread_pairs_per_s": 1.0 / dcs,
+                                "note": "ORBmatcher.cpp:948-1171 batched: one thread per (pair, direction, map point), grid-window walk in the "
+                                        "reference's order; 8 distinct synthetic pairs cycled; bit-identical to the oracle"}
+    except Exception as err:
+        ex["search_by_sim3_error"] = repr(err)
     # ---- ORBmatcher::SearchByBoW, 1024 candidate keyframes against one frame (Tracking.cpp:1207-1232)
     try:
         Fb = synth.bow_frame(11, 1500, 100)

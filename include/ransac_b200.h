@@ -460,6 +460,55 @@ int rsac_kfdb_detect(rsac_engine* e, const rsac_kfdb_queries* q, int32_t* counts
 /* mRelocScore of every keyframe after the queries run so far */
 int rsac_kfdb_get_state(rsac_engine* e, float* score_state);
 
+/* ------------------------------------------------ ORBmatcher::SearchBySim3 (batched) */
+/* the guided matching between Sim3Solver and Optimizer::OptimizeSim3 in LoopClosing::ComputeSim3
+ * (LoopClosing.cpp:286-311: SearchBySim3(mpCurrentKF, pKF, vpMapPointMatches, R, t, 7.5)); src/ORBmatcher.cpp:948-1171.
+ * A keyframe view is what the function reads from a KeyFrame and its MapPoints (KeyFrame::GetFeaturesInArea
+ * src/KeyFrame.cpp:560-599, IsInImage :601-604, MapPoint::PredictScale src/MapPoint.cpp:367-382). */
+typedef struct {
+    int32_t n_feat;
+    const float* kp_xy;          /* [n_feat][2] mvKeysUn[i].pt */
+    const int32_t* kp_octave;    /* [n_feat] mvKeysUn[i].octave */
+    const uint32_t* desc;        /* [n_feat][8] mDescriptors rows */
+    const uint8_t* mp_valid;     /* [n_feat] the feature has a MapPoint that is not bad */
+    const float* mp_xyz;         /* [n_feat][3] MapPoint::GetWorldPos() */
+    const uint32_t* mp_desc;     /* [n_feat][8] MapPoint::GetDescriptor() */
+    const float* mp_maxdist;     /* [n_feat] MapPoint::mfMaxDistance */
+    const float* mp_mindist;     /* [n_feat] MapPoint::mfMinDistance */
+    float Rcw[9], tcw[3];        /* GetRotation(), GetTranslation() */
+    float bounds[4];             /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+    int32_t grid_cols, grid_rows;/* mnGridCols, mnGridRows */
+    float grid_w_inv, grid_h_inv;/* mfGridElementWidthInv, mfGridElementHeightInv */
+    const int32_t* grid_off;     /* [grid_cols*grid_rows + 1] mGrid[ix][iy] at ix*grid_rows + iy */
+    const int32_t* grid_idx;     /* feature indices per cell in insertion order */
+    int32_t n_levels;            /* mnScaleLevels (<= 16) */
+    const float* scale_factors;  /* [n_levels] mvScaleFactors */
+    float log_scale_factor;      /* mfLogScaleFactor */
+} rsac_kf_view;
+
+typedef struct {
+    int32_t n_views;
+    const rsac_kf_view* views;
+    int32_t C;                   /* keyframe pairs */
+    const int32_t* kf1;          /* [C] view index of pKF1 */
+    const int32_t* kf2;          /* [C] */
+    const float* K;              /* [C][4] pKF1's fx, fy, cx, cy (the reference projects with them in both directions) */
+    const float* R12;            /* [C][9] */
+    const float* t12;            /* [C][3] */
+    const float* s12;            /* [C] or NULL = 1 (the reference is fixed-scale; upstream's s12 is supported) */
+    float th;                    /* 7.5 in ComputeSim3 */
+    const int32_t* matched12_in; /* optional, concatenated per pair [views[kf1[c]].n_feat]: vpMatches12 on entry as the KF2 feature
+                                    index of the matched MapPoint (GetIndexInKeyFrame(pKF2)), -2 = a MapPoint KF2 does not observe,
+                                    -1 = no match */
+} rsac_sim3_search_batch;
+
+int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b);
+int rsac_sim3_search_run(rsac_engine* e);
+/* match12: concatenated per pair [views[kf1[c]].n_feat]: the KF2 feature newly matched to each KF1 feature
+ * (vpMatches12[i1] = vpMapPoints2[idx2], ORBmatcher.cpp:1164) or -1; n_found[C]: the return values */
+int rsac_sim3_search_download(rsac_engine* e, int32_t* match12, int32_t* n_found);
+int rsac_sim3_search(rsac_engine* e, const rsac_sim3_search_batch* b, int32_t* match12, int32_t* n_found);
+
 /* ------------------------------------------------ multi-GPU (candidates shard) */
 /* contiguous block partition of C problems over `world` ranks: rank r owns [*first, *first + *count) */
 int rsac_shard_range(int C, int rank, int world, int* first, int* count);

@@ -249,8 +249,36 @@ typedef struct {
     const int32_t *covis;        /* [K][10] KeyFrame::GetBestCovisibilityKeyFrames(10), -1 padded */
 } orc_kfdb;
 double orc_bow_l1_score(int n1, const uint32_t *w1, const double *v1, int n2, const uint32_t *w2, const double *v2);
+double orc_kfdb_last_query_seconds(void);
 int orc_detect_candidates(const orc_kfdb *db, int mode, int nq, const uint32_t *qword, const double *qval, int n_conn,
                           const int32_t *conn, float min_score, float *score_state, int32_t *out, int cap);
+
+/* ------------------------------------------------ guided matching */
+/* what SearchBySim3 / SearchByProjection read from a KeyFrame (or Frame) and its MapPoints */
+typedef struct {
+    int n_feat;
+    const float *kp_xy;          /* [n][2] mvKeysUn[i].pt */
+    const int32_t *kp_octave;    /* [n] mvKeysUn[i].octave */
+    const uint32_t *desc;        /* [n][8] mDescriptors rows */
+    const uint8_t *mp_valid;     /* [n] feature has a MapPoint that is not bad */
+    const float *mp_xyz;         /* [n][3] MapPoint::GetWorldPos() */
+    const uint32_t *mp_desc;     /* [n][8] MapPoint::GetDescriptor() */
+    const float *mp_maxdist;     /* [n] mfMaxDistance */
+    const float *mp_mindist;     /* [n] mfMinDistance */
+    float Rcw[9], tcw[3];        /* GetRotation(), GetTranslation() */
+    float bounds[4];             /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+    int grid_cols, grid_rows;    /* mnGridCols, mnGridRows */
+    float grid_w_inv, grid_h_inv;/* mfGridElementWidthInv, mfGridElementHeightInv */
+    const int32_t *grid_off;     /* [cols*rows + 1], cell (ix, iy) at ix*rows + iy */
+    const int32_t *grid_idx;     /* feature indices per cell, ascending (AssignFeaturesToGrid order) */
+    int n_levels;                /* mnScaleLevels */
+    const float *scale_factors;  /* [n_levels] mvScaleFactors */
+    float log_scale_factor;      /* mfLogScaleFactor */
+} orc_kf_view;
+int orc_features_in_area(const orc_kf_view *kf, float x, float y, float r, int32_t *out);
+int orc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);
+int orc_search_by_sim3(const orc_kf_view *kf1, const orc_kf_view *kf2, const float K[4], const float R12[9], const float t12[3],
+                       float s12, float th, const int32_t *matched12_in, int32_t *match12_out);
 
 /* ------------------------------------------------ Optimizer::PoseOptimization */
 /* one frame: what Optimizer.cpp:244-323 reads from the Frame and its MapPoints */

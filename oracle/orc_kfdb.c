@@ -25,7 +25,19 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "orc.h"
+
+/* seconds the last orc_detect_candidates call spent AFTER rebuilding the inverted file (the reference maintains its
+ * inverted file incrementally, so only the walk and the scoring are its per-query cost); bench.py's CPU figure */
+static double g_last_query_seconds = 0.0;
+double orc_kfdb_last_query_seconds(void) { return g_last_query_seconds; }
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 /* L1Scoring::score (ScoringObject.cpp:23-66) on two ascending (word, value) arrays */
 double orc_bow_l1_score(int n1, const uint32_t *w1, const double *v1, int n2, const uint32_t *w2, const double *v2)
@@ -80,6 +92,7 @@ int orc_detect_candidates(const orc_kfdb *db, int mode, int nq, const uint32_t *
     int64_t *inv_off = NULL;
     int32_t *inv_kf = NULL;
     if (build_inverted(db, &mw, &inv_off, &inv_kf)) return -1;
+    const double t_query0 = now_s();
     int *query = (int *)calloc((size_t)(K > 0 ? K : 1), sizeof(int));        /* mnRelocQuery / mnLoopQuery == this query */
     int *words = (int *)calloc((size_t)(K > 0 ? K : 1), sizeof(int));        /* mnRelocWords / mnLoopWords */
     char *connected = (char *)calloc((size_t)(K > 0 ? K : 1), 1);
@@ -172,6 +185,7 @@ int orc_detect_candidates(const orc_kfdb *db, int mode, int nq, const uint32_t *
     }
     if (mode == 0 && score_state) memcpy(score_state, score, sizeof(float) * (size_t)K);
 done:
+    g_last_query_seconds = now_s() - t_query0;
     free(inv_off); free(inv_kf); free(query); free(words); free(connected); free(share); free(score);
     free(sm_kf); free(sm_s); free(acc_kf); free(acc_s); free(added);
     return n_out;

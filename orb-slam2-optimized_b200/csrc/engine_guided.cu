@@ -1,0 +1,159 @@
+// engine_guided.cu -- C ABI for the batched ORBmatcher::SearchBySim3 (include/ransac_b200.h).
+#include "engine_shared.cuh"
+#include "guided.cuh"
+
+int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b)
+{
+    if (!e || !b || b->n_views < 0 || b->C < 0 || (b->n_views > 0 && !b->views)) return RSAC_ERR_INVALID;
+    if (b->C > 0 && (!b->kf1 || !b->kf2 || !b->K || !b->R12 || !b->t12)) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    GuidedState& s = e->guided;
+    s.uploaded = false; s.ran = false;
+    const int V = b->n_views, C = b->C;
+    std::vector<KfViewDev> views(std::max(V, 1));
+    int64_t nfeat = 0, ngoff = 0, ngidx = 0;
+    for (int i = 0; i < V; ++i) {
+        const rsac_kf_view& v = b->views[i];
+        const int64_t cells = (int64_t)v.grid_cols * v.grid_rows;
+        if (v.n_feat < 0 || v.grid_cols <= 0 || v.grid_rows <= 0 || cells > (1 << 20) || !v.grid_off || v.n_levels < 1 || v.n_levels > kGuidedMaxLevels ||
+            !v.scale_factors || (v.n_feat > 0 && (!v.kp_xy || !v.kp_octave || !v.desc || !v.mp_valid || !v.mp_xyz || !v.mp_desc || !v.mp_maxdist || !v.mp_mindist))) {
+            e->err = "bad keyframe view"; return RSAC_ERR_INVALID;
+        }
+        if (v.grid_off[0] != 0 || v.grid_off[cells] < 0 || (v.grid_off[cells] > 0 && !v.grid_idx)) { e->err = "bad keyframe grid"; return RSAC_ERR_INVALID; }
+        for (int64_t k = 0; k < cells; ++k)
+            if (v.grid_off[k + 1] < v.grid_off[k]) { e->err = "grid_off must ascend"; return RSAC_ERR_INVALID; }
+        for (int k = 0; k < v.grid_off[cells]; ++k)
+            if (v.grid_idx[k] < 0 || v.grid_idx[k] >= v.n_feat) { e->err = "grid index out of range"; return RSAC_ERR_INVALID; }
+        KfViewDev& d = views[i];
+        memset(&d, 0, sizeof(d));
+        d.feat_off = (int32_t)nfeat; d.n_feat = v.n_feat;
+        d.goff_off = (int32_t)ngoff; d.gidx_off = (int32_t)ngidx;
+        d.grid_cols = v.grid_cols; d.grid_rows = v.grid_rows; d.n_levels = v.n_levels;
+        d.grid_w_inv = v.grid_w_inv; d.grid_h_inv = v.grid_h_inv; d.log_scale_factor = v.log_scale_factor;
+        memcpy(d.Rcw, v.Rcw, sizeof(d.Rcw)); memcpy(d.tcw, v.tcw, sizeof(d.tcw)); memcpy(d.bounds, v.bounds, sizeof(d.bounds));
+        for (int k = 0; k < v.n_levels; ++k) d.scale_factors[k] = v.scale_factors[k];
+        nfeat += v.n_feat; ngoff += cells + 1; ngidx += v.grid_off[cells];
+        if (nfeat > INT32_MAX / 8 || ngoff > INT32_MAX || ngidx > INT32_MAX) { e->err = "batch too large"; return RSAC_ERR_INVALID; }
+    }
+    std::vector<int64_t> off1(C + 1, 0), off2(C + 1, 0);
+    s.maxN1 = 0; s.maxN = 0;
+    for (int c = 0; c < C; ++c) {
+        const int a = b->kf1[c], q = b->kf2[c];
+        if (a < 0 || a >= V || q < 0 || q >= V) { e->err = "view index out of range"; return RSAC_ERR_INVALID; }
+        off1[c + 1] = off1[c] + views[a].n_feat;
+        off2[c + 1] = off2[c] + views[q].n_feat;
+        s.maxN1 = std::max(s.maxN1, views[a].n_feat);
+        s.maxN = std::max(s.maxN, std::max(views[a].n_feat, views[q].n_feat));
+    }
+    s.C = C; s.n_views = V; s.total1 = off1[C]; s.total2 = off2[C]; s.th = b->th;
+    s.have_matched = b->matched12_in != nullptr && s.total1 > 0;
+    s.have_scale = b->s12 != nullptr;
+
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t nf = (size_t)std::max<int64_t>(nfeat, 1), c1 = (size_t)std::max(C, 1);
+    struct Seg { DevBuf* d; size_t bytes, off; };
+    Seg seg[] = {{&s.d_views, sizeof(KfViewDev) * views.size(), 0}, {&s.d_kp_xy, 8 * nf, 0}, {&s.d_kp_octave, 4 * nf, 0}, {&s.d_desc, 32 * nf, 0},
+                 {&s.d_mp_valid, nf, 0}, {&s.d_mp_xyz, 12 * nf, 0}, {&s.d_mp_desc, 32 * nf, 0}, {&s.d_mp_maxdist, 4 * nf, 0},
+                 {&s.d_mp_mindist, 4 * nf, 0}, {&s.d_grid_off, 4 * (size_t)std::max<int64_t>(ngoff, 1), 0},
+                 {&s.d_grid_idx, 4 * (size_t)std::max<int64_t>(ngidx, 1), 0}, {&s.d_kf1, 4 * c1, 0}, {&s.d_kf2, 4 * c1, 0}, {&s.d_K, 16 * c1, 0},
+                 {&s.d_R12, 36 * c1, 0}, {&s.d_t12, 12 * c1, 0}, {&s.d_s12, 4 * c1, 0}, {&s.d_off1, 8 * (c1 + 1), 0}, {&s.d_off2, 8 * (c1 + 1), 0},
+                 {&s.d_matched_in, 4 * (size_t)std::max<int64_t>(s.total1, 1), 0}};
+    size_t total = 0;
+    for (auto& g : seg) { g.off = total; total = al(total + g.bytes); }
+    char* h = (char*)s.h_stage.ensure(total);
+    if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
+    memset(h, 0, total);
+    memcpy(h + seg[0].off, views.data(), sizeof(KfViewDev) * views.size());
+    for (int i = 0; i < V; ++i) {
+        const rsac_kf_view& v = b->views[i];
+        const KfViewDev& d = views[i];
+        const size_t f = (size_t)d.feat_off, n = (size_t)v.n_feat;
+        const int64_t cells = (int64_t)v.grid_cols * v.grid_rows;
+        if (n > 0) {
+            memcpy(h + seg[1].off + 8 * f, v.kp_xy, 8 * n); memcpy(h + seg[2].off + 4 * f, v.kp_octave, 4 * n);
+            memcpy(h + seg[3].off + 32 * f, v.desc, 32 * n); memcpy(h + seg[4].off + f, v.mp_valid, n);
+            memcpy(h + seg[5].off + 12 * f, v.mp_xyz, 12 * n); memcpy(h + seg[6].off + 32 * f, v.mp_desc, 32 * n);
+            memcpy(h + seg[7].off + 4 * f, v.mp_maxdist, 4 * n); memcpy(h + seg[8].off + 4 * f, v.mp_mindist, 4 * n);
+        }
+        memcpy(h + seg[9].off + 4 * (size_t)d.goff_off, v.grid_off, 4 * (size_t)(cells + 1));
+        if (v.grid_off[cells] > 0) memcpy(h + seg[10].off + 4 * (size_t)d.gidx_off, v.grid_idx, 4 * (size_t)v.grid_off[cells]);
+    }
+    if (C > 0) {
+        memcpy(h + seg[11].off, b->kf1, 4 * (size_t)C); memcpy(h + seg[12].off, b->kf2, 4 * (size_t)C);
+        memcpy(h + seg[13].off, b->K, 16 * (size_t)C); memcpy(h + seg[14].off, b->R12, 36 * (size_t)C); memcpy(h + seg[15].off, b->t12, 12 * (size_t)C);
+        if (b->s12) memcpy(h + seg[16].off, b->s12, 4 * (size_t)C);
+    }
+    memcpy(h + seg[17].off, off1.data(), 8 * (size_t)(C + 1));
+    memcpy(h + seg[18].off, off2.data(), 8 * (size_t)(C + 1));
+    if (s.have_matched) memcpy(h + seg[19].off, b->matched12_in, 4 * (size_t)s.total1);
+    for (auto& g : seg) {
+        RSAC_TRY(g.d->ensure(e, g.bytes));
+        RSAC_CUDA(e, cudaMemcpyAsync(g.d->p, h + g.off, g.bytes, cudaMemcpyHostToDevice, e->stream));
+    }
+    s.h_stage.mark(e->stream);
+    const size_t t1 = (size_t)std::max<int64_t>(s.total1, 1), t2 = (size_t)std::max<int64_t>(s.total2, 1);
+    RSAC_TRY(s.d_already1.ensure(e, t1)); RSAC_TRY(s.d_already2.ensure(e, t2));
+    RSAC_TRY(s.d_m1.ensure(e, 4 * t1)); RSAC_TRY(s.d_m2.ensure(e, 4 * t2));
+    RSAC_TRY(s.d_match12.ensure(e, 4 * t1)); RSAC_TRY(s.d_n_found.ensure(e, 4 * c1));
+    s.uploaded = true;
+    return RSAC_OK;
+}
+
+int rsac_sim3_search_run(rsac_engine* e)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    GuidedState& s = e->guided;
+    if (!s.uploaded) { e->err = "rsac_sim3_search_run before rsac_sim3_search_upload"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    s.ran = true;
+    if (s.C == 0) return RSAC_OK;
+    Sim3SearchArgs a;
+    a.views = (const KfViewDev*)s.d_views.p; a.kp_xy = (const float*)s.d_kp_xy.p; a.kp_octave = (const int32_t*)s.d_kp_octave.p;
+    a.desc = (const uint32_t*)s.d_desc.p; a.mp_valid = (const uint8_t*)s.d_mp_valid.p; a.mp_xyz = (const float*)s.d_mp_xyz.p;
+    a.mp_desc = (const uint32_t*)s.d_mp_desc.p; a.mp_maxdist = (const float*)s.d_mp_maxdist.p; a.mp_mindist = (const float*)s.d_mp_mindist.p;
+    a.grid_off = (const int32_t*)s.d_grid_off.p; a.grid_idx = (const int32_t*)s.d_grid_idx.p;
+    a.C = s.C; a.kf1 = (const int32_t*)s.d_kf1.p; a.kf2 = (const int32_t*)s.d_kf2.p; a.K = (const float*)s.d_K.p;
+    a.R12 = (const float*)s.d_R12.p; a.t12 = (const float*)s.d_t12.p; a.s12 = s.have_scale ? (const float*)s.d_s12.p : nullptr; a.th = s.th;
+    a.off1 = (const int64_t*)s.d_off1.p; a.off2 = (const int64_t*)s.d_off2.p;
+    a.matched_in = s.have_matched ? (const int32_t*)s.d_matched_in.p : nullptr;
+    a.already1 = (uint8_t*)s.d_already1.p; a.already2 = (uint8_t*)s.d_already2.p; a.m1 = (int32_t*)s.d_m1.p; a.m2 = (int32_t*)s.d_m2.p;
+    a.match12 = (int32_t*)s.d_match12.p; a.n_found = (int32_t*)s.d_n_found.p;
+    RSAC_CUDA(e, cudaMemsetAsync(s.d_already2.p, 0, (size_t)std::max<int64_t>(s.total2, 1), st));
+    RSAC_CUDA(e, cudaMemsetAsync(s.d_n_found.p, 0, 4 * (size_t)s.C, st));
+    const dim3 g1((unsigned)std::max(1, (s.maxN1 + 255) / 256), (unsigned)s.C);
+    const dim3 gs((unsigned)std::max(1, (s.maxN + 127) / 128), (unsigned)(2 * s.C));
+    e->stage_begin(RSAC_STAGE_PACK);
+    sim3_search_prepare_kernel<<<g1, 256, 0, st>>>(a);
+    e->stage_end(RSAC_STAGE_PACK);
+    e->stage_begin(RSAC_STAGE_SOLVE);
+    sim3_search_kernel<<<gs, 128, 0, st>>>(a);
+    e->stage_end(RSAC_STAGE_SOLVE);
+    e->stage_begin(RSAC_STAGE_SELECT);
+    sim3_search_agree_kernel<<<g1, 256, 0, st>>>(a);
+    e->stage_end(RSAC_STAGE_SELECT);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+int rsac_sim3_search_download(rsac_engine* e, int32_t* match12, int32_t* n_found)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    GuidedState& s = e->guided;
+    if (!s.ran) { e->err = "rsac_sim3_search_download before rsac_sim3_search_run"; return RSAC_ERR_STATE; }
+    if (s.C > 0) {
+        if (match12 && s.total1 > 0) RSAC_CUDA(e, cudaMemcpyAsync(match12, s.d_match12.p, 4 * (size_t)s.total1, cudaMemcpyDeviceToHost, e->stream));
+        if (n_found) RSAC_CUDA(e, cudaMemcpyAsync(n_found, s.d_n_found.p, 4 * (size_t)s.C, cudaMemcpyDeviceToHost, e->stream));
+    }
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_sim3_search(rsac_engine* e, const rsac_sim3_search_batch* b, int32_t* match12, int32_t* n_found)
+{
+    int rc = rsac_sim3_search_upload(e, b);
+    if (rc) return rc;
+    rc = rsac_sim3_search_run(e);
+    if (rc) return rc;
+    return rsac_sim3_search_download(e, match12, n_found);
+}

@@ -234,6 +234,25 @@ struct KfdbState {
     }
 };
 
+struct GuidedState {
+    bool uploaded = false, ran = false;
+    int C = 0, n_views = 0, maxN1 = 0, maxN = 0;
+    int64_t total1 = 0, total2 = 0;
+    bool have_matched = false, have_scale = false;
+    float th = 7.5f;
+    DevBuf d_views, d_kp_xy, d_kp_octave, d_desc, d_mp_valid, d_mp_xyz, d_mp_desc, d_mp_maxdist, d_mp_mindist, d_grid_off, d_grid_idx,
+        d_kf1, d_kf2, d_K, d_R12, d_t12, d_s12, d_off1, d_off2, d_matched_in, d_already1, d_already2, d_m1, d_m2, d_match12, d_n_found;
+    PinnedBuf h_stage;
+    void release()
+    {
+        DevBuf* all[] = {&d_views, &d_kp_xy, &d_kp_octave, &d_desc, &d_mp_valid, &d_mp_xyz, &d_mp_desc, &d_mp_maxdist, &d_mp_mindist,
+                         &d_grid_off, &d_grid_idx, &d_kf1, &d_kf2, &d_K, &d_R12, &d_t12, &d_s12, &d_off1, &d_off2, &d_matched_in,
+                         &d_already1, &d_already2, &d_m1, &d_m2, &d_match12, &d_n_found};
+        for (DevBuf* b : all) b->release();
+        h_stage.release();
+    }
+};
+
 struct ProfPair {
     int stage;
     cudaEvent_t a, b;
@@ -269,6 +288,7 @@ struct rsac_engine {
     rsac::Sim3OptState sim3opt;
     rsac::BowState bow;
     rsac::KfdbState kfdb;
+    rsac::GuidedState guided;
     rsac::DevBuf d_exact, d_scratch, d_resume, d_problem_ids;
     int32_t n_problem_ids = 0;                   // > 0: rsac_set_problem_ids is in force for batches of exactly this many problems
     uint64_t alloc_epoch = 0;                    // bumped by every device (re)allocation: captured graphs hold raw pointers
@@ -294,7 +314,7 @@ struct rsac_engine {
     }
     void free_all()
     {
-        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release(); sim3opt.release(); bow.release(); kfdb.release();
+        pnp.release(); mlpnp.release(); score.release(); sim3.release(); poseopt.release(); sim3opt.release(); bow.release(); kfdb.release(); guided.release();
         d_exact.release(); d_scratch.release(); d_resume.release(); d_problem_ids.release();
     }
 };

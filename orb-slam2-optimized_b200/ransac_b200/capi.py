@@ -120,6 +120,19 @@ class KfDbQueries(C.Structure):
                 ("min_score", C.c_void_p), ("conn_off", C.c_void_p), ("conn", C.c_void_p)]
 
 
+class KfView(C.Structure):
+    _fields_ = [("n_feat", C.c_int32), ("kp_xy", C.c_void_p), ("kp_octave", C.c_void_p), ("desc", C.c_void_p), ("mp_valid", C.c_void_p),
+                ("mp_xyz", C.c_void_p), ("mp_desc", C.c_void_p), ("mp_maxdist", C.c_void_p), ("mp_mindist", C.c_void_p),
+                ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("bounds", C.c_float * 4), ("grid_cols", C.c_int32), ("grid_rows", C.c_int32),
+                ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float), ("grid_off", C.c_void_p), ("grid_idx", C.c_void_p),
+                ("n_levels", C.c_int32), ("scale_factors", C.c_void_p), ("log_scale_factor", C.c_float)]
+
+
+class Sim3SearchBatch(C.Structure):
+    _fields_ = [("n_views", C.c_int32), ("views", C.c_void_p), ("C", C.c_int32), ("kf1", C.c_void_p), ("kf2", C.c_void_p), ("K", C.c_void_p),
+                ("R12", C.c_void_p), ("t12", C.c_void_p), ("s12", C.c_void_p), ("th", C.c_float), ("matched12_in", C.c_void_p)]
+
+
 class RsacError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__(f"ransac_b200 error {code}: {msg}")
@@ -687,6 +700,50 @@ class Engine:
         st = np.zeros(max(self._kfdb_K, 1), np.float32)
         self._ck(self.L.rsac_kfdb_get_state(self.h, _p(st)), "rsac_kfdb_get_state")
         return st[:self._kfdb_K]
+
+    # -- guided matching: ORBmatcher::SearchBySim3
+    def sim3_search_upload(self, views, kf1, kf2, K, R12, t12, th=7.5, matched12_in=None, s12=None):
+        """views: list of keyframe-view dicts (synth.kf_view); kf1 / kf2: view index per pair; K [C,4], R12 [C,9], t12 [C,3];
+        matched12_in: list of per-pair int32 arrays (or None)"""
+        keep = []
+        arr = (KfView * max(len(views), 1))()
+        for i, v in enumerate(views):
+            a = [np.ascontiguousarray(v["kp_xy"], np.float32), np.ascontiguousarray(v["kp_octave"], np.int32), np.ascontiguousarray(v["desc"], np.uint32),
+                 np.ascontiguousarray(v["mp_valid"], np.uint8), np.ascontiguousarray(v["mp_xyz"], np.float32), np.ascontiguousarray(v["mp_desc"], np.uint32),
+                 np.ascontiguousarray(v["mp_maxdist"], np.float32), np.ascontiguousarray(v["mp_mindist"], np.float32),
+                 np.ascontiguousarray(v["grid_off"], np.int32), np.ascontiguousarray(v["grid_idx"], np.int32), np.ascontiguousarray(v["scale_factors"], np.float32)]
+            keep += a
+            arr[i] = KfView(int(v["n_feat"]), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]),
+                            (C.c_float * 9)(*np.asarray(v["Rcw"], np.float32).reshape(-1)), (C.c_float * 3)(*np.asarray(v["tcw"], np.float32).reshape(-1)),
+                            (C.c_float * 4)(*np.asarray(v["bounds"], np.float32)), int(v["grid_cols"]), int(v["grid_rows"]), float(v["grid_w_inv"]),
+                            float(v["grid_h_inv"]), _p(a[8]), _p(a[9]), int(v["n_levels"]), _p(a[10]), float(v["log_scale_factor"]))
+        k1, k2 = np.ascontiguousarray(kf1, np.int32), np.ascontiguousarray(kf2, np.int32)
+        Kc = np.ascontiguousarray(K, np.float32).reshape(-1, 4)
+        R = np.ascontiguousarray(R12, np.float32).reshape(-1, 9)
+        t = np.ascontiguousarray(t12, np.float32).reshape(-1, 3)
+        sc = None if s12 is None else np.ascontiguousarray(s12, np.float32)
+        mi = None if matched12_in is None else np.ascontiguousarray(np.concatenate([np.asarray(m, np.int32) for m in matched12_in]) if len(k1) else [], np.int32)
+        b = Sim3SearchBatch(len(views), C.cast(arr, C.c_void_p), len(k1), _p(k1), _p(k2), _p(Kc), _p(R), _p(t), _p(sc), C.c_float(th),
+                            _p(mi) if mi is not None and len(mi) else None)
+        self._ck(self.L.rsac_sim3_search_upload(self.h, C.byref(b)), "rsac_sim3_search_upload")
+        self._s3s_n1 = [int(views[i]["n_feat"]) for i in k1]
+
+    def sim3_search_run(self):
+        self._ck(self.L.rsac_sim3_search_run(self.h), "rsac_sim3_search_run")
+
+    def sim3_search_download(self):
+        """(list of per-pair match12 arrays, n_found [C])"""
+        n1 = self._s3s_n1
+        flat = np.empty(max(int(sum(n1)), 1), np.int32)
+        nf = np.zeros(max(len(n1), 1), np.int32)
+        self._ck(self.L.rsac_sim3_search_download(self.h, _p(flat), _p(nf)), "rsac_sim3_search_download")
+        offs = np.concatenate([[0], np.cumsum(n1)]).astype(np.int64)
+        return [flat[offs[i]:offs[i + 1]].copy() for i in range(len(n1))], nf[:len(n1)]
+
+    def sim3_search(self, views, kf1, kf2, K, R12, t12, th=7.5, matched12_in=None, s12=None):
+        self.sim3_search_upload(views, kf1, kf2, K, R12, t12, th, matched12_in, s12)
+        self.sim3_search_run()
+        return self.sim3_search_download()
 
     def score_exact_evals(self) -> int:
         return self.L.rsac_score_exact_evals(self.h)

@@ -356,3 +356,93 @@ def kf_query(seed: int, db: dict, place: int, n_words: int = 1000):
     b = rng.choice(db["pools"][q], int(n_words * 0.25), replace=False)
     c = rng.integers(0, db["vocab"], n_words - len(a) - len(b))
     return _bow_vector(rng, np.concatenate([a, b, c]))
+
+
+# ---------------------------------------------------------------- keyframe views for guided matching
+GRID_COLS, GRID_ROWS = 64, 48      # FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.hpp:20-21)
+
+
+def _grid_csr(xy: np.ndarray, cam=EUROC):
+    """Frame::AssignFeaturesToGrid (src/Frame.cpp:293-318) + PosInGrid (:449-459): cell (ix, iy) at ix*ROWS + iy, features in index order"""
+    w_inv = np.float32(GRID_COLS) / np.float32(cam["width"] - 0.0)
+    h_inv = np.float32(GRID_ROWS) / np.float32(cam["height"] - 0.0)
+    px = np.round((xy[:, 0] - np.float32(0)) * w_inv).astype(np.int64)
+    py = np.round((xy[:, 1] - np.float32(0)) * h_inv).astype(np.int64)
+    ok = (px >= 0) & (px < GRID_COLS) & (py >= 0) & (py < GRID_ROWS)
+    cell = np.where(ok, px * GRID_ROWS + py, -1)
+    off = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
+    idx = []
+    for c in range(GRID_COLS * GRID_ROWS):
+        members = np.flatnonzero(cell == c)
+        idx.append(members)
+        off[c + 1] = off[c] + len(members)
+    return off, (np.concatenate(idx) if idx else np.zeros(0)).astype(np.int32), float(w_inv), float(h_inv)
+
+
+def kf_view(rng, R, t, mp_xyz, mp_desc, mp_maxdist, mp_mindist, visible, n_extra=400, flip_bits=20, cam=EUROC, pix_noise=0.7):
+    """What ORBmatcher reads from one keyframe: features = the visible map points (projected, noisy pixel, octave predicted from
+    the distance, descriptor = the map point's with a few bits flipped) followed by n_extra features without a map point."""
+    sf = np.array([1.2 ** i for i in range(8)], np.float32)
+    Xc = mp_xyz[visible].astype(np.float64) @ R.T + t
+    uv = project(Xc, cam) + rng.normal(size=(len(visible), 2)) * pix_noise
+    dist = np.linalg.norm(Xc, axis=1)
+    lvl = np.clip(np.ceil(np.log(mp_maxdist[visible] / dist) / np.log(1.2)) - rng.integers(0, 2, len(visible)), 0, 7).astype(np.int32)
+    inside = (uv[:, 0] > 1) & (uv[:, 0] < cam["width"] - 1) & (uv[:, 1] > 1) & (uv[:, 1] < cam["height"] - 1) & (Xc[:, 2] > 0.1)
+    visible = visible[inside]
+    uv, lvl = uv[inside], lvl[inside]
+    n_mp = len(visible)
+    d = mp_desc[visible].copy()
+    for i in range(n_mp):
+        bits = rng.choice(256, rng.integers(0, flip_bits + 1), replace=False)
+        for b in bits:
+            d[i, b >> 5] ^= np.uint32(1) << np.uint32(b & 31)
+    ex_uv = np.stack([rng.uniform(1, cam["width"] - 1, n_extra), rng.uniform(1, cam["height"] - 1, n_extra)], 1)
+    ex_d = rng.integers(0, 2 ** 32, (n_extra, 8), dtype=np.uint64).astype(np.uint32)
+    n = n_mp + n_extra
+    perm = rng.permutation(n)                                  # features in detection order, not map-point order
+    kp_xy = np.concatenate([uv, ex_uv]).astype(np.float32)[perm]
+    octave = np.concatenate([lvl, rng.integers(0, 8, n_extra).astype(np.int32)])[perm]
+    desc = np.concatenate([d, ex_d])[perm]
+    mp_id = np.concatenate([visible, np.full(n_extra, -1)]).astype(np.int64)[perm]
+    valid = (mp_id >= 0).astype(np.uint8)
+    bad = (rng.random(n) < 0.03) & (mp_id >= 0)                # a few bad map points (isBad)
+    valid[bad] = 0
+    safe = np.maximum(mp_id, 0)
+    off, idx, w_inv, h_inv = _grid_csr(kp_xy, cam)
+    return dict(n_feat=n, kp_xy=kp_xy, kp_octave=octave.astype(np.int32), desc=np.ascontiguousarray(desc), mp_valid=valid, mp_id=mp_id,
+                mp_xyz=np.ascontiguousarray(mp_xyz[safe], np.float32), mp_desc=np.ascontiguousarray(mp_desc[safe]),
+                mp_maxdist=np.ascontiguousarray(mp_maxdist[safe], np.float32), mp_mindist=np.ascontiguousarray(mp_mindist[safe], np.float32),
+                Rcw=R.astype(np.float32), tcw=t.astype(np.float32), bounds=np.array([0.0, cam["width"], 0.0, cam["height"]], np.float32),
+                grid_cols=GRID_COLS, grid_rows=GRID_ROWS, grid_w_inv=w_inv, grid_h_inv=h_inv, grid_off=off, grid_idx=idx,
+                n_levels=8, scale_factors=sf, log_scale_factor=float(np.float32(np.log(np.float32(1.2)))))
+
+
+def kf_view_pair(seed: int, n_points: int = 1200, n_extra: int = 400, pose_noise: float = 0.01, prematched: float = 0.3, cam=EUROC):
+    """Two keyframes of a loop closure looking at the same n_points map points from nearby poses, the Sim3 (R12, t12, s = 1)
+    that Sim3Solver would hand over (ground truth + a small perturbation), and the matches SearchByBoW already found
+    (matched12_in: KF2 feature index, -2 = a map point KF2 does not observe, -1 = none)."""
+    rng = np.random.default_rng(seed)
+    R1, t1 = random_pose(rng, 0.3, 0.5)
+    dR, dt = random_pose(rng, 0.15, 0.6)
+    R2, t2 = dR @ R1, dR @ t1 + dt
+    Xc1 = frustum_points(rng, n_points, cam, 2.0, 15.0)
+    Xw = (Xc1 - t1) @ R1
+    mp_desc = rng.integers(0, 2 ** 32, (n_points, 8), dtype=np.uint64).astype(np.uint32)
+    ref_dist = np.linalg.norm(Xc1, axis=1)
+    ref_lvl = rng.integers(0, 5, n_points)
+    mp_maxdist = (ref_dist * (1.2 ** ref_lvl)).astype(np.float32)          # MapPoint::UpdateNormalAndDepth: dist * levelScaleFactor
+    mp_mindist = (mp_maxdist / np.float32(1.2 ** 7)).astype(np.float32)
+    vis = np.arange(n_points)
+    kf1 = kf_view(rng, R1, t1, Xw, mp_desc, mp_maxdist, mp_mindist, vis[rng.random(n_points) < 0.9], n_extra, cam=cam)
+    kf2 = kf_view(rng, R2, t2, Xw, mp_desc, mp_maxdist, mp_mindist, vis[rng.random(n_points) < 0.9], n_extra, cam=cam)
+    # T12 = T1w * T2w^-1 (+ noise)
+    nR, nt = random_pose(rng, pose_noise, pose_noise * 3)
+    R12 = nR @ R1 @ R2.T
+    t12 = nR @ (t1 - R1 @ R2.T @ t2) + nt
+    idx2_of = {int(m): i for i, m in enumerate(kf2["mp_id"]) if m >= 0}
+    matched = np.full(kf1["n_feat"], -1, np.int32)
+    for i, m in enumerate(kf1["mp_id"]):
+        if m >= 0 and rng.random() < prematched:
+            matched[i] = idx2_of.get(int(m), -2)
+    K = np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32)
+    return dict(kf1=kf1, kf2=kf2, K=K, R12=R12.astype(np.float32), t12=t12.astype(np.float32), matched12_in=matched)

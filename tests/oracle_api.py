@@ -492,6 +492,12 @@ def bow_l1_score(w1, v1, w2, v2):
     return f(C.c_int(len(w1)), _p(w1), _p(v1), C.c_int(len(w2)), _p(w2), _p(v2))
 
 
+def kfdb_last_query_seconds():
+    f = lib().orc_kfdb_last_query_seconds
+    f.restype = C.c_double
+    return f()
+
+
 def detect_candidates(db: _Keep, qword, qval, mode=0, conn=None, min_score=0.0, score_state=None):
     """KeyFrameDatabase::DetectRelocalizationCandidates (mode 0) / DetectLoopCandidates (mode 1): candidate keyframe
     indices in the reference's order.  score_state (float32 [K]) is updated in place (mode 0)."""
@@ -505,6 +511,49 @@ def detect_candidates(db: _Keep, qword, qval, mode=0, conn=None, min_score=0.0, 
                                     C.c_float(min_score), None if score_state is None else _p(score_state), _p(out), C.c_int(len(out)))
     assert n >= 0
     return out[:n].copy()
+
+
+class KfView(C.Structure):
+    _fields_ = [("n_feat", C.c_int), ("kp_xy", C.c_void_p), ("kp_octave", C.c_void_p), ("desc", C.c_void_p), ("mp_valid", C.c_void_p),
+                ("mp_xyz", C.c_void_p), ("mp_desc", C.c_void_p), ("mp_maxdist", C.c_void_p), ("mp_mindist", C.c_void_p),
+                ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("bounds", C.c_float * 4), ("grid_cols", C.c_int), ("grid_rows", C.c_int),
+                ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float), ("grid_off", C.c_void_p), ("grid_idx", C.c_void_p),
+                ("n_levels", C.c_int), ("scale_factors", C.c_void_p), ("log_scale_factor", C.c_float)]
+
+
+def kf_view(v):
+    a = dict(kp_xy=np.ascontiguousarray(v["kp_xy"], np.float32), kp_octave=np.ascontiguousarray(v["kp_octave"], np.int32),
+             desc=np.ascontiguousarray(v["desc"], np.uint32), mp_valid=np.ascontiguousarray(v["mp_valid"], np.uint8),
+             mp_xyz=np.ascontiguousarray(v["mp_xyz"], np.float32), mp_desc=np.ascontiguousarray(v["mp_desc"], np.uint32),
+             mp_maxdist=np.ascontiguousarray(v["mp_maxdist"], np.float32), mp_mindist=np.ascontiguousarray(v["mp_mindist"], np.float32),
+             grid_off=np.ascontiguousarray(v["grid_off"], np.int32), grid_idx=np.ascontiguousarray(v["grid_idx"], np.int32),
+             scale_factors=np.ascontiguousarray(v["scale_factors"], np.float32))
+    st = KfView(int(v["n_feat"]), _p(a["kp_xy"]), _p(a["kp_octave"]), _p(a["desc"]), _p(a["mp_valid"]), _p(a["mp_xyz"]), _p(a["mp_desc"]),
+                _p(a["mp_maxdist"]), _p(a["mp_mindist"]), (C.c_float * 9)(*np.asarray(v["Rcw"], np.float32).reshape(-1)),
+                (C.c_float * 3)(*np.asarray(v["tcw"], np.float32).reshape(-1)), (C.c_float * 4)(*np.asarray(v["bounds"], np.float32)),
+                int(v["grid_cols"]), int(v["grid_rows"]), float(v["grid_w_inv"]), float(v["grid_h_inv"]), _p(a["grid_off"]), _p(a["grid_idx"]),
+                int(v["n_levels"]), _p(a["scale_factors"]), float(v["log_scale_factor"]))
+    return _Keep(st, *a.values())
+
+
+def features_in_area(kf: _Keep, x, y, r):
+    out = np.empty(max(kf.st.n_feat, 1), np.int32)
+    n = lib().orc_features_in_area(C.byref(kf.st), C.c_float(x), C.c_float(y), C.c_float(r), _p(out))
+    return out[:n].copy()
+
+
+def predict_scale(max_distance, current_dist, log_scale_factor, n_levels):
+    return lib().orc_predict_scale(C.c_float(max_distance), C.c_float(current_dist), C.c_float(log_scale_factor), C.c_int(n_levels))
+
+
+def search_by_sim3(kf1: _Keep, kf2: _Keep, K, R12, t12, th=7.5, matched12_in=None, s12=1.0):
+    """ORBmatcher::SearchBySim3: (match12 [N1] = KF2 feature newly matched to each KF1 feature or -1, nFound)"""
+    K = np.ascontiguousarray(K, np.float32); R12 = np.ascontiguousarray(R12, np.float32).reshape(9); t12 = np.ascontiguousarray(t12, np.float32)
+    mi = None if matched12_in is None else np.ascontiguousarray(matched12_in, np.int32)
+    out = np.empty(max(kf1.st.n_feat, 1), np.int32)
+    n = lib().orc_search_by_sim3(C.byref(kf1.st), C.byref(kf2.st), _p(K), _p(R12), _p(t12), C.c_float(s12), C.c_float(th), None if mi is None else _p(mi), _p(out))
+    assert n >= 0
+    return out[:kf1.st.n_feat].copy(), n
 
 
 class PoseOptProblem(C.Structure):

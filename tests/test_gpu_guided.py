@@ -1,0 +1,67 @@
+"""GPU parity: batched ORBmatcher::SearchBySim3 (CUDA, through the C ABI) vs the CPU oracle.
+Index output: the match arrays must be equal element for element."""
+import numpy as np
+import pytest
+
+from ransac_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_pairs(oracle, pairs, th, with_matched=True, s12=None):
+    out = []
+    for i, p in enumerate(pairs):
+        k1, k2 = oracle.kf_view(p["kf1"]), oracle.kf_view(p["kf2"])
+        out.append(oracle.search_by_sim3(k1, k2, p["K"], p["R12"], p["t12"], th, p["matched12_in"] if with_matched else None,
+                                         s12=1.0 if s12 is None else float(s12[i])))
+    return out
+
+
+def test_search_by_sim3_batch_equals_oracle(engine, oracle):
+    """six keyframe pairs of different sizes in one batch, with the matches SearchByBoW already found"""
+    pairs = [synth.kf_view_pair(10 + i, n_points=300 + 250 * i, n_extra=100 + 60 * i, prematched=0.1 * i) for i in range(6)]
+    views = [v for p in pairs for v in (p["kf1"], p["kf2"])]
+    kf1, kf2 = [2 * i for i in range(6)], [2 * i + 1 for i in range(6)]
+    got, nf = engine.sim3_search(views, kf1, kf2, [p["K"] for p in pairs], [p["R12"] for p in pairs], [p["t12"] for p in pairs], 7.5,
+                                 [p["matched12_in"] for p in pairs])
+    want = _oracle_pairs(oracle, pairs, 7.5)
+    total = 0
+    for i in range(6):
+        assert got[i].tolist() == want[i][0].tolist(), i
+        assert nf[i] == want[i][1]
+        total += int(nf[i])
+    assert total > 600
+    # same batch without prior matches, a different window
+    got, nf = engine.sim3_search(views, kf1, kf2, [p["K"] for p in pairs], [p["R12"] for p in pairs], [p["t12"] for p in pairs], 4.0)
+    want = _oracle_pairs(oracle, pairs, 4.0, with_matched=False)
+    for i in range(6):
+        assert got[i].tolist() == want[i][0].tolist() and nf[i] == want[i][1], i
+
+
+def test_search_by_sim3_shared_views_scale_and_edges(engine, oracle):
+    """one current keyframe against three candidates (views referenced by index), an upstream-style scale s12 != 1, a pair
+    whose transform is wrong (few matches), an empty keyframe"""
+    base = synth.kf_view_pair(31, n_points=500, n_extra=200, prematched=0.0)
+    others = [synth.kf_view_pair(32 + i, n_points=400, n_extra=150, prematched=0.2) for i in range(2)]
+    empty = dict(base["kf2"])
+    for k in ("kp_xy", "kp_octave", "desc", "mp_valid", "mp_xyz", "mp_desc", "mp_maxdist", "mp_mindist"):
+        empty[k] = base["kf2"][k][:0]
+    empty["n_feat"] = 0
+    empty["grid_off"] = np.zeros_like(base["kf2"]["grid_off"]); empty["grid_idx"] = np.zeros(0, np.int32)
+    views = [base["kf1"], base["kf2"], others[0]["kf1"], others[0]["kf2"], others[1]["kf1"], others[1]["kf2"], empty]
+    kf1 = [0, 2, 4, 0, 0]
+    kf2 = [1, 3, 5, 1, 6]
+    t_bad = base["t12"] + np.float32([1.2, -0.9, 0.7])
+    Ks = [base["K"], others[0]["K"], others[1]["K"], base["K"], base["K"]]
+    Rs = [base["R12"], others[0]["R12"], others[1]["R12"], base["R12"], base["R12"]]
+    ts = [base["t12"], others[0]["t12"], others[1]["t12"], t_bad, base["t12"]]
+    s12 = np.float32([1.0, 1.03, 0.97, 1.0, 1.0])
+    mins = [np.full(views[a]["n_feat"], -1, np.int32) for a in kf1]
+    mins[1] = others[0]["matched12_in"]; mins[2] = others[1]["matched12_in"]
+    got, nf = engine.sim3_search(views, kf1, kf2, Ks, Rs, ts, 7.5, mins, s12=s12)
+    for c in range(5):
+        k1, k2 = oracle.kf_view(views[kf1[c]]), oracle.kf_view(views[kf2[c]])
+        w, n = oracle.search_by_sim3(k1, k2, Ks[c], Rs[c], ts[c], 7.5, mins[c], s12=float(s12[c]))
+        assert got[c].tolist() == w.tolist(), c
+        assert nf[c] == n
+    assert nf[0] > 100 and nf[3] < 40 and nf[4] == 0
