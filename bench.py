@@ -964,6 +964,36 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                                         "reference's order; 8 distinct synthetic pairs cycled; bit-identical to the oracle"}
     except Exception as err:
         ex["search_by_sim3_error"] = repr(err)
+    # ---- ORBmatcher::SearchByProjection(Frame, KeyFrame, sAlreadyFound, 10, 100) (ORBmatcher.cpp:1317-1444), 64 pairs
+    try:
+        cs = [synth.proj_search_case(800 + i, n_points=1200, n_extra=400, clones=0.1) for i in range(8)]
+        vwp = [v for c_ in cs for v in (c_["frame"], c_["kf"])]
+        NPp = 64
+        fi, ki = [2 * (i % 8) for i in range(NPp)], [2 * (i % 8) + 1 for i in range(NPp)]
+        eng.proj_search_upload(vwp, fi, ki, [cs[i % 8]["K"] for i in range(NPp)], [cs[i % 8]["Rcw"] for i in range(NPp)],
+                               [cs[i % 8]["tcw"] for i in range(NPp)], 10.0, 100, True, [cs[i % 8]["occupied"] for i in range(NPp)],
+                               [cs[i % 8]["already_found"] for i in range(NPp)])
+        for _ in range(3):
+            eng.proj_search_run()
+        eng.sync()
+        eng.timer_begin()
+        for _ in range(20):
+            eng.proj_search_run()
+        msp = eng.timer_end() / 20
+        gmp, gnp, fellp, rndp = eng.proj_search_download()
+        of, okf = O.kf_view(cs[0]["frame"]), O.kf_view(cs[0]["kf"])
+        t0 = time.perf_counter()
+        for _ in range(5):
+            wmp, wnp = O.search_by_projection(of, okf, cs[0]["K"], cs[0]["Rcw"], cs[0]["tcw"], 10.0, 100, True, cs[0]["occupied"], cs[0]["already_found"])
+        dcp = (time.perf_counter() - t0) / 5
+        ex["search_by_projection"] = {"pairs": NPp, "ms_per_batch": msp, "pairs_per_s": NPp / (msp * 1e-3), "matches_mean": float(np.mean(gnp)),
+                                      "assignment_rounds_max": int(rndp.max()), "sequential_fallbacks": int(fellp.sum()),
+                                      "pair_0_equals_oracle": bool(gmp[0].tolist() == wmp.tolist() and int(gnp[0]) == wnp),
+                                      "cpu_port_single_thread_pairs_per_s": 1.0 / dcp,
+                                      "note": "ORBmatcher.cpp:1317-1444 batched; the reference's greedy keyframe-order assignment is reproduced "
+                                              "exactly by preference lists + rounds (csrc/guided.cuh); bit-identical to the oracle"}
+    except Exception as err:
+        ex["search_by_projection_error"] = repr(err)
     # ---- ORBmatcher::SearchByBoW, 1024 candidate keyframes against one frame (Tracking.cpp:1207-1232)
     try:
         Fb = synth.bow_frame(11, 1500, 100)

@@ -469,6 +469,7 @@ typedef struct {
     int32_t n_feat;
     const float* kp_xy;          /* [n_feat][2] mvKeysUn[i].pt */
     const int32_t* kp_octave;    /* [n_feat] mvKeysUn[i].octave */
+    const float* kp_angle;       /* [n_feat] mvKeysUn[i].angle (rsac_proj_search_* only; may be NULL for rsac_sim3_search_*) */
     const uint32_t* desc;        /* [n_feat][8] mDescriptors rows */
     const uint8_t* mp_valid;     /* [n_feat] the feature has a MapPoint that is not bad */
     const float* mp_xyz;         /* [n_feat][3] MapPoint::GetWorldPos() */
@@ -508,6 +509,36 @@ int rsac_sim3_search_run(rsac_engine* e);
  * (vpMatches12[i1] = vpMapPoints2[idx2], ORBmatcher.cpp:1164) or -1; n_found[C]: the return values */
 int rsac_sim3_search_download(rsac_engine* e, int32_t* match12, int32_t* n_found);
 int rsac_sim3_search(rsac_engine* e, const rsac_sim3_search_batch* b, int32_t* match12, int32_t* n_found);
+
+/* ------------------------------------------------ ORBmatcher::SearchByProjection(Frame, KeyFrame, ...) (batched) */
+/* SURVEY 8(f) N3, second half: src/ORBmatcher.cpp:1317-1444, called by Tracking::Relocalization for a candidate whose pose
+ * PoseOptimization left with 10 <= nGood < 50 inliers (Tracking.cpp:1296: th = 10, ORBdist = 100; :1310: th = 3, ORBdist = 64).
+ * The frame is a view too (its keypoints, descriptors, grid, scale pyramid; Frame::GetFeaturesInArea src/Frame.cpp:393-446);
+ * the keyframe view supplies the MapPoints.  The reference's assignment is greedy in keyframe-feature order; the device
+ * reproduces it exactly (csrc/guided.cuh). */
+typedef struct {
+    int32_t n_views;
+    const rsac_kf_view* views;
+    int32_t C;                     /* (frame, keyframe) pairs */
+    const int32_t* frame;          /* [C] view index of CurrentFrame */
+    const int32_t* kf;             /* [C] view index of the candidate keyframe */
+    const float* K;                /* [C][4] CurrentFrame.fx, fy, cx, cy */
+    const float* Rcw;              /* [C][9] CurrentFrame.mTcw */
+    const float* tcw;              /* [C][3] */
+    float th;
+    int32_t orb_dist;              /* ORBdist */
+    int32_t check_orientation;     /* mbCheckOrientation */
+    const uint8_t* occupied;       /* optional, concatenated per pair [views[frame[c]].n_feat]: CurrentFrame.mvpMapPoints[i] != nullptr on entry */
+    const uint8_t* already_found;  /* optional, concatenated per pair [views[kf[c]].n_feat]: sAlreadyFound.count(pMP) */
+} rsac_proj_search_batch;
+
+int rsac_proj_search_upload(rsac_engine* e, const rsac_proj_search_batch* b);
+int rsac_proj_search_run(rsac_engine* e);
+/* frame_match: concatenated per pair [views[frame[c]].n_feat]: the keyframe feature whose MapPoint this call assigned to the
+ * frame keypoint (CurrentFrame.mvpMapPoints[i2] = pMP), else -1; n_matches[C]: the return values; info (optional) [2][C]:
+ * pairs that took the sequential fall-back, assignment rounds */
+int rsac_proj_search_download(rsac_engine* e, int32_t* frame_match, int32_t* n_matches, int32_t* info);
+int rsac_proj_search(rsac_engine* e, const rsac_proj_search_batch* b, int32_t* frame_match, int32_t* n_matches);
 
 /* ------------------------------------------------ multi-GPU (candidates shard) */
 /* contiguous block partition of C problems over `world` ranks: rank r owns [*first, *first + *count) */

@@ -259,6 +259,7 @@ typedef struct {
     int n_feat;
     const float *kp_xy;          /* [n][2] mvKeysUn[i].pt */
     const int32_t *kp_octave;    /* [n] mvKeysUn[i].octave */
+    const float *kp_angle;       /* [n] mvKeysUn[i].angle (SearchByProjection's rotation histogram; may be NULL for SearchBySim3) */
     const uint32_t *desc;        /* [n][8] mDescriptors rows */
     const uint8_t *mp_valid;     /* [n] feature has a MapPoint that is not bad */
     const float *mp_xyz;         /* [n][3] MapPoint::GetWorldPos() */
@@ -277,6 +278,10 @@ typedef struct {
 } orc_kf_view;
 int orc_features_in_area(const orc_kf_view *kf, float x, float y, float r, int32_t *out);
 int orc_predict_scale(float max_distance, float current_dist, float log_scale_factor, int n_levels);
+/* ORBmatcher::SearchByProjection(Frame&, KeyFrame, sAlreadyFound, th, ORBdist) (ORBmatcher.cpp:1317-1444) */
+int orc_search_by_projection(const orc_kf_view *frame, const orc_kf_view *kf, const float K[4], const float Rcw[9], const float tcw[3],
+                             float th, int orb_dist, int check_orientation, const uint8_t *occupied, const uint8_t *already_found,
+                             int32_t *frame_match);
 int orc_search_by_sim3(const orc_kf_view *kf1, const orc_kf_view *kf2, const float K[4], const float R12[9], const float t12[3],
                        float s12, float th, const int32_t *matched12_in, int32_t *match12_out);
 

@@ -142,3 +142,119 @@ done:
     free(am1); free(am2); free(m1); free(m2); free(scratch);
     return nFound;
 }
+
+/* Frame::GetFeaturesInArea (src/Frame.cpp:393-446) with the level window */
+static int frame_features_in_area(const orc_kf_view *f, float x, float y, float r, int minLevel, int maxLevel, int32_t *out)
+{
+    int n = 0;
+    const float mnMinX = f->bounds[0], mnMinY = f->bounds[2];
+    int nMinCellX = (int)floorf((x - mnMinX - r) * f->grid_w_inv);
+    if (nMinCellX < 0) nMinCellX = 0;
+    if (nMinCellX >= f->grid_cols) return 0;
+    int nMaxCellX = (int)ceilf((x - mnMinX + r) * f->grid_w_inv);
+    if (nMaxCellX > f->grid_cols - 1) nMaxCellX = f->grid_cols - 1;
+    if (nMaxCellX < 0) return 0;
+    int nMinCellY = (int)floorf((y - mnMinY - r) * f->grid_h_inv);
+    if (nMinCellY < 0) nMinCellY = 0;
+    if (nMinCellY >= f->grid_rows) return 0;
+    int nMaxCellY = (int)ceilf((y - mnMinY + r) * f->grid_h_inv);
+    if (nMaxCellY > f->grid_rows - 1) nMaxCellY = f->grid_rows - 1;
+    if (nMaxCellY < 0) return 0;
+    const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const int c = ix * f->grid_rows + iy;
+            for (int j = f->grid_off[c]; j < f->grid_off[c + 1]; j++) {
+                const int idx = f->grid_idx[j];
+                if (bCheckLevels) {
+                    if (f->kp_octave[idx] < minLevel) continue;
+                    if (maxLevel >= 0 && f->kp_octave[idx] > maxLevel) continue;
+                }
+                const float distx = f->kp_xy[2 * idx] - x, disty = f->kp_xy[2 * idx + 1] - y;
+                if (fabsf(distx) < r && fabsf(disty) < r) out[n++] = idx;
+            }
+        }
+    return n;
+}
+
+/*
+ * ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist)   src/ORBmatcher.cpp:1317-1444
+ * (Tracking::Relocalization, Tracking.cpp:1296 with th = 10, ORBdist = 100 and :1310 with th = 3, ORBdist = 64: more
+ * matches for a candidate whose pose PoseOptimization left with 10 <= nGood < 50 inliers).
+ *   frame          the current frame: keypoints, descriptors, grid, scale pyramid (view fields of the Frame)
+ *   kf             the candidate keyframe: its MapPoints (mp_*), the angles of its keypoints
+ *   Rcw, tcw, K    CurrentFrame.mTcw and intrinsics
+ *   occupied       [frame->n_feat] CurrentFrame.mvpMapPoints[i2] != nullptr on entry
+ *   already_found  [kf->n_feat] sAlreadyFound.count(pMP)
+ *   frame_match    [frame->n_feat] out: the keyframe feature whose MapPoint this call assigned to the frame keypoint, else -1
+ * Returns nmatches.  GREEDY and sequential: a frame keypoint taken by an earlier map point is skipped by the later ones (:1389).
+ */
+int orc_search_by_projection(const orc_kf_view *frame, const orc_kf_view *kf, const float K[4], const float Rcw[9], const float tcw[3],
+                             float th, int orb_dist, int check_orientation, const uint8_t *occupied, const uint8_t *already_found,
+                             int32_t *frame_match)
+{
+    const int NF = frame->n_feat;
+    int nmatches = 0;
+    uint8_t *taken = (uint8_t *)calloc((size_t)(NF > 0 ? NF : 1), 1);
+    int32_t *scratch = (int32_t *)malloc(sizeof(int32_t) * (size_t)(NF + 1));
+    int8_t *bin_of = (int8_t *)malloc((size_t)(NF > 0 ? NF : 1));
+    if (!taken || !scratch || !bin_of) { free(taken); free(scratch); free(bin_of); return -1; }
+    for (int i = 0; i < NF; i++) { taken[i] = occupied ? occupied[i] : 0; frame_match[i] = -1; bin_of[i] = -1; }
+    /* Ow = -Rcw^T * tcw (:1323) */
+    float Ow[3];
+    for (int i = 0; i < 3; i++) Ow[i] = (-Rcw[i] * tcw[0] + -Rcw[3 + i] * tcw[1]) + -Rcw[6 + i] * tcw[2];
+    int histo[30];
+    memset(histo, 0, sizeof(histo));
+    const float factor = 1.0f / 30;
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    for (int i = 0; i < kf->n_feat; i++) {
+        if (!kf->mp_valid[i] || (already_found && already_found[i])) continue;
+        const float *x3Dw = kf->mp_xyz + 3 * (size_t)i;
+        float x3Dc[3];
+        mat3_vec(Rcw, x3Dw, tcw, x3Dc);
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = (float)(1.0 / (double)x3Dc[2]);
+        const float u = fx * xc * invzc + cx;
+        const float v = fy * yc * invzc + cy;
+        if (u < frame->bounds[0] || u > frame->bounds[1]) continue;
+        if (v < frame->bounds[2] || v > frame->bounds[3]) continue;
+        const float PO[3] = {x3Dw[0] - Ow[0], x3Dw[1] - Ow[1], x3Dw[2] - Ow[2]};
+        const float dist3D = sqrtf((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        const float maxDistance = 1.2f * kf->mp_maxdist[i], minDistance = 0.8f * kf->mp_mindist[i];
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = orc_predict_scale(kf->mp_maxdist[i], dist3D, frame->log_scale_factor, frame->n_levels);
+        const float radius = th * frame->scale_factors[nPredictedLevel];
+        const int nc = frame_features_in_area(frame, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, scratch);
+        if (nc == 0) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = scratch[c];
+            if (taken[i2]) continue;                                     /* CurrentFrame.mvpMapPoints[i2] */
+            const int dist = orc_descriptor_distance(kf->mp_desc + 8 * (size_t)i, frame->desc + 8 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            taken[bestIdx2] = 1;
+            frame_match[bestIdx2] = i;
+            nmatches++;
+            if (check_orientation) {
+                float rot = kf->kp_angle[i] - frame->kp_angle[bestIdx2];
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == 30) bin = 0;
+                bin_of[bestIdx2] = (int8_t)bin;
+                histo[bin]++;
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1, ind2, ind3;
+        orc_three_maxima(histo, 30, &ind1, &ind2, &ind3);
+        for (int i2 = 0; i2 < NF; i2++) {
+            const int b = bin_of[i2];
+            if (b >= 0 && b != ind1 && b != ind2 && b != ind3) { frame_match[i2] = -1; nmatches--; }
+        }
+    }
+    free(taken); free(scratch); free(bin_of);
+    return nmatches;
+}

@@ -2,21 +2,18 @@
 #include "engine_shared.cuh"
 #include "guided.cuh"
 
-int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b)
+// keyframe / frame views -> concatenated device arrays (shared by rsac_sim3_search_* and rsac_proj_search_*)
+static int guided_upload_views(rsac_engine* e, int V, const rsac_kf_view* in, bool need_angle, std::vector<KfViewDev>& views)
 {
-    if (!e || !b || b->n_views < 0 || b->C < 0 || (b->n_views > 0 && !b->views)) return RSAC_ERR_INVALID;
-    if (b->C > 0 && (!b->kf1 || !b->kf2 || !b->K || !b->R12 || !b->t12)) return RSAC_ERR_INVALID;
-    RSAC_CUDA(e, cudaSetDevice(e->device));
     GuidedState& s = e->guided;
-    s.uploaded = false; s.ran = false;
-    const int V = b->n_views, C = b->C;
-    std::vector<KfViewDev> views(std::max(V, 1));
+    views.assign(std::max(V, 1), KfViewDev());
     int64_t nfeat = 0, ngoff = 0, ngidx = 0;
     for (int i = 0; i < V; ++i) {
-        const rsac_kf_view& v = b->views[i];
+        const rsac_kf_view& v = in[i];
         const int64_t cells = (int64_t)v.grid_cols * v.grid_rows;
         if (v.n_feat < 0 || v.grid_cols <= 0 || v.grid_rows <= 0 || cells > (1 << 20) || !v.grid_off || v.n_levels < 1 || v.n_levels > kGuidedMaxLevels ||
-            !v.scale_factors || (v.n_feat > 0 && (!v.kp_xy || !v.kp_octave || !v.desc || !v.mp_valid || !v.mp_xyz || !v.mp_desc || !v.mp_maxdist || !v.mp_mindist))) {
+            !v.scale_factors || (v.n_feat > 0 && (!v.kp_xy || !v.kp_octave || !v.desc || !v.mp_valid || !v.mp_xyz || !v.mp_desc || !v.mp_maxdist || !v.mp_mindist)) ||
+            (need_angle && v.n_feat > 0 && !v.kp_angle) || v.n_feat >= (1 << 20)) {
             e->err = "bad keyframe view"; return RSAC_ERR_INVALID;
         }
         if (v.grid_off[0] != 0 || v.grid_off[cells] < 0 || (v.grid_off[cells] > 0 && !v.grid_idx)) { e->err = "bad keyframe grid"; return RSAC_ERR_INVALID; }
@@ -35,6 +32,53 @@ int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b)
         nfeat += v.n_feat; ngoff += cells + 1; ngidx += v.grid_off[cells];
         if (nfeat > INT32_MAX / 8 || ngoff > INT32_MAX || ngidx > INT32_MAX) { e->err = "batch too large"; return RSAC_ERR_INVALID; }
     }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t nf = (size_t)std::max<int64_t>(nfeat, 1);
+    struct Seg { DevBuf* d; size_t bytes, off; };
+    Seg seg[] = {{&s.d_views, sizeof(KfViewDev) * views.size(), 0}, {&s.d_kp_xy, 8 * nf, 0}, {&s.d_kp_octave, 4 * nf, 0}, {&s.d_desc, 32 * nf, 0},
+                 {&s.d_mp_valid, nf, 0}, {&s.d_mp_xyz, 12 * nf, 0}, {&s.d_mp_desc, 32 * nf, 0}, {&s.d_mp_maxdist, 4 * nf, 0},
+                 {&s.d_mp_mindist, 4 * nf, 0}, {&s.d_grid_off, 4 * (size_t)std::max<int64_t>(ngoff, 1), 0},
+                 {&s.d_grid_idx, 4 * (size_t)std::max<int64_t>(ngidx, 1), 0}, {&s.d_kp_angle, 4 * nf, 0}};
+    size_t total = 0;
+    for (auto& g : seg) { g.off = total; total = al(total + g.bytes); }
+    char* h = (char*)s.h_stage.ensure(total);
+    if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
+    memset(h, 0, total);
+    memcpy(h + seg[0].off, views.data(), sizeof(KfViewDev) * views.size());
+    for (int i = 0; i < V; ++i) {
+        const rsac_kf_view& v = in[i];
+        const KfViewDev& d = views[i];
+        const size_t f = (size_t)d.feat_off, n = (size_t)v.n_feat;
+        const int64_t cells = (int64_t)v.grid_cols * v.grid_rows;
+        if (n > 0) {
+            memcpy(h + seg[1].off + 8 * f, v.kp_xy, 8 * n); memcpy(h + seg[2].off + 4 * f, v.kp_octave, 4 * n);
+            memcpy(h + seg[3].off + 32 * f, v.desc, 32 * n); memcpy(h + seg[4].off + f, v.mp_valid, n);
+            memcpy(h + seg[5].off + 12 * f, v.mp_xyz, 12 * n); memcpy(h + seg[6].off + 32 * f, v.mp_desc, 32 * n);
+            memcpy(h + seg[7].off + 4 * f, v.mp_maxdist, 4 * n); memcpy(h + seg[8].off + 4 * f, v.mp_mindist, 4 * n);
+            if (v.kp_angle) memcpy(h + seg[11].off + 4 * f, v.kp_angle, 4 * n);
+        }
+        memcpy(h + seg[9].off + 4 * (size_t)d.goff_off, v.grid_off, 4 * (size_t)(cells + 1));
+        if (v.grid_off[cells] > 0) memcpy(h + seg[10].off + 4 * (size_t)d.gidx_off, v.grid_idx, 4 * (size_t)v.grid_off[cells]);
+    }
+    for (auto& g : seg) {
+        RSAC_TRY(g.d->ensure(e, g.bytes));
+        RSAC_CUDA(e, cudaMemcpyAsync(g.d->p, h + g.off, g.bytes, cudaMemcpyHostToDevice, e->stream));
+    }
+    s.h_stage.mark(e->stream);
+    s.n_views = V;
+    return RSAC_OK;
+}
+
+int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b)
+{
+    if (!e || !b || b->n_views < 0 || b->C < 0 || (b->n_views > 0 && !b->views)) return RSAC_ERR_INVALID;
+    if (b->C > 0 && (!b->kf1 || !b->kf2 || !b->K || !b->R12 || !b->t12)) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    GuidedState& s = e->guided;
+    s.uploaded = false; s.ran = false; s.proj_uploaded = false; s.proj_ran = false;
+    const int V = b->n_views, C = b->C;
+    std::vector<KfViewDev> views;
+    RSAC_TRY(guided_upload_views(e, V, b->views, false, views));
     std::vector<int64_t> off1(C + 1, 0), off2(C + 1, 0);
     s.maxN1 = 0; s.maxN = 0;
     for (int c = 0; c < C; ++c) {
@@ -45,52 +89,32 @@ int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b)
         s.maxN1 = std::max(s.maxN1, views[a].n_feat);
         s.maxN = std::max(s.maxN, std::max(views[a].n_feat, views[q].n_feat));
     }
-    s.C = C; s.n_views = V; s.total1 = off1[C]; s.total2 = off2[C]; s.th = b->th;
+    s.C = C; s.total1 = off1[C]; s.total2 = off2[C]; s.th = b->th;
     s.have_matched = b->matched12_in != nullptr && s.total1 > 0;
     s.have_scale = b->s12 != nullptr;
-
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t nf = (size_t)std::max<int64_t>(nfeat, 1), c1 = (size_t)std::max(C, 1);
+    const size_t c1 = (size_t)std::max(C, 1);
     struct Seg { DevBuf* d; size_t bytes, off; };
-    Seg seg[] = {{&s.d_views, sizeof(KfViewDev) * views.size(), 0}, {&s.d_kp_xy, 8 * nf, 0}, {&s.d_kp_octave, 4 * nf, 0}, {&s.d_desc, 32 * nf, 0},
-                 {&s.d_mp_valid, nf, 0}, {&s.d_mp_xyz, 12 * nf, 0}, {&s.d_mp_desc, 32 * nf, 0}, {&s.d_mp_maxdist, 4 * nf, 0},
-                 {&s.d_mp_mindist, 4 * nf, 0}, {&s.d_grid_off, 4 * (size_t)std::max<int64_t>(ngoff, 1), 0},
-                 {&s.d_grid_idx, 4 * (size_t)std::max<int64_t>(ngidx, 1), 0}, {&s.d_kf1, 4 * c1, 0}, {&s.d_kf2, 4 * c1, 0}, {&s.d_K, 16 * c1, 0},
-                 {&s.d_R12, 36 * c1, 0}, {&s.d_t12, 12 * c1, 0}, {&s.d_s12, 4 * c1, 0}, {&s.d_off1, 8 * (c1 + 1), 0}, {&s.d_off2, 8 * (c1 + 1), 0},
-                 {&s.d_matched_in, 4 * (size_t)std::max<int64_t>(s.total1, 1), 0}};
+    Seg seg[] = {{&s.d_kf1, 4 * c1, 0}, {&s.d_kf2, 4 * c1, 0}, {&s.d_K, 16 * c1, 0}, {&s.d_R12, 36 * c1, 0}, {&s.d_t12, 12 * c1, 0}, {&s.d_s12, 4 * c1, 0},
+                 {&s.d_off1, 8 * (c1 + 1), 0}, {&s.d_off2, 8 * (c1 + 1), 0}, {&s.d_matched_in, 4 * (size_t)std::max<int64_t>(s.total1, 1), 0}};
     size_t total = 0;
     for (auto& g : seg) { g.off = total; total = al(total + g.bytes); }
-    char* h = (char*)s.h_stage.ensure(total);
+    char* h = (char*)s.h_stage2.ensure(total);
     if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
     memset(h, 0, total);
-    memcpy(h + seg[0].off, views.data(), sizeof(KfViewDev) * views.size());
-    for (int i = 0; i < V; ++i) {
-        const rsac_kf_view& v = b->views[i];
-        const KfViewDev& d = views[i];
-        const size_t f = (size_t)d.feat_off, n = (size_t)v.n_feat;
-        const int64_t cells = (int64_t)v.grid_cols * v.grid_rows;
-        if (n > 0) {
-            memcpy(h + seg[1].off + 8 * f, v.kp_xy, 8 * n); memcpy(h + seg[2].off + 4 * f, v.kp_octave, 4 * n);
-            memcpy(h + seg[3].off + 32 * f, v.desc, 32 * n); memcpy(h + seg[4].off + f, v.mp_valid, n);
-            memcpy(h + seg[5].off + 12 * f, v.mp_xyz, 12 * n); memcpy(h + seg[6].off + 32 * f, v.mp_desc, 32 * n);
-            memcpy(h + seg[7].off + 4 * f, v.mp_maxdist, 4 * n); memcpy(h + seg[8].off + 4 * f, v.mp_mindist, 4 * n);
-        }
-        memcpy(h + seg[9].off + 4 * (size_t)d.goff_off, v.grid_off, 4 * (size_t)(cells + 1));
-        if (v.grid_off[cells] > 0) memcpy(h + seg[10].off + 4 * (size_t)d.gidx_off, v.grid_idx, 4 * (size_t)v.grid_off[cells]);
-    }
     if (C > 0) {
-        memcpy(h + seg[11].off, b->kf1, 4 * (size_t)C); memcpy(h + seg[12].off, b->kf2, 4 * (size_t)C);
-        memcpy(h + seg[13].off, b->K, 16 * (size_t)C); memcpy(h + seg[14].off, b->R12, 36 * (size_t)C); memcpy(h + seg[15].off, b->t12, 12 * (size_t)C);
-        if (b->s12) memcpy(h + seg[16].off, b->s12, 4 * (size_t)C);
+        memcpy(h + seg[0].off, b->kf1, 4 * (size_t)C); memcpy(h + seg[1].off, b->kf2, 4 * (size_t)C);
+        memcpy(h + seg[2].off, b->K, 16 * (size_t)C); memcpy(h + seg[3].off, b->R12, 36 * (size_t)C); memcpy(h + seg[4].off, b->t12, 12 * (size_t)C);
+        if (b->s12) memcpy(h + seg[5].off, b->s12, 4 * (size_t)C);
     }
-    memcpy(h + seg[17].off, off1.data(), 8 * (size_t)(C + 1));
-    memcpy(h + seg[18].off, off2.data(), 8 * (size_t)(C + 1));
-    if (s.have_matched) memcpy(h + seg[19].off, b->matched12_in, 4 * (size_t)s.total1);
+    memcpy(h + seg[6].off, off1.data(), 8 * (size_t)(C + 1));
+    memcpy(h + seg[7].off, off2.data(), 8 * (size_t)(C + 1));
+    if (s.have_matched) memcpy(h + seg[8].off, b->matched12_in, 4 * (size_t)s.total1);
     for (auto& g : seg) {
         RSAC_TRY(g.d->ensure(e, g.bytes));
         RSAC_CUDA(e, cudaMemcpyAsync(g.d->p, h + g.off, g.bytes, cudaMemcpyHostToDevice, e->stream));
     }
-    s.h_stage.mark(e->stream);
+    s.h_stage2.mark(e->stream);
     const size_t t1 = (size_t)std::max<int64_t>(s.total1, 1), t2 = (size_t)std::max<int64_t>(s.total2, 1);
     RSAC_TRY(s.d_already1.ensure(e, t1)); RSAC_TRY(s.d_already2.ensure(e, t2));
     RSAC_TRY(s.d_m1.ensure(e, 4 * t1)); RSAC_TRY(s.d_m2.ensure(e, 4 * t2));
@@ -109,7 +133,7 @@ int rsac_sim3_search_run(rsac_engine* e)
     s.ran = true;
     if (s.C == 0) return RSAC_OK;
     Sim3SearchArgs a;
-    a.views = (const KfViewDev*)s.d_views.p; a.kp_xy = (const float*)s.d_kp_xy.p; a.kp_octave = (const int32_t*)s.d_kp_octave.p;
+    a.views = (const KfViewDev*)s.d_views.p; a.kp_xy = (const float*)s.d_kp_xy.p; a.kp_octave = (const int32_t*)s.d_kp_octave.p; a.kp_angle = (const float*)s.d_kp_angle.p;
     a.desc = (const uint32_t*)s.d_desc.p; a.mp_valid = (const uint8_t*)s.d_mp_valid.p; a.mp_xyz = (const float*)s.d_mp_xyz.p;
     a.mp_desc = (const uint32_t*)s.d_mp_desc.p; a.mp_maxdist = (const float*)s.d_mp_maxdist.p; a.mp_mindist = (const float*)s.d_mp_mindist.p;
     a.grid_off = (const int32_t*)s.d_grid_off.p; a.grid_idx = (const int32_t*)s.d_grid_idx.p;
@@ -156,4 +180,117 @@ int rsac_sim3_search(rsac_engine* e, const rsac_sim3_search_batch* b, int32_t* m
     rc = rsac_sim3_search_run(e);
     if (rc) return rc;
     return rsac_sim3_search_download(e, match12, n_found);
+}
+
+// ---------------------------------------------------------------- ORBmatcher::SearchByProjection(Frame, KeyFrame, ...)
+int rsac_proj_search_upload(rsac_engine* e, const rsac_proj_search_batch* b)
+{
+    if (!e || !b || b->n_views < 0 || b->C < 0 || (b->n_views > 0 && !b->views)) return RSAC_ERR_INVALID;
+    if (b->C > 0 && (!b->frame || !b->kf || !b->K || !b->Rcw || !b->tcw)) return RSAC_ERR_INVALID;
+    if (b->orb_dist < 0 || b->orb_dist > 256) { e->err = "ORBdist must be in [0, 256]"; return RSAC_ERR_INVALID; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    GuidedState& s = e->guided;
+    s.uploaded = false; s.ran = false; s.proj_uploaded = false; s.proj_ran = false;
+    const int V = b->n_views, C = b->C;
+    std::vector<KfViewDev> views;
+    RSAC_TRY(guided_upload_views(e, V, b->views, b->check_orientation != 0, views));
+    std::vector<int64_t> offF(C + 1, 0), offK(C + 1, 0);
+    s.maxN = 0;
+    for (int c = 0; c < C; ++c) {
+        const int f = b->frame[c], k = b->kf[c];
+        if (f < 0 || f >= V || k < 0 || k >= V) { e->err = "view index out of range"; return RSAC_ERR_INVALID; }
+        offF[c + 1] = offF[c] + views[f].n_feat;
+        offK[c + 1] = offK[c] + views[k].n_feat;
+        s.maxN = std::max(s.maxN, views[k].n_feat);
+    }
+    s.proj_C = C; s.totalF = offF[C]; s.totalK = offK[C]; s.th = b->th; s.orb_dist = b->orb_dist; s.check_orientation = b->check_orientation;
+    s.have_occupied = b->occupied != nullptr && s.totalF > 0;
+    s.have_found = b->already_found != nullptr && s.totalK > 0;
+    s.cap = std::max(1, std::min(32, env_int("RSAC_PROJ_CAP", 16)));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t c1 = (size_t)std::max(C, 1), tF = (size_t)std::max<int64_t>(s.totalF, 1), tK = (size_t)std::max<int64_t>(s.totalK, 1);
+    struct Seg { DevBuf* d; size_t bytes, off; };
+    Seg seg[] = {{&s.d_kf1, 4 * c1, 0}, {&s.d_kf2, 4 * c1, 0}, {&s.d_K, 16 * c1, 0}, {&s.d_R12, 36 * c1, 0}, {&s.d_t12, 12 * c1, 0},
+                 {&s.d_off1, 8 * (c1 + 1), 0}, {&s.d_off2, 8 * (c1 + 1), 0}, {&s.d_already1, tF, 0}, {&s.d_already2, tK, 0}};
+    size_t total = 0;
+    for (auto& g : seg) { g.off = total; total = al(total + g.bytes); }
+    char* h = (char*)s.h_stage2.ensure(total);
+    if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
+    memset(h, 0, total);
+    if (C > 0) {
+        memcpy(h + seg[0].off, b->frame, 4 * (size_t)C); memcpy(h + seg[1].off, b->kf, 4 * (size_t)C);
+        memcpy(h + seg[2].off, b->K, 16 * (size_t)C); memcpy(h + seg[3].off, b->Rcw, 36 * (size_t)C); memcpy(h + seg[4].off, b->tcw, 12 * (size_t)C);
+    }
+    memcpy(h + seg[5].off, offF.data(), 8 * (size_t)(C + 1));
+    memcpy(h + seg[6].off, offK.data(), 8 * (size_t)(C + 1));
+    if (s.have_occupied) memcpy(h + seg[7].off, b->occupied, (size_t)s.totalF);
+    if (s.have_found) memcpy(h + seg[8].off, b->already_found, (size_t)s.totalK);
+    for (auto& g : seg) {
+        RSAC_TRY(g.d->ensure(e, g.bytes));
+        RSAC_CUDA(e, cudaMemcpyAsync(g.d->p, h + g.off, g.bytes, cudaMemcpyHostToDevice, e->stream));
+    }
+    s.h_stage2.mark(e->stream);
+    RSAC_TRY(s.d_cand.ensure(e, 4 * tK * (size_t)s.cap)); RSAC_TRY(s.d_cand_n.ensure(e, 4 * tK));
+    RSAC_TRY(s.d_taken.ensure(e, tF)); RSAC_TRY(s.d_minidx.ensure(e, 4 * tF)); RSAC_TRY(s.d_match12.ensure(e, 4 * tF));
+    RSAC_TRY(s.d_n_found.ensure(e, 4 * 3 * c1));
+    s.proj_uploaded = true;
+    return RSAC_OK;
+}
+
+int rsac_proj_search_run(rsac_engine* e)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    GuidedState& s = e->guided;
+    if (!s.proj_uploaded) { e->err = "rsac_proj_search_run before rsac_proj_search_upload"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    s.proj_ran = true;
+    if (s.proj_C == 0) return RSAC_OK;
+    ProjSearchArgs a;
+    a.views = (const KfViewDev*)s.d_views.p; a.kp_xy = (const float*)s.d_kp_xy.p; a.kp_octave = (const int32_t*)s.d_kp_octave.p;
+    a.kp_angle = (const float*)s.d_kp_angle.p; a.desc = (const uint32_t*)s.d_desc.p; a.mp_valid = (const uint8_t*)s.d_mp_valid.p;
+    a.mp_xyz = (const float*)s.d_mp_xyz.p; a.mp_desc = (const uint32_t*)s.d_mp_desc.p; a.mp_maxdist = (const float*)s.d_mp_maxdist.p;
+    a.mp_mindist = (const float*)s.d_mp_mindist.p; a.grid_off = (const int32_t*)s.d_grid_off.p; a.grid_idx = (const int32_t*)s.d_grid_idx.p;
+    a.C = s.proj_C; a.vframe = (const int32_t*)s.d_kf1.p; a.vkf = (const int32_t*)s.d_kf2.p; a.K = (const float*)s.d_K.p;
+    a.Rcw = (const float*)s.d_R12.p; a.tcw = (const float*)s.d_t12.p; a.th = s.th; a.orb_dist = s.orb_dist; a.check_orientation = s.check_orientation;
+    a.cap = s.cap;
+    a.offF = (const int64_t*)s.d_off1.p; a.offK = (const int64_t*)s.d_off2.p;
+    a.occupied = s.have_occupied ? (const uint8_t*)s.d_already1.p : nullptr;
+    a.already_found = s.have_found ? (const uint8_t*)s.d_already2.p : nullptr;
+    a.cand = (int32_t*)s.d_cand.p; a.cand_n = (int32_t*)s.d_cand_n.p; a.taken = (uint8_t*)s.d_taken.p; a.minidx = (int32_t*)s.d_minidx.p;
+    a.frame_match = (int32_t*)s.d_match12.p;
+    a.nmatches = (int32_t*)s.d_n_found.p; a.overflow = a.nmatches + s.proj_C; a.rounds = a.nmatches + 2 * (size_t)s.proj_C;
+    RSAC_CUDA(e, cudaMemsetAsync(s.d_n_found.p, 0, 4 * 3 * (size_t)s.proj_C, st));
+    const dim3 gc((unsigned)std::max(1, (s.maxN + 127) / 128), (unsigned)s.proj_C);
+    e->stage_begin(RSAC_STAGE_SOLVE);
+    proj_candidates_kernel<<<gc, 128, 0, st>>>(a);
+    e->stage_end(RSAC_STAGE_SOLVE);
+    e->stage_begin(RSAC_STAGE_SELECT);
+    proj_assign_kernel<<<s.proj_C, 256, 0, st>>>(a);
+    e->stage_end(RSAC_STAGE_SELECT);
+    RSAC_CUDA(e, cudaGetLastError());
+    return RSAC_OK;
+}
+
+int rsac_proj_search_download(rsac_engine* e, int32_t* frame_match, int32_t* n_matches, int32_t* info)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    GuidedState& s = e->guided;
+    if (!s.proj_ran) { e->err = "rsac_proj_search_download before rsac_proj_search_run"; return RSAC_ERR_STATE; }
+    if (s.proj_C > 0) {
+        if (frame_match && s.totalF > 0) RSAC_CUDA(e, cudaMemcpyAsync(frame_match, s.d_match12.p, 4 * (size_t)s.totalF, cudaMemcpyDeviceToHost, e->stream));
+        if (n_matches) RSAC_CUDA(e, cudaMemcpyAsync(n_matches, s.d_n_found.p, 4 * (size_t)s.proj_C, cudaMemcpyDeviceToHost, e->stream));
+        if (info) RSAC_CUDA(e, cudaMemcpyAsync(info, (int32_t*)s.d_n_found.p + s.proj_C, 8 * (size_t)s.proj_C, cudaMemcpyDeviceToHost, e->stream));
+    }
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
+}
+
+int rsac_proj_search(rsac_engine* e, const rsac_proj_search_batch* b, int32_t* frame_match, int32_t* n_matches)
+{
+    int rc = rsac_proj_search_upload(e, b);
+    if (rc) return rc;
+    rc = rsac_proj_search_run(e);
+    if (rc) return rc;
+    return rsac_proj_search_download(e, frame_match, n_matches, nullptr);
 }

@@ -240,6 +240,12 @@ struct GuidedState {
     int64_t total1 = 0, total2 = 0;
     bool have_matched = false, have_scale = false;
     float th = 7.5f;
+    // SearchByProjection(Frame, KeyFrame): shares the view buffers and the small per-pair arrays
+    bool proj_uploaded = false, proj_ran = false, have_occupied = false, have_found = false;
+    int proj_C = 0, orb_dist = 100, check_orientation = 1, cap = 16;
+    int64_t totalF = 0, totalK = 0;
+    DevBuf d_kp_angle, d_cand, d_cand_n, d_taken, d_minidx;
+    PinnedBuf h_stage2;
     DevBuf d_views, d_kp_xy, d_kp_octave, d_desc, d_mp_valid, d_mp_xyz, d_mp_desc, d_mp_maxdist, d_mp_mindist, d_grid_off, d_grid_idx,
         d_kf1, d_kf2, d_K, d_R12, d_t12, d_s12, d_off1, d_off2, d_matched_in, d_already1, d_already2, d_m1, d_m2, d_match12, d_n_found;
     PinnedBuf h_stage;
@@ -247,9 +253,10 @@ struct GuidedState {
     {
         DevBuf* all[] = {&d_views, &d_kp_xy, &d_kp_octave, &d_desc, &d_mp_valid, &d_mp_xyz, &d_mp_desc, &d_mp_maxdist, &d_mp_mindist,
                          &d_grid_off, &d_grid_idx, &d_kf1, &d_kf2, &d_K, &d_R12, &d_t12, &d_s12, &d_off1, &d_off2, &d_matched_in,
-                         &d_already1, &d_already2, &d_m1, &d_m2, &d_match12, &d_n_found};
+                         &d_already1, &d_already2, &d_m1, &d_m2, &d_match12, &d_n_found, &d_kp_angle, &d_cand, &d_cand_n, &d_taken, &d_minidx};
         for (DevBuf* b : all) b->release();
         h_stage.release();
+        h_stage2.release();
     }
 };
 

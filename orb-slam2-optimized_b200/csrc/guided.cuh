@@ -34,6 +34,7 @@ struct Sim3SearchArgs {
     const KfViewDev* views;
     const float* kp_xy;                // [.][2]
     const int32_t* kp_octave;
+    const float* kp_angle;
     const uint32_t* desc;              // [.][8]
     const uint8_t* mp_valid;
     const float* mp_xyz;               // [.][3]
@@ -187,6 +188,273 @@ static __global__ void __launch_bounds__(256) sim3_search_agree_kernel(Sim3Searc
     }
     found = __reduce_add_sync(0xffffffffu, found);
     if ((threadIdx.x & 31) == 0 && found) atomicAdd(a.n_found + c, found);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(Frame&, KeyFrame, sAlreadyFound, th, ORBdist)   (src/ORBmatcher.cpp:1317-1444;
+// Tracking::Relocalization, Tracking.cpp:1296,1310).  GREEDY in the reference: map points are taken in keyframe-feature
+// order and a frame keypoint that an earlier map point took is skipped by the later ones (:1389, :1403).  Reproduced
+// exactly, in parallel:
+//   1. every map point (thread) projects itself, walks its window in Frame::GetFeaturesInArea's order and keeps the
+//      candidates that could ever be accepted -- free on entry and within ORBdist -- as a PREFERENCE LIST sorted by
+//      (distance, position in the walk): the reference's scan picks the first minimum among the keypoints still free;
+//   2. rounds (one CTA per pair): every undecided map point i marks each free keypoint of its list with the smallest
+//      interested index (atomicMin) and looks at its first free entry b; i is FINAL iff no undecided j < i has b anywhere in
+//      its list -- no earlier point can ever take b, and losing other entries does not change i's first choice.  The
+//      smallest undecided index is always final, so the rounds terminate; dense frames need a handful;
+//   3. rotation histogram over the assigned keypoints, ComputeThreeMaxima, the other bins dropped (:1420-1441).
+// A map point with more than `cap` acceptable candidates makes the pair fall back to the literal sequential scan on one
+// thread (never seen with ORBdist <= 100: unrelated descriptors are 128 +- 8 bits apart).
+struct ProjSearchArgs {
+    const KfViewDev* views;
+    const float* kp_xy;
+    const int32_t* kp_octave;
+    const float* kp_angle;
+    const uint32_t* desc;
+    const uint8_t* mp_valid;
+    const float* mp_xyz;
+    const uint32_t* mp_desc;
+    const float* mp_maxdist;
+    const float* mp_mindist;
+    const int32_t* grid_off;
+    const int32_t* grid_idx;
+    int32_t C;
+    const int32_t* vframe;             // [C] view index of the frame
+    const int32_t* vkf;                // [C] view index of the keyframe
+    const float* K;                    // [C][4]
+    const float* Rcw;                  // [C][9] CurrentFrame.mTcw
+    const float* tcw;                  // [C][3]
+    float th;
+    int32_t orb_dist, check_orientation, cap;
+    const int64_t* offF;               // [C+1] frame-indexed arrays
+    const int64_t* offK;               // [C+1] keyframe-indexed arrays
+    const uint8_t* occupied;           // frame-indexed (or nullptr)
+    const uint8_t* already_found;      // keyframe-indexed (or nullptr)
+    int32_t* cand;                     // [sumK][cap] preference lists (frame keypoint indices)
+    int32_t* cand_n;                   // [sumK]
+    uint8_t* taken;                    // frame-indexed
+    int32_t* minidx;                   // frame-indexed
+    int32_t* frame_match;              // frame-indexed output
+    int32_t* nmatches;                 // [C]
+    int32_t* overflow;                 // [C] (zeroed by the host)
+    int32_t* rounds;                   // [C] diagnostic
+};
+
+// the projection of keyframe feature i of pair c into the frame: false if the reference `continue`s before the window search
+__device__ __forceinline__ bool proj_project(const ProjSearchArgs& a, int c, const KfViewDev& fr, size_t g, float& u, float& v, int& lvl, float& radius)
+{
+    const float* Rcw = a.Rcw + 9 * (size_t)c;
+    const float* tcw = a.tcw + 3 * (size_t)c;
+    const float fx = a.K[4 * c], fy = a.K[4 * c + 1], cx = a.K[4 * c + 2], cy = a.K[4 * c + 3];
+    const float pw[3] = {a.mp_xyz[3 * g], a.mp_xyz[3 * g + 1], a.mp_xyz[3 * g + 2]};
+    float pc[3];
+    guided_mat3_vec(Rcw, pw, tcw, pc);
+    const float invzc = (float)(1.0 / (double)pc[2]);
+    u = fx * pc[0] * invzc + cx;
+    v = fy * pc[1] * invzc + cy;
+    if (u < fr.bounds[0] || u > fr.bounds[1]) return false;
+    if (v < fr.bounds[2] || v > fr.bounds[3]) return false;
+    float Ow[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Ow[i] = (-Rcw[i] * tcw[0] + -Rcw[3 + i] * tcw[1]) + -Rcw[6 + i] * tcw[2];
+    const float P0 = pw[0] - Ow[0], P1 = pw[1] - Ow[1], P2 = pw[2] - Ow[2];
+    const float dist3D = sqrtf((P0 * P0 + P1 * P1) + P2 * P2);
+    const float maxD = 1.2f * a.mp_maxdist[g], minD = 0.8f * a.mp_mindist[g];
+    if (dist3D < minD || dist3D > maxD) return false;
+    lvl = guided_predict_scale(a.mp_maxdist[g], dist3D, fr.log_scale_factor, fr.n_levels);
+    radius = a.th * fr.scale_factors[lvl];
+    return true;
+}
+
+// Frame::GetFeaturesInArea(u, v, r, lvl - 1, lvl + 1) (Frame.cpp:393-446): calls f(idx) for every keypoint, in its order
+template <typename F>
+__device__ __forceinline__ void proj_walk_window(const ProjSearchArgs& a, const KfViewDev& fr, float u, float v, float r, int lvl, F f)
+{
+    const float mnMinX = fr.bounds[0], mnMinY = fr.bounds[2];
+    const int nMinCellX = max(0, (int)floorf((u - mnMinX - r) * fr.grid_w_inv));
+    const int nMaxCellX = min(fr.grid_cols - 1, (int)ceilf((u - mnMinX + r) * fr.grid_w_inv));
+    const int nMinCellY = max(0, (int)floorf((v - mnMinY - r) * fr.grid_h_inv));
+    const int nMaxCellY = min(fr.grid_rows - 1, (int)ceilf((v - mnMinY + r) * fr.grid_h_inv));
+    if (nMinCellX >= fr.grid_cols || nMaxCellX < 0 || nMinCellY >= fr.grid_rows || nMaxCellY < 0) return;
+    const int minLevel = lvl - 1, maxLevel = lvl + 1;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+        for (int iy = nMinCellY; iy <= nMaxCellY; ++iy) {
+            const int cell = fr.goff_off + ix * fr.grid_rows + iy;
+            for (int j = a.grid_off[cell]; j < a.grid_off[cell + 1]; ++j) {
+                const int idx = a.grid_idx[fr.gidx_off + j];
+                const size_t gd = (size_t)fr.feat_off + idx;
+                if (bCheckLevels) {
+                    const int oct = a.kp_octave[gd];
+                    if (oct < minLevel) continue;
+                    if (maxLevel >= 0 && oct > maxLevel) continue;
+                }
+                const float distx = a.kp_xy[2 * gd] - u, disty = a.kp_xy[2 * gd + 1] - v;
+                if (fabsf(distx) < r && fabsf(disty) < r) f(idx, gd);
+            }
+        }
+}
+
+// 1. preference lists.  grid (ceil(maxK / 128), C)
+static __global__ void __launch_bounds__(128) proj_candidates_kernel(ProjSearchArgs a)
+{
+    const int c = blockIdx.y;
+    const KfViewDev& fr = a.views[a.vframe[c]];
+    const KfViewDev& kf = a.views[a.vkf[c]];
+    const uint8_t* occ = a.occupied ? a.occupied + a.offF[c] : nullptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kf.n_feat; i += gridDim.x * blockDim.x) {
+        const size_t g = (size_t)kf.feat_off + i;
+        int n = 0;
+        int32_t* list = a.cand + ((size_t)a.offK[c] + i) * a.cap;
+        float u, v, r;
+        int lvl;
+        if (a.mp_valid[g] && !(a.already_found && a.already_found[a.offK[c] + i]) && proj_project(a, c, fr, g, u, v, lvl, r)) {
+            const uint32_t* dMP = a.mp_desc + 8 * g;
+            // sorted insertion by (distance, walk position): keys of the kept entries live beside the list in registers' stead
+            // -- the distances are recomputed from the list when needed is avoided by packing (dist << 20 | idx)
+            bool over = false;
+            proj_walk_window(a, fr, u, v, r, lvl, [&](int idx, size_t gd) {
+                if (occ && occ[idx]) return;
+                const int dist = guided_descriptor_distance(dMP, a.desc + 8 * gd);
+                if (dist > a.orb_dist) return;
+                // insert behind every entry with distance <= dist (equal distances keep walk order)
+                int pos = n;
+                while (pos > 0 && (list[pos - 1] >> 20) > dist) --pos;
+                if (n == a.cap) {
+                    over = true;
+                    if (pos == n) return;            // would be last: dropped (the pair falls back anyway)
+                    for (int k = n - 1; k > pos; --k) list[k] = list[k - 1];
+                } else {
+                    for (int k = n; k > pos; --k) list[k] = list[k - 1];
+                    ++n;
+                }
+                list[pos] = (dist << 20) | idx;
+            });
+            if (over) a.overflow[c] = 1;
+        }
+        a.cand_n[a.offK[c] + i] = n;
+    }
+}
+
+// ORBmatcher::ComputeThreeMaxima (:1445-1488) on the bin sizes
+__device__ inline void guided_three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3)
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < L; ++i) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+__device__ __forceinline__ int proj_rot_bin(float angle_kf, float angle_f)
+{
+    float rot = angle_kf - angle_f;
+    if (rot < 0.0f) rot += 360.0f;
+    int bin = (int)roundf(rot * (1.0f / 30));
+    if (bin == 30) bin = 0;
+    return bin;
+}
+
+// 2 + 3. one CTA per pair
+static __global__ void __launch_bounds__(256) proj_assign_kernel(ProjSearchArgs a)
+{
+    __shared__ int s_undecided, s_histo[30], s_ind[3], s_n;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const KfViewDev& fr = a.views[a.vframe[c]];
+    const KfViewDev& kf = a.views[a.vkf[c]];
+    const int NF = fr.n_feat, NK = kf.n_feat;
+    uint8_t* taken = a.taken + a.offF[c];
+    int32_t* minidx = a.minidx + a.offF[c];
+    int32_t* fmatch = a.frame_match + a.offF[c];
+    int32_t* cn = a.cand_n + a.offK[c];                // becomes -1 once a map point is decided
+    const int32_t* cand = a.cand + (size_t)a.offK[c] * a.cap;
+    const uint8_t* occ = a.occupied ? a.occupied + a.offF[c] : nullptr;
+    for (int f = tid; f < NF; f += blockDim.x) { taken[f] = occ ? occ[f] : 0; fmatch[f] = -1; }
+    if (tid < 30) s_histo[tid] = 0;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    int rounds = 0;
+    if (a.overflow[c]) {
+        // literal sequential scan (one thread): :1335-1417
+        if (tid == 0) {
+            for (int i = 0; i < NK; ++i) {
+                const size_t g = (size_t)kf.feat_off + i;
+                float u, v, r;
+                int lvl;
+                if (!a.mp_valid[g] || (a.already_found && a.already_found[a.offK[c] + i]) || !proj_project(a, c, fr, g, u, v, lvl, r)) continue;
+                const uint32_t* dMP = a.mp_desc + 8 * g;
+                int bestDist = 256, bestIdx2 = -1;
+                proj_walk_window(a, fr, u, v, r, lvl, [&](int idx, size_t gd) {
+                    if (taken[idx]) return;
+                    const int dist = guided_descriptor_distance(dMP, a.desc + 8 * gd);
+                    if (dist < bestDist) { bestDist = dist; bestIdx2 = idx; }
+                });
+                if (bestDist <= a.orb_dist) { taken[bestIdx2] = 1; fmatch[bestIdx2] = i; }
+            }
+        }
+        __syncthreads();
+    } else {
+        for (;;) {
+            for (int f = tid; f < NF; f += blockDim.x) minidx[f] = INT_MAX;
+            if (tid == 0) s_undecided = 0;
+            __syncthreads();
+            for (int i = tid; i < NK; i += blockDim.x) {
+                const int n = cn[i];
+                if (n <= 0) continue;
+                bool any = false;
+                for (int k = 0; k < n; ++k) {
+                    const int idx = cand[(size_t)i * a.cap + k] & 0xfffff;
+                    if (!taken[idx]) { atomicMin(minidx + idx, i); any = true; }
+                }
+                if (!any) cn[i] = -1;                         // everything it could accept is gone: no match
+            }
+            __syncthreads();
+            for (int i = tid; i < NK; i += blockDim.x) {
+                const int n = cn[i];
+                if (n <= 0) continue;
+                int b = -1;
+                for (int k = 0; k < n && b < 0; ++k) {
+                    const int idx = cand[(size_t)i * a.cap + k] & 0xfffff;
+                    if (!taken[idx]) b = idx;
+                }
+                if (minidx[b] == i) { fmatch[b] = i; cn[i] = -1; }      // final (taken[] is written after the barrier below)
+                else atomicAdd(&s_undecided, 1);
+            }
+            __syncthreads();
+            for (int f = tid; f < NF; f += blockDim.x)
+                if (fmatch[f] >= 0) taken[f] = 1;
+            ++rounds;
+            const int left = s_undecided;
+            __syncthreads();
+            if (left == 0) break;
+        }
+    }
+    // 3. rotation consistency (:1405-1441)
+    int mine = 0;
+    if (a.check_orientation) {
+        for (int f = tid; f < NF; f += blockDim.x)
+            if (fmatch[f] >= 0) atomicAdd(&s_histo[proj_rot_bin(a.kp_angle[(size_t)kf.feat_off + fmatch[f]], a.kp_angle[(size_t)fr.feat_off + f])], 1);
+        __syncthreads();
+        if (tid == 0) guided_three_maxima(s_histo, 30, s_ind[0], s_ind[1], s_ind[2]);
+        __syncthreads();
+        for (int f = tid; f < NF; f += blockDim.x)
+            if (fmatch[f] >= 0) {
+                const int b = proj_rot_bin(a.kp_angle[(size_t)kf.feat_off + fmatch[f]], a.kp_angle[(size_t)fr.feat_off + f]);
+                if (b != s_ind[0] && b != s_ind[1] && b != s_ind[2]) fmatch[f] = -1;
+                else ++mine;
+            }
+    } else {
+        for (int f = tid; f < NF; f += blockDim.x) mine += fmatch[f] >= 0;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((tid & 31) == 0 && mine) atomicAdd(&s_n, mine);
+    __syncthreads();
+    if (tid == 0) { a.nmatches[c] = s_n; a.rounds[c] = rounds; }
 }
 
 }  // namespace rsac

@@ -121,7 +121,7 @@ class KfDbQueries(C.Structure):
 
 
 class KfView(C.Structure):
-    _fields_ = [("n_feat", C.c_int32), ("kp_xy", C.c_void_p), ("kp_octave", C.c_void_p), ("desc", C.c_void_p), ("mp_valid", C.c_void_p),
+    _fields_ = [("n_feat", C.c_int32), ("kp_xy", C.c_void_p), ("kp_octave", C.c_void_p), ("kp_angle", C.c_void_p), ("desc", C.c_void_p), ("mp_valid", C.c_void_p),
                 ("mp_xyz", C.c_void_p), ("mp_desc", C.c_void_p), ("mp_maxdist", C.c_void_p), ("mp_mindist", C.c_void_p),
                 ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("bounds", C.c_float * 4), ("grid_cols", C.c_int32), ("grid_rows", C.c_int32),
                 ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float), ("grid_off", C.c_void_p), ("grid_idx", C.c_void_p),
@@ -131,6 +131,12 @@ class KfView(C.Structure):
 class Sim3SearchBatch(C.Structure):
     _fields_ = [("n_views", C.c_int32), ("views", C.c_void_p), ("C", C.c_int32), ("kf1", C.c_void_p), ("kf2", C.c_void_p), ("K", C.c_void_p),
                 ("R12", C.c_void_p), ("t12", C.c_void_p), ("s12", C.c_void_p), ("th", C.c_float), ("matched12_in", C.c_void_p)]
+
+
+class ProjSearchBatch(C.Structure):
+    _fields_ = [("n_views", C.c_int32), ("views", C.c_void_p), ("C", C.c_int32), ("frame", C.c_void_p), ("kf", C.c_void_p), ("K", C.c_void_p),
+                ("Rcw", C.c_void_p), ("tcw", C.c_void_p), ("th", C.c_float), ("orb_dist", C.c_int32), ("check_orientation", C.c_int32),
+                ("occupied", C.c_void_p), ("already_found", C.c_void_p)]
 
 
 class RsacError(RuntimeError):
@@ -705,18 +711,7 @@ class Engine:
     def sim3_search_upload(self, views, kf1, kf2, K, R12, t12, th=7.5, matched12_in=None, s12=None):
         """views: list of keyframe-view dicts (synth.kf_view); kf1 / kf2: view index per pair; K [C,4], R12 [C,9], t12 [C,3];
         matched12_in: list of per-pair int32 arrays (or None)"""
-        keep = []
-        arr = (KfView * max(len(views), 1))()
-        for i, v in enumerate(views):
-            a = [np.ascontiguousarray(v["kp_xy"], np.float32), np.ascontiguousarray(v["kp_octave"], np.int32), np.ascontiguousarray(v["desc"], np.uint32),
-                 np.ascontiguousarray(v["mp_valid"], np.uint8), np.ascontiguousarray(v["mp_xyz"], np.float32), np.ascontiguousarray(v["mp_desc"], np.uint32),
-                 np.ascontiguousarray(v["mp_maxdist"], np.float32), np.ascontiguousarray(v["mp_mindist"], np.float32),
-                 np.ascontiguousarray(v["grid_off"], np.int32), np.ascontiguousarray(v["grid_idx"], np.int32), np.ascontiguousarray(v["scale_factors"], np.float32)]
-            keep += a
-            arr[i] = KfView(int(v["n_feat"]), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]),
-                            (C.c_float * 9)(*np.asarray(v["Rcw"], np.float32).reshape(-1)), (C.c_float * 3)(*np.asarray(v["tcw"], np.float32).reshape(-1)),
-                            (C.c_float * 4)(*np.asarray(v["bounds"], np.float32)), int(v["grid_cols"]), int(v["grid_rows"]), float(v["grid_w_inv"]),
-                            float(v["grid_h_inv"]), _p(a[8]), _p(a[9]), int(v["n_levels"]), _p(a[10]), float(v["log_scale_factor"]))
+        arr, keep = self._kf_views(views)
         k1, k2 = np.ascontiguousarray(kf1, np.int32), np.ascontiguousarray(kf2, np.int32)
         Kc = np.ascontiguousarray(K, np.float32).reshape(-1, 4)
         R = np.ascontiguousarray(R12, np.float32).reshape(-1, 9)
@@ -727,6 +722,57 @@ class Engine:
                             _p(mi) if mi is not None and len(mi) else None)
         self._ck(self.L.rsac_sim3_search_upload(self.h, C.byref(b)), "rsac_sim3_search_upload")
         self._s3s_n1 = [int(views[i]["n_feat"]) for i in k1]
+
+    @staticmethod
+    def _kf_views(views):
+        keep = []
+        arr = (KfView * max(len(views), 1))()
+        for i, v in enumerate(views):
+            ang = np.ascontiguousarray(v["kp_angle"], np.float32)
+            keep.append(ang)
+            a = [np.ascontiguousarray(v["kp_xy"], np.float32), np.ascontiguousarray(v["kp_octave"], np.int32), np.ascontiguousarray(v["desc"], np.uint32),
+                 np.ascontiguousarray(v["mp_valid"], np.uint8), np.ascontiguousarray(v["mp_xyz"], np.float32), np.ascontiguousarray(v["mp_desc"], np.uint32),
+                 np.ascontiguousarray(v["mp_maxdist"], np.float32), np.ascontiguousarray(v["mp_mindist"], np.float32),
+                 np.ascontiguousarray(v["grid_off"], np.int32), np.ascontiguousarray(v["grid_idx"], np.int32), np.ascontiguousarray(v["scale_factors"], np.float32)]
+            keep += a
+            arr[i] = KfView(int(v["n_feat"]), _p(a[0]), _p(a[1]), _p(ang), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]),
+                            (C.c_float * 9)(*np.asarray(v["Rcw"], np.float32).reshape(-1)), (C.c_float * 3)(*np.asarray(v["tcw"], np.float32).reshape(-1)),
+                            (C.c_float * 4)(*np.asarray(v["bounds"], np.float32)), int(v["grid_cols"]), int(v["grid_rows"]), float(v["grid_w_inv"]),
+                            float(v["grid_h_inv"]), _p(a[8]), _p(a[9]), int(v["n_levels"]), _p(a[10]), float(v["log_scale_factor"]))
+        return arr, keep
+
+    # -- guided matching: ORBmatcher::SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist)
+    def proj_search_upload(self, views, frame, kf, K, Rcw, tcw, th=10.0, orb_dist=100, check_orientation=True, occupied=None, already_found=None):
+        arr, keep = self._kf_views(views)
+        fi, ki = np.ascontiguousarray(frame, np.int32), np.ascontiguousarray(kf, np.int32)
+        Kc = np.ascontiguousarray(K, np.float32).reshape(-1, 4)
+        R = np.ascontiguousarray(Rcw, np.float32).reshape(-1, 9)
+        t = np.ascontiguousarray(tcw, np.float32).reshape(-1, 3)
+        oc = None if occupied is None else np.ascontiguousarray(np.concatenate([np.asarray(o, np.uint8) for o in occupied]) if len(fi) else [], np.uint8)
+        af = None if already_found is None else np.ascontiguousarray(np.concatenate([np.asarray(o, np.uint8) for o in already_found]) if len(fi) else [], np.uint8)
+        b = ProjSearchBatch(len(views), C.cast(arr, C.c_void_p), len(fi), _p(fi), _p(ki), _p(Kc), _p(R), _p(t), C.c_float(th), int(orb_dist),
+                            int(check_orientation), _p(oc) if oc is not None and len(oc) else None, _p(af) if af is not None and len(af) else None)
+        self._ck(self.L.rsac_proj_search_upload(self.h, C.byref(b)), "rsac_proj_search_upload")
+        self._sbp_nf = [int(views[i]["n_feat"]) for i in fi]
+
+    def proj_search_run(self):
+        self._ck(self.L.rsac_proj_search_run(self.h), "rsac_proj_search_run")
+
+    def proj_search_download(self):
+        """(list of per-pair frame_match arrays, n_matches [C], fell_back [C], rounds [C])"""
+        nf = self._sbp_nf
+        Cn = len(nf)
+        flat = np.empty(max(int(sum(nf)), 1), np.int32)
+        nm = np.zeros(max(Cn, 1), np.int32)
+        info = np.zeros((2, max(Cn, 1)), np.int32)
+        self._ck(self.L.rsac_proj_search_download(self.h, _p(flat), _p(nm), _p(info)), "rsac_proj_search_download")
+        offs = np.concatenate([[0], np.cumsum(nf)]).astype(np.int64)
+        return [flat[offs[i]:offs[i + 1]].copy() for i in range(Cn)], nm[:Cn], info[0, :Cn], info[1, :Cn]
+
+    def proj_search(self, views, frame, kf, K, Rcw, tcw, th=10.0, orb_dist=100, check_orientation=True, occupied=None, already_found=None):
+        self.proj_search_upload(views, frame, kf, K, Rcw, tcw, th, orb_dist, check_orientation, occupied, already_found)
+        self.proj_search_run()
+        return self.proj_search_download()
 
     def sim3_search_run(self):
         self._ck(self.L.rsac_sim3_search_run(self.h), "rsac_sim3_search_run")

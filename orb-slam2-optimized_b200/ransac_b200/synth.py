@@ -379,7 +379,8 @@ def _grid_csr(xy: np.ndarray, cam=EUROC):
     return off, (np.concatenate(idx) if idx else np.zeros(0)).astype(np.int32), float(w_inv), float(h_inv)
 
 
-def kf_view(rng, R, t, mp_xyz, mp_desc, mp_maxdist, mp_mindist, visible, n_extra=400, flip_bits=20, cam=EUROC, pix_noise=0.7):
+def kf_view(rng, R, t, mp_xyz, mp_desc, mp_maxdist, mp_mindist, visible, n_extra=400, flip_bits=20, cam=EUROC, pix_noise=0.7,
+            mp_angle=None, roll=0.0):
     """What ORBmatcher reads from one keyframe: features = the visible map points (projected, noisy pixel, octave predicted from
     the distance, descriptor = the map point's with a few bits flipped) followed by n_extra features without a map point."""
     sf = np.array([1.2 ** i for i in range(8)], np.float32)
@@ -402,6 +403,11 @@ def kf_view(rng, R, t, mp_xyz, mp_desc, mp_maxdist, mp_mindist, visible, n_extra
     perm = rng.permutation(n)                                  # features in detection order, not map-point order
     kp_xy = np.concatenate([uv, ex_uv]).astype(np.float32)[perm]
     octave = np.concatenate([lvl, rng.integers(0, 8, n_extra).astype(np.int32)])[perm]
+    # keypoint orientation: the map point's canonical angle seen under this keyframe's in-plane rotation (+ noise); a few wrong
+    ang_mp = (mp_angle[visible] + roll + rng.normal(0.0, 3.0, n_mp)) if mp_angle is not None else rng.uniform(0, 360, n_mp)
+    odd = rng.random(n_mp) < 0.08
+    ang_mp = np.where(odd, ang_mp + rng.uniform(40, 320, n_mp), ang_mp)
+    angle = np.mod(np.concatenate([ang_mp, rng.uniform(0, 360, n_extra)]), 360.0).astype(np.float32)[perm]
     desc = np.concatenate([d, ex_d])[perm]
     mp_id = np.concatenate([visible, np.full(n_extra, -1)]).astype(np.int64)[perm]
     valid = (mp_id >= 0).astype(np.uint8)
@@ -409,7 +415,7 @@ def kf_view(rng, R, t, mp_xyz, mp_desc, mp_maxdist, mp_mindist, visible, n_extra
     valid[bad] = 0
     safe = np.maximum(mp_id, 0)
     off, idx, w_inv, h_inv = _grid_csr(kp_xy, cam)
-    return dict(n_feat=n, kp_xy=kp_xy, kp_octave=octave.astype(np.int32), desc=np.ascontiguousarray(desc), mp_valid=valid, mp_id=mp_id,
+    return dict(n_feat=n, kp_xy=kp_xy, kp_octave=octave.astype(np.int32), kp_angle=angle, desc=np.ascontiguousarray(desc), mp_valid=valid, mp_id=mp_id,
                 mp_xyz=np.ascontiguousarray(mp_xyz[safe], np.float32), mp_desc=np.ascontiguousarray(mp_desc[safe]),
                 mp_maxdist=np.ascontiguousarray(mp_maxdist[safe], np.float32), mp_mindist=np.ascontiguousarray(mp_mindist[safe], np.float32),
                 Rcw=R.astype(np.float32), tcw=t.astype(np.float32), bounds=np.array([0.0, cam["width"], 0.0, cam["height"]], np.float32),
@@ -433,8 +439,9 @@ def kf_view_pair(seed: int, n_points: int = 1200, n_extra: int = 400, pose_noise
     mp_maxdist = (ref_dist * (1.2 ** ref_lvl)).astype(np.float32)          # MapPoint::UpdateNormalAndDepth: dist * levelScaleFactor
     mp_mindist = (mp_maxdist / np.float32(1.2 ** 7)).astype(np.float32)
     vis = np.arange(n_points)
-    kf1 = kf_view(rng, R1, t1, Xw, mp_desc, mp_maxdist, mp_mindist, vis[rng.random(n_points) < 0.9], n_extra, cam=cam)
-    kf2 = kf_view(rng, R2, t2, Xw, mp_desc, mp_maxdist, mp_mindist, vis[rng.random(n_points) < 0.9], n_extra, cam=cam)
+    mp_angle = rng.uniform(0, 360, n_points)
+    kf1 = kf_view(rng, R1, t1, Xw, mp_desc, mp_maxdist, mp_mindist, vis[rng.random(n_points) < 0.9], n_extra, cam=cam, mp_angle=mp_angle, roll=0.0)
+    kf2 = kf_view(rng, R2, t2, Xw, mp_desc, mp_maxdist, mp_mindist, vis[rng.random(n_points) < 0.9], n_extra, cam=cam, mp_angle=mp_angle, roll=25.0)
     # T12 = T1w * T2w^-1 (+ noise)
     nR, nt = random_pose(rng, pose_noise, pose_noise * 3)
     R12 = nR @ R1 @ R2.T
@@ -446,3 +453,51 @@ def kf_view_pair(seed: int, n_points: int = 1200, n_extra: int = 400, pose_noise
             matched[i] = idx2_of.get(int(m), -2)
     K = np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32)
     return dict(kf1=kf1, kf2=kf2, K=K, R12=R12.astype(np.float32), t12=t12.astype(np.float32), matched12_in=matched)
+
+
+def _clone_kf_features(rng, kf: dict, frac: float):
+    """append near-duplicates of a fraction of the keyframe's map-point features (same 3D point up to millimetres, descriptor
+    with a few flipped bits): they compete for the SAME frame keypoint, which is what makes SearchByProjection's greedy,
+    order-dependent assignment (ORBmatcher.cpp:1389,1403) observable"""
+    src = np.flatnonzero(kf["mp_valid"] > 0)
+    src = rng.choice(src, int(len(src) * frac), replace=False) if len(src) else src
+    if len(src) == 0:
+        return kf
+    out = dict(kf)
+    d = kf["mp_desc"][src].copy()
+    for i in range(len(src)):
+        for b in rng.choice(256, rng.integers(0, 6), replace=False):
+            d[i, b >> 5] ^= np.uint32(1) << np.uint32(b & 31)
+    app = dict(kp_xy=kf["kp_xy"][src], kp_octave=kf["kp_octave"][src], kp_angle=kf["kp_angle"][src], desc=kf["desc"][src],
+               mp_valid=kf["mp_valid"][src], mp_id=-2 - np.arange(len(src)), mp_desc=d,
+               mp_xyz=(kf["mp_xyz"][src] + rng.normal(0, 0.002, (len(src), 3))).astype(np.float32),
+               mp_maxdist=kf["mp_maxdist"][src], mp_mindist=kf["mp_mindist"][src])
+    for k_, v in app.items():
+        out[k_] = np.ascontiguousarray(np.concatenate([kf[k_], v]))
+    out["n_feat"] = kf["n_feat"] + len(src)
+    # interleave: clones must not all come last (the greedy order matters)
+    perm = rng.permutation(out["n_feat"])
+    for k_ in app:
+        out[k_] = np.ascontiguousarray(out[k_][perm])
+    off, idx, w_inv, h_inv = _grid_csr(out["kp_xy"])
+    out["grid_off"], out["grid_idx"] = off, idx
+    return out
+
+
+def proj_search_case(seed: int, n_points: int = 1000, n_extra: int = 400, found: float = 0.25, pose_noise: float = 0.004, clones: float = 0.15,
+                     cam=EUROC):
+    """Tracking::Relocalization after the first PoseOptimization of a candidate (Tracking.cpp:1285-1296): the current frame with a
+    pose estimate, some of its keypoints already holding map points (`occupied`, the inliers so far = sFound), and the candidate
+    keyframe whose remaining map points SearchByProjection tries to add."""
+    rng = np.random.default_rng(seed)
+    p = kf_view_pair(seed, n_points=n_points, n_extra=n_extra, prematched=0.0, cam=cam)
+    frame, kf = p["kf2"], _clone_kf_features(rng, p["kf1"], clones)
+    nR, nt = random_pose(rng, pose_noise, pose_noise * 2)
+    Rcw = (nR @ frame["Rcw"].astype(np.float64)).astype(np.float32)
+    tcw = (nR @ frame["tcw"].astype(np.float64) + nt).astype(np.float32)
+    common = np.intersect1d(frame["mp_id"][frame["mp_id"] >= 0], kf["mp_id"][kf["mp_id"] >= 0])
+    sfound = set(rng.choice(common, int(len(common) * found), replace=False).tolist()) if len(common) else set()
+    occupied = np.array([1 if int(m) in sfound else 0 for m in frame["mp_id"]], np.uint8)
+    occupied |= (rng.random(frame["n_feat"]) < 0.02).astype(np.uint8)          # keypoints holding map points of other keyframes
+    already = np.array([1 if int(m) in sfound else 0 for m in kf["mp_id"]], np.uint8)
+    return dict(frame=frame, kf=kf, K=p["K"], Rcw=Rcw, tcw=tcw, occupied=occupied, already_found=already)

@@ -514,7 +514,7 @@ def detect_candidates(db: _Keep, qword, qval, mode=0, conn=None, min_score=0.0, 
 
 
 class KfView(C.Structure):
-    _fields_ = [("n_feat", C.c_int), ("kp_xy", C.c_void_p), ("kp_octave", C.c_void_p), ("desc", C.c_void_p), ("mp_valid", C.c_void_p),
+    _fields_ = [("n_feat", C.c_int), ("kp_xy", C.c_void_p), ("kp_octave", C.c_void_p), ("kp_angle", C.c_void_p), ("desc", C.c_void_p), ("mp_valid", C.c_void_p),
                 ("mp_xyz", C.c_void_p), ("mp_desc", C.c_void_p), ("mp_maxdist", C.c_void_p), ("mp_mindist", C.c_void_p),
                 ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("bounds", C.c_float * 4), ("grid_cols", C.c_int), ("grid_rows", C.c_int),
                 ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float), ("grid_off", C.c_void_p), ("grid_idx", C.c_void_p),
@@ -523,12 +523,13 @@ class KfView(C.Structure):
 
 def kf_view(v):
     a = dict(kp_xy=np.ascontiguousarray(v["kp_xy"], np.float32), kp_octave=np.ascontiguousarray(v["kp_octave"], np.int32),
+             kp_angle=np.ascontiguousarray(v["kp_angle"], np.float32),
              desc=np.ascontiguousarray(v["desc"], np.uint32), mp_valid=np.ascontiguousarray(v["mp_valid"], np.uint8),
              mp_xyz=np.ascontiguousarray(v["mp_xyz"], np.float32), mp_desc=np.ascontiguousarray(v["mp_desc"], np.uint32),
              mp_maxdist=np.ascontiguousarray(v["mp_maxdist"], np.float32), mp_mindist=np.ascontiguousarray(v["mp_mindist"], np.float32),
              grid_off=np.ascontiguousarray(v["grid_off"], np.int32), grid_idx=np.ascontiguousarray(v["grid_idx"], np.int32),
              scale_factors=np.ascontiguousarray(v["scale_factors"], np.float32))
-    st = KfView(int(v["n_feat"]), _p(a["kp_xy"]), _p(a["kp_octave"]), _p(a["desc"]), _p(a["mp_valid"]), _p(a["mp_xyz"]), _p(a["mp_desc"]),
+    st = KfView(int(v["n_feat"]), _p(a["kp_xy"]), _p(a["kp_octave"]), _p(a["kp_angle"]), _p(a["desc"]), _p(a["mp_valid"]), _p(a["mp_xyz"]), _p(a["mp_desc"]),
                 _p(a["mp_maxdist"]), _p(a["mp_mindist"]), (C.c_float * 9)(*np.asarray(v["Rcw"], np.float32).reshape(-1)),
                 (C.c_float * 3)(*np.asarray(v["tcw"], np.float32).reshape(-1)), (C.c_float * 4)(*np.asarray(v["bounds"], np.float32)),
                 int(v["grid_cols"]), int(v["grid_rows"]), float(v["grid_w_inv"]), float(v["grid_h_inv"]), _p(a["grid_off"]), _p(a["grid_idx"]),
@@ -544,6 +545,18 @@ def features_in_area(kf: _Keep, x, y, r):
 
 def predict_scale(max_distance, current_dist, log_scale_factor, n_levels):
     return lib().orc_predict_scale(C.c_float(max_distance), C.c_float(current_dist), C.c_float(log_scale_factor), C.c_int(n_levels))
+
+
+def search_by_projection(frame: _Keep, kf: _Keep, K, Rcw, tcw, th=10.0, orb_dist=100, check_orientation=True, occupied=None, already_found=None):
+    """ORBmatcher::SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist): (frame_match [N_frame], nmatches)"""
+    K = np.ascontiguousarray(K, np.float32); R = np.ascontiguousarray(Rcw, np.float32).reshape(9); t = np.ascontiguousarray(tcw, np.float32)
+    oc = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    af = None if already_found is None else np.ascontiguousarray(already_found, np.uint8)
+    out = np.empty(max(frame.st.n_feat, 1), np.int32)
+    n = lib().orc_search_by_projection(C.byref(frame.st), C.byref(kf.st), _p(K), _p(R), _p(t), C.c_float(th), C.c_int(orb_dist),
+                                       C.c_int(int(check_orientation)), None if oc is None else _p(oc), None if af is None else _p(af), _p(out))
+    assert n >= 0
+    return out[:frame.st.n_feat].copy(), n
 
 
 def search_by_sim3(kf1: _Keep, kf2: _Keep, K, R12, t12, th=7.5, matched12_in=None, s12=1.0):

@@ -65,3 +65,45 @@ def test_search_by_sim3_shared_views_scale_and_edges(engine, oracle):
         assert got[c].tolist() == w.tolist(), c
         assert nf[c] == n
     assert nf[0] > 100 and nf[3] < 40 and nf[4] == 0
+
+
+def _sbp_check(engine, oracle, cases, th, od, co):
+    views = [v for c in cases for v in (c["frame"], c["kf"])]
+    fr, kf = [2 * i for i in range(len(cases))], [2 * i + 1 for i in range(len(cases))]
+    got, nm, fell, rounds = engine.proj_search(views, fr, kf, [c["K"] for c in cases], [c["Rcw"] for c in cases], [c["tcw"] for c in cases],
+                                               th, od, co, [c["occupied"] for c in cases], [c["already_found"] for c in cases])
+    for i, c in enumerate(cases):
+        w, n = oracle.search_by_projection(oracle.kf_view(c["frame"]), oracle.kf_view(c["kf"]), c["K"], c["Rcw"], c["tcw"], th, od, co,
+                                           c["occupied"], c["already_found"])
+        assert got[i].tolist() == w.tolist(), (i, th, od, co)
+        assert nm[i] == n
+    return nm, fell, rounds
+
+
+def test_search_by_projection_greedy_order_reproduced(engine, oracle):
+    """ORBmatcher::SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist) is greedy in keyframe-feature order.  The
+    keyframes hold near-duplicate map points that compete for the same frame keypoint (reversing the order changes ~15 % of
+    the assignments on this data, tests/test_cpu_guided.py), so an implementation that resolved conflicts any other way
+    would fail here.  Both of Relocalization's calls: (th 10, ORBdist 100) and (th 3, ORBdist 64)."""
+    cases = [synth.proj_search_case(40 + i, n_points=500 + 200 * i, n_extra=150 + 80 * i, clones=0.1 + 0.05 * i) for i in range(5)]
+    for th, od, co in ((10.0, 100, True), (3.0, 64, True), (10.0, 100, False)):
+        nm, fell, rounds = _sbp_check(engine, oracle, cases, th, od, co)
+        assert (nm > 100).all() and not fell.any()
+        assert (rounds >= 2).all(), "no conflict ever needed a second round: the test data does not exercise the greedy order"
+
+
+def test_search_by_projection_sequential_fallback_and_edges(engine, oracle, monkeypatch):
+    """wide windows with a permissive ORBdist give every map point several acceptable keypoints: with preference lists of one
+    entry (RSAC_PROJ_CAP=1) they overflow, the pairs take the literal one-thread scan and must still agree; the same with the
+    default capacity; a frame whose keypoints are all occupied; a wrong pose"""
+    cases = [synth.proj_search_case(60 + i, n_points=400, n_extra=120, clones=0.3) for i in range(3)]
+    monkeypatch.setenv("RSAC_PROJ_CAP", "1")
+    nm, fell, _ = _sbp_check(engine, oracle, cases, 25.0, 140, True)            # many acceptable candidates per map point
+    assert fell.all()
+    monkeypatch.delenv("RSAC_PROJ_CAP")
+    nm, fell, rounds = _sbp_check(engine, oracle, cases, 25.0, 140, True)       # the same through the preference lists
+    assert not fell.any()
+    full = dict(cases[0], occupied=np.ones_like(cases[0]["occupied"]))
+    wrong = dict(cases[1], tcw=cases[1]["tcw"] + np.float32([2.0, 1.0, -1.5]))
+    nm, fell, rounds = _sbp_check(engine, oracle, [full, wrong], 10.0, 100, True)
+    assert nm[0] == 0
