@@ -25,6 +25,23 @@ struct ProblemMeta {
 
 constexpr float kUnitRoundoff = 5.9604644775390625e-08f;   // 2^-24
 
+// Checked build (-DRSAC_CHECKED; scripts/run_checked.sh): compute-sanitizer is closed on this GPU pool, so the hand-written
+// mbarrier ring, the list-driven launches and the index arithmetic carry their own assertions -- a violated one prints its
+// location and traps (the CUDA error surfaces through the C ABI and fails the test), and the scoring ring is poison-filled
+// before every bulk copy so that a short or misplaced copy cannot go unnoticed.  The default build compiles all of it away.
+#if defined(RSAC_CHECKED) && defined(__CUDA_ARCH__)
+#include <cstdio>
+#define RSAC_ASSERT(cond)                                                                                        \
+    do {                                                                                                         \
+        if (!(cond)) {                                                                                           \
+            printf("RSAC_CHECKED: %s failed at %s:%d (block %d, thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                                            \
+        }                                                                                                        \
+    } while (0)
+#else
+#define RSAC_ASSERT(cond) ((void)0)
+#endif
+
 #ifdef __CUDACC__
 // problem that owns global hypothesis g (binary search over hyp_off)
 __device__ __forceinline__ int find_problem(const ProblemMeta* metas, int C, int64_t g)

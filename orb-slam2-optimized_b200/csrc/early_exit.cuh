@@ -59,7 +59,11 @@ static __global__ void __launch_bounds__(128) early_exit_flag_kernel(const Probl
             bool any = false;
             for (int h = lane; h < lim; h += 32) any = any || (counts[m.hyp_off + h] >= m.min_inl);
             any = __any_sync(0xffffffffu, any);
-            if (!any && lane == 0) v.list(stage + 1)[atomicAdd(v.counters + stage + 1, 1)] = p;
+            if (!any && lane == 0) {
+                const int slot = atomicAdd(v.counters + stage + 1, 1);
+                RSAC_ASSERT(slot >= 0 && slot < C && stage + 1 < kMaxStages && p >= 0 && p < C);
+                v.list(stage + 1)[slot] = p;
+            }
         }
         if (lane == 0) v.upto[p] = min(m.H, lim);
     } else {

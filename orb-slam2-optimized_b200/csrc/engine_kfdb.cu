@@ -11,13 +11,16 @@ int rsac_kfdb_upload(rsac_engine* e, const rsac_kfdb* db)
     if (db->bow_off[0] != 0 || nnz < 0 || (nnz > 0 && (!db->bow_word || !db->bow_val)) || (K > 0 && !db->covis)) {
         e->err = "bad keyframe database"; return RSAC_ERR_INVALID;
     }
+    uint32_t max_word = 0;
     for (int k = 0; k < K; ++k) {
         if (db->bow_off[k + 1] < db->bow_off[k] || db->bow_off[k + 1] - db->bow_off[k] > INT32_MAX) { e->err = "bow_off must ascend"; return RSAC_ERR_INVALID; }
         for (int64_t i = db->bow_off[k] + 1; i < db->bow_off[k + 1]; ++i)
             if (db->bow_word[i] <= db->bow_word[i - 1]) { e->err = "BowVector word ids must ascend (std::map order)"; return RSAC_ERR_INVALID; }
+        if (db->bow_off[k + 1] > db->bow_off[k]) max_word = std::max(max_word, db->bow_word[db->bow_off[k + 1] - 1]);
     }
     RSAC_CUDA(e, cudaSetDevice(e->device));
     KfdbState& s = e->kfdb;
+    s.bm_words = (int64_t)max_word / 32 + 1;
     s.db_ready = false; s.ran = false;
     cudaStream_t st = e->stream;
     const size_t k1 = (size_t)std::max(K, 1), nz = (size_t)std::max<int64_t>(nnz, 1);
@@ -99,6 +102,11 @@ int rsac_kfdb_query_upload(rsac_engine* e, const rsac_kfdb_queries* qs)
     RSAC_TRY(s.d_firstpos.ensure(e, 4 * qk)); RSAC_TRY(s.d_out.ensure(e, 4 * qk));
     RSAC_TRY(s.d_keys.ensure(e, 8 * q1 * (size_t)s.K2));
     RSAC_TRY(s.d_min_common.ensure(e, 4 * q1)); RSAC_TRY(s.d_best_acc.ensure(e, 4 * q1)); RSAC_TRY(s.d_n_out.ensure(e, 4 * q1));
+    // membership bitmaps: up to 2 MB per query (a 16 M-word vocabulary; ORBvoc has 10^6) and 1 GB per batch, else binary search
+    s.use_bitmap = env_int("RSAC_KFDB_BITMAP", 1) != 0 && s.bm_words <= (1 << 19) && (int64_t)q1 * s.bm_words * 4 <= (1ll << 30);
+    if (s.use_bitmap) RSAC_TRY(s.d_bitmap.ensure(e, 4 * q1 * (size_t)s.bm_words));
+    s.max_nq = 0;
+    for (int q = 0; q < Q; ++q) s.max_nq = std::max<int64_t>(s.max_nq, qs->bow_off[q + 1] - qs->bow_off[q]);
     s.Q = Q; s.mode = qs->mode;
     s.queries_ready = true;
     return RSAC_OK;
@@ -125,6 +133,14 @@ int rsac_kfdb_run(rsac_engine* e)
     a.min_common = (int32_t*)s.d_min_common.p; a.best_acc = (float*)s.d_best_acc.p; a.n_out = (int32_t*)s.d_n_out.p;
     if (s.K == 0) { RSAC_CUDA(e, cudaMemsetAsync(s.d_n_out.p, 0, 4 * (size_t)s.Q, st)); return RSAC_OK; }
     RSAC_CUDA(e, cudaMemsetAsync(s.d_firstpos.p, 0x7f, 4 * (size_t)s.Q * s.K, st));
+    a.q_bitmap = nullptr; a.bm_words = (int32_t)s.bm_words;
+    if (s.use_bitmap && s.max_nq > 0) {
+        a.q_bitmap = (uint32_t*)s.d_bitmap.p;
+        RSAC_CUDA(e, cudaMemsetAsync(s.d_bitmap.p, 0, 4 * (size_t)s.Q * (size_t)s.bm_words, st));
+        e->stage_begin(RSAC_STAGE_PACK);
+        kfdb_bitmap_kernel<<<dim3((unsigned)std::min<int64_t>((s.max_nq + 255) / 256, 64), (unsigned)s.Q), 256, 0, st>>>(a);
+        e->stage_end(RSAC_STAGE_PACK);
+    }
     const dim3 gw((unsigned)((s.K + kKfdbWarps - 1) / kKfdbWarps), (unsigned)s.Q), gt((unsigned)((s.K + 255) / 256), (unsigned)s.Q);
     e->stage_begin(RSAC_STAGE_SOLVE);
     kfdb_common_kernel<<<gw, kKfdbWarps * 32, 0, st>>>(a);

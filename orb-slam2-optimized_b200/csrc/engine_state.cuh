@@ -220,6 +220,9 @@ struct BowState {
 struct KfdbState {
     bool db_ready = false, queries_ready = false, ran = false;
     int K = 0, K2 = 1, Q = 0, mode = 0;
+    int64_t bm_words = 1, max_nq = 0;
+    bool use_bitmap = false;
+    DevBuf d_bitmap;
     DevBuf d_kf_off, d_kf_word, d_kf_val, d_covis, d_state;
     DevBuf d_q_off, d_q_word, d_q_val, d_min_score, d_conn_off, d_conn;
     DevBuf d_cw, d_wstar, d_si, d_eff, d_acc, d_best, d_firstpos, d_keys, d_out, d_min_common, d_best_acc, d_n_out;
@@ -228,7 +231,7 @@ struct KfdbState {
     {
         DevBuf* all[] = {&d_kf_off, &d_kf_word, &d_kf_val, &d_covis, &d_state, &d_q_off, &d_q_word, &d_q_val, &d_min_score, &d_conn_off,
                          &d_conn, &d_cw, &d_wstar, &d_si, &d_eff, &d_acc, &d_best, &d_firstpos, &d_keys, &d_out, &d_min_common,
-                         &d_best_acc, &d_n_out};
+                         &d_best_acc, &d_n_out, &d_bitmap};
         for (DevBuf* b : all) b->release();
         h_stage.release();
     }

@@ -186,6 +186,7 @@ epnp_minimal_subwarp_kernel(const ProblemMeta* __restrict__ metas, int C, const 
                 float4 a = make_float4((float)(i & 1), (float)(i >> 1), 5.0f + 0.75f * (float)(i * i), 0.0f);
                 float4 q = make_float4(300.0f + 90.0f * (float)(i & 1), 200.0f + 80.0f * (float)(i >> 1), 0.0f, 0.0f);
                 if (real) {
+                    RSAC_ASSERT(p >= 0 && p < C && h >= 0 && h < m.H && idx[i] < (uint32_t)m.n);
                     const size_t ci = (size_t)m.corr_off + idx[i];
                     a = cA[ci];
                     q = cC[ci];

@@ -15,6 +15,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "common.cuh"
 
 namespace rsac {
 
@@ -422,6 +423,7 @@ static __global__ void __launch_bounds__(256) proj_assign_kernel(ProjSearchArgs 
                     const int idx = cand[(size_t)i * a.cap + k] & 0xfffff;
                     if (!taken[idx]) b = idx;
                 }
+                RSAC_ASSERT(b >= 0 && b < NF && minidx[b] <= i);
                 if (minidx[b] == i) { fmatch[b] = i; cn[i] = -1; }      // final (taken[] is written after the barrier below)
                 else atomicAdd(&s_undecided, 1);
             }

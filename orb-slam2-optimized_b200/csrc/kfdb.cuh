@@ -27,6 +27,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "common.cuh"
 
 namespace rsac {
 
@@ -57,6 +58,9 @@ struct KfdbArgs {
     unsigned long long* keys;    // [Q][K2] sort keys (w* << 32 | keyframe)
     int32_t K2;                  // K rounded up to a power of two
     int32_t* out;                // [Q][K] candidates
+    // membership bitmaps of the queries' words over [0, bm_words * 32) (nullptr: binary search in the sorted word list)
+    uint32_t* q_bitmap;          // [Q][bm_words]
+    int32_t bm_words;
     // per query
     int32_t* min_common;         // [Q]
     float* best_acc;             // [Q] (initialised by the threshold kernel)
@@ -87,6 +91,21 @@ __device__ __forceinline__ bool kfdb_in_sorted(const int32_t* a, int n, int32_t 
     return lo < n && a[lo] == v;
 }
 
+// 0. membership bitmap of every query's words (the vocabulary has ~10^6 words: 128 KB per query, L2-resident): step 1 then
+// costs one load and a bit test per keyframe word instead of a ten-step binary search.  grid (ceil(max nq / 256), Q); the
+// bitmaps are zeroed by the host
+static __global__ void __launch_bounds__(256) kfdb_bitmap_kernel(KfdbArgs a)
+{
+    const int q = blockIdx.y;
+    const int64_t q0 = a.q_off[q];
+    const int nq = (int)(a.q_off[q + 1] - q0);
+    uint32_t* bm = a.q_bitmap + (size_t)q * a.bm_words;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        const uint32_t w = a.q_word[q0 + i];
+        if ((w >> 5) < (uint32_t)a.bm_words) atomicOr(bm + (w >> 5), 1u << (w & 31));     // words beyond the database's largest cannot match
+    }
+}
+
 // 1. shared words of every (query, keyframe) pair.  grid (ceil(K / kKfdbWarps), Q), kKfdbWarps warps
 static __global__ void __launch_bounds__(kKfdbWarps * 32) kfdb_common_kernel(KfdbArgs a)
 {
@@ -94,7 +113,8 @@ static __global__ void __launch_bounds__(kKfdbWarps * 32) kfdb_common_kernel(Kfd
     const int q = blockIdx.y;
     const int64_t q0 = a.q_off[q];
     const int nq = (int)(a.q_off[q + 1] - q0);
-    const bool staged = nq <= kKfdbQMax;
+    const uint32_t* bm = a.q_bitmap ? a.q_bitmap + (size_t)q * a.bm_words : nullptr;
+    const bool staged = !bm && nq <= kKfdbQMax;
     if (staged)
         for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[i] = a.q_word[q0 + i];
     __syncthreads();
@@ -118,7 +138,7 @@ static __global__ void __launch_bounds__(kKfdbWarps * 32) kfdb_common_kernel(Kfd
             uint32_t w = 0xffffffffu;
             if (i < nk) {
                 w = a.kf_word[k0 + i];
-                found = kfdb_find(qw, nq, w) >= 0;
+                found = bm ? ((bm[w >> 5] >> (w & 31)) & 1u) != 0 : kfdb_find(qw, nq, w) >= 0;      // w <= the database's largest word: inside the bitmap
             }
             cnt += __popc(__ballot_sync(0xffffffffu, found));
             first = min(first, __reduce_min_sync(0xffffffffu, found ? w : 0xffffffffu));
@@ -275,7 +295,11 @@ static __global__ void __launch_bounds__(kKfdbEmitThreads) kfdb_emit_kernel(Kfdb
     __syncthreads();
     unsigned long long* gkeys = a.keys + (size_t)q * a.K2;      // K2 = K rounded up to a power of two slots per query
     for (int k = tid; k < a.K; k += blockDim.x)
-        if (kfdb_listed(a, q, k)) gkeys[atomicAdd(&s_n, 1)] = ((unsigned long long)a.wstar[row + k] << 32) | (unsigned)k;
+        if (kfdb_listed(a, q, k)) {
+            const int slot = atomicAdd(&s_n, 1);
+            RSAC_ASSERT(slot < a.K && a.wstar[row + k] != 0xffffffffu);
+            gkeys[slot] = ((unsigned long long)a.wstar[row + k] << 32) | (unsigned)k;
+        }
     __syncthreads();
     const int n = s_n;
     if (n == 0) { if (tid == 0) a.n_out[q] = 0; return; }
@@ -322,6 +346,7 @@ static __global__ void __launch_bounds__(kKfdbEmitThreads) kfdb_emit_kernel(Kfdb
             s_scan[tid] += v;
             __syncthreads();
         }
+        RSAC_ASSERT(!flag || (s_base + s_scan[tid] - 1 >= 0 && s_base + s_scan[tid] - 1 < a.K && b >= 0 && b < a.K));
         if (flag) a.out[row + s_base + s_scan[tid] - 1] = b;
         __syncthreads();
         if (tid == blockDim.x - 1) s_base += s_scan[tid];

@@ -266,6 +266,13 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
                     const int nw = min(grp.chunk_words, grp.words - w0);
                     const int nc = min(nw * 32, grp.n - w0 * 32);
                     float4* dst = sbuf + (size_t)stage * cap * 3;
+                    RSAC_ASSERT(nw > 0 && nc > 0 && nw * 32 <= cap && grp.chunk_words * 32 <= cap && grp.words == (grp.n + 31) / 32);
+                    RSAC_ASSERT(grp.hyp0 >= 0 && grp.hyp0 < grp.H && grp.nchunks == (grp.words + grp.chunk_words - 1) / grp.chunk_words);
+#ifdef RSAC_CHECKED
+                    // poison the slot: whatever the bulk copies do not overwrite would be scored as NaN
+                    for (int q = 0; q < cap * 3; ++q) dst[q] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nw * 1024u + (uint32_t)nc * 16u);
                     tma_load_1d(dst, args.cP + ((size_t)grp.word_off + w0) * 64, (uint32_t)nw * 1024u, &full_bar[stage]);
                     tma_load_1d(dst + 2 * cap, args.cC + (size_t)grp.corr_off + (size_t)w0 * 32, (uint32_t)nc * 16u, &full_bar[stage]);
@@ -378,6 +385,7 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
         if (hdr.x < 0) break;
         if (cit == 0) RSAC_SCORE_MARK(1);
         ++dbg_chunks;
+        RSAC_ASSERT(hdr.y >= 0 && (hdr.y == cur_k || hdr.y > cur_k || args.list != nullptr));     // the producer walks its list forwards
         if (hdr.y != cur_k) {
             // ---- new group: flush the finished tile, take the record from the slot header
             if (cur_k >= 0) flush();
@@ -392,6 +400,7 @@ __global__ void __launch_bounds__(kScoreMaxThreads, 1) score_kernel(ScoreArgs ar
             const int w0 = hdr.x * g_cw;
             const int nw = min(g_cw, g_words - w0);
             const int nc = min(nw * 32, g_n - w0 * 32);
+            RSAC_ASSERT(hdr.x >= 0 && w0 < g_words && nw > 0 && nc > 0 && nw * 32 <= cap);
             for (int w = 0; w < nw; ++w) {
                 uint32_t inl[HPL], cert[HPL];
 #pragma unroll

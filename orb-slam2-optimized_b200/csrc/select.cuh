@@ -768,6 +768,7 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
             while (bits) {
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1;
+                RSAC_ASSERT(w * 32 + b < N && o < N);
                 sel[o++] = (uint32_t)(w * 32 + b);
             }
         }
@@ -846,7 +847,9 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
         if (tid == 0) {
             int32_t* counters = a.ee + 4 * (size_t)a.C;
             a.ee[blockIdx.x] = -(H + 1);
-            (a.ee + 3 * (size_t)a.C)[atomicAdd(counters + 15, 1)] = blockIdx.x;   // kCleanupCounter
+            const int slot = atomicAdd(counters + 15, 1);                           // kCleanupCounter
+            RSAC_ASSERT(slot >= 0 && slot < a.C);
+            (a.ee + 3 * (size_t)a.C)[slot] = blockIdx.x;
             res.reserved[0] = 1;   // not decided yet
             reinterpret_cast<ResultRec*>(a.results)[blockIdx.x] = res;
         }

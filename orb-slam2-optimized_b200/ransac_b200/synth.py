@@ -299,7 +299,12 @@ def reloc_frame(seed: int, C: int, n_kp: int = 2000, n_match: int = 500, outlier
         ks = rng.choice(n_kp, n_match, replace=False)
         ms = true_id[ks].copy()
         out = rng.random(n_match) < outlier_ratio
-        ms[out] = rng.integers(0, n_map, int(out.sum()))
+        # wrong matches: distinct map points, none of them one of this candidate's true points -- SearchByBoW hands every
+        # keyframe map point to at most one frame keypoint (ORBmatcher.cpp:162,219), so a candidate's set never holds a map
+        # point twice (a duplicate would make the minimal sets that draw both copies degenerate)
+        n_out = int(out.sum())
+        pool = np.setdiff1d(rng.choice(n_map, 2 * n_out + 16, replace=False), ms, assume_unique=False)
+        ms[out] = rng.permutation(pool)[:n_out]
         kp_idx[c], mp_idx[c] = ks, ms
     flat = dict(p3d=mp[mp_idx], p2d=uv[kp_idx], sigma2=sigma2[kp_idx])
     return dict(K=np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float64), R=R, t=t, kp_uv=uv, kp_sigma2=sigma2, mp_xyz=mp, kp_idx=kp_idx, mp_idx=mp_idx,

@@ -54,3 +54,38 @@ if os.environ.get("RSAC_PROF_ALL") == "1":
         eng.bow_run()
     eng.sync()
     print("all ok")
+
+# ---- round 2, second session: retrieval and guided matching (RSAC_PROF_NEW=1)
+if os.environ.get("RSAC_PROF_NEW") == "1":
+    dbk = synth.kf_database(21, K=2048, n_places=128)
+    eng.kfdb_upload(dbk)
+    eng.kfdb_query_upload([synth.kf_query(500 + i, dbk, (37 * i) % 128) for i in range(16)], mode=0)
+    for _ in range(reps):
+        eng.kfdb_run()
+    prs = [synth.kf_view_pair(700 + i, n_points=1200, n_extra=400, prematched=0.3) for i in range(4)]
+    vws = [v for p_ in prs for v in (p_["kf1"], p_["kf2"])]
+    k1i, k2i = [2 * (i % 4) for i in range(32)], [2 * (i % 4) + 1 for i in range(32)]
+    eng.sim3_search_upload(vws, k1i, k2i, [prs[i % 4]["K"] for i in range(32)], [prs[i % 4]["R12"] for i in range(32)],
+                           [prs[i % 4]["t12"] for i in range(32)], 7.5, [prs[i % 4]["matched12_in"] for i in range(32)])
+    for _ in range(reps):
+        eng.sim3_search_run()
+    cs = [synth.proj_search_case(800 + i, n_points=1200, n_extra=400, clones=0.1) for i in range(4)]
+    vwp = [v for c_ in cs for v in (c_["frame"], c_["kf"])]
+    eng.proj_search_upload(vwp, k1i, k2i, [cs[i % 4]["K"] for i in range(32)], [cs[i % 4]["Rcw"] for i in range(32)],
+                           [cs[i % 4]["tcw"] for i in range(32)], 10.0, 100, True, [cs[i % 4]["occupied"] for i in range(32)],
+                           [cs[i % 4]["already_found"] for i in range(32)])
+    for _ in range(reps):
+        eng.proj_search_run()
+    # staged MLPnP
+    C2, N2 = 64, 1000
+    b2 = synth.pnp_batch(2, C2, N2, 0.5)
+    cov = np.stack([synth.bearing_covariances(dict(K=b2["K"], sigma2=b2["sigma2"][c])) for c in range(C2)])
+    eng.set_stages([128])
+    eng.mlpnp_upload((np.arange(C2 + 1) * N2).astype(np.int32), b2["p3d"], b2["p2d"], b2["sigma2"], np.array([b2["K"]], np.float32),
+                     capi.ransac_params(0.99, 10, 300, 6, 0.2, 5.991), cov=cov, seeds=b2["seeds"])
+    eng.set_graphs(False)
+    for _ in range(reps):
+        eng.mlpnp_run(capi.FLAG_EARLY_EXIT)
+    eng.set_stages([])
+    eng.sync()
+    print("new ok")

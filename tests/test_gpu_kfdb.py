@@ -52,7 +52,11 @@ def test_loop_candidates(engine, oracle):
     assert found > 10
 
 
-def test_retrieval_edge_cases(engine, oracle):
+@pytest.mark.parametrize("bitmap", ["1", "0"])
+def test_retrieval_edge_cases(engine, oracle, monkeypatch, bitmap):
+    """both membership tests of the shared-word kernel: the per-query bitmap over the vocabulary (default) and the binary
+    search in the query's word list (vocabularies too large for a bitmap; RSAC_KFDB_BITMAP=0 forces it)"""
+    monkeypatch.setenv("RSAC_KFDB_BITMAP", bitmap)
     db = synth.kf_database(3, K=40, n_places=4)
     odb = oracle.kfdb(db)
     engine.kfdb_upload(db)
