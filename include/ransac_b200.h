@@ -383,6 +383,15 @@ int rsac_sim3opt_run(rsac_engine* e);
 /* removed: [total] 1 where the reference sets vpMatches1[idx] = nullptr */
 int rsac_sim3opt_download(rsac_engine* e, rsac_sim3opt_result* results, uint8_t* removed);
 int rsac_sim3opt_solve(rsac_engine* e, const rsac_sim3opt_batch* b, rsac_sim3opt_result* results, uint8_t* removed);
+/* Device-side chaining behind SearchBySim3 (LoopClosing::ComputeSim3, LoopClosing.cpp:309-311: the guided matching extends
+ * vpMapPointMatches, OptimizeSim3 then runs on every non-null entry): pair c = pair c of the engine's last rsac_sim3_search_run,
+ * matches = vpMatches12 on entry (matched12_in >= 0) plus the ones SearchBySim3 added, filtered as Optimizer.cpp:1107-1121 does,
+ * camera-frame points / observations / inverse level sigmas gathered from the resident keyframe views, g2oS12 = the (R12, t12, s12)
+ * the search ran with.  K2: [C][4] intrinsics of pKF2 (NULL: the search's K).  Nothing crosses PCIe.  Then rsac_sim3opt_run and
+ * rsac_sim3opt_download_chained: flags per KF1 feature of every pair (concatenated like match12): 0 = match kept, 1 = removed by
+ * the optimiser, 2 = no match; n_edges[C] (optional) = nCorrespondences. */
+int rsac_sim3opt_from_search(rsac_engine* e, float th2, int fix_scale, const float* K2);
+int rsac_sim3opt_download_chained(rsac_engine* e, rsac_sim3opt_result* results, uint8_t* flags, int32_t* n_edges);
 
 /* ------------------------------------------------ ORBmatcher::SearchByBoW (batched) */
 /* the producer of every correspondence set the RANSAC engine verifies.  Both overloads of the reference:

@@ -1,6 +1,7 @@
 // engine_guided.cu -- C ABI for the batched ORBmatcher::SearchBySim3 (include/ransac_b200.h).
 #include "engine_shared.cuh"
 #include "guided.cuh"
+#include "sim3opt.cuh"
 
 // keyframe / frame views -> concatenated device arrays (shared by rsac_sim3_search_* and rsac_proj_search_*)
 static int guided_upload_views(rsac_engine* e, int V, const rsac_kf_view* in, bool need_angle, std::vector<KfViewDev>& views)
@@ -293,4 +294,92 @@ int rsac_proj_search(rsac_engine* e, const rsac_proj_search_batch* b, int32_t* f
     rc = rsac_proj_search_run(e);
     if (rc) return rc;
     return rsac_proj_search_download(e, frame_match, n_matches, nullptr);
+}
+
+// ---------------------------------------------------------------- OptimizeSim3 chained behind SearchBySim3
+static __global__ void sim3opt_chain_meta_kernel(Sim3OptMeta* metas, int C, const int64_t* off1, const int32_t* n_edges, const float* K1,
+                                                 const float* K2, const float* R12, const float* t12, const float* s12, float th2, int fix_scale)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    Sim3OptMeta m;
+    m.off = off1[c];
+    m.n = n_edges[c];
+    m.fix_scale = fix_scale;
+    m.th2 = th2;
+    for (int k = 0; k < 4; ++k) { m.K1[k] = K1[4 * c + k]; m.K2[k] = K2[4 * c + k]; }
+    for (int k = 0; k < 9; ++k) m.R12[k] = R12[9 * c + k];
+    for (int k = 0; k < 3; ++k) m.t12[k] = t12[3 * c + k];
+    m.s12 = s12 ? s12[c] : 1.0f;
+    metas[c] = m;
+}
+
+int rsac_sim3opt_from_search(rsac_engine* e, float th2, int fix_scale, const float* K2)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    GuidedState& g = e->guided;
+    if (!g.ran) { e->err = "rsac_sim3opt_from_search before rsac_sim3_search_run"; return RSAC_ERR_STATE; }
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    Sim3OptState& s = e->sim3opt;
+    s.uploaded = false; s.ran = false;
+    const int C = g.C;
+    s.C = C; s.total = g.total1; s.chained = true;
+    const size_t tot = (size_t)std::max<int64_t>(g.total1, 1), c1 = (size_t)std::max(C, 1);
+    RSAC_TRY(s.d_metas.ensure(e, sizeof(Sim3OptMeta) * c1));
+    RSAC_TRY(s.d_x1.ensure(e, tot * 12)); RSAC_TRY(s.d_x2.ensure(e, tot * 12));
+    RSAC_TRY(s.d_o1.ensure(e, tot * 8)); RSAC_TRY(s.d_o2.ensure(e, tot * 8));
+    RSAC_TRY(s.d_is1.ensure(e, tot * 4)); RSAC_TRY(s.d_is2.ensure(e, tot * 4));
+    RSAC_TRY(s.d_removed.ensure(e, tot)); RSAC_TRY(s.d_src.ensure(e, tot * 4)); RSAC_TRY(s.d_full.ensure(e, tot));
+    RSAC_TRY(s.d_nedges.ensure(e, 4 * c1)); RSAC_TRY(s.d_K2.ensure(e, 16 * c1));
+    RSAC_TRY(s.d_results.ensure(e, sizeof(rsac_sim3opt_result) * c1));
+    if (C == 0) { s.uploaded = true; return RSAC_OK; }
+    cudaStream_t st = e->stream;
+    if (K2) {
+        float* h = (float*)s.h_metas.ensure(16 * c1);
+        if (!h) { e->err = "pinned allocation failed"; return RSAC_ERR_ALLOC; }
+        memcpy(h, K2, 16 * (size_t)C);
+        RSAC_CUDA(e, cudaMemcpyAsync(s.d_K2.p, h, 16 * (size_t)C, cudaMemcpyHostToDevice, st));
+        s.h_metas.mark(st);
+    }
+    Sim3OptChainArgs a;
+    a.views = (const KfViewDev*)g.d_views.p; a.kp_xy = (const float*)g.d_kp_xy.p; a.kp_octave = (const int32_t*)g.d_kp_octave.p;
+    a.mp_valid = (const uint8_t*)g.d_mp_valid.p; a.mp_xyz = (const float*)g.d_mp_xyz.p;
+    a.C = C; a.kf1 = (const int32_t*)g.d_kf1.p; a.kf2 = (const int32_t*)g.d_kf2.p; a.off1 = (const int64_t*)g.d_off1.p;
+    a.matched_in = g.have_matched ? (const int32_t*)g.d_matched_in.p : nullptr; a.match12 = (const int32_t*)g.d_match12.p;
+    a.x1c = (float*)s.d_x1.p; a.x2c = (float*)s.d_x2.p; a.o1 = (float*)s.d_o1.p; a.o2 = (float*)s.d_o2.p; a.is1 = (float*)s.d_is1.p; a.is2 = (float*)s.d_is2.p;
+    a.src = (int32_t*)s.d_src.p; a.n_edges = (int32_t*)s.d_nedges.p;
+    e->stage_begin(RSAC_STAGE_PACK);
+    sim3opt_from_search_kernel<<<C, 128, 0, st>>>(a);
+    e->stage_end(RSAC_STAGE_PACK);
+    e->stage_begin(RSAC_STAGE_PACK);
+    sim3opt_chain_meta_kernel<<<(C + 127) / 128, 128, 0, st>>>((Sim3OptMeta*)s.d_metas.p, C, a.off1, a.n_edges, (const float*)g.d_K.p,
+                                                            K2 ? (const float*)s.d_K2.p : (const float*)g.d_K.p, (const float*)g.d_R12.p,
+                                                            (const float*)g.d_t12.p, g.have_scale ? (const float*)g.d_s12.p : nullptr, th2, fix_scale);
+    e->stage_end(RSAC_STAGE_PACK);
+    RSAC_CUDA(e, cudaGetLastError());
+    s.uploaded = true;
+    return RSAC_OK;
+}
+
+// after rsac_sim3opt_run on a chained batch: results [C] and, per KF1 feature of every pair, 0 = match kept, 1 = match removed by
+// the optimiser (vpMatches1[i] = nullptr, Optimizer.cpp:1196-1207), 2 = no match / not an edge; n_edges [C] (optional)
+int rsac_sim3opt_download_chained(rsac_engine* e, rsac_sim3opt_result* results, uint8_t* flags, int32_t* n_edges)
+{
+    if (!e) return RSAC_ERR_INVALID;
+    Sim3OptState& s = e->sim3opt;
+    GuidedState& g = e->guided;
+    if (!s.ran || !s.chained) { e->err = "rsac_sim3opt_download_chained needs rsac_sim3opt_from_search + rsac_sim3opt_run"; return RSAC_ERR_STATE; }
+    if (s.C > 0) {
+        e->stage_begin(RSAC_STAGE_PACK);
+        sim3opt_scatter_flags_kernel<<<s.C, 128, 0, e->stream>>>((const KfViewDev*)g.d_views.p, (const int32_t*)g.d_kf1.p, (const int64_t*)g.d_off1.p,
+                                                                 (const int32_t*)s.d_nedges.p, (const uint8_t*)s.d_removed.p, (const int32_t*)s.d_src.p,
+                                                                 (uint8_t*)s.d_full.p);
+        e->stage_end(RSAC_STAGE_PACK);
+        RSAC_CUDA(e, cudaGetLastError());
+        if (results) RSAC_CUDA(e, cudaMemcpyAsync(results, s.d_results.p, sizeof(rsac_sim3opt_result) * (size_t)s.C, cudaMemcpyDeviceToHost, e->stream));
+        if (flags && s.total > 0) RSAC_CUDA(e, cudaMemcpyAsync(flags, s.d_full.p, (size_t)s.total, cudaMemcpyDeviceToHost, e->stream));
+        if (n_edges) RSAC_CUDA(e, cudaMemcpyAsync(n_edges, s.d_nedges.p, 4 * (size_t)s.C, cudaMemcpyDeviceToHost, e->stream));
+    }
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return RSAC_OK;
 }

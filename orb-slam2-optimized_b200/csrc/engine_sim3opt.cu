@@ -19,7 +19,7 @@ int rsac_sim3opt_upload(rsac_engine* e, const rsac_sim3opt_batch* b)
     if (!e || !b || b->C < 0 || !b->offsets || !b->K1 || !b->K2 || !b->S12 || !b->th2) return RSAC_ERR_INVALID;
     RSAC_CUDA(e, cudaSetDevice(e->device));
     Sim3OptState& s = e->sim3opt;
-    s.uploaded = false; s.ran = false;
+    s.uploaded = false; s.ran = false; s.chained = false;
     const int C = b->C;
     const int64_t total = b->offsets[C];
     if (total < 0 || (total > 0 && (!b->x1c || !b->x2c || !b->obs1 || !b->obs2 || !b->inv_sigma2_1 || !b->inv_sigma2_2))) return RSAC_ERR_INVALID;

@@ -186,13 +186,14 @@ struct PoseOptState {
 
 struct Sim3OptState {
     bool uploaded = false, ran = false;
+    bool chained = false;      // the batch was built on the device from the last SearchBySim3 run (rsac_sim3opt_from_search)
     int C = 0;
     int64_t total = 0;
-    DevBuf d_metas, d_x1, d_x2, d_o1, d_o2, d_is1, d_is2, d_removed, d_results;
+    DevBuf d_metas, d_x1, d_x2, d_o1, d_o2, d_is1, d_is2, d_removed, d_results, d_src, d_full, d_nedges, d_K2;
     PinnedBuf h_metas;
     void release()
     {
-        DevBuf* all[] = {&d_metas, &d_x1, &d_x2, &d_o1, &d_o2, &d_is1, &d_is2, &d_removed, &d_results};
+        DevBuf* all[] = {&d_metas, &d_x1, &d_x2, &d_o1, &d_o2, &d_is1, &d_is2, &d_removed, &d_results, &d_src, &d_full, &d_nedges, &d_K2};
         for (DevBuf* b : all) b->release();
         h_metas.release();
     }

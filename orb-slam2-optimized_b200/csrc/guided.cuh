@@ -459,4 +459,88 @@ static __global__ void __launch_bounds__(256) proj_assign_kernel(ProjSearchArgs 
     if (tid == 0) { a.nmatches[c] = s_n; a.rounds[c] = rounds; }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Optimizer::OptimizeSim3 chained behind SearchBySim3 on the device (LoopClosing::ComputeSim3, LoopClosing.cpp:309-311:
+// SearchBySim3 extends vpMapPointMatches, OptimizeSim3 then uses every non-null entry).  One CTA per pair walks the KF1
+// features in order and compacts the matches -- vpMatches12 on entry (matched_in >= 0) or the one SearchBySim3 just added
+// (match12) -- that pass Optimizer.cpp:1107-1121 (pMP1 and pMP2 exist, neither is bad, pMP2 is observed by KF2) into the
+// optimiser's flat arrays, exactly as the reference builds its vertices and edges (:1122-1176): camera-frame points
+// R_iw * P_w + t_iw in float, keypoint observations, mvInvLevelSigma2[octave] = 1 / (scale_factor[octave]^2).
+struct Sim3OptChainArgs {
+    const KfViewDev* views;
+    const float* kp_xy;
+    const int32_t* kp_octave;
+    const uint8_t* mp_valid;
+    const float* mp_xyz;
+    int32_t C;
+    const int32_t* kf1;
+    const int32_t* kf2;
+    const int64_t* off1;
+    const int32_t* matched_in;         // or nullptr
+    const int32_t* match12;
+    float* x1c; float* x2c; float* o1; float* o2; float* is1; float* is2;   // optimiser arrays, pair c at off1[c]
+    int32_t* src;                      // KF1 feature of every compacted match
+    int32_t* n_edges;                  // [C]
+};
+
+static __global__ void __launch_bounds__(128) sim3opt_from_search_kernel(Sim3OptChainArgs a)
+{
+    __shared__ int s_base, s_warp[4];
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const KfViewDev& v1 = a.views[a.kf1[c]];
+    const KfViewDev& v2 = a.views[a.kf2[c]];
+    const int64_t base = a.off1[c];
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < v1.n_feat; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        int i2 = -1;
+        if (i < v1.n_feat) {
+            const int mi = a.matched_in ? a.matched_in[base + i] : -1;
+            i2 = mi != -1 ? mi : a.match12[base + i];                  // -2: a MapPoint KF2 does not observe (i2 < 0: skipped, :1110,1114)
+            if (i2 >= v2.n_feat) i2 = -1;
+            if (i2 >= 0 && !(a.mp_valid[(size_t)v1.feat_off + i] && a.mp_valid[(size_t)v2.feat_off + i2])) i2 = -1;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, i2 >= 0);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        const int k = before + __popc(m & ((1u << lane) - 1u));
+        if (i2 >= 0) {
+            const size_t g1 = (size_t)v1.feat_off + i, g2 = (size_t)v2.feat_off + i2, o = (size_t)base + k;
+            const float p1[3] = {a.mp_xyz[3 * g1], a.mp_xyz[3 * g1 + 1], a.mp_xyz[3 * g1 + 2]};
+            const float p2[3] = {a.mp_xyz[3 * g2], a.mp_xyz[3 * g2 + 1], a.mp_xyz[3 * g2 + 2]};
+            float c1[3], c2[3];
+            guided_mat3_vec(v1.Rcw, p1, v1.tcw, c1);
+            guided_mat3_vec(v2.Rcw, p2, v2.tcw, c2);
+            a.x1c[3 * o] = c1[0]; a.x1c[3 * o + 1] = c1[1]; a.x1c[3 * o + 2] = c1[2];
+            a.x2c[3 * o] = c2[0]; a.x2c[3 * o + 1] = c2[1]; a.x2c[3 * o + 2] = c2[2];
+            a.o1[2 * o] = a.kp_xy[2 * g1]; a.o1[2 * o + 1] = a.kp_xy[2 * g1 + 1];
+            a.o2[2 * o] = a.kp_xy[2 * g2]; a.o2[2 * o + 1] = a.kp_xy[2 * g2 + 1];
+            const float sf1 = v1.scale_factors[a.kp_octave[g1]], sf2 = v2.scale_factors[a.kp_octave[g2]];
+            a.is1[o] = 1.0f / (sf1 * sf1);                              // ORBextractor: mvLevelSigma2 = scale^2, mvInvLevelSigma2 = 1.0f / it
+            a.is2[o] = 1.0f / (sf2 * sf2);
+            a.src[o] = i;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 4; ++w) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) a.n_edges[c] = s_base;
+}
+
+// flags of a chained run back in the KF1 feature index space: 2 = not an edge, 1 = removed by the optimiser, 0 = kept
+static __global__ void __launch_bounds__(128) sim3opt_scatter_flags_kernel(const KfViewDev* views, const int32_t* kf1, const int64_t* off1,
+                                                                   const int32_t* n_edges, const uint8_t* removed, const int32_t* src,
+                                                                   uint8_t* full)
+{
+    const int c = blockIdx.x;
+    const int n1 = views[kf1[c]].n_feat;
+    const int64_t base = off1[c];
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) full[base + i] = 2;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_edges[c]; k += blockDim.x) full[base + src[base + k]] = removed[base + k];
+}
+
 }  // namespace rsac

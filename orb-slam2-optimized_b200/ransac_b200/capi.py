@@ -592,6 +592,22 @@ class Engine:
     def sim3opt_run(self):
         self._ck(self.L.rsac_sim3opt_run(self.h), "sim3opt_run")
 
+    def sim3opt_from_search(self, th2=10.0, fix_scale=True, K2=None):
+        """OptimizeSim3 on the device behind the last sim3_search_run (LoopClosing.cpp:309-311)"""
+        k2 = None if K2 is None else np.ascontiguousarray(K2, np.float32).reshape(-1, 4)
+        self._ck(self.L.rsac_sim3opt_from_search(self.h, C.c_float(th2), C.c_int(1 if fix_scale else 0), _p(k2)), "rsac_sim3opt_from_search")
+
+    def sim3opt_download_chained(self):
+        """(results [C], list of per-pair KF1-indexed flag arrays (0 kept, 1 removed, 2 no match), n_edges [C])"""
+        n1 = self._s3s_n1
+        Cn = len(n1)
+        res = np.zeros(max(Cn, 1), SIM3OPT_DTYPE)
+        flags = np.zeros(max(int(sum(n1)), 1), np.uint8)
+        ne = np.zeros(max(Cn, 1), np.int32)
+        self._ck(self.L.rsac_sim3opt_download_chained(self.h, _p(res), _p(flags), _p(ne)), "rsac_sim3opt_download_chained")
+        offs = np.concatenate([[0], np.cumsum(n1)]).astype(np.int64)
+        return res[:Cn], [flags[offs[i]:offs[i + 1]].copy() for i in range(Cn)], ne[:Cn]
+
     # -- scoring stress
     def score_pnp_upload(self, poses, p3d, p2d, max_err, K):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)

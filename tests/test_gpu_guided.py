@@ -107,3 +107,58 @@ def test_search_by_projection_sequential_fallback_and_edges(engine, oracle, monk
     wrong = dict(cases[1], tcw=cases[1]["tcw"] + np.float32([2.0, 1.0, -1.5]))
     nm, fell, rounds = _sbp_check(engine, oracle, [full, wrong], 10.0, 100, True)
     assert nm[0] == 0
+
+
+def _mv32(R, p, t):
+    F = np.float32
+    R = np.asarray(R, F).reshape(3, 3)
+    return np.array([F(F(F(R[i, 0] * p[0]) + F(R[i, 1] * p[1])) + F(R[i, 2] * p[2])) + F(t[i]) for i in range(3)], F)
+
+
+def test_optimize_sim3_chained_behind_search_by_sim3(engine, oracle):
+    """LoopClosing::ComputeSim3 (LoopClosing.cpp:309-311): SearchBySim3 extends vpMapPointMatches, OptimizeSim3 runs on every
+    non-null entry -- on the device, from the resident keyframe views, nothing crossing PCIe in between.  The oracle side
+    composes orc_search_by_sim3 with the vertex / edge construction of Optimizer.cpp:1100-1176 (float camera-frame points,
+    keypoint observations, inverse level sigmas) and orc_optimize_sim3."""
+    F = np.float32
+    pairs = [synth.kf_view_pair(90 + i, n_points=350 + 150 * i, n_extra=100, prematched=0.25, pose_noise=0.006) for i in range(4)]
+    views = [v for p in pairs for v in (p["kf1"], p["kf2"])]
+    kf1, kf2 = [2 * i for i in range(4)], [2 * i + 1 for i in range(4)]
+    engine.sim3_search_upload(views, kf1, kf2, [p["K"] for p in pairs], [p["R12"] for p in pairs], [p["t12"] for p in pairs], 7.5,
+                              [p["matched12_in"] for p in pairs])
+    engine.sim3_search_run()
+    new, nf = engine.sim3_search_download()
+    engine.sim3opt_from_search(10.0, True)
+    engine.sim3opt_run()
+    res, flags, n_edges = engine.sim3opt_download_chained()
+    for c, p in enumerate(pairs):
+        k1, k2 = p["kf1"], p["kf2"]
+        wn, _ = oracle.search_by_sim3(oracle.kf_view(k1), oracle.kf_view(k2), p["K"], p["R12"], p["t12"], 7.5, p["matched12_in"])
+        assert new[c].tolist() == wn.tolist()
+        i2_of = np.where(p["matched12_in"] != -1, p["matched12_in"], wn)
+        src, x1c, x2c, o1, o2, is1, is2 = [], [], [], [], [], [], []
+        for i in range(k1["n_feat"]):
+            i2 = int(i2_of[i])
+            if i2 < 0 or not k1["mp_valid"][i] or not k2["mp_valid"][i2]:
+                continue
+            src.append(i)
+            x1c.append(_mv32(k1["Rcw"], k1["mp_xyz"][i], k1["tcw"])); x2c.append(_mv32(k2["Rcw"], k2["mp_xyz"][i2], k2["tcw"]))
+            o1.append(k1["kp_xy"][i]); o2.append(k2["kp_xy"][i2])
+            s1, s2 = k1["scale_factors"][k1["kp_octave"][i]], k2["scale_factors"][k2["kp_octave"][i2]]
+            is1.append(F(1.0) / F(s1 * s1)); is2.append(F(1.0) / F(s2 * s2))
+        assert n_edges[c] == len(src) and len(src) > 100, c
+        S12 = np.concatenate([p["R12"].reshape(-1), p["t12"], [1.0]]).astype(F)
+        o, orem = oracle.optimize_sim3(oracle.sim3opt_problem(np.array(x1c), np.array(x2c), np.array(o1), np.array(o2), np.array(is1), np.array(is2),
+                                                              p["K"], p["K"], S12, th2=10.0, fix_scale=True))
+        want = np.full(k1["n_feat"], 2, np.uint8)
+        want[np.array(src)] = orem
+        diff = np.flatnonzero(flags[c] != want)
+        assert not ((flags[c] == 2) != (want == 2)).any(), c                    # the same edges
+        if diff.size == 0:                                                       # (a chi2 within rounding of th2 may flip a flag)
+            r = res[c]
+            assert r["optimized"] == o["optimized"] and r["n_inliers"] == o["n_inliers"] and r["n_bad"] == o["n_bad"], c
+            d = max(np.abs(r["R"].reshape(3, 3) - o["R"]).max(), np.abs(r["t"] - o["t"]).max())
+            assert d < 1e-6, (c, d)
+            assert r["n_inliers"] >= 20                                          # ComputeSim3 would accept this candidate (:314)
+        else:
+            assert diff.size <= 2, (c, diff)
