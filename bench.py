@@ -994,6 +994,43 @@ def extras_single_gpu(eng, peaks, peak_src, fp32_pk, line):
                                               "exactly by preference lists + rounds (csrc/guided.cuh); bit-identical to the oracle"}
     except Exception as err:
         ex["search_by_projection_error"] = repr(err)
+    # ---- the body of Tracking::Relocalization on the device (Tracking.cpp:1207-1284): SearchByBoW for every candidate -> PnP batch
+    # built from the match arrays on the device (only the match counts visit the host) -> EPnP RANSAC sweep -> PoseOptimization
+    try:
+        Cw = 256
+        wr = synth.reloc_world(77, C=Cw, n_kp=1500, n_kf_feat=1200)
+        setsw = [wr["frame"]] + wr["kfs"]
+        prmw = capi.ransac_params(0.99, 10, 300, 4, 0.5, 5.991)
+
+        def reloc_once(first=False):
+            eng.bow_upload(setsw, list(range(1, Cw + 1)), [0] * Cw, 0.75, True, 0) if first else None
+            eng.bow_run()
+            _, nmw = eng.bow_download()
+            eng.pnp_upload_from_bow(nmw, wr["K"], prmw, wr["seeds"], 15, kp_uv=wr["kp_uv"] if first else None,
+                                    kp_sigma2=wr["kp_sigma2"] if first else None, mp_xyz=wr["mp_xyz"] if first else None)
+            eng.pnp_run(capi.FLAG_EARLY_EXIT)
+            eng.poseopt_from_pnp()
+            eng.poseopt_run()
+            return eng.poseopt_download(), nmw
+
+        (pow_, _), nmw = reloc_once(True)
+        for _ in range(2):
+            reloc_once()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            reloc_once()
+        msw = (time.perf_counter() - t0) / 10 * 1e3
+        Rw = np.stack([r_["Rf"].reshape(3, 3) for r_ in pow_])
+        good = [int(c_) for c_ in range(Cw) if nmw[c_] >= 15 and pow_[c_]["n_inliers"] >= 50 and np.abs(Rw[c_] - wr["R"]).max() < 0.02]
+        ex["relocalisation_pipeline"] = {"candidates": Cw, "frame_keypoints": 1500, "keyframe_features": 1200, "ms_per_relocalisation": msw,
+                                         "candidates_per_s": Cw / (msw * 1e-3), "bow_matches_mean": float(np.mean(nmw)),
+                                         "candidates_relocalised": len(good),
+                                         "note": "SearchByBoW (resident keyframe sets) -> rsac_pnp_upload_from_bow -> EPnP RANSAC -> PoseOptimization, "
+                                                 "wall clock per relocalisation of one frame against 256 candidates incl. the download of the "
+                                                 "match counts and of the final records; a candidate counts as relocalised with >= 50 inliers "
+                                                 "(Tracking.cpp:1318) at the true pose"}
+    except Exception as err:
+        ex["relocalisation_pipeline_error"] = repr(err)
     # ---- ORBmatcher::SearchByBoW, 1024 candidate keyframes against one frame (Tracking.cpp:1207-1232)
     try:
         Fb = synth.bow_frame(11, 1500, 100)

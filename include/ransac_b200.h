@@ -214,6 +214,25 @@ typedef struct {
     const int64_t* table_offsets;
 } rsac_pnp_indexed_batch;
 int rsac_pnp_upload_indexed(rsac_engine* e, const rsac_pnp_indexed_batch* b);
+/* The same batch built ON THE DEVICE from the engine's last rsac_bow_run (mode 0, every pair against the same frame): candidate
+ * c = pair c, its correspondences = the frame keypoints SearchByBoW matched, in keypoint order (the order PnPsolver's constructor
+ * walks vpMapPointMatches, PnPsolver.cpp:25-50), each paired with mp_index[] of the matched keyframe feature -- the matches never
+ * leave the device; the host only needs their COUNTS (n_matches from rsac_bow_download) to shape the batch (Tracking.cpp:1207-1232:
+ * SearchByBoW, then a PnPsolver per candidate with at least 15 matches -- candidates below min_matches become empty problems).
+ * One parameter set (n_params = 1).  kp_uv / mp_xyz == NULL keep the resident tables. */
+typedef struct {
+    const int32_t* n_matches;    /* [C] as downloaded */
+    int32_t min_matches;         /* nmatches < min_matches: vbDiscarded (15 in Relocalization) */
+    int32_t n_keypoints;
+    const float* kp_uv;
+    const float* kp_sigma2;
+    int32_t n_mappoints;
+    const float* mp_xyz;
+    const double* K;             /* [4] */
+    const rsac_ransac_params* params;
+    const uint32_t* seeds;       /* [C] */
+} rsac_pnp_from_bow;
+int rsac_pnp_upload_from_bow(rsac_engine* e, const rsac_pnp_from_bow* b);
 /* stage 2: all hypotheses of all problems: EPnP minimal solves, CheckInliers scoring,
  * sequential-semantics replay with Refine (PnPsolver::iterate, PnPsolver.cpp:102-238).
  * Device-resident, asynchronous.  d_results_out: optional device buffer of C rsac_result
@@ -409,6 +428,8 @@ typedef struct {
     const uint32_t* node_ids;    /* [n_nodes] NodeIds, ascending (std::map order) */
     const int32_t* node_off;     /* [n_nodes + 1] */
     const uint32_t* node_feat;   /* [node_off[n_nodes]] feature indices, per node in insertion order */
+    const uint32_t* mp_index;    /* optional [n_feat]: slot of every feature's MapPoint in the map-point table of
+                                    rsac_pnp_upload_indexed (keyframes only; used by rsac_pnp_upload_from_bow) */
 } rsac_bow_features;
 
 typedef struct {

@@ -59,7 +59,7 @@ __device__ __forceinline__ int bow_distance(const uint4 a0, const uint4 a1, cons
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-__global__ void __launch_bounds__(128) bow_match_kernel(BowArgs a)
+static __global__ void __launch_bounds__(128) bow_match_kernel(BowArgs a)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) bow_match_kernel(BowArgs a)
 }
 
 // rotation consistency (:214-234) and the final count, one CTA per pair
-__global__ void __launch_bounds__(128) bow_orient_kernel(BowArgs a)
+static __global__ void __launch_bounds__(128) bow_orient_kernel(BowArgs a)
 {
     __shared__ int histo[kBowHisto];
     __shared__ int s_ind[3], s_count;

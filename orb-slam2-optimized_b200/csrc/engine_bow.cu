@@ -13,7 +13,7 @@ int rsac_bow_upload(rsac_engine* e, const rsac_bow_batch* b)
     const int S = b->n_sets, C = b->C;
     std::vector<BowSet> sets(std::max(S, 1));
     int64_t nfeat = 0, nnodes = 0, nnf = 0;
-    bool any_valid = false;
+    bool any_valid = false, any_mp = false;
     for (int i = 0; i < S; ++i) {
         const rsac_bow_features& f = b->sets[i];
         if (f.n_feat < 0 || f.n_nodes < 0 || (f.n_feat > 0 && (!f.desc || !f.angle)) || (f.n_nodes > 0 && (!f.node_ids || !f.node_off || !f.node_feat))) {
@@ -32,6 +32,7 @@ int rsac_bow_upload(rsac_engine* e, const rsac_bow_batch* b)
         d.nf_off = (int32_t)nnf;
         nfeat += f.n_feat; nnodes += f.n_nodes; nnf += f.n_nodes > 0 ? f.node_off[f.n_nodes] : 0;
         any_valid = any_valid || f.valid != nullptr;
+        any_mp = any_mp || f.mp_index != nullptr;
         if (nfeat > INT32_MAX / 8 || nnf > INT32_MAX) { e->err = "batch too large"; return RSAC_ERR_INVALID; }
     }
     // work items: (pair, query node); per-pair output offsets
@@ -47,6 +48,13 @@ int rsac_bow_upload(rsac_engine* e, const rsac_bow_batch* b)
     s.C = C; s.n_items = (int)items.size(); s.mode = b->mode; s.check_orientation = b->check_orientation; s.nn_ratio = b->nn_ratio;
     s.total_t = s.t2q_off[C]; s.total_q = s.q2t_off[C];
     s.have_valid = any_valid;
+    s.have_mp_index = any_mp;
+    s.one_target = true;
+    s.target_n_feat.assign(C, 0);
+    for (int p = 0; p < C; ++p) {
+        s.one_target = s.one_target && b->target_set[p] == b->target_set[0];
+        s.target_n_feat[p] = sets[b->target_set[p]].n_feat;
+    }
 
     // one pinned staging buffer, one layout, a handful of copies
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -90,6 +98,16 @@ int rsac_bow_upload(rsac_engine* e, const rsac_bow_batch* b)
         RSAC_CUDA(e, cudaMemcpyAsync(c.d->p, h + c.off, c.bytes, cudaMemcpyHostToDevice, e->stream));
     }
     s.h_stage.mark(e->stream);
+    if (any_mp) {
+        // map-point table slots of the keyframes' features (rsac_pnp_upload_from_bow): pageable copies, made before returning
+        RSAC_TRY(s.d_mp_index.ensure(e, 4 * (size_t)std::max<int64_t>(nfeat, 1)));
+        RSAC_CUDA(e, cudaMemsetAsync(s.d_mp_index.p, 0xff, 4 * (size_t)std::max<int64_t>(nfeat, 1), e->stream));
+        for (int i = 0; i < S; ++i)
+            if (b->sets[i].mp_index && b->sets[i].n_feat > 0)
+                RSAC_CUDA(e, cudaMemcpyAsync((uint32_t*)s.d_mp_index.p + sets[i].feat_off, b->sets[i].mp_index, 4 * (size_t)b->sets[i].n_feat,
+                                             cudaMemcpyHostToDevice, e->stream));
+        RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    }
     RSAC_TRY(s.d_t2q.ensure(e, 4 * (size_t)std::max<int64_t>(s.total_t, 1)));
     RSAC_TRY(s.d_q2t.ensure(e, 4 * (size_t)std::max<int64_t>(s.total_q, 1)));
     RSAC_TRY(s.d_bin.ensure(e, (size_t)std::max<int64_t>(s.total_t, 1)));

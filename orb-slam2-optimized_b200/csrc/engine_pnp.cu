@@ -5,6 +5,7 @@
 #include "pnp_pipeline.cuh"
 #include "epnp_subwarp.cuh"
 #include "select.cuh"
+#include "bow.cuh"
 
 // The 4-point minimal solver: three lanes per hypothesis (epnp_subwarp.cuh); RSAC_SOLVE_IMPL=thread selects the
 // round-1 one-thread-per-hypothesis kernel (A/B timing only)
@@ -256,13 +257,102 @@ static int pnp_pack(rsac_engine* e)
     return RSAC_OK;
 }
 
-static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_pnp_indexed_batch* ib);
+static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_pnp_indexed_batch* ib, bool idx_on_device = false);
 
 int rsac_pnp_upload(rsac_engine* e, const rsac_pnp_batch* b) { return pnp_upload_impl(e, b, nullptr); }
+
+// (keypoint, map point) index pairs of every candidate straight from SearchByBoW's match arrays: one CTA per pair walks the
+// frame's features in order and compacts the matched ones (ballot + prefix) to offsets[c] ..; a candidate the host discarded
+// (fewer than min_matches: offsets[c + 1] == offsets[c]) writes nothing
+static __global__ void __launch_bounds__(128) pnp_pairs_from_bow_kernel(int C, const int64_t* __restrict__ t2q_off, const int32_t* __restrict__ t2q,
+                                                                 const BowSet* __restrict__ sets, const int32_t* __restrict__ qset,
+                                                                 const int32_t* __restrict__ tset, const uint32_t* __restrict__ mp_index,
+                                                                 const int32_t* __restrict__ offsets, uint16_t* __restrict__ kp_idx,
+                                                                 uint32_t* __restrict__ mp_idx)
+{
+    __shared__ int s_base, s_warp[4];
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = offsets[c + 1] - offsets[c];
+    if (cap <= 0) return;
+    const BowSet Q = sets[qset[c]], T = sets[tset[c]];
+    const int32_t* m = t2q + t2q_off[c];
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < T.n_feat; j0 += blockDim.x) {
+        const int j = j0 + tid;
+        const int q = j < T.n_feat ? m[j] : -1;
+        const unsigned b = __ballot_sync(0xffffffffu, q >= 0);
+        if (lane == 0) s_warp[warp] = __popc(b);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        const int k = before + __popc(b & ((1u << lane) - 1u));
+        if (q >= 0 && k < cap) {
+            kp_idx[offsets[c] + k] = (uint16_t)j;
+            mp_idx[offsets[c] + k] = mp_index[Q.feat_off + q];
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 4; ++w) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+}
+
+int rsac_pnp_upload_from_bow(rsac_engine* e, const rsac_pnp_from_bow* fb)
+{
+    if (!e || !fb || !fb->n_matches || !fb->K || !fb->params || !fb->seeds) return RSAC_ERR_INVALID;
+    BowState& bw = e->bow;
+    if (!bw.ran) { e->err = "rsac_pnp_upload_from_bow before rsac_bow_run"; return RSAC_ERR_STATE; }
+    if (bw.mode != 0 || !bw.one_target || !bw.have_mp_index) {
+        e->err = "rsac_pnp_upload_from_bow needs a mode-0 SearchByBoW batch against ONE frame whose keyframe sets carry mp_index";
+        return RSAC_ERR_STATE;
+    }
+    const int C = bw.C;
+    if (C > 0 && bw.target_n_feat[0] > 65536) { e->err = "the frame has more than 65536 keypoints"; return RSAC_ERR_INVALID; }
+    std::vector<int32_t> offsets((size_t)C + 1, 0);
+    for (int c = 0; c < C; ++c) {
+        const int n = fb->n_matches[c];
+        if (n < 0 || n > bw.target_n_feat[c]) { e->err = "n_matches does not belong to the last SearchByBoW run"; return RSAC_ERR_INVALID; }
+        if ((int64_t)offsets[c] + n > INT32_MAX) { e->err = "batch too large"; return RSAC_ERR_INVALID; }
+        offsets[c + 1] = offsets[c] + (n >= fb->min_matches ? n : 0);            // Tracking.cpp:1215-1219: nmatches < 15 -> vbDiscarded
+    }
+    rsac_pnp_indexed_batch ib;
+    memset(&ib, 0, sizeof(ib));
+    ib.n_keypoints = fb->n_keypoints; ib.kp_uv = fb->kp_uv; ib.kp_sigma2 = fb->kp_sigma2;
+    ib.n_mappoints = fb->n_mappoints; ib.mp_xyz = fb->mp_xyz;
+    ib.C = C; ib.offsets = offsets.data(); ib.K = fb->K; ib.params = fb->params; ib.n_params = 1; ib.seeds = fb->seeds;
+    PnpState& s = e->pnp;
+    if ((!ib.kp_uv && s.n_keypoints == 0) || (!ib.mp_xyz && s.n_mappoints == 0)) { e->err = "no resident keypoint / map-point table"; return RSAC_ERR_STATE; }
+    if ((ib.kp_uv && (ib.n_keypoints <= 0 || ib.n_keypoints > 65536 || !ib.kp_sigma2)) || (ib.mp_xyz && ib.n_mappoints <= 0)) {
+        e->err = "bad keypoint / map-point table"; return RSAC_ERR_INVALID;
+    }
+    std::vector<double> K((size_t)std::max(C, 1) * 4);
+    for (int c = 0; c < C; ++c)
+        for (int k = 0; k < 4; ++k) K[4 * (size_t)c + k] = fb->K[k];
+    rsac_pnp_batch b;
+    memset(&b, 0, sizeof(b));
+    b.C = C; b.offsets = offsets.data(); b.K = K.data(); b.params = fb->params; b.n_params = 1; b.seeds = fb->seeds;
+    RSAC_TRY(pnp_upload_impl(e, &b, &ib, true));
+    if (!s.indexed_fused) { e->err = "rsac_pnp_upload_from_bow needs the fused indexed path (RSAC_INDEXED_FUSED=0 is set)"; return RSAC_ERR_STATE; }
+    if (C > 0 && s.d.total > 0) {
+        RSAC_TRY(e->d_scratch.ensure(e, 4 * ((size_t)C + 1)));
+        int32_t* h = (int32_t*)s.h_fromBow.ensure(4 * ((size_t)C + 1));
+        if (!h) { e->err = "cudaHostAlloc failed"; return RSAC_ERR_ALLOC; }
+        memcpy(h, offsets.data(), 4 * ((size_t)C + 1));
+        RSAC_CUDA(e, cudaMemcpyAsync(e->d_scratch.p, h, 4 * ((size_t)C + 1), cudaMemcpyHostToDevice, e->stream));
+        s.h_fromBow.mark(e->stream);
+        ++e->launches;
+        pnp_pairs_from_bow_kernel<<<C, 128, 0, e->stream>>>(C, (const int64_t*)bw.d_t2q_off.p, (const int32_t*)bw.d_t2q.p, (const BowSet*)bw.d_sets.p,
+                                                           (const int32_t*)bw.d_qset.p, (const int32_t*)bw.d_tset.p, (const uint32_t*)bw.d_mp_index.p,
+                                                           (const int32_t*)e->d_scratch.p, (uint16_t*)s.d_kp_idx.p, (uint32_t*)s.d_mp_idx.p);
+        RSAC_CUDA(e, cudaGetLastError());
+    }
+    return RSAC_OK;
+}
 
 int rsac_pnp_upload_indexed(rsac_engine* e, const rsac_pnp_indexed_batch* ib)
 {
     if (!e || !ib || ib->C < 0 || !ib->offsets || !ib->K) return RSAC_ERR_INVALID;
+    if (ib->n_params < 1 || !ib->params) return RSAC_ERR_INVALID;
     const int64_t total = ib->offsets[ib->C];
     if (total > 0 && (!ib->kp_idx || !ib->mp_idx)) { e->err = "kp_idx / mp_idx is NULL"; return RSAC_ERR_INVALID; }
     PnpState& s = e->pnp;
@@ -280,7 +370,7 @@ int rsac_pnp_upload_indexed(rsac_engine* e, const rsac_pnp_indexed_batch* ib)
     return pnp_upload_impl(e, &b, ib);
 }
 
-static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_pnp_indexed_batch* ib)
+static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_pnp_indexed_batch* ib, bool idx_on_device)
 {
     if (!e || !b || b->C < 0 || !b->offsets || !b->params || b->n_params < 1) return RSAC_ERR_INVALID;
     if (!b->seeds && !b->tables) { if (e) e->err = "need seeds or tables"; return RSAC_ERR_INVALID; }
@@ -374,9 +464,11 @@ static int pnp_upload_impl(rsac_engine* e, const rsac_pnp_batch* b, const rsac_p
         if (d.total > 0) {
             RSAC_TRY(s.d_kp_idx.ensure(e, (size_t)d.total * 2));
             RSAC_TRY(s.d_mp_idx.ensure(e, (size_t)d.total * 4));
-            RSAC_CUDA(e, cudaMemcpyAsync(s.d_kp_idx.p, ib->kp_idx, (size_t)d.total * 2, cudaMemcpyHostToDevice, st));
-            RSAC_CUDA(e, cudaMemcpyAsync(s.d_mp_idx.p, ib->mp_idx, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));
-            if (!s.indexed_fused) RSAC_TRY(rsac_internal_pnp_ensure_flat(e));
+            if (!idx_on_device) {       // (rsac_pnp_upload_from_bow writes the pairs with a kernel, after this function)
+                RSAC_CUDA(e, cudaMemcpyAsync(s.d_kp_idx.p, ib->kp_idx, (size_t)d.total * 2, cudaMemcpyHostToDevice, st));
+                RSAC_CUDA(e, cudaMemcpyAsync(s.d_mp_idx.p, ib->mp_idx, (size_t)d.total * 4, cudaMemcpyHostToDevice, st));
+                if (!s.indexed_fused) RSAC_TRY(rsac_internal_pnp_ensure_flat(e));
+            }
         }
     } else if (d.total > 0) {
         s.indexed_fused = false;

@@ -99,7 +99,7 @@ struct PnpState {
     uint64_t h2d_bytes = 0;
     DevBuf d_metas, d_cP, d_th2, d_p3d, d_p2d, d_sigma2, d_cA, d_cB, d_uv, d_tables, d_poses, d_counts,
         d_results, d_masks, d_hmasks, d_sel, d_pw, d_us, d_al, d_cov, d_extra, d_visit;
-    PinnedBuf h_stage;
+    PinnedBuf h_stage, h_fromBow;
     // indexed wire format: the frame's keypoint table and the map-point table stay resident between uploads
     DevBuf d_kp_uv, d_kp_s2, d_mp_xyz, d_kp_idx, d_mp_idx, d_kpA, d_kpB;
     int n_keypoints = 0, n_mappoints = 0;
@@ -133,6 +133,7 @@ struct PnpState {
     {
         if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
         h_stage.release();
+        h_fromBow.release();
         h_stageEE.release();
         d_ee.release();
         for (auto& b : ee_visit) b.release();
@@ -206,13 +207,14 @@ struct BowState {
     int64_t total_t = 0, total_q = 0;          // sizes of the per-pair target- / query-indexed arrays
     std::vector<int64_t> t2q_off, q2t_off;
     DevBuf d_sets, d_qset, d_tset, d_t2q_off, d_q2t_off, d_items, d_desc, d_angle, d_valid, d_node_ids, d_node_start, d_node_feat,
-        d_t2q, d_q2t, d_bin, d_nmatches;
+        d_t2q, d_q2t, d_bin, d_nmatches, d_mp_index;
     PinnedBuf h_stage;
-    bool have_valid = false;
+    bool have_valid = false, have_mp_index = false, one_target = false;
+    std::vector<int32_t> target_n_feat;        // [C] features of every pair's target set
     void release()
     {
         DevBuf* all[] = {&d_sets, &d_qset, &d_tset, &d_t2q_off, &d_q2t_off, &d_items, &d_desc, &d_angle, &d_valid, &d_node_ids,
-                         &d_node_start, &d_node_feat, &d_t2q, &d_q2t, &d_bin, &d_nmatches};
+                         &d_node_start, &d_node_feat, &d_t2q, &d_q2t, &d_bin, &d_nmatches, &d_mp_index};
         for (DevBuf* b : all) b->release();
         h_stage.release();
     }

@@ -102,7 +102,14 @@ SIM3OPT_DTYPE = np.dtype([("n_inliers", np.int32), ("n_bad", np.int32), ("optimi
 
 class BowFeatures(C.Structure):
     _fields_ = [("n_feat", C.c_int32), ("desc", C.c_void_p), ("angle", C.c_void_p), ("valid", C.c_void_p),
-                ("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("node_off", C.c_void_p), ("node_feat", C.c_void_p)]
+                ("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("node_off", C.c_void_p), ("node_feat", C.c_void_p),
+                ("mp_index", C.c_void_p)]
+
+
+class PnPFromBow(C.Structure):
+    _fields_ = [("n_matches", C.c_void_p), ("min_matches", C.c_int32), ("n_keypoints", C.c_int32), ("kp_uv", C.c_void_p),
+                ("kp_sigma2", C.c_void_p), ("n_mappoints", C.c_int32), ("mp_xyz", C.c_void_p), ("K", C.c_void_p), ("params", C.c_void_p),
+                ("seeds", C.c_void_p)]
 
 
 class BowBatch(C.Structure):
@@ -390,6 +397,25 @@ class Engine:
         self._pnp_words = ((np.diff(offsets) + 31) // 32).astype(np.int64)
         return Cn
 
+    def pnp_upload_from_bow(self, n_matches, K, params, seeds, min_matches=15, kp_uv=None, kp_sigma2=None, mp_xyz=None):
+        """the PnP batch built on the device from the last bow_run (mode 0, one frame): only the match COUNTS come from the host"""
+        nm = np.ascontiguousarray(n_matches, np.int32)
+        K = np.ascontiguousarray(K, np.float64).reshape(4)
+        parr = (RansacParams * 1)(params)
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        kp_uv = None if kp_uv is None else np.ascontiguousarray(kp_uv, np.float32).reshape(-1, 2)
+        kp_sigma2 = None if kp_sigma2 is None else np.ascontiguousarray(kp_sigma2, np.float32).reshape(-1)
+        mp_xyz = None if mp_xyz is None else np.ascontiguousarray(mp_xyz, np.float32).reshape(-1, 3)
+        d = PnPFromBow(_p(nm), int(min_matches), 0 if kp_uv is None else kp_uv.shape[0], _p(kp_uv), _p(kp_sigma2),
+                       0 if mp_xyz is None else mp_xyz.shape[0], _p(mp_xyz), _p(K), C.cast(parr, C.c_void_p), _p(seeds))
+        self._ck(self.L.rsac_pnp_upload_from_bow(self.h, C.byref(d)), "rsac_pnp_upload_from_bow")
+        counts = np.where(nm >= min_matches, nm, 0).astype(np.int64)
+        offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        self._pnp_C = len(nm)
+        self._pnp_total = int(offsets[-1])
+        self._pnp_words = ((np.diff(offsets) + 31) // 32).astype(np.int64)
+        return offsets
+
     def pnp_run(self, flags=0, d_results_out: int | None = None):
         self._ck(self.L.rsac_pnp_run(self.h, C.c_int(flags), C.c_void_p(d_results_out or 0)), "pnp_run")
 
@@ -644,8 +670,9 @@ class Engine:
             nid = np.ascontiguousarray(f["node_ids"], np.uint32)
             noff = np.ascontiguousarray(f["node_off"], np.int32)
             nfe = np.ascontiguousarray(f["node_feat"], np.uint32)
-            keep += [desc, ang, val, nid, noff, nfe]
-            arr[i] = BowFeatures(desc.shape[0], _p(desc), _p(ang), _p(val), len(nid), _p(nid), _p(noff), _p(nfe))
+            mpi = None if f.get("mp_index") is None else np.ascontiguousarray(f["mp_index"], np.uint32)
+            keep += [desc, ang, val, nid, noff, nfe, mpi]
+            arr[i] = BowFeatures(desc.shape[0], _p(desc), _p(ang), _p(val), len(nid), _p(nid), _p(noff), _p(nfe), _p(mpi))
         qs, ts = np.ascontiguousarray(query_set, np.int32), np.ascontiguousarray(target_set, np.int32)
         keep += [qs, ts, arr]
         b = BowBatch(len(sets), C.cast(arr, C.c_void_p), len(qs), _p(qs), _p(ts), C.c_float(nn_ratio), int(check_orientation), int(mode))

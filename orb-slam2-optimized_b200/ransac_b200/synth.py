@@ -506,3 +506,35 @@ def proj_search_case(seed: int, n_points: int = 1000, n_extra: int = 400, found:
     occupied |= (rng.random(frame["n_feat"]) < 0.02).astype(np.uint8)          # keypoints holding map points of other keyframes
     already = np.array([1 if int(m) in sfound else 0 for m in kf["mp_id"]], np.uint8)
     return dict(frame=frame, kf=kf, K=p["K"], Rcw=Rcw, tcw=tcw, occupied=occupied, already_found=already)
+
+
+# ---------------------------------------------------------------- a relocalisation with descriptors AND geometry
+def reloc_world(seed: int, C: int = 24, n_kp: int = 1500, n_kf_feat: int = 1200, n_map: int = 60000, n_nodes: int = 100, cam=EUROC):
+    """One lost frame and C candidate keyframes, consistent across the stages of Tracking::Relocalization: the frame's keypoints
+    carry descriptors, vocabulary nodes and angles (SearchByBoW's input) AND are projections of map points under the true pose
+    (the PnP solver's input).  Keyframe c re-observes a share of the frame's features (descriptor with flipped bits, same node)
+    and its features point at map-point table slots through mp_index: a re-observed feature at the frame keypoint's true map
+    point, the others at unrelated points.  Candidates 0, 5, 10, ... share next to nothing with the frame (discarded: < 15 matches)."""
+    rng = np.random.default_rng(seed)
+    R, t = random_pose(rng)
+    frame = bow_frame(seed + 1, n_kp, n_nodes)
+    Xc = frustum_points(rng, n_kp, cam)
+    octave = rng.choice(N_LEVELS, size=n_kp, p=_LEVEL_P)
+    sigma2 = np.ascontiguousarray(_SIGMA2[octave], np.float32)
+    uv = (project(Xc, cam) + rng.normal(size=(n_kp, 2)) * np.sqrt(sigma2)[:, None]).astype(np.float32)
+    mp = ((frustum_points(rng, n_map, cam) - t) @ R).astype(np.float32)
+    true_id = rng.choice(n_map, n_kp, replace=False)                  # map-point table slot of every frame keypoint's true point
+    mp[true_id] = ((Xc - t) @ R).astype(np.float32)
+    kfs = []
+    for c in range(C):
+        shared = 0.01 if c % 5 == 0 else float(rng.uniform(0.15, 0.4))
+        kf = bow_keyframe(seed * 1000 + c, frame, n_kf_feat, shared=shared, rot=float(rng.uniform(0, 360)), valid_ratio=0.85)
+        dst, src = kf["truth"]
+        mpi = rng.choice(n_map, n_kf_feat, replace=False).astype(np.uint32)       # unrelated points (distinct per keyframe)
+        good = rng.random(len(dst)) < 0.8                                          # 20 % of the re-observations are wrong associations
+        mpi[dst[good]] = true_id[src[good]].astype(np.uint32)
+        kf["mp_index"] = mpi
+        kfs.append(kf)
+    return dict(frame=frame, kfs=kfs, kp_uv=uv, kp_sigma2=sigma2, mp_xyz=mp,
+                K=np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float64), R=R, t=t,
+                seeds=(np.arange(C) + 31 * seed + 5).astype(np.uint32))

@@ -50,3 +50,47 @@ def test_edge_cases_empty_ragged_and_big_nodes(engine, oracle):
     _check(engine, oracle, sets, [1, 2, 1, 3, 4, 4], [0, 0, 2, 0, 0, 4], 0, True)
     _check(engine, oracle, sets, [1, 4], [4, 1], 1, True)
     _check(engine, oracle, sets, [1], [0], 0, True, ratio=0.95)
+
+
+def test_pnp_batch_built_on_device_from_search_by_bow(engine):
+    """Tracking::Relocalization (Tracking.cpp:1207-1232): SearchByBoW per candidate, a PnPsolver for every candidate with at least
+    15 matches.  rsac_pnp_upload_from_bow builds that PnP batch on the device from the match arrays of the last rsac_bow_run
+    -- only the match counts visit the host.  It must equal the batch a host would build from the downloaded matches
+    (rsac_pnp_upload_indexed): same records and masks; and the candidates that really saw the place recover the true pose."""
+    from ransac_b200 import capi
+    w = synth.reloc_world(7, C=24)
+    C = len(w["kfs"])
+    sets = [w["frame"]] + w["kfs"]
+    engine.bow_upload(sets, list(range(1, C + 1)), [0] * C, 0.75, True, 0)
+    engine.bow_run()
+    matches, nm = engine.bow_download()
+    prm = capi.ransac_params(0.99, 10, 300, 4, 0.5, 5.991)              # Tracking.cpp:1226
+    # (a) on the device
+    offsets = engine.pnp_upload_from_bow(nm, w["K"], prm, w["seeds"], min_matches=15, kp_uv=w["kp_uv"], kp_sigma2=w["kp_sigma2"], mp_xyz=w["mp_xyz"])
+    engine.pnp_run(capi.FLAG_EARLY_EXIT)
+    res_a, m_a = engine.pnp_download()
+    engine.poseopt_from_pnp()
+    engine.poseopt_run()
+    po_a, fl_a = engine.poseopt_download()
+    # (b) the same batch from the downloaded matches
+    kp_idx, mp_idx, off_b = [], [], [0]
+    for c in range(C):
+        js = np.flatnonzero(matches[c] >= 0) if nm[c] >= 15 else np.zeros(0, np.int64)
+        kp_idx.append(js.astype(np.uint16)); mp_idx.append(w["kfs"][c]["mp_index"][matches[c][js]].astype(np.uint32))
+        off_b.append(off_b[-1] + len(js))
+    assert offsets.tolist() == off_b
+    engine.pnp_upload_indexed(np.array(off_b, np.int32), np.concatenate(kp_idx), np.concatenate(mp_idx), w["K"], prm, seeds=w["seeds"])
+    engine.pnp_run(capi.FLAG_EARLY_EXIT)
+    res_b, m_b = engine.pnp_download()
+    assert res_a.tobytes() == res_b.tobytes() and (m_a == m_b).all()
+    engine.poseopt_from_pnp()
+    engine.poseopt_run()
+    po_b, fl_b = engine.poseopt_download()
+    assert po_a.tobytes() == po_b.tobytes() and (fl_a == fl_b).all()
+    discarded = np.array([nm[c] < 15 for c in range(C)])
+    assert discarded.sum() >= 3 and not res_a["ok"][discarded].any() and (res_a["no_more"][discarded] == 1).all()
+    ok = res_a["ok"] == 1
+    assert ok.sum() >= C // 2
+    for c in np.flatnonzero(ok):
+        assert np.abs(res_a[c]["R"].reshape(3, 3) - w["R"]).max() < 0.03, c
+        assert np.abs(po_a[c]["Rf"].reshape(3, 3) - w["R"]).max() < 0.02, c
