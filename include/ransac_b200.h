@@ -110,16 +110,16 @@ int rsac_set_problem_ids(rsac_engine* e, const int32_t* ids, int C);
 /* CUDA graphs for the staged PnP sweep (default on; RSAC_GRAPH=0 in the environment turns them off): the second run of
  * a (batch shape, flags, output buffer) combination captures its 18 launches, later runs replay them with one call */
 int rsac_set_graphs(rsac_engine* e, int on);
-/* RSAC_FLAG_EARLY_EXIT: hypotheses per problem in the first stage (later stages double); 0 (default) = three quarters
- * of one wave of the minimal-solver kernel over the batch (a batch that fits one wave runs all hypotheses at once) */
+/* RSAC_FLAG_EARLY_EXIT: hypotheses per problem in the first stage (later stages double); 0 (default) = two full waves
+ * of the minimal-solver kernel over the batch (a batch that fits one wave runs all hypotheses at once) */
 int rsac_set_first_phase(rsac_engine* e, int hypotheses);
 /* two explicit boundaries: hypotheses [0, first) for every problem, [first, second) for the problems still without an
  * acceptable hypothesis, [second, H) for those still without one after that (second >= H: two stages only, the lower
  * latency for a single sweep); 0, 0 = automatic */
 int rsac_set_phases(rsac_engine* e, int first, int second);
 /* any number of stages (n <= 7 boundaries, strictly increasing; [b(n-1), H) is the last stage); n = 0: automatic =
- * first stage three quarters of a solver wave, every further stage doubles the hypotheses a problem has (cfg4: 41, 82,
- * 164, 300); fewer stages = lower latency of a single sweep, more stages = less work when sweeps overlap */
+ * first stage two full waves of the minimal-solver kernel, every further stage doubles the hypotheses a problem has (cfg4: 46,
+ * 92, 184, 300); fewer stages = lower latency of a single sweep, more stages = less work when sweeps overlap */
 int rsac_set_stages(rsac_engine* e, int n, const int32_t* bounds);
 /* diagnostic (synchronises): after an early-exit run: out[0] = first_phase used (0: the run was exhaustive),
  * out[1] = problems that went on to the second stage, out[2] = problems handed to the clean-up phase by the

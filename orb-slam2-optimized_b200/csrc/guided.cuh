@@ -424,6 +424,7 @@ static __global__ void __launch_bounds__(256) proj_assign_kernel(ProjSearchArgs 
                     if (!taken[idx]) b = idx;
                 }
                 RSAC_ASSERT(b >= 0 && b < NF && minidx[b] <= i);
+                if (b < 0) { cn[i] = -1; continue; }                     // (cannot happen: step b left only points with a free entry)
                 if (minidx[b] == i) { fmatch[b] = i; cn[i] = -1; }      // final (taken[] is written after the barrier below)
                 else atomicAdd(&s_undecided, 1);
             }
@@ -433,7 +434,8 @@ static __global__ void __launch_bounds__(256) proj_assign_kernel(ProjSearchArgs 
             ++rounds;
             const int left = s_undecided;
             __syncthreads();
-            if (left == 0) break;
+            RSAC_ASSERT(rounds <= NK);
+            if (left == 0 || rounds > NK) break;                         // every round decides the smallest undecided index at least
         }
     }
     // 3. rotation consistency (:1405-1441)
