@@ -591,6 +591,9 @@ int rsac_nccl_destroy(rsac_engine* e);
  * oracle bit-for-bit without a GPU.  Not a fallback: nothing in the engine calls these. */
 /* diagnostic: clock64() stamps of the replay kernel's phases (block 0 of the last launch) */
 int rsac_debug_select_clocks(rsac_engine* e, long long out[16]);
+/* diagnostic: clock64() stamps of the MLPnP 6-point solve's phases (hypothesis 0 of the last exhaustive launch): entry, null spaces +
+ * weights, A^T P A built, eigen-solve, pose recovery, Gauss-Newton, exit; out[7] = Gauss-Newton iterations */
+int rsac_debug_mlpnp_clocks(rsac_engine* e, long long out[8]);
 /* diagnostic: clock64() stamps of the EPnP minimal solve's phases (thread 0 of block 0 of the last launch) */
 int rsac_debug_solve_clocks(rsac_engine* e, long long out[16]);
 /* diagnostic: globaltimer stamps (ns) of the first and last four CTAs of the last scoring launch:

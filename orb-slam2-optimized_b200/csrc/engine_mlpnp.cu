@@ -273,3 +273,11 @@ int rsac_debug_host_mlpnp6(const float K[4], const float p3d[18], const float p2
     mlpnp_compute_pose_small<6>(f, pw, cov54, R, t, rec.data());
     return RSAC_OK;
 }
+
+int rsac_debug_mlpnp_clocks(rsac_engine* e, long long out[8])
+{
+    if (!e || !out) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaStreamSynchronize(e->stream));
+    RSAC_CUDA(e, cudaMemcpyFromSymbol(out, g_mlpnp_clocks, sizeof(long long) * 8));
+    return RSAC_OK;
+}

@@ -272,9 +272,21 @@ __host__ __device__ inline int mlpnp_gn_decide(const double* dx, double max_dl)
 
 // Whole MLPnPsolver::computePose (:321-623) for NPTS thread-private observations.
 // f, p: NPTS x 3 (double); cov: NPTS x 9 or nullptr.  Writes R (9) and t (3).
+#if defined(__CUDA_ARCH__)
+#define RSAC_MLPNP_MARK(i) do { if (clk) clk[i] = clock64(); } while (0)
+#else
+#define RSAC_MLPNP_MARK(i) ((void)0)
+#endif
+// clk: optional clock64() stamps of the phases (rsac_debug_mlpnp_clocks).  Measured on B200 (cfg2, hypothesis 0): null spaces +
+// weights 11 k cycles, A^T P A 7 k, the 12 x 12 eigen-solve 669 k (72 %: 78 doubles of matrix beside ~100 live doubles of the
+// caller under a 255-register cap, 260 KB of unrolled code per sweep), pose recovery 34 k, Gauss-Newton 211 k.  Tried and
+// measured slower: the matrix in shared memory, one column per thread, with the step loop rolled (LSU-bound: 998 k), and the
+// eigen-solve out of line (1.3 M); the next step is the eigen-solve on six lanes per hypothesis.
 template <int NPTS>
-__host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const double* p, const double* cov, double* Rres, double* tres, double2* rec)
+__host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const double* p, const double* cov, double* Rres, double* tres, double2* rec,
+                                                         long long* clk = nullptr)
 {
+    RSAC_MLPNP_MARK(0);
     double nulls[NPTS * 6], pts3[NPTS * 3], P[NPTS * 4];
     for (int i = 0; i < NPTS; ++i) mlpnp_nullspace(f + 3 * i, nulls + 6 * i);
     for (int i = 0; i < NPTS * 3; ++i) pts3[i] = p[i];
@@ -299,6 +311,7 @@ __host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const 
     }
     if (cov)
         for (int i = 0; i < NPTS; ++i) mlpnp_weight(nulls + 6 * i, cov + 9 * i, P + 4 * i);
+    RSAC_MLPNP_MARK(1);
 
     double result1[12], ev[1];
     if (planar) {
@@ -330,10 +343,13 @@ __host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const 
                     AtPA[tri_idx(12, a, b)] = rfma(a1[a], w1[b], AtPA[tri_idx(12, a, b)]);
                 }
         }
+        RSAC_MLPNP_MARK(2);
         jacobi_lowest<12, 1>(AtPA, ev, result1, rec);
     }
+    RSAC_MLPNP_MARK(3);
     double Rout[9], tout[3];
     mlpnp_recover(result1, planar, eigenRot, p, f, Rout, tout);
+    RSAC_MLPNP_MARK(4);
 
     // Gauss-Newton (MLPnPsolver.cpp:607-622, 659-723)
     double x[6];
@@ -384,8 +400,11 @@ __host__ __device__ inline void mlpnp_compute_pose_small(const double* f, const 
         if (dec == 2) break;
         ++it_cnt;
     }
+    RSAC_MLPNP_MARK(5);
+    if (clk) clk[7] = it_cnt;
     rodrigues2rot(x, Rres);
     tres[0] = x[3]; tres[1] = x[4]; tres[2] = x[5];
+    RSAC_MLPNP_MARK(6);
 }
 
 }  // namespace rsac

@@ -5,6 +5,9 @@
 
 namespace rsac {
 
+// diagnostic: clock64() stamps of the 6-point solve's phases (hypothesis 0 of the last exhaustive launch; rsac_debug_mlpnp_clocks)
+static __device__ long long g_mlpnp_clocks[8];
+
 // ---- MLPnP minimal solve: one thread per hypothesis (MLPnPsolver.cpp:76-120) ----
 static __global__ void __launch_bounds__(128) mlpnp_minimal_kernel(const ProblemMeta* metas, int C, int64_t sumH,
                                                             const uint32_t* tables, const float4* cA,
@@ -28,7 +31,7 @@ static __global__ void __launch_bounds__(128) mlpnp_minimal_kernel(const Problem
     }
     double R[9], t[3];
     double2 rec[kMaxSweepsRec * 66];
-    mlpnp_compute_pose_small<6>(f, pw, cov ? cv : nullptr, R, t, rec);
+    mlpnp_compute_pose_small<6>(f, pw, cov ? cv : nullptr, R, t, rec, g == 0 ? g_mlpnp_clocks : nullptr);
     double* out = poses + g * 12;
     for (int i = 0; i < 9; ++i) out[i] = R[i];
     out[9] = t[0]; out[10] = t[1]; out[11] = t[2];
