@@ -261,7 +261,7 @@ def main():
         kpi = np.concatenate([b_["kp_idx"][first:first + count].astype(np.int64) + i * N_KP for i, b_ in enumerate(sel)]).astype(np.uint16)
         mpi = np.concatenate([b_["mp_idx"][first:first + count].astype(np.int64) + (j * world + i) * N_MAP
                               for i, b_ in enumerate(sel)]).astype(np.uint32)
-        batches.append(dict(p3d=cat("p3d", (-1, 3)), p2d=cat("p2d", (-1, 2)), s2=cat("sigma2", (-1,)),
+        batches.append(dict(p3d=pin(cat("p3d", (-1, 3))).numpy(), p2d=pin(cat("p2d", (-1, 2))).numpy(), s2=pin(cat("sigma2", (-1,))).numpy(),
                             kp_idx=pin(kpi.reshape(-1)), mp_idx=pin(mpi.reshape(-1)),
                             kp_uv=pin(np.concatenate([b_["kp_uv"] for b_ in sel])), kp_s2=pin(np.concatenate([b_["kp_sigma2"] for b_ in sel])),
                             seeds=np.concatenate([b_["seeds"][first:first + count] for b_ in sel]), K=sel[0]["K"], ids=ids))
@@ -355,6 +355,18 @@ def main():
 
     issue_ms = [0.0]
 
+    def run_e2e_flat(k):
+        """the same with the flat wire format (24 B per correspondence, no resident map): reported beside the headline e2e"""
+        i = k % NSLOT
+        with torch.cuda.stream(streams[i]):
+            upload(i, k)
+            bound_in_flight(i, k, e2e_ring)
+            run_and_gather(i, k)
+            ev = torch.cuda.Event()
+            ev.record(streams[i])
+            e2e_ring[k % len(e2e_ring)] = ev
+            engines[i].pnp_download_async(h_res[i].data_ptr(), h_msk[i].data_ptr())
+
     def timed(fn, steps):
         """`steps` steps = steps * RUNS batches on this rank; device time, max over ranks"""
         for r in (res_ring, e2e_ring):
@@ -440,6 +452,9 @@ def main():
     timed(run_e2e, 1)
     ms_e2e = timed(run_e2e, args.steps)
     issue_e2e = issue_ms[0]
+    timed(run_e2e_flat, 1)
+    ms_e2e_flat = timed(run_e2e_flat, max(1, args.steps // 2))
+    steps_flat = max(1, args.steps // 2)
     with torch.cuda.stream(streams[0]):
         upload_indexed(0, 0)
         engines[0].pnp_run(RUN_FLAGS, d_local[0].data_ptr())
@@ -524,7 +539,10 @@ def main():
             "e2e": {"value": e2e_v, "unit": "candidates/s", "h2d_bytes_per_step": h2d * RUNS * world, "d2h_bytes_per_step": d2h * RUNS * world,
                     "ms_per_step": ms_e2e / args.steps,
                     "ms_per_batch": ms_e2e / args.steps / RUNS, "host_issue_ms_per_batch": issue_e2e,
-                    "resident_ms_per_batch": ms / args.steps / RUNS, "resident_host_issue_ms_per_batch": issue_res},
+                    "resident_ms_per_batch": ms / args.steps / RUNS, "resident_host_issue_ms_per_batch": issue_res,
+                    "flat_upload": {"value": C_STEP * steps_flat / (ms_e2e_flat * 1e-3), "unit": "candidates/s",
+                                    "h2d_bytes_per_step": int(C_RUN * N_MATCH * 24 + C_RUN * 160) * RUNS * world,
+                                    "note": "the same end-to-end pass with rsac_pnp_upload (24 B per correspondence, nothing resident)"}},
             "gpu_launches": int(launches),
             "checks": checks,
             "host_binding": ("rank 0 bound to NUMA node %d of its GPU (every rank binds itself the same way)" % numa_node) if numa_node is not None
