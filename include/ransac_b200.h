@@ -533,6 +533,26 @@ typedef struct {
                                     -1 = no match */
 } rsac_sim3_search_batch;
 
+/* keyframe views resident on the device: batches with n_views = 0 and views = NULL (rsac_sim3_search_batch, rsac_proj_search_batch)
+ * and rsac_sim3_upload_from_views reference them by index */
+int rsac_views_upload(rsac_engine* e, int n_views, const rsac_kf_view* views);
+/* The Sim3Solver constructor (Sim3Solver.cpp:6-85) over the resident views: pair c = (views[kf1[c]], views[kf2[c]]) with
+ * vpMatched12 given as matches12 (concatenated per pair [n_feat(kf1)]: the KF2 feature of the matched MapPoint, -1 = none).  The
+ * host walks the matches (which ones survive :31-44 decides the batch's shape) and sends 12 B per correspondence; camera-frame
+ * points and level sigmas are gathered on the device.  offsets_out [C+1], idx1_out / idx2_out (optional, [offsets_out[C]]):
+ * mvnIndices1 and the KF2 features, i.e. what bit k of a result mask refers to.  Then rsac_sim3_run / rsac_sim3_download. */
+typedef struct {
+    int32_t C;
+    const int32_t* kf1;
+    const int32_t* kf2;
+    const int32_t* matches12;
+    const float* K1;             /* [C][4] */
+    const float* K2;
+    const rsac_sim3_params* params;
+    int32_t n_params;
+    const uint32_t* seeds;       /* [C] */
+} rsac_sim3_from_views;
+int rsac_sim3_upload_from_views(rsac_engine* e, const rsac_sim3_from_views* b, int32_t* offsets_out, int32_t* idx1_out, int32_t* idx2_out);
 int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b);
 int rsac_sim3_search_run(rsac_engine* e);
 /* match12: concatenated per pair [views[kf1[c]].n_feat]: the KF2 feature newly matched to each KF1 feature

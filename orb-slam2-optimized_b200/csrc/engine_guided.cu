@@ -67,7 +67,38 @@ static int guided_upload_views(rsac_engine* e, int V, const rsac_kf_view* in, bo
     }
     s.h_stage.mark(e->stream);
     s.n_views = V;
+    s.views_have_angle = true;
+    for (int i = 0; i < V; ++i) s.views_have_angle = s.views_have_angle && (in[i].kp_angle != nullptr || in[i].n_feat == 0);
+    s.view_n_feat.assign(V, 0); s.view_feat_off.assign(V, 0);
+    s.view_mp_valid.assign((size_t)nfeat, 0);
+    for (int i = 0; i < V; ++i) {
+        s.view_n_feat[i] = views[i].n_feat; s.view_feat_off[i] = views[i].feat_off;
+        if (in[i].n_feat > 0) memcpy(s.view_mp_valid.data() + views[i].feat_off, in[i].mp_valid, (size_t)in[i].n_feat);
+    }
     return RSAC_OK;
+}
+
+// the views of a batch: uploaded when given, else the resident ones (n_views == 0 && views == NULL)
+static int guided_views_for_batch(rsac_engine* e, int n_views, const rsac_kf_view* in, bool need_angle, std::vector<KfViewDev>& views)
+{
+    GuidedState& s = e->guided;
+    if (n_views == 0 && !in && s.n_views > 0) {
+        if (need_angle && !s.views_have_angle) { e->err = "the resident views carry no keypoint angles"; return RSAC_ERR_STATE; }
+        views.assign(s.n_views, KfViewDev());
+        for (int i = 0; i < s.n_views; ++i) { views[i].n_feat = s.view_n_feat[i]; views[i].feat_off = s.view_feat_off[i]; }
+        return RSAC_OK;
+    }
+    return guided_upload_views(e, n_views, in, need_angle, views);
+}
+
+int rsac_views_upload(rsac_engine* e, int n_views, const rsac_kf_view* views)
+{
+    if (!e || n_views < 0 || (n_views > 0 && !views)) return RSAC_ERR_INVALID;
+    RSAC_CUDA(e, cudaSetDevice(e->device));
+    GuidedState& s = e->guided;
+    s.uploaded = false; s.ran = false; s.proj_uploaded = false; s.proj_ran = false;
+    std::vector<KfViewDev> tmp;
+    return guided_upload_views(e, n_views, views, false, tmp);
 }
 
 int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b)
@@ -77,9 +108,10 @@ int rsac_sim3_search_upload(rsac_engine* e, const rsac_sim3_search_batch* b)
     RSAC_CUDA(e, cudaSetDevice(e->device));
     GuidedState& s = e->guided;
     s.uploaded = false; s.ran = false; s.proj_uploaded = false; s.proj_ran = false;
-    const int V = b->n_views, C = b->C;
+    const int C = b->C;
     std::vector<KfViewDev> views;
-    RSAC_TRY(guided_upload_views(e, V, b->views, false, views));
+    RSAC_TRY(guided_views_for_batch(e, b->n_views, b->views, false, views));
+    const int V = (int)s.n_views;
     std::vector<int64_t> off1(C + 1, 0), off2(C + 1, 0);
     s.maxN1 = 0; s.maxN = 0;
     for (int c = 0; c < C; ++c) {
@@ -192,9 +224,10 @@ int rsac_proj_search_upload(rsac_engine* e, const rsac_proj_search_batch* b)
     RSAC_CUDA(e, cudaSetDevice(e->device));
     GuidedState& s = e->guided;
     s.uploaded = false; s.ran = false; s.proj_uploaded = false; s.proj_ran = false;
-    const int V = b->n_views, C = b->C;
+    const int C = b->C;
     std::vector<KfViewDev> views;
-    RSAC_TRY(guided_upload_views(e, V, b->views, b->check_orientation != 0, views));
+    RSAC_TRY(guided_views_for_batch(e, b->n_views, b->views, b->check_orientation != 0, views));
+    const int V = (int)s.n_views;
     std::vector<int64_t> offF(C + 1, 0), offK(C + 1, 0);
     s.maxN = 0;
     for (int c = 0; c < C; ++c) {

@@ -160,13 +160,17 @@ struct ScoreState {
 
 struct Sim3State {
     bool uploaded = false, ran = false, have_tables = false, tables_ready = false;
+    DevBuf d_idx1, d_idx2;               // rsac_sim3_upload_from_views: KF1 / KF2 feature of every correspondence
+    PinnedBuf h_idx;
     BatchDims d;
     std::vector<ProblemMeta> metas;
     DevBuf d_metas, d_x1, d_x2, d_s1, d_s2, d_c1, d_c2, d_tables, d_poses, d_counts, d_hmasks, d_results, d_masks, d_done;
     void release()
     {
-        DevBuf* all[] = {&d_metas, &d_x1, &d_x2, &d_s1, &d_s2, &d_c1, &d_c2, &d_tables, &d_poses, &d_counts, &d_hmasks, &d_results, &d_masks, &d_done};
+        DevBuf* all[] = {&d_metas, &d_x1, &d_x2, &d_s1, &d_s2, &d_c1, &d_c2, &d_tables, &d_poses, &d_counts, &d_hmasks, &d_results, &d_masks, &d_done,
+                         &d_idx1, &d_idx2};
         for (DevBuf* b : all) b->release();
+        h_idx.release();
     }
 };
 
@@ -252,6 +256,10 @@ struct GuidedState {
     int64_t totalF = 0, totalK = 0;
     DevBuf d_kp_angle, d_cand, d_cand_n, d_taken, d_minidx;
     PinnedBuf h_stage2;
+    // host-side facts about the resident views (rsac_sim3_upload_from_views, batches that reference the resident views)
+    bool views_have_angle = false;
+    std::vector<int32_t> view_n_feat, view_feat_off;
+    std::vector<uint8_t> view_mp_valid;     // concatenated
     DevBuf d_views, d_kp_xy, d_kp_octave, d_desc, d_mp_valid, d_mp_xyz, d_mp_desc, d_mp_maxdist, d_mp_mindist, d_grid_off, d_grid_idx,
         d_kf1, d_kf2, d_K, d_R12, d_t12, d_s12, d_off1, d_off2, d_matched_in, d_already1, d_already2, d_m1, d_m2, d_match12, d_n_found;
     PinnedBuf h_stage;

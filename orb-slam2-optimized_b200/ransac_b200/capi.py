@@ -146,6 +146,11 @@ class ProjSearchBatch(C.Structure):
                 ("occupied", C.c_void_p), ("already_found", C.c_void_p)]
 
 
+class Sim3FromViews(C.Structure):
+    _fields_ = [("C", C.c_int32), ("kf1", C.c_void_p), ("kf2", C.c_void_p), ("matches12", C.c_void_p), ("K1", C.c_void_p), ("K2", C.c_void_p),
+                ("params", C.c_void_p), ("n_params", C.c_int32), ("seeds", C.c_void_p)]
+
+
 class RsacError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__(f"ransac_b200 error {code}: {msg}")
@@ -750,21 +755,46 @@ class Engine:
         self._ck(self.L.rsac_kfdb_get_state(self.h, _p(st)), "rsac_kfdb_get_state")
         return st[:self._kfdb_K]
 
+    # -- resident keyframe views and the Sim3Solver constructor over them
+    def views_upload(self, views):
+        arr, keep = self._kf_views(views)
+        self._ck(self.L.rsac_views_upload(self.h, C.c_int(len(views)), C.cast(arr, C.c_void_p)), "rsac_views_upload")
+        self._views_n = [int(v["n_feat"]) for v in views]
+
+    def sim3_upload_from_views(self, kf1, kf2, matches12, K1, K2, params, seeds):
+        """matches12: list of per-pair int32 arrays (KF2 feature per KF1 feature, -1 none).  Returns (offsets, idx1, idx2)."""
+        k1, k2 = np.ascontiguousarray(kf1, np.int32), np.ascontiguousarray(kf2, np.int32)
+        Cn = len(k1)
+        m = np.ascontiguousarray(np.concatenate([np.asarray(x, np.int32) for x in matches12]) if Cn else [], np.int32)
+        K1 = np.ascontiguousarray(K1, np.float32).reshape(-1, 4); K2 = np.ascontiguousarray(K2, np.float32).reshape(-1, 4)
+        parr = (Sim3Params * 1)(params)
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        offs = np.zeros(Cn + 1, np.int32)
+        idx1 = np.zeros(max(len(m), 1), np.int32); idx2 = np.zeros(max(len(m), 1), np.int32)
+        d = Sim3FromViews(Cn, _p(k1), _p(k2), _p(m) if len(m) else None, _p(K1), _p(K2), C.cast(parr, C.c_void_p), 1, _p(seeds))
+        self._ck(self.L.rsac_sim3_upload_from_views(self.h, C.byref(d), _p(offs), _p(idx1), _p(idx2)), "rsac_sim3_upload_from_views")
+        n = int(offs[-1])
+        self._sim3_C = Cn
+        self._sim3_total = n
+        self._sim3_words = ((np.diff(offs) + 31) // 32).astype(np.int64)
+        return offs, idx1[:n].copy(), idx2[:n].copy()
+
     # -- guided matching: ORBmatcher::SearchBySim3
     def sim3_search_upload(self, views, kf1, kf2, K, R12, t12, th=7.5, matched12_in=None, s12=None):
         """views: list of keyframe-view dicts (synth.kf_view); kf1 / kf2: view index per pair; K [C,4], R12 [C,9], t12 [C,3];
         matched12_in: list of per-pair int32 arrays (or None)"""
-        arr, keep = self._kf_views(views)
+        resident = views is None
+        arr, keep = (None, []) if resident else self._kf_views(views)
         k1, k2 = np.ascontiguousarray(kf1, np.int32), np.ascontiguousarray(kf2, np.int32)
         Kc = np.ascontiguousarray(K, np.float32).reshape(-1, 4)
         R = np.ascontiguousarray(R12, np.float32).reshape(-1, 9)
         t = np.ascontiguousarray(t12, np.float32).reshape(-1, 3)
         sc = None if s12 is None else np.ascontiguousarray(s12, np.float32)
         mi = None if matched12_in is None else np.ascontiguousarray(np.concatenate([np.asarray(m, np.int32) for m in matched12_in]) if len(k1) else [], np.int32)
-        b = Sim3SearchBatch(len(views), C.cast(arr, C.c_void_p), len(k1), _p(k1), _p(k2), _p(Kc), _p(R), _p(t), _p(sc), C.c_float(th),
-                            _p(mi) if mi is not None and len(mi) else None)
+        b = Sim3SearchBatch(0 if resident else len(views), None if resident else C.cast(arr, C.c_void_p), len(k1), _p(k1), _p(k2), _p(Kc), _p(R), _p(t),
+                            _p(sc), C.c_float(th), _p(mi) if mi is not None and len(mi) else None)
         self._ck(self.L.rsac_sim3_search_upload(self.h, C.byref(b)), "rsac_sim3_search_upload")
-        self._s3s_n1 = [int(views[i]["n_feat"]) for i in k1]
+        self._s3s_n1 = [self._views_n[i] for i in k1] if resident else [int(views[i]["n_feat"]) for i in k1]
 
     @staticmethod
     def _kf_views(views):

@@ -162,3 +162,67 @@ def test_optimize_sim3_chained_behind_search_by_sim3(engine, oracle):
             assert r["n_inliers"] >= 20                                          # ComputeSim3 would accept this candidate (:314)
         else:
             assert diff.size <= 2, (c, diff)
+
+
+def test_loop_verification_chain_on_resident_views(engine, oracle):
+    """LoopClosing::ComputeSim3 for a batch of candidates with the keyframe views resident on the device:
+    Sim3Solver constructor (rsac_sim3_upload_from_views: 12 B per correspondence, camera-frame points gathered on the device) ->
+    RANSAC -> SearchBySim3 on the accepted Sim3 with the RANSAC inliers as vpMapPointMatches -> OptimizeSim3 chained on the device.
+    The Sim3 stage must equal the flat upload of host-computed arrays bit for bit; the rest is checked against the oracle."""
+    F = np.float32
+    pairs = [synth.kf_view_pair(120 + i, n_points=500 + 100 * i, n_extra=150, prematched=0.0, pose_noise=0.0) for i in range(3)]
+    views = [v for p in pairs for v in (p["kf1"], p["kf2"])]
+    kf1, kf2 = [0, 2, 4], [1, 3, 5]
+    # vvpMapPointMatches as SearchByBoW would leave them: most of the co-observed map points, a tenth of them wrong
+    rng = np.random.default_rng(3)
+    matches12 = []
+    for p in pairs:
+        i2_of = {int(m): j for j, m in enumerate(p["kf2"]["mp_id"]) if m >= 0}
+        m12 = np.full(p["kf1"]["n_feat"], -1, np.int32)
+        for i, m in enumerate(p["kf1"]["mp_id"]):
+            if m >= 0 and int(m) in i2_of and rng.random() < 0.6:
+                m12[i] = i2_of[int(m)] if rng.random() < 0.9 else int(rng.integers(0, p["kf2"]["n_feat"]))
+        matches12.append(m12)
+    Ks = np.stack([p["K"] for p in pairs])
+    prm = capi.Sim3Params(0.99, 20, 300, 1)
+    seeds = np.arange(3, dtype=np.uint32) + 77
+    engine.views_upload(views)
+    offs, idx1, idx2 = engine.sim3_upload_from_views(kf1, kf2, matches12, Ks, Ks, prm, seeds)
+    engine.sim3_run()
+    res, masks = engine.sim3_download()
+    # (a) the same Sim3 batch from host-computed arrays
+    x1c, x2c, s1, s2 = [], [], [], []
+    for c, p in enumerate(pairs):
+        k1, k2 = p["kf1"], p["kf2"]
+        want_idx = [(i, int(matches12[c][i])) for i in range(k1["n_feat"])
+                    if matches12[c][i] >= 0 and k1["mp_valid"][i] and k2["mp_valid"][matches12[c][i]]]
+        assert [int(a) for a in idx1[offs[c]:offs[c + 1]]] == [a for a, _ in want_idx]
+        assert [int(b) for b in idx2[offs[c]:offs[c + 1]]] == [b for _, b in want_idx]
+        for i, i2 in want_idx:
+            x1c.append(_mv32(k1["Rcw"], k1["mp_xyz"][i], k1["tcw"])); x2c.append(_mv32(k2["Rcw"], k2["mp_xyz"][i2], k2["tcw"]))
+            f1, f2 = k1["scale_factors"][k1["kp_octave"][i]], k2["scale_factors"][k2["kp_octave"][i2]]
+            s1.append(F(f1 * f1)); s2.append(F(f2 * f2))
+    res_b, masks_b = engine.sim3_solve(offs, np.array(x1c), np.array(x2c), np.array(s1), np.array(s2), Ks, Ks, prm, seeds=seeds)
+    assert res.tobytes() == res_b.tobytes() and (masks == masks_b).all()
+    assert (res["ok"] == 1).all()
+    # (b) SearchBySim3 with the inliers as vpMapPointMatches and the accepted Sim3, on the resident views, then OptimizeSim3 chained
+    ml = engine.split_masks(masks, offs)
+    matched_in, R12, t12 = [], [], []
+    for c, p in enumerate(pairs):
+        mi = np.full(p["kf1"]["n_feat"], -1, np.int32)
+        inl = np.flatnonzero(ml[c])
+        mi[idx1[offs[c]:offs[c + 1]][inl]] = idx2[offs[c]:offs[c + 1]][inl]
+        matched_in.append(mi); R12.append(res[c]["R"]); t12.append(res[c]["t"])
+    engine.sim3_search_upload(None, kf1, kf2, Ks, R12, t12, 7.5, matched_in)
+    engine.sim3_search_run()
+    new, nf = engine.sim3_search_download()
+    engine.sim3opt_from_search(10.0, True)
+    engine.sim3opt_run()
+    ores, flags, n_edges = engine.sim3opt_download_chained()
+    for c, p in enumerate(pairs):
+        w, n = oracle.search_by_sim3(oracle.kf_view(p["kf1"]), oracle.kf_view(p["kf2"]), p["K"], R12[c], t12[c], 7.5, matched_in[c])
+        assert new[c].tolist() == w.tolist() and nf[c] == n
+        assert ores[c]["n_inliers"] >= 20, c                                     # LoopClosing.cpp:314: the candidate is accepted
+        assert n_edges[c] >= (matched_in[c] >= 0).sum()
+        Rt = p["R12"].reshape(3, 3)                                               # (pose_noise = 0: the true relative pose)
+        assert np.abs(ores[c]["R"].reshape(3, 3) - Rt).max() < 0.01 and np.abs(ores[c]["t"] - p["t12"]).max() < 0.05, c
