@@ -553,6 +553,28 @@ static int pnp_launch_select(rsac_engine* e, int flags, const int32_t* d_resume,
         const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024) + 2);
         RSAC_TRY(set_func_attr_max(e, (const void*)ransac_select_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
+    // the main replay of a sweep split around the first Refine's eigen-solve (select.cuh, SelectArgs::split_phase); later
+    // iterate() calls and the clean-up replay run in one launch
+    static const bool split_default = env_int("RSAC_SELECT_SPLIT", 1) != 0;
+    if (split_default && only_phase < 0 && !d_resume && d.C > 0) {
+        RSAC_TRY(s.d_carry.ensure(e, sizeof(SelectCarry) * (size_t)d.C));
+        if (kSelEigSmemPerWarp * kSelEigWarps > 48 * 1024)
+            RSAC_TRY(set_func_attr_max(e, (const void*)select_eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSelEigSmemPerWarp * kSelEigWarps)));
+        a.carry = (SelectCarry*)s.d_carry.p;
+        a.split_phase = 1;
+        e->stage_begin(RSAC_STAGE_SELECT);
+        ransac_select_kernel<0><<<d.C, kSelectThreads, smem, e->stream>>>(a);
+        e->stage_end(RSAC_STAGE_SELECT);
+        e->stage_begin(RSAC_STAGE_SELECT);
+        select_eigen_kernel<<<(d.C + kSelEigWarps - 1) / kSelEigWarps, kSelEigWarps * 32, kSelEigSmemPerWarp * kSelEigWarps, e->stream>>>(a.carry, d.C);
+        e->stage_end(RSAC_STAGE_SELECT);
+        a.split_phase = 2;
+        e->stage_begin(RSAC_STAGE_SELECT);
+        ransac_select_kernel<0><<<d.C, kSelectThreads, smem, e->stream>>>(a);
+        e->stage_end(RSAC_STAGE_SELECT);
+        RSAC_CUDA(e, cudaGetLastError());
+        return RSAC_OK;
+    }
     e->stage_begin(RSAC_STAGE_SELECT);
     ransac_select_kernel<0><<<d.C, kSelectThreads, smem, e->stream>>>(a);
     e->stage_end(RSAC_STAGE_SELECT);

@@ -101,7 +101,7 @@ struct PnpState {
         d_results, d_masks, d_hmasks, d_sel, d_pw, d_us, d_al, d_cov, d_extra, d_visit;
     PinnedBuf h_stage, h_fromBow;
     // indexed wire format: the frame's keypoint table and the map-point table stay resident between uploads
-    DevBuf d_kp_uv, d_kp_s2, d_mp_xyz, d_kp_idx, d_mp_idx, d_kpA, d_kpB;
+    DevBuf d_kp_uv, d_kp_s2, d_mp_xyz, d_kp_idx, d_mp_idx, d_kpA, d_kpB, d_carry;
     int n_keypoints = 0, n_mappoints = 0;
     bool indexed_fused = false;             // the batch is packed straight from the index pairs (pnp_pack)
     bool flat_valid = true;                 // d_p3d / d_p2d / d_sigma2 hold the batch (always for flat uploads)
@@ -139,7 +139,7 @@ struct PnpState {
         for (auto& b : ee_visit) b.release();
         DevBuf* all[] = {&d_metas, &d_cP, &d_th2, &d_p3d, &d_p2d, &d_sigma2, &d_cA, &d_cB, &d_uv, &d_tables, &d_poses,
                          &d_counts, &d_results, &d_masks, &d_hmasks, &d_sel, &d_pw, &d_us, &d_al, &d_cov, &d_extra, &d_visit,
-                         &d_kp_uv, &d_kp_s2, &d_mp_xyz, &d_kp_idx, &d_mp_idx, &d_kpA, &d_kpB};
+                         &d_kp_uv, &d_kp_s2, &d_mp_xyz, &d_kp_idx, &d_mp_idx, &d_kpA, &d_kpB, &d_carry};
         for (DevBuf* b : all) b->release();
     }
 };

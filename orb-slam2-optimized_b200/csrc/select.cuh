@@ -47,6 +47,20 @@ struct SelectArgs {
     int32_t first_phase = 0;   // HA: hypotheses every problem has after phase A
     int32_t only_phase = -1;   // >= 0: the phase-C replay: only problems marked undecided run; they resume where they stopped
     const int32_t* problem_ids = nullptr;   // optional [C]: global problem index of every problem (rsac_set_problem_ids)
+    // The replay split around the first Refine's 12x12 eigen-solve (PnP, main replay of a sweep): split_phase 1 runs up to
+    // M^T M and parks the problem in `carry`; select_eigen_kernel (one warp per problem) solves; split_phase 2 picks up
+    // behind the eigen-solve and finishes the scan (any further Refine of the same problem runs its eigen-solve in place).
+    // 0 = the whole replay in one launch.  The eigen-solve is 36 % of the replay's critical path and uses one warp of the
+    // CTA's three: on its own it holds a sixth of the registers for that time, which is what other sweeps in flight get.
+    struct SelectCarry* carry = nullptr;
+    int32_t split_phase = 0;
+};
+
+struct SelectCarry {
+    int32_t waiting;          // 1: parked in front of the eigen-solve
+    int32_t best, bestH, lastRefH, lastCntR, mSel, cursor, h, n_refines, pad[3];
+    float bestpose[12];
+    double C0[3], A[9], cws[12], CCi[9], MtM[78], U4[48], w4[4], pad2;
 };
 
 struct ResultRec {   // mirrors rsac_result (include/ransac_b200.h)
@@ -226,7 +240,12 @@ __device__ inline void epnp_gauss_newton_warp(const double* L, const double* rho
 
 // PnPsolver::Refine's compute_pose on the n selected points (PnPsolver.cpp:206-217, 359-415);
 // result as float R|t in pose_out[12] (shared)
-__device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, int n, EpnpShared& S, double2* s_rec, float* pose_out)
+constexpr int kSelTile = 64, kSelTP = kSelTile + 1;          // padded rows: entries of different rows fall into different banks
+constexpr int kSelRowTile = 32, kSelRP = kSelRowTile + 1;    // MtM: 24 row entries per point
+constexpr int kSelTileDoubles = 24 * kSelRP > 12 * kSelTP ? 24 * kSelRP : 12 * kSelTP;
+
+// front half: add_correspondence .. M^T M (PnPsolver.cpp:206-217, 296-343, 364-379)
+__device__ inline void refine_epnp_front(const ProblemMeta* m, const SelectArgs& a, int n, EpnpShared& S, double* s_tile)
 {
     const int tid = threadIdx.x;
     const Cam cam = {m->fx, m->fy, m->cx, m->cy};
@@ -234,14 +253,12 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     double* pw = a.pw_s + (size_t)m->corr_off * 3;
     double* us = a.us_s + (size_t)m->corr_off * 2;
     double* al = a.al_s + (size_t)m->corr_off * 4;
+    constexpr int kTile = kSelTile, kTP = kSelTP, kRowTile = kSelRowTile, kRP = kSelRP;
     RSAC_SEL_MARK(2);
     // Every n-point sum below is formed by ONE thread per output entry that adds the per-point terms in index
     // order (the checker's serial order).  The terms travel through a shared-memory tile: the whole CTA loads /
     // computes the terms of kTile points (coalesced, independent), then the few summing threads add them from
     // shared memory -- the dependent chain is the additions alone, not a global-memory load per point.
-    constexpr int kTile = 64, kTP = kTile + 1;          // padded rows: entries of different rows fall into different banks
-    constexpr int kRowTile = 32, kRP = kRowTile + 1;    // MtM: 24 row entries per point
-    __shared__ double s_tile[24 * kRP > 12 * kTP ? 24 * kRP : 12 * kTP];
     for (int i = tid; i < n; i += blockDim.x) {       // add_correspondence
         const size_t g = (size_t)m->corr_off + sel[i];
         const float4 c = a.cA[g];
@@ -340,11 +357,28 @@ __device__ inline void refine_epnp(const ProblemMeta* m, const SelectArgs& a, in
     }
     __syncthreads();
     RSAC_SEL_MARK(4);
-    if (n == 4 && !(a.flags & 8)) {                    // RSAC_FLAG_EPNP_EIGEN clear: QR null space for a 4-point system
+}
+
+// a 4-point best set in the default mode takes the QR null space: no eigen-solve to split off
+__device__ __forceinline__ bool refine_epnp_has_eigen(const SelectArgs& a, int n) { return !(n == 4 && !(a.flags & 8)); }
+
+// back half: null space (do_eigen: the 12x12 eigen-solve runs here; false: S.U4 / S.w4 already hold its result), betas,
+// R and t of the three candidates, the best one as float R|t in pose_out[12] (shared) (PnPsolver.cpp:380-415)
+__device__ inline void refine_epnp_back(const ProblemMeta* m, const SelectArgs& a, int n, EpnpShared& S, double2* s_rec, float* pose_out,
+                                        double* s_tile, bool do_eigen)
+{
+    // do_eigen == false: select_eigen_kernel has left S.U4 and S.w4 (the split replay)
+    const int tid = threadIdx.x;
+    const Cam cam = {m->fx, m->fy, m->cx, m->cy};
+    double* pw = a.pw_s + (size_t)m->corr_off * 3;
+    double* us = a.us_s + (size_t)m->corr_off * 2;
+    double* al = a.al_s + (size_t)m->corr_off * 4;
+    constexpr int kTile = kSelTile, kTP = kSelTP;
+    if (!refine_epnp_has_eigen(a, n)) {                // RSAC_FLAG_EPNP_EIGEN clear: QR null space for a 4-point system
         if (tid == 0) epnp_solve_betas_qr4(al, us, cam, S.cws, S.U4, S.betas);
     } else {
         // 12x12 eigen-solve (:380): warp 0, cooperative schedule of the same rotations
-        if (tid < 32) jacobi_lowest_warp<12, 4>(S.MtM, S.w4, S.U4, s_rec, tid, blockIdx.x == 0 ? g_select_clocks + 11 : nullptr);
+        if (do_eigen && tid < 32) jacobi_lowest_warp<12, 4>(S.MtM, S.w4, S.U4, s_rec, tid, blockIdx.x == 0 ? g_select_clocks + 11 : nullptr);
         __syncthreads();
         RSAC_SEL_MARK(5);
         // L (6x10, :604-637) and rho (:639-647) entry-parallel into shared memory: 72 control-point differences,
@@ -690,6 +724,36 @@ __device__ inline void refine_mlpnp(const ProblemMeta* m, const SelectArgs& a, i
     __syncthreads();
 }
 
+// ------------------------------------------------------------- the split replay's eigen-solve
+// One warp per parked problem: the 12x12 eigen-solve of M^T M (PnPsolver.cpp:380), the same cooperative schedule as inside the
+// replay kernel (bit-identical), with a sixth of the replay CTA's registers.  kSelEigWarps problems per CTA.
+#ifndef RSAC_SEL_EIG_WARPS
+#define RSAC_SEL_EIG_WARPS 4
+#endif
+constexpr int kSelEigWarps = RSAC_SEL_EIG_WARPS;
+constexpr size_t kSelEigSmemPerWarp = sizeof(double) * (78 + 48 + 4) + sizeof(double2) * kMaxSweepsRec * 66;
+// (measured and rejected: the beta branches in this kernel too -- 0.370 instead of 0.364 ms per sweep in flight, the narrow kernel
+// gets longer than what it frees; the recorded rotations in global memory instead of 12.7 KB of shared memory per warp -- 0.386)
+static __global__ void __launch_bounds__(kSelEigWarps * 32) select_eigen_kernel(SelectCarry* carry, int C)
+{
+    extern __shared__ __align__(16) unsigned char eig_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kSelEigWarps + warp;
+    if (c >= C) return;
+    SelectCarry* cr = carry + c;
+    if (!cr->waiting) return;
+    double2* rec = reinterpret_cast<double2*>(eig_smem + (size_t)warp * kSelEigSmemPerWarp);
+    double* MtM = reinterpret_cast<double*>(rec + kMaxSweepsRec * 66);
+    double* U4 = MtM + 78;
+    double* w4 = U4 + 48;
+    for (int i = lane; i < 78; i += 32) MtM[i] = cr->MtM[i];
+    __syncwarp();
+    jacobi_lowest_warp<12, 4>(MtM, w4, U4, rec, lane);
+    __syncwarp();
+    for (int i = lane; i < 48; i += 32) cr->U4[i] = U4[i];
+    if (lane < 4) cr->w4[lane] = w4[lane];
+}
+
 // ------------------------------------------------------------- the replay kernel
 template <int MODEL>
 __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ransac_select_kernel(SelectArgs a)
@@ -707,6 +771,10 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
     __shared__ PT s_pose[12], s_bestpose[12];
     __shared__ typename std::conditional<MODEL == 0, EpnpShared, MlpnpShared>::type S;
     __shared__ double2 s_rec[kMaxSweepsRec * 66];       // recorded rotations of the refine eigen-solve
+    __shared__ double s_tile[MODEL == 0 ? kSelTileDoubles : 1];
+    SelectCarry* const cr = (MODEL == 0 && a.carry && a.split_phase != 0) ? a.carry + blockIdx.x : nullptr;
+    if (cr && a.split_phase == 2 && !cr->waiting) return;       // decided in the first pass
+    if (cr && a.split_phase == 1 && threadIdx.x == 0) cr->waiting = 0;
 
     ResultRec res;
     res.ok = 0; res.no_more = 0; res.n_inliers = 0; res.best_hyp = -1; res.refined = 0; res.n_refines = 0;
@@ -775,6 +843,24 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
         __syncthreads();
     };
 
+    // second pass of the split replay: back where the first pass parked the problem, behind the eigen-solve
+    bool resume_refine = false;
+    int h_resume = 0;
+    if constexpr (MODEL == 0) {
+        if (cr && a.split_phase == 2) {
+            resume_refine = true;
+            best = cr->best; bestH = cr->bestH; lastRefH = cr->lastRefH; lastCntR = cr->lastCntR; mSel = cr->mSel;
+            cursor = cr->cursor; h_resume = cr->h; res.n_refines = cr->n_refines;
+            if (tid < 12) s_bestpose[tid] = cr->bestpose[tid];
+            for (int w = tid; w < words; w += blockDim.x) bestmask[w] = final_mask[w];      // parked there by the first pass
+            for (int i = tid; i < 3; i += blockDim.x) S.C0[i] = cr->C0[i];
+            for (int i = tid; i < 9; i += blockDim.x) { S.A[i] = cr->A[i]; S.CCi[i] = cr->CCi[i]; }
+            for (int i = tid; i < 12; i += blockDim.x) S.cws[i] = cr->cws[i];
+            for (int i = tid; i < 48; i += blockDim.x) S.U4[i] = cr->U4[i];
+            for (int i = tid; i < 4; i += blockDim.x) S.w4[i] = cr->w4[i];
+            __syncthreads();
+        }
+    }
     const int resume_at = resume_phase ? resume_stop : ((a.resume && !finished) ? a.resume[blockIdx.x] : 0);
     if (!finished && resume_at > 0) {
         // a later iterate() call (or the phase-C continuation): rebuild mnBestInliers / mvbBestInliers as the
@@ -792,23 +878,27 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
     }
 
     while (!finished) {
-        // next hypothesis with cnt >= minInliers (PnPsolver.cpp:146)
-        if (tid == 0) s_found = H;
-        __syncthreads();
         int h = H;
-        for (int base = cursor; base < H; base += blockDim.x) {   // uniform trip count: h is read after a barrier
-            const int hc = base + tid;
-            if (hc < H && counts[hc] >= minInl) atomicMin(&s_found, hc);
+        if (resume_refine) {
+            h = h_resume;                                       // the hypothesis whose Refine is under way
+        } else {
+            // next hypothesis with cnt >= minInliers (PnPsolver.cpp:146)
+            if (tid == 0) s_found = H;
             __syncthreads();
-            h = s_found;
-            __syncthreads();
-            if (h < H) break;
-        }
-        if (h >= H) break;
+            for (int base = cursor; base < H; base += blockDim.x) {   // uniform trip count: h is read after a barrier
+                const int hc = base + tid;
+                if (hc < H && counts[hc] >= minInl) atomicMin(&s_found, hc);
+                __syncthreads();
+                h = s_found;
+                __syncthreads();
+                if (h < H) break;
+            }
+            if (h >= H) break;
 
-        RSAC_SEL_MARK(1);
-        if (counts[h] > best) set_best(h);   // :149 strict: first maximum wins (Refine uses this set, :195-204)
-        res.n_refines++;
+            RSAC_SEL_MARK(1);
+            if (counts[h] > best) set_best(h);   // :149 strict: first maximum wins (Refine uses this set, :195-204)
+            res.n_refines++;
+        }
 
         if (discard) {
             // MLPnPsolver::Refine as shipped never copies its result into mRi/mti
@@ -820,14 +910,39 @@ __global__ void __launch_bounds__(select_threads<MODEL>(), kSelectCtasPerSm) ran
                 lastCntR = s_cnt;
                 lastRefH = h;
             }
-        } else if (bestH != lastRefBestH) {
-            if constexpr (MODEL == 0) refine_epnp(m, a, mSel, S, s_rec, s_pose);
-            else refine_mlpnp(m, a, mSel, S, s_rec, s_pose);
+        } else if (resume_refine || bestH != lastRefBestH) {
+            if constexpr (MODEL == 0) {
+                bool do_eigen = true;
+                if (!resume_refine) {
+                    refine_epnp_front(m, a, mSel, S, s_tile);
+                    if (cr && a.split_phase == 1 && refine_epnp_has_eigen(a, mSel)) {
+                        // park the problem in front of its eigen-solve: scan state, the best set's pose and mask, the front half's results
+                        if (tid == 0) {
+                            cr->waiting = 1;
+                            cr->best = best; cr->bestH = bestH; cr->lastRefH = lastRefH; cr->lastCntR = lastCntR; cr->mSel = mSel;
+                            cr->cursor = cursor; cr->h = h; cr->n_refines = res.n_refines;
+                        }
+                        if (tid < 12) cr->bestpose[tid] = s_bestpose[tid];
+                        for (int w = tid; w < words; w += blockDim.x) final_mask[w] = bestmask[w];
+                        for (int i = tid; i < 3; i += blockDim.x) cr->C0[i] = S.C0[i];
+                        for (int i = tid; i < 9; i += blockDim.x) { cr->A[i] = S.A[i]; cr->CCi[i] = S.CCi[i]; }
+                        for (int i = tid; i < 12; i += blockDim.x) cr->cws[i] = S.cws[i];
+                        for (int i = tid; i < 78; i += blockDim.x) cr->MtM[i] = S.MtM[i];
+                        return;
+                    }
+                } else {
+                    do_eigen = false;                           // select_eigen_kernel did it
+                }
+                refine_epnp_back(m, a, mSel, S, s_rec, s_pose, s_tile, do_eigen);
+            } else {
+                refine_mlpnp(m, a, mSel, S, s_rec, s_pose);
+            }
             RSAC_SEL_MARK(8);
             cta_score_exact<MODEL>(m, a, s_pose, refmask, &s_cnt);   // :220
             RSAC_SEL_MARK(9);
             lastCntR = s_cnt;
             lastRefBestH = bestH;
+            resume_refine = false;
         }
 
         if (lastCntR > minInl) {                               // :225 strict
