@@ -1,0 +1,288 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// C entry points around the REFERENCE's own classes, compiled from the reference's sources where they lie:
+//   /root/reference/src/PnPsolver.cpp, /root/reference/src/Sim3Solver.cpp      (unmodified, against oracle/shim/)
+//   /root/reference/Thirdparty/DBoW2/DUtils/Random.cpp, Timestamp.cpp          (unmodified, no stand-ins needed)
+// Built by `make -C oracle ref` into oracle/_ref/libref_solvers.so; loaded only by tests/test_cpu_reference_build.py
+// through tests/ref_api.py.  The stand-in headers (oracle/shim/) and what a build against them does and does not pin
+// are described in oracle/shim/Eigen/Dense.
+//
+// Private / protected members are reached by redefining the access keywords for this translation unit only (the
+// solver sources themselves are compiled as they are): the tests call compute_pose / CheckInliers / ComputeSim3 on
+// chosen inputs and read the RANSAC state.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <mutex>
+#include <vector>
+#include <Eigen/Dense>
+
+#define private public
+#define protected public
+#include "PnPsolver.hpp"
+#include "Sim3Solver.hpp"
+#undef private
+#undef protected
+
+using namespace ORB_SLAM_CUSTOM;
+
+namespace {
+
+struct PnpBox {
+    Frame frame;
+    std::vector<std::shared_ptr<MapPoint>> matches;
+    std::unique_ptr<PnPsolver> solver;
+};
+
+struct Sim3Box {
+    std::shared_ptr<KeyFrame> kf1, kf2;
+    std::vector<std::shared_ptr<MapPoint>> matched12;
+    std::unique_ptr<Sim3Solver> solver;
+};
+
+// recorded 12 x 12 eigen-problems of the current thread's solver calls (shim hook)
+std::vector<double> g_eig_basis;   // 48 doubles per call
+int g_eig_calls = 0;
+bool g_eig_record = false;
+void eig_hook(const double *, double *U, double *)
+{
+    ++g_eig_calls;
+    if (g_eig_record) g_eig_basis.insert(g_eig_basis.end(), U, U + 48);
+}
+
+void store_T(const Eigen::Matrix4f &T, float *out)
+{
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) out[i * 4 + j] = T(i, j);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- DUtils::Random (the reference's own Random.cpp) ----
+void ref_seed(int seed) { DUtils::Random::SeedRand(seed); }
+int ref_random_int(int lo, int hi) { return DUtils::Random::RandomInt(lo, hi); }
+
+// ---- 12 x 12 eigen-problem recorder ----
+void ref_eig_record(int on)
+{
+    Eigen::shim_eig12_hook() = eig_hook;
+    g_eig_record = on != 0;
+    g_eig_basis.clear();
+    g_eig_calls = 0;
+}
+int ref_eig_calls(void) { return g_eig_calls; }
+int ref_eig_take(double *out, int max_calls)
+{
+    const int n = std::min<int>(max_calls, (int)(g_eig_basis.size() / 48));
+    if (out && n > 0) std::memcpy(out, g_eig_basis.data(), sizeof(double) * 48 * (size_t)n);
+    return n;
+}
+
+// ---- PnPsolver ----
+// state[i]: 0 = keypoint i has no map point, 1 = map point, 2 = bad map point (PnPsolver.cpp:23-29)
+void *ref_pnp_create(int n_kp, const float *kp_xy, const int *octave, const float *level_sigma2, int n_levels,
+                     const float *mp_xyz, const uint8_t *state, float fx, float fy, float cx, float cy)
+{
+    PnpBox *b = new PnpBox;
+    b->frame.fx = fx; b->frame.fy = fy; b->frame.cx = cx; b->frame.cy = cy;
+    b->frame.mvLevelSigma2.assign(level_sigma2, level_sigma2 + n_levels);
+    b->frame.mvKeysUn.resize(n_kp);
+    b->frame.mvpMapPoints.resize(n_kp);
+    b->matches.resize(n_kp);
+    for (int i = 0; i < n_kp; ++i) {
+        b->frame.mvKeysUn[i].pt = cv::Point2f(kp_xy[2 * i], kp_xy[2 * i + 1]);
+        b->frame.mvKeysUn[i].octave = octave[i];
+        if (state[i]) {
+            auto mp = std::make_shared<MapPoint>();
+            mp->mWorldPos = Eigen::Vector3f(mp_xyz[3 * i], mp_xyz[3 * i + 1], mp_xyz[3 * i + 2]);
+            mp->mbBad = state[i] == 2;
+            b->matches[i] = mp;
+        }
+    }
+    b->solver.reset(new PnPsolver(b->frame, b->matches));
+    return b;
+}
+void ref_pnp_destroy(void *h) { delete static_cast<PnpBox *>(h); }
+
+void ref_pnp_set_params(void *h, double prob, int min_inliers, int max_its, int min_set, float eps, float th2)
+{
+    static_cast<PnpBox *>(h)->solver->SetRansacParameters(prob, min_inliers, max_its, min_set, eps, th2);
+}
+// N, adjusted mRansacMinInliers / mRansacMaxIts / mRansacEpsilon, mvMaxError[N], mvKeyPointIndices[N]
+void ref_pnp_get_params(void *h, int *N, int *min_inliers, int *max_its, float *eps, float *max_err, int *kp_index)
+{
+    PnPsolver &s = *static_cast<PnpBox *>(h)->solver;
+    *N = (int)s.mvP2D.size();
+    *min_inliers = s.mRansacMinInliers;
+    *max_its = s.mRansacMaxIts;
+    *eps = s.mRansacEpsilon;
+    if (max_err)
+        for (size_t i = 0; i < s.mvMaxError.size(); ++i) max_err[i] = s.mvMaxError[i];
+    if (kp_index)
+        for (size_t i = 0; i < s.mvKeyPointIndices.size(); ++i) kp_index[i] = (int)s.mvKeyPointIndices[i];
+}
+int ref_pnp_iterate(void *h, int n_iterations, int *no_more, uint8_t *inliers /* n_kp */, int *n_inliers, float *T16)
+{
+    PnpBox *b = static_cast<PnpBox *>(h);
+    bool bNoMore = false;
+    std::vector<bool> vb;
+    int nInl = 0;
+    Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+    const bool ok = b->solver->iterate(n_iterations, bNoMore, vb, nInl, T);
+    *no_more = bNoMore ? 1 : 0;
+    *n_inliers = nInl;
+    std::memset(inliers, 0, b->matches.size());
+    for (size_t i = 0; i < vb.size() && i < b->matches.size(); ++i) inliers[i] = vb[i] ? 1 : 0;
+    store_T(T, T16);
+    return ok ? 1 : 0;
+}
+// RANSAC state after a call: mnIterations, mnBestInliers, mnRefinedInliers, mBestTcw, mvbBestInliers[N]
+void ref_pnp_state(void *h, int *iterations, int *best_inliers, int *refined_inliers, float *best_T16, uint8_t *best_mask)
+{
+    PnPsolver &s = *static_cast<PnpBox *>(h)->solver;
+    *iterations = s.mnIterations;
+    *best_inliers = s.mnBestInliers;
+    *refined_inliers = s.mnRefinedInliers;
+    if (best_T16) store_T(s.mBestTcw, best_T16);
+    if (best_mask)
+        for (size_t i = 0; i < s.mvbBestInliers.size(); ++i) best_mask[i] = s.mvbBestInliers[i] ? 1 : 0;
+}
+// PnPsolver::compute_pose on the subset idx[0..m) of the solver's correspondences, driven exactly as iterate() /
+// Refine() drive it (PnPsolver.cpp:109,122,131 / :208-217)
+double ref_pnp_compute_pose(void *h, const int *idx, int m, float *R9, float *t3)
+{
+    PnPsolver &s = *static_cast<PnpBox *>(h)->solver;
+    s.set_maximum_number_of_correspondences(m);
+    s.reset_correspondences();
+    for (int i = 0; i < m; ++i) s.add_correspondence(s.mvP3Dw[idx[i]], s.mvP2D[idx[i]]);
+    const double err = s.compute_pose(s.mRi, s.mti);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R9[i * 3 + j] = s.mRi(i, j);
+        t3[i] = s.mti(i);
+    }
+    return err;
+}
+// PnPsolver::CheckInliers for a given pose; returns mnInliersi, mask = mvbInliersi
+int ref_pnp_check_inliers(void *h, const float *R9, const float *t3, uint8_t *mask)
+{
+    PnPsolver &s = *static_cast<PnpBox *>(h)->solver;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) s.mRi(i, j) = R9[i * 3 + j];
+        s.mti(i) = t3[i];
+    }
+    s.CheckInliers();
+    for (size_t i = 0; i < s.mvbInliersi.size(); ++i) mask[i] = s.mvbInliersi[i] ? 1 : 0;
+    return s.mnInliersi;
+}
+
+// ---- Sim3Solver ----
+// Both keyframes sit at the world origin with identity rotation, so the constructor's camera-frame points
+// (Sim3Solver.cpp:57-63) are the given ones exactly.  state[i] as above, for the matched point of keypoint i of KF1;
+// keypoint i of KF1 always holds map point i.
+void *ref_sim3_create(int n, const float *x1, const float *x2, const int *octave1, const int *octave2,
+                      const float *level_sigma2, int n_levels, const uint8_t *state, const float *K1 /* fx fy cx cy */,
+                      const float *K2)
+{
+    Sim3Box *b = new Sim3Box;
+    b->kf1 = std::make_shared<KeyFrame>();
+    b->kf2 = std::make_shared<KeyFrame>();
+    KeyFrame *kfs[2] = {b->kf1.get(), b->kf2.get()};
+    const float *Ks[2] = {K1, K2};
+    for (int k = 0; k < 2; ++k) {
+        kfs[k]->mRcw.setIdentity();
+        kfs[k]->mtcw.setZero();
+        kfs[k]->mK.setIdentity();
+        kfs[k]->mK(0, 0) = Ks[k][0]; kfs[k]->mK(1, 1) = Ks[k][1]; kfs[k]->mK(0, 2) = Ks[k][2]; kfs[k]->mK(1, 2) = Ks[k][3];
+        kfs[k]->mvLevelSigma2.assign(level_sigma2, level_sigma2 + n_levels);
+        kfs[k]->mvKeysUn.resize(n);
+        kfs[k]->mvpMapPoints.resize(n);
+    }
+    b->matched12.resize(n);
+    for (int i = 0; i < n; ++i) {
+        b->kf1->mvKeysUn[i].octave = octave1[i];
+        b->kf2->mvKeysUn[i].octave = octave2[i];
+        auto mp1 = std::make_shared<MapPoint>();
+        mp1->mWorldPos = Eigen::Vector3f(x1[3 * i], x1[3 * i + 1], x1[3 * i + 2]);
+        mp1->mpKF1 = b->kf1.get(); mp1->mIndexKF1 = i;
+        b->kf1->mvpMapPoints[i] = mp1;
+        if (state[i]) {
+            auto mp2 = std::make_shared<MapPoint>();
+            mp2->mWorldPos = Eigen::Vector3f(x2[3 * i], x2[3 * i + 1], x2[3 * i + 2]);
+            mp2->mpKF2 = b->kf2.get(); mp2->mIndexKF2 = i;
+            mp2->mbBad = state[i] == 2;
+            b->kf2->mvpMapPoints[i] = mp2;
+            b->matched12[i] = mp2;
+        }
+    }
+    b->solver.reset(new Sim3Solver(b->kf1, b->kf2, b->matched12));
+    return b;
+}
+void ref_sim3_destroy(void *h) { delete static_cast<Sim3Box *>(h); }
+void ref_sim3_set_params(void *h, double prob, int min_inliers, int max_its)
+{
+    static_cast<Sim3Box *>(h)->solver->SetRansacParameters(prob, min_inliers, max_its);
+}
+// N, mRansacMaxIts, the integer thresholds mvnMaxError1/2 (Sim3Solver.hpp: vector<size_t>)
+void ref_sim3_get_params(void *h, int *N, int *max_its, uint64_t *max_err1, uint64_t *max_err2)
+{
+    Sim3Solver &s = *static_cast<Sim3Box *>(h)->solver;
+    *N = s.N;
+    *max_its = s.mRansacMaxIts;
+    for (size_t i = 0; i < s.mvnMaxError1.size(); ++i) {
+        if (max_err1) max_err1[i] = s.mvnMaxError1[i];
+        if (max_err2) max_err2[i] = s.mvnMaxError2[i];
+    }
+}
+int ref_sim3_iterate(void *h, int n_iterations, int *no_more, uint8_t *inliers /* n */, int *n_inliers)
+{
+    Sim3Box *b = static_cast<Sim3Box *>(h);
+    bool bNoMore = false;
+    std::vector<bool> vb;
+    int nInl = 0;
+    const bool ok = b->solver->iterate(n_iterations, bNoMore, vb, nInl);
+    *no_more = bNoMore ? 1 : 0;
+    *n_inliers = nInl;
+    std::memset(inliers, 0, b->matched12.size());
+    for (size_t i = 0; i < vb.size() && i < b->matched12.size(); ++i) inliers[i] = vb[i] ? 1 : 0;
+    return ok ? 1 : 0;
+}
+// mnIterations, mnBestInliers, GetEstimatedRotation / GetEstimatedTranslation, mvbBestInliers[N]
+void ref_sim3_state(void *h, int *iterations, int *best_inliers, float *R9, float *t3, uint8_t *best_mask)
+{
+    Sim3Solver &s = *static_cast<Sim3Box *>(h)->solver;
+    *iterations = s.mnIterations;
+    *best_inliers = s.mnBestInliers;
+    const Eigen::Matrix3f R = s.GetEstimatedRotation();
+    const Eigen::Vector3f t = s.GetEstimatedTranslation();
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R9[i * 3 + j] = R(i, j);
+        t3[i] = t(i);
+    }
+    if (best_mask)
+        for (size_t i = 0; i < s.mvbBestInliers.size(); ++i) best_mask[i] = s.mvbBestInliers[i] ? 1 : 0;
+}
+// Sim3Solver::ComputeSim3 on three pairs (columns of P are points, Sim3Solver.cpp:142-143) followed by CheckInliers
+int ref_sim3_compute_and_check(void *h, const int *idx3, float *R9, float *t3, uint8_t *mask)
+{
+    Sim3Solver &s = *static_cast<Sim3Box *>(h)->solver;
+    Eigen::Matrix3f P1, P2;
+    for (int i = 0; i < 3; ++i) {
+        P1.col(i) = s.mvX3Dc1[idx3[i]];
+        P2.col(i) = s.mvX3Dc2[idx3[i]];
+    }
+    s.ComputeSim3(P1, P2);
+    s.CheckInliers();
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R9[i * 3 + j] = s.mR12i(i, j);
+        t3[i] = s.mt12i(i);
+    }
+    for (size_t i = 0; i < s.mvbInliersi.size(); ++i) mask[i] = s.mvbInliersi[i] ? 1 : 0;
+    return s.mnInliersi;
+}
+
+}  // extern "C"

@@ -1,0 +1,17 @@
+// oracle/shim/orbslam/Frame.hpp -- TEST INFRASTRUCTURE ONLY.
+// Stand-in for the reference's include/Frame.hpp with the members PnPsolver's constructor reads
+// (Frame.hpp:102-105 fx, fy, cx, cy as float; :127 mvKeysUn; :142 mvpMapPoints; mvLevelSigma2).
+#pragma once
+#include "MapPoint.hpp"
+
+namespace ORB_SLAM_CUSTOM {
+
+class Frame {
+public:
+    float fx = 0.f, fy = 0.f, cx = 0.f, cy = 0.f;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<std::shared_ptr<MapPoint>> mvpMapPoints;
+    std::vector<float> mvLevelSigma2;
+};
+
+}  // namespace ORB_SLAM_CUSTOM

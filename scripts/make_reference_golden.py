@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Generates tests/golden/reference_build.npz: outputs of THE REFERENCE'S OWN PnPsolver.cpp / Sim3Solver.cpp, compiled
+unmodified by `make -C oracle ref` (stand-in Eigen / OpenCV headers under oracle/shim/, see oracle/shim/Eigen/Dense),
+on seeded synthetic inputs -- the inputs are stored with them, so the file is self-contained.
+
+Runs only where /root/reference exists (this container).  The oracle is checked against the file by
+tests/test_cpu_reference_build.py::test_oracle_equals_reference_golden (no reference needed) and the CUDA engine by
+tests/test_gpu_reference_golden.py on the GPU box.
+
+    python scripts/make_reference_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "orb-slam2-optimized_b200"))
+import ref_api  # noqa: E402
+from ransac_b200 import synth  # noqa: E402
+
+CFG4 = dict(prob=0.99, min_inliers=10, max_its=300, min_set=4, eps=0.2, th2=5.991)
+SIM3 = dict(prob=0.99, min_inliers=20, max_its=300)
+
+
+def main():
+    assert ref_api.available(), "oracle/_ref/libref_solvers.so could not be built (needs /root/reference)"
+    ls2 = synth.level_sigma2()
+    out = {"level_sigma2": ls2}
+
+    # ---- PnPsolver: 16 cfg4 problems (500 matches, 50 % outliers), Relocalization's first iterate() call
+    Cn, n = 16, 500
+    seeds = np.arange(4000, 4000 + Cn, dtype=np.uint32)
+    ps = [synth.pnp_problem(int(s), n, 0.5) for s in seeds]
+    K = np.array([np.float32(k) for k in ps[0]["K"]], np.float32)
+    rec = dict(ok=[], no_more=[], n_inliers=[], iterations=[], best_inliers=[], n_refines=[], T=[], inliers=[], min_inliers=[], max_its=[])
+    for s, p in zip(seeds, ps):
+        sol = ref_api.PnP(p["p2d"], p["octave"], ls2, p["p3d"], K)
+        sol.set_params(**CFG4)
+        rp = sol.params()
+        ref_api.seed(int(s))
+        ref_api.eig_record(False)
+        r = sol.iterate(rp["max_its"])
+        st = sol.state(n)
+        rec["ok"].append(r["ok"]); rec["no_more"].append(r["no_more"]); rec["n_inliers"].append(r["n_inliers"])
+        rec["iterations"].append(st["iterations"]); rec["best_inliers"].append(st["best_inliers"])
+        rec["n_refines"].append(ref_api.eig_calls() - st["iterations"])
+        rec["T"].append(r["T"]); rec["inliers"].append(r["inliers"])
+        rec["min_inliers"].append(rp["min_inliers"]); rec["max_its"].append(rp["max_its"])
+    assert all(rec["ok"]) and all(k == 1 for k in rec["n_refines"]), "golden PnP runs must succeed at their first Refine (no stale rows, SURVEY Q1)"
+    out.update(pnp_seeds=seeds, pnp_K=K, pnp_params=np.array([CFG4[k] for k in ("prob", "min_inliers", "max_its", "min_set", "eps", "th2")], np.float64),
+               pnp_p3d=np.stack([p["p3d"] for p in ps]), pnp_p2d=np.stack([p["p2d"] for p in ps]),
+               pnp_octave=np.stack([p["octave"] for p in ps]).astype(np.int32))
+    for k, v in rec.items():
+        out["pnp_" + k] = np.array(v)
+
+    # per-call EPnP poses (PnPsolver::compute_pose) on subsets of problem 0: m = 4 .. 250
+    rng = np.random.default_rng(1)
+    inl = np.flatnonzero(ps[0]["inlier"])
+    sets, Rs, ts = [], [], []
+    for m in (4, 4, 4, 4, 5, 6, 8, 20, 100, 250):
+        idx = (rng.permutation(n)[:4] if m == 4 else rng.permutation(inl)[:m]).astype(np.int32)
+        sol = ref_api.PnP(ps[0]["p2d"], ps[0]["octave"], ls2, ps[0]["p3d"], K)
+        sol.set_params(**CFG4)
+        R, t, _ = sol.compute_pose(idx)
+        sets.append(np.pad(idx, (0, 250 - m), constant_values=-1)); Rs.append(R); ts.append(t)
+    out.update(pose_sets=np.stack(sets), pose_R=np.stack(Rs), pose_t=np.stack(ts))
+
+    # ---- Sim3Solver: 12 loop candidates (200 matches, 40 - 80 % outliers), iterate(5) until done (LoopClosing.cpp:275)
+    Cs, ns = 12, 200
+    sseeds = np.arange(5200, 5200 + Cs, dtype=np.uint32)
+    srec = dict(ok=[], n_inliers=[], iterations=[], best_inliers=[], R=[], t=[], inliers=[], max_its=[])
+    sp = []
+    for c, s in enumerate(sseeds):
+        p = synth.sim3_problem(int(s), ns, (0.4, 0.6, 0.8)[c % 3])
+        o1 = np.searchsorted(ls2, p["sigma2_1"]).astype(np.int32)
+        o2 = np.searchsorted(ls2, p["sigma2_2"]).astype(np.int32)
+        p["o1"], p["o2"] = o1, o2
+        sp.append(p)
+        sol = ref_api.Sim3(p["x1c"], p["x2c"], o1, o2, ls2, p["K"], p["K"])
+        sol.set_params(**SIM3)
+        ref_api.seed(int(s))
+        while True:
+            r = sol.iterate(5)
+            if r["ok"] or r["no_more"]:
+                break
+        st = sol.state(ns)
+        srec["ok"].append(r["ok"]); srec["n_inliers"].append(r["n_inliers"]); srec["iterations"].append(st["iterations"])
+        srec["best_inliers"].append(st["best_inliers"]); srec["R"].append(st["R"]); srec["t"].append(st["t"])
+        srec["inliers"].append(r["inliers"]); srec["max_its"].append(sol.params()["max_its"])
+    out.update(sim3_seeds=sseeds, sim3_K=np.array(sp[0]["K"], np.float32), sim3_params=np.array([SIM3["prob"], SIM3["min_inliers"], SIM3["max_its"]], np.float64),
+               sim3_x1c=np.stack([p["x1c"] for p in sp]), sim3_x2c=np.stack([p["x2c"] for p in sp]),
+               sim3_oct1=np.stack([p["o1"] for p in sp]), sim3_oct2=np.stack([p["o2"] for p in sp]))
+    for k, v in srec.items():
+        out["sim3_" + k] = np.array(v)
+
+    path = os.path.join(ROOT, "tests", "golden", "reference_build.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;",
+          "PnP iterations", out["pnp_iterations"].tolist(), "inliers", out["pnp_n_inliers"].tolist(),
+          "| Sim3 ok", out["sim3_ok"].astype(int).tolist(), "iterations", out["sim3_iterations"].tolist())
+
+
+if __name__ == "__main__":
+    main()

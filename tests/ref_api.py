@@ -1,0 +1,176 @@
+"""ctypes binding of oracle/_ref/libref_solvers.so -- TEST INFRASTRUCTURE ONLY.
+
+The library holds the REFERENCE's own PnPsolver.cpp, Sim3Solver.cpp and DUtils/Random.cpp, compiled unmodified from
+/root/reference by `make -C oracle ref` against the stand-in headers under oracle/shim/ (Eigen and OpenCV are not
+installed in this image; what the stand-ins pin and what they cannot is stated in oracle/shim/Eigen/Dense).
+It exists to check the oracle; nothing in the product, bench.py or the GPU tests loads it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+PATH = os.environ.get("REF_SO", os.path.join(ORACLE_DIR, "_ref", "libref_solvers.so"))
+_LIB = None
+
+
+def available() -> bool:
+    """built here (needs /root/reference) or shipped prebuilt"""
+    if not os.path.exists(PATH) and os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "orc_linalg.o"], check=False)
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref"], check=False)
+    return os.path.exists(PATH)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(PATH)
+        _LIB.ref_pnp_create.restype = C.c_void_p
+        _LIB.ref_sim3_create.restype = C.c_void_p
+        _LIB.ref_pnp_compute_pose.restype = C.c_double
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def random_ints(seed, lo, hi, count):
+    L = lib()
+    L.ref_seed(C.c_int(seed))
+    return [L.ref_random_int(C.c_int(lo), C.c_int(hi)) for _ in range(count)]
+
+
+def seed(s):
+    lib().ref_seed(C.c_int(s))
+
+
+class PnP:
+    """The reference's PnPsolver over one frame: keypoint i carries map point i unless state[i] == 0 (none) / 2 (bad)."""
+
+    def __init__(self, kp_xy, octave, level_sigma2, mp_xyz, K, state=None):
+        kp_xy = np.ascontiguousarray(kp_xy, np.float32)
+        mp_xyz = np.ascontiguousarray(mp_xyz, np.float32)
+        octave = np.ascontiguousarray(octave, np.int32)
+        ls2 = np.ascontiguousarray(level_sigma2, np.float32)
+        self.n_kp = kp_xy.shape[0]
+        st = np.ones(self.n_kp, np.uint8) if state is None else np.ascontiguousarray(state, np.uint8)
+        self.h = C.c_void_p(lib().ref_pnp_create(C.c_int(self.n_kp), _p(kp_xy), _p(octave), _p(ls2), C.c_int(len(ls2)), _p(mp_xyz), _p(st),
+                                                 C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3])))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_pnp_destroy(self.h)
+            self.h = None
+
+    def set_params(self, prob=0.99, min_inliers=8, max_its=300, min_set=4, eps=0.4, th2=5.991):
+        lib().ref_pnp_set_params(self.h, C.c_double(prob), C.c_int(min_inliers), C.c_int(max_its), C.c_int(min_set), C.c_float(eps), C.c_float(th2))
+
+    def params(self):
+        N, mi, its = C.c_int(), C.c_int(), C.c_int()
+        eps = C.c_float()
+        lib().ref_pnp_get_params(self.h, C.byref(N), C.byref(mi), C.byref(its), C.byref(eps), None, None)
+        max_err = np.zeros(max(N.value, 1), np.float32)
+        kpi = np.zeros(max(N.value, 1), np.int32)
+        lib().ref_pnp_get_params(self.h, C.byref(N), C.byref(mi), C.byref(its), C.byref(eps), _p(max_err), _p(kpi))
+        return dict(N=N.value, min_inliers=mi.value, max_its=its.value, eps=eps.value, max_err=max_err[:N.value], kp_index=kpi[:N.value])
+
+    def iterate(self, n_iterations):
+        no_more, n_inl = C.c_int(), C.c_int()
+        inl = np.zeros(max(self.n_kp, 1), np.uint8)
+        T = np.zeros(16, np.float32)
+        ok = lib().ref_pnp_iterate(self.h, C.c_int(n_iterations), C.byref(no_more), _p(inl), C.byref(n_inl), _p(T))
+        return dict(ok=bool(ok), no_more=bool(no_more.value), n_inliers=n_inl.value, inliers=inl[:self.n_kp].astype(bool), T=T.reshape(4, 4))
+
+    def state(self, N):
+        it, best, refd = C.c_int(), C.c_int(), C.c_int()
+        T = np.zeros(16, np.float32)
+        mask = np.zeros(max(N, 1), np.uint8)
+        lib().ref_pnp_state(self.h, C.byref(it), C.byref(best), C.byref(refd), _p(T), _p(mask))
+        return dict(iterations=it.value, best_inliers=best.value, refined_inliers=refd.value, best_T=T.reshape(4, 4), best_mask=mask[:N].astype(bool))
+
+    def compute_pose(self, idx):
+        idx = np.ascontiguousarray(idx, np.int32)
+        R, t = np.zeros(9, np.float32), np.zeros(3, np.float32)
+        err = lib().ref_pnp_compute_pose(self.h, _p(idx), C.c_int(len(idx)), _p(R), _p(t))
+        return R.reshape(3, 3), t, err
+
+    def check_inliers(self, R, t, N):
+        R = np.ascontiguousarray(R, np.float32).reshape(-1)
+        t = np.ascontiguousarray(t, np.float32)
+        mask = np.zeros(max(N, 1), np.uint8)
+        cnt = lib().ref_pnp_check_inliers(self.h, _p(R), _p(t), _p(mask))
+        return cnt, mask[:N].astype(bool)
+
+
+class Sim3:
+    """The reference's Sim3Solver over two keyframes at the origin (camera-frame points given directly)."""
+
+    def __init__(self, x1c, x2c, octave1, octave2, level_sigma2, K1, K2, state=None):
+        x1c = np.ascontiguousarray(x1c, np.float32)
+        x2c = np.ascontiguousarray(x2c, np.float32)
+        o1 = np.ascontiguousarray(octave1, np.int32)
+        o2 = np.ascontiguousarray(octave2, np.int32)
+        ls2 = np.ascontiguousarray(level_sigma2, np.float32)
+        self.n = x1c.shape[0]
+        st = np.ones(self.n, np.uint8) if state is None else np.ascontiguousarray(state, np.uint8)
+        k1 = np.ascontiguousarray(K1, np.float32)
+        k2 = np.ascontiguousarray(K2, np.float32)
+        self.h = C.c_void_p(lib().ref_sim3_create(C.c_int(self.n), _p(x1c), _p(x2c), _p(o1), _p(o2), _p(ls2), C.c_int(len(ls2)), _p(st), _p(k1), _p(k2)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_sim3_destroy(self.h)
+            self.h = None
+
+    def set_params(self, prob=0.99, min_inliers=6, max_its=300):
+        lib().ref_sim3_set_params(self.h, C.c_double(prob), C.c_int(min_inliers), C.c_int(max_its))
+
+    def params(self):
+        N, its = C.c_int(), C.c_int()
+        lib().ref_sim3_get_params(self.h, C.byref(N), C.byref(its), None, None)
+        e1 = np.zeros(max(N.value, 1), np.uint64)
+        e2 = np.zeros(max(N.value, 1), np.uint64)
+        lib().ref_sim3_get_params(self.h, C.byref(N), C.byref(its), _p(e1), _p(e2))
+        return dict(N=N.value, max_its=its.value, max_err1=e1[:N.value], max_err2=e2[:N.value])
+
+    def iterate(self, n_iterations):
+        no_more, n_inl = C.c_int(), C.c_int()
+        inl = np.zeros(max(self.n, 1), np.uint8)
+        ok = lib().ref_sim3_iterate(self.h, C.c_int(n_iterations), C.byref(no_more), _p(inl), C.byref(n_inl))
+        return dict(ok=bool(ok), no_more=bool(no_more.value), n_inliers=n_inl.value, inliers=inl[:self.n].astype(bool))
+
+    def state(self, N):
+        it, best = C.c_int(), C.c_int()
+        R, t = np.zeros(9, np.float32), np.zeros(3, np.float32)
+        mask = np.zeros(max(N, 1), np.uint8)
+        lib().ref_sim3_state(self.h, C.byref(it), C.byref(best), _p(R), _p(t), _p(mask))
+        return dict(iterations=it.value, best_inliers=best.value, R=R.reshape(3, 3), t=t, best_mask=mask[:N].astype(bool))
+
+    def compute_and_check(self, idx3, N):
+        idx3 = np.ascontiguousarray(idx3, np.int32)
+        R, t = np.zeros(9, np.float32), np.zeros(3, np.float32)
+        mask = np.zeros(max(N, 1), np.uint8)
+        cnt = lib().ref_sim3_compute_and_check(self.h, _p(idx3), _p(R), _p(t), _p(mask))
+        return R.reshape(3, 3), t, cnt, mask[:N].astype(bool)
+
+
+def eig_record(on=True):
+    lib().ref_eig_record(C.c_int(1 if on else 0))
+
+
+def eig_calls():
+    """12 x 12 eigen-problems solved since eig_record(): one per compute_pose call (PnPsolver.cpp:380)"""
+    return lib().ref_eig_calls()
+
+
+def eig_take(max_calls=4096):
+    out = np.zeros((max_calls, 12, 4), np.float64)
+    n = lib().ref_eig_take(_p(out), C.c_int(max_calls))
+    return out[:n]

@@ -1,0 +1,58 @@
+"""GPU parity against outputs of THE REFERENCE'S OWN SOURCES: tests/golden/reference_build.npz holds what the
+reference's PnPsolver.cpp / Sim3Solver.cpp -- compiled unmodified by `make -C oracle ref` against the stand-in headers of
+oracle/shim/ -- return on stored inputs (scripts/make_reference_golden.py; the CPU suite checks the oracle against the
+same file and against the live library).  Here the CUDA engine is compared with the file directly, through the C ABI:
+PnP in the reference's own structure (RSAC_FLAG_EPNP_EIGEN: 12 x 12 eigen-solve per hypothesis), exhaustive and with
+the staged early exit, and Sim3.  Bit for bit: return value, inlier count, iteration at which the reference stopped,
+inlier vector, pose."""
+import os
+
+import numpy as np
+import pytest
+
+from ransac_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_build.npz"))
+
+
+@pytest.mark.parametrize("early_exit", [False, True])
+def test_pnp_engine_equals_compiled_reference(engine, early_exit):
+    C, n = G["pnp_p3d"].shape[:2]
+    ls2 = G["level_sigma2"]
+    sigma2 = ls2[G["pnp_octave"]]
+    offsets = np.arange(C + 1, dtype=np.int32) * n
+    pr = G["pnp_params"]
+    prm = capi.ransac_params(pr[0], int(pr[1]), int(pr[2]), int(pr[3]), float(pr[4]), float(pr[5]))
+    flags = capi.FLAG_EPNP_EIGEN | (capi.FLAG_EARLY_EXIT if early_exit else 0)
+    res, masks = engine.pnp_solve(offsets, G["pnp_p3d"], G["pnp_p2d"], sigma2, [G["pnp_K"]], prm, seeds=G["pnp_seeds"], flags=flags)
+    ml = engine.split_masks(masks, offsets)
+    for c in range(C):
+        r = res[c]
+        assert (bool(r["ok"]), bool(r["no_more"]), int(r["n_inliers"]), int(r["best_count"]), int(r["n_refines"])) == \
+               (bool(G["pnp_ok"][c]), bool(G["pnp_no_more"][c]), int(G["pnp_n_inliers"][c]), int(G["pnp_best_inliers"][c]), int(G["pnp_n_refines"][c])), c
+        assert int(r["n_hyp"]) == int(G["pnp_iterations"][c]), (c, int(r["n_hyp"]), int(G["pnp_iterations"][c]))
+        T = G["pnp_T"][c]
+        assert (r["R"].reshape(3, 3).view(np.uint32) == T[:3, :3].view(np.uint32)).all(), c
+        assert (r["t"].view(np.uint32) == T[:3, 3].view(np.uint32)).all(), c
+        assert (ml[c] == G["pnp_inliers"][c]).all(), c
+
+
+def test_sim3_engine_equals_compiled_reference(engine):
+    C, n = G["sim3_x1c"].shape[:2]
+    ls2 = G["level_sigma2"]
+    offsets = np.arange(C + 1, dtype=np.int32) * n
+    sp = G["sim3_params"]
+    K = np.array([G["sim3_K"]], np.float32)
+    res, masks = engine.sim3_solve(offsets, G["sim3_x1c"], G["sim3_x2c"], ls2[G["sim3_oct1"]], ls2[G["sim3_oct2"]], K, K,
+                                   capi.Sim3Params(sp[0], int(sp[1]), int(sp[2]), 1), seeds=G["sim3_seeds"])
+    ml = engine.split_masks(masks, offsets)
+    for c in range(C):
+        r = res[c]
+        assert (bool(r["ok"]), int(r["n_inliers"])) == (bool(G["sim3_ok"][c]), int(G["sim3_n_inliers"][c])), c
+        assert int(r["n_hyp"]) == int(G["sim3_iterations"][c]), (c, int(r["n_hyp"]), int(G["sim3_iterations"][c]))
+        if r["ok"]:
+            assert (r["R"].reshape(3, 3).view(np.uint32) == G["sim3_R"][c].view(np.uint32)).all(), c
+            assert (r["t"].view(np.uint32) == G["sim3_t"][c].view(np.uint32)).all(), c
+            assert (ml[c] == G["sim3_inliers"][c]).all(), c
