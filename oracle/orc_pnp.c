@@ -3,7 +3,8 @@
  *
  * Plain-C restatement of the reference's src/PnPsolver.cpp (the Eigen rewrite
  * of EPnP + RANSAC).  Function by function; every function cites the
- * reference lines it follows.  PARITY UNPINNED against an Eigen-built binary.
+ * reference lines it follows.  Pinned bit for bit against the reference's own source compiled with stand-in
+ * Eigen headers (oracle/_ref, tests/test_cpu_reference_build.py); Eigen's own rounding stays unpinned (orc.h).
  */
 #include <math.h>
 #include <stdlib.h>

@@ -4,8 +4,11 @@
  * Plain-C restatement of the reference's src/Sim3Solver.cpp (Horn 1987 on three
  * pairs + two-way reprojection scoring, all f32).  The reference has no scale
  * step (Sim3Solver.cpp:250); fix_scale=0 adds Horn's scale as
- * upstream ORB-SLAM2 does -- PARITY UNPINNED for that variant and for the
- * Eigen-backed 4x4 eigen-solve.
+ * upstream ORB-SLAM2 does -- PARITY UNPINNED for that variant.  The fixed-scale
+ * path (the reference's) equals the reference's own Sim3Solver.cpp, compiled
+ * with stand-in Eigen headers, bit for bit (oracle/_ref,
+ * tests/test_cpu_reference_build.py); the 4x4 eigen-solve is orc_linalg.c's on
+ * both sides (Eigen's own rounding unpinned, orc.h).
  */
 #include <math.h>
 #include <stdlib.h>

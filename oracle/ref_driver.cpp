@@ -286,3 +286,83 @@ int ref_sim3_compute_and_check(void *h, const int *idx3, float *R9, float *t3, u
 }
 
 }  // extern "C"
+
+// ---- KeyFrameDatabase ----
+#include "KeyFrameDatabase.hpp"
+
+namespace {
+struct KfdbBox {
+    std::shared_ptr<ORBVocabulary> voc;
+    std::vector<std::shared_ptr<KeyFrame>> kfs;
+    std::unique_ptr<KeyFrameDatabase> db;
+};
+int emit(const std::vector<std::shared_ptr<KeyFrame>> &cands, const KfdbBox *b, int32_t *out, int cap)
+{
+    int n = 0;
+    for (const auto &kf : cands) {
+        int idx = -1;
+        for (size_t k = 0; k < b->kfs.size(); ++k)
+            if (b->kfs[k] == kf) { idx = (int)k; break; }
+        if (n < cap) out[n] = idx;
+        ++n;
+    }
+    return n;
+}
+}  // namespace
+
+extern "C" {
+
+// keyframe k: BowVector = (bow_word, bow_val)[bow_off[k] .. bow_off[k+1]), GetBestCovisibilityKeyFrames(10) = covis[k][0..10)
+// (-1 padded); keyframes are add()-ed in index order (KeyFrameDatabase.cpp:15-22)
+void *ref_kfdb_create(int K, const int64_t *bow_off, const uint32_t *bow_word, const double *bow_val, const int32_t *covis, unsigned n_words)
+{
+    KfdbBox *b = new KfdbBox;
+    b->voc = std::make_shared<ORBVocabulary>(n_words);
+    b->kfs.resize(K);
+    for (int k = 0; k < K; ++k) {
+        b->kfs[k] = std::make_shared<KeyFrame>();
+        b->kfs[k]->mnId = (unsigned long)k + 1000000000ul;
+        for (int64_t i = bow_off[k]; i < bow_off[k + 1]; ++i) b->kfs[k]->mBowVec.addWeight(bow_word[i], bow_val[i]);
+    }
+    for (int k = 0; k < K; ++k)
+        for (int j = 0; j < 10 && covis[k * 10 + j] >= 0; ++j) b->kfs[k]->mvpOrderedConnected.push_back(b->kfs[covis[k * 10 + j]]);
+    b->db.reset(new KeyFrameDatabase(b->voc));
+    for (int k = 0; k < K; ++k) b->db->add(b->kfs[k]);
+    return b;
+}
+void ref_kfdb_destroy(void *h) { delete static_cast<KfdbBox *>(h); }
+
+// KeyFrameDatabase::DetectRelocalizationCandidates(Frame*): candidate keyframe indices in the returned order
+int ref_kfdb_reloc(void *h, int nq, const uint32_t *qword, const double *qval, unsigned long frame_id, int32_t *out, int cap)
+{
+    KfdbBox *b = static_cast<KfdbBox *>(h);
+    Frame F;
+    F.mnId = frame_id;
+    for (int i = 0; i < nq; ++i) F.mBowVec.addWeight(qword[i], qval[i]);
+    return emit(b->db->DetectRelocalizationCandidates(&F), b, out, cap);
+}
+// KeyFrameDatabase::DetectLoopCandidates(pKF, minScore) for database keyframe q, which takes the id query_id for the
+// call; conn = GetConnectedKeyFrames()
+int ref_kfdb_loop(void *h, int q, unsigned long query_id, int n_conn, const int32_t *conn, float min_score, int32_t *out, int cap)
+{
+    KfdbBox *b = static_cast<KfdbBox *>(h);
+    std::shared_ptr<KeyFrame> kf = b->kfs[q];
+    kf->mnId = query_id;
+    kf->mvpConnected.clear();
+    for (int i = 0; i < n_conn; ++i) kf->mvpConnected.push_back(b->kfs[conn[i]]);
+    return emit(b->db->DetectLoopCandidates(kf, min_score), b, out, cap);
+}
+void ref_kfdb_reloc_scores(void *h, float *scores)
+{
+    KfdbBox *b = static_cast<KfdbBox *>(h);
+    for (size_t k = 0; k < b->kfs.size(); ++k) scores[k] = b->kfs[k]->mRelocScore;
+}
+double ref_bow_l1_score(int n1, const uint32_t *w1, const double *v1, int n2, const uint32_t *w2, const double *v2)
+{
+    DBoW2::BowVector a, c;
+    for (int i = 0; i < n1; ++i) a.addWeight(w1[i], v1[i]);
+    for (int i = 0; i < n2; ++i) c.addWeight(w2[i], v2[i]);
+    return DBoW2::L1Scoring().score(a, c);
+}
+
+}  // extern "C"

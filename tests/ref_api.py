@@ -174,3 +174,54 @@ def eig_take(max_calls=4096):
     out = np.zeros((max_calls, 12, 4), np.float64)
     n = lib().ref_eig_take(_p(out), C.c_int(max_calls))
     return out[:n]
+
+
+class KfDb:
+    """The reference's KeyFrameDatabase (KeyFrameDatabase.cpp) over its own DBoW2 BowVector / L1Scoring; the keyframes
+    of `db` (synth.kf_database) are add()-ed in index order and keep their query marks between calls, as in a running
+    system."""
+
+    def __init__(self, db):
+        self.K = int(db["K"])
+        off = np.ascontiguousarray(db["bow_off"], np.int64)
+        w = np.ascontiguousarray(db["bow_word"], np.uint32)
+        v = np.ascontiguousarray(db["bow_val"], np.float64)
+        cov = np.ascontiguousarray(db["covis"], np.int32)
+        assert cov.shape == (self.K, 10)
+        self.h = C.c_void_p(lib_kfdb().ref_kfdb_create(C.c_int(self.K), _p(off), _p(w), _p(v), _p(cov), C.c_uint(int(db["vocab"]) + 16)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_kfdb_destroy(self.h)
+            self.h = None
+
+    def reloc(self, qword, qval, frame_id):
+        qw = np.ascontiguousarray(qword, np.uint32)
+        qv = np.ascontiguousarray(qval, np.float64)
+        out = np.empty(max(self.K, 1), np.int32)
+        n = lib().ref_kfdb_reloc(self.h, C.c_int(len(qw)), _p(qw), _p(qv), C.c_ulong(frame_id), _p(out), C.c_int(len(out)))
+        return out[:n].tolist()
+
+    def loop(self, q, query_id, conn, min_score):
+        cn = np.ascontiguousarray(conn, np.int32)
+        out = np.empty(max(self.K, 1), np.int32)
+        n = lib().ref_kfdb_loop(self.h, C.c_int(q), C.c_ulong(query_id), C.c_int(len(cn)), _p(cn), C.c_float(min_score), _p(out), C.c_int(len(out)))
+        return out[:n].tolist()
+
+    def reloc_scores(self):
+        s = np.zeros(max(self.K, 1), np.float32)
+        lib().ref_kfdb_reloc_scores(self.h, _p(s))
+        return s[:self.K]
+
+
+def lib_kfdb():
+    L = lib()
+    L.ref_kfdb_create.restype = C.c_void_p
+    L.ref_bow_l1_score.restype = C.c_double
+    return L
+
+
+def bow_l1_score(w1, v1, w2, v2):
+    w1, w2 = np.ascontiguousarray(w1, np.uint32), np.ascontiguousarray(w2, np.uint32)
+    v1, v2 = np.ascontiguousarray(v1, np.float64), np.ascontiguousarray(v2, np.float64)
+    return lib_kfdb().ref_bow_l1_score(C.c_int(len(w1)), _p(w1), _p(v1), C.c_int(len(w2)), _p(w2), _p(v2))

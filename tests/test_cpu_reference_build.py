@@ -308,3 +308,56 @@ def test_reference_golden_is_current(oracle):
         ref_api.seed(int(g["pnp_seeds"][c]))
         r = s.iterate(300)
         assert np.array_equal(r["T"], g["pnp_T"][c]) and np.array_equal(r["inliers"], g["pnp_inliers"][c])
+
+
+# ------------------------------------------------------------------ KeyFrameDatabase
+def test_l1_score_is_the_reference_dbow2_score(oracle):
+    """DBoW2::L1Scoring::score (the reference's vendored ScoringObject.cpp:23-66, compiled as it is)"""
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        w1, v1 = synth._bow_vector(rng, rng.integers(0, 5000, 800))
+        w2, v2 = synth._bow_vector(rng, rng.integers(0, 5000, 700))
+        assert oracle.bow_l1_score(w1, v1, w2, v2) == ref_api.bow_l1_score(w1, v1, w2, v2)
+
+
+def test_relocalization_candidates_equal_compiled_reference(oracle):
+    """KeyFrameDatabase::DetectRelocalizationCandidates (KeyFrameDatabase.cpp:174-284): a sequence of queries against
+    one database -- candidate lists equal, order included; the per-keyframe mRelocScore the reference carries from query
+    to query (quirk Q11) equals the oracle's explicit state after every query"""
+    db = synth.kf_database(1, K=300, n_places=30)
+    odb = oracle.kfdb(db)
+    rdb = ref_api.KfDb(db)
+    state = np.zeros(db["K"], np.float32)
+    n_total = 0
+    for q in range(24):
+        qw, qv = synth.kf_query(100 + q, db, place=(q * 7) % 30)
+        got = oracle.detect_candidates(odb, qw, qv, mode=0, score_state=state)
+        want = rdb.reloc(qw, qv, frame_id=7000 + q)
+        assert got.tolist() == want, q
+        assert np.array_equal(state, rdb.reloc_scores()), q
+        n_total += len(want)
+    assert n_total >= 24
+
+
+def test_loop_candidates_equal_compiled_reference(oracle):
+    """KeyFrameDatabase::DetectLoopCandidates (KeyFrameDatabase.cpp:51-172) with LoopClosing's minScore, 0 and 0.9"""
+    db = synth.kf_database(2, K=300, n_places=30)
+    odb = oracle.kfdb(db)
+    rdb = ref_api.KfDb(db)
+    found, qid = 0, 5000
+    for q in range(270, 300, 3):
+        qw = db["bow_word"][db["bow_off"][q]:db["bow_off"][q + 1]]
+        qv = db["bow_val"][db["bow_off"][q]:db["bow_off"][q + 1]]
+        conn = [int(c) for c in db["covis"][q] if c >= 0] + [q]
+        sl = lambda c: slice(db["bow_off"][c], db["bow_off"][c + 1])
+        min_score = min([1.0] + [float(oracle.bow_l1_score(qw, qv, db["bow_word"][sl(c)], db["bow_val"][sl(c)])) for c in conn if c != q])
+        for ms in (min_score, 0.0, 0.9):
+            qid += 1
+            got = oracle.detect_candidates(odb, qw, qv, mode=1, conn=conn, min_score=ms)
+            want = rdb.loop(q, qid, conn, ms)
+            assert got.tolist() == want, (q, ms)
+            found += len(want)
+    assert found > 0
+    # nothing shared / everything connected
+    assert rdb.reloc(np.array([db["vocab"] + 5], np.uint32), np.array([1.0]), 9999) == []
+    assert rdb.loop(5, 9998, list(range(300)), 0.0) == []
