@@ -7,6 +7,7 @@
 //     static int select(e, flags, d_resume, d_results_out, only_phase) the replay kernel
 //     static int setup(e)                                              kernel attributes (outside a graph capture)
 //     static int stage0_hpl()                                          hypotheses per lane of the stage-0 scoring plan (0: default)
+//     static int stage_hpl(), stage_chunk_words()                      the same for the later stages; chunk size of every stage plan (0: default)
 #pragma once
 #include "engine_shared.cuh"
 #include "early_exit.cuh"
@@ -29,8 +30,8 @@ static int early_plan(rsac_engine* e, PnpState& s, const std::vector<int>& bound
     // stage 0: few hypotheses per problem -- one hypothesis per lane (two consumer warps per problem) measured
     // best for PnP (0.045 ms against 0.066 with two per lane at 1024 x 55)
     RSAC_TRY(plan_score<MODEL>(e, s.metas, d.maxH, s.ee_groups[0], s.ee_plans[0], 0, bounds[0],
-                               env_int("RSAC_EE_HPL_A", EarlyHooks<MODEL>::stage0_hpl()), env_int("RSAC_EE_CW_A", 0)));
-    const int hplB = env_int("RSAC_EE_HPL_B", 0), cwB = env_int("RSAC_EE_CW_B", 0);
+                               env_int("RSAC_EE_HPL_A", EarlyHooks<MODEL>::stage0_hpl()), env_int("RSAC_EE_CW_A", EarlyHooks<MODEL>::stage_chunk_words())));
+    const int hplB = env_int("RSAC_EE_HPL_B", EarlyHooks<MODEL>::stage_hpl()), cwB = env_int("RSAC_EE_CW_B", EarlyHooks<MODEL>::stage_chunk_words());
     for (int j = 1; j < K; ++j)
         RSAC_TRY(plan_score<MODEL>(e, s.metas, d.maxH, s.ee_groups[j], s.ee_plans[j], bounds[j - 1], bounds[j], hplB, cwB, true));
     RSAC_TRY(plan_score<MODEL>(e, s.metas, d.maxH, s.ee_groups[K], s.ee_plans[K], bounds[0], INT32_MAX, hplB, cwB, true));   // clean-up

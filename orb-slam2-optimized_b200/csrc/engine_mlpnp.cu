@@ -149,6 +149,8 @@ template <> struct EarlyHooks<1> {
     { return mlpnp_launch_select(e, flags, d_resume, d_results_out, only_phase); }
     static int setup(rsac_engine* e) { return mlpnp_select_setup(e); }
     static int stage0_hpl() { return 0; }
+    static int stage_hpl() { return 0; }
+    static int stage_chunk_words() { return 0; }
 };
 
 int rsac_mlpnp_rerun(rsac_engine* e, int flags, const int32_t* resume_from, void* d_results_out)
