@@ -3,7 +3,10 @@
  *
  * Plain-C restatement of the reference's src/MLPnPsolver.cpp (an ORB-SLAM3
  * transplant that the reference neither compiles nor calls, SURVEY F6: this
- * file is spec-by-source).  PARITY UNPINNED for the whole path.
+ * file is spec-by-source).  Pinned (round 2) against the reference's own
+ * MLPnPsolver.cpp compiled with stand-in Eigen / OpenCV headers (oracle/_ref, tests/test_cpu_reference_build.py:
+ * generated Jacobian 1e-12, computePose median 3e-12, whole runs exact in counts and stopping iteration with Q6
+ * reproduced); Eigen's own SVD / LDLT rounding stays unpinned (orc.h).
  *
  * The 2x6 Jacobian (MLPnPsolver.cpp:773-1020) is a machine-generated symbolic
  * derivative of  r = N^T (R(w) p + t)/|R(w) p + t|  w.r.t. (w, t); it is

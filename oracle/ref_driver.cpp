@@ -1,7 +1,8 @@
 // oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY.
 //
 // C entry points around the REFERENCE's own classes, compiled from the reference's sources where they lie:
-//   /root/reference/src/PnPsolver.cpp, /root/reference/src/Sim3Solver.cpp      (unmodified, against oracle/shim/)
+//   /root/reference/src/PnPsolver.cpp, Sim3Solver.cpp, MLPnPsolver.cpp,
+//   KeyFrameDatabase.cpp                                                       (unmodified, against oracle/shim/)
 //   /root/reference/Thirdparty/DBoW2/DUtils/Random.cpp, Timestamp.cpp          (unmodified, no stand-ins needed)
 // Built by `make -C oracle ref` into oracle/_ref/libref_solvers.so; loaded only by tests/test_cpu_reference_build.py
 // through tests/ref_api.py.  The stand-in headers (oracle/shim/) and what a build against them does and does not pin
@@ -24,6 +25,7 @@
 #define protected public
 #include "PnPsolver.hpp"
 #include "Sim3Solver.hpp"
+#include "MLPnPsolver.hpp"
 #undef private
 #undef protected
 
@@ -363,6 +365,135 @@ double ref_bow_l1_score(int n1, const uint32_t *w1, const double *v1, int n2, co
     for (int i = 0; i < n1; ++i) a.addWeight(w1[i], v1[i]);
     for (int i = 0; i < n2; ++i) c.addWeight(w2[i], v2[i]);
     return DBoW2::L1Scoring().score(a, c);
+}
+
+}  // extern "C"
+
+// ---- MLPnPsolver (commented out of the reference's own CMakeLists.txt:75; compiled here all the same) ----
+namespace {
+struct MlpnpBox {
+    Frame frame;
+    std::vector<std::shared_ptr<MapPoint>> matches;
+    std::unique_ptr<MLPnPsolver> solver;
+};
+}  // namespace
+
+extern "C" {
+
+void *ref_mlpnp_create(int n_kp, const float *kp_xy, const int *octave, const float *level_sigma2, int n_levels,
+                       const float *mp_xyz, const uint8_t *state, float fx, float fy, float cx, float cy)
+{
+    MlpnpBox *b = new MlpnpBox;
+    b->frame.fx = fx; b->frame.fy = fy; b->frame.cx = cx; b->frame.cy = cy;
+    b->frame.mvLevelSigma2.assign(level_sigma2, level_sigma2 + n_levels);
+    b->frame.mvKeysUn.resize(n_kp);
+    b->frame.mvpMapPoints.resize(n_kp);
+    b->matches.resize(n_kp);
+    for (int i = 0; i < n_kp; ++i) {
+        b->frame.mvKeysUn[i].pt = cv::Point2f(kp_xy[2 * i], kp_xy[2 * i + 1]);
+        b->frame.mvKeysUn[i].octave = octave[i];
+        if (state[i]) {
+            auto mp = std::make_shared<MapPoint>();
+            mp->mWorldPos = Eigen::Vector3f(mp_xyz[3 * i], mp_xyz[3 * i + 1], mp_xyz[3 * i + 2]);
+            mp->mbBad = state[i] == 2;
+            b->matches[i] = mp;
+        }
+    }
+    b->solver.reset(new MLPnPsolver(b->frame, b->matches));
+    return b;
+}
+void ref_mlpnp_destroy(void *h) { delete static_cast<MlpnpBox *>(h); }
+void ref_mlpnp_set_params(void *h, double prob, int min_inliers, int max_its, int min_set, float eps, float th2)
+{
+    static_cast<MlpnpBox *>(h)->solver->SetRansacParameters(prob, min_inliers, max_its, min_set, eps, th2);
+}
+void ref_mlpnp_get_params(void *h, int *N, int *min_inliers, int *max_its, float *max_err, int *kp_index)
+{
+    MLPnPsolver &s = *static_cast<MlpnpBox *>(h)->solver;
+    *N = s.N;
+    *min_inliers = s.mRansacMinInliers;
+    *max_its = s.mRansacMaxIts;
+    if (max_err)
+        for (size_t i = 0; i < s.mvMaxError.size(); ++i) max_err[i] = s.mvMaxError[i];
+    if (kp_index)
+        for (size_t i = 0; i < s.mvKeyPointIndices.size(); ++i) kp_index[i] = (int)s.mvKeyPointIndices[i];
+}
+int ref_mlpnp_iterate(void *h, int n_iterations, int *no_more, uint8_t *inliers, int *n_inliers, float *T16)
+{
+    MlpnpBox *b = static_cast<MlpnpBox *>(h);
+    bool bNoMore = false;
+    std::vector<bool> vb;
+    int nInl = 0;
+    Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+    const bool ok = b->solver->iterate(n_iterations, bNoMore, vb, nInl, T);
+    *no_more = bNoMore ? 1 : 0;
+    *n_inliers = nInl;
+    std::memset(inliers, 0, b->matches.size());
+    for (size_t i = 0; i < vb.size() && i < b->matches.size(); ++i) inliers[i] = vb[i] ? 1 : 0;
+    store_T(T, T16);
+    return ok ? 1 : 0;
+}
+void ref_mlpnp_state(void *h, int *iterations, int *best_inliers, int *refined_inliers)
+{
+    MLPnPsolver &s = *static_cast<MlpnpBox *>(h)->solver;
+    *iterations = s.mnIterations;
+    *best_inliers = s.mnBestInliers;
+    *refined_inliers = s.mnRefinedInliers;
+}
+// MLPnPsolver::computePose on the subset idx[0..m), driven as iterate() / Refine() drive it (MLPnPsolver.cpp:80-105);
+// cov != NULL: m bearing covariances (3 x 3 each) -- the use_cov branch (:375-388) iterate() itself never takes
+void ref_mlpnp_compute_pose(void *h, const int *idx, int m, const double *cov, double *R9, double *t3)
+{
+    MLPnPsolver &s = *static_cast<MlpnpBox *>(h)->solver;
+    MLPnPsolver::bearingVectors_t f(m);
+    MLPnPsolver::points_t p(m);
+    std::vector<int> indexes(m);
+    for (int i = 0; i < m; ++i) { f[i] = s.mvBearingVecs[idx[i]]; p[i] = s.mvP3Dw[idx[i]]; indexes[i] = i; }
+    MLPnPsolver::cov3_mats_t covs(cov ? m : 1);
+    if (cov)
+        for (int i = 0; i < m; ++i)
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) covs[i](r, c) = cov[9 * i + 3 * r + c];
+    MLPnPsolver::transformation_t result;
+    s.computePose(f, p, covs, indexes, result);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) R9[r * 3 + c] = result(r, c);
+        t3[r] = result(r, 3);
+    }
+}
+int ref_mlpnp_check_inliers(void *h, const double *R9, const double *t3, uint8_t *mask)
+{
+    MLPnPsolver &s = *static_cast<MlpnpBox *>(h)->solver;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) s.mRi[r][c] = R9[r * 3 + c];
+        s.mti[r] = t3[r];
+    }
+    s.CheckInliers();
+    for (size_t i = 0; i < s.mvbInliersi.size(); ++i) mask[i] = s.mvbInliersi[i] ? 1 : 0;
+    return s.mnInliersi;
+}
+// MLPnPsolver::mlpnpJacs (:773-1020, the generated polynomial) and the residual pair of :736-742
+void ref_mlpnp_res_jac(void *h, const double *pt, const double *nr, const double *ns, const double *w, const double *t, double *r2, double *J12)
+{
+    MLPnPsolver &s = *static_cast<MlpnpBox *>(h)->solver;
+    const Eigen::Vector3d P(pt[0], pt[1], pt[2]), NR(nr[0], nr[1], nr[2]), NS(ns[0], ns[1], ns[2]), W(w[0], w[1], w[2]), T(t[0], t[1], t[2]);
+    Eigen::MatrixXd jacs(2, 6);
+    s.mlpnpJacs(P, NR, NS, W, T, jacs);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 6; ++j) J12[i * 6 + j] = jacs(i, j);
+    Eigen::Vector3d ptCam = s.rodrigues2rot(W) * P + T;
+    ptCam /= ptCam.norm();
+    r2[0] = NR.transpose() * ptCam;
+    r2[1] = NS.transpose() * ptCam;
+}
+void ref_mlpnp_rodrigues(void *h, const double *w, double *R9, double *w_back)
+{
+    MLPnPsolver &s = *static_cast<MlpnpBox *>(h)->solver;
+    const Eigen::Matrix3d R = s.rodrigues2rot(Eigen::Vector3d(w[0], w[1], w[2]));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R9[i * 3 + j] = R(i, j);
+    const Eigen::Vector3d wb = s.rot2rodrigues(R);
+    for (int i = 0; i < 3; ++i) w_back[i] = wb(i);
 }
 
 }  // extern "C"

@@ -2,7 +2,11 @@
 // The handful of OpenCV names the reference's PnPsolver / Sim3Solver sources mention (cv::KeyPoint with pt and
 // octave; a cv::Mat that PnPsolver::Refine constructs and never reads, PnPsolver.cpp:228-231).  Not OpenCV.
 #pragma once
+#include <cstring>
+#include <memory>
+#include <vector>
 #define CV_32F 5
+#define CV_64F 6
 namespace cv {
 struct Point2f {
     float x, y;
@@ -15,9 +19,32 @@ struct KeyPoint {
     int octave, class_id;
     KeyPoint() : size(0.f), angle(-1.f), response(0.f), octave(0), class_id(-1) {}
 };
+struct Point3f {
+    float x, y, z;
+    Point3f() : x(0.f), y(0.f), z(0.f) {}
+    Point3f(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
+};
+// a dense row-major CV_32F / CV_64F matrix: owns its storage or wraps caller memory (MLPnPsolver.cpp:133-136)
 struct Mat {
     int rows, cols, type;
-    Mat() : rows(0), cols(0), type(0) {}
-    Mat(int r, int c, int t) : rows(r), cols(c), type(t) {}
+    void *data;
+    std::shared_ptr<std::vector<double>> own;      // storage (doubles are large and aligned enough for floats too)
+    Mat() : rows(0), cols(0), type(0), data(nullptr) {}
+    Mat(int r, int c, int t) : rows(r), cols(c), type(t), own(std::make_shared<std::vector<double>>((size_t)r * c, 0.0)) { data = own->data(); }
+    Mat(int r, int c, int t, void *p) : rows(r), cols(c), type(t), data(p) {}
+    double get(int i, int j) const
+    {
+        return type == CV_64F ? static_cast<const double *>(data)[i * cols + j] : (double)static_cast<const float *>(data)[i * cols + j];
+    }
+    void convertTo(Mat &dst, int t) const
+    {
+        Mat out(rows, cols, t);
+        for (int i = 0; i < rows; ++i)
+            for (int j = 0; j < cols; ++j) {
+                if (t == CV_64F) static_cast<double *>(out.data)[i * cols + j] = get(i, j);
+                else static_cast<float *>(out.data)[i * cols + j] = (float)get(i, j);      // saturate_cast<float>(double): a plain conversion
+            }
+        dst = out;
+    }
 };
 }  // namespace cv

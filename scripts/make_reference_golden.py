@@ -95,11 +95,34 @@ def main():
     for k, v in srec.items():
         out["sim3_" + k] = np.array(v)
 
+    # ---- MLPnPsolver: 6 cfg2-shaped frames (1000 matches, 50 % outliers, no covariances: the path iterate() takes)
+    MLP = dict(prob=0.99, min_inliers=10, max_its=300, min_set=6, eps=0.2, th2=5.991)
+    Cm, nm = 6, 1000
+    mseeds = np.arange(2000, 2000 + Cm, dtype=np.uint32)
+    mps = [synth.pnp_problem(int(s), nm, 0.5) for s in mseeds]
+    mrec = dict(ok=[], no_more=[], n_inliers=[], iterations=[], best_inliers=[], T=[], inliers=[], max_its=[])
+    for s, p in zip(mseeds, mps):
+        sol = ref_api.MLPnP(p["p2d"], p["octave"], ls2, p["p3d"], K)
+        sol.set_params(**MLP)
+        H = sol.params()["max_its"]
+        ref_api.seed(int(s))
+        r = sol.iterate(H)
+        st = sol.state()
+        mrec["ok"].append(r["ok"]); mrec["no_more"].append(r["no_more"]); mrec["n_inliers"].append(r["n_inliers"])
+        mrec["iterations"].append(st["iterations"]); mrec["best_inliers"].append(st["best_inliers"]); mrec["T"].append(r["T"])
+        mrec["inliers"].append(r["inliers"]); mrec["max_its"].append(H)
+    out.update(mlpnp_seeds=mseeds, mlpnp_params=np.array([MLP[k] for k in ("prob", "min_inliers", "max_its", "min_set", "eps", "th2")], np.float64),
+               mlpnp_p3d=np.stack([p["p3d"] for p in mps]), mlpnp_p2d=np.stack([p["p2d"] for p in mps]),
+               mlpnp_octave=np.stack([p["octave"] for p in mps]).astype(np.int32))
+    for k, v in mrec.items():
+        out["mlpnp_" + k] = np.array(v)
+
     path = os.path.join(ROOT, "tests", "golden", "reference_build.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;",
           "PnP iterations", out["pnp_iterations"].tolist(), "inliers", out["pnp_n_inliers"].tolist(),
-          "| Sim3 ok", out["sim3_ok"].astype(int).tolist(), "iterations", out["sim3_iterations"].tolist())
+          "| Sim3 ok", out["sim3_ok"].astype(int).tolist(), "iterations", out["sim3_iterations"].tolist(),
+          "| MLPnP iterations", out["mlpnp_iterations"].tolist(), "inliers", out["mlpnp_n_inliers"].tolist())
 
 
 if __name__ == "__main__":

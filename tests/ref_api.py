@@ -225,3 +225,73 @@ def bow_l1_score(w1, v1, w2, v2):
     w1, w2 = np.ascontiguousarray(w1, np.uint32), np.ascontiguousarray(w2, np.uint32)
     v1, v2 = np.ascontiguousarray(v1, np.float64), np.ascontiguousarray(v2, np.float64)
     return lib_kfdb().ref_bow_l1_score(C.c_int(len(w1)), _p(w1), _p(v1), C.c_int(len(w2)), _p(w2), _p(v2))
+
+
+class MLPnP:
+    """The reference's MLPnPsolver (left out of its own build, CMakeLists.txt:75) over one frame."""
+
+    def __init__(self, kp_xy, octave, level_sigma2, mp_xyz, K, state=None):
+        kp_xy = np.ascontiguousarray(kp_xy, np.float32)
+        mp_xyz = np.ascontiguousarray(mp_xyz, np.float32)
+        octave = np.ascontiguousarray(octave, np.int32)
+        ls2 = np.ascontiguousarray(level_sigma2, np.float32)
+        self.n_kp = kp_xy.shape[0]
+        st = np.ones(self.n_kp, np.uint8) if state is None else np.ascontiguousarray(state, np.uint8)
+        L = lib()
+        L.ref_mlpnp_create.restype = C.c_void_p
+        self.h = C.c_void_p(L.ref_mlpnp_create(C.c_int(self.n_kp), _p(kp_xy), _p(octave), _p(ls2), C.c_int(len(ls2)), _p(mp_xyz), _p(st),
+                                               C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3])))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_mlpnp_destroy(self.h)
+            self.h = None
+
+    def set_params(self, prob=0.99, min_inliers=8, max_its=300, min_set=6, eps=0.4, th2=5.991):
+        lib().ref_mlpnp_set_params(self.h, C.c_double(prob), C.c_int(min_inliers), C.c_int(max_its), C.c_int(min_set), C.c_float(eps), C.c_float(th2))
+
+    def params(self):
+        N, mi, its = C.c_int(), C.c_int(), C.c_int()
+        lib().ref_mlpnp_get_params(self.h, C.byref(N), C.byref(mi), C.byref(its), None, None)
+        max_err = np.zeros(max(N.value, 1), np.float32)
+        kpi = np.zeros(max(N.value, 1), np.int32)
+        lib().ref_mlpnp_get_params(self.h, C.byref(N), C.byref(mi), C.byref(its), _p(max_err), _p(kpi))
+        return dict(N=N.value, min_inliers=mi.value, max_its=its.value, max_err=max_err[:N.value], kp_index=kpi[:N.value])
+
+    def iterate(self, n_iterations):
+        no_more, n_inl = C.c_int(), C.c_int()
+        inl = np.zeros(max(self.n_kp, 1), np.uint8)
+        T = np.zeros(16, np.float32)
+        ok = lib().ref_mlpnp_iterate(self.h, C.c_int(n_iterations), C.byref(no_more), _p(inl), C.byref(n_inl), _p(T))
+        return dict(ok=bool(ok), no_more=bool(no_more.value), n_inliers=n_inl.value, inliers=inl[:self.n_kp].astype(bool), T=T.reshape(4, 4))
+
+    def state(self):
+        it, best, refd = C.c_int(), C.c_int(), C.c_int()
+        lib().ref_mlpnp_state(self.h, C.byref(it), C.byref(best), C.byref(refd))
+        return dict(iterations=it.value, best_inliers=best.value, refined_inliers=refd.value)
+
+    def compute_pose(self, idx, cov=None):
+        idx = np.ascontiguousarray(idx, np.int32)
+        covc = None if cov is None else np.ascontiguousarray(cov, np.float64)
+        R, t = np.zeros(9), np.zeros(3)
+        lib().ref_mlpnp_compute_pose(self.h, _p(idx), C.c_int(len(idx)), None if covc is None else _p(covc), _p(R), _p(t))
+        return R.reshape(3, 3), t
+
+    def check_inliers(self, R, t, N):
+        R = np.ascontiguousarray(R, np.float64).reshape(-1)
+        t = np.ascontiguousarray(t, np.float64)
+        mask = np.zeros(max(N, 1), np.uint8)
+        cnt = lib().ref_mlpnp_check_inliers(self.h, _p(R), _p(t), _p(mask))
+        return cnt, mask[:N].astype(bool)
+
+    def res_jac(self, pt, nr, ns, w, t):
+        a = [np.ascontiguousarray(x, np.float64) for x in (pt, nr, ns, w, t)]
+        r, J = np.zeros(2), np.zeros(12)
+        lib().ref_mlpnp_res_jac(self.h, *[_p(x) for x in a], _p(r), _p(J))
+        return r, J.reshape(2, 6)
+
+    def rodrigues(self, w):
+        w = np.ascontiguousarray(w, np.float64)
+        R, wb = np.zeros(9), np.zeros(3)
+        lib().ref_mlpnp_rodrigues(self.h, _p(w), _p(R), _p(wb))
+        return R.reshape(3, 3), wb

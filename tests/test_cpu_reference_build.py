@@ -295,6 +295,27 @@ def test_oracle_equals_reference_golden(oracle):
             assert np.array_equal(o["mask"], g["sim3_inliers"][c]), c
 
 
+def test_oracle_equals_reference_golden_mlpnp(oracle):
+    """the MLPnP part of the golden file: as-shipped semantics (Q6, ORC_FLAG_MLPNP_DISCARD_REFINE); counts and the
+    stopping iteration exact, pose to 1e-6 (libm + SVD conventions, see the MLPnP tests below)"""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_build.npz"))
+    ls2 = g["level_sigma2"]
+    K = tuple(float(k) for k in g["pnp_K"])
+    pr = g["mlpnp_params"]
+    prm = oracle.params(pr[0], int(pr[1]), int(pr[2]), int(pr[3]), float(pr[4]), float(pr[5]))
+    for c, seed in enumerate(g["mlpnp_seeds"]):
+        pb = oracle.mlpnp_problem(g["mlpnp_p3d"][c], g["mlpnp_p2d"][c], ls2[g["mlpnp_octave"][c]], K)
+        _, H = oracle.ransac_setup_pnp(1000, prm)
+        assert H == int(g["mlpnp_max_its"][c])
+        o = oracle.mlpnp_ransac(pb, prm, oracle.index_table(int(seed), 1000, 6, H), oracle.FLAG_MLPNP_DISCARD_REFINE)
+        assert (bool(o["ok"]), o["n_inliers"], o["n_hyp"], o["best_count"]) == \
+               (bool(g["mlpnp_ok"][c]), int(g["mlpnp_n_inliers"][c]), int(g["mlpnp_iterations"][c]), int(g["mlpnp_best_inliers"][c])), c
+        assert np.abs(o["T"][:3] - g["mlpnp_T"][c][:3]).max() < 1e-6 * max(1.0, np.abs(g["mlpnp_T"][c]).max())
+        assert (o["mask"] != g["mlpnp_inliers"][c]).sum() <= 1
+
+
 def test_reference_golden_is_current(oracle):
     """the committed golden file is what the compiled reference produces today (guards against a stale fixture)"""
     import os
@@ -361,3 +382,155 @@ def test_loop_candidates_equal_compiled_reference(oracle):
     # nothing shared / everything connected
     assert rdb.reloc(np.array([db["vocab"] + 5], np.uint32), np.array([1.0]), 9999) == []
     assert rdb.loop(5, 9998, list(range(300)), 0.0) == []
+
+
+# ------------------------------------------------------------------ MLPnPsolver (M01-M12)
+# The reference leaves MLPnPsolver.cpp out of its own build (CMakeLists.txt:75); it is compiled here all the same.  Its
+# dense steps are Eigen SVDs whose singular VECTORS are only defined up to sign / rotation inside a repeated singular
+# value (the stand-in JacobiSVD takes them from an eigen-decomposition), and it calls libm; so agreement is stated with
+# tolerances -- the ones tests/test_gpu_mlpnp.py uses between the engine and the oracle (pose 1e-9 relative).
+MLPRM = dict(prob=0.99, min_inliers=10, max_its=300, min_set=6, eps=0.2, th2=5.991)   # cfg2
+
+
+def _ref_mlpnp(p, prm=MLPRM, state=None):
+    s = ref_api.MLPnP(p["p2d"], p["octave"], LS2, p["p3d"], _K32(p["K"]), state)
+    s.set_params(**prm)
+    return s
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+def test_mlpnp_constructor_and_parameters(oracle):
+    p = synth.pnp_problem(70, 1000, 0.5)
+    for prm in (MLPRM, dict(MLPRM, eps=0.5), dict(prob=0.9, min_inliers=50, max_its=40, min_set=6, eps=0.05, th2=7.815)):
+        r = _ref_mlpnp(p, prm).params()
+        mi, its = oracle.ransac_setup_pnp(1000, oracle.params(**prm))
+        assert (r["N"], r["min_inliers"], r["max_its"]) == (1000, mi, its)
+        assert np.array_equal(r["max_err"], (p["sigma2"] * np.float32(prm["th2"])).astype(np.float32))
+
+
+def test_mlpnp_rodrigues_and_generated_jacobian(oracle):
+    """rodrigues2rot / rot2rodrigues (MLPnPsolver.cpp:625-657) and mlpnpJacs (:773-1020, 250 lines of generated
+    polynomial) against the oracle's restatement -- which re-derives the Jacobian from the Rodrigues formula instead of
+    transcribing t5..t216 (M11): the compiled original is the check that the two are the same function"""
+    s = _ref_mlpnp(synth.pnp_problem(71, 50, 0.0))
+    rng = np.random.default_rng(5)
+    worst_J = worst_r = 0.0
+    for k in range(400):
+        w = rng.normal(size=3) * 10 ** rng.uniform(-3, 0.4)
+        R, wb = s.rodrigues(w)
+        Ro = oracle.rodrigues2rot(w)
+        assert np.abs(R - Ro).max() < 1e-15
+        assert np.abs(wb - oracle.rot2rodrigues(Ro)).max() < 1e-9 * max(1.0, 1.0 / max(1e-3, np.pi - np.linalg.norm(w) % (2 * np.pi)))
+        pt = rng.normal(size=3) * 5 + np.array([0, 0, 8.0])
+        f = rng.normal(size=3); f /= np.linalg.norm(f)
+        nr = np.cross(f, rng.normal(size=3)); nr /= np.linalg.norm(nr)
+        ns = np.cross(f, nr)
+        t = rng.normal(size=3)
+        r_ref, J_ref = s.res_jac(pt, nr, ns, w, t)
+        r_o, J_o = oracle.mlpnp_res_jac(pt, nr, ns, w, t)
+        worst_r = max(worst_r, float(np.abs(r_ref - r_o).max()))
+        worst_J = max(worst_J, float(np.max(np.abs(J_ref - J_o) / np.maximum(1.0, np.abs(J_o)))))
+    print("\nmlpnpJacs (generated) vs the oracle's re-derived Jacobian: max relative difference %.2e over 400 points; residuals %.2e" % (worst_J, worst_r))
+    assert worst_r < 1e-13 and worst_J < 1e-9
+
+
+def test_mlpnp_check_inliers_bit_identical(oracle):
+    """MLPnPsolver::CheckInliers (MLPnPsolver.cpp:222-255): f64 pose, f32 expression"""
+    p = synth.pnp_problem(72, 2000, 0.5)
+    s = _ref_mlpnp(p)
+    pb = oracle.mlpnp_problem(p["p3d"], p["p2d"], p["sigma2"], _K32(p["K"]))
+    thr = s.params()["max_err"]
+    rng = np.random.default_rng(72)
+    for k in range(40):
+        R = p["R"] @ synth.rodrigues(rng.normal(size=3) * 0.003 * k)
+        t = p["t"] + rng.normal(size=3) * 0.005 * k
+        cr, mr = s.check_inliers(R, t, 2000)
+        co, mo, _ = oracle.mlpnp_check_inliers(pb, thr, R, t)
+        assert cr == co and np.array_equal(mr, mo), k
+
+
+def test_mlpnp_compute_pose(oracle):
+    """MLPnPsolver::computePose (MLPnPsolver.cpp:321-623): the path iterate() takes (no covariances) on RANSAC's own
+    minimal sets (wrong matches included) and on larger inlier sets; planar scenes; and the use_cov branch (:375-388),
+    which iterate() never reaches (it passes one covariance for n points, :99) but BASELINE cfg2 and the engine use"""
+    rel, rel_cov, rel_big = [], [], []
+    for seed in range(200, 206):
+        p = synth.pnp_problem(seed, 1000, 0.5)
+        s = _ref_mlpnp(p)
+        K = _K32(p["K"])
+        cov = synth.bearing_covariances(p)
+        pb = oracle.mlpnp_problem(p["p3d"], p["p2d"], p["sigma2"], K)
+        pbc = oracle.mlpnp_problem(p["p3d"], p["p2d"], p["sigma2"], K, cov)
+        table = oracle.index_table(seed, 1000, 6, 100)
+        inl = np.flatnonzero(p["inlier"])
+        rng = np.random.default_rng(seed)
+        for h in range(100):
+            Rr, tr = s.compute_pose(table[h])
+            Ro, to = oracle.mlpnp_pose(pb, table[h])
+            rel.append(max(_rel(Rr, Ro), _rel(tr, to)))
+            Rr, tr = s.compute_pose(table[h], cov[table[h]])
+            Ro, to = oracle.mlpnp_pose(pbc, table[h])
+            rel_cov.append(max(_rel(Rr, Ro), _rel(tr, to)))
+        for m in (8, 20, 100, 400):
+            idx = rng.permutation(inl)[:m]
+            for c_, pb_ in ((None, pb), (cov[idx], pbc)):
+                Rr, tr = s.compute_pose(idx, c_)
+                Ro, to = oracle.mlpnp_pose(pb_, idx)
+                rel_big.append(max(_rel(Rr, Ro), _rel(tr, to)))
+                assert np.abs(Ro - p["R"]).max() < 0.05
+    rel, rel_cov, rel_big = np.array(rel), np.array(rel_cov), np.array(rel_big)
+    print("\ncomputePose, compiled reference vs oracle, relative pose difference: 6-point sets median %.1e, 99th percentile %.1e, max %.1e; "
+          "with covariances median %.1e, 90th %.1e (ill-conditioned weighted 12 x 12 systems amplify the rounding of the two eigen-solvers); "
+          "8..400 inliers max %.1e" % (np.median(rel), np.percentile(rel, 99), rel.max(), np.median(rel_cov), np.percentile(rel_cov, 90), rel_big.max()))
+    assert np.median(rel) < 1e-10 and np.mean(rel < 1e-9) > 0.95 and rel.max() < 1e-4      # north_star: 1e-4 on R, t
+    assert np.median(rel_big) < 1e-13 and rel_big.max() < 1e-6
+    assert np.median(rel_cov) < 1e-6 and np.mean(rel_cov < 1e-4) > 0.8
+    # planar scene (rank-2 planarTest, :354-364, :497-558): world points exactly on the plane Z_w = 0
+    pp = synth.pnp_problem(77, 300, 0.0, noise=False)
+    R, t = pp["R"], pp["t"] + np.array([0, 0, 9.0])
+    rng = np.random.default_rng(77)
+    Xw = np.stack([rng.uniform(-4, 4, 300), rng.uniform(-3, 3, 300), np.zeros(300)], axis=1).astype(np.float32)
+    pp["p3d"] = Xw
+    pp["p2d"] = synth.project(Xw.astype(np.float64) @ R.T + t).astype(np.float32)
+    s = _ref_mlpnp(pp)
+    pb = oracle.mlpnp_problem(pp["p3d"], pp["p2d"], pp["sigma2"], _K32(pp["K"]))
+    for m in (6, 12, 100):
+        idx = rng.permutation(300)[:m]
+        Rr, tr = s.compute_pose(idx)
+        Ro, to = oracle.mlpnp_pose(pb, idx)
+        assert max(_rel(Rr, Ro), _rel(tr, to)) < 1e-8, m
+        # (the transplanted planar branch does not reproject this scene well on either side -- 100 px on six
+        # noise-free points -- which is the reference's behaviour, reproduced, not this test's concern)
+
+
+def test_mlpnp_ransac_runs(oracle):
+    """MLPnPsolver::iterate + Refine (MLPnPsolver.cpp:56-160, 257-318) on cfg2-shaped frames.  The compiled reference
+    confirms quirk Q6: Refine() never stores the pose it computes (:290 writes `result`, :293 scores mRi), so the
+    'refined' answer is the winning hypothesis itself -- the oracle reproduces that behind ORC_FLAG_MLPNP_DISCARD_REFINE
+    and only then equals the reference: return value, iteration, counts exactly; pose to 1e-9; inlier vector except
+    evaluations within rounding of the threshold"""
+    differs_without_flag = 0
+    for c in range(12):
+        seed = 2000 + c
+        p = synth.pnp_problem(seed, 1000, 0.5)
+        s = _ref_mlpnp(p)
+        prm = oracle.params(**MLPRM)
+        _, H = oracle.ransac_setup_pnp(1000, prm)
+        pb = oracle.mlpnp_problem(p["p3d"], p["p2d"], p["sigma2"], _K32(p["K"]))
+        table = oracle.index_table(seed, 1000, 6, H)
+        o = oracle.mlpnp_ransac(pb, prm, table, oracle.FLAG_MLPNP_DISCARD_REFINE)
+        o_clean = oracle.mlpnp_ransac(pb, prm, table, 0)
+        ref_api.seed(seed)
+        r = s.iterate(H)
+        st = s.state()
+        assert (r["ok"], r["no_more"], r["n_inliers"], st["iterations"], st["best_inliers"]) == \
+               (bool(o["ok"]), bool(o["no_more"]), o["n_inliers"], o["n_hyp"], o["best_count"]), (seed, r, o)
+        assert r["ok"]
+        assert _rel(r["T"][:3].astype(np.float64), o["T"][:3].astype(np.float64)) < 1e-6
+        assert (r["inliers"] != o["mask"]).sum() <= 1, seed
+        differs_without_flag += int(o_clean["n_inliers"] != r["n_inliers"])
+    print("\nMLPnP runs: %d of 12 differ from the compiled reference without ORC_FLAG_MLPNP_DISCARD_REFINE (Q6)" % differs_without_flag)
+    assert differs_without_flag >= 6

@@ -56,3 +56,24 @@ def test_sim3_engine_equals_compiled_reference(engine):
             assert (r["R"].reshape(3, 3).view(np.uint32) == G["sim3_R"][c].view(np.uint32)).all(), c
             assert (r["t"].view(np.uint32) == G["sim3_t"][c].view(np.uint32)).all(), c
             assert (ml[c] == G["sim3_inliers"][c]).all(), c
+
+
+def test_mlpnp_engine_equals_compiled_reference(engine):
+    """MLPnPsolver as shipped (Refine() discards its pose, quirk Q6 => RSAC_FLAG_MLPNP_DISCARD_REFINE); the reference's
+    MLPnPsolver.cpp calls libm and Eigen SVDs, so: return value, inlier count, stopping iteration exact; pose 1e-6"""
+    C, n = G["mlpnp_p3d"].shape[:2]
+    ls2 = G["level_sigma2"]
+    offsets = np.arange(C + 1, dtype=np.int32) * n
+    pr = G["mlpnp_params"]
+    prm = capi.ransac_params(pr[0], int(pr[1]), int(pr[2]), int(pr[3]), float(pr[4]), float(pr[5]))
+    for flags in (capi.FLAG_MLPNP_DISCARD_REFINE, capi.FLAG_MLPNP_DISCARD_REFINE | capi.FLAG_EARLY_EXIT):
+        res, masks = engine.mlpnp_solve(offsets, G["mlpnp_p3d"], G["mlpnp_p2d"], ls2[G["mlpnp_octave"]], np.array([G["pnp_K"]], np.float32), prm,
+                                        seeds=G["mlpnp_seeds"], flags=flags)
+        ml = engine.split_masks(masks, offsets)
+        for c in range(C):
+            r = res[c]
+            assert (bool(r["ok"]), int(r["n_inliers"]), int(r["best_count"]), int(r["n_hyp"])) == \
+                   (bool(G["mlpnp_ok"][c]), int(G["mlpnp_n_inliers"][c]), int(G["mlpnp_best_inliers"][c]), int(G["mlpnp_iterations"][c])), (c, flags)
+            T = G["mlpnp_T"][c]
+            assert np.abs(r["R"].reshape(3, 3) - T[:3, :3]).max() < 1e-6 and np.abs(r["t"] - T[:3, 3]).max() < 1e-6 * max(1.0, np.abs(T[:3, 3]).max()), c
+            assert (ml[c] != G["mlpnp_inliers"][c]).sum() <= 1, c
