@@ -14,10 +14,12 @@
  *
  * PARITY PIN (round 2): `make -C oracle ref` compiles the reference's OWN sources, unmodified and from where they
  * lie under /root/reference -- src/PnPsolver.cpp, src/Sim3Solver.cpp, src/MLPnPsolver.cpp, src/KeyFrameDatabase.cpp,
- * Thirdparty/DBoW2/DUtils/Random.cpp, Thirdparty/DBoW2/DBoW2/{BowVector,ScoringObject}.cpp -- into
+ * src/ORBmatcher.cpp, Thirdparty/DBoW2/DUtils/Random.cpp, Thirdparty/DBoW2/DBoW2/{BowVector,FeatureVector,
+ * ScoringObject}.cpp -- into
  * oracle/_ref/libref_solvers.so, against stand-in headers for what this image lacks (oracle/shim/: Eigen, OpenCV,
  * Frame / KeyFrame / MapPoint / ORBVocabulary).  The oracle equals that library BIT FOR BIT: per call (compute_pose on
- * 4..250 points, CheckInliers, ComputeSim3, SetRansacParameters, the L1 score) and for whole RANSAC / retrieval runs
+ * 4..250 points, CheckInliers, ComputeSim3, SetRansacParameters, the L1 score, DescriptorDistance) and for whole RANSAC /
+ * retrieval / matching runs (SearchByBoW, SearchBySim3, SearchByProjection(Frame, KeyFrame): match arrays equal)
  * (tests/test_cpu_reference_build.py); golden vectors generated from it are committed
  * (tests/golden/reference_build.npz) and the CUDA engine is compared with them directly
  * (tests/test_gpu_reference_golden.py).  MLPnPsolver.cpp (which the reference's own CMakeLists.txt:75 leaves out) is
@@ -29,8 +31,9 @@
  * (cyclic / tournament Jacobi, Householder-QR least squares with a Jacobi-SVD fallback, cofactor inverse) and
  * evaluates products in index order; an Eigen-built binary will differ from both in rounding -- for 4-point EPnP
  * that means a different (equally valid) null-space basis per hypothesis (outcome-level
- * agreement across bases).  Optimizer.cpp (g2o on Eigen) and ORBmatcher.cpp (the whole Frame / KeyFrame API) are
- * not compiled: their restatements are pinned by independent checks only (numpy / scipy / cv2, literal transcriptions, ground truth), as listed in DESIGN.md.
+ * agreement across bases).  Optimizer.cpp (the vendored g2o is templated on Eigen throughout) is not compiled: its
+ * restatement is pinned by independent checks only; the Frame / KeyFrame / MapPoint helpers ORBmatcher.cpp calls
+ * (GetFeaturesInArea, PredictScale: other translation units of the reference) are the oracle's restatements (numpy / scipy / cv2, literal transcriptions, ground truth), as listed in DESIGN.md.
  *
  * Arithmetic contract shared with the CUDA kernels (DESIGN.md "arithmetic
  * contract"): only + - * / sqrt in IEEE double/float, no FMA contraction

@@ -497,3 +497,187 @@ void ref_mlpnp_rodrigues(void *h, const double *w, double *R9, double *w_back)
 }
 
 }  // extern "C"
+
+// ---- ORBmatcher: SearchByBoW (both overloads), SearchBySim3, SearchByProjection(Frame, KeyFrame) ----
+#include "ORBmatcher.hpp"
+
+namespace {
+
+cv::Mat make_descriptors(const uint32_t *desc, int n)
+{
+    cv::Mat m(n > 0 ? n : 1, 32, CV_8U);
+    if (n > 0) std::memcpy(m.data, desc, (size_t)n * 32);
+    return m;
+}
+std::shared_ptr<MapPoint> make_point(const KeyFrame *owner, int idx, const uint32_t *desc8)
+{
+    auto mp = std::make_shared<MapPoint>();
+    mp->mpKF1 = owner;
+    mp->mIndexKF1 = idx;
+    mp->mDescriptor = make_descriptors(desc8, 1);
+    mp->mWorldPos.setZero();
+    mp->mNormalVector.setZero();
+    return mp;
+}
+void fill_feature_vector(DBoW2::FeatureVector &fv, const orc_bow_features *f)
+{
+    for (int k = 0; k < f->n_nodes; ++k)
+        for (int j = f->node_off[k]; j < f->node_off[k + 1]; ++j) fv.addFeature(f->node_ids[k], f->node_feat[j]);
+}
+// a keyframe as SearchByBoW reads it: descriptors, angles, map points (where valid), feature vector
+std::shared_ptr<KeyFrame> kf_from_bow(const orc_bow_features *f)
+{
+    auto kf = std::make_shared<KeyFrame>();
+    kf->N = f->n_feat;
+    kf->mvKeysUn.resize(f->n_feat);
+    kf->mvKeys.resize(f->n_feat);
+    kf->mvpMapPoints.resize(f->n_feat);
+    kf->mDescriptors = make_descriptors(f->desc, f->n_feat);
+    for (int i = 0; i < f->n_feat; ++i) {
+        kf->mvKeysUn[i].angle = kf->mvKeys[i].angle = f->angle[i];
+        if (!f->valid || f->valid[i]) kf->mvpMapPoints[i] = make_point(kf.get(), i, f->desc + 8 * (size_t)i);
+    }
+    fill_feature_vector(kf->mFeatVec, f);
+    return kf;
+}
+// a keyframe / frame as the guided searches read it (orc_kf_view)
+void fill_view_common(const orc_kf_view *v, const float *K, std::vector<cv::KeyPoint> &keys, cv::Mat &desc, std::vector<float> &uright,
+                      std::vector<float> &scale, std::vector<float> &sig2, std::vector<float> &isig2)
+{
+    keys.resize(v->n_feat);
+    for (int i = 0; i < v->n_feat; ++i) {
+        keys[i].pt = cv::Point2f(v->kp_xy[2 * i], v->kp_xy[2 * i + 1]);
+        keys[i].octave = v->kp_octave[i];
+        keys[i].angle = v->kp_angle ? v->kp_angle[i] : 0.f;
+    }
+    desc = make_descriptors(v->desc, v->n_feat);
+    uright.assign(v->n_feat, -1.f);                         // monocular: no right coordinate anywhere
+    scale.assign(v->scale_factors, v->scale_factors + v->n_levels);
+    sig2.resize(v->n_levels);
+    isig2.resize(v->n_levels);
+    for (int l = 0; l < v->n_levels; ++l) { sig2[l] = scale[l] * scale[l]; isig2[l] = 1.0f / sig2[l]; }
+    (void)K;
+}
+std::shared_ptr<KeyFrame> kf_from_view(const orc_kf_view *v, const float *K)
+{
+    auto kf = std::make_shared<KeyFrame>();
+    kf->N = v->n_feat;
+    kf->mpView = v;
+    fill_view_common(v, K, kf->mvKeysUn, kf->mDescriptors, kf->mvuRight, kf->mvScaleFactors, kf->mvLevelSigma2, kf->mvInvLevelSigma2);
+    kf->mvKeys = kf->mvKeysUn;
+    kf->mnScaleLevels = v->n_levels;
+    kf->mfLogScaleFactor = v->log_scale_factor;
+    kf->fx = K[0]; kf->fy = K[1]; kf->cx = K[2]; kf->cy = K[3];
+    kf->mnMinX = (int)v->bounds[0]; kf->mnMaxX = (int)v->bounds[1]; kf->mnMinY = (int)v->bounds[2]; kf->mnMaxY = (int)v->bounds[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) kf->mRcw(i, j) = v->Rcw[i * 3 + j];
+        kf->mtcw(i) = v->tcw[i];
+    }
+    kf->mvpMapPoints.resize(v->n_feat);
+    for (int i = 0; i < v->n_feat; ++i) {
+        if (!v->mp_valid[i]) continue;
+        auto mp = make_point(kf.get(), i, v->mp_desc + 8 * (size_t)i);
+        mp->mWorldPos = Eigen::Vector3f(v->mp_xyz[3 * i], v->mp_xyz[3 * i + 1], v->mp_xyz[3 * i + 2]);
+        mp->mfMaxDistance = v->mp_maxdist[i];
+        mp->mfMinDistance = v->mp_mindist[i];
+        kf->mvpMapPoints[i] = mp;
+    }
+    return kf;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ORBmatcher::SearchByBoW: mode 0 (KeyFrame q, Frame t): match_out[frame feature] = keyframe feature or -1;
+// mode 1 (KeyFrame q, KeyFrame t): match_out[q feature] = t feature or -1.  Returns nmatches.
+int ref_search_by_bow(const orc_bow_features *q, const orc_bow_features *t, float nn_ratio, int check_orientation, int mode, int32_t *match_out)
+{
+    ORBmatcher matcher(nn_ratio, check_orientation != 0);
+    std::shared_ptr<KeyFrame> kq = kf_from_bow(q);
+    std::vector<std::shared_ptr<MapPoint>> matches;
+    int n = 0;
+    if (mode == 0) {
+        Frame F;
+        F.N = t->n_feat;
+        F.mvKeys.resize(t->n_feat);
+        F.mvKeysUn.resize(t->n_feat);
+        for (int i = 0; i < t->n_feat; ++i) F.mvKeys[i].angle = F.mvKeysUn[i].angle = t->angle[i];
+        F.mDescriptors = make_descriptors(t->desc, t->n_feat);
+        F.mvpMapPoints.resize(t->n_feat);
+        fill_feature_vector(F.mFeatVec, t);
+        n = matcher.SearchByBoW(kq, F, matches);
+        for (int i = 0; i < t->n_feat; ++i) match_out[i] = (i < (int)matches.size() && matches[i]) ? matches[i]->mIndexKF1 : -1;
+    } else {
+        std::shared_ptr<KeyFrame> kt = kf_from_bow(t);
+        n = matcher.SearchByBoW(kq, kt, matches);
+        for (int i = 0; i < q->n_feat; ++i) match_out[i] = (i < (int)matches.size() && matches[i]) ? matches[i]->mIndexKF1 : -1;
+    }
+    return n;
+}
+int ref_descriptor_distance(const uint32_t *a, const uint32_t *b)
+{
+    return ORBmatcher::DescriptorDistance(make_descriptors(a, 1), make_descriptors(b, 1));
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, R12, t12, th) (the reference has no scale argument: s12 = 1)
+int ref_search_by_sim3(const orc_kf_view *v1, const orc_kf_view *v2, const float *K, const float *R12, const float *t12, float th,
+                       const int32_t *matched12_in, int32_t *match12_out)
+{
+    ORBmatcher matcher(0.75f, true);
+    std::shared_ptr<KeyFrame> k1 = kf_from_view(v1, K), k2 = kf_from_view(v2, K);
+    std::vector<std::shared_ptr<MapPoint>> m12(v1->n_feat);
+    for (int i = 0; i < v1->n_feat; ++i)
+        if (matched12_in && matched12_in[i] >= 0) m12[i] = k2->mvpMapPoints[matched12_in[i]];
+    Eigen::Matrix3f R;
+    Eigen::Vector3f t;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R(i, j) = R12[i * 3 + j];
+        t(i) = t12[i];
+    }
+    const int n = matcher.SearchBySim3(k1, k2, m12, R, t, th);
+    for (int i = 0; i < v1->n_feat; ++i) match12_out[i] = m12[i] ? m12[i]->mIndexKF1 : -1;
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, pKF, sAlreadyFound, th, ORBdist): occupied[i] = the frame's
+// keypoint i already holds a map point; already_found[j] = keyframe map point j is in sAlreadyFound;
+// frame_match[i] = keyframe feature whose map point the call assigned to frame keypoint i, else -1
+int ref_search_by_projection(const orc_kf_view *vf, const orc_kf_view *vk, const float *K, const float *Rcw, const float *tcw, float th, int orb_dist,
+                             int check_orientation, const uint8_t *occupied, const uint8_t *already_found, int32_t *frame_match)
+{
+    ORBmatcher matcher(0.9f, check_orientation != 0);
+    std::shared_ptr<KeyFrame> kf = kf_from_view(vk, K);
+    Frame F;
+    F.N = vf->n_feat;
+    F.mpView = vf;
+    fill_view_common(vf, K, F.mvKeysUn, F.mDescriptors, F.mvuRight, F.mvScaleFactors, F.mvLevelSigma2, F.mvInvLevelSigma2);
+    F.mvKeys = F.mvKeysUn;
+    F.mnScaleLevels = vf->n_levels;
+    F.mfLogScaleFactor = vf->log_scale_factor;
+    F.fx = K[0]; F.fy = K[1]; F.cx = K[2]; F.cy = K[3];
+    F.mnMinX = vf->bounds[0]; F.mnMaxX = vf->bounds[1]; F.mnMinY = vf->bounds[2]; F.mnMaxY = vf->bounds[3];
+    F.mvpMapPoints.resize(vf->n_feat);
+    F.mvbOutlier.assign(vf->n_feat, false);
+    auto placeholder = std::make_shared<MapPoint>();          // "this keypoint is taken" (any non-null pointer)
+    for (int i = 0; i < vf->n_feat; ++i)
+        if (occupied && occupied[i]) F.mvpMapPoints[i] = placeholder;
+    Eigen::Matrix3f R;
+    Eigen::Vector3f t;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R(i, j) = Rcw[i * 3 + j];
+        t(i) = tcw[i];
+    }
+    F.mTcw.setIdentity();
+    F.mTcw.linear() = R;
+    F.mTcw.translation() = t;
+    std::set<std::shared_ptr<MapPoint>> found;
+    for (int j = 0; j < vk->n_feat; ++j)
+        if (already_found && already_found[j] && kf->mvpMapPoints[j]) found.insert(kf->mvpMapPoints[j]);
+    const int n = matcher.SearchByProjection(F, kf, found, th, orb_dist);
+    for (int i = 0; i < vf->n_feat; ++i)
+        frame_match[i] = (F.mvpMapPoints[i] && F.mvpMapPoints[i] != placeholder) ? F.mvpMapPoints[i]->mIndexKF1 : -1;
+    return n;
+}
+
+}  // extern "C"

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <memory>
 #include <vector>
+#define CV_8U 0
 #define CV_32F 5
 #define CV_64F 6
 namespace cv {
@@ -30,8 +31,24 @@ struct Mat {
     void *data;
     std::shared_ptr<std::vector<double>> own;      // storage (doubles are large and aligned enough for floats too)
     Mat() : rows(0), cols(0), type(0), data(nullptr) {}
-    Mat(int r, int c, int t) : rows(r), cols(c), type(t), own(std::make_shared<std::vector<double>>((size_t)r * c, 0.0)) { data = own->data(); }
+    Mat(int r, int c, int t) : rows(r), cols(c), type(t), own(std::make_shared<std::vector<double>>((size_t)r * c + 1, 0.0)) { data = own->data(); }
     Mat(int r, int c, int t, void *p) : rows(r), cols(c), type(t), data(p) {}
+    size_t elem_size() const { return type == CV_64F ? 8 : (type == CV_32F ? 4 : 1); }
+    // a view of row i (shares the storage), the typed row pointer, a copy (ORBmatcher.cpp: descriptor rows)
+    Mat row(int i) const
+    {
+        Mat r(1, cols, type, static_cast<unsigned char *>(data) + (size_t)i * cols * elem_size());
+        r.own = own;
+        return r;
+    }
+    template <class T> T *ptr(int i = 0) { return reinterpret_cast<T *>(static_cast<unsigned char *>(data) + (size_t)i * cols * elem_size()); }
+    template <class T> const T *ptr(int i = 0) const { return reinterpret_cast<const T *>(static_cast<const unsigned char *>(data) + (size_t)i * cols * elem_size()); }
+    Mat clone() const
+    {
+        Mat c(rows, cols, type);
+        std::memcpy(c.data, data, (size_t)rows * cols * elem_size());
+        return c;
+    }
     double get(int i, int j) const
     {
         return type == CV_64F ? static_cast<const double *>(data)[i * cols + j] : (double)static_cast<const float *>(data)[i * cols + j];

@@ -1,6 +1,7 @@
 """ctypes binding of oracle/_ref/libref_solvers.so -- TEST INFRASTRUCTURE ONLY.
 
-The library holds the REFERENCE's own PnPsolver.cpp, Sim3Solver.cpp and DUtils/Random.cpp, compiled unmodified from
+The library holds the REFERENCE's own PnPsolver.cpp, Sim3Solver.cpp, MLPnPsolver.cpp, KeyFrameDatabase.cpp, ORBmatcher.cpp,
+DUtils/Random.cpp and the vendored DBoW2 BowVector / FeatureVector / ScoringObject, compiled unmodified from
 /root/reference by `make -C oracle ref` against the stand-in headers under oracle/shim/ (Eigen and OpenCV are not
 installed in this image; what the stand-ins pin and what they cannot is stated in oracle/shim/Eigen/Dense).
 It exists to check the oracle; nothing in the product, bench.py or the GPU tests loads it.
@@ -22,7 +23,7 @@ _LIB = None
 def available() -> bool:
     """built here (needs /root/reference) or shipped prebuilt"""
     if not os.path.exists(PATH) and os.path.isdir("/root/reference/src"):
-        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "orc_linalg.o"], check=False)
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "orc_linalg.o", "orc_guided.o", "orc_bow.o"], check=False)
         subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref"], check=False)
     return os.path.exists(PATH)
 
@@ -295,3 +296,34 @@ class MLPnP:
         R, wb = np.zeros(9), np.zeros(3)
         lib().ref_mlpnp_rodrigues(self.h, _p(w), _p(R), _p(wb))
         return R.reshape(3, 3), wb
+
+
+# ---- ORBmatcher (takes the oracle binding's struct wrappers: oracle_api.bow_features / kf_view) ----
+def search_by_bow(q, t, nn_ratio=0.75, check_orientation=True, mode=0):
+    n_out = t.st.n_feat if mode == 0 else q.st.n_feat
+    out = np.empty(max(n_out, 1), np.int32)
+    n = lib().ref_search_by_bow(C.byref(q.st), C.byref(t.st), C.c_float(nn_ratio), C.c_int(int(check_orientation)), C.c_int(mode), _p(out))
+    return out[:n_out], n
+
+
+def descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint32), np.ascontiguousarray(b, np.uint32)
+    return lib().ref_descriptor_distance(_p(a), _p(b))
+
+
+def search_by_sim3(kf1, kf2, K, R12, t12, th=7.5, matched12_in=None):
+    K = np.ascontiguousarray(K, np.float32); R12 = np.ascontiguousarray(R12, np.float32).reshape(9); t12 = np.ascontiguousarray(t12, np.float32)
+    mi = None if matched12_in is None else np.ascontiguousarray(matched12_in, np.int32)
+    out = np.empty(max(kf1.st.n_feat, 1), np.int32)
+    n = lib().ref_search_by_sim3(C.byref(kf1.st), C.byref(kf2.st), _p(K), _p(R12), _p(t12), C.c_float(th), None if mi is None else _p(mi), _p(out))
+    return out[:kf1.st.n_feat].copy(), n
+
+
+def search_by_projection(frame, kf, K, Rcw, tcw, th=10.0, orb_dist=100, check_orientation=True, occupied=None, already_found=None):
+    K = np.ascontiguousarray(K, np.float32); R = np.ascontiguousarray(Rcw, np.float32).reshape(9); t = np.ascontiguousarray(tcw, np.float32)
+    oc = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    af = None if already_found is None else np.ascontiguousarray(already_found, np.uint8)
+    out = np.empty(max(frame.st.n_feat, 1), np.int32)
+    n = lib().ref_search_by_projection(C.byref(frame.st), C.byref(kf.st), _p(K), _p(R), _p(t), C.c_float(th), C.c_int(orb_dist), C.c_int(int(check_orientation)),
+                                       None if oc is None else _p(oc), None if af is None else _p(af), _p(out))
+    return out[:frame.st.n_feat].copy(), n
