@@ -26,6 +26,10 @@
  * compared with tolerances -- it calls libm and takes singular vectors from Eigen SVDs, which are defined only up to
  * sign / rotation: generated Jacobian vs the re-derived one 1e-12, computePose median 3e-12 (6-point sets, 99 % within
  * 4e-9), whole runs exact in return value / counts / stopping iteration once quirk Q6 is reproduced.
+ * A second build (`make ref-lapack`) sends every dense solve to LAPACK (dsyev = Eigen's eigen-solver algorithm, dgelsd =
+ * bdcSvd's class) and shares no kernel with this oracle: outcome-level agreement is asserted against it (Sim3 runs
+ * identical; PnP: same candidates accepted, poses at the pixel-noise level -- DESIGN.md section 2 explains why an
+ * Eigen-built reference cannot be matched more closely: EPnP depends on the signs of the 3 x 3 principal axes).
  * STILL UNPINNED: Eigen's own rounding.  Eigen is not installed and cannot be fetched, so the stand-in forwards the
  * dense solves the sources call (SelfAdjointEigenSolver, bdcSvd().solve, inverse()) to the kernels in orc_linalg.c
  * (cyclic / tournament Jacobi, Householder-QR least squares with a Jacobi-SVD fallback, cofactor inverse) and
