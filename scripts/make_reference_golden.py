@@ -125,5 +125,94 @@ def main():
           "| MLPnP iterations", out["mlpnp_iterations"].tolist(), "inliers", out["mlpnp_n_inliers"].tolist())
 
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# second file: retrieval and matching.  The inputs are large (descriptors, grids, bag-of-words vectors)
+# and come from seeded generators (ransac_b200.synth), so only the generator arguments, a SHA-1 of the generated arrays and the
+# compiled reference's OUTPUTS are stored: tests/golden/reference_build_matching.npz
+def matching_cases():
+    """the cases, as (name, builder) -- shared with tests/test_gpu_reference_golden.py"""
+    def bow0():
+        F = synth.bow_frame(11, 600, 40)
+        kfs = [synth.bow_keyframe(1000 + i, F, 500 + 37 * (i % 5), shared=0.1 + 0.05 * (i % 7), rot=10.0 * i) for i in range(6)]
+        return F, kfs
+
+    def bow1():
+        cur = synth.bow_frame(21, 500, 40)
+        cur["valid"] = (np.random.default_rng(5).random(500) < 0.75).astype(np.uint8)
+        kfs = [synth.bow_keyframe(2000 + i, cur, 450, shared=0.3, rot=5.0 * i) for i in range(4)]
+        return cur, kfs
+
+    def pairs():
+        return [synth.kf_view_pair(10 + i, n_points=300 + 250 * i, n_extra=100 + 60 * i, prematched=0.1 * i) for i in range(3)]
+
+    def proj():
+        return [synth.proj_search_case(s, n_points=450, n_extra=150) for s in (1, 2, 3)]
+
+    def kfdb():
+        db = synth.kf_database(1, K=300, n_places=30)
+        return db, [synth.kf_query(100 + q, db, place=(q * 7) % 30) for q in range(12)]
+
+    return dict(bow0=bow0, bow1=bow1, pairs=pairs, proj=proj, kfdb=kfdb)
+
+
+def digest(*arrays):
+    import hashlib
+
+    h = hashlib.sha1()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def matching_digests(cases):
+    F, kfs = cases["bow0"]()
+    cur, kfs1 = cases["bow1"]()
+    prs = cases["pairs"]()
+    pj = cases["proj"]()
+    db, qs = cases["kfdb"]()
+    return dict(
+        bow0=digest(F["desc"], F["angle"], F["node_feat"], *[k["desc"] for k in kfs], *[k["node_feat"] for k in kfs]),
+        bow1=digest(cur["desc"], cur["valid"], *[k["desc"] for k in kfs1]),
+        pairs=digest(*[p["kf1"]["desc"] for p in prs], *[p["kf2"]["mp_xyz"] for p in prs], *[p["R12"] for p in prs], *[p["matched12_in"] for p in prs]),
+        proj=digest(*[c["frame"]["desc"] for c in pj], *[c["kf"]["mp_xyz"] for c in pj], *[c["Rcw"] for c in pj], *[c["occupied"] for c in pj]),
+        kfdb=digest(db["bow_word"], db["bow_val"], db["covis"], *[q[0] for q in qs], *[q[1] for q in qs]))
+
+
+def main_matching():
+    import oracle_api as O
+
+    cases = matching_cases()
+    out = {("sha1_" + k): np.array(v) for k, v in matching_digests(cases).items()}
+    F, kfs = cases["bow0"]()
+    tF = O.bow_features(F)
+    res = [ref_api.search_by_bow(O.bow_features(k), tF, 0.75, True, 0) for k in kfs]
+    out["bow0_match"] = np.stack([r[0] for r in res]); out["bow0_n"] = np.array([r[1] for r in res])
+    cur, kfs1 = cases["bow1"]()
+    qC = O.bow_features(cur)
+    res = [ref_api.search_by_bow(qC, O.bow_features(k), 0.75, True, 1) for k in kfs1]
+    out["bow1_match"] = np.stack([r[0] for r in res]); out["bow1_n"] = np.array([r[1] for r in res])
+    for i, p in enumerate(cases["pairs"]()):
+        k1, k2 = O.kf_view(p["kf1"]), O.kf_view(p["kf2"])
+        m, n = ref_api.search_by_sim3(k1, k2, p["K"], p["R12"], p["t12"], 7.5, p["matched12_in"])
+        m = m.copy(); m[np.asarray(p["matched12_in"]) >= 0] = -1          # the new matches only (the reference leaves the old ones in place)
+        out["sim3s_match_%d" % i] = m; out["sim3s_n_%d" % i] = np.array(n)
+    for i, c in enumerate(cases["proj"]()):
+        m, n = ref_api.search_by_projection(O.kf_view(c["frame"]), O.kf_view(c["kf"]), c["K"], c["Rcw"], c["tcw"], 10.0, 100, True, c["occupied"], c["already_found"])
+        out["proj_match_%d" % i] = m; out["proj_n_%d" % i] = np.array(n)
+    db, qs = cases["kfdb"]()
+    rdb = ref_api.KfDb(db)
+    for q, (qw, qv) in enumerate(qs):
+        out["kfdb_cand_%d" % q] = np.array(rdb.reloc(qw, qv, frame_id=7000 + q), np.int32)
+    out["kfdb_state"] = rdb.reloc_scores()
+    path = os.path.join(ROOT, "tests", "golden", "reference_build_matching.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes; SearchByBoW matches", out["bow0_n"].tolist(), out["bow1_n"].tolist(),
+          "| SearchBySim3", [int(out["sim3s_n_%d" % i]) for i in range(3)], "| SearchByProjection", [int(out["proj_n_%d" % i]) for i in range(3)],
+          "| candidates per query", [len(out["kfdb_cand_%d" % q]) for q in range(12)])
+
+
 if __name__ == "__main__":
     main()
+    main_matching()

@@ -726,3 +726,37 @@ def test_lapack_build_no_dense_kernel_paths_are_identical(oracle):
         # float products use the other fusion convention here: a projection may move by an ulp, which can flip a
         # radius / distance decision for a feature on the boundary -- allow a handful
         assert abs(n - nw) <= 2 and (got != want).sum() <= 3
+
+
+def test_matching_golden_is_current_and_equals_oracle(oracle):
+    """tests/golden/reference_build_matching.npz: the seeded inputs are still the ones the stored outputs belong to, the
+    compiled reference still produces them, and the oracle equals them"""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(root, "scripts", "make_reference_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(root, "tests", "golden", "reference_build_matching.npz"))
+    cases = mod.matching_cases()
+    for k, v in mod.matching_digests(cases).items():
+        assert str(g["sha1_" + k]) == v, k
+    F, kfs = cases["bow0"]()
+    for i, k in enumerate(kfs):
+        for side in (oracle, ref_api):
+            m, n = side.search_by_bow(oracle.bow_features(k), oracle.bow_features(F), 0.75, True, 0)
+            assert n == g["bow0_n"][i] and np.array_equal(m, g["bow0_match"][i])
+    for i, p in enumerate(cases["pairs"]()):
+        m, n = oracle.search_by_sim3(oracle.kf_view(p["kf1"]), oracle.kf_view(p["kf2"]), p["K"], p["R12"], p["t12"], 7.5, p["matched12_in"])
+        assert n == int(g["sim3s_n_%d" % i]) and np.array_equal(m, g["sim3s_match_%d" % i])
+    for i, c in enumerate(cases["proj"]()):
+        m, n = oracle.search_by_projection(oracle.kf_view(c["frame"]), oracle.kf_view(c["kf"]), c["K"], c["Rcw"], c["tcw"], 10.0, 100, True,
+                                           c["occupied"], c["already_found"])
+        assert n == int(g["proj_n_%d" % i]) and np.array_equal(m, g["proj_match_%d" % i])
+    db, qs = cases["kfdb"]()
+    odb = oracle.kfdb(db)
+    state = np.zeros(db["K"], np.float32)
+    for q, (qw, qv) in enumerate(qs):
+        assert oracle.detect_candidates(odb, qw, qv, mode=0, score_state=state).tolist() == g["kfdb_cand_%d" % q].tolist()
+    assert np.array_equal(state, g["kfdb_state"])

@@ -77,3 +77,53 @@ def test_mlpnp_engine_equals_compiled_reference(engine):
             T = G["mlpnp_T"][c]
             assert np.abs(r["R"].reshape(3, 3) - T[:3, :3]).max() < 1e-6 and np.abs(r["t"] - T[:3, 3]).max() < 1e-6 * max(1.0, np.abs(T[:3, 3]).max()), c
             assert (ml[c] != G["mlpnp_inliers"][c]).sum() <= 1, c
+
+
+# ---- retrieval and matching: tests/golden/reference_build_matching.npz holds the compiled reference's
+# outputs for seeded generator cases (scripts/make_reference_golden.py::matching_cases) and a SHA-1 of the generated inputs
+def _matching():
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(root, "scripts", "make_reference_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(root, "tests", "golden", "reference_build_matching.npz"))
+    cases = mod.matching_cases()
+    dig = mod.matching_digests(cases)
+    for k, v in dig.items():
+        assert str(g["sha1_" + k]) == v, "the seeded generator no longer produces the inputs the golden outputs belong to: " + k
+    return g, cases
+
+
+def test_matching_and_retrieval_engine_equals_compiled_reference(engine):
+    """ORBmatcher::SearchByBoW (both overloads), SearchBySim3, SearchByProjection(Frame, KeyFrame) and
+    KeyFrameDatabase::DetectRelocalizationCandidates: the engine against outputs of the reference's own ORBmatcher.cpp /
+    KeyFrameDatabase.cpp, element for element"""
+    g, cases = _matching()
+    F, kfs = cases["bow0"]()
+    m, n = engine.bow_match([F] + kfs, list(range(1, 7)), [0] * 6, 0.75, True, 0)
+    for i in range(6):
+        assert n[i] == g["bow0_n"][i] and (m[i] == g["bow0_match"][i]).all(), ("bow0", i)
+    cur, kfs1 = cases["bow1"]()
+    m, n = engine.bow_match([cur] + kfs1, [0] * 4, list(range(1, 5)), 0.75, True, 1)
+    for i in range(4):
+        assert n[i] == g["bow1_n"][i] and (m[i] == g["bow1_match"][i]).all(), ("bow1", i)
+    prs = cases["pairs"]()
+    views = [v for p in prs for v in (p["kf1"], p["kf2"])]
+    got, nf = engine.sim3_search(views, [0, 2, 4], [1, 3, 5], [p["K"] for p in prs], [p["R12"] for p in prs], [p["t12"] for p in prs], 7.5,
+                                 [p["matched12_in"] for p in prs])
+    for i in range(3):
+        assert nf[i] == int(g["sim3s_n_%d" % i]) and got[i].tolist() == g["sim3s_match_%d" % i].tolist(), ("sim3 search", i)
+    pj = cases["proj"]()
+    views = [v for c in pj for v in (c["frame"], c["kf"])]
+    got, nm, fell, rounds = engine.proj_search(views, [0, 2, 4], [1, 3, 5], [c["K"] for c in pj], [c["Rcw"] for c in pj], [c["tcw"] for c in pj],
+                                               10.0, 100, True, [c["occupied"] for c in pj], [c["already_found"] for c in pj])
+    for i in range(3):
+        assert nm[i] == int(g["proj_n_%d" % i]) and got[i].tolist() == g["proj_match_%d" % i].tolist(), ("projection search", i)
+    db, qs = cases["kfdb"]()
+    engine.kfdb_upload(db)
+    got = engine.kfdb_detect(qs, mode=0)
+    for q in range(len(qs)):
+        assert got[q].tolist() == g["kfdb_cand_%d" % q].tolist(), ("retrieval", q)
+    assert (engine.kfdb_state().view(np.uint32) == g["kfdb_state"].view(np.uint32)).all()
