@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Randomised differential soak on the GPU box: the CUDA engine (through the C ABI) against the CPU oracle on randomly drawn
 batch shapes, sizes, outlier ratios, RANSAC parameters and engine modes -- PnP (QR / eigen null space x exhaustive / staged
-early exit), Sim3 (fixed / free scale), MLPnP (with / without covariances x exhaustive / staged).  Every record field, pose bit
+early exit), Sim3 (fixed / free scale), MLPnP (with / without covariances x exhaustive / staged), and the matcher /
+retrieval entry points (SearchByBoW, SearchBySim3, SearchByProjection, DetectRelocalization/LoopCandidates).  Every record field, pose bit
 and mask bit is compared for PnP and Sim3; MLPnP (libm on one side, CUDA math on the other) with the tolerances of
 tests/test_gpu_mlpnp.py.  Prints one summary line per family; exits non-zero on the first divergence.
 
@@ -162,9 +163,80 @@ def mlpnp_family():
     assert flips <= max(3, cands // 50)
 
 
+def matching_family():
+    """SearchByBoW, SearchBySim3, SearchByProjection(Frame, KeyFrame), DetectRelocalizationCandidates / DetectLoopCandidates:
+    integer outputs, compared element for element"""
+    t0, nb, ns, npj, nk, matches = time.time(), 0, 0, 0, 0, 0
+    while time.time() - t0 < BUDGET:
+        seed0 = int(rng.integers(1, 2 ** 30))
+        # --- SearchByBoW: one frame / keyframe against several keyframes, both overloads
+        mode = int(rng.integers(0, 2))
+        nf = int(rng.integers(40, 900))
+        F = synth.bow_frame(seed0, nf, int(rng.integers(3, 60)))
+        if mode == 1:
+            F["valid"] = (rng.random(nf) < rng.uniform(0.3, 1.0)).astype(np.uint8)
+        kfs = [synth.bow_keyframe(seed0 + 1 + i, F, int(rng.integers(30, 900)), shared=float(rng.uniform(0.0, 0.6)), flip_bits=int(rng.integers(5, 60)),
+                                  rot=float(rng.uniform(0, 360))) for i in range(int(rng.integers(1, 6)))]
+        orient, ratio = bool(rng.random() < 0.7), float(rng.choice([0.6, 0.75, 0.9]))
+        qs, ts = ([i + 1 for i in range(len(kfs))], [0] * len(kfs)) if mode == 0 else ([0] * len(kfs), [i + 1 for i in range(len(kfs))])
+        m, n = eng.bow_match([F] + kfs, qs, ts, ratio, orient, mode)
+        keeps = [O.bow_features(x) for x in [F] + kfs]
+        for i, (q, t) in enumerate(zip(qs, ts)):
+            w, wn = O.search_by_bow(keeps[q], keeps[t], ratio, orient, mode)
+            assert n[i] == wn and (m[i] == w).all(), ("bow", seed0, i, mode)
+            matches += wn
+        nb += len(kfs)
+        # --- SearchBySim3
+        prs = [synth.kf_view_pair(seed0 + 10 + i, n_points=int(rng.integers(60, 700)), n_extra=int(rng.integers(0, 300)), prematched=float(rng.uniform(0, 0.7)))
+               for i in range(int(rng.integers(1, 4)))]
+        views = [v for p in prs for v in (p["kf1"], p["kf2"])]
+        th = float(rng.choice([3.0, 7.5, 12.0]))
+        k1, k2 = [2 * i for i in range(len(prs))], [2 * i + 1 for i in range(len(prs))]
+        got, nfound = eng.sim3_search(views, k1, k2, [p["K"] for p in prs], [p["R12"] for p in prs], [p["t12"] for p in prs], th, [p["matched12_in"] for p in prs])
+        for i, p in enumerate(prs):
+            w, wn = O.search_by_sim3(O.kf_view(p["kf1"]), O.kf_view(p["kf2"]), p["K"], p["R12"], p["t12"], th, p["matched12_in"])
+            assert nfound[i] == wn and got[i].tolist() == w.tolist(), ("sim3 search", seed0, i)
+            matches += wn
+        ns += len(prs)
+        # --- SearchByProjection(Frame, KeyFrame)
+        cs = [synth.proj_search_case(seed0 + 20 + i, n_points=int(rng.integers(60, 700)), n_extra=int(rng.integers(0, 300))) for i in range(int(rng.integers(1, 4)))]
+        views = [v for c in cs for v in (c["frame"], c["kf"])]
+        thp, od, co = float(rng.choice([3.0, 10.0, 15.0])), int(rng.choice([64, 100])), bool(rng.random() < 0.7)
+        got, nm, fell, rounds = eng.proj_search(views, [2 * i for i in range(len(cs))], [2 * i + 1 for i in range(len(cs))], [c["K"] for c in cs],
+                                                [c["Rcw"] for c in cs], [c["tcw"] for c in cs], thp, od, co, [c["occupied"] for c in cs], [c["already_found"] for c in cs])
+        for i, c in enumerate(cs):
+            w, wn = O.search_by_projection(O.kf_view(c["frame"]), O.kf_view(c["kf"]), c["K"], c["Rcw"], c["tcw"], thp, od, co, c["occupied"], c["already_found"])
+            assert nm[i] == wn and got[i].tolist() == w.tolist(), ("projection search", seed0, i)
+            matches += wn
+        npj += len(cs)
+        # --- candidate retrieval: a query sequence against one database, relocalisation mode with carried state, then loop mode
+        Kdb, places = int(rng.integers(20, 400)), int(rng.integers(2, 30))
+        db = synth.kf_database(seed0 % 100000, K=Kdb, n_places=places, words_per_kf=int(rng.integers(100, 900)))
+        odb = O.kfdb(db)
+        eng.kfdb_upload(db)
+        state = np.zeros(db["K"], np.float32)
+        qsq = [synth.kf_query(seed0 + 40 + q, db, place=int(rng.integers(0, places))) for q in range(int(rng.integers(1, 8)))]
+        got = eng.kfdb_detect(qsq, mode=0)
+        for q, (qw, qv) in enumerate(qsq):
+            assert got[q].tolist() == O.detect_candidates(odb, qw, qv, mode=0, score_state=state).tolist(), ("retrieval", seed0, q)
+        assert (eng.kfdb_state().view(np.uint32) == state.view(np.uint32)).all(), ("retrieval state", seed0)
+        ql = [int(x) for x in rng.integers(0, Kdb, int(rng.integers(1, 5)))]
+        sl = lambda c: slice(db["bow_off"][c], db["bow_off"][c + 1])
+        loopq = [(db["bow_word"][sl(q)], db["bow_val"][sl(q)]) for q in ql]
+        conns = [[int(c) for c in db["covis"][q] if c >= 0] + [q] for q in ql]
+        mss = [float(rng.choice([0.0, 0.01, 0.05])) for _ in ql]
+        got = eng.kfdb_detect(loopq, mode=1, min_score=mss, conn=conns)
+        for i, q in enumerate(ql):
+            assert got[i].tolist() == O.detect_candidates(odb, loopq[i][0], loopq[i][1], mode=1, conn=conns[i], min_score=mss[i]).tolist(), ("loop retrieval", seed0, i)
+        nk += len(qsq) + len(ql)
+    print("match : %d SearchByBoW pairs, %d SearchBySim3 pairs, %d SearchByProjection cases (%d matches in all), %d retrieval queries: "
+          "match arrays, candidate lists (order included) and carried score state equal to the oracle's" % (nb, ns, npj, matches, nk))
+
+
 if __name__ == "__main__":
     print("differential soak, %.0f s per family, %d oracle threads, device %s" % (BUDGET, THREADS, "cuda:0"))
     pnp_family()
     sim3_family()
     mlpnp_family()
+    matching_family()
     print("soak ok")
