@@ -156,6 +156,10 @@ public:
     void SetSeed(uint32_t seed) { seed_ = seed; table_.clear(); cached_ = false; epoch_ = 0; }
     // explicit minimal sets, H x minSet indices into the compact correspondence list
     void SetIndexTable(const std::vector<uint32_t>& t) { table_ = t; cached_ = false; epoch_ = 0; }
+    // engine mode bits ORed into every run of this solver, e.g. RSAC_FLAG_EPNP_EIGEN: the reference's own 12 x 12
+    // eigen-solve per hypothesis instead of the default QR null space -- with it the class returns
+    // what the reference's PnPsolver returns bit for bit (tests/cpp/dropin_vs_reference.cpp)
+    void SetEngineFlags(int flags) { flags_ = flags; cached_ = false; epoch_ = 0; }
 
     // PnPsolver.cpp:96-100
     bool find(std::vector<bool>& vbInliers, int& nInliers, Matrix4f& T)
@@ -187,7 +191,7 @@ public:
             ensure_resident();
             if (cursor_ > 0) {
                 int32_t resume = cursor_;
-                check(rsac_pnp_rerun(eng_->handle(), 0, &resume, nullptr), eng_->handle(), "rsac_pnp_rerun");
+                check(rsac_pnp_rerun(eng_->handle(), flags_, &resume, nullptr), eng_->handle(), "rsac_pnp_rerun");
             }
             check(rsac_pnp_download(eng_->handle(), &r, words.data()), eng_->handle(), "rsac_pnp_download");
         }
@@ -250,7 +254,7 @@ public:
         std::vector<uint32_t> masks((size_t)std::max<int64_t>(nwords, 1));
         // early exit in phases: identical records, hypotheses behind the reference's stopping point are not computed
         // (batches too small to fill one solver wave run all hypotheses at once)
-        check(rsac_pnp_solve(eng->handle(), &b, RSAC_FLAG_EARLY_EXIT, res.data(), masks.data()), eng->handle(), "rsac_pnp_solve");
+        check(rsac_pnp_solve(eng->handle(), &b, RSAC_FLAG_EARLY_EXIT | solvers[0]->flags_, res.data(), masks.data()), eng->handle(), "rsac_pnp_solve");
         eng->next_epoch();
         size_t w0 = 0;
         for (int c = 0; c < C; ++c) {
@@ -279,7 +283,7 @@ private:
         int64_t toff[2] = {0, (int64_t)table_.size()};
         if (!table_.empty()) { b.tables = table_.data(); b.table_offsets = toff; }
         check(rsac_pnp_upload(eng_->handle(), &b), eng_->handle(), "rsac_pnp_upload");
-        check(rsac_pnp_run(eng_->handle(), 0, nullptr), eng_->handle(), "rsac_pnp_run");
+        check(rsac_pnp_run(eng_->handle(), flags_, nullptr), eng_->handle(), "rsac_pnp_run");
         epoch_ = eng_->next_epoch();
     }
 
@@ -291,6 +295,7 @@ private:
     rsac_ransac_params prm_;
     int mRansacMinInliers = 0, mRansacMaxIts = 0;
     uint32_t seed_ = 1;     // glibc: an unseeded rand() behaves like srand(1)
+    int flags_ = 0;         // SetEngineFlags
     std::vector<uint32_t> table_;
     int cursor_ = 0;        // hypotheses consumed so far (mnIterations)
     uint64_t epoch_ = 0;
