@@ -9,13 +9,16 @@
 // The drop-in runs with RSAC_FLAG_EPNP_EIGEN (the reference's own 12 x 12 eigen-solve per hypothesis); rand() is
 // seeded identically on both sides (the reference: srand through DUtils::Random::SeedRand; the drop-in: SetSeed).
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
+#include <string>
 #include <fstream>
 #include <memory>
 #include <vector>
 
 #include "PnPsolver.hpp"      // the reference's header (oracle/_ref/inc/ -> /root/reference/include/PnPsolver.hpp)
 #include "Sim3Solver.hpp"     // the reference's header
+#include "MLPnPsolver.hpp"    // the reference's header
 #include "ransac_b200/solvers.hpp"
 
 namespace rb = ransac_b200;
@@ -78,7 +81,9 @@ template <typename T> static void rd(std::ifstream& f, T* p, size_t n) { f.read(
 
 static int fail(const char* what, int call) { std::printf("{\"equal\":0,\"where\":\"%s\",\"call\":%d}\n", what, call); return 1; }
 
-static int run_pnp(std::ifstream& f)
+// MODE 0: PnPsolver (bit for bit); MODE 1: MLPnPsolver (return values, counts and inlier vectors exact; the pose to 1e-6 relative:
+// the 6-point solve runs sin / cos / acos of the device's libm, tests/test_gpu_mlpnp.py states the same tolerance)
+template <int MODE> static int run_pnp(std::ifstream& f)
 {
     int n; float K[4];
     rd(f, &n, 1); rd(f, K, 4);
@@ -100,29 +105,47 @@ static int run_pnp(std::ifstream& f)
             mps[i]->mbBad = state[i] == 2;
         }
     }
-    // reference
-    ORB_SLAM_CUSTOM::PnPsolver ref(F, mps);
-    ref.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);
-    // drop-in
     FrameSnapshot snap(F, mps);
-    rb::PnPsolver dr(snap.F, snap.M);
-    dr.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);
-    dr.SetSeed(seed);
-    dr.SetEngineFlags(RSAC_FLAG_EPNP_EIGEN);
-    DUtils::Random::SeedRand((int)seed);
-    // the first iterate(step) consumes the whole budget on both sides (the `||` of PnPsolver.cpp:119); calls after a
-    // Refine() are not compared: there the as-shipped reference sums stale rows, the drop-in does not
-    std::vector<bool> in_r, in_d; int n_r = 0, n_d = 0; bool nm_r = false, nm_d = false;
+    // the first iterate(step) consumes the whole budget on both sides (the `||` of PnPsolver.cpp:119 / MLPnPsolver.cpp:71); calls
+    // after a Refine() are not compared: there the as-shipped PnPsolver sums stale rows, the drop-in does not
+    std::vector<bool> in_r, in_d; int n_r = 0, n_d = 0; bool nm_r = false, nm_d = false, ok_r, ok_d;
     Eigen::Matrix4f T_r; rb::Matrix4f T_d;
-    const bool ok_r = ref.iterate(step, nm_r, in_r, n_r, T_r);
-    const bool ok_d = dr.iterate(step, nm_d, in_d, n_d, T_d);
-    if (ok_r != ok_d || nm_r != nm_d || n_r != n_d) return fail("pnp return values", 0);
-    if (ok_r) {
-        if (in_r.size() != in_d.size()) return fail("pnp inlier vector length", 0);
-        for (size_t i = 0; i < in_r.size(); ++i) if (in_r[i] != in_d[i]) return fail("pnp inlier vector", 0);
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) if (T_r(i, j) != T_d(i, j)) return fail("pnp pose", 0);
+    if (MODE == 0) {
+        ORB_SLAM_CUSTOM::PnPsolver ref(F, mps);
+        ref.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);
+        rb::PnPsolver dr(snap.F, snap.M);
+        dr.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);
+        dr.SetSeed(seed);
+        dr.SetEngineFlags(RSAC_FLAG_EPNP_EIGEN);
+        DUtils::Random::SeedRand((int)seed);
+        ok_r = ref.iterate(step, nm_r, in_r, n_r, T_r);
+        ok_d = dr.iterate(step, nm_d, in_d, n_d, T_d);
+    } else {
+        ORB_SLAM_CUSTOM::MLPnPsolver ref(F, mps);
+        ref.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);
+        rb::MLPnPsolver dr(snap.F, snap.M);
+        dr.SetRansacParameters(prob, minInl, maxIts, minSet, eps, th2);
+        dr.SetSeed(seed);
+        dr.SetDiscardRefine(true);                          // MLPnPsolver::Refine as shipped never stores its pose
+        DUtils::Random::SeedRand((int)seed);
+        ok_r = ref.iterate(step, nm_r, in_r, n_r, T_r);
+        ok_d = dr.iterate(step, nm_d, in_d, n_d, T_d);
     }
-    std::printf("{\"equal\":1,\"ok\":%d,\"noMore\":%d,\"nInliers\":%d}\n", (int)ok_r, (int)nm_r, n_r);
+    if (ok_r != ok_d || nm_r != nm_d || n_r != n_d) return fail("return values", 0);
+    double worst = 0.0;
+    if (ok_r) {
+        if (in_r.size() != in_d.size()) return fail("inlier vector length", 0);
+        for (size_t i = 0; i < in_r.size(); ++i) if (in_r[i] != in_d[i]) return fail("inlier vector", 0);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) {
+            if (MODE == 0) { if (T_r(i, j) != T_d(i, j)) return fail("pose", 0); }
+            else {
+                const double d = std::fabs((double)T_r(i, j) - (double)T_d(i, j)) / (1.0 + std::fabs((double)T_r(i, j)));
+                if (d > worst) worst = d;
+            }
+        }
+        if (worst > 1e-6) return fail("pose tolerance", 0);
+    }
+    std::printf("{\"equal\":1,\"ok\":%d,\"noMore\":%d,\"nInliers\":%d,\"pose_dev\":%.3g}\n", (int)ok_r, (int)nm_r, n_r, worst);
     return 0;
 }
 
@@ -179,11 +202,12 @@ static int run_sim3(std::ifstream& f)
 
 int main(int argc, char** argv)
 {
-    if (argc < 3) { std::fprintf(stderr, "usage: dropin_vs_reference pnp|sim3 file\n"); return 2; }
+    if (argc < 3) { std::fprintf(stderr, "usage: dropin_vs_reference pnp|mlpnp|sim3 file\n"); return 2; }
     std::ifstream f(argv[2], std::ios::binary);
     if (!f) { std::fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
     try {
-        return std::string(argv[1]) == "pnp" ? run_pnp(f) : run_sim3(f);
+        const std::string mode(argv[1]);
+        return mode == "pnp" ? run_pnp<0>(f) : mode == "mlpnp" ? run_pnp<1>(f) : run_sim3(f);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return 3;

@@ -38,31 +38,51 @@ def _run(driver, mode, blob, tmp_path, tag):
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
+def _frame_blob(seed, n, outl, prm):
+    """a Frame with n matched keypoints among n + 120 slots (unmatched slots and bad map points in between)"""
+    s2 = synth.level_sigma2()
+    p = synth.pnp_problem(seed, n, outl)
+    rng = np.random.default_rng(seed)
+    n_slots = n + 120
+    slot_of = np.sort(rng.permutation(n_slots)[:n])
+    xy = rng.uniform(0, 700, size=(n_slots, 2)).astype(np.float32)
+    octave = rng.integers(0, 8, size=n_slots).astype(np.int32)
+    state = np.zeros(n_slots, np.uint8)
+    state[rng.permutation(n_slots)[:40]] = 2                      # bad map points on unrelated keypoints
+    world = rng.normal(size=(n_slots, 3)).astype(np.float32)
+    xy[slot_of], octave[slot_of], state[slot_of], world[slot_of] = p["p2d"], p["octave"], 1, p["p3d"]
+    K = np.array(p["K"], np.float32)
+    blob = struct.pack("<i", n_slots) + K.tobytes() + xy.tobytes() + octave.tobytes() + state.tobytes() + world.tobytes() + s2.tobytes()
+    return blob + struct.pack("<diiiffIi", prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], seed, 5)
+
+
 def test_pnpsolver_class_equals_reference_class(dropin, tmp_path):
     """Tracking::Relocalization's call on each candidate: SetRansacParameters(0.99, 10, 300, 4, 0.5, 5.991), iterate(5, ...)"""
-    s2 = synth.level_sigma2()
     n_ok = 0
     cases = [(4000 + i, 500, 0.5, (0.99, 10, 300, 4, 0.2, 5.991)) for i in range(8)]            # cfg4
     cases += [(12000 + i, 200, 0.3, (0.99, 10, 300, 4, 0.5, 5.991)) for i in range(6)]          # Tracking.cpp:1228
     cases += [(7300, 30, 0.4, (0.99, 10, 300, 4, 0.2, 5.991)), (7301, 9, 0.0, (0.99, 10, 300, 4, 0.2, 5.991))]
     for seed, n, outl, prm in cases:
-        p = synth.pnp_problem(seed, n, outl)
-        rng = np.random.default_rng(seed)
-        n_slots = n + 120
-        slot_of = np.sort(rng.permutation(n_slots)[:n])
-        xy = rng.uniform(0, 700, size=(n_slots, 2)).astype(np.float32)
-        octave = rng.integers(0, 8, size=n_slots).astype(np.int32)
-        state = np.zeros(n_slots, np.uint8)
-        state[rng.permutation(n_slots)[:40]] = 2                      # bad map points on unrelated keypoints
-        world = rng.normal(size=(n_slots, 3)).astype(np.float32)
-        xy[slot_of], octave[slot_of], state[slot_of], world[slot_of] = p["p2d"], p["octave"], 1, p["p3d"]
-        K = np.array(p["K"], np.float32)
-        blob = struct.pack("<i", n_slots) + K.tobytes() + xy.tobytes() + octave.tobytes() + state.tobytes() + world.tobytes() + s2.tobytes()
-        blob += struct.pack("<diiiffIi", prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], seed, 5)
-        r = _run(dropin, "pnp", blob, tmp_path, str(seed))
+        r = _run(dropin, "pnp", _frame_blob(seed, n, outl, prm), tmp_path, str(seed))
         assert r["equal"] == 1, (seed, r)
         n_ok += r["ok"]
     assert n_ok >= 12
+
+
+def test_mlpnpsolver_class_equals_reference_class(dropin, tmp_path):
+    """MLPnPsolver (MLPnPsolver.hpp:14-21) driven like PnPsolver: return values, inlier count and inlier vector equal, pose
+    within 1e-6 relative (device libm in the 6-point solve; the driver states the tolerance)"""
+    n_ok = 0
+    worst = 0.0
+    cases = [(21000 + i, 1000, 0.4, (0.99, 10, 300, 6, 0.5, 5.991)) for i in range(4)]          # cfg2
+    cases += [(22000 + i, 200, 0.3, (0.99, 10, 300, 6, 0.5, 5.991)) for i in range(6)]
+    cases += [(23000, 40, 0.3, (0.99, 8, 300, 6, 0.4, 5.991)), (23001, 7, 0.0, (0.99, 8, 300, 6, 0.4, 5.991))]
+    for seed, n, outl, prm in cases:
+        r = _run(dropin, "mlpnp", _frame_blob(seed, n, outl, prm), tmp_path, str(seed))
+        assert r["equal"] == 1, (seed, r)
+        n_ok += r["ok"]
+        worst = max(worst, r["pose_dev"])
+    assert n_ok >= 4 and worst <= 1e-6       # how many frames verify is the generator's business; each one compared equal above
 
 
 def test_sim3solver_class_equals_reference_class(dropin, tmp_path):
