@@ -188,7 +188,12 @@ def run_reference(args):
             ev_tot += ev
             n_tot += len(pbs)
     val = n_tot / t_tot
-    compiled = compiled_reference_leg(blocks_raw[0], cores) if os.environ.get("RSAC_BENCH_COMPILED_REF", "1") == "1" else None
+    compiled = None
+    if os.environ.get("RSAC_BENCH_COMPILED_REF", "1") == "1":
+        try:
+            compiled = compiled_reference_leg(blocks_raw[0], cores)
+        except Exception as err:
+            compiled = {"unavailable": repr(err)}
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "candidates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 solve / f32 score",
@@ -247,7 +252,13 @@ def compiled_reference_leg(bj, cores):
     procs = [ctx.Process(target=_compiled_ref_worker, args=(bj, min(n, w * per), min(n, (w + 1) * per), barrier, out)) for w in range(nproc)]
     for q in procs:
         q.start()
-    got = [out.get(timeout=600) for _ in procs]
+    try:
+        got = [out.get(timeout=120) for _ in procs]
+    except Exception as err:                                # a worker died: report it, never lose the reference line over this leg
+        for q in procs:
+            if q.is_alive():
+                q.kill()
+        return {"unavailable": "compiled-reference worker failed: %r" % (err,)}
     for q in procs:
         q.join()
     wall = max(g[1] for g in got) - min(g[0] for g in got)
